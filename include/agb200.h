@@ -1,0 +1,231 @@
+/*
+ * agb200.h — C ABI of the B200-native (sm_100a) execution backend for rust-autograd's
+ * op-evaluation hot path.
+ *
+ * This is the drop-in boundary: every function below is what a built-in
+ * `Op::compute` (reference `src/op.rs:90-101`, called from `src/evaluation.rs:323-324`) binds through
+ * a thin `extern "C"` module — the same seam where the reference declares its optional CPU
+ * accelerator today (`src/tensor_ops/blas_ffi.rs:17-158`, `cblas_sgemm` call sites
+ * `src/tensor_ops/dot_ops.rs:209-224`).  Plain pointers and sizes only: no torch types, no C++.
+ *
+ * Conventions
+ *   - All tensors are f32 in device memory (HBM).  Index-valued tensors (argmax, pool indices,
+ *     labels, gather ids) are f32 too, exactly as in the reference (`src/ndarray_ext.rs:29-31`).
+ *   - `agb_tensor` = borrowed device view {ptr, rank, shape, stride}; strides are in ELEMENTS and
+ *     may be 0 (broadcast) or permuted (transpose views), mirroring `NdArrayView`.
+ *   - Outputs are caller-allocated, C-contiguous unless stated otherwise.
+ *   - Every call is asynchronous on the context's CUDA stream; only agb_d2h / agb_sync block.
+ *   - Return value: 0 = ok; 1..5 = the five `OpError` variants of `src/op.rs:67-73`;
+ *     >= 100 = CUDA / NCCL / driver failure.  `agb_last_error()` gives the message.
+ *   - There is no CPU fallback: without a CUDA device agb_init fails with AGB_ERR_CUDA.
+ */
+#ifndef AGB200_H
+#define AGB200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define AGB_MAX_RANK 8
+
+/* ---- status codes (1..5 mirror OpError, src/op.rs:67-73) ---- */
+enum {
+  AGB_OK = 0,
+  AGB_ERR_NDARRAY = 1,            /* OpError::NdArrayError      */
+  AGB_ERR_INCOMPATIBLE_SHAPE = 2, /* OpError::IncompatibleShape */
+  AGB_ERR_TYPE_UNSUPPORTED = 3,   /* OpError::TypeUnsupported   */
+  AGB_ERR_INVALID_DIMS = 4,       /* OpError::InvalidDims       */
+  AGB_ERR_OUT_OF_BOUNDS = 5,      /* OpError::OutOfBounds       */
+  AGB_ERR_CUDA = 100,
+  AGB_ERR_NCCL = 101,
+  AGB_ERR_UNSUPPORTED = 102       /* shape/stride combination the device path rejects */
+};
+
+typedef struct agb_ctx agb_ctx;
+
+typedef struct agb_tensor {
+  float*  ptr;
+  int32_t rank;
+  int64_t shape[AGB_MAX_RANK];
+  int64_t stride[AGB_MAX_RANK]; /* elements */
+} agb_tensor;
+
+/* ---- GEMM / conv arithmetic modes (north_star: "f32-faithful 3xTF32 mode and a plain TF32 mode") ---- */
+enum {
+  AGB_MATH_3XTF32 = 0, /* tcgen05 kind::tf32, hi/lo split, 3 MMAs per product: ~1e-6 rel  */
+  AGB_MATH_TF32   = 1, /* tcgen05 kind::tf32, single MMA: ~1e-3 rel                       */
+  AGB_MATH_FP32   = 2  /* CUDA-core FMA path (also used automatically for shapes TMA rejects) */
+};
+
+/* ======================= runtime ======================= */
+/* one host thread <-> one context <-> one CUDA stream (SURVEY §8b "Threading") */
+int  agb_init(int device, agb_ctx** out);
+int  agb_destroy(agb_ctx* ctx);
+const char* agb_last_error(void);
+int  agb_device_count(int* out);
+int  agb_sm_count(agb_ctx* ctx, int* out);
+int  agb_set_math_mode(agb_ctx* ctx, int mode);
+int  agb_get_math_mode(agb_ctx* ctx, int* mode);
+/* number of kernels this library has launched on ctx since agb_init (bench "gpu_launches") */
+int  agb_launch_count(agb_ctx* ctx, int64_t* out);
+
+int  agb_alloc(agb_ctx* ctx, size_t bytes, void** out);    /* stream-ordered caching arena */
+int  agb_free(agb_ctx* ctx, void* ptr);
+int  agb_trim(agb_ctx* ctx);                                /* release cached blocks to the driver */
+int  agb_mem_stats(agb_ctx* ctx, size_t* live_bytes, size_t* cached_bytes, size_t* peak_bytes);
+int  agb_host_alloc(size_t bytes, void** out);              /* pinned host memory for feeds */
+int  agb_host_free(void* ptr);
+int  agb_h2d(agb_ctx* ctx, void* dst, const void* src, size_t bytes); /* async on ctx stream */
+int  agb_d2h(agb_ctx* ctx, void* dst, const void* src, size_t bytes); /* async + stream sync  */
+int  agb_d2d(agb_ctx* ctx, void* dst, const void* src, size_t bytes);
+int  agb_memset0(agb_ctx* ctx, void* dst, size_t bytes);
+int  agb_sync(agb_ctx* ctx);
+int  agb_flush_l2(agb_ctx* ctx);                            /* writes a >L2 scratch buffer */
+
+/* CUDA-event timing on the context's own stream (torch.cuda.Event would not see it) */
+int  agb_event_create(void** ev);
+int  agb_event_destroy(void* ev);
+int  agb_event_record(agb_ctx* ctx, void* ev);
+int  agb_event_elapsed_ms(void* start, void* stop, float* ms); /* synchronises on stop */
+
+/* CUDA-graph capture of a launch sequence */
+int  agb_graph_begin(agb_ctx* ctx);
+int  agb_graph_end(agb_ctx* ctx, void** graph_exec);
+int  agb_graph_launch(agb_ctx* ctx, void* graph_exec);
+int  agb_graph_destroy(void* graph_exec);
+
+/* ======================= dense contractions ======================= */
+/* replaces MatMul::compute / BatchMatMul::compute (src/tensor_ops/dot_ops.rs:565-606, 632-695) and the
+ * cblas_sgemm / matrixmultiply::sgemm call sites (dot_ops.rs:209-224, 400).
+ * a, b: rank-2 (or rank>=3 with identical leading batch dims) views, any strides;
+ * c: C-contiguous [.., m, n].  beta in {0,1}.  Transposes are applied to the LAST TWO axes. */
+int  agb_gemm_f32(agb_ctx* ctx, int trans_a, int trans_b,
+                  const agb_tensor* a, const agb_tensor* b, agb_tensor* c, float beta);
+
+/* replaces Conv2D::compute (conv_ops/conv2d.rs:532-554): x [B,C,H,W], w [O,C,kh,kw] -> y [B,O,yh,yw].
+ * Implicit GEMM: the im2col buffer (conv_ops/mod.rs:73-124) is never materialised. */
+int  agb_conv2d_fprop_f32(agb_ctx* ctx, const agb_tensor* x, const agb_tensor* w, agb_tensor* y,
+                          int pad, int stride, int dilation);
+/* replaces Conv2DTranspose::compute (conv_ops/conv2d_transpose.rs:250-272): gy [B,O,yh,yw],
+ * w [O,C,kh,kw] -> gx [B,C,xh,xw], xh = s(yh-1) - 2p + d(kh-1) + 1 (conv2d_transpose.rs:55-56). */
+int  agb_conv2d_dgrad_f32(agb_ctx* ctx, const agb_tensor* gy, const agb_tensor* w, agb_tensor* gx,
+                          int pad, int stride, int dilation);
+/* replaces Conv2DFilterGrad::compute (conv2d.rs:737-744) and Conv2DTransposeFilterGrad::compute
+ * (conv2d_transpose.rs:433-451): gw[O,C,kh,kw] = sum_b g[b] (x) im2col(img[b]).
+ * img [B,C,H,W] is the tensor that gets im2col'd, g [B,O,yh,yw] the one that multiplies it. */
+int  agb_conv2d_wgrad_f32(agb_ctx* ctx, const agb_tensor* img, const agb_tensor* g, agb_tensor* gw,
+                          int pad, int stride, int dilation);
+/* materialise im2col(x) = Conv2D output #1, [B,C,kh,kw,yh,yw] (only when user code evaluates it) */
+int  agb_im2col_f32(agb_ctx* ctx, const agb_tensor* x, agb_tensor* cols, int kh, int kw,
+                    int pad, int stride, int dilation);
+
+/* ======================= pooling ======================= */
+/* MaxPool2D::compute (conv_ops/max_pool2d.rs:166-227): strict '>' scan, index = flat offset into the
+ * whole input, stored as float in idx_f32 (may be NULL) and as int32 in idx_i32 (may be NULL). */
+int  agb_maxpool2d_fwd(agb_ctx* ctx, const agb_tensor* x, agb_tensor* y, float* idx_f32, int32_t* idx_i32,
+                       int size, int pad, int stride);
+/* MaxPool2DGrad::compute (max_pool2d.rs:245-279): gx = 0; gx[idx[i]] += gy[i]. exactly one of idx_* non-NULL */
+int  agb_maxpool2d_bwd(agb_ctx* ctx, const agb_tensor* gy, const float* idx_f32, const int32_t* idx_i32,
+                       agb_tensor* gx);
+/* MaxPool2DGradGrad::compute (max_pool2d.rs:297-331): ggy[i] = ggx[idx[i]] */
+int  agb_maxpool2d_gradgrad(agb_ctx* ctx, const agb_tensor* ggx, const float* idx_f32, const int32_t* idx_i32,
+                            agb_tensor* ggy);
+
+/* ======================= elementwise ======================= */
+enum { /* unary ops: math_ops.rs:277-1019, activation_ops.rs:113-226, array_ops.rs:537-574 */
+  AGB_U_COPY = 0, AGB_U_ABS, AGB_U_NEG, AGB_U_SQUARE, AGB_U_INV, AGB_U_INVSQRT, AGB_U_SIGN, AGB_U_FLOOR,
+  AGB_U_CEIL, AGB_U_SQRT, AGB_U_POW /*p0*/, AGB_U_LN, AGB_U_LOG2, AGB_U_LOG10, AGB_U_EXP, AGB_U_EXP2,
+  AGB_U_EXP10, AGB_U_SIN, AGB_U_COS, AGB_U_TAN, AGB_U_ASIN, AGB_U_ACOS, AGB_U_ATAN, AGB_U_SINH, AGB_U_COSH,
+  AGB_U_TANH, AGB_U_ASINH, AGB_U_ACOSH, AGB_U_ATANH, AGB_U_SIGMOID, AGB_U_RELU, AGB_U_SOFTPLUS,
+  AGB_U_ELU /*p0=alpha*/, AGB_U_CLIP /*p0=min,p1=max*/, AGB_U_SCALE /* x*p0 */, AGB_U_ADD_SCALAR /* x+p0 */,
+  AGB_U_RSUB_SCALAR /* p0-x */, AGB_U_RDIV_SCALAR /* p0/x */, AGB_U_COUNT
+};
+enum { /* binary ops: binary_ops.rs:147-290, math_ops.rs:86-184, activation_ops.rs:204-226, array_ops.rs:556-574 */
+  AGB_B_ADD = 0, AGB_B_SUB, AGB_B_MUL, AGB_B_DIV, AGB_B_EQ, AGB_B_NE, AGB_B_GT, AGB_B_LT, AGB_B_GE, AGB_B_LE,
+  AGB_B_MAX, AGB_B_MIN, AGB_B_ELU_GRAD /* (x, gy), p0=alpha */, AGB_B_CLIP_GRAD /* (x, gy), p0,p1 */,
+  AGB_B_SIGMOID_XENT /* (x, t) xent_ops.rs:33-46 */, AGB_B_RELU_GRAD /* (x, gy): (x>0)*gy */,
+  AGB_B_COUNT
+};
+/* y = f(x); x may be any strided view, y is C-contiguous with x's shape */
+int  agb_unary(agb_ctx* ctx, int op, float p0, float p1, const agb_tensor* x, agb_tensor* y);
+/* y = f(a, b) with numpy-style broadcasting expressed by the caller as zero strides: a and b must
+ * already have y's rank and shape (stride 0 on broadcast axes). */
+int  agb_binary(agb_ctx* ctx, int op, float p0, float p1, const agb_tensor* a, const agb_tensor* b, agb_tensor* y);
+/* AddN::compute (array_ops.rs:503-528): y = xs[0] + ... + xs[n-1], all same shape, left fold */
+int  agb_add_n(agb_ctx* ctx, int n, const agb_tensor* const* xs, agb_tensor* y);
+int  agb_fill(agb_ctx* ctx, agb_tensor* y, float value);
+/* dst (any strides, e.g. a sliced region of a larger buffer) <- src (any strides), same shape.
+ * Serves deep_copy, Concat/Tile, SliceGrad/SplitGrad (array_ops.rs:576-825), MaybeBroadcast. */
+int  agb_copy_strided(agb_ctx* ctx, const agb_tensor* src, agb_tensor* dst);
+/* Dropout::compute (random_ops.rs:218-237): train: y = x*mask (NOT rescaled); mask is supplied in
+ * `mask` when seed==0, otherwise generated on device (Philox, (seed,offset)) and written to `mask`. */
+int  agb_dropout(agb_ctx* ctx, const agb_tensor* x, agb_tensor* y, agb_tensor* mask,
+                 float ratio, uint64_t seed, uint64_t offset);
+
+/* ======================= reductions ======================= */
+enum { AGB_R_SUM = 0, AGB_R_MEAN, AGB_R_PROD, AGB_R_MIN, AGB_R_MAX };
+/* impl_reduce_forward!/ReduceMean (reduction_ops.rs:54-108,187-215): x is viewed as [outer, r, inner]
+ * (C-contiguous), reduced over r into y [outer, inner].  Multi-axis reductions are expressed by the
+ * caller as one call per contiguous axis group, highest axis first, like the reference's fold order. */
+int  agb_reduce(agb_ctx* ctx, int op, const float* x, float* y, int64_t outer, int64_t r, int64_t inner);
+/* ArgMax/ArgMin (reduction_ops.rs:365-457): first occurrence, result as float */
+int  agb_argreduce(agb_ctx* ctx, int is_max, const float* x, float* y, int64_t outer, int64_t r, int64_t inner);
+
+/* ======================= softmax family ======================= */
+/* softmax_impl (activation_ops.rs:61-96), LogSoftmax (xent_ops.rs:17-22), logsumexp_forward
+ * (math_ops.rs:540-593), all over [outer, r, inner] reducing r */
+int  agb_softmax(agb_ctx* ctx, const float* x, float* y, int64_t outer, int64_t r, int64_t inner);
+int  agb_log_softmax(agb_ctx* ctx, const float* x, float* y, int64_t outer, int64_t r, int64_t inner);
+int  agb_logsumexp(agb_ctx* ctx, const float* x, float* y, int64_t outer, int64_t r, int64_t inner);
+/* SparseSoftmaxCrossEntropy::compute (xent_ops.rs:63-113): logits [B,C], labels [B] as float ->
+ * loss [B] (= [B,1]), log_x [B,C] */
+int  agb_sparse_xent_fwd(agb_ctx* ctx, const float* logits, const float* labels, float* loss, float* log_x,
+                         int64_t batch, int64_t classes);
+/* SparseSoftmaxCrossEntropyGrad::compute (xent_ops.rs:139-152): gx = (exp(log_x) - onehot(t)) * gy,
+ * gy has gy_len elements (B or 1) and is broadcast over classes */
+int  agb_sparse_xent_bwd(agb_ctx* ctx, const float* log_x, const float* labels, const float* gy, int64_t gy_len,
+                         float* gx, int64_t batch, int64_t classes);
+/* SoftmaxCrossEntropy::compute (xent_ops.rs:160-177): dense labels t [B,C] -> loss [B], log_x [B,C] */
+int  agb_softmax_xent_fwd(agb_ctx* ctx, const float* logits, const float* t, float* loss, float* log_x,
+                          int64_t batch, int64_t classes);
+
+/* ======================= gather / scatter ======================= */
+/* Gather::compute (array_ops.rs:353-384): param viewed as [pre, axis_len, post] (C-contiguous),
+ * out [pre, n_idx, post]; negative indices are wrapped when normalize_negative != 0 */
+int  agb_gather(agb_ctx* ctx, const float* param, const float* indices, float* out,
+                int64_t pre, int64_t axis_len, int64_t post, int64_t n_idx, int normalize_negative);
+/* GatherGrad::compute (array_ops.rs:401-466): gx = 0; gx[:, idx[j], :] += gy[:, j, :] */
+int  agb_gather_grad(agb_ctx* ctx, const float* gy, const float* indices, float* gx,
+                     int64_t pre, int64_t axis_len, int64_t post, int64_t n_idx);
+
+/* ======================= optimizers ======================= */
+/* One fused multi-tensor launch replaces n AdamOp::compute calls (gradient_descent_ops/adam.rs:11-58):
+ * m = b1 m + (1-b1) g; v = b2 v + (1-b2) g^2; p -= alpha * (m/(1-b1^t)) / (sqrt(v/(1-b2^t)) + eps); t += 1.
+ * t[i] points at the per-variable 0-d step counter living in HBM (optimizers/adam.rs:97).
+ * grad_scale multiplies g on read (1/world after the NCCL sum; 1.0 on one GPU). */
+int  agb_multi_tensor_adam(agb_ctx* ctx, int n, float* const* p, const float* const* g, float* const* m,
+                           float* const* v, float* const* t, const int64_t* sizes,
+                           float alpha, float eps, float b1, float b2, float grad_scale);
+/* SGDOp (sgd.rs:14-26): p -= alpha*g */
+int  agb_multi_tensor_sgd(agb_ctx* ctx, int n, float* const* p, const float* const* g, const int64_t* sizes,
+                          float alpha, float grad_scale);
+/* MomentumSGDOp (sgd.rs:28-40): v = momentum*v - lr*g; p += v */
+int  agb_multi_tensor_momentum(agb_ctx* ctx, int n, float* const* p, const float* const* g, float* const* v,
+                               const int64_t* sizes, float lr, float momentum, float grad_scale);
+/* AdaGradOp (adagrad.rs:8-21): h += g^2; p -= lr*g/(sqrt(h)+1e-7) */
+int  agb_multi_tensor_adagrad(agb_ctx* ctx, int n, float* const* p, const float* const* g, float* const* h,
+                              const int64_t* sizes, float lr, float grad_scale);
+
+/* ======================= data parallel ======================= */
+int  agb_nccl_unique_id(void* id128);                           /* rank 0: fills 128 bytes */
+int  agb_nccl_init(agb_ctx* ctx, int rank, int world, const void* id128);
+int  agb_allreduce_sum(agb_ctx* ctx, float* buf, int64_t n);    /* in place, on ctx stream */
+int  agb_nccl_destroy(agb_ctx* ctx);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* AGB200_H */

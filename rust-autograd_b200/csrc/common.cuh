@@ -1,0 +1,86 @@
+// common.cuh — shared internals of libagb200 (not part of the C ABI).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <string.h>
+#include <string>
+#include <map>
+#include <unordered_map>
+#include <vector>
+#include "../../include/agb200.h"
+
+struct agb_ctx {
+  int device = 0;
+  int sm_count = 148;
+  cudaStream_t stream = nullptr;
+  int math_mode = AGB_MATH_3XTF32;
+  int64_t launches = 0;
+  // stream-ordered caching arena: every block is only ever used on `stream`, so a freed block can be
+  // handed out again immediately (work is ordered by the stream).
+  std::multimap<size_t, void*> free_blocks;
+  std::unordered_map<void*, size_t> block_size;   // every block we own (live or cached)
+  std::unordered_map<void*, bool> is_live;
+  size_t live_bytes = 0, cached_bytes = 0, peak_bytes = 0;
+  // scratch for two-stage reductions / split-K / descriptor tables
+  void* scratch = nullptr; size_t scratch_bytes = 0;
+  void* flush_buf = nullptr; size_t flush_bytes = 0;
+  // optimizer descriptor-table cache (key = hash of pointer lists)
+  std::unordered_map<uint64_t, void*> optim_tables;
+  // device-side error flag (bad labels / indices)
+  int* dev_err = nullptr;
+  // nccl
+  void* nccl_comm = nullptr;
+  int rank = 0, world = 1;
+  bool capturing = false;
+};
+
+void agb_set_error(const char* fmt, ...);
+int  agb_cuda_fail(cudaError_t e, const char* what, const char* file, int line);
+int  agb_scratch(agb_ctx* ctx, size_t bytes, void** out);
+
+#define AGB_CUDA(x) do { cudaError_t _e = (x); if (_e != cudaSuccess) return agb_cuda_fail(_e, #x, __FILE__, __LINE__); } while (0)
+#define AGB_CHECK(cond, code, ...) do { if (!(cond)) { agb_set_error(__VA_ARGS__); return (code); } } while (0)
+#define AGB_TRY(x) do { int _r = (x); if (_r != AGB_OK) return _r; } while (0)
+#define AGB_LAUNCHED(ctx) do { (ctx)->launches++; cudaError_t _e = cudaPeekAtLastError(); if (_e != cudaSuccess) return agb_cuda_fail(_e, "kernel launch", __FILE__, __LINE__); } while (0)
+
+static inline int64_t agb_numel(const agb_tensor* t) {
+  int64_t n = 1; for (int i = 0; i < t->rank; i++) n *= t->shape[i]; return n;
+}
+static inline bool agb_is_contig(const agb_tensor* t) {
+  int64_t s = 1;
+  for (int i = t->rank - 1; i >= 0; i--) {
+    if (t->shape[i] != 1 && t->stride[i] != s) return false;
+    s *= t->shape[i];
+  }
+  return true;
+}
+static inline int agb_grid_for(int64_t work_items, int threads, int sm_count, int per_sm = 8) {
+  int64_t b = (work_items + threads - 1) / threads;
+  int64_t cap = (int64_t)sm_count * per_sm;
+  if (b > cap) b = cap;
+  if (b < 1) b = 1;
+  return (int)b;
+}
+
+// ---- device helpers ----
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+__device__ __forceinline__ float warp_max(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, o));
+  return v;
+}
+__device__ __forceinline__ float4 ldg_stream4(const float* p) {
+  float4 r;
+  asm volatile("ld.global.nc.L1::no_allocate.v4.f32 {%0,%1,%2,%3}, [%4];"
+               : "=f"(r.x), "=f"(r.y), "=f"(r.z), "=f"(r.w) : "l"(p));
+  return r;
+}
+__device__ __forceinline__ void stg_stream4(float* p, float4 v) {
+  asm volatile("st.global.L1::no_allocate.v4.f32 [%0], {%1,%2,%3,%4};"
+               :: "l"(p), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w) : "memory");
+}

@@ -1,0 +1,183 @@
+// conv.cu — conv2d fprop / dgrad / wgrad entry points (NCHW, f32, square pad/stride/dilation) and the
+// general CUDA-core implicit-GEMM path.  The im2col matrix (reference: conv_ops/mod.rs:73-124) is never
+// materialised: loaders compute the (channel, tap, pixel) -> input address mapping on the fly.
+// 3x3 / stride 1 / pad 1 layers with channel counts TMA accepts go to the tcgen05 kernels (tc_conv.cu).
+//
+// Reference semantics followed (src/tensor_ops/conv_ops/):
+//   conv2d_extract_params + yh/yw formula          conv2d.rs:346-404
+//   Conv2D: y[b] = W[O, C*kh*kw] . im2col(x[b])    conv2d.rs:115-211, mod.rs:73-124
+//   Conv2DTranspose: cols = W^T . gy[b]; col2im     conv2d_transpose.rs:89-247, mod.rs:178-223
+//     xh = s(yh-1) - 2p + d(kh-1) + 1                conv2d_transpose.rs:55-56
+//   Conv2DFilterGrad: gw = sum_b gy[b] . cols[b]^T   conv2d.rs:631-734
+//   Conv2DTransposeFilterGrad (roles swapped)        conv2d_transpose.rs:303-431
+//   quirk: im2col uses `ph` for the x start (mod.rs:98); pads are always square so it is unobservable.
+#include "simt_gemm.cuh"
+
+int agb_tc_conv_fprop(agb_ctx* ctx, int mode, const float* x, const float* w, float* y,
+                      int B, int C, int H, int W, int O, int kh, int kw, int pad, int stride, int dil, int flip_transpose);
+int agb_tc_conv_wgrad(agb_ctx* ctx, int mode, const float* img, const float* g, float* gw,
+                      int B, int C, int H, int W, int O, int kh, int kw, int pad, int stride, int dil);
+
+struct ConvGeom { int B, C, H, W, O, kh, kw, yh, yw, pad, stride, dil; };
+
+// ---- fprop ----
+struct FpropA { const float* w; int64_t K; static const bool K_CONTIG = true;
+  __device__ __forceinline__ float load(int, int64_t m, int64_t k) const { return __ldg(w + m * K + k); } };
+struct FpropB { const float* x; ConvGeom g; static const bool K_CONTIG = false;
+  __device__ __forceinline__ float load(int, int64_t k, int64_t n) const {
+    int kk = g.kh * g.kw; int c = (int)(k / kk); int r = (int)(k - (int64_t)c * kk); int i = r / g.kw, j = r - i * g.kw;
+    int P = g.yh * g.yw; int b = (int)(n / P); int pix = (int)(n - (int64_t)b * P); int oy = pix / g.yw, ox = pix - oy * g.yw;
+    int iy = oy * g.stride - g.pad + i * g.dil, ix = ox * g.stride - g.pad + j * g.dil;
+    if ((unsigned)iy >= (unsigned)g.H || (unsigned)ix >= (unsigned)g.W) return 0.0f;
+    return __ldg(x + (((int64_t)b * g.C + c) * g.H + iy) * g.W + ix);
+  } };
+struct FpropC { float* y; ConvGeom g;
+  __device__ __forceinline__ void store(int, int64_t m, int64_t n, float v) const {
+    int P = g.yh * g.yw; int64_t b = n / P; int64_t pix = n - b * P;
+    y[(b * g.O + m) * P + pix] = v;
+  } };
+
+// ---- dgrad: gx[b,c,iy,ix] = sum_{o,i,j} W[o,c,i,j] * gy[b,o,oy,ox],  oy*s - p + i*d == iy ----
+struct DgradA { const float* w; ConvGeom g; static const bool K_CONTIG = true;
+  __device__ __forceinline__ float load(int, int64_t m, int64_t k) const {
+    int kk = g.kh * g.kw; int o = (int)(k / kk); int r = (int)(k - (int64_t)o * kk);
+    return __ldg(w + ((int64_t)o * g.C + m) * kk + r);
+  } };
+struct DgradB { const float* gy; ConvGeom g; static const bool K_CONTIG = false;
+  __device__ __forceinline__ float load(int, int64_t k, int64_t n) const {
+    int kk = g.kh * g.kw; int o = (int)(k / kk); int r = (int)(k - (int64_t)o * kk); int i = r / g.kw, j = r - i * g.kw;
+    int P = g.H * g.W; int b = (int)(n / P); int pix = (int)(n - (int64_t)b * P); int iy = pix / g.W, ix = pix - iy * g.W;
+    int ty = iy + g.pad - i * g.dil, tx = ix + g.pad - j * g.dil;
+    if (ty < 0 || tx < 0) return 0.0f;
+    int oy = ty / g.stride, ox = tx / g.stride;
+    if (oy * g.stride != ty || ox * g.stride != tx || oy >= g.yh || ox >= g.yw) return 0.0f;
+    return __ldg(gy + (((int64_t)b * g.O + o) * g.yh + oy) * g.yw + ox);
+  } };
+struct DgradC { float* gx; ConvGeom g;
+  __device__ __forceinline__ void store(int, int64_t m, int64_t n, float v) const {
+    int P = g.H * g.W; int64_t b = n / P; int64_t pix = n - b * P;
+    gx[(b * g.C + m) * P + pix] = v;
+  } };
+
+// ---- wgrad: gw[o,(c,i,j)] = sum_{b,oy,ox} gr[b,o,oy,ox] * img[b,c,oy*s-p+i*d, ox*s-p+j*d]; split over batch ----
+struct WgradA { const float* gr; ConvGeom g; int bchunk; static const bool K_CONTIG = true;
+  __device__ __forceinline__ float load(int z, int64_t m, int64_t k) const {
+    int P = g.yh * g.yw; int bl = (int)(k / P); int pix = (int)(k - (int64_t)bl * P); int b = z * bchunk + bl;
+    if (b >= g.B) return 0.0f;
+    return __ldg(gr + ((int64_t)b * g.O + m) * P + pix);
+  } };
+struct WgradB { const float* img; ConvGeom g; int bchunk; static const bool K_CONTIG = true;
+  __device__ __forceinline__ float load(int z, int64_t k, int64_t n) const {
+    int P = g.yh * g.yw; int bl = (int)(k / P); int pix = (int)(k - (int64_t)bl * P); int b = z * bchunk + bl;
+    if (b >= g.B) return 0.0f;
+    int oy = pix / g.yw, ox = pix - oy * g.yw;
+    int kk = g.kh * g.kw; int c = (int)(n / kk); int r = (int)(n - (int64_t)c * kk); int i = r / g.kw, j = r - i * g.kw;
+    int iy = oy * g.stride - g.pad + i * g.dil, ix = ox * g.stride - g.pad + j * g.dil;
+    if ((unsigned)iy >= (unsigned)g.H || (unsigned)ix >= (unsigned)g.W) return 0.0f;
+    return __ldg(img + (((int64_t)b * g.C + c) * g.H + iy) * g.W + ix);
+  } };
+struct WgradC { float* gw; int64_t N; int atomic;
+  __device__ __forceinline__ void store(int, int64_t m, int64_t n, float v) const {
+    if (atomic) atomicAdd(gw + m * N + n, v); else gw[m * N + n] = v;
+  } };
+
+static int check_geom(const char* who, const agb_tensor* x, const agb_tensor* w, int pad, int stride, int dil, ConvGeom& g) {
+  AGB_CHECK(x->rank == 4, AGB_ERR_INCOMPATIBLE_SHAPE, "%s: lhs input must be 4D (got rank %d)", who, x->rank);
+  AGB_CHECK(w->rank == 4, AGB_ERR_INCOMPATIBLE_SHAPE, "%s: filter must be 4D (got rank %d)", who, w->rank);
+  AGB_CHECK(stride >= 1 && dil >= 1 && pad >= 0, AGB_ERR_INVALID_DIMS, "%s: stride/dilation must be >= 1, pad >= 0", who);
+  g.B = (int)x->shape[0]; g.C = (int)x->shape[1]; g.H = (int)x->shape[2]; g.W = (int)x->shape[3];
+  g.O = (int)w->shape[0]; g.kh = (int)w->shape[2]; g.kw = (int)w->shape[3];
+  g.pad = pad; g.stride = stride; g.dil = dil;
+  AGB_CHECK(x->shape[1] == w->shape[1], AGB_ERR_INCOMPATIBLE_SHAPE, "%s: input channel dim (%lld) must match filter's second dim (%lld)", who,
+            (long long)x->shape[1], (long long)w->shape[1]);
+  int eh = dil * (g.kh - 1) + 1, ew = dil * (g.kw - 1) + 1;
+  AGB_CHECK(g.H + 2 * pad >= eh && g.W + 2 * pad >= ew, AGB_ERR_INCOMPATIBLE_SHAPE, "%s: kernel larger than padded input", who);
+  g.yh = (g.H + 2 * pad - eh) / stride + 1; g.yw = (g.W + 2 * pad - ew) / stride + 1;
+  return AGB_OK;
+}
+
+extern "C" int agb_conv2d_fprop_f32(agb_ctx* ctx, const agb_tensor* x, const agb_tensor* w, agb_tensor* y, int pad, int stride, int dilation) {
+  ConvGeom g; AGB_TRY(check_geom("conv2d", x, w, pad, stride, dilation, g));
+  AGB_CHECK(agb_is_contig(x) && agb_is_contig(w) && agb_is_contig(y), AGB_ERR_UNSUPPORTED, "conv2d: tensors must be C-contiguous (the reference deep-copies, conv2d.rs:436-452)");
+  AGB_CHECK(y->rank == 4 && y->shape[0] == g.B && y->shape[1] == g.O && y->shape[2] == g.yh && y->shape[3] == g.yw, AGB_ERR_INCOMPATIBLE_SHAPE,
+            "conv2d: output must be [%d,%d,%d,%d]", g.B, g.O, g.yh, g.yw);
+  if (agb_numel(y) == 0) return AGB_OK;
+  if (ctx->math_mode != AGB_MATH_FP32) {
+    int r = agb_tc_conv_fprop(ctx, ctx->math_mode, x->ptr, w->ptr, y->ptr, g.B, g.C, g.H, g.W, g.O, g.kh, g.kw, pad, stride, dilation, 0);
+    if (r != AGB_ERR_UNSUPPORTED) return r;
+  }
+  int64_t K = (int64_t)g.C * g.kh * g.kw;
+  return simt_gemm_launch(ctx, FpropA{w->ptr, K}, FpropB{x->ptr, g}, FpropC{y->ptr, g}, g.O, (int64_t)g.B * g.yh * g.yw, K, 1);
+}
+
+extern "C" int agb_conv2d_dgrad_f32(agb_ctx* ctx, const agb_tensor* gy, const agb_tensor* w, agb_tensor* gx, int pad, int stride, int dilation) {
+  AGB_CHECK(gy->rank == 4, AGB_ERR_INCOMPATIBLE_SHAPE, "conv2d_transpose: Input must be 4D (got rank %d)", gy->rank);
+  AGB_CHECK(w->rank == 4, AGB_ERR_INCOMPATIBLE_SHAPE, "conv2d_transpose: Filter must be 4D (got rank %d)", w->rank);
+  AGB_CHECK(gy->shape[1] == w->shape[0], AGB_ERR_INCOMPATIBLE_SHAPE,
+            "conv2d_transpose: Number of input channels (%lld) must match second filter dim (%lld)", (long long)gy->shape[1], (long long)w->shape[0]);
+  AGB_CHECK(stride >= 1 && dilation >= 1 && pad >= 0, AGB_ERR_INVALID_DIMS, "conv2d_transpose: bad pad/stride/dilation");
+  ConvGeom g;
+  g.B = (int)gy->shape[0]; g.O = (int)gy->shape[1]; g.yh = (int)gy->shape[2]; g.yw = (int)gy->shape[3];
+  g.C = (int)w->shape[1]; g.kh = (int)w->shape[2]; g.kw = (int)w->shape[3]; g.pad = pad; g.stride = stride; g.dil = dilation;
+  g.H = stride * (g.yh - 1) - 2 * pad + (dilation * (g.kh - 1) + 1);
+  g.W = stride * (g.yw - 1) - 2 * pad + (dilation * (g.kw - 1) + 1);
+  AGB_CHECK(g.H > 0 && g.W > 0, AGB_ERR_INCOMPATIBLE_SHAPE, "conv2d_transpose: non-positive output size");
+  AGB_CHECK(gx->rank == 4 && gx->shape[0] == g.B && gx->shape[1] == g.C && gx->shape[2] == g.H && gx->shape[3] == g.W, AGB_ERR_INCOMPATIBLE_SHAPE,
+            "conv2d_transpose: output must be [%d,%d,%d,%d]", g.B, g.C, g.H, g.W);
+  AGB_CHECK(agb_is_contig(gy) && agb_is_contig(w) && agb_is_contig(gx), AGB_ERR_UNSUPPORTED, "conv2d_transpose: tensors must be C-contiguous");
+  if (agb_numel(gx) == 0) return AGB_OK;
+  if (ctx->math_mode != AGB_MATH_FP32 && stride == 1 && g.H == g.yh && g.W == g.yw) {
+    // stride-1 "same" dgrad == fprop of gy with the spatially flipped, channel-transposed filter
+    int r = agb_tc_conv_fprop(ctx, ctx->math_mode, gy->ptr, w->ptr, gx->ptr, g.B, g.O, g.yh, g.yw, g.C, g.kh, g.kw, pad, stride, dilation, 1);
+    if (r != AGB_ERR_UNSUPPORTED) return r;
+  }
+  int64_t K = (int64_t)g.O * g.kh * g.kw;
+  return simt_gemm_launch(ctx, DgradA{w->ptr, g}, DgradB{gy->ptr, g}, DgradC{gx->ptr, g}, g.C, (int64_t)g.B * g.H * g.W, K, 1);
+}
+
+extern "C" int agb_conv2d_wgrad_f32(agb_ctx* ctx, const agb_tensor* img, const agb_tensor* gr, agb_tensor* gw, int pad, int stride, int dilation) {
+  ConvGeom g; AGB_TRY(check_geom("conv2d_filter_grad", img, gw, pad, stride, dilation, g));
+  AGB_CHECK(gr->rank == 4 && gr->shape[0] == g.B && gr->shape[1] == g.O && gr->shape[2] == g.yh && gr->shape[3] == g.yw, AGB_ERR_INCOMPATIBLE_SHAPE,
+            "conv2d_filter_grad: gradient must be [%d,%d,%d,%d]", g.B, g.O, g.yh, g.yw);
+  AGB_CHECK(agb_is_contig(img) && agb_is_contig(gr) && agb_is_contig(gw), AGB_ERR_UNSUPPORTED, "conv2d_filter_grad: tensors must be C-contiguous");
+  if (agb_numel(gw) == 0) return AGB_OK;
+  if (ctx->math_mode != AGB_MATH_FP32) {
+    int r = agb_tc_conv_wgrad(ctx, ctx->math_mode, img->ptr, gr->ptr, gw->ptr, g.B, g.C, g.H, g.W, g.O, g.kh, g.kw, pad, stride, dilation);
+    if (r != AGB_ERR_UNSUPPORTED) return r;
+  }
+  int64_t N = (int64_t)g.C * g.kh * g.kw; int64_t P = (int64_t)g.yh * g.yw;
+  bool big = (g.O >= 96 && N >= 96); int tile = big ? 128 : 64;
+  int64_t tiles = ((g.O + tile - 1) / tile) * ((N + tile - 1) / tile);
+  int64_t Z = (2 * (int64_t)ctx->sm_count + tiles - 1) / tiles; if (Z > g.B) Z = g.B; if (Z < 1) Z = 1;
+  int bchunk = (int)((g.B + Z - 1) / Z); Z = (g.B + bchunk - 1) / bchunk;
+  if (Z > 1) AGB_TRY(agb_memset0(ctx, gw->ptr, agb_numel(gw) * sizeof(float)));
+  return simt_gemm_launch(ctx, WgradA{gr->ptr, g, bchunk}, WgradB{img->ptr, g, bchunk}, WgradC{gw->ptr, N, Z > 1}, g.O, N, (int64_t)bchunk * P, Z);
+}
+
+// ---- im2col materialisation (only for user-visible evaluation of Conv2D's 2nd output) ----
+__global__ void __launch_bounds__(256) im2col_kernel(const float* __restrict__ x, float* __restrict__ cols, ConvGeom g, int64_t n) {
+  int64_t tid = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  int64_t gs = (int64_t)gridDim.x * blockDim.x;
+  for (int64_t o = tid; o < n; o += gs) {
+    // cols [B, C, kh, kw, yh, yw]  (conv_ops/mod.rs:93-121: for c, kh, kw, yh, yw)
+    int ox = (int)(o % g.yw); int64_t t = o / g.yw; int oy = (int)(t % g.yh); t /= g.yh;
+    int j = (int)(t % g.kw); t /= g.kw; int i = (int)(t % g.kh); t /= g.kh; int c = (int)(t % g.C); int64_t b = t / g.C;
+    int iy = oy * g.stride - g.pad + i * g.dil, ix = ox * g.stride - g.pad + j * g.dil;
+    float v = 0.0f;
+    if ((unsigned)iy < (unsigned)g.H && (unsigned)ix < (unsigned)g.W) v = __ldg(x + ((b * g.C + c) * g.H + iy) * g.W + ix);
+    cols[o] = v;
+  }
+}
+extern "C" int agb_im2col_f32(agb_ctx* ctx, const agb_tensor* x, agb_tensor* cols, int kh, int kw, int pad, int stride, int dilation) {
+  AGB_CHECK(x->rank == 4 && cols->rank == 6, AGB_ERR_INCOMPATIBLE_SHAPE, "im2col: x must be 4D and cols 6D");
+  AGB_CHECK(agb_is_contig(x) && agb_is_contig(cols), AGB_ERR_UNSUPPORTED, "im2col: tensors must be contiguous");
+  ConvGeom g; g.B = (int)x->shape[0]; g.C = (int)x->shape[1]; g.H = (int)x->shape[2]; g.W = (int)x->shape[3];
+  g.O = 0; g.kh = kh; g.kw = kw; g.pad = pad; g.stride = stride; g.dil = dilation;
+  g.yh = (g.H + 2 * pad - (dilation * (kh - 1) + 1)) / stride + 1; g.yw = (g.W + 2 * pad - (dilation * (kw - 1) + 1)) / stride + 1;
+  int64_t n = (int64_t)g.B * g.C * kh * kw * g.yh * g.yw;
+  AGB_CHECK(agb_numel(cols) == n, AGB_ERR_INCOMPATIBLE_SHAPE, "im2col: cols must have %lld elements", (long long)n);
+  if (n == 0) return AGB_OK;
+  im2col_kernel<<<agb_grid_for(n, 256, ctx->sm_count, 8), 256, 0, ctx->stream>>>(x->ptr, cols->ptr, g, n);
+  AGB_LAUNCHED(ctx);
+  return AGB_OK;
+}

@@ -1,0 +1,387 @@
+// ewise.cu — bandwidth-bound elementwise kernels: unary / binary-with-broadcast / add_n / fill /
+// strided copy / dropout.  HBM roofline: unary 8 B/elem, binary 12 B/elem.
+// 128-bit vectorised streaming loads/stores on the contiguous fast paths, grid = SMs x 8 grid-stride.
+//
+// Reference semantics followed:
+//   binary arithmetic + broadcasting     src/tensor_ops/binary_ops.rs:147-290,304-347
+//   compare/select (0/1 floats)          src/tensor_ops/math_ops.rs:86-184
+//   unary math                           src/tensor_ops/math_ops.rs:277-1019
+//   Sigmoid/ReLU/Softplus/ELU(+Grad)     src/tensor_ops/activation_ops.rs:113-226
+//   Clip/ClipGrad, AddN                  src/tensor_ops/array_ops.rs:503-574
+//   SigmoidCrossEntropy                  src/tensor_ops/xent_ops.rs:33-46
+//   Dropout (non-inverted)               src/tensor_ops/random_ops.rs:218-237
+#include "common.cuh"
+
+// ----------------------------------------------------------------------------------------------
+// functors
+// ----------------------------------------------------------------------------------------------
+__device__ __forceinline__ float unary_apply(int op, float x, float p0, float p1) {
+  switch (op) {
+    case AGB_U_COPY: return x;
+    case AGB_U_ABS: return fabsf(x);
+    case AGB_U_NEG: return -x;
+    case AGB_U_SQUARE: return x * x;
+    case AGB_U_INV: return 1.0f / x;
+    case AGB_U_INVSQRT: return 1.0f / sqrtf(x);           // math_ops.rs: a.sqrt().recip()
+    case AGB_U_SIGN: return (x == 0.0f) ? 0.0f : (x != x ? x : copysignf(1.0f, x));   // math_ops.rs:370-381: 0 -> 0, else signum
+    case AGB_U_FLOOR: return floorf(x);
+    case AGB_U_CEIL: return ceilf(x);
+    case AGB_U_SQRT: return sqrtf(x);
+    case AGB_U_POW: return powf(x, p0);
+    case AGB_U_LN: return logf(x);
+    case AGB_U_LOG2: return log2f(x);
+    case AGB_U_LOG10: return log10f(x);
+    case AGB_U_EXP: return expf(x);
+    case AGB_U_EXP2: return exp2f(x);
+    case AGB_U_EXP10: return exp10f(x);
+    case AGB_U_SIN: return sinf(x);
+    case AGB_U_COS: return cosf(x);
+    case AGB_U_TAN: return tanf(x);
+    case AGB_U_ASIN: return asinf(x);
+    case AGB_U_ACOS: return acosf(x);
+    case AGB_U_ATAN: return atanf(x);
+    case AGB_U_SINH: return sinhf(x);
+    case AGB_U_COSH: return coshf(x);
+    case AGB_U_TANH: return tanhf(x);
+    case AGB_U_ASINH: return asinhf(x);
+    case AGB_U_ACOSH: return acoshf(x);
+    case AGB_U_ATANH: return atanhf(x);
+    case AGB_U_SIGMOID: return tanhf(x * 0.5f) * 0.5f + 0.5f;        // activation_ops.rs:138-141
+    case AGB_U_RELU: return fmaxf(x, 0.0f);                           // Float::max: NaN -> 0
+    case AGB_U_SOFTPLUS: return logf(expf(x) + 1.0f);                 // unguarded, as the reference
+    case AGB_U_ELU: return x > 0.0f ? x : p0 * (expf(x) - 1.0f);
+    case AGB_U_CLIP: return fmaxf(fminf(x, p1), p0);                  // a.min(max).max(min)
+    case AGB_U_SCALE: return x * p0;
+    case AGB_U_ADD_SCALAR: return x + p0;
+    case AGB_U_RSUB_SCALAR: return p0 - x;
+    case AGB_U_RDIV_SCALAR: return p0 / x;
+  }
+  return x;
+}
+
+__device__ __forceinline__ float binary_apply(int op, float a, float b, float p0, float p1) {
+  switch (op) {
+    case AGB_B_ADD: return a + b;
+    case AGB_B_SUB: return a - b;
+    case AGB_B_MUL: return a * b;
+    case AGB_B_DIV: return a / b;
+    case AGB_B_EQ: return a == b ? 1.0f : 0.0f;
+    case AGB_B_NE: return a != b ? 1.0f : 0.0f;
+    case AGB_B_GT: return a > b ? 1.0f : 0.0f;
+    case AGB_B_LT: return a < b ? 1.0f : 0.0f;
+    case AGB_B_GE: return a >= b ? 1.0f : 0.0f;
+    case AGB_B_LE: return a <= b ? 1.0f : 0.0f;
+    case AGB_B_MAX: return a > b ? a : b;                 // math_ops.rs maximum_fn
+    case AGB_B_MIN: return a < b ? a : b;
+    case AGB_B_ELU_GRAD: return (a > 0.0f ? 1.0f : p0 * (expf(a) - 1.0f) + p0) * b;
+    case AGB_B_CLIP_GRAD: return ((a > p0) ? 1.0f : 0.0f) * ((a < p1) ? 1.0f : 0.0f) * b;
+    case AGB_B_SIGMOID_XENT: return logf(expf(-fabsf(a)) + 1.0f) + fmaxf(0.0f, a) - b * a;
+    case AGB_B_RELU_GRAD: return a > 0.0f ? b : 0.0f * b;
+  }
+  return 0.0f;
+}
+
+// ----------------------------------------------------------------------------------------------
+// contiguous unary
+// ----------------------------------------------------------------------------------------------
+template <int OP>
+__global__ void __launch_bounds__(256) unary_contig_kernel(const float* __restrict__ x, float* __restrict__ y,
+                                                           int64_t n, float p0, float p1) {
+  int64_t n4 = n >> 2;
+  int64_t tid = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  // 2 independent 128-bit loads in flight per thread per iteration
+  int64_t i = tid;
+  for (; i + stride < n4; i += 2 * stride) {
+    float4 a = ldg_stream4(x + 4 * i);
+    float4 b = ldg_stream4(x + 4 * (i + stride));
+    a.x = unary_apply(OP, a.x, p0, p1); a.y = unary_apply(OP, a.y, p0, p1);
+    a.z = unary_apply(OP, a.z, p0, p1); a.w = unary_apply(OP, a.w, p0, p1);
+    b.x = unary_apply(OP, b.x, p0, p1); b.y = unary_apply(OP, b.y, p0, p1);
+    b.z = unary_apply(OP, b.z, p0, p1); b.w = unary_apply(OP, b.w, p0, p1);
+    stg_stream4(y + 4 * i, a);
+    stg_stream4(y + 4 * (i + stride), b);
+  }
+  for (; i < n4; i += stride) {
+    float4 a = ldg_stream4(x + 4 * i);
+    a.x = unary_apply(OP, a.x, p0, p1); a.y = unary_apply(OP, a.y, p0, p1);
+    a.z = unary_apply(OP, a.z, p0, p1); a.w = unary_apply(OP, a.w, p0, p1);
+    stg_stream4(y + 4 * i, a);
+  }
+  for (int64_t j = (n4 << 2) + tid; j < n; j += stride) y[j] = unary_apply(OP, x[j], p0, p1);
+}
+
+template <int OP>
+__global__ void __launch_bounds__(256) unary_scalar_kernel(const float* __restrict__ x, float* __restrict__ y,
+                                                           int64_t n, float p0, float p1) {
+  int64_t tid = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  for (int64_t j = tid; j < n; j += stride) y[j] = unary_apply(OP, x[j], p0, p1);
+}
+
+typedef void (*unary_fn)(const float*, float*, int64_t, float, float);
+template <int... I> struct useq {};
+template <int N, int... I> struct make_useq : make_useq<N - 1, N - 1, I...> {};
+template <int... I> struct make_useq<0, I...> { typedef useq<I...> type; };
+template <int... I> static const unary_fn* unary_table_v(useq<I...>) { static const unary_fn t[] = {unary_contig_kernel<I>...}; return t; }
+template <int... I> static const unary_fn* unary_table_s(useq<I...>) { static const unary_fn t[] = {unary_scalar_kernel<I>...}; return t; }
+
+// ----------------------------------------------------------------------------------------------
+// generic strided binary (broadcast by zero strides); output contiguous (or strided for copy)
+// ----------------------------------------------------------------------------------------------
+#define AGB_EW_MAXD 6
+struct StridedParams {
+  int rank;                      // collapsed rank (>=1)
+  int64_t shape[AGB_EW_MAXD];    // collapsed shape; innermost is dim rank-1 (already divided by 4 for vec)
+  int64_t sa[AGB_EW_MAXD], sb[AGB_EW_MAXD], sy[AGB_EW_MAXD];
+};
+
+template <int OP, bool VEC, typename IDX>
+__global__ void __launch_bounds__(256) binary_strided_kernel(const float* __restrict__ a, const float* __restrict__ b,
+                                                             float* __restrict__ y, StridedParams P, int64_t total,
+                                                             float p0, float p1) {
+  IDX tid = (IDX)blockIdx.x * blockDim.x + threadIdx.x;
+  IDX stride = (IDX)gridDim.x * blockDim.x;
+  for (IDX i = tid; i < (IDX)total; i += stride) {
+    IDX rem = i; int64_t oa = 0, ob = 0, oy = 0;
+#pragma unroll
+    for (int d = AGB_EW_MAXD - 1; d >= 0; d--) {
+      if (d < P.rank) {
+        IDX q = (d == 0) ? 0 : rem / (IDX)P.shape[d];
+        IDX c = (d == 0) ? rem : rem - q * (IDX)P.shape[d];
+        rem = q;
+        if (VEC && d == P.rank - 1) { oa += (int64_t)c * 4 * P.sa[d]; ob += (int64_t)c * 4 * P.sb[d]; oy += (int64_t)c * 4 * P.sy[d]; }
+        else { oa += (int64_t)c * P.sa[d]; ob += (int64_t)c * P.sb[d]; oy += (int64_t)c * P.sy[d]; }
+      }
+    }
+    if (VEC) {
+      const int last = P.rank - 1;
+      float4 va, vb, r;
+      if (P.sa[last] == 1) va = ldg_stream4(a + oa); else { float s = __ldg(a + oa); va = make_float4(s, s, s, s); }
+      if (OP == -1) { vb = va; }
+      else if (P.sb[last] == 1) vb = ldg_stream4(b + ob); else { float s = __ldg(b + ob); vb = make_float4(s, s, s, s); }
+      if (OP == -1) r = va;
+      else {
+        r.x = binary_apply(OP, va.x, vb.x, p0, p1); r.y = binary_apply(OP, va.y, vb.y, p0, p1);
+        r.z = binary_apply(OP, va.z, vb.z, p0, p1); r.w = binary_apply(OP, va.w, vb.w, p0, p1);
+      }
+      stg_stream4(y + oy, r);
+    } else {
+      float va = __ldg(a + oa);
+      if (OP == -1) y[oy] = va;
+      else y[oy] = binary_apply(OP, va, __ldg(b + ob), p0, p1);
+    }
+  }
+}
+
+// collapse adjacent dims whenever all three stride sets allow it; drop size-1 dims
+static void collapse(int rank, const int64_t* shape, const int64_t* sa, const int64_t* sb, const int64_t* sy, StridedParams& P) {
+  int64_t sh[AGB_MAX_RANK], a[AGB_MAX_RANK], b[AGB_MAX_RANK], y[AGB_MAX_RANK]; int r = 0;
+  for (int i = 0; i < rank; i++) {
+    if (shape[i] == 1) continue;
+    if (r > 0 && a[r - 1] == shape[i] * sa[i] && b[r - 1] == shape[i] * sb[i] && y[r - 1] == shape[i] * sy[i]) {
+      sh[r - 1] *= shape[i]; a[r - 1] = sa[i]; b[r - 1] = sb[i]; y[r - 1] = sy[i];
+    } else { sh[r] = shape[i]; a[r] = sa[i]; b[r] = sb[i]; y[r] = sy[i]; r++; }
+  }
+  if (r == 0) { sh[0] = 1; a[0] = b[0] = y[0] = 1; r = 1; }
+  P.rank = r;
+  for (int i = 0; i < r; i++) { P.shape[i] = sh[i]; P.sa[i] = a[i]; P.sb[i] = b[i]; P.sy[i] = y[i]; }
+}
+
+template <int OP>
+static int launch_strided(agb_ctx* ctx, const float* a, const float* b, float* y, int rank, const int64_t* shape,
+                          const int64_t* sa, const int64_t* sb, const int64_t* sy, float p0, float p1) {
+  StridedParams P; collapse(rank, shape, sa, sb, sy, P);
+  AGB_CHECK(P.rank <= AGB_EW_MAXD, AGB_ERR_UNSUPPORTED, "elementwise: more than %d non-collapsible dims", AGB_EW_MAXD);
+  int64_t total = 1; for (int i = 0; i < P.rank; i++) total *= P.shape[i];
+  if (total == 0) return AGB_OK;
+  const int last = P.rank - 1;
+  auto al16 = [](const void* p) { return ((uintptr_t)p & 15) == 0; };
+  bool vec = (P.shape[last] % 4 == 0) && (P.sa[last] == 1 || P.sa[last] == 0) && (P.sb[last] == 1 || P.sb[last] == 0) &&
+             P.sy[last] == 1 && al16(y) && (P.sa[last] == 0 || al16(a)) && (P.sb[last] == 0 || al16(b));
+  for (int i = 0; i < last && vec; i++) {
+    if (P.sa[last] == 1 && P.sa[i] % 4) vec = false;
+    if (P.sb[last] == 1 && P.sb[i] % 4) vec = false;
+    if (P.sy[i] % 4) vec = false;
+  }
+  if (vec) { P.shape[last] /= 4; total /= 4; }
+  int grid = agb_grid_for(total, 256, ctx->sm_count, 8);
+  bool small = total * (vec ? 4 : 1) < (1ll << 31) ;
+  for (int i = 0; i < P.rank && small; i++) {
+    if (llabs(P.sa[i]) * P.shape[i] >= (1ll << 31) || llabs(P.sb[i]) * P.shape[i] >= (1ll << 31)) small = false;
+  }
+  if (vec) {
+    if (small) binary_strided_kernel<OP, true, uint32_t><<<grid, 256, 0, ctx->stream>>>(a, b, y, P, total, p0, p1);
+    else binary_strided_kernel<OP, true, int64_t><<<grid, 256, 0, ctx->stream>>>(a, b, y, P, total, p0, p1);
+  } else {
+    if (small) binary_strided_kernel<OP, false, uint32_t><<<grid, 256, 0, ctx->stream>>>(a, b, y, P, total, p0, p1);
+    else binary_strided_kernel<OP, false, int64_t><<<grid, 256, 0, ctx->stream>>>(a, b, y, P, total, p0, p1);
+  }
+  AGB_LAUNCHED(ctx);
+  return AGB_OK;
+}
+
+typedef int (*strided_fn)(agb_ctx*, const float*, const float*, float*, int, const int64_t*, const int64_t*, const int64_t*, const int64_t*, float, float);
+template <int... I> static const strided_fn* binary_table(useq<I...>) { static const strided_fn t[] = {launch_strided<I>...}; return t; }
+
+static void contig_strides(int rank, const int64_t* shape, int64_t* st) {
+  int64_t s = 1; for (int i = rank - 1; i >= 0; i--) { st[i] = s; s *= shape[i]; }
+}
+
+extern "C" int agb_unary(agb_ctx* ctx, int op, float p0, float p1, const agb_tensor* x, agb_tensor* y) {
+  AGB_CHECK(op >= 0 && op < AGB_U_COUNT, AGB_ERR_INVALID_DIMS, "agb_unary: bad op %d", op);
+  AGB_CHECK(x->rank == y->rank, AGB_ERR_INCOMPATIBLE_SHAPE, "agb_unary: rank mismatch");
+  for (int i = 0; i < x->rank; i++) AGB_CHECK(x->shape[i] == y->shape[i], AGB_ERR_INCOMPATIBLE_SHAPE, "agb_unary: shape mismatch on axis %d", i);
+  AGB_CHECK(agb_is_contig(y), AGB_ERR_UNSUPPORTED, "agb_unary: output must be C-contiguous");
+  int64_t n = agb_numel(x);
+  if (n == 0) return AGB_OK;
+  const float* xp = x->ptr; float* tmp = nullptr;
+  if (!agb_is_contig(x)) {       // materialise the view first (reference: ndarray map over a strided view)
+    if (op == AGB_U_COPY) return agb_copy_strided(ctx, x, y);
+    agb_tensor t = *y; AGB_TRY(agb_alloc(ctx, n * sizeof(float), (void**)&tmp)); t.ptr = tmp;
+    AGB_TRY(agb_copy_strided(ctx, x, &t)); xp = tmp;
+  }
+  int grid = agb_grid_for((n + 3) / 4, 256, ctx->sm_count, 8);
+  bool aligned = (((uintptr_t)xp | (uintptr_t)y->ptr) & 15) == 0;
+  const unary_fn* tv = unary_table_v(make_useq<AGB_U_COUNT>::type());
+  const unary_fn* ts = unary_table_s(make_useq<AGB_U_COUNT>::type());
+  if (aligned) tv[op]<<<grid, 256, 0, ctx->stream>>>(xp, y->ptr, n, p0, p1);
+  else ts[op]<<<agb_grid_for(n, 256, ctx->sm_count, 8), 256, 0, ctx->stream>>>(xp, y->ptr, n, p0, p1);
+  AGB_LAUNCHED(ctx);
+  if (tmp) AGB_TRY(agb_free(ctx, tmp));
+  return AGB_OK;
+}
+
+extern "C" int agb_binary(agb_ctx* ctx, int op, float p0, float p1, const agb_tensor* a, const agb_tensor* b, agb_tensor* y) {
+  AGB_CHECK(op >= 0 && op < AGB_B_COUNT, AGB_ERR_INVALID_DIMS, "agb_binary: bad op %d", op);
+  AGB_CHECK(a->rank == y->rank && b->rank == y->rank, AGB_ERR_INCOMPATIBLE_SHAPE, "agb_binary: operands must be pre-broadcast to the output rank");
+  for (int i = 0; i < y->rank; i++)
+    AGB_CHECK(a->shape[i] == y->shape[i] && b->shape[i] == y->shape[i], AGB_ERR_INCOMPATIBLE_SHAPE,
+              "agb_binary: operands must be pre-broadcast to the output shape (axis %d)", i);
+  AGB_CHECK(agb_is_contig(y), AGB_ERR_UNSUPPORTED, "agb_binary: output must be C-contiguous");
+  int64_t sy[AGB_MAX_RANK]; contig_strides(y->rank, y->shape, sy);
+  const strided_fn* t = binary_table(make_useq<AGB_B_COUNT>::type());
+  return t[op](ctx, a->ptr, b->ptr, y->ptr, y->rank, y->shape, a->stride, b->stride, sy, p0, p1);
+}
+
+extern "C" int agb_copy_strided(agb_ctx* ctx, const agb_tensor* src, agb_tensor* dst) {
+  AGB_CHECK(src->rank == dst->rank, AGB_ERR_INCOMPATIBLE_SHAPE, "agb_copy_strided: rank mismatch %d vs %d", src->rank, dst->rank);
+  for (int i = 0; i < src->rank; i++) AGB_CHECK(src->shape[i] == dst->shape[i], AGB_ERR_INCOMPATIBLE_SHAPE, "agb_copy_strided: shape mismatch on axis %d", i);
+  if (agb_is_contig(src) && agb_is_contig(dst)) return agb_d2d(ctx, dst->ptr, src->ptr, agb_numel(src) * sizeof(float));
+  return launch_strided<-1>(ctx, src->ptr, src->ptr, dst->ptr, src->rank, src->shape, src->stride, src->stride, dst->stride, 0.f, 0.f);
+}
+
+// ----------------------------------------------------------------------------------------------
+// add_n, fill
+// ----------------------------------------------------------------------------------------------
+#define AGB_ADDN_MAX 8
+struct AddNPtrs { const float* p[AGB_ADDN_MAX]; };
+__global__ void __launch_bounds__(256) add_n_kernel(AddNPtrs P, int n, float* __restrict__ y, int64_t numel, int accumulate) {
+  int64_t n4 = numel >> 2;
+  int64_t tid = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  for (int64_t i = tid; i < n4; i += stride) {
+    float4 acc = accumulate ? *(const float4*)(y + 4 * i) : ldg_stream4(P.p[0] + 4 * i);
+    for (int k = accumulate ? 0 : 1; k < n; k++) {
+      float4 v = ldg_stream4(P.p[k] + 4 * i);
+      acc.x += v.x; acc.y += v.y; acc.z += v.z; acc.w += v.w;   // left fold, like `base += &ctx.input(i)`
+    }
+    *(float4*)(y + 4 * i) = acc;
+  }
+  for (int64_t j = (n4 << 2) + tid; j < numel; j += stride) {
+    float acc = accumulate ? y[j] : P.p[0][j];
+    for (int k = accumulate ? 0 : 1; k < n; k++) acc += P.p[k][j];
+    y[j] = acc;
+  }
+}
+
+extern "C" int agb_add_n(agb_ctx* ctx, int n, const agb_tensor* const* xs, agb_tensor* y) {
+  AGB_CHECK(n >= 1, AGB_ERR_INVALID_DIMS, "agb_add_n: n must be >= 1");
+  int64_t numel = agb_numel(y);
+  AGB_CHECK(agb_is_contig(y), AGB_ERR_UNSUPPORTED, "agb_add_n: output must be contiguous");
+  for (int i = 0; i < n; i++) {
+    AGB_CHECK(agb_numel(xs[i]) == numel && agb_is_contig(xs[i]), AGB_ERR_INCOMPATIBLE_SHAPE, "agb_add_n: input %d must be contiguous with the output's size", i);
+    AGB_CHECK((((uintptr_t)xs[i]->ptr) & 15) == 0, AGB_ERR_UNSUPPORTED, "agb_add_n: input %d not 16B aligned", i);
+  }
+  if (numel == 0) return AGB_OK;
+  int grid = agb_grid_for((numel + 3) / 4, 256, ctx->sm_count, 8);
+  for (int base = 0; base < n; base += AGB_ADDN_MAX) {
+    AddNPtrs P; int m = n - base < AGB_ADDN_MAX ? n - base : AGB_ADDN_MAX;
+    for (int i = 0; i < m; i++) P.p[i] = xs[base + i]->ptr;
+    add_n_kernel<<<grid, 256, 0, ctx->stream>>>(P, m, y->ptr, numel, base > 0);
+    AGB_LAUNCHED(ctx);
+  }
+  return AGB_OK;
+}
+
+__global__ void __launch_bounds__(256) fill_kernel(float* __restrict__ y, int64_t n, float v) {
+  int64_t tid = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  int64_t n4 = n >> 2;
+  float4 v4 = make_float4(v, v, v, v);
+  if ((((uintptr_t)y) & 15) == 0) {
+    for (int64_t i = tid; i < n4; i += stride) stg_stream4(y + 4 * i, v4);
+    for (int64_t j = (n4 << 2) + tid; j < n; j += stride) y[j] = v;
+  } else {
+    for (int64_t j = tid; j < n; j += stride) y[j] = v;
+  }
+}
+extern "C" int agb_fill(agb_ctx* ctx, agb_tensor* y, float value) {
+  AGB_CHECK(agb_is_contig(y), AGB_ERR_UNSUPPORTED, "agb_fill: output must be contiguous");
+  int64_t n = agb_numel(y); if (n == 0) return AGB_OK;
+  if (value == 0.0f) return agb_memset0(ctx, y->ptr, n * sizeof(float));
+  fill_kernel<<<agb_grid_for((n + 3) / 4, 256, ctx->sm_count, 8), 256, 0, ctx->stream>>>(y->ptr, n, value);
+  AGB_LAUNCHED(ctx);
+  return AGB_OK;
+}
+
+// ----------------------------------------------------------------------------------------------
+// dropout: y = x * mask, mask = (u < 1 - ratio) as float.  Not rescaled (random_ops.rs:224-237).
+// seed == 0: the caller supplies `mask` (parity runs: same mask as the oracle).
+// seed != 0: Philox-4x32-10 counter RNG; the reference's XorShift stream is parity-unpinned.
+// ----------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint4 philox4x32_10(uint4 ctr, uint2 key) {
+  const uint32_t M0 = 0xD2511F53u, M1 = 0xCD9E8D57u, W0 = 0x9E3779B9u, W1 = 0xBB67AE85u;
+#pragma unroll
+  for (int r = 0; r < 10; r++) {
+    uint32_t hi0 = __umulhi(M0, ctr.x), lo0 = M0 * ctr.x;
+    uint32_t hi1 = __umulhi(M1, ctr.z), lo1 = M1 * ctr.z;
+    ctr = make_uint4(hi1 ^ ctr.y ^ key.x, lo1, hi0 ^ ctr.w ^ key.y, lo0);
+    key.x += W0; key.y += W1;
+  }
+  return ctr;
+}
+__global__ void __launch_bounds__(256) dropout_gen_kernel(const float* __restrict__ x, float* __restrict__ y,
+                                                          float* __restrict__ mask, int64_t n, float keep,
+                                                          uint64_t seed, uint64_t offset) {
+  int64_t tid = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  int64_t n4 = (n + 3) >> 2;
+  for (int64_t i = tid; i < n4; i += stride) {
+    uint64_t c = offset + (uint64_t)i;
+    uint4 r = philox4x32_10(make_uint4((uint32_t)c, (uint32_t)(c >> 32), 0u, 0u), make_uint2((uint32_t)seed, (uint32_t)(seed >> 32)));
+    uint32_t rr[4] = {r.x, r.y, r.z, r.w};
+#pragma unroll
+    for (int k = 0; k < 4; k++) {
+      int64_t j = 4 * i + k;
+      if (j < n) {
+        float u = (rr[k] >> 8) * (1.0f / 16777216.0f);   // U[0,1)
+        float m = u < keep ? 1.0f : 0.0f;
+        mask[j] = m; y[j] = x[j] * m;
+      }
+    }
+  }
+}
+extern "C" int agb_dropout(agb_ctx* ctx, const agb_tensor* x, agb_tensor* y, agb_tensor* mask, float ratio, uint64_t seed, uint64_t offset) {
+  AGB_CHECK(agb_is_contig(x) && agb_is_contig(y) && agb_is_contig(mask), AGB_ERR_UNSUPPORTED, "agb_dropout: tensors must be contiguous");
+  int64_t n = agb_numel(x);
+  AGB_CHECK(agb_numel(y) == n && agb_numel(mask) == n, AGB_ERR_INCOMPATIBLE_SHAPE, "agb_dropout: size mismatch");
+  if (n == 0) return AGB_OK;
+  if (seed == 0) {
+    agb_tensor xm = *x, mm = *mask, ym = *y;
+    return agb_binary(ctx, AGB_B_MUL, 0.f, 0.f, &mm, &xm, &ym);    // mask * x
+  }
+  dropout_gen_kernel<<<agb_grid_for((n + 3) / 4, 256, ctx->sm_count, 8), 256, 0, ctx->stream>>>(x->ptr, y->ptr, mask->ptr, n, 1.0f - ratio, seed, offset);
+  AGB_LAUNCHED(ctx);
+  return AGB_OK;
+}

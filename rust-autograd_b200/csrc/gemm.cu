@@ -1,0 +1,83 @@
+// gemm.cu — agb_gemm_f32: MatMul / BatchMatMul entry point and dispatch.
+//
+// Reference semantics followed (src/tensor_ops/dot_ops.rs):
+//   MatMul::compute       :565-606  2-D only, transposes = stride swap (:574-579), k mismatch -> IncompatibleShape
+//   BatchMatMul::compute  :632-695  rank >= 2, identical leading dims (no broadcast, :661), transposes on last two axes
+// Output layout: always C-contiguous (the reference may emit Fortran order, dot_ops.rs:585-594; SURVEY §9.17 lets
+// the device path pick one layout and carry strides in the descriptor).
+//
+// Dispatch: tcgen05 tensor-core kernel (tc_gemm.cu; TF32 or 3xTF32) when the operands satisfy TMA's
+// alignment rules and the problem is big enough to fill a 128-lane tile; otherwise the CUDA-core fp32 kernel.
+#include "simt_gemm.cuh"
+
+int agb_tc_gemm(agb_ctx* ctx, int mode, const float* A, const float* B, float* C,
+                int64_t M, int64_t N, int64_t K, int64_t batch,
+                int64_t rsa, int64_t csa, int64_t bsa, int64_t rsb, int64_t csb, int64_t bsb, int64_t bsc, float beta);
+
+struct StridedA { const float* p; int64_t rs, cs, bs; static const bool K_CONTIG = true;
+  __device__ __forceinline__ float load(int z, int64_t m, int64_t k) const { return __ldg(p + z * bs + m * rs + k * cs); } };
+struct StridedA_M { const float* p; int64_t rs, cs, bs; static const bool K_CONTIG = false;
+  __device__ __forceinline__ float load(int z, int64_t m, int64_t k) const { return __ldg(p + z * bs + m * rs + k * cs); } };
+struct StridedB { const float* p; int64_t rs, cs, bs; static const bool K_CONTIG = false;   // n contiguous
+  __device__ __forceinline__ float load(int z, int64_t k, int64_t n) const { return __ldg(p + z * bs + k * rs + n * cs); } };
+struct StridedB_K { const float* p; int64_t rs, cs, bs; static const bool K_CONTIG = true;
+  __device__ __forceinline__ float load(int z, int64_t k, int64_t n) const { return __ldg(p + z * bs + k * rs + n * cs); } };
+struct StoreC { float* p; int64_t ld, bs; int accumulate;
+  __device__ __forceinline__ void store(int z, int64_t m, int64_t n, float v) const {
+    float* q = p + z * bs + m * ld + n; *q = accumulate ? *q + v : v; } };
+
+static int simt_gemm(agb_ctx* ctx, const float* A, const float* B, float* C, int64_t M, int64_t N, int64_t K, int64_t batch,
+                     int64_t rsa, int64_t csa, int64_t bsa, int64_t rsb, int64_t csb, int64_t bsb, int64_t bsc, float beta) {
+  StoreC cs{C, N, bsc, beta != 0.0f};
+  bool a_kc = (csa == 1) || (rsa != 1), b_kc = (rsb == 1) && (csb != 1);
+  for (int64_t z0 = 0; z0 < batch; z0 += 65535) {
+    int64_t zc = batch - z0 < 65535 ? batch - z0 : 65535;
+    const float* a = A + z0 * bsa; const float* b = B + z0 * bsb; StoreC c = cs; c.p = C + z0 * bsc;
+    int r;
+    if (a_kc && !b_kc) r = simt_gemm_launch(ctx, StridedA{a, rsa, csa, bsa}, StridedB{b, rsb, csb, bsb}, c, M, N, K, zc);
+    else if (a_kc && b_kc) r = simt_gemm_launch(ctx, StridedA{a, rsa, csa, bsa}, StridedB_K{b, rsb, csb, bsb}, c, M, N, K, zc);
+    else if (!a_kc && !b_kc) r = simt_gemm_launch(ctx, StridedA_M{a, rsa, csa, bsa}, StridedB{b, rsb, csb, bsb}, c, M, N, K, zc);
+    else r = simt_gemm_launch(ctx, StridedA_M{a, rsa, csa, bsa}, StridedB_K{b, rsb, csb, bsb}, c, M, N, K, zc);
+    AGB_TRY(r);
+  }
+  return AGB_OK;
+}
+
+extern "C" int agb_gemm_f32(agb_ctx* ctx, int trans_a, int trans_b, const agb_tensor* a, const agb_tensor* b, agb_tensor* c, float beta) {
+  AGB_CHECK(a->rank >= 2 && b->rank >= 2, AGB_ERR_INCOMPATIBLE_SHAPE, "matmul: inputs must have ndim >= 2 (got %d and %d)", a->rank, b->rank);
+  AGB_CHECK(a->rank == b->rank && c->rank == a->rank, AGB_ERR_INCOMPATIBLE_SHAPE, "matmul: rank mismatch: %d vs %d (out %d)", a->rank, b->rank, c->rank);
+  AGB_CHECK(beta == 0.0f || beta == 1.0f, AGB_ERR_INVALID_DIMS, "matmul: beta must be 0 or 1");
+  const int R = a->rank;
+  int64_t m = a->shape[R - 2], k = a->shape[R - 1], rsa = a->stride[R - 2], csa = a->stride[R - 1];
+  if (trans_a) { int64_t t = m; m = k; k = t; t = rsa; rsa = csa; csa = t; }
+  int64_t k2 = b->shape[R - 2], n = b->shape[R - 1], rsb = b->stride[R - 2], csb = b->stride[R - 1];
+  if (trans_b) { int64_t t = k2; k2 = n; n = t; t = rsb; rsb = csb; csb = t; }
+  AGB_CHECK(k == k2, AGB_ERR_INCOMPATIBLE_SHAPE, "inputs %lld x %lld and %lld x %lld are not compatible for matrix multiplication",
+            (long long)m, (long long)k, (long long)k2, (long long)n);    // dot_shape_error text, dot_ops.rs
+  int64_t batch = 1;
+  for (int i = 0; i < R - 2; i++) {
+    AGB_CHECK(a->shape[i] == b->shape[i], AGB_ERR_INCOMPATIBLE_SHAPE, "Input shapes mismatch on batch axis %d: %lld vs %lld", i, (long long)a->shape[i], (long long)b->shape[i]);
+    AGB_CHECK(c->shape[i] == a->shape[i], AGB_ERR_INCOMPATIBLE_SHAPE, "matmul: output batch axis %d mismatch", i);
+    batch *= a->shape[i];
+  }
+  AGB_CHECK(c->shape[R - 2] == m && c->shape[R - 1] == n, AGB_ERR_INCOMPATIBLE_SHAPE, "matmul: output must be [.., %lld, %lld]", (long long)m, (long long)n);
+  AGB_CHECK(agb_is_contig(c), AGB_ERR_UNSUPPORTED, "matmul: output must be C-contiguous");
+  // batch dims must collapse to a single stride (the reference deep-copies otherwise, dot_ops.rs:444-453,524-531;
+  // the host evaluator does the same before calling here)
+  int64_t bsa = 0, bsb = 0;
+  if (R > 2) {
+    bsa = a->stride[R - 3]; bsb = b->stride[R - 3];
+    for (int i = R - 4; i >= 0; i--) {
+      AGB_CHECK(a->shape[i] == 1 || a->stride[i] == a->stride[i + 1] * a->shape[i + 1], AGB_ERR_UNSUPPORTED, "batch_matmul: lhs batch dims are not collapsible; copy first");
+      AGB_CHECK(b->shape[i] == 1 || b->stride[i] == b->stride[i + 1] * b->shape[i + 1], AGB_ERR_UNSUPPORTED, "batch_matmul: rhs batch dims are not collapsible; copy first");
+    }
+  }
+  if (m == 0 || n == 0 || batch == 0) return AGB_OK;
+  if (k == 0) { if (beta == 0.0f) return agb_memset0(ctx, c->ptr, agb_numel(c) * sizeof(float)); return AGB_OK; }
+  int mode = ctx->math_mode;
+  if (mode != AGB_MATH_FP32) {
+    int r = agb_tc_gemm(ctx, mode, a->ptr, b->ptr, c->ptr, m, n, k, batch, rsa, csa, bsa, rsb, csb, bsb, m * n, beta);
+    if (r != AGB_ERR_UNSUPPORTED) return r;
+  }
+  return simt_gemm(ctx, a->ptr, b->ptr, c->ptr, m, n, k, batch, rsa, csa, bsa, rsb, csb, bsb, m * n, beta);
+}

@@ -1,0 +1,254 @@
+// runtime.cu — context, stream-ordered caching arena, copies, events, CUDA graphs, NCCL plumbing.
+// Replaces nothing numeric in the reference; it is the device-side counterpart of the evaluator's
+// per-run heap allocations (`src/evaluation.rs:183-223`) and of `VariableEnvironment` storage
+// (`src/variable.rs:152-155`): variables and intermediates live in HBM.
+#include "common.cuh"
+#include <stdarg.h>
+#include <dlfcn.h>
+
+static thread_local char g_err[1024] = "";
+
+void agb_set_error(const char* fmt, ...) {
+  va_list ap; va_start(ap, fmt); vsnprintf(g_err, sizeof(g_err), fmt, ap); va_end(ap);
+}
+int agb_cuda_fail(cudaError_t e, const char* what, const char* file, int line) {
+  agb_set_error("CUDA error %d (%s) at %s:%d: %s", (int)e, cudaGetErrorString(e), file, line, what);
+  return AGB_ERR_CUDA;
+}
+extern "C" const char* agb_last_error(void) { return g_err; }
+
+extern "C" int agb_device_count(int* out) {
+  int n = 0; cudaError_t e = cudaGetDeviceCount(&n);
+  if (e != cudaSuccess) { *out = 0; return agb_cuda_fail(e, "cudaGetDeviceCount", __FILE__, __LINE__); }
+  *out = n; return AGB_OK;
+}
+
+extern "C" int agb_init(int device, agb_ctx** out) {
+  *out = nullptr;
+  int n = 0;
+  AGB_CUDA(cudaGetDeviceCount(&n));
+  AGB_CHECK(n > 0 && device < n, AGB_ERR_CUDA, "agb_init: no CUDA device %d (count=%d); there is no CPU fallback", device, n);
+  AGB_CUDA(cudaSetDevice(device));
+  cudaDeviceProp prop; AGB_CUDA(cudaGetDeviceProperties(&prop, device));
+  AGB_CHECK(prop.major == 10, AGB_ERR_CUDA, "agb_init: device is sm_%d%d; this library is built for sm_100a only", prop.major, prop.minor);
+  agb_ctx* ctx = new agb_ctx();
+  ctx->device = device; ctx->sm_count = prop.multiProcessorCount;
+  AGB_CUDA(cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking));
+  AGB_CUDA(cudaMalloc(&ctx->dev_err, sizeof(int)));
+  AGB_CUDA(cudaMemsetAsync(ctx->dev_err, 0, sizeof(int), ctx->stream));
+  *out = ctx;
+  return AGB_OK;
+}
+
+extern "C" int agb_trim(agb_ctx* ctx) {
+  cudaStreamSynchronize(ctx->stream);
+  for (auto& kv : ctx->free_blocks) { cudaFree(kv.second); ctx->block_size.erase(kv.second); ctx->is_live.erase(kv.second); }
+  ctx->free_blocks.clear(); ctx->cached_bytes = 0;
+  return AGB_OK;
+}
+
+extern "C" int agb_destroy(agb_ctx* ctx) {
+  if (!ctx) return AGB_OK;
+  cudaSetDevice(ctx->device);
+  cudaStreamSynchronize(ctx->stream);
+  agb_nccl_destroy(ctx);
+  for (auto& kv : ctx->block_size) cudaFree(kv.first);
+  for (auto& kv : ctx->optim_tables) cudaFree(kv.second);
+  if (ctx->scratch) cudaFree(ctx->scratch);
+  if (ctx->flush_buf) cudaFree(ctx->flush_buf);
+  if (ctx->dev_err) cudaFree(ctx->dev_err);
+  cudaStreamDestroy(ctx->stream);
+  delete ctx;
+  return AGB_OK;
+}
+
+extern "C" int agb_sm_count(agb_ctx* ctx, int* out) { *out = ctx->sm_count; return AGB_OK; }
+extern "C" int agb_set_math_mode(agb_ctx* ctx, int mode) {
+  AGB_CHECK(mode >= 0 && mode <= 2, AGB_ERR_INVALID_DIMS, "agb_set_math_mode: bad mode %d", mode);
+  ctx->math_mode = mode; return AGB_OK;
+}
+extern "C" int agb_get_math_mode(agb_ctx* ctx, int* mode) { *mode = ctx->math_mode; return AGB_OK; }
+extern "C" int agb_launch_count(agb_ctx* ctx, int64_t* out) { *out = ctx->launches; return AGB_OK; }
+
+static size_t round_block(size_t bytes) {
+  if (bytes == 0) bytes = 1;
+  if (bytes <= (1u << 20)) return (bytes + 511) & ~(size_t)511;              // 512 B granules
+  return (bytes + ((1u << 21) - 1)) & ~(size_t)((1u << 21) - 1);             // 2 MiB granules
+}
+
+extern "C" int agb_alloc(agb_ctx* ctx, size_t bytes, void** out) {
+  size_t sz = round_block(bytes);
+  auto it = ctx->free_blocks.lower_bound(sz);
+  // accept a cached block up to 25% larger than requested
+  if (it != ctx->free_blocks.end() && it->first <= sz + sz / 4) {
+    void* p = it->second; size_t got = it->first;
+    ctx->free_blocks.erase(it);
+    ctx->cached_bytes -= got; ctx->live_bytes += got; ctx->is_live[p] = true;
+    if (ctx->live_bytes > ctx->peak_bytes) ctx->peak_bytes = ctx->live_bytes;
+    *out = p; return AGB_OK;
+  }
+  void* p = nullptr;
+  cudaError_t e = cudaMalloc(&p, sz);
+  if (e != cudaSuccess) {   // give cached memory back and retry once
+    cudaGetLastError();
+    agb_trim(ctx);
+    e = cudaMalloc(&p, sz);
+    if (e != cudaSuccess) return agb_cuda_fail(e, "cudaMalloc", __FILE__, __LINE__);
+  }
+  ctx->block_size[p] = sz; ctx->is_live[p] = true; ctx->live_bytes += sz;
+  if (ctx->live_bytes > ctx->peak_bytes) ctx->peak_bytes = ctx->live_bytes;
+  *out = p; return AGB_OK;
+}
+
+extern "C" int agb_free(agb_ctx* ctx, void* ptr) {
+  if (!ptr) return AGB_OK;
+  auto it = ctx->block_size.find(ptr);
+  AGB_CHECK(it != ctx->block_size.end(), AGB_ERR_INVALID_DIMS, "agb_free: pointer %p not owned by this context", ptr);
+  AGB_CHECK(ctx->is_live[ptr], AGB_ERR_INVALID_DIMS, "agb_free: double free of %p", ptr);
+  ctx->is_live[ptr] = false;
+  ctx->live_bytes -= it->second; ctx->cached_bytes += it->second;
+  ctx->free_blocks.insert({it->second, ptr});
+  return AGB_OK;
+}
+
+extern "C" int agb_mem_stats(agb_ctx* ctx, size_t* live, size_t* cached, size_t* peak) {
+  if (live) *live = ctx->live_bytes; if (cached) *cached = ctx->cached_bytes; if (peak) *peak = ctx->peak_bytes;
+  return AGB_OK;
+}
+
+int agb_scratch(agb_ctx* ctx, size_t bytes, void** out) {
+  if (bytes > ctx->scratch_bytes) {
+    AGB_CHECK(!ctx->capturing, AGB_ERR_CUDA, "scratch growth during graph capture; run the step once eagerly first");
+    if (ctx->scratch) { AGB_CUDA(cudaStreamSynchronize(ctx->stream)); AGB_CUDA(cudaFree(ctx->scratch)); }
+    size_t sz = bytes < (8u << 20) ? (8u << 20) : round_block(bytes);
+    AGB_CUDA(cudaMalloc(&ctx->scratch, sz)); ctx->scratch_bytes = sz;
+  }
+  *out = ctx->scratch; return AGB_OK;
+}
+
+extern "C" int agb_host_alloc(size_t bytes, void** out) { AGB_CUDA(cudaMallocHost(out, bytes ? bytes : 1)); return AGB_OK; }
+extern "C" int agb_host_free(void* p) { if (p) AGB_CUDA(cudaFreeHost(p)); return AGB_OK; }
+
+extern "C" int agb_h2d(agb_ctx* ctx, void* dst, const void* src, size_t bytes) {
+  if (bytes) AGB_CUDA(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyHostToDevice, ctx->stream));
+  return AGB_OK;
+}
+extern "C" int agb_d2h(agb_ctx* ctx, void* dst, const void* src, size_t bytes) {
+  if (bytes) AGB_CUDA(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDeviceToHost, ctx->stream));
+  AGB_CUDA(cudaStreamSynchronize(ctx->stream));
+  return AGB_OK;
+}
+extern "C" int agb_d2d(agb_ctx* ctx, void* dst, const void* src, size_t bytes) {
+  if (bytes) AGB_CUDA(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDeviceToDevice, ctx->stream));
+  return AGB_OK;
+}
+extern "C" int agb_memset0(agb_ctx* ctx, void* dst, size_t bytes) {
+  if (bytes) AGB_CUDA(cudaMemsetAsync(dst, 0, bytes, ctx->stream));
+  return AGB_OK;
+}
+extern "C" int agb_sync(agb_ctx* ctx) {
+  AGB_CUDA(cudaStreamSynchronize(ctx->stream));
+  int flag = 0;
+  AGB_CUDA(cudaMemcpy(&flag, ctx->dev_err, sizeof(int), cudaMemcpyDeviceToHost));
+  if (flag) {
+    cudaMemset(ctx->dev_err, 0, sizeof(int));
+    agb_set_error("device-side index check failed (code %d): label / gather index out of range", flag);
+    return AGB_ERR_OUT_OF_BOUNDS;
+  }
+  return AGB_OK;
+}
+
+__global__ void flush_kernel(float4* p, size_t n4) {
+  size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x;
+  size_t stride = (size_t)gridDim.x * blockDim.x;
+  for (; i < n4; i += stride) p[i] = make_float4(1.f, 2.f, 3.f, 4.f);
+}
+extern "C" int agb_flush_l2(agb_ctx* ctx) {
+  const size_t bytes = 256u << 20;   // 256 MiB > 126 MB L2
+  if (!ctx->flush_buf) { AGB_CUDA(cudaMalloc(&ctx->flush_buf, bytes)); ctx->flush_bytes = bytes; }
+  flush_kernel<<<ctx->sm_count * 4, 256, 0, ctx->stream>>>((float4*)ctx->flush_buf, bytes / 16);
+  AGB_CUDA(cudaPeekAtLastError());
+  return AGB_OK;
+}
+
+// ---- events ----
+extern "C" int agb_event_create(void** ev) { cudaEvent_t e; AGB_CUDA(cudaEventCreate(&e)); *ev = e; return AGB_OK; }
+extern "C" int agb_event_destroy(void* ev) { AGB_CUDA(cudaEventDestroy((cudaEvent_t)ev)); return AGB_OK; }
+extern "C" int agb_event_record(agb_ctx* ctx, void* ev) { AGB_CUDA(cudaEventRecord((cudaEvent_t)ev, ctx->stream)); return AGB_OK; }
+extern "C" int agb_event_elapsed_ms(void* a, void* b, float* ms) {
+  AGB_CUDA(cudaEventSynchronize((cudaEvent_t)b));
+  AGB_CUDA(cudaEventElapsedTime(ms, (cudaEvent_t)a, (cudaEvent_t)b));
+  return AGB_OK;
+}
+
+// ---- CUDA graphs ----
+extern "C" int agb_graph_begin(agb_ctx* ctx) {
+  AGB_CUDA(cudaStreamBeginCapture(ctx->stream, cudaStreamCaptureModeThreadLocal));
+  ctx->capturing = true; return AGB_OK;
+}
+extern "C" int agb_graph_end(agb_ctx* ctx, void** graph_exec) {
+  cudaGraph_t g = nullptr; ctx->capturing = false;
+  AGB_CUDA(cudaStreamEndCapture(ctx->stream, &g));
+  cudaGraphExec_t ge = nullptr;
+  AGB_CUDA(cudaGraphInstantiate(&ge, g, 0));
+  cudaGraphDestroy(g);
+  *graph_exec = ge; return AGB_OK;
+}
+extern "C" int agb_graph_launch(agb_ctx* ctx, void* graph_exec) {
+  AGB_CUDA(cudaGraphLaunch((cudaGraphExec_t)graph_exec, ctx->stream)); return AGB_OK;
+}
+extern "C" int agb_graph_destroy(void* graph_exec) { AGB_CUDA(cudaGraphExecDestroy((cudaGraphExec_t)graph_exec)); return AGB_OK; }
+
+// ---- NCCL (dlopen'ed so the library loads on boxes without it; torch's bundled copy is reused when
+//      torch is already imported in the process) ----
+typedef struct { char internal[128]; } nccl_uid;
+typedef int (*fn_ncclGetUniqueId)(nccl_uid*);
+typedef int (*fn_ncclCommInitRank)(void**, int, nccl_uid, int);
+typedef int (*fn_ncclAllReduce)(const void*, void*, size_t, int, int, void*, cudaStream_t);
+typedef int (*fn_ncclCommDestroy)(void*);
+typedef const char* (*fn_ncclGetErrorString)(int);
+static struct {
+  void* h = nullptr; fn_ncclGetUniqueId uid; fn_ncclCommInitRank init; fn_ncclAllReduce ar; fn_ncclCommDestroy destroy;
+  fn_ncclGetErrorString errstr;
+} g_nccl;
+
+static int nccl_load() {
+  if (g_nccl.h) return AGB_OK;
+  const char* names[] = {"libnccl.so.2", "libnccl.so", nullptr};
+  for (int i = 0; names[i] && !g_nccl.h; i++) g_nccl.h = dlopen(names[i], RTLD_NOW | RTLD_GLOBAL);
+  AGB_CHECK(g_nccl.h, AGB_ERR_NCCL, "dlopen(libnccl.so.2) failed: %s", dlerror());
+  g_nccl.uid = (fn_ncclGetUniqueId)dlsym(g_nccl.h, "ncclGetUniqueId");
+  g_nccl.init = (fn_ncclCommInitRank)dlsym(g_nccl.h, "ncclCommInitRank");
+  g_nccl.ar = (fn_ncclAllReduce)dlsym(g_nccl.h, "ncclAllReduce");
+  g_nccl.destroy = (fn_ncclCommDestroy)dlsym(g_nccl.h, "ncclCommDestroy");
+  g_nccl.errstr = (fn_ncclGetErrorString)dlsym(g_nccl.h, "ncclGetErrorString");
+  AGB_CHECK(g_nccl.uid && g_nccl.init && g_nccl.ar && g_nccl.destroy, AGB_ERR_NCCL, "libnccl is missing symbols");
+  return AGB_OK;
+}
+#define AGB_NCCL(x) do { int _r = (x); if (_r != 0) { agb_set_error("NCCL error %d (%s): %s", _r, g_nccl.errstr ? g_nccl.errstr(_r) : "?", #x); return AGB_ERR_NCCL; } } while (0)
+
+extern "C" int agb_nccl_unique_id(void* id128) {
+  AGB_TRY(nccl_load());
+  AGB_NCCL(g_nccl.uid((nccl_uid*)id128));
+  return AGB_OK;
+}
+extern "C" int agb_nccl_init(agb_ctx* ctx, int rank, int world, const void* id128) {
+  AGB_TRY(nccl_load());
+  AGB_CUDA(cudaSetDevice(ctx->device));
+  nccl_uid id; memcpy(&id, id128, sizeof(id));
+  AGB_NCCL(g_nccl.init(&ctx->nccl_comm, world, id, rank));
+  ctx->rank = rank; ctx->world = world;
+  return AGB_OK;
+}
+extern "C" int agb_allreduce_sum(agb_ctx* ctx, float* buf, int64_t n) {
+  if (ctx->world <= 1) return AGB_OK;
+  AGB_CHECK(ctx->nccl_comm, AGB_ERR_NCCL, "agb_allreduce_sum: agb_nccl_init was not called");
+  // ncclFloat32 = 7, ncclSum = 0
+  AGB_NCCL(g_nccl.ar(buf, buf, (size_t)n, 7, 0, ctx->nccl_comm, ctx->stream));
+  ctx->launches++;
+  return AGB_OK;
+}
+extern "C" int agb_nccl_destroy(agb_ctx* ctx) {
+  if (ctx->nccl_comm && g_nccl.destroy) { g_nccl.destroy(ctx->nccl_comm); ctx->nccl_comm = nullptr; }
+  return AGB_OK;
+}

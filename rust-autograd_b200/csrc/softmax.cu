@@ -1,0 +1,239 @@
+// softmax.cu — softmax / log_softmax / logsumexp over a [outer, r, inner] view and the fused
+// sparse-softmax-cross-entropy forward/backward.  HBM roofline: 8 B/elem (read once + write once,
+// SURVEY §8d) — rows are staged once in shared memory / registers so x is read from HBM exactly once
+// whenever a row fits on chip (<= 48 K floats); longer rows take a second (L2-served) read.
+//
+// Reference semantics followed:
+//   softmax_impl (max-subtract, exp, sum, divide)      src/tensor_ops/activation_ops.rs:61-96
+//   logsumexp_forward (max, exp, sum, ln, + max)       src/tensor_ops/math_ops.rs:540-593
+//   LogSoftmax = x - logsumexp(x)                      src/tensor_ops/xent_ops.rs:17-22
+//   SparseSoftmaxCrossEntropy (loss [B,1], log_x)      src/tensor_ops/xent_ops.rs:63-113
+//   SparseSoftmaxCrossEntropyGrad                      src/tensor_ops/xent_ops.rs:139-152
+//   SoftmaxCrossEntropy                                src/tensor_ops/xent_ops.rs:160-177
+// The reference max-fold starts from T::min_value() (= -FLT_MAX); so does this one.
+#include "common.cuh"
+#include <float.h>
+
+enum { SM_SOFTMAX = 0, SM_LOGSOFTMAX = 1, SM_LSE = 2, SM_SPARSE_XENT = 3, SM_DENSE_XENT = 4 };
+
+__device__ __forceinline__ float block_max(float v, float* sm) {
+  v = warp_max(v);
+  int w = threadIdx.x >> 5, l = threadIdx.x & 31, nw = blockDim.x >> 5;
+  if (l == 0) sm[w] = v;
+  __syncthreads();
+  float r = (l < nw) ? sm[l] : -FLT_MAX;
+  r = warp_max(r);
+  __syncthreads();
+  return r;
+}
+__device__ __forceinline__ float block_sum(float v, float* sm) {
+  v = warp_sum(v);
+  int w = threadIdx.x >> 5, l = threadIdx.x & 31, nw = blockDim.x >> 5;
+  if (l == 0) sm[w] = v;
+  __syncthreads();
+  float r = (l < nw) ? sm[l] : 0.0f;
+  r = warp_sum(r);
+  __syncthreads();
+  return r;
+}
+
+// finalise one row element
+template <int MODE> __device__ __forceinline__ float sm_out(float x, float mx, float sum, float lse) {
+  if (MODE == SM_SOFTMAX) return expf(x - mx) / sum;
+  return x - lse;
+}
+
+// ---- short rows: one warp per row, row cached in registers (r <= 32*CAP) ----
+template <int MODE, int CAP>
+__global__ void __launch_bounds__(256) softmax_warp_kernel(const float* __restrict__ x, float* __restrict__ y,
+                                                           const float* __restrict__ aux, float* __restrict__ loss,
+                                                           int64_t rows, int r, int* err) {
+  int64_t row = blockIdx.x * (int64_t)(blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (row >= rows) return;
+  int l = threadIdx.x & 31;
+  const float* p = x + row * (int64_t)r;
+  float v[CAP];
+  float mx = -FLT_MAX;
+#pragma unroll
+  for (int k = 0; k < CAP; k++) { int i = l + 32 * k; v[k] = (i < r) ? __ldg(p + i) : -FLT_MAX; if (i < r) mx = fmaxf(mx, v[k]); }
+  mx = warp_max(mx);
+  float s = 0.0f;
+#pragma unroll
+  for (int k = 0; k < CAP; k++) { int i = l + 32 * k; if (i < r) s += expf(v[k] - mx); }
+  s = warp_sum(s);
+  float lse = logf(s) + mx;
+  if (MODE == SM_LSE) { if (l == 0) y[row] = lse; return; }
+  float* q = y + row * (int64_t)r;
+  float dense = 0.0f;
+#pragma unroll
+  for (int k = 0; k < CAP; k++) {
+    int i = l + 32 * k;
+    if (i < r) {
+      float o = sm_out<MODE>(v[k], mx, s, lse);
+      q[i] = o;
+      if (MODE == SM_DENSE_XENT) dense += __ldg(aux + row * (int64_t)r + i) * o;
+    }
+  }
+  if (MODE == SM_SPARSE_XENT && l == 0) {
+    float tf = __ldg(aux + row); int t = (int)tf;
+    if (tf < 0.0f || t >= r || tf != tf) { atomicExch(err, 1); loss[row] = nanf(""); }
+    else loss[row] = -(__ldg(p + t) - lse);
+  }
+  if (MODE == SM_DENSE_XENT) { dense = warp_sum(dense); if (l == 0) loss[row] = -dense; }
+}
+
+// ---- long rows: one block per row; the row is staged in dynamic shared memory when it fits ----
+template <int MODE, bool CACHED>
+__global__ void __launch_bounds__(512) softmax_block_kernel(const float* __restrict__ x, float* __restrict__ y,
+                                                            const float* __restrict__ aux, float* __restrict__ loss,
+                                                            int64_t r, int* err) {
+  extern __shared__ __align__(16) float rowbuf[];
+  __shared__ float red[32];
+  int64_t row = blockIdx.x;
+  const float* p = x + row * r;
+  const int T = blockDim.x;
+  bool vec = ((((uintptr_t)p) & 15) == 0) && (r % 4 == 0);
+  float mx = -FLT_MAX;
+  if (vec) {
+    for (int64_t i = threadIdx.x; i < (r >> 2); i += T) {
+      float4 v = ldg_stream4(p + 4 * i);
+      if (CACHED) *(float4*)(rowbuf + 4 * i) = v;
+      mx = fmaxf(mx, fmaxf(fmaxf(v.x, v.y), fmaxf(v.z, v.w)));
+    }
+  } else {
+    for (int64_t i = threadIdx.x; i < r; i += T) { float v = __ldg(p + i); if (CACHED) rowbuf[i] = v; mx = fmaxf(mx, v); }
+  }
+  mx = block_max(mx, red);    // also orders the rowbuf writes (syncthreads inside)
+  const float* src = CACHED ? rowbuf : p;
+  float s = 0.0f;
+  for (int64_t i = threadIdx.x; i < r; i += T) s += expf(src[i] - mx);
+  s = block_sum(s, red);
+  float lse = logf(s) + mx;
+  if (MODE == SM_LSE) { if (threadIdx.x == 0) y[row] = lse; return; }
+  float* q = y + row * r;
+  float dense = 0.0f;
+  bool vecq = vec && ((((uintptr_t)q) & 15) == 0);
+  if (vecq && MODE != SM_DENSE_XENT) {
+    for (int64_t i = threadIdx.x; i < (r >> 2); i += T) {
+      float4 v = CACHED ? *(const float4*)(rowbuf + 4 * i) : *(const float4*)(p + 4 * i);
+      v.x = sm_out<MODE>(v.x, mx, s, lse); v.y = sm_out<MODE>(v.y, mx, s, lse);
+      v.z = sm_out<MODE>(v.z, mx, s, lse); v.w = sm_out<MODE>(v.w, mx, s, lse);
+      stg_stream4(q + 4 * i, v);
+    }
+  } else {
+    for (int64_t i = threadIdx.x; i < r; i += T) {
+      float o = sm_out<MODE>(src[i], mx, s, lse);
+      q[i] = o;
+      if (MODE == SM_DENSE_XENT) dense += __ldg(aux + row * r + i) * o;
+    }
+  }
+  if (MODE == SM_SPARSE_XENT && threadIdx.x == 0) {
+    float tf = __ldg(aux + row); int64_t t = (int64_t)tf;
+    if (tf < 0.0f || t >= r || tf != tf) { atomicExch(err, 1); loss[row] = nanf(""); }
+    else loss[row] = -(src[t] - lse);
+  }
+  if (MODE == SM_DENSE_XENT) { dense = block_sum(dense, red); if (threadIdx.x == 0) loss[row] = -dense; }
+}
+
+// ---- inner > 1: one thread per (outer, inner) column, three strided passes (coalesced across inner) ----
+template <int MODE>
+__global__ void __launch_bounds__(256) softmax_cols_kernel(const float* __restrict__ x, float* __restrict__ y, int64_t r, int64_t inner) {
+  int64_t col = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  if (col >= inner) return;
+  int64_t o = blockIdx.y;
+  const float* p = x + o * r * inner + col;
+  float mx = -FLT_MAX;
+  for (int64_t k = 0; k < r; k++) mx = fmaxf(mx, __ldg(p + k * inner));
+  float s = 0.0f;
+  for (int64_t k = 0; k < r; k++) s += expf(__ldg(p + k * inner) - mx);
+  float lse = logf(s) + mx;
+  if (MODE == SM_LSE) { y[o * inner + col] = lse; return; }
+  float* q = y + o * r * inner + col;
+  for (int64_t k = 0; k < r; k++) q[k * inner] = sm_out<MODE>(__ldg(p + k * inner), mx, s, lse);
+}
+
+template <int MODE>
+static int softmax_rows(agb_ctx* ctx, const float* x, float* y, const float* aux, float* loss, int64_t rows, int64_t r) {
+  if (rows == 0) return AGB_OK;
+  AGB_CHECK(r > 0, AGB_ERR_INCOMPATIBLE_SHAPE, "softmax: reduction axis has length 0");
+  if (r <= 32 * 4 ) {
+    unsigned blocks = (unsigned)((rows + 7) / 8);
+    if (r <= 32) softmax_warp_kernel<MODE, 1><<<blocks, 256, 0, ctx->stream>>>(x, y, aux, loss, rows, (int)r, ctx->dev_err);
+    else softmax_warp_kernel<MODE, 4><<<blocks, 256, 0, ctx->stream>>>(x, y, aux, loss, rows, (int)r, ctx->dev_err);
+    AGB_LAUNCHED(ctx); return AGB_OK;
+  }
+  if (r <= 1024) {
+    unsigned blocks = (unsigned)((rows + 7) / 8);
+    softmax_warp_kernel<MODE, 32><<<blocks, 256, 0, ctx->stream>>>(x, y, aux, loss, rows, (int)r, ctx->dev_err);
+    AGB_LAUNCHED(ctx); return AGB_OK;
+  }
+  AGB_CHECK(rows < (1ll << 31), AGB_ERR_UNSUPPORTED, "softmax: too many rows");
+  int threads = r >= 8192 ? 512 : 256;
+  size_t smem = (size_t)r * sizeof(float);
+  if (smem <= 200 * 1024) {
+    static bool attr_set[8] = {false};
+    if (smem > 48 * 1024 && !attr_set[MODE]) {
+      AGB_CUDA(cudaFuncSetAttribute(softmax_block_kernel<MODE, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+      attr_set[MODE] = true;
+    }
+    softmax_block_kernel<MODE, true><<<(unsigned)rows, threads, smem, ctx->stream>>>(x, y, aux, loss, r, ctx->dev_err);
+  } else {
+    softmax_block_kernel<MODE, false><<<(unsigned)rows, 512, 0, ctx->stream>>>(x, y, aux, loss, r, ctx->dev_err);
+  }
+  AGB_LAUNCHED(ctx);
+  return AGB_OK;
+}
+
+template <int MODE>
+static int softmax_any(agb_ctx* ctx, const float* x, float* y, int64_t outer, int64_t r, int64_t inner) {
+  if (outer * inner == 0) return AGB_OK;
+  if (inner == 1) return softmax_rows<MODE>(ctx, x, y, nullptr, nullptr, outer, r);
+  AGB_CHECK(outer <= 65535, AGB_ERR_UNSUPPORTED, "softmax: outer too large for the strided path");
+  AGB_CHECK(r > 0, AGB_ERR_INCOMPATIBLE_SHAPE, "softmax: reduction axis has length 0");
+  softmax_cols_kernel<MODE><<<dim3((unsigned)((inner + 255) / 256), (unsigned)outer), 256, 0, ctx->stream>>>(x, y, r, inner);
+  AGB_LAUNCHED(ctx);
+  return AGB_OK;
+}
+
+extern "C" int agb_softmax(agb_ctx* ctx, const float* x, float* y, int64_t outer, int64_t r, int64_t inner) {
+  return softmax_any<SM_SOFTMAX>(ctx, x, y, outer, r, inner);
+}
+extern "C" int agb_log_softmax(agb_ctx* ctx, const float* x, float* y, int64_t outer, int64_t r, int64_t inner) {
+  return softmax_any<SM_LOGSOFTMAX>(ctx, x, y, outer, r, inner);
+}
+extern "C" int agb_logsumexp(agb_ctx* ctx, const float* x, float* y, int64_t outer, int64_t r, int64_t inner) {
+  return softmax_any<SM_LSE>(ctx, x, y, outer, r, inner);
+}
+extern "C" int agb_sparse_xent_fwd(agb_ctx* ctx, const float* logits, const float* labels, float* loss, float* log_x,
+                                   int64_t batch, int64_t classes) {
+  return softmax_rows<SM_SPARSE_XENT>(ctx, logits, log_x, labels, loss, batch, classes);
+}
+extern "C" int agb_softmax_xent_fwd(agb_ctx* ctx, const float* logits, const float* t, float* loss, float* log_x,
+                                    int64_t batch, int64_t classes) {
+  return softmax_rows<SM_DENSE_XENT>(ctx, logits, log_x, t, loss, batch, classes);
+}
+
+// gx[b,c] = (exp(log_x[b,c]) - (c == t[b])) * gy[b]
+__global__ void __launch_bounds__(256) sparse_xent_bwd_kernel(const float* __restrict__ log_x, const float* __restrict__ labels,
+                                                              const float* __restrict__ gy, int64_t gy_len, float* __restrict__ gx,
+                                                              int64_t batch, int64_t classes) {
+  int64_t n = batch * classes;
+  int64_t tid = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  for (int64_t i = tid; i < n; i += stride) {
+    int64_t b = i / classes, c = i - b * classes;
+    float g = __ldg(gy + (gy_len == 1 ? 0 : b));
+    int64_t t = (int64_t)__ldg(labels + b);
+    float v = expf(__ldg(log_x + i));
+    if (c == t) v -= 1.0f;
+    gx[i] = v * g;
+  }
+}
+extern "C" int agb_sparse_xent_bwd(agb_ctx* ctx, const float* log_x, const float* labels, const float* gy, int64_t gy_len,
+                                   float* gx, int64_t batch, int64_t classes) {
+  AGB_CHECK(gy_len == 1 || gy_len == batch, AGB_ERR_INCOMPATIBLE_SHAPE, "sparse_xent_bwd: gy must have 1 or batch elements (got %lld)", (long long)gy_len);
+  int64_t n = batch * classes; if (n == 0) return AGB_OK;
+  sparse_xent_bwd_kernel<<<agb_grid_for(n, 256, ctx->sm_count, 8), 256, 0, ctx->stream>>>(log_x, labels, gy, gy_len, gx, batch, classes);
+  AGB_LAUNCHED(ctx);
+  return AGB_OK;
+}

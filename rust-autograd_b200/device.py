@@ -1,0 +1,358 @@
+"""Kernel-level Python handle on the C ABI: a ``Device`` (context + stream + HBM arena) and ``DArray``
+(device-resident f32 array with shape/strides, the device analogue of ``NdArray``/``NdArrayView``).
+
+Only plumbing lives here (allocation, H2D/D2H, view arithmetic, output-shape computation for the kernel
+entry points); every number is produced by ``libagb200.so``.
+"""
+import ctypes as C
+
+import numpy as np
+
+from . import ffi
+
+
+class DArray:
+    """f32 array in HBM.  ``owner`` keeps the backing block alive for views."""
+
+    def __init__(self, dev, ptr, shape, strides=None, owner=None, owns=False):
+        self.dev, self.ptr, self.shape = dev, int(ptr) if ptr else 0, tuple(int(d) for d in shape)
+        if strides is None:
+            strides, s = [], 1
+            for d in reversed(self.shape):
+                strides.append(s)
+                s *= d
+            strides = tuple(reversed(strides))
+        self.strides = tuple(int(s) for s in strides)
+        self.owner, self.owns = owner, owns
+
+    @property
+    def size(self):
+        n = 1
+        for d in self.shape:
+            n *= d
+        return n
+
+    @property
+    def ndim(self):
+        return len(self.shape)
+
+    def desc(self):
+        return ffi.make_tensor(self.ptr, self.shape, self.strides)
+
+    def is_contiguous(self):
+        s = 1
+        for d, st in zip(reversed(self.shape), reversed(self.strides)):
+            if d != 1 and st != s:
+                return False
+            s *= d
+        return True
+
+    # zero-copy views (reference: OpOutput::View, Transpose = stride permutation math_ops.rs:448)
+    def reshape(self, shape):
+        assert self.is_contiguous()
+        return DArray(self.dev, self.ptr, shape, owner=self)
+
+    def transpose(self, perm=None):
+        perm = perm or tuple(reversed(range(self.ndim)))
+        return DArray(self.dev, self.ptr, [self.shape[p] for p in perm], [self.strides[p] for p in perm], owner=self)
+
+    def broadcast_to(self, shape):
+        shape = tuple(shape)
+        pad = len(shape) - self.ndim
+        sh = (1,) * pad + self.shape
+        st = (0,) * pad + self.strides
+        strides = []
+        for d, t, s in zip(sh, shape, st):
+            if d == t:
+                strides.append(s)
+            elif d == 1:
+                strides.append(0)
+            else:
+                raise ffi.OpError(ffi.ERR_INCOMPATIBLE_SHAPE, "cannot broadcast %s to %s" % (self.shape, shape))
+        return DArray(self.dev, self.ptr, shape, strides, owner=self)
+
+    def slice(self, axis, start, stop):
+        shape = list(self.shape)
+        shape[axis] = stop - start
+        return DArray(self.dev, self.ptr + 4 * start * self.strides[axis], shape, self.strides, owner=self)
+
+    def numpy(self):
+        return self.dev.download(self)
+
+    def free(self):
+        if self.owns and self.ptr:
+            ffi.check(self.dev.lib.agb_free(self.dev.ctx, self.ptr))
+            self.ptr, self.owns = 0, False
+
+    def __del__(self):
+        try:
+            self.free()
+        except Exception:
+            pass
+
+
+class Device:
+    def __init__(self, index=0):
+        self.lib = ffi.load_library()
+        ctx = C.c_void_p()
+        ffi.check(self.lib.agb_init(index, C.byref(ctx)))
+        self.ctx = ctx
+        self.index = index
+
+    def close(self):
+        if self.ctx:
+            self.lib.agb_destroy(self.ctx)
+            self.ctx = None
+
+    # ---- memory ----
+    def empty(self, shape):
+        n = 1
+        for d in shape:
+            n *= int(d)
+        p = C.c_void_p()
+        ffi.check(self.lib.agb_alloc(self.ctx, max(n, 1) * 4, C.byref(p)))
+        return DArray(self, p.value, shape, owns=True)
+
+    def upload(self, a):
+        a = np.ascontiguousarray(a, dtype=np.float32)
+        t = self.empty(a.shape)
+        ffi.check(self.lib.agb_h2d(self.ctx, t.ptr, ffi.np_ptr(a), a.nbytes))
+        self.sync()          # the numpy temporary may die right after this call
+        return t
+
+    def download(self, t):
+        if not t.is_contiguous():
+            c = self.empty(t.shape)
+            ffi.check(self.lib.agb_copy_strided(self.ctx, t.desc(), c.desc()))
+            t = c
+        out = np.empty(t.shape, dtype=np.float32)
+        ffi.check(self.lib.agb_d2h(self.ctx, ffi.np_ptr(out), t.ptr, out.nbytes))
+        ffi.check(self.lib.agb_sync(self.ctx))
+        return out
+
+    def sync(self):
+        ffi.check(self.lib.agb_sync(self.ctx))
+
+    def set_math_mode(self, mode):
+        ffi.check(self.lib.agb_set_math_mode(self.ctx, mode))
+
+    def launch_count(self):
+        v = C.c_int64()
+        ffi.check(self.lib.agb_launch_count(self.ctx, C.byref(v)))
+        return v.value
+
+    def sm_count(self):
+        v = C.c_int()
+        ffi.check(self.lib.agb_sm_count(self.ctx, C.byref(v)))
+        return v.value
+
+    # ---- timing on the context's stream ----
+    def event(self):
+        e = C.c_void_p()
+        ffi.check(self.lib.agb_event_create(C.byref(e)))
+        return e
+
+    def record(self, e):
+        ffi.check(self.lib.agb_event_record(self.ctx, e))
+
+    def elapsed_ms(self, a, b):
+        ms = C.c_float()
+        ffi.check(self.lib.agb_event_elapsed_ms(a, b, C.byref(ms)))
+        return ms.value
+
+    def flush_l2(self):
+        ffi.check(self.lib.agb_flush_l2(self.ctx))
+
+    # ---- kernels (thin: compute the output shape, call C) ----
+    def unary(self, op, x, p0=0.0, p1=0.0):
+        y = self.empty(x.shape)
+        ffi.check(self.lib.agb_unary(self.ctx, ffi.U[op], p0, p1, x.desc(), y.desc()))
+        return y
+
+    def binary(self, op, a, b, p0=0.0, p1=0.0):
+        shape = np.broadcast_shapes(a.shape, b.shape)
+        y = self.empty(shape)
+        ffi.check(self.lib.agb_binary(self.ctx, ffi.B[op], p0, p1, a.broadcast_to(shape).desc(), b.broadcast_to(shape).desc(), y.desc()))
+        return y
+
+    def add_n(self, xs):
+        y = self.empty(xs[0].shape)
+        descs = [x.desc() for x in xs]
+        arr = (C.POINTER(ffi.AgbTensor) * len(xs))(*[C.pointer(d) for d in descs])
+        ffi.check(self.lib.agb_add_n(self.ctx, len(xs), arr, y.desc()))
+        return y
+
+    def fill(self, shape, v):
+        y = self.empty(shape)
+        ffi.check(self.lib.agb_fill(self.ctx, y.desc(), v))
+        return y
+
+    def copy(self, x):
+        y = self.empty(x.shape)
+        ffi.check(self.lib.agb_copy_strided(self.ctx, x.desc(), y.desc()))
+        return y
+
+    def _axis_view(self, shape, axis):
+        outer = 1
+        for d in shape[:axis]:
+            outer *= d
+        inner = 1
+        for d in shape[axis + 1:]:
+            inner *= d
+        return outer, shape[axis], inner
+
+    def reduce(self, op, x, axis, keep_dims=False):
+        assert x.is_contiguous()
+        axis %= x.ndim
+        o, r, i = self._axis_view(x.shape, axis)
+        shape = list(x.shape)
+        if keep_dims:
+            shape[axis] = 1
+        else:
+            shape.pop(axis)
+        y = self.empty(shape)
+        ffi.check(self.lib.agb_reduce(self.ctx, ffi.R[op], x.ptr, y.ptr, o, r, i))
+        return y
+
+    def argreduce(self, is_max, x, axis, keep_dims=False):
+        assert x.is_contiguous()
+        axis %= x.ndim
+        o, r, i = self._axis_view(x.shape, axis)
+        shape = list(x.shape)
+        if keep_dims:
+            shape[axis] = 1
+        else:
+            shape.pop(axis)
+        y = self.empty(shape)
+        ffi.check(self.lib.agb_argreduce(self.ctx, int(is_max), x.ptr, y.ptr, o, r, i))
+        return y
+
+    def softmax_like(self, kind, x, axis):
+        assert x.is_contiguous()
+        axis %= x.ndim
+        o, r, i = self._axis_view(x.shape, axis)
+        if kind == "logsumexp":
+            shape = list(x.shape)
+            shape[axis] = 1
+            y = self.empty(shape)
+        else:
+            y = self.empty(x.shape)
+        fn = {"softmax": self.lib.agb_softmax, "log_softmax": self.lib.agb_log_softmax, "logsumexp": self.lib.agb_logsumexp}[kind]
+        ffi.check(fn(self.ctx, x.ptr, y.ptr, o, r, i))
+        return y
+
+    def sparse_xent_fwd(self, logits, labels):
+        b, c = logits.shape
+        loss, log_x = self.empty((b, 1)), self.empty((b, c))
+        ffi.check(self.lib.agb_sparse_xent_fwd(self.ctx, logits.ptr, labels.ptr, loss.ptr, log_x.ptr, b, c))
+        return loss, log_x
+
+    def sparse_xent_bwd(self, log_x, labels, gy):
+        b, c = log_x.shape
+        gx = self.empty((b, c))
+        ffi.check(self.lib.agb_sparse_xent_bwd(self.ctx, log_x.ptr, labels.ptr, gy.ptr, gy.size, gx.ptr, b, c))
+        return gx
+
+    def softmax_xent_fwd(self, logits, t):
+        b, c = logits.shape
+        loss, log_x = self.empty((b,)), self.empty((b, c))
+        ffi.check(self.lib.agb_softmax_xent_fwd(self.ctx, logits.ptr, t.ptr, loss.ptr, log_x.ptr, b, c))
+        return loss, log_x
+
+    def gemm(self, a, b, trans_a=False, trans_b=False, out=None, beta=0.0):
+        ash, bsh = list(a.shape), list(b.shape)
+        m, k = (ash[-1], ash[-2]) if trans_a else (ash[-2], ash[-1])
+        n = bsh[-2] if trans_b else bsh[-1]
+        c = out if out is not None else self.empty(ash[:-2] + [m, n])
+        ffi.check(self.lib.agb_gemm_f32(self.ctx, int(trans_a), int(trans_b), a.desc(), b.desc(), c.desc(), beta))
+        return c
+
+    @staticmethod
+    def conv_out(x, k, pad, stride, dil):
+        return (x + 2 * pad - (dil * (k - 1) + 1)) // stride + 1
+
+    def conv2d(self, x, w, pad=0, stride=1, dil=1):
+        b, _, h, wd = x.shape
+        o, _, kh, kw = w.shape
+        y = self.empty((b, o, self.conv_out(h, kh, pad, stride, dil), self.conv_out(wd, kw, pad, stride, dil)))
+        ffi.check(self.lib.agb_conv2d_fprop_f32(self.ctx, x.desc(), w.desc(), y.desc(), pad, stride, dil))
+        return y
+
+    def conv2d_transpose(self, gy, w, pad=0, stride=1, dil=1):
+        b, _, yh, yw = gy.shape
+        _, c, kh, kw = w.shape
+        xh = stride * (yh - 1) - 2 * pad + (dil * (kh - 1) + 1)
+        xw = stride * (yw - 1) - 2 * pad + (dil * (kw - 1) + 1)
+        gx = self.empty((b, c, xh, xw))
+        ffi.check(self.lib.agb_conv2d_dgrad_f32(self.ctx, gy.desc(), w.desc(), gx.desc(), pad, stride, dil))
+        return gx
+
+    def conv2d_filter_grad(self, img, g, wshape, pad=0, stride=1, dil=1):
+        gw = self.empty(wshape)
+        ffi.check(self.lib.agb_conv2d_wgrad_f32(self.ctx, img.desc(), g.desc(), gw.desc(), pad, stride, dil))
+        return gw
+
+    def im2col(self, x, kh, kw, pad=0, stride=1, dil=1):
+        b, c, h, w = x.shape
+        cols = self.empty((b, c, kh, kw, self.conv_out(h, kh, pad, stride, dil), self.conv_out(w, kw, pad, stride, dil)))
+        ffi.check(self.lib.agb_im2col_f32(self.ctx, x.desc(), cols.desc(), kh, kw, pad, stride, dil))
+        return cols
+
+    def max_pool2d(self, x, size, pad=0, stride=1):
+        b, c, h, w = x.shape
+        yh, yw = (h + 2 * pad - size) // stride + 1, (w + 2 * pad - size) // stride + 1
+        y, idx = self.empty((b, c, yh, yw)), self.empty((b, c, yh, yw))
+        ffi.check(self.lib.agb_maxpool2d_fwd(self.ctx, x.desc(), y.desc(), idx.ptr, None, size, pad, stride))
+        return y, idx
+
+    def max_pool2d_grad(self, gy, idx, size, pad=0, stride=1):
+        b, c, yh, yw = gy.shape
+        gx = self.empty((b, c, stride * (yh - 1) - 2 * pad + size, stride * (yw - 1) - 2 * pad + size))
+        ffi.check(self.lib.agb_maxpool2d_bwd(self.ctx, gy.desc(), idx.ptr, None, gx.desc()))
+        return gx
+
+    def max_pool2d_grad_grad(self, ggx, idx, size, pad=0, stride=1):
+        b, c, h, w = ggx.shape
+        ggy = self.empty((b, c, (h + 2 * pad - size) // stride + 1, (w + 2 * pad - size) // stride + 1))
+        ffi.check(self.lib.agb_maxpool2d_gradgrad(self.ctx, ggx.desc(), idx.ptr, None, ggy.desc()))
+        return ggy
+
+    def gather(self, param, indices, axis, normalize_negative=True):
+        axis %= param.ndim
+        pre, al, post = self._axis_view(param.shape, axis)
+        out = self.empty(tuple(param.shape[:axis]) + tuple(indices.shape) + tuple(param.shape[axis + 1:]))
+        ffi.check(self.lib.agb_gather(self.ctx, param.ptr, indices.ptr, out.ptr, pre, al, post, indices.size, int(normalize_negative)))
+        return out
+
+    def gather_grad(self, gy, indices, param_shape, axis):
+        axis %= len(param_shape)
+        pre, al, post = self._axis_view(tuple(param_shape), axis)
+        gx = self.empty(param_shape)
+        ffi.check(self.lib.agb_gather_grad(self.ctx, gy.ptr, indices.ptr, gx.ptr, pre, al, post, indices.size))
+        return gx
+
+    def dropout(self, x, ratio, mask=None, seed=0, offset=0):
+        y = self.empty(x.shape)
+        m = mask if mask is not None else self.empty(x.shape)
+        ffi.check(self.lib.agb_dropout(self.ctx, x.desc(), y.desc(), m.desc(), ratio, seed, offset))
+        return y, m
+
+    def _plist(self, arrs):
+        return (C.c_void_p * len(arrs))(*[a.ptr for a in arrs])
+
+    def adam(self, ps, gs, ms, vs, ts, alpha=1e-3, eps=1e-8, b1=0.9, b2=0.999, grad_scale=1.0):
+        sizes = (C.c_int64 * len(ps))(*[p.size for p in ps])
+        ffi.check(self.lib.agb_multi_tensor_adam(self.ctx, len(ps), self._plist(ps), self._plist(gs), self._plist(ms),
+                                                 self._plist(vs), self._plist(ts), sizes, alpha, eps, b1, b2, grad_scale))
+
+    def sgd(self, ps, gs, alpha, grad_scale=1.0):
+        sizes = (C.c_int64 * len(ps))(*[p.size for p in ps])
+        ffi.check(self.lib.agb_multi_tensor_sgd(self.ctx, len(ps), self._plist(ps), self._plist(gs), sizes, alpha, grad_scale))
+
+    def momentum(self, ps, gs, vs, lr, momentum, grad_scale=1.0):
+        sizes = (C.c_int64 * len(ps))(*[p.size for p in ps])
+        ffi.check(self.lib.agb_multi_tensor_momentum(self.ctx, len(ps), self._plist(ps), self._plist(gs), self._plist(vs), sizes, lr, momentum, grad_scale))
+
+    def adagrad(self, ps, gs, hs, lr, grad_scale=1.0):
+        sizes = (C.c_int64 * len(ps))(*[p.size for p in ps])
+        ffi.check(self.lib.agb_multi_tensor_adagrad(self.ctx, len(ps), self._plist(ps), self._plist(gs), self._plist(hs), sizes, lr, grad_scale))

@@ -1,0 +1,432 @@
+"""-m gpu parity tests, kernel level: every entry point of include/agb200.h (called through the C ABI via ctypes) against
+the oracle (oracle/ref_ops.py) on the same seeded inputs, plus the reference's own known-answer vectors replayed on the GPU.
+
+Tolerances (BASELINE.json north_star): bit-exact for index/integer-valued outputs; f32 within 1e-5 relative for
+3xTF32 / fp32 GEMM-conv and for elementwise / reduction kernels; 1e-2 relative in TF32 mode.  For contractions
+"relative" is taken against the largest output magnitude (forward-error convention for sums with cancellation)."""
+import json
+import os
+
+import numpy as np
+import pytest
+
+from oracle import ref_ops as R
+
+pytestmark = pytest.mark.gpu
+KATS = json.load(open(os.path.join(os.path.dirname(__file__), "golden", "reference_kats.json")))
+TOL = {0: 1e-5, 1: 1e-2, 2: 1e-5}      # math mode -> relative tolerance
+MODES = [0, 1, 2]                        # 3xTF32, TF32, FP32
+
+
+def rel_err(got, ref):
+    got, ref = np.asarray(got, np.float64), np.asarray(ref, np.float64)
+    assert got.shape == ref.shape, (got.shape, ref.shape)
+    if ref.size == 0:
+        return 0.0
+    return float(np.abs(got - ref).max() / max(np.abs(ref).max(), 1e-30))
+
+
+def close(got, ref, tol=1e-5):
+    np.testing.assert_allclose(np.asarray(got, np.float64), np.asarray(ref, np.float64), rtol=tol, atol=tol * 1e-1)
+
+
+# ------------------------------------------------------------------------------------------------ runtime
+def test_runtime_roundtrip_and_arena(dev):
+    rng = np.random.default_rng(0)
+    a = rng.standard_normal((37, 129)).astype(np.float32)
+    d = dev.upload(a)
+    assert np.array_equal(d.numpy(), a)
+    assert np.array_equal(d.transpose().numpy(), a.T)
+    assert np.array_equal(d.slice(1, 5, 77).numpy(), a[:, 5:77])
+    assert dev.sm_count() == 148
+    assert dev.launch_count() > 0
+
+
+# ------------------------------------------------------------------------------------------------ GEMM
+@pytest.mark.parametrize("k", KATS["matmul"])
+@pytest.mark.parametrize("mode", MODES)
+def test_matmul_kats(dev, k, mode):
+    dev.set_math_mode(mode)
+    c = dev.gemm(dev.upload(np.array(k["a"], np.float32)), dev.upload(np.array(k["b"], np.float32)), k["ta"], k["tb"])
+    assert np.array_equal(c.numpy(), np.array(k["expected"], np.float32))
+
+
+@pytest.mark.parametrize("k", KATS["batch_matmul"])
+def test_batch_matmul_kats(dev, k):
+    dev.set_math_mode(0)
+    c = dev.gemm(dev.upload(np.array(k["a"], np.float32)), dev.upload(np.array(k["b"], np.float32)), k["ta"], k["tb"])
+    assert np.array_equal(c.numpy(), np.array(k["expected"], np.float32))
+
+
+GEMM_SHAPES = [(200, 10, 784), (784, 10, 200), (200, 784, 10), (128, 128, 128), (256, 512, 64), (130, 70, 33), (257, 129, 100),
+               (512, 1024, 2048), (1, 1, 1), (5, 3, 7), (128, 4096, 1024), (1000, 1000, 1000), (64, 64, 32), (16, 64, 40)]
+
+
+@pytest.mark.parametrize("mode", MODES)
+@pytest.mark.parametrize("ta,tb", [(False, False), (True, False), (False, True), (True, True)])
+@pytest.mark.parametrize("m,n,k", GEMM_SHAPES)
+def test_matmul_vs_oracle(dev, m, n, k, ta, tb, mode):
+    dev.set_math_mode(mode)
+    rng = np.random.default_rng(m * 31 + n * 7 + k)
+    a = rng.standard_normal((k, m) if ta else (m, k)).astype(np.float32)
+    b = rng.standard_normal((n, k) if tb else (k, n)).astype(np.float32)
+    c = dev.gemm(dev.upload(a), dev.upload(b), ta, tb).numpy()
+    assert rel_err(c, R.matmul(a, b, ta, tb)) <= TOL[mode]
+
+
+@pytest.mark.parametrize("mode", MODES)
+def test_matmul_transposed_views_and_beta(dev, mode):
+    """Transpose is a stride permutation (math_ops.rs:448): the kernel must consume such views without copies;
+    beta=1 accumulates (used by the conv filter-grad batch loop, conv2d.rs:703-722)."""
+    dev.set_math_mode(mode)
+    rng = np.random.default_rng(5)
+    a, b = rng.standard_normal((96, 160)).astype(np.float32), rng.standard_normal((96, 192)).astype(np.float32)
+    da, db = dev.upload(a), dev.upload(b)
+    c = dev.gemm(da.transpose(), db)                       # [160,96] x [96,192]
+    assert rel_err(c.numpy(), R.matmul(a.T, b)) <= TOL[mode]
+    c2 = dev.gemm(da.transpose(), db, out=c, beta=1.0)
+    assert rel_err(c2.numpy(), 2 * R.matmul(a.T, b).astype(np.float64)) <= TOL[mode]
+
+
+@pytest.mark.parametrize("mode", MODES)
+@pytest.mark.parametrize("batch,m,n,k", [((3,), 64, 128, 96), ((2, 3), 33, 17, 9), ((4,), 256, 256, 256)])
+def test_batch_matmul_vs_oracle(dev, batch, m, n, k, mode):
+    dev.set_math_mode(mode)
+    rng = np.random.default_rng(11)
+    a, b = rng.standard_normal(batch + (m, k)).astype(np.float32), rng.standard_normal(batch + (n, k)).astype(np.float32)
+    c = dev.gemm(dev.upload(a), dev.upload(b), False, True).numpy()
+    assert rel_err(c, R.batch_matmul(a, b, False, True)) <= TOL[mode]
+
+
+def test_matmul_errors(dev):
+    import rust_autograd_b200 as agb
+    with pytest.raises(agb.OpError) as e:
+        dev.gemm(dev.upload(np.zeros((3, 4), np.float32)), dev.upload(np.zeros((5, 6), np.float32)))
+    assert e.value.kind == "IncompatibleShape"          # dot_ops.rs:580-584
+
+
+def test_gemm_linearity_full_size(dev):
+    """Size-independent property at BASELINE's largest microbench size (8192^3): C(a, b1+b2) == C(a,b1) + C(a,b2)."""
+    dev.set_math_mode(0)
+    n = 8192
+    rng = np.random.default_rng(3)
+    a = dev.upload(rng.standard_normal((n, n)).astype(np.float32))
+    b1h, b2h = rng.standard_normal((n, n)).astype(np.float32), rng.standard_normal((n, n)).astype(np.float32)
+    b1, b2 = dev.upload(b1h), dev.upload(b2h)
+    c12 = dev.gemm(a, dev.binary("add", b1, b2))
+    c1 = dev.gemm(a, b1)
+    c = dev.gemm(a, b2, out=c1, beta=1.0)
+    s = dev.reduce("max", dev.unary("abs", dev.binary("sub", c12, c)).reshape((n * n,)), 0).numpy()
+    scale = dev.reduce("max", dev.unary("abs", c12).reshape((n * n,)), 0).numpy()
+    assert float(s) <= 2e-5 * float(scale)
+
+
+# ------------------------------------------------------------------------------------------------ conv family
+def test_im2col_kat(dev):
+    k = KATS["im2col_batch"]
+    x = np.tile(np.arange(k["xch"] * k["xh"] * k["xw"], dtype=np.float32).reshape(1, k["xch"], k["xh"], k["xw"]), (k["batch"], 1, 1, 1))
+    cols = dev.im2col(dev.upload(x), k["kh"], k["kw"], k["pad"], k["stride"], k["dilation"]).numpy()
+    assert cols.ravel().tolist() == [float(v) for v in k["expected"]]
+
+
+@pytest.mark.parametrize("mode", MODES)
+def test_deconv_kat(dev, mode):
+    dev.set_math_mode(mode)
+    k = KATS["deconv"]
+    out = dev.conv2d_transpose(dev.upload(np.ones((k["batch"], k["ych"], k["yh"], k["yw"]), np.float32)),
+                               dev.upload(np.ones((k["ych"], k["xch"], k["kh"], k["kw"]), np.float32)), k["pad"], k["stride"]).numpy()
+    assert out.shape == (2, 3, 3, 3)
+    assert np.array_equal(out, np.tile(np.array(k["expected_per_channel"], np.float32).reshape(1, 1, 3, 3), (2, 3, 1, 1)))
+
+
+CONV_CASES = [  # B, C, H, W, O, kh, kw, pad, stride, dil
+    (2, 1, 28, 28, 32, 3, 3, 1, 1, 1),      # cnn_mnist conv1
+    (3, 32, 14, 14, 64, 3, 3, 1, 1, 1),     # cnn_mnist conv2
+    (2, 3, 9, 7, 4, 3, 2, 0, 1, 1),
+    (2, 3, 9, 9, 5, 3, 3, 1, 2, 1),
+    (2, 4, 10, 10, 6, 3, 3, 2, 1, 2),
+    (1, 2, 5, 5, 3, 1, 1, 0, 1, 1),
+    (2, 64, 32, 32, 64, 3, 3, 1, 1, 1),     # VGG-like tile-sized layer
+    (2, 64, 16, 16, 128, 3, 3, 1, 1, 1),
+    (1, 128, 8, 8, 256, 3, 3, 1, 1, 1),
+    (2, 3, 32, 32, 64, 3, 3, 1, 1, 1),      # VGG L0 (C=3)
+    (2, 16, 12, 12, 24, 5, 5, 2, 1, 1),
+    (2, 8, 15, 15, 8, 3, 3, 1, 2, 1),
+]
+
+
+@pytest.mark.parametrize("mode", MODES)
+@pytest.mark.parametrize("case", CONV_CASES)
+def test_conv2d_family_vs_oracle(dev, case, mode):
+    dev.set_math_mode(mode)
+    B, C, H, W, O, kh, kw, pad, stride, dil = case
+    rng = np.random.default_rng(sum(case))
+    x = rng.standard_normal((B, C, H, W)).astype(np.float32)
+    w = (rng.standard_normal((O, C, kh, kw)) * 0.1).astype(np.float32)
+    dx, dw = dev.upload(x), dev.upload(w)
+    y_ref = R.conv2d(x, w, pad, stride, dil)
+    y = dev.conv2d(dx, dw, pad, stride, dil).numpy()
+    assert rel_err(y, y_ref) <= TOL[mode], "fprop"
+    gy = rng.standard_normal(y_ref.shape).astype(np.float32)
+    dgy = dev.upload(gy)
+    gx = dev.conv2d_transpose(dgy, dw, pad, stride, dil).numpy()
+    assert rel_err(gx, R.conv2d_transpose(gy, w, pad, stride, dil)) <= TOL[mode], "dgrad"
+    gw = dev.conv2d_filter_grad(dx, dgy, w.shape, pad, stride, dil).numpy()
+    assert rel_err(gw, R.conv2d_filter_grad(x, gy, w.shape, pad, stride, dil)) <= TOL[mode], "wgrad"
+
+
+def test_conv_errors(dev):
+    import rust_autograd_b200 as agb
+    with pytest.raises(agb.OpError) as e:
+        dev.conv2d(dev.upload(np.zeros((1, 3, 5, 5), np.float32)), dev.upload(np.zeros((2, 4, 3, 3), np.float32)))
+    assert e.value.kind == "IncompatibleShape"
+
+
+# ------------------------------------------------------------------------------------------------ pooling (bit-exact)
+def test_max_pool_kat(dev):
+    k = KATS["max_pool"]
+    y, idx = dev.max_pool2d(dev.upload(np.array(k["x"], np.float32).reshape(1, 1, k["h"], k["w"])), k["size"], k["pad"], k["stride"])
+    assert y.numpy().ravel().tolist() == k["output"] and idx.numpy().ravel().tolist() == k["argmax"]
+
+
+@pytest.mark.parametrize("shape,size,stride", [((200, 32, 28, 28), 2, 2), ((4, 3, 7, 9), 3, 2), ((2, 5, 8, 8), 2, 1), ((3, 2, 9, 9), 3, 3)])
+def test_max_pool_family_bit_exact(dev, shape, size, stride):
+    rng = np.random.default_rng(1)
+    x = rng.integers(-3, 4, shape).astype(np.float32)          # many ties -> exercises "first maximum wins"
+    x[0, 0, :size, :size] = -np.inf                               # all -inf window keeps max_i = 0 (max_pool2d.rs:51-52)
+    y_ref, idx_ref, _ = R.max_pool2d(x, size, 0, stride)
+    y, idx = dev.max_pool2d(dev.upload(x), size, 0, stride)
+    assert np.array_equal(y.numpy(), y_ref) and np.array_equal(idx.numpy(), idx_ref)
+    gy = rng.standard_normal(y_ref.shape).astype(np.float32)
+    gx = dev.max_pool2d_grad(dev.upload(gy), idx, size, 0, stride).numpy()
+    close(gx, R.max_pool2d_grad(gy, idx_ref, size, 0, stride))
+    gshape = gx.shape
+    ggx = rng.standard_normal(gshape).astype(np.float32)
+    ggy = dev.max_pool2d_grad_grad(dev.upload(ggx), idx, size, 0, stride).numpy() if gshape == x.shape else None
+    if ggy is not None:
+        assert np.array_equal(ggy, R.max_pool2d_grad_grad(ggx, idx_ref, size, 0, stride))
+
+
+# ------------------------------------------------------------------------------------------------ elementwise
+UNARY = {"abs": (-3, 3), "neg": (-3, 3), "square": (-3, 3), "inv": (0.5, 3), "invsqrt": (0.5, 3), "sign": (-3, 3), "floor": (-3, 3),
+         "ceil": (-3, 3), "sqrt": (0.1, 9), "ln": (0.1, 9), "log2": (0.1, 9), "log10": (0.1, 9), "exp": (-3, 3), "exp2": (-3, 3),
+         "exp10": (-2, 2), "sin": (-3, 3), "cos": (-3, 3), "tan": (-1, 1), "asin": (-0.9, 0.9), "acos": (-0.9, 0.9), "atan": (-3, 3),
+         "sinh": (-3, 3), "cosh": (-3, 3), "tanh": (-3, 3), "asinh": (-3, 3), "acosh": (1.1, 5), "atanh": (-0.9, 0.9),
+         "sigmoid": (-6, 6), "relu": (-3, 3), "softplus": (-6, 6)}
+
+
+@pytest.mark.parametrize("op", sorted(UNARY))
+def test_unary_vs_oracle(dev, op):
+    lo, hi = UNARY[op]
+    rng = np.random.default_rng(len(op))
+    x = rng.uniform(lo, hi, (13, 1031)).astype(np.float32)
+    x[0, :3] = [0.0 if lo < 0 < hi else lo, lo, hi]
+    y = dev.unary(op, dev.upload(x)).numpy()
+    close(y, R.unary(op, x), 1e-5)
+    yt = dev.unary(op, dev.upload(x).transpose()).numpy()        # strided input view
+    close(yt, R.unary(op, x.T), 1e-5)
+
+
+def test_unary_param_ops(dev):
+    rng = np.random.default_rng(7)
+    x = rng.uniform(0.2, 3, (1000,)).astype(np.float32)
+    d = dev.upload(x)
+    close(dev.unary("pow", d, 2.5).numpy(), R.unary("pow", x, 2.5))
+    close(dev.unary("elu", dev.upload(x - 1.5), 0.7).numpy(), R.unary("elu", x - 1.5, 0.7))
+    assert np.array_equal(dev.unary("clip", d, 1.0, 2.0).numpy(), R.unary("clip", x, 1.0, 2.0))
+    k = KATS["clip"]
+    assert dev.unary("clip", dev.upload(np.array(k["x"], np.float32)), k["min"], k["max"]).numpy().tolist() == k["expected"]
+    k = KATS["sign"]
+    assert dev.unary("sign", dev.upload(np.array(k["x"], np.float32))).numpy().tolist() == k["expected"]
+    gy = rng.standard_normal(1000).astype(np.float32)
+    close(dev.binary("elu_grad", dev.upload(x - 1.5), dev.upload(gy), 0.7).numpy(), R.elu_grad(x - 1.5, gy, 0.7))
+    assert np.array_equal(dev.binary("clip_grad", d, dev.upload(gy), 1.0, 2.0).numpy(), R.clip_grad(x, gy, 1.0, 2.0))
+
+
+BIN = {"add": "add", "sub": "sub", "mul": "mul", "div": "div"}
+CMP = {"eq": "equal", "ne": "not_equal", "gt": "greater", "lt": "lesser", "ge": "greater_equal", "le": "lesser_equal", "max": "maximum", "min": "minimum"}
+
+
+@pytest.mark.parametrize("sa,sb", [((200, 32, 28, 28), (1, 32, 28, 28)), ((128, 64), (1, 64)), ((7, 5, 3), (7, 1, 3)), ((1000,), (1000,)),
+                                   ((4, 1, 6), (1, 5, 6)), ((33, 17), (33, 1)), ((3, 4), ())])
+def test_binary_broadcast_vs_oracle(dev, sa, sb):
+    rng = np.random.default_rng(len(sa) * 10 + len(sb))
+    a = rng.integers(-4, 5, sa).astype(np.float32) + rng.integers(0, 2, sa).astype(np.float32) * 0.5
+    b = rng.integers(1, 5, sb).astype(np.float32)
+    da, db = dev.upload(a), dev.upload(b)
+    for op, ref in BIN.items():
+        close(dev.binary(op, da, db).numpy(), R.binary_arith(ref, a, b), 1e-6)
+        if op != "div":
+            close(dev.binary(op, db, da).numpy(), R.binary_arith(ref, b, a), 1e-6)
+    for op, ref in CMP.items():
+        assert np.array_equal(dev.binary(op, da, db).numpy(), R.compare(ref, a, b)), op
+
+
+@pytest.mark.parametrize("k", KATS["compare"])
+def test_compare_kats(dev, k):
+    op = {v: kk for kk, v in CMP.items()}[k["op"]]
+    assert dev.binary(op, dev.upload(np.array(k["a"], np.float32)), dev.upload(np.array(k["b"], np.float32))).numpy().tolist() == k["expected"]
+
+
+def test_add_n_fill_copy_dropout(dev):
+    rng = np.random.default_rng(9)
+    xs = [rng.standard_normal((17, 33)).astype(np.float32) for _ in range(11)]
+    close(dev.add_n([dev.upload(x) for x in xs]).numpy(), R.add_n(xs), 1e-6)
+    k = KATS["add_n"]
+    assert np.array_equal(dev.add_n([dev.fill(k["shape"], 1.0) for _ in range(k["n"])]).numpy(), np.array(k["expected"], np.float32))
+    assert np.array_equal(dev.fill((5, 7), 2.5).numpy(), np.full((5, 7), 2.5, np.float32))
+    assert np.array_equal(dev.fill((5, 7), 0.0).numpy(), np.zeros((5, 7), np.float32))
+    x = rng.standard_normal((6, 10, 14)).astype(np.float32)
+    d = dev.upload(x)
+    assert np.array_equal(dev.copy(d.transpose((2, 0, 1))).numpy(), x.transpose(2, 0, 1))
+    assert np.array_equal(dev.copy(d.slice(2, 3, 11)).numpy(), x[:, :, 3:11])
+    mask = (rng.uniform(size=x.shape) < 0.75).astype(np.float32)
+    y, _ = dev.dropout(d, 0.25, mask=dev.upload(mask))
+    assert np.array_equal(y.numpy(), R.dropout(x, mask, 0.25))
+    big = dev.upload(np.ones((1 << 20,), np.float32))
+    y, m = dev.dropout(big, 0.25, seed=1234)
+    m = m.numpy()
+    assert set(np.unique(m)) == {0.0, 1.0} and abs(m.mean() - 0.75) < 5e-3 and np.array_equal(y.numpy(), m)
+
+
+# ------------------------------------------------------------------------------------------------ reductions
+@pytest.mark.parametrize("k", KATS["reduce"])
+def test_reduce_kats(dev, k):
+    x = np.array(k["x"], np.float32)
+    assert np.array_equal(dev.reduce(k["op"], dev.upload(x), k["axes"][0]).numpy(), np.array(k["expected"], np.float32))
+
+
+@pytest.mark.parametrize("op", ["sum", "mean", "prod", "min", "max"])
+@pytest.mark.parametrize("shape,axis", [((200, 1), 0), ((200, 32, 28, 28), 0), ((128, 4096), 1), ((128, 4096), 0), ((7, 13, 5), 1), ((1 << 20,), 0),
+                                        ((3, 100000), 1), ((100000, 3), 0)])
+def test_reduce_vs_oracle(dev, op, shape, axis):
+    rng = np.random.default_rng(axis + len(shape))
+    x = (rng.uniform(0.97, 1.03, shape) if op == "prod" else rng.standard_normal(shape)).astype(np.float32)
+    if op == "prod" and shape[axis] > 5000:
+        x = np.ones(shape, np.float32)
+    y = dev.reduce(op, dev.upload(x), axis).numpy()
+    ref = R.reduce(op, x, [axis])
+    if op in ("min", "max"):
+        assert np.array_equal(y, ref)
+    else:
+        assert rel_err(y, ref) <= 1e-5
+
+
+@pytest.mark.parametrize("k", KATS["argmax"] + KATS["argmin"])
+def test_arg_kats(dev, k):
+    is_max = k in KATS["argmax"]
+    x = np.array(k["x"], np.float32)
+    got = dev.argreduce(is_max, dev.upload(x), k["axis"]).numpy()
+    assert np.array_equal(got, np.array(k["expected"], np.float32))
+
+
+@pytest.mark.parametrize("shape,axis", [((1000, 10), 1), ((10, 1000), 0), ((4, 7, 9), 1), ((3, 100000), 1)])
+def test_argreduce_bit_exact_with_ties(dev, shape, axis):
+    rng = np.random.default_rng(4)
+    x = rng.integers(0, 5, shape).astype(np.float32)
+    for is_max in (True, False):
+        assert np.array_equal(dev.argreduce(is_max, dev.upload(x), axis).numpy(), R.arg_reduce(x, axis, False, is_max))
+
+
+# ------------------------------------------------------------------------------------------------ softmax family
+@pytest.mark.parametrize("shape,axis", [((200, 10), 1), ((128, 8192), 1), ((7, 13, 5), 1), ((64, 100), 0), ((4, 40000), 1)])
+def test_softmax_family_vs_oracle(dev, shape, axis):
+    rng = np.random.default_rng(8)
+    x = (rng.standard_normal(shape) * 4).astype(np.float32)
+    d = dev.upload(x)
+    close(dev.softmax_like("softmax", d, axis).numpy(), R.softmax(x, axis), 1e-5)
+    close(dev.softmax_like("log_softmax", d, axis).numpy(), R.log_softmax(x, axis), 1e-5)
+    close(dev.softmax_like("logsumexp", d, axis).numpy(), R.logsumexp(x, axis, True), 1e-5)
+
+
+@pytest.mark.parametrize("b,c", [(200, 10), (128, 8192), (1, 3), (1000, 1000)])
+def test_sparse_xent_vs_oracle(dev, b, c):
+    rng = np.random.default_rng(b + c)
+    x = (rng.standard_normal((b, c)) * 3).astype(np.float32)
+    t = rng.integers(0, c, (b,)).astype(np.float32)
+    loss_ref, logx_ref = R.sparse_softmax_cross_entropy(x, t)
+    loss, log_x = dev.sparse_xent_fwd(dev.upload(x), dev.upload(t))
+    assert loss.shape == (b, 1)
+    close(loss.numpy(), loss_ref, 1e-5)
+    close(log_x.numpy(), logx_ref, 1e-5)
+    gy = rng.standard_normal((b, 1)).astype(np.float32)
+    gx = dev.sparse_xent_bwd(log_x, dev.upload(t), dev.upload(gy)).numpy()
+    close(gx, R.sparse_softmax_cross_entropy_grad(logx_ref, t, gy), 1e-5)
+    onehot = np.eye(c, dtype=np.float32)[t.astype(int)]
+    l2, lx2 = dev.softmax_xent_fwd(dev.upload(x), dev.upload(onehot))
+    assert l2.shape == (b,)
+    close(l2.numpy(), R.softmax_cross_entropy(x, onehot)[0], 1e-5)
+    close(dev.binary("sigmoid_xent", dev.upload(x), dev.upload(onehot)).numpy(), R.sigmoid_cross_entropy(x, onehot), 1e-5)
+
+
+def test_sparse_xent_bad_label_is_out_of_bounds(dev):
+    import rust_autograd_b200 as agb
+    x = np.zeros((4, 3), np.float32)
+    t = np.array([0, 1, 7, 2], np.float32)        # "Wrong label value" panic in the reference (xent_ops.rs:104)
+    dev.sparse_xent_fwd(dev.upload(x), dev.upload(t))
+    with pytest.raises(agb.OpError) as e:
+        dev.sync()
+    assert e.value.kind == "OutOfBounds"
+
+
+# ------------------------------------------------------------------------------------------------ gather
+@pytest.mark.parametrize("pshape,ishape,axis", [((8192, 64), (128, 1), 0), ((5, 7, 3), (4,), 1), ((6, 4), (2, 3), -1)])
+def test_gather_family_bit_exact(dev, pshape, ishape, axis):
+    rng = np.random.default_rng(6)
+    p = rng.standard_normal(pshape).astype(np.float32)
+    ax = axis % len(pshape)
+    idx = rng.integers(-pshape[ax], pshape[ax], ishape).astype(np.float32)
+    idx.ravel()[:2] = idx.ravel()[0]          # duplicates accumulate in the grad
+    out = dev.gather(dev.upload(p), dev.upload(idx), axis).numpy()
+    ref = R.gather(p, idx, axis)
+    assert np.array_equal(out, ref)
+    gy = rng.integers(-3, 4, ref.shape).astype(np.float32)
+    gx = dev.gather_grad(dev.upload(gy), dev.upload(idx), pshape, axis).numpy()
+    assert np.array_equal(gx, R.gather_grad(idx, pshape, gy, axis))
+
+
+# ------------------------------------------------------------------------------------------------ optimizers
+def test_multi_tensor_optimizers_vs_oracle(dev):
+    rng = np.random.default_rng(10)
+    shapes = [(32, 1, 3, 3), (1, 32, 28, 28), (64, 32, 3, 3), (3136, 10), (1, 10), (7,)]
+    ps = [rng.standard_normal(s).astype(np.float32) for s in shapes]
+    gs = [rng.standard_normal(s).astype(np.float32) for s in shapes]
+    ms = [rng.standard_normal(s).astype(np.float32) * 0.1 for s in shapes]
+    vs = [np.abs(rng.standard_normal(s)).astype(np.float32) * 0.1 for s in shapes]
+    ts = [np.array([float(i + 1)], np.float32) for i in range(len(shapes))]
+    up = lambda l: [dev.upload(a) for a in l]
+    dp, dg, dm, dv, dt = up(ps), up(gs), up(ms), up(vs), up(ts)
+    dev.adam(dp, dg, dm, dv, dt)
+    for i in range(len(shapes)):
+        p2, m2, v2, t2 = R.adam_update(ps[i], gs[i], ms[i], vs[i], ts[i])
+        close(dp[i].numpy(), p2, 1e-5), close(dm[i].numpy(), m2, 1e-5), close(dv[i].numpy(), v2, 1e-5)
+        assert dt[i].numpy()[0] == t2[0]
+    dp = up(ps)
+    dev.adam(dp, dg, up(ms), up(vs), up(ts), grad_scale=0.25)      # 1/world after the NCCL sum
+    close(dp[3].numpy(), R.adam_update(ps[3], gs[3] * np.float32(0.25), ms[3], vs[3], ts[3])[0], 1e-5)
+    dp = up(ps)
+    dev.sgd(dp, dg, 0.1)
+    for i in range(len(shapes)):
+        close(dp[i].numpy(), R.sgd_update(ps[i], gs[i], 0.1), 1e-6)
+    dp, dv2 = up(ps), up(ms)
+    dev.momentum(dp, dg, dv2, 0.01, 0.9)
+    for i in range(len(shapes)):
+        p2, v2 = R.momentum_sgd_update(ps[i], gs[i], ms[i], 0.01, 0.9)
+        close(dp[i].numpy(), p2, 1e-6), close(dv2[i].numpy(), v2, 1e-6)
+    dp, dh = up(ps), up(vs)
+    dev.adagrad(dp, dg, dh, 0.01)
+    for i in range(len(shapes)):
+        p2, h2 = R.adagrad_update(ps[i], gs[i], vs[i], 0.01)
+        close(dp[i].numpy(), p2, 1e-5), close(dh[i].numpy(), h2, 1e-6)
+
+
+# ------------------------------------------------------------------------------------------------ full-size properties
+def test_reduce_sum_full_size_checksum(dev):
+    """2^28 f32 (1 GiB) reduce_sum of an exactly representable pattern: the sum is known in closed form."""
+    n = 1 << 28
+    x = dev.fill((n,), 0.5)
+    assert float(dev.reduce("sum", x, 0).numpy()) == n * 0.5
+    x2 = x.reshape((1 << 14, 1 << 14))
+    assert np.array_equal(dev.reduce("sum", x2, 1).numpy(), np.full((1 << 14,), (1 << 14) * 0.5, np.float32))
+    sm = dev.softmax_like("softmax", x2, 1)
+    assert float(dev.reduce("sum", sm.reshape((n,)), 0).numpy()) == float(1 << 14)
