@@ -1,0 +1,233 @@
+// capi.cc — flat C ABI (include/agx200.h) over the C++ host engine; bound from Python with ctypes for the re-hosted
+// reference test-suite, the benchmarks and smoke().  No logic lives here beyond argument marshalling and the
+// name -> tensor_ops constructor table.
+#include "agx.h"
+#include "../../../include/agx200.h"
+#include <fstream>
+#include <sstream>
+#include <string.h>
+
+using namespace agx;
+
+struct agx_env { VariableEnvironment* env; };
+struct agx_graph { Graph g; };
+struct agx_opt { Optimizer* o; };
+struct agx_results { std::vector<EvalResult> rs; };
+
+static thread_local std::string g_err;
+extern "C" const char* agx_last_error(void) { return g_err.c_str(); }
+
+#define AGX_TRY try {
+#define AGX_CATCH                                                                                   \
+  return 0; }                                                                                       \
+  catch (const OpError& e) { g_err = e.msg; return e.code ? e.code : AGB_ERR_NDARRAY; }             \
+  catch (const Panic& e) { g_err = std::string("panic: ") + e.msg; return AGX_ERR_PANIC; }          \
+  catch (const std::exception& e) { g_err = std::string("internal error: ") + e.what(); return AGX_ERR_PANIC; }
+
+static std::vector<Tensor> tv(agx_graph* g, const int* ids, int n) {
+  std::vector<Tensor> r;
+  for (int i = 0; i < n; i++) {
+    if (ids[i] < 0 || ids[i] >= (int)g->g.node_set.size()) throw Panic("tensor id out of range");
+    r.push_back(g->g.tensor(ids[i]));
+  }
+  return r;
+}
+static std::vector<Feed> fv(agx_graph* g, const agx_feed* feeds, int n) {
+  std::vector<Feed> r; Device* dev = g->g.env->dev;
+  for (int i = 0; i < n; i++) {
+    Feed f; f.by_name = feeds[i].name != nullptr; if (f.by_name) f.name = feeds[i].name; f.id = feeds[i].tensor_id;
+    Shape shp(feeds[i].shape, feeds[i].shape + feeds[i].rank);
+    if (feeds[i].on_device) {          // value already resident in HBM (owned by the caller): wrap, no copy
+      f.value.shape = shp; f.value.stride = NdArray::contiguous_strides(shp); f.value.dptr = const_cast<float*>(feeds[i].data);
+    } else {                           // evaluation.rs:296: the feed view enters the graph -> one H2D copy on the run's stream
+      f.value = dev->empty(shp);
+      if (f.value.size() > 0) check_status(agb_h2d(dev->ctx, f.value.dptr, feeds[i].data, (size_t)f.value.size() * sizeof(float)));
+    }
+    r.push_back(std::move(f));
+  }
+  return r;
+}
+
+// ================================================================================================ environment
+extern "C" int agx_env_new(int device, agx_env** out) { AGX_TRY *out = nullptr; auto* e = new agx_env(); e->env = new VariableEnvironment(device); *out = e; AGX_CATCH }
+extern "C" int agx_env_free(agx_env* env) { AGX_TRY if (env) { delete env->env; delete env; } AGX_CATCH }
+extern "C" int agx_env_ctx(agx_env* env, agb_ctx** out) { AGX_TRY *out = env->env->dev->ctx; AGX_CATCH }
+extern "C" int agx_env_set(agx_env* env, const char* ns, const char* name, const float* data, const int64_t* shape, int rank, int* vid) {
+  AGX_TRY *vid = env->env->set(ns ? ns : "", name, Shape(shape, shape + rank), data).v; AGX_CATCH
+}
+extern "C" int agx_env_find(agx_env* env, const char* ns, const char* name, int* vid) { AGX_TRY *vid = env->env->find(ns ? ns : "", name).v; AGX_CATCH }
+extern "C" int agx_env_var_count(agx_env* env, int* n) { AGX_TRY *n = (int)env->env->array_list.size(); AGX_CATCH }
+extern "C" int agx_env_var_ids(agx_env* env, const char* ns, int* out, int cap, int* n) {
+  AGX_TRY auto v = env->env->current_var_ids(ns ? ns : ""); *n = (int)v.size(); for (int i = 0; i < (int)v.size() && i < cap; i++) out[i] = v[i].v; AGX_CATCH
+}
+extern "C" int agx_env_var_shape(agx_env* env, int vid, int64_t* shape, int* rank) {
+  AGX_TRY const NdArray& a = env->env->array_list.at(vid); *rank = a.ndim(); for (int i = 0; i < a.ndim(); i++) shape[i] = a.shape[i]; AGX_CATCH
+}
+extern "C" int agx_env_get(agx_env* env, int vid, float* out, int64_t cap) {
+  AGX_TRY std::vector<float> h = env->env->get(VariableID{vid}); if ((int64_t)h.size() > cap) throw OpError(AGB_ERR_INVALID_DIMS, "agx_env_get: buffer too small"); memcpy(out, h.data(), h.size() * sizeof(float)); AGX_CATCH
+}
+extern "C" int agx_env_put(agx_env* env, int vid, const float* data, int64_t n) { AGX_TRY env->env->put(VariableID{vid}, data, (size_t)n); AGX_CATCH }
+extern "C" int agx_env_var_ptr(agx_env* env, int vid, float** dptr) { AGX_TRY *dptr = env->env->array_list.at(vid).dptr; AGX_CATCH }
+extern "C" int agx_env_save(agx_env* env, const char* path) {
+  AGX_TRY std::ofstream f(path); if (!f) throw OpError(AGB_ERR_NDARRAY, std::string("save: cannot open ") + path); f << env->env->save_json(); AGX_CATCH
+}
+extern "C" int agx_env_load(agx_env* env, const char* path) {
+  AGX_TRY std::ifstream f(path); if (!f) throw OpError(AGB_ERR_NDARRAY, std::string("load: cannot open ") + path); std::stringstream ss; ss << f.rdbuf(); env->env->load_json(ss.str()); AGX_CATCH
+}
+extern "C" int agx_env_set_data_parallel(agx_env* env, int rank, int world, const void* id) {
+  AGX_TRY if (world > 1) check_status(agb_nccl_init(env->env->dev->ctx, rank, world, id)); env->env->rank = rank; env->env->world = world; AGX_CATCH
+}
+
+// ================================================================================================ graph
+extern "C" int agx_graph_new(agx_env* env, agx_graph** out) { AGX_TRY auto* g = new agx_graph(); g->g.env = env->env; g->g.node_set.reserve(512); *out = g; AGX_CATCH }
+extern "C" int agx_graph_free(agx_graph* g) { AGX_TRY delete g; AGX_CATCH }
+extern "C" int agx_graph_clear(agx_graph* g) { AGX_TRY g->g.clear(); AGX_CATCH }
+extern "C" int agx_graph_size(agx_graph* g, int* n) { AGX_TRY *n = (int)g->g.node_set.size(); AGX_CATCH }
+extern "C" int agx_placeholder(agx_graph* g, const char* name, const int64_t* shape, int rank, int* tid) {
+  AGX_TRY *tid = g->g.placeholder(name, std::vector<int64_t>(shape, shape + rank)).id; AGX_CATCH
+}
+extern "C" int agx_variable(agx_graph* g, int vid, int* tid) { AGX_TRY *tid = g->g.variable_by_id(VariableID{vid}).id; AGX_CATCH }
+extern "C" int agx_variable_by_name(agx_graph* g, const char* ns, const char* name, int* tid) { AGX_TRY *tid = g->g.variable_by_name(name, ns ? ns : "").id; AGX_CATCH }
+extern "C" int agx_convert_to_tensor(agx_graph* g, const float* data, const int64_t* shape, int rank, int* tid) {
+  AGX_TRY Shape s(shape, shape + rank); int64_t n = 1; for (auto d : s) n *= d;
+  *tid = T::convert_to_tensor(&g->g, s, std::vector<float>(data, data + n)).id; AGX_CATCH
+}
+extern "C" int agx_tensor_op_name(agx_graph* g, int tid, char* buf, int cap) { AGX_TRY snprintf(buf, cap, "%s", g->g.inner(tid).op->name()); AGX_CATCH }
+extern "C" int agx_tensor_variable_id(agx_graph* g, int tid, int* vid) { AGX_TRY *vid = g->g.inner(tid).variable_id.v; AGX_CATCH }
+
+extern "C" int agx_call(agx_graph* gg, const char* fn_, const int* tensors, int nt, const int64_t* I, int ni, const double* F, int nf, int* out, int cap, int* nout) {
+  AGX_TRY
+  Graph* g = &gg->g; std::string fn = fn_;
+  std::vector<Tensor> t = tv(gg, tensors, nt); std::vector<Tensor> r;
+  auto need = [&](int a, int b, int c) { if (nt < a || ni < b || nf < c) throw Panic("agx_call(" + fn + "): expected at least " + std::to_string(a) + " tensors, " + std::to_string(b) + " ints, " + std::to_string(c) + " floats"); };
+  auto ints = [&](int from) { return std::vector<int64_t>(I + from, I + ni); };
+  static const char* unary_names[] = {"sin", "cos", "tan", "asin", "acos", "atan", "sinh", "cosh", "tanh", "asinh", "acosh", "atanh", "exp", "exp2", "exp10", "ln", "log2",
+                                      "log10", "sqrt", "neg", "abs", "sign", "floor", "ceil", "inv", "inv_sqrt", "square", "sigmoid", "relu", "softplus"};
+  static const char* cmp_names[] = {"equal", "not_equal", "greater", "lesser", "greater_equal", "lesser_equal", "maximum", "minimum"};
+  bool done = false;
+  for (auto u : unary_names) if (fn == u) { need(1, 0, 0); r = {T::unary(fn, t[0])}; done = true; }
+  for (auto u : cmp_names) if (fn == u) { need(2, 0, 0); r = {T::cmp(fn, t[0], t[1])}; done = true; }
+  if (done) {}
+  else if (fn == "pow") { need(1, 0, 1); r = {T::unary("pow", t[0], (float)F[0])}; }
+  else if (fn == "elu") { need(1, 0, 1); r = {T::unary("elu", t[0], (float)F[0])}; }
+  else if (fn == "leaky_relu") { need(1, 0, 1); r = {T::leaky_relu(t[0], (float)F[0])}; }
+  else if (fn == "clip") { need(1, 0, 2); r = {T::clip(t[0], (float)F[0], (float)F[1])}; }
+  else if (fn == "add") { need(2, 0, 0); r = {T::add(t[0], t[1])}; }
+  else if (fn == "sub") { need(2, 0, 0); r = {T::sub(t[0], t[1])}; }
+  else if (fn == "mul") { need(2, 0, 0); r = {T::mul(t[0], t[1])}; }
+  else if (fn == "div") { need(2, 0, 0); r = {T::div(t[0], t[1])}; }
+  else if (fn == "add_n") { need(1, 0, 0); r = {T::add_n(t)}; }
+  else if (fn == "scalar") { need(0, 0, 1); r = {T::scalar(g, (float)F[0])}; }
+  else if (fn == "as_tensor") { r = {T::as_tensor(g, ints(0))}; }                    // integer literal arrays (axes / shapes)
+  else if (fn == "zeros") { need(1, 0, 0); r = {T::zeros(g, t[0])}; }
+  else if (fn == "ones") { need(1, 0, 0); r = {T::ones(g, t[0])}; }
+  else if (fn == "shape") { need(1, 0, 0); r = {T::shape(t[0])}; }
+  else if (fn == "rank") { need(1, 0, 0); r = {T::rank(t[0])}; }
+  else if (fn == "size") { need(1, 0, 0); r = {T::size(t[0])}; }
+  else if (fn == "identity") { need(1, 0, 0); r = {T::identity(t[0])}; }
+  else if (fn == "nth_tensor") { need(1, 1, 0); r = {T::nth_tensor(t[0], (int)I[0])}; }
+  else if (fn == "stop_gradient") { need(1, 0, 0); r = {T::stop_gradient(t[0])}; }
+  else if (fn == "reduce_sum" || fn == "reduce_mean" || fn == "reduce_prod" || fn == "reduce_min" || fn == "reduce_max") { need(2, 1, 0); r = {T::reduce(fn.substr(7), t[0], t[1], I[0] != 0)}; }
+  else if (fn == "reduce_variance") { need(2, 1, 0); r = {T::reduce_variance(t[0], t[1], I[0] != 0)}; }
+  else if (fn == "sum_all") { need(1, 0, 0); r = {T::sum_all(t[0])}; }
+  else if (fn == "mean_all") { need(1, 0, 0); r = {T::mean_all(t[0])}; }
+  else if (fn == "argmax") { need(1, 2, 0); r = {T::argmax(t[0], (int)I[0], I[1] != 0)}; }
+  else if (fn == "argmin") { need(1, 2, 0); r = {T::argmin(t[0], (int)I[0], I[1] != 0)}; }
+  else if (fn == "reduce_logsumexp") { need(1, 2, 0); r = {T::reduce_logsumexp(t[0], (int)I[0], I[1] != 0)}; }
+  else if (fn == "softmax") { need(1, 1, 0); r = {T::softmax(t[0], (int)I[0])}; }
+  else if (fn == "log_softmax") { need(1, 1, 0); r = {T::log_softmax(t[0], (int)I[0])}; }
+  else if (fn == "sigmoid_cross_entropy") { need(2, 0, 0); r = {T::sigmoid_cross_entropy(t[0], t[1])}; }
+  else if (fn == "softmax_cross_entropy") { need(2, 0, 0); r = {T::softmax_cross_entropy(t[0], t[1])}; }
+  else if (fn == "sparse_softmax_cross_entropy") { need(2, 0, 0); r = {T::sparse_softmax_cross_entropy(t[0], t[1])}; }
+  else if (fn == "mean_squared_error") { need(2, 0, 0); r = {T::mean_squared_error(t[0], t[1])}; }
+  else if (fn == "matmul") { need(2, 0, 0); r = {T::matmul(t[0], t[1])}; }
+  else if (fn == "batch_matmul") { need(2, 0, 0); r = {T::batch_matmul_t(t[0], t[1], false, false)}; }
+  else if (fn == "batch_matmul_t") { need(2, 2, 0); r = {T::batch_matmul_t(t[0], t[1], I[0] != 0, I[1] != 0)}; }
+  else if (fn == "tensordot") { need(4, 0, 0); r = {T::tensordot(t[0], t[1], t[2], t[3])}; }
+  else if (fn == "reshape") { need(2, 0, 0); r = {T::reshape(t[0], t[1])}; }
+  else if (fn == "flatten") { need(1, 0, 0); r = {T::flatten(t[0])}; }
+  else if (fn == "transpose") { need(2, 0, 0); r = {T::transpose(t[0], t[1])}; }
+  else if (fn == "squeeze") { need(2, 0, 0); r = {T::squeeze(t[0], t[1])}; }
+  else if (fn == "expand_dims") { need(2, 0, 0); r = {T::expand_dims(t[0], t[1])}; }
+  else if (fn == "slice") { need(1, 2, 0); std::vector<int64_t> all = ints(0); size_t h = all.size() / 2; r = {T::slice(t[0], std::vector<int64_t>(all.begin(), all.begin() + h), std::vector<int64_t>(all.begin() + h, all.end()))}; }
+  else if (fn == "split") { need(1, 2, 0); r = T::split(t[0], ints(1), (int)I[0]); }                         // ints: axis, sizes...
+  else if (fn == "concat") { need(1, 1, 0); r = {T::concat(t, (int)I[0])}; }
+  else if (fn == "tile") { need(1, 2, 0); r = {T::tile(t[0], (int)I[0], (int)I[1])}; }
+  else if (fn == "gather_common") { need(2, 1, 0); r = {T::gather_common(t[0], t[1], (int)I[0])}; }
+  else if (fn == "gather") { need(2, 1, 0); r = {T::gather(t[0], t[1], (int)I[0])}; }
+  else if (fn == "access_elem") { need(1, 1, 0); r = {T::access_elem(t[0], I[0])}; }
+  else if (fn == "setdiff1d") { need(2, 0, 0); r = {T::setdiff1d(t[0], t[1])}; }
+  else if (fn == "conv2d") { need(2, 2, 0); r = {T::conv2d(t[0], t[1], (int)I[0], (int)I[1], 1)}; }
+  else if (fn == "dilated_conv2d") { need(2, 3, 0); r = {T::conv2d(t[0], t[1], (int)I[0], (int)I[1], (int)I[2])}; }
+  else if (fn == "conv2d_transpose") { need(2, 2, 0); r = {T::conv2d_transpose(t[0], t[1], (int)I[0], (int)I[1], 1)}; }
+  else if (fn == "dilated_conv2d_transpose") { need(2, 3, 0); r = {T::conv2d_transpose(t[0], t[1], (int)I[0], (int)I[1], (int)I[2])}; }
+  else if (fn == "max_pool2d") { need(1, 3, 0); r = {T::max_pool2d(t[0], (int)I[0], (int)I[1], (int)I[2])}; }
+  else if (fn == "dropout") { need(1, 1, 1); r = {T::dropout(t[0], (float)F[0], I[0] != 0, ni > 1 ? (uint64_t)I[1] : 0)}; }
+  else if (fn == "normalize") { need(2, 0, 0); r = {T::normalize(t[0], t[1])}; }
+  else if (fn == "batch_norm") { need(3, 0, 0); r = {T::batch_norm(t[0], t[1], t[2])}; }
+  else if (fn == "assign") { need(2, 0, 0); r = {T::assign(t[0], t[1])}; }
+  else if (fn == "control_dependencies") { need(1, 0, 0); r = {T::control_dependencies(t[0], std::vector<Tensor>(t.begin() + 1, t.end()))}; }
+  else throw Panic("agx_call: unknown tensor_ops function `" + fn + "`");
+  *nout = (int)r.size();
+  for (int i = 0; i < (int)r.size() && i < cap; i++) out[i] = r[i].id;
+  AGX_CATCH
+}
+
+extern "C" int agx_grad(agx_graph* g, const int* ys, int ny, const int* xs, int nx, const int* gys, int* out) {
+  AGX_TRY
+  std::vector<Tensor> r = gys ? T::grad_with_default(tv(g, ys, ny), tv(g, xs, nx), tv(g, gys, ny)) : T::grad(tv(g, ys, ny), tv(g, xs, nx));
+  for (int i = 0; i < nx; i++) out[i] = r[i].id;
+  AGX_CATCH
+}
+extern "C" int agx_grad_helper(agx_graph* g, const int* losses, int n, const char* ns, int* vars, int* grads, int cap, int* nout) {
+  AGX_TRY
+  std::vector<Tensor> vs, gs; grad_helper(tv(g, losses, n), ns ? ns : "", &g->g, vs, gs);
+  *nout = (int)vs.size();
+  for (int i = 0; i < (int)vs.size() && i < cap; i++) { vars[i] = vs[i].id; grads[i] = gs[i].id; }
+  AGX_CATCH
+}
+
+// ================================================================================================ evaluation
+extern "C" int agx_eval(agx_graph* g, const int* targets, int n, const agx_feed* feeds, int nfeeds, agx_results** out) {
+  AGX_TRY *out = nullptr; auto* r = new agx_results(); r->rs = eval(&g->g, tv(g, targets, n), fv(g, feeds, nfeeds), true); *out = r; AGX_CATCH
+}
+extern "C" int agx_run(agx_graph* g, const int* targets, int n, const agx_feed* feeds, int nfeeds) {
+  AGX_TRY
+  std::vector<EvalResult> rs = eval(&g->g, tv(g, targets, n), fv(g, feeds, nfeeds), false);
+  for (auto& r : rs) if (!r.ok) throw OpError(r.err_code, r.err_msg);
+  AGX_CATCH
+}
+extern "C" int agx_results_count(agx_results* r, int* n) { *n = (int)r->rs.size(); return 0; }
+extern "C" int agx_results_status(agx_results* r, int i, int* code, const char** msg) { *code = r->rs[i].ok ? 0 : r->rs[i].err_code; *msg = r->rs[i].err_msg.c_str(); return 0; }
+extern "C" int agx_results_shape(agx_results* r, int i, int64_t* shape, int* rank) {
+  const NdArray& a = r->rs[i].value; *rank = a.ndim(); for (int k = 0; k < a.ndim(); k++) shape[k] = a.shape[k]; return 0;
+}
+extern "C" int agx_results_data(agx_results* r, int i, const float** data, int64_t* n) {
+  const NdArray& a = r->rs[i].value;
+  if (!a.host) { g_err = "result has no host copy"; return AGX_ERR_PANIC; }
+  *data = a.host->data(); *n = (int64_t)a.host->size(); return 0;
+}
+extern "C" int agx_results_free(agx_results* r) { delete r; return 0; }
+
+// ================================================================================================ optimizers
+static std::vector<VariableID> vids(const int* v, int n) { std::vector<VariableID> r; for (int i = 0; i < n; i++) r.push_back(VariableID{v[i]}); return r; }
+extern "C" int agx_opt_adam(agx_env* env, const int* v, int n, const char* ns, float alpha, float eps, float b1, float b2, agx_opt** out) {
+  AGX_TRY auto* o = new agx_opt(); o->o = make_adam(env->env, vids(v, n), ns, alpha, eps, b1, b2); *out = o; AGX_CATCH
+}
+extern "C" int agx_opt_sgd(float lr, agx_opt** out) { AGX_TRY auto* o = new agx_opt(); o->o = make_sgd(lr); *out = o; AGX_CATCH }
+extern "C" int agx_opt_momentum_sgd(agx_env* env, const int* v, int n, const char* ns, float lr, float momentum, agx_opt** out) {
+  AGX_TRY auto* o = new agx_opt(); o->o = make_momentum_sgd(env->env, vids(v, n), ns, lr, momentum); *out = o; AGX_CATCH
+}
+extern "C" int agx_opt_adagrad(agx_env* env, const int* v, int n, const char* ns, float lr, agx_opt** out) {
+  AGX_TRY auto* o = new agx_opt(); o->o = make_adagrad(env->env, vids(v, n), ns, lr); *out = o; AGX_CATCH
+}
+extern "C" int agx_opt_compute_updates(agx_opt* o, agx_graph* g, const int* params, const int* grads, int n, int* out) {
+  AGX_TRY std::vector<Tensor> r = o->o->compute_updates(tv(g, params, n), tv(g, grads, n), &g->g); for (int i = 0; i < n; i++) out[i] = r[i].id; AGX_CATCH
+}
+extern "C" int agx_opt_get_update_op(agx_opt* o, agx_graph* g, const int* params, const int* grads, int n, int* tid) {
+  AGX_TRY *tid = o->o->get_update_op(tv(g, params, n), tv(g, grads, n), &g->g).id; AGX_CATCH
+}
+extern "C" int agx_opt_update(agx_opt* o, agx_graph* g, const int* params, const int* grads, int n, const agx_feed* feeds, int nfeeds) {
+  AGX_TRY o->o->update(tv(g, params, n), tv(g, grads, n), &g->g, fv(g, feeds, nfeeds)); AGX_CATCH
+}
+extern "C" int agx_opt_free(agx_opt* o) { AGX_TRY if (o) { delete o->o; delete o; } AGX_CATCH }

@@ -1,0 +1,498 @@
+// core.cc — arrays, graph, reverse-mode gradient builder, evaluator, variable environment (see agx.h for the reference map).
+#include "agx.h"
+#include <algorithm>
+#include <queue>
+#include <sstream>
+#include <stdio.h>
+#include <string.h>
+
+namespace agx {
+
+void check_status(int status) {
+  if (status != AGB_OK) throw OpError(status, agb_last_error());
+}
+
+// ================================================================================================ NdArray / Device
+Buffer::Buffer(agb_ctx* c, size_t b) : ctx(c), ptr(nullptr), bytes(b) {
+  void* p = nullptr; check_status(agb_alloc(c, b ? b : 4, &p)); ptr = (float*)p;
+}
+Buffer::~Buffer() { if (ptr) agb_free(ctx, ptr); }
+
+Shape NdArray::contiguous_strides(const Shape& s) {
+  Shape st(s.size()); int64_t acc = 1;
+  for (int i = (int)s.size() - 1; i >= 0; i--) { st[i] = acc; acc *= s[i]; }
+  return st;
+}
+bool NdArray::is_contiguous() const {
+  if (!on_device()) return true;
+  int64_t acc = 1;
+  for (int i = ndim() - 1; i >= 0; i--) { if (shape[i] != 1 && stride[i] != acc) return false; acc *= shape[i]; }
+  return true;
+}
+agb_tensor NdArray::desc() const {
+  agb_tensor t; t.ptr = dptr; t.rank = ndim();
+  if (t.rank > AGB_MAX_RANK) throw OpError(AGB_ERR_INVALID_DIMS, "tensor rank exceeds AGB_MAX_RANK");
+  for (int i = 0; i < t.rank; i++) { t.shape[i] = shape[i]; t.stride[i] = stride[i]; }
+  return t;
+}
+NdArray NdArray::from_host(const Shape& shape, std::vector<float> v, bool meta) {
+  NdArray a; a.shape = shape; a.stride = contiguous_strides(shape);
+  a.host = std::make_shared<std::vector<float>>(std::move(v)); a.meta = meta;
+  return a;
+}
+NdArray NdArray::reshaped(const Shape& s) const {
+  NdArray r = *this; r.shape = s; r.stride = contiguous_strides(s); r.virt.reset();
+  return r;
+}
+NdArray NdArray::permuted(const std::vector<int>& perm) const {
+  NdArray r = *this; r.host.reset(); r.virt.reset();
+  for (size_t i = 0; i < perm.size(); i++) { r.shape[i] = shape[perm[i]]; r.stride[i] = stride[perm[i]]; }
+  return r;
+}
+NdArray NdArray::sliced(int axis, int64_t start, int64_t len) const {
+  NdArray r = *this; r.host.reset(); r.virt.reset();
+  r.dptr = dptr + start * stride[axis]; r.shape[axis] = len;
+  return r;
+}
+
+Device::Device(int index) { check_status(agb_init(index, &ctx)); }
+Device::~Device() { if (ctx) agb_destroy(ctx); }
+NdArray Device::empty(const Shape& s) {
+  NdArray a; a.shape = s; a.stride = NdArray::contiguous_strides(s);
+  a.buf = std::make_shared<Buffer>(ctx, (size_t)std::max<int64_t>(a.size(), 1) * sizeof(float)); a.dptr = a.buf->ptr;
+  return a;
+}
+NdArray Device::zeros(const Shape& s) {
+  NdArray a = empty(s);
+  check_status(agb_memset0(ctx, a.dptr, (size_t)a.size() * sizeof(float)));
+  return a;
+}
+NdArray Device::full(const Shape& s, float v) {
+  NdArray a = empty(s); agb_tensor t = a.desc();
+  check_status(agb_fill(ctx, &t, v));
+  return a;
+}
+void Device::ensure_device(NdArray& a) {
+  if (a.on_device()) return;
+  if (a.virt) throw Panic("virtual im2col tensor used where a materialised array is required");
+  if (!a.host) throw Panic("array has neither device nor host storage");
+  NdArray d = empty(a.shape);
+  if (a.size() == 1) { agb_tensor t = d.desc(); check_status(agb_fill(ctx, &t, (*a.host)[0])); }   // scalars: no H2D at all
+  else if (a.size() > 0) check_status(agb_h2d(ctx, d.dptr, a.host->data(), (size_t)a.size() * sizeof(float)));
+  a.buf = d.buf; a.dptr = d.dptr; a.stride = d.stride;
+}
+const std::vector<float>& Device::ensure_host(NdArray& a) {
+  if (a.host) return *a.host;
+  NdArray c = a.is_contiguous() ? a : contiguous(a);
+  auto h = std::make_shared<std::vector<float>>((size_t)c.size());
+  check_status(agb_d2h(ctx, h->data(), c.dptr, (size_t)c.size() * sizeof(float)));
+  check_status(agb_sync(ctx));
+  a.host = h;
+  return *a.host;
+}
+NdArray Device::contiguous(const NdArray& a) {
+  if (a.is_contiguous()) return a;
+  return copy(a);
+}
+NdArray Device::copy(const NdArray& a_) {
+  NdArray a = a_; ensure_device(a);
+  NdArray c = empty(a.shape);
+  agb_tensor s = a.desc(), d = c.desc();
+  check_status(agb_copy_strided(ctx, &s, &d));
+  c.meta = a.meta;
+  return c;
+}
+void Device::sync() { check_status(agb_sync(ctx)); }
+
+Shape as_shape(Device* dev, NdArray& a) {
+  const std::vector<float>& h = dev->ensure_host(a);
+  Shape s(h.size()); for (size_t i = 0; i < h.size(); i++) s[i] = (int64_t)h[i];
+  return s;
+}
+std::vector<int64_t> as_ints(Device* dev, NdArray& a) { return as_shape(dev, a); }
+
+// ================================================================================================ Graph / builder
+TensorID Graph::install(std::unique_ptr<TensorInternal> node) {
+  size_t id = node_set.size();
+  if (id == NUM_NODES_WARN)
+    fprintf(stderr, "Too many tensors in this graph: %zu. Use Graph::clear, or move the training loop out of the `run` block\n", NUM_NODES_WARN);
+  if (id > NUM_NODES_CRITICAL)
+    throw Panic("Maximum graph size exceeded: 500000. Use Graph::clear, or move the training loop out of the `run` block");   // graph.rs:36-41
+  node->id = (TensorID)id;
+  node_set.push_back(std::move(node));
+  return (TensorID)id;
+}
+
+TensorBuilder& TensorBuilder::append_input_with_selector(Tensor t, bool allow_mut, int sel) {
+  if (t.graph != graph) throw Panic("Detected tensors belonging to different graphs");     // graph.rs:229-236
+  in_nodes.push_back(IncomingTensor{t.id, allow_mut, sel});
+  return *this;
+}
+TensorBuilder& TensorBuilder::append_backprop_input(Tensor t) {
+  if (t.graph != graph) throw Panic("Detected tensors belonging to different graphs");
+  has_bp = true; bp.push_back(IncomingTensor{t.id, false, 0});
+  return *this;
+}
+TensorBuilder& TensorBuilder::set_known_shape(const std::vector<int64_t>& s) {
+  for (auto a : s) if (a != -1 && a <= 0) throw Panic("Given shape contains invalid dim size(s)");   // tensor.rs:629-640
+  has_known = true; known = s; return *this;
+}
+Tensor TensorBuilder::build(Op* op) {
+  auto n = std::make_unique<TensorInternal>();
+  int rank = 0;
+  for (auto& in : in_nodes) rank = std::max(rank, graph->inner(in.id).topo_rank + 1);   // tensor.rs:773-783
+  n->op.reset(op); n->incoming_nodes = in_nodes; n->topo_rank = rank; n->shape = shape;
+  n->is_differentiable = differentiable; n->has_backprop_inputs = has_bp; n->backprop_inputs = bp;
+  n->has_known_shape = has_known; n->known_shape = known; n->variable_id = variable_id;
+  n->placeholder_name = placeholder; n->is_placeholder = is_ph;
+  return graph->tensor(graph->install(std::move(n)));
+}
+
+// marker ops whose compute is unreachable (basic_source_ops.rs:3-23)
+struct SourceOp : Op {
+  const char* nm; explicit SourceOp(const char* n) : nm(n) {}
+  const char* name() const override { return nm; }
+  void compute(ComputeContext&) override { throw Panic("unreachable: source op computed"); }
+  void grad(GradientContext&) override {}
+};
+
+Tensor Graph::placeholder(const std::string& name, const std::vector<int64_t>& shp) {
+  TensorBuilder b(this);
+  b.set_placeholder_name(name);
+  if (shp.empty() || shp[0] != -1) b.set_shape(T::as_tensor(this, shp));          // graph.rs:182-196
+  b.set_known_shape(shp);
+  return b.build(new SourceOp("autograd::tensor_ops::basic_source_ops::Placeholder"));
+}
+Tensor Graph::variable_by_id(VariableID vid) {
+  auto it = variable2node.find(vid.v);
+  if (it != variable2node.end()) return tensor(it->second);
+  if (!env || vid.v < 0 || vid.v >= (int)env->array_list.size()) throw Panic("variable array not found");
+  const NdArray& arr = env->array_list[vid.v];
+  TensorBuilder b(this);
+  b.set_shape(T::as_tensor(this, arr.shape)).set_variable(vid);
+  Tensor t = b.build(new SourceOp("autograd::tensor_ops::basic_source_ops::Variable"));
+  variable2node[vid.v] = t.id;
+  return t;
+}
+Tensor Graph::variable_by_name(const std::string& name, const std::string& ns) {
+  VariableID v = env->find(ns, name);
+  if (!v.valid()) throw Panic("variable array not found in `" + ns + "`: " + name);        // variable.rs:742-752
+  return variable_by_id(v);
+}
+
+// ================================================================================================ contexts
+NdArray ComputeContext::input(int i) {
+  if (i < 0 || i >= (int)xs.size()) throw Panic("Bad op impl: input index out of range.");
+  OpInput& x = xs[i];
+  if (x.kind == InputKind::RdWrVariable) throw Panic("Bad op impl: cannot perform mutable borrowing for input. Use input_mut() instead.");
+  if (x.taken) throw Panic("Bad op impl: input()/input_mut() cannot be called twice");
+  x.taken = true; return x.arr;
+}
+NdArray ComputeContext::input_mut(int i) {
+  if (i < 0 || i >= (int)xs.size()) throw Panic("Bad op impl: input doesn't exist.");
+  OpInput& x = xs[i];
+  if (x.kind != InputKind::RdWrVariable) throw Panic("Bad op impl: cannot perform mutable borrowing for input");
+  if (x.taken) throw Panic("Bad op impl: input()/input_mut() cannot be called twice");
+  x.taken = true; return x.arr;
+}
+void ComputeContext::append_output_view(NdArray y) {
+  bool has_var = false;
+  for (auto& x : xs) if (x.kind != InputKind::NonVariable) has_var = true;
+  if (has_var && y.on_device()) ys.push_back(dev->copy(y));      // copy beforehand, like op.rs:273-287
+  else ys.push_back(std::move(y));
+}
+void ComputeContext::append_empty_output() { ys.push_back(NdArray::scalar_host(0.0f)); }
+
+Tensor GradientContext::input(int i) const {
+  auto& in = g->inner(y.id).incoming_nodes;
+  if (i < 0 || i >= (int)in.size()) throw Panic("bad Op::grad impl");
+  return g->tensor(in[i].id);
+}
+std::vector<Tensor> GradientContext::inputs() const {
+  std::vector<Tensor> r; for (auto& in : g->inner(y.id).incoming_nodes) r.push_back(g->tensor(in.id)); return r;
+}
+int GradientContext::num_inputs() const { return (int)g->inner(y.id).incoming_nodes.size(); }
+
+// ================================================================================================ gradients (gradient.rs)
+namespace {
+struct GradInfo { std::vector<Tensor> gradients; bool on_path = false; bool present = false; };
+struct HeapNode { TensorID id; int rank; bool operator<(const HeapNode& o) const { return rank < o.rank; } };
+}
+
+std::vector<Tensor> compute_gradients(const std::vector<Tensor>& ys, const std::vector<Tensor>& xs, const std::vector<Tensor>* gys, Graph* g) {
+  std::unordered_map<TensorID, GradInfo> map;
+  auto is_xs = [&](TensorID id) { for (auto& x : xs) if (x.id == id) return true; return false; };
+  // init_gradient_map (gradient.rs:203-248): DFS from ys, mark nodes between ys and xs
+  std::vector<std::pair<TensorID, bool>> st;
+  for (auto& y : ys) st.push_back({y.id, false});
+  while (!st.empty()) {
+    auto [cur, visit] = st.back(); st.pop_back();
+    TensorInternal& n = g->inner(cur);
+    if (visit) {
+      bool child_on = false;
+      for (auto& c : n.get_backprop_inputs()) { auto it = map.find(c.id); if (it != map.end() && it->second.on_path) child_on = true; }
+      GradInfo gi; gi.present = true; gi.on_path = n.is_differentiable && (is_xs(cur) || child_on);
+      map[cur] = gi;
+    } else {
+      st.push_back({cur, true});
+      for (auto& c : n.get_backprop_inputs()) {
+        if (map.find(cur) != map.end()) continue;
+        TensorInternal& ch = g->inner(c.id);
+        if (ch.is_source() || !ch.is_differentiable) {
+          GradInfo gi; gi.present = true; gi.on_path = ch.is_differentiable && is_xs(c.id);
+          map[c.id] = gi;
+        } else st.push_back({c.id, false});
+      }
+    }
+  }
+  auto gradient_of = [&](GradInfo& gi) -> Tensor {
+    if (gi.gradients.size() > 1) { Tensor s = T::add_n(gi.gradients); gi.gradients.clear(); gi.gradients.push_back(s); }   // :168-173
+    return gi.gradients[0];
+  };
+  if (gys) {
+    if (gys->size() != ys.size()) throw Panic("`ys.len()` must match `gys.len()`");
+    for (size_t i = 0; i < ys.size(); i++) map[ys[i].id].gradients.push_back((*gys)[i]);
+  } else {
+    Tensor one = T::scalar(g, 1.0f);
+    for (auto& y : ys) map[y.id].gradients.push_back(one);
+  }
+  std::priority_queue<HeapNode> heap;
+  for (auto& y : ys) heap.push(HeapNode{y.id, g->inner(y.id).topo_rank});
+  while (!heap.empty()) {
+    HeapNode y = heap.top(); heap.pop();
+    Tensor gy = gradient_of(map[y.id]);
+    GradientContext ctx; ctx.gy = gy; ctx.y = g->tensor(y.id); ctx.g = g;
+    Op* op = g->inner(y.id).op.get();            // (the reference temporarily steals the boxed op, op.rs:365-380)
+    op->grad(ctx);
+    // copy: Op::grad may have appended nodes and reallocated node storage
+    std::vector<IncomingTensor> bins = g->inner(y.id).get_backprop_inputs();
+    size_t n = std::min(bins.size(), ctx.gxs.size());
+    for (size_t i = 0; i < n; i++) {
+      TensorID xid = bins[i].id;
+      auto it = map.find(xid);
+      if (it == map.end() || !it->second.on_path) continue;
+      if (!ctx.gxs[i].valid()) continue;
+      bool not_visited = it->second.gradients.empty();
+      it->second.gradients.push_back(ctx.gxs[i]);
+      if (!g->inner(xid).is_source() && not_visited) heap.push(HeapNode{xid, g->inner(xid).topo_rank});
+    }
+  }
+  std::vector<Tensor> ret;
+  for (auto& x : xs) {
+    auto it = map.find(x.id);
+    if (it != map.end() && it->second.on_path && !it->second.gradients.empty()) ret.push_back(gradient_of(it->second));
+    else ret.push_back(Tensor{});     // None: not differentiable
+  }
+  return ret;
+}
+
+// ================================================================================================ evaluation (evaluation.rs)
+namespace {
+struct Stored { bool ok = true; int code = 0; std::string msg; std::vector<NdArray> ys; };
+
+NdArray find_placeholder_value(const std::vector<Feed>& feeds, Graph* g, TensorID id) {
+  TensorInternal& n = g->inner(id);
+  for (auto& f : feeds) {
+    bool hit = f.by_name ? (f.name == n.placeholder_name) : (f.id == id);
+    if (!hit) continue;
+    if (n.has_known_shape) {              // validate_using_known_shape, tensor.rs:374-386
+      bool ok = n.known_shape.size() == f.value.shape.size();
+      for (size_t i = 0; ok && i < n.known_shape.size(); i++) if (n.known_shape[i] > 0 && n.known_shape[i] != f.value.shape[i]) ok = false;
+      if (!ok) throw Panic("Shape error: placeholder required a different shape than the value fed to `" + n.placeholder_name + "`");
+    }
+    return f.value;
+  }
+  throw Panic("Placeholder unfilled");    // evaluation.rs:248
+}
+}  // namespace
+
+std::vector<EvalResult> eval(Graph* g, const std::vector<Tensor>& targets, const std::vector<Feed>& feeds, bool fetch_to_host) {
+  VariableEnvironment* env = g->env; Device* dev = env->dev;
+  std::unordered_map<TensorID, Stored> storage;
+  Evaluation run; run.graph = g; run.dev = dev;
+  auto would_not_visit = [&](TensorID id) {
+    TensorInternal& n = g->inner(id);
+    return n.is_placeholder || n.is_variable() || storage.count(id) > 0;
+  };
+  std::vector<std::pair<TensorID, bool>> st; st.reserve(1 << 10);
+  for (auto& t : targets) { if (t.graph != g) throw Panic("Detected tensors belonging to different graphs"); st.push_back({t.id, false}); }
+  while (!st.empty()) {
+    auto [id, visit] = st.back(); st.pop_back();
+    if (visit) {
+      if (would_not_visit(id)) continue;
+      TensorInternal& n = g->inner(id);
+      Stored out;
+      ComputeContext ctx; ctx.dev = dev; ctx.run = &run; ctx.node = id;
+      for (auto& in : n.incoming_nodes) {
+        TensorInternal& x = g->inner(in.id);
+        if (x.is_placeholder) ctx.xs.push_back(OpInput{find_placeholder_value(feeds, g, in.id), InputKind::NonVariable});
+        else if (x.is_variable()) ctx.xs.push_back(OpInput{env->array_list[x.variable_id.v], in.allow_mut ? InputKind::RdWrVariable : InputKind::RdOnlyVariable});
+        else {
+          Stored& s = storage[in.id];
+          if (!s.ok) { out.ok = false; out.code = s.code; out.msg = s.msg; break; }     // errors propagate to dependents (:202-211)
+          if (in.array_selector >= (int)s.ys.size()) throw Panic("Bad op implementation: output selector out of range");
+          ctx.xs.push_back(OpInput{s.ys[in.array_selector], InputKind::NonVariable});
+        }
+      }
+      if (out.ok) {
+        try {
+          n.op->compute(ctx);
+          if (ctx.ys.empty()) throw Panic("Bad op implementation: empty return value");
+          out.ys = std::move(ctx.ys);
+        } catch (const OpError& e) { out.ok = false; out.code = e.code; out.msg = e.msg; }
+      }
+      storage[id] = std::move(out);
+    } else {
+      st.push_back({id, true});
+      for (auto& c : g->inner(id).incoming_nodes) if (!would_not_visit(c.id)) st.push_back({c.id, false});
+    }
+  }
+  // all gradients of this run exist now: (allreduce +) ONE fused multi-tensor optimizer launch (north_star item 5)
+  flush_pending_updates(run, env);
+
+  std::vector<EvalResult> ret;
+  for (auto& t : targets) {
+    EvalResult r; TensorInternal& n = g->inner(t.id);
+    if (n.is_variable()) r.value = env->array_list[n.variable_id.v];                      // case 1 (:347-349) (cloned on fetch)
+    else if (n.is_placeholder) r.value = find_placeholder_value(feeds, g, t.id);          // case 2
+    else {
+      auto it = storage.find(t.id);
+      if (it == storage.end()) throw Panic("eval: the same tensor was requested twice");   // storage.take(..).unwrap()
+      if (!it->second.ok) { r.ok = false; r.err_code = it->second.code; r.err_msg = it->second.msg; }
+      else r.value = it->second.ys[0];
+      storage.erase(it);
+    }
+    if (r.ok && r.value.virt && !r.value.on_device() && !r.value.has_host()) {
+      extern NdArray materialize_im2col(Device*, const NdArray&);
+      r.value = materialize_im2col(dev, r.value);
+    }
+    if (r.ok && fetch_to_host) dev->ensure_host(r.value);
+    ret.push_back(std::move(r));
+  }
+  if (!fetch_to_host) return ret;
+  dev->sync();      // surfaces device-side index errors (bad labels / gather ids) as OutOfBounds
+  return ret;
+}
+
+// ================================================================================================ variables
+VariableEnvironment::VariableEnvironment(int device_index) { dev = new Device(device_index); owns_dev = true; }
+VariableEnvironment::~VariableEnvironment() { array_list.clear(); if (owns_dev) delete dev; }
+
+VariableID VariableEnvironment::set(const std::string& ns, const std::string& name, const Shape& shape, const float* data) {
+  NdArray a = dev->empty(shape);
+  if (a.size() > 0) { check_status(agb_h2d(dev->ctx, a.dptr, data, (size_t)a.size() * sizeof(float))); dev->sync(); }
+  VariableID id{(int)array_list.size()};
+  name_to_id[{ns, name}] = id.v;               // register_variable, variable.rs:347-358 (a re-used name re-points to the new slot)
+  names.push_back({ns, name});
+  array_list.push_back(a);
+  return id;
+}
+VariableID VariableEnvironment::find(const std::string& ns, const std::string& name) const {
+  auto it = name_to_id.find({ns, name});
+  return it == name_to_id.end() ? VariableID{} : VariableID{it->second};
+}
+std::vector<VariableID> VariableEnvironment::current_var_ids(const std::string& ns) const {
+  std::vector<VariableID> r;
+  for (auto& kv : name_to_id) if (kv.first.first == ns) r.push_back(VariableID{kv.second});
+  std::sort(r.begin(), r.end(), [](VariableID a, VariableID b) { return a.v < b.v; });   // deterministic (the reference's FxHashMap order is unspecified)
+  return r;
+}
+std::vector<float> VariableEnvironment::get(VariableID v) {
+  NdArray a = array_list.at(v.v); a.host.reset();
+  return dev->ensure_host(a);
+}
+void VariableEnvironment::put(VariableID v, const float* data, size_t n) {
+  NdArray& a = array_list.at(v.v);
+  if ((int64_t)n != a.size()) throw OpError(AGB_ERR_INCOMPATIBLE_SHAPE, "VariableEnvironment::put: size mismatch");
+  if (n) { check_status(agb_h2d(dev->ctx, a.dptr, data, n * sizeof(float))); dev->sync(); }
+}
+
+// JSON checkpoint in the reference's serde layout (variable.rs:549-598; ndarray's {"v":1,"dim":[..],"data":[..]}),
+// names serialised as "namespacename" (variable.rs:225-229).
+std::string VariableEnvironment::save_json() {
+  std::ostringstream o; o.precision(9);
+  o << "{\"array_list\":[";
+  for (size_t i = 0; i < array_list.size(); i++) {
+    std::vector<float> h = get(VariableID{(int)i});
+    if (i) o << ",";
+    o << "{\"v\":1,\"dim\":[";
+    for (size_t d = 0; d < array_list[i].shape.size(); d++) { if (d) o << ","; o << array_list[i].shape[d]; }
+    o << "],\"data\":[";
+    for (size_t k = 0; k < h.size(); k++) { if (k) o << ","; o << h[k]; }
+    o << "]}";
+  }
+  o << "],\"name_to_id\":{";
+  bool first = true;
+  for (auto& kv : name_to_id) {
+    if (!first) o << ","; first = false;
+    o << "\"" << kv.first.first << "\\u0001" << kv.first.second << "\":" << kv.second;
+  }
+  o << "}}";
+  return o.str();
+}
+
+namespace {
+struct JsonCur {
+  const std::string& s; size_t i = 0;
+  explicit JsonCur(const std::string& str) : s(str) {}
+  void ws() { while (i < s.size() && (s[i] == ' ' || s[i] == '\n' || s[i] == '\t' || s[i] == '\r')) i++; }
+  bool eat(char c) { ws(); if (i < s.size() && s[i] == c) { i++; return true; } return false; }
+  void expect(char c) { if (!eat(c)) throw OpError(AGB_ERR_NDARRAY, std::string("load: malformed checkpoint near '") + c + "'"); }
+  std::string str() {
+    expect('"'); std::string r;
+    while (i < s.size() && s[i] != '"') {
+      if (s[i] == '\\' && i + 5 < s.size() && s[i + 1] == 'u') { r.push_back((char)strtol(s.substr(i + 2, 4).c_str(), nullptr, 16)); i += 6; }
+      else if (s[i] == '\\' && i + 1 < s.size()) { r.push_back(s[i + 1]); i += 2; }
+      else r.push_back(s[i++]);
+    }
+    expect('"'); return r;
+  }
+  double num() { ws(); size_t j = i; while (j < s.size() && (isdigit((unsigned char)s[j]) || strchr("+-.eE", s[j]))) j++; double v = atof(s.substr(i, j - i).c_str()); i = j; return v; }
+};
+}  // namespace
+
+void VariableEnvironment::load_json(const std::string& js) {
+  JsonCur c(js);
+  std::vector<std::pair<Shape, std::vector<float>>> arrays; std::map<std::string, int> ids;
+  c.expect('{');
+  do {
+    std::string key = c.str(); c.expect(':');
+    if (key == "array_list") {
+      c.expect('[');
+      if (!c.eat(']')) {
+        do {
+          Shape dim; std::vector<float> data;
+          c.expect('{');
+          do {
+            std::string k = c.str(); c.expect(':');
+            if (k == "dim") { c.expect('['); if (!c.eat(']')) { do dim.push_back((int64_t)c.num()); while (c.eat(',')); c.expect(']'); } }
+            else if (k == "data") { c.expect('['); if (!c.eat(']')) { do data.push_back((float)c.num()); while (c.eat(',')); c.expect(']'); } }
+            else c.num();
+          } while (c.eat(','));
+          c.expect('}');
+          arrays.push_back({dim, data});
+        } while (c.eat(','));
+        c.expect(']');
+      }
+    } else if (key == "name_to_id") {
+      c.expect('{');
+      if (!c.eat('}')) { do { std::string k = c.str(); c.expect(':'); ids[k] = (int)c.num(); } while (c.eat(',')); c.expect('}'); }
+    }
+  } while (c.eat(','));
+  array_list.clear(); names.assign(arrays.size(), {"", ""}); name_to_id.clear();
+  for (auto& a : arrays) {
+    NdArray d = dev->empty(a.first);
+    if (d.size() != (int64_t)a.second.size()) throw OpError(AGB_ERR_NDARRAY, "load: dim/data mismatch");
+    if (d.size()) check_status(agb_h2d(dev->ctx, d.dptr, a.second.data(), a.second.size() * sizeof(float)));
+    array_list.push_back(d);
+  }
+  dev->sync();
+  for (auto& kv : ids) {
+    size_t p = kv.first.find('\x01');
+    std::string ns = p == std::string::npos ? "" : kv.first.substr(0, p), nm = p == std::string::npos ? kv.first : kv.first.substr(p + 1);
+    name_to_id[{ns, nm}] = kv.second;
+    if (kv.second >= 0 && kv.second < (int)names.size()) names[kv.second] = {ns, nm};
+  }
+}
+
+}  // namespace agx

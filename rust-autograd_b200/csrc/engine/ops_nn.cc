@@ -1,0 +1,445 @@
+// ops_nn.cc — dense contractions, convolution family, pooling, dropout, optimizer update ops and the Optimizer trait.
+// Reference files mirrored: tensor_ops/dot_ops.rs, tensor_ops/conv_ops/{conv2d,conv2d_transpose,max_pool2d}.rs,
+// tensor_ops/random_ops.rs:218-245, tensor_ops/gradient_descent_ops/*.rs, optimizers/*.rs.
+#include "agx.h"
+#include <algorithm>
+
+namespace agx {
+#define REFNAME(mod, nm) "autograd::tensor_ops::" mod "::" nm
+static NdArray on_dev(Device* d, NdArray a) { d->ensure_device(a); return a; }
+
+// ================================================================================================ MatMul / BatchMatMul
+struct MatMul : Op {                   // dot_ops.rs:554-629.  Transposes = stride swaps; the kernel consumes strided views directly.
+  bool ta, tb, batched;
+  const char* name() const override { return batched ? REFNAME("dot_ops", "BatchMatMul") : REFNAME("dot_ops", "MatMul"); }
+  void compute(ComputeContext& c) override {
+    NdArray a = on_dev(c.dev, c.input(0)), b = on_dev(c.dev, c.input(1));
+    if (!batched) {
+      if (a.ndim() != 2) throw OpError(AGB_ERR_INCOMPATIBLE_SHAPE, "matmul: lhs input's ndim must be 2");     // :568-573
+      if (b.ndim() != 2) throw OpError(AGB_ERR_INCOMPATIBLE_SHAPE, "matmul: rhs input's ndim must be 2");
+    } else {
+      if (a.ndim() < 2) throw OpError(AGB_ERR_INCOMPATIBLE_SHAPE, "BatchMatMul: Left-hand-side input's ndim must be >= 2");
+      if (b.ndim() < 2) throw OpError(AGB_ERR_INCOMPATIBLE_SHAPE, "BatchMatMul: Right-hand-side input's ndim must be >= 2");
+      if (a.ndim() != b.ndim()) throw OpError(AGB_ERR_INCOMPATIBLE_SHAPE, "Input shapes mismatch: ranks differ");
+      // non-collapsible batch dims are deep-copied, like batch_mat_mul_requires_copy (dot_ops.rs:444-453,524-531)
+      auto collapsible = [](const NdArray& t) { for (int i = t.ndim() - 4; i >= 0; i--) if (t.shape[i] != 1 && t.stride[i] != t.stride[i + 1] * t.shape[i + 1]) return false; return true; };
+      if (!collapsible(a)) a = c.dev->copy(a);
+      if (!collapsible(b)) b = c.dev->copy(b);
+    }
+    int R = a.ndim();
+    int64_t m = ta ? a.shape[R - 1] : a.shape[R - 2], n = tb ? b.shape[R - 2] : b.shape[R - 1];
+    Shape out(a.shape.begin(), a.shape.end() - 2); out.push_back(m); out.push_back(n);
+    NdArray y = c.dev->empty(out);
+    agb_tensor da = a.desc(), db = b.desc(), dy = y.desc();
+    check_status(agb_gemm_f32(c.dev->ctx, ta ? 1 : 0, tb ? 1 : 0, &da, &db, &dy, 0.0f));
+    c.append_output(y);
+  }
+  void grad(GradientContext& c) override {       // dot_ops.rs:608-628,697-717: the forward op's own flags are ignored (sic)
+    Tensor gy = c.output_grad();
+    auto mk = [&](Tensor l, Tensor r, bool tl, bool tr) { auto* op = new MatMul(); op->ta = tl; op->tb = tr; op->batched = batched; return TensorBuilder(c.graph()).append_input(l, false).append_input(r, false).build(op); };
+    c.append_input_grad(mk(gy, c.input(1), false, true));
+    c.append_input_grad(mk(c.input(0), gy, true, false));
+  }
+};
+Tensor T::matmul(Tensor a, Tensor b) { auto* op = new MatMul(); op->ta = op->tb = false; op->batched = false; return TensorBuilder(a.graph).append_input(a, false).append_input(b, false).build(op); }
+Tensor T::batch_matmul_t(Tensor a, Tensor b, bool ta, bool tb) { auto* op = new MatMul(); op->ta = ta; op->tb = tb; op->batched = true; return TensorBuilder(a.graph).append_input(a, false).append_input(b, false).build(op); }
+
+struct TensordotPreprocess : Op {      // dot_ops.rs:720-799: host shape math, 5 tiny outputs
+  const char* name() const override { return REFNAME("dot_ops", "TensordotPreprocess"); }
+  void compute(ComputeContext& c) override {
+    NdArray x0 = c.input(0), x1 = c.input(1), a0 = c.input(2), a1 = c.input(3);
+    auto norm = [&](NdArray& ax, int nd) { std::vector<int64_t> v = as_ints(c.dev, ax); for (auto& e : v) e = e < 0 ? e + nd : e; return v; };
+    std::vector<int64_t> axes0 = norm(a0, x0.ndim()), axes1 = norm(a1, x1.ndim());
+    auto pre = [&](const Shape& shp, const std::vector<int64_t>& axes, bool flip, std::vector<float>& perm, std::vector<float>& new_shape, std::vector<float>& free_dims) {
+      std::vector<int64_t> free;
+      for (int64_t i = 0; i < (int64_t)shp.size(); i++) if (std::find(axes.begin(), axes.end(), i) == axes.end()) free.push_back(i);
+      int64_t pf = 1, pa = 1;
+      for (auto i : free) { pf *= shp[i]; free_dims.push_back((float)shp[i]); }
+      for (auto i : axes) pa *= shp[i];
+      std::vector<int64_t> first = flip ? axes : free, second = flip ? free : axes;
+      for (auto i : first) perm.push_back((float)i);
+      for (auto i : second) perm.push_back((float)i);
+      new_shape = flip ? std::vector<float>{(float)pa, (float)pf} : std::vector<float>{(float)pf, (float)pa};
+    };
+    std::vector<float> perm0, ns0, fd0, perm1, ns1, fd1;
+    pre(x0.shape, axes0, false, perm0, ns0, fd0); pre(x1.shape, axes1, true, perm1, ns1, fd1);
+    fd0.insert(fd0.end(), fd1.begin(), fd1.end());
+    auto H = [](std::vector<float> v) { int64_t n = (int64_t)v.size(); return NdArray::from_host({n}, std::move(v), true); };
+    c.append_output(H(fd0)); c.append_output(H(perm0)); c.append_output(H(perm1)); c.append_output(H(ns0)); c.append_output(H(ns1));
+  }
+  void grad(GradientContext& c) override { for (int i = 0; i < 4; i++) c.append_none(); }
+};
+Tensor T::tensordot(Tensor a, Tensor b, Tensor a_axes, Tensor b_axes) {      // mod.rs:1914-1946
+  Graph* g = a.graph;
+  Tensor pre = TensorBuilder(g).append_input(a, false).append_input(b, false).append_input(a_axes, false).append_input(b_axes, false).build(new TensordotPreprocess());
+  Tensor final_shape = nth_tensor(pre, 0), perm_a = nth_tensor(pre, 1), perm_b = nth_tensor(pre, 2), nsa = nth_tensor(pre, 3), nsb = nth_tensor(pre, 4);
+  Tensor ar = reshape(transpose(a, perm_a), nsa), br = reshape(transpose(b, perm_b), nsb);
+  return reshape(matmul(ar, br), final_shape);
+}
+
+// ================================================================================================ convolution family
+// Conv2D's second output in the reference is the materialised im2col buffer (conv2d.rs:484, consumed by Conv2DFilterGrad via
+// nth_tensor(y, 1), :571-582).  north_star forbids materialising it, so output #1 is a VIRTUAL tensor: a descriptor holding a
+// reference to x plus the window geometry.  Conv2DFilterGrad / Conv2DWithCols recognise it and run implicit GEMM on x.
+struct Im2colRef { NdArray x; int kh, kw, pad, stride, dil; };
+
+NdArray materialize_im2col(Device* dev, const NdArray& cols) {      // only when user code evaluates nth_tensor(conv, 1)
+  const Im2colRef& r = *cols.virt;
+  NdArray x = dev->contiguous(r.x), out = dev->empty(cols.shape);
+  agb_tensor tx = x.desc(), tc = out.desc();
+  check_status(agb_im2col_f32(dev->ctx, &tx, &tc, r.kh, r.kw, r.pad, r.stride, r.dil));
+  return out;
+}
+static NdArray real_cols(Device* dev, const NdArray& cols) { return cols.virt && !cols.on_device() ? materialize_im2col(dev, cols) : cols; }
+
+struct ConvParams { int pad, stride, dilation; };
+static Tensor mk_conv_transpose(Graph* g, Tensor gy, Tensor w, ConvParams p);
+static Tensor mk_conv(Graph* g, Tensor x, Tensor w, ConvParams p);
+static Tensor mk_filter_grad(Graph* g, Tensor cols, Tensor gy, Tensor w, Tensor bp_x, Tensor bp_gy, ConvParams p);
+static Tensor mk_conv_with_cols(Graph* g, Tensor cols, Tensor w, Tensor bp_x, Tensor bp_w, ConvParams p);
+
+static int64_t conv_out(int64_t x, int64_t k, ConvParams p) { return (x + 2 * p.pad - (p.dilation * (k - 1) + 1)) / p.stride + 1; }
+
+struct Conv2D : Op {                   // conv2d.rs:531-586
+  ConvParams p;
+  const char* name() const override { return REFNAME("conv_ops::conv2d", "Conv2D"); }
+  void compute(ComputeContext& c) override {
+    NdArray x = c.dev->contiguous(on_dev(c.dev, c.input(0))), w = c.dev->contiguous(on_dev(c.dev, c.input(1)));   // deep_copy if not standard layout (:436-452)
+    if (x.ndim() != 4) throw OpError(AGB_ERR_INCOMPATIBLE_SHAPE, "conv2d: lhs input must be 4D");
+    if (w.ndim() != 4) throw OpError(AGB_ERR_INCOMPATIBLE_SHAPE, "conv2d: filter must be 4D");
+    if (x.shape[1] != w.shape[1]) throw OpError(AGB_ERR_INCOMPATIBLE_SHAPE, "conv2d: input channel dim must match filter's second dim");
+    int64_t yh = conv_out(x.shape[2], w.shape[2], p), yw = conv_out(x.shape[3], w.shape[3], p);
+    NdArray y = c.dev->empty({x.shape[0], w.shape[0], yh, yw});
+    agb_tensor tx = x.desc(), tw = w.desc(), ty = y.desc();
+    check_status(agb_conv2d_fprop_f32(c.dev->ctx, &tx, &tw, &ty, p.pad, p.stride, p.dilation));
+    NdArray cols; cols.shape = {x.shape[0], x.shape[1], w.shape[2], w.shape[3], yh, yw}; cols.stride = NdArray::contiguous_strides(cols.shape);
+    cols.virt = std::make_shared<Im2colRef>(Im2colRef{x, (int)w.shape[2], (int)w.shape[3], p.pad, p.stride, p.dilation});
+    c.append_output(y); c.append_output(cols);
+  }
+  void grad(GradientContext& c) override {
+    Graph* g = c.graph(); Tensor gy = c.output_grad(), y = c.output(), x = c.input(0), w = c.input(1);
+    c.append_input_grad(mk_conv_transpose(g, gy, w, p));
+    c.append_input_grad(mk_filter_grad(g, T::nth_tensor(y, 1), gy, w, x, gy, p));
+  }
+};
+struct Conv2DWithCols : Op {           // conv2d.rs:589-628
+  ConvParams p;
+  const char* name() const override { return REFNAME("conv_ops::conv2d", "Conv2DWithCols"); }
+  void compute(ComputeContext& c) override {
+    NdArray cols = c.input(0), w = c.dev->contiguous(on_dev(c.dev, c.input(1)));
+    if (cols.ndim() != 6 || w.ndim() != 4) throw OpError(AGB_ERR_INCOMPATIBLE_SHAPE, "Conv2DWithCols: cols must be 6-D and the filter 4-D");
+    if (cols.virt) {
+      NdArray x = c.dev->contiguous(cols.virt->x);
+      NdArray y = c.dev->empty({x.shape[0], w.shape[0], cols.shape[4], cols.shape[5]});
+      agb_tensor tx = x.desc(), tw = w.desc(), ty = y.desc();
+      check_status(agb_conv2d_fprop_f32(c.dev->ctx, &tx, &tw, &ty, cols.virt->pad, cols.virt->stride, cols.virt->dil));
+      c.append_output(y); return;
+    }
+    cols = c.dev->contiguous(on_dev(c.dev, cols));       // materialised cols supplied by the caller: y[b] = W . cols[b]
+    int64_t B = cols.shape[0], K = cols.shape[1] * cols.shape[2] * cols.shape[3], P = cols.shape[4] * cols.shape[5], O = w.shape[0];
+    NdArray y = c.dev->empty({B, O, cols.shape[4], cols.shape[5]});
+    NdArray w2 = w.reshaped({1, O, K}); w2.stride[0] = 0;  NdArray wb = w2; wb.shape[0] = B;
+    NdArray c3 = cols.reshaped({B, K, P}), y3 = y.reshaped({B, O, P});
+    agb_tensor ta = wb.desc(), tb = c3.desc(), ty = y3.desc();
+    check_status(agb_gemm_f32(c.dev->ctx, 0, 0, &ta, &tb, &ty, 0.0f));
+    c.append_output(y);
+  }
+  void grad(GradientContext& c) override {
+    Graph* g = c.graph(); Tensor cols = c.input(0), w = c.input(1), y = c.output(), gy = c.output_grad();
+    c.append_input_grad(mk_conv_transpose(g, gy, w, p));
+    Tensor bp0 = g->tensor(g->inner(y.id).get_backprop_inputs()[0].id);
+    c.append_input_grad(mk_filter_grad(g, cols, gy, w, bp0, gy, p));
+  }
+};
+struct Conv2DFilterGrad : Op {         // conv2d.rs:736-776
+  ConvParams p;
+  const char* name() const override { return REFNAME("conv_ops::conv2d", "Conv2DFilterGrad"); }
+  void compute(ComputeContext& c) override {
+    NdArray cols = c.input(0), gy = c.dev->contiguous(on_dev(c.dev, c.input(1))), w = c.input(2);
+    NdArray gw = c.dev->empty(w.shape);
+    if (cols.virt) {
+      NdArray x = c.dev->contiguous(cols.virt->x);
+      agb_tensor tx = x.desc(), tg = gy.desc(), tw = gw.desc();
+      check_status(agb_conv2d_wgrad_f32(c.dev->ctx, &tx, &tg, &tw, cols.virt->pad, cols.virt->stride, cols.virt->dil));
+      c.append_output(gw); return;
+    }
+    cols = c.dev->contiguous(on_dev(c.dev, cols));       // gw = sum_b gy[b] . cols[b]^T, beta = 1 over the batch like conv2d.rs:703-722
+    int64_t B = cols.shape[0], K = cols.shape[1] * cols.shape[2] * cols.shape[3], P = cols.shape[4] * cols.shape[5], O = gy.shape[1];
+    NdArray g3 = gy.reshaped({B, O, P}), c3 = cols.reshaped({B, K, P}), gw2 = gw.reshaped({O, K});
+    for (int64_t b = 0; b < B; b++) {
+      NdArray gb = g3.sliced(0, b, 1).reshaped({O, P}), cb = c3.sliced(0, b, 1).reshaped({K, P});
+      gb.dptr = g3.dptr + b * O * P; cb.dptr = c3.dptr + b * K * P;
+      agb_tensor ta = gb.desc(), tb = cb.desc(), ty = gw2.desc();
+      check_status(agb_gemm_f32(c.dev->ctx, 0, 1, &ta, &tb, &ty, b == 0 ? 0.0f : 1.0f));
+    }
+    c.append_output(gw);
+  }
+  void grad(GradientContext& c) override {
+    Graph* g = c.graph(); Tensor cols = c.input(0), gy = c.input(1), ggw = c.output_grad(), y = c.output();
+    c.append_input_grad(mk_conv_transpose(g, gy, ggw, p));
+    Tensor bp0 = g->tensor(g->inner(y.id).get_backprop_inputs()[0].id);
+    c.append_input_grad(mk_conv_with_cols(g, cols, ggw, bp0, ggw, p));
+  }
+};
+struct Conv2DTransposeFilterGrad;
+struct Conv2DTranspose : Op {          // conv2d_transpose.rs:249-300
+  ConvParams p;
+  const char* name() const override { return REFNAME("conv_ops::conv2d_transpose", "Conv2DTranspose"); }
+  void compute(ComputeContext& c) override {
+    NdArray gy = c.dev->contiguous(on_dev(c.dev, c.input(0))), w = c.dev->contiguous(on_dev(c.dev, c.input(1)));
+    if (gy.ndim() != 4) throw OpError(AGB_ERR_INCOMPATIBLE_SHAPE, "conv2d_transpose: Input must be 4D");
+    if (w.ndim() != 4) throw OpError(AGB_ERR_INCOMPATIBLE_SHAPE, "conv2d_transpose: Filter must be 4D");
+    if (gy.shape[1] != w.shape[0]) throw OpError(AGB_ERR_INCOMPATIBLE_SHAPE, "conv2d_transpose: Number of input channels must match second filter dim");
+    int64_t xh = p.stride * (gy.shape[2] - 1) - 2 * p.pad + (p.dilation * (w.shape[2] - 1) + 1);     // follows the code (:55-56)
+    int64_t xw = p.stride * (gy.shape[3] - 1) - 2 * p.pad + (p.dilation * (w.shape[3] - 1) + 1);
+    NdArray gx = c.dev->empty({gy.shape[0], w.shape[1], xh, xw});
+    agb_tensor tg = gy.desc(), tw = w.desc(), tx = gx.desc();
+    check_status(agb_conv2d_dgrad_f32(c.dev->ctx, &tg, &tw, &tx, p.pad, p.stride, p.dilation));
+    c.append_output(gx);
+  }
+  void grad(GradientContext& c) override;
+};
+struct Conv2DTransposeFilterGrad : Op {   // conv2d_transpose.rs:433-480: inputs (gy, x, w)
+  ConvParams p;
+  const char* name() const override { return REFNAME("conv_ops::conv2d_transpose", "Conv2DTransposeFilterGrad"); }
+  void compute(ComputeContext& c) override {
+    NdArray gy = c.dev->contiguous(on_dev(c.dev, c.input(0))), x = c.dev->contiguous(on_dev(c.dev, c.input(1))), w = c.input(2);
+    NdArray gw = c.dev->empty(w.shape);
+    agb_tensor ti = gy.desc(), tg = x.desc(), tw = gw.desc();     // roles swapped: gy is im2col'd, x multiplies it
+    check_status(agb_conv2d_wgrad_f32(c.dev->ctx, &ti, &tg, &tw, p.pad, p.stride, p.dilation));
+    c.append_output(gw);
+  }
+  void grad(GradientContext& c) override {
+    Graph* g = c.graph(); Tensor gy = c.input(0), gw = c.output_grad(), x = c.input(1);
+    c.append_input_grad(mk_conv_transpose(g, x, gw, p));
+    c.append_input_grad(mk_conv(g, gy, gw, p));
+    c.append_none();
+  }
+};
+void Conv2DTranspose::grad(GradientContext& c) {
+  Graph* g = c.graph(); Tensor x = c.input(0), w = c.input(1), gy = c.output_grad();
+  c.append_input_grad(mk_conv(g, gy, w, p));
+  auto* op = new Conv2DTransposeFilterGrad(); op->p = p;
+  c.append_input_grad(TensorBuilder(g).append_input(gy, false).append_input(x, false).append_input(T::stop_gradient(w), false).build(op));
+}
+static Tensor mk_conv(Graph* g, Tensor x, Tensor w, ConvParams p) { auto* op = new Conv2D(); op->p = p; return TensorBuilder(g).append_input(x, false).append_input(w, false).build(op); }
+static Tensor mk_conv_transpose(Graph* g, Tensor gy, Tensor w, ConvParams p) { auto* op = new Conv2DTranspose(); op->p = p; return TensorBuilder(g).append_input(gy, false).append_input(w, false).build(op); }
+static Tensor mk_filter_grad(Graph* g, Tensor cols, Tensor gy, Tensor w, Tensor bp_x, Tensor bp_gy, ConvParams p) {
+  auto* op = new Conv2DFilterGrad(); op->p = p;
+  return TensorBuilder(g).append_input(cols, false).append_input(gy, false).append_input(w, false).append_backprop_input(bp_x).append_backprop_input(bp_gy).build(op);
+}
+static Tensor mk_conv_with_cols(Graph* g, Tensor cols, Tensor w, Tensor bp_x, Tensor bp_w, ConvParams p) {
+  auto* op = new Conv2DWithCols(); op->p = p;
+  return TensorBuilder(g).append_input(cols, false).append_input(w, false).append_backprop_input(bp_x).append_backprop_input(bp_w).build(op);
+}
+Tensor T::conv2d(Tensor x, Tensor w, int pad, int stride, int dilation) { return mk_conv(x.graph, x, w, ConvParams{pad, stride, dilation}); }
+Tensor T::conv2d_transpose(Tensor x, Tensor w, int pad, int stride, int dilation) { return mk_conv_transpose(x.graph, x, w, ConvParams{pad, stride, dilation}); }
+
+// ================================================================================================ max pooling
+struct MaxPool2DGradGrad : Op {        // max_pool2d.rs:297-337
+  int size, pad, stride;
+  const char* name() const override { return REFNAME("conv_ops::max_pool2d", "MaxPool2DGradGrad"); }
+  void compute(ComputeContext& c) override {
+    NdArray ggx = c.dev->contiguous(on_dev(c.dev, c.input(0))), idx = c.dev->contiguous(on_dev(c.dev, c.input(1)));
+    int64_t yh = (ggx.shape[2] + 2 * pad - size) / stride + 1, yw = (ggx.shape[3] + 2 * pad - size) / stride + 1;
+    NdArray ggy = c.dev->empty({ggx.shape[0], ggx.shape[1], yh, yw});
+    agb_tensor tx = ggx.desc(), ty = ggy.desc();
+    check_status(agb_maxpool2d_gradgrad(c.dev->ctx, &tx, idx.dptr, nullptr, &ty));
+    c.append_output(ggy);
+  }
+  void grad(GradientContext& c) override { c.append_none(); c.append_none(); }
+};
+struct MaxPool2DGrad : Op {            // max_pool2d.rs:245-295
+  int size, pad, stride;
+  const char* name() const override { return REFNAME("conv_ops::max_pool2d", "MaxPool2DGrad"); }
+  void compute(ComputeContext& c) override {
+    NdArray gy = c.dev->contiguous(on_dev(c.dev, c.input(0))), idx = c.dev->contiguous(on_dev(c.dev, c.input(1)));
+    int64_t xh = stride * (gy.shape[2] - 1) - 2 * pad + size, xw = stride * (gy.shape[3] - 1) - 2 * pad + size;     // (:263-264)
+    NdArray gx = c.dev->empty({gy.shape[0], gy.shape[1], xh, xw});
+    agb_tensor tg = gy.desc(), tx = gx.desc();
+    check_status(agb_maxpool2d_bwd(c.dev->ctx, &tg, idx.dptr, nullptr, &tx));
+    c.append_output(gx);
+  }
+  void grad(GradientContext& c) override {
+    auto* op = new MaxPool2DGradGrad(); op->size = size; op->pad = pad; op->stride = stride;
+    c.append_input_grad(TensorBuilder(c.graph()).append_input(c.output_grad(), false).append_input(c.input(1), false).build(op));
+    c.append_none();
+  }
+};
+struct MaxPool2D : Op {                // max_pool2d.rs:166-243
+  int size, pad, stride;
+  const char* name() const override { return REFNAME("conv_ops::max_pool2d", "MaxPool2D"); }
+  void compute(ComputeContext& c) override {
+    NdArray x = c.dev->contiguous(on_dev(c.dev, c.input(0)));
+    if (x.ndim() != 4) throw OpError(AGB_ERR_INCOMPATIBLE_SHAPE, "max_pool2d: input must be 4-D");
+    int64_t yh = (x.shape[2] + 2 * pad - size) / stride + 1, yw = (x.shape[3] + 2 * pad - size) / stride + 1;
+    NdArray y = c.dev->empty({x.shape[0], x.shape[1], yh, yw}), idx = c.dev->empty({x.shape[0], x.shape[1], yh, yw});
+    agb_tensor tx = x.desc(), ty = y.desc();
+    check_status(agb_maxpool2d_fwd(c.dev->ctx, &tx, &ty, idx.dptr, nullptr, size, pad, stride));
+    c.append_output(y); c.append_output(idx);
+  }
+  void grad(GradientContext& c) override {
+    auto* op = new MaxPool2DGrad(); op->size = size; op->pad = pad; op->stride = stride;
+    c.append_input_grad(TensorBuilder(c.graph()).append_input(c.output_grad(), false).append_input(T::nth_tensor(c.output(), 1), false).build(op));
+  }
+};
+Tensor T::max_pool2d(Tensor x, int size, int pad, int stride) { auto* op = new MaxPool2D(); op->size = size; op->pad = pad; op->stride = stride; return TensorBuilder(x.graph).append_input(x, false).build(op); }
+
+// ================================================================================================ dropout
+struct Dropout : Op {                  // random_ops.rs:218-245: NOT inverted; outputs (y, mask); eval mode scales by (1 - ratio)
+  float ratio; bool train; uint64_t seed;
+  const char* name() const override { return REFNAME("random_ops", "Dropout"); }
+  void compute(ComputeContext& c) override {
+    NdArray x = c.dev->contiguous(on_dev(c.dev, c.input(0)));
+    if (!train) { NdArray y = c.dev->empty(x.shape); agb_tensor tx = x.desc(), ty = y.desc(); check_status(agb_unary(c.dev->ctx, AGB_U_SCALE, 1.0f - ratio, 0.f, &tx, &ty)); c.append_output(y); return; }
+    NdArray y = c.dev->empty(x.shape), mask = c.dev->empty(x.shape);
+    agb_tensor tx = x.desc(), ty = y.desc(), tm = mask.desc();
+    // The reference re-seeds a XorShift stream with a constant at every op construction (mod.rs:2895-2905), so every step
+    // draws the same mask; that stream is parity-unpinned.  Here: device Philox keyed by (seed, node id).
+    check_status(agb_dropout(c.dev->ctx, &tx, &ty, &tm, ratio, seed ? seed : 0x5EEDull, (uint64_t)c.node << 32));
+    c.append_output(y); c.append_output(mask);
+  }
+  void grad(GradientContext& c) override { c.append_input_grad(T::mul(c.output_grad(), T::nth_tensor(c.output(), 1))); }
+};
+Tensor T::dropout(Tensor x, float ratio, bool train, uint64_t seed) { auto* op = new Dropout(); op->ratio = ratio; op->train = train; op->seed = seed; return TensorBuilder(x.graph).append_input(x, false).build(op); }
+
+// ================================================================================================ optimizer update ops
+// One op node per variable as in the reference (AdamOp inputs: param(mut), grad, m(mut), v(mut), t(mut); adam.rs:11-58), but
+// compute() only REGISTERS the update; Graph::eval flushes all registered updates of the run as a single fused multi-tensor
+// kernel once every gradient exists (preceded by the NCCL gradient all-reduce in data-parallel runs).  This is the "clean"
+// ordering of SURVEY §3.5: every gradient is taken at the pre-update weights.
+enum { OPT_ADAM = 0, OPT_SGD = 1, OPT_MOMENTUM = 2, OPT_ADAGRAD = 3 };
+struct UpdateOp : Op {
+  int kind; float h[4];
+  const char* name() const override {
+    return kind == OPT_ADAM ? REFNAME("gradient_descent_ops::adam", "AdamOp") : kind == OPT_SGD ? REFNAME("gradient_descent_ops::sgd", "SGDOp")
+         : kind == OPT_MOMENTUM ? REFNAME("gradient_descent_ops::sgd", "MomentumSGDOp") : REFNAME("gradient_descent_ops::adagrad", "AdaGradOp");
+  }
+  void compute(ComputeContext& c) override {
+    PendingUpdate u; u.kind = kind; for (int i = 0; i < 4; i++) u.h[i] = h[i];
+    u.p = c.input_mut(0); u.g = c.dev->contiguous(on_dev(c.dev, c.input(1)));
+    if (u.g.shape != u.p.shape) { if (u.g.size() != u.p.size()) throw OpError(AGB_ERR_INCOMPATIBLE_SHAPE, "optimizer: gradient shape does not match the variable"); }
+    if (kind == OPT_ADAM) { u.s0 = c.input_mut(2); u.s1 = c.input_mut(3); u.t = c.input_mut(4); }
+    else if (kind != OPT_SGD) u.s0 = c.input_mut(2);
+    c.run->pending.push_back(u);
+    c.append_empty_output();
+  }
+  void grad(GradientContext& c) override { for (int i = 0; i < c.num_inputs(); i++) c.append_none(); }
+};
+
+void flush_pending_updates(Evaluation& run, VariableEnvironment* env) {
+  if (run.pending.empty()) return;
+  Device* dev = run.dev;
+  float gscale = 1.0f;
+  if (env->world > 1) {
+    // data parallel: pack all gradients into one contiguous arena, ONE NCCL all-reduce (sum), read them back
+    // scaled by 1/world inside the optimizer kernel
+    int64_t total = 0; for (auto& u : run.pending) total += (u.g.size() + 3) / 4 * 4;
+    NdArray arena = dev->empty({total}); int64_t off = 0;
+    for (auto& u : run.pending) {
+      check_status(agb_d2d(dev->ctx, arena.dptr + off, u.g.dptr, (size_t)u.g.size() * sizeof(float)));
+      NdArray v = arena.sliced(0, off, u.g.size()); v.shape = u.g.shape; v.stride = NdArray::contiguous_strides(v.shape);
+      off += (u.g.size() + 3) / 4 * 4; u.g = v;
+    }
+    check_status(agb_allreduce_sum(dev->ctx, arena.dptr, total));
+    gscale = 1.0f / (float)env->world;
+  }
+  for (int kind = 0; kind < 4; kind++) {
+    std::vector<PendingUpdate*> us; for (auto& u : run.pending) if (u.kind == kind) us.push_back(&u);
+    size_t i = 0;
+    while (i < us.size()) {       // one launch per group of updates sharing hyper-parameters (normally: all of them)
+      size_t j = i; std::vector<float*> p, s0, s1, t; std::vector<const float*> g; std::vector<int64_t> n;
+      while (j < us.size() && std::equal(us[j]->h, us[j]->h + 4, us[i]->h)) {
+        p.push_back(us[j]->p.dptr); g.push_back(us[j]->g.dptr); n.push_back(us[j]->p.size());
+        s0.push_back(us[j]->s0.dptr); s1.push_back(us[j]->s1.dptr); t.push_back(us[j]->t.dptr); j++;
+      }
+      const float* h = us[i]->h; int cnt = (int)p.size();
+      if (kind == OPT_ADAM) check_status(agb_multi_tensor_adam(dev->ctx, cnt, p.data(), g.data(), s0.data(), s1.data(), t.data(), n.data(), h[0], h[1], h[2], h[3], gscale));
+      else if (kind == OPT_SGD) check_status(agb_multi_tensor_sgd(dev->ctx, cnt, p.data(), g.data(), n.data(), h[0], gscale));
+      else if (kind == OPT_MOMENTUM) check_status(agb_multi_tensor_momentum(dev->ctx, cnt, p.data(), g.data(), s0.data(), n.data(), h[0], h[1], gscale));
+      else check_status(agb_multi_tensor_adagrad(dev->ctx, cnt, p.data(), g.data(), s0.data(), n.data(), h[0], gscale));
+      i = j;
+    }
+  }
+  run.pending.clear();
+}
+
+// ---- Optimizer trait (optimizers/mod.rs:49-99) ----
+void Optimizer::update(const std::vector<Tensor>& params, const std::vector<Tensor>& grads, Graph* g, const std::vector<Feed>& feeds) {
+  std::vector<Tensor> ups = compute_updates(params, grads, g);
+  std::vector<EvalResult> rs = eval(g, ups, feeds, false);
+  for (auto& r : rs) if (!r.ok) throw OpError(r.err_code, r.err_msg);      // `r.unwrap()`
+}
+Tensor Optimizer::get_update_op(const std::vector<Tensor>& params, const std::vector<Tensor>& grads, Graph* g) { return T::add_n(compute_updates(params, grads, g)); }
+
+namespace {
+std::string vid_name(VariableID v, const char* suffix) { return std::to_string(v.v) + suffix; }
+VariableID var_of(Tensor t) { VariableID v = t.graph->inner(t.id).variable_id; if (!v.valid()) throw Panic("Got non-variable tensor"); return v; }
+Tensor update_node(Graph* g, int kind, const float h[4], Tensor param, Tensor grad, const std::vector<Tensor>& state) {
+  auto* op = new UpdateOp(); op->kind = kind; for (int i = 0; i < 4; i++) op->h[i] = h[i];
+  TensorBuilder b(g); b.append_input(param, true).append_input(grad, false);
+  for (auto& s : state) b.append_input(s, true);
+  return b.build(op);
+}
+void make_state(VariableEnvironment* env, const std::vector<VariableID>& vars, const std::string& ns, const std::vector<const char*>& suffixes, bool with_t) {
+  for (auto vid : vars) {          // optimizers/adam.rs:84-103: "{vid}m", "{vid}v" zeros like the variable, "{vid}t" = 1.0 (0-d)
+    if (vid.v < 0 || vid.v >= (int)env->array_list.size()) throw Panic("variable array not found");
+    Shape shp = env->array_list[vid.v].shape; int64_t n = env->array_list[vid.v].size();
+    std::vector<float> z((size_t)n, 0.f);
+    for (auto sfx : suffixes) env->set(ns, vid_name(vid, sfx), shp, z.data());
+    if (with_t) { float one = 1.0f; env->set(ns, vid_name(vid, "t"), {}, &one); }
+  }
+}
+struct Adam : Optimizer {
+  float alpha, eps, b1, b2; std::string ns;
+  std::vector<Tensor> compute_updates(const std::vector<Tensor>& params, const std::vector<Tensor>& grads, Graph* g) override {   // optimizers/adam.rs:116-153
+    if (params.size() != grads.size()) throw Panic("assertion failed: num_params == grads.len()");
+    std::vector<Tensor> ret; float h[4] = {alpha, eps, b1, b2};
+    for (size_t i = 0; i < params.size(); i++) {
+      VariableID v = var_of(params[i]);
+      ret.push_back(update_node(g, OPT_ADAM, h, params[i], grads[i], {g->variable_by_name(vid_name(v, "m"), ns), g->variable_by_name(vid_name(v, "v"), ns), g->variable_by_name(vid_name(v, "t"), ns)}));
+    }
+    return ret;
+  }
+};
+struct SGD : Optimizer {               // optimizers/sgd.rs
+  float lr;
+  std::vector<Tensor> compute_updates(const std::vector<Tensor>& params, const std::vector<Tensor>& grads, Graph* g) override {
+    if (params.size() != grads.size()) throw Panic("assertion failed: num_params == grads.len()");
+    std::vector<Tensor> ret; float h[4] = {lr, 0, 0, 0};
+    for (size_t i = 0; i < params.size(); i++) { var_of(params[i]); ret.push_back(update_node(g, OPT_SGD, h, params[i], grads[i], {})); }
+    return ret;
+  }
+};
+struct StatefulSGD : Optimizer {       // MomentumSGD ("{vid}v", optimizers/momentum_sgd.rs) and AdaGrad ("{vid}h", optimizers/adagrad.rs)
+  int kind; float lr, momentum; std::string ns; const char* sfx;
+  std::vector<Tensor> compute_updates(const std::vector<Tensor>& params, const std::vector<Tensor>& grads, Graph* g) override {
+    if (params.size() != grads.size()) throw Panic("assertion failed: num_params == grads.len()");
+    std::vector<Tensor> ret; float h[4] = {lr, momentum, 0, 0};
+    for (size_t i = 0; i < params.size(); i++) { VariableID v = var_of(params[i]); ret.push_back(update_node(g, kind, h, params[i], grads[i], {g->variable_by_name(vid_name(v, sfx), ns)})); }
+    return ret;
+  }
+};
+}  // namespace
+Optimizer* make_adam(VariableEnvironment* env, const std::vector<VariableID>& vars, const std::string& ns, float alpha, float eps, float b1, float b2) {
+  make_state(env, vars, ns, {"m", "v"}, true);
+  auto* a = new Adam(); a->alpha = alpha; a->eps = eps; a->b1 = b1; a->b2 = b2; a->ns = ns; return a;
+}
+Optimizer* make_sgd(float lr) { auto* s = new SGD(); s->lr = lr; return s; }
+Optimizer* make_momentum_sgd(VariableEnvironment* env, const std::vector<VariableID>& vars, const std::string& ns, float lr, float momentum) {
+  make_state(env, vars, ns, {""}, false);      // state is named "{vid}" (optimizers/momentum_sgd.rs:65)
+  auto* s = new StatefulSGD(); s->kind = OPT_MOMENTUM; s->lr = lr; s->momentum = momentum; s->ns = ns; s->sfx = ""; return s;
+}
+Optimizer* make_adagrad(VariableEnvironment* env, const std::vector<VariableID>& vars, const std::string& ns, float lr) {
+  make_state(env, vars, ns, {""}, false);      // state is named "{vid}" (optimizers/adagrad.rs:48)
+  auto* s = new StatefulSGD(); s->kind = OPT_ADAGRAD; s->lr = lr; s->momentum = 0; s->ns = ns; s->sfx = ""; return s;
+}
+
+void grad_helper(const std::vector<Tensor>& losses, const std::string& ns, Graph* g, std::vector<Tensor>& vars, std::vector<Tensor>& grads) {   // optimizers/mod.rs:21-46
+  std::vector<Tensor> ys; for (auto& l : losses) ys.push_back(T::sum_all(l));
+  std::vector<Tensor> xs; for (auto vid : g->env->current_var_ids(ns)) xs.push_back(g->variable_by_id(vid));     // var_tensors_by_name (variable.rs:768-780)
+  std::vector<Tensor> gs = compute_gradients(ys, xs, nullptr, g);
+  for (size_t i = 0; i < xs.size(); i++) if (gs[i].valid()) { vars.push_back(xs[i]); grads.push_back(gs[i]); }
+}
+
+}  // namespace agx

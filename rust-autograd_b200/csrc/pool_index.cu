@@ -130,6 +130,7 @@ __global__ void __launch_bounds__(256) gather_grad_kernel(const float* __restric
     int64_t q = o % post; int64_t t = o / post; int64_t j = t % n_idx; int64_t p = t / n_idx;
     float f = __ldg(indices + j);
     int64_t k = (int64_t)f;
+    if (k < 0) k += axis_len;      // ndarray slices with a negative start count from the end (array_ops.rs:431-436)
     if (k < 0 || k >= axis_len || f != f) { atomicExch(err, 2); continue; }
     atomicAdd(gx + (p * axis_len + k) * post + q, __ldg(gy + o));
   }

@@ -5,6 +5,7 @@
 #pragma once
 #include "common.cuh"
 #include <cuda.h>
+#include <stdlib.h>
 
 // ------------------------------------------------------------------ host: tensor maps
 typedef CUresult (*PFN_encodeTiled)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
@@ -20,15 +21,18 @@ static inline PFN_encodeTiled agb_get_encode() {
   return fn;
 }
 // rank-N f32 tensor map, 128-byte swizzle, zero OOB fill.  dims/strides innermost first; strides in bytes for dims 1..N-1.
+// swizzle_atom32: false -> SWIZZLE_128B (16-byte chunks; K-major operands), true -> SWIZZLE_128B_ATOM_32B (32-byte chunks;
+// the only shared-memory layout tcgen05 accepts for MN-major TF32 operands, UMMA layout type 128B_BASE32B).
 static inline int agb_make_tmap(CUtensorMap* m, const void* base, int rank, const uint64_t* dims, const uint64_t* strides_bytes,
-                                const uint32_t* box) {
+                                const uint32_t* box, bool swizzle_atom32 = false) {
   PFN_encodeTiled enc = agb_get_encode();
   AGB_CHECK(enc, AGB_ERR_CUDA, "cuTensorMapEncodeTiled is not available from the driver");
   cuuint64_t d[5], s[4]; cuuint32_t b[5], e[5];
   for (int i = 0; i < rank; i++) { d[i] = dims[i]; b[i] = box[i]; e[i] = 1; }
   for (int i = 0; i + 1 < rank; i++) s[i] = strides_bytes[i];
   CUresult r = enc(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, (cuuint32_t)rank, const_cast<void*>(base), d, s, b, e,
-                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                   CU_TENSOR_MAP_INTERLEAVE_NONE, swizzle_atom32 ? CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B : CU_TENSOR_MAP_SWIZZLE_128B,
+                   CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                    CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) { agb_set_error("cuTensorMapEncodeTiled failed with CUresult %d", (int)r); return AGB_ERR_UNSUPPORTED; }
   return AGB_OK;
@@ -108,14 +112,14 @@ __device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.
 
 // ---- UMMA descriptors ----
 // shared-memory matrix descriptor (64-bit): [0,14) addr>>4, [16,30) LBO>>4, [32,46) SBO>>4, [46,48) version=1,
-// [61,64) layout (2 = SWIZZLE_128B).
-__device__ __forceinline__ uint64_t umma_smem_desc(uint32_t saddr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
+// [61,64) layout (2 = SWIZZLE_128B, 1 = SWIZZLE_128B_BASE32B).
+__device__ __forceinline__ uint64_t umma_smem_desc(uint32_t saddr, uint32_t lbo_bytes, uint32_t sbo_bytes, uint32_t layout = 2) {
   uint64_t d = 0;
   d |= (uint64_t)((saddr >> 4) & 0x3FFF);
   d |= (uint64_t)((lbo_bytes >> 4) & 0x3FFF) << 16;
   d |= (uint64_t)((sbo_bytes >> 4) & 0x3FFF) << 32;
   d |= (uint64_t)1 << 46;
-  d |= (uint64_t)2 << 61;
+  d |= (uint64_t)layout << 61;
   return d;
 }
 // instruction descriptor (32-bit) for kind::tf32, fp32 accumulate: c_format[4,6)=1, a_format[7,10)=2, b_format[10,13)=2,
@@ -124,14 +128,28 @@ __host__ __device__ constexpr uint32_t umma_idesc_tf32(int M, int N, int a_mn_ma
   return (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)a_mn_major << 15) | ((uint32_t)b_mn_major << 16) |
          ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
 }
-// SW128 tile geometry (f32): a K-major tile is rows x 32 k (128 B per row, 8-row groups of 1024 B);
-// an MN-major tile is made of [32 k][32 mn] boxes of 4096 B, one per 32 mn.
+// Tile geometry (f32): a K-major tile is rows x 32 k (128 B per row, SWIZZLE_128B atoms = 8 rows of 1024 B, SBO = 1024);
+// an MN-major tile is made of [32 k][32 mn] boxes of 4096 B, one per 32 mn (LBO = 4096); inside a box every k is a
+// 128-byte row and the 128B_BASE32B swizzle atom is 4 k-rows = 512 B (SBO = 512); one MMA (K = 8) consumes 8 rows.
 #define TC_BK 32
 __device__ __forceinline__ uint64_t umma_desc_kmajor(uint32_t tile_saddr, int kstep /*0..3*/) {
   return umma_smem_desc(tile_saddr + kstep * 32, 16, 1024);
 }
-__device__ __forceinline__ uint64_t umma_desc_mnmajor(uint32_t tile_saddr, int kstep /*0..3*/) {
-  return umma_smem_desc(tile_saddr + kstep * 1024, 4096, 1024);
+struct MnDescCfg { uint32_t lbo, sbo, layout, kadv; };     // bring-up knob (AGB_MN_VARIANT); defaults = the documented layout
+static inline MnDescCfg agb_mn_cfg(bool* atom32 = nullptr) {
+  static MnDescCfg c = {4096, 512, 1, 1024}; static bool a32 = true; static bool init = false;
+  if (!init) {
+    init = true;
+    if (const char* e = getenv("AGB_MN_VARIANT")) {
+      unsigned l, s, t, k, a;
+      if (sscanf(e, "%u,%u,%u,%u,%u", &l, &s, &t, &k, &a) == 5) { c = {l, s, t, k}; a32 = a != 0; }
+    }
+  }
+  if (atom32) *atom32 = a32;
+  return c;
+}
+__device__ __forceinline__ uint64_t umma_desc_mnmajor(uint32_t tile_saddr, int kstep /*0..3*/, MnDescCfg c) {
+  return umma_smem_desc(tile_saddr + kstep * c.kadv, c.lbo, c.sbo, c.layout);
 }
 __device__ __forceinline__ float tf32_rna(float x) {
   uint32_t r; asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(x)); return __uint_as_float(r);

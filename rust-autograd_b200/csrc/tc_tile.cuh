@@ -1,0 +1,194 @@
+// tc_tile.cuh — the shared tcgen05 "tile engine" behind the GEMM and implicit-GEMM convolution kernels.
+//
+//   D[lane, col] = sum_k P[lane, k] * Q[col, k]        128 TMEM lanes x TN TMEM columns per CTA, fp32 accumulators in TMEM
+//
+// Warp roles (one CTA per output tile):
+//   warp 0      TMA producer: a Policy functor issues the `cp.async.bulk.tensor` loads of one 32-wide k-block of P and Q
+//               into a multi-stage mbarrier ring (128-byte swizzled tiles, zero fill out of bounds)
+//   warp 1      allocates TMEM, then ONE thread issues `tcgen05.mma.kind::tf32` (K = 8 per instruction) and
+//               `tcgen05.commit`s ring slots back to the producer and accumulators to the drain warps
+//   warps 2-5   SPLIT (3xTF32) only: split every landed tile in place into hi = rna_tf32(x), lo = rna_tf32(x - hi);
+//               the issuer then runs lo*hi + hi*lo + hi*hi (dropped lo*lo ~ 2^-22)
+//   last 4      drain/epilogue: `tcgen05.ld` the accumulator and hand 32-column strips to the Policy's store functor
+//
+// fp32-faithful accumulation (SPLIT): the tensor core adds into the TMEM accumulator with truncation, which biases long
+// sums toward zero (measured on B200: relative bias ~5e-9 * K, i.e. 1e-4 at K = 16k).  The 3xTF32 mode therefore
+// accumulates at most TC_KC k-blocks (256 k) per TMEM buffer, ping-pongs two buffers, and the drain warps add each finished
+// chunk into fp32 registers with round-to-nearest CUDA-core adds while the tensor core works on the other buffer.
+#pragma once
+#include "tc_common.cuh"
+
+#define TC_LANES 128
+#define TC_KC 8            // k-blocks per TMEM accumulation chunk in SPLIT mode (8 * 32 = 256 k)
+
+template <int TN, bool SPLIT> struct TcCfg {
+  static constexpr int P_BYTES = TC_LANES * TC_BK * 4;                 // 16 KB
+  static constexpr int Q_BYTES = TN * TC_BK * 4;
+  static constexpr int STAGE_BYTES = (P_BYTES + Q_BYTES) * (SPLIT ? 2 : 1);
+  static constexpr int STAGES = (200 * 1024) / STAGE_BYTES > 6 ? 6 : (200 * 1024) / STAGE_BYTES;
+  static constexpr int SMEM = STAGES * STAGE_BYTES + 1024 /*align*/ + 256 /*barriers*/;
+  static constexpr int THREADS = SPLIT ? 320 : 192;
+  static constexpr int TMEM_COLS = SPLIT ? 2 * TN : TN;                // power of two >= 32 for TN in {32,64,128,256}
+  static_assert(!SPLIT || TN <= 128, "3xTF32 keeps TN fp32 partial sums per thread in registers");
+};
+
+// Policy interface:
+//   static constexpr int TN; static constexpr bool SPLIT, P_MN, Q_MN;
+//   struct Params { ... CUtensorMap members ...; MnDescCfg mnc; };
+//   struct Tile { ... };                                               per-CTA coordinates
+//   __device__ static Tile tile(const Params&);                        from blockIdx
+//   __device__ static int  num_kblocks(const Params&, const Tile&);
+//   __device__ static void prefetch(const Params&);
+//   __device__ static void load(const Params&, const Tile&, int kb, uint8_t* pP, uint8_t* pQ, uint64_t* bar);   one thread
+//   __device__ static void store(const Params&, const Tile&, int lane /*0..127*/, int c0 /*0..TN-32*/, const float* v /*[32]*/);
+template <class Pol>
+__global__ void __launch_bounds__(TcCfg<Pol::TN, Pol::SPLIT>::THREADS, 1) tc_tile_kernel(const __grid_constant__ typename Pol::Params prm) {
+  constexpr int TN = Pol::TN; constexpr bool SPLIT = Pol::SPLIT, P_MN = Pol::P_MN, Q_MN = Pol::Q_MN;
+  using Cfg = TcCfg<TN, SPLIT>;
+  constexpr int S = Cfg::STAGES;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
+  uint64_t* bars = (uint64_t*)(smem + S * Cfg::STAGE_BYTES);
+  uint64_t* full = bars; uint64_t* ready = bars + S; uint64_t* empty = bars + 2 * S;
+  uint64_t* acc_full = bars + 3 * S; uint64_t* acc_empty = bars + 3 * S + 2;
+  uint32_t* tmem_slot = (uint32_t*)(bars + 3 * S + 4);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const typename Pol::Tile tl = Pol::tile(prm);
+  const int nk = Pol::num_kblocks(prm, tl);
+
+  if (warp == 0 && lane == 0) {
+    Pol::prefetch(prm);
+    for (int s = 0; s < S; s++) { mbar_init(&full[s], 1); mbar_init(&ready[s], 128); mbar_init(&empty[s], 1); }
+    for (int b = 0; b < 2; b++) { mbar_init(&acc_full[b], 1); mbar_init(&acc_empty[b], 128); }
+    fence_barrier_init();
+  }
+  if (warp == 1) { tmem_alloc(tmem_slot, Cfg::TMEM_COLS); tmem_relinquish(); }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    // ===================== TMA producer =====================
+    if (lane == 0) {
+      for (int kb = 0; kb < nk; kb++) {
+        const int s = kb % S; const uint32_t ph = (kb / S) & 1;
+        mbar_wait(&empty[s], ph ^ 1);
+        uint8_t* st = smem + s * Cfg::STAGE_BYTES;
+        mbar_expect_tx(&full[s], Cfg::P_BYTES + Cfg::Q_BYTES);
+        Pol::load(prm, tl, kb, st, st + Cfg::P_BYTES, &full[s]);
+      }
+    }
+  } else if (warp == 1) {
+    // ===================== MMA issuer =====================
+    if (lane == 0) {
+      constexpr uint32_t idesc = umma_idesc_tf32(TC_LANES, TN, P_MN ? 1 : 0, Q_MN ? 1 : 0);
+      const MnDescCfg mnc = prm.mnc;
+      for (int kb = 0; kb < nk; kb++) {
+        const int s = kb % S; const uint32_t ph = (kb / S) & 1;
+        uint32_t tacc = tmem_base; bool first = (kb == 0);
+        if (SPLIT) {
+          const int chunk = kb / TC_KC, buf = chunk & 1;
+          tacc = tmem_base + (uint32_t)(buf * TN);
+          first = (kb % TC_KC) == 0;
+          if (first) { mbar_wait(&acc_empty[buf], (uint32_t)(((chunk >> 1) & 1) ^ 1)); tc_fence_after(); }
+        }
+        mbar_wait(SPLIT ? &ready[s] : &full[s], ph);
+        tc_fence_after();
+        const uint32_t st = smem_u32(smem + s * Cfg::STAGE_BYTES);
+        const uint32_t aP = st, aQ = st + Cfg::P_BYTES;
+        const uint32_t aPl = st + Cfg::P_BYTES + Cfg::Q_BYTES, aQl = aPl + Cfg::P_BYTES;
+#pragma unroll
+        for (int k = 0; k < TC_BK / 8; k++) {
+          const uint64_t dP = P_MN ? umma_desc_mnmajor(aP, k, mnc) : umma_desc_kmajor(aP, k);
+          const uint64_t dQ = Q_MN ? umma_desc_mnmajor(aQ, k, mnc) : umma_desc_kmajor(aQ, k);
+          if (SPLIT) {
+            const uint64_t dPl = P_MN ? umma_desc_mnmajor(aPl, k, mnc) : umma_desc_kmajor(aPl, k);
+            const uint64_t dQl = Q_MN ? umma_desc_mnmajor(aQl, k, mnc) : umma_desc_kmajor(aQl, k);
+            umma_tf32(tacc, dPl, dQ, idesc, !(first && k == 0));
+            umma_tf32(tacc, dP, dQl, idesc, 1);
+            umma_tf32(tacc, dP, dQ, idesc, 1);
+          } else {
+            umma_tf32(tacc, dP, dQ, idesc, !(first && k == 0));
+          }
+        }
+        umma_commit(&empty[s]);            // ring slot reusable once these MMAs have read it
+        if (SPLIT) { if ((kb % TC_KC) == TC_KC - 1 || kb == nk - 1) umma_commit(&acc_full[(kb / TC_KC) & 1]); }
+        else if (kb == nk - 1) umma_commit(&acc_full[0]);
+      }
+    }
+  } else if (SPLIT && warp < 6) {
+    // ===================== splitter (3xTF32) =====================
+    const int t = threadIdx.x - 64;        // 0..127
+    for (int kb = 0; kb < nk; kb++) {
+      const int s = kb % S; const uint32_t ph = (kb / S) & 1;
+      mbar_wait(&full[s], ph);
+      float4* hi = (float4*)(smem + s * Cfg::STAGE_BYTES);
+      float4* lo = (float4*)(smem + s * Cfg::STAGE_BYTES + Cfg::P_BYTES + Cfg::Q_BYTES);
+      constexpr int N4 = (Cfg::P_BYTES + Cfg::Q_BYTES) / 16;
+#pragma unroll 4
+      for (int i = t; i < N4; i += 128) {
+        float4 x = hi[i], h, l;
+        h.x = tf32_rna(x.x); h.y = tf32_rna(x.y); h.z = tf32_rna(x.z); h.w = tf32_rna(x.w);
+        l.x = tf32_rna(x.x - h.x); l.y = tf32_rna(x.y - h.y); l.z = tf32_rna(x.z - h.z); l.w = tf32_rna(x.w - h.w);
+        hi[i] = h; lo[i] = l;
+      }
+      fence_proxy_async();               // generic-proxy writes -> visible to the tensor core (async proxy)
+      mbar_arrive(&ready[s]);
+    }
+  } else {
+    // ===================== drain / epilogue =====================
+    const int q = warp & 3;                // TMEM lane quarter this warp may access
+    const int row = 32 * q + lane;         // accumulator lane handled by this thread
+    const uint32_t tlane = tmem_base + ((uint32_t)(32 * q) << 16);
+    if (SPLIT) {
+      float racc[TN];
+#pragma unroll
+      for (int j = 0; j < TN; j++) racc[j] = 0.0f;
+      const int nchunks = (nk + TC_KC - 1) / TC_KC;
+      for (int c = 0; c < nchunks; c++) {
+        const int buf = c & 1;
+        mbar_wait(&acc_full[buf], (uint32_t)((c >> 1) & 1));
+        tc_fence_after();
+#pragma unroll
+        for (int c0 = 0; c0 < TN; c0 += 32) {
+          float v[32];
+          tmem_ld32(tlane + (uint32_t)(buf * TN + c0), v);
+          tmem_ld_wait();
+#pragma unroll
+          for (int j = 0; j < 32; j++) racc[c0 + j] += v[j];
+        }
+        tc_fence_before();
+        mbar_arrive(&acc_empty[buf]);
+      }
+      if (nk > 0) {
+#pragma unroll
+        for (int c0 = 0; c0 < TN; c0 += 32) Pol::store(prm, tl, row, c0, &racc[c0]);
+      }
+    } else if (nk > 0) {
+      mbar_wait(&acc_full[0], 0);
+      tc_fence_after();
+#pragma unroll 1
+      for (int c0 = 0; c0 < TN; c0 += 32) {
+        float v[32];
+        tmem_ld32(tlane + (uint32_t)c0, v);
+        tmem_ld_wait();
+        Pol::store(prm, tl, row, c0, v);
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) tmem_dealloc(tmem_base, Cfg::TMEM_COLS);
+}
+
+template <class Pol>
+static int tc_tile_launch(agb_ctx* ctx, const typename Pol::Params& prm, dim3 grid) {
+  using Cfg = TcCfg<Pol::TN, Pol::SPLIT>;
+  static bool attr = false;
+  if (!attr) { AGB_CUDA(cudaFuncSetAttribute(tc_tile_kernel<Pol>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM)); attr = true; }
+  tc_tile_kernel<Pol><<<grid, Cfg::THREADS, Cfg::SMEM, ctx->stream>>>(prm);
+  AGB_LAUNCHED(ctx);
+  return AGB_OK;
+}

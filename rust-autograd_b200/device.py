@@ -80,7 +80,7 @@ class DArray:
         return self.dev.download(self)
 
     def free(self):
-        if self.owns and self.ptr:
+        if self.owns and self.ptr and self.dev.ctx:
             ffi.check(self.dev.lib.agb_free(self.dev.ctx, self.ptr))
             self.ptr, self.owns = 0, False
 
@@ -101,8 +101,8 @@ class Device:
 
     def close(self):
         if self.ctx:
-            self.lib.agb_destroy(self.ctx)
-            self.ctx = None
+            ctx, self.ctx = self.ctx, None      # DArrays that outlive the context must not call agb_free on it
+            self.lib.agb_destroy(ctx)
 
     # ---- memory ----
     def empty(self, shape):
