@@ -1,0 +1,290 @@
+"""bench.py — headline benchmark: CNN training samples/s on B200 (BASELINE.json metric), VGG-style conv stack
+(configs[3]: 64-256 ch, 3x128x128 synthetic images, batch 256 per GPU, Adam, data-parallel with NCCL gradient all-reduce).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--mode tf32|3xtf32|fp32] [--batch B]
+
+One process per GPU (torchrun for N > 1).  Prints ONE JSON line on rank 0.
+  value     whole-job samples/s with the batch already resident in HBM (CUDA events on the library's own stream, max over ranks)
+  e2e       the same step driven through the public graph API with HOST feeds: H2D of the batch and D2H of the loss inside the timed region
+  roofline  the dominant kernel class (conv implicit GEMM) timed live with CUDA event pairs around every call (agb_prof_*)
+  cpu_baseline  the oracle (CPU restatement of the reference, numpy/OpenBLAS) on a bounded sample of the same workload
+--impl reference times that oracle alone (the Rust crate cannot be built in this image: no cargo/rustc).
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+WORKLOAD = "vgg_stack_3x128x128_b256_per_gpu"
+METRIC = "cnn_train_samples_per_s"
+
+
+def peaks():
+    p = {"hbm_gbs": 6650.0, "bf16_tflops": 1590.0, "bf16_tflops_sustained": 1400.0, "src": "fallback"}
+    f = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(f):
+        try:
+            p.update(json.load(open(f)))
+            p["src"] = "measured"
+        except Exception:
+            pass
+    return p
+
+
+class ClockSampler(threading.Thread):
+    """nvidia-smi clocks + throttle reasons during the timed region (B200_PROFILING.md recipe)."""
+
+    def __init__(self, index):
+        super().__init__(daemon=True)
+        self.index, self.stop_flag, self.rows = index, False, []
+
+    def run(self):
+        q = "clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
+        while not self.stop_flag:
+            try:
+                out = subprocess.run(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + q, "--format=csv,noheader,nounits"],
+                                     capture_output=True, text=True, timeout=5).stdout.strip()
+                if out:
+                    self.rows.append([c.strip() for c in out.split(",")])
+            except Exception:
+                pass
+            time.sleep(0.2)
+
+    def summary(self):
+        sm = [float(r[0]) for r in self.rows if r and r[0].replace(".", "").isdigit()]
+        mx = [float(r[1]) for r in self.rows if len(r) > 1 and r[1].replace(".", "").isdigit()]
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        reasons = sorted({names[i] for r in self.rows for i in range(4) if len(r) > 2 + i and r[2 + i].lower().startswith("active")})
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None, "reasons": reasons, "samples": len(sm)}
+
+
+# ------------------------------------------------------------------------------------------------ reference arm (oracle on host cores)
+def run_reference(args, rank):
+    if rank != 0:
+        return
+    from oracle import ref_graph as OG
+    from rust_autograd_b200 import workloads as W
+    rng = np.random.default_rng(0)
+    bs = args.cpu_batch
+    env = OG.VariableEnvironment()
+    W.vgg_init(env, rng)
+    adam = OG.optimizers.Adam.default("adam", env.default_namespace().current_var_ids(), env)
+    x = rng.standard_normal((bs, 3, 128, 128)).astype(np.float32)
+    y = rng.integers(0, 10, (bs, 1)).astype(np.float32)
+
+    def step(g):
+        loss, _ = W.vgg_loss(OG, g)
+        params, grads = OG.optimizers.grad_helper([loss], g.default_namespace())
+        upd = adam.get_update_op(params, grads, g)
+        return float(np.asarray(g.evaluator().push(loss).push(upd).feed("x", x).feed("y", y).run()[0].unwrap()).ravel()[0])
+    for _ in range(args.warmup_ref):
+        env.run(step)
+    t0 = time.time()
+    for _ in range(args.steps_ref):
+        env.run(step)
+    dt = (time.time() - t0) / args.steps_ref
+    cores = os.cpu_count()
+    sample = "oracle (numpy/OpenBLAS restatement of the reference CPU path) on batch %d of the VGG stack, %d step(s)" % (bs, args.steps_ref)
+    v = bs / dt
+    print(json.dumps({"impl": "reference", "metric": METRIC, "value": v, "unit": "samples/s", "n_gpus": args.gpus, "steps": args.steps_ref, "warmup": args.warmup_ref,
+                      "ms_per_step": dt * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+                      "config": {"workload": WORKLOAD, "sample_batch": bs},
+                      "cpu_baseline": {"value": v, "unit": "samples/s", "cores": cores, "kind": "port", "sample": sample},
+                      "e2e": {"value": v, "unit": "samples/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}), flush=True)
+
+
+def cpu_baseline(batch, steps=1):
+    from oracle import ref_graph as OG
+    from rust_autograd_b200 import workloads as W
+    rng = np.random.default_rng(0)
+    env = OG.VariableEnvironment()
+    W.vgg_init(env, rng)
+    adam = OG.optimizers.Adam.default("adam", env.default_namespace().current_var_ids(), env)
+    x = rng.standard_normal((batch, 3, 128, 128)).astype(np.float32)
+    y = rng.integers(0, 10, (batch, 1)).astype(np.float32)
+
+    def step(g):
+        loss, _ = W.vgg_loss(OG, g)
+        params, grads = OG.optimizers.grad_helper([loss], g.default_namespace())
+        g.evaluator().push(loss).push(adam.get_update_op(params, grads, g)).feed("x", x).feed("y", y).run()[0].unwrap()
+    t0 = time.time()
+    for _ in range(steps):
+        env.run(step)
+    dt = (time.time() - t0) / steps
+    return {"value": batch / dt, "unit": "samples/s", "cores": os.cpu_count(), "kind": "port",
+            "sample": "oracle (numpy/OpenBLAS restatement of the reference CPU path), batch %d of the same VGG stack, %d step(s), %.1f s" % (batch, steps, dt * steps)}
+
+
+# ------------------------------------------------------------------------------------------------ our arm
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours")
+    ap.add_argument("--mode", default="tf32", choices=["tf32", "3xtf32", "fp32"])
+    ap.add_argument("--batch", type=int, default=256, help="per-GPU batch")
+    ap.add_argument("--cpu-batch", type=int, default=4)
+    ap.add_argument("--steps-ref", type=int, default=2)
+    ap.add_argument("--warmup-ref", type=int, default=1)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    rank, world, local = int(os.environ.get("RANK", 0)), int(os.environ.get("WORLD_SIZE", 1)), int(os.environ.get("LOCAL_RANK", 0))
+    if args.impl == "reference":
+        run_reference(args, rank)
+        return
+    args.warmup = max(args.warmup, 3)
+
+    import ctypes as C
+    import torch
+    import torch.distributed as dist
+    from rust_autograd_b200 import autograd as ag, ffi, workloads as W
+    torch.cuda.set_device(local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    lib = ffi.load_library()
+    env = ag.VariableEnvironment(local)
+    ctx = env.agb_ctx()
+    ffi.check(lib.agb_set_math_mode(ctx, {"3xtf32": 0, "tf32": 1, "fp32": 2}[args.mode]))
+    if world > 1:          # ncclUniqueId from rank 0 to everybody over torch.distributed (plumbing only)
+        idbuf = C.create_string_buffer(128)
+        if rank == 0:
+            ffi.check(lib.agb_nccl_unique_id(idbuf))
+        t = torch.frombuffer(bytearray(idbuf.raw), dtype=torch.uint8).cuda()
+        dist.broadcast(t, 0)
+        env.set_data_parallel(rank, world, bytes(t.cpu().numpy().tobytes()))
+
+    rng = np.random.default_rng(0)         # identical replicas on every rank
+    W.vgg_init(env, rng)
+    adam = ag.optimizers.Adam.default("adam", env.default_namespace().current_var_ids(), env)
+    B = args.batch
+    drng = np.random.default_rng(1000 + rank)   # each rank feeds its own shard of the global batch
+    n_host = 4
+    xs = [drng.standard_normal((B, 3, 128, 128)).astype(np.float32) for _ in range(n_host)]
+    ys = [drng.integers(0, 10, (B, 1)).astype(np.float32) for _ in range(n_host)]
+    # pinned host staging for the e2e leg
+    pin = []
+    for a in xs + ys:
+        p = C.c_void_p()
+        ffi.check(lib.agb_host_alloc(a.nbytes, C.byref(p)))
+        C.memmove(p, a.ctypes.data, a.nbytes)
+        pin.append(np.ctypeslib.as_array(C.cast(p, C.POINTER(C.c_float)), shape=a.shape))
+    xs_p, ys_p = pin[:n_host], pin[n_host:]
+    # device-resident copies for the `value` leg
+    dev_x, dev_y = [], []
+    for a in xs:
+        p = C.c_void_p(); ffi.check(lib.agb_alloc(ctx, a.nbytes, C.byref(p))); ffi.check(lib.agb_h2d(ctx, p, a.ctypes.data, a.nbytes)); dev_x.append(ag.DeviceArray(p.value, a.shape))
+    for a in ys:
+        p = C.c_void_p(); ffi.check(lib.agb_alloc(ctx, a.nbytes, C.byref(p))); ffi.check(lib.agb_h2d(ctx, p, a.ctypes.data, a.nbytes)); dev_y.append(ag.DeviceArray(p.value, a.shape))
+    ffi.check(lib.agb_sync(ctx))
+
+    g = ag.Context(env)                   # the graph is built once; the training loop lives outside (README: "move the loop out")
+    loss, _ = W.vgg_loss(ag, g)
+    params, grads = ag.optimizers.grad_helper([loss], g.default_namespace())
+    upd = adam.get_update_op(params, grads, g)
+
+    def step_resident(i):
+        g.evaluator().push(loss).push(upd).feed("x", dev_x[i % n_host]).feed("y", dev_y[i % n_host]).run_async()
+
+    def step_e2e(i):
+        r = g.evaluator().push(loss).push(upd).feed("x", xs_p[i % n_host]).feed("y", ys_p[i % n_host]).run()
+        return float(np.asarray(r[0].unwrap()).ravel()[0])
+
+    def barrier():
+        ffi.check(lib.agb_sync(ctx))
+        if world > 1:
+            dist.barrier()
+            torch.cuda.synchronize()
+
+    def timed(fn, steps, warm):
+        for i in range(warm):
+            fn(i)
+        barrier()
+        ev0, ev1 = C.c_void_p(), C.c_void_p()
+        ffi.check(lib.agb_event_create(C.byref(ev0))); ffi.check(lib.agb_event_create(C.byref(ev1)))
+        l0 = C.c_int64(); ffi.check(lib.agb_launch_count(ctx, C.byref(l0)))
+        t0 = time.time()
+        ffi.check(lib.agb_event_record(ctx, ev0))
+        for i in range(steps):
+            fn(warm + i)
+        ffi.check(lib.agb_event_record(ctx, ev1))
+        ms = C.c_float(); ffi.check(lib.agb_event_elapsed_ms(ev0, ev1, C.byref(ms)))
+        barrier()
+        wall = (time.time() - t0) * 1e3
+        l1 = C.c_int64(); ffi.check(lib.agb_launch_count(ctx, C.byref(l1)))
+        dev_ms = float(ms.value)
+        if world > 1:
+            t = torch.tensor([dev_ms, wall], device="cuda"); dist.all_reduce(t, op=dist.ReduceOp.MAX); dev_ms, wall = float(t[0]), float(t[1])
+        return dev_ms, wall, l1.value - l0.value
+
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    # ---- leg 1: inputs resident in HBM (value) with the live kernel profiler on
+    ffi.check(lib.agb_prof_reset(ctx))
+    for i in range(args.warmup):
+        step_resident(i)
+    ffi.check(lib.agb_prof_enable(ctx, 1)); ffi.check(lib.agb_prof_reset(ctx))
+    dev_ms, wall_ms, launches = timed(step_resident, args.steps, 0)
+    ffi.check(lib.agb_prof_enable(ctx, 0))
+    prof = {}
+    names = ["gemm", "conv_fprop", "conv_dgrad", "conv_wgrad", "ewise", "reduce", "softmax", "pool", "optim"]
+    for cls, nm in enumerate(names):
+        t, n, w = C.c_double(), C.c_int64(), C.c_double()
+        ffi.check(lib.agb_prof_collect(ctx, cls, C.byref(t), C.byref(n), C.byref(w)))
+        if n.value:
+            prof[nm] = {"ms": t.value, "calls": n.value, "work": w.value}
+    ffi.check(lib.agb_prof_reset(ctx))
+    # ---- leg 2: end to end through the public API with host feeds
+    e2e_ms, e2e_wall, _ = timed(step_e2e, args.steps, 1)
+    e2e_time = max(e2e_ms, e2e_wall)       # the D2H of the loss serialises host and device: wall time is the honest figure
+    sampler.stop_flag = True
+
+    if rank == 0:
+        pk = peaks()
+        step_ms = max(dev_ms, 0.0) / args.steps
+        value = world * B * args.steps / (dev_ms / 1e3)
+        e2e_value = world * B * args.steps / (e2e_time / 1e3)
+        conv = {k: v for k, v in prof.items() if k.startswith("conv")}
+        roof = None
+        if conv:
+            top = max(conv, key=lambda k: conv[k]["ms"])
+            tot_ms = sum(v["ms"] for v in conv.values()); tot_w = sum(v["work"] for v in conv.values())
+            achieved = conv[top]["work"] / (conv[top]["ms"] / 1e3) / 1e12
+            tf32_peak = pk["bf16_tflops_sustained"] / 2.0
+            roof = {"bound": "tensor", "kernel": top + " (implicit-GEMM conv, %s)" % args.mode, "achieved": achieved, "peak": tf32_peak, "unit": "TFLOP/s",
+                    "frac": achieved / tf32_peak, "traffic": None,
+                    "peak_source": "%s bf16 sustained / 2 (dense TF32 = half the bf16 rate), MEASURED_PEAKS.json" % pk["src"],
+                    "per_launch_ms": conv[top]["ms"] / conv[top]["calls"], "flops_per_launch": conv[top]["work"] / conv[top]["calls"],
+                    "all_conv": {"achieved": tot_w / (tot_ms / 1e3) / 1e12, "share_of_step": tot_ms / max(dev_ms, 1e-9)},
+                    "classes": {k: {"ms_per_step": v["ms"] / args.steps, "calls_per_step": v["calls"] / args.steps} for k, v in prof.items()}}
+        out = {"metric": METRIC, "value": value, "unit": "samples/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": step_ms,
+               "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32 (%s tensor-core contractions)" % args.mode, "data": "synthetic",
+               "config": {"workload": WORKLOAD, "per_gpu_batch": B, "global_batch": B * world, "optimizer": "adam", "parallelism": "dp%d" % world,
+                          "l2": "inputs and activations (>= 1 GB per layer) exceed the 126 MB L2", "math_mode": args.mode,
+                          "flops_per_step_per_gpu": W.vgg_flops_per_sample() * B},
+               "e2e": {"value": e2e_value, "unit": "samples/s", "h2d_bytes_per_step": int(xs[0].nbytes + ys[0].nbytes), "d2h_bytes_per_step": 4,
+                       "ms_per_step": e2e_time / args.steps},
+               "gpu_launches": int(launches), "clocks": sampler.summary(), "roofline": roof,
+               "model_tflops": W.vgg_flops_per_sample() * B / (step_ms / 1e3) / 1e12}
+        if not args.no_cpu_baseline and world == 1:
+            try:
+                out["cpu_baseline"] = cpu_baseline(args.cpu_batch)
+            except Exception as e:      # the baseline is reported, never the product path
+                out["cpu_baseline"] = {"error": repr(e)}
+        print(json.dumps(out), flush=True)
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

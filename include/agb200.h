@@ -72,6 +72,15 @@ int  agb_get_math_mode(agb_ctx* ctx, int* mode);
 /* number of kernels this library has launched on ctx since agb_init (bench "gpu_launches") */
 int  agb_launch_count(agb_ctx* ctx, int64_t* out);
 
+/* Live per-entry-point timing with CUDA events on the context's own stream (bench.py roofline): while enabled, every call
+ * of the profiled classes below is bracketed by an event pair and its algorithmic work (FLOPs for contractions, bytes for
+ * bandwidth kernels) is accumulated.  agb_prof_collect synchronises and returns totals for one class. */
+enum { AGB_PROF_GEMM = 0, AGB_PROF_CONV_FPROP, AGB_PROF_CONV_DGRAD, AGB_PROF_CONV_WGRAD, AGB_PROF_EWISE, AGB_PROF_REDUCE, AGB_PROF_SOFTMAX,
+       AGB_PROF_POOL, AGB_PROF_OPTIM, AGB_PROF_COUNT };
+int  agb_prof_enable(agb_ctx* ctx, int on);
+int  agb_prof_collect(agb_ctx* ctx, int cls, double* total_ms, int64_t* calls, double* work /* FLOPs or bytes */);
+int  agb_prof_reset(agb_ctx* ctx);
+
 int  agb_alloc(agb_ctx* ctx, size_t bytes, void** out);    /* stream-ordered caching arena */
 int  agb_free(agb_ctx* ctx, void* ptr);
 int  agb_trim(agb_ctx* ctx);                                /* release cached blocks to the driver */

@@ -22,8 +22,17 @@ F32_MIN = np.finfo(np.float32).min     # T::min_value() for floats = most negati
 F32_MAX = np.finfo(np.float32).max
 
 
+OUT_DTYPE = np.float32        # the reference tests run their finite-difference checks with F = f64: tests may switch this
+
+
+def set_out_dtype(dt):
+    """Results are rounded once to this dtype (float32 = the product's element type; float64 for FD self-checks)."""
+    global OUT_DTYPE
+    OUT_DTYPE = dt
+
+
 def _f32(a):
-    return np.asarray(a, dtype=np.float64).astype(np.float32)
+    return np.asarray(a, dtype=np.float64).astype(OUT_DTYPE)
 
 
 def _f64(a):
@@ -174,11 +183,11 @@ def max_pool2d(x, size, pad=0, stride=1):
     """MaxPool2D::compute :166-227 / impl_max_pool! :21-88.  Strict `>` scan starting from T::min_value(), first maximum
     in row-major window order wins (:62-69); index = flat offset into the WHOLE input buffer incl. batch and channel
     (:61 `index = w + xw*(h + xh*(c + b*ch))`), returned as float (:74-75).  Only pad == 0 is meaningful (usize wrap :43,53)."""
-    x = np.asarray(x, dtype=np.float32)
+    x = np.asarray(x, dtype=OUT_DTYPE)
     assert pad == 0, "reference underflows usize for pad > 0 (max_pool2d.rs:43,53)"
     B, C, H, W = x.shape
     yh, yw = (H + 2 * pad - size) // stride + 1, (W + 2 * pad - size) // stride + 1
-    best = np.full((B, C, yh, yw), F32_MIN, dtype=np.float32)
+    best = np.full((B, C, yh, yw), F32_MIN, dtype=OUT_DTYPE)
     besti = np.zeros((B, C, yh, yw), dtype=np.int64)
     base = (np.arange(B * C, dtype=np.int64) * (H * W)).reshape(B, C, 1, 1)
     oy = (np.arange(yh) * stride).reshape(1, 1, yh, 1)
@@ -192,7 +201,7 @@ def max_pool2d(x, size, pad=0, stride=1):
             take = valid & (v > best)             # NaN > x is False, like the reference
             best = np.where(take, v, best)
             besti = np.where(take, base + hc * W + wc, besti)
-    return best, besti.astype(np.float32), besti
+    return best, besti.astype(OUT_DTYPE), besti
 
 
 def max_pool2d_grad(gy, idx, size, pad=0, stride=1):
@@ -208,7 +217,7 @@ def max_pool2d_grad(gy, idx, size, pad=0, stride=1):
 
 def max_pool2d_grad_grad(ggx, idx, size, pad=0, stride=1):
     """MaxPool2DGradGrad::compute :297-331 / impl_max_pool_grad_grad! :137-159: ggy[i] = ggx[idx[i]]."""
-    ggx = np.asarray(ggx, dtype=np.float32)
+    ggx = np.asarray(ggx, dtype=OUT_DTYPE)
     return ggx.ravel()[np.asarray(idx).astype(np.int64)].reshape(np.asarray(idx).shape)
 
 
@@ -223,7 +232,7 @@ def _is_scalar_shape(shape):
 def binary_arith(op, a, b):
     """AddOp/SubOp/MulOp/DivOp::compute, binary_ops.rs:147-290 + macro :304-347: scalar fast paths (rank-0 or shape [0];
     Div by scalar = multiply by reciprocal :251-255), otherwise ndarray broadcasting arithmetic (equal rank)."""
-    a, b = np.asarray(a, dtype=np.float32), np.asarray(b, dtype=np.float32)
+    a, b = np.asarray(a, dtype=OUT_DTYPE), np.asarray(b, dtype=OUT_DTYPE)
     a64, b64 = _f64(a), _f64(b)
     if op == "add":
         r = a64 + b64
@@ -243,29 +252,29 @@ def binary_arith(op, a, b):
 
 def compare(op, a, b):
     """impl_cmp_op!, math_ops.rs:86-184: 0/1-valued floats; Maximum/Minimum select."""
-    a, b = np.asarray(a, dtype=np.float32), np.asarray(b, dtype=np.float32)
+    a, b = np.asarray(a, dtype=OUT_DTYPE), np.asarray(b, dtype=OUT_DTYPE)
     if op == "equal":
-        return (a == b).astype(F32)
+        return (a == b).astype(OUT_DTYPE)
     if op == "not_equal":
-        return (a != b).astype(F32)
+        return (a != b).astype(OUT_DTYPE)
     if op == "greater":
-        return (a > b).astype(F32)
+        return (a > b).astype(OUT_DTYPE)
     if op == "lesser":
-        return (a < b).astype(F32)
+        return (a < b).astype(OUT_DTYPE)
     if op == "greater_equal":
-        return (a >= b).astype(F32)
+        return (a >= b).astype(OUT_DTYPE)
     if op == "lesser_equal":
-        return (a <= b).astype(F32)
+        return (a <= b).astype(OUT_DTYPE)
     if op == "maximum":
-        return np.where(a > b, a, b).astype(F32)      # math_ops.rs:160-167 `if a > b {a} else {b}`
+        return np.where(a > b, a, b).astype(OUT_DTYPE)      # math_ops.rs:160-167 `if a > b {a} else {b}`
     if op == "minimum":
-        return np.where(a < b, a, b).astype(F32)
+        return np.where(a < b, a, b).astype(OUT_DTYPE)
     raise ValueError(op)
 
 
 def unary(op, x, p0=0.0, p1=0.0):
     """math_ops.rs:277-1019 (x.map(f)), activation_ops.rs:113-226, array_ops.rs:537-574 (Clip)."""
-    x32 = np.asarray(x, dtype=np.float32)
+    x32 = np.asarray(x, dtype=OUT_DTYPE)
     x = _f64(x32)
     with np.errstate(all="ignore"):
         if op == "abs":
@@ -309,7 +318,7 @@ def unary(op, x, p0=0.0, p1=0.0):
         elif op == "relu":                           # activation_ops.rs:156  x.max(0): NaN -> 0
             r = np.where(np.isnan(x), 0.0, np.maximum(x, 0.0))
         elif op == "softplus":                       # activation_ops.rs:115 (unguarded; evaluated in f32 range)
-            r = np.log(np.exp(x32).astype(np.float64) + 1.0)
+            r = np.log(np.exp(x32.astype(np.float32) if OUT_DTYPE == np.float32 else x32).astype(np.float64) + 1.0)
         elif op == "elu":                            # activation_ops.rs:188-198
             r = np.where(x > 0, x, p0 * (np.exp(x) - 1.0))
         elif op == "clip":                           # array_ops.rs:540-545  a.min(max).max(min)
@@ -329,7 +338,7 @@ def elu_grad(x, gy, alpha):
 
 def clip_grad(x, gy, lo, hi):
     """ClipGrad::compute, array_ops.rs:556-574"""
-    x = np.asarray(x, dtype=np.float32)
+    x = np.asarray(x, dtype=OUT_DTYPE)
     return _f32(((x > F32(lo)) & (x < F32(hi))).astype(np.float64) * _f64(gy))
 
 
@@ -358,7 +367,7 @@ def _norm_axes(axes, ndim):
 def reduce(op, x, axes, keep_dims=False):
     """impl_reduce_forward!, reduction_ops.rs:54-108 (sorted axes folded highest first; empty axes / rank-0 -> view of x :63-70);
     ReduceMean :187-215: sum then multiply by 1/len with len accumulated as f32 (:198-209)."""
-    x32 = np.asarray(x, dtype=np.float32)
+    x32 = np.asarray(x, dtype=OUT_DTYPE)
     if x32.ndim == 0 or np.asarray(axes).size == 0:
         return x32
     ax = tuple(_norm_axes(axes, x32.ndim))
@@ -388,21 +397,21 @@ def sum_all(x):
 
 def arg_reduce(x, axis, keep_dim=False, is_max=True):
     """ArgMax/ArgMin via argx_helper, reduction_ops.rs:365-429: FIRST occurrence of the extreme along `axis`, as float."""
-    x = np.asarray(x, dtype=np.float32)
+    x = np.asarray(x, dtype=OUT_DTYPE)
     axis = axis + x.ndim if axis < 0 else axis
     r = np.argmax(x, axis=axis) if is_max else np.argmin(x, axis=axis)     # numpy returns the first occurrence
-    r = r.astype(np.float32)
+    r = r.astype(OUT_DTYPE)
     return np.expand_dims(r, axis) if keep_dim else r
 
 
 def broadcast_to(x, shape):
     """ReduceGradCommon / MaybeBroadcast, reduction_ops.rs:459-496, binary_ops.rs:108-137"""
-    return np.ascontiguousarray(np.broadcast_to(np.asarray(x, dtype=np.float32), shape))
+    return np.ascontiguousarray(np.broadcast_to(np.asarray(x, dtype=OUT_DTYPE), shape))
 
 
 def reduce_grad_common(gy, x_shape, axes, keep_dims=False):
     """ReduceGradCommon::compute, reduction_ops.rs:459-496: re-insert reduced axes (unless keep_dims) and broadcast to x_shape."""
-    gy = np.asarray(gy, dtype=np.float32)
+    gy = np.asarray(gy, dtype=OUT_DTYPE)
     if len(x_shape) == 0 or tuple(gy.shape) == tuple(x_shape):
         return gy.reshape(x_shape)
     if not keep_dims:
@@ -414,7 +423,7 @@ def reduce_grad_common(gy, x_shape, axes, keep_dims=False):
 def maybe_reduce_sum(gy, target_shape):
     """MaybeReduceSum::compute, binary_ops.rs:39-94: identity when shapes match; scalar target -> full sum reshaped;
     else sum over every axis where target == 1 < gy (keeping the axis)."""
-    gy32 = np.asarray(gy, dtype=np.float32)
+    gy32 = np.asarray(gy, dtype=OUT_DTYPE)
     target_shape = tuple(int(s) for s in target_shape)
     if tuple(gy32.shape) == target_shape:
         return gy32
@@ -432,7 +441,7 @@ def maybe_reduce_sum(gy, target_shape):
 # ----------------------------------------------------------------------------------------------------------------
 def logsumexp(x, axis, keep_dims=True):
     """logsumexp_forward, math_ops.rs:540-593: max (fold from T::min_value()) -> exp(x-max) -> sum -> ln -> + max"""
-    x = _f64(np.asarray(x, dtype=np.float32))
+    x = _f64(np.asarray(x, dtype=OUT_DTYPE))
     m = np.maximum(x.max(axis=axis, keepdims=True), F32_MIN)
     r = np.log(np.exp(x - m).sum(axis=axis, keepdims=True)) + m
     return _f32(r if keep_dims else np.squeeze(r, axis))
@@ -440,7 +449,7 @@ def logsumexp(x, axis, keep_dims=True):
 
 def softmax(x, axis):
     """softmax_impl, activation_ops.rs:61-96"""
-    x = _f64(np.asarray(x, dtype=np.float32))
+    x = _f64(np.asarray(x, dtype=OUT_DTYPE))
     m = np.maximum(x.max(axis=axis, keepdims=True), F32_MIN)
     e = np.exp(x - m)
     return _f32(e / e.sum(axis=axis, keepdims=True))
@@ -448,7 +457,7 @@ def softmax(x, axis):
 
 def log_softmax(x, axis):
     """LogSoftmax::compute, xent_ops.rs:17-22: x - logsumexp(x, axis, keep)"""
-    x = _f64(np.asarray(x, dtype=np.float32))
+    x = _f64(np.asarray(x, dtype=OUT_DTYPE))
     m = np.maximum(x.max(axis=axis, keepdims=True), F32_MIN)
     return _f32(x - (np.log(np.exp(x - m).sum(axis=axis, keepdims=True)) + m))
 
@@ -456,7 +465,7 @@ def log_softmax(x, axis):
 def sparse_softmax_cross_entropy(x, t):
     """SparseSoftmaxCrossEntropy::compute, xent_ops.rs:63-113: axis 1, 2-D logits, labels [B] or [B,1] as floats;
     outputs (loss [B,1], log_x [B,C])."""
-    x = np.asarray(x, dtype=np.float32)
+    x = np.asarray(x, dtype=OUT_DTYPE)
     t = np.asarray(t)
     if x.ndim != 2:
         raise OpError("IncompatibleShape", "SparseSoftmaxCrossEntropy: given first argument's ndim is not 2: shape=%s" % (x.shape,))
@@ -480,7 +489,7 @@ def sparse_softmax_cross_entropy_grad(log_x, t, gy):
 
 def softmax_cross_entropy(x, t):
     """SoftmaxCrossEntropy::compute, xent_ops.rs:160-177: outputs (loss (B,), log_x (B,C))"""
-    x64 = _f64(np.asarray(x, dtype=np.float32))
+    x64 = _f64(np.asarray(x, dtype=OUT_DTYPE))
     m = np.maximum(x64.max(axis=1, keepdims=True), F32_MIN)
     log_x = x64 - (np.log(np.exp(x64 - m).sum(axis=1, keepdims=True)) + m)
     return _f32(-(_f64(t) * log_x).sum(axis=1)), _f32(log_x)
@@ -488,7 +497,7 @@ def softmax_cross_entropy(x, t):
 
 def sigmoid_cross_entropy(x, t):
     """SigmoidCrossEntropy::compute, xent_ops.rs:33-46"""
-    x, t = _f64(np.asarray(x, dtype=np.float32)), _f64(t)
+    x, t = _f64(np.asarray(x, dtype=OUT_DTYPE)), _f64(t)
     return _f32(np.log(np.exp(-np.abs(x)) + 1.0) + np.maximum(0.0, x) - t * x)
 
 
@@ -497,7 +506,7 @@ def sigmoid_cross_entropy(x, t):
 # ----------------------------------------------------------------------------------------------------------------
 def gather(param, indices, axis):
     """Gather::compute, array_ops.rs:353-384: out shape = param[..axis] + indices.shape + param[axis+1..]; negative ids wrap."""
-    param = np.asarray(param, dtype=np.float32)
+    param = np.asarray(param, dtype=OUT_DTYPE)
     idx = np.asarray(indices).astype(np.int64)
     axis = axis + param.ndim if axis < 0 else axis
     idx = np.where(idx < 0, idx + param.shape[axis], idx)

@@ -33,6 +33,25 @@ struct agb_ctx {
   void* nccl_comm = nullptr;
   int rank = 0, world = 1;
   bool capturing = false;
+  // live profiler (agb_prof_*): event pairs per profiled entry-point call
+  bool prof_on = false;
+  struct ProfRec { int cls; cudaEvent_t a, b; double work; };
+  std::vector<ProfRec> prof_recs;
+  std::vector<cudaEvent_t> prof_pool;
+};
+
+// RAII bracket used by the profiled entry points: records an event pair around the launches issued in its scope
+struct AgbProfScope {
+  agb_ctx* ctx; int idx = -1;
+  AgbProfScope(agb_ctx* c, int cls, double work) : ctx(c) {
+    if (!c->prof_on || c->capturing) return;
+    agb_ctx::ProfRec r; r.cls = cls; r.work = work;
+    auto get = [&]() { cudaEvent_t e; if (!c->prof_pool.empty()) { e = c->prof_pool.back(); c->prof_pool.pop_back(); } else cudaEventCreate(&e); return e; };
+    r.a = get(); r.b = get();
+    cudaEventRecord(r.a, c->stream);
+    idx = (int)c->prof_recs.size(); c->prof_recs.push_back(r);
+  }
+  ~AgbProfScope() { if (idx >= 0) cudaEventRecord(ctx->prof_recs[idx].b, ctx->stream); }
 };
 
 void agb_set_error(const char* fmt, ...);

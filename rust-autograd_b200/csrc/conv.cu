@@ -102,6 +102,7 @@ extern "C" int agb_conv2d_fprop_f32(agb_ctx* ctx, const agb_tensor* x, const agb
   AGB_CHECK(y->rank == 4 && y->shape[0] == g.B && y->shape[1] == g.O && y->shape[2] == g.yh && y->shape[3] == g.yw, AGB_ERR_INCOMPATIBLE_SHAPE,
             "conv2d: output must be [%d,%d,%d,%d]", g.B, g.O, g.yh, g.yw);
   if (agb_numel(y) == 0) return AGB_OK;
+  AgbProfScope prof(ctx, AGB_PROF_CONV_FPROP, 2.0 * (double)agb_numel(y) * g.C * g.kh * g.kw);
   if (ctx->math_mode != AGB_MATH_FP32) {
     int r = agb_tc_conv_fprop(ctx, ctx->math_mode, x->ptr, w->ptr, y->ptr, g.B, g.C, g.H, g.W, g.O, g.kh, g.kw, pad, stride, dilation, 0);
     if (r != AGB_ERR_UNSUPPORTED) return r;
@@ -126,6 +127,7 @@ extern "C" int agb_conv2d_dgrad_f32(agb_ctx* ctx, const agb_tensor* gy, const ag
             "conv2d_transpose: output must be [%d,%d,%d,%d]", g.B, g.C, g.H, g.W);
   AGB_CHECK(agb_is_contig(gy) && agb_is_contig(w) && agb_is_contig(gx), AGB_ERR_UNSUPPORTED, "conv2d_transpose: tensors must be C-contiguous");
   if (agb_numel(gx) == 0) return AGB_OK;
+  AgbProfScope prof(ctx, AGB_PROF_CONV_DGRAD, 2.0 * (double)agb_numel(gy) * g.C * g.kh * g.kw);
   if (ctx->math_mode != AGB_MATH_FP32 && stride == 1 && g.H == g.yh && g.W == g.yw) {
     // stride-1 "same" dgrad == fprop of gy with the spatially flipped, channel-transposed filter
     int r = agb_tc_conv_fprop(ctx, ctx->math_mode, gy->ptr, w->ptr, gx->ptr, g.B, g.O, g.yh, g.yw, g.C, g.kh, g.kw, pad, stride, dilation, 1);
@@ -141,6 +143,7 @@ extern "C" int agb_conv2d_wgrad_f32(agb_ctx* ctx, const agb_tensor* img, const a
             "conv2d_filter_grad: gradient must be [%d,%d,%d,%d]", g.B, g.O, g.yh, g.yw);
   AGB_CHECK(agb_is_contig(img) && agb_is_contig(gr) && agb_is_contig(gw), AGB_ERR_UNSUPPORTED, "conv2d_filter_grad: tensors must be C-contiguous");
   if (agb_numel(gw) == 0) return AGB_OK;
+  AgbProfScope prof(ctx, AGB_PROF_CONV_WGRAD, 2.0 * (double)agb_numel(gr) * g.C * g.kh * g.kw);
   if (ctx->math_mode != AGB_MATH_FP32) {
     int r = agb_tc_conv_wgrad(ctx, ctx->math_mode, img->ptr, gr->ptr, gw->ptr, g.B, g.C, g.H, g.W, g.O, g.kh, g.kw, pad, stride, dilation);
     if (r != AGB_ERR_UNSUPPORTED) return r;

@@ -235,6 +235,7 @@ extern "C" int agb_unary(agb_ctx* ctx, int op, float p0, float p1, const agb_ten
   AGB_CHECK(agb_is_contig(y), AGB_ERR_UNSUPPORTED, "agb_unary: output must be C-contiguous");
   int64_t n = agb_numel(x);
   if (n == 0) return AGB_OK;
+  AgbProfScope prof(ctx, AGB_PROF_EWISE, 8.0 * (double)n);
   const float* xp = x->ptr; float* tmp = nullptr;
   if (!agb_is_contig(x)) {       // materialise the view first (reference: ndarray map over a strided view)
     if (op == AGB_U_COPY) return agb_copy_strided(ctx, x, y);
@@ -260,6 +261,7 @@ extern "C" int agb_binary(agb_ctx* ctx, int op, float p0, float p1, const agb_te
               "agb_binary: operands must be pre-broadcast to the output shape (axis %d)", i);
   AGB_CHECK(agb_is_contig(y), AGB_ERR_UNSUPPORTED, "agb_binary: output must be C-contiguous");
   int64_t sy[AGB_MAX_RANK]; contig_strides(y->rank, y->shape, sy);
+  AgbProfScope prof(ctx, AGB_PROF_EWISE, 12.0 * (double)agb_numel(y));
   const strided_fn* t = binary_table(make_useq<AGB_B_COUNT>::type());
   return t[op](ctx, a->ptr, b->ptr, y->ptr, y->rank, y->shape, a->stride, b->stride, sy, p0, p1);
 }

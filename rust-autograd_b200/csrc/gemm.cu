@@ -74,6 +74,7 @@ extern "C" int agb_gemm_f32(agb_ctx* ctx, int trans_a, int trans_b, const agb_te
   }
   if (m == 0 || n == 0 || batch == 0) return AGB_OK;
   if (k == 0) { if (beta == 0.0f) return agb_memset0(ctx, c->ptr, agb_numel(c) * sizeof(float)); return AGB_OK; }
+  AgbProfScope prof(ctx, AGB_PROF_GEMM, 2.0 * (double)m * (double)n * (double)k * (double)batch);
   int mode = ctx->math_mode;
   if (mode != AGB_MATH_FP32) {
     int r = agb_tc_gemm(ctx, mode, a->ptr, b->ptr, c->ptr, m, n, k, batch, rsa, csa, bsa, rsb, csb, bsb, m * n, beta);

@@ -171,6 +171,21 @@ extern "C" int agb_flush_l2(agb_ctx* ctx) {
   return AGB_OK;
 }
 
+// ---- live profiler ----
+extern "C" int agb_prof_enable(agb_ctx* ctx, int on) { ctx->prof_on = on != 0; return AGB_OK; }
+extern "C" int agb_prof_reset(agb_ctx* ctx) {
+  AGB_CUDA(cudaStreamSynchronize(ctx->stream));
+  for (auto& r : ctx->prof_recs) { ctx->prof_pool.push_back(r.a); ctx->prof_pool.push_back(r.b); }
+  ctx->prof_recs.clear(); return AGB_OK;
+}
+extern "C" int agb_prof_collect(agb_ctx* ctx, int cls, double* total_ms, int64_t* calls, double* work) {
+  AGB_CUDA(cudaStreamSynchronize(ctx->stream));
+  double t = 0, w = 0; int64_t n = 0;
+  for (auto& r : ctx->prof_recs) if (r.cls == cls) { float ms = 0; AGB_CUDA(cudaEventElapsedTime(&ms, r.a, r.b)); t += ms; w += r.work; n++; }
+  if (total_ms) *total_ms = t; if (calls) *calls = n; if (work) *work = w;
+  return AGB_OK;
+}
+
 // ---- events ----
 extern "C" int agb_event_create(void** ev) { cudaEvent_t e; AGB_CUDA(cudaEventCreate(&e)); *ev = e; return AGB_OK; }
 extern "C" int agb_event_destroy(void* ev) { AGB_CUDA(cudaEventDestroy((cudaEvent_t)ev)); return AGB_OK; }
