@@ -143,6 +143,9 @@ int  agb_maxpool2d_bwd(agb_ctx* ctx, const agb_tensor* gy, const float* idx_f32,
 int  agb_maxpool2d_gradgrad(agb_ctx* ctx, const agb_tensor* ggx, const float* idx_f32, const int32_t* idx_i32,
                             agb_tensor* ggy);
 
+/* index buffers are kept as int32 on the device (exact for any size); API-visible float copies are made on demand */
+int  agb_convert_i32_f32(agb_ctx* ctx, const int32_t* src, float* dst, int64_t n);
+
 /* ======================= elementwise ======================= */
 enum { /* unary ops: math_ops.rs:277-1019, activation_ops.rs:113-226, array_ops.rs:537-574 */
   AGB_U_COPY = 0, AGB_U_ABS, AGB_U_NEG, AGB_U_SQUARE, AGB_U_INV, AGB_U_INVSQRT, AGB_U_SIGN, AGB_U_FLOOR,

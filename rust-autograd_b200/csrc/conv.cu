@@ -13,10 +13,54 @@
 //   quirk: im2col uses `ph` for the x start (mod.rs:98); pads are always square so it is unobservable.
 #include "simt_gemm.cuh"
 
+// tcgen05 kernels (tc_conv.cu): operate on channels-last activation buffers
 int agb_tc_conv_fprop(agb_ctx* ctx, int mode, const float* x, const float* w, float* y,
                       int B, int C, int H, int W, int O, int kh, int kw, int pad, int stride, int dil, int flip_transpose);
 int agb_tc_conv_wgrad(agb_ctx* ctx, int mode, const float* img, const float* g, float* gw,
                       int B, int C, int H, int W, int O, int kh, int kw, int pad, int stride, int dil);
+bool agb_tc_conv_eligible(int C, int O, int kh, int kw, int stride, int yw);
+
+// ---- activation layouts.  A logical [B,C,H,W] tensor is accepted in two dense memory orders: NCHW (C-contiguous, the
+// reference's layout) and channels-last (N,H,W,C).  Each kernel family has a native order (tcgen05: channels-last, CUDA-core
+// implicit GEMM: NCHW); operands in the other order go through one tiled transpose (agb_copy_strided) into an arena temporary.
+static bool is_nchw(const agb_tensor* t) { return agb_is_contig(t); }
+static bool is_channels_last(const agb_tensor* t) {
+  if (t->rank != 4) return false;
+  const int64_t C = t->shape[1], H = t->shape[2], W = t->shape[3];
+  return (C == 1 || t->stride[1] == 1) && (W == 1 || t->stride[3] == C) && (H == 1 || t->stride[2] == W * C) && (t->shape[0] == 1 || t->stride[0] == H * W * C);
+}
+static void set_layout(agb_tensor* t, bool channels_last) {
+  const int64_t C = t->shape[1], H = t->shape[2], W = t->shape[3];
+  if (channels_last) { t->stride[0] = H * W * C; t->stride[1] = 1; t->stride[2] = W * C; t->stride[3] = C; }
+  else { t->stride[0] = C * H * W; t->stride[1] = H * W; t->stride[2] = W; t->stride[3] = 1; }
+}
+struct LayoutTmp {     // an input converted on entry, or an output converted back on exit
+  agb_ctx* ctx; float* tmp = nullptr; agb_tensor view; const agb_tensor* user = nullptr; bool copy_back = false;
+  explicit LayoutTmp(agb_ctx* c) : ctx(c) {}
+  int input(const agb_tensor* t, bool want_cl) {
+    view = *t;
+    if (want_cl ? is_channels_last(t) : is_nchw(t)) return AGB_OK;
+    AGB_CHECK(is_nchw(t) || is_channels_last(t), AGB_ERR_UNSUPPORTED, "conv: activations must be dense NCHW or channels-last");
+    AGB_TRY(agb_alloc(ctx, (size_t)agb_numel(t) * sizeof(float), (void**)&tmp));
+    view.ptr = tmp; set_layout(&view, want_cl);
+    return agb_copy_strided(ctx, t, &view);
+  }
+  int output(agb_tensor* t, bool want_cl) {
+    view = *t; user = t;
+    if (want_cl ? is_channels_last(t) : is_nchw(t)) return AGB_OK;
+    AGB_CHECK(is_nchw(t) || is_channels_last(t), AGB_ERR_UNSUPPORTED, "conv: activations must be dense NCHW or channels-last");
+    AGB_TRY(agb_alloc(ctx, (size_t)agb_numel(t) * sizeof(float), (void**)&tmp));
+    view.ptr = tmp; set_layout(&view, want_cl); copy_back = true;
+    return AGB_OK;
+  }
+  int finish() {
+    int r = AGB_OK;
+    if (copy_back) { agb_tensor dst = *user; r = agb_copy_strided(ctx, &view, &dst); copy_back = false; }
+    if (tmp) { agb_free(ctx, tmp); tmp = nullptr; }
+    return r;
+  }
+  ~LayoutTmp() { if (tmp) agb_free(ctx, tmp); }
+};
 
 struct ConvGeom { int B, C, H, W, O, kh, kw, yh, yw, pad, stride, dil; };
 
@@ -98,17 +142,23 @@ static int check_geom(const char* who, const agb_tensor* x, const agb_tensor* w,
 
 extern "C" int agb_conv2d_fprop_f32(agb_ctx* ctx, const agb_tensor* x, const agb_tensor* w, agb_tensor* y, int pad, int stride, int dilation) {
   ConvGeom g; AGB_TRY(check_geom("conv2d", x, w, pad, stride, dilation, g));
-  AGB_CHECK(agb_is_contig(x) && agb_is_contig(w) && agb_is_contig(y), AGB_ERR_UNSUPPORTED, "conv2d: tensors must be C-contiguous (the reference deep-copies, conv2d.rs:436-452)");
+  AGB_CHECK(agb_is_contig(w), AGB_ERR_UNSUPPORTED, "conv2d: the filter must be C-contiguous");
   AGB_CHECK(y->rank == 4 && y->shape[0] == g.B && y->shape[1] == g.O && y->shape[2] == g.yh && y->shape[3] == g.yw, AGB_ERR_INCOMPATIBLE_SHAPE,
             "conv2d: output must be [%d,%d,%d,%d]", g.B, g.O, g.yh, g.yw);
   if (agb_numel(y) == 0) return AGB_OK;
   AgbProfScope prof(ctx, AGB_PROF_CONV_FPROP, 2.0 * (double)agb_numel(y) * g.C * g.kh * g.kw);
-  if (ctx->math_mode != AGB_MATH_FP32) {
-    int r = agb_tc_conv_fprop(ctx, ctx->math_mode, x->ptr, w->ptr, y->ptr, g.B, g.C, g.H, g.W, g.O, g.kh, g.kw, pad, stride, dilation, 0);
+  if (ctx->math_mode != AGB_MATH_FP32 && agb_tc_conv_eligible(g.C, g.O, g.kh, g.kw, stride, g.yw)) {
+    LayoutTmp lx(ctx), ly(ctx);
+    AGB_TRY(lx.input(x, true)); AGB_TRY(ly.output(y, true));
+    int r = agb_tc_conv_fprop(ctx, ctx->math_mode, lx.view.ptr, w->ptr, ly.view.ptr, g.B, g.C, g.H, g.W, g.O, g.kh, g.kw, pad, stride, dilation, 0);
+    if (r == AGB_OK) { AGB_TRY(ly.finish()); return lx.finish(); }
     if (r != AGB_ERR_UNSUPPORTED) return r;
   }
+  LayoutTmp lx(ctx), ly(ctx);
+  AGB_TRY(lx.input(x, false)); AGB_TRY(ly.output(y, false));
   int64_t K = (int64_t)g.C * g.kh * g.kw;
-  return simt_gemm_launch(ctx, FpropA{w->ptr, K}, FpropB{x->ptr, g}, FpropC{y->ptr, g}, g.O, (int64_t)g.B * g.yh * g.yw, K, 1);
+  AGB_TRY(simt_gemm_launch(ctx, FpropA{w->ptr, K}, FpropB{lx.view.ptr, g}, FpropC{ly.view.ptr, g}, g.O, (int64_t)g.B * g.yh * g.yw, K, 1));
+  AGB_TRY(ly.finish()); return lx.finish();
 }
 
 extern "C" int agb_conv2d_dgrad_f32(agb_ctx* ctx, const agb_tensor* gy, const agb_tensor* w, agb_tensor* gx, int pad, int stride, int dilation) {
@@ -125,36 +175,48 @@ extern "C" int agb_conv2d_dgrad_f32(agb_ctx* ctx, const agb_tensor* gy, const ag
   AGB_CHECK(g.H > 0 && g.W > 0, AGB_ERR_INCOMPATIBLE_SHAPE, "conv2d_transpose: non-positive output size");
   AGB_CHECK(gx->rank == 4 && gx->shape[0] == g.B && gx->shape[1] == g.C && gx->shape[2] == g.H && gx->shape[3] == g.W, AGB_ERR_INCOMPATIBLE_SHAPE,
             "conv2d_transpose: output must be [%d,%d,%d,%d]", g.B, g.C, g.H, g.W);
-  AGB_CHECK(agb_is_contig(gy) && agb_is_contig(w) && agb_is_contig(gx), AGB_ERR_UNSUPPORTED, "conv2d_transpose: tensors must be C-contiguous");
+  AGB_CHECK(agb_is_contig(w), AGB_ERR_UNSUPPORTED, "conv2d_transpose: the filter must be C-contiguous");
   if (agb_numel(gx) == 0) return AGB_OK;
   AgbProfScope prof(ctx, AGB_PROF_CONV_DGRAD, 2.0 * (double)agb_numel(gy) * g.C * g.kh * g.kw);
-  if (ctx->math_mode != AGB_MATH_FP32 && stride == 1 && g.H == g.yh && g.W == g.yw) {
-    // stride-1 "same" dgrad == fprop of gy with the spatially flipped, channel-transposed filter
-    int r = agb_tc_conv_fprop(ctx, ctx->math_mode, gy->ptr, w->ptr, gx->ptr, g.B, g.O, g.yh, g.yw, g.C, g.kh, g.kw, pad, stride, dilation, 1);
+  if (ctx->math_mode != AGB_MATH_FP32 && stride == 1 && dilation * (g.kh - 1) - pad >= 0 && agb_tc_conv_eligible(g.O, g.C, g.kh, g.kw, stride, g.W)) {
+    // stride-1 dgrad == fprop of gy with the spatially flipped, channel-transposed filter and pad' = d(k-1) - p
+    LayoutTmp lg(ctx), lx(ctx);
+    AGB_TRY(lg.input(gy, true)); AGB_TRY(lx.output(gx, true));
+    int r = agb_tc_conv_fprop(ctx, ctx->math_mode, lg.view.ptr, w->ptr, lx.view.ptr, g.B, g.O, g.yh, g.yw, g.C, g.kh, g.kw, pad, stride, dilation, 1);
+    if (r == AGB_OK) { AGB_TRY(lx.finish()); return lg.finish(); }
     if (r != AGB_ERR_UNSUPPORTED) return r;
   }
+  LayoutTmp lg(ctx), lx(ctx);
+  AGB_TRY(lg.input(gy, false)); AGB_TRY(lx.output(gx, false));
   int64_t K = (int64_t)g.O * g.kh * g.kw;
-  return simt_gemm_launch(ctx, DgradA{w->ptr, g}, DgradB{gy->ptr, g}, DgradC{gx->ptr, g}, g.C, (int64_t)g.B * g.H * g.W, K, 1);
+  AGB_TRY(simt_gemm_launch(ctx, DgradA{w->ptr, g}, DgradB{lg.view.ptr, g}, DgradC{lx.view.ptr, g}, g.C, (int64_t)g.B * g.H * g.W, K, 1));
+  AGB_TRY(lx.finish()); return lg.finish();
 }
 
 extern "C" int agb_conv2d_wgrad_f32(agb_ctx* ctx, const agb_tensor* img, const agb_tensor* gr, agb_tensor* gw, int pad, int stride, int dilation) {
   ConvGeom g; AGB_TRY(check_geom("conv2d_filter_grad", img, gw, pad, stride, dilation, g));
   AGB_CHECK(gr->rank == 4 && gr->shape[0] == g.B && gr->shape[1] == g.O && gr->shape[2] == g.yh && gr->shape[3] == g.yw, AGB_ERR_INCOMPATIBLE_SHAPE,
             "conv2d_filter_grad: gradient must be [%d,%d,%d,%d]", g.B, g.O, g.yh, g.yw);
-  AGB_CHECK(agb_is_contig(img) && agb_is_contig(gr) && agb_is_contig(gw), AGB_ERR_UNSUPPORTED, "conv2d_filter_grad: tensors must be C-contiguous");
+  AGB_CHECK(agb_is_contig(gw), AGB_ERR_UNSUPPORTED, "conv2d_filter_grad: the filter gradient must be C-contiguous");
   if (agb_numel(gw) == 0) return AGB_OK;
   AgbProfScope prof(ctx, AGB_PROF_CONV_WGRAD, 2.0 * (double)agb_numel(gr) * g.C * g.kh * g.kw);
-  if (ctx->math_mode != AGB_MATH_FP32) {
-    int r = agb_tc_conv_wgrad(ctx, ctx->math_mode, img->ptr, gr->ptr, gw->ptr, g.B, g.C, g.H, g.W, g.O, g.kh, g.kw, pad, stride, dilation);
+  if (ctx->math_mode != AGB_MATH_FP32 && agb_tc_conv_eligible(g.C, g.O, g.kh, g.kw, stride, g.yw)) {
+    LayoutTmp li(ctx), lg(ctx);
+    AGB_TRY(li.input(img, true)); AGB_TRY(lg.input(gr, true));
+    int r = agb_tc_conv_wgrad(ctx, ctx->math_mode, li.view.ptr, lg.view.ptr, gw->ptr, g.B, g.C, g.H, g.W, g.O, g.kh, g.kw, pad, stride, dilation);
+    if (r == AGB_OK) { AGB_TRY(li.finish()); return lg.finish(); }
     if (r != AGB_ERR_UNSUPPORTED) return r;
   }
+  LayoutTmp li(ctx), lg(ctx);
+  AGB_TRY(li.input(img, false)); AGB_TRY(lg.input(gr, false));
   int64_t N = (int64_t)g.C * g.kh * g.kw; int64_t P = (int64_t)g.yh * g.yw;
   bool big = (g.O >= 96 && N >= 96); int tile = big ? 128 : 64;
   int64_t tiles = ((g.O + tile - 1) / tile) * ((N + tile - 1) / tile);
   int64_t Z = (2 * (int64_t)ctx->sm_count + tiles - 1) / tiles; if (Z > g.B) Z = g.B; if (Z < 1) Z = 1;
   int bchunk = (int)((g.B + Z - 1) / Z); Z = (g.B + bchunk - 1) / bchunk;
   if (Z > 1) AGB_TRY(agb_memset0(ctx, gw->ptr, agb_numel(gw) * sizeof(float)));
-  return simt_gemm_launch(ctx, WgradA{gr->ptr, g, bchunk}, WgradB{img->ptr, g, bchunk}, WgradC{gw->ptr, N, Z > 1}, g.O, N, (int64_t)bchunk * P, Z);
+  AGB_TRY(simt_gemm_launch(ctx, WgradA{lg.view.ptr, g, bchunk}, WgradB{li.view.ptr, g, bchunk}, WgradC{gw->ptr, N, Z > 1}, g.O, N, (int64_t)bchunk * P, Z));
+  AGB_TRY(li.finish()); return lg.finish();
 }
 
 // ---- im2col materialisation (only for user-visible evaluation of Conv2D's 2nd output) ----

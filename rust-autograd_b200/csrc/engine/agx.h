@@ -59,6 +59,8 @@ struct NdArray {
   BufferP buf; float* dptr = nullptr;
   std::shared_ptr<std::vector<float>> host;
   bool meta = false;              // shape-derived value: arithmetic on it stays on the host
+  bool i32 = false;               // the buffer holds int32 indices (max-pool argmax): exact beyond 2^24, converted to f32 only when a
+                                  // float consumer or the user asks (the reference stores indices as floats, max_pool2d.rs:74-75)
   std::shared_ptr<Im2colRef> virt;
 
   int ndim() const { return (int)shape.size(); }
@@ -85,6 +87,7 @@ struct Device {                   // thin C++ handle on the kernel C ABI context
   void ensure_device(NdArray& a);               // upload the host copy if there is no device copy yet
   const std::vector<float>& ensure_host(NdArray& a);   // D2H (+ stream sync) if there is no host copy yet
   NdArray contiguous(const NdArray& a);         // materialise a strided view (reference: ndarray_ext::deep_copy)
+  NdArray i32_to_f32(const NdArray& a);         // float copy of an int32 index buffer
   NdArray copy(const NdArray& a);
   void sync();
 };
@@ -162,6 +165,7 @@ struct Evaluation;                // per-run state (pending optimizer updates, d
 struct ComputeContext {           // src/op.rs:186-309
   std::vector<OpInput> xs; std::vector<NdArray> ys;
   Device* dev; Evaluation* run; TensorID node;
+  bool accept_i32 = false;        // set by ops that consume int32 index buffers natively
   NdArray input(int i);           // each input may be taken once (:206-233)
   NdArray input_mut(int i);       // only RdWrVariable edges (:239-259)
   int num_inputs() const { return (int)xs.size(); }

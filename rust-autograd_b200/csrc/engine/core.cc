@@ -83,6 +83,7 @@ void Device::ensure_device(NdArray& a) {
 }
 const std::vector<float>& Device::ensure_host(NdArray& a) {
   if (a.host) return *a.host;
+  if (a.i32) { NdArray f = i32_to_f32(a); a.buf = f.buf; a.dptr = f.dptr; a.stride = f.stride; a.i32 = false; }
   NdArray c = a.is_contiguous() ? a : contiguous(a);
   auto h = std::make_shared<std::vector<float>>((size_t)c.size());
   check_status(agb_d2h(ctx, h->data(), c.dptr, (size_t)c.size() * sizeof(float)));
@@ -99,8 +100,15 @@ NdArray Device::copy(const NdArray& a_) {
   NdArray c = empty(a.shape);
   agb_tensor s = a.desc(), d = c.desc();
   check_status(agb_copy_strided(ctx, &s, &d));
-  c.meta = a.meta;
+  c.meta = a.meta; c.i32 = a.i32;
   return c;
+}
+NdArray Device::i32_to_f32(const NdArray& a) {
+  if (!a.i32) return a;
+  NdArray s = a; s.i32 = false; s = contiguous(s);       // bit patterns are copied verbatim by the strided copy
+  NdArray d = empty(a.shape);
+  check_status(agb_convert_i32_f32(ctx, (const int32_t*)s.dptr, d.dptr, s.size()));
+  return d;
 }
 void Device::sync() { check_status(agb_sync(ctx)); }
 
@@ -186,7 +194,9 @@ NdArray ComputeContext::input(int i) {
   OpInput& x = xs[i];
   if (x.kind == InputKind::RdWrVariable) throw Panic("Bad op impl: cannot perform mutable borrowing for input. Use input_mut() instead.");
   if (x.taken) throw Panic("Bad op impl: input()/input_mut() cannot be called twice");
-  x.taken = true; return x.arr;
+  x.taken = true;
+  if (x.arr.i32 && !accept_i32) return dev->i32_to_f32(x.arr);
+  return x.arr;
 }
 NdArray ComputeContext::input_mut(int i) {
   if (i < 0 || i >= (int)xs.size()) throw Panic("Bad op impl: input doesn't exist.");

@@ -227,7 +227,7 @@ static Tensor infer_bin_op_shape(Graph* g, Tensor sa, Tensor sb) { return Tensor
 // ================================================================================================ pass-through ops
 struct IdentityOp : Op {               // activation_ops.rs:169-181 (also nth_tensor)
   const char* name() const override { return REFNAME("activation_ops", "Identity"); }
-  void compute(ComputeContext& c) override { c.append_output_view(c.input(0)); }
+  void compute(ComputeContext& c) override { c.accept_i32 = true; c.append_output_view(c.input(0)); }
   void grad(GradientContext& c) override { c.append_input_grad(c.output_grad()); }
 };
 struct StopGradient : Op {             // gradient_ops.rs:4-16

@@ -240,11 +240,12 @@ struct MaxPool2DGradGrad : Op {        // max_pool2d.rs:297-337
   int size, pad, stride;
   const char* name() const override { return REFNAME("conv_ops::max_pool2d", "MaxPool2DGradGrad"); }
   void compute(ComputeContext& c) override {
+    c.accept_i32 = true;
     NdArray ggx = c.dev->contiguous(on_dev(c.dev, c.input(0))), idx = c.dev->contiguous(on_dev(c.dev, c.input(1)));
     int64_t yh = (ggx.shape[2] + 2 * pad - size) / stride + 1, yw = (ggx.shape[3] + 2 * pad - size) / stride + 1;
     NdArray ggy = c.dev->empty({ggx.shape[0], ggx.shape[1], yh, yw});
     agb_tensor tx = ggx.desc(), ty = ggy.desc();
-    check_status(agb_maxpool2d_gradgrad(c.dev->ctx, &tx, idx.dptr, nullptr, &ty));
+    check_status(agb_maxpool2d_gradgrad(c.dev->ctx, &tx, idx.i32 ? nullptr : idx.dptr, idx.i32 ? (const int32_t*)idx.dptr : nullptr, &ty));
     c.append_output(ggy);
   }
   void grad(GradientContext& c) override { c.append_none(); c.append_none(); }
@@ -253,11 +254,12 @@ struct MaxPool2DGrad : Op {            // max_pool2d.rs:245-295
   int size, pad, stride;
   const char* name() const override { return REFNAME("conv_ops::max_pool2d", "MaxPool2DGrad"); }
   void compute(ComputeContext& c) override {
+    c.accept_i32 = true;
     NdArray gy = c.dev->contiguous(on_dev(c.dev, c.input(0))), idx = c.dev->contiguous(on_dev(c.dev, c.input(1)));
     int64_t xh = stride * (gy.shape[2] - 1) - 2 * pad + size, xw = stride * (gy.shape[3] - 1) - 2 * pad + size;     // (:263-264)
     NdArray gx = c.dev->empty({gy.shape[0], gy.shape[1], xh, xw});
     agb_tensor tg = gy.desc(), tx = gx.desc();
-    check_status(agb_maxpool2d_bwd(c.dev->ctx, &tg, idx.dptr, nullptr, &tx));
+    check_status(agb_maxpool2d_bwd(c.dev->ctx, &tg, idx.i32 ? nullptr : idx.dptr, idx.i32 ? (const int32_t*)idx.dptr : nullptr, &tx));
     c.append_output(gx);
   }
   void grad(GradientContext& c) override {
@@ -275,7 +277,10 @@ struct MaxPool2D : Op {                // max_pool2d.rs:166-243
     int64_t yh = (x.shape[2] + 2 * pad - size) / stride + 1, yw = (x.shape[3] + 2 * pad - size) / stride + 1;
     NdArray y = c.dev->empty({x.shape[0], x.shape[1], yh, yw}), idx = c.dev->empty({x.shape[0], x.shape[1], yh, yw});
     agb_tensor tx = x.desc(), ty = y.desc();
-    check_status(agb_maxpool2d_fwd(c.dev->ctx, &tx, &ty, idx.dptr, nullptr, size, pad, stride));
+    // indices stay int32 on the device: the reference's float-encoded flat offsets lose bits above 2^24 elements
+    // (max_pool2d.rs:74-75; a 256x64x128x128 VGG activation has 2.7e8), API-visible values are converted on fetch
+    if (x.size() < (1ll << 31)) { check_status(agb_maxpool2d_fwd(c.dev->ctx, &tx, &ty, nullptr, (int32_t*)idx.dptr, size, pad, stride)); idx.i32 = true; }
+    else check_status(agb_maxpool2d_fwd(c.dev->ctx, &tx, &ty, idx.dptr, nullptr, size, pad, stride));
     c.append_output(y); c.append_output(idx);
   }
   void grad(GradientContext& c) override {

@@ -266,10 +266,45 @@ extern "C" int agb_binary(agb_ctx* ctx, int op, float p0, float p1, const agb_te
   return t[op](ctx, a->ptr, b->ptr, y->ptr, y->rank, y->shape, a->stride, b->stride, sy, p0, p1);
 }
 
+// batched 2-D transpose through shared memory: src [B][R][S] (S contiguous) -> dst [B][S][R] (R contiguous).  Both sides are
+// read / written in 128-byte rows; this is the NCHW <-> channels-last layout change (R = C, S = H*W or the reverse).
+__global__ void __launch_bounds__(256) transpose_batched_kernel(const float* __restrict__ src, float* __restrict__ dst, int64_t R, int64_t S) {
+  __shared__ float tile[32][33];
+  const int64_t b = blockIdx.z; const int64_t s0 = (int64_t)blockIdx.x * 32, r0 = (int64_t)blockIdx.y * 32;
+  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;     // 32 x 8
+  const float* sp = src + b * R * S; float* dp = dst + b * R * S;
+#pragma unroll
+  for (int k = 0; k < 32; k += 8) { int64_t r = r0 + ty + k, s = s0 + tx; if (r < R && s < S) tile[ty + k][tx] = __ldg(sp + r * S + s); }
+  __syncthreads();
+#pragma unroll
+  for (int k = 0; k < 32; k += 8) { int64_t s = s0 + ty + k, r = r0 + tx; if (r < R && s < S) dp[s * R + r] = tile[tx][ty + k]; }
+}
+static int launch_transpose(agb_ctx* ctx, const float* src, float* dst, int64_t B, int64_t R, int64_t S) {
+  for (int64_t b0 = 0; b0 < B; b0 += 65535) {
+    int64_t nb = B - b0 < 65535 ? B - b0 : 65535;
+    dim3 grid((unsigned)((S + 31) / 32), (unsigned)((R + 31) / 32), (unsigned)nb);
+    AGB_CHECK(grid.y <= 65535, AGB_ERR_UNSUPPORTED, "transpose: too many row tiles");
+    transpose_batched_kernel<<<grid, 256, 0, ctx->stream>>>(src + b0 * R * S, dst + b0 * R * S, R, S);
+    AGB_LAUNCHED(ctx);
+  }
+  return AGB_OK;
+}
+
 extern "C" int agb_copy_strided(agb_ctx* ctx, const agb_tensor* src, agb_tensor* dst) {
   AGB_CHECK(src->rank == dst->rank, AGB_ERR_INCOMPATIBLE_SHAPE, "agb_copy_strided: rank mismatch %d vs %d", src->rank, dst->rank);
   for (int i = 0; i < src->rank; i++) AGB_CHECK(src->shape[i] == dst->shape[i], AGB_ERR_INCOMPATIBLE_SHAPE, "agb_copy_strided: shape mismatch on axis %d", i);
   if (agb_is_contig(src) && agb_is_contig(dst)) return agb_d2d(ctx, dst->ptr, src->ptr, agb_numel(src) * sizeof(float));
+  {   // [B][R][S] <-> [B][S][R] pattern (layout changes): tiled transpose instead of the generic gather
+    StridedParams P; collapse(src->rank, src->shape, src->stride, src->stride, dst->stride, P);
+    if (P.rank == 2 || P.rank == 3) {
+      const int o = P.rank - 2; const int64_t B = o ? P.shape[0] : 1, d1 = P.shape[o], d2 = P.shape[o + 1];
+      const bool bs_ok = !o || (P.sa[0] == d1 * d2 && P.sy[0] == d1 * d2);
+      if (bs_ok && d1 >= 8 && d2 >= 8) {
+        if (P.sa[o] == d2 && P.sa[o + 1] == 1 && P.sy[o] == 1 && P.sy[o + 1] == d1) return launch_transpose(ctx, src->ptr, dst->ptr, B, d1, d2);      // src row-major, dst transposed
+        if (P.sa[o] == 1 && P.sa[o + 1] == d1 && P.sy[o] == d2 && P.sy[o + 1] == 1) return launch_transpose(ctx, src->ptr, dst->ptr, B, d2, d1);      // src transposed, dst row-major
+      }
+    }
+  }
   return launch_strided<-1>(ctx, src->ptr, src->ptr, dst->ptr, src->rank, src->shape, src->stride, src->stride, dst->stride, 0.f, 0.f);
 }
 

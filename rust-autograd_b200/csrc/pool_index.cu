@@ -143,3 +143,13 @@ extern "C" int agb_gather_grad(agb_ctx* ctx, const float* gy, const float* indic
   AGB_LAUNCHED(ctx);
   return AGB_OK;
 }
+
+__global__ void __launch_bounds__(256) i32_to_f32_kernel(const int32_t* __restrict__ s, float* __restrict__ d, int64_t n) {
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) d[i] = (float)s[i];
+}
+extern "C" int agb_convert_i32_f32(agb_ctx* ctx, const int32_t* src, float* dst, int64_t n) {
+  if (n == 0) return AGB_OK;
+  i32_to_f32_kernel<<<agb_grid_for(n, 256, ctx->sm_count, 8), 256, 0, ctx->stream>>>(src, dst, n);
+  AGB_LAUNCHED(ctx);
+  return AGB_OK;
+}

@@ -1,5 +1,210 @@
-// tc_conv.cu — tcgen05 implicit-GEMM convolutions (placeholder until the kernels land; returns UNSUPPORTED so
-// conv.cu routes to the CUDA-core implicit-GEMM path).
-#include "tc_common.cuh"
-int agb_tc_conv_fprop(agb_ctx*, int, const float*, const float*, float*, int, int, int, int, int, int, int, int, int, int, int) { return AGB_ERR_UNSUPPORTED; }
-int agb_tc_conv_wgrad(agb_ctx*, int, const float*, const float*, float*, int, int, int, int, int, int, int, int, int, int) { return AGB_ERR_UNSUPPORTED; }
+// tc_conv.cu — tcgen05 implicit-GEMM convolutions for sm_100a on CHANNELS-LAST activations (logical NCHW tensors whose
+// memory order is N,H,W,C), stride 1, square pad / dilation, built on the tile engine in tc_tile.cuh.
+//
+// Why channels-last: TMA requires the innermost box coordinate to be 16-byte aligned (measured: a 4-byte-shifted start raises
+// an illegal-instruction fault).  In NCHW the 3x3 taps shift the innermost (W) axis by +-1 element, in channels-last they shift
+// H and W which are outer axes, and the innermost axis (C) only ever moves in steps of 32 channels.  The im2col matrix of the
+// reference (conv_ops/mod.rs:73-124; 9x the input for 3x3) is never materialised: TMA boxes with out-of-bounds zero fill ARE
+// the im2col rows (padding = zero fill).
+//
+// fprop  (Conv2D::compute, conv2d.rs:115-211)   y[b,o,oy,ox] = sum_{c,i,j} w[o,c,i,j] x[b,c,oy+i*d-p,ox+j*d-p]
+//   D[lane = pixel, col = o]: a CTA owns a 4x32 pixel patch of one image (128 TMEM lanes) x TN output channels.
+//   k-block = (tap (i,j), 32 input channels).  P operand (K-major): ONE 4-D TMA box {32 c, 32 w, 4 h, 1 b} at the tap's offset
+//   lands as [pixel][32 c] rows of 128 B (SWIZZLE_128B).  Q operand (K-major): filter repacked per call to wr[tap][o][c].
+//   Epilogue: thread = pixel owns 32 consecutive output channels per tcgen05.ld = 128 contiguous bytes of y (float4 stores).
+// dgrad  (Conv2DTranspose::compute, conv2d_transpose.rs:89-247), stride 1: the same kernel on gy with the filter repacked
+//   flipped and channel-transposed (wr[tap'][c][o]) and pad' = d(k-1) - p.
+// wgrad  (Conv2DFilterGrad::compute, conv2d.rs:631-734; the reference loops the batch sequentially with beta = 1):
+//   gw[o,c,i,j] = sum_{b,oy,ox} gy[b,o,oy,ox] x[b,c,oy+i*d-p,ox+j*d-p]
+//   D[lane = c, col = o] per tap, K = pixels: k-block = 32 consecutive ox of one (b, oy) row.  Both operands are MN-major
+//   (channels contiguous): [32 px][32 ch] TMA boxes {32 c, 32 w, 1, 1} (128B_BASE32B swizzle).  With C == 64 two taps share
+//   the 128 lanes.  Split-K over (b, oy) across CTAs, fp32 `red.global.add` into the zeroed gw.
+#include "tc_tile.cuh"
+
+// ------------------------------------------------------------------------------------------------ filter repack
+// mode 0 (fprop): wr[t][o][c] = w[o][c][t];  mode 1 (dgrad): wr[T-1-t][c][o] = w[o][c][t]   (rows = output channel of the GEMM)
+__global__ void __launch_bounds__(256) repack_filter_kernel(const float* __restrict__ w, float* __restrict__ wr, int O, int C, int T, int mode) {
+  int64_t n = (int64_t)O * C * T;
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+    int t = (int)(i % T); int64_t r = i / T; int c = (int)(r % C); int o = (int)(r / C);
+    float v = __ldg(w + i);
+    if (mode == 0) wr[((int64_t)t * O + o) * C + c] = v;
+    else wr[((int64_t)(T - 1 - t) * C + c) * O + o] = v;
+  }
+}
+
+// ------------------------------------------------------------------------------------------------ fprop / dgrad policy
+template <int TN_, bool SPLIT_> struct ConvFpropPol {
+  static constexpr int TN = TN_; static constexpr bool SPLIT = SPLIT_, P_MN = false, Q_MN = false;
+  static constexpr int OCC = (SPLIT_ || TN_ > 128) ? 1 : 2;
+  struct Params { CUtensorMap tmX, tmW; float* y; int Cout, yh, yw, kw, pad, dil, tiles_x, tiles_y, cblocks, taps; MnDescCfg mnc; };
+  struct Tile { int b, oy0, ox0, o0; };
+  __device__ static Tile tile(const Params& p) {
+    int bx = (int)blockIdx.x; int tx = bx % p.tiles_x; int r = bx / p.tiles_x; int ty = r % p.tiles_y;
+    return Tile{r / p.tiles_y, ty * 4, tx * 32, (int)blockIdx.y * TN};
+  }
+  __device__ static int num_kblocks(const Params& p, const Tile&) { return p.taps * p.cblocks; }
+  __device__ static void prefetch(const Params& p) { tma_prefetch_desc(&p.tmX); tma_prefetch_desc(&p.tmW); }
+  __device__ static void load(const Params& p, const Tile& t, int kb, uint8_t* pP, uint8_t* pQ, uint64_t* bar) {
+    const int tap = kb / p.cblocks, cb = kb - tap * p.cblocks; const int i = tap / p.kw, j = tap - i * p.kw;
+    tma_load_4d(pP, &p.tmX, bar, cb * 32, t.ox0 + j * p.dil - p.pad, t.oy0 + i * p.dil - p.pad, t.b);     // dims {c, w, h, b}
+    tma_load_3d(pQ, &p.tmW, bar, cb * 32, t.o0, tap);
+  }
+  __device__ static void store(const Params& p, const Tile& t, int lane, int c0, const float* v) {
+    const int oy = t.oy0 + (lane >> 5), ox = t.ox0 + (lane & 31);
+    if (oy >= p.yh || ox >= p.yw) return;
+    const int o = t.o0 + c0;
+    float* dst = p.y + (((int64_t)t.b * p.yh + oy) * p.yw + ox) * p.Cout + o;
+    if (o + 32 <= p.Cout) {
+#pragma unroll
+      for (int j = 0; j < 32; j += 4) *(float4*)(dst + j) = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
+    } else {
+#pragma unroll
+      for (int j = 0; j < 32; j++) if (o + j < p.Cout) dst[j] = v[j];
+    }
+  }
+};
+
+// ------------------------------------------------------------------------------------------------ wgrad policy
+template <int TN_, bool SPLIT_, bool PAIR_> struct ConvWgradPol {
+  static constexpr int TN = TN_; static constexpr bool SPLIT = SPLIT_, P_MN = true, Q_MN = true;
+  static constexpr int OCC = (SPLIT_ || TN_ > 128) ? 1 : 2;
+  struct Params { CUtensorMap tmX, tmG; float* gw; int C, O, T, kw, pad, dil, yh, xblocks, kb_total, kb_per_split; MnDescCfg mnc; };
+  struct Tile { int c0, tapA, tapB, o0, q0, q1; };
+  __device__ static Tile tile(const Params& p) {
+    Tile t; t.o0 = (int)blockIdx.y * TN;
+    if (PAIR_) { t.c0 = 0; t.tapA = 2 * (int)blockIdx.x; t.tapB = t.tapA + 1; }
+    else { int ctiles = (p.C + 127) / 128; t.c0 = ((int)blockIdx.x % ctiles) * 128; t.tapA = (int)blockIdx.x / ctiles; t.tapB = -1; }
+    t.q0 = (int)blockIdx.z * p.kb_per_split; t.q1 = min(t.q0 + p.kb_per_split, p.kb_total);
+    return t;
+  }
+  __device__ static int num_kblocks(const Params&, const Tile& t) { return t.q1 > t.q0 ? t.q1 - t.q0 : 0; }
+  __device__ static void prefetch(const Params& p) { tma_prefetch_desc(&p.tmX); tma_prefetch_desc(&p.tmG); }
+  __device__ static void load(const Params& p, const Tile& t, int kb, uint8_t* pP, uint8_t* pQ, uint64_t* bar) {
+    const int q = t.q0 + kb; const int xb = q % p.xblocks; const int r = q / p.xblocks; const int oy = r % p.yh, b = r / p.yh;
+    const int ox0 = xb * 32;
+    const int iA = t.tapA / p.kw, jA = t.tapA - iA * p.kw;
+    const int xA = ox0 + jA * p.dil - p.pad, yA = oy + iA * p.dil - p.pad;
+    if (PAIR_) {      // lanes 0-63: channels 0..63 at tap A, lanes 64-127: channels 0..63 at tap B
+      int xB = xA, yB = yA, cB = p.C + 64;                                   // tap B absent (odd tap count): fully out of bounds = zero rows
+      if (t.tapB < p.T) { const int iB = t.tapB / p.kw, jB = t.tapB - iB * p.kw; xB = ox0 + jB * p.dil - p.pad; yB = oy + iB * p.dil - p.pad; cB = 0; }
+      tma_load_4d(pP, &p.tmX, bar, 0, xA, yA, b);
+      tma_load_4d(pP + 4096, &p.tmX, bar, 32, xA, yA, b);
+      tma_load_4d(pP + 8192, &p.tmX, bar, cB, xB, yB, b);
+      tma_load_4d(pP + 12288, &p.tmX, bar, cB + 32, xB, yB, b);
+    } else {
+#pragma unroll
+      for (int g = 0; g < 4; g++) tma_load_4d(pP + g * 4096, &p.tmX, bar, t.c0 + 32 * g, xA, yA, b);
+    }
+#pragma unroll
+    for (int g = 0; g < TN / 32; g++) tma_load_4d(pQ + g * 4096, &p.tmG, bar, t.o0 + 32 * g, ox0, oy, b);
+  }
+  __device__ static void store(const Params& p, const Tile& t, int lane, int c0, const float* v) {
+    int c, tap;
+    if (PAIR_) { c = lane & 63; tap = lane < 64 ? t.tapA : t.tapB; } else { c = t.c0 + lane; tap = t.tapA; }
+    if (c >= p.C || tap >= p.T) return;
+#pragma unroll
+    for (int j = 0; j < 32; j++) { const int o = t.o0 + c0 + j; if (o < p.O) red_add_f32(p.gw + ((int64_t)o * p.C + c) * p.T + tap, v[j]); }
+  }
+};
+
+// ------------------------------------------------------------------------------------------------ host side
+// channels-last tensor map of a logical [B, C, H, W] activation: dims {c, w, h, b}
+static int make_cl_map(CUtensorMap* m, const float* p, int B, int C, int H, int W, uint32_t bc, uint32_t bw, uint32_t bh, bool atom32) {
+  uint64_t dims[4] = {(uint64_t)C, (uint64_t)W, (uint64_t)H, (uint64_t)B};
+  uint64_t str[3] = {(uint64_t)C * 4, (uint64_t)W * C * 4, (uint64_t)H * W * C * 4};
+  uint32_t box[4] = {bc, bw, bh, 1};
+  return agb_make_tmap(m, p, 4, dims, str, box, atom32);
+}
+
+bool agb_tc_conv_eligible(int C, int O, int kh, int kw, int stride, int yw) {
+  return stride == 1 && kh == kw && C >= 32 && C % 4 == 0 && O >= 32 && O % 4 == 0 && yw >= 16;
+}
+
+template <int TN, bool SPLIT>
+static int fprop_launch(agb_ctx* ctx, const float* x, const float* wr, float* y, int B, int Cin, int H, int W, int Cout, int yh, int yw, int kh, int kw,
+                        int pad, int dil) {
+  using Pol = ConvFpropPol<TN, SPLIT>;
+  typename Pol::Params p;
+  AGB_TRY(make_cl_map(&p.tmX, x, B, Cin, H, W, 32, 32, 4, false));
+  {  // wr[tap][o][c]
+    uint64_t dims[3] = {(uint64_t)Cin, (uint64_t)Cout, (uint64_t)(kh * kw)};
+    uint64_t str[2] = {(uint64_t)Cin * 4, (uint64_t)Cin * Cout * 4};
+    uint32_t box[3] = {32, (uint32_t)TN, 1};
+    AGB_TRY(agb_make_tmap(&p.tmW, wr, 3, dims, str, box, false));
+  }
+  p.y = y; p.Cout = Cout; p.yh = yh; p.yw = yw; p.kw = kw; p.pad = pad; p.dil = dil;
+  p.tiles_x = (yw + 31) / 32; p.tiles_y = (yh + 3) / 4; p.cblocks = (Cin + 31) / 32; p.taps = kh * kw; p.mnc = agb_mn_cfg();
+  int64_t nb = (int64_t)p.tiles_x * p.tiles_y * B;
+  if (nb > 2147483647ll) return AGB_ERR_UNSUPPORTED;
+  dim3 grid((unsigned)nb, (unsigned)((Cout + TN - 1) / TN), 1);
+  return tc_tile_launch<Pol>(ctx, p, grid);
+}
+
+// fprop on channels-last buffers: x [B,H,W,C], w [O,C,kh,kw] (plain) -> y [B,yh,yw,O].  flip_transpose != 0: dgrad — `x` is gy
+// with C = filter dim 0, w [C, O(=out channels of this GEMM), kh, kw]; the effective padding is dil*(k-1) - pad.
+int agb_tc_conv_fprop(agb_ctx* ctx, int mode, const float* x, const float* w, float* y, int B, int C, int H, int W, int O, int kh, int kw,
+                      int pad, int stride, int dil, int flip_transpose) {
+  const int epad = flip_transpose ? dil * (kh - 1) - pad : pad;
+  if (epad < 0) return AGB_ERR_UNSUPPORTED;
+  const int yh = H + 2 * epad - (dil * (kh - 1) + 1) + 1, yw = W + 2 * epad - (dil * (kw - 1) + 1) + 1;
+  if (yh < 1 || yw < 1 || !agb_tc_conv_eligible(C, O, kh, kw, stride, yw)) return AGB_ERR_UNSUPPORTED;
+  if ((((uintptr_t)x | (uintptr_t)y) & 15) != 0) return AGB_ERR_UNSUPPORTED;
+  const int T = kh * kw;
+  float* wr = nullptr;
+  AGB_TRY(agb_scratch(ctx, (size_t)T * O * C * sizeof(float), (void**)&wr));
+  {
+    int64_t n = (int64_t)O * C * T;
+    // fprop: w is [O][C][T] -> wr[t][O][C];  dgrad: w is [C(in)][O(out)][T] -> wr[T-1-t][O(out)][C(in)]
+    if (!flip_transpose) repack_filter_kernel<<<agb_grid_for(n, 256, ctx->sm_count, 4), 256, 0, ctx->stream>>>(w, wr, O, C, T, 0);
+    else repack_filter_kernel<<<agb_grid_for(n, 256, ctx->sm_count, 4), 256, 0, ctx->stream>>>(w, wr, C, O, T, 1);
+    AGB_LAUNCHED(ctx);
+  }
+  const bool split = mode == AGB_MATH_3XTF32;
+  if (split) {
+    if (O > 64) return fprop_launch<128, true>(ctx, x, wr, y, B, C, H, W, O, yh, yw, kh, kw, epad, dil);
+    return fprop_launch<64, true>(ctx, x, wr, y, B, C, H, W, O, yh, yw, kh, kw, epad, dil);
+  }
+  if (O > 128) return fprop_launch<256, false>(ctx, x, wr, y, B, C, H, W, O, yh, yw, kh, kw, epad, dil);
+  if (O > 64) return fprop_launch<128, false>(ctx, x, wr, y, B, C, H, W, O, yh, yw, kh, kw, epad, dil);
+  return fprop_launch<64, false>(ctx, x, wr, y, B, C, H, W, O, yh, yw, kh, kw, epad, dil);
+}
+
+template <int TN, bool SPLIT, bool PAIR>
+static int wgrad_launch(agb_ctx* ctx, const float* img, const float* g, float* gw, int B, int C, int H, int W, int O, int yh, int yw, int kh, int kw, int pad, int dil) {
+  using Pol = ConvWgradPol<TN, SPLIT, PAIR>;
+  typename Pol::Params p;
+  AGB_TRY(make_cl_map(&p.tmX, img, B, C, H, W, 32, 32, 1, true));
+  AGB_TRY(make_cl_map(&p.tmG, g, B, O, yh, yw, 32, 32, 1, true));
+  const int T = kh * kw;
+  p.gw = gw; p.C = C; p.O = O; p.T = T; p.kw = kw; p.pad = pad; p.dil = dil; p.yh = yh; p.xblocks = (yw + 31) / 32;
+  int64_t kb_total = (int64_t)B * yh * p.xblocks;
+  if (kb_total > 2147483647ll) return AGB_ERR_UNSUPPORTED;
+  p.kb_total = (int)kb_total; p.mnc = agb_mn_cfg();
+  const int gx = PAIR ? (T + 1) / 2 : ((C + 127) / 128) * T, gy_ = (O + TN - 1) / TN;
+  int64_t want = 2ll * ctx->sm_count * Pol::OCC / ((int64_t)gx * gy_); if (want < 1) want = 1;
+  int64_t per = (kb_total + want - 1) / want; if (per < 16) per = 16; if (per > kb_total) per = kb_total;
+  p.kb_per_split = (int)per;
+  int splits = (int)((kb_total + per - 1) / per);
+  if (splits > 65535) return AGB_ERR_UNSUPPORTED;
+  AGB_TRY(agb_memset0(ctx, gw, (size_t)O * C * T * sizeof(float)));
+  dim3 grid((unsigned)gx, (unsigned)gy_, (unsigned)splits);
+  return tc_tile_launch<Pol>(ctx, p, grid);
+}
+
+// wgrad on channels-last buffers: img [B,H,W,C] (the im2col'd operand), g [B,yh,yw,O] -> gw [O,C,kh,kw] (plain)
+int agb_tc_conv_wgrad(agb_ctx* ctx, int mode, const float* img, const float* g, float* gw, int B, int C, int H, int W, int O, int kh, int kw,
+                      int pad, int stride, int dil) {
+  const int yh = H + 2 * pad - (dil * (kh - 1) + 1) + 1, yw = W + 2 * pad - (dil * (kw - 1) + 1) + 1;
+  if (yh < 1 || yw < 1 || !agb_tc_conv_eligible(C, O, kh, kw, stride, yw)) return AGB_ERR_UNSUPPORTED;
+  if ((((uintptr_t)img | (uintptr_t)g) & 15) != 0) return AGB_ERR_UNSUPPORTED;
+  const bool split = mode == AGB_MATH_3XTF32;
+  const bool pair = C <= 64;
+#define WG(TN_, SP_) (pair ? wgrad_launch<TN_, SP_, true>(ctx, img, g, gw, B, C, H, W, O, yh, yw, kh, kw, pad, dil) \
+                           : wgrad_launch<TN_, SP_, false>(ctx, img, g, gw, B, C, H, W, O, yh, yw, kh, kw, pad, dil))
+  if (split) { if (O > 64) return WG(128, true); return WG(64, true); }
+  if (O > 128) return WG(256, false);
+  if (O > 64) return WG(128, false);
+  return WG(64, false);
+#undef WG
+}

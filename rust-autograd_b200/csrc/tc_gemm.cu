@@ -22,6 +22,7 @@
 
 template <int TN_, bool P_MN_, bool Q_MN_, bool SPLIT_> struct GemmPol {
   static constexpr int TN = TN_; static constexpr bool SPLIT = SPLIT_, P_MN = P_MN_, Q_MN = Q_MN_;
+  static constexpr int OCC = (SPLIT_ || TN_ > 128) ? 1 : 2;
   struct Params { CUtensorMap tmP, tmQ; float* C; int NL, NC, K; int64_t ldc, bsc; int accumulate; MnDescCfg mnc; };
   struct Tile { int lane0, col0, bz; };
   __device__ static Tile tile(const Params&) { return Tile{(int)blockIdx.x * TC_LANES, (int)blockIdx.y * TN, (int)blockIdx.z}; }

@@ -21,11 +21,15 @@
 #define TC_LANES 128
 #define TC_KC 8            // k-blocks per TMEM accumulation chunk in SPLIT mode (8 * 32 = 256 k)
 
-template <int TN, bool SPLIT> struct TcCfg {
+// OCC = CTAs co-resident per SM.  Two co-resident CTAs overlap one CTA's prologue / epilogue (TMEM drain, global stores) with the
+// other's MMA main loop without a persistent tile scheduler; the ring depth is what fits in 1/OCC of the 227 KB shared memory.
+template <int TN, bool SPLIT, int OCC = 1> struct TcCfg {
   static constexpr int P_BYTES = TC_LANES * TC_BK * 4;                 // 16 KB
   static constexpr int Q_BYTES = TN * TC_BK * 4;
   static constexpr int STAGE_BYTES = (P_BYTES + Q_BYTES) * (SPLIT ? 2 : 1);
-  static constexpr int STAGES = (200 * 1024) / STAGE_BYTES > 6 ? 6 : (200 * 1024) / STAGE_BYTES;
+  static constexpr int BUDGET = (224 * 1024) / OCC - 2048;
+  static constexpr int STAGES = BUDGET / STAGE_BYTES > 6 ? 6 : BUDGET / STAGE_BYTES;
+  static_assert(STAGES >= 2, "tile does not fit the shared-memory budget");
   static constexpr int SMEM = STAGES * STAGE_BYTES + 1024 /*align*/ + 256 /*barriers*/;
   static constexpr int THREADS = SPLIT ? 320 : 192;
   static constexpr int TMEM_COLS = SPLIT ? 2 * TN : TN;                // power of two >= 32 for TN in {32,64,128,256}
@@ -33,7 +37,7 @@ template <int TN, bool SPLIT> struct TcCfg {
 };
 
 // Policy interface:
-//   static constexpr int TN; static constexpr bool SPLIT, P_MN, Q_MN;
+//   static constexpr int TN, OCC; static constexpr bool SPLIT, P_MN, Q_MN;
 //   struct Params { ... CUtensorMap members ...; MnDescCfg mnc; };
 //   struct Tile { ... };                                               per-CTA coordinates
 //   __device__ static Tile tile(const Params&);                        from blockIdx
@@ -42,9 +46,9 @@ template <int TN, bool SPLIT> struct TcCfg {
 //   __device__ static void load(const Params&, const Tile&, int kb, uint8_t* pP, uint8_t* pQ, uint64_t* bar);   one thread
 //   __device__ static void store(const Params&, const Tile&, int lane /*0..127*/, int c0 /*0..TN-32*/, const float* v /*[32]*/);
 template <class Pol>
-__global__ void __launch_bounds__(TcCfg<Pol::TN, Pol::SPLIT>::THREADS, 1) tc_tile_kernel(const __grid_constant__ typename Pol::Params prm) {
+__global__ void __launch_bounds__(TcCfg<Pol::TN, Pol::SPLIT, Pol::OCC>::THREADS, Pol::OCC) tc_tile_kernel(const __grid_constant__ typename Pol::Params prm) {
   constexpr int TN = Pol::TN; constexpr bool SPLIT = Pol::SPLIT, P_MN = Pol::P_MN, Q_MN = Pol::Q_MN;
-  using Cfg = TcCfg<TN, SPLIT>;
+  using Cfg = TcCfg<TN, SPLIT, Pol::OCC>;
   constexpr int S = Cfg::STAGES;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
@@ -185,7 +189,7 @@ __global__ void __launch_bounds__(TcCfg<Pol::TN, Pol::SPLIT>::THREADS, 1) tc_til
 
 template <class Pol>
 static int tc_tile_launch(agb_ctx* ctx, const typename Pol::Params& prm, dim3 grid) {
-  using Cfg = TcCfg<Pol::TN, Pol::SPLIT>;
+  using Cfg = TcCfg<Pol::TN, Pol::SPLIT, Pol::OCC>;
   static bool attr = false;
   if (!attr) { AGB_CUDA(cudaFuncSetAttribute(tc_tile_kernel<Pol>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM)); attr = true; }
   tc_tile_kernel<Pol><<<grid, Cfg::THREADS, Cfg::SMEM, ctx->stream>>>(prm);

@@ -67,6 +67,7 @@ SIGNATURES = {
     "agb_conv2d_wgrad_f32": [_P, _T, _T, _T, _i, _i, _i], "agb_im2col_f32": [_P, _T, _T, _i, _i, _i, _i, _i],
     "agb_maxpool2d_fwd": [_P, _T, _T, _P, _P, _i, _i, _i], "agb_maxpool2d_bwd": [_P, _T, _P, _P, _T],
     "agb_maxpool2d_gradgrad": [_P, _T, _P, _P, _T],
+    "agb_convert_i32_f32": [_P, _P, _P, _i64],
     "agb_unary": [_P, _i, _f, _f, _T, _T], "agb_binary": [_P, _i, _f, _f, _T, _T, _T],
     "agb_add_n": [_P, _i, C.POINTER(_T), _T], "agb_fill": [_P, _T, _f], "agb_copy_strided": [_P, _T, _T],
     "agb_dropout": [_P, _T, _T, _T, _f, _u64, _u64],

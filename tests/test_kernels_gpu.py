@@ -152,6 +152,16 @@ CONV_CASES = [  # B, C, H, W, O, kh, kw, pad, stride, dil
     (2, 3, 32, 32, 64, 3, 3, 1, 1, 1),      # VGG L0 (C=3)
     (2, 16, 12, 12, 24, 5, 5, 2, 1, 1),
     (2, 8, 15, 15, 8, 3, 3, 1, 2, 1),
+    # shapes that take the tcgen05 implicit-GEMM path (stride 1, W >= 32, C, O >= 32)
+    (2, 32, 32, 32, 32, 3, 3, 1, 1, 1),
+    (1, 64, 64, 64, 128, 3, 3, 1, 1, 1),
+    (2, 128, 32, 32, 256, 3, 3, 1, 1, 1),
+    (1, 256, 32, 32, 256, 3, 3, 1, 1, 1),
+    (2, 64, 36, 40, 64, 3, 3, 1, 1, 1),     # partial pixel tiles
+    (2, 32, 40, 40, 32, 3, 3, 2, 1, 2),     # dilation 2
+    (1, 32, 32, 32, 64, 5, 5, 2, 1, 1),     # 5x5
+    (1, 32, 34, 34, 32, 3, 3, 0, 1, 1),     # no padding
+    (3, 48, 32, 64, 96, 3, 3, 1, 1, 1),     # channel counts that are not multiples of 32 / 64
 ]
 
 
