@@ -127,6 +127,12 @@ int  agb_conv2d_dgrad_f32(agb_ctx* ctx, const agb_tensor* gy, const agb_tensor* 
  * img [B,C,H,W] is the tensor that gets im2col'd, g [B,O,yh,yw] the one that multiplies it. */
 int  agb_conv2d_wgrad_f32(agb_ctx* ctx, const agb_tensor* img, const agb_tensor* g, agb_tensor* gw,
                           int pad, int stride, int dilation);
+/* Activation layouts.  Logical [B,C,H,W] tensors are accepted by the conv and pooling entry points in two dense memory orders:
+ * NCHW (C-contiguous, the reference's layout) and channels-last (strides {H*W*C, 1, W*C, C}).  The tcgen05 conv kernels are
+ * native channels-last (TMA needs 16-byte aligned innermost coordinates; the 3x3 taps shift W by one element), operands in
+ * the other order are converted through a tiled transpose.  Returns 1 when a conv of this geometry runs on the tensor cores,
+ * i.e. when the caller should keep its activations channels-last. */
+int  agb_conv_prefers_channels_last(int in_channels, int out_channels, int kh, int kw, int stride, int out_w);
 /* materialise im2col(x) = Conv2D output #1, [B,C,kh,kw,yh,yw] (only when user code evaluates it) */
 int  agb_im2col_f32(agb_ctx* ctx, const agb_tensor* x, agb_tensor* cols, int kh, int kw,
                     int pad, int stride, int dilation);

@@ -219,6 +219,10 @@ extern "C" int agb_conv2d_wgrad_f32(agb_ctx* ctx, const agb_tensor* img, const a
   AGB_TRY(li.finish()); return lg.finish();
 }
 
+extern "C" int agb_conv_prefers_channels_last(int in_channels, int out_channels, int kh, int kw, int stride, int out_w) {
+  return agb_tc_conv_eligible(in_channels, out_channels, kh, kw, stride, out_w) ? 1 : 0;
+}
+
 // ---- im2col materialisation (only for user-visible evaluation of Conv2D's 2nd output) ----
 __global__ void __launch_bounds__(256) im2col_kernel(const float* __restrict__ x, float* __restrict__ cols, ConvGeom g, int64_t n) {
   int64_t tid = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;

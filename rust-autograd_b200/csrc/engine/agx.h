@@ -72,6 +72,9 @@ struct NdArray {
   static Shape contiguous_strides(const Shape& s);
   static NdArray from_host(const Shape& shape, std::vector<float> v, bool meta = false);
   static NdArray scalar_host(float v, bool meta = false) { return from_host({}, {v}, meta); }
+  // Memory-order permutation of a dense array: order[0] is the slowest axis.  Returns false when the view is not dense
+  // (slices, broadcasts).  A C-contiguous array yields the identity; a channels-last [B,C,H,W] yields {0,2,3,1}.
+  bool dense_order(std::vector<int>& order) const;
   NdArray reshaped(const Shape& s) const;      // contiguous only (device) / always (host)
   NdArray permuted(const std::vector<int>& perm) const;
   NdArray sliced(int axis, int64_t start, int64_t len) const;
@@ -82,6 +85,7 @@ struct Device {                   // thin C++ handle on the kernel C ABI context
   explicit Device(int index);
   ~Device();
   NdArray empty(const Shape& s);
+  NdArray empty_ordered(const Shape& s, const std::vector<int>& order);   // dense, memory order = `order` (e.g. channels-last)
   NdArray zeros(const Shape& s);
   NdArray full(const Shape& s, float v);
   void ensure_device(NdArray& a);               // upload the host copy if there is no device copy yet

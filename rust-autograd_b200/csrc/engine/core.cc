@@ -29,6 +29,20 @@ bool NdArray::is_contiguous() const {
   for (int i = ndim() - 1; i >= 0; i--) { if (shape[i] != 1 && stride[i] != acc) return false; acc *= shape[i]; }
   return true;
 }
+bool NdArray::dense_order(std::vector<int>& order) const {
+  const int n = ndim();
+  order.resize(n);
+  for (int i = 0; i < n; i++) order[i] = i;
+  if (!on_device()) return true;
+  std::vector<int> big;                       // non-unit axes by descending stride; unit axes keep their logical slot
+  for (int i = 0; i < n; i++) if (shape[i] != 1) big.push_back(i);
+  std::sort(big.begin(), big.end(), [&](int a, int b) { return stride[a] != stride[b] ? stride[a] > stride[b] : a < b; });
+  int bi = 0;
+  for (int i = 0; i < n; i++) order[i] = shape[i] == 1 ? i : big[bi++];
+  int64_t acc = 1;
+  for (int i = n - 1; i >= 0; i--) { int a = order[i]; if (shape[a] != 1 && stride[a] != acc) return false; acc *= shape[a]; }
+  return true;
+}
 agb_tensor NdArray::desc() const {
   agb_tensor t; t.ptr = dptr; t.rank = ndim();
   if (t.rank > AGB_MAX_RANK) throw OpError(AGB_ERR_INVALID_DIMS, "tensor rank exceeds AGB_MAX_RANK");
@@ -60,6 +74,11 @@ Device::~Device() { if (ctx) agb_destroy(ctx); }
 NdArray Device::empty(const Shape& s) {
   NdArray a; a.shape = s; a.stride = NdArray::contiguous_strides(s);
   a.buf = std::make_shared<Buffer>(ctx, (size_t)std::max<int64_t>(a.size(), 1) * sizeof(float)); a.dptr = a.buf->ptr;
+  return a;
+}
+NdArray Device::empty_ordered(const Shape& s, const std::vector<int>& order) {
+  NdArray a = empty(s); int64_t acc = 1;
+  for (int i = (int)s.size() - 1; i >= 0; i--) { a.stride[order[i]] = acc; acc *= s[order[i]]; }
   return a;
 }
 NdArray Device::zeros(const Shape& s) {

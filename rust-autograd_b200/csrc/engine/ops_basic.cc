@@ -13,8 +13,22 @@ namespace agx {
 // ================================================================================================ device helpers
 static NdArray on_dev(Device* d, NdArray a) { d->ensure_device(a); return a; }
 
+// Elementwise kernels preserve the memory order of their (dominant) input: a channels-last activation stays channels-last
+// through bias add / ReLU / gradient masks, so no layout change is ever paid between two tensor-core convolutions.
+static bool is_identity(const std::vector<int>& o) { for (size_t i = 0; i < o.size(); i++) if (o[i] != (int)i) return false; return true; }
+static agb_tensor flat_desc(const NdArray& a) { agb_tensor t; t.ptr = a.dptr; t.rank = 1; t.shape[0] = a.size(); t.stride[0] = 1; return t; }
+static agb_tensor permuted_desc(const agb_tensor& t, const std::vector<int>& order) {
+  agb_tensor r = t; for (int i = 0; i < t.rank; i++) { r.shape[i] = t.shape[order[i]]; r.stride[i] = t.stride[order[i]]; } return r;
+}
 static NdArray dev_unary(Device* d, int op, NdArray x, float p0 = 0.f, float p1 = 0.f) {
   d->ensure_device(x);
+  std::vector<int> order;
+  if (x.dense_order(order) && !is_identity(order)) {          // dense but permuted: run on the flat memory, keep the strides
+    NdArray y = d->empty_ordered(x.shape, order);
+    agb_tensor tx = flat_desc(x), ty = flat_desc(y);
+    check_status(agb_unary(d->ctx, op, p0, p1, &tx, &ty));
+    return y;
+  }
   NdArray y = d->empty(x.shape);
   agb_tensor tx = x.desc(), ty = y.desc();
   check_status(agb_unary(d->ctx, op, p0, p1, &tx, &ty));
@@ -43,8 +57,20 @@ static agb_tensor broadcast_desc(const NdArray& a, const Shape& out) {
 static NdArray dev_binary(Device* d, int op, NdArray a, NdArray b, float p0 = 0.f, float p1 = 0.f, const char* who = "binary op") {
   d->ensure_device(a); d->ensure_device(b);
   Shape out = broadcast_shape(a.shape, b.shape, who);
+  agb_tensor ta = broadcast_desc(a, out), tb = broadcast_desc(b, out);
+  // output memory order = that of the first full-size operand with a permuted dense layout
+  std::vector<int> order;
+  const NdArray* dom = nullptr;
+  if (a.shape == out && a.dense_order(order) && !is_identity(order)) dom = &a;
+  else if (b.shape == out && b.dense_order(order) && !is_identity(order)) dom = &b;
+  if (dom) {
+    NdArray y = d->empty_ordered(out, order);
+    agb_tensor pa = permuted_desc(ta, order), pb = permuted_desc(tb, order), py = permuted_desc(y.desc(), order);
+    check_status(agb_binary(d->ctx, op, p0, p1, &pa, &pb, &py));
+    return y;
+  }
   NdArray y = d->empty(out);
-  agb_tensor ta = broadcast_desc(a, out), tb = broadcast_desc(b, out), ty = y.desc();
+  agb_tensor ty = y.desc();
   check_status(agb_binary(d->ctx, op, p0, p1, &ta, &tb, &ty));
   return y;
 }
@@ -91,7 +117,25 @@ static std::vector<int> norm_axes(Device* d, NdArray& axes, int ndim) {     // n
 // reduce `x` (contiguous) over the sorted axis set, highest group first (impl_reduce_forward!, reduction_ops.rs:54-108)
 static NdArray dev_reduce_axes(Device* d, int op, NdArray x, std::vector<int> axes, bool keep_dims) {
   std::sort(axes.begin(), axes.end()); axes.erase(std::unique(axes.begin(), axes.end()), axes.end());
-  x = d->contiguous(on_dev(d, x));
+  x = on_dev(d, x);
+  {   // dense permuted input (channels-last): reduce in memory order, hand the result back as a strided logical view
+    std::vector<int> order;
+    if (x.dense_order(order) && !is_identity(order)) {
+      NdArray xp = x; std::vector<int> pos(order.size());
+      for (size_t i = 0; i < order.size(); i++) { xp.shape[i] = x.shape[order[i]]; xp.stride[i] = x.stride[order[i]]; pos[order[i]] = (int)i; }
+      std::vector<int> paxes; for (int a : axes) paxes.push_back(pos[a]);
+      NdArray rp = dev_reduce_axes(d, op, xp, paxes, true);           // physical order, reduced axes kept as 1
+      NdArray r = rp;                                                   // un-permute: logical axis a lives at physical slot pos[a]
+      for (size_t a = 0; a < order.size(); a++) { r.shape[a] = rp.shape[pos[a]]; r.stride[a] = rp.stride[pos[a]]; }
+      if (!keep_dims) {
+        Shape s2, st2;
+        for (size_t a = 0; a < order.size(); a++) if (std::find(axes.begin(), axes.end(), (int)a) == axes.end()) { s2.push_back(r.shape[a]); st2.push_back(r.stride[a]); }
+        r.shape = s2; r.stride = st2;
+      }
+      return r;
+    }
+  }
+  x = d->contiguous(x);
   Shape cur = x.shape; NdArray curr = x;
   int i = (int)axes.size() - 1;
   while (i >= 0) {
@@ -329,6 +373,7 @@ struct MaybeReduceSum : Op {           // binary_ops.rs:39-105
     }
     NdArray r = dev_reduce_axes(c.dev, AGB_R_SUM, gy, axes, true);
     Shape fin = orig_.size() == 1 && orig_[0] == 0 ? Shape{} : orig_;     // shape [0] (scalar_shape) denotes a 0-d target
+    if (!r.is_contiguous()) r = c.dev->contiguous(r);
     c.append_output(r.reshaped(fin));
   }
   static NdArray d_reshape(ComputeContext& c, NdArray a, const Shape& s) {
@@ -506,7 +551,17 @@ struct AddN : Op {                     // array_ops.rs:503-535
     }
     if (same) {
       std::vector<agb_tensor> ds; std::vector<const agb_tensor*> ps;
-      for (auto& x : xs) { x = c.dev->contiguous(on_dev(c.dev, x)); ds.push_back(x.desc()); }
+      for (auto& x : xs) c.dev->ensure_device(x);
+      std::vector<int> order; bool same_layout = xs[0].dense_order(order) && !is_identity(order);
+      for (auto& x : xs) if (x.stride != xs[0].stride) same_layout = false;
+      if (same_layout) {          // all inputs share one permuted dense layout: add the flat buffers
+        for (auto& x : xs) ds.push_back(flat_desc(x));
+        for (auto& dd : ds) ps.push_back(&dd);
+        NdArray y = c.dev->empty_ordered(xs[0].shape, order); agb_tensor ty = flat_desc(y);
+        check_status(agb_add_n(c.dev->ctx, n, ps.data(), &ty));
+        c.append_output(y); return;
+      }
+      for (auto& x : xs) { x = c.dev->contiguous(x); ds.push_back(x.desc()); }
       for (auto& d : ds) ps.push_back(&d);
       NdArray y = c.dev->empty(xs[0].shape); agb_tensor ty = y.desc();
       check_status(agb_add_n(c.dev->ctx, n, ps.data(), &ty));

@@ -93,6 +93,10 @@ NdArray materialize_im2col(Device* dev, const NdArray& cols) {      // only when
 static NdArray real_cols(Device* dev, const NdArray& cols) { return cols.virt && !cols.on_device() ? materialize_im2col(dev, cols) : cols; }
 
 struct ConvParams { int pad, stride, dilation; };
+// activations enter the conv / pool entry points either NCHW-contiguous or channels-last; anything else is deep-copied
+static bool is_cl4(const NdArray& a) { std::vector<int> o; return a.ndim() == 4 && a.on_device() && a.dense_order(o) && o == std::vector<int>({0, 2, 3, 1}) && !a.is_contiguous(); }
+static NdArray act_layout(Device* dev, NdArray a) { if (a.ndim() == 4 && (a.is_contiguous() || is_cl4(a))) return a; return dev->contiguous(a); }
+static NdArray act_empty(Device* dev, const Shape& s, bool channels_last) { return channels_last ? dev->empty_ordered(s, {0, 2, 3, 1}) : dev->empty(s); }
 static Tensor mk_conv_transpose(Graph* g, Tensor gy, Tensor w, ConvParams p);
 static Tensor mk_conv(Graph* g, Tensor x, Tensor w, ConvParams p);
 static Tensor mk_filter_grad(Graph* g, Tensor cols, Tensor gy, Tensor w, Tensor bp_x, Tensor bp_gy, ConvParams p);
@@ -104,12 +108,12 @@ struct Conv2D : Op {                   // conv2d.rs:531-586
   ConvParams p;
   const char* name() const override { return REFNAME("conv_ops::conv2d", "Conv2D"); }
   void compute(ComputeContext& c) override {
-    NdArray x = c.dev->contiguous(on_dev(c.dev, c.input(0))), w = c.dev->contiguous(on_dev(c.dev, c.input(1)));   // deep_copy if not standard layout (:436-452)
+    NdArray x = act_layout(c.dev, on_dev(c.dev, c.input(0))), w = c.dev->contiguous(on_dev(c.dev, c.input(1)));   // deep_copy if not a dense layout (:436-452)
     if (x.ndim() != 4) throw OpError(AGB_ERR_INCOMPATIBLE_SHAPE, "conv2d: lhs input must be 4D");
     if (w.ndim() != 4) throw OpError(AGB_ERR_INCOMPATIBLE_SHAPE, "conv2d: filter must be 4D");
     if (x.shape[1] != w.shape[1]) throw OpError(AGB_ERR_INCOMPATIBLE_SHAPE, "conv2d: input channel dim must match filter's second dim");
     int64_t yh = conv_out(x.shape[2], w.shape[2], p), yw = conv_out(x.shape[3], w.shape[3], p);
-    NdArray y = c.dev->empty({x.shape[0], w.shape[0], yh, yw});
+    NdArray y = act_empty(c.dev, {x.shape[0], w.shape[0], yh, yw}, agb_conv_prefers_channels_last((int)x.shape[1], (int)w.shape[0], (int)w.shape[2], (int)w.shape[3], p.stride, (int)yw));
     agb_tensor tx = x.desc(), tw = w.desc(), ty = y.desc();
     check_status(agb_conv2d_fprop_f32(c.dev->ctx, &tx, &tw, &ty, p.pad, p.stride, p.dilation));
     NdArray cols; cols.shape = {x.shape[0], x.shape[1], w.shape[2], w.shape[3], yh, yw}; cols.stride = NdArray::contiguous_strides(cols.shape);
@@ -129,8 +133,8 @@ struct Conv2DWithCols : Op {           // conv2d.rs:589-628
     NdArray cols = c.input(0), w = c.dev->contiguous(on_dev(c.dev, c.input(1)));
     if (cols.ndim() != 6 || w.ndim() != 4) throw OpError(AGB_ERR_INCOMPATIBLE_SHAPE, "Conv2DWithCols: cols must be 6-D and the filter 4-D");
     if (cols.virt) {
-      NdArray x = c.dev->contiguous(cols.virt->x);
-      NdArray y = c.dev->empty({x.shape[0], w.shape[0], cols.shape[4], cols.shape[5]});
+      NdArray x = act_layout(c.dev, cols.virt->x);
+      NdArray y = act_empty(c.dev, {x.shape[0], w.shape[0], cols.shape[4], cols.shape[5]}, is_cl4(x));
       agb_tensor tx = x.desc(), tw = w.desc(), ty = y.desc();
       check_status(agb_conv2d_fprop_f32(c.dev->ctx, &tx, &tw, &ty, cols.virt->pad, cols.virt->stride, cols.virt->dil));
       c.append_output(y); return;
@@ -155,15 +159,15 @@ struct Conv2DFilterGrad : Op {         // conv2d.rs:736-776
   ConvParams p;
   const char* name() const override { return REFNAME("conv_ops::conv2d", "Conv2DFilterGrad"); }
   void compute(ComputeContext& c) override {
-    NdArray cols = c.input(0), gy = c.dev->contiguous(on_dev(c.dev, c.input(1))), w = c.input(2);
+    NdArray cols = c.input(0), gy = act_layout(c.dev, on_dev(c.dev, c.input(1))), w = c.input(2);
     NdArray gw = c.dev->empty(w.shape);
     if (cols.virt) {
-      NdArray x = c.dev->contiguous(cols.virt->x);
+      NdArray x = act_layout(c.dev, cols.virt->x);
       agb_tensor tx = x.desc(), tg = gy.desc(), tw = gw.desc();
       check_status(agb_conv2d_wgrad_f32(c.dev->ctx, &tx, &tg, &tw, cols.virt->pad, cols.virt->stride, cols.virt->dil));
       c.append_output(gw); return;
     }
-    cols = c.dev->contiguous(on_dev(c.dev, cols));       // gw = sum_b gy[b] . cols[b]^T, beta = 1 over the batch like conv2d.rs:703-722
+    cols = c.dev->contiguous(on_dev(c.dev, cols)); gy = c.dev->contiguous(gy);       // gw = sum_b gy[b] . cols[b]^T, beta = 1 over the batch like conv2d.rs:703-722
     int64_t B = cols.shape[0], K = cols.shape[1] * cols.shape[2] * cols.shape[3], P = cols.shape[4] * cols.shape[5], O = gy.shape[1];
     NdArray g3 = gy.reshaped({B, O, P}), c3 = cols.reshaped({B, K, P}), gw2 = gw.reshaped({O, K});
     for (int64_t b = 0; b < B; b++) {
@@ -186,13 +190,13 @@ struct Conv2DTranspose : Op {          // conv2d_transpose.rs:249-300
   ConvParams p;
   const char* name() const override { return REFNAME("conv_ops::conv2d_transpose", "Conv2DTranspose"); }
   void compute(ComputeContext& c) override {
-    NdArray gy = c.dev->contiguous(on_dev(c.dev, c.input(0))), w = c.dev->contiguous(on_dev(c.dev, c.input(1)));
+    NdArray gy = act_layout(c.dev, on_dev(c.dev, c.input(0))), w = c.dev->contiguous(on_dev(c.dev, c.input(1)));
     if (gy.ndim() != 4) throw OpError(AGB_ERR_INCOMPATIBLE_SHAPE, "conv2d_transpose: Input must be 4D");
     if (w.ndim() != 4) throw OpError(AGB_ERR_INCOMPATIBLE_SHAPE, "conv2d_transpose: Filter must be 4D");
     if (gy.shape[1] != w.shape[0]) throw OpError(AGB_ERR_INCOMPATIBLE_SHAPE, "conv2d_transpose: Number of input channels must match second filter dim");
     int64_t xh = p.stride * (gy.shape[2] - 1) - 2 * p.pad + (p.dilation * (w.shape[2] - 1) + 1);     // follows the code (:55-56)
     int64_t xw = p.stride * (gy.shape[3] - 1) - 2 * p.pad + (p.dilation * (w.shape[3] - 1) + 1);
-    NdArray gx = c.dev->empty({gy.shape[0], w.shape[1], xh, xw});
+    NdArray gx = act_empty(c.dev, {gy.shape[0], w.shape[1], xh, xw}, p.stride == 1 && agb_conv_prefers_channels_last((int)w.shape[0], (int)w.shape[1], (int)w.shape[2], (int)w.shape[3], 1, (int)xw));
     agb_tensor tg = gy.desc(), tw = w.desc(), tx = gx.desc();
     check_status(agb_conv2d_dgrad_f32(c.dev->ctx, &tg, &tw, &tx, p.pad, p.stride, p.dilation));
     c.append_output(gx);
@@ -203,7 +207,7 @@ struct Conv2DTransposeFilterGrad : Op {   // conv2d_transpose.rs:433-480: inputs
   ConvParams p;
   const char* name() const override { return REFNAME("conv_ops::conv2d_transpose", "Conv2DTransposeFilterGrad"); }
   void compute(ComputeContext& c) override {
-    NdArray gy = c.dev->contiguous(on_dev(c.dev, c.input(0))), x = c.dev->contiguous(on_dev(c.dev, c.input(1))), w = c.input(2);
+    NdArray gy = act_layout(c.dev, on_dev(c.dev, c.input(0))), x = act_layout(c.dev, on_dev(c.dev, c.input(1))), w = c.input(2);
     NdArray gw = c.dev->empty(w.shape);
     agb_tensor ti = gy.desc(), tg = x.desc(), tw = gw.desc();     // roles swapped: gy is im2col'd, x multiplies it
     check_status(agb_conv2d_wgrad_f32(c.dev->ctx, &ti, &tg, &tw, p.pad, p.stride, p.dilation));
@@ -241,9 +245,9 @@ struct MaxPool2DGradGrad : Op {        // max_pool2d.rs:297-337
   const char* name() const override { return REFNAME("conv_ops::max_pool2d", "MaxPool2DGradGrad"); }
   void compute(ComputeContext& c) override {
     c.accept_i32 = true;
-    NdArray ggx = c.dev->contiguous(on_dev(c.dev, c.input(0))), idx = c.dev->contiguous(on_dev(c.dev, c.input(1)));
+    NdArray ggx = act_layout(c.dev, on_dev(c.dev, c.input(0))), idx = act_layout(c.dev, on_dev(c.dev, c.input(1)));
     int64_t yh = (ggx.shape[2] + 2 * pad - size) / stride + 1, yw = (ggx.shape[3] + 2 * pad - size) / stride + 1;
-    NdArray ggy = c.dev->empty({ggx.shape[0], ggx.shape[1], yh, yw});
+    NdArray ggy = act_empty(c.dev, {ggx.shape[0], ggx.shape[1], yh, yw}, is_cl4(idx));      // laid out like the index buffer
     agb_tensor tx = ggx.desc(), ty = ggy.desc();
     check_status(agb_maxpool2d_gradgrad(c.dev->ctx, &tx, idx.i32 ? nullptr : idx.dptr, idx.i32 ? (const int32_t*)idx.dptr : nullptr, &ty));
     c.append_output(ggy);
@@ -255,9 +259,16 @@ struct MaxPool2DGrad : Op {            // max_pool2d.rs:245-295
   const char* name() const override { return REFNAME("conv_ops::max_pool2d", "MaxPool2DGrad"); }
   void compute(ComputeContext& c) override {
     c.accept_i32 = true;
-    NdArray gy = c.dev->contiguous(on_dev(c.dev, c.input(0))), idx = c.dev->contiguous(on_dev(c.dev, c.input(1)));
+    NdArray gy = on_dev(c.dev, c.input(0)), idx = act_layout(c.dev, on_dev(c.dev, c.input(1)));
+    {   // the kernel walks gy and the index buffer together: bring gy into the index buffer's memory order
+      const bool icl = is_cl4(idx);
+      if (icl != is_cl4(gy) || !(gy.is_contiguous() || is_cl4(gy))) {
+        NdArray t = act_empty(c.dev, gy.shape, icl); agb_tensor ts = gy.desc(), td = t.desc();
+        check_status(agb_copy_strided(c.dev->ctx, &ts, &td)); gy = t;
+      }
+    }
     int64_t xh = stride * (gy.shape[2] - 1) - 2 * pad + size, xw = stride * (gy.shape[3] - 1) - 2 * pad + size;     // (:263-264)
-    NdArray gx = c.dev->empty({gy.shape[0], gy.shape[1], xh, xw});
+    NdArray gx = act_empty(c.dev, {gy.shape[0], gy.shape[1], xh, xw}, is_cl4(idx));
     agb_tensor tg = gy.desc(), tx = gx.desc();
     check_status(agb_maxpool2d_bwd(c.dev->ctx, &tg, idx.i32 ? nullptr : idx.dptr, idx.i32 ? (const int32_t*)idx.dptr : nullptr, &tx));
     c.append_output(gx);
@@ -272,10 +283,12 @@ struct MaxPool2D : Op {                // max_pool2d.rs:166-243
   int size, pad, stride;
   const char* name() const override { return REFNAME("conv_ops::max_pool2d", "MaxPool2D"); }
   void compute(ComputeContext& c) override {
-    NdArray x = c.dev->contiguous(on_dev(c.dev, c.input(0)));
+    NdArray x = on_dev(c.dev, c.input(0));
     if (x.ndim() != 4) throw OpError(AGB_ERR_INCOMPATIBLE_SHAPE, "max_pool2d: input must be 4-D");
+    x = act_layout(c.dev, x);
     int64_t yh = (x.shape[2] + 2 * pad - size) / stride + 1, yw = (x.shape[3] + 2 * pad - size) / stride + 1;
-    NdArray y = c.dev->empty({x.shape[0], x.shape[1], yh, yw}), idx = c.dev->empty({x.shape[0], x.shape[1], yh, yw});
+    const bool cl = is_cl4(x);
+    NdArray y = act_empty(c.dev, {x.shape[0], x.shape[1], yh, yw}, cl), idx = act_empty(c.dev, {x.shape[0], x.shape[1], yh, yw}, cl);
     agb_tensor tx = x.desc(), ty = y.desc();
     // indices stay int32 on the device: the reference's float-encoded flat offsets lose bits above 2^24 elements
     // (max_pool2d.rs:74-75; a 256x64x128x128 VGG activation has 2.7e8), API-visible values are converted on fetch

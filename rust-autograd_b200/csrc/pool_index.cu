@@ -14,29 +14,48 @@
 #include "common.cuh"
 #include <float.h>
 
+// Layouts: the activation tensors may be dense NCHW or channels-last (N,H,W,C memory order); x and y of one call share the
+// layout, index buffers are laid out like the POOLED tensor (y / gy / ggy).  Index VALUES are always the reference's logical
+// NCHW flat offsets.  Threads walk the pooled tensor in its memory order (coalesced), strides do the rest.
+struct PoolDims { int C, xh, xw, yh, yw; int64_t xs[4], ys[4]; };   // strides of x-like and y-like tensors (b, c, h, w)
+template <bool CL> __device__ __forceinline__ void pool_decode(int64_t o, const PoolDims& d, int& b, int& c, int& i, int& j) {
+  if (CL) { c = (int)(o % d.C); int64_t t = o / d.C; j = (int)(t % d.yw); t /= d.yw; i = (int)(t % d.yh); b = (int)(t / d.yh); }
+  else { j = (int)(o % d.yw); int64_t t = o / d.yw; i = (int)(t % d.yh); t /= d.yh; c = (int)(t % d.C); b = (int)(t / d.C); }
+}
+template <bool CL>
 __global__ void __launch_bounds__(256) maxpool_fwd_kernel(const float* __restrict__ x, float* __restrict__ y,
                                                           float* __restrict__ idx_f, int32_t* __restrict__ idx_i,
-                                                          int64_t n_out, int xh, int xw, int yh, int yw, int size, int stride) {
+                                                          int64_t n_out, PoolDims d, int size, int stride) {
   int64_t tid = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
   int64_t gstride = (int64_t)gridDim.x * blockDim.x;
   for (int64_t o = tid; o < n_out; o += gstride) {
-    int j = (int)(o % yw); int64_t t = o / yw; int i = (int)(t % yh); int64_t bc = t / yh;
+    int b, c, i, j; pool_decode<CL>(o, d, b, c, i, j);
     int h0 = i * stride, w0 = j * stride;
-    int h1 = h0 + size > xh ? xh : h0 + size;
-    int w1 = w0 + size > xw ? xw : w0 + size;
-    const int64_t base = bc * (int64_t)xh * xw;
+    int h1 = h0 + size > d.xh ? d.xh : h0 + size;
+    int w1 = w0 + size > d.xw ? d.xw : w0 + size;
+    const float* xp = x + b * d.xs[0] + c * d.xs[1];
+    const int64_t lbase = ((int64_t)b * d.C + c) * d.xh * d.xw;
     float mx = -FLT_MAX; int64_t mi = 0;
-    for (int h = h0; h < h1; h++) {
-      const float* row = x + base + (int64_t)h * xw;
+    for (int h = h0; h < h1; h++)
       for (int w = w0; w < w1; w++) {
-        float v = __ldg(row + w);
-        if (v > mx) { mx = v; mi = base + (int64_t)h * xw + w; }
+        float v = __ldg(xp + h * d.xs[2] + w * d.xs[3]);
+        if (v > mx) { mx = v; mi = lbase + (int64_t)h * d.xw + w; }
       }
-    }
     y[o] = mx;
     if (idx_f) idx_f[o] = (float)mi;
     if (idx_i) idx_i[o] = (int32_t)mi;
   }
+}
+
+static bool pool_is_cl(const agb_tensor* t) {
+  const int64_t C = t->shape[1], H = t->shape[2], W = t->shape[3];
+  return !agb_is_contig(t) && (C == 1 || t->stride[1] == 1) && (W == 1 || t->stride[3] == C) && (H == 1 || t->stride[2] == W * C) && (t->shape[0] == 1 || t->stride[0] == H * W * C);
+}
+static int pool_layout(const char* who, const agb_tensor* t, bool* cl) {
+  AGB_CHECK(t->rank == 4, AGB_ERR_INCOMPATIBLE_SHAPE, "%s: tensors must be 4-D", who);
+  if (agb_is_contig(t)) { *cl = false; return AGB_OK; }
+  AGB_CHECK(pool_is_cl(t), AGB_ERR_UNSUPPORTED, "%s: tensors must be dense NCHW or channels-last", who);
+  *cl = true; return AGB_OK;
 }
 
 extern "C" int agb_maxpool2d_fwd(agb_ctx* ctx, const agb_tensor* x, agb_tensor* y, float* idx_f32, int32_t* idx_i32,
@@ -44,7 +63,7 @@ extern "C" int agb_maxpool2d_fwd(agb_ctx* ctx, const agb_tensor* x, agb_tensor* 
   AGB_CHECK(x->rank == 4 && y->rank == 4, AGB_ERR_INCOMPATIBLE_SHAPE, "max_pool2d: input and output must be 4-D");
   AGB_CHECK(pad == 0, AGB_ERR_UNSUPPORTED, "max_pool2d: pad > 0 underflows in the reference (max_pool2d.rs:43,53); only pad == 0 is defined");
   AGB_CHECK(size >= 1 && stride >= 1, AGB_ERR_INVALID_DIMS, "max_pool2d: size and stride must be >= 1");
-  AGB_CHECK(agb_is_contig(x) && agb_is_contig(y), AGB_ERR_UNSUPPORTED, "max_pool2d: tensors must be C-contiguous");
+  bool xcl, ycl; AGB_TRY(pool_layout("max_pool2d", x, &xcl)); AGB_TRY(pool_layout("max_pool2d", y, &ycl));
   int xh = (int)x->shape[2], xw = (int)x->shape[3];
   AGB_CHECK(xh >= size && xw >= size, AGB_ERR_INCOMPATIBLE_SHAPE, "max_pool2d: window larger than input");
   int yh = (xh + 2 * pad - size) / stride + 1, yw = (xw + 2 * pad - size) / stride + 1;
@@ -52,44 +71,62 @@ extern "C" int agb_maxpool2d_fwd(agb_ctx* ctx, const agb_tensor* x, agb_tensor* 
             AGB_ERR_INCOMPATIBLE_SHAPE, "max_pool2d: output shape must be [%lld,%lld,%d,%d]", (long long)x->shape[0], (long long)x->shape[1], yh, yw);
   AGB_CHECK(!idx_i32 || agb_numel(x) < (1ll << 31), AGB_ERR_UNSUPPORTED, "max_pool2d: input too large for int32 indices");
   int64_t n = agb_numel(y); if (n == 0) return AGB_OK;
-  maxpool_fwd_kernel<<<agb_grid_for(n, 256, ctx->sm_count, 8), 256, 0, ctx->stream>>>(x->ptr, y->ptr, idx_f32, idx_i32, n, xh, xw, yh, yw, size, stride);
+  AgbProfScope prof(ctx, AGB_PROF_POOL, 4.0 * (double)(agb_numel(x) + 2 * n));
+  PoolDims d; d.C = (int)x->shape[1]; d.xh = xh; d.xw = xw; d.yh = yh; d.yw = yw;
+  for (int k = 0; k < 4; k++) { d.xs[k] = x->stride[k]; d.ys[k] = y->stride[k]; }
+  int grid = agb_grid_for(n, 256, ctx->sm_count, 8);
+  if (ycl) maxpool_fwd_kernel<true><<<grid, 256, 0, ctx->stream>>>(x->ptr, y->ptr, idx_f32, idx_i32, n, d, size, stride);
+  else maxpool_fwd_kernel<false><<<grid, 256, 0, ctx->stream>>>(x->ptr, y->ptr, idx_f32, idx_i32, n, d, size, stride);
   AGB_LAUNCHED(ctx);
   return AGB_OK;
 }
 
+// logical NCHW flat offset -> memory offset of a tensor with strides xs
+__device__ __forceinline__ int64_t pool_phys(int64_t k, const PoolDims& d, bool x_cl) {
+  if (!x_cl) return k;
+  int w = (int)(k % d.xw); int64_t t = k / d.xw; int h = (int)(t % d.xh); t /= d.xh; int c = (int)(t % d.C); int64_t b = t / d.C;
+  return b * d.xs[0] + c * d.xs[1] + h * d.xs[2] + w * d.xs[3];
+}
 __global__ void __launch_bounds__(256) maxpool_bwd_kernel(const float* __restrict__ gy, const float* __restrict__ idx_f,
-                                                          const int32_t* __restrict__ idx_i, float* __restrict__ gx, int64_t n) {
+                                                          const int32_t* __restrict__ idx_i, float* __restrict__ gx, int64_t n, PoolDims d, bool x_cl) {
   int64_t tid = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
   int64_t gstride = (int64_t)gridDim.x * blockDim.x;
   for (int64_t o = tid; o < n; o += gstride) {
     int64_t k = idx_i ? (int64_t)__ldg(idx_i + o) : (int64_t)__ldg(idx_f + o);
-    atomicAdd(gx + k, __ldg(gy + o));
+    atomicAdd(gx + pool_phys(k, d, x_cl), __ldg(gy + o));
   }
 }
+// gy and the index buffer share one layout (either); gx may be NCHW or channels-last
 extern "C" int agb_maxpool2d_bwd(agb_ctx* ctx, const agb_tensor* gy, const float* idx_f32, const int32_t* idx_i32, agb_tensor* gx) {
   AGB_CHECK((idx_f32 != nullptr) != (idx_i32 != nullptr), AGB_ERR_INVALID_DIMS, "max_pool2d_grad: exactly one index buffer must be given");
-  AGB_CHECK(agb_is_contig(gy) && agb_is_contig(gx), AGB_ERR_UNSUPPORTED, "max_pool2d_grad: tensors must be C-contiguous");
+  bool gcl, xcl; AGB_TRY(pool_layout("max_pool2d_grad", gy, &gcl)); AGB_TRY(pool_layout("max_pool2d_grad", gx, &xcl));
   AGB_TRY(agb_memset0(ctx, gx->ptr, agb_numel(gx) * sizeof(float)));
   int64_t n = agb_numel(gy); if (n == 0) return AGB_OK;
-  maxpool_bwd_kernel<<<agb_grid_for(n, 256, ctx->sm_count, 8), 256, 0, ctx->stream>>>(gy->ptr, idx_f32, idx_i32, gx->ptr, n);
+  AgbProfScope prof(ctx, AGB_PROF_POOL, 4.0 * (double)(agb_numel(gx) + 3 * n));
+  PoolDims d; d.C = (int)gx->shape[1]; d.xh = (int)gx->shape[2]; d.xw = (int)gx->shape[3]; d.yh = (int)gy->shape[2]; d.yw = (int)gy->shape[3];
+  for (int k = 0; k < 4; k++) { d.xs[k] = gx->stride[k]; d.ys[k] = gy->stride[k]; }
+  maxpool_bwd_kernel<<<agb_grid_for(n, 256, ctx->sm_count, 8), 256, 0, ctx->stream>>>(gy->ptr, idx_f32, idx_i32, gx->ptr, n, d, xcl);
   AGB_LAUNCHED(ctx);
   return AGB_OK;
 }
 
 __global__ void __launch_bounds__(256) maxpool_gg_kernel(const float* __restrict__ ggx, const float* __restrict__ idx_f,
-                                                         const int32_t* __restrict__ idx_i, float* __restrict__ ggy, int64_t n) {
+                                                         const int32_t* __restrict__ idx_i, float* __restrict__ ggy, int64_t n, PoolDims d, bool x_cl) {
   int64_t tid = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
   int64_t gstride = (int64_t)gridDim.x * blockDim.x;
   for (int64_t o = tid; o < n; o += gstride) {
     int64_t k = idx_i ? (int64_t)__ldg(idx_i + o) : (int64_t)__ldg(idx_f + o);
-    ggy[o] = __ldg(ggx + k);
+    ggy[o] = __ldg(ggx + pool_phys(k, d, x_cl));
   }
 }
+// ggy and the index buffer share one layout; ggx may be NCHW or channels-last
 extern "C" int agb_maxpool2d_gradgrad(agb_ctx* ctx, const agb_tensor* ggx, const float* idx_f32, const int32_t* idx_i32, agb_tensor* ggy) {
   AGB_CHECK((idx_f32 != nullptr) != (idx_i32 != nullptr), AGB_ERR_INVALID_DIMS, "max_pool2d_grad_grad: exactly one index buffer must be given");
-  AGB_CHECK(agb_is_contig(ggx) && agb_is_contig(ggy), AGB_ERR_UNSUPPORTED, "max_pool2d_grad_grad: tensors must be C-contiguous");
+  bool xcl, ycl; AGB_TRY(pool_layout("max_pool2d_grad_grad", ggx, &xcl)); AGB_TRY(pool_layout("max_pool2d_grad_grad", ggy, &ycl));
   int64_t n = agb_numel(ggy); if (n == 0) return AGB_OK;
-  maxpool_gg_kernel<<<agb_grid_for(n, 256, ctx->sm_count, 8), 256, 0, ctx->stream>>>(ggx->ptr, idx_f32, idx_i32, ggy->ptr, n);
+  PoolDims d; d.C = (int)ggx->shape[1]; d.xh = (int)ggx->shape[2]; d.xw = (int)ggx->shape[3]; d.yh = (int)ggy->shape[2]; d.yw = (int)ggy->shape[3];
+  for (int k = 0; k < 4; k++) { d.xs[k] = ggx->stride[k]; d.ys[k] = ggy->stride[k]; }
+  maxpool_gg_kernel<<<agb_grid_for(n, 256, ctx->sm_count, 8), 256, 0, ctx->stream>>>(ggx->ptr, idx_f32, idx_i32, ggy->ptr, n, d, xcl);
   AGB_LAUNCHED(ctx);
   return AGB_OK;
 }

@@ -1,0 +1,256 @@
+"""-m gpu parity tests, graph level: the re-hosted reference tests (tests/refcases.py) run on the CUDA engine through the
+graph-level C ABI (include/agx200.h) and are compared, forward and after `grad`, with the oracle (oracle/ref_graph.py) on the
+same seeded inputs.  Tolerances: 1e-5 relative (to the largest magnitude of the tensor) in the default 3xTF32 mode and for
+elementwise / reduction work, 1e-2 in TF32 mode; index-valued outputs exact (BASELINE.json north_star)."""
+import json
+import os
+
+import numpy as np
+import pytest
+
+import refcases
+from oracle import ref_graph as OG
+
+pytestmark = pytest.mark.gpu
+KATS = json.load(open(os.path.join(os.path.dirname(__file__), "golden", "reference_kats.json")))
+
+
+@pytest.fixture(scope="module")
+def ag():
+    from rust_autograd_b200 import autograd
+    return autograd
+
+
+def rel(got, ref):
+    got, ref = np.asarray(got, np.float64), np.asarray(ref, np.float64)
+    assert got.shape == ref.shape, (got.shape, ref.shape)
+    if ref.size == 0:
+        return 0.0
+    return float(np.abs(got - ref).max() / max(np.abs(ref).max(), 1e-6))
+
+
+def run_case(mod, case, mode=None):
+    env = mod.VariableEnvironment()
+    if mode is not None:
+        from rust_autograd_b200 import ffi
+        ffi.check(ffi.load_library().agb_set_math_mode(env.agb_ctx(), mode))
+    rng = np.random.default_rng(1234)
+
+    def body(g):
+        z, grads, vids, feeds = case(mod, env, g, rng)
+        return [r.unwrap() for r in g.evaluator().push(z).extend(grads).feeds(feeds).run()]
+    try:
+        return env.run(body)
+    finally:
+        env.close()
+
+
+@pytest.mark.parametrize("case", refcases.CASES, ids=lambda c: c.__name__)
+def test_reference_case_engine_vs_oracle(ag, case):
+    got, ref = run_case(ag, case), run_case(OG, case)
+    assert len(got) == len(ref)
+    for a, b in zip(got, ref):
+        assert rel(a, b) <= 2e-5, case.__name__
+
+
+@pytest.mark.parametrize("name", ["matmul", "conv2d", "conv2d_filter_grad", "tensordot", "cnn_block", "lstm_step"])
+def test_contraction_cases_in_tf32_mode(ag, name):
+    case = [c for c in refcases.CASES if c.__name__ == name][0]
+    got, ref = run_case(ag, case, mode=1), run_case(OG, case)
+    for a, b in zip(got, ref):
+        assert rel(a, b) <= 1e-2
+
+
+# ------------------------------------------------------------------------------------------------ known-answer tests through the graph API
+def test_eval_kats(ag):
+    def body(g):
+        c = lambda a: ag.convert_to_tensor(np.array(a, np.float32), g)
+        for k in KATS["argmax"]:
+            assert np.array_equal(ag.argmax(c(k["x"]), k["axis"], False).eval(g), np.array(k["expected"], np.float32)), k["cite"]
+        for k in KATS["argmin"]:
+            assert np.array_equal(ag.argmin(c(k["x"]), k["axis"], False).eval(g), np.array(k["expected"], np.float32))
+        # tests/test_tensor_ops_eval.rs:71-93: transposes are views, matmul consumes them
+        x, w = c([[0., 1.], [2., 3.]]), c([[0., 1.], [2., 3.]])
+        assert ag.matmul(x, ag.transpose(w, [1, 0])).eval(g).ravel().tolist() == [1., 3., 3., 13.]
+        x = c([[0., 1., 2.], [3., 4., 5.]])
+        assert ag.matmul(ag.transpose(x, [1, 0]), w).eval(g).ravel().tolist() == [6., 9., 8., 13., 10., 17.]
+        assert ag.matmul(ag.ones([2, 5], g), ag.ones([5, 1], g)).eval(g).ravel().tolist() == [5., 5.]       # :96-104
+        for k in KATS["batch_matmul"]:
+            a, b = c(k["a"]), c(k["b"])
+            a = ag.transpose(a, [0, 2, 1]) if k["ta"] else a
+            b = ag.transpose(b, [0, 2, 1]) if k["tb"] else b
+            assert np.array_equal(ag.batch_matmul(a, b).eval(g), np.array(k["expected"], np.float32)), k["cite"]
+        for k in KATS["compare"]:
+            assert getattr(ag, k["op"])(c(k["a"]), c(k["b"])).eval(g).tolist() == k["expected"]
+        for k in KATS["reduce"]:
+            assert np.array_equal(getattr(ag, "reduce_" + k["op"])(c(k["x"]), k["axes"], False).eval(g), np.array(k["expected"], np.float32)), k["cite"]
+        k = KATS["sum_all"]
+        assert float(ag.sum_all(c(k["x"])).eval(g)) == k["expected"] and float(ag.mean_all(c(k["x"])).eval(g)) == k["mean_all"]
+        k = KATS["add_n"]
+        assert np.array_equal(ag.add_n([ag.ones(k["shape"], g) for _ in range(k["n"])]).eval(g), np.array(k["expected"], np.float32))
+        k = KATS["clip"]
+        assert ag.clip(c(k["x"]), k["min"], k["max"]).eval(g).tolist() == k["expected"]
+        k = KATS["sign"]
+        assert ag.sign(c(k["x"])).eval(g).tolist() == k["expected"]
+        k = KATS["tile"]
+        assert np.array_equal(ag.tile(c(k["x"]), k["axis"], k["num"]).eval(g), np.array(k["expected"], np.float32))
+        k = KATS["max_pool"]
+        y = ag.max_pool2d(ag.reshape(c(k["x"]), [1, 1, k["h"], k["w"]]), k["size"], k["pad"], k["stride"])
+        assert y.eval(g).ravel().tolist() == k["output"] and ag.nth_tensor(y, 1).eval(g).ravel().tolist() == k["argmax"]
+        k = KATS["im2col_batch"]
+        x = np.tile(np.arange(18, dtype=np.float32).reshape(1, 2, 3, 3), (2, 1, 1, 1))
+        cols = ag.nth_tensor(ag.conv2d(c(x), ag.ones([1, 2, 2, 2], g), 0, 1), 1).eval(g)      # the virtual `cols` output, materialised on demand
+        assert cols.shape == (2, 2, 2, 2, 2, 2) and cols.ravel().tolist() == [float(v) for v in k["expected"]]
+        k = KATS["deconv"]
+        out = ag.conv2d_transpose(ag.ones([2, 2, 2, 2], g), ag.ones([2, 3, 2, 2], g), 0, 1).eval(g)
+        assert np.array_equal(out, np.tile(np.array(k["expected_per_channel"], np.float32).reshape(1, 1, 3, 3), (2, 3, 1, 1)))
+        # scalar / shape behaviour (tests/test_binary_ops_eval.rs:7-57, tests/test_tensor_ops_eval.rs:10-17)
+        assert (ag.scalar(3., g) + 2.).eval(g).shape == () and float((2. * ag.scalar(3., g) - 1.).eval(g)) == 5.
+        assert ag.slice(ag.zeros([4, 4], g), [0, 0], [-1, 2]).eval(g).shape == (4, 2)
+        assert ag.reduce_sum(ag.zeros([3, 4, 5], g), [0, -1], True).eval(g).shape == (1, 4, 1)
+        assert ag.shape(ag.zeros([2, 3], g)).eval(g).tolist() == [2., 3.] and float(ag.size(ag.zeros([2, 3], g)).eval(g)) == 6.
+        assert ag.setdiff1d(c([4., 1., 5., 2., 3., 6.]), c([1., 3., 5.])).eval(g).tolist() == [2., 4., 6.]     # mod.rs:2034-2040
+    ag.run(body)
+
+
+def test_eval_semantics(ag):
+    """src/evaluation.rs:373-454 + error propagation (:202-211) + multi-output ops (tests/test_core.rs:27-36)"""
+    env = ag.VariableEnvironment()
+    v = env.slot().set(np.array([[0., 1.], [2., 3.]]))
+
+    def body(g):
+        a = g.placeholder("a", [-1, 2])
+        x = a + a
+        r = g.evaluator().push(x).push(g.variable(v)).push(a).feed("a", np.ones((3, 2))).run()
+        assert np.array_equal(r[0].unwrap(), 2 * np.ones((3, 2), np.float32))
+        assert np.array_equal(r[1].unwrap(), np.array([[0., 1.], [2., 3.]], np.float32))
+        assert np.array_equal(r[2].unwrap(), np.ones((3, 2), np.float32))
+        r = g.evaluator().push(x).feed(a, np.full((1, 2), 4.)).run()             # feed by tensor handle (PlaceholderKey::ID)
+        assert r[0].unwrap().tolist() == [[8., 8.]]
+        bad = ag.matmul(x, ag.convert_to_tensor(np.ones((3, 3)), g))
+        r = g.evaluator().push(bad + x).push(x).feed("a", np.ones((3, 2))).run()
+        assert not r[0].is_ok() and r[0].code == 2 and r[1].is_ok()                 # IncompatibleShape reaches the dependent only
+        with pytest.raises(ag.Panic):
+            x.eval(g)                                                               # "Placeholder unfilled" (evaluation.rs:248)
+        with pytest.raises(ag.Panic):
+            g.evaluator().push(x).feed("a", np.ones((3, 3))).run()                  # known-shape validation (tensor.rs:374-386)
+        names = [ag.matmul(x, x).op_name(), x.op_name(), ag.relu(x).op_name()]
+        assert names == ["autograd::tensor_ops::dot_ops::MatMul", "autograd::tensor_ops::binary_ops::AddOp", "autograd::tensor_ops::activation_ops::ReLU"]
+    env.run(body)
+    env.close()
+
+
+def test_mixed_graph_panics(ag):
+    """src/graph.rs:238-248"""
+    env = ag.VariableEnvironment()
+    g1, g2 = ag.Context(env), ag.Context(env)
+    with pytest.raises(ag.Panic):
+        ag.add(ag.zeros([1], g1), ag.zeros([1], g2))
+    env.close()
+
+
+@pytest.mark.parametrize("name", ["Adam", "AdaGrad", "MomentumSGD", "SGD"])
+def test_optimizers_match_oracle(ag, name):
+    """tests/test_optimizers.rs:10-64 builds a 2x2 softmax regression and calls update once (asserting nothing); here three
+    updates are applied on both backends and every variable, including optimizer state, must agree."""
+    def run(mod):
+        env = mod.VariableEnvironment()
+        rng = np.random.default_rng(5)
+        w = env.slot().name("w").set(rng.standard_normal((2, 2)))
+        b = env.slot().name("b").set(np.zeros((1, 2)))
+        ids = env.default_namespace().current_var_ids()
+        opt = mod.optimizers.SGD(0.1) if name == "SGD" else getattr(mod.optimizers, name).default("opt", ids, env)
+
+        def body(g):
+            x = g.placeholder("x", [-1, 2])
+            y = mod.convert_to_tensor(np.array([1., 0., 1.]), g)
+            wt, bt = g.variable(w), g.variable(b)
+            loss = mod.sparse_softmax_cross_entropy(mod.matmul(x, wt) + bt, y)
+            opt.update([wt, bt], mod.grad([loss], [wt, bt]), g, mod.Feeder().push("x", rng.standard_normal((3, 2))))
+        for _ in range(3):
+            env.run(body)
+        n = len(env.default_namespace().current_var_ids()) + len(env.namespace("opt").current_var_ids())
+        out = [env.get_array_by_id(i) for i in range(n)]
+        env.close()
+        return out
+    got, ref = run(ag), run(OG)
+    assert len(got) == len(ref) and len(got) >= 2
+    for a, b in zip(got, ref):
+        assert rel(a, b) <= 1e-5
+
+
+def test_channels_last_network_matches_oracle(ag):
+    """A VGG-style block big enough for the tcgen05 / channels-last path (C >= 32, W >= 32): conv-bias-relu x2, pool, conv,
+    pool, FC, xent; loss, logits, pool indices and every parameter gradient against the oracle, in both tensor-core modes."""
+    from rust_autograd_b200 import ffi, workloads as W
+    layers = [(3, 32), (32, 32), "pool", (32, 64), "pool"]
+    rng0 = np.random.default_rng(3)
+    x = rng0.standard_normal((2, 3, 32, 32)).astype(np.float32)
+    y = rng0.integers(0, 10, (2, 1)).astype(np.float32)
+
+    def run(mod, mode):
+        env = mod.VariableEnvironment()
+        if mode is not None:
+            ffi.check(ffi.load_library().agb_set_math_mode(env.agb_ctx(), mode))
+        W.vgg_init(env, np.random.default_rng(0), size=32, layers=layers)
+
+        def body(g):
+            loss, logits = W.vgg_loss(mod, g, size=32, layers=layers)
+            params, grads = mod.optimizers.grad_helper([loss], g.default_namespace())
+            return [r.unwrap() for r in g.evaluator().push(loss).push(logits).extend(grads).feed("x", x).feed("y", y).run()]
+        out = env.run(body)
+        env.close()
+        return out
+    ref = run(OG, None)
+    for mode, tol in ((0, 2e-5), (1, 1e-2)):
+        got = run(ag, mode)
+        assert len(got) == len(ref)
+        for a, b in zip(got, ref):
+            assert rel(a, b) <= tol, (mode, a.shape)
+
+
+def test_training_reduces_loss_and_checkpoint_roundtrip(ag, tmp_path):
+    """examples/mlp_mnist.rs flow on synthetic data + VariableEnvironment::save/load (src/variable.rs:470-598, test :810-840)."""
+    from rust_autograd_b200 import workloads as W
+    env = ag.VariableEnvironment()
+    rng = np.random.default_rng(0)
+    W.mlp_init(env, rng)
+    adam = ag.optimizers.Adam.default("adam", env.default_namespace().current_var_ids(), env)
+    xb = rng.uniform(size=(200, 784)).astype(np.float32)
+    yb = rng.integers(0, 10, (200, 1)).astype(np.float32)
+
+    def step(g):
+        loss, _ = W.mlp_loss(ag, g)
+        params, grads = ag.optimizers.grad_helper([loss], g.default_namespace())
+        l = loss.eval(g, {"x": xb, "y": yb})
+        adam.update(params, grads, g, ag.Feeder().push("x", xb).push("y", yb))
+        return float(np.asarray(l).ravel()[0])
+    losses = [env.run(step) for _ in range(30)]
+    assert losses[-1] < 0.7 * losses[0]
+    path = str(tmp_path / "ckpt.json")
+    env.save(path)
+    js = json.load(open(path))
+    assert set(js) == {"array_list", "name_to_id"} and js["array_list"][0]["v"] == 1 and "w" in js["name_to_id"]
+    env2 = ag.VariableEnvironment.load(path)
+    n = len(js["array_list"])
+    for i in range(n):
+        assert np.array_equal(env.get_array_by_id(i), env2.get_array_by_id(i))
+    assert float(env2.namespace("adam").get_array_by_name("0t")) == 31.0          # t starts at 1 (optimizers/adam.rs:97)
+    env.close()
+    env2.close()
+
+
+def test_dropout_semantics(ag):
+    """random_ops.rs:218-245: not inverted; eval mode scales by (1 - ratio); grad = gy * mask"""
+    env = ag.VariableEnvironment()
+    v = env.slot().set(np.ones((64, 64)))
+
+    def body(g):
+        x = g.variable(v)
+        d = ag.dropout(x, 0.25, True)
+        y, mask, gx = [r.unwrap() for r in g.evaluator().push(d).push(ag.nth_tensor(d, 1)).extend(ag.grad([d], [x])).run()]
+        assert set(np.unique(mask)) <= {0., 1.} and abs(mask.mean() - 0.75) < 0.05
+        assert np.array_equal(y, mask) and np.array_equal(gx, mask)
+        assert np.allclose(ag.dropout(x, 0.25, False).eval(g), 0.75)
+    env.run(body)
+    env.close()
