@@ -76,6 +76,11 @@ def _check(status):
     raise ffi.OpError(status, msg)
 
 
+def _f32c(value):
+    """float32, C-contiguous, rank preserved (np.ascontiguousarray would turn a 0-d scalar into shape (1,))."""
+    return np.require(np.asarray(value, dtype=np.float32), requirements=["C", "A"])
+
+
 def _ints(v):
     return (C.c_int * len(v))(*[int(x) for x in v])
 
@@ -191,7 +196,7 @@ def _make_feeds(items):
             f.data, f.shape, f.rank, f.on_device = value.ptr, shp, len(value.shape), 1
             keep.append(shp)
         else:
-            a = np.ascontiguousarray(value, dtype=np.float32)
+            a = _f32c(value)
             shp = _i64s(a.shape)
             f.data, f.shape, f.rank, f.on_device = a.ctypes.data, shp, a.ndim, 0
             keep += [a, shp]
@@ -321,7 +326,7 @@ class _Slot:
 
     def set(self, value):
         import uuid
-        a = np.ascontiguousarray(value, dtype=np.float32)
+        a = _f32c(value)
         v = C.c_int()
         nm = self._name if self._name is not None else str(uuid.uuid4())      # DefaultVariableSlot::set (variable.rs:262-270)
         _check(lib().agx_env_set(self.env.h, self.ns.encode(), nm.encode(), a.ctypes.data, _i64s(a.shape), a.ndim, C.byref(v)))
@@ -383,7 +388,7 @@ class VariableEnvironment:
         return out
 
     def set_array_by_id(self, vid, value):
-        a = np.ascontiguousarray(value, dtype=np.float32)
+        a = _f32c(value)
         _check(lib().agx_env_put(self.h, vid, a.ctypes.data, a.size))
 
     def var_ptr(self, vid):
@@ -457,7 +462,7 @@ def as_tensor(v, g):
 
 
 def convert_to_tensor(arr, g):
-    a = np.ascontiguousarray(arr, dtype=np.float32)
+    a = _f32c(arr)
     t = C.c_int()
     _check(lib().agx_convert_to_tensor(g.h, a.ctypes.data, _i64s(a.shape), a.ndim, C.byref(t)))
     return Tensor(g, t.value)

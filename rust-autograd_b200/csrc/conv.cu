@@ -19,6 +19,10 @@ int agb_tc_conv_fprop(agb_ctx* ctx, int mode, const float* x, const float* w, fl
 int agb_tc_conv_wgrad(agb_ctx* ctx, int mode, const float* img, const float* g, float* gw,
                       int B, int C, int H, int W, int O, int kh, int kw, int pad, int stride, int dil);
 bool agb_tc_conv_eligible(int C, int O, int kh, int kw, int stride, int yw);
+// direct kernels for very small input-channel counts (conv_small_c.cu)
+bool agb_small_c_eligible(int C, int O, int kh, int kw);
+int agb_small_c_fprop(agb_ctx* ctx, const float* x, const float* w, agb_tensor* y, int B, int C, int H, int W, int O, int kh, int kw, int yh, int yw, int pad, int stride, int dil);
+int agb_small_c_wgrad(agb_ctx* ctx, const float* x, const agb_tensor* gy, float* gw, int B, int C, int H, int W, int O, int kh, int kw, int yh, int yw, int pad, int stride, int dil);
 
 // ---- activation layouts.  A logical [B,C,H,W] tensor is accepted in two dense memory orders: NCHW (C-contiguous, the
 // reference's layout) and channels-last (N,H,W,C).  Each kernel family has a native order (tcgen05: channels-last, CUDA-core
@@ -154,6 +158,12 @@ extern "C" int agb_conv2d_fprop_f32(agb_ctx* ctx, const agb_tensor* x, const agb
     if (r == AGB_OK) { AGB_TRY(ly.finish()); return lx.finish(); }
     if (r != AGB_ERR_UNSUPPORTED) return r;
   }
+  if (agb_small_c_eligible(g.C, g.O, g.kh, g.kw) && (is_nchw(y) || is_channels_last(y))) {
+    LayoutTmp lx(ctx); AGB_TRY(lx.input(x, false));
+    int r = agb_small_c_fprop(ctx, lx.view.ptr, w->ptr, y, g.B, g.C, g.H, g.W, g.O, g.kh, g.kw, g.yh, g.yw, pad, stride, dilation);
+    if (r == AGB_OK) return lx.finish();
+    if (r != AGB_ERR_UNSUPPORTED) return r;
+  }
   LayoutTmp lx(ctx), ly(ctx);
   AGB_TRY(lx.input(x, false)); AGB_TRY(ly.output(y, false));
   int64_t K = (int64_t)g.C * g.kh * g.kw;
@@ -207,6 +217,12 @@ extern "C" int agb_conv2d_wgrad_f32(agb_ctx* ctx, const agb_tensor* img, const a
     if (r == AGB_OK) { AGB_TRY(li.finish()); return lg.finish(); }
     if (r != AGB_ERR_UNSUPPORTED) return r;
   }
+  if (agb_small_c_eligible(g.C, g.O, g.kh, g.kw) && (is_nchw(gr) || is_channels_last(gr))) {
+    LayoutTmp li(ctx); AGB_TRY(li.input(img, false));
+    int r = agb_small_c_wgrad(ctx, li.view.ptr, gr, gw->ptr, g.B, g.C, g.H, g.W, g.O, g.kh, g.kw, g.yh, g.yw, pad, stride, dilation);
+    if (r == AGB_OK) return li.finish();
+    if (r != AGB_ERR_UNSUPPORTED) return r;
+  }
   LayoutTmp li(ctx), lg(ctx);
   AGB_TRY(li.input(img, false)); AGB_TRY(lg.input(gr, false));
   int64_t N = (int64_t)g.C * g.kh * g.kw; int64_t P = (int64_t)g.yh * g.yw;
@@ -220,7 +236,8 @@ extern "C" int agb_conv2d_wgrad_f32(agb_ctx* ctx, const agb_tensor* img, const a
 }
 
 extern "C" int agb_conv_prefers_channels_last(int in_channels, int out_channels, int kh, int kw, int stride, int out_w) {
-  return agb_tc_conv_eligible(in_channels, out_channels, kh, kw, stride, out_w) ? 1 : 0;
+  if (agb_tc_conv_eligible(in_channels, out_channels, kh, kw, stride, out_w)) return 1;
+  return (agb_small_c_eligible(in_channels, out_channels, kh, kw) && out_channels >= 32 && out_channels % 4 == 0 && out_w >= 16) ? 1 : 0;
 }
 
 // ---- im2col materialisation (only for user-visible evaluation of Conv2D's 2nd output) ----

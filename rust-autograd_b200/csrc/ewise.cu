@@ -174,6 +174,24 @@ __global__ void __launch_bounds__(256) binary_strided_kernel(const float* __rest
   }
 }
 
+// ---- row / channel broadcast fast paths (bias add and friends): y[r, c] = f(a[r, c], b[c]) on contiguous a, y.
+//      CSTRIDE == 1: b varies with the innermost index (channels-last bias, [rows, C] + [C]);
+//      CSTRIDE  > 1: b varies with the middle index of [outer, C, inner] (NCHW bias [1,C,1,1]); inner % 4 == 0.
+template <int OP, bool SWAP>
+__global__ void __launch_bounds__(256) binary_bias_kernel(const float* __restrict__ a, const float* __restrict__ b, float* __restrict__ y,
+                                                          int64_t n4, int C, int inner4, float p0, float p1) {
+  int64_t tid = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  for (int64_t i = tid; i < n4; i += stride) {
+    float4 va = ldg_stream4(a + 4 * i), vb, r;
+    if (inner4 == 0) { int c = (int)((4 * i) % C); vb = __ldg((const float4*)(b + c)); }
+    else { float s = __ldg(b + (int)((i / inner4) % C)); vb = make_float4(s, s, s, s); }
+    if (!SWAP) { r.x = binary_apply(OP, va.x, vb.x, p0, p1); r.y = binary_apply(OP, va.y, vb.y, p0, p1); r.z = binary_apply(OP, va.z, vb.z, p0, p1); r.w = binary_apply(OP, va.w, vb.w, p0, p1); }
+    else { r.x = binary_apply(OP, vb.x, va.x, p0, p1); r.y = binary_apply(OP, vb.y, va.y, p0, p1); r.z = binary_apply(OP, vb.z, va.z, p0, p1); r.w = binary_apply(OP, vb.w, va.w, p0, p1); }
+    stg_stream4(y + 4 * i, r);
+  }
+}
+
 // collapse adjacent dims whenever all three stride sets allow it; drop size-1 dims
 static void collapse(int rank, const int64_t* shape, const int64_t* sa, const int64_t* sb, const int64_t* sy, StridedParams& P) {
   int64_t sh[AGB_MAX_RANK], a[AGB_MAX_RANK], b[AGB_MAX_RANK], y[AGB_MAX_RANK]; int r = 0;
@@ -197,6 +215,27 @@ static int launch_strided(agb_ctx* ctx, const float* a, const float* b, float* y
   if (total == 0) return AGB_OK;
   const int last = P.rank - 1;
   auto al16 = [](const void* p) { return ((uintptr_t)p & 15) == 0; };
+  if (OP >= 0 && total < (1ll << 40) && al16(a) && al16(b) && al16(y)) {
+    // bias patterns: one operand full and contiguous, the other a [C] vector broadcast along rows (rank 2) or along
+    // [outer, C, inner] (rank 3); output contiguous
+    for (int swap = 0; swap < 2; swap++) {
+      const int64_t* sf = swap ? P.sb : P.sa; const int64_t* sv = swap ? P.sa : P.sb;
+      const float* full = swap ? b : a; const float* vecp = swap ? a : b;
+      if (P.rank == 2 && sf[0] == P.shape[1] && sf[1] == 1 && P.sy[0] == P.shape[1] && P.sy[1] == 1 && sv[0] == 0 && sv[1] == 1 && P.shape[1] % 4 == 0 && P.shape[1] < (1ll << 30)) {
+        int64_t n4 = total / 4; int grid = agb_grid_for(n4, 256, ctx->sm_count, 8);
+        if (swap) binary_bias_kernel<OP, true><<<grid, 256, 0, ctx->stream>>>(full, vecp, y, n4, (int)P.shape[1], 0, p0, p1);
+        else binary_bias_kernel<OP, false><<<grid, 256, 0, ctx->stream>>>(full, vecp, y, n4, (int)P.shape[1], 0, p0, p1);
+        AGB_LAUNCHED(ctx); return AGB_OK;
+      }
+      if (P.rank == 3 && sf[2] == 1 && sf[1] == P.shape[2] && sf[0] == P.shape[1] * P.shape[2] && P.sy[2] == 1 && P.sy[1] == P.shape[2] && P.sy[0] == P.shape[1] * P.shape[2] &&
+          sv[0] == 0 && sv[1] == 1 && sv[2] == 0 && P.shape[2] % 4 == 0 && P.shape[1] < (1ll << 30) && P.shape[2] < (1ll << 32)) {
+        int64_t n4 = total / 4; int grid = agb_grid_for(n4, 256, ctx->sm_count, 8);
+        if (swap) binary_bias_kernel<OP, true><<<grid, 256, 0, ctx->stream>>>(full, vecp, y, n4, (int)P.shape[1], (int)(P.shape[2] / 4), p0, p1);
+        else binary_bias_kernel<OP, false><<<grid, 256, 0, ctx->stream>>>(full, vecp, y, n4, (int)P.shape[1], (int)(P.shape[2] / 4), p0, p1);
+        AGB_LAUNCHED(ctx); return AGB_OK;
+      }
+    }
+  }
   bool vec = (P.shape[last] % 4 == 0) && (P.sa[last] == 1 || P.sa[last] == 0) && (P.sb[last] == 1 || P.sb[last] == 0) &&
              P.sy[last] == 1 && al16(y) && (P.sa[last] == 0 || al16(a)) && (P.sb[last] == 0 || al16(b));
   for (int i = 0; i < last && vec; i++) {

@@ -14,22 +14,44 @@ int agb_tc_gemm(agb_ctx* ctx, int mode, const float* A, const float* B, float* C
                 int64_t M, int64_t N, int64_t K, int64_t batch,
                 int64_t rsa, int64_t csa, int64_t bsa, int64_t rsb, int64_t csb, int64_t bsb, int64_t bsc, float beta);
 
-struct StridedA { const float* p; int64_t rs, cs, bs; static const bool K_CONTIG = true;
-  __device__ __forceinline__ float load(int z, int64_t m, int64_t k) const { return __ldg(p + z * bs + m * rs + k * cs); } };
-struct StridedA_M { const float* p; int64_t rs, cs, bs; static const bool K_CONTIG = false;
-  __device__ __forceinline__ float load(int z, int64_t m, int64_t k) const { return __ldg(p + z * bs + m * rs + k * cs); } };
-struct StridedB { const float* p; int64_t rs, cs, bs; static const bool K_CONTIG = false;   // n contiguous
-  __device__ __forceinline__ float load(int z, int64_t k, int64_t n) const { return __ldg(p + z * bs + k * rs + n * cs); } };
-struct StridedB_K { const float* p; int64_t rs, cs, bs; static const bool K_CONTIG = true;
-  __device__ __forceinline__ float load(int z, int64_t k, int64_t n) const { return __ldg(p + z * bs + k * rs + n * cs); } };
-struct StoreC { float* p; int64_t ld, bs; int accumulate;
+// loaders: element (z, m, k) of op(A) / (z, k, n) of op(B).  Split-K (kchunk > 0): z indexes a K slab instead of a batch entry.
+#define LOADER_FIELDS const float* p; int64_t rs, cs, bs; int64_t kchunk = 0, ktot = 0;
+struct StridedA { LOADER_FIELDS static const bool K_CONTIG = true;
+  __device__ __forceinline__ float load(int z, int64_t m, int64_t k) const { if (kchunk && z * kchunk + k >= ktot) return 0.0f; return __ldg(p + z * bs + m * rs + k * cs); } };
+struct StridedA_M { LOADER_FIELDS static const bool K_CONTIG = false;
+  __device__ __forceinline__ float load(int z, int64_t m, int64_t k) const { if (kchunk && z * kchunk + k >= ktot) return 0.0f; return __ldg(p + z * bs + m * rs + k * cs); } };
+struct StridedB { LOADER_FIELDS static const bool K_CONTIG = false;   // n contiguous
+  __device__ __forceinline__ float load(int z, int64_t k, int64_t n) const { if (kchunk && z * kchunk + k >= ktot) return 0.0f; return __ldg(p + z * bs + k * rs + n * cs); } };
+struct StridedB_K { LOADER_FIELDS static const bool K_CONTIG = true;
+  __device__ __forceinline__ float load(int z, int64_t k, int64_t n) const { if (kchunk && z * kchunk + k >= ktot) return 0.0f; return __ldg(p + z * bs + k * rs + n * cs); } };
+struct StoreC { float* p; int64_t ld, bs; int accumulate; int atomic = 0;
   __device__ __forceinline__ void store(int z, int64_t m, int64_t n, float v) const {
+    if (atomic) { atomicAdd(p + m * ld + n, v); return; }
     float* q = p + z * bs + m * ld + n; *q = accumulate ? *q + v : v; } };
 
 static int simt_gemm(agb_ctx* ctx, const float* A, const float* B, float* C, int64_t M, int64_t N, int64_t K, int64_t batch,
                      int64_t rsa, int64_t csa, int64_t bsa, int64_t rsb, int64_t csb, int64_t bsb, int64_t bsc, float beta) {
   StoreC cs{C, N, bsc, beta != 0.0f};
   bool a_kc = (csa == 1) || (rsa != 1), b_kc = (rsb == 1) && (csb != 1);
+  // skinny outputs with a long reduction (e.g. the classifier of a CNN: [256 x 65536] . [65536 x 10]): split K across the
+  // SMs, fp32 atomics into the (zeroed) result
+  int64_t tile = (M >= 96 && N >= 96) ? 128 : 64;
+  int64_t tiles = ((M + tile - 1) / tile) * ((N + tile - 1) / tile);
+  if (batch == 1 && K >= 2048 && tiles * 2 <= ctx->sm_count) {
+    int64_t splits = (2 * (int64_t)ctx->sm_count + tiles - 1) / tiles;
+    int64_t kchunk = (K + splits - 1) / splits; kchunk = (kchunk + 15) / 16 * 16; if (kchunk < 256) kchunk = 256;
+    splits = (K + kchunk - 1) / kchunk;
+    if (splits > 1 && splits <= 65535) {
+      if (beta == 0.0f) AGB_TRY(agb_memset0(ctx, C, (size_t)M * N * sizeof(float)));
+      StoreC ca{C, N, 0, 1, 1};
+      int r;
+      if (a_kc && !b_kc) r = simt_gemm_launch(ctx, StridedA{A, rsa, csa, kchunk * csa, kchunk, K}, StridedB{B, rsb, csb, kchunk * rsb, kchunk, K}, ca, M, N, kchunk, splits);
+      else if (a_kc && b_kc) r = simt_gemm_launch(ctx, StridedA{A, rsa, csa, kchunk * csa, kchunk, K}, StridedB_K{B, rsb, csb, kchunk * rsb, kchunk, K}, ca, M, N, kchunk, splits);
+      else if (!a_kc && !b_kc) r = simt_gemm_launch(ctx, StridedA_M{A, rsa, csa, kchunk * csa, kchunk, K}, StridedB{B, rsb, csb, kchunk * rsb, kchunk, K}, ca, M, N, kchunk, splits);
+      else r = simt_gemm_launch(ctx, StridedA_M{A, rsa, csa, kchunk * csa, kchunk, K}, StridedB_K{B, rsb, csb, kchunk * rsb, kchunk, K}, ca, M, N, kchunk, splits);
+      return r;
+    }
+  }
   for (int64_t z0 = 0; z0 < batch; z0 += 65535) {
     int64_t zc = batch - z0 < 65535 ? batch - z0 : 65535;
     const float* a = A + z0 * bsa; const float* b = B + z0 * bsb; StoreC c = cs; c.p = C + z0 * bsc;

@@ -47,6 +47,37 @@ __global__ void __launch_bounds__(256) maxpool_fwd_kernel(const float* __restric
   }
 }
 
+// channels-last, C % 4 == 0: one thread owns 4 consecutive channels of one output pixel (128-bit loads / stores, 32-bit indexing)
+__global__ void __launch_bounds__(256) maxpool_fwd_cl4_kernel(const float* __restrict__ x, float* __restrict__ y, float* __restrict__ idx_f, int32_t* __restrict__ idx_i,
+                                                              uint32_t n4, int C, int xh, int xw, int yh, int yw, int size, int stride) {
+  const uint32_t c4n = (uint32_t)C >> 2;
+  for (uint32_t o = blockIdx.x * blockDim.x + threadIdx.x; o < n4; o += gridDim.x * blockDim.x) {
+    uint32_t c4 = o % c4n, t = o / c4n; uint32_t j = t % (uint32_t)yw; t /= (uint32_t)yw; uint32_t i = t % (uint32_t)yh, b = t / (uint32_t)yh;
+    int h0 = (int)i * stride, w0 = (int)j * stride;
+    int h1 = h0 + size > xh ? xh : h0 + size, w1 = w0 + size > xw ? xw : w0 + size;
+    const int c = (int)c4 * 4;
+    float mx[4] = {-FLT_MAX, -FLT_MAX, -FLT_MAX, -FLT_MAX}; int mi[4] = {0, 0, 0, 0};
+    for (int h = h0; h < h1; h++)
+      for (int w = w0; w < w1; w++) {
+        float4 v = ldg_stream4(x + (((size_t)b * xh + h) * xw + w) * C + c);
+        const int hw = h * xw + w;
+        if (v.x > mx[0]) { mx[0] = v.x; mi[0] = hw; }
+        if (v.y > mx[1]) { mx[1] = v.y; mi[1] = hw; }
+        if (v.z > mx[2]) { mx[2] = v.z; mi[2] = hw; }
+        if (v.w > mx[3]) { mx[3] = v.w; mi[3] = hw; }
+      }
+    // logical NCHW flat offset = ((b*C + c)*xh + h)*xw + w ; a window that never fired keeps index 0 (max_pool2d.rs:51-52)
+    int64_t lb = ((int64_t)b * C + c) * xh * xw; const int64_t plane = (int64_t)xh * xw;
+    int64_t li[4];
+#pragma unroll
+    for (int q = 0; q < 4; q++) li[q] = mx[q] == -FLT_MAX ? 0 : lb + q * plane + mi[q];
+    const size_t off = (size_t)o * 4;
+    *(float4*)(y + off) = make_float4(mx[0], mx[1], mx[2], mx[3]);
+    if (idx_f) *(float4*)(idx_f + off) = make_float4((float)li[0], (float)li[1], (float)li[2], (float)li[3]);
+    if (idx_i) *(int4*)(idx_i + off) = make_int4((int)li[0], (int)li[1], (int)li[2], (int)li[3]);
+  }
+}
+
 static bool pool_is_cl(const agb_tensor* t) {
   const int64_t C = t->shape[1], H = t->shape[2], W = t->shape[3];
   return !agb_is_contig(t) && (C == 1 || t->stride[1] == 1) && (W == 1 || t->stride[3] == C) && (H == 1 || t->stride[2] == W * C) && (t->shape[0] == 1 || t->stride[0] == H * W * C);
@@ -75,6 +106,11 @@ extern "C" int agb_maxpool2d_fwd(agb_ctx* ctx, const agb_tensor* x, agb_tensor* 
   PoolDims d; d.C = (int)x->shape[1]; d.xh = xh; d.xw = xw; d.yh = yh; d.yw = yw;
   for (int k = 0; k < 4; k++) { d.xs[k] = x->stride[k]; d.ys[k] = y->stride[k]; }
   int grid = agb_grid_for(n, 256, ctx->sm_count, 8);
+  if (ycl && xcl && d.C % 4 == 0 && n / 4 < (1ll << 31) && agb_numel(x) < (1ll << 32) && ((((uintptr_t)x->ptr | (uintptr_t)y->ptr | (uintptr_t)idx_f32 | (uintptr_t)idx_i32) & 15) == 0)) {
+    maxpool_fwd_cl4_kernel<<<agb_grid_for(n / 4, 256, ctx->sm_count, 8), 256, 0, ctx->stream>>>(x->ptr, y->ptr, idx_f32, idx_i32, (uint32_t)(n / 4), d.C, xh, xw, yh, yw, size, stride);
+    AGB_LAUNCHED(ctx);
+    return AGB_OK;
+  }
   if (ycl) maxpool_fwd_kernel<true><<<grid, 256, 0, ctx->stream>>>(x->ptr, y->ptr, idx_f32, idx_i32, n, d, size, stride);
   else maxpool_fwd_kernel<false><<<grid, 256, 0, ctx->stream>>>(x->ptr, y->ptr, idx_f32, idx_i32, n, d, size, stride);
   AGB_LAUNCHED(ctx);

@@ -105,6 +105,42 @@ __global__ void __launch_bounds__(256) reduce_cols_kernel(const float* __restric
   out[(o * splits + s) * inner + col] = (splits == 1) ? v * scale : v;
 }
 
+// ---- columns with a SHORT inner extent (inner <= 1024, multiple of 4; e.g. bias gradients of channels-last activations,
+//      [B*H*W, C] -> [C]): a thread-per-column mapping would leave most of the block idle, so 256 threads tile
+//      (1024 / inner) rows x inner columns with 128-bit loads, then fold the row groups through shared memory.
+template <int OP>
+__global__ void __launch_bounds__(256) reduce_cols_small_kernel(const float* __restrict__ x, float* __restrict__ out,
+                                                                int64_t r, int inner, int64_t rchunk, int splits, float scale) {
+  __shared__ float4 sm[256];
+  const int vec = inner >> 2;                 // float4 per row
+  const int rows_per_it = 256 / vec;          // vec divides 256 (inner in {4..1024} power-of-two multiples) or leaves idle threads
+  const int tr = threadIdx.x / vec, tc = threadIdx.x - tr * vec;
+  const int64_t o = blockIdx.z, s = blockIdx.y;
+  int64_t beg = s * rchunk, end = beg + rchunk; if (end > r) end = r;
+  const float* p = x + (o * r) * inner;
+  float4 a = make_float4(r_init<OP>(), r_init<OP>(), r_init<OP>(), r_init<OP>()), b = a;
+  if (tr < rows_per_it) {
+    int64_t k = beg + tr;
+    for (; k + rows_per_it < end; k += 2 * rows_per_it) {
+      float4 v0 = ldg_stream4(p + k * inner + 4 * tc), v1 = ldg_stream4(p + (k + rows_per_it) * inner + 4 * tc);
+      a.x = r_comb<OP>(a.x, v0.x); a.y = r_comb<OP>(a.y, v0.y); a.z = r_comb<OP>(a.z, v0.z); a.w = r_comb<OP>(a.w, v0.w);
+      b.x = r_comb<OP>(b.x, v1.x); b.y = r_comb<OP>(b.y, v1.y); b.z = r_comb<OP>(b.z, v1.z); b.w = r_comb<OP>(b.w, v1.w);
+    }
+    for (; k < end; k += rows_per_it) {
+      float4 v0 = ldg_stream4(p + k * inner + 4 * tc);
+      a.x = r_comb<OP>(a.x, v0.x); a.y = r_comb<OP>(a.y, v0.y); a.z = r_comb<OP>(a.z, v0.z); a.w = r_comb<OP>(a.w, v0.w);
+    }
+  }
+  a.x = r_comb<OP>(a.x, b.x); a.y = r_comb<OP>(a.y, b.y); a.z = r_comb<OP>(a.z, b.z); a.w = r_comb<OP>(a.w, b.w);
+  sm[threadIdx.x] = a;
+  __syncthreads();
+  if (tr == 0 && tc < vec) {
+    for (int g = 1; g < rows_per_it; g++) { float4 v = sm[g * vec + tc]; a.x = r_comb<OP>(a.x, v.x); a.y = r_comb<OP>(a.y, v.y); a.z = r_comb<OP>(a.z, v.z); a.w = r_comb<OP>(a.w, v.w); }
+    if (splits == 1) { a.x *= scale; a.y *= scale; a.z *= scale; a.w *= scale; }
+    *(float4*)(out + (o * splits + s) * inner + 4 * tc) = a;
+  }
+}
+
 template <int OP>
 static int reduce_impl(agb_ctx* ctx, const float* x, float* y, int64_t outer, int64_t r, int64_t inner, float scale) {
   if (outer * inner == 0) return AGB_OK;
@@ -144,6 +180,21 @@ static int reduce_impl(agb_ctx* ctx, const float* x, float* y, int64_t outer, in
   int64_t maxs = (r + 63) / 64;
   int splits = (int)(want < maxs ? want : maxs); if (splits < 1) splits = 1; if (splits > 1024) splits = 1024;
   int64_t rchunk = (r + splits - 1) / splits; splits = (int)((r + rchunk - 1) / rchunk);
+  if (inner <= 1024 && inner % 4 == 0 && r >= 64 && (((uintptr_t)x | (uintptr_t)y) & 15) == 0 && outer <= 65535) {
+    int64_t want = (4ll * sms + outer - 1) / outer; int64_t maxs = (r + 255) / 256;
+    int sp = (int)(want < maxs ? want : maxs); if (sp < 1) sp = 1; if (sp > 65535) sp = 65535;
+    int64_t rc = (r + sp - 1) / sp; sp = (int)((r + rc - 1) / rc);
+    if (sp == 1) {
+      reduce_cols_small_kernel<OP><<<dim3(1, 1, (unsigned)outer), 256, 0, ctx->stream>>>(x, y, r, (int)inner, rc, 1, scale);
+      AGB_LAUNCHED(ctx); return AGB_OK;
+    }
+    float* part; AGB_TRY(agb_scratch(ctx, sizeof(float) * outer * sp * inner, (void**)&part));
+    reduce_cols_small_kernel<OP><<<dim3(1, sp, (unsigned)outer), 256, 0, ctx->stream>>>(x, part, r, (int)inner, rc, sp, 1.0f);
+    AGB_LAUNCHED(ctx);
+    reduce_cols_kernel<OP><<<dim3((unsigned)((inner + 255) / 256), 1, (unsigned)outer), 256, 0, ctx->stream>>>(part, y, sp, inner, sp, 1, scale);
+    AGB_LAUNCHED(ctx);
+    return AGB_OK;
+  }
   if (splits == 1) {
     reduce_cols_kernel<OP><<<dim3((unsigned)cblocks, 1, (unsigned)outer), 256, 0, ctx->stream>>>(x, y, r, inner, rchunk, 1, scale);
     AGB_LAUNCHED(ctx); return AGB_OK;
