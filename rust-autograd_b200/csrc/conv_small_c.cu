@@ -11,41 +11,67 @@
 #define SC_MAXK 36
 struct SmallGeom { int B, C, H, W, O, kh, kw, yh, yw, pad, stride, dil; int64_t ys[4]; /* y strides (b,o,h,w) */ };
 
-template <int K>
-__global__ void __launch_bounds__(128) small_c_fprop_kernel(const float* __restrict__ x, const float* __restrict__ w, float* __restrict__ y, SmallGeom g) {
-  extern __shared__ float ws[];                       // [O][K]
-  for (int i = threadIdx.x; i < g.O * K; i += blockDim.x) ws[i] = __ldg(w + i);
-  __syncthreads();
-  const int64_t P = (int64_t)g.yh * g.yw, total = (int64_t)g.B * P;
-  const int64_t pix = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
-  if (pix >= total) return;
-  const int b = (int)(pix / P); const int r = (int)(pix - (int64_t)b * P); const int oy = r / g.yw, ox = r - oy * g.yw;
-  float v[K];
+// ---- fprop: per CTA a [64 pixels] x [K] patch matrix times the [K] x [O] filter, both staged in shared memory, each thread
+//      a 4 (pixel) x 4 (o) register tile: two 128-bit shared loads per 16 FMAs.
+#define SCF_PIX 64
+__global__ void __launch_bounds__(256) small_c_fprop_kernel(const float* __restrict__ x, const float* __restrict__ w, float* __restrict__ y, SmallGeom g, int K) {
+  extern __shared__ __align__(16) float sm[];
+  float* ws = sm;                                     // [K][O]   (transposed filter)
+  float* vs = sm + K * g.O;                           // [K][SCF_PIX]
+  __shared__ int64_t s_xoff[SCF_PIX], s_yoff[SCF_PIX];
+  __shared__ int s_oy[SCF_PIX], s_ox[SCF_PIX];
+  __shared__ int s_tc[SC_MAXK], s_ti[SC_MAXK], s_tj[SC_MAXK];
   const int kk = g.kh * g.kw;
-#pragma unroll
-  for (int k = 0; k < K; k++) {
-    const int c = k / kk, t = k - c * kk, i = t / g.kw, j = t - i * g.kw;
-    const int iy = oy * g.stride - g.pad + i * g.dil, ix = ox * g.stride - g.pad + j * g.dil;
-    v[k] = ((unsigned)iy < (unsigned)g.H && (unsigned)ix < (unsigned)g.W) ? __ldg(x + (((int64_t)b * g.C + c) * g.H + iy) * g.W + ix) : 0.0f;
+  for (int i = threadIdx.x; i < g.O * K; i += blockDim.x) { int o = i / K, k = i - o * K; ws[k * g.O + o] = __ldg(w + i); }
+  if (threadIdx.x < K) { int k = threadIdx.x; int c = k / kk, t = k - c * kk; s_tc[k] = c; s_ti[k] = (t / g.kw) * g.dil - g.pad; s_tj[k] = (t % g.kw) * g.dil - g.pad; }
+  const int64_t P = (int64_t)g.yh * g.yw, total = (int64_t)g.B * P;
+  const int64_t base = (int64_t)blockIdx.x * SCF_PIX;
+  if (threadIdx.x < SCF_PIX) {
+    int64_t pix = base + threadIdx.x; if (pix >= total) pix = total - 1;
+    const int b = (int)(pix / P); const int r = (int)(pix - (int64_t)b * P); const int oy = r / g.yw, ox = r - oy * g.yw;
+    s_xoff[threadIdx.x] = (int64_t)b * g.C * g.H * g.W; s_yoff[threadIdx.x] = b * g.ys[0] + oy * g.ys[2] + ox * g.ys[3];
+    s_oy[threadIdx.x] = oy * g.stride; s_ox[threadIdx.x] = ox * g.stride;
   }
-  float* yp = y + b * g.ys[0] + oy * g.ys[2] + ox * g.ys[3];
+  __syncthreads();
+  for (int i = threadIdx.x; i < K * SCF_PIX; i += blockDim.x) {
+    const int k = i / SCF_PIX, pi = i - k * SCF_PIX;
+    const int iy = s_oy[pi] + s_ti[k], ix = s_ox[pi] + s_tj[k];
+    vs[i] = ((unsigned)iy < (unsigned)g.H && (unsigned)ix < (unsigned)g.W) ? __ldg(x + s_xoff[pi] + ((int64_t)s_tc[k] * g.H + iy) * g.W + ix) : 0.0f;
+  }
+  __syncthreads();
+  const int to = threadIdx.x & 15, tp = threadIdx.x >> 4;          // 16 o-quads x 16 pixel-quads
   const bool cl = g.ys[1] == 1;
-  for (int o0 = 0; o0 < g.O; o0 += 4) {
-    float acc[4] = {0.f, 0.f, 0.f, 0.f};
+  for (int o0 = 0; o0 < g.O; o0 += 64) {
+    const int o = o0 + 4 * to;
+    float acc[4][4];
 #pragma unroll
-    for (int q = 0; q < 4; q++) {
-      if (o0 + q < g.O) {
-        const float* wr = ws + (o0 + q) * K;
+    for (int a = 0; a < 4; a++)
 #pragma unroll
-        for (int k = 0; k < K; k++) acc[q] = fmaf(wr[k], v[k], acc[q]);
+      for (int q = 0; q < 4; q++) acc[a][q] = 0.f;
+    if (o < g.O) {
+      for (int k = 0; k < K; k++) {
+        const float4 pv = *(const float4*)(vs + k * SCF_PIX + 4 * tp);
+        const float4 wv = *(const float4*)(ws + k * g.O + o);
+        const float p_[4] = {pv.x, pv.y, pv.z, pv.w}, w_[4] = {wv.x, wv.y, wv.z, wv.w};
+#pragma unroll
+        for (int a = 0; a < 4; a++)
+#pragma unroll
+          for (int q = 0; q < 4; q++) acc[a][q] = fmaf(p_[a], w_[q], acc[a][q]);
+      }
+#pragma unroll
+      for (int a = 0; a < 4; a++) {
+        const int pi = 4 * tp + a;
+        if (base + pi < total) {
+          float* yp = y + s_yoff[pi];
+          if (cl) *(float4*)(yp + o) = make_float4(acc[a][0], acc[a][1], acc[a][2], acc[a][3]);
+          else { for (int q = 0; q < 4; q++) yp[(o + q) * g.ys[1]] = acc[a][q]; }
+        }
       }
     }
-    if (cl && o0 + 4 <= g.O) *(float4*)(yp + o0) = make_float4(acc[0], acc[1], acc[2], acc[3]);
-    else { for (int q = 0; q < 4; q++) if (o0 + q < g.O) yp[(o0 + q) * g.ys[1]] = acc[q]; }
   }
 }
 
-// gy strides gs (b,o,h,w) in either layout; K <= SC_MAXK, O <= 256 (multiple of 4).
+// gy strides gs (b,o,h,w) in either layout; K <= 32, O <= 256 (multiple of 4).
 // Register tiling: thread (to, tk) owns a 4 (o) x 2 (k) block of gw for every 64-channel slab of O, so one slab pixel costs
 // one 128-bit + one 64-bit shared-memory read per 8 FMAs (a thread-per-output mapping would be shared-memory bound).
 #define SCW_PIX 64
@@ -54,9 +80,13 @@ __global__ void __launch_bounds__(256) small_c_wgrad_kernel(const float* __restr
   extern __shared__ __align__(16) float sm[];
   float* gs = sm;                                     // [SCW_PIX][O]
   float* ps = sm + SCW_PIX * g.O;                     // [SCW_PIX][K2]
+  __shared__ int64_t s_xoff[SCW_PIX], s_goff[SCW_PIX];
+  __shared__ int s_oy[SCW_PIX], s_ox[SCW_PIX];
+  __shared__ int s_tc[SC_MAXK], s_ti[SC_MAXK], s_tj[SC_MAXK];
   const int64_t P = (int64_t)g.yh * g.yw, total = (int64_t)g.B * P;
   const int64_t p0 = blockIdx.x * chunk, p1 = min(p0 + chunk, total);
   const int kk = g.kh * g.kw;
+  if (threadIdx.x < K2) { int k = threadIdx.x; int c = k / kk, t = k - c * kk; s_tc[k] = c; s_ti[k] = (t / g.kw) * g.dil - g.pad; s_tj[k] = (t % g.kw) * g.dil - g.pad; }
   const int to = threadIdx.x & 15, tk = threadIdx.x >> 4;          // 16 o-quads x 16 k-pairs per 64-channel slab
   const int nslab = (g.O + 63) / 64;
   const bool active = 2 * tk < K2;
@@ -68,21 +98,24 @@ __global__ void __launch_bounds__(256) small_c_wgrad_kernel(const float* __restr
   const bool gy_cl = g.ys[1] == 1;
   for (int64_t base = p0; base < p1; base += SCW_PIX) {
     const int np = (int)min((int64_t)SCW_PIX, p1 - base);
+    if (threadIdx.x < np) {
+      const int64_t pix = base + threadIdx.x;
+      const int b = (int)(pix / P); const int r = (int)(pix - (int64_t)b * P); const int oy = r / g.yw, ox = r - oy * g.yw;
+      s_xoff[threadIdx.x] = (int64_t)b * g.C * g.H * g.W; s_goff[threadIdx.x] = b * g.ys[0] + oy * g.ys[2] + ox * g.ys[3];
+      s_oy[threadIdx.x] = oy * g.stride; s_ox[threadIdx.x] = ox * g.stride;
+    }
+    __syncthreads();
     for (int i = threadIdx.x; i < np * g.O; i += blockDim.x) {
       int pi, o;
       if (gy_cl) { pi = i / g.O; o = i - pi * g.O; } else { o = i / np; pi = i - o * np; }      // coalesced in either layout
-      const int64_t pix = base + pi;
-      const int b = (int)(pix / P); const int r = (int)(pix - (int64_t)b * P); const int oy = r / g.yw, ox = r - oy * g.yw;
-      gs[pi * g.O + o] = __ldg(gy + b * g.ys[0] + o * g.ys[1] + oy * g.ys[2] + ox * g.ys[3]);
+      gs[pi * g.O + o] = __ldg(gy + s_goff[pi] + o * g.ys[1]);
     }
     for (int i = threadIdx.x; i < np * K2; i += blockDim.x) {
-      const int k = i / np, pi = i - k * np; const int64_t pix = base + pi;        // consecutive threads -> consecutive pixels (coalesced x reads)
+      const int k = i / np, pi = i - k * np;           // consecutive threads -> consecutive pixels (coalesced x reads)
       float v = 0.0f;
       if (k < K) {
-        const int b = (int)(pix / P); const int r = (int)(pix - (int64_t)b * P); const int oy = r / g.yw, ox = r - oy * g.yw;
-        const int c = k / kk, t = k - c * kk, ii = t / g.kw, jj = t - ii * g.kw;
-        const int iy = oy * g.stride - g.pad + ii * g.dil, ix = ox * g.stride - g.pad + jj * g.dil;
-        if ((unsigned)iy < (unsigned)g.H && (unsigned)ix < (unsigned)g.W) v = __ldg(x + (((int64_t)b * g.C + c) * g.H + iy) * g.W + ix);
+        const int iy = s_oy[pi] + s_ti[k], ix = s_ox[pi] + s_tj[k];
+        if ((unsigned)iy < (unsigned)g.H && (unsigned)ix < (unsigned)g.W) v = __ldg(x + s_xoff[pi] + ((int64_t)s_tc[k] * g.H + iy) * g.W + ix);
       }
       ps[pi * K2 + k] = v;
     }
@@ -129,14 +162,12 @@ int agb_small_c_fprop(agb_ctx* ctx, const float* x, const float* w, agb_tensor* 
                       int pad, int stride, int dil) {
   SmallGeom g; fill_geom(g, B, C, H, W, O, kh, kw, yh, yw, pad, stride, dil, y);
   const int K = C * kh * kw; const int64_t total = (int64_t)B * yh * yw;
-  const size_t smem = (size_t)O * K * sizeof(float);
-  dim3 grid((unsigned)((total + 127) / 128));
-  switch (K) {
-#define SC_CASE(KK) case KK: small_c_fprop_kernel<KK><<<grid, 128, smem, ctx->stream>>>(x, w, y->ptr, g); break;
-    SC_CASE(1) SC_CASE(2) SC_CASE(3) SC_CASE(4) SC_CASE(8) SC_CASE(9) SC_CASE(12) SC_CASE(16) SC_CASE(18) SC_CASE(25) SC_CASE(27) SC_CASE(32) SC_CASE(36)
-#undef SC_CASE
-    default: return AGB_ERR_UNSUPPORTED;
-  }
+  if (O % 4 != 0 || K > SC_MAXK || (((uintptr_t)y->ptr) & 15) != 0) return AGB_ERR_UNSUPPORTED;
+  const size_t smem = (size_t)K * (O + SCF_PIX) * sizeof(float);
+  if (smem > 48 * 1024) return AGB_ERR_UNSUPPORTED;
+  int64_t blocks = (total + SCF_PIX - 1) / SCF_PIX;
+  if (blocks > 2147483647ll) return AGB_ERR_UNSUPPORTED;
+  small_c_fprop_kernel<<<(unsigned)blocks, 256, smem, ctx->stream>>>(x, w, y->ptr, g, K);
   AGB_LAUNCHED(ctx);
   return AGB_OK;
 }
