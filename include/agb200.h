@@ -118,6 +118,11 @@ int  agb_gemm_f32(agb_ctx* ctx, int trans_a, int trans_b,
  * Implicit GEMM: the im2col buffer (conv_ops/mod.rs:73-124) is never materialised. */
 int  agb_conv2d_fprop_f32(agb_ctx* ctx, const agb_tensor* x, const agb_tensor* w, agb_tensor* y,
                           int pad, int stride, int dilation);
+/* fused form of Conv2D -> AddOp(bias) -> ReLU (reference graph: examples/cnn_mnist.rs:38-45; ops conv2d.rs:532, binary_ops.rs:147,
+ * activation_ops.rs:154): y = [relu](conv(x, w) [+ bias[o]]).  bias = NULL or O contiguous floats; the epilogue runs on the accumulator
+ * registers, the pre-activation tensors never reach HBM. */
+int  agb_conv2d_fprop_fused_f32(agb_ctx* ctx, const agb_tensor* x, const agb_tensor* w, const float* bias, int relu, agb_tensor* y,
+                                int pad, int stride, int dilation);
 /* replaces Conv2DTranspose::compute (conv_ops/conv2d_transpose.rs:250-272): gy [B,O,yh,yw],
  * w [O,C,kh,kw] -> gx [B,C,xh,xw], xh = s(yh-1) - 2p + d(kh-1) + 1 (conv2d_transpose.rs:55-56). */
 int  agb_conv2d_dgrad_f32(agb_ctx* ctx, const agb_tensor* gy, const agb_tensor* w, agb_tensor* gx,

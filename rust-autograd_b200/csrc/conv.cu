@@ -15,13 +15,13 @@
 
 // tcgen05 kernels (tc_conv.cu): operate on channels-last activation buffers
 int agb_tc_conv_fprop(agb_ctx* ctx, int mode, const float* x, const float* w, float* y,
-                      int B, int C, int H, int W, int O, int kh, int kw, int pad, int stride, int dil, int flip_transpose);
+                      int B, int C, int H, int W, int O, int kh, int kw, int pad, int stride, int dil, int flip_transpose, const float* bias, int relu);
 int agb_tc_conv_wgrad(agb_ctx* ctx, int mode, const float* img, const float* g, float* gw,
                       int B, int C, int H, int W, int O, int kh, int kw, int pad, int stride, int dil);
 bool agb_tc_conv_eligible(int C, int O, int kh, int kw, int stride, int yw);
 // direct kernels for very small input-channel counts (conv_small_c.cu)
 bool agb_small_c_eligible(int C, int O, int kh, int kw);
-int agb_small_c_fprop(agb_ctx* ctx, const float* x, const float* w, agb_tensor* y, int B, int C, int H, int W, int O, int kh, int kw, int yh, int yw, int pad, int stride, int dil);
+int agb_small_c_fprop(agb_ctx* ctx, const float* x, const float* w, agb_tensor* y, int B, int C, int H, int W, int O, int kh, int kw, int yh, int yw, int pad, int stride, int dil, const float* bias, int relu);
 int agb_small_c_wgrad(agb_ctx* ctx, const float* x, const agb_tensor* gy, float* gw, int B, int C, int H, int W, int O, int kh, int kw, int yh, int yw, int pad, int stride, int dil);
 
 // ---- activation layouts.  A logical [B,C,H,W] tensor is accepted in two dense memory orders: NCHW (C-contiguous, the
@@ -145,6 +145,12 @@ static int check_geom(const char* who, const agb_tensor* x, const agb_tensor* w,
 }
 
 extern "C" int agb_conv2d_fprop_f32(agb_ctx* ctx, const agb_tensor* x, const agb_tensor* w, agb_tensor* y, int pad, int stride, int dilation) {
+  return agb_conv2d_fprop_fused_f32(ctx, x, w, nullptr, 0, y, pad, stride, dilation);
+}
+
+// y = [relu](conv(x, w) [+ bias[o]]): the fused form of Conv2D -> AddOp(bias [1,O,1,1]) -> ReLU (examples/cnn_mnist.rs:38-45)
+extern "C" int agb_conv2d_fprop_fused_f32(agb_ctx* ctx, const agb_tensor* x, const agb_tensor* w, const float* bias, int relu, agb_tensor* y,
+                                         int pad, int stride, int dilation) {
   ConvGeom g; AGB_TRY(check_geom("conv2d", x, w, pad, stride, dilation, g));
   AGB_CHECK(agb_is_contig(w), AGB_ERR_UNSUPPORTED, "conv2d: the filter must be C-contiguous");
   AGB_CHECK(y->rank == 4 && y->shape[0] == g.B && y->shape[1] == g.O && y->shape[2] == g.yh && y->shape[3] == g.yw, AGB_ERR_INCOMPATIBLE_SHAPE,
@@ -154,13 +160,13 @@ extern "C" int agb_conv2d_fprop_f32(agb_ctx* ctx, const agb_tensor* x, const agb
   if (ctx->math_mode != AGB_MATH_FP32 && agb_tc_conv_eligible(g.C, g.O, g.kh, g.kw, stride, g.yw)) {
     LayoutTmp lx(ctx), ly(ctx);
     AGB_TRY(lx.input(x, true)); AGB_TRY(ly.output(y, true));
-    int r = agb_tc_conv_fprop(ctx, ctx->math_mode, lx.view.ptr, w->ptr, ly.view.ptr, g.B, g.C, g.H, g.W, g.O, g.kh, g.kw, pad, stride, dilation, 0);
+    int r = agb_tc_conv_fprop(ctx, ctx->math_mode, lx.view.ptr, w->ptr, ly.view.ptr, g.B, g.C, g.H, g.W, g.O, g.kh, g.kw, pad, stride, dilation, 0, bias, relu);
     if (r == AGB_OK) { AGB_TRY(ly.finish()); return lx.finish(); }
     if (r != AGB_ERR_UNSUPPORTED) return r;
   }
   if (agb_small_c_eligible(g.C, g.O, g.kh, g.kw) && (is_nchw(y) || is_channels_last(y))) {
     LayoutTmp lx(ctx); AGB_TRY(lx.input(x, false));
-    int r = agb_small_c_fprop(ctx, lx.view.ptr, w->ptr, y, g.B, g.C, g.H, g.W, g.O, g.kh, g.kw, g.yh, g.yw, pad, stride, dilation);
+    int r = agb_small_c_fprop(ctx, lx.view.ptr, w->ptr, y, g.B, g.C, g.H, g.W, g.O, g.kh, g.kw, g.yh, g.yw, pad, stride, dilation, bias, relu);
     if (r == AGB_OK) return lx.finish();
     if (r != AGB_ERR_UNSUPPORTED) return r;
   }
@@ -168,6 +174,16 @@ extern "C" int agb_conv2d_fprop_f32(agb_ctx* ctx, const agb_tensor* x, const agb
   AGB_TRY(lx.input(x, false)); AGB_TRY(ly.output(y, false));
   int64_t K = (int64_t)g.C * g.kh * g.kw;
   AGB_TRY(simt_gemm_launch(ctx, FpropA{w->ptr, K}, FpropB{lx.view.ptr, g}, FpropC{ly.view.ptr, g}, g.O, (int64_t)g.B * g.yh * g.yw, K, 1));
+  if (bias != nullptr || relu) {       // CUDA-core path: epilogue as in-place elementwise passes over the NCHW result
+    agb_tensor yv = ly.view;
+    if (bias != nullptr) {
+      agb_tensor bt; bt.ptr = const_cast<float*>(bias); bt.rank = 4;
+      for (int i = 0; i < 4; i++) { bt.shape[i] = yv.shape[i]; bt.stride[i] = 0; }
+      bt.stride[1] = 1;
+      AGB_TRY(agb_binary(ctx, AGB_B_ADD, 0.f, 0.f, &yv, &bt, &yv));
+    }
+    if (relu) AGB_TRY(agb_unary(ctx, AGB_U_RELU, 0.f, 0.f, &yv, &yv));
+  }
   AGB_TRY(ly.finish()); return lx.finish();
 }
 
@@ -192,7 +208,7 @@ extern "C" int agb_conv2d_dgrad_f32(agb_ctx* ctx, const agb_tensor* gy, const ag
     // stride-1 dgrad == fprop of gy with the spatially flipped, channel-transposed filter and pad' = d(k-1) - p
     LayoutTmp lg(ctx), lx(ctx);
     AGB_TRY(lg.input(gy, true)); AGB_TRY(lx.output(gx, true));
-    int r = agb_tc_conv_fprop(ctx, ctx->math_mode, lg.view.ptr, w->ptr, lx.view.ptr, g.B, g.O, g.yh, g.yw, g.C, g.kh, g.kw, pad, stride, dilation, 1);
+    int r = agb_tc_conv_fprop(ctx, ctx->math_mode, lg.view.ptr, w->ptr, lx.view.ptr, g.B, g.O, g.yh, g.yw, g.C, g.kh, g.kw, pad, stride, dilation, 1, nullptr, 0);
     if (r == AGB_OK) { AGB_TRY(lx.finish()); return lg.finish(); }
     if (r != AGB_ERR_UNSUPPORTED) return r;
   }

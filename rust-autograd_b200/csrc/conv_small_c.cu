@@ -14,7 +14,8 @@ struct SmallGeom { int B, C, H, W, O, kh, kw, yh, yw, pad, stride, dil; int64_t 
 // ---- fprop: per CTA a [64 pixels] x [K] patch matrix times the [K] x [O] filter, both staged in shared memory, each thread
 //      a 4 (pixel) x 4 (o) register tile: two 128-bit shared loads per 16 FMAs.
 #define SCF_PIX 64
-__global__ void __launch_bounds__(256) small_c_fprop_kernel(const float* __restrict__ x, const float* __restrict__ w, float* __restrict__ y, SmallGeom g, int K) {
+__global__ void __launch_bounds__(256) small_c_fprop_kernel(const float* __restrict__ x, const float* __restrict__ w, float* __restrict__ y, SmallGeom g, int K,
+                                                            const float* __restrict__ bias, int relu) {
   extern __shared__ __align__(16) float sm[];
   float* ws = sm;                                     // [K][O]   (transposed filter)
   float* vs = sm + K * g.O;                           // [K][SCF_PIX]
@@ -22,7 +23,7 @@ __global__ void __launch_bounds__(256) small_c_fprop_kernel(const float* __restr
   __shared__ int s_oy[SCF_PIX], s_ox[SCF_PIX];
   __shared__ int s_tc[SC_MAXK], s_ti[SC_MAXK], s_tj[SC_MAXK];
   const int kk = g.kh * g.kw;
-  for (int i = threadIdx.x; i < g.O * K; i += blockDim.x) { int o = i / K, k = i - o * K; ws[k * g.O + o] = __ldg(w + i); }
+  for (int i = threadIdx.x; i < g.O * K; i += blockDim.x) { int k = i / g.O, o = i - k * g.O; ws[i] = __ldg(w + o * K + k); }     // o fastest: conflict-free stores
   if (threadIdx.x < K) { int k = threadIdx.x; int c = k / kk, t = k - c * kk; s_tc[k] = c; s_ti[k] = (t / g.kw) * g.dil - g.pad; s_tj[k] = (t % g.kw) * g.dil - g.pad; }
   const int64_t P = (int64_t)g.yh * g.yw, total = (int64_t)g.B * P;
   const int64_t base = (int64_t)blockIdx.x * SCF_PIX;
@@ -57,6 +58,17 @@ __global__ void __launch_bounds__(256) small_c_fprop_kernel(const float* __restr
         for (int a = 0; a < 4; a++)
 #pragma unroll
           for (int q = 0; q < 4; q++) acc[a][q] = fmaf(p_[a], w_[q], acc[a][q]);
+      }
+      if (bias != nullptr) {
+        const float4 bv = __ldg((const float4*)(bias + o));
+#pragma unroll
+        for (int a = 0; a < 4; a++) { acc[a][0] += bv.x; acc[a][1] += bv.y; acc[a][2] += bv.z; acc[a][3] += bv.w; }
+      }
+      if (relu) {
+#pragma unroll
+        for (int a = 0; a < 4; a++)
+#pragma unroll
+          for (int q = 0; q < 4; q++) acc[a][q] = fmaxf(acc[a][q], 0.0f);
       }
 #pragma unroll
       for (int a = 0; a < 4; a++) {
@@ -159,7 +171,7 @@ bool agb_small_c_eligible(int C, int O, int kh, int kw) { return C <= 4 && C * k
 
 // x must be NCHW-contiguous (a first-layer input); y may be NCHW or channels-last (strides taken from the descriptor)
 int agb_small_c_fprop(agb_ctx* ctx, const float* x, const float* w, agb_tensor* y, int B, int C, int H, int W, int O, int kh, int kw, int yh, int yw,
-                      int pad, int stride, int dil) {
+                      int pad, int stride, int dil, const float* bias, int relu) {
   SmallGeom g; fill_geom(g, B, C, H, W, O, kh, kw, yh, yw, pad, stride, dil, y);
   const int K = C * kh * kw; const int64_t total = (int64_t)B * yh * yw;
   if (O % 4 != 0 || K > SC_MAXK || (((uintptr_t)y->ptr) & 15) != 0) return AGB_ERR_UNSUPPORTED;
@@ -167,7 +179,8 @@ int agb_small_c_fprop(agb_ctx* ctx, const float* x, const float* w, agb_tensor* 
   if (smem > 48 * 1024) return AGB_ERR_UNSUPPORTED;
   int64_t blocks = (total + SCF_PIX - 1) / SCF_PIX;
   if (blocks > 2147483647ll) return AGB_ERR_UNSUPPORTED;
-  small_c_fprop_kernel<<<(unsigned)blocks, 256, smem, ctx->stream>>>(x, w, y->ptr, g, K);
+  if (bias && (((uintptr_t)bias) & 15)) return AGB_ERR_UNSUPPORTED;
+  small_c_fprop_kernel<<<(unsigned)blocks, 256, smem, ctx->stream>>>(x, w, y->ptr, g, K, bias, relu);
   AGB_LAUNCHED(ctx);
   return AGB_OK;
 }

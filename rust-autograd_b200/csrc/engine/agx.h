@@ -48,7 +48,8 @@ typedef std::shared_ptr<Buffer> BufferP;
 typedef std::vector<int64_t> Shape;
 
 struct NdArray;
-struct Im2colRef;                 // virtual `cols` tensor (Conv2D output #1), see ops_conv.cc
+struct Im2colRef;                 // virtual `cols` tensor (Conv2D output #1), see ops_nn.cc
+struct Lazy;                      // deferred epilogue (conv [+bias] awaiting a ReLU, "x > 0" mask awaiting a multiply), see ops_nn.cc
 
 // f32 array: a strided view on an HBM block and/or a small contiguous host vector.
 //   - data arrays live on the device (dptr != null);
@@ -62,6 +63,8 @@ struct NdArray {
   bool i32 = false;               // the buffer holds int32 indices (max-pool argmax): exact beyond 2^24, converted to f32 only when a
                                   // float consumer or the user asks (the reference stores indices as floats, max_pool2d.rs:74-75)
   std::shared_ptr<Im2colRef> virt;
+  std::shared_ptr<Lazy> lazy;     // value not computed yet: only `shape` is valid.  ComputeContext::input() materialises it unless the
+                                  // consuming op declared accept_lazy (the ops that can fuse it into their own kernel)
 
   int ndim() const { return (int)shape.size(); }
   int64_t size() const { int64_t n = 1; for (auto d : shape) n *= d; return n; }
@@ -170,6 +173,7 @@ struct ComputeContext {           // src/op.rs:186-309
   std::vector<OpInput> xs; std::vector<NdArray> ys;
   Device* dev; Evaluation* run; TensorID node;
   bool accept_i32 = false;        // set by ops that consume int32 index buffers natively
+  bool accept_lazy = false;       // set by ops that fuse a deferred producer (AddOp / ReLU / greater / MulOp / Shape)
   NdArray input(int i);           // each input may be taken once (:206-233)
   NdArray input_mut(int i);       // only RdWrVariable edges (:239-259)
   int num_inputs() const { return (int)xs.size(); }
@@ -285,6 +289,7 @@ Shape as_shape(Device* dev, NdArray& a);                         // ndarray_ext:
 std::vector<int64_t> as_ints(Device* dev, NdArray& a);
 inline bool is_scalar_shape(const Shape& s) { return s.empty() || (s.size() == 1 && s[0] == 0); }   // ndarray_ext.rs:120-122
 inline int normalize_negative_axis(int64_t axis, int ndim) { return (int)(axis < 0 ? ndim + axis : axis); }
+NdArray materialize_lazy(Device* dev, const NdArray& a);      // runs the deferred producer un-fused (always correct)
 Op* make_optimizer_op(int kind, float h0, float h1, float h2, float h3);
 void flush_pending_updates(Evaluation& run, VariableEnvironment* env);
 

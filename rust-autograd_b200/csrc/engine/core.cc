@@ -214,6 +214,7 @@ NdArray ComputeContext::input(int i) {
   if (x.kind == InputKind::RdWrVariable) throw Panic("Bad op impl: cannot perform mutable borrowing for input. Use input_mut() instead.");
   if (x.taken) throw Panic("Bad op impl: input()/input_mut() cannot be called twice");
   x.taken = true;
+  if (x.arr.lazy && !accept_lazy) return materialize_lazy(dev, x.arr);
   if (x.arr.i32 && !accept_i32) return dev->i32_to_f32(x.arr);
   return x.arr;
 }
@@ -391,6 +392,7 @@ std::vector<EvalResult> eval(Graph* g, const std::vector<Tensor>& targets, const
       else r.value = it->second.ys[0];
       storage.erase(it);
     }
+    if (r.ok && r.value.lazy) r.value = materialize_lazy(dev, r.value);
     if (r.ok && r.value.virt && !r.value.on_device() && !r.value.has_host()) {
       extern NdArray materialize_im2col(Device*, const NdArray&);
       r.value = materialize_im2col(dev, r.value);

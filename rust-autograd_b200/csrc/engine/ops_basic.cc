@@ -10,6 +10,14 @@
 
 namespace agx {
 
+// deferred-epilogue hooks (ops_nn.cc)
+NdArray lazy_conv_add_bias(const NdArray& conv, const NdArray& bias);
+NdArray lazy_conv_relu(Device* dev, const NdArray& a);
+NdArray lazy_gt0_mask(const NdArray& src_or_lazy);
+bool lazy_is_mask(const NdArray& a);
+bool lazy_is_conv(const NdArray& a);
+const NdArray& lazy_mask_src(const NdArray& a);
+
 // ================================================================================================ device helpers
 static NdArray on_dev(Device* d, NdArray a) { d->ensure_device(a); return a; }
 
@@ -219,7 +227,7 @@ Tensor T::ones(Graph* g, Tensor shape) { auto* op = new FillOp(); op->v = 1.f; r
 // ================================================================================================ metadata ops (host)
 struct ShapeOp : Op {                  // array_ops.rs:148-159
   const char* name() const override { return REFNAME("array_ops", "Shape"); }
-  void compute(ComputeContext& c) override { NdArray x = c.input(0); std::vector<float> v; for (auto s : x.shape) v.push_back((float)s); c.append_output(NdArray::from_host({(int64_t)v.size()}, v, true)); }
+  void compute(ComputeContext& c) override { c.accept_lazy = true; NdArray x = c.input(0); std::vector<float> v; for (auto s : x.shape) v.push_back((float)s); c.append_output(NdArray::from_host({(int64_t)v.size()}, v, true)); }
   void grad(GradientContext& c) override { c.append_none(); }
 };
 struct RankOp : Op {
@@ -317,7 +325,20 @@ struct BinArith : Op {                 // AddOp/SubOp/MulOp/DivOp, binary_ops.rs
     return kind == AGB_B_ADD ? REFNAME("binary_ops", "AddOp") : kind == AGB_B_SUB ? REFNAME("binary_ops", "SubOp") : kind == AGB_B_MUL ? REFNAME("binary_ops", "MulOp") : REFNAME("binary_ops", "DivOp");
   }
   void compute(ComputeContext& c) override {
+    c.accept_lazy = (kind == AGB_B_ADD || kind == AGB_B_MUL);
     NdArray a = c.input(0), b = c.input(1);
+    if (a.lazy || b.lazy) {
+      if (kind == AGB_B_ADD) {            // Conv2D + bias[1,O,1,1]: stays deferred, the bias joins the conv epilogue
+        NdArray bb = lazy_is_conv(a) ? b : a; if (!bb.lazy) c.dev->ensure_device(bb);
+        NdArray r = lazy_is_conv(a) && !b.lazy ? lazy_conv_add_bias(a, bb) : (lazy_is_conv(b) && !a.lazy ? lazy_conv_add_bias(b, bb) : NdArray());
+        if (r.lazy) { c.append_output(r); return; }
+      } else {                            // (x > 0) * gy: one ReLU-grad kernel instead of compare + multiply
+        const NdArray& m = lazy_is_mask(a) ? a : b; const NdArray& o = lazy_is_mask(a) ? b : a;
+        if (lazy_is_mask(m) && !o.lazy && o.shape == m.shape) { c.append_output(dev_binary(c.dev, AGB_B_RELU_GRAD, lazy_mask_src(m), o)); return; }
+      }
+      if (a.lazy) a = materialize_lazy(c.dev, a);
+      if (b.lazy) b = materialize_lazy(c.dev, b);
+    }
     if (all_meta(a) && all_meta(b)) { c.append_output(host_binary(kind, a, b)); return; }
     float s;
     const bool a_sc = a.ndim() == 0 && scalar_value(a, &s);
@@ -430,7 +451,12 @@ struct UnaryOp : Op {
   const UnaryInfo* info; float p0;
   const char* name() const override { return info->ref; }
   void compute(ComputeContext& c) override {
+    c.accept_lazy = info->op == AGB_U_RELU;
     NdArray x = c.input(0);
+    if (x.lazy) {
+      if (lazy_is_conv(x)) { NdArray y = lazy_conv_relu(c.dev, x); if (y.on_device()) { c.append_output(y); return; } }
+      x = materialize_lazy(c.dev, x);
+    }
     if (info->op == AGB_U_NEG && all_meta(x)) { std::vector<float> v = *x.host; for (auto& e : v) e = -e; c.append_output(NdArray::from_host(x.shape, v, true)); return; }
     c.append_output(dev_unary(c.dev, info->op, x, p0));
   }
@@ -513,7 +539,17 @@ struct CmpOp : Op {                    // impl_cmp_op!, math_ops.rs:86-184
   const CmpInfo* info;
   const char* name() const override { return info->ref; }
   void compute(ComputeContext& c) override {
+    c.accept_lazy = info->op == AGB_B_GT;
     NdArray a = c.input(0), b = c.input(1);
+    if (info->op == AGB_B_GT) {          // greater(x, scalar 0): the ReLU-gradient mask; deferred until its multiply arrives
+      float z;
+      if (!b.lazy && b.ndim() == 0 && scalar_value(b, &z) && z == 0.0f && a.ndim() > 0 && (a.lazy || a.on_device())) {
+        NdArray r = lazy_gt0_mask(a);
+        if (r.lazy) { c.append_output(r); return; }
+      }
+      if (a.lazy) a = materialize_lazy(c.dev, a);
+      if (b.lazy) b = materialize_lazy(c.dev, b);
+    }
     bool as = is_scalar_shape(a.shape), bs = is_scalar_shape(b.shape);
     if (!as && !bs) {
       if (a.ndim() != b.ndim()) throw Panic(std::string("Tensor ranks mismatch: ") + info->ref);

@@ -93,6 +93,23 @@ NdArray materialize_im2col(Device* dev, const NdArray& cols) {      // only when
 static NdArray real_cols(Device* dev, const NdArray& cols) { return cols.virt && !cols.on_device() ? materialize_im2col(dev, cols) : cols; }
 
 struct ConvParams { int pad, stride, dilation; };
+
+// ---- deferred epilogues ("elementwise fusion ... must keep unfused intermediates available").
+// The reference graph of a conv layer is Conv2D -> AddOp(bias [1,O,1,1]) -> ReLU, and ReLU's gradient is
+// mul(greater(pre_activation, 0), gy) (activation_ops.rs:161-166).  Conv2D / AddOp / `greater(., 0)` return a LAZY array (shape
+// only); the op that completes the pattern runs ONE fused kernel:
+//     ReLU(lazy conv[+bias])      -> conv kernel with bias + ReLU in its epilogue (agb_conv2d_fprop_fused_f32)
+//     MulOp(lazy mask, gy)        -> AGB_B_RELU_GRAD
+//     greater(lazy conv+bias, 0)  -> mask of the ReLU OUTPUT (x > 0  <=>  relu(x) > 0), no pre-activation needed
+// Any other consumer gets the exact un-fused value through materialize_lazy (ComputeContext::input), so every intermediate of
+// the reference graph remains observable; fusion only removes HBM round trips.
+struct Lazy {
+  int kind = 0;                        // 1 = conv [+ bias], 2 = (src > 0) mask
+  NdArray x, w, bias; bool has_bias = false; ConvParams p{0, 1, 1};
+  NdArray relu_out; bool has_relu = false;       // filled by the ReLU consumer that ran the fused kernel
+  NdArray src;                                    // kind 2
+  NdArray value; bool has_value = false;          // cache of the un-fused value
+};
 // activations enter the conv / pool entry points either NCHW-contiguous or channels-last; anything else is deep-copied
 static bool is_cl4(const NdArray& a) { std::vector<int> o; return a.ndim() == 4 && a.on_device() && a.dense_order(o) && o == std::vector<int>({0, 2, 3, 1}) && !a.is_contiguous(); }
 static NdArray act_layout(Device* dev, NdArray a) { if (a.ndim() == 4 && (a.is_contiguous() || is_cl4(a))) return a; return dev->contiguous(a); }
@@ -101,6 +118,67 @@ static Tensor mk_conv_transpose(Graph* g, Tensor gy, Tensor w, ConvParams p);
 static Tensor mk_conv(Graph* g, Tensor x, Tensor w, ConvParams p);
 static Tensor mk_filter_grad(Graph* g, Tensor cols, Tensor gy, Tensor w, Tensor bp_x, Tensor bp_gy, ConvParams p);
 static Tensor mk_conv_with_cols(Graph* g, Tensor cols, Tensor w, Tensor bp_x, Tensor bp_w, ConvParams p);
+
+static NdArray run_conv_fused(Device* dev, const Lazy& L, bool relu) {
+  const NdArray &x = L.x, &w = L.w;
+  int64_t yh = (x.shape[2] + 2 * L.p.pad - (L.p.dilation * (w.shape[2] - 1) + 1)) / L.p.stride + 1;
+  int64_t yw = (x.shape[3] + 2 * L.p.pad - (L.p.dilation * (w.shape[3] - 1) + 1)) / L.p.stride + 1;
+  NdArray y = act_empty(dev, {x.shape[0], w.shape[0], yh, yw}, agb_conv_prefers_channels_last((int)x.shape[1], (int)w.shape[0], (int)w.shape[2], (int)w.shape[3], L.p.stride, (int)yw));
+  agb_tensor tx = x.desc(), tw = w.desc(), ty = y.desc();
+  check_status(agb_conv2d_fprop_fused_f32(dev->ctx, &tx, &tw, L.has_bias ? L.bias.dptr : nullptr, relu ? 1 : 0, &ty, L.p.pad, L.p.stride, L.p.dilation));
+  return y;
+}
+NdArray materialize_lazy(Device* dev, const NdArray& a) {
+  Lazy& L = *a.lazy;
+  if (!L.has_value) {
+    if (L.kind == 1) L.value = run_conv_fused(dev, L, false);
+    else {
+      NdArray zero = dev->full({}, 0.0f), src = L.src;
+      std::vector<int> order;
+      if (!src.dense_order(order)) { src = dev->contiguous(src); src.dense_order(order); }
+      NdArray y = dev->empty_ordered(src.shape, order);          // same memory order as the source
+      agb_tensor ta, tb, ty;
+      ta.ptr = src.dptr; ta.rank = 1; ta.shape[0] = src.size(); ta.stride[0] = 1;
+      tb.ptr = zero.dptr; tb.rank = 1; tb.shape[0] = src.size(); tb.stride[0] = 0;
+      ty.ptr = y.dptr; ty.rank = 1; ty.shape[0] = src.size(); ty.stride[0] = 1;
+      check_status(agb_binary(dev->ctx, AGB_B_GT, 0.f, 0.f, &ta, &tb, &ty));
+      L.value = y;
+    }
+    L.has_value = true;
+  }
+  return L.value;
+}
+// hooks used by ops_basic.cc (AddOp / ReLU / greater / MulOp)
+NdArray lazy_conv_add_bias(const NdArray& conv, const NdArray& bias) {      // returns an invalid (no lazy) array when the pattern does not apply
+  NdArray r;
+  if (!conv.lazy || conv.lazy->kind != 1 || conv.lazy->has_bias || conv.lazy->has_relu || conv.lazy->has_value) return r;
+  if (conv.ndim() != 4 || bias.ndim() != 4 || !bias.on_device() || !bias.is_contiguous()) return r;
+  if (bias.shape[0] != 1 || bias.shape[1] != conv.shape[1] || bias.shape[2] != 1 || bias.shape[3] != 1) return r;
+  if (((uintptr_t)bias.dptr) & 15) return r;
+  auto L = std::make_shared<Lazy>(*conv.lazy); L->bias = bias; L->has_bias = true;
+  r.shape = conv.shape; r.stride = NdArray::contiguous_strides(r.shape); r.lazy = L;
+  return r;
+}
+NdArray lazy_conv_relu(Device* dev, const NdArray& a) {                      // ReLU(conv [+ bias]) in one kernel
+  Lazy& L = *a.lazy;
+  if (L.has_value) return NdArray();          // already materialised un-fused: the caller applies a plain ReLU to that value
+  NdArray y = run_conv_fused(dev, L, true);
+  L.relu_out = y; L.has_relu = true;
+  return y;
+}
+NdArray lazy_gt0_mask(const NdArray& src_or_lazy) {                          // greater(x, 0) whose multiply has not arrived yet
+  NdArray src = src_or_lazy;
+  if (src.lazy) {
+    if (src.lazy->kind != 1 || !src.lazy->has_relu) return NdArray();
+    src = src.lazy->relu_out;                                                // x > 0  <=>  relu(x) > 0
+  }
+  NdArray r; auto L = std::make_shared<Lazy>(); L->kind = 2; L->src = src;
+  r.shape = src.shape; r.stride = NdArray::contiguous_strides(r.shape); r.lazy = L;
+  return r;
+}
+bool lazy_is_mask(const NdArray& a) { return a.lazy && a.lazy->kind == 2 && !a.lazy->has_value; }
+bool lazy_is_conv(const NdArray& a) { return a.lazy && a.lazy->kind == 1; }
+const NdArray& lazy_mask_src(const NdArray& a) { return a.lazy->src; }
 
 static int64_t conv_out(int64_t x, int64_t k, ConvParams p) { return (x + 2 * p.pad - (p.dilation * (k - 1) + 1)) / p.stride + 1; }
 
@@ -113,9 +191,10 @@ struct Conv2D : Op {                   // conv2d.rs:531-586
     if (w.ndim() != 4) throw OpError(AGB_ERR_INCOMPATIBLE_SHAPE, "conv2d: filter must be 4D");
     if (x.shape[1] != w.shape[1]) throw OpError(AGB_ERR_INCOMPATIBLE_SHAPE, "conv2d: input channel dim must match filter's second dim");
     int64_t yh = conv_out(x.shape[2], w.shape[2], p), yw = conv_out(x.shape[3], w.shape[3], p);
-    NdArray y = act_empty(c.dev, {x.shape[0], w.shape[0], yh, yw}, agb_conv_prefers_channels_last((int)x.shape[1], (int)w.shape[0], (int)w.shape[2], (int)w.shape[3], p.stride, (int)yw));
-    agb_tensor tx = x.desc(), tw = w.desc(), ty = y.desc();
-    check_status(agb_conv2d_fprop_f32(c.dev->ctx, &tx, &tw, &ty, p.pad, p.stride, p.dilation));
+    if (yh < 1 || yw < 1) throw OpError(AGB_ERR_INCOMPATIBLE_SHAPE, "conv2d: kernel larger than padded input");
+    NdArray y;      // deferred: the bias add / ReLU that usually follow are folded into the conv kernel's epilogue
+    y.shape = {x.shape[0], w.shape[0], yh, yw}; y.stride = NdArray::contiguous_strides(y.shape);
+    y.lazy = std::make_shared<Lazy>(); y.lazy->kind = 1; y.lazy->x = x; y.lazy->w = w; y.lazy->p = p;
     NdArray cols; cols.shape = {x.shape[0], x.shape[1], w.shape[2], w.shape[3], yh, yw}; cols.stride = NdArray::contiguous_strides(cols.shape);
     cols.virt = std::make_shared<Im2colRef>(Im2colRef{x, (int)w.shape[2], (int)w.shape[3], p.pad, p.stride, p.dilation});
     c.append_output(y); c.append_output(cols);

@@ -37,7 +37,7 @@ __global__ void __launch_bounds__(256) repack_filter_kernel(const float* __restr
 template <int TN_, bool SPLIT_> struct ConvFpropPol {
   static constexpr int TN = TN_; static constexpr bool SPLIT = SPLIT_, P_MN = false, Q_MN = false;
   static constexpr int OCC = (SPLIT_ || TN_ > 128) ? 1 : 2;
-  struct Params { CUtensorMap tmX, tmW; float* y; int Cout, yh, yw, kw, pad, dil, tiles_x, tiles_y, cblocks, taps; MnDescCfg mnc; };
+  struct Params { CUtensorMap tmX, tmW; float* y; const float* bias; int relu; int Cout, yh, yw, kw, pad, dil, tiles_x, tiles_y, cblocks, taps; MnDescCfg mnc; };
   struct Tile { int b, oy0, ox0, o0; };
   __device__ static Tile tile(const Params& p) {
     int bx = (int)blockIdx.x; int tx = bx % p.tiles_x; int r = bx / p.tiles_x; int ty = r % p.tiles_y;
@@ -55,12 +55,21 @@ template <int TN_, bool SPLIT_> struct ConvFpropPol {
     if (oy >= p.yh || ox >= p.yw) return;
     const int o = t.o0 + c0;
     float* dst = p.y + (((int64_t)t.b * p.yh + oy) * p.yw + ox) * p.Cout + o;
+    // fused epilogue: per-channel bias and ReLU applied to the accumulator registers, so the
+    // pre-activation tensors of conv -> add -> relu never travel through HBM
+    float r[32];
+#pragma unroll
+    for (int j = 0; j < 32; j++) {
+      float a = v[j];
+      if (p.bias != nullptr && o + j < p.Cout) a += __ldg(p.bias + o + j);
+      r[j] = p.relu ? fmaxf(a, 0.0f) : a;
+    }
     if (o + 32 <= p.Cout) {
 #pragma unroll
-      for (int j = 0; j < 32; j += 4) *(float4*)(dst + j) = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
+      for (int j = 0; j < 32; j += 4) *(float4*)(dst + j) = make_float4(r[j], r[j + 1], r[j + 2], r[j + 3]);
     } else {
 #pragma unroll
-      for (int j = 0; j < 32; j++) if (o + j < p.Cout) dst[j] = v[j];
+      for (int j = 0; j < 32; j++) if (o + j < p.Cout) dst[j] = r[j];
     }
   }
 };
@@ -123,7 +132,7 @@ bool agb_tc_conv_eligible(int C, int O, int kh, int kw, int stride, int yw) {
 
 template <int TN, bool SPLIT>
 static int fprop_launch(agb_ctx* ctx, const float* x, const float* wr, float* y, int B, int Cin, int H, int W, int Cout, int yh, int yw, int kh, int kw,
-                        int pad, int dil) {
+                        int pad, int dil, const float* bias, int relu) {
   using Pol = ConvFpropPol<TN, SPLIT>;
   typename Pol::Params p;
   AGB_TRY(make_cl_map(&p.tmX, x, B, Cin, H, W, 32, 32, 4, false));
@@ -133,7 +142,7 @@ static int fprop_launch(agb_ctx* ctx, const float* x, const float* wr, float* y,
     uint32_t box[3] = {32, (uint32_t)TN, 1};
     AGB_TRY(agb_make_tmap(&p.tmW, wr, 3, dims, str, box, false));
   }
-  p.y = y; p.Cout = Cout; p.yh = yh; p.yw = yw; p.kw = kw; p.pad = pad; p.dil = dil;
+  p.y = y; p.bias = bias; p.relu = relu; p.Cout = Cout; p.yh = yh; p.yw = yw; p.kw = kw; p.pad = pad; p.dil = dil;
   p.tiles_x = (yw + 31) / 32; p.tiles_y = (yh + 3) / 4; p.cblocks = (Cin + 31) / 32; p.taps = kh * kw; p.mnc = agb_mn_cfg();
   int64_t nb = (int64_t)p.tiles_x * p.tiles_y * B;
   if (nb > 2147483647ll) return AGB_ERR_UNSUPPORTED;
@@ -144,7 +153,7 @@ static int fprop_launch(agb_ctx* ctx, const float* x, const float* wr, float* y,
 // fprop on channels-last buffers: x [B,H,W,C], w [O,C,kh,kw] (plain) -> y [B,yh,yw,O].  flip_transpose != 0: dgrad — `x` is gy
 // with C = filter dim 0, w [C, O(=out channels of this GEMM), kh, kw]; the effective padding is dil*(k-1) - pad.
 int agb_tc_conv_fprop(agb_ctx* ctx, int mode, const float* x, const float* w, float* y, int B, int C, int H, int W, int O, int kh, int kw,
-                      int pad, int stride, int dil, int flip_transpose) {
+                      int pad, int stride, int dil, int flip_transpose, const float* bias, int relu) {
   const int epad = flip_transpose ? dil * (kh - 1) - pad : pad;
   if (epad < 0) return AGB_ERR_UNSUPPORTED;
   const int yh = H + 2 * epad - (dil * (kh - 1) + 1) + 1, yw = W + 2 * epad - (dil * (kw - 1) + 1) + 1;
@@ -162,12 +171,12 @@ int agb_tc_conv_fprop(agb_ctx* ctx, int mode, const float* x, const float* w, fl
   }
   const bool split = mode == AGB_MATH_3XTF32;
   if (split) {
-    if (O > 64) return fprop_launch<128, true>(ctx, x, wr, y, B, C, H, W, O, yh, yw, kh, kw, epad, dil);
-    return fprop_launch<64, true>(ctx, x, wr, y, B, C, H, W, O, yh, yw, kh, kw, epad, dil);
+    if (O > 64) return fprop_launch<128, true>(ctx, x, wr, y, B, C, H, W, O, yh, yw, kh, kw, epad, dil, bias, relu);
+    return fprop_launch<64, true>(ctx, x, wr, y, B, C, H, W, O, yh, yw, kh, kw, epad, dil, bias, relu);
   }
-  if (O > 128) return fprop_launch<256, false>(ctx, x, wr, y, B, C, H, W, O, yh, yw, kh, kw, epad, dil);
-  if (O > 64) return fprop_launch<128, false>(ctx, x, wr, y, B, C, H, W, O, yh, yw, kh, kw, epad, dil);
-  return fprop_launch<64, false>(ctx, x, wr, y, B, C, H, W, O, yh, yw, kh, kw, epad, dil);
+  if (O > 128) return fprop_launch<256, false>(ctx, x, wr, y, B, C, H, W, O, yh, yw, kh, kw, epad, dil, bias, relu);
+  if (O > 64) return fprop_launch<128, false>(ctx, x, wr, y, B, C, H, W, O, yh, yw, kh, kw, epad, dil, bias, relu);
+  return fprop_launch<64, false>(ctx, x, wr, y, B, C, H, W, O, yh, yw, kh, kw, epad, dil, bias, relu);
 }
 
 template <int TN, bool SPLIT, bool PAIR>
