@@ -84,29 +84,31 @@ __global__ void __launch_bounds__(256) small_c_fprop_kernel(const float* __restr
 }
 
 // gy strides gs (b,o,h,w) in either layout; K <= 32, O <= 256 (multiple of 4).
-// Register tiling: thread (to, tk) owns a 4 (o) x 2 (k) block of gw for every 64-channel slab of O, so one slab pixel costs
-// one 128-bit + one 64-bit shared-memory read per 8 FMAs (a thread-per-output mapping would be shared-memory bound).
-#define SCW_PIX 64
-__global__ void __launch_bounds__(256) small_c_wgrad_kernel(const float* __restrict__ x, const float* __restrict__ gy, float* __restrict__ gw, SmallGeom g,
-                                                            int K, int K2 /* K rounded up to even */, int64_t chunk) {
+// Register tiling: thread (to, tk) owns a 4 (o) x 4 (k) block of gw for every 64-channel slab of O, so one slab pixel costs
+// two 128-bit shared-memory reads per 16 FMAs (a thread-per-output mapping would be shared-memory bound).
+#define SCW_PIX 128
+__global__ void __launch_bounds__(128) small_c_wgrad_kernel(const float* __restrict__ x, const float* __restrict__ gy, float* __restrict__ gw, SmallGeom g,
+                                                            int K, int K4 /* K rounded up to a multiple of 4 */, int64_t chunk) {
   extern __shared__ __align__(16) float sm[];
   float* gs = sm;                                     // [SCW_PIX][O]
-  float* ps = sm + SCW_PIX * g.O;                     // [SCW_PIX][K2]
+  float* ps = sm + SCW_PIX * g.O;                     // [SCW_PIX][K4]
   __shared__ int64_t s_xoff[SCW_PIX], s_goff[SCW_PIX];
   __shared__ int s_oy[SCW_PIX], s_ox[SCW_PIX];
   __shared__ int s_tc[SC_MAXK], s_ti[SC_MAXK], s_tj[SC_MAXK];
   const int64_t P = (int64_t)g.yh * g.yw, total = (int64_t)g.B * P;
   const int64_t p0 = blockIdx.x * chunk, p1 = min(p0 + chunk, total);
   const int kk = g.kh * g.kw;
-  if (threadIdx.x < K2) { int k = threadIdx.x; int c = k / kk, t = k - c * kk; s_tc[k] = c; s_ti[k] = (t / g.kw) * g.dil - g.pad; s_tj[k] = (t % g.kw) * g.dil - g.pad; }
-  const int to = threadIdx.x & 15, tk = threadIdx.x >> 4;          // 16 o-quads x 16 k-pairs per 64-channel slab
+  if (threadIdx.x < K4) { int k = threadIdx.x; int c = k / kk, t = k - c * kk; s_tc[k] = c; s_ti[k] = (t / g.kw) * g.dil - g.pad; s_tj[k] = (t % g.kw) * g.dil - g.pad; }
+  const int to = threadIdx.x & 15, tk = threadIdx.x >> 4;          // 16 o-quads x 8 k-quads per 64-channel slab
   const int nslab = (g.O + 63) / 64;
-  const bool active = 2 * tk < K2;
-  float acc[4][4][2];                                  // [slab][o in quad][k in pair]
+  const bool active = 4 * tk < K4;
+  float acc[4][4][4];                                  // [slab][o in quad][k in quad]
 #pragma unroll
   for (int s = 0; s < 4; s++)
 #pragma unroll
-    for (int q = 0; q < 4; q++) { acc[s][q][0] = 0.f; acc[s][q][1] = 0.f; }
+    for (int q = 0; q < 4; q++)
+#pragma unroll
+      for (int e = 0; e < 4; e++) acc[s][q][e] = 0.f;
   const bool gy_cl = g.ys[1] == 1;
   for (int64_t base = p0; base < p1; base += SCW_PIX) {
     const int np = (int)min((int64_t)SCW_PIX, p1 - base);
@@ -117,32 +119,42 @@ __global__ void __launch_bounds__(256) small_c_wgrad_kernel(const float* __restr
       s_oy[threadIdx.x] = oy * g.stride; s_ox[threadIdx.x] = ox * g.stride;
     }
     __syncthreads();
-    for (int i = threadIdx.x; i < np * g.O; i += blockDim.x) {
-      int pi, o;
-      if (gy_cl) { pi = i / g.O; o = i - pi * g.O; } else { o = i / np; pi = i - o * np; }      // coalesced in either layout
-      gs[pi * g.O + o] = __ldg(gy + s_goff[pi] + o * g.ys[1]);
+    if (gy_cl && (g.O & 3) == 0) {                     // channels-last gy: 128-bit coalesced copies
+      const int o4n = g.O >> 2;
+      for (int i = threadIdx.x; i < np * o4n; i += blockDim.x) {
+        const int pi = i / o4n, o4 = i - pi * o4n;
+        *(float4*)(gs + pi * g.O + 4 * o4) = __ldg((const float4*)(gy + s_goff[pi] + 4 * o4));
+      }
+    } else {
+      for (int i = threadIdx.x; i < np * g.O; i += blockDim.x) {
+        int pi, o;
+        if (gy_cl) { pi = i / g.O; o = i - pi * g.O; } else { o = i / np; pi = i - o * np; }
+        gs[pi * g.O + o] = __ldg(gy + s_goff[pi] + o * g.ys[1]);
+      }
     }
-    for (int i = threadIdx.x; i < np * K2; i += blockDim.x) {
+    for (int i = threadIdx.x; i < np * K4; i += blockDim.x) {
       const int k = i / np, pi = i - k * np;           // consecutive threads -> consecutive pixels (coalesced x reads)
       float v = 0.0f;
       if (k < K) {
         const int iy = s_oy[pi] + s_ti[k], ix = s_ox[pi] + s_tj[k];
         if ((unsigned)iy < (unsigned)g.H && (unsigned)ix < (unsigned)g.W) v = __ldg(x + s_xoff[pi] + ((int64_t)s_tc[k] * g.H + iy) * g.W + ix);
       }
-      ps[pi * K2 + k] = v;
+      ps[pi * K4 + k] = v;
     }
     __syncthreads();
     if (active) {
       for (int pi = 0; pi < np; pi++) {
-        const float2 pv = *(const float2*)(ps + pi * K2 + 2 * tk);
+        const float4 pv = *(const float4*)(ps + pi * K4 + 4 * tk);
+        const float p_[4] = {pv.x, pv.y, pv.z, pv.w};
 #pragma unroll
         for (int s = 0; s < 4; s++) {
           if (s < nslab) {
             const float4 gv = *(const float4*)(gs + pi * g.O + s * 64 + 4 * to);
-            acc[s][0][0] = fmaf(gv.x, pv.x, acc[s][0][0]); acc[s][0][1] = fmaf(gv.x, pv.y, acc[s][0][1]);
-            acc[s][1][0] = fmaf(gv.y, pv.x, acc[s][1][0]); acc[s][1][1] = fmaf(gv.y, pv.y, acc[s][1][1]);
-            acc[s][2][0] = fmaf(gv.z, pv.x, acc[s][2][0]); acc[s][2][1] = fmaf(gv.z, pv.y, acc[s][2][1]);
-            acc[s][3][0] = fmaf(gv.w, pv.x, acc[s][3][0]); acc[s][3][1] = fmaf(gv.w, pv.y, acc[s][3][1]);
+            const float g_[4] = {gv.x, gv.y, gv.z, gv.w};
+#pragma unroll
+            for (int q = 0; q < 4; q++)
+#pragma unroll
+              for (int e = 0; e < 4; e++) acc[s][q][e] = fmaf(g_[q], p_[e], acc[s][q][e]);
           }
         }
       }
@@ -155,8 +167,8 @@ __global__ void __launch_bounds__(256) small_c_wgrad_kernel(const float* __restr
 #pragma unroll
       for (int q = 0; q < 4; q++)
 #pragma unroll
-        for (int e = 0; e < 2; e++) {
-          const int o = s * 64 + 4 * to + q, k = 2 * tk + e;
+        for (int e = 0; e < 4; e++) {
+          const int o = s * 64 + 4 * to + q, k = 4 * tk + e;
           if (s < nslab && o < g.O && k < K) atomicAdd(gw + o * K + k, acc[s][q][e]);
         }
   }
@@ -191,15 +203,15 @@ int agb_small_c_wgrad(agb_ctx* ctx, const float* x, const agb_tensor* gy, float*
   SmallGeom g; fill_geom(g, B, C, H, W, O, kh, kw, yh, yw, pad, stride, dil, gy);
   const int K = C * kh * kw; const int64_t total = (int64_t)B * yh * yw;
   if (O % 4 != 0 || O > 256 || K > 32) return AGB_ERR_UNSUPPORTED;       // 16 k-pairs per thread row
-  const int K2 = (K + 1) & ~1;
+  const int K2 = (K + 3) & ~3;
   AGB_TRY(agb_memset0(ctx, gw, (size_t)O * K * sizeof(float)));
-  int64_t blocks = 4ll * ctx->sm_count; int64_t chunk = (total + blocks - 1) / blocks; chunk = (chunk + 63) / 64 * 64; if (chunk < 64) chunk = 64;
+  int64_t blocks = 8ll * ctx->sm_count; int64_t chunk = (total + blocks - 1) / blocks; chunk = (chunk + SCW_PIX - 1) / SCW_PIX * SCW_PIX; if (chunk < SCW_PIX) chunk = SCW_PIX;
   blocks = (total + chunk - 1) / chunk;
   const size_t smem = (size_t)SCW_PIX * (O + K2) * sizeof(float);
   static bool attr = false;
   if (!attr) { AGB_CUDA(cudaFuncSetAttribute(small_c_wgrad_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024)); attr = true; }
   if (smem > 96 * 1024) return AGB_ERR_UNSUPPORTED;
-  small_c_wgrad_kernel<<<(unsigned)blocks, 256, smem, ctx->stream>>>(x, gy->ptr, gw, g, K, K2, chunk);
+  small_c_wgrad_kernel<<<(unsigned)blocks, 128, smem, ctx->stream>>>(x, gy->ptr, gw, g, K, K2, chunk);
   AGB_LAUNCHED(ctx);
   return AGB_OK;
 }
