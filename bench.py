@@ -236,7 +236,8 @@ def main():
     dev_ms, wall_ms, launches = timed(step_resident, args.steps, 0)
     ffi.check(lib.agb_prof_enable(ctx, 0))
     prof = {}
-    names = ["gemm", "conv_fprop", "conv_dgrad", "conv_wgrad", "ewise", "reduce", "softmax", "pool", "optim"]
+    names = ["gemm", "conv_fprop", "conv_dgrad", "conv_wgrad", "ewise", "reduce", "softmax", "pool", "optim",
+             "conv_small_c_fprop", "conv_small_c_wgrad", "conv_simt"]
     for cls, nm in enumerate(names):
         t, n, w = C.c_double(), C.c_int64(), C.c_double()
         ffi.check(lib.agb_prof_collect(ctx, cls, C.byref(t), C.byref(n), C.byref(w)))
@@ -255,15 +256,25 @@ def main():
         e2e_value = world * B * args.steps / (e2e_time / 1e3)
         conv = {k: v for k, v in prof.items() if k.startswith("conv")}
         roof = None
-        if conv:
-            top = max(conv, key=lambda k: conv[k]["ms"])
+        # dominant kernel: tc_tile_kernel<ConvFpropPol<TN>> — the tcgen05 implicit-GEMM conv that serves Conv2D fprop and (flipped filter)
+        # Conv2DTranspose / dgrad.  Classes conv_fprop + conv_dgrad hold exactly its launches (small-C and SIMT paths are re-labelled).
+        dom = [conv[k] for k in ("conv_fprop", "conv_dgrad") if k in conv]
+        if dom:
+            d_ms = sum(v["ms"] for v in dom); d_w = sum(v["work"] for v in dom); d_n = sum(v["calls"] for v in dom)
             tot_ms = sum(v["ms"] for v in conv.values()); tot_w = sum(v["work"] for v in conv.values())
-            achieved = conv[top]["work"] / (conv[top]["ms"] / 1e3) / 1e12
+            achieved = d_w / (d_ms / 1e3) / 1e12
             tf32_peak = pk["bf16_tflops_sustained"] / 2.0
-            roof = {"bound": "tensor", "kernel": top + " (implicit-GEMM conv, %s)" % args.mode, "achieved": achieved, "peak": tf32_peak, "unit": "TFLOP/s",
-                    "frac": achieved / tf32_peak, "traffic": None,
+            traffic, traffic_src = None, None
+            tpath = os.path.join(ROOT, "profiles", "ncu_conv_traffic.json")     # dram bytes per launch from the committed ncu --set full capture
+            if os.path.exists(tpath) and world == 1:
+                tj = json.load(open(tpath))
+                if tj.get("workload") == WORKLOAD and tj.get("math_mode") == args.mode:
+                    traffic, traffic_src = tj["dram_bytes_per_launch"], tj["source"]
+            roof = {"bound": "tensor", "kernel": "tc_tile_kernel<ConvFpropPol> (tcgen05 implicit-GEMM conv: fprop + dgrad, %s)" % args.mode,
+                    "achieved": achieved, "peak": tf32_peak, "unit": "TFLOP/s", "frac": achieved / tf32_peak, "traffic": traffic, "traffic_source": traffic_src,
                     "peak_source": "%s bf16 sustained / 2 (dense TF32 = half the bf16 rate), MEASURED_PEAKS.json" % pk["src"],
-                    "per_launch_ms": conv[top]["ms"] / conv[top]["calls"], "flops_per_launch": conv[top]["work"] / conv[top]["calls"],
+                    "per_launch_ms": d_ms / d_n, "flops_per_launch": d_w / d_n, "launches_per_step": d_n / args.steps,
+                    "share_of_step": d_ms / max(dev_ms, 1e-9),
                     "all_conv": {"achieved": tot_w / (tot_ms / 1e3) / 1e12, "share_of_step": tot_ms / max(dev_ms, 1e-9)},
                     "classes": {k: {"ms_per_step": v["ms"] / args.steps, "calls_per_step": v["calls"] / args.steps} for k, v in prof.items()}}
         out = {"metric": METRIC, "value": value, "unit": "samples/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": step_ms,

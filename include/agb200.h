@@ -76,7 +76,7 @@ int  agb_launch_count(agb_ctx* ctx, int64_t* out);
  * of the profiled classes below is bracketed by an event pair and its algorithmic work (FLOPs for contractions, bytes for
  * bandwidth kernels) is accumulated.  agb_prof_collect synchronises and returns totals for one class. */
 enum { AGB_PROF_GEMM = 0, AGB_PROF_CONV_FPROP, AGB_PROF_CONV_DGRAD, AGB_PROF_CONV_WGRAD, AGB_PROF_EWISE, AGB_PROF_REDUCE, AGB_PROF_SOFTMAX,
-       AGB_PROF_POOL, AGB_PROF_OPTIM, AGB_PROF_COUNT };
+       AGB_PROF_POOL, AGB_PROF_OPTIM, AGB_PROF_CONV_SMALLC_FPROP, AGB_PROF_CONV_SMALLC_WGRAD, AGB_PROF_CONV_SIMT, AGB_PROF_COUNT };
 int  agb_prof_enable(agb_ctx* ctx, int on);
 int  agb_prof_collect(agb_ctx* ctx, int cls, double* total_ms, int64_t* calls, double* work /* FLOPs or bytes */);
 int  agb_prof_reset(agb_ctx* ctx);

@@ -51,6 +51,7 @@ struct AgbProfScope {
     cudaEventRecord(r.a, c->stream);
     idx = (int)c->prof_recs.size(); c->prof_recs.push_back(r);
   }
+  void set_cls(int cls) { if (idx >= 0) ctx->prof_recs[idx].cls = cls; }   // the dispatcher re-labels the bracket with the kernel that ran
   ~AgbProfScope() { if (idx >= 0) cudaEventRecord(ctx->prof_recs[idx].b, ctx->stream); }
 };
 

@@ -167,9 +167,10 @@ extern "C" int agb_conv2d_fprop_fused_f32(agb_ctx* ctx, const agb_tensor* x, con
   if (agb_small_c_eligible(g.C, g.O, g.kh, g.kw) && (is_nchw(y) || is_channels_last(y))) {
     LayoutTmp lx(ctx); AGB_TRY(lx.input(x, false));
     int r = agb_small_c_fprop(ctx, lx.view.ptr, w->ptr, y, g.B, g.C, g.H, g.W, g.O, g.kh, g.kw, g.yh, g.yw, pad, stride, dilation, bias, relu);
-    if (r == AGB_OK) return lx.finish();
+    if (r == AGB_OK) { prof.set_cls(AGB_PROF_CONV_SMALLC_FPROP); return lx.finish(); }
     if (r != AGB_ERR_UNSUPPORTED) return r;
   }
+  prof.set_cls(AGB_PROF_CONV_SIMT);
   LayoutTmp lx(ctx), ly(ctx);
   AGB_TRY(lx.input(x, false)); AGB_TRY(ly.output(y, false));
   int64_t K = (int64_t)g.C * g.kh * g.kw;
@@ -212,6 +213,7 @@ extern "C" int agb_conv2d_dgrad_f32(agb_ctx* ctx, const agb_tensor* gy, const ag
     if (r == AGB_OK) { AGB_TRY(lx.finish()); return lg.finish(); }
     if (r != AGB_ERR_UNSUPPORTED) return r;
   }
+  prof.set_cls(AGB_PROF_CONV_SIMT);
   LayoutTmp lg(ctx), lx(ctx);
   AGB_TRY(lg.input(gy, false)); AGB_TRY(lx.output(gx, false));
   int64_t K = (int64_t)g.O * g.kh * g.kw;
@@ -236,9 +238,10 @@ extern "C" int agb_conv2d_wgrad_f32(agb_ctx* ctx, const agb_tensor* img, const a
   if (agb_small_c_eligible(g.C, g.O, g.kh, g.kw) && (is_nchw(gr) || is_channels_last(gr))) {
     LayoutTmp li(ctx); AGB_TRY(li.input(img, false));
     int r = agb_small_c_wgrad(ctx, li.view.ptr, gr, gw->ptr, g.B, g.C, g.H, g.W, g.O, g.kh, g.kw, g.yh, g.yw, pad, stride, dilation);
-    if (r == AGB_OK) return li.finish();
+    if (r == AGB_OK) { prof.set_cls(AGB_PROF_CONV_SMALLC_WGRAD); return li.finish(); }
     if (r != AGB_ERR_UNSUPPORTED) return r;
   }
+  prof.set_cls(AGB_PROF_CONV_SIMT);
   LayoutTmp li(ctx), lg(ctx);
   AGB_TRY(li.input(img, false)); AGB_TRY(lg.input(gr, false));
   int64_t N = (int64_t)g.C * g.kh * g.kw; int64_t P = (int64_t)g.yh * g.yw;

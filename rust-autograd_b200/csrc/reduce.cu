@@ -157,7 +157,14 @@ static int reduce_impl(agb_ctx* ctx, const float* x, float* y, int64_t outer, in
       reduce_rows_warp_kernel<OP><<<(unsigned)blocks, 256, 0, ctx->stream>>>(x, y, rows, r, scale);
       AGB_LAUNCHED(ctx); return AGB_OK;
     }
-    AGB_CHECK(rows <= 65535, AGB_ERR_UNSUPPORTED, "agb_reduce: too many long rows (%lld)", (long long)rows);
+    if (rows > 65535) {   // grid.y limit: more rows than that already fill the machine with one block per row, launch in slabs
+      for (int64_t r0 = 0; r0 < rows; r0 += 65535) {
+        int64_t nr = rows - r0 < 65535 ? rows - r0 : 65535;
+        reduce_rows_kernel<OP><<<dim3(1, (unsigned)nr), 256, 0, ctx->stream>>>(x + r0 * r, y + r0, r, (r + 3) & ~(int64_t)3, 1, scale);
+        AGB_LAUNCHED(ctx);
+      }
+      return AGB_OK;
+    }
     // chunks per row so that the grid covers >= 4 blocks per SM; each chunk >= 4096 elements
     int64_t want = ((int64_t)sms * 4 + rows - 1) / rows;
     int64_t maxc = (r + 4095) / 4096;

@@ -82,47 +82,83 @@ __global__ void __launch_bounds__(256) softmax_warp_kernel(const float* __restri
   if (MODE == SM_DENSE_XENT) { dense = warp_sum(dense); if (l == 0) loss[row] = -dense; }
 }
 
-// ---- long rows: one block per row; the row is staged in dynamic shared memory when it fits ----
+// ---- long rows: one block per row.  Online (single-pass) max + sum: one block reduction instead of two.
+//      CACHED (row <= 48 KB, several CTAs per SM): the row is staged in shared memory, HBM sees it exactly once.
+//      !CACHED (longer rows): the row is re-read for the output pass — it is at most a few MB and still L2-resident, so HBM
+//      traffic stays at the algorithmic 8 B/elem while 4+ CTAs per SM keep the load / reduce / store phases of different rows
+//      overlapped (a 128 KB shared-memory row would pin the SM to one row at a time).
+struct MaxSum { float m, s; };
+__device__ __forceinline__ MaxSum ms_comb(MaxSum a, MaxSum b) {
+  MaxSum r; r.m = fmaxf(a.m, b.m);
+  r.s = a.s * __expf(a.m - r.m) + b.s * __expf(b.m - r.m);
+  return r;
+}
+__device__ __forceinline__ MaxSum block_maxsum(MaxSum v, MaxSum* sm) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) { MaxSum t; t.m = __shfl_xor_sync(0xffffffffu, v.m, o); t.s = __shfl_xor_sync(0xffffffffu, v.s, o); v = ms_comb(v, t); }
+  int w = threadIdx.x >> 5, l = threadIdx.x & 31, nw = blockDim.x >> 5;
+  if (l == 0) sm[w] = v;
+  __syncthreads();
+  MaxSum r; r.m = -FLT_MAX; r.s = 0.0f;
+  if (l < nw) r = sm[l];
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) { MaxSum t; t.m = __shfl_xor_sync(0xffffffffu, r.m, o); t.s = __shfl_xor_sync(0xffffffffu, r.s, o); r = ms_comb(r, t); }
+  __syncthreads();
+  return r;
+}
+__device__ __forceinline__ void ms_push4(MaxSum& a, float4 v) {
+  float m4 = fmaxf(fmaxf(v.x, v.y), fmaxf(v.z, v.w));
+  float m = fmaxf(a.m, m4);
+  a.s = a.s * __expf(a.m - m) + __expf(v.x - m) + __expf(v.y - m) + __expf(v.z - m) + __expf(v.w - m);
+  a.m = m;
+}
+__device__ __forceinline__ void ms_push1(MaxSum& a, float v) {
+  float m = fmaxf(a.m, v);
+  a.s = a.s * __expf(a.m - m) + __expf(v - m);
+  a.m = m;
+}
+
 template <int MODE, bool CACHED>
 __global__ void __launch_bounds__(512) softmax_block_kernel(const float* __restrict__ x, float* __restrict__ y,
                                                             const float* __restrict__ aux, float* __restrict__ loss,
                                                             int64_t r, int* err) {
   extern __shared__ __align__(16) float rowbuf[];
-  __shared__ float red[32];
+  __shared__ MaxSum red[32];
   int64_t row = blockIdx.x;
   const float* p = x + row * r;
   const int T = blockDim.x;
   bool vec = ((((uintptr_t)p) & 15) == 0) && (r % 4 == 0);
-  float mx = -FLT_MAX;
+  MaxSum acc; acc.m = -FLT_MAX; acc.s = 0.0f;
   if (vec) {
-    for (int64_t i = threadIdx.x; i < (r >> 2); i += T) {
-      float4 v = ldg_stream4(p + 4 * i);
-      if (CACHED) *(float4*)(rowbuf + 4 * i) = v;
-      mx = fmaxf(mx, fmaxf(fmaxf(v.x, v.y), fmaxf(v.z, v.w)));
+    const int64_t n4 = r >> 2;
+    int64_t i = threadIdx.x;
+    for (; i + T < n4; i += 2 * T) {               // two independent 128-bit loads in flight
+      float4 v0 = ldg_stream4(p + 4 * i), v1 = ldg_stream4(p + 4 * (i + T));
+      if (CACHED) { *(float4*)(rowbuf + 4 * i) = v0; *(float4*)(rowbuf + 4 * (i + T)) = v1; }
+      ms_push4(acc, v0); ms_push4(acc, v1);
     }
+    for (; i < n4; i += T) { float4 v = ldg_stream4(p + 4 * i); if (CACHED) *(float4*)(rowbuf + 4 * i) = v; ms_push4(acc, v); }
   } else {
-    for (int64_t i = threadIdx.x; i < r; i += T) { float v = __ldg(p + i); if (CACHED) rowbuf[i] = v; mx = fmaxf(mx, v); }
+    for (int64_t i = threadIdx.x; i < r; i += T) { float v = __ldg(p + i); if (CACHED) rowbuf[i] = v; ms_push1(acc, v); }
   }
-  mx = block_max(mx, red);    // also orders the rowbuf writes (syncthreads inside)
-  const float* src = CACHED ? rowbuf : p;
-  float s = 0.0f;
-  for (int64_t i = threadIdx.x; i < r; i += T) s += expf(src[i] - mx);
-  s = block_sum(s, red);
-  float lse = logf(s) + mx;
+  acc = block_maxsum(acc, red);                     // also orders the rowbuf writes (syncthreads inside)
+  const float mx = acc.m, s = acc.s;
+  const float lse = logf(s) + mx, inv = 1.0f / s;
   if (MODE == SM_LSE) { if (threadIdx.x == 0) y[row] = lse; return; }
+  const float* src = CACHED ? rowbuf : p;
   float* q = y + row * r;
   float dense = 0.0f;
   bool vecq = vec && ((((uintptr_t)q) & 15) == 0);
   if (vecq && MODE != SM_DENSE_XENT) {
     for (int64_t i = threadIdx.x; i < (r >> 2); i += T) {
-      float4 v = CACHED ? *(const float4*)(rowbuf + 4 * i) : *(const float4*)(p + 4 * i);
-      v.x = sm_out<MODE>(v.x, mx, s, lse); v.y = sm_out<MODE>(v.y, mx, s, lse);
-      v.z = sm_out<MODE>(v.z, mx, s, lse); v.w = sm_out<MODE>(v.w, mx, s, lse);
+      float4 v = CACHED ? *(const float4*)(rowbuf + 4 * i) : __ldg((const float4*)(p + 4 * i));
+      if (MODE == SM_SOFTMAX) { v.x = __expf(v.x - mx) * inv; v.y = __expf(v.y - mx) * inv; v.z = __expf(v.z - mx) * inv; v.w = __expf(v.w - mx) * inv; }
+      else { v.x -= lse; v.y -= lse; v.z -= lse; v.w -= lse; }
       stg_stream4(q + 4 * i, v);
     }
   } else {
     for (int64_t i = threadIdx.x; i < r; i += T) {
-      float o = sm_out<MODE>(src[i], mx, s, lse);
+      float o = (MODE == SM_SOFTMAX) ? __expf(src[i] - mx) * inv : src[i] - lse;
       q[i] = o;
       if (MODE == SM_DENSE_XENT) dense += __ldg(aux + row * r + i) * o;
     }
@@ -132,7 +168,10 @@ __global__ void __launch_bounds__(512) softmax_block_kernel(const float* __restr
     if (tf < 0.0f || t >= r || tf != tf) { atomicExch(err, 1); loss[row] = nanf(""); }
     else loss[row] = -(src[t] - lse);
   }
-  if (MODE == SM_DENSE_XENT) { dense = block_sum(dense, red); if (threadIdx.x == 0) loss[row] = -dense; }
+  if (MODE == SM_DENSE_XENT) {
+    __shared__ float redf[32];
+    dense = block_sum(dense, redf); if (threadIdx.x == 0) loss[row] = -dense;
+  }
 }
 
 // ---- inner > 1: one thread per (outer, inner) column, three strided passes (coalesced across inner) ----
@@ -170,12 +209,7 @@ static int softmax_rows(agb_ctx* ctx, const float* x, float* y, const float* aux
   AGB_CHECK(rows < (1ll << 31), AGB_ERR_UNSUPPORTED, "softmax: too many rows");
   int threads = r >= 8192 ? 512 : 256;
   size_t smem = (size_t)r * sizeof(float);
-  if (smem <= 200 * 1024) {
-    static bool attr_set[8] = {false};
-    if (smem > 48 * 1024 && !attr_set[MODE]) {
-      AGB_CUDA(cudaFuncSetAttribute(softmax_block_kernel<MODE, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
-      attr_set[MODE] = true;
-    }
+  if (smem <= 48 * 1024) {
     softmax_block_kernel<MODE, true><<<(unsigned)rows, threads, smem, ctx->stream>>>(x, y, aux, loss, r, ctx->dev_err);
   } else {
     softmax_block_kernel<MODE, false><<<(unsigned)rows, 512, 0, ctx->stream>>>(x, y, aux, loss, r, ctx->dev_err);
