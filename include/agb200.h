@@ -127,6 +127,11 @@ int  agb_conv2d_fprop_fused_f32(agb_ctx* ctx, const agb_tensor* x, const agb_ten
  * w [O,C,kh,kw] -> gx [B,C,xh,xw], xh = s(yh-1) - 2p + d(kh-1) + 1 (conv2d_transpose.rs:55-56). */
 int  agb_conv2d_dgrad_f32(agb_ctx* ctx, const agb_tensor* gy, const agb_tensor* w, agb_tensor* gx,
                           int pad, int stride, int dilation);
+/* fused form of Conv2DTranspose followed by the ReLU backward of the layer below, mul(greater(a, 0), gx)
+ * (activation_ops.rs:161-166): gx = conv2d_transpose(gy, w) * (mask_src > 0).  mask_src (NULL = no mask) is [B,C,xh,xw] with
+ * the same strides as gx; the compare-and-zero runs on the accumulator registers of the tensor-core epilogue. */
+int  agb_conv2d_dgrad_fused_f32(agb_ctx* ctx, const agb_tensor* gy, const agb_tensor* w, const agb_tensor* mask_src, agb_tensor* gx,
+                                int pad, int stride, int dilation);
 /* replaces Conv2DFilterGrad::compute (conv2d.rs:737-744) and Conv2DTransposeFilterGrad::compute
  * (conv2d_transpose.rs:433-451): gw[O,C,kh,kw] = sum_b g[b] (x) im2col(img[b]).
  * img [B,C,H,W] is the tensor that gets im2col'd, g [B,O,yh,yw] the one that multiplies it. */
@@ -150,6 +155,12 @@ int  agb_maxpool2d_fwd(agb_ctx* ctx, const agb_tensor* x, agb_tensor* y, float* 
 /* MaxPool2DGrad::compute (max_pool2d.rs:245-279): gx = 0; gx[idx[i]] += gy[i]. exactly one of idx_* non-NULL */
 int  agb_maxpool2d_bwd(agb_ctx* ctx, const agb_tensor* gy, const float* idx_f32, const int32_t* idx_i32,
                        agb_tensor* gx);
+/* same, given the forward window (size, stride; 0 = unknown) and an optional gate laid out like gy: gx = scatter(gy * (gate > 0)).
+ * Windows that tile gx exactly (size == stride) are written gather-form: no zero-fill, no atomics.  With gate = the pooled forward
+ * output of a ReLU activation this also performs the ReLU backward that follows in conv -> relu -> pool stacks
+ * (relu'(x[argmax]) == (max > 0)). */
+int  agb_maxpool2d_bwd_fused(agb_ctx* ctx, const agb_tensor* gy, const float* idx_f32, const int32_t* idx_i32, const float* gate,
+                             agb_tensor* gx, int size, int stride);
 /* MaxPool2DGradGrad::compute (max_pool2d.rs:297-331): ggy[i] = ggx[idx[i]] */
 int  agb_maxpool2d_gradgrad(agb_ctx* ctx, const agb_tensor* ggx, const float* idx_f32, const int32_t* idx_i32,
                             agb_tensor* ggy);

@@ -15,7 +15,7 @@
 
 // tcgen05 kernels (tc_conv.cu): operate on channels-last activation buffers
 int agb_tc_conv_fprop(agb_ctx* ctx, int mode, const float* x, const float* w, float* y,
-                      int B, int C, int H, int W, int O, int kh, int kw, int pad, int stride, int dil, int flip_transpose, const float* bias, int relu);
+                      int B, int C, int H, int W, int O, int kh, int kw, int pad, int stride, int dil, int flip_transpose, const float* bias, int relu, const float* mask);
 int agb_tc_conv_wgrad(agb_ctx* ctx, int mode, const float* img, const float* g, float* gw,
                       int B, int C, int H, int W, int O, int kh, int kw, int pad, int stride, int dil);
 bool agb_tc_conv_eligible(int C, int O, int kh, int kw, int stride, int yw);
@@ -160,7 +160,7 @@ extern "C" int agb_conv2d_fprop_fused_f32(agb_ctx* ctx, const agb_tensor* x, con
   if (ctx->math_mode != AGB_MATH_FP32 && agb_tc_conv_eligible(g.C, g.O, g.kh, g.kw, stride, g.yw)) {
     LayoutTmp lx(ctx), ly(ctx);
     AGB_TRY(lx.input(x, true)); AGB_TRY(ly.output(y, true));
-    int r = agb_tc_conv_fprop(ctx, ctx->math_mode, lx.view.ptr, w->ptr, ly.view.ptr, g.B, g.C, g.H, g.W, g.O, g.kh, g.kw, pad, stride, dilation, 0, bias, relu);
+    int r = agb_tc_conv_fprop(ctx, ctx->math_mode, lx.view.ptr, w->ptr, ly.view.ptr, g.B, g.C, g.H, g.W, g.O, g.kh, g.kw, pad, stride, dilation, 0, bias, relu, nullptr);
     if (r == AGB_OK) { AGB_TRY(ly.finish()); return lx.finish(); }
     if (r != AGB_ERR_UNSUPPORTED) return r;
   }
@@ -189,6 +189,33 @@ extern "C" int agb_conv2d_fprop_fused_f32(agb_ctx* ctx, const agb_tensor* x, con
 }
 
 extern "C" int agb_conv2d_dgrad_f32(agb_ctx* ctx, const agb_tensor* gy, const agb_tensor* w, agb_tensor* gx, int pad, int stride, int dilation) {
+  return agb_conv2d_dgrad_fused_f32(ctx, gy, w, nullptr, gx, pad, stride, dilation);
+}
+
+// un-fused tail of the fused entry point: gx = (mask_src > 0) * gx in place (AGB_B_RELU_GRAD); gx is dense NCHW or channels-last
+static int apply_relu_mask(agb_ctx* ctx, const agb_tensor* mask_src, agb_tensor* gx) {
+  if (mask_src == nullptr) return AGB_OK;
+  if (agb_is_contig(gx)) return agb_binary(ctx, AGB_B_RELU_GRAD, 0.f, 0.f, mask_src, gx, gx);
+  // channels-last gx: elementwise over raw memory; a mask in another memory order is first brought into gx's order
+  bool same = true;
+  for (int i = 0; i < 4; i++) if (gx->shape[i] != 1 && mask_src->stride[i] != gx->stride[i]) same = false;
+  const int64_t n = agb_numel(gx);
+  float* tmp = nullptr; const float* mptr = mask_src->ptr;
+  if (!same) {
+    AGB_TRY(agb_alloc(ctx, (size_t)n * sizeof(float), (void**)&tmp));
+    agb_tensor tv = *gx; tv.ptr = tmp;
+    int r = agb_copy_strided(ctx, mask_src, &tv);
+    if (r != AGB_OK) { agb_free(ctx, tmp); return r; }
+    mptr = tmp;
+  }
+  agb_tensor fm, fg; fm.ptr = const_cast<float*>(mptr); fg.ptr = gx->ptr; fm.rank = fg.rank = 1; fm.shape[0] = fg.shape[0] = n; fm.stride[0] = fg.stride[0] = 1;
+  int r = agb_binary(ctx, AGB_B_RELU_GRAD, 0.f, 0.f, &fm, &fg, &fg);
+  if (tmp) agb_free(ctx, tmp);
+  return r;
+}
+
+extern "C" int agb_conv2d_dgrad_fused_f32(agb_ctx* ctx, const agb_tensor* gy, const agb_tensor* w, const agb_tensor* mask_src, agb_tensor* gx,
+                                         int pad, int stride, int dilation) {
   AGB_CHECK(gy->rank == 4, AGB_ERR_INCOMPATIBLE_SHAPE, "conv2d_transpose: Input must be 4D (got rank %d)", gy->rank);
   AGB_CHECK(w->rank == 4, AGB_ERR_INCOMPATIBLE_SHAPE, "conv2d_transpose: Filter must be 4D (got rank %d)", w->rank);
   AGB_CHECK(gy->shape[1] == w->shape[0], AGB_ERR_INCOMPATIBLE_SHAPE,
@@ -203,14 +230,23 @@ extern "C" int agb_conv2d_dgrad_f32(agb_ctx* ctx, const agb_tensor* gy, const ag
   AGB_CHECK(gx->rank == 4 && gx->shape[0] == g.B && gx->shape[1] == g.C && gx->shape[2] == g.H && gx->shape[3] == g.W, AGB_ERR_INCOMPATIBLE_SHAPE,
             "conv2d_transpose: output must be [%d,%d,%d,%d]", g.B, g.C, g.H, g.W);
   AGB_CHECK(agb_is_contig(w), AGB_ERR_UNSUPPORTED, "conv2d_transpose: the filter must be C-contiguous");
+  if (mask_src != nullptr) {
+    AGB_CHECK(mask_src->rank == 4, AGB_ERR_INCOMPATIBLE_SHAPE, "conv2d_transpose: mask_src must be 4-D");
+    for (int i = 0; i < 4; i++)
+      AGB_CHECK(mask_src->shape[i] == gx->shape[i], AGB_ERR_INCOMPATIBLE_SHAPE, "conv2d_transpose: mask_src must have the shape of the output");
+  }
+  bool same_strides = mask_src != nullptr;
+  if (mask_src != nullptr) for (int i = 0; i < 4; i++) if (gx->shape[i] != 1 && mask_src->stride[i] != gx->stride[i]) same_strides = false;
   if (agb_numel(gx) == 0) return AGB_OK;
   AgbProfScope prof(ctx, AGB_PROF_CONV_DGRAD, 2.0 * (double)agb_numel(gy) * g.C * g.kh * g.kw);
   if (ctx->math_mode != AGB_MATH_FP32 && stride == 1 && dilation * (g.kh - 1) - pad >= 0 && agb_tc_conv_eligible(g.O, g.C, g.kh, g.kw, stride, g.W)) {
     // stride-1 dgrad == fprop of gy with the spatially flipped, channel-transposed filter and pad' = d(k-1) - p
     LayoutTmp lg(ctx), lx(ctx);
     AGB_TRY(lg.input(gy, true)); AGB_TRY(lx.output(gx, true));
-    int r = agb_tc_conv_fprop(ctx, ctx->math_mode, lg.view.ptr, w->ptr, lx.view.ptr, g.B, g.O, g.yh, g.yw, g.C, g.kh, g.kw, pad, stride, dilation, 1, nullptr, 0);
-    if (r == AGB_OK) { AGB_TRY(lx.finish()); return lg.finish(); }
+    const bool fuse = same_strides && lx.view.ptr == gx->ptr && ((((uintptr_t)mask_src->ptr) & 15) == 0);     // output written in place, channels-last
+    int r = agb_tc_conv_fprop(ctx, ctx->math_mode, lg.view.ptr, w->ptr, lx.view.ptr, g.B, g.O, g.yh, g.yw, g.C, g.kh, g.kw, pad, stride, dilation, 1, nullptr, 0,
+                              fuse ? mask_src->ptr : nullptr);
+    if (r == AGB_OK) { AGB_TRY(lx.finish()); AGB_TRY(lg.finish()); return fuse ? AGB_OK : apply_relu_mask(ctx, mask_src, gx); }
     if (r != AGB_ERR_UNSUPPORTED) return r;
   }
   prof.set_cls(AGB_PROF_CONV_SIMT);
@@ -218,7 +254,8 @@ extern "C" int agb_conv2d_dgrad_f32(agb_ctx* ctx, const agb_tensor* gy, const ag
   AGB_TRY(lg.input(gy, false)); AGB_TRY(lx.output(gx, false));
   int64_t K = (int64_t)g.O * g.kh * g.kw;
   AGB_TRY(simt_gemm_launch(ctx, DgradA{w->ptr, g}, DgradB{lg.view.ptr, g}, DgradC{lx.view.ptr, g}, g.C, (int64_t)g.B * g.H * g.W, K, 1));
-  AGB_TRY(lx.finish()); return lg.finish();
+  AGB_TRY(lx.finish()); AGB_TRY(lg.finish());
+  return apply_relu_mask(ctx, mask_src, gx);
 }
 
 extern "C" int agb_conv2d_wgrad_f32(agb_ctx* ctx, const agb_tensor* img, const agb_tensor* gr, agb_tensor* gw, int pad, int stride, int dilation) {

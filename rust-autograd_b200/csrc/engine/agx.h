@@ -49,6 +49,7 @@ typedef std::vector<int64_t> Shape;
 
 struct NdArray;
 struct Im2colRef;                 // virtual `cols` tensor (Conv2D output #1), see ops_nn.cc
+struct PoolRef;                   // (max-pool index buffers) the pooled forward output + identity of the pooled input, see ops_nn.cc
 struct Lazy;                      // deferred epilogue (conv [+bias] awaiting a ReLU, "x > 0" mask awaiting a multiply), see ops_nn.cc
 
 // f32 array: a strided view on an HBM block and/or a small contiguous host vector.
@@ -63,6 +64,7 @@ struct NdArray {
   bool i32 = false;               // the buffer holds int32 indices (max-pool argmax): exact beyond 2^24, converted to f32 only when a
                                   // float consumer or the user asks (the reference stores indices as floats, max_pool2d.rs:74-75)
   std::shared_ptr<Im2colRef> virt;
+  std::shared_ptr<PoolRef> pool;
   std::shared_ptr<Lazy> lazy;     // value not computed yet: only `shape` is valid.  ComputeContext::input() materialises it unless the
                                   // consuming op declared accept_lazy (the ops that can fuse it into their own kernel)
 

@@ -15,6 +15,7 @@ NdArray lazy_conv_add_bias(const NdArray& conv, const NdArray& bias);
 NdArray lazy_conv_relu(Device* dev, const NdArray& a);
 NdArray lazy_gt0_mask(const NdArray& src_or_lazy);
 bool lazy_is_mask(const NdArray& a);
+NdArray lazy_fuse_mask(Device* dev, const NdArray& mask, const NdArray& prod);
 bool lazy_is_conv(const NdArray& a);
 const NdArray& lazy_mask_src(const NdArray& a);
 
@@ -333,8 +334,15 @@ struct BinArith : Op {                 // AddOp/SubOp/MulOp/DivOp, binary_ops.rs
         NdArray r = lazy_is_conv(a) && !b.lazy ? lazy_conv_add_bias(a, bb) : (lazy_is_conv(b) && !a.lazy ? lazy_conv_add_bias(b, bb) : NdArray());
         if (r.lazy) { c.append_output(r); return; }
       } else {                            // (x > 0) * gy: one ReLU-grad kernel instead of compare + multiply
-        const NdArray& m = lazy_is_mask(a) ? a : b; const NdArray& o = lazy_is_mask(a) ? b : a;
-        if (lazy_is_mask(m) && !o.lazy && o.shape == m.shape) { c.append_output(dev_binary(c.dev, AGB_B_RELU_GRAD, lazy_mask_src(m), o)); return; }
+        const NdArray& m = lazy_is_mask(a) ? a : b; NdArray o = lazy_is_mask(a) ? b : a;
+        if (lazy_is_mask(m) && o.shape == m.shape && (o.lazy || o.on_device())) {
+          if (o.lazy) {                   // the producer of gy is itself deferred (dgrad / pool backward): fuse the mask into it
+            NdArray r = lazy_fuse_mask(c.dev, m, o);
+            if (r.on_device()) { c.append_output(r); return; }
+            o = materialize_lazy(c.dev, o);
+          }
+          c.append_output(dev_binary(c.dev, AGB_B_RELU_GRAD, lazy_mask_src(m), o)); return;
+        }
       }
       if (a.lazy) a = materialize_lazy(c.dev, a);
       if (b.lazy) b = materialize_lazy(c.dev, b);

@@ -101,13 +101,16 @@ struct ConvParams { int pad, stride, dilation; };
 //     ReLU(lazy conv[+bias])      -> conv kernel with bias + ReLU in its epilogue (agb_conv2d_fprop_fused_f32)
 //     MulOp(lazy mask, gy)        -> AGB_B_RELU_GRAD
 //     greater(lazy conv+bias, 0)  -> mask of the ReLU OUTPUT (x > 0  <=>  relu(x) > 0), no pre-activation needed
+//     MulOp(lazy mask, lazy Conv2DTranspose)  -> dgrad kernel with the compare-and-zero in its epilogue (agb_conv2d_dgrad_fused_f32)
+//     MulOp(lazy mask, lazy MaxPool2DGrad)    -> gather-form pool backward gated by (pooled output > 0) (agb_maxpool2d_bwd_fused)
 // Any other consumer gets the exact un-fused value through materialize_lazy (ComputeContext::input), so every intermediate of
 // the reference graph remains observable; fusion only removes HBM round trips.
 struct Lazy {
-  int kind = 0;                        // 1 = conv [+ bias], 2 = (src > 0) mask
+  int kind = 0;                        // 1 = conv [+ bias], 2 = (src > 0) mask, 3 = Conv2DTranspose(x = gy, w), 4 = MaxPool2DGrad(x = gy, idx)
   NdArray x, w, bias; bool has_bias = false; ConvParams p{0, 1, 1};
   NdArray relu_out; bool has_relu = false;       // filled by the ReLU consumer that ran the fused kernel
   NdArray src;                                    // kind 2
+  NdArray idx; int pool_size = 0, pool_stride = 0; // kind 4
   NdArray value; bool has_value = false;          // cache of the un-fused value
 };
 // activations enter the conv / pool entry points either NCHW-contiguous or channels-last; anything else is deep-copied
@@ -119,6 +122,35 @@ static Tensor mk_conv(Graph* g, Tensor x, Tensor w, ConvParams p);
 static Tensor mk_filter_grad(Graph* g, Tensor cols, Tensor gy, Tensor w, Tensor bp_x, Tensor bp_gy, ConvParams p);
 static Tensor mk_conv_with_cols(Graph* g, Tensor cols, Tensor w, Tensor bp_x, Tensor bp_w, ConvParams p);
 
+struct PoolRef { NdArray y; const float* x_dptr; Shape x_shape, x_stride; };
+// gx = conv2d_transpose(gy, w) [* (mask_src > 0)]
+static NdArray run_dgrad(Device* dev, const Lazy& L, const NdArray* mask_src) {
+  const NdArray &gy = L.x, &w = L.w; const ConvParams& p = L.p;
+  int64_t xh = p.stride * (gy.shape[2] - 1) - 2 * p.pad + (p.dilation * (w.shape[2] - 1) + 1);     // follows the code (conv2d_transpose.rs:55-56)
+  int64_t xw = p.stride * (gy.shape[3] - 1) - 2 * p.pad + (p.dilation * (w.shape[3] - 1) + 1);
+  bool cl = p.stride == 1 && agb_conv_prefers_channels_last((int)w.shape[0], (int)w.shape[1], (int)w.shape[2], (int)w.shape[3], 1, (int)xw);
+  if (mask_src) cl = !mask_src->is_contiguous();          // write gx in the mask's memory order so the epilogue can read it in place
+  NdArray gx = act_empty(dev, {gy.shape[0], w.shape[1], xh, xw}, cl);
+  agb_tensor tg = gy.desc(), tw = w.desc(), tx = gx.desc(), tm;
+  if (mask_src) tm = mask_src->desc();
+  check_status(agb_conv2d_dgrad_fused_f32(dev->ctx, &tg, &tw, mask_src ? &tm : nullptr, &tx, p.pad, p.stride, p.dilation));
+  return gx;
+}
+// gx = max_pool2d_grad(gy, idx) [gated by pooled output > 0]
+static NdArray run_pool_grad(Device* dev, const Lazy& L, bool gated) {
+  NdArray gy = L.x; const NdArray& idx = L.idx;
+  const bool icl = is_cl4(idx);
+  if (icl != is_cl4(gy) || !(gy.is_contiguous() || is_cl4(gy))) {     // the kernel walks gy and the index buffer together
+    NdArray t = act_empty(dev, gy.shape, icl); agb_tensor ts = gy.desc(), td = t.desc();
+    check_status(agb_copy_strided(dev->ctx, &ts, &td)); gy = t;
+  }
+  int64_t xh = L.pool_stride * (gy.shape[2] - 1) - 2 * L.p.pad + L.pool_size, xw = L.pool_stride * (gy.shape[3] - 1) - 2 * L.p.pad + L.pool_size;     // (max_pool2d.rs:263-264)
+  NdArray gx = act_empty(dev, {gy.shape[0], gy.shape[1], xh, xw}, icl);
+  agb_tensor tg = gy.desc(), tx = gx.desc();
+  check_status(agb_maxpool2d_bwd_fused(dev->ctx, &tg, idx.i32 ? nullptr : idx.dptr, idx.i32 ? (const int32_t*)idx.dptr : nullptr,
+                                       gated ? idx.pool->y.dptr : nullptr, &tx, L.pool_size, L.pool_stride));
+  return gx;
+}
 static NdArray run_conv_fused(Device* dev, const Lazy& L, bool relu) {
   const NdArray &x = L.x, &w = L.w;
   int64_t yh = (x.shape[2] + 2 * L.p.pad - (L.p.dilation * (w.shape[2] - 1) + 1)) / L.p.stride + 1;
@@ -132,6 +164,8 @@ NdArray materialize_lazy(Device* dev, const NdArray& a) {
   Lazy& L = *a.lazy;
   if (!L.has_value) {
     if (L.kind == 1) L.value = run_conv_fused(dev, L, false);
+    else if (L.kind == 3) L.value = run_dgrad(dev, L, nullptr);
+    else if (L.kind == 4) L.value = run_pool_grad(dev, L, false);
     else {
       NdArray zero = dev->full({}, 0.0f), src = L.src;
       std::vector<int> order;
@@ -175,6 +209,23 @@ NdArray lazy_gt0_mask(const NdArray& src_or_lazy) {                          // 
   NdArray r; auto L = std::make_shared<Lazy>(); L->kind = 2; L->src = src;
   r.shape = src.shape; r.stride = NdArray::contiguous_strides(r.shape); r.lazy = L;
   return r;
+}
+// MulOp(mask, lazy producer of gy): returns the fused result, or an invalid array when the pattern does not apply
+NdArray lazy_fuse_mask(Device* dev, const NdArray& mask, const NdArray& prod) {
+  Lazy& L = *prod.lazy;
+  if (L.has_value) return NdArray();
+  const NdArray& src = mask.lazy->src;
+  if (src.shape != prod.shape || src.ndim() != 4 || !src.on_device() || !(src.is_contiguous() || is_cl4(src))) return NdArray();
+  if (L.kind == 3) return run_dgrad(dev, L, &src);
+  if (L.kind == 4) {
+    // the gate is the pooled OUTPUT: valid only when the mask source is the very tensor that was pooled (then x[argmax] == y)
+    const NdArray& idx = L.idx;
+    if (!idx.pool || idx.pool->x_dptr != src.dptr || idx.pool->x_shape != src.shape || idx.pool->x_stride != src.stride) return NdArray();
+    if (L.pool_size != L.pool_stride || L.p.pad != 0) return NdArray();
+    if (is_cl4(idx) != is_cl4(idx.pool->y) || idx.pool->y.shape != idx.shape) return NdArray();
+    return run_pool_grad(dev, L, true);
+  }
+  return NdArray();
 }
 bool lazy_is_mask(const NdArray& a) { return a.lazy && a.lazy->kind == 2 && !a.lazy->has_value; }
 bool lazy_is_conv(const NdArray& a) { return a.lazy && a.lazy->kind == 1; }
@@ -275,9 +326,10 @@ struct Conv2DTranspose : Op {          // conv2d_transpose.rs:249-300
     if (gy.shape[1] != w.shape[0]) throw OpError(AGB_ERR_INCOMPATIBLE_SHAPE, "conv2d_transpose: Number of input channels must match second filter dim");
     int64_t xh = p.stride * (gy.shape[2] - 1) - 2 * p.pad + (p.dilation * (w.shape[2] - 1) + 1);     // follows the code (:55-56)
     int64_t xw = p.stride * (gy.shape[3] - 1) - 2 * p.pad + (p.dilation * (w.shape[3] - 1) + 1);
-    NdArray gx = act_empty(c.dev, {gy.shape[0], w.shape[1], xh, xw}, p.stride == 1 && agb_conv_prefers_channels_last((int)w.shape[0], (int)w.shape[1], (int)w.shape[2], (int)w.shape[3], 1, (int)xw));
-    agb_tensor tg = gy.desc(), tw = w.desc(), tx = gx.desc();
-    check_status(agb_conv2d_dgrad_f32(c.dev->ctx, &tg, &tw, &tx, p.pad, p.stride, p.dilation));
+    if (xh < 1 || xw < 1) throw OpError(AGB_ERR_INCOMPATIBLE_SHAPE, "conv2d_transpose: non-positive output size");
+    NdArray gx;     // deferred: when this is a backward conv, the ReLU-grad multiply that usually follows joins the kernel's epilogue
+    gx.shape = {gy.shape[0], w.shape[1], xh, xw}; gx.stride = NdArray::contiguous_strides(gx.shape);
+    gx.lazy = std::make_shared<Lazy>(); gx.lazy->kind = 3; gx.lazy->x = gy; gx.lazy->w = w; gx.lazy->p = p;
     c.append_output(gx);
   }
   void grad(GradientContext& c) override;
@@ -339,17 +391,11 @@ struct MaxPool2DGrad : Op {            // max_pool2d.rs:245-295
   void compute(ComputeContext& c) override {
     c.accept_i32 = true;
     NdArray gy = on_dev(c.dev, c.input(0)), idx = act_layout(c.dev, on_dev(c.dev, c.input(1)));
-    {   // the kernel walks gy and the index buffer together: bring gy into the index buffer's memory order
-      const bool icl = is_cl4(idx);
-      if (icl != is_cl4(gy) || !(gy.is_contiguous() || is_cl4(gy))) {
-        NdArray t = act_empty(c.dev, gy.shape, icl); agb_tensor ts = gy.desc(), td = t.desc();
-        check_status(agb_copy_strided(c.dev->ctx, &ts, &td)); gy = t;
-      }
-    }
+    if (gy.ndim() != 4 || idx.ndim() != 4 || gy.shape != idx.shape) throw OpError(AGB_ERR_INCOMPATIBLE_SHAPE, "max_pool2d_grad: gy and the index buffer must be 4-D and of one shape");
     int64_t xh = stride * (gy.shape[2] - 1) - 2 * pad + size, xw = stride * (gy.shape[3] - 1) - 2 * pad + size;     // (:263-264)
-    NdArray gx = act_empty(c.dev, {gy.shape[0], gy.shape[1], xh, xw}, is_cl4(idx));
-    agb_tensor tg = gy.desc(), tx = gx.desc();
-    check_status(agb_maxpool2d_bwd(c.dev->ctx, &tg, idx.i32 ? nullptr : idx.dptr, idx.i32 ? (const int32_t*)idx.dptr : nullptr, &tx));
+    NdArray gx;     // deferred: a following ReLU-grad multiply is folded into the scatter (see Lazy)
+    gx.shape = {gy.shape[0], gy.shape[1], xh, xw}; gx.stride = NdArray::contiguous_strides(gx.shape);
+    gx.lazy = std::make_shared<Lazy>(); gx.lazy->kind = 4; gx.lazy->x = gy; gx.lazy->idx = idx; gx.lazy->pool_size = size; gx.lazy->pool_stride = stride; gx.lazy->p.pad = pad;
     c.append_output(gx);
   }
   void grad(GradientContext& c) override {
@@ -373,6 +419,7 @@ struct MaxPool2D : Op {                // max_pool2d.rs:166-243
     // (max_pool2d.rs:74-75; a 256x64x128x128 VGG activation has 2.7e8), API-visible values are converted on fetch
     if (x.size() < (1ll << 31)) { check_status(agb_maxpool2d_fwd(c.dev->ctx, &tx, &ty, nullptr, (int32_t*)idx.dptr, size, pad, stride)); idx.i32 = true; }
     else check_status(agb_maxpool2d_fwd(c.dev->ctx, &tx, &ty, idx.dptr, nullptr, size, pad, stride));
+    idx.pool = std::make_shared<PoolRef>(PoolRef{y, x.dptr, x.shape, x.stride});
     c.append_output(y); c.append_output(idx);
   }
   void grad(GradientContext& c) override {

@@ -124,24 +124,99 @@ __device__ __forceinline__ int64_t pool_phys(int64_t k, const PoolDims& d, bool 
   return b * d.xs[0] + c * d.xs[1] + h * d.xs[2] + w * d.xs[3];
 }
 __global__ void __launch_bounds__(256) maxpool_bwd_kernel(const float* __restrict__ gy, const float* __restrict__ idx_f,
-                                                          const int32_t* __restrict__ idx_i, float* __restrict__ gx, int64_t n, PoolDims d, bool x_cl) {
+                                                          const int32_t* __restrict__ idx_i, const float* __restrict__ gate,
+                                                          float* __restrict__ gx, int64_t n, PoolDims d, bool x_cl) {
   int64_t tid = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
   int64_t gstride = (int64_t)gridDim.x * blockDim.x;
   for (int64_t o = tid; o < n; o += gstride) {
     int64_t k = idx_i ? (int64_t)__ldg(idx_i + o) : (int64_t)__ldg(idx_f + o);
-    atomicAdd(gx + pool_phys(k, d, x_cl), __ldg(gy + o));
+    float g = __ldg(gy + o);
+    if (gate != nullptr) g = __ldg(gate + o) > 0.0f ? g : 0.0f * g;      // 0*g keeps NaN/Inf propagation of the un-fused multiply
+    atomicAdd(gx + pool_phys(k, d, x_cl), g);
+  }
+}
+// Non-overlapping windows that tile gx exactly (size == stride, xh == yh*size, xw == yw*size — every VGG / cnn_mnist pool): each
+// gx element belongs to exactly one window, so the scatter becomes a gather-form full write: no memset, no atomics.
+// The reference accumulates gx[idx[i]] += gy[i] (max_pool2d.rs:111-135); with disjoint windows at most one term lands on an
+// element, except for windows whose scan never fired (index 0, NaN-only windows) — those are sent down the scatter path.
+template <bool CL>
+__global__ void __launch_bounds__(256) maxpool_bwd_tiled_kernel(const float* __restrict__ gy, const float* __restrict__ idx_f,
+                                                                const int32_t* __restrict__ idx_i, const float* __restrict__ gate,
+                                                                float* __restrict__ gx, int64_t n, PoolDims d, int size) {
+  int64_t tid = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  int64_t gstride = (int64_t)gridDim.x * blockDim.x;
+  for (int64_t o = tid; o < n; o += gstride) {
+    int b, c, i, j; pool_decode<CL>(o, d, b, c, i, j);
+    const int64_t k = idx_i ? (int64_t)__ldg(idx_i + o) : (int64_t)__ldg(idx_f + o);
+    float g = __ldg(gy + o);
+    if (gate != nullptr) g = __ldg(gate + o) > 0.0f ? g : 0.0f * g;
+    const int64_t lbase = ((int64_t)b * d.C + c) * d.xh * d.xw;
+    float* xp = gx + b * d.xs[0] + c * d.xs[1];
+    for (int dh = 0; dh < size; dh++)
+      for (int dw = 0; dw < size; dw++) {
+        const int h = i * size + dh, w = j * size + dw;
+        xp[h * d.xs[2] + w * d.xs[3]] = (lbase + (int64_t)h * d.xw + w == k) ? g : 0.0f;
+      }
+  }
+}
+// channels-last, C % 4 == 0, int32 indices: 4 channels per thread, 128-bit accesses
+__global__ void __launch_bounds__(256) maxpool_bwd_tiled_cl4_kernel(const float* __restrict__ gy, const int32_t* __restrict__ idx_i,
+                                                                    const float* __restrict__ gate, float* __restrict__ gx,
+                                                                    uint32_t n4, int C, int xh, int xw, int yh, int yw, int size) {
+  const uint32_t c4n = (uint32_t)C >> 2;
+  for (uint32_t o = blockIdx.x * blockDim.x + threadIdx.x; o < n4; o += gridDim.x * blockDim.x) {
+    uint32_t c4 = o % c4n, t = o / c4n; uint32_t j = t % (uint32_t)yw; t /= (uint32_t)yw; uint32_t i = t % (uint32_t)yh, b = t / (uint32_t)yh;
+    const int c = (int)c4 * 4;
+    const size_t off = (size_t)o * 4;
+    float4 g = ldg_stream4(gy + off);
+    const int4 k = __ldg((const int4*)(idx_i + off));
+    if (gate != nullptr) {
+      const float4 m = ldg_stream4(gate + off);
+      g.x = m.x > 0.0f ? g.x : 0.0f * g.x; g.y = m.y > 0.0f ? g.y : 0.0f * g.y; g.z = m.z > 0.0f ? g.z : 0.0f * g.z; g.w = m.w > 0.0f ? g.w : 0.0f * g.w;
+    }
+    const int plane = xh * xw; const int lb = (int)((b * (uint32_t)C + c) * (uint32_t)plane);     // host checks numel(gx) < 2^31
+    for (int dh = 0; dh < size; dh++)
+      for (int dw = 0; dw < size; dw++) {
+        const int h = (int)i * size + dh, w = (int)j * size + dw;
+        const int li = lb + h * xw + w;
+        float4 v;
+        v.x = (li == k.x) ? g.x : 0.0f; v.y = (li + plane == k.y) ? g.y : 0.0f; v.z = (li + 2 * plane == k.z) ? g.z : 0.0f; v.w = (li + 3 * plane == k.w) ? g.w : 0.0f;
+        stg_stream4(gx + (((size_t)b * xh + h) * xw + w) * C + c, v);
+      }
   }
 }
 // gy and the index buffer share one layout (either); gx may be NCHW or channels-last
 extern "C" int agb_maxpool2d_bwd(agb_ctx* ctx, const agb_tensor* gy, const float* idx_f32, const int32_t* idx_i32, agb_tensor* gx) {
+  return agb_maxpool2d_bwd_fused(ctx, gy, idx_f32, idx_i32, nullptr, gx, 0, 0);
+}
+// gx = scatter(gy * (gate > 0)) — `gate` (nullable, laid out like gy) is the POOLED forward output when the pooled input was a
+// ReLU output: relu'(x[argmax]) == (max > 0), so the ReLU backward that follows a pool backward in conv->relu->pool stacks
+// (activation_ops.rs:161-166) costs one extra read of a 1/size^2-sized tensor instead of a 3-array pass.
+// size/stride = the forward window (0 = unknown: always the scatter form).
+extern "C" int agb_maxpool2d_bwd_fused(agb_ctx* ctx, const agb_tensor* gy, const float* idx_f32, const int32_t* idx_i32, const float* gate,
+                                       agb_tensor* gx, int size, int stride) {
   AGB_CHECK((idx_f32 != nullptr) != (idx_i32 != nullptr), AGB_ERR_INVALID_DIMS, "max_pool2d_grad: exactly one index buffer must be given");
   bool gcl, xcl; AGB_TRY(pool_layout("max_pool2d_grad", gy, &gcl)); AGB_TRY(pool_layout("max_pool2d_grad", gx, &xcl));
-  AGB_TRY(agb_memset0(ctx, gx->ptr, agb_numel(gx) * sizeof(float)));
-  int64_t n = agb_numel(gy); if (n == 0) return AGB_OK;
-  AgbProfScope prof(ctx, AGB_PROF_POOL, 4.0 * (double)(agb_numel(gx) + 3 * n));
+  int64_t n = agb_numel(gy);
   PoolDims d; d.C = (int)gx->shape[1]; d.xh = (int)gx->shape[2]; d.xw = (int)gx->shape[3]; d.yh = (int)gy->shape[2]; d.yw = (int)gy->shape[3];
   for (int k = 0; k < 4; k++) { d.xs[k] = gx->stride[k]; d.ys[k] = gy->stride[k]; }
-  maxpool_bwd_kernel<<<agb_grid_for(n, 256, ctx->sm_count, 8), 256, 0, ctx->stream>>>(gy->ptr, idx_f32, idx_i32, gx->ptr, n, d, xcl);
+  const bool tiled = size >= 1 && size == stride && gcl == xcl && n > 0 && gy->shape[0] == gx->shape[0] && gy->shape[1] == gx->shape[1] &&
+                     (int64_t)d.yh * size == d.xh && (int64_t)d.yw * size == d.xw;
+  if (tiled) {
+    AgbProfScope prof(ctx, AGB_PROF_POOL, 4.0 * (double)(agb_numel(gx) + (gate ? 3 : 2) * n));
+    if (gcl && idx_i32 && d.C % 4 == 0 && agb_numel(gx) < (1ll << 31) &&
+        ((((uintptr_t)gy->ptr | (uintptr_t)gx->ptr | (uintptr_t)idx_i32 | (uintptr_t)gate) & 15) == 0)) {
+      maxpool_bwd_tiled_cl4_kernel<<<agb_grid_for(n / 4, 256, ctx->sm_count, 8), 256, 0, ctx->stream>>>(gy->ptr, idx_i32, gate, gx->ptr, (uint32_t)(n / 4),
+                                                                                                       d.C, d.xh, d.xw, d.yh, d.yw, size);
+    } else if (gcl) maxpool_bwd_tiled_kernel<true><<<agb_grid_for(n, 256, ctx->sm_count, 8), 256, 0, ctx->stream>>>(gy->ptr, idx_f32, idx_i32, gate, gx->ptr, n, d, size);
+    else maxpool_bwd_tiled_kernel<false><<<agb_grid_for(n, 256, ctx->sm_count, 8), 256, 0, ctx->stream>>>(gy->ptr, idx_f32, idx_i32, gate, gx->ptr, n, d, size);
+    AGB_LAUNCHED(ctx);
+    return AGB_OK;
+  }
+  AGB_TRY(agb_memset0(ctx, gx->ptr, agb_numel(gx) * sizeof(float)));
+  if (n == 0) return AGB_OK;
+  AgbProfScope prof(ctx, AGB_PROF_POOL, 4.0 * (double)(agb_numel(gx) + 3 * n));
+  maxpool_bwd_kernel<<<agb_grid_for(n, 256, ctx->sm_count, 8), 256, 0, ctx->stream>>>(gy->ptr, idx_f32, idx_i32, gate, gx->ptr, n, d, xcl);
   AGB_LAUNCHED(ctx);
   return AGB_OK;
 }

@@ -37,7 +37,7 @@ __global__ void __launch_bounds__(256) repack_filter_kernel(const float* __restr
 template <int TN_, bool SPLIT_> struct ConvFpropPol {
   static constexpr int TN = TN_; static constexpr bool SPLIT = SPLIT_, P_MN = false, Q_MN = false;
   static constexpr int OCC = (SPLIT_ || TN_ > 128) ? 1 : 2;
-  struct Params { CUtensorMap tmX, tmW; float* y; const float* bias; int relu; int Cout, yh, yw, kw, pad, dil, tiles_x, tiles_y, cblocks, taps; MnDescCfg mnc; };
+  struct Params { CUtensorMap tmX, tmW; float* y; const float* bias; const float* mask; int relu; int Cout, yh, yw, kw, pad, dil, tiles_x, tiles_y, cblocks, taps; MnDescCfg mnc; };
   struct Tile { int b, oy0, ox0, o0; };
   __device__ static Tile tile(const Params& p) {
     int bx = (int)blockIdx.x; int tx = bx % p.tiles_x; int r = bx / p.tiles_x; int ty = r % p.tiles_y;
@@ -50,7 +50,31 @@ template <int TN_, bool SPLIT_> struct ConvFpropPol {
     tma_load_4d(pP, &p.tmX, bar, cb * 32, t.ox0 + j * p.dil - p.pad, t.oy0 + i * p.dil - p.pad, t.b);     // dims {c, w, h, b}
     tma_load_3d(pQ, &p.tmW, bar, cb * 32, t.o0, tap);
   }
-  __device__ static void store(const Params& p, const Tile& t, int lane, int c0, const float* v) {
+  // dgrad + ReLU backward of the layer below: bit j of pre[c] = (mask_src[pixel, o0 + 32c + j] > 0).  Read while the MMAs run, so the
+  // strided (one pixel per thread) loads cost no epilogue latency; default-cached so both halves of a 32-byte sector are used.
+  __device__ static void pre_epilogue(const Params& p, const Tile& t, int lane, uint32_t* pre) {
+    if (p.mask == nullptr) return;
+    const int oy = t.oy0 + (lane >> 5), ox = t.ox0 + (lane & 31);
+    const bool in = oy < p.yh && ox < p.yw;
+    const float* m = p.mask + (((int64_t)t.b * p.yh + (in ? oy : 0)) * p.yw + (in ? ox : 0)) * p.Cout + t.o0;
+#pragma unroll
+    for (int c = 0; c < TN / 32; c++) {
+      uint32_t bits = 0;
+      const int o = t.o0 + 32 * c;
+      if (in && o + 32 <= p.Cout) {
+#pragma unroll
+        for (int j = 0; j < 32; j += 4) {
+          const float4 mv = __ldg((const float4*)(m + 32 * c + j));
+          bits |= (mv.x > 0.0f ? 1u : 0u) << j; bits |= (mv.y > 0.0f ? 1u : 0u) << (j + 1);
+          bits |= (mv.z > 0.0f ? 1u : 0u) << (j + 2); bits |= (mv.w > 0.0f ? 1u : 0u) << (j + 3);
+        }
+      } else if (in) {
+        for (int j = 0; j < 32; j++) if (o + j < p.Cout && __ldg(m + 32 * c + j) > 0.0f) bits |= 1u << j;
+      }
+      pre[c] = bits;
+    }
+  }
+  __device__ static void store(const Params& p, const Tile& t, int lane, int c0, const float* v, uint32_t pre) {
     const int oy = t.oy0 + (lane >> 5), ox = t.ox0 + (lane & 31);
     if (oy >= p.yh || ox >= p.yw) return;
     const int o = t.o0 + c0;
@@ -63,6 +87,10 @@ template <int TN_, bool SPLIT_> struct ConvFpropPol {
       float a = v[j];
       if (p.bias != nullptr && o + j < p.Cout) a += __ldg(p.bias + o + j);
       r[j] = p.relu ? fmaxf(a, 0.0f) : a;
+    }
+    if (p.mask != nullptr) {           // gx *= (mask_src > 0); 0*r keeps the NaN/Inf semantics of the un-fused multiply
+#pragma unroll
+      for (int j = 0; j < 32; j++) r[j] = ((pre >> j) & 1u) ? r[j] : 0.0f * r[j];
     }
     if (o + 32 <= p.Cout) {
 #pragma unroll
@@ -108,7 +136,8 @@ template <int TN_, bool SPLIT_, bool PAIR_> struct ConvWgradPol {
 #pragma unroll
     for (int g = 0; g < TN / 32; g++) tma_load_4d(pQ + g * 4096, &p.tmG, bar, t.o0 + 32 * g, ox0, oy, b);
   }
-  __device__ static void store(const Params& p, const Tile& t, int lane, int c0, const float* v) {
+  __device__ static void pre_epilogue(const Params&, const Tile&, int, uint32_t*) {}
+  __device__ static void store(const Params& p, const Tile& t, int lane, int c0, const float* v, uint32_t) {
     int c, tap;
     if (PAIR_) { c = lane & 63; tap = lane < 64 ? t.tapA : t.tapB; } else { c = t.c0 + lane; tap = t.tapA; }
     if (c >= p.C || tap >= p.T) return;
@@ -132,7 +161,7 @@ bool agb_tc_conv_eligible(int C, int O, int kh, int kw, int stride, int yw) {
 
 template <int TN, bool SPLIT>
 static int fprop_launch(agb_ctx* ctx, const float* x, const float* wr, float* y, int B, int Cin, int H, int W, int Cout, int yh, int yw, int kh, int kw,
-                        int pad, int dil, const float* bias, int relu) {
+                        int pad, int dil, const float* bias, int relu, const float* mask) {
   using Pol = ConvFpropPol<TN, SPLIT>;
   typename Pol::Params p;
   AGB_TRY(make_cl_map(&p.tmX, x, B, Cin, H, W, 32, 32, 4, false));
@@ -142,7 +171,7 @@ static int fprop_launch(agb_ctx* ctx, const float* x, const float* wr, float* y,
     uint32_t box[3] = {32, (uint32_t)TN, 1};
     AGB_TRY(agb_make_tmap(&p.tmW, wr, 3, dims, str, box, false));
   }
-  p.y = y; p.bias = bias; p.relu = relu; p.Cout = Cout; p.yh = yh; p.yw = yw; p.kw = kw; p.pad = pad; p.dil = dil;
+  p.y = y; p.bias = bias; p.mask = mask; p.relu = relu; p.Cout = Cout; p.yh = yh; p.yw = yw; p.kw = kw; p.pad = pad; p.dil = dil;
   p.tiles_x = (yw + 31) / 32; p.tiles_y = (yh + 3) / 4; p.cblocks = (Cin + 31) / 32; p.taps = kh * kw; p.mnc = agb_mn_cfg();
   int64_t nb = (int64_t)p.tiles_x * p.tiles_y * B;
   if (nb > 2147483647ll) return AGB_ERR_UNSUPPORTED;
@@ -153,7 +182,7 @@ static int fprop_launch(agb_ctx* ctx, const float* x, const float* wr, float* y,
 // fprop on channels-last buffers: x [B,H,W,C], w [O,C,kh,kw] (plain) -> y [B,yh,yw,O].  flip_transpose != 0: dgrad — `x` is gy
 // with C = filter dim 0, w [C, O(=out channels of this GEMM), kh, kw]; the effective padding is dil*(k-1) - pad.
 int agb_tc_conv_fprop(agb_ctx* ctx, int mode, const float* x, const float* w, float* y, int B, int C, int H, int W, int O, int kh, int kw,
-                      int pad, int stride, int dil, int flip_transpose, const float* bias, int relu) {
+                      int pad, int stride, int dil, int flip_transpose, const float* bias, int relu, const float* mask) {
   const int epad = flip_transpose ? dil * (kh - 1) - pad : pad;
   if (epad < 0) return AGB_ERR_UNSUPPORTED;
   const int yh = H + 2 * epad - (dil * (kh - 1) + 1) + 1, yw = W + 2 * epad - (dil * (kw - 1) + 1) + 1;
@@ -171,12 +200,12 @@ int agb_tc_conv_fprop(agb_ctx* ctx, int mode, const float* x, const float* w, fl
   }
   const bool split = mode == AGB_MATH_3XTF32;
   if (split) {
-    if (O > 64) return fprop_launch<128, true>(ctx, x, wr, y, B, C, H, W, O, yh, yw, kh, kw, epad, dil, bias, relu);
-    return fprop_launch<64, true>(ctx, x, wr, y, B, C, H, W, O, yh, yw, kh, kw, epad, dil, bias, relu);
+    if (O > 64) return fprop_launch<128, true>(ctx, x, wr, y, B, C, H, W, O, yh, yw, kh, kw, epad, dil, bias, relu, mask);
+    return fprop_launch<64, true>(ctx, x, wr, y, B, C, H, W, O, yh, yw, kh, kw, epad, dil, bias, relu, mask);
   }
-  if (O > 128) return fprop_launch<256, false>(ctx, x, wr, y, B, C, H, W, O, yh, yw, kh, kw, epad, dil, bias, relu);
-  if (O > 64) return fprop_launch<128, false>(ctx, x, wr, y, B, C, H, W, O, yh, yw, kh, kw, epad, dil, bias, relu);
-  return fprop_launch<64, false>(ctx, x, wr, y, B, C, H, W, O, yh, yw, kh, kw, epad, dil, bias, relu);
+  if (O > 128) return fprop_launch<256, false>(ctx, x, wr, y, B, C, H, W, O, yh, yw, kh, kw, epad, dil, bias, relu, mask);
+  if (O > 64) return fprop_launch<128, false>(ctx, x, wr, y, B, C, H, W, O, yh, yw, kh, kw, epad, dil, bias, relu, mask);
+  return fprop_launch<64, false>(ctx, x, wr, y, B, C, H, W, O, yh, yw, kh, kw, epad, dil, bias, relu, mask);
 }
 
 template <int TN, bool SPLIT, bool PAIR>

@@ -146,6 +146,9 @@ __global__ void __launch_bounds__(TcCfg<Pol::TN, Pol::SPLIT, Pol::OCC>::THREADS,
     const int q = warp & 3;                // TMEM lane quarter this warp may access
     const int row = 32 * q + lane;         // accumulator lane handled by this thread
     const uint32_t tlane = tmem_base + ((uint32_t)(32 * q) << 16);
+    // per-thread epilogue side input (e.g. the ReLU mask bits of the dgrad epilogue), fetched while the MMAs are still running
+    uint32_t pre[TN / 32];
+    Pol::pre_epilogue(prm, tl, row, pre);
     if (SPLIT) {
       float racc[TN];
 #pragma unroll
@@ -168,17 +171,17 @@ __global__ void __launch_bounds__(TcCfg<Pol::TN, Pol::SPLIT, Pol::OCC>::THREADS,
       }
       if (nk > 0) {
 #pragma unroll
-        for (int c0 = 0; c0 < TN; c0 += 32) Pol::store(prm, tl, row, c0, &racc[c0]);
+        for (int c0 = 0; c0 < TN; c0 += 32) Pol::store(prm, tl, row, c0, &racc[c0], pre[c0 / 32]);
       }
     } else if (nk > 0) {
       mbar_wait(&acc_full[0], 0);
       tc_fence_after();
-#pragma unroll 1
+#pragma unroll
       for (int c0 = 0; c0 < TN; c0 += 32) {
         float v[32];
         tmem_ld32(tlane + (uint32_t)c0, v);
         tmem_ld_wait();
-        Pol::store(prm, tl, row, c0, v);
+        Pol::store(prm, tl, row, c0, v, pre[c0 / 32]);
       }
     }
   }

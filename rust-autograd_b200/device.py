@@ -271,20 +271,35 @@ class Device:
     def conv_out(x, k, pad, stride, dil):
         return (x + 2 * pad - (dil * (k - 1) + 1)) // stride + 1
 
-    def conv2d(self, x, w, pad=0, stride=1, dil=1):
+    def empty_channels_last(self, shape):
+        """logical [B,C,H,W] array whose memory order is N,H,W,C (strides {HWC, 1, WC, C})"""
+        b, c, h, w = shape
+        return self.empty((b, h, w, c)).transpose((0, 3, 1, 2))
+
+    def upload_channels_last(self, a):
+        return self.upload(np.ascontiguousarray(np.transpose(a, (0, 2, 3, 1)))).transpose((0, 3, 1, 2))
+
+    def conv2d(self, x, w, pad=0, stride=1, dil=1, bias=None, relu=False, channels_last=False):
         b, _, h, wd = x.shape
         o, _, kh, kw = w.shape
-        y = self.empty((b, o, self.conv_out(h, kh, pad, stride, dil), self.conv_out(wd, kw, pad, stride, dil)))
-        ffi.check(self.lib.agb_conv2d_fprop_f32(self.ctx, x.desc(), w.desc(), y.desc(), pad, stride, dil))
+        shape = (b, o, self.conv_out(h, kh, pad, stride, dil), self.conv_out(wd, kw, pad, stride, dil))
+        y = self.empty_channels_last(shape) if channels_last else self.empty(shape)
+        if bias is None and not relu:
+            ffi.check(self.lib.agb_conv2d_fprop_f32(self.ctx, x.desc(), w.desc(), y.desc(), pad, stride, dil))
+        else:
+            ffi.check(self.lib.agb_conv2d_fprop_fused_f32(self.ctx, x.desc(), w.desc(), bias.ptr if bias is not None else None, int(relu), y.desc(), pad, stride, dil))
         return y
 
-    def conv2d_transpose(self, gy, w, pad=0, stride=1, dil=1):
+    def conv2d_transpose(self, gy, w, pad=0, stride=1, dil=1, mask_src=None, channels_last=False):
         b, _, yh, yw = gy.shape
         _, c, kh, kw = w.shape
         xh = stride * (yh - 1) - 2 * pad + (dil * (kh - 1) + 1)
         xw = stride * (yw - 1) - 2 * pad + (dil * (kw - 1) + 1)
-        gx = self.empty((b, c, xh, xw))
-        ffi.check(self.lib.agb_conv2d_dgrad_f32(self.ctx, gy.desc(), w.desc(), gx.desc(), pad, stride, dil))
+        gx = self.empty_channels_last((b, c, xh, xw)) if channels_last else self.empty((b, c, xh, xw))
+        if mask_src is None:
+            ffi.check(self.lib.agb_conv2d_dgrad_f32(self.ctx, gy.desc(), w.desc(), gx.desc(), pad, stride, dil))
+        else:
+            ffi.check(self.lib.agb_conv2d_dgrad_fused_f32(self.ctx, gy.desc(), w.desc(), mask_src.desc(), gx.desc(), pad, stride, dil))
         return gx
 
     def conv2d_filter_grad(self, img, g, wshape, pad=0, stride=1, dil=1):
@@ -298,17 +313,26 @@ class Device:
         ffi.check(self.lib.agb_im2col_f32(self.ctx, x.desc(), cols.desc(), kh, kw, pad, stride, dil))
         return cols
 
-    def max_pool2d(self, x, size, pad=0, stride=1):
+    def max_pool2d(self, x, size, pad=0, stride=1, int32_index=False):
+        """idx holds float-encoded offsets (the reference's format) or, with int32_index, raw int32 (DArray.numpy().view(np.int32));
+        y and idx take the memory order of x (NCHW or channels-last)"""
         b, c, h, w = x.shape
         yh, yw = (h + 2 * pad - size) // stride + 1, (w + 2 * pad - size) // stride + 1
-        y, idx = self.empty((b, c, yh, yw)), self.empty((b, c, yh, yw))
-        ffi.check(self.lib.agb_maxpool2d_fwd(self.ctx, x.desc(), y.desc(), idx.ptr, None, size, pad, stride))
+        mk = self.empty if x.is_contiguous() else self.empty_channels_last
+        y, idx = mk((b, c, yh, yw)), mk((b, c, yh, yw))
+        ffi.check(self.lib.agb_maxpool2d_fwd(self.ctx, x.desc(), y.desc(), None if int32_index else idx.ptr, idx.ptr if int32_index else None, size, pad, stride))
         return y, idx
 
-    def max_pool2d_grad(self, gy, idx, size, pad=0, stride=1):
+    def max_pool2d_grad(self, gy, idx, size, pad=0, stride=1, gate=None, int32_index=False, window_known=True):
+        """gx = scatter(gy [* (gate > 0)]); gx takes the memory order of gy / idx"""
         b, c, yh, yw = gy.shape
-        gx = self.empty((b, c, stride * (yh - 1) - 2 * pad + size, stride * (yw - 1) - 2 * pad + size))
-        ffi.check(self.lib.agb_maxpool2d_bwd(self.ctx, gy.desc(), idx.ptr, None, gx.desc()))
+        shape = (b, c, stride * (yh - 1) - 2 * pad + size, stride * (yw - 1) - 2 * pad + size)
+        gx = self.empty(shape) if gy.is_contiguous() else self.empty_channels_last(shape)
+        fi, ii = (None, idx.ptr) if int32_index else (idx.ptr, None)
+        if gate is None and not window_known:
+            ffi.check(self.lib.agb_maxpool2d_bwd(self.ctx, gy.desc(), fi, ii, gx.desc()))
+        else:
+            ffi.check(self.lib.agb_maxpool2d_bwd_fused(self.ctx, gy.desc(), fi, ii, gate.ptr if gate is not None else None, gx.desc(), size, stride))
         return gx
 
     def max_pool2d_grad_grad(self, ggx, idx, size, pad=0, stride=1):

@@ -87,6 +87,31 @@ def main():
             row("conv2d_transpose_" + tag, timeit(dev, lambda: ffi.check(lib.agb_conv2d_dgrad_f32(dev.ctx, gy.desc(), w.desc(), gx.desc(), 1, 1, 1)), iters=5, flush=False), flops=fl)
             row("conv2d_filter_grad_" + tag, timeit(dev, lambda: ffi.check(lib.agb_conv2d_wgrad_f32(dev.ctx, x.desc(), gy.desc(), gw.desc(), 1, 1, 1)), iters=5, flush=False), flops=fl)
             x = gy = y = gx = None
+    # first layer (C = 3, warp-MMA kernels), max-pool forward / gather-form backward with the ReLU gate, long softmax rows
+    for mode, nm in ((1, "tf32"), (0, "3xtf32"), (2, "fp32")):
+        dev.set_math_mode(mode)
+        B, H, O = 256, 128, 64
+        x = dev.fill((B, 3, H, H), 0.01)
+        y, gy = cl(dev, (B, O, H, H)), cl(dev, (B, O, H, H))
+        w, gw = dev.fill((O, 3, 3, 3), 0.01), dev.empty((O, 3, 3, 3))
+        ybytes = 4.0 * B * O * H * H
+        row("conv2d_fprop_firstlayer_%s_B256_C3_H128_O64" % nm, timeit(dev, lambda: ffi.check(lib.agb_conv2d_fprop_f32(dev.ctx, x.desc(), w.desc(), y.desc(), 1, 1, 1)), iters=5), bytes_=ybytes + 4.0 * B * 3 * H * H)
+        row("conv2d_filter_grad_firstlayer_%s_B256_C3_H128_O64" % nm, timeit(dev, lambda: ffi.check(lib.agb_conv2d_wgrad_f32(dev.ctx, x.desc(), gy.desc(), gw.desc(), 1, 1, 1)), iters=5), bytes_=ybytes + 4.0 * B * 3 * H * H)
+        x = y = gy = None
+    dev.set_math_mode(1)
+    for (B, Cc, H) in ((256, 64, 128), (256, 128, 64), (256, 256, 32)):
+        x, gx = cl(dev, (B, Cc, H, H)), cl(dev, (B, Cc, H, H))
+        y, idx, gy = cl(dev, (B, Cc, H // 2, H // 2)), cl(dev, (B, Cc, H // 2, H // 2)), cl(dev, (B, Cc, H // 2, H // 2))
+        nx = 4.0 * B * Cc * H * H
+        row("max_pool2d_fwd_B%d_C%d_H%d" % (B, Cc, H), timeit(dev, lambda: ffi.check(lib.agb_maxpool2d_fwd(dev.ctx, x.desc(), y.desc(), None, idx.ptr, 2, 0, 2)), iters=5), bytes_=nx * 1.5)
+        row("max_pool2d_grad_scatter_B%d_C%d_H%d" % (B, Cc, H), timeit(dev, lambda: ffi.check(lib.agb_maxpool2d_bwd(dev.ctx, gy.desc(), None, idx.ptr, gx.desc())), iters=5), bytes_=nx * 1.5)
+        row("max_pool2d_grad_tiled_relu_gate_B%d_C%d_H%d" % (B, Cc, H), timeit(dev, lambda: ffi.check(lib.agb_maxpool2d_bwd_fused(dev.ctx, gy.desc(), None, idx.ptr, y.ptr, gx.desc(), 2, 2)), iters=5), bytes_=nx * 1.75)
+        x = gx = y = idx = gy = None
+    for cols in (1024, 4096, 16384, 32768, 131072):
+        n = 1 << 28
+        x, z = dev.fill((n,), 1.0), dev.empty((n,))
+        row("softmax_rows%d_2^28" % cols, timeit(dev, lambda: ffi.check(lib.agb_softmax(dev.ctx, x.ptr, z.ptr, n // cols, cols, 1)), iters=5), bytes_=8.0 * n)
+        x.free(); z.free()
     for logn in (20, 24, 28, 30):
         n = 1 << logn
         x, z = dev.fill((n,), 1.0), dev.empty((n,))

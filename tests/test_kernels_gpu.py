@@ -186,6 +186,58 @@ def test_conv2d_family_vs_oracle(dev, case, mode):
     assert rel_err(gw, R.conv2d_filter_grad(x, gy, w.shape, pad, stride, dil)) <= TOL[mode], "wgrad"
 
 
+FUSED_CASES = [  # B, C, H, W, O, kh, kw, pad, dil — stride 1 ("same"-style backward convs) + one SIMT-path shape
+    (2, 64, 32, 32, 64, 3, 3, 1, 1), (1, 128, 32, 32, 256, 3, 3, 1, 1), (2, 48, 36, 40, 96, 3, 3, 1, 1), (2, 8, 12, 12, 16, 3, 3, 1, 1),
+]
+
+
+@pytest.mark.parametrize("mode", MODES)
+@pytest.mark.parametrize("cl", [False, True])
+@pytest.mark.parametrize("case", FUSED_CASES)
+def test_conv2d_fused_epilogues_vs_oracle(dev, case, cl, mode):
+    """conv + bias + ReLU (fprop epilogue) and conv2d_transpose * (mask_src > 0) (dgrad epilogue), both memory orders"""
+    dev.set_math_mode(mode)
+    B, C, H, W, O, kh, kw, pad, dil = case
+    rng = np.random.default_rng(sum(case))
+    x = rng.standard_normal((B, C, H, W)).astype(np.float32)
+    w = (rng.standard_normal((O, C, kh, kw)) * 0.1).astype(np.float32)
+    bias = rng.standard_normal(O).astype(np.float32)
+    up = dev.upload_channels_last if cl else dev.upload
+    dw = dev.upload(w)
+    y_ref = np.maximum(R.conv2d(x, w, pad, 1, dil) + bias.reshape(1, O, 1, 1), 0)
+    y = dev.conv2d(up(x), dw, pad, 1, dil, bias=dev.upload(bias), relu=True, channels_last=cl).numpy()
+    assert rel_err(y, y_ref) <= TOL[mode], "fprop+bias+relu"
+    gy = rng.standard_normal(y_ref.shape).astype(np.float32)
+    mask_src = rng.standard_normal(x.shape).astype(np.float32)
+    mask_src[0, 0, 0, :4] = 0.0                                    # exactly-zero entries are masked out (x > 0 is strict)
+    gx_ref = R.conv2d_transpose(gy, w, pad, 1, dil) * (mask_src > 0)
+    gx = dev.conv2d_transpose(up(gy), dw, pad, 1, dil, mask_src=up(mask_src), channels_last=cl).numpy()
+    assert rel_err(gx, gx_ref) <= TOL[mode], "dgrad*mask"
+    assert np.all(gx[mask_src <= 0] == 0.0)
+    # mask in the other memory order than the output: still correct (un-fused tail)
+    gx2 = dev.conv2d_transpose(up(gy), dw, pad, 1, dil, mask_src=(dev.upload if cl else dev.upload_channels_last)(mask_src), channels_last=cl).numpy()
+    assert rel_err(gx2, gx_ref) <= TOL[mode]
+
+
+@pytest.mark.parametrize("mode", MODES)
+@pytest.mark.parametrize("case", [(2, 1, 28, 28, 32, 3, 3, 1, 1, 1), (2, 3, 32, 32, 64, 3, 3, 1, 1, 1), (3, 3, 17, 13, 48, 3, 3, 1, 2, 1), (2, 2, 11, 11, 24, 3, 3, 2, 1, 2),
+                                  (1, 4, 9, 9, 8, 2, 2, 0, 1, 1), (2, 3, 20, 20, 200, 3, 3, 1, 1, 1), (5, 1, 6, 6, 10, 5, 5, 2, 1, 1)])
+def test_small_channel_conv_channels_last(dev, case, mode):
+    """first-layer kernels (C <= 4): NCHW input, channels-last output / output-gradient, ragged pixel groups, O not a multiple of 64"""
+    dev.set_math_mode(mode)
+    B, C, H, W, O, kh, kw, pad, stride, dil = case
+    rng = np.random.default_rng(sum(case) + 1)
+    x = rng.standard_normal((B, C, H, W)).astype(np.float32)
+    w = (rng.standard_normal((O, C, kh, kw)) * 0.3).astype(np.float32)
+    bias = rng.standard_normal(O).astype(np.float32)
+    y_ref = np.maximum(R.conv2d(x, w, pad, stride, dil) + bias.reshape(1, O, 1, 1), 0)
+    y = dev.conv2d(dev.upload(x), dev.upload(w), pad, stride, dil, bias=dev.upload(bias), relu=True, channels_last=True).numpy()
+    assert rel_err(y, y_ref) <= TOL[mode]
+    gy = rng.standard_normal(y_ref.shape).astype(np.float32)
+    gw = dev.conv2d_filter_grad(dev.upload(x), dev.upload_channels_last(gy), w.shape, pad, stride, dil).numpy()
+    assert rel_err(gw, R.conv2d_filter_grad(x, gy, w.shape, pad, stride, dil)) <= TOL[mode]
+
+
 def test_conv_errors(dev):
     import rust_autograd_b200 as agb
     with pytest.raises(agb.OpError) as e:
@@ -216,6 +268,29 @@ def test_max_pool_family_bit_exact(dev, shape, size, stride):
     ggy = dev.max_pool2d_grad_grad(dev.upload(ggx), idx, size, 0, stride).numpy() if gshape == x.shape else None
     if ggy is not None:
         assert np.array_equal(ggy, R.max_pool2d_grad_grad(ggx, idx_ref, size, 0, stride))
+
+
+@pytest.mark.parametrize("cl", [False, True])
+@pytest.mark.parametrize("shape,size,stride", [((6, 32, 28, 28), 2, 2), ((3, 8, 9, 9), 3, 3), ((2, 6, 8, 10), 2, 2), ((2, 5, 8, 8), 2, 1), ((2, 4, 7, 9), 3, 2)])
+def test_max_pool_grad_fused_bit_exact(dev, shape, size, stride, cl):
+    """gather-form backward for windows that tile the input, int32 indices, ReLU gate = (pooled output > 0); both memory orders"""
+    rng = np.random.default_rng(2)
+    x = np.maximum(rng.integers(-3, 4, shape), 0).astype(np.float32)          # a ReLU output: zeros and ties everywhere
+    y_ref, idx_ref, _ = R.max_pool2d(x, size, 0, stride)
+    up = dev.upload_channels_last if cl else dev.upload
+    dx = up(x)
+    y, idx = dev.max_pool2d(dx, size, 0, stride, int32_index=True)
+    assert np.array_equal(y.numpy(), y_ref) and np.array_equal(idx.numpy().view(np.int32), idx_ref.astype(np.int32))
+    gy = rng.standard_normal(y_ref.shape).astype(np.float32)
+    gx_ref = R.max_pool2d_grad(gy, idx_ref, size, 0, stride)
+    gx = dev.max_pool2d_grad(up(gy), idx, size, 0, stride, int32_index=True).numpy()
+    close(gx, gx_ref)
+    if gx_ref.shape == x.shape:
+        gated = dev.max_pool2d_grad(up(gy), idx, size, 0, stride, gate=y, int32_index=True).numpy()
+        close(gated, gx_ref * (x > 0))                                       # == relu_grad(x, max_pool2d_grad(gy))
+    _, idx_f = dev.max_pool2d(dx, size, 0, stride)
+    close(dev.max_pool2d_grad(up(gy), idx_f, size, 0, stride).numpy(), gx_ref)
+    close(dev.max_pool2d_grad(up(gy), idx_f, size, 0, stride, window_known=False).numpy(), gx_ref)
 
 
 # ------------------------------------------------------------------------------------------------ elementwise
