@@ -123,6 +123,11 @@ __device__ __forceinline__ uint64_t umma_smem_desc(uint32_t saddr, uint32_t lbo_
   d |= (uint64_t)layout << 61;
   return d;
 }
+// descriptor from its two 32-bit halves (lo: start address >> 4 | LBO >> 4 << 16; hi: SBO >> 4 | version << 14 | layout << 29):
+// issue loops keep `hi` constant and step only the address field with one 32-bit add per MMA
+__device__ __forceinline__ uint64_t umma_desc_pack(uint32_t lo, uint32_t hi) {
+  uint64_t d; asm("mov.b64 %0, {%1, %2};" : "=l"(d) : "r"(lo), "r"(hi)); return d;
+}
 // instruction descriptor (32-bit) for kind::tf32, fp32 accumulate: c_format[4,6)=1, a_format[7,10)=2, b_format[10,13)=2,
 // a_major[15], b_major[16] (0 = K-major, 1 = MN-major), n_dim[17,23) = N>>3, m_dim[24,29) = M>>4
 __host__ __device__ constexpr uint32_t umma_idesc_tf32(int M, int N, int a_mn_major, int b_mn_major) {

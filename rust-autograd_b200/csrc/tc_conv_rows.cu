@@ -1,0 +1,270 @@
+// tc_conv_rows.cu — persistent, halo-reusing tcgen05 implicit-GEMM convolution for WIDE feature maps (output width >= 128,
+// stride 1, channels-last activations).  Serves Conv2D fprop and Conv2DTranspose/dgrad (flipped filter) exactly like
+// ConvFpropPol in tc_conv.cu, for the layers where that kernel is bound by L2 -> shared-memory bandwidth.
+//
+// Why a second kernel (measured, profiles/ncu_conv_full_r1.csv): the per-tap kernel re-fetches its 128-pixel input window from
+// L2 once per filter tap — 9x for 3x3 — and its filter slice once per CTA.  On the 64-channel 128x128 VGG layers that is 432 KB
+// of TMA traffic per 9.4 MFLOP tile, 14.5 GB per launch at ~10 TB/s: the kernel sits on the chip's L2->SM throughput cap
+// (~6300 B/clk) with the tensor pipe 20 % busy.  DRAM traffic is already minimal (x once, y once); the waste is on-chip.
+//
+// This kernel loads each input element into shared memory ONCE per 32-channel block:
+//   * tile = R output rows x 128 consecutive output pixels of one image x TN output channels;
+//   * per 32-channel block ONE 4-D TMA box {32 c, 128 + d(kw-1) w, R + d(kh-1) h, 1 b} brings the haloed input window
+//     (SWIZZLE_128B, one 128-byte row per pixel, zero fill = padding);
+//   * every tap (i, j) of every output row r reads that window through a K-major UMMA descriptor whose start address is shifted
+//     by ((r + i d) * pitch + j d) pixel rows.  The 128B swizzle is a function of absolute shared-memory address bits, so a
+//     start address that is 128-byte but not 1024-byte aligned addresses the TMA-written data correctly (verified on B200 by
+//     scripts/cuda/umma_shift_probe.cu for every shift, base_offset field 0);
+//   * the filter tap tiles [TN o][32 c] stream through a small ring and are shared by the R rows (R MMAs per tap and k-step).
+//   L2 -> smem traffic per 128-pixel x 64-channel output strip: (R+2)/R * 33 KB + 147/R KB = 140 KB at R = 2 (was 432 KB).
+// Persistent CTAs (one per SM) walk the tile list; two TMEM accumulator sets (2 x R x TN columns) let the epilogue of tile t
+// (tcgen05.ld, bias / ReLU / ReLU-mask, 128-byte channel runs per pixel) overlap the MMAs of tile t+1.
+//
+// Reference semantics: Conv2D::compute conv2d.rs:115-211, Conv2DTranspose::compute conv2d_transpose.rs:89-247.
+#include "tc_common.cuh"
+
+#define ROWS_R 2
+struct RowsParams {
+  CUtensorMap tmX, tmW;
+  float* y; const float* bias; const float* mask; int relu;
+  int Cout, yh, yw, kw, pad, dil, tiles_x, tiles_y, otiles, cblocks, taps, pitch, a_box_bytes, a_slot_bytes;
+  long long num_tiles;
+};
+template <int TN> struct RowsCfg {
+  static constexpr int NB = TN <= 64 ? 6 : 4;                 // filter-tap ring depth
+  static constexpr int B_BYTES = TN * 128;
+  static constexpr int TMEM_COLS = 2 * ROWS_R * TN;            // 256 (TN = 64) / 512 (TN = 128)
+  static constexpr int THREADS = 256;            // warps: 0 TMA-A, 1 MMA row 0, 2-5 epilogue, 6 TMA-B, 7 MMA row 1
+};
+
+template <int TN>
+__global__ void __launch_bounds__(256, 1) conv_rows_kernel(const __grid_constant__ RowsParams p) {
+  using Cfg = RowsCfg<TN>;
+  constexpr int NB = Cfg::NB, R = ROWS_R;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
+  uint8_t* sA = smem;                                          // [2][a_slot_bytes]
+  uint8_t* sB = smem + 2 * p.a_slot_bytes;                     // [NB][TN * 128]
+  uint64_t* bars = (uint64_t*)(sB + NB * Cfg::B_BYTES);
+  uint64_t* a_full = bars; uint64_t* a_empty = bars + 2;
+  uint64_t* b_full = bars + 4; uint64_t* b_empty = bars + 4 + NB;
+  uint64_t* acc_full = bars + 4 + 2 * NB; uint64_t* acc_empty = bars + 6 + 2 * NB;
+  uint32_t* tmem_slot = (uint32_t*)(bars + 8 + 2 * NB);
+  float* stage = (float*)((uint8_t*)bars + 256);               // [4 warps][32][36] epilogue transpose tiles
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&p.tmX); tma_prefetch_desc(&p.tmW);
+    for (int s = 0; s < 2; s++) { mbar_init(&a_full[s], 1); mbar_init(&a_empty[s], R); mbar_init(&acc_full[s], R); mbar_init(&acc_empty[s], 128); }
+    for (int s = 0; s < NB; s++) { mbar_init(&b_full[s], 1); mbar_init(&b_empty[s], R); }
+    fence_barrier_init();
+  }
+  if (warp == 1) { tmem_alloc(tmem_slot, Cfg::TMEM_COLS); tmem_relinquish(); }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+  const long long tiles_per_img = (long long)p.tiles_x * p.tiles_y * p.otiles;
+
+  if (warp == 0) {
+    // ===================== TMA producer A: haloed input windows =====================
+    // (own warp: the next window is requested the moment its slot frees, independent of the filter-tap ring's back-pressure)
+    if (lane == 0) {
+      uint32_t ai = 0;
+      for (long long t = blockIdx.x; t < p.num_tiles; t += gridDim.x) {
+        const int b = (int)(t / tiles_per_img); int r = (int)(t - (long long)b * tiles_per_img);
+        r /= p.otiles; const int tx = r % p.tiles_x, ty = r / p.tiles_x;
+        const int oy0 = ty * R, ox0 = tx * 128;
+        for (int cb = 0; cb < p.cblocks; cb++, ai++) {
+          const uint32_t as = ai & 1;
+          mbar_wait(&a_empty[as], ((ai >> 1) & 1) ^ 1);
+          mbar_expect_tx(&a_full[as], (uint32_t)p.a_box_bytes);
+          tma_load_4d(sA + as * p.a_slot_bytes, &p.tmX, &a_full[as], cb * 32, ox0 - p.pad, oy0 - p.pad, b);       // dims {c, w, h, b}
+        }
+      }
+    }
+  } else if (warp == 6) {
+    // ===================== TMA producer B: filter taps =====================
+    if (lane == 0) {
+      uint32_t bs = 0, bph = 0;
+      for (long long t = blockIdx.x; t < p.num_tiles; t += gridDim.x) {
+        const int o0 = (int)(t % p.otiles) * TN;
+        for (int cb = 0; cb < p.cblocks; cb++)
+          for (int tap = 0; tap < p.taps; tap++) {
+            mbar_wait(&b_empty[bs], bph ^ 1);
+            mbar_expect_tx(&b_full[bs], Cfg::B_BYTES);
+            tma_load_3d(sB + bs * Cfg::B_BYTES, &p.tmW, &b_full[bs], cb * 32, o0, tap);
+            if (++bs == NB) { bs = 0; bph ^= 1; }
+          }
+      }
+    }
+  } else if (warp == 1 || warp == 7) {
+    // ===================== MMA issuers: one warp per output row =====================
+    // A tcgen05.mma of N = 64 occupies the tensor pipe for only ~32 clocks; a single issuing thread (wait + descriptor adds + loop
+    // bookkeeping, ~11 instructions per MMA) could not keep up (measured: issuer-bound at 40 % tensor activity).  Row r of the tile
+    // has its own accumulator, so each row gets its own issuer warp; ring slots are released when BOTH have committed.
+    // Converged warp, one elected lane issues (uniform-register descriptors; see tc_tile.cuh).
+    const int r = warp == 1 ? 0 : 1;
+    constexpr uint32_t idesc = umma_idesc_tf32(128, TN, 0, 0);
+    const uint32_t hi = (1024u >> 4) | (1u << 14) | (2u << 29), lo0 = (16u >> 4) << 16;     // K-major SWIZZLE_128B, LBO 16 B, SBO 1024 B
+    const uint32_t row4 = (uint32_t)(p.pitch * 128) >> 4;            // one input row of the halo window, in 16-byte units
+    const uint32_t sA4 = (smem_u32(sA) >> 4) + lo0 + (uint32_t)r * row4, sB4 = (smem_u32(sB) >> 4) + lo0;
+    const uint32_t dj4 = (uint32_t)(p.dil * 128) >> 4, di4 = (uint32_t)p.dil * row4;
+    uint32_t ai = 0, bs = 0, bph = 0, it = 0;
+    for (long long t = blockIdx.x; t < p.num_tiles; t += gridDim.x, it++) {
+      const uint32_t acs = it & 1;
+      mbar_wait(&acc_empty[acs], ((it >> 1) & 1) ^ 1);
+      tc_fence_after();
+      const uint32_t tacc = tmem_base + (acs * (uint32_t)R + (uint32_t)r) * (uint32_t)TN;
+      for (int cb = 0; cb < p.cblocks; cb++, ai++) {
+        const uint32_t as = ai & 1;
+        mbar_wait(&a_full[as], (ai >> 1) & 1);
+        tc_fence_after();
+        const uint32_t a0 = sA4 + as * ((uint32_t)p.a_slot_bytes >> 4);
+        uint32_t arow = a0, atap = a0; int j = 0;                      // window origin of tap (i, j) for this row
+        for (int tap = 0; tap < p.taps; tap++) {
+          mbar_wait(&b_full[bs], bph);
+          tc_fence_after();
+          if (elect_one()) {
+            const uint32_t q0 = sB4 + bs * (uint32_t)(Cfg::B_BYTES >> 4);
+#pragma unroll
+            for (int ks = 0; ks < 4; ks++)
+              umma_tf32(tacc, umma_desc_pack(atap + ks * 2, hi), umma_desc_pack(q0 + ks * 2, hi), idesc, !(cb == 0 && tap == 0 && ks == 0));
+            umma_commit(&b_empty[bs]);
+            if (tap == p.taps - 1) {
+              umma_commit(&a_empty[as]);
+              if (cb == p.cblocks - 1) umma_commit(&acc_full[acs]);
+            }
+          }
+          __syncwarp();
+          if (++bs == NB) { bs = 0; bph ^= 1; }
+          if (++j == p.kw) { j = 0; arow += di4; atap = arow; } else atap += dj4;
+        }
+      }
+    }
+  } else if (warp < 6) {
+    // ===================== epilogue =====================
+    // tcgen05.ld hands every thread one pixel x 32 channels; written out like that a warp store touches 32 separate sectors.
+    // Each warp therefore transposes its 32 x 32 strip through a padded shared-memory tile (conflict-free both ways) and works in
+    // the transposed layout: lane -> (pixel = 4 it + lane / 8, channels 4 (lane % 8) .. +3), so every 128-bit global access of a
+    // warp covers 4 pixels x 128 contiguous bytes.  Bias / ReLU / ReLU-mask are applied in that layout (4 fixed channels per lane).
+    const int q = warp & 3;
+    const uint32_t tlane = tmem_base + ((uint32_t)(32 * q) << 16);
+    float* stg = stage + q * (32 * 36);
+    const int pl0 = lane >> 3, ch4 = lane & 7;
+    uint32_t it = 0;
+    for (long long t = blockIdx.x; t < p.num_tiles; t += gridDim.x, it++) {
+      const int b = (int)(t / tiles_per_img); int rr = (int)(t - (long long)b * tiles_per_img);
+      const int ot = rr % p.otiles; rr /= p.otiles; const int tx = rr % p.tiles_x, ty = rr / p.tiles_x;
+      const int oy0 = ty * R, ox0 = tx * 128 + 32 * q, o0 = ot * TN;
+      // ReLU-mask bits of the dgrad epilogue, fetched (coalesced) before the accumulator is ready:
+      // bit 4 it + e of pre[r][c]  <=>  mask_src[b, oy0 + r, ox0 + 4 it + pl0, o0 + 32 c + 4 ch4 + e] > 0
+      uint32_t pre[R][TN / 32];
+      if (p.mask != nullptr) {
+#pragma unroll
+        for (int r = 0; r < R; r++) {
+          const int oy = oy0 + r;
+#pragma unroll
+          for (int c = 0; c < TN / 32; c++) {
+            // unconditional loads from clamped addresses (bits of out-of-range pixels / channels are never used): the 8 loads
+            // of a strip are independent and issue back to back
+            uint32_t bits = 0; const int o = min(o0 + 32 * c + 4 * ch4, p.Cout - 4);
+            const float* mrow = p.mask + (((long long)b * p.yh + min(oy, p.yh - 1)) * p.yw) * p.Cout + o;
+            float4 mv[8];
+#pragma unroll
+            for (int k = 0; k < 8; k++) mv[k] = __ldg((const float4*)(mrow + (long long)min(ox0 + 4 * k + pl0, p.yw - 1) * p.Cout));
+#pragma unroll
+            for (int k = 0; k < 8; k++)
+              bits |= ((mv[k].x > 0.0f ? 1u : 0u) | (mv[k].y > 0.0f ? 2u : 0u) | (mv[k].z > 0.0f ? 4u : 0u) | (mv[k].w > 0.0f ? 8u : 0u)) << (4 * k);
+            pre[r][c] = bits;
+          }
+        }
+      }
+      float4 bv[TN / 32];
+#pragma unroll
+      for (int c = 0; c < TN / 32; c++) {
+        const int o = o0 + 32 * c + 4 * ch4;
+        bv[c] = (p.bias != nullptr && o + 4 <= p.Cout) ? __ldg((const float4*)(p.bias + o)) : make_float4(0.f, 0.f, 0.f, 0.f);
+      }
+      const uint32_t acs = it & 1;
+      mbar_wait(&acc_full[acs], (it >> 1) & 1);
+      tc_fence_after();
+#pragma unroll
+      for (int r = 0; r < R; r++) {
+        const int oy = oy0 + r;
+#pragma unroll
+        for (int c = 0; c < TN / 32; c++) {
+          float v[32];
+          tmem_ld32(tlane + (uint32_t)((acs * R + r) * TN + 32 * c), v);
+          tmem_ld_wait();
+#pragma unroll
+          for (int k = 0; k < 8; k++) *(float4*)(stg + lane * 36 + 4 * k) = make_float4(v[4 * k], v[4 * k + 1], v[4 * k + 2], v[4 * k + 3]);
+          __syncwarp();
+          const int o = o0 + 32 * c + 4 * ch4;
+#pragma unroll
+          for (int k = 0; k < 8; k++) {
+            const int pl = 4 * k + pl0, ox = ox0 + pl;
+            float4 a = *(const float4*)(stg + pl * 36 + 4 * ch4);
+            a.x += bv[c].x; a.y += bv[c].y; a.z += bv[c].z; a.w += bv[c].w;
+            if (p.relu) { a.x = fmaxf(a.x, 0.0f); a.y = fmaxf(a.y, 0.0f); a.z = fmaxf(a.z, 0.0f); a.w = fmaxf(a.w, 0.0f); }
+            if (p.mask != nullptr) {      // 0*a keeps the NaN/Inf semantics of the un-fused multiply
+              const uint32_t m = pre[r][c] >> (4 * k);
+              a.x = (m & 1u) ? a.x : 0.0f * a.x; a.y = (m & 2u) ? a.y : 0.0f * a.y; a.z = (m & 4u) ? a.z : 0.0f * a.z; a.w = (m & 8u) ? a.w : 0.0f * a.w;
+            }
+            if (oy < p.yh && ox < p.yw && o + 4 <= p.Cout) *(float4*)(p.y + (((long long)b * p.yh + oy) * p.yw + ox) * p.Cout + o) = a;
+          }
+          __syncwarp();
+        }
+      }
+      tc_fence_before();
+      mbar_arrive(&acc_empty[acs]);
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) tmem_dealloc(tmem_base, Cfg::TMEM_COLS);
+}
+
+template <int TN>
+static int rows_launch(agb_ctx* ctx, RowsParams& p, size_t smem) {
+  static bool attr = false;
+  if (!attr) { AGB_CUDA(cudaFuncSetAttribute(conv_rows_kernel<TN>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024)); attr = true; }
+  long long grid = p.num_tiles < ctx->sm_count ? p.num_tiles : ctx->sm_count;
+  conv_rows_kernel<TN><<<(unsigned)grid, RowsCfg<TN>::THREADS, smem, ctx->stream>>>(p);
+  AGB_LAUNCHED(ctx);
+  return AGB_OK;
+}
+
+// x [B,H,W,Cin] channels-last, wr = filter repacked to [tap][Cout][Cin] (see tc_conv.cu), y [B,yh,yw,Cout] channels-last.
+// Returns AGB_ERR_UNSUPPORTED when the geometry is outside this kernel's envelope (the caller falls back to the per-tap kernel).
+int agb_tc_conv_rows(agb_ctx* ctx, const float* x, const float* wr, float* y, int B, int Cin, int H, int W, int Cout, int yh, int yw, int kh, int kw,
+                     int pad, int dil, const float* bias, int relu, const float* mask) {
+  static int enabled = -1;
+  if (enabled < 0) { const char* e = getenv("AGB_CONV_ROWS"); enabled = (e && e[0] == '0') ? 0 : 1; }
+  if (!enabled || yw < 128 || Cout > 128 || Cin % 4 != 0 || Cout % 4 != 0) return AGB_ERR_UNSUPPORTED;
+  const int pitch = 128 + dil * (kw - 1), hrows = ROWS_R + dil * (kh - 1);
+  if (pitch > 256 || hrows > 256) return AGB_ERR_UNSUPPORTED;
+  RowsParams p;
+  p.a_box_bytes = pitch * hrows * 128; p.a_slot_bytes = (p.a_box_bytes + 1023) & ~1023;
+  const int TN = Cout > 64 ? 128 : 64;
+  const int nb = TN <= 64 ? RowsCfg<64>::NB : RowsCfg<128>::NB;
+  const size_t smem = 2 * (size_t)p.a_slot_bytes + (size_t)nb * TN * 128 + 1024 + 256 + 4 * 32 * 36 * 4;
+  if (smem > 227 * 1024) return AGB_ERR_UNSUPPORTED;
+  {
+    uint64_t dims[4] = {(uint64_t)Cin, (uint64_t)W, (uint64_t)H, (uint64_t)B};
+    uint64_t str[3] = {(uint64_t)Cin * 4, (uint64_t)W * Cin * 4, (uint64_t)H * W * Cin * 4};
+    uint32_t box[4] = {32, (uint32_t)pitch, (uint32_t)hrows, 1};
+    AGB_TRY(agb_make_tmap(&p.tmX, x, 4, dims, str, box, false));
+  }
+  {
+    uint64_t dims[3] = {(uint64_t)Cin, (uint64_t)Cout, (uint64_t)(kh * kw)};
+    uint64_t str[2] = {(uint64_t)Cin * 4, (uint64_t)Cin * Cout * 4};
+    uint32_t box[3] = {32, (uint32_t)TN, 1};
+    AGB_TRY(agb_make_tmap(&p.tmW, wr, 3, dims, str, box, false));
+  }
+  p.y = y; p.bias = bias; p.mask = mask; p.relu = relu; p.Cout = Cout; p.yh = yh; p.yw = yw; p.kw = kw; p.pad = pad; p.dil = dil;
+  p.tiles_x = (yw + 127) / 128; p.tiles_y = (yh + ROWS_R - 1) / ROWS_R; p.otiles = (Cout + TN - 1) / TN;
+  p.cblocks = (Cin + 31) / 32; p.taps = kh * kw; p.pitch = pitch;
+  p.num_tiles = (long long)B * p.tiles_x * p.tiles_y * p.otiles;
+  return TN == 64 ? rows_launch<64>(ctx, p, smem) : rows_launch<128>(ctx, p, smem);
+}

@@ -86,30 +86,38 @@ __global__ void __launch_bounds__(TcCfg<Pol::TN, Pol::SPLIT, Pol::OCC>::THREADS,
     }
   } else if (warp == 1) {
     // ===================== MMA issuer =====================
-    if (lane == 0) {
-      constexpr uint32_t idesc = umma_idesc_tf32(TC_LANES, TN, P_MN ? 1 : 0, Q_MN ? 1 : 0);
-      const MnDescCfg mnc = prm.mnc;
-      for (int kb = 0; kb < nk; kb++) {
-        const int s = kb % S; const uint32_t ph = (kb / S) & 1;
-        uint32_t tacc = tmem_base; bool first = (kb == 0);
-        if (SPLIT) {
-          const int chunk = kb / TC_KC, buf = chunk & 1;
-          tacc = tmem_base + (uint32_t)(buf * TN);
-          first = (kb % TC_KC) == 0;
-          if (first) { mbar_wait(&acc_empty[buf], (uint32_t)(((chunk >> 1) & 1) ^ 1)); tc_fence_after(); }
-        }
-        mbar_wait(SPLIT ? &ready[s] : &full[s], ph);
-        tc_fence_after();
-        const uint32_t st = smem_u32(smem + s * Cfg::STAGE_BYTES);
-        const uint32_t aP = st, aQ = st + Cfg::P_BYTES;
-        const uint32_t aPl = st + Cfg::P_BYTES + Cfg::Q_BYTES, aQl = aPl + Cfg::P_BYTES;
+    // The whole warp walks the loop converged and ONE elected lane issues: with warp-uniform control flow the descriptors live in
+    // uniform registers and a tcgen05.mma costs ~4 issue slots.  (Issuing from inside an `if (lane == 0)` branch made the compiler
+    // wrap every MMA in an ELECT / R2UR.BROADCAST waterfall, ~25 instructions per MMA: measured, the issuer thread — not the
+    // tensor pipe or L2 — was the bottleneck of every TN <= 128 kernel.)
+    constexpr uint32_t idesc = umma_idesc_tf32(TC_LANES, TN, P_MN ? 1 : 0, Q_MN ? 1 : 0);
+    const MnDescCfg mnc = prm.mnc;
+    // descriptor = {lo: addr>>4 | LBO>>4 << 16, hi: SBO>>4 | version 1 << 14 | layout << 29}; only the address field changes
+    const uint32_t hiK = (1024u >> 4) | (1u << 14) | (2u << 29), loK = (16u >> 4) << 16, stepK = 32u >> 4;
+    const uint32_t hiM = (mnc.sbo >> 4) | (1u << 14) | (mnc.layout << 29), loM = (mnc.lbo >> 4) << 16, stepM = mnc.kadv >> 4;
+    const uint32_t hiP = P_MN ? hiM : hiK, loP = P_MN ? loM : loK, stepP = P_MN ? stepM : stepK;
+    const uint32_t hiQ = Q_MN ? hiM : hiK, loQ = Q_MN ? loM : loK, stepQ = Q_MN ? stepM : stepK;
+    const uint32_t smem0 = smem_u32(smem) >> 4;
+    int s = 0; uint32_t ph = 0;
+    for (int kb = 0; kb < nk; kb++) {
+      uint32_t tacc = tmem_base; bool first = (kb == 0);
+      if (SPLIT) {
+        const int chunk = kb / TC_KC, buf = chunk & 1;
+        tacc = tmem_base + (uint32_t)(buf * TN);
+        first = (kb % TC_KC) == 0;
+        if (first) { mbar_wait(&acc_empty[buf], (uint32_t)(((chunk >> 1) & 1) ^ 1)); tc_fence_after(); }
+      }
+      mbar_wait(SPLIT ? &ready[s] : &full[s], ph);
+      tc_fence_after();
+      if (elect_one()) {
+        const uint32_t st = smem0 + (uint32_t)s * (Cfg::STAGE_BYTES >> 4);
+        const uint32_t aP = st + loP, aQ = st + (Cfg::P_BYTES >> 4) + loQ;
+        const uint32_t aPl = aP + ((Cfg::P_BYTES + Cfg::Q_BYTES) >> 4), aQl = aQ + ((Cfg::P_BYTES + Cfg::Q_BYTES) >> 4);
 #pragma unroll
         for (int k = 0; k < TC_BK / 8; k++) {
-          const uint64_t dP = P_MN ? umma_desc_mnmajor(aP, k, mnc) : umma_desc_kmajor(aP, k);
-          const uint64_t dQ = Q_MN ? umma_desc_mnmajor(aQ, k, mnc) : umma_desc_kmajor(aQ, k);
+          const uint64_t dP = umma_desc_pack(aP + k * stepP, hiP), dQ = umma_desc_pack(aQ + k * stepQ, hiQ);
           if (SPLIT) {
-            const uint64_t dPl = P_MN ? umma_desc_mnmajor(aPl, k, mnc) : umma_desc_kmajor(aPl, k);
-            const uint64_t dQl = Q_MN ? umma_desc_mnmajor(aQl, k, mnc) : umma_desc_kmajor(aQl, k);
+            const uint64_t dPl = umma_desc_pack(aPl + k * stepP, hiP), dQl = umma_desc_pack(aQl + k * stepQ, hiQ);
             umma_tf32(tacc, dPl, dQ, idesc, !(first && k == 0));
             umma_tf32(tacc, dP, dQl, idesc, 1);
             umma_tf32(tacc, dP, dQ, idesc, 1);
@@ -121,6 +129,8 @@ __global__ void __launch_bounds__(TcCfg<Pol::TN, Pol::SPLIT, Pol::OCC>::THREADS,
         if (SPLIT) { if ((kb % TC_KC) == TC_KC - 1 || kb == nk - 1) umma_commit(&acc_full[(kb / TC_KC) & 1]); }
         else if (kb == nk - 1) umma_commit(&acc_full[0]);
       }
+      __syncwarp();
+      if (++s == S) { s = 0; ph ^= 1; }
     }
   } else if (SPLIT && warp < 6) {
     // ===================== splitter (3xTF32) =====================

@@ -163,6 +163,14 @@ CONV_CASES = [  # B, C, H, W, O, kh, kw, pad, stride, dil
     (1, 32, 32, 32, 64, 5, 5, 2, 1, 1),     # 5x5
     (1, 32, 34, 34, 32, 3, 3, 0, 1, 1),     # no padding
     (3, 48, 32, 64, 96, 3, 3, 1, 1, 1),     # channel counts that are not multiples of 32 / 64
+    # wide feature maps (output width >= 128): persistent halo-reusing kernel in TF32 mode
+    (1, 64, 6, 128, 64, 3, 3, 1, 1, 1),
+    (2, 32, 5, 160, 48, 3, 3, 1, 1, 1),     # odd row count, partial second 128-pixel strip, 48 channels
+    (1, 64, 4, 256, 128, 3, 3, 1, 1, 1),    # TN = 128
+    (1, 32, 8, 130, 32, 3, 3, 0, 1, 1),     # no padding
+    (1, 32, 9, 136, 32, 3, 3, 2, 1, 2),     # dilation 2
+    (3, 96, 7, 128, 160, 3, 3, 1, 1, 1),    # three c-blocks, two o-tiles (the second partial)
+    (1, 32, 6, 128, 32, 5, 5, 2, 1, 1),     # 5x5
 ]
 
 
@@ -188,6 +196,7 @@ def test_conv2d_family_vs_oracle(dev, case, mode):
 
 FUSED_CASES = [  # B, C, H, W, O, kh, kw, pad, dil — stride 1 ("same"-style backward convs) + one SIMT-path shape
     (2, 64, 32, 32, 64, 3, 3, 1, 1), (1, 128, 32, 32, 256, 3, 3, 1, 1), (2, 48, 36, 40, 96, 3, 3, 1, 1), (2, 8, 12, 12, 16, 3, 3, 1, 1),
+    (2, 64, 7, 128, 64, 3, 3, 1, 1), (1, 32, 4, 192, 80, 3, 3, 1, 1),      # wide maps: halo-reusing kernel
 ]
 
 
