@@ -128,10 +128,12 @@ int  agb_conv2d_fprop_fused_f32(agb_ctx* ctx, const agb_tensor* x, const agb_ten
 int  agb_conv2d_dgrad_f32(agb_ctx* ctx, const agb_tensor* gy, const agb_tensor* w, agb_tensor* gx,
                           int pad, int stride, int dilation);
 /* fused form of Conv2DTranspose followed by the ReLU backward of the layer below, mul(greater(a, 0), gx)
- * (activation_ops.rs:161-166): gx = conv2d_transpose(gy, w) * (mask_src > 0).  mask_src (NULL = no mask) is [B,C,xh,xw] with
- * the same strides as gx; the compare-and-zero runs on the accumulator registers of the tensor-core epilogue. */
-int  agb_conv2d_dgrad_fused_f32(agb_ctx* ctx, const agb_tensor* gy, const agb_tensor* w, const agb_tensor* mask_src, agb_tensor* gx,
-                                int pad, int stride, int dilation);
+ * (activation_ops.rs:161-166): gx = conv2d_transpose(gy, w) * (mask_src > 0).  mask_src (NULL = no mask) is [B,C,xh,xw]; when it
+ * has the strides of gx the compare-and-zero runs on the accumulator registers of the tensor-core epilogue.
+ * chan_sum (NULL = not wanted): C floats that receive sum_{b,h,w} gx[b,c,h,w] — the bias gradient of the layer below
+ * (MaybeReduceSum of the broadcast AddOp operand, binary_ops.rs:39-105), accumulated in the same epilogue. */
+int  agb_conv2d_dgrad_fused_f32(agb_ctx* ctx, const agb_tensor* gy, const agb_tensor* w, const agb_tensor* mask_src, float* chan_sum,
+                                agb_tensor* gx, int pad, int stride, int dilation);
 /* replaces Conv2DFilterGrad::compute (conv2d.rs:737-744) and Conv2DTransposeFilterGrad::compute
  * (conv2d_transpose.rs:433-451): gw[O,C,kh,kw] = sum_b g[b] (x) im2col(img[b]).
  * img [B,C,H,W] is the tensor that gets im2col'd, g [B,O,yh,yw] the one that multiplies it. */
@@ -160,6 +162,7 @@ int  agb_maxpool2d_bwd(agb_ctx* ctx, const agb_tensor* gy, const float* idx_f32,
  * output of a ReLU activation this also performs the ReLU backward that follows in conv -> relu -> pool stacks
  * (relu'(x[argmax]) == (max > 0)). */
 int  agb_maxpool2d_bwd_fused(agb_ctx* ctx, const agb_tensor* gy, const float* idx_f32, const int32_t* idx_i32, const float* gate,
+                             float* chan_sum /* NULL or C floats: sum_{b,h,w} gx, see agb_conv2d_dgrad_fused_f32 */,
                              agb_tensor* gx, int size, int stride);
 /* MaxPool2DGradGrad::compute (max_pool2d.rs:297-331): ggy[i] = ggx[idx[i]] */
 int  agb_maxpool2d_gradgrad(agb_ctx* ctx, const agb_tensor* ggx, const float* idx_f32, const int32_t* idx_i32,

@@ -15,7 +15,7 @@
 
 // tcgen05 kernels (tc_conv.cu): operate on channels-last activation buffers
 int agb_tc_conv_fprop(agb_ctx* ctx, int mode, const float* x, const float* w, float* y,
-                      int B, int C, int H, int W, int O, int kh, int kw, int pad, int stride, int dil, int flip_transpose, const float* bias, int relu, const float* mask);
+                      int B, int C, int H, int W, int O, int kh, int kw, int pad, int stride, int dil, int flip_transpose, const float* bias, int relu, const float* mask, float* csum);
 int agb_tc_conv_wgrad(agb_ctx* ctx, int mode, const float* img, const float* g, float* gw,
                       int B, int C, int H, int W, int O, int kh, int kw, int pad, int stride, int dil);
 bool agb_tc_conv_eligible(int C, int O, int kh, int kw, int stride, int yw);
@@ -160,7 +160,7 @@ extern "C" int agb_conv2d_fprop_fused_f32(agb_ctx* ctx, const agb_tensor* x, con
   if (ctx->math_mode != AGB_MATH_FP32 && agb_tc_conv_eligible(g.C, g.O, g.kh, g.kw, stride, g.yw)) {
     LayoutTmp lx(ctx), ly(ctx);
     AGB_TRY(lx.input(x, true)); AGB_TRY(ly.output(y, true));
-    int r = agb_tc_conv_fprop(ctx, ctx->math_mode, lx.view.ptr, w->ptr, ly.view.ptr, g.B, g.C, g.H, g.W, g.O, g.kh, g.kw, pad, stride, dilation, 0, bias, relu, nullptr);
+    int r = agb_tc_conv_fprop(ctx, ctx->math_mode, lx.view.ptr, w->ptr, ly.view.ptr, g.B, g.C, g.H, g.W, g.O, g.kh, g.kw, pad, stride, dilation, 0, bias, relu, nullptr, nullptr);
     if (r == AGB_OK) { AGB_TRY(ly.finish()); return lx.finish(); }
     if (r != AGB_ERR_UNSUPPORTED) return r;
   }
@@ -189,7 +189,18 @@ extern "C" int agb_conv2d_fprop_fused_f32(agb_ctx* ctx, const agb_tensor* x, con
 }
 
 extern "C" int agb_conv2d_dgrad_f32(agb_ctx* ctx, const agb_tensor* gy, const agb_tensor* w, agb_tensor* gx, int pad, int stride, int dilation) {
-  return agb_conv2d_dgrad_fused_f32(ctx, gy, w, nullptr, gx, pad, stride, dilation);
+  return agb_conv2d_dgrad_fused_f32(ctx, gy, w, nullptr, nullptr, gx, pad, stride, dilation);
+}
+
+// chan_sum[c] = sum over (b, h, w) of t[b, c, h, w] for a dense NCHW or channels-last tensor (un-fused form of the side output)
+static int channel_sums(agb_ctx* ctx, const agb_tensor* t, float* chan_sum) {
+  const int64_t B = t->shape[0], C = t->shape[1], HW = t->shape[2] * t->shape[3];
+  if (!agb_is_contig(t)) return agb_reduce(ctx, AGB_R_SUM, t->ptr, chan_sum, 1, B * HW, C);          // channels-last: [pixels, C]
+  float* tmp; AGB_TRY(agb_alloc(ctx, (size_t)(B * C) * sizeof(float), (void**)&tmp));
+  int r = agb_reduce(ctx, AGB_R_SUM, t->ptr, tmp, B * C, HW, 1);
+  if (r == AGB_OK) r = agb_reduce(ctx, AGB_R_SUM, tmp, chan_sum, 1, B, C);
+  agb_free(ctx, tmp);
+  return r;
 }
 
 // un-fused tail of the fused entry point: gx = (mask_src > 0) * gx in place (AGB_B_RELU_GRAD); gx is dense NCHW or channels-last
@@ -214,8 +225,8 @@ static int apply_relu_mask(agb_ctx* ctx, const agb_tensor* mask_src, agb_tensor*
   return r;
 }
 
-extern "C" int agb_conv2d_dgrad_fused_f32(agb_ctx* ctx, const agb_tensor* gy, const agb_tensor* w, const agb_tensor* mask_src, agb_tensor* gx,
-                                         int pad, int stride, int dilation) {
+extern "C" int agb_conv2d_dgrad_fused_f32(agb_ctx* ctx, const agb_tensor* gy, const agb_tensor* w, const agb_tensor* mask_src, float* chan_sum,
+                                         agb_tensor* gx, int pad, int stride, int dilation) {
   AGB_CHECK(gy->rank == 4, AGB_ERR_INCOMPATIBLE_SHAPE, "conv2d_transpose: Input must be 4D (got rank %d)", gy->rank);
   AGB_CHECK(w->rank == 4, AGB_ERR_INCOMPATIBLE_SHAPE, "conv2d_transpose: Filter must be 4D (got rank %d)", w->rank);
   AGB_CHECK(gy->shape[1] == w->shape[0], AGB_ERR_INCOMPATIBLE_SHAPE,
@@ -243,10 +254,17 @@ extern "C" int agb_conv2d_dgrad_fused_f32(agb_ctx* ctx, const agb_tensor* gy, co
     // stride-1 dgrad == fprop of gy with the spatially flipped, channel-transposed filter and pad' = d(k-1) - p
     LayoutTmp lg(ctx), lx(ctx);
     AGB_TRY(lg.input(gy, true)); AGB_TRY(lx.output(gx, true));
-    const bool fuse = same_strides && lx.view.ptr == gx->ptr && ((((uintptr_t)mask_src->ptr) & 15) == 0);     // output written in place, channels-last
+    const bool in_place = lx.view.ptr == gx->ptr;                                                               // output written channels-last, no conversion
+    const bool fuse = same_strides && in_place && ((((uintptr_t)mask_src->ptr) & 15) == 0);
+    const bool fuse_sum = chan_sum != nullptr && in_place && (mask_src == nullptr || fuse);                     // sums of the FINAL (masked) values
+    if (fuse_sum) AGB_TRY(agb_memset0(ctx, chan_sum, (size_t)g.C * sizeof(float)));
     int r = agb_tc_conv_fprop(ctx, ctx->math_mode, lg.view.ptr, w->ptr, lx.view.ptr, g.B, g.O, g.yh, g.yw, g.C, g.kh, g.kw, pad, stride, dilation, 1, nullptr, 0,
-                              fuse ? mask_src->ptr : nullptr);
-    if (r == AGB_OK) { AGB_TRY(lx.finish()); AGB_TRY(lg.finish()); return fuse ? AGB_OK : apply_relu_mask(ctx, mask_src, gx); }
+                              fuse ? mask_src->ptr : nullptr, fuse_sum ? chan_sum : nullptr);
+    if (r == AGB_OK) {
+      AGB_TRY(lx.finish()); AGB_TRY(lg.finish());
+      if (!fuse) AGB_TRY(apply_relu_mask(ctx, mask_src, gx));
+      return (chan_sum != nullptr && !fuse_sum) ? channel_sums(ctx, gx, chan_sum) : AGB_OK;
+    }
     if (r != AGB_ERR_UNSUPPORTED) return r;
   }
   prof.set_cls(AGB_PROF_CONV_SIMT);
@@ -255,7 +273,8 @@ extern "C" int agb_conv2d_dgrad_fused_f32(agb_ctx* ctx, const agb_tensor* gy, co
   int64_t K = (int64_t)g.O * g.kh * g.kw;
   AGB_TRY(simt_gemm_launch(ctx, DgradA{w->ptr, g}, DgradB{lg.view.ptr, g}, DgradC{lx.view.ptr, g}, g.C, (int64_t)g.B * g.H * g.W, K, 1));
   AGB_TRY(lx.finish()); AGB_TRY(lg.finish());
-  return apply_relu_mask(ctx, mask_src, gx);
+  AGB_TRY(apply_relu_mask(ctx, mask_src, gx));
+  return chan_sum != nullptr ? channel_sums(ctx, gx, chan_sum) : AGB_OK;
 }
 
 extern "C" int agb_conv2d_wgrad_f32(agb_ctx* ctx, const agb_tensor* img, const agb_tensor* gr, agb_tensor* gw, int pad, int stride, int dilation) {

@@ -65,6 +65,8 @@ struct NdArray {
                                   // float consumer or the user asks (the reference stores indices as floats, max_pool2d.rs:74-75)
   std::shared_ptr<Im2colRef> virt;
   std::shared_ptr<PoolRef> pool;
+  std::shared_ptr<NdArray> chan_sum;   // (4-D activations gradients) per-channel sums over (b, h, w), produced for free by the fused dgrad /
+                                       // pool-backward epilogues; MaybeReduceSum (the bias gradient) takes it instead of re-reading the tensor
   std::shared_ptr<Lazy> lazy;     // value not computed yet: only `shape` is valid.  ComputeContext::input() materialises it unless the
                                   // consuming op declared accept_lazy (the ops that can fuse it into their own kernel)
 

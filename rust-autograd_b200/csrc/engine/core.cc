@@ -55,16 +55,16 @@ NdArray NdArray::from_host(const Shape& shape, std::vector<float> v, bool meta) 
   return a;
 }
 NdArray NdArray::reshaped(const Shape& s) const {
-  NdArray r = *this; r.shape = s; r.stride = contiguous_strides(s); r.virt.reset();
+  NdArray r = *this; r.shape = s; r.stride = contiguous_strides(s); r.virt.reset(); r.chan_sum.reset(); r.pool.reset();
   return r;
 }
 NdArray NdArray::permuted(const std::vector<int>& perm) const {
-  NdArray r = *this; r.host.reset(); r.virt.reset();
+  NdArray r = *this; r.host.reset(); r.virt.reset(); r.chan_sum.reset(); r.pool.reset();
   for (size_t i = 0; i < perm.size(); i++) { r.shape[i] = shape[perm[i]]; r.stride[i] = stride[perm[i]]; }
   return r;
 }
 NdArray NdArray::sliced(int axis, int64_t start, int64_t len) const {
-  NdArray r = *this; r.host.reset(); r.virt.reset();
+  NdArray r = *this; r.host.reset(); r.virt.reset(); r.chan_sum.reset(); r.pool.reset();
   r.dptr = dptr + start * stride[axis]; r.shape[axis] = len;
   return r;
 }

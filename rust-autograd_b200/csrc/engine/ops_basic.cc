@@ -400,8 +400,11 @@ struct MaybeReduceSum : Op {           // binary_ops.rs:39-105
       if (orig[i] == 1 && gy.shape[i] > 1) axes.push_back((int)i);
       else if (orig[i] != gy.shape[i]) throw Panic("bug of MaybeReduceSum probably");
     }
-    NdArray r = dev_reduce_axes(c.dev, AGB_R_SUM, gy, axes, true);
     Shape fin = orig_.size() == 1 && orig_[0] == 0 ? Shape{} : orig_;     // shape [0] (scalar_shape) denotes a 0-d target
+    if (gy.chan_sum && gy.ndim() == 4 && axes == std::vector<int>({0, 2, 3}) && gy.chan_sum->size() == gy.shape[1]) {
+      c.append_output(gy.chan_sum->reshaped(fin)); return;               // bias gradient already produced by the fused epilogue that wrote gy
+    }
+    NdArray r = dev_reduce_axes(c.dev, AGB_R_SUM, gy, axes, true);
     if (!r.is_contiguous()) r = c.dev->contiguous(r);
     c.append_output(r.reshaped(fin));
   }

@@ -133,7 +133,11 @@ static NdArray run_dgrad(Device* dev, const Lazy& L, const NdArray* mask_src) {
   NdArray gx = act_empty(dev, {gy.shape[0], w.shape[1], xh, xw}, cl);
   agb_tensor tg = gy.desc(), tw = w.desc(), tx = gx.desc(), tm;
   if (mask_src) tm = mask_src->desc();
-  check_status(agb_conv2d_dgrad_fused_f32(dev->ctx, &tg, &tw, mask_src ? &tm : nullptr, &tx, p.pad, p.stride, p.dilation));
+  // with the ReLU mask fused this is the gradient of a conv -> add(bias) -> relu layer's pre-activation: its per-channel sums
+  // (the bias gradient) come out of the same epilogue
+  NdArray cs; if (mask_src) cs = dev->empty({gx.shape[1]});
+  check_status(agb_conv2d_dgrad_fused_f32(dev->ctx, &tg, &tw, mask_src ? &tm : nullptr, mask_src ? cs.dptr : nullptr, &tx, p.pad, p.stride, p.dilation));
+  if (mask_src) gx.chan_sum = std::make_shared<NdArray>(cs);
   return gx;
 }
 // gx = max_pool2d_grad(gy, idx) [gated by pooled output > 0]
@@ -147,8 +151,10 @@ static NdArray run_pool_grad(Device* dev, const Lazy& L, bool gated) {
   int64_t xh = L.pool_stride * (gy.shape[2] - 1) - 2 * L.p.pad + L.pool_size, xw = L.pool_stride * (gy.shape[3] - 1) - 2 * L.p.pad + L.pool_size;     // (max_pool2d.rs:263-264)
   NdArray gx = act_empty(dev, {gy.shape[0], gy.shape[1], xh, xw}, icl);
   agb_tensor tg = gy.desc(), tx = gx.desc();
+  NdArray cs; if (gated) cs = dev->empty({gx.shape[1]});
   check_status(agb_maxpool2d_bwd_fused(dev->ctx, &tg, idx.i32 ? nullptr : idx.dptr, idx.i32 ? (const int32_t*)idx.dptr : nullptr,
-                                       gated ? idx.pool->y.dptr : nullptr, &tx, L.pool_size, L.pool_stride));
+                                       gated ? idx.pool->y.dptr : nullptr, gated ? cs.dptr : nullptr, &tx, L.pool_size, L.pool_stride));
+  if (gated) gx.chan_sum = std::make_shared<NdArray>(cs);
   return gx;
 }
 static NdArray run_conv_fused(Device* dev, const Lazy& L, bool relu) {

@@ -161,9 +161,12 @@ __global__ void __launch_bounds__(256) maxpool_bwd_tiled_kernel(const float* __r
 }
 // channels-last, C % 4 == 0, int32 indices: 4 channels per thread, 128-bit accesses
 __global__ void __launch_bounds__(256) maxpool_bwd_tiled_cl4_kernel(const float* __restrict__ gy, const int32_t* __restrict__ idx_i,
-                                                                    const float* __restrict__ gate, float* __restrict__ gx,
+                                                                    const float* __restrict__ gate, float* __restrict__ gx, float* __restrict__ csum,
                                                                     uint32_t n4, int C, int xh, int xw, int yh, int yw, int size) {
   const uint32_t c4n = (uint32_t)C >> 2;
+  // csum != NULL (host guarantees 256 % c4n == 0): a thread meets the same 4 channels at every grid-stride step, so the per-channel
+  // sums of gx (= sums of the gated gy: every other window element is 0) accumulate in registers
+  float4 cs = make_float4(0.f, 0.f, 0.f, 0.f);
   for (uint32_t o = blockIdx.x * blockDim.x + threadIdx.x; o < n4; o += gridDim.x * blockDim.x) {
     uint32_t c4 = o % c4n, t = o / c4n; uint32_t j = t % (uint32_t)yw; t /= (uint32_t)yw; uint32_t i = t % (uint32_t)yh, b = t / (uint32_t)yh;
     const int c = (int)c4 * 4;
@@ -182,19 +185,38 @@ __global__ void __launch_bounds__(256) maxpool_bwd_tiled_cl4_kernel(const float*
         float4 v;
         v.x = (li == k.x) ? g.x : 0.0f; v.y = (li + plane == k.y) ? g.y : 0.0f; v.z = (li + 2 * plane == k.z) ? g.z : 0.0f; v.w = (li + 3 * plane == k.w) ? g.w : 0.0f;
         stg_stream4(gx + (((size_t)b * xh + h) * xw + w) * C + c, v);
+        cs.x += v.x; cs.y += v.y; cs.z += v.z; cs.w += v.w;
       }
+  }
+  if (csum != nullptr) {
+    __shared__ float cs_s[1024];                       // C <= 1024
+    for (int i = threadIdx.x; i < C; i += blockDim.x) cs_s[i] = 0.0f;
+    __syncthreads();
+    const int c = (int)(threadIdx.x % c4n) * 4;
+    atomicAdd(cs_s + c, cs.x); atomicAdd(cs_s + c + 1, cs.y); atomicAdd(cs_s + c + 2, cs.z); atomicAdd(cs_s + c + 3, cs.w);
+    __syncthreads();
+    for (int i = threadIdx.x; i < C; i += blockDim.x) atomicAdd(csum + i, cs_s[i]);
   }
 }
 // gy and the index buffer share one layout (either); gx may be NCHW or channels-last
 extern "C" int agb_maxpool2d_bwd(agb_ctx* ctx, const agb_tensor* gy, const float* idx_f32, const int32_t* idx_i32, agb_tensor* gx) {
-  return agb_maxpool2d_bwd_fused(ctx, gy, idx_f32, idx_i32, nullptr, gx, 0, 0);
+  return agb_maxpool2d_bwd_fused(ctx, gy, idx_f32, idx_i32, nullptr, nullptr, gx, 0, 0);
 }
 // gx = scatter(gy * (gate > 0)) — `gate` (nullable, laid out like gy) is the POOLED forward output when the pooled input was a
 // ReLU output: relu'(x[argmax]) == (max > 0), so the ReLU backward that follows a pool backward in conv->relu->pool stacks
 // (activation_ops.rs:161-166) costs one extra read of a 1/size^2-sized tensor instead of a 3-array pass.
 // size/stride = the forward window (0 = unknown: always the scatter form).
+static int pool_channel_sums(agb_ctx* ctx, const agb_tensor* t, bool cl, float* chan_sum) {
+  const int64_t B = t->shape[0], C = t->shape[1], HW = t->shape[2] * t->shape[3];
+  if (cl) return agb_reduce(ctx, AGB_R_SUM, t->ptr, chan_sum, 1, B * HW, C);
+  float* tmp; AGB_TRY(agb_alloc(ctx, (size_t)(B * C) * sizeof(float), (void**)&tmp));
+  int r = agb_reduce(ctx, AGB_R_SUM, t->ptr, tmp, B * C, HW, 1);
+  if (r == AGB_OK) r = agb_reduce(ctx, AGB_R_SUM, tmp, chan_sum, 1, B, C);
+  agb_free(ctx, tmp);
+  return r;
+}
 extern "C" int agb_maxpool2d_bwd_fused(agb_ctx* ctx, const agb_tensor* gy, const float* idx_f32, const int32_t* idx_i32, const float* gate,
-                                       agb_tensor* gx, int size, int stride) {
+                                       float* chan_sum, agb_tensor* gx, int size, int stride) {
   AGB_CHECK((idx_f32 != nullptr) != (idx_i32 != nullptr), AGB_ERR_INVALID_DIMS, "max_pool2d_grad: exactly one index buffer must be given");
   bool gcl, xcl; AGB_TRY(pool_layout("max_pool2d_grad", gy, &gcl)); AGB_TRY(pool_layout("max_pool2d_grad", gx, &xcl));
   int64_t n = agb_numel(gy);
@@ -206,19 +228,23 @@ extern "C" int agb_maxpool2d_bwd_fused(agb_ctx* ctx, const agb_tensor* gy, const
     AgbProfScope prof(ctx, AGB_PROF_POOL, 4.0 * (double)(agb_numel(gx) + (gate ? 3 : 2) * n));
     if (gcl && idx_i32 && d.C % 4 == 0 && agb_numel(gx) < (1ll << 31) &&
         ((((uintptr_t)gy->ptr | (uintptr_t)gx->ptr | (uintptr_t)idx_i32 | (uintptr_t)gate) & 15) == 0)) {
-      maxpool_bwd_tiled_cl4_kernel<<<agb_grid_for(n / 4, 256, ctx->sm_count, 8), 256, 0, ctx->stream>>>(gy->ptr, idx_i32, gate, gx->ptr, (uint32_t)(n / 4),
-                                                                                                       d.C, d.xh, d.xw, d.yh, d.yw, size);
+      const bool fuse_sum = chan_sum != nullptr && d.C <= 1024 && 256 % (d.C / 4) == 0;
+      if (fuse_sum) AGB_TRY(agb_memset0(ctx, chan_sum, (size_t)d.C * sizeof(float)));
+      maxpool_bwd_tiled_cl4_kernel<<<agb_grid_for(n / 4, 256, ctx->sm_count, 8), 256, 0, ctx->stream>>>(gy->ptr, idx_i32, gate, gx->ptr, fuse_sum ? chan_sum : nullptr,
+                                                                                                       (uint32_t)(n / 4), d.C, d.xh, d.xw, d.yh, d.yw, size);
+      AGB_LAUNCHED(ctx);
+      return (chan_sum != nullptr && !fuse_sum) ? pool_channel_sums(ctx, gx, true, chan_sum) : AGB_OK;
     } else if (gcl) maxpool_bwd_tiled_kernel<true><<<agb_grid_for(n, 256, ctx->sm_count, 8), 256, 0, ctx->stream>>>(gy->ptr, idx_f32, idx_i32, gate, gx->ptr, n, d, size);
     else maxpool_bwd_tiled_kernel<false><<<agb_grid_for(n, 256, ctx->sm_count, 8), 256, 0, ctx->stream>>>(gy->ptr, idx_f32, idx_i32, gate, gx->ptr, n, d, size);
     AGB_LAUNCHED(ctx);
-    return AGB_OK;
+    return chan_sum != nullptr ? pool_channel_sums(ctx, gx, gcl, chan_sum) : AGB_OK;
   }
   AGB_TRY(agb_memset0(ctx, gx->ptr, agb_numel(gx) * sizeof(float)));
-  if (n == 0) return AGB_OK;
+  if (n == 0) return chan_sum != nullptr ? agb_memset0(ctx, chan_sum, (size_t)gx->shape[1] * sizeof(float)) : AGB_OK;
   AgbProfScope prof(ctx, AGB_PROF_POOL, 4.0 * (double)(agb_numel(gx) + 3 * n));
   maxpool_bwd_kernel<<<agb_grid_for(n, 256, ctx->sm_count, 8), 256, 0, ctx->stream>>>(gy->ptr, idx_f32, idx_i32, gate, gx->ptr, n, d, xcl);
   AGB_LAUNCHED(ctx);
-  return AGB_OK;
+  return chan_sum != nullptr ? pool_channel_sums(ctx, gx, xcl, chan_sum) : AGB_OK;
 }
 
 __global__ void __launch_bounds__(256) maxpool_gg_kernel(const float* __restrict__ ggx, const float* __restrict__ idx_f,

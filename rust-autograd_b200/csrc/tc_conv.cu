@@ -37,7 +37,7 @@ __global__ void __launch_bounds__(256) repack_filter_kernel(const float* __restr
 template <int TN_, bool SPLIT_> struct ConvFpropPol {
   static constexpr int TN = TN_; static constexpr bool SPLIT = SPLIT_, P_MN = false, Q_MN = false;
   static constexpr int OCC = (SPLIT_ || TN_ > 128) ? 1 : 2;
-  struct Params { CUtensorMap tmX, tmW; float* y; const float* bias; const float* mask; int relu; int Cout, yh, yw, kw, pad, dil, tiles_x, tiles_y, cblocks, taps; MnDescCfg mnc; };
+  struct Params { CUtensorMap tmX, tmW; float* y; const float* bias; const float* mask; float* csum; int relu; int Cout, yh, yw, kw, pad, dil, tiles_x, tiles_y, cblocks, taps; MnDescCfg mnc; };
   struct Tile { int b, oy0, ox0, o0; };
   __device__ static Tile tile(const Params& p) {
     int bx = (int)blockIdx.x; int tx = bx % p.tiles_x; int r = bx / p.tiles_x; int ty = r % p.tiles_y;
@@ -74,11 +74,12 @@ template <int TN_, bool SPLIT_> struct ConvFpropPol {
       pre[c] = bits;
     }
   }
-  __device__ static void store(const Params& p, const Tile& t, int lane, int c0, const float* v, uint32_t pre) {
+  __device__ static void store(const Params& p, const Tile& t, int lane, int c0, const float* v, uint32_t pre, float* csum_s) {
     const int oy = t.oy0 + (lane >> 5), ox = t.ox0 + (lane & 31);
-    if (oy >= p.yh || ox >= p.yw) return;
+    const bool in = oy < p.yh && ox < p.yw;
+    if (!in && p.csum == nullptr) return;
     const int o = t.o0 + c0;
-    float* dst = p.y + (((int64_t)t.b * p.yh + oy) * p.yw + ox) * p.Cout + o;
+    float* dst = p.y + (((int64_t)t.b * p.yh + (in ? oy : 0)) * p.yw + (in ? ox : 0)) * p.Cout + o;
     // fused epilogue: per-channel bias and ReLU applied to the accumulator registers, so the
     // pre-activation tensors of conv -> add -> relu never travel through HBM
     float r[32];
@@ -92,13 +93,37 @@ template <int TN_, bool SPLIT_> struct ConvFpropPol {
 #pragma unroll
       for (int j = 0; j < 32; j++) r[j] = ((pre >> j) & 1u) ? r[j] : 0.0f * r[j];
     }
-    if (o + 32 <= p.Cout) {
+    if (in) {
+      if (o + 32 <= p.Cout) {
 #pragma unroll
-      for (int j = 0; j < 32; j += 4) *(float4*)(dst + j) = make_float4(r[j], r[j + 1], r[j + 2], r[j + 3]);
-    } else {
+        for (int j = 0; j < 32; j += 4) *(float4*)(dst + j) = make_float4(r[j], r[j + 1], r[j + 2], r[j + 3]);
+      } else {
 #pragma unroll
-      for (int j = 0; j < 32; j++) if (o + j < p.Cout) dst[j] = r[j];
+        for (int j = 0; j < 32; j++) if (o + j < p.Cout) dst[j] = r[j];
+      }
     }
+    if (p.csum != nullptr) {
+      // per-channel sums of the stored tile (the bias gradient of the layer below, reduce_sum over b,h,w): butterfly
+      // transpose-reduce across the warp — 31 shuffles leave the sum of channel l in lane l — then one shared-memory add per lane
+      const int wl = lane & 31;
+#pragma unroll
+      for (int j = 0; j < 32; j++) r[j] = in ? r[j] : 0.0f;
+#pragma unroll
+      for (int off = 16, n = 32; off >= 1; off >>= 1, n >>= 1) {
+        const bool upper = (wl & off) != 0;
+#pragma unroll
+        for (int i = 0; i < 16; i++) {
+          if (i < n / 2) {
+            const float send = upper ? r[i] : r[i + n / 2], keep = upper ? r[i + n / 2] : r[i];
+            r[i] = keep + __shfl_xor_sync(0xffffffffu, send, off);
+          }
+        }
+      }
+      if (o + wl < p.Cout) atomicAdd(csum_s + c0 + wl, r[0]);
+    }
+  }
+  __device__ static void finish(const Params& p, const Tile& t, const float* csum_s) {
+    if (p.csum != nullptr && (int)threadIdx.x < TN && t.o0 + (int)threadIdx.x < p.Cout) atomicAdd(p.csum + t.o0 + threadIdx.x, csum_s[threadIdx.x]);
   }
 };
 
@@ -137,7 +162,8 @@ template <int TN_, bool SPLIT_, bool PAIR_> struct ConvWgradPol {
     for (int g = 0; g < TN / 32; g++) tma_load_4d(pQ + g * 4096, &p.tmG, bar, t.o0 + 32 * g, ox0, oy, b);
   }
   __device__ static void pre_epilogue(const Params&, const Tile&, int, uint32_t*) {}
-  __device__ static void store(const Params& p, const Tile& t, int lane, int c0, const float* v, uint32_t) {
+  __device__ static void finish(const Params&, const Tile&, const float*) {}
+  __device__ static void store(const Params& p, const Tile& t, int lane, int c0, const float* v, uint32_t, float*) {
     int c, tap;
     if (PAIR_) { c = lane & 63; tap = lane < 64 ? t.tapA : t.tapB; } else { c = t.c0 + lane; tap = t.tapA; }
     if (c >= p.C || tap >= p.T) return;
@@ -148,7 +174,7 @@ template <int TN_, bool SPLIT_, bool PAIR_> struct ConvWgradPol {
 
 // ------------------------------------------------------------------------------------------------ host side
 int agb_tc_conv_rows(agb_ctx* ctx, const float* x, const float* wr, float* y, int B, int Cin, int H, int W, int Cout, int yh, int yw, int kh, int kw,
-                     int pad, int dil, const float* bias, int relu, const float* mask);
+                     int pad, int dil, const float* bias, int relu, const float* mask, float* csum);
 // channels-last tensor map of a logical [B, C, H, W] activation: dims {c, w, h, b}
 static int make_cl_map(CUtensorMap* m, const float* p, int B, int C, int H, int W, uint32_t bc, uint32_t bw, uint32_t bh, bool atom32) {
   uint64_t dims[4] = {(uint64_t)C, (uint64_t)W, (uint64_t)H, (uint64_t)B};
@@ -163,7 +189,7 @@ bool agb_tc_conv_eligible(int C, int O, int kh, int kw, int stride, int yw) {
 
 template <int TN, bool SPLIT>
 static int fprop_launch(agb_ctx* ctx, const float* x, const float* wr, float* y, int B, int Cin, int H, int W, int Cout, int yh, int yw, int kh, int kw,
-                        int pad, int dil, const float* bias, int relu, const float* mask) {
+                        int pad, int dil, const float* bias, int relu, const float* mask, float* csum) {
   using Pol = ConvFpropPol<TN, SPLIT>;
   typename Pol::Params p;
   AGB_TRY(make_cl_map(&p.tmX, x, B, Cin, H, W, 32, 32, 4, false));
@@ -173,7 +199,7 @@ static int fprop_launch(agb_ctx* ctx, const float* x, const float* wr, float* y,
     uint32_t box[3] = {32, (uint32_t)TN, 1};
     AGB_TRY(agb_make_tmap(&p.tmW, wr, 3, dims, str, box, false));
   }
-  p.y = y; p.bias = bias; p.mask = mask; p.relu = relu; p.Cout = Cout; p.yh = yh; p.yw = yw; p.kw = kw; p.pad = pad; p.dil = dil;
+  p.y = y; p.bias = bias; p.mask = mask; p.csum = csum; p.relu = relu; p.Cout = Cout; p.yh = yh; p.yw = yw; p.kw = kw; p.pad = pad; p.dil = dil;
   p.tiles_x = (yw + 31) / 32; p.tiles_y = (yh + 3) / 4; p.cblocks = (Cin + 31) / 32; p.taps = kh * kw; p.mnc = agb_mn_cfg();
   int64_t nb = (int64_t)p.tiles_x * p.tiles_y * B;
   if (nb > 2147483647ll) return AGB_ERR_UNSUPPORTED;
@@ -184,7 +210,7 @@ static int fprop_launch(agb_ctx* ctx, const float* x, const float* wr, float* y,
 // fprop on channels-last buffers: x [B,H,W,C], w [O,C,kh,kw] (plain) -> y [B,yh,yw,O].  flip_transpose != 0: dgrad — `x` is gy
 // with C = filter dim 0, w [C, O(=out channels of this GEMM), kh, kw]; the effective padding is dil*(k-1) - pad.
 int agb_tc_conv_fprop(agb_ctx* ctx, int mode, const float* x, const float* w, float* y, int B, int C, int H, int W, int O, int kh, int kw,
-                      int pad, int stride, int dil, int flip_transpose, const float* bias, int relu, const float* mask) {
+                      int pad, int stride, int dil, int flip_transpose, const float* bias, int relu, const float* mask, float* csum) {
   const int epad = flip_transpose ? dil * (kh - 1) - pad : pad;
   if (epad < 0) return AGB_ERR_UNSUPPORTED;
   const int yh = H + 2 * epad - (dil * (kh - 1) + 1) + 1, yw = W + 2 * epad - (dil * (kw - 1) + 1) + 1;
@@ -202,16 +228,16 @@ int agb_tc_conv_fprop(agb_ctx* ctx, int mode, const float* x, const float* w, fl
   }
   const bool split = mode == AGB_MATH_3XTF32;
   if (!split) {       // wide feature maps: persistent halo-reusing kernel (tc_conv_rows.cu), 3x less L2 -> smem traffic
-    int r = agb_tc_conv_rows(ctx, x, wr, y, B, C, H, W, O, yh, yw, kh, kw, epad, dil, bias, relu, mask);
+    int r = agb_tc_conv_rows(ctx, x, wr, y, B, C, H, W, O, yh, yw, kh, kw, epad, dil, bias, relu, mask, csum);
     if (r != AGB_ERR_UNSUPPORTED) return r;
   }
   if (split) {
-    if (O > 64) return fprop_launch<128, true>(ctx, x, wr, y, B, C, H, W, O, yh, yw, kh, kw, epad, dil, bias, relu, mask);
-    return fprop_launch<64, true>(ctx, x, wr, y, B, C, H, W, O, yh, yw, kh, kw, epad, dil, bias, relu, mask);
+    if (O > 64) return fprop_launch<128, true>(ctx, x, wr, y, B, C, H, W, O, yh, yw, kh, kw, epad, dil, bias, relu, mask, csum);
+    return fprop_launch<64, true>(ctx, x, wr, y, B, C, H, W, O, yh, yw, kh, kw, epad, dil, bias, relu, mask, csum);
   }
-  if (O > 128) return fprop_launch<256, false>(ctx, x, wr, y, B, C, H, W, O, yh, yw, kh, kw, epad, dil, bias, relu, mask);
-  if (O > 64) return fprop_launch<128, false>(ctx, x, wr, y, B, C, H, W, O, yh, yw, kh, kw, epad, dil, bias, relu, mask);
-  return fprop_launch<64, false>(ctx, x, wr, y, B, C, H, W, O, yh, yw, kh, kw, epad, dil, bias, relu, mask);
+  if (O > 128) return fprop_launch<256, false>(ctx, x, wr, y, B, C, H, W, O, yh, yw, kh, kw, epad, dil, bias, relu, mask, csum);
+  if (O > 64) return fprop_launch<128, false>(ctx, x, wr, y, B, C, H, W, O, yh, yw, kh, kw, epad, dil, bias, relu, mask, csum);
+  return fprop_launch<64, false>(ctx, x, wr, y, B, C, H, W, O, yh, yw, kh, kw, epad, dil, bias, relu, mask, csum);
 }
 
 template <int TN, bool SPLIT, bool PAIR>

@@ -26,7 +26,7 @@
 #define ROWS_R 2
 struct RowsParams {
   CUtensorMap tmX, tmW;
-  float* y; const float* bias; const float* mask; int relu;
+  float* y; const float* bias; const float* mask; float* csum; int relu;
   int Cout, yh, yw, kw, pad, dil, tiles_x, tiles_y, otiles, cblocks, taps, pitch, a_box_bytes, a_slot_bytes;
   long long num_tiles;
 };
@@ -51,6 +51,8 @@ __global__ void __launch_bounds__(256, 1) conv_rows_kernel(const __grid_constant
   uint64_t* acc_full = bars + 4 + 2 * NB; uint64_t* acc_empty = bars + 6 + 2 * NB;
   uint32_t* tmem_slot = (uint32_t*)(bars + 8 + 2 * NB);
   float* stage = (float*)((uint8_t*)bars + 256);               // [4 warps][32][36] epilogue transpose tiles
+  float* csum_s = stage + 4 * 32 * 36;                         // [TN] per-channel sums of this CTA
+  if ((int)threadIdx.x < TN) csum_s[threadIdx.x] = 0.0f;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
 
   if (warp == 0 && lane == 0) {
@@ -152,6 +154,9 @@ __global__ void __launch_bounds__(256, 1) conv_rows_kernel(const __grid_constant
     const uint32_t tlane = tmem_base + ((uint32_t)(32 * q) << 16);
     float* stg = stage + q * (32 * 36);
     const int pl0 = lane >> 3, ch4 = lane & 7;
+    float4 cs[TN / 32];                                          // per-channel sums of the stored values (csum side output; otiles == 1)
+#pragma unroll
+    for (int c = 0; c < TN / 32; c++) cs[c] = make_float4(0.f, 0.f, 0.f, 0.f);
     uint32_t it = 0;
     for (long long t = blockIdx.x; t < p.num_tiles; t += gridDim.x, it++) {
       const int b = (int)(t / tiles_per_img); int rr = (int)(t - (long long)b * tiles_per_img);
@@ -211,7 +216,10 @@ __global__ void __launch_bounds__(256, 1) conv_rows_kernel(const __grid_constant
               const uint32_t m = pre[r][c] >> (4 * k);
               a.x = (m & 1u) ? a.x : 0.0f * a.x; a.y = (m & 2u) ? a.y : 0.0f * a.y; a.z = (m & 4u) ? a.z : 0.0f * a.z; a.w = (m & 8u) ? a.w : 0.0f * a.w;
             }
-            if (oy < p.yh && ox < p.yw && o + 4 <= p.Cout) *(float4*)(p.y + (((long long)b * p.yh + oy) * p.yw + ox) * p.Cout + o) = a;
+            if (oy < p.yh && ox < p.yw && o + 4 <= p.Cout) {
+              *(float4*)(p.y + (((long long)b * p.yh + oy) * p.yw + ox) * p.Cout + o) = a;
+              cs[c].x += a.x; cs[c].y += a.y; cs[c].z += a.z; cs[c].w += a.w;
+            }
           }
           __syncwarp();
         }
@@ -219,9 +227,25 @@ __global__ void __launch_bounds__(256, 1) conv_rows_kernel(const __grid_constant
       tc_fence_before();
       mbar_arrive(&acc_empty[acs]);
     }
+    if (p.csum != nullptr) {       // lanes with equal ch4 (4 per warp) -> shared-memory sums of the CTA
+#pragma unroll
+      for (int c = 0; c < TN / 32; c++) {
+        float4 v = cs[c];
+#pragma unroll
+        for (int off = 8; off <= 16; off <<= 1) {
+          v.x += __shfl_xor_sync(0xffffffffu, v.x, off); v.y += __shfl_xor_sync(0xffffffffu, v.y, off);
+          v.z += __shfl_xor_sync(0xffffffffu, v.z, off); v.w += __shfl_xor_sync(0xffffffffu, v.w, off);
+        }
+        if (lane < 8) {
+          float* d = csum_s + 32 * c + 4 * ch4;
+          atomicAdd(d, v.x); atomicAdd(d + 1, v.y); atomicAdd(d + 2, v.z); atomicAdd(d + 3, v.w);
+        }
+      }
+    }
   }
   tc_fence_before();
   __syncthreads();
+  if (p.csum != nullptr && (int)threadIdx.x < TN && (int)threadIdx.x < p.Cout) atomicAdd(p.csum + threadIdx.x, csum_s[threadIdx.x]);
   if (warp == 1) tmem_dealloc(tmem_base, Cfg::TMEM_COLS);
 }
 
@@ -238,7 +262,7 @@ static int rows_launch(agb_ctx* ctx, RowsParams& p, size_t smem) {
 // x [B,H,W,Cin] channels-last, wr = filter repacked to [tap][Cout][Cin] (see tc_conv.cu), y [B,yh,yw,Cout] channels-last.
 // Returns AGB_ERR_UNSUPPORTED when the geometry is outside this kernel's envelope (the caller falls back to the per-tap kernel).
 int agb_tc_conv_rows(agb_ctx* ctx, const float* x, const float* wr, float* y, int B, int Cin, int H, int W, int Cout, int yh, int yw, int kh, int kw,
-                     int pad, int dil, const float* bias, int relu, const float* mask) {
+                     int pad, int dil, const float* bias, int relu, const float* mask, float* csum) {
   static int enabled = -1;
   if (enabled < 0) { const char* e = getenv("AGB_CONV_ROWS"); enabled = (e && e[0] == '0') ? 0 : 1; }
   if (!enabled || yw < 128 || Cout > 128 || Cin % 4 != 0 || Cout % 4 != 0) return AGB_ERR_UNSUPPORTED;
@@ -248,7 +272,7 @@ int agb_tc_conv_rows(agb_ctx* ctx, const float* x, const float* wr, float* y, in
   p.a_box_bytes = pitch * hrows * 128; p.a_slot_bytes = (p.a_box_bytes + 1023) & ~1023;
   const int TN = Cout > 64 ? 128 : 64;
   const int nb = TN <= 64 ? RowsCfg<64>::NB : RowsCfg<128>::NB;
-  const size_t smem = 2 * (size_t)p.a_slot_bytes + (size_t)nb * TN * 128 + 1024 + 256 + 4 * 32 * 36 * 4;
+  const size_t smem = 2 * (size_t)p.a_slot_bytes + (size_t)nb * TN * 128 + 1024 + 256 + 4 * 32 * 36 * 4 + 128 * 4;
   if (smem > 227 * 1024) return AGB_ERR_UNSUPPORTED;
   {
     uint64_t dims[4] = {(uint64_t)Cin, (uint64_t)W, (uint64_t)H, (uint64_t)B};
@@ -262,7 +286,7 @@ int agb_tc_conv_rows(agb_ctx* ctx, const float* x, const float* wr, float* y, in
     uint32_t box[3] = {32, (uint32_t)TN, 1};
     AGB_TRY(agb_make_tmap(&p.tmW, wr, 3, dims, str, box, false));
   }
-  p.y = y; p.bias = bias; p.mask = mask; p.relu = relu; p.Cout = Cout; p.yh = yh; p.yw = yw; p.kw = kw; p.pad = pad; p.dil = dil;
+  p.y = y; p.bias = bias; p.mask = mask; p.csum = csum; p.relu = relu; p.Cout = Cout; p.yh = yh; p.yw = yw; p.kw = kw; p.pad = pad; p.dil = dil;
   p.tiles_x = (yw + 127) / 128; p.tiles_y = (yh + ROWS_R - 1) / ROWS_R; p.otiles = (Cout + TN - 1) / TN;
   p.cblocks = (Cin + 31) / 32; p.taps = kh * kw; p.pitch = pitch;
   p.num_tiles = (long long)B * p.tiles_x * p.tiles_y * p.otiles;

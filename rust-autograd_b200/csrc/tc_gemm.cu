@@ -38,7 +38,8 @@ template <int TN_, bool P_MN_, bool Q_MN_, bool SPLIT_> struct GemmPol {
   // thread `lane` owns C column n = lane0 + lane; v[j] belongs to C row m = col0 + c0 + j: a warp stores 32 consecutive
   // floats of one C row per instruction (128-byte coalesced), no shared-memory staging
   __device__ static void pre_epilogue(const Params&, const Tile&, int, uint32_t*) {}
-  __device__ static void store(const Params& p, const Tile& t, int lane, int c0, const float* v, uint32_t) {
+  __device__ static void finish(const Params&, const Tile&, const float*) {}
+  __device__ static void store(const Params& p, const Tile& t, int lane, int c0, const float* v, uint32_t, float*) {
     const int n = t.lane0 + lane;
     if (n >= p.NL) return;
     float* cbase = p.C + (int64_t)t.bz * p.bsc + n;

@@ -30,7 +30,7 @@ template <int TN, bool SPLIT, int OCC = 1> struct TcCfg {
   static constexpr int BUDGET = (224 * 1024) / OCC - 2048;
   static constexpr int STAGES = BUDGET / STAGE_BYTES > 6 ? 6 : BUDGET / STAGE_BYTES;
   static_assert(STAGES >= 2, "tile does not fit the shared-memory budget");
-  static constexpr int SMEM = STAGES * STAGE_BYTES + 1024 /*align*/ + 256 /*barriers*/;
+  static constexpr int SMEM = STAGES * STAGE_BYTES + 1024 /*align*/ + 256 /*barriers*/ + 1024 /*policy scratch: TN floats, zeroed*/;
   static constexpr int THREADS = SPLIT ? 320 : 192;
   static constexpr int TMEM_COLS = SPLIT ? 2 * TN : TN;                // power of two >= 32 for TN in {32,64,128,256}
   static_assert(!SPLIT || TN <= 128, "3xTF32 keeps TN fp32 partial sums per thread in registers");
@@ -56,6 +56,8 @@ __global__ void __launch_bounds__(TcCfg<Pol::TN, Pol::SPLIT, Pol::OCC>::THREADS,
   uint64_t* full = bars; uint64_t* ready = bars + S; uint64_t* empty = bars + 2 * S;
   uint64_t* acc_full = bars + 3 * S; uint64_t* acc_empty = bars + 3 * S + 2;
   uint32_t* tmem_slot = (uint32_t*)(bars + 3 * S + 4);
+  float* pol_smem = (float*)((uint8_t*)bars + 256);           // TN floats of policy scratch (e.g. per-channel sums), zeroed here
+  for (int i = threadIdx.x; i < 256; i += blockDim.x) pol_smem[i] = 0.0f;
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const typename Pol::Tile tl = Pol::tile(prm);
@@ -181,7 +183,7 @@ __global__ void __launch_bounds__(TcCfg<Pol::TN, Pol::SPLIT, Pol::OCC>::THREADS,
       }
       if (nk > 0) {
 #pragma unroll
-        for (int c0 = 0; c0 < TN; c0 += 32) Pol::store(prm, tl, row, c0, &racc[c0], pre[c0 / 32]);
+        for (int c0 = 0; c0 < TN; c0 += 32) Pol::store(prm, tl, row, c0, &racc[c0], pre[c0 / 32], pol_smem);
       }
     } else if (nk > 0) {
       mbar_wait(&acc_full[0], 0);
@@ -191,12 +193,13 @@ __global__ void __launch_bounds__(TcCfg<Pol::TN, Pol::SPLIT, Pol::OCC>::THREADS,
         float v[32];
         tmem_ld32(tlane + (uint32_t)c0, v);
         tmem_ld_wait();
-        Pol::store(prm, tl, row, c0, v, pre[c0 / 32]);
+        Pol::store(prm, tl, row, c0, v, pre[c0 / 32], pol_smem);
       }
     }
   }
   tc_fence_before();
   __syncthreads();
+  Pol::finish(prm, tl, pol_smem);                              // all threads, after every store of the CTA
   if (warp == 1) tmem_dealloc(tmem_base, Cfg::TMEM_COLS);
 }
 

@@ -290,17 +290,20 @@ class Device:
             ffi.check(self.lib.agb_conv2d_fprop_fused_f32(self.ctx, x.desc(), w.desc(), bias.ptr if bias is not None else None, int(relu), y.desc(), pad, stride, dil))
         return y
 
-    def conv2d_transpose(self, gy, w, pad=0, stride=1, dil=1, mask_src=None, channels_last=False):
+    def conv2d_transpose(self, gy, w, pad=0, stride=1, dil=1, mask_src=None, channels_last=False, chan_sum=False):
+        """gx = conv2d_transpose(gy, w) [* (mask_src > 0)]; with chan_sum also returns sum_{b,h,w} gx as a [C] array"""
         b, _, yh, yw = gy.shape
         _, c, kh, kw = w.shape
         xh = stride * (yh - 1) - 2 * pad + (dil * (kh - 1) + 1)
         xw = stride * (yw - 1) - 2 * pad + (dil * (kw - 1) + 1)
         gx = self.empty_channels_last((b, c, xh, xw)) if channels_last else self.empty((b, c, xh, xw))
-        if mask_src is None:
+        if mask_src is None and not chan_sum:
             ffi.check(self.lib.agb_conv2d_dgrad_f32(self.ctx, gy.desc(), w.desc(), gx.desc(), pad, stride, dil))
-        else:
-            ffi.check(self.lib.agb_conv2d_dgrad_fused_f32(self.ctx, gy.desc(), w.desc(), mask_src.desc(), gx.desc(), pad, stride, dil))
-        return gx
+            return gx
+        cs = self.empty((c,)) if chan_sum else None
+        ffi.check(self.lib.agb_conv2d_dgrad_fused_f32(self.ctx, gy.desc(), w.desc(), mask_src.desc() if mask_src is not None else None,
+                                                      cs.ptr if chan_sum else None, gx.desc(), pad, stride, dil))
+        return (gx, cs) if chan_sum else gx
 
     def conv2d_filter_grad(self, img, g, wshape, pad=0, stride=1, dil=1):
         gw = self.empty(wshape)
@@ -323,17 +326,19 @@ class Device:
         ffi.check(self.lib.agb_maxpool2d_fwd(self.ctx, x.desc(), y.desc(), None if int32_index else idx.ptr, idx.ptr if int32_index else None, size, pad, stride))
         return y, idx
 
-    def max_pool2d_grad(self, gy, idx, size, pad=0, stride=1, gate=None, int32_index=False, window_known=True):
+    def max_pool2d_grad(self, gy, idx, size, pad=0, stride=1, gate=None, int32_index=False, window_known=True, chan_sum=False):
         """gx = scatter(gy [* (gate > 0)]); gx takes the memory order of gy / idx"""
         b, c, yh, yw = gy.shape
         shape = (b, c, stride * (yh - 1) - 2 * pad + size, stride * (yw - 1) - 2 * pad + size)
         gx = self.empty(shape) if gy.is_contiguous() else self.empty_channels_last(shape)
         fi, ii = (None, idx.ptr) if int32_index else (idx.ptr, None)
-        if gate is None and not window_known:
+        if gate is None and not window_known and not chan_sum:
             ffi.check(self.lib.agb_maxpool2d_bwd(self.ctx, gy.desc(), fi, ii, gx.desc()))
-        else:
-            ffi.check(self.lib.agb_maxpool2d_bwd_fused(self.ctx, gy.desc(), fi, ii, gate.ptr if gate is not None else None, gx.desc(), size, stride))
-        return gx
+            return gx
+        cs = self.empty((c,)) if chan_sum else None
+        ffi.check(self.lib.agb_maxpool2d_bwd_fused(self.ctx, gy.desc(), fi, ii, gate.ptr if gate is not None else None, cs.ptr if chan_sum else None,
+                                                   gx.desc(), size if window_known else 0, stride if window_known else 0))
+        return (gx, cs) if chan_sum else gx
 
     def max_pool2d_grad_grad(self, ggx, idx, size, pad=0, stride=1):
         b, c, h, w = ggx.shape

@@ -20,9 +20,10 @@ def main():
     dev.set_math_mode(1)
     x, gy, y, gx, m = cl(dev, (B, Cc, H, H)), cl(dev, (B, O, H, H)), cl(dev, (B, O, H, H)), cl(dev, (B, Cc, H, H)), cl(dev, (B, Cc, H, H))
     w, gw = dev.fill((O, Cc, 3, 3), 0.01), dev.empty((O, Cc, 3, 3))
+    cs = dev.empty((Cc,))
     fl = 2.0 * B * O * H * H * Cc * 9
     for name, fn in (("fprop", lambda: ffi.check(lib.agb_conv2d_fprop_f32(dev.ctx, x.desc(), w.desc(), y.desc(), 1, 1, 1))),
-                     ("dgrad_mask", lambda: ffi.check(lib.agb_conv2d_dgrad_fused_f32(dev.ctx, gy.desc(), w.desc(), m.desc(), gx.desc(), 1, 1, 1))),
+                     ("dgrad_mask", lambda: ffi.check(lib.agb_conv2d_dgrad_fused_f32(dev.ctx, gy.desc(), w.desc(), m.desc(), cs.ptr, gx.desc(), 1, 1, 1))),
                      ("wgrad", lambda: ffi.check(lib.agb_conv2d_wgrad_f32(dev.ctx, x.desc(), gy.desc(), gw.desc(), 1, 1, 1)))):
         ms = timeit(dev, fn, iters=iters, warm=2, flush=False)
         print("%s B%d C%d H%d O%d: %.3f ms  %.1f TFLOP/s" % (name, B, Cc, H, O, ms, fl / ms / 1e9), flush=True)

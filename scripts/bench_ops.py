@@ -105,7 +105,7 @@ def main():
         nx = 4.0 * B * Cc * H * H
         row("max_pool2d_fwd_B%d_C%d_H%d" % (B, Cc, H), timeit(dev, lambda: ffi.check(lib.agb_maxpool2d_fwd(dev.ctx, x.desc(), y.desc(), None, idx.ptr, 2, 0, 2)), iters=5), bytes_=nx * 1.5)
         row("max_pool2d_grad_scatter_B%d_C%d_H%d" % (B, Cc, H), timeit(dev, lambda: ffi.check(lib.agb_maxpool2d_bwd(dev.ctx, gy.desc(), None, idx.ptr, gx.desc())), iters=5), bytes_=nx * 1.5)
-        row("max_pool2d_grad_tiled_relu_gate_B%d_C%d_H%d" % (B, Cc, H), timeit(dev, lambda: ffi.check(lib.agb_maxpool2d_bwd_fused(dev.ctx, gy.desc(), None, idx.ptr, y.ptr, gx.desc(), 2, 2)), iters=5), bytes_=nx * 1.75)
+        row("max_pool2d_grad_tiled_relu_gate_B%d_C%d_H%d" % (B, Cc, H), timeit(dev, lambda: ffi.check(lib.agb_maxpool2d_bwd_fused(dev.ctx, gy.desc(), None, idx.ptr, y.ptr, None, gx.desc(), 2, 2)), iters=5), bytes_=nx * 1.75)
         x = gx = y = idx = gy = None
     for cols in (1024, 4096, 16384, 32768, 131072):
         n = 1 << 28

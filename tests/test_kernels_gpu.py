@@ -220,12 +220,15 @@ def test_conv2d_fused_epilogues_vs_oracle(dev, case, cl, mode):
     mask_src = rng.standard_normal(x.shape).astype(np.float32)
     mask_src[0, 0, 0, :4] = 0.0                                    # exactly-zero entries are masked out (x > 0 is strict)
     gx_ref = R.conv2d_transpose(gy, w, pad, 1, dil) * (mask_src > 0)
-    gx = dev.conv2d_transpose(up(gy), dw, pad, 1, dil, mask_src=up(mask_src), channels_last=cl).numpy()
+    gx, cs = dev.conv2d_transpose(up(gy), dw, pad, 1, dil, mask_src=up(mask_src), channels_last=cl, chan_sum=True)
+    gx = gx.numpy()
     assert rel_err(gx, gx_ref) <= TOL[mode], "dgrad*mask"
     assert np.all(gx[mask_src <= 0] == 0.0)
+    assert rel_err(cs.numpy(), gx.astype(np.float64).sum(axis=(0, 2, 3))) <= 1e-5, "per-channel sums of the stored values (bias gradient)"
     # mask in the other memory order than the output: still correct (un-fused tail)
-    gx2 = dev.conv2d_transpose(up(gy), dw, pad, 1, dil, mask_src=(dev.upload if cl else dev.upload_channels_last)(mask_src), channels_last=cl).numpy()
-    assert rel_err(gx2, gx_ref) <= TOL[mode]
+    gx2, cs2 = dev.conv2d_transpose(up(gy), dw, pad, 1, dil, mask_src=(dev.upload if cl else dev.upload_channels_last)(mask_src), channels_last=cl, chan_sum=True)
+    assert rel_err(gx2.numpy(), gx_ref) <= TOL[mode]
+    assert rel_err(cs2.numpy(), gx2.numpy().astype(np.float64).sum(axis=(0, 2, 3))) <= 1e-5
 
 
 @pytest.mark.parametrize("mode", MODES)
@@ -295,8 +298,10 @@ def test_max_pool_grad_fused_bit_exact(dev, shape, size, stride, cl):
     gx = dev.max_pool2d_grad(up(gy), idx, size, 0, stride, int32_index=True).numpy()
     close(gx, gx_ref)
     if gx_ref.shape == x.shape:
-        gated = dev.max_pool2d_grad(up(gy), idx, size, 0, stride, gate=y, int32_index=True).numpy()
+        gated, cs = dev.max_pool2d_grad(up(gy), idx, size, 0, stride, gate=y, int32_index=True, chan_sum=True)
+        gated = gated.numpy()
         close(gated, gx_ref * (x > 0))                                       # == relu_grad(x, max_pool2d_grad(gy))
+        assert rel_err(cs.numpy(), gated.astype(np.float64).sum(axis=(0, 2, 3))) <= 1e-5
     _, idx_f = dev.max_pool2d(dx, size, 0, stride)
     close(dev.max_pool2d_grad(up(gy), idx_f, size, 0, stride).numpy(), gx_ref)
     close(dev.max_pool2d_grad(up(gy), idx_f, size, 0, stride, window_known=False).numpy(), gx_ref)
