@@ -34,14 +34,16 @@ __global__ void __launch_bounds__(256) repack_filter_kernel(const float* __restr
 }
 
 // ------------------------------------------------------------------------------------------------ fprop / dgrad policy
-template <int TN_, bool SPLIT_> struct ConvFpropPol {
-  static constexpr int TN = TN_; static constexpr bool SPLIT = SPLIT_, P_MN = false, Q_MN = false;
-  static constexpr int OCC = (SPLIT_ || TN_ > 128) ? 1 : 2;
+// MT_ = 2: the CTA owns an 8x32 pixel patch = two 128-lane M-tiles (rows 0-3 / 4-7, ONE {32 c, 32 w, 8 h} box per k-block) that
+// share every filter tile: 1.33x (TN 128) / 1.5x (TN 256) fewer bytes through L2 -> smem per output, the bound of these kernels.
+template <int TN_, bool SPLIT_, int MT_ = 1> struct ConvFpropPol {
+  static constexpr int TN = TN_, MT = MT_; static constexpr bool SPLIT = SPLIT_, P_MN = false, Q_MN = false;
+  static constexpr int OCC = (SPLIT_ || TN_ > 128 || MT_ > 1) ? 1 : 2;
   struct Params { CUtensorMap tmX, tmW; float* y; const float* bias; const float* mask; float* csum; int relu; int Cout, yh, yw, kw, pad, dil, tiles_x, tiles_y, cblocks, taps; MnDescCfg mnc; };
   struct Tile { int b, oy0, ox0, o0; };
-  __device__ static Tile tile(const Params& p) {
-    int bx = (int)blockIdx.x; int tx = bx % p.tiles_x; int r = bx / p.tiles_x; int ty = r % p.tiles_y;
-    return Tile{r / p.tiles_y, ty * 4, tx * 32, (int)blockIdx.y * TN};
+  __device__ static Tile tile(const Params& p, uint3 blk) {
+    int bx = (int)blk.x; int tx = bx % p.tiles_x; int r = bx / p.tiles_x; int ty = r % p.tiles_y;
+    return Tile{r / p.tiles_y, ty * 4 * MT, tx * 32, (int)blk.y * TN};
   }
   __device__ static int num_kblocks(const Params& p, const Tile&) { return p.taps * p.cblocks; }
   __device__ static void prefetch(const Params& p) { tma_prefetch_desc(&p.tmX); tma_prefetch_desc(&p.tmW); }
@@ -54,28 +56,31 @@ template <int TN_, bool SPLIT_> struct ConvFpropPol {
   // strided (one pixel per thread) loads cost no epilogue latency; default-cached so both halves of a 32-byte sector are used.
   __device__ static void pre_epilogue(const Params& p, const Tile& t, int lane, uint32_t* pre) {
     if (p.mask == nullptr) return;
-    const int oy = t.oy0 + (lane >> 5), ox = t.ox0 + (lane & 31);
-    const bool in = oy < p.yh && ox < p.yw;
-    const float* m = p.mask + (((int64_t)t.b * p.yh + (in ? oy : 0)) * p.yw + (in ? ox : 0)) * p.Cout + t.o0;
 #pragma unroll
-    for (int c = 0; c < TN / 32; c++) {
-      uint32_t bits = 0;
-      const int o = t.o0 + 32 * c;
-      if (in && o + 32 <= p.Cout) {
+    for (int mt = 0; mt < MT; mt++) {
+      const int oy = t.oy0 + 4 * mt + (lane >> 5), ox = t.ox0 + (lane & 31);
+      const bool in = oy < p.yh && ox < p.yw;
+      const float* m = p.mask + (((int64_t)t.b * p.yh + (in ? oy : 0)) * p.yw + (in ? ox : 0)) * p.Cout + t.o0;
 #pragma unroll
-        for (int j = 0; j < 32; j += 4) {
-          const float4 mv = __ldg((const float4*)(m + 32 * c + j));
-          bits |= (mv.x > 0.0f ? 1u : 0u) << j; bits |= (mv.y > 0.0f ? 1u : 0u) << (j + 1);
-          bits |= (mv.z > 0.0f ? 1u : 0u) << (j + 2); bits |= (mv.w > 0.0f ? 1u : 0u) << (j + 3);
+      for (int c = 0; c < TN / 32; c++) {
+        uint32_t bits = 0;
+        const int o = t.o0 + 32 * c;
+        if (in && o + 32 <= p.Cout) {
+#pragma unroll
+          for (int j = 0; j < 32; j += 4) {
+            const float4 mv = __ldg((const float4*)(m + 32 * c + j));
+            bits |= (mv.x > 0.0f ? 1u : 0u) << j; bits |= (mv.y > 0.0f ? 1u : 0u) << (j + 1);
+            bits |= (mv.z > 0.0f ? 1u : 0u) << (j + 2); bits |= (mv.w > 0.0f ? 1u : 0u) << (j + 3);
+          }
+        } else if (in) {
+          for (int j = 0; j < 32; j++) if (o + j < p.Cout && __ldg(m + 32 * c + j) > 0.0f) bits |= 1u << j;
         }
-      } else if (in) {
-        for (int j = 0; j < 32; j++) if (o + j < p.Cout && __ldg(m + 32 * c + j) > 0.0f) bits |= 1u << j;
+        pre[mt * (TN / 32) + c] = bits;
       }
-      pre[c] = bits;
     }
   }
-  __device__ static void store(const Params& p, const Tile& t, int lane, int c0, const float* v, uint32_t pre, float* csum_s) {
-    const int oy = t.oy0 + (lane >> 5), ox = t.ox0 + (lane & 31);
+  __device__ static void store(const Params& p, const Tile& t, int mt, int lane, int c0, const float* v, uint32_t pre) {
+    const int oy = t.oy0 + 4 * mt + (lane >> 5), ox = t.ox0 + (lane & 31);
     const bool in = oy < p.yh && ox < p.yw;
     if (!in && p.csum == nullptr) return;
     const int o = t.o0 + c0;
@@ -104,7 +109,7 @@ template <int TN_, bool SPLIT_> struct ConvFpropPol {
     }
     if (p.csum != nullptr) {
       // per-channel sums of the stored tile (the bias gradient of the layer below, reduce_sum over b,h,w): butterfly
-      // transpose-reduce across the warp — 31 shuffles leave the sum of channel l in lane l — then one shared-memory add per lane
+      // transpose-reduce across the warp — 31 shuffles leave the sum of channel l in lane l — then one red.global.add per lane
       const int wl = lane & 31;
 #pragma unroll
       for (int j = 0; j < 32; j++) r[j] = in ? r[j] : 0.0f;
@@ -119,25 +124,22 @@ template <int TN_, bool SPLIT_> struct ConvFpropPol {
           }
         }
       }
-      if (o + wl < p.Cout) atomicAdd(csum_s + c0 + wl, r[0]);
+      if (o + wl < p.Cout) red_add_f32(p.csum + o + wl, r[0]);
     }
-  }
-  __device__ static void finish(const Params& p, const Tile& t, const float* csum_s) {
-    if (p.csum != nullptr && (int)threadIdx.x < TN && t.o0 + (int)threadIdx.x < p.Cout) atomicAdd(p.csum + t.o0 + threadIdx.x, csum_s[threadIdx.x]);
   }
 };
 
 // ------------------------------------------------------------------------------------------------ wgrad policy
 template <int TN_, bool SPLIT_, bool PAIR_> struct ConvWgradPol {
-  static constexpr int TN = TN_; static constexpr bool SPLIT = SPLIT_, P_MN = true, Q_MN = true;
+  static constexpr int TN = TN_, MT = 1; static constexpr bool SPLIT = SPLIT_, P_MN = true, Q_MN = true;
   static constexpr int OCC = (SPLIT_ || TN_ > 128) ? 1 : 2;
   struct Params { CUtensorMap tmX, tmG; float* gw; int C, O, T, kw, pad, dil, yh, xblocks, kb_total, kb_per_split; MnDescCfg mnc; };
   struct Tile { int c0, tapA, tapB, o0, q0, q1; };
-  __device__ static Tile tile(const Params& p) {
-    Tile t; t.o0 = (int)blockIdx.y * TN;
-    if (PAIR_) { t.c0 = 0; t.tapA = 2 * (int)blockIdx.x; t.tapB = t.tapA + 1; }
-    else { int ctiles = (p.C + 127) / 128; t.c0 = ((int)blockIdx.x % ctiles) * 128; t.tapA = (int)blockIdx.x / ctiles; t.tapB = -1; }
-    t.q0 = (int)blockIdx.z * p.kb_per_split; t.q1 = min(t.q0 + p.kb_per_split, p.kb_total);
+  __device__ static Tile tile(const Params& p, uint3 blk) {
+    Tile t; t.o0 = (int)blk.y * TN;
+    if (PAIR_) { t.c0 = 0; t.tapA = 2 * (int)blk.x; t.tapB = t.tapA + 1; }
+    else { int ctiles = (p.C + 127) / 128; t.c0 = ((int)blk.x % ctiles) * 128; t.tapA = (int)blk.x / ctiles; t.tapB = -1; }
+    t.q0 = (int)blk.z * p.kb_per_split; t.q1 = min(t.q0 + p.kb_per_split, p.kb_total);
     return t;
   }
   __device__ static int num_kblocks(const Params&, const Tile& t) { return t.q1 > t.q0 ? t.q1 - t.q0 : 0; }
@@ -162,8 +164,7 @@ template <int TN_, bool SPLIT_, bool PAIR_> struct ConvWgradPol {
     for (int g = 0; g < TN / 32; g++) tma_load_4d(pQ + g * 4096, &p.tmG, bar, t.o0 + 32 * g, ox0, oy, b);
   }
   __device__ static void pre_epilogue(const Params&, const Tile&, int, uint32_t*) {}
-  __device__ static void finish(const Params&, const Tile&, const float*) {}
-  __device__ static void store(const Params& p, const Tile& t, int lane, int c0, const float* v, uint32_t, float*) {
+  __device__ static void store(const Params& p, const Tile& t, int, int lane, int c0, const float* v, uint32_t) {
     int c, tap;
     if (PAIR_) { c = lane & 63; tap = lane < 64 ? t.tapA : t.tapB; } else { c = t.c0 + lane; tap = t.tapA; }
     if (c >= p.C || tap >= p.T) return;
@@ -187,12 +188,12 @@ bool agb_tc_conv_eligible(int C, int O, int kh, int kw, int stride, int yw) {
   return stride == 1 && kh == kw && C >= 32 && C % 4 == 0 && O >= 32 && O % 4 == 0 && yw >= 16;
 }
 
-template <int TN, bool SPLIT>
+template <int TN, bool SPLIT, int MT = 1>
 static int fprop_launch(agb_ctx* ctx, const float* x, const float* wr, float* y, int B, int Cin, int H, int W, int Cout, int yh, int yw, int kh, int kw,
                         int pad, int dil, const float* bias, int relu, const float* mask, float* csum) {
-  using Pol = ConvFpropPol<TN, SPLIT>;
+  using Pol = ConvFpropPol<TN, SPLIT, MT>;
   typename Pol::Params p;
-  AGB_TRY(make_cl_map(&p.tmX, x, B, Cin, H, W, 32, 32, 4, false));
+  AGB_TRY(make_cl_map(&p.tmX, x, B, Cin, H, W, 32, 32, 4 * MT, false));
   {  // wr[tap][o][c]
     uint64_t dims[3] = {(uint64_t)Cin, (uint64_t)Cout, (uint64_t)(kh * kw)};
     uint64_t str[2] = {(uint64_t)Cin * 4, (uint64_t)Cin * Cout * 4};
@@ -200,7 +201,7 @@ static int fprop_launch(agb_ctx* ctx, const float* x, const float* wr, float* y,
     AGB_TRY(agb_make_tmap(&p.tmW, wr, 3, dims, str, box, false));
   }
   p.y = y; p.bias = bias; p.mask = mask; p.csum = csum; p.relu = relu; p.Cout = Cout; p.yh = yh; p.yw = yw; p.kw = kw; p.pad = pad; p.dil = dil;
-  p.tiles_x = (yw + 31) / 32; p.tiles_y = (yh + 3) / 4; p.cblocks = (Cin + 31) / 32; p.taps = kh * kw; p.mnc = agb_mn_cfg();
+  p.tiles_x = (yw + 31) / 32; p.tiles_y = (yh + 4 * MT - 1) / (4 * MT); p.cblocks = (Cin + 31) / 32; p.taps = kh * kw; p.mnc = agb_mn_cfg();
   int64_t nb = (int64_t)p.tiles_x * p.tiles_y * B;
   if (nb > 2147483647ll) return AGB_ERR_UNSUPPORTED;
   dim3 grid((unsigned)nb, (unsigned)((Cout + TN - 1) / TN), 1);
@@ -235,8 +236,13 @@ int agb_tc_conv_fprop(agb_ctx* ctx, int mode, const float* x, const float* w, fl
     if (O > 64) return fprop_launch<128, true>(ctx, x, wr, y, B, C, H, W, O, yh, yw, kh, kw, epad, dil, bias, relu, mask, csum);
     return fprop_launch<64, true>(ctx, x, wr, y, B, C, H, W, O, yh, yw, kh, kw, epad, dil, bias, relu, mask, csum);
   }
-  if (O > 128) return fprop_launch<256, false>(ctx, x, wr, y, B, C, H, W, O, yh, yw, kh, kw, epad, dil, bias, relu, mask, csum);
-  if (O > 64) return fprop_launch<128, false>(ctx, x, wr, y, B, C, H, W, O, yh, yw, kh, kw, epad, dil, bias, relu, mask, csum);
+  static int m2 = -1;     // two M-tiles per CTA: measured slower than one (3-stage ring, doubled epilogue) — kept as an opt-in experiment
+  if (m2 < 0) { const char* e = getenv("AGB_CONV_M2"); m2 = (e && e[0] == '1') ? 1 : 0; }
+  const bool tall = m2 && yh >= 8 && (int64_t)B * ((yh + 7) / 8) * ((yw + 31) / 32) >= ctx->sm_count;       // enough 8-row patches to fill the machine
+  if (O > 128) return tall ? fprop_launch<256, false, 2>(ctx, x, wr, y, B, C, H, W, O, yh, yw, kh, kw, epad, dil, bias, relu, mask, csum)
+                           : fprop_launch<256, false>(ctx, x, wr, y, B, C, H, W, O, yh, yw, kh, kw, epad, dil, bias, relu, mask, csum);
+  if (O > 64) return tall ? fprop_launch<128, false, 2>(ctx, x, wr, y, B, C, H, W, O, yh, yw, kh, kw, epad, dil, bias, relu, mask, csum)
+                          : fprop_launch<128, false>(ctx, x, wr, y, B, C, H, W, O, yh, yw, kh, kw, epad, dil, bias, relu, mask, csum);
   return fprop_launch<64, false>(ctx, x, wr, y, B, C, H, W, O, yh, yw, kh, kw, epad, dil, bias, relu, mask, csum);
 }
 

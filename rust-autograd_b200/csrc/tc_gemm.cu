@@ -21,11 +21,11 @@
 #include "tc_tile.cuh"
 
 template <int TN_, bool P_MN_, bool Q_MN_, bool SPLIT_> struct GemmPol {
-  static constexpr int TN = TN_; static constexpr bool SPLIT = SPLIT_, P_MN = P_MN_, Q_MN = Q_MN_;
+  static constexpr int TN = TN_, MT = 1; static constexpr bool SPLIT = SPLIT_, P_MN = P_MN_, Q_MN = Q_MN_;
   static constexpr int OCC = (SPLIT_ || TN_ > 128) ? 1 : 2;
   struct Params { CUtensorMap tmP, tmQ; float* C; int NL, NC, K; int64_t ldc, bsc; int accumulate; MnDescCfg mnc; };
   struct Tile { int lane0, col0, bz; };
-  __device__ static Tile tile(const Params&) { return Tile{(int)blockIdx.x * TC_LANES, (int)blockIdx.y * TN, (int)blockIdx.z}; }
+  __device__ static Tile tile(const Params&, uint3 blk) { return Tile{(int)blk.x * TC_LANES, (int)blk.y * TN, (int)blk.z}; }
   __device__ static int num_kblocks(const Params& p, const Tile&) { return (p.K + TC_BK - 1) / TC_BK; }
   __device__ static void prefetch(const Params& p) { tma_prefetch_desc(&p.tmP); tma_prefetch_desc(&p.tmQ); }
   __device__ static void load(const Params& p, const Tile& t, int kb, uint8_t* pP, uint8_t* pQ, uint64_t* bar) {
@@ -38,8 +38,7 @@ template <int TN_, bool P_MN_, bool Q_MN_, bool SPLIT_> struct GemmPol {
   // thread `lane` owns C column n = lane0 + lane; v[j] belongs to C row m = col0 + c0 + j: a warp stores 32 consecutive
   // floats of one C row per instruction (128-byte coalesced), no shared-memory staging
   __device__ static void pre_epilogue(const Params&, const Tile&, int, uint32_t*) {}
-  __device__ static void finish(const Params&, const Tile&, const float*) {}
-  __device__ static void store(const Params& p, const Tile& t, int lane, int c0, const float* v, uint32_t, float*) {
+  __device__ static void store(const Params& p, const Tile& t, int, int lane, int c0, const float* v, uint32_t) {
     const int n = t.lane0 + lane;
     if (n >= p.NL) return;
     float* cbase = p.C + (int64_t)t.bz * p.bsc + n;

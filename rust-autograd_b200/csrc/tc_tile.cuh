@@ -23,16 +23,19 @@
 
 // OCC = CTAs co-resident per SM.  Two co-resident CTAs overlap one CTA's prologue / epilogue (TMEM drain, global stores) with the
 // other's MMA main loop without a persistent tile scheduler; the ring depth is what fits in 1/OCC of the 227 KB shared memory.
-template <int TN, bool SPLIT, int OCC = 1> struct TcCfg {
-  static constexpr int P_BYTES = TC_LANES * TC_BK * 4;                 // 16 KB
+// MT = 128-lane M-tiles per CTA (1 or 2): MT = 2 shares every Q (filter / B) tile between two accumulators, halving the Q bytes a
+// CTA pulls from L2 per output element — the tile engine kernels are bound by L2 -> shared-memory ingest, not by the tensor pipe.
+template <int TN, bool SPLIT, int OCC = 1, int MT = 1> struct TcCfg {
+  static constexpr int P_BYTES = MT * TC_LANES * TC_BK * 4;            // 16 KB per M-tile
   static constexpr int Q_BYTES = TN * TC_BK * 4;
   static constexpr int STAGE_BYTES = (P_BYTES + Q_BYTES) * (SPLIT ? 2 : 1);
   static constexpr int BUDGET = (224 * 1024) / OCC - 2048;
   static constexpr int STAGES = BUDGET / STAGE_BYTES > 6 ? 6 : BUDGET / STAGE_BYTES;
   static_assert(STAGES >= 2, "tile does not fit the shared-memory budget");
-  static constexpr int SMEM = STAGES * STAGE_BYTES + 1024 /*align*/ + 256 /*barriers*/ + 1024 /*policy scratch: TN floats, zeroed*/;
+  static constexpr int SMEM = STAGES * STAGE_BYTES + 1024 /*align*/ + 256 /*barriers*/;
   static constexpr int THREADS = SPLIT ? 320 : 192;
-  static constexpr int TMEM_COLS = SPLIT ? 2 * TN : TN;                // power of two >= 32 for TN in {32,64,128,256}
+  static constexpr int TMEM_COLS = SPLIT ? 2 * TN : MT * TN;           // power of two >= 32 for TN in {32,64,128,256}
+  static_assert(MT == 1 || (!SPLIT && MT == 2 && MT * TN <= 512), "two M-tiles need 2*TN TMEM columns and the single-pass mode");
   static_assert(!SPLIT || TN <= 128, "3xTF32 keeps TN fp32 partial sums per thread in registers");
 };
 
@@ -40,15 +43,16 @@ template <int TN, bool SPLIT, int OCC = 1> struct TcCfg {
 //   static constexpr int TN, OCC; static constexpr bool SPLIT, P_MN, Q_MN;
 //   struct Params { ... CUtensorMap members ...; MnDescCfg mnc; };
 //   struct Tile { ... };                                               per-CTA coordinates
-//   __device__ static Tile tile(const Params&);                        from blockIdx
+//   __device__ static Tile tile(const Params&, uint3 blk);             blk = block coordinates in the logical grid
 //   __device__ static int  num_kblocks(const Params&, const Tile&);
 //   __device__ static void prefetch(const Params&);
 //   __device__ static void load(const Params&, const Tile&, int kb, uint8_t* pP, uint8_t* pQ, uint64_t* bar);   one thread
 //   __device__ static void store(const Params&, const Tile&, int lane /*0..127*/, int c0 /*0..TN-32*/, const float* v /*[32]*/);
 template <class Pol>
-__global__ void __launch_bounds__(TcCfg<Pol::TN, Pol::SPLIT, Pol::OCC>::THREADS, Pol::OCC) tc_tile_kernel(const __grid_constant__ typename Pol::Params prm) {
+__global__ void __launch_bounds__(TcCfg<Pol::TN, Pol::SPLIT, Pol::OCC, Pol::MT>::THREADS, Pol::OCC) tc_tile_kernel(const __grid_constant__ typename Pol::Params prm) {
   constexpr int TN = Pol::TN; constexpr bool SPLIT = Pol::SPLIT, P_MN = Pol::P_MN, Q_MN = Pol::Q_MN;
-  using Cfg = TcCfg<TN, SPLIT, Pol::OCC>;
+  constexpr int MT = Pol::MT;
+  using Cfg = TcCfg<TN, SPLIT, Pol::OCC, MT>;
   constexpr int S = Cfg::STAGES;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
@@ -56,11 +60,9 @@ __global__ void __launch_bounds__(TcCfg<Pol::TN, Pol::SPLIT, Pol::OCC>::THREADS,
   uint64_t* full = bars; uint64_t* ready = bars + S; uint64_t* empty = bars + 2 * S;
   uint64_t* acc_full = bars + 3 * S; uint64_t* acc_empty = bars + 3 * S + 2;
   uint32_t* tmem_slot = (uint32_t*)(bars + 3 * S + 4);
-  float* pol_smem = (float*)((uint8_t*)bars + 256);           // TN floats of policy scratch (e.g. per-channel sums), zeroed here
-  for (int i = threadIdx.x; i < 256; i += blockDim.x) pol_smem[i] = 0.0f;
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const typename Pol::Tile tl = Pol::tile(prm);
+  const typename Pol::Tile tl = Pol::tile(prm, blockIdx);
   const int nk = Pol::num_kblocks(prm, tl);
 
   if (warp == 0 && lane == 0) {
@@ -124,7 +126,9 @@ __global__ void __launch_bounds__(TcCfg<Pol::TN, Pol::SPLIT, Pol::OCC>::THREADS,
             umma_tf32(tacc, dP, dQl, idesc, 1);
             umma_tf32(tacc, dP, dQ, idesc, 1);
           } else {
-            umma_tf32(tacc, dP, dQ, idesc, !(first && k == 0));
+#pragma unroll
+            for (int mt = 0; mt < MT; mt++)
+              umma_tf32(tacc + (uint32_t)(mt * TN), umma_desc_pack(aP + (uint32_t)(mt * ((TC_LANES * TC_BK * 4) >> 4)) + k * stepP, hiP), dQ, idesc, !(first && k == 0));
           }
         }
         umma_commit(&empty[s]);            // ring slot reusable once these MMAs have read it
@@ -159,7 +163,7 @@ __global__ void __launch_bounds__(TcCfg<Pol::TN, Pol::SPLIT, Pol::OCC>::THREADS,
     const int row = 32 * q + lane;         // accumulator lane handled by this thread
     const uint32_t tlane = tmem_base + ((uint32_t)(32 * q) << 16);
     // per-thread epilogue side input (e.g. the ReLU mask bits of the dgrad epilogue), fetched while the MMAs are still running
-    uint32_t pre[TN / 32];
+    uint32_t pre[MT * (TN / 32)];
     Pol::pre_epilogue(prm, tl, row, pre);
     if (SPLIT) {
       float racc[TN];
@@ -183,31 +187,177 @@ __global__ void __launch_bounds__(TcCfg<Pol::TN, Pol::SPLIT, Pol::OCC>::THREADS,
       }
       if (nk > 0) {
 #pragma unroll
-        for (int c0 = 0; c0 < TN; c0 += 32) Pol::store(prm, tl, row, c0, &racc[c0], pre[c0 / 32], pol_smem);
+        for (int c0 = 0; c0 < TN; c0 += 32) Pol::store(prm, tl, 0, row, c0, &racc[c0], pre[c0 / 32]);
       }
     } else if (nk > 0) {
       mbar_wait(&acc_full[0], 0);
       tc_fence_after();
 #pragma unroll
-      for (int c0 = 0; c0 < TN; c0 += 32) {
-        float v[32];
-        tmem_ld32(tlane + (uint32_t)c0, v);
-        tmem_ld_wait();
-        Pol::store(prm, tl, row, c0, v, pre[c0 / 32], pol_smem);
+      for (int mt = 0; mt < MT; mt++) {
+#pragma unroll
+        for (int c0 = 0; c0 < TN; c0 += 32) {
+          float v[32];
+          tmem_ld32(tlane + (uint32_t)(mt * TN + c0), v);
+          tmem_ld_wait();
+          Pol::store(prm, tl, mt, row, c0, v, pre[mt * (TN / 32) + c0 / 32]);
+        }
       }
     }
   }
   tc_fence_before();
   __syncthreads();
-  Pol::finish(prm, tl, pol_smem);                              // all threads, after every store of the CTA
   if (warp == 1) tmem_dealloc(tmem_base, Cfg::TMEM_COLS);
+}
+
+// ------------------------------------------------------------------------------------------------ persistent variant
+// Single-pass (non-SPLIT) tiles only.  CTAs (OCC per SM) walk the logical grid; when two accumulator sets fit in TMEM
+// (2 * MT * TN <= 512 columns) the drain / epilogue of tile t overlaps the MMAs of tile t+1, and the per-CTA prologue (barrier
+// init, TMEM allocation, descriptor prefetch, pipeline fill) is paid once per SM instead of once per tile.  Measured on the
+// one-tile-per-CTA kernel with TN = 256 (one CTA per SM, nothing to overlap with): 17 % of a CTA's life is the epilogue and
+// ~10 % the prologue (profiles/ncu_conv_full_r1.csv: tensor pipe 53 % active).
+template <class Pol>
+__global__ void __launch_bounds__(TcCfg<Pol::TN, false, Pol::OCC, Pol::MT>::THREADS, Pol::OCC)
+tc_tile_persist_kernel(const __grid_constant__ typename Pol::Params prm, const uint3 lgrid) {
+  constexpr int TN = Pol::TN; constexpr bool P_MN = Pol::P_MN, Q_MN = Pol::Q_MN;
+  constexpr int MT = Pol::MT;
+  static_assert(!Pol::SPLIT, "the persistent kernel serves the single-pass mode");
+  using Cfg = TcCfg<TN, false, Pol::OCC, MT>;
+  constexpr int S = Cfg::STAGES;
+  constexpr int NACC = (2 * MT * TN * Pol::OCC <= 512) ? 2 : 1;       // accumulator sets per CTA (all co-resident CTAs share 512 columns)
+  constexpr int TCOLS = NACC * MT * TN;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
+  uint64_t* bars = (uint64_t*)(smem + S * Cfg::STAGE_BYTES);
+  uint64_t* full = bars; uint64_t* empty = bars + S;
+  uint64_t* acc_full = bars + 2 * S; uint64_t* acc_empty = bars + 2 * S + 2;
+  uint32_t* tmem_slot = (uint32_t*)(bars + 2 * S + 4);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const uint32_t total = lgrid.x * lgrid.y * lgrid.z;
+
+  if (warp == 0 && lane == 0) {
+    Pol::prefetch(prm);
+    for (int s = 0; s < S; s++) { mbar_init(&full[s], 1); mbar_init(&empty[s], 1); }
+    for (int b = 0; b < 2; b++) { mbar_init(&acc_full[b], 1); mbar_init(&acc_empty[b], 128); }
+    fence_barrier_init();
+  }
+  if (warp == 1) { tmem_alloc(tmem_slot, TCOLS); tmem_relinquish(); }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+  auto blk_of = [&](uint32_t t) { uint3 b; b.x = t % lgrid.x; const uint32_t r = t / lgrid.x; b.y = r % lgrid.y; b.z = r / lgrid.y; return b; };
+
+  if (warp == 0) {
+    // ===================== TMA producer =====================
+    if (lane == 0) {
+      int s = 0; uint32_t ph = 0;
+      for (uint32_t t = blockIdx.x; t < total; t += gridDim.x) {
+        const typename Pol::Tile tl = Pol::tile(prm, blk_of(t));
+        const int nk = Pol::num_kblocks(prm, tl);
+        for (int kb = 0; kb < nk; kb++) {
+          mbar_wait(&empty[s], ph ^ 1);
+          uint8_t* st = smem + s * Cfg::STAGE_BYTES;
+          mbar_expect_tx(&full[s], Cfg::P_BYTES + Cfg::Q_BYTES);
+          Pol::load(prm, tl, kb, st, st + Cfg::P_BYTES, &full[s]);
+          if (++s == S) { s = 0; ph ^= 1; }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ===================== MMA issuer (converged warp, elected lane; see tc_tile_kernel) =====================
+    constexpr uint32_t idesc = umma_idesc_tf32(TC_LANES, TN, P_MN ? 1 : 0, Q_MN ? 1 : 0);
+    const MnDescCfg mnc = prm.mnc;
+    const uint32_t hiK = (1024u >> 4) | (1u << 14) | (2u << 29), loK = (16u >> 4) << 16, stepK = 32u >> 4;
+    const uint32_t hiM = (mnc.sbo >> 4) | (1u << 14) | (mnc.layout << 29), loM = (mnc.lbo >> 4) << 16, stepM = mnc.kadv >> 4;
+    const uint32_t hiP = P_MN ? hiM : hiK, loP = P_MN ? loM : loK, stepP = P_MN ? stepM : stepK;
+    const uint32_t hiQ = Q_MN ? hiM : hiK, loQ = Q_MN ? loM : loK, stepQ = Q_MN ? stepM : stepK;
+    const uint32_t smem0 = smem_u32(smem) >> 4;
+    int s = 0; uint32_t ph = 0, ti = 0;
+    for (uint32_t t = blockIdx.x; t < total; t += gridDim.x) {
+      const typename Pol::Tile tl = Pol::tile(prm, blk_of(t));
+      const int nk = Pol::num_kblocks(prm, tl);
+      if (nk <= 0) continue;
+      const uint32_t ab = ti % NACC;
+      mbar_wait(&acc_empty[ab], ((ti / NACC) & 1) ^ 1);
+      tc_fence_after();
+      const uint32_t tacc = tmem_base + ab * (uint32_t)(MT * TN);
+      for (int kb = 0; kb < nk; kb++) {
+        mbar_wait(&full[s], ph);
+        tc_fence_after();
+        if (elect_one()) {
+          const uint32_t st = smem0 + (uint32_t)s * (Cfg::STAGE_BYTES >> 4);
+          const uint32_t aP = st + loP, aQ = st + (Cfg::P_BYTES >> 4) + loQ;
+#pragma unroll
+          for (int k = 0; k < TC_BK / 8; k++) {
+            const uint64_t dQ = umma_desc_pack(aQ + k * stepQ, hiQ);
+#pragma unroll
+            for (int mt = 0; mt < MT; mt++)
+              umma_tf32(tacc + (uint32_t)(mt * TN), umma_desc_pack(aP + (uint32_t)(mt * ((TC_LANES * TC_BK * 4) >> 4)) + k * stepP, hiP), dQ, idesc, !(kb == 0 && k == 0));
+          }
+          umma_commit(&empty[s]);
+          if (kb == nk - 1) umma_commit(&acc_full[ab]);
+        }
+        __syncwarp();
+        if (++s == S) { s = 0; ph ^= 1; }
+      }
+      ti++;
+    }
+  } else {
+    // ===================== drain / epilogue =====================
+    const int q = warp & 3;
+    const int row = 32 * q + lane;
+    const uint32_t tlane = tmem_base + ((uint32_t)(32 * q) << 16);
+    uint32_t ti = 0;
+    for (uint32_t t = blockIdx.x; t < total; t += gridDim.x) {
+      const typename Pol::Tile tl = Pol::tile(prm, blk_of(t));
+      const int nk = Pol::num_kblocks(prm, tl);
+      if (nk <= 0) continue;
+      uint32_t pre[MT * (TN / 32)];
+      Pol::pre_epilogue(prm, tl, row, pre);
+      const uint32_t ab = ti % NACC;
+      mbar_wait(&acc_full[ab], (ti / NACC) & 1);
+      tc_fence_after();
+#pragma unroll
+      for (int mt = 0; mt < MT; mt++) {
+#pragma unroll
+        for (int c0 = 0; c0 < TN; c0 += 32) {
+          float v[32];
+          tmem_ld32(tlane + ab * (uint32_t)(MT * TN) + (uint32_t)(mt * TN + c0), v);
+          tmem_ld_wait();
+          Pol::store(prm, tl, mt, row, c0, v, pre[mt * (TN / 32) + c0 / 32]);
+        }
+      }
+      tc_fence_before();
+      mbar_arrive(&acc_empty[ab]);
+      ti++;
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) tmem_dealloc(tmem_base, TCOLS);
 }
 
 template <class Pol>
 static int tc_tile_launch(agb_ctx* ctx, const typename Pol::Params& prm, dim3 grid) {
-  using Cfg = TcCfg<Pol::TN, Pol::SPLIT, Pol::OCC>;
+  using Cfg = TcCfg<Pol::TN, Pol::SPLIT, Pol::OCC, Pol::MT>;
   static bool attr = false;
   if (!attr) { AGB_CUDA(cudaFuncSetAttribute(tc_tile_kernel<Pol>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM)); attr = true; }
+  static int persist = -1;
+  if (persist < 0) { const char* e = getenv("AGB_TC_PERSIST"); persist = (e && e[0] == '0') ? 0 : 1; }
+  if constexpr (!Pol::SPLIT) {
+    if (persist) {
+      static bool attr2 = false;
+      if (!attr2) { AGB_CUDA(cudaFuncSetAttribute(tc_tile_persist_kernel<Pol>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM)); attr2 = true; }
+      const uint64_t total = (uint64_t)grid.x * grid.y * grid.z;
+      if (total < (1ull << 31)) {
+        const uint64_t cap = (uint64_t)ctx->sm_count * Pol::OCC;
+        const unsigned n = (unsigned)(total < cap ? total : cap);
+        tc_tile_persist_kernel<Pol><<<n, Cfg::THREADS, Cfg::SMEM, ctx->stream>>>(prm, make_uint3(grid.x, grid.y, grid.z));
+        AGB_LAUNCHED(ctx);
+        return AGB_OK;
+      }
+    }
+  }
   tc_tile_kernel<Pol><<<grid, Cfg::THREADS, Cfg::SMEM, ctx->stream>>>(prm);
   AGB_LAUNCHED(ctx);
   return AGB_OK;

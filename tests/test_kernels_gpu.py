@@ -171,6 +171,9 @@ CONV_CASES = [  # B, C, H, W, O, kh, kw, pad, stride, dil
     (1, 32, 9, 136, 32, 3, 3, 2, 1, 2),     # dilation 2
     (3, 96, 7, 128, 160, 3, 3, 1, 1, 1),    # three c-blocks, two o-tiles (the second partial)
     (1, 32, 6, 128, 32, 5, 5, 2, 1, 1),     # 5x5
+    # enough 8-row patches to fill the machine: two M-tiles per CTA sharing the filter tiles (TF32 mode)
+    (16, 128, 44, 64, 128, 3, 3, 1, 1, 1),  # TN = 128, last patch has 4 of 8 rows
+    (40, 64, 28, 32, 256, 3, 3, 1, 1, 1),   # TN = 256
 ]
 
 
@@ -197,6 +200,7 @@ def test_conv2d_family_vs_oracle(dev, case, mode):
 FUSED_CASES = [  # B, C, H, W, O, kh, kw, pad, dil — stride 1 ("same"-style backward convs) + one SIMT-path shape
     (2, 64, 32, 32, 64, 3, 3, 1, 1), (1, 128, 32, 32, 256, 3, 3, 1, 1), (2, 48, 36, 40, 96, 3, 3, 1, 1), (2, 8, 12, 12, 16, 3, 3, 1, 1),
     (2, 64, 7, 128, 64, 3, 3, 1, 1), (1, 32, 4, 192, 80, 3, 3, 1, 1),      # wide maps: halo-reusing kernel
+    (40, 64, 28, 32, 160, 3, 3, 1, 1),                                      # two M-tiles per CTA
 ]
 
 
