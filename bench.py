@@ -256,7 +256,7 @@ def main():
         e2e_value = world * B * args.steps / (e2e_time / 1e3)
         conv = {k: v for k, v in prof.items() if k.startswith("conv")}
         roof = None
-        # dominant kernel: tc_tile_kernel<ConvFpropPol<TN>> — the tcgen05 implicit-GEMM conv that serves Conv2D fprop and (flipped filter)
+        # dominant kernel: the tcgen05 implicit-GEMM conv (tc_tile_persist_kernel<ConvFpropPol<TN>>, conv_rows_kernel for wide maps) that serves Conv2D fprop and (flipped filter)
         # Conv2DTranspose / dgrad.  Classes conv_fprop + conv_dgrad hold exactly its launches (small-C and SIMT paths are re-labelled).
         dom = [conv[k] for k in ("conv_fprop", "conv_dgrad") if k in conv]
         if dom:
@@ -270,7 +270,7 @@ def main():
                 tj = json.load(open(tpath))
                 if tj.get("workload") == WORKLOAD and tj.get("math_mode") == args.mode:
                     traffic, traffic_src = tj["dram_bytes_per_launch"], tj["source"]
-            roof = {"bound": "tensor", "kernel": "tc_tile_kernel<ConvFpropPol> (tcgen05 implicit-GEMM conv: fprop + dgrad, %s)" % args.mode,
+            roof = {"bound": "tensor", "kernel": "tc_tile_persist_kernel<ConvFpropPol> + conv_rows_kernel (tcgen05 implicit-GEMM conv: fprop + dgrad, %s)" % args.mode,
                     "achieved": achieved, "peak": tf32_peak, "unit": "TFLOP/s", "frac": achieved / tf32_peak, "traffic": traffic, "traffic_source": traffic_src,
                     "peak_source": "%s bf16 sustained / 2 (dense TF32 = half the bf16 rate), MEASURED_PEAKS.json" % pk["src"],
                     "per_launch_ms": d_ms / d_n, "flops_per_launch": d_w / d_n, "launches_per_step": d_n / args.steps,

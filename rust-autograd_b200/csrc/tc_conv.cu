@@ -130,14 +130,21 @@ template <int TN_, bool SPLIT_, int MT_ = 1> struct ConvFpropPol {
 };
 
 // ------------------------------------------------------------------------------------------------ wgrad policy
-template <int TN_, bool SPLIT_, bool PAIR_> struct ConvWgradPol {
-  static constexpr int TN = TN_, MT = 1; static constexpr bool SPLIT = SPLIT_, P_MN = true, Q_MN = true;
-  static constexpr int OCC = (SPLIT_ || TN_ > 128) ? 1 : 2;
+// MT_ = 2 (non-PAIR): the CTA owns two (tap, 128-channel tile) units — two M-tiles that share every gy tile, so gy is pulled from
+// L2 half as often (the TN = 256 wgrad moved 48 KB per 4 MMAs: bound by L2 -> smem ingest at 43 % tensor activity).
+template <int TN_, bool SPLIT_, bool PAIR_, int MT_ = 1> struct ConvWgradPol {
+  static constexpr int TN = TN_, MT = MT_; static constexpr bool SPLIT = SPLIT_, P_MN = true, Q_MN = true;
+  static constexpr int OCC = (SPLIT_ || TN_ > 128 || MT_ > 1) ? 1 : 2;
+  static_assert(!(PAIR_ && MT_ > 1), "tap pairing within one M-tile and two M-tiles are alternatives");
   struct Params { CUtensorMap tmX, tmG; float* gw; int C, O, T, kw, pad, dil, yh, xblocks, kb_total, kb_per_split; MnDescCfg mnc; };
-  struct Tile { int c0, tapA, tapB, o0, q0, q1; };
+  struct Tile { int c0, tapA, tapB, o0, q0, q1, c1; };       // MT == 2: unit 0 = (tapA, c0), unit 1 = (tapB, c1)
   __device__ static Tile tile(const Params& p, uint3 blk) {
-    Tile t; t.o0 = (int)blk.y * TN;
+    Tile t; t.o0 = (int)blk.y * TN; t.c1 = 0;
     if (PAIR_) { t.c0 = 0; t.tapA = 2 * (int)blk.x; t.tapB = t.tapA + 1; }
+    else if (MT == 2) {
+      const int ctiles = (p.C + 127) / 128, u0 = 2 * (int)blk.x, u1 = u0 + 1;
+      t.c0 = (u0 % ctiles) * 128; t.tapA = u0 / ctiles; t.c1 = (u1 % ctiles) * 128; t.tapB = u1 / ctiles;      // tapB may be >= T: absent unit
+    }
     else { int ctiles = (p.C + 127) / 128; t.c0 = ((int)blk.x % ctiles) * 128; t.tapA = (int)blk.x / ctiles; t.tapB = -1; }
     t.q0 = (int)blk.z * p.kb_per_split; t.q1 = min(t.q0 + p.kb_per_split, p.kb_total);
     return t;
@@ -159,14 +166,22 @@ template <int TN_, bool SPLIT_, bool PAIR_> struct ConvWgradPol {
     } else {
 #pragma unroll
       for (int g = 0; g < 4; g++) tma_load_4d(pP + g * 4096, &p.tmX, bar, t.c0 + 32 * g, xA, yA, b);
+      if (MT == 2) {
+        int xB = xA, yB = yA, cB = p.C + 128;                                // absent unit: fully out of bounds = zero rows
+        if (t.tapB < p.T) { const int iB = t.tapB / p.kw, jB = t.tapB - iB * p.kw; xB = ox0 + jB * p.dil - p.pad; yB = oy + iB * p.dil - p.pad; cB = t.c1; }
+#pragma unroll
+        for (int g = 0; g < 4; g++) tma_load_4d(pP + 16384 + g * 4096, &p.tmX, bar, cB + 32 * g, xB, yB, b);
+      }
     }
 #pragma unroll
     for (int g = 0; g < TN / 32; g++) tma_load_4d(pQ + g * 4096, &p.tmG, bar, t.o0 + 32 * g, ox0, oy, b);
   }
   __device__ static void pre_epilogue(const Params&, const Tile&, int, uint32_t*) {}
-  __device__ static void store(const Params& p, const Tile& t, int, int lane, int c0, const float* v, uint32_t) {
+  __device__ static void store(const Params& p, const Tile& t, int mt, int lane, int c0, const float* v, uint32_t) {
     int c, tap;
-    if (PAIR_) { c = lane & 63; tap = lane < 64 ? t.tapA : t.tapB; } else { c = t.c0 + lane; tap = t.tapA; }
+    if (PAIR_) { c = lane & 63; tap = lane < 64 ? t.tapA : t.tapB; }
+    else if (MT == 2 && mt == 1) { c = t.c1 + lane; tap = t.tapB; }
+    else { c = t.c0 + lane; tap = t.tapA; }
     if (c >= p.C || tap >= p.T) return;
 #pragma unroll
     for (int j = 0; j < 32; j++) { const int o = t.o0 + c0 + j; if (o < p.O) red_add_f32(p.gw + ((int64_t)o * p.C + c) * p.T + tap, v[j]); }
@@ -246,9 +261,9 @@ int agb_tc_conv_fprop(agb_ctx* ctx, int mode, const float* x, const float* w, fl
   return fprop_launch<64, false>(ctx, x, wr, y, B, C, H, W, O, yh, yw, kh, kw, epad, dil, bias, relu, mask, csum);
 }
 
-template <int TN, bool SPLIT, bool PAIR>
+template <int TN, bool SPLIT, bool PAIR, int MT = 1>
 static int wgrad_launch(agb_ctx* ctx, const float* img, const float* g, float* gw, int B, int C, int H, int W, int O, int yh, int yw, int kh, int kw, int pad, int dil) {
-  using Pol = ConvWgradPol<TN, SPLIT, PAIR>;
+  using Pol = ConvWgradPol<TN, SPLIT, PAIR, MT>;
   typename Pol::Params p;
   AGB_TRY(make_cl_map(&p.tmX, img, B, C, H, W, 32, 32, 1, true));
   AGB_TRY(make_cl_map(&p.tmG, g, B, O, yh, yw, 32, 32, 1, true));
@@ -257,7 +272,8 @@ static int wgrad_launch(agb_ctx* ctx, const float* img, const float* g, float* g
   int64_t kb_total = (int64_t)B * yh * p.xblocks;
   if (kb_total > 2147483647ll) return AGB_ERR_UNSUPPORTED;
   p.kb_total = (int)kb_total; p.mnc = agb_mn_cfg();
-  const int gx = PAIR ? (T + 1) / 2 : ((C + 127) / 128) * T, gy_ = (O + TN - 1) / TN;
+  const int units = ((C + 127) / 128) * T;
+  const int gx = PAIR ? (T + 1) / 2 : (MT == 2 ? (units + 1) / 2 : units), gy_ = (O + TN - 1) / TN;
   int64_t want = 2ll * ctx->sm_count * Pol::OCC / ((int64_t)gx * gy_); if (want < 1) want = 1;
   int64_t per = (kb_total + want - 1) / want; if (per < 16) per = 16; if (per > kb_total) per = kb_total;
   p.kb_per_split = (int)per;
@@ -279,6 +295,11 @@ int agb_tc_conv_wgrad(agb_ctx* ctx, int mode, const float* img, const float* g, 
 #define WG(TN_, SP_) (pair ? wgrad_launch<TN_, SP_, true>(ctx, img, g, gw, B, C, H, W, O, yh, yw, kh, kw, pad, dil) \
                            : wgrad_launch<TN_, SP_, false>(ctx, img, g, gw, B, C, H, W, O, yh, yw, kh, kw, pad, dil))
   if (split) { if (O > 64) return WG(128, true); return WG(64, true); }
+  static int m2 = -1;
+  if (m2 < 0) { const char* e = getenv("AGB_WGRAD_M2"); m2 = (e && e[0] == '0') ? 0 : 1; }
+  // measured (B200, B = 256): C256/O256 0.66 -> 0.54 ms, C128/O256 0.37 -> 0.32 ms; with TN = 128 the one-M-tile kernel at two CTAs
+  // per SM is faster (0.57 vs 0.78 ms), so only the 256-wide tiles pair up
+  if (m2 && !pair && O > 128) return wgrad_launch<256, false, false, 2>(ctx, img, g, gw, B, C, H, W, O, yh, yw, kh, kw, pad, dil);
   if (O > 128) return WG(256, false);
   if (O > 64) return WG(128, false);
   return WG(64, false);
