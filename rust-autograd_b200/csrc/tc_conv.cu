@@ -191,6 +191,8 @@ template <int TN_, bool SPLIT_, bool PAIR_, int MT_ = 1> struct ConvWgradPol {
 // ------------------------------------------------------------------------------------------------ host side
 int agb_tc_conv_rows(agb_ctx* ctx, const float* x, const float* wr, float* y, int B, int Cin, int H, int W, int Cout, int yh, int yw, int kh, int kw,
                      int pad, int dil, const float* bias, int relu, const float* mask, float* csum);
+int agb_tc_conv_wgrad_taps(agb_ctx* ctx, const float* img, const float* g, float* gw, int B, int C, int H, int W, int O, int yh, int yw,
+                           int kh, int kw, int pad, int dil);
 // channels-last tensor map of a logical [B, C, H, W] activation: dims {c, w, h, b}
 static int make_cl_map(CUtensorMap* m, const float* p, int B, int C, int H, int W, uint32_t bc, uint32_t bw, uint32_t bh, bool atom32) {
   uint64_t dims[4] = {(uint64_t)C, (uint64_t)W, (uint64_t)H, (uint64_t)B};
@@ -291,6 +293,10 @@ int agb_tc_conv_wgrad(agb_ctx* ctx, int mode, const float* img, const float* g, 
   if (yh < 1 || yw < 1 || !agb_tc_conv_eligible(C, O, kh, kw, stride, yw)) return AGB_ERR_UNSUPPORTED;
   if ((((uintptr_t)img | (uintptr_t)g) & 15) != 0) return AGB_ERR_UNSUPPORTED;
   const bool split = mode == AGB_MATH_3XTF32;
+  if (!split) {       // narrow layers: all taps per CTA from one haloed window (tc_conv_wgrad_taps.cu)
+    int r = agb_tc_conv_wgrad_taps(ctx, img, g, gw, B, C, H, W, O, yh, yw, kh, kw, pad, dil);
+    if (r != AGB_ERR_UNSUPPORTED) return r;
+  }
   const bool pair = C <= 64;
 #define WG(TN_, SP_) (pair ? wgrad_launch<TN_, SP_, true>(ctx, img, g, gw, B, C, H, W, O, yh, yw, kh, kw, pad, dil) \
                            : wgrad_launch<TN_, SP_, false>(ctx, img, g, gw, B, C, H, W, O, yh, yw, kh, kw, pad, dil))
