@@ -92,6 +92,20 @@ int  agb_d2h(agb_ctx* ctx, void* dst, const void* src, size_t bytes); /* async +
 int  agb_d2d(agb_ctx* ctx, void* dst, const void* src, size_t bytes);
 int  agb_memset0(agb_ctx* ctx, void* dst, size_t bytes);
 int  agb_sync(agb_ctx* ctx);
+/* Host-feed staging: the device analogue of handing the evaluator a host array per step (Feeder::push, evaluation.rs:296) without
+ * serialising the copy in front of the step.  The caller keeps two device buffers per placeholder:
+ *   agb_stage_wait  — the compute stream waits for every copy staged so far (call before launching the step that reads them);
+ *   agb_stage_mark  — records "everything enqueued on the compute stream so far has been issued" (call before launching step i:
+ *                     the buffers of step i-1 are free once the mark passes);
+ *   agb_stage_h2d   — async copy from PINNED host memory on a second stream, ordered after the last mark. */
+int  agb_stage_mark(agb_ctx* ctx);
+int  agb_stage_h2d(agb_ctx* ctx, void* dst, const void* src, size_t bytes);
+int  agb_stage_wait(agb_ctx* ctx);
+/* results: agb_stage_d2h copies src (device) to PINNED host memory on a third stream, ordered after the compute work enqueued so
+ * far; *done_event is complete when the bytes are on the host (agb_event_sync, then agb_event_destroy).  Lets the host read step i's
+ * loss while step i+1 runs. */
+int  agb_stage_d2h(agb_ctx* ctx, void* dst_pinned, const void* src, size_t bytes, void** done_event);
+int  agb_event_sync(void* ev);
 int  agb_flush_l2(agb_ctx* ctx);                            /* writes a >L2 scratch buffer */
 
 /* CUDA-event timing on the context's own stream (torch.cuda.Event would not see it) */

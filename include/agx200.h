@@ -69,6 +69,11 @@ int agx_tensor_variable_id(agx_graph* g, int tid, int* vid);
 
 /* ---- Evaluation ---- */
 int agx_eval(agx_graph* g, const int* targets, int n, const agx_feed* feeds, int nfeeds, agx_results** out);
+/* the same evaluation without the host sync: kernels and the results' D2H copies (copy stream, pinned staging) are enqueued and the
+ * call returns; agx_results_fetch(r) completes the copies later — e.g. after the NEXT step has been launched — and only then may
+ * agx_results_data be read.  Device-side index errors of the run surface at the next synchronising call. */
+int agx_eval_launch(agx_graph* g, const int* targets, int n, const agx_feed* feeds, int nfeeds, agx_results** out);
+int agx_results_fetch(agx_results* r);
 int agx_results_count(agx_results* r, int* n);
 int agx_results_status(agx_results* r, int i, int* code, const char** msg);
 int agx_results_shape(agx_results* r, int i, int64_t* shape, int* rank);

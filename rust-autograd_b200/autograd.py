@@ -41,6 +41,7 @@ SIGNATURES = {
     "agx_grad": [_P, _pi, _i, _pi, _i, _pi, _pi], "agx_grad_helper": [_P, _pi, _i, C.c_char_p, _pi, _pi, _i, _pi],
     "agx_tensor_op_name": [_P, _i, C.c_char_p, _i], "agx_tensor_variable_id": [_P, _i, _pi],
     "agx_eval": [_P, _pi, _i, _pfeed, _i, C.POINTER(_P)], "agx_run": [_P, _pi, _i, _pfeed, _i],
+    "agx_eval_launch": [_P, _pi, _i, _pfeed, _i, C.POINTER(_P)], "agx_results_fetch": [_P],
     "agx_results_count": [_P, _pi], "agx_results_status": [_P, _i, _pi, C.POINTER(C.c_char_p)], "agx_results_shape": [_P, _i, _pi64, _pi],
     "agx_results_data": [_P, _i, C.POINTER(_pf), _pi64], "agx_results_free": [_P],
     "agx_opt_adam": [_P, _pi, _i, C.c_char_p, _f, _f, _f, _f, C.POINTER(_P)], "agx_opt_sgd": [_f, C.POINTER(_P)],
@@ -183,6 +184,56 @@ class DeviceArray:
         self.ptr, self.shape = int(ptr), tuple(int(s) for s in shape)
 
 
+class HostPrefetcher:
+    """Double-buffered host -> HBM feed staging (the device-side form of Feeder::push with host arrays, evaluation.rs:296).
+
+        pf = HostPrefetcher(env, [x_shape, y_shape]); pf.stage([x0, y0])
+        for i in range(steps):
+            x, y = pf.acquire()                                   # DeviceArrays of step i
+            pending = ev.feed("x", x).feed("y", y).run_deferred()   # kernels + result copies enqueued, no host sync
+            pf.stage([x_next, y_next])                              # H2D of step i+1 runs under the kernels of step i
+            ... previous.get() ...; previous = pending              # read step i-1's loss while step i runs
+
+    stage() copies from (ideally pinned) host arrays on a second CUDA stream, so the transfer of step i+1 runs under the kernels of
+    step i; acquire() makes the compute stream wait for it.  Values and results are identical to feeding the host arrays directly."""
+
+    def __init__(self, env, shapes):
+        from . import ffi as _ffi
+        self._ffi, self._lib, self._ctx = _ffi, _ffi.load_library(), env.agb_ctx()
+        self.shapes = [tuple(int(d) for d in s) for s in shapes]
+        self.bufs = []
+        for _ in range(2):
+            row = []
+            for s in self.shapes:
+                p = C.c_void_p()
+                _ffi.check(self._lib.agb_alloc(self._ctx, max(int(np.prod(s)), 1) * 4, C.byref(p)))
+                row.append(DeviceArray(p.value, s))
+            self.bufs.append(row)
+        self.staged, self.cur = 0, 0        # buffer index the next stage() writes / the last acquire() returned
+        self._keep = [None, None]           # host arrays of the in-flight copies (must outlive the async transfer)
+
+    def stage(self, host_arrays):
+        keep = []
+        for d, a in zip(self.bufs[self.staged], host_arrays):
+            a = _f32c(a)
+            assert tuple(a.shape) == d.shape, "staged array must have the placeholder's shape"
+            self._ffi.check(self._lib.agb_stage_h2d(self._ctx, d.ptr, a.ctypes.data, a.nbytes))
+            keep.append(a)
+        self._keep[self.staged] = keep
+        self.cur, self.staged = self.staged, self.staged ^ 1
+
+    def acquire(self):
+        self._ffi.check(self._lib.agb_stage_wait(self._ctx))     # compute waits for the staged copy
+        self._ffi.check(self._lib.agb_stage_mark(self._ctx))     # everything enqueued before this step may still read the other buffer
+        return list(self.bufs[self.cur])
+
+    def close(self):
+        for row in self.bufs:
+            for d in row:
+                self._lib.agb_free(self._ctx, d.ptr)
+        self.bufs = []
+
+
 def _make_feeds(items):
     keep, arr = [], (AgxFeed * max(len(items), 1))()
     for k, (key, value) in enumerate(items):
@@ -201,6 +252,27 @@ def _make_feeds(items):
             f.data, f.shape, f.rank, f.on_device = a.ctypes.data, shp, a.ndim, 0
             keep += [a, shp]
     return arr, len(items), keep
+
+
+class Deferred:
+    """Pending results of Evaluator.run_deferred()."""
+
+    def __init__(self, ev, res):
+        self._ev, self._res, self._out = ev, res, None
+
+    def get(self):
+        if self._out is None:
+            _check(lib().agx_results_fetch(self._res))
+            self._out = self._ev._collect(self._res)
+            self._res = None
+        return self._out
+
+    def __del__(self):
+        try:
+            if self._res is not None:
+                lib().agx_results_free(self._res)
+        except Exception:
+            pass
 
 
 class Evaluator:
@@ -233,10 +305,7 @@ class Evaluator:
         self.feeder = feeder
         return self
 
-    def run(self):
-        arr, n, keep = _make_feeds(self.feeder.items)
-        res = C.c_void_p()
-        _check(lib().agx_eval(self.graph.h, _ints([t.id for t in self.targets]), len(self.targets), arr, n, C.byref(res)))
+    def _collect(self, res):
         out = []
         try:
             for i in range(len(self.targets)):
@@ -254,6 +323,21 @@ class Evaluator:
         finally:
             lib().agx_results_free(res)
         return out
+
+    def run(self):
+        arr, n, keep = _make_feeds(self.feeder.items)
+        res = C.c_void_p()
+        _check(lib().agx_eval(self.graph.h, _ints([t.id for t in self.targets]), len(self.targets), arr, n, C.byref(res)))
+        return self._collect(res)
+
+    def run_deferred(self):
+        """Launch the evaluation and queue the results' device -> host copies on the copy stream WITHOUT a host sync; returns a
+        Deferred whose .get() yields what run() would have returned.  Calling .get() after the NEXT step has been launched keeps the
+        GPU busy while the host reads the loss (the reference's evaluator is synchronous: evaluation.rs:150-172)."""
+        arr, n, keep = _make_feeds(self.feeder.items)
+        res = C.c_void_p()
+        _check(lib().agx_eval_launch(self.graph.h, _ints([t.id for t in self.targets]), len(self.targets), arr, n, C.byref(res)))
+        return Deferred(self, res)
 
     def run_async(self):
         """Evaluate for side effects only (training step): nothing is copied back, no host sync."""

@@ -14,6 +14,8 @@ struct agb_ctx {
   int device = 0;
   int sm_count = 148;
   cudaStream_t stream = nullptr;
+  // host-feed staging (agb_stage_*): a copy stream that runs H2D of the NEXT step's inputs under the current step's kernels
+  cudaStream_t copy_stream = nullptr, d2h_stream = nullptr; cudaEvent_t stage_mark = nullptr, stage_done = nullptr; bool stage_pending = false, stage_marked = false;
   int math_mode = AGB_MATH_3XTF32;
   int64_t launches = 0;
   // stream-ordered caching arena: every block is only ever used on `stream`, so a freed block can be

@@ -12,7 +12,18 @@ using namespace agx;
 struct agx_env { VariableEnvironment* env; };
 struct agx_graph { Graph g; };
 struct agx_opt { Optimizer* o; };
-struct agx_results { std::vector<EvalResult> rs; };
+struct agx_results {
+  std::vector<EvalResult> rs;
+  // deferred fetch (agx_eval_launch / agx_results_fetch): pinned staging blocks of the in-flight D2H copies
+  Device* dev = nullptr; std::vector<void*> pinned, events; std::vector<size_t> bytes; std::vector<NdArray> keep;
+};
+// small pinned-block pool: cudaHostAlloc / cudaFreeHost synchronise the device, so blocks are recycled
+static std::multimap<size_t, void*> g_pinned_pool;
+static void* pinned_get(size_t bytes) {
+  auto it = g_pinned_pool.lower_bound(bytes);
+  if (it != g_pinned_pool.end() && it->first <= 4 * bytes + 4096) { void* p = it->second; g_pinned_pool.erase(it); return p; }
+  void* p = nullptr; check_status(agb_host_alloc(bytes ? bytes : 4, &p)); return p;
+}
 
 static thread_local std::string g_err;
 extern "C" const char* agx_last_error(void) { return g_err.c_str(); }
@@ -191,6 +202,41 @@ extern "C" int agx_grad_helper(agx_graph* g, const int* losses, int n, const cha
 extern "C" int agx_eval(agx_graph* g, const int* targets, int n, const agx_feed* feeds, int nfeeds, agx_results** out) {
   AGX_TRY *out = nullptr; auto* r = new agx_results(); r->rs = eval(&g->g, tv(g, targets, n), fv(g, feeds, nfeeds), true); *out = r; AGX_CATCH
 }
+// launch-only evaluation: every kernel of the run is enqueued, each result's D2H is queued on the copy stream into pinned memory,
+// and the call returns without a host sync; agx_results_fetch completes it later (after more work has been enqueued)
+extern "C" int agx_eval_launch(agx_graph* g, const int* targets, int n, const agx_feed* feeds, int nfeeds, agx_results** out) {
+  AGX_TRY
+  *out = nullptr; auto* r = new agx_results(); r->dev = g->g.env->dev;
+  r->rs = eval(&g->g, tv(g, targets, n), fv(g, feeds, nfeeds), false);
+  for (auto& e : r->rs) {
+    void* pin = nullptr; void* ev = nullptr; size_t nb = 0;
+    if (e.ok && !e.value.host && e.value.on_device()) {
+      NdArray c = e.value;
+      if (c.i32) c = r->dev->i32_to_f32(c);
+      c = r->dev->contiguous(c);
+      nb = (size_t)c.size() * sizeof(float); pin = pinned_get(nb);
+      check_status(agb_stage_d2h(r->dev->ctx, pin, c.dptr, nb, &ev));
+      r->keep.push_back(c);
+    }
+    r->pinned.push_back(pin); r->events.push_back(ev); r->bytes.push_back(nb);
+  }
+  *out = r;
+  AGX_CATCH
+}
+extern "C" int agx_results_fetch(agx_results* r) {
+  AGX_TRY
+  for (size_t i = 0; i < r->rs.size(); i++) {
+    if (i < r->pinned.size() && r->pinned[i]) {
+      check_status(agb_event_sync(r->events[i])); agb_event_destroy(r->events[i]); r->events[i] = nullptr;
+      auto h = std::make_shared<std::vector<float>>(r->bytes[i] / sizeof(float));
+      memcpy(h->data(), r->pinned[i], r->bytes[i]);
+      r->rs[i].value.host = h;
+      g_pinned_pool.insert({r->bytes[i] ? r->bytes[i] : 4, r->pinned[i]}); r->pinned[i] = nullptr;
+    }
+  }
+  r->keep.clear();
+  AGX_CATCH
+}
 extern "C" int agx_run(agx_graph* g, const int* targets, int n, const agx_feed* feeds, int nfeeds) {
   AGX_TRY
   std::vector<EvalResult> rs = eval(&g->g, tv(g, targets, n), fv(g, feeds, nfeeds), false);
@@ -207,7 +253,10 @@ extern "C" int agx_results_data(agx_results* r, int i, const float** data, int64
   if (!a.host) { g_err = "result has no host copy"; return AGX_ERR_PANIC; }
   *data = a.host->data(); *n = (int64_t)a.host->size(); return 0;
 }
-extern "C" int agx_results_free(agx_results* r) { delete r; return 0; }
+extern "C" int agx_results_free(agx_results* r) {
+  if (r) { for (size_t i = 0; i < r->pinned.size(); i++) if (r->pinned[i]) { if (r->events[i]) { agb_event_sync(r->events[i]); agb_event_destroy(r->events[i]); } g_pinned_pool.insert({r->bytes[i] ? r->bytes[i] : 4, r->pinned[i]}); } }
+  delete r; return 0;
+}
 
 // ================================================================================================ optimizers
 static std::vector<VariableID> vids(const int* v, int n) { std::vector<VariableID> r; for (int i = 0; i < n; i++) r.push_back(VariableID{v[i]}); return r; }

@@ -57,6 +57,7 @@ extern "C" int agb_destroy(agb_ctx* ctx) {
   if (ctx->scratch) cudaFree(ctx->scratch);
   if (ctx->flush_buf) cudaFree(ctx->flush_buf);
   if (ctx->dev_err) cudaFree(ctx->dev_err);
+  if (ctx->copy_stream) { cudaStreamSynchronize(ctx->copy_stream); cudaStreamDestroy(ctx->copy_stream); cudaStreamSynchronize(ctx->d2h_stream); cudaStreamDestroy(ctx->d2h_stream); cudaEventDestroy(ctx->stage_mark); cudaEventDestroy(ctx->stage_done); }
   cudaStreamDestroy(ctx->stream);
   delete ctx;
   return AGB_OK;
@@ -131,6 +132,48 @@ extern "C" int agb_host_free(void* p) { if (p) AGB_CUDA(cudaFreeHost(p)); return
 
 extern "C" int agb_h2d(agb_ctx* ctx, void* dst, const void* src, size_t bytes) {
   if (bytes) AGB_CUDA(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyHostToDevice, ctx->stream));
+  return AGB_OK;
+}
+// ---- host-feed staging: double-buffered inputs, copy of step i+1 overlapped with the kernels of step i --------------------------
+static int stage_init(agb_ctx* ctx) {
+  if (ctx->copy_stream) return AGB_OK;
+  AGB_CUDA(cudaStreamCreateWithFlags(&ctx->copy_stream, cudaStreamNonBlocking));
+  AGB_CUDA(cudaStreamCreateWithFlags(&ctx->d2h_stream, cudaStreamNonBlocking));
+  AGB_CUDA(cudaEventCreateWithFlags(&ctx->stage_mark, cudaEventDisableTiming));
+  AGB_CUDA(cudaEventCreateWithFlags(&ctx->stage_done, cudaEventDisableTiming));
+  return AGB_OK;
+}
+extern "C" int agb_stage_mark(agb_ctx* ctx) {
+  AGB_TRY(stage_init(ctx));
+  AGB_CUDA(cudaEventRecord(ctx->stage_mark, ctx->stream)); ctx->stage_marked = true;
+  return AGB_OK;
+}
+extern "C" int agb_stage_h2d(agb_ctx* ctx, void* dst, const void* src, size_t bytes) {
+  AGB_TRY(stage_init(ctx));
+  if (ctx->stage_marked) AGB_CUDA(cudaStreamWaitEvent(ctx->copy_stream, ctx->stage_mark, 0));      // readers of dst enqueued before the mark
+  if (bytes) AGB_CUDA(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyHostToDevice, ctx->copy_stream));
+  AGB_CUDA(cudaEventRecord(ctx->stage_done, ctx->copy_stream)); ctx->stage_pending = true;
+  return AGB_OK;
+}
+// D2H of a result on its own stream (separate from the H2D staging stream, so a result copy that waits for step i never delays the
+// input copy of step i+1), ordered after everything enqueued on the compute stream so far.  dst must be pinned: a pageable
+// destination would block the host until the copy runs.  *done receives an event (agb_event_sync / agb_event_destroy).
+extern "C" int agb_stage_d2h(agb_ctx* ctx, void* dst_pinned, const void* src, size_t bytes, void** done) {
+  AGB_TRY(stage_init(ctx));
+  cudaEvent_t e = nullptr, d = nullptr;
+  AGB_CUDA(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+  AGB_CUDA(cudaEventRecord(e, ctx->stream));
+  AGB_CUDA(cudaStreamWaitEvent(ctx->d2h_stream, e, 0));
+  AGB_CUDA(cudaEventDestroy(e));                       // released by the driver once the wait has consumed it
+  if (bytes) AGB_CUDA(cudaMemcpyAsync(dst_pinned, src, bytes, cudaMemcpyDeviceToHost, ctx->d2h_stream));
+  AGB_CUDA(cudaEventCreateWithFlags(&d, cudaEventDisableTiming | cudaEventBlockingSync));
+  AGB_CUDA(cudaEventRecord(d, ctx->d2h_stream));
+  *done = d;
+  return AGB_OK;
+}
+extern "C" int agb_event_sync(void* ev) { AGB_CUDA(cudaEventSynchronize((cudaEvent_t)ev)); return AGB_OK; }
+extern "C" int agb_stage_wait(agb_ctx* ctx) {
+  if (ctx->stage_pending) { AGB_CUDA(cudaStreamWaitEvent(ctx->stream, ctx->stage_done, 0)); ctx->stage_pending = false; }
   return AGB_OK;
 }
 extern "C" int agb_d2h(agb_ctx* ctx, void* dst, const void* src, size_t bytes) {

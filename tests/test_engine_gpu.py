@@ -246,6 +246,51 @@ def test_training_reduces_loss_and_checkpoint_roundtrip(ag, tmp_path):
     env2.close()
 
 
+def test_host_prefetcher_matches_direct_feeds(ag):
+    """HostPrefetcher (copy of step i+1 on a second stream under step i) + run_deferred (loss of step i read while step i+1 runs)
+    must give bit-identical training trajectories to feeding
+    the host arrays directly (Feeder::push, evaluation.rs:296)."""
+    from rust_autograd_b200 import workloads as W
+    rng = np.random.default_rng(3)
+    batches = [(rng.uniform(size=(64, 784)).astype(np.float32), rng.integers(0, 10, (64, 1)).astype(np.float32)) for _ in range(5)]
+
+    def train(prefetch):
+        env = ag.VariableEnvironment()
+        W.mlp_init(env, np.random.default_rng(0))
+        adam = ag.optimizers.Adam.default("adam", env.default_namespace().current_var_ids(), env)
+        g = ag.Context(env)
+        loss, _ = W.mlp_loss(ag, g)
+        params, grads = ag.optimizers.grad_helper([loss], g.default_namespace())
+        upd = adam.get_update_op(params, grads, g)
+        out, pending = [], None
+        if prefetch:
+            pf = ag.HostPrefetcher(env, [batches[0][0].shape, batches[0][1].shape])
+            pf.stage(list(batches[0]))
+        for i in range(12):
+            if prefetch:          # pipelined: launch step i, stage batch i+1, then read step i-1's loss
+                x, y = pf.acquire()
+                d = g.evaluator().push(loss).push(upd).feed("x", x).feed("y", y).run_deferred()
+                pf.stage(list(batches[(i + 1) % len(batches)]))
+                if pending is not None:
+                    out.append(float(np.asarray(pending.get()[0].unwrap()).ravel()[0]))
+                pending = d
+            else:
+                xb, yb = batches[i % len(batches)]
+                r = g.evaluator().push(loss).push(upd).feed("x", xb).feed("y", yb).run()
+                out.append(float(np.asarray(r[0].unwrap()).ravel()[0]))
+        if pending is not None:
+            out.append(float(np.asarray(pending.get()[0].unwrap()).ravel()[0]))
+        w = env.get_array_by_id(0).copy()
+        if prefetch:
+            pf.close()
+        g.close()
+        env.close()
+        return out, w
+    l0, w0 = train(False)
+    l1, w1 = train(True)
+    assert l0 == l1 and np.array_equal(w0, w1)
+
+
 def test_dropout_semantics(ag):
     """random_ops.rs:218-245: not inverted; eval mode scales by (1 - ratio); grad = gy * mask"""
     env = ag.VariableEnvironment()
