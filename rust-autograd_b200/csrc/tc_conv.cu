@@ -191,6 +191,8 @@ template <int TN_, bool SPLIT_, bool PAIR_, int MT_ = 1> struct ConvWgradPol {
 // ------------------------------------------------------------------------------------------------ host side
 int agb_tc_conv_rows(agb_ctx* ctx, const float* x, const float* wr, float* y, int B, int Cin, int H, int W, int Cout, int yh, int yw, int kh, int kw,
                      int pad, int dil, const float* bias, int relu, const float* mask, float* csum);
+int agb_tc_conv_cols(agb_ctx* ctx, const float* x, const float* wr, float* y, int B, int Cin, int H, int W, int Cout, int yh, int yw, int kh, int kw,
+                     int pad, int dil, const float* bias, int relu, const float* mask, float* csum);
 int agb_tc_conv_wgrad_taps(agb_ctx* ctx, const float* img, const float* g, float* gw, int B, int C, int H, int W, int O, int yh, int yw,
                            int kh, int kw, int pad, int dil);
 // channels-last tensor map of a logical [B, C, H, W] activation: dims {c, w, h, b}
@@ -247,6 +249,8 @@ int agb_tc_conv_fprop(agb_ctx* ctx, int mode, const float* x, const float* w, fl
   const bool split = mode == AGB_MATH_3XTF32;
   if (!split) {       // wide feature maps: persistent halo-reusing kernel (tc_conv_rows.cu), 3x less L2 -> smem traffic
     int r = agb_tc_conv_rows(ctx, x, wr, y, B, C, H, W, O, yh, yw, kh, kw, epad, dil, bias, relu, mask, csum);
+    if (r != AGB_ERR_UNSUPPORTED) return r;
+    r = agb_tc_conv_cols(ctx, x, wr, y, B, C, H, W, O, yh, yw, kh, kw, epad, dil, bias, relu, mask, csum);     // narrow maps, Cout <= 128
     if (r != AGB_ERR_UNSUPPORTED) return r;
   }
   if (split) {

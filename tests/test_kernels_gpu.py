@@ -174,6 +174,12 @@ CONV_CASES = [  # B, C, H, W, O, kh, kw, pad, stride, dil
     # enough 8-row patches to fill the machine: two M-tiles per CTA sharing the filter tiles (TF32 mode)
     (16, 128, 44, 64, 128, 3, 3, 1, 1, 1),  # TN = 128, last patch has 4 of 8 rows
     (40, 64, 28, 32, 256, 3, 3, 1, 1, 1),   # TN = 256
+    # narrow maps (output width 16 / 32 / 64, Cout <= 128) with enough tiles: column-copies window kernel (TF32 mode)
+    (40, 64, 30, 32, 96, 3, 3, 1, 1, 1),    # yw = 32: 8-row tiles, last tile 6 rows, 96 of 128 channels
+    (80, 32, 24, 16, 64, 3, 3, 1, 1, 1),    # yw = 16: 16-row tiles, TN = 64
+    (40, 32, 32, 32, 32, 3, 3, 2, 1, 2),    # dilation 2
+    (40, 40, 32, 32, 64, 3, 3, 1, 1, 1),    # Cin = 40: three 16-channel blocks, the last one partial
+    (38, 64, 16, 64, 128, 3, 3, 1, 1, 1),   # yw = 64
 ]
 
 
@@ -201,6 +207,7 @@ FUSED_CASES = [  # B, C, H, W, O, kh, kw, pad, dil — stride 1 ("same"-style ba
     (2, 64, 32, 32, 64, 3, 3, 1, 1), (1, 128, 32, 32, 256, 3, 3, 1, 1), (2, 48, 36, 40, 96, 3, 3, 1, 1), (2, 8, 12, 12, 16, 3, 3, 1, 1),
     (2, 64, 7, 128, 64, 3, 3, 1, 1), (1, 32, 4, 192, 80, 3, 3, 1, 1),      # wide maps: halo-reusing kernel
     (40, 64, 28, 32, 160, 3, 3, 1, 1),                                      # two M-tiles per CTA
+    (80, 32, 16, 32, 96, 3, 3, 1, 1), (38, 64, 16, 64, 64, 3, 3, 1, 1),     # narrow maps: column-copies window kernel
 ]
 
 
