@@ -247,12 +247,12 @@ def main():
     sampler = ClockSampler(local)
     if rank == 0:
         sampler.start()
-    # ---- leg 1: inputs resident in HBM (value) with the live kernel profiler on
+    # ---- leg 1: inputs resident in HBM (value); then the same steps once more with the live kernel profiler on (event pairs around
+    # every profiled call: that pass feeds `roofline`, not `value`)
     ffi.check(lib.agb_prof_reset(ctx))
-    for i in range(args.warmup):
-        step_resident(i)
+    dev_ms, wall_ms, launches = timed(step_resident, args.steps, args.warmup)
     ffi.check(lib.agb_prof_enable(ctx, 1)); ffi.check(lib.agb_prof_reset(ctx))
-    dev_ms, wall_ms, launches = timed(step_resident, args.steps, 0)
+    prof_ms, _, _ = timed(step_resident, args.steps, 0)
     ffi.check(lib.agb_prof_enable(ctx, 0))
     prof = {}
     names = ["gemm", "conv_fprop", "conv_dgrad", "conv_wgrad", "ewise", "reduce", "softmax", "pool", "optim",
@@ -293,8 +293,8 @@ def main():
                     "achieved": achieved, "peak": tf32_peak, "unit": "TFLOP/s", "frac": achieved / tf32_peak, "traffic": traffic, "traffic_source": traffic_src,
                     "peak_source": "%s bf16 sustained / 2 (dense TF32 = half the bf16 rate), MEASURED_PEAKS.json" % pk["src"],
                     "per_launch_ms": d_ms / d_n, "flops_per_launch": d_w / d_n, "launches_per_step": d_n / args.steps,
-                    "share_of_step": d_ms / max(dev_ms, 1e-9),
-                    "all_conv": {"achieved": tot_w / (tot_ms / 1e3) / 1e12, "share_of_step": tot_ms / max(dev_ms, 1e-9)},
+                    "share_of_step": d_ms / max(prof_ms, 1e-9),
+                    "all_conv": {"achieved": tot_w / (tot_ms / 1e3) / 1e12, "share_of_step": tot_ms / max(prof_ms, 1e-9)},
                     "classes": {k: {"ms_per_step": v["ms"] / args.steps, "calls_per_step": v["calls"] / args.steps} for k, v in prof.items()}}
         out = {"metric": METRIC, "value": value, "unit": "samples/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": step_ms,
                "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32 (%s tensor-core contractions)" % args.mode, "data": "synthetic",

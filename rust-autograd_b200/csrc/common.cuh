@@ -85,6 +85,15 @@ static inline int agb_grid_for(int64_t work_items, int threads, int sm_count, in
   return (int)b;
 }
 
+// grid for a grid-stride kernel = ONE full wave of the blocks that are actually co-resident (registers / shared memory decide, not the
+// 2048-thread limit): a grid of 8 blocks per SM on a kernel that fits 6 runs a second, quarter-full wave as long as the first.
+template <class K>
+static inline int agb_grid_occ(agb_ctx* ctx, K kernel, int64_t work_items, int threads, size_t smem = 0) {
+  int nb = 0;
+  if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, kernel, threads, smem) != cudaSuccess || nb < 1) nb = 1;
+  return agb_grid_for(work_items, threads, ctx->sm_count, nb);
+}
+
 // ---- device helpers ----
 __device__ __forceinline__ float warp_sum(float v) {
 #pragma unroll

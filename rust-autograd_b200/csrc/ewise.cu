@@ -281,11 +281,10 @@ extern "C" int agb_unary(agb_ctx* ctx, int op, float p0, float p1, const agb_ten
     agb_tensor t = *y; AGB_TRY(agb_alloc(ctx, n * sizeof(float), (void**)&tmp)); t.ptr = tmp;
     AGB_TRY(agb_copy_strided(ctx, x, &t)); xp = tmp;
   }
-  int grid = agb_grid_for((n + 3) / 4, 256, ctx->sm_count, 8);
   bool aligned = (((uintptr_t)xp | (uintptr_t)y->ptr) & 15) == 0;
   const unary_fn* tv = unary_table_v(make_useq<AGB_U_COUNT>::type());
   const unary_fn* ts = unary_table_s(make_useq<AGB_U_COUNT>::type());
-  if (aligned) tv[op]<<<grid, 256, 0, ctx->stream>>>(xp, y->ptr, n, p0, p1);
+  if (aligned) tv[op]<<<agb_grid_occ(ctx, tv[op], (n + 3) / 4, 256), 256, 0, ctx->stream>>>(xp, y->ptr, n, p0, p1);
   else ts[op]<<<agb_grid_for(n, 256, ctx->sm_count, 8), 256, 0, ctx->stream>>>(xp, y->ptr, n, p0, p1);
   AGB_LAUNCHED(ctx);
   if (tmp) AGB_TRY(agb_free(ctx, tmp));

@@ -107,7 +107,7 @@ extern "C" int agb_maxpool2d_fwd(agb_ctx* ctx, const agb_tensor* x, agb_tensor* 
   for (int k = 0; k < 4; k++) { d.xs[k] = x->stride[k]; d.ys[k] = y->stride[k]; }
   int grid = agb_grid_for(n, 256, ctx->sm_count, 8);
   if (ycl && xcl && d.C % 4 == 0 && n / 4 < (1ll << 31) && agb_numel(x) < (1ll << 32) && ((((uintptr_t)x->ptr | (uintptr_t)y->ptr | (uintptr_t)idx_f32 | (uintptr_t)idx_i32) & 15) == 0)) {
-    maxpool_fwd_cl4_kernel<<<agb_grid_for(n / 4, 256, ctx->sm_count, 8), 256, 0, ctx->stream>>>(x->ptr, y->ptr, idx_f32, idx_i32, (uint32_t)(n / 4), d.C, xh, xw, yh, yw, size, stride);
+    maxpool_fwd_cl4_kernel<<<agb_grid_occ(ctx, maxpool_fwd_cl4_kernel, n / 4, 256), 256, 0, ctx->stream>>>(x->ptr, y->ptr, idx_f32, idx_i32, (uint32_t)(n / 4), d.C, xh, xw, yh, yw, size, stride);
     AGB_LAUNCHED(ctx);
     return AGB_OK;
   }
@@ -230,7 +230,7 @@ extern "C" int agb_maxpool2d_bwd_fused(agb_ctx* ctx, const agb_tensor* gy, const
         ((((uintptr_t)gy->ptr | (uintptr_t)gx->ptr | (uintptr_t)idx_i32 | (uintptr_t)gate) & 15) == 0)) {
       const bool fuse_sum = chan_sum != nullptr && d.C <= 1024 && 256 % (d.C / 4) == 0;
       if (fuse_sum) AGB_TRY(agb_memset0(ctx, chan_sum, (size_t)d.C * sizeof(float)));
-      maxpool_bwd_tiled_cl4_kernel<<<agb_grid_for(n / 4, 256, ctx->sm_count, 8), 256, 0, ctx->stream>>>(gy->ptr, idx_i32, gate, gx->ptr, fuse_sum ? chan_sum : nullptr,
+      maxpool_bwd_tiled_cl4_kernel<<<agb_grid_occ(ctx, maxpool_bwd_tiled_cl4_kernel, n / 4, 256), 256, 0, ctx->stream>>>(gy->ptr, idx_i32, gate, gx->ptr, fuse_sum ? chan_sum : nullptr,
                                                                                                        (uint32_t)(n / 4), d.C, d.xh, d.xw, d.yh, d.yw, size);
       AGB_LAUNCHED(ctx);
       return (chan_sum != nullptr && !fuse_sum) ? pool_channel_sums(ctx, gx, true, chan_sum) : AGB_OK;
