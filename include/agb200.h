@@ -137,6 +137,13 @@ int  agb_conv2d_fprop_f32(agb_ctx* ctx, const agb_tensor* x, const agb_tensor* w
  * registers, the pre-activation tensors never reach HBM. */
 int  agb_conv2d_fprop_fused_f32(agb_ctx* ctx, const agb_tensor* x, const agb_tensor* w, const float* bias, int relu, agb_tensor* y,
                                 int pad, int stride, int dilation);
+/* Conv2D -> AddOp(bias) -> ReLU -> MaxPool2D(size 2, pad 0, stride 2) (examples/cnn_mnist.rs:38-45) with the pooling in the conv
+ * epilogue: y_pooled [B,O,yh/2,yw/2] channels-last and idx_i32 (same layout; MaxPool2D's argmax = flat offsets into the [B,O,yh,yw]
+ * activation, max_pool2d.rs:21-88) are written, the full-size activation never reaches HBM.  Returns AGB_ERR_UNSUPPORTED — before
+ * launching anything — when the layer is outside the fused kernel's envelope (TF32 mode, stride 1, output width >= 128, O <= 128,
+ * channels-last x); the caller then runs agb_conv2d_fprop_fused_f32 + agb_maxpool2d_fwd. */
+int  agb_conv2d_fprop_pool_f32(agb_ctx* ctx, const agb_tensor* x, const agb_tensor* w, const float* bias, int relu, agb_tensor* y_pooled,
+                               int32_t* idx_i32, int pad, int stride, int dilation);
 /* replaces Conv2DTranspose::compute (conv_ops/conv2d_transpose.rs:250-272): gy [B,O,yh,yw],
  * w [O,C,kh,kw] -> gx [B,C,xh,xw], xh = s(yh-1) - 2p + d(kh-1) + 1 (conv2d_transpose.rs:55-56). */
 int  agb_conv2d_dgrad_f32(agb_ctx* ctx, const agb_tensor* gy, const agb_tensor* w, agb_tensor* gx,

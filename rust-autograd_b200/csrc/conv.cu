@@ -15,7 +15,7 @@
 
 // tcgen05 kernels (tc_conv.cu): operate on channels-last activation buffers
 int agb_tc_conv_fprop(agb_ctx* ctx, int mode, const float* x, const float* w, float* y,
-                      int B, int C, int H, int W, int O, int kh, int kw, int pad, int stride, int dil, int flip_transpose, const float* bias, int relu, const float* mask, float* csum);
+                      int B, int C, int H, int W, int O, int kh, int kw, int pad, int stride, int dil, int flip_transpose, const float* bias, int relu, const float* mask, float* csum, float* pool_y, int* pool_idx);
 int agb_tc_conv_wgrad(agb_ctx* ctx, int mode, const float* img, const float* g, float* gw,
                       int B, int C, int H, int W, int O, int kh, int kw, int pad, int stride, int dil);
 bool agb_tc_conv_eligible(int C, int O, int kh, int kw, int stride, int yw);
@@ -160,7 +160,7 @@ extern "C" int agb_conv2d_fprop_fused_f32(agb_ctx* ctx, const agb_tensor* x, con
   if (ctx->math_mode != AGB_MATH_FP32 && agb_tc_conv_eligible(g.C, g.O, g.kh, g.kw, stride, g.yw)) {
     LayoutTmp lx(ctx), ly(ctx);
     AGB_TRY(lx.input(x, true)); AGB_TRY(ly.output(y, true));
-    int r = agb_tc_conv_fprop(ctx, ctx->math_mode, lx.view.ptr, w->ptr, ly.view.ptr, g.B, g.C, g.H, g.W, g.O, g.kh, g.kw, pad, stride, dilation, 0, bias, relu, nullptr, nullptr);
+    int r = agb_tc_conv_fprop(ctx, ctx->math_mode, lx.view.ptr, w->ptr, ly.view.ptr, g.B, g.C, g.H, g.W, g.O, g.kh, g.kw, pad, stride, dilation, 0, bias, relu, nullptr, nullptr, nullptr, nullptr);
     if (r == AGB_OK) { AGB_TRY(ly.finish()); return lx.finish(); }
     if (r != AGB_ERR_UNSUPPORTED) return r;
   }
@@ -186,6 +186,25 @@ extern "C" int agb_conv2d_fprop_fused_f32(agb_ctx* ctx, const agb_tensor* x, con
     if (relu) AGB_TRY(agb_unary(ctx, AGB_U_RELU, 0.f, 0.f, &yv, &yv));
   }
   AGB_TRY(ly.finish()); return lx.finish();
+}
+
+// y_pooled = max_pool2d([relu](conv(x, w) [+ bias]), size 2, pad 0, stride 2) with the pooling done in the conv epilogue: the full-size
+// activation is never written.  Only the tensor-core wide-map kernel has this epilogue; everything else answers AGB_ERR_UNSUPPORTED
+// BEFORE launching anything, and the caller runs conv and pool separately.
+extern "C" int agb_conv2d_fprop_pool_f32(agb_ctx* ctx, const agb_tensor* x, const agb_tensor* w, const float* bias, int relu, agb_tensor* y_pooled,
+                                        int32_t* idx_i32, int pad, int stride, int dilation) {
+  ConvGeom g; AGB_TRY(check_geom("conv2d", x, w, pad, stride, dilation, g));
+  AGB_CHECK(agb_is_contig(w), AGB_ERR_UNSUPPORTED, "conv2d: the filter must be C-contiguous");
+  const int ph = g.yh / 2, pw = g.yw / 2;
+  AGB_CHECK(y_pooled->rank == 4 && y_pooled->shape[0] == g.B && y_pooled->shape[1] == g.O && y_pooled->shape[2] == ph && y_pooled->shape[3] == pw,
+            AGB_ERR_INCOMPATIBLE_SHAPE, "conv2d+max_pool2d: pooled output must be [%d,%d,%d,%d]", g.B, g.O, ph, pw);
+  if (ctx->math_mode != AGB_MATH_TF32 || stride != 1 || g.yw < 128 || g.O > 128 || ph < 1 || pw < 1 || idx_i32 == nullptr ||
+      !agb_tc_conv_eligible(g.C, g.O, g.kh, g.kw, stride, g.yw) || !is_channels_last(x) || !is_channels_last(y_pooled) || agb_is_contig(y_pooled) ||
+      (bias != nullptr && (((uintptr_t)bias) & 15) != 0))
+    return AGB_ERR_UNSUPPORTED;
+  AgbProfScope prof(ctx, AGB_PROF_CONV_FPROP, 2.0 * (double)g.B * g.O * g.yh * g.yw * g.C * g.kh * g.kw);
+  return agb_tc_conv_fprop(ctx, ctx->math_mode, x->ptr, w->ptr, nullptr, g.B, g.C, g.H, g.W, g.O, g.kh, g.kw, pad, stride, dilation, 0, bias, relu, nullptr, nullptr,
+                           y_pooled->ptr, idx_i32);
 }
 
 extern "C" int agb_conv2d_dgrad_f32(agb_ctx* ctx, const agb_tensor* gy, const agb_tensor* w, agb_tensor* gx, int pad, int stride, int dilation) {
@@ -259,7 +278,7 @@ extern "C" int agb_conv2d_dgrad_fused_f32(agb_ctx* ctx, const agb_tensor* gy, co
     const bool fuse_sum = chan_sum != nullptr && in_place && (mask_src == nullptr || fuse);                     // sums of the FINAL (masked) values
     if (fuse_sum) AGB_TRY(agb_memset0(ctx, chan_sum, (size_t)g.C * sizeof(float)));
     int r = agb_tc_conv_fprop(ctx, ctx->math_mode, lg.view.ptr, w->ptr, lx.view.ptr, g.B, g.O, g.yh, g.yw, g.C, g.kh, g.kw, pad, stride, dilation, 1, nullptr, 0,
-                              fuse ? mask_src->ptr : nullptr, fuse_sum ? chan_sum : nullptr);
+                              fuse ? mask_src->ptr : nullptr, fuse_sum ? chan_sum : nullptr, nullptr, nullptr);
     if (r == AGB_OK) {
       AGB_TRY(lx.finish()); AGB_TRY(lg.finish());
       if (!fuse) AGB_TRY(apply_relu_mask(ctx, mask_src, gx));

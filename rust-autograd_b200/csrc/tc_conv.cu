@@ -190,7 +190,7 @@ template <int TN_, bool SPLIT_, bool PAIR_, int MT_ = 1> struct ConvWgradPol {
 
 // ------------------------------------------------------------------------------------------------ host side
 int agb_tc_conv_rows(agb_ctx* ctx, const float* x, const float* wr, float* y, int B, int Cin, int H, int W, int Cout, int yh, int yw, int kh, int kw,
-                     int pad, int dil, const float* bias, int relu, const float* mask, float* csum);
+                     int pad, int dil, const float* bias, int relu, const float* mask, float* csum, float* pool_y, int* pool_idx);
 int agb_tc_conv_cols(agb_ctx* ctx, const float* x, const float* wr, float* y, int B, int Cin, int H, int W, int Cout, int yh, int yw, int kh, int kw,
                      int pad, int dil, const float* bias, int relu, const float* mask, float* csum);
 int agb_tc_conv_wgrad_taps(agb_ctx* ctx, const float* img, const float* g, float* gw, int B, int C, int H, int W, int O, int yh, int yw,
@@ -230,7 +230,7 @@ static int fprop_launch(agb_ctx* ctx, const float* x, const float* wr, float* y,
 // fprop on channels-last buffers: x [B,H,W,C], w [O,C,kh,kw] (plain) -> y [B,yh,yw,O].  flip_transpose != 0: dgrad — `x` is gy
 // with C = filter dim 0, w [C, O(=out channels of this GEMM), kh, kw]; the effective padding is dil*(k-1) - pad.
 int agb_tc_conv_fprop(agb_ctx* ctx, int mode, const float* x, const float* w, float* y, int B, int C, int H, int W, int O, int kh, int kw,
-                      int pad, int stride, int dil, int flip_transpose, const float* bias, int relu, const float* mask, float* csum) {
+                      int pad, int stride, int dil, int flip_transpose, const float* bias, int relu, const float* mask, float* csum, float* pool_y, int* pool_idx) {
   const int epad = flip_transpose ? dil * (kh - 1) - pad : pad;
   if (epad < 0) return AGB_ERR_UNSUPPORTED;
   const int yh = H + 2 * epad - (dil * (kh - 1) + 1) + 1, yw = W + 2 * epad - (dil * (kw - 1) + 1) + 1;
@@ -247,9 +247,11 @@ int agb_tc_conv_fprop(agb_ctx* ctx, int mode, const float* x, const float* w, fl
     AGB_LAUNCHED(ctx);
   }
   const bool split = mode == AGB_MATH_3XTF32;
+  if (split && pool_y != nullptr) return AGB_ERR_UNSUPPORTED;
   if (!split) {       // wide feature maps: persistent halo-reusing kernel (tc_conv_rows.cu), 3x less L2 -> smem traffic
-    int r = agb_tc_conv_rows(ctx, x, wr, y, B, C, H, W, O, yh, yw, kh, kw, epad, dil, bias, relu, mask, csum);
+    int r = agb_tc_conv_rows(ctx, x, wr, y, B, C, H, W, O, yh, yw, kh, kw, epad, dil, bias, relu, mask, csum, pool_y, pool_idx);
     if (r != AGB_ERR_UNSUPPORTED) return r;
+    if (pool_y != nullptr) return AGB_ERR_UNSUPPORTED;          // the fused pooling epilogue exists in the wide-map kernel only
     r = agb_tc_conv_cols(ctx, x, wr, y, B, C, H, W, O, yh, yw, kh, kw, epad, dil, bias, relu, mask, csum);     // narrow maps, Cout <= 128
     if (r != AGB_ERR_UNSUPPORTED) return r;
   }

@@ -22,11 +22,13 @@
 //
 // Reference semantics: Conv2D::compute conv2d.rs:115-211, Conv2DTranspose::compute conv2d_transpose.rs:89-247.
 #include "tc_common.cuh"
+#include <float.h>
 
 #define ROWS_R 2
 struct RowsParams {
   CUtensorMap tmX, tmW;
   float* y; const float* bias; const float* mask; float* csum; int relu;
+  float* pool_y; int* pool_idx; int ph, pw;      // fused max_pool2d(2, 0, 2): pooled output + int32 argmax (logical NCHW offsets into y), y itself not written
   int Cout, yh, yw, kw, pad, dil, tiles_x, tiles_y, otiles, cblocks, taps, pitch, a_box_bytes, a_slot_bytes;
   long long num_tiles;
 };
@@ -194,6 +196,59 @@ __global__ void __launch_bounds__(256, 1) conv_rows_kernel(const __grid_constant
       const uint32_t acs = it & 1;
       mbar_wait(&acc_full[acs], (it >> 1) & 1);
       tc_fence_after();
+      if (p.pool_y != nullptr) {
+        // conv -> (+bias) -> ReLU -> max_pool2d(2, 0, 2) in one epilogue (examples/cnn_mnist.rs:38-45 layer pattern): the tile's two
+        // rows are the two rows of every window, horizontal neighbours sit 8 lanes apart in the transposed layout.  Scan order and
+        // tie-breaking follow MaxPool2D::compute (max_pool2d.rs:21-88): strict '>' from -FLT_MAX over (h0,w0), (h0,w0+1), (h1,w0),
+        // (h1,w0+1); index = flat offset into the (never materialised) [B,C,yh,yw] conv output.
+        const int py = oy0 >> 1;
+#pragma unroll
+        for (int c = 0; c < TN / 32; c++) {
+          float4 a0[8], a1[8];
+#pragma unroll
+          for (int r = 0; r < 2; r++) {
+            float v[32];
+            tmem_ld32(tlane + (uint32_t)((acs * R + r) * TN + 32 * c), v);
+            tmem_ld_wait();
+#pragma unroll
+            for (int k = 0; k < 8; k++) *(float4*)(stg + lane * 36 + 4 * k) = make_float4(v[4 * k], v[4 * k + 1], v[4 * k + 2], v[4 * k + 3]);
+            __syncwarp();
+#pragma unroll
+            for (int k = 0; k < 8; k++) {
+              float4 a = *(const float4*)(stg + (4 * k + pl0) * 36 + 4 * ch4);
+              a.x += bv[c].x; a.y += bv[c].y; a.z += bv[c].z; a.w += bv[c].w;
+              if (p.relu) { a.x = fmaxf(a.x, 0.0f); a.y = fmaxf(a.y, 0.0f); a.z = fmaxf(a.z, 0.0f); a.w = fmaxf(a.w, 0.0f); }
+              if (r == 0) a0[k] = a; else a1[k] = a;
+            }
+            __syncwarp();
+          }
+          const int o = o0 + 32 * c + 4 * ch4;
+#pragma unroll
+          for (int k = 0; k < 8; k++) {
+            float4 b0, b1;                 // the odd-column neighbour (lane ^ 8)
+            b0.x = __shfl_xor_sync(0xffffffffu, a0[k].x, 8); b0.y = __shfl_xor_sync(0xffffffffu, a0[k].y, 8);
+            b0.z = __shfl_xor_sync(0xffffffffu, a0[k].z, 8); b0.w = __shfl_xor_sync(0xffffffffu, a0[k].w, 8);
+            b1.x = __shfl_xor_sync(0xffffffffu, a1[k].x, 8); b1.y = __shfl_xor_sync(0xffffffffu, a1[k].y, 8);
+            b1.z = __shfl_xor_sync(0xffffffffu, a1[k].z, 8); b1.w = __shfl_xor_sync(0xffffffffu, a1[k].w, 8);
+            const int ox = ox0 + 4 * k + pl0, px = ox >> 1;
+            if ((pl0 & 1) == 0 && py < p.ph && px < p.pw && o + 4 <= p.Cout) {
+              const float w4[4][4] = {{a0[k].x, b0.x, a1[k].x, b1.x}, {a0[k].y, b0.y, a1[k].y, b1.y}, {a0[k].z, b0.z, a1[k].z, b1.z}, {a0[k].w, b0.w, a1[k].w, b1.w}};
+              float mx[4]; int mi[4];
+#pragma unroll
+              for (int e = 0; e < 4; e++) {
+                mx[e] = -FLT_MAX; int pos = -1;
+#pragma unroll
+                for (int u = 0; u < 4; u++) if (w4[e][u] > mx[e]) { mx[e] = w4[e][u]; pos = u; }
+                const long long plane = (long long)p.yh * p.yw;
+                mi[e] = pos < 0 ? 0 : (int)(((long long)b * p.Cout + (o + e)) * plane + (long long)(oy0 + (pos >> 1)) * p.yw + ox + (pos & 1));
+              }
+              const long long off = (((long long)b * p.ph + py) * p.pw + px) * p.Cout + o;
+              *(float4*)(p.pool_y + off) = make_float4(mx[0], mx[1], mx[2], mx[3]);
+              *(int4*)(p.pool_idx + off) = make_int4(mi[0], mi[1], mi[2], mi[3]);
+            }
+          }
+        }
+      } else {
 #pragma unroll
       for (int r = 0; r < R; r++) {
         const int oy = oy0 + r;
@@ -223,6 +278,7 @@ __global__ void __launch_bounds__(256, 1) conv_rows_kernel(const __grid_constant
           }
           __syncwarp();
         }
+      }
       }
       tc_fence_before();
       mbar_arrive(&acc_empty[acs]);
@@ -262,10 +318,11 @@ static int rows_launch(agb_ctx* ctx, RowsParams& p, size_t smem) {
 // x [B,H,W,Cin] channels-last, wr = filter repacked to [tap][Cout][Cin] (see tc_conv.cu), y [B,yh,yw,Cout] channels-last.
 // Returns AGB_ERR_UNSUPPORTED when the geometry is outside this kernel's envelope (the caller falls back to the per-tap kernel).
 int agb_tc_conv_rows(agb_ctx* ctx, const float* x, const float* wr, float* y, int B, int Cin, int H, int W, int Cout, int yh, int yw, int kh, int kw,
-                     int pad, int dil, const float* bias, int relu, const float* mask, float* csum) {
+                     int pad, int dil, const float* bias, int relu, const float* mask, float* csum, float* pool_y, int* pool_idx) {
   static int enabled = -1;
   if (enabled < 0) { const char* e = getenv("AGB_CONV_ROWS"); enabled = (e && e[0] == '0') ? 0 : 1; }
   if (!enabled || yw < 128 || Cout > 128 || Cin % 4 != 0 || Cout % 4 != 0) return AGB_ERR_UNSUPPORTED;
+  if (pool_y != nullptr && ((int64_t)B * Cout * yh * yw >= (1ll << 31) || (((uintptr_t)pool_y | (uintptr_t)pool_idx) & 15) != 0)) return AGB_ERR_UNSUPPORTED;     // int32 argmax offsets
   const int pitch = 128 + dil * (kw - 1), hrows = ROWS_R + dil * (kh - 1);
   if (pitch > 256 || hrows > 256) return AGB_ERR_UNSUPPORTED;
   RowsParams p;
@@ -286,7 +343,7 @@ int agb_tc_conv_rows(agb_ctx* ctx, const float* x, const float* wr, float* y, in
     uint32_t box[3] = {32, (uint32_t)TN, 1};
     AGB_TRY(agb_make_tmap(&p.tmW, wr, 3, dims, str, box, false));
   }
-  p.y = y; p.bias = bias; p.mask = mask; p.csum = csum; p.relu = relu; p.Cout = Cout; p.yh = yh; p.yw = yw; p.kw = kw; p.pad = pad; p.dil = dil;
+  p.y = y; p.bias = bias; p.mask = mask; p.csum = csum; p.relu = relu; p.pool_y = pool_y; p.pool_idx = pool_idx; p.ph = yh / 2; p.pw = yw / 2; p.Cout = Cout; p.yh = yh; p.yw = yw; p.kw = kw; p.pad = pad; p.dil = dil;
   p.tiles_x = (yw + 127) / 128; p.tiles_y = (yh + ROWS_R - 1) / ROWS_R; p.otiles = (Cout + TN - 1) / TN;
   p.cblocks = (Cin + 31) / 32; p.taps = kh * kw; p.pitch = pitch;
   p.num_tiles = (long long)B * p.tiles_x * p.tiles_y * p.otiles;

@@ -290,6 +290,19 @@ class Device:
             ffi.check(self.lib.agb_conv2d_fprop_fused_f32(self.ctx, x.desc(), w.desc(), bias.ptr if bias is not None else None, int(relu), y.desc(), pad, stride, dil))
         return y
 
+    def conv2d_pool(self, x, w, pad=0, stride=1, dil=1, bias=None, relu=True):
+        """max_pool2d([relu](conv2d(x, w) [+ bias]), 2, 0, 2) in one kernel; returns (y_pooled, idx_int32) channels-last, or None when the
+        fused kernel does not take the layer (AGB_ERR_UNSUPPORTED)"""
+        b, _, h, wd = x.shape
+        o, _, kh, kw = w.shape
+        yh, yw = self.conv_out(h, kh, pad, stride, dil), self.conv_out(wd, kw, pad, stride, dil)
+        y, idx = self.empty_channels_last((b, o, yh // 2, yw // 2)), self.empty_channels_last((b, o, yh // 2, yw // 2))
+        st = self.lib.agb_conv2d_fprop_pool_f32(self.ctx, x.desc(), w.desc(), bias.ptr if bias is not None else None, int(relu), y.desc(), idx.ptr, pad, stride, dil)
+        if st == ffi.ERR_UNSUPPORTED:
+            return None
+        ffi.check(st)
+        return y, idx
+
     def conv2d_transpose(self, gy, w, pad=0, stride=1, dil=1, mask_src=None, channels_last=False, chan_sum=False):
         """gx = conv2d_transpose(gy, w) [* (mask_src > 0)]; with chan_sum also returns sum_{b,h,w} gx as a [C] array"""
         b, _, yh, yw = gy.shape

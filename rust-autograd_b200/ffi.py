@@ -63,7 +63,7 @@ SIGNATURES = {
     "agb_event_elapsed_ms": [_P, _P, C.POINTER(_f)],
     "agb_graph_begin": [_P], "agb_graph_end": [_P, C.POINTER(_P)], "agb_graph_launch": [_P, _P], "agb_graph_destroy": [_P],
     "agb_gemm_f32": [_P, _i, _i, _T, _T, _T, _f],
-    "agb_conv2d_fprop_f32": [_P, _T, _T, _T, _i, _i, _i], "agb_conv2d_fprop_fused_f32": [_P, _T, _T, _P, _i, _T, _i, _i, _i], "agb_conv2d_dgrad_f32": [_P, _T, _T, _T, _i, _i, _i],
+    "agb_conv2d_fprop_f32": [_P, _T, _T, _T, _i, _i, _i], "agb_conv2d_fprop_fused_f32": [_P, _T, _T, _P, _i, _T, _i, _i, _i], "agb_conv2d_fprop_pool_f32": [_P, _T, _T, _P, _i, _T, _P, _i, _i, _i], "agb_conv2d_dgrad_f32": [_P, _T, _T, _T, _i, _i, _i],
     "agb_conv2d_dgrad_fused_f32": [_P, _T, _T, _T, _P, _T, _i, _i, _i], "agb_maxpool2d_bwd_fused": [_P, _T, _P, _P, _P, _P, _T, _i, _i],
     "agb_conv2d_wgrad_f32": [_P, _T, _T, _T, _i, _i, _i], "agb_conv_prefers_channels_last": [_i, _i, _i, _i, _i, _i], "agb_im2col_f32": [_P, _T, _T, _i, _i, _i, _i, _i],
     "agb_maxpool2d_fwd": [_P, _T, _T, _P, _P, _i, _i, _i], "agb_maxpool2d_bwd": [_P, _T, _P, _P, _T],

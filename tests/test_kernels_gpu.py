@@ -261,6 +261,29 @@ def test_small_channel_conv_channels_last(dev, case, mode):
     assert rel_err(gw, R.conv2d_filter_grad(x, gy, w.shape, pad, stride, dil)) <= TOL[mode]
 
 
+@pytest.mark.parametrize("case", [(2, 64, 8, 128, 64, 1), (1, 32, 7, 256, 96, 1), (2, 32, 6, 130, 48, 0)])
+def test_conv_relu_pool_fused_matches_separate_kernels(dev, case):
+    """conv+bias+ReLU+max_pool2d(2,0,2) in one epilogue must be bit-identical (values AND argmax) to the conv kernel followed by the
+    pooling kernel, and within the TF32 tolerance of the oracle; odd heights / widths drop the last row / column like the reference."""
+    dev.set_math_mode(1)
+    B, C, H, W, O, pad = case
+    rng = np.random.default_rng(sum(case))
+    x = rng.standard_normal((B, C, H, W)).astype(np.float32)
+    w = (rng.standard_normal((O, C, 3, 3)) * 0.1).astype(np.float32)
+    bias = rng.standard_normal(O).astype(np.float32)
+    dx, dw, db = dev.upload_channels_last(x), dev.upload(w), dev.upload(bias)
+    fused = dev.conv2d_pool(dx, dw, pad, 1, 1, bias=db, relu=True)
+    assert fused is not None, "the wide-map kernel should take this layer"
+    y = dev.conv2d(dx, dw, pad, 1, 1, bias=db, relu=True, channels_last=True)
+    py, pidx = dev.max_pool2d(y, 2, 0, 2, int32_index=True)
+    assert np.array_equal(fused[0].numpy(), py.numpy())
+    assert np.array_equal(fused[1].numpy().view(np.int32), pidx.numpy().view(np.int32))
+    y_ref = np.maximum(R.conv2d(x, w, pad, 1, 1) + bias.reshape(1, O, 1, 1), 0)
+    assert rel_err(fused[0].numpy(), R.max_pool2d(y_ref, 2, 0, 2)[0]) <= TOL[1]
+    dev.set_math_mode(0)
+    assert dev.conv2d_pool(dx, dw, pad, 1, 1, bias=db, relu=True) is None      # 3xTF32 mode: not fused, the caller falls back
+
+
 def test_conv_errors(dev):
     import rust_autograd_b200 as agb
     with pytest.raises(agb.OpError) as e:
