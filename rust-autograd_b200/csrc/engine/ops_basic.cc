@@ -17,7 +17,7 @@ NdArray lazy_gt0_mask(const NdArray& src_or_lazy);
 bool lazy_is_mask(const NdArray& a);
 NdArray lazy_fuse_mask(Device* dev, const NdArray& mask, const NdArray& prod);
 bool lazy_is_conv(const NdArray& a);
-const NdArray& lazy_mask_src(const NdArray& a);
+NdArray lazy_mask_src(Device* dev, const NdArray& a);
 
 // ================================================================================================ device helpers
 static NdArray on_dev(Device* d, NdArray a) { d->ensure_device(a); return a; }
@@ -341,7 +341,7 @@ struct BinArith : Op {                 // AddOp/SubOp/MulOp/DivOp, binary_ops.rs
             if (r.on_device()) { c.append_output(r); return; }
             o = materialize_lazy(c.dev, o);
           }
-          c.append_output(dev_binary(c.dev, AGB_B_RELU_GRAD, lazy_mask_src(m), o)); return;
+          c.append_output(dev_binary(c.dev, AGB_B_RELU_GRAD, lazy_mask_src(c.dev, m), o)); return;
         }
       }
       if (a.lazy) a = materialize_lazy(c.dev, a);
@@ -465,7 +465,7 @@ struct UnaryOp : Op {
     c.accept_lazy = info->op == AGB_U_RELU;
     NdArray x = c.input(0);
     if (x.lazy) {
-      if (lazy_is_conv(x)) { NdArray y = lazy_conv_relu(c.dev, x); if (y.on_device()) { c.append_output(y); return; } }
+      if (lazy_is_conv(x)) { NdArray y = lazy_conv_relu(c.dev, x); if (y.lazy) { c.append_output(y); return; } }      // stays deferred (ops_nn.cc)
       x = materialize_lazy(c.dev, x);
     }
     if (info->op == AGB_U_NEG && all_meta(x)) { std::vector<float> v = *x.host; for (auto& e : v) e = -e; c.append_output(NdArray::from_host(x.shape, v, true)); return; }

@@ -103,13 +103,20 @@ struct ConvParams { int pad, stride, dilation; };
 //     greater(lazy conv+bias, 0)  -> mask of the ReLU OUTPUT (x > 0  <=>  relu(x) > 0), no pre-activation needed
 //     MulOp(lazy mask, lazy Conv2DTranspose)  -> dgrad kernel with the compare-and-zero in its epilogue (agb_conv2d_dgrad_fused_f32)
 //     MulOp(lazy mask, lazy MaxPool2DGrad)    -> gather-form pool backward gated by (pooled output > 0) (agb_maxpool2d_bwd_fused)
+//     MaxPool2D(lazy ReLU(conv [+ bias]))     -> pooling in the conv epilogue (agb_conv2d_fprop_pool_f32): the full-size activation
+//                                                is written only if some other consumer asks for it
+// ReLU itself stays deferred (`relu_deferred`) until its first consumer shows what it is: MaxPool2D fuses, anything else runs the
+// conv + bias + ReLU kernel once and caches the value.  The ReLU-gradient mask refers to that deferred node (`src_lazy`), so the
+// backward pass of a conv -> relu -> pool block needs neither the pre-activation nor the activation.
 // Any other consumer gets the exact un-fused value through materialize_lazy (ComputeContext::input), so every intermediate of
 // the reference graph remains observable; fusion only removes HBM round trips.
 struct Lazy {
   int kind = 0;                        // 1 = conv [+ bias], 2 = (src > 0) mask, 3 = Conv2DTranspose(x = gy, w), 4 = MaxPool2DGrad(x = gy, idx)
   NdArray x, w, bias; bool has_bias = false; ConvParams p{0, 1, 1};
-  NdArray relu_out; bool has_relu = false;       // filled by the ReLU consumer that ran the fused kernel
-  NdArray src;                                    // kind 2
+  NdArray relu_out; bool has_relu = false;       // filled when the fused conv + bias + ReLU kernel ran
+  bool relu_deferred = false;                     // kind 1: this node is ReLU(conv [+ bias]); `value` (when computed) is the activation
+  std::shared_ptr<Lazy> relu_child;               // kind 1, pre-activation node: the deferred ReLU that consumed it
+  NdArray src; std::shared_ptr<Lazy> src_lazy;    // kind 2: mask source as an array, or as a deferred ReLU node
   NdArray idx; int pool_size = 0, pool_stride = 0; // kind 4
   NdArray value; bool has_value = false;          // cache of the un-fused value
 };
@@ -122,7 +129,7 @@ static Tensor mk_conv(Graph* g, Tensor x, Tensor w, ConvParams p);
 static Tensor mk_filter_grad(Graph* g, Tensor cols, Tensor gy, Tensor w, Tensor bp_x, Tensor bp_gy, ConvParams p);
 static Tensor mk_conv_with_cols(Graph* g, Tensor cols, Tensor w, Tensor bp_x, Tensor bp_w, ConvParams p);
 
-struct PoolRef { NdArray y; const float* x_dptr; Shape x_shape, x_stride; };
+struct PoolRef { NdArray y; const float* x_dptr; Shape x_shape, x_stride; std::shared_ptr<Lazy> x_lazy; };      // x_lazy: the pooled input was a deferred ReLU (fused conv + pool)
 // gx = conv2d_transpose(gy, w) [* (mask_src > 0)]
 static NdArray run_dgrad(Device* dev, const Lazy& L, const NdArray* mask_src) {
   const NdArray &gy = L.x, &w = L.w; const ConvParams& p = L.p;
@@ -157,6 +164,7 @@ static NdArray run_pool_grad(Device* dev, const Lazy& L, bool gated) {
   if (gated) gx.chan_sum = std::make_shared<NdArray>(cs);
   return gx;
 }
+NdArray lazy_mask_src(Device* dev, const NdArray& m);
 static NdArray run_conv_fused(Device* dev, const Lazy& L, bool relu) {
   const NdArray &x = L.x, &w = L.w;
   int64_t yh = (x.shape[2] + 2 * L.p.pad - (L.p.dilation * (w.shape[2] - 1) + 1)) / L.p.stride + 1;
@@ -169,11 +177,14 @@ static NdArray run_conv_fused(Device* dev, const Lazy& L, bool relu) {
 NdArray materialize_lazy(Device* dev, const NdArray& a) {
   Lazy& L = *a.lazy;
   if (!L.has_value) {
-    if (L.kind == 1) L.value = run_conv_fused(dev, L, false);
+    if (L.kind == 1) {
+      L.value = run_conv_fused(dev, L, L.relu_deferred);
+      if (L.relu_deferred) { L.relu_out = L.value; L.has_relu = true; }
+    }
     else if (L.kind == 3) L.value = run_dgrad(dev, L, nullptr);
     else if (L.kind == 4) L.value = run_pool_grad(dev, L, false);
     else {
-      NdArray zero = dev->full({}, 0.0f), src = L.src;
+      NdArray zero = dev->full({}, 0.0f), src = lazy_mask_src(dev, a);
       std::vector<int> order;
       if (!src.dense_order(order)) { src = dev->contiguous(src); src.dense_order(order); }
       NdArray y = dev->empty_ordered(src.shape, order);          // same memory order as the source
@@ -191,7 +202,7 @@ NdArray materialize_lazy(Device* dev, const NdArray& a) {
 // hooks used by ops_basic.cc (AddOp / ReLU / greater / MulOp)
 NdArray lazy_conv_add_bias(const NdArray& conv, const NdArray& bias) {      // returns an invalid (no lazy) array when the pattern does not apply
   NdArray r;
-  if (!conv.lazy || conv.lazy->kind != 1 || conv.lazy->has_bias || conv.lazy->has_relu || conv.lazy->has_value) return r;
+  if (!conv.lazy || conv.lazy->kind != 1 || conv.lazy->has_bias || conv.lazy->has_relu || conv.lazy->relu_deferred || conv.lazy->has_value) return r;
   if (conv.ndim() != 4 || bias.ndim() != 4 || !bias.on_device() || !bias.is_contiguous()) return r;
   if (bias.shape[0] != 1 || bias.shape[1] != conv.shape[1] || bias.shape[2] != 1 || bias.shape[3] != 1) return r;
   if (((uintptr_t)bias.dptr) & 15) return r;
@@ -199,43 +210,62 @@ NdArray lazy_conv_add_bias(const NdArray& conv, const NdArray& bias) {      // r
   r.shape = conv.shape; r.stride = NdArray::contiguous_strides(r.shape); r.lazy = L;
   return r;
 }
-NdArray lazy_conv_relu(Device* dev, const NdArray& a) {                      // ReLU(conv [+ bias]) in one kernel
+NdArray lazy_conv_relu(Device* dev, const NdArray& a) {                      // ReLU(conv [+ bias]): stays deferred, see above
+  (void)dev;
   Lazy& L = *a.lazy;
-  if (L.has_value) return NdArray();          // already materialised un-fused: the caller applies a plain ReLU to that value
-  NdArray y = run_conv_fused(dev, L, true);
-  L.relu_out = y; L.has_relu = true;
-  return y;
+  if (L.has_value || L.relu_deferred) return NdArray();          // pre-activation already materialised / ReLU of a ReLU: plain kernel
+  auto L2 = std::make_shared<Lazy>(L); L2->relu_deferred = true; L2->relu_child.reset();
+  a.lazy->relu_child = L2;
+  NdArray r; r.shape = a.shape; r.stride = NdArray::contiguous_strides(r.shape); r.lazy = L2;
+  return r;
 }
 NdArray lazy_gt0_mask(const NdArray& src_or_lazy) {                          // greater(x, 0) whose multiply has not arrived yet
-  NdArray src = src_or_lazy;
-  if (src.lazy) {
-    if (src.lazy->kind != 1 || !src.lazy->has_relu) return NdArray();
-    src = src.lazy->relu_out;                                                // x > 0  <=>  relu(x) > 0
-  }
-  NdArray r; auto L = std::make_shared<Lazy>(); L->kind = 2; L->src = src;
-  r.shape = src.shape; r.stride = NdArray::contiguous_strides(r.shape); r.lazy = L;
+  NdArray r; auto M = std::make_shared<Lazy>(); M->kind = 2;
+  if (src_or_lazy.lazy) {
+    Lazy& S = *src_or_lazy.lazy;
+    if (S.kind != 1) return NdArray();
+    if (S.relu_deferred) M->src_lazy = src_or_lazy.lazy;                     // greater(relu(x), 0)
+    else if (S.relu_child) M->src_lazy = S.relu_child;                       // greater(x, 0) with relu(x) deferred: x > 0 <=> relu(x) > 0
+    else if (S.has_relu) M->src = S.relu_out;
+    else return NdArray();
+  } else M->src = src_or_lazy;
+  r.shape = src_or_lazy.shape; r.stride = NdArray::contiguous_strides(r.shape); r.lazy = M;
   return r;
+}
+// the array a mask compares with 0 (materialises a deferred ReLU on first use; cached there)
+NdArray lazy_mask_src(Device* dev, const NdArray& m) {
+  Lazy& M = *m.lazy;
+  if (!M.src_lazy) return M.src;
+  NdArray t; t.shape = m.shape; t.stride = NdArray::contiguous_strides(t.shape); t.lazy = M.src_lazy;
+  return materialize_lazy(dev, t);
 }
 // MulOp(mask, lazy producer of gy): returns the fused result, or an invalid array when the pattern does not apply
 NdArray lazy_fuse_mask(Device* dev, const NdArray& mask, const NdArray& prod) {
   Lazy& L = *prod.lazy;
-  if (L.has_value) return NdArray();
-  const NdArray& src = mask.lazy->src;
-  if (src.shape != prod.shape || src.ndim() != 4 || !src.on_device() || !(src.is_contiguous() || is_cl4(src))) return NdArray();
-  if (L.kind == 3) return run_dgrad(dev, L, &src);
+  if (L.has_value || mask.shape != prod.shape || mask.ndim() != 4) return NdArray();
+  Lazy& M = *mask.lazy;
   if (L.kind == 4) {
     // the gate is the pooled OUTPUT: valid only when the mask source is the very tensor that was pooled (then x[argmax] == y)
     const NdArray& idx = L.idx;
-    if (!idx.pool || idx.pool->x_dptr != src.dptr || idx.pool->x_shape != src.shape || idx.pool->x_stride != src.stride) return NdArray();
-    if (L.pool_size != L.pool_stride || L.p.pad != 0) return NdArray();
+    if (!idx.pool || L.pool_size != L.pool_stride || L.p.pad != 0) return NdArray();
     if (is_cl4(idx) != is_cl4(idx.pool->y) || idx.pool->y.shape != idx.shape) return NdArray();
+    bool same = false;
+    if (M.src_lazy) {
+      if (idx.pool->x_lazy == M.src_lazy) same = true;                       // fused conv + pool: identity of the deferred ReLU node
+      else if (M.src_lazy->has_value) { const NdArray& v = M.src_lazy->value; same = idx.pool->x_dptr == v.dptr && idx.pool->x_shape == v.shape && idx.pool->x_stride == v.stride; }
+    } else same = idx.pool->x_dptr != nullptr && idx.pool->x_dptr == M.src.dptr && idx.pool->x_shape == M.src.shape && idx.pool->x_stride == M.src.stride;
+    if (!same) return NdArray();
     return run_pool_grad(dev, L, true);
+  }
+  if (L.kind == 3) {
+    const NdArray src = lazy_mask_src(dev, mask);
+    if (src.shape != prod.shape || !src.on_device() || !(src.is_contiguous() || is_cl4(src))) return NdArray();
+    return run_dgrad(dev, L, &src);
   }
   return NdArray();
 }
 bool lazy_is_mask(const NdArray& a) { return a.lazy && a.lazy->kind == 2 && !a.lazy->has_value; }
 bool lazy_is_conv(const NdArray& a) { return a.lazy && a.lazy->kind == 1; }
-const NdArray& lazy_mask_src(const NdArray& a) { return a.lazy->src; }
 
 static int64_t conv_out(int64_t x, int64_t k, ConvParams p) { return (x + 2 * p.pad - (p.dilation * (k - 1) + 1)) / p.stride + 1; }
 
@@ -414,9 +444,27 @@ struct MaxPool2D : Op {                // max_pool2d.rs:166-243
   int size, pad, stride;
   const char* name() const override { return REFNAME("conv_ops::max_pool2d", "MaxPool2D"); }
   void compute(ComputeContext& c) override {
-    NdArray x = on_dev(c.dev, c.input(0));
+    c.accept_lazy = true;
+    NdArray x = c.input(0);
     if (x.ndim() != 4) throw OpError(AGB_ERR_INCOMPATIBLE_SHAPE, "max_pool2d: input must be 4-D");
-    x = act_layout(c.dev, x);
+    if (x.lazy) {
+      // ReLU(conv [+ bias]) feeding a 2x2 / stride-2 pool: pooling runs in the conv epilogue, the activation is not written
+      Lazy& L = *x.lazy;
+      if (L.kind == 1 && L.relu_deferred && !L.has_value && size == 2 && pad == 0 && stride == 2 && x.shape[2] >= 2 && x.shape[3] >= 2 && is_cl4(L.x)) {
+        const Shape ps = {x.shape[0], x.shape[1], x.shape[2] / 2, x.shape[3] / 2};
+        NdArray y = act_empty(c.dev, ps, true), idx = act_empty(c.dev, ps, true);
+        agb_tensor tx = L.x.desc(), tw = L.w.desc(), ty = y.desc();
+        int st = agb_conv2d_fprop_pool_f32(c.dev->ctx, &tx, &tw, L.has_bias ? L.bias.dptr : nullptr, 1, &ty, (int32_t*)idx.dptr, L.p.pad, L.p.stride, L.p.dilation);
+        if (st == AGB_OK) {
+          idx.i32 = true;
+          idx.pool = std::make_shared<PoolRef>(PoolRef{y, nullptr, x.shape, NdArray::contiguous_strides(x.shape), x.lazy});
+          c.append_output(y); c.append_output(idx); return;
+        }
+        if (st != AGB_ERR_UNSUPPORTED) check_status(st);
+      }
+      x = materialize_lazy(c.dev, x);
+    }
+    x = act_layout(c.dev, on_dev(c.dev, x));
     int64_t yh = (x.shape[2] + 2 * pad - size) / stride + 1, yw = (x.shape[3] + 2 * pad - size) / stride + 1;
     const bool cl = is_cl4(x);
     NdArray y = act_empty(c.dev, {x.shape[0], x.shape[1], yh, yw}, cl), idx = act_empty(c.dev, {x.shape[0], x.shape[1], yh, yw}, cl);
@@ -425,7 +473,7 @@ struct MaxPool2D : Op {                // max_pool2d.rs:166-243
     // (max_pool2d.rs:74-75; a 256x64x128x128 VGG activation has 2.7e8), API-visible values are converted on fetch
     if (x.size() < (1ll << 31)) { check_status(agb_maxpool2d_fwd(c.dev->ctx, &tx, &ty, nullptr, (int32_t*)idx.dptr, size, pad, stride)); idx.i32 = true; }
     else check_status(agb_maxpool2d_fwd(c.dev->ctx, &tx, &ty, idx.dptr, nullptr, size, pad, stride));
-    idx.pool = std::make_shared<PoolRef>(PoolRef{y, x.dptr, x.shape, x.stride});
+    idx.pool = std::make_shared<PoolRef>(PoolRef{y, x.dptr, x.shape, x.stride, nullptr});
     c.append_output(y); c.append_output(idx);
   }
   void grad(GradientContext& c) override {
