@@ -289,7 +289,7 @@ def main():
                 tj = json.load(open(tpath))
                 if tj.get("workload") == WORKLOAD and tj.get("math_mode") == args.mode:
                     traffic, traffic_src = tj["dram_bytes_per_launch"], tj["source"]
-            roof = {"bound": "tensor", "kernel": "tc_tile_persist_kernel<ConvFpropPol> + conv_rows_kernel (tcgen05 implicit-GEMM conv: fprop + dgrad, %s)" % args.mode,
+            roof = {"bound": "tensor", "kernel": "tc_tile_persist_kernel<ConvFpropPol> + conv_rows_kernel + conv_cols_kernel (tcgen05 implicit-GEMM conv: fprop + dgrad, %s)" % args.mode,
                     "achieved": achieved, "peak": tf32_peak, "unit": "TFLOP/s", "frac": achieved / tf32_peak, "traffic": traffic, "traffic_source": traffic_src,
                     "peak_source": "%s bf16 sustained / 2 (dense TF32 = half the bf16 rate), MEASURED_PEAKS.json" % pk["src"],
                     "per_launch_ms": d_ms / d_n, "flops_per_launch": d_w / d_n, "launches_per_step": d_n / args.steps,
