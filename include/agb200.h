@@ -98,6 +98,8 @@ int  agb_sync(agb_ctx* ctx);
  *   agb_stage_mark  — records "everything enqueued on the compute stream so far has been issued" (call before launching step i:
  *                     the buffers of step i-1 are free once the mark passes);
  *   agb_stage_h2d   — async copy from PINNED host memory on a second stream, ordered after the last mark. */
+/* arena blocks referenced by instantiated step graphs must stay mapped: +1 / -1 pins (agb_trim and out-of-memory trimming are disabled while > 0) */
+int  agb_arena_pin(agb_ctx* ctx, int delta);
 int  agb_stage_mark(agb_ctx* ctx);
 int  agb_stage_h2d(agb_ctx* ctx, void* dst, const void* src, size_t bytes);
 int  agb_stage_wait(agb_ctx* ctx);
@@ -116,6 +118,7 @@ int  agb_event_elapsed_ms(void* start, void* stop, float* ms); /* synchronises o
 
 /* CUDA-graph capture of a launch sequence */
 int  agb_graph_begin(agb_ctx* ctx);
+/* graph_exec == NULL aborts the capture (nothing is instantiated) */
 int  agb_graph_end(agb_ctx* ctx, void** graph_exec);
 int  agb_graph_launch(agb_ctx* ctx, void* graph_exec);
 int  agb_graph_destroy(void* graph_exec);

@@ -75,6 +75,13 @@ int agx_eval(agx_graph* g, const int* targets, int n, const agx_feed* feeds, int
 int agx_eval_launch(agx_graph* g, const int* targets, int n, const agx_feed* feeds, int nfeeds, agx_results** out);
 int agx_results_fetch(agx_results* r);
 int agx_results_count(agx_results* r, int* n);
+/* Step graphs (the reference rebuilds and re-walks its graph every step, mlp_mnist.rs:74, cnn_mnist.rs:96): one
+ * evaluation for side effects (agx_run semantics) is captured into a CUDA graph after two eager warm-up runs; agx_step_launch replays
+ * it with no host-side graph walk.  All feeds must be device-resident and are re-read at the same addresses on every launch. */
+typedef struct agx_step agx_step;
+int agx_step_capture(agx_graph* g, const int* targets, int n, const agx_feed* feeds, int nfeeds, agx_step** out);
+int agx_step_launch(agx_step* s);
+int agx_step_free(agx_step* s);
 int agx_results_status(agx_results* r, int i, int* code, const char** msg);
 int agx_results_shape(agx_results* r, int i, int64_t* shape, int* rank);
 int agx_results_data(agx_results* r, int i, const float** data, int64_t* n);

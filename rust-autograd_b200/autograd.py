@@ -42,6 +42,7 @@ SIGNATURES = {
     "agx_tensor_op_name": [_P, _i, C.c_char_p, _i], "agx_tensor_variable_id": [_P, _i, _pi],
     "agx_eval": [_P, _pi, _i, _pfeed, _i, C.POINTER(_P)], "agx_run": [_P, _pi, _i, _pfeed, _i],
     "agx_eval_launch": [_P, _pi, _i, _pfeed, _i, C.POINTER(_P)], "agx_results_fetch": [_P],
+    "agx_step_capture": [_P, _pi, _i, _pfeed, _i, C.POINTER(_P)], "agx_step_launch": [_P], "agx_step_free": [_P],
     "agx_results_count": [_P, _pi], "agx_results_status": [_P, _i, _pi, C.POINTER(C.c_char_p)], "agx_results_shape": [_P, _i, _pi64, _pi],
     "agx_results_data": [_P, _i, C.POINTER(_pf), _pi64], "agx_results_free": [_P],
     "agx_opt_adam": [_P, _pi, _i, C.c_char_p, _f, _f, _f, _f, C.POINTER(_P)], "agx_opt_sgd": [_f, C.POINTER(_P)],
@@ -254,6 +255,27 @@ def _make_feeds(items):
     return arr, len(items), keep
 
 
+class StepGraph:
+    """A captured training / evaluation step (Evaluator.capture)."""
+
+    def __init__(self, h):
+        self.h = h
+
+    def launch(self):
+        _check(lib().agx_step_launch(self.h))
+
+    def close(self):
+        if self.h:
+            lib().agx_step_free(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
 class Deferred:
     """Pending results of Evaluator.run_deferred()."""
 
@@ -338,6 +360,14 @@ class Evaluator:
         res = C.c_void_p()
         _check(lib().agx_eval_launch(self.graph.h, _ints([t.id for t in self.targets]), len(self.targets), arr, n, C.byref(res)))
         return Deferred(self, res)
+
+    def capture(self):
+        """Capture this evaluation (run_async semantics, device-resident feeds only) into a CUDA graph; returns a StepGraph whose
+        .launch() replays the whole step — forward, backward, optimizer — without walking the graph on the host."""
+        arr, n, keep = _make_feeds(self.feeder.items)
+        h = C.c_void_p()
+        _check(lib().agx_step_capture(self.graph.h, _ints([t.id for t in self.targets]), len(self.targets), arr, n, C.byref(h)))
+        return StepGraph(h)
 
     def run_async(self):
         """Evaluate for side effects only (training step): nothing is copied back, no host sync."""

@@ -35,6 +35,7 @@ struct agb_ctx {
   void* nccl_comm = nullptr;
   int rank = 0, world = 1;
   bool capturing = false;
+  int pinned_graphs = 0;            // live agx_step graphs: the arena must not return blocks to the driver while they exist
   // live profiler (agb_prof_*): event pairs per profiled entry-point call
   bool prof_on = false;
   struct ProfRec { int cls; cudaEvent_t a, b; double work; };

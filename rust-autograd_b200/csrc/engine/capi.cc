@@ -237,6 +237,33 @@ extern "C" int agx_results_fetch(agx_results* r) {
   r->keep.clear();
   AGX_CATCH
 }
+// ---- step graphs: the kernels of one evaluation captured into a CUDA graph and replayed without walking the
+// graph on the host.  Every feed must be device-resident (the replay reads the same addresses: refill them in place), the step must
+// not need a host decision that depends on device data, and nothing is read back (fetch results from variables / fed buffers).
+struct agx_step { Device* dev; void* exec; };
+extern "C" int agx_step_capture(agx_graph* g, const int* targets, int n, const agx_feed* feeds, int nfeeds, agx_step** out) {
+  AGX_TRY
+  *out = nullptr;
+  for (int i = 0; i < nfeeds; i++) if (!feeds[i].on_device) throw OpError(AGB_ERR_UNSUPPORTED, "agx_step_capture: every feed must be device-resident");
+  Device* dev = g->g.env->dev;
+  // two eager runs: the first grows the arena / scratch / descriptor tables, the second starts from the free-list state the captured
+  // run will start from, so cached tables keyed by buffer addresses hit during capture
+  for (int w = 0; w < 2; w++) { auto rs = eval(&g->g, tv(g, targets, n), fv(g, feeds, nfeeds), false); for (auto& r : rs) if (!r.ok) throw OpError(r.err_code, r.err_msg); }
+  dev->sync();
+  check_status(agb_graph_begin(dev->ctx));
+  void* exec = nullptr;
+  try {
+    auto rs = eval(&g->g, tv(g, targets, n), fv(g, feeds, nfeeds), false);
+    for (auto& r : rs) if (!r.ok) throw OpError(r.err_code, r.err_msg);
+  } catch (...) { agb_graph_end(dev->ctx, nullptr); throw; }
+  check_status(agb_graph_end(dev->ctx, &exec));
+  agb_arena_pin(dev->ctx, +1);
+  *out = new agx_step{dev, exec};
+  AGX_CATCH
+}
+extern "C" int agx_step_launch(agx_step* s) { AGX_TRY check_status(agb_graph_launch(s->dev->ctx, s->exec)); AGX_CATCH }
+extern "C" int agx_step_free(agx_step* s) { if (s) { agb_graph_destroy(s->exec); agb_arena_pin(s->dev->ctx, -1); delete s; } return 0; }
+
 extern "C" int agx_run(agx_graph* g, const int* targets, int n, const agx_feed* feeds, int nfeeds) {
   AGX_TRY
   std::vector<EvalResult> rs = eval(&g->g, tv(g, targets, n), fv(g, feeds, nfeeds), false);

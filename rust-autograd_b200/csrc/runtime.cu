@@ -41,6 +41,7 @@ extern "C" int agb_init(int device, agb_ctx** out) {
 }
 
 extern "C" int agb_trim(agb_ctx* ctx) {
+  if (ctx->pinned_graphs > 0) return AGB_OK;       // instantiated step graphs hold raw addresses of arena blocks
   cudaStreamSynchronize(ctx->stream);
   for (auto& kv : ctx->free_blocks) { cudaFree(kv.second); ctx->block_size.erase(kv.second); ctx->is_live.erase(kv.second); }
   ctx->free_blocks.clear(); ctx->cached_bytes = 0;
@@ -88,6 +89,7 @@ extern "C" int agb_alloc(agb_ctx* ctx, size_t bytes, void** out) {
     if (ctx->live_bytes > ctx->peak_bytes) ctx->peak_bytes = ctx->live_bytes;
     *out = p; return AGB_OK;
   }
+  AGB_CHECK(!ctx->capturing, AGB_ERR_CUDA, "arena growth during graph capture; run the step eagerly (twice) first");
   void* p = nullptr;
   cudaError_t e = cudaMalloc(&p, sz);
   if (e != cudaSuccess) {   // give cached memory back and retry once
@@ -246,12 +248,14 @@ extern "C" int agb_graph_begin(agb_ctx* ctx) {
 }
 extern "C" int agb_graph_end(agb_ctx* ctx, void** graph_exec) {
   cudaGraph_t g = nullptr; ctx->capturing = false;
+  if (graph_exec == nullptr) { cudaStreamEndCapture(ctx->stream, &g); if (g) cudaGraphDestroy(g); cudaGetLastError(); return AGB_OK; }     // abort
   AGB_CUDA(cudaStreamEndCapture(ctx->stream, &g));
   cudaGraphExec_t ge = nullptr;
   AGB_CUDA(cudaGraphInstantiate(&ge, g, 0));
   cudaGraphDestroy(g);
   *graph_exec = ge; return AGB_OK;
 }
+extern "C" int agb_arena_pin(agb_ctx* ctx, int delta) { ctx->pinned_graphs += delta; if (ctx->pinned_graphs < 0) ctx->pinned_graphs = 0; return AGB_OK; }
 extern "C" int agb_graph_launch(agb_ctx* ctx, void* graph_exec) {
   AGB_CUDA(cudaGraphLaunch((cudaGraphExec_t)graph_exec, ctx->stream)); return AGB_OK;
 }

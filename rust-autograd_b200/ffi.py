@@ -58,7 +58,7 @@ SIGNATURES = {
     "agb_mem_stats": [_P, C.POINTER(_sz), C.POINTER(_sz), C.POINTER(_sz)],
     "agb_host_alloc": [_sz, C.POINTER(_P)], "agb_host_free": [_P],
     "agb_h2d": [_P, _P, _P, _sz], "agb_d2h": [_P, _P, _P, _sz], "agb_d2d": [_P, _P, _P, _sz], "agb_memset0": [_P, _P, _sz],
-    "agb_sync": [_P], "agb_flush_l2": [_P], "agb_stage_mark": [_P], "agb_stage_h2d": [_P, _P, _P, _sz], "agb_stage_wait": [_P], "agb_stage_d2h": [_P, _P, _P, _sz, C.POINTER(_P)], "agb_event_sync": [_P],
+    "agb_sync": [_P], "agb_flush_l2": [_P], "agb_arena_pin": [_P, _i], "agb_stage_mark": [_P], "agb_stage_h2d": [_P, _P, _P, _sz], "agb_stage_wait": [_P], "agb_stage_d2h": [_P, _P, _P, _sz, C.POINTER(_P)], "agb_event_sync": [_P],
     "agb_event_create": [C.POINTER(_P)], "agb_event_destroy": [_P], "agb_event_record": [_P, _P],
     "agb_event_elapsed_ms": [_P, _P, C.POINTER(_f)],
     "agb_graph_begin": [_P], "agb_graph_end": [_P, C.POINTER(_P)], "agb_graph_launch": [_P, _P], "agb_graph_destroy": [_P],
