@@ -54,6 +54,39 @@ def cnn_mnist_loss(T, g, train=True, masks=None):
     return T.reduce_mean(T.sparse_softmax_cross_entropy(logits, g.placeholder("y", [-1, 1])), [0], False), logits
 
 
+# ------------------------------------------------------------------------------------------------ examples/lstm_lm.rs:18-125
+def lstm_init(env, rng, dim, vocab, scale=0.01):
+    """init_vars (lstm_lm.rs:55-82): N(0, 0.01) tables / gate weights, zero bias, U(0, 0.01) prediction weights"""
+    ns = env.default_namespace_mut()
+    ns.slot().name("lookup_table").set((rng.standard_normal((vocab, dim)) * scale).astype(np.float32))
+    ns.slot().name("wx").set((rng.standard_normal((dim, 4 * dim)) * scale).astype(np.float32))
+    ns.slot().name("wh").set((rng.standard_normal((dim, 4 * dim)) * scale).astype(np.float32))
+    ns.slot().name("b").set(np.zeros((1, 4 * dim), np.float32))
+    ns.slot().name("w_pred").set(rng.uniform(0, scale, (dim, vocab)).astype(np.float32))
+
+
+def lstm_loss(T, g, dim, seq):
+    """Unrolled LSTM language model (lstm_lm.rs:18-52,96-113): per step gather -> two gate GEMMs -> 4 slices -> sigmoid/tanh cell ->
+    prediction GEMM -> sparse softmax cross-entropy; loss = add_n of the per-step losses.  h0 / c0 are zeros_like the first x."""
+    v = {k: g.variable(k) for k in ("lookup_table", "wx", "wh", "b", "w_pred")}
+    sents = g.placeholder("sents", [-1, seq])
+    h = c = None
+    losses = []
+    for i in range(seq - 1):
+        cur = T.slice(sents, [0, i], [-1, i + 1])
+        nxt = T.slice(sents, [0, i + 1], [-1, i + 2])
+        x = T.squeeze(T.gather(v["lookup_table"], cur, 0), [1])
+        if h is None:
+            h = T.zeros(T.shape(x), g)
+            c = T.zeros(T.shape(x), g)
+        xh = T.matmul(x, v["wx"]) + T.matmul(h, v["wh"]) + v["b"]
+        i_, f_, c_, o_ = (T.slice(xh, [0, k * dim], [-1, (k + 1) * dim]) for k in range(4))
+        c = T.sigmoid(f_) * c + T.sigmoid(i_) * T.tanh(c_)
+        h = T.sigmoid(o_) * T.tanh(c)
+        losses.append(T.sparse_softmax_cross_entropy(T.matmul(h, v["w_pred"]), nxt))
+    return T.add_n(losses), None
+
+
 # ------------------------------------------------------------------------------------------------ VGG-style stack (configs[3])
 def vgg_init(env, rng, size=128, classes=10, layers=VGG_LAYERS):
     ns = env.default_namespace_mut()

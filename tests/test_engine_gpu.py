@@ -215,6 +215,35 @@ def test_channels_last_network_matches_oracle(ag):
                 assert l2 <= 1e-1, (mode, a.shape, l2)
 
 
+def test_lstm_language_model_matches_oracle(ag):
+    """examples/lstm_lm.rs unrolled LSTM LM (gather, two gate GEMMs, slices, sigmoid/tanh cell, prediction GEMM, sparse xent, add_n) at a
+    size where the tensor-core GEMMs engage (batch 32, dim 64, vocab 96, 5 steps): loss and all five parameter gradients vs the oracle."""
+    from rust_autograd_b200 import ffi, workloads as W
+    D, V, S, B = 64, 96, 5, 32
+    sents = np.random.default_rng(9).integers(0, V, (B, S)).astype(np.float32)
+
+    def run(mod, mode):
+        env = mod.VariableEnvironment()
+        if mode is not None:
+            ffi.check(ffi.load_library().agb_set_math_mode(env.agb_ctx(), mode))
+        W.lstm_init(env, np.random.default_rng(0), D, V, scale=0.2)     # larger than the example's 0.01: gates and gradients well away from 0
+
+        def body(g):
+            loss, _ = W.lstm_loss(mod, g, D, S)
+            vs = [g.variable(k) for k in ("wx", "wh", "b", "lookup_table", "w_pred")]
+            grads = mod.grad([loss], vs)
+            return [r_.unwrap() for r_ in g.evaluator().push(loss).extend(grads).feed("sents", sents).run()]
+        out = env.run(body)
+        env.close()
+        return out
+    ref = run(OG, None)
+    for mode, tol in ((0, 5e-5), (1, 2e-2)):
+        got = run(ag, mode)
+        assert len(got) == len(ref) == 6
+        for a, b in zip(got, ref):
+            assert rel(a, b) <= tol, (mode, np.asarray(a).shape, rel(a, b))
+
+
 def test_training_reduces_loss_and_checkpoint_roundtrip(ag, tmp_path):
     """examples/mlp_mnist.rs flow on synthetic data + VariableEnvironment::save/load (src/variable.rs:470-598, test :810-840)."""
     from rust_autograd_b200 import workloads as W
