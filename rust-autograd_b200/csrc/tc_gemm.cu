@@ -23,13 +23,20 @@
 template <int TN_, bool P_MN_, bool Q_MN_, bool SPLIT_> struct GemmPol {
   static constexpr int TN = TN_, MT = 1; static constexpr bool SPLIT = SPLIT_, P_MN = P_MN_, Q_MN = Q_MN_;
   static constexpr int OCC = (SPLIT_ || TN_ > 128) ? 1 : 2;
-  struct Params { CUtensorMap tmP, tmQ; float* C; int NL, NC, K; int64_t ldc, bsc; int accumulate; MnDescCfg mnc; };
-  struct Tile { int lane0, col0, bz; };
-  __device__ static Tile tile(const Params&, uint3 blk) { return Tile{(int)blk.x * TC_LANES, (int)blk.y * TN, (int)blk.z}; }
-  __device__ static int num_kblocks(const Params& p, const Tile&) { return (p.K + TC_BK - 1) / TC_BK; }
+  // splits > 1: split-K for problems with too few output tiles to fill the machine (e.g. the LSTM's 128 x 1024 x 8192 dgrad GEMM is
+  // 8 tiles): grid.z = batch * splits, every CTA reduces kb_per_split k-blocks and adds its partial with red.global.add (C pre-zeroed)
+  struct Params { CUtensorMap tmP, tmQ; float* C; int NL, NC, K; int64_t ldc, bsc; int accumulate; int splits, kb_per_split; MnDescCfg mnc; };
+  struct Tile { int lane0, col0, bz, kb0, nkb; };
+  __device__ static Tile tile(const Params& p, uint3 blk) {
+    const int kb_total = (p.K + TC_BK - 1) / TC_BK;
+    const int bz = (int)blk.z / p.splits, ks = (int)blk.z - bz * p.splits;
+    const int kb0 = ks * p.kb_per_split;
+    return Tile{(int)blk.x * TC_LANES, (int)blk.y * TN, bz, kb0, max(0, min(p.kb_per_split, kb_total - kb0))};
+  }
+  __device__ static int num_kblocks(const Params&, const Tile& t) { return t.nkb; }
   __device__ static void prefetch(const Params& p) { tma_prefetch_desc(&p.tmP); tma_prefetch_desc(&p.tmQ); }
   __device__ static void load(const Params& p, const Tile& t, int kb, uint8_t* pP, uint8_t* pQ, uint64_t* bar) {
-    const int k0 = kb * TC_BK;
+    const int k0 = (t.kb0 + kb) * TC_BK;
     if (P_MN) { for (int j = 0; j < TC_LANES / 32; j++) tma_load_3d(pP + j * 4096, &p.tmP, bar, t.lane0 + 32 * j, k0, t.bz); }
     else tma_load_3d(pP, &p.tmP, bar, k0, t.lane0, t.bz);
     if (Q_MN) { for (int j = 0; j < TN / 32; j++) tma_load_3d(pQ + j * 4096, &p.tmQ, bar, t.col0 + 32 * j, k0, t.bz); }
@@ -45,7 +52,10 @@ template <int TN_, bool P_MN_, bool Q_MN_, bool SPLIT_> struct GemmPol {
 #pragma unroll
     for (int j = 0; j < 32; j++) {
       const int m = t.col0 + c0 + j;
-      if (m < p.NC) { float* q = cbase + (int64_t)m * p.ldc; *q = p.accumulate ? (*q + v[j]) : v[j]; }
+      if (m < p.NC) {
+        float* q = cbase + (int64_t)m * p.ldc;
+        if (p.splits > 1) red_add_f32(q, v[j]); else *q = p.accumulate ? (*q + v[j]) : v[j];
+      }
     }
   }
 };
@@ -75,8 +85,19 @@ template <int TN, bool P_MN, bool Q_MN, bool SPLIT>
 static int tc_launch(agb_ctx* ctx, const CUtensorMap& tmP, const CUtensorMap& tmQ, float* C, int NL, int NC, int K, int64_t ldc, int64_t bsc,
                      int64_t batch, int accumulate) {
   using Pol = GemmPol<TN, P_MN, Q_MN, SPLIT>;
-  typename Pol::Params prm{tmP, tmQ, C, NL, NC, K, ldc, bsc, accumulate, agb_mn_cfg()};
-  dim3 grid((NL + TC_LANES - 1) / TC_LANES, (NC + TN - 1) / TN, (unsigned)batch);
+  const int gx = (NL + TC_LANES - 1) / TC_LANES, gy = (NC + TN - 1) / TN;
+  const int kb_total = (K + TC_BK - 1) / TC_BK;
+  // split-K when the output tiles cannot fill the machine and there is K to share (>= 4 k-blocks per split)
+  int64_t tiles = (int64_t)gx * gy * batch, cap = (int64_t)ctx->sm_count * Pol::OCC;
+  int splits = 1;
+  if (tiles * 2 <= cap && kb_total >= 8 && ldc == NL && (batch == 1 || bsc == (int64_t)NC * NL)) {
+    int64_t s = cap / tiles; if (s > kb_total / 4) s = kb_total / 4; if (s > 1) splits = (int)s;
+  }
+  int kb_per = (kb_total + splits - 1) / splits; splits = (kb_total + kb_per - 1) / kb_per;
+  if ((int64_t)batch * splits > 65535) { splits = 1; kb_per = kb_total; }
+  if (splits > 1 && !accumulate) AGB_TRY(agb_memset0(ctx, C, (size_t)batch * NC * NL * sizeof(float)));
+  typename Pol::Params prm{tmP, tmQ, C, NL, NC, K, ldc, bsc, accumulate, splits, kb_per, agb_mn_cfg()};
+  dim3 grid(gx, gy, (unsigned)(batch * splits));
   return tc_tile_launch<Pol>(ctx, prm, grid);
 }
 
