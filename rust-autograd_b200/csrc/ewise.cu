@@ -356,10 +356,14 @@ __global__ void __launch_bounds__(256) add_n_kernel(AddNPtrs P, int n, float* __
   int64_t tid = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
   int64_t stride = (int64_t)gridDim.x * blockDim.x;
   for (int64_t i = tid; i < n4; i += stride) {
-    float4 acc = accumulate ? *(const float4*)(y + 4 * i) : ldg_stream4(P.p[0] + 4 * i);
-    for (int k = accumulate ? 0 : 1; k < n; k++) {
-      float4 v = ldg_stream4(P.p[k] + 4 * i);
-      acc.x += v.x; acc.y += v.y; acc.z += v.z; acc.w += v.w;   // left fold, like `base += &ctx.input(i)`
+    // all operand loads are issued before the first add (a runtime-length loop would serialise n memory round trips)
+    float4 v[AGB_ADDN_MAX];
+#pragma unroll
+    for (int k = 0; k < AGB_ADDN_MAX; k++) if (k < n) v[k] = ldg_stream4(P.p[k] + 4 * i);
+    float4 acc = accumulate ? *(const float4*)(y + 4 * i) : v[0];
+#pragma unroll
+    for (int k = 0; k < AGB_ADDN_MAX; k++) {
+      if (k < n && (accumulate || k > 0)) { acc.x += v[k].x; acc.y += v[k].y; acc.z += v[k].z; acc.w += v[k].w; }   // left fold, like `base += &ctx.input(i)`
     }
     *(float4*)(y + 4 * i) = acc;
   }

@@ -122,7 +122,8 @@ int agb_tc_gemm(agb_ctx* ctx, int mode, const float* A, const float* B, float* C
   bool pmn, qmn;
   if (!tc_operand_ok(P, K, batch, pmn) || !tc_operand_ok(Q, K, batch, qmn)) return AGB_ERR_UNSUPPORTED;
   const bool split = (mode == AGB_MATH_3XTF32);
-  const int TN = (M >= 192 && !split) ? 256 : (M > 64 ? 128 : 64);
+  // 256-wide tiles (one CTA per SM, 128 KB epilogue per tile) only pay off when the k-loop is long enough to hide the epilogue behind it
+  const int TN = (M >= 192 && !split && K >= 512) ? 256 : (M > 64 ? 128 : 64);
   CUtensorMap tmP, tmQ;
   int r = tc_make_map(&tmP, P, K, batch, pmn, TC_LANES); if (r != AGB_OK) return r;
   r = tc_make_map(&tmQ, Q, K, batch, qmn, TN); if (r != AGB_OK) return r;
