@@ -39,11 +39,22 @@ __global__ void __launch_bounds__(256) repack_filter_kernel(const float* __restr
 template <int TN_, bool SPLIT_, int MT_ = 1> struct ConvFpropPol {
   static constexpr int TN = TN_, MT = MT_; static constexpr bool SPLIT = SPLIT_, P_MN = false, Q_MN = false;
   static constexpr int OCC = (SPLIT_ || TN_ > 128 || MT_ > 1) ? 1 : 2;
-  struct Params { CUtensorMap tmX, tmW; float* y; const float* bias; const float* mask; float* csum; int relu; int Cout, yh, yw, kw, pad, dil, tiles_x, tiles_y, cblocks, taps; MnDescCfg mnc; };
+  // The 128 lanes of an M-tile are a {bw w, bh h, bb images} pixel box (TMA writes box elements in exactly that order): 32x4x1 for
+  // maps at least 32 wide; narrow maps take whole rows and, when a whole image is smaller than the tile, several images
+  // (14x14 -> 14x9x1, 7x7 -> 7x7x2).  Lanes past bw*bh*bb read stale shared memory and are never stored.
+  struct Params { CUtensorMap tmX, tmW; float* y; const float* bias; const float* mask; float* csum; int relu; int B, Cout, yh, yw, kw, pad, dil, tiles_x, tiles_y, cblocks, taps;
+                  int bw, bh, bb; uint32_t p_bytes; MnDescCfg mnc; };
   struct Tile { int b, oy0, ox0, o0; };
   __device__ static Tile tile(const Params& p, uint3 blk) {
     int bx = (int)blk.x; int tx = bx % p.tiles_x; int r = bx / p.tiles_x; int ty = r % p.tiles_y;
-    return Tile{r / p.tiles_y, ty * 4 * MT, tx * 32, (int)blk.y * TN};
+    return Tile{(r / p.tiles_y) * p.bb, ty * p.bh * MT, tx * p.bw, (int)blk.y * TN};
+  }
+  __device__ static uint32_t p_bytes(const Params& p, uint32_t) { return p.p_bytes; }
+  // lane -> pixel of M-tile mt
+  __device__ static bool pixel(const Params& p, const Tile& t, int mt, int lane, int& b, int& oy, int& ox) {
+    const int w = lane % p.bw, q = lane / p.bw, h = q % p.bh, bi = q / p.bh;
+    b = t.b + bi; oy = t.oy0 + p.bh * mt + h; ox = t.ox0 + w;
+    return bi < p.bb && b < p.B && oy < p.yh && ox < p.yw;
   }
   __device__ static int num_kblocks(const Params& p, const Tile&) { return p.taps * p.cblocks; }
   __device__ static void prefetch(const Params& p) { tma_prefetch_desc(&p.tmX); tma_prefetch_desc(&p.tmW); }
@@ -58,9 +69,9 @@ template <int TN_, bool SPLIT_, int MT_ = 1> struct ConvFpropPol {
     if (p.mask == nullptr) return;
 #pragma unroll
     for (int mt = 0; mt < MT; mt++) {
-      const int oy = t.oy0 + 4 * mt + (lane >> 5), ox = t.ox0 + (lane & 31);
-      const bool in = oy < p.yh && ox < p.yw;
-      const float* m = p.mask + (((int64_t)t.b * p.yh + (in ? oy : 0)) * p.yw + (in ? ox : 0)) * p.Cout + t.o0;
+      int b, oy, ox;
+      const bool in = pixel(p, t, mt, lane, b, oy, ox);
+      const float* m = p.mask + (((int64_t)(in ? b : 0) * p.yh + (in ? oy : 0)) * p.yw + (in ? ox : 0)) * p.Cout + t.o0;
 #pragma unroll
       for (int c = 0; c < TN / 32; c++) {
         uint32_t bits = 0;
@@ -80,11 +91,11 @@ template <int TN_, bool SPLIT_, int MT_ = 1> struct ConvFpropPol {
     }
   }
   __device__ static void store(const Params& p, const Tile& t, int mt, int lane, int c0, const float* v, uint32_t pre) {
-    const int oy = t.oy0 + 4 * mt + (lane >> 5), ox = t.ox0 + (lane & 31);
-    const bool in = oy < p.yh && ox < p.yw;
+    int b, oy, ox;
+    const bool in = pixel(p, t, mt, lane, b, oy, ox);
     if (!in && p.csum == nullptr) return;
     const int o = t.o0 + c0;
-    float* dst = p.y + (((int64_t)t.b * p.yh + (in ? oy : 0)) * p.yw + (in ? ox : 0)) * p.Cout + o;
+    float* dst = p.y + (((int64_t)(in ? b : 0) * p.yh + (in ? oy : 0)) * p.yw + (in ? ox : 0)) * p.Cout + o;
     // fused epilogue: per-channel bias and ReLU applied to the accumulator registers, so the
     // pre-activation tensors of conv -> add -> relu never travel through HBM
     float r[32];
@@ -150,6 +161,7 @@ template <int TN_, bool SPLIT_, bool PAIR_, int MT_ = 1> struct ConvWgradPol {
     return t;
   }
   __device__ static int num_kblocks(const Params&, const Tile& t) { return t.q1 > t.q0 ? t.q1 - t.q0 : 0; }
+  __device__ static uint32_t p_bytes(const Params&, uint32_t full) { return full; }
   __device__ static void prefetch(const Params& p) { tma_prefetch_desc(&p.tmX); tma_prefetch_desc(&p.tmG); }
   __device__ static void load(const Params& p, const Tile& t, int kb, uint8_t* pP, uint8_t* pQ, uint64_t* bar) {
     const int q = t.q0 + kb; const int xb = q % p.xblocks; const int r = q / p.xblocks; const int oy = r % p.yh, b = r / p.yh;
@@ -204,7 +216,7 @@ static int make_cl_map(CUtensorMap* m, const float* p, int B, int C, int H, int 
 }
 
 bool agb_tc_conv_eligible(int C, int O, int kh, int kw, int stride, int yw) {
-  return stride == 1 && kh == kw && C >= 32 && C % 4 == 0 && O >= 32 && O % 4 == 0 && yw >= 8;      // narrow maps waste lanes (14 of 32 columns) but still beat the CUDA-core path 10x
+  return stride == 1 && kh == kw && C >= 32 && C % 4 == 0 && O >= 32 && O % 4 == 0 && yw >= 4;       // narrow maps: see ConvFpropPol::Params (whole rows / several images per tile)
 }
 
 template <int TN, bool SPLIT, int MT = 1>
@@ -212,7 +224,16 @@ static int fprop_launch(agb_ctx* ctx, const float* x, const float* wr, float* y,
                         int pad, int dil, const float* bias, int relu, const float* mask, float* csum) {
   using Pol = ConvFpropPol<TN, SPLIT, MT>;
   typename Pol::Params p;
-  AGB_TRY(make_cl_map(&p.tmX, x, B, Cin, H, W, 32, 32, 4 * MT, false));
+  int bw = 32, bh = 4, bb = 1;
+  if (yw < 32) { bw = yw; bh = yh < 128 / bw ? yh : 128 / bw; bb = bh == yh ? 128 / (bw * bh) : 1; if (bb > B) bb = B; if (bb < 1) bb = 1; }
+  if (MT > 1 && (bw != 32 || bb != 1)) return AGB_ERR_UNSUPPORTED;
+  {
+    uint64_t dims[4] = {(uint64_t)Cin, (uint64_t)W, (uint64_t)H, (uint64_t)B};
+    uint64_t str[3] = {(uint64_t)Cin * 4, (uint64_t)W * Cin * 4, (uint64_t)H * W * Cin * 4};
+    uint32_t box[4] = {32, (uint32_t)bw, (uint32_t)(bh * MT), (uint32_t)bb};
+    AGB_TRY(agb_make_tmap(&p.tmX, x, 4, dims, str, box, false));
+  }
+  p.bw = bw; p.bh = bh; p.bb = bb; p.B = B; p.p_bytes = (uint32_t)(128 * bw * bh * MT * bb);
   {  // wr[tap][o][c]
     uint64_t dims[3] = {(uint64_t)Cin, (uint64_t)Cout, (uint64_t)(kh * kw)};
     uint64_t str[2] = {(uint64_t)Cin * 4, (uint64_t)Cin * Cout * 4};
@@ -220,8 +241,8 @@ static int fprop_launch(agb_ctx* ctx, const float* x, const float* wr, float* y,
     AGB_TRY(agb_make_tmap(&p.tmW, wr, 3, dims, str, box, false));
   }
   p.y = y; p.bias = bias; p.mask = mask; p.csum = csum; p.relu = relu; p.Cout = Cout; p.yh = yh; p.yw = yw; p.kw = kw; p.pad = pad; p.dil = dil;
-  p.tiles_x = (yw + 31) / 32; p.tiles_y = (yh + 4 * MT - 1) / (4 * MT); p.cblocks = (Cin + 31) / 32; p.taps = kh * kw; p.mnc = agb_mn_cfg();
-  int64_t nb = (int64_t)p.tiles_x * p.tiles_y * B;
+  p.tiles_x = (yw + bw - 1) / bw; p.tiles_y = (yh + bh * MT - 1) / (bh * MT); p.cblocks = (Cin + 31) / 32; p.taps = kh * kw; p.mnc = agb_mn_cfg();
+  int64_t nb = (int64_t)p.tiles_x * p.tiles_y * ((B + bb - 1) / bb);
   if (nb > 2147483647ll) return AGB_ERR_UNSUPPORTED;
   dim3 grid((unsigned)nb, (unsigned)((Cout + TN - 1) / TN), 1);
   return tc_tile_launch<Pol>(ctx, p, grid);
@@ -261,7 +282,7 @@ int agb_tc_conv_fprop(agb_ctx* ctx, int mode, const float* x, const float* w, fl
   }
   static int m2 = -1;     // two M-tiles per CTA: measured slower than one (3-stage ring, doubled epilogue) — kept as an opt-in experiment
   if (m2 < 0) { const char* e = getenv("AGB_CONV_M2"); m2 = (e && e[0] == '1') ? 1 : 0; }
-  const bool tall = m2 && yh >= 8 && (int64_t)B * ((yh + 7) / 8) * ((yw + 31) / 32) >= ctx->sm_count;       // enough 8-row patches to fill the machine
+  const bool tall = m2 && yh >= 8 && yw >= 32 && (int64_t)B * ((yh + 7) / 8) * ((yw + 31) / 32) >= ctx->sm_count;       // enough 8-row patches to fill the machine
   if (O > 128) return tall ? fprop_launch<256, false, 2>(ctx, x, wr, y, B, C, H, W, O, yh, yw, kh, kw, epad, dil, bias, relu, mask, csum)
                            : fprop_launch<256, false>(ctx, x, wr, y, B, C, H, W, O, yh, yw, kh, kw, epad, dil, bias, relu, mask, csum);
   if (O > 64) return tall ? fprop_launch<128, false, 2>(ctx, x, wr, y, B, C, H, W, O, yh, yw, kh, kw, epad, dil, bias, relu, mask, csum)

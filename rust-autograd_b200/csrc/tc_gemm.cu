@@ -34,6 +34,7 @@ template <int TN_, bool P_MN_, bool Q_MN_, bool SPLIT_> struct GemmPol {
     return Tile{(int)blk.x * TC_LANES, (int)blk.y * TN, bz, kb0, max(0, min(p.kb_per_split, kb_total - kb0))};
   }
   __device__ static int num_kblocks(const Params&, const Tile& t) { return t.nkb; }
+  __device__ static uint32_t p_bytes(const Params&, uint32_t full) { return full; }
   __device__ static void prefetch(const Params& p) { tma_prefetch_desc(&p.tmP); tma_prefetch_desc(&p.tmQ); }
   __device__ static void load(const Params& p, const Tile& t, int kb, uint8_t* pP, uint8_t* pQ, uint64_t* bar) {
     const int k0 = (t.kb0 + kb) * TC_BK;

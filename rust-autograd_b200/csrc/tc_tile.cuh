@@ -84,7 +84,7 @@ __global__ void __launch_bounds__(TcCfg<Pol::TN, Pol::SPLIT, Pol::OCC, Pol::MT>:
         const int s = kb % S; const uint32_t ph = (kb / S) & 1;
         mbar_wait(&empty[s], ph ^ 1);
         uint8_t* st = smem + s * Cfg::STAGE_BYTES;
-        mbar_expect_tx(&full[s], Cfg::P_BYTES + Cfg::Q_BYTES);
+        mbar_expect_tx(&full[s], Pol::p_bytes(prm, Cfg::P_BYTES) + Cfg::Q_BYTES);
         Pol::load(prm, tl, kb, st, st + Cfg::P_BYTES, &full[s]);
       }
     }
@@ -257,7 +257,7 @@ tc_tile_persist_kernel(const __grid_constant__ typename Pol::Params prm, const u
         for (int kb = 0; kb < nk; kb++) {
           mbar_wait(&empty[s], ph ^ 1);
           uint8_t* st = smem + s * Cfg::STAGE_BYTES;
-          mbar_expect_tx(&full[s], Cfg::P_BYTES + Cfg::Q_BYTES);
+          mbar_expect_tx(&full[s], Pol::p_bytes(prm, Cfg::P_BYTES) + Cfg::Q_BYTES);
           Pol::load(prm, tl, kb, st, st + Cfg::P_BYTES, &full[s]);
           if (++s == S) { s = 0; ph ^= 1; }
         }

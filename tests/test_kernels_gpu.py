@@ -180,6 +180,11 @@ CONV_CASES = [  # B, C, H, W, O, kh, kw, pad, stride, dil
     (40, 32, 32, 32, 32, 3, 3, 2, 1, 2),    # dilation 2
     (40, 40, 32, 32, 64, 3, 3, 1, 1, 1),    # Cin = 40: three 16-channel blocks, the last one partial
     (38, 64, 16, 64, 128, 3, 3, 1, 1, 1),   # yw = 64
+    # narrow maps on the per-tap kernel: whole rows / several images per 128-lane tile
+    (5, 64, 7, 7, 64, 3, 3, 1, 1, 1),       # 7x7: two images per tile, odd batch
+    (3, 32, 14, 14, 256, 3, 3, 1, 1, 1),    # 14x14: 9 + 5 rows
+    (2, 512, 7, 7, 512, 3, 3, 1, 1, 1),     # ResNet-style deep layer
+    (4, 32, 5, 6, 32, 3, 3, 1, 1, 1),       # 5x6
 ]
 
 
@@ -208,6 +213,7 @@ FUSED_CASES = [  # B, C, H, W, O, kh, kw, pad, dil — stride 1 ("same"-style ba
     (2, 64, 7, 128, 64, 3, 3, 1, 1), (1, 32, 4, 192, 80, 3, 3, 1, 1),      # wide maps: halo-reusing kernel
     (40, 64, 28, 32, 160, 3, 3, 1, 1),                                      # two M-tiles per CTA
     (80, 32, 16, 32, 96, 3, 3, 1, 1), (38, 64, 16, 64, 64, 3, 3, 1, 1),     # narrow maps: column-copies window kernel
+    (5, 32, 7, 7, 64, 3, 3, 1, 1), (3, 64, 14, 14, 48, 3, 3, 1, 1),          # narrow maps on the per-tap kernel (partial tiles in lanes)
 ]
 
 
