@@ -19,6 +19,7 @@ int agb_tc_conv_fprop(agb_ctx* ctx, int mode, const float* x, const float* w, fl
 int agb_tc_conv_wgrad(agb_ctx* ctx, int mode, const float* img, const float* g, float* gw,
                       int B, int C, int H, int W, int O, int kh, int kw, int pad, int stride, int dil);
 bool agb_tc_conv_eligible(int C, int O, int kh, int kw, int stride, int yw);
+bool agb_tc_conv_fprop_eligible(int C, int O, int kh, int kw, int stride, int yw);
 // direct kernels for very small input-channel counts (conv_small_c.cu)
 bool agb_small_c_eligible(int C, int O, int kh, int kw);
 int agb_small_c_fprop(agb_ctx* ctx, const float* x, const float* w, agb_tensor* y, int B, int C, int H, int W, int O, int kh, int kw, int yh, int yw, int pad, int stride, int dil, const float* bias, int relu);
@@ -157,7 +158,7 @@ extern "C" int agb_conv2d_fprop_fused_f32(agb_ctx* ctx, const agb_tensor* x, con
             "conv2d: output must be [%d,%d,%d,%d]", g.B, g.O, g.yh, g.yw);
   if (agb_numel(y) == 0) return AGB_OK;
   AgbProfScope prof(ctx, AGB_PROF_CONV_FPROP, 2.0 * (double)agb_numel(y) * g.C * g.kh * g.kw);
-  if (ctx->math_mode != AGB_MATH_FP32 && agb_tc_conv_eligible(g.C, g.O, g.kh, g.kw, stride, g.yw)) {
+  if (ctx->math_mode != AGB_MATH_FP32 && agb_tc_conv_fprop_eligible(g.C, g.O, g.kh, g.kw, stride, g.yw)) {
     LayoutTmp lx(ctx), ly(ctx);
     AGB_TRY(lx.input(x, true)); AGB_TRY(ly.output(y, true));
     int r = agb_tc_conv_fprop(ctx, ctx->math_mode, lx.view.ptr, w->ptr, ly.view.ptr, g.B, g.C, g.H, g.W, g.O, g.kh, g.kw, pad, stride, dilation, 0, bias, relu, nullptr, nullptr, nullptr, nullptr);
@@ -330,7 +331,7 @@ extern "C" int agb_conv2d_wgrad_f32(agb_ctx* ctx, const agb_tensor* img, const a
 }
 
 extern "C" int agb_conv_prefers_channels_last(int in_channels, int out_channels, int kh, int kw, int stride, int out_w) {
-  if (agb_tc_conv_eligible(in_channels, out_channels, kh, kw, stride, out_w)) return 1;
+  if (agb_tc_conv_fprop_eligible(in_channels, out_channels, kh, kw, stride, out_w)) return 1;
   return (agb_small_c_eligible(in_channels, out_channels, kh, kw) && out_channels >= 32 && out_channels % 4 == 0 && out_w >= 16) ? 1 : 0;
 }
 

@@ -24,11 +24,12 @@ static inline PFN_encodeTiled agb_get_encode() {
 // swizzle_atom32: false -> SWIZZLE_128B (16-byte chunks; K-major operands), true -> SWIZZLE_128B_ATOM_32B (32-byte chunks;
 // the only shared-memory layout tcgen05 accepts for MN-major TF32 operands, UMMA layout type 128B_BASE32B).
 static inline int agb_make_tmap(CUtensorMap* m, const void* base, int rank, const uint64_t* dims, const uint64_t* strides_bytes,
-                                const uint32_t* box, bool swizzle_atom32 = false) {
+                                const uint32_t* box, bool swizzle_atom32 = false, const uint32_t* elem_strides = nullptr) {
   PFN_encodeTiled enc = agb_get_encode();
   AGB_CHECK(enc, AGB_ERR_CUDA, "cuTensorMapEncodeTiled is not available from the driver");
   cuuint64_t d[5], s[4]; cuuint32_t b[5], e[5];
-  for (int i = 0; i < rank; i++) { d[i] = dims[i]; b[i] = box[i]; e[i] = 1; }
+  // elem_strides: traversal stride per dimension — a box of boxDim elements delivers every stride-th one (strided convolutions)
+  for (int i = 0; i < rank; i++) { d[i] = dims[i]; b[i] = box[i]; e[i] = elem_strides ? elem_strides[i] : 1; }
   for (int i = 0; i + 1 < rank; i++) s[i] = strides_bytes[i];
   CUresult r = enc(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, (cuuint32_t)rank, const_cast<void*>(base), d, s, b, e,
                    CU_TENSOR_MAP_INTERLEAVE_NONE, swizzle_atom32 ? CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B : CU_TENSOR_MAP_SWIZZLE_128B,

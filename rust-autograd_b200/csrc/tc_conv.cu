@@ -42,7 +42,7 @@ template <int TN_, bool SPLIT_, int MT_ = 1> struct ConvFpropPol {
   // The 128 lanes of an M-tile are a {bw w, bh h, bb images} pixel box (TMA writes box elements in exactly that order): 32x4x1 for
   // maps at least 32 wide; narrow maps take whole rows and, when a whole image is smaller than the tile, several images
   // (14x14 -> 14x9x1, 7x7 -> 7x7x2).  Lanes past bw*bh*bb read stale shared memory and are never stored.
-  struct Params { CUtensorMap tmX, tmW; float* y; const float* bias; const float* mask; float* csum; int relu; int B, Cout, yh, yw, kw, pad, dil, tiles_x, tiles_y, cblocks, taps;
+  struct Params { CUtensorMap tmX, tmW; float* y; const float* bias; const float* mask; float* csum; int relu; int B, Cout, yh, yw, kw, pad, dil, stride, tiles_x, tiles_y, cblocks, taps;
                   int bw, bh, bb; uint32_t p_bytes; MnDescCfg mnc; };
   struct Tile { int b, oy0, ox0, o0; };
   __device__ static Tile tile(const Params& p, uint3 blk) {
@@ -60,8 +60,8 @@ template <int TN_, bool SPLIT_, int MT_ = 1> struct ConvFpropPol {
   __device__ static void prefetch(const Params& p) { tma_prefetch_desc(&p.tmX); tma_prefetch_desc(&p.tmW); }
   __device__ static void load(const Params& p, const Tile& t, int kb, uint8_t* pP, uint8_t* pQ, uint64_t* bar) {
     const int tap = kb / p.cblocks, cb = kb - tap * p.cblocks; const int i = tap / p.kw, j = tap - i * p.kw;
-    tma_load_4d(pP, &p.tmX, bar, cb * 32, t.ox0 + j * p.dil - p.pad, t.oy0 + i * p.dil - p.pad, t.b);     // dims {c, w, h, b}
-    tma_load_3d(pQ, &p.tmW, bar, cb * 32, t.o0, tap);
+    tma_load_4d(pP, &p.tmX, bar, cb * 32, t.ox0 * p.stride + j * p.dil - p.pad, t.oy0 * p.stride + i * p.dil - p.pad, t.b);     // dims {c, w, h, b}; a strided
+    tma_load_3d(pQ, &p.tmW, bar, cb * 32, t.o0, tap);                                                                             // conv walks the box with element stride s
   }
   // dgrad + ReLU backward of the layer below: bit j of pre[c] = (mask_src[pixel, o0 + 32c + j] > 0).  Read while the MMAs run, so the
   // strided (one pixel per thread) loads cost no epilogue latency; default-cached so both halves of a 32-byte sector are used.
@@ -203,6 +203,7 @@ template <int TN_, bool SPLIT_, bool PAIR_, int MT_ = 1> struct ConvWgradPol {
 // ------------------------------------------------------------------------------------------------ host side
 int agb_tc_conv_rows(agb_ctx* ctx, const float* x, const float* wr, float* y, int B, int Cin, int H, int W, int Cout, int yh, int yw, int kh, int kw,
                      int pad, int dil, const float* bias, int relu, const float* mask, float* csum, float* pool_y, int* pool_idx);
+bool agb_tc_conv_eligible(int C, int O, int kh, int kw, int stride, int yw);
 int agb_tc_conv_cols(agb_ctx* ctx, const float* x, const float* wr, float* y, int B, int Cin, int H, int W, int Cout, int yh, int yw, int kh, int kw,
                      int pad, int dil, const float* bias, int relu, const float* mask, float* csum);
 int agb_tc_conv_wgrad_taps(agb_ctx* ctx, const float* img, const float* g, float* gw, int B, int C, int H, int W, int O, int yh, int yw,
@@ -215,13 +216,16 @@ static int make_cl_map(CUtensorMap* m, const float* p, int B, int C, int H, int 
   return agb_make_tmap(m, p, 4, dims, str, box, atom32);
 }
 
+bool agb_tc_conv_fprop_eligible(int C, int O, int kh, int kw, int stride, int yw) {       // forward: strides 1..4
+  return stride >= 1 && stride <= 4 && agb_tc_conv_eligible(C, O, kh, kw, 1, yw);
+}
 bool agb_tc_conv_eligible(int C, int O, int kh, int kw, int stride, int yw) {
   return stride == 1 && kh == kw && C >= 32 && C % 4 == 0 && O >= 32 && O % 4 == 0 && yw >= 4;       // narrow maps: see ConvFpropPol::Params (whole rows / several images per tile)
 }
 
 template <int TN, bool SPLIT, int MT = 1>
 static int fprop_launch(agb_ctx* ctx, const float* x, const float* wr, float* y, int B, int Cin, int H, int W, int Cout, int yh, int yw, int kh, int kw,
-                        int pad, int dil, const float* bias, int relu, const float* mask, float* csum) {
+                        int pad, int dil, const float* bias, int relu, const float* mask, float* csum, int stride = 1) {
   using Pol = ConvFpropPol<TN, SPLIT, MT>;
   typename Pol::Params p;
   int bw = 32, bh = 4, bb = 1;
@@ -230,10 +234,12 @@ static int fprop_launch(agb_ctx* ctx, const float* x, const float* wr, float* y,
   {
     uint64_t dims[4] = {(uint64_t)Cin, (uint64_t)W, (uint64_t)H, (uint64_t)B};
     uint64_t str[3] = {(uint64_t)Cin * 4, (uint64_t)W * Cin * 4, (uint64_t)H * W * Cin * 4};
-    uint32_t box[4] = {32, (uint32_t)bw, (uint32_t)(bh * MT), (uint32_t)bb};
-    AGB_TRY(agb_make_tmap(&p.tmX, x, 4, dims, str, box, false));
+    const uint32_t su = (uint32_t)stride;
+    uint32_t box[4] = {32, (uint32_t)(bw - 1) * su + 1, (uint32_t)(bh * MT - 1) * su + 1, (uint32_t)bb}, es[4] = {1, su, su, 1};
+    if (box[1] > 256 || box[2] > 256) return AGB_ERR_UNSUPPORTED;
+    AGB_TRY(agb_make_tmap(&p.tmX, x, 4, dims, str, box, false, stride > 1 ? es : nullptr));
   }
-  p.bw = bw; p.bh = bh; p.bb = bb; p.B = B; p.p_bytes = (uint32_t)(128 * bw * bh * MT * bb);
+  p.stride = stride; p.bw = bw; p.bh = bh; p.bb = bb; p.B = B; p.p_bytes = (uint32_t)(128 * bw * bh * MT * bb);
   {  // wr[tap][o][c]
     uint64_t dims[3] = {(uint64_t)Cin, (uint64_t)Cout, (uint64_t)(kh * kw)};
     uint64_t str[2] = {(uint64_t)Cin * 4, (uint64_t)Cin * Cout * 4};
@@ -254,8 +260,9 @@ int agb_tc_conv_fprop(agb_ctx* ctx, int mode, const float* x, const float* w, fl
                       int pad, int stride, int dil, int flip_transpose, const float* bias, int relu, const float* mask, float* csum, float* pool_y, int* pool_idx) {
   const int epad = flip_transpose ? dil * (kh - 1) - pad : pad;
   if (epad < 0) return AGB_ERR_UNSUPPORTED;
-  const int yh = H + 2 * epad - (dil * (kh - 1) + 1) + 1, yw = W + 2 * epad - (dil * (kw - 1) + 1) + 1;
-  if (yh < 1 || yw < 1 || !agb_tc_conv_eligible(C, O, kh, kw, stride, yw)) return AGB_ERR_UNSUPPORTED;
+  const int yh = (H + 2 * epad - (dil * (kh - 1) + 1)) / stride + 1, yw = (W + 2 * epad - (dil * (kw - 1) + 1)) / stride + 1;
+  // strided convolutions: forward only (the tile's TMA box walks the input with element stride s); dgrad of a strided conv is not a conv
+  if (yh < 1 || yw < 1 || stride < 1 || stride > 4 || (stride > 1 && flip_transpose) || !agb_tc_conv_eligible(C, O, kh, kw, 1, yw)) return AGB_ERR_UNSUPPORTED;
   if ((((uintptr_t)x | (uintptr_t)y) & 15) != 0) return AGB_ERR_UNSUPPORTED;
   const int T = kh * kw;
   float* wr = nullptr;
@@ -268,8 +275,8 @@ int agb_tc_conv_fprop(agb_ctx* ctx, int mode, const float* x, const float* w, fl
     AGB_LAUNCHED(ctx);
   }
   const bool split = mode == AGB_MATH_3XTF32;
-  if (split && pool_y != nullptr) return AGB_ERR_UNSUPPORTED;
-  if (!split) {       // wide feature maps: persistent halo-reusing kernel (tc_conv_rows.cu), 3x less L2 -> smem traffic
+  if ((split || stride > 1) && pool_y != nullptr) return AGB_ERR_UNSUPPORTED;
+  if (!split && stride == 1) {       // wide feature maps: persistent halo-reusing kernel (tc_conv_rows.cu), 3x less L2 -> smem traffic
     int r = agb_tc_conv_rows(ctx, x, wr, y, B, C, H, W, O, yh, yw, kh, kw, epad, dil, bias, relu, mask, csum, pool_y, pool_idx);
     if (r != AGB_ERR_UNSUPPORTED) return r;
     if (pool_y != nullptr) return AGB_ERR_UNSUPPORTED;          // the fused pooling epilogue exists in the wide-map kernel only
@@ -277,17 +284,17 @@ int agb_tc_conv_fprop(agb_ctx* ctx, int mode, const float* x, const float* w, fl
     if (r != AGB_ERR_UNSUPPORTED) return r;
   }
   if (split) {
-    if (O > 64) return fprop_launch<128, true>(ctx, x, wr, y, B, C, H, W, O, yh, yw, kh, kw, epad, dil, bias, relu, mask, csum);
-    return fprop_launch<64, true>(ctx, x, wr, y, B, C, H, W, O, yh, yw, kh, kw, epad, dil, bias, relu, mask, csum);
+    if (O > 64) return fprop_launch<128, true>(ctx, x, wr, y, B, C, H, W, O, yh, yw, kh, kw, epad, dil, bias, relu, mask, csum, stride);
+    return fprop_launch<64, true>(ctx, x, wr, y, B, C, H, W, O, yh, yw, kh, kw, epad, dil, bias, relu, mask, csum, stride);
   }
   static int m2 = -1;     // two M-tiles per CTA: measured slower than one (3-stage ring, doubled epilogue) — kept as an opt-in experiment
   if (m2 < 0) { const char* e = getenv("AGB_CONV_M2"); m2 = (e && e[0] == '1') ? 1 : 0; }
-  const bool tall = m2 && yh >= 8 && yw >= 32 && (int64_t)B * ((yh + 7) / 8) * ((yw + 31) / 32) >= ctx->sm_count;       // enough 8-row patches to fill the machine
+  const bool tall = m2 && stride == 1 && yh >= 8 && yw >= 32 && (int64_t)B * ((yh + 7) / 8) * ((yw + 31) / 32) >= ctx->sm_count;       // enough 8-row patches to fill the machine
   if (O > 128) return tall ? fprop_launch<256, false, 2>(ctx, x, wr, y, B, C, H, W, O, yh, yw, kh, kw, epad, dil, bias, relu, mask, csum)
-                           : fprop_launch<256, false>(ctx, x, wr, y, B, C, H, W, O, yh, yw, kh, kw, epad, dil, bias, relu, mask, csum);
+                           : fprop_launch<256, false>(ctx, x, wr, y, B, C, H, W, O, yh, yw, kh, kw, epad, dil, bias, relu, mask, csum, stride);
   if (O > 64) return tall ? fprop_launch<128, false, 2>(ctx, x, wr, y, B, C, H, W, O, yh, yw, kh, kw, epad, dil, bias, relu, mask, csum)
-                          : fprop_launch<128, false>(ctx, x, wr, y, B, C, H, W, O, yh, yw, kh, kw, epad, dil, bias, relu, mask, csum);
-  return fprop_launch<64, false>(ctx, x, wr, y, B, C, H, W, O, yh, yw, kh, kw, epad, dil, bias, relu, mask, csum);
+                          : fprop_launch<128, false>(ctx, x, wr, y, B, C, H, W, O, yh, yw, kh, kw, epad, dil, bias, relu, mask, csum, stride);
+  return fprop_launch<64, false>(ctx, x, wr, y, B, C, H, W, O, yh, yw, kh, kw, epad, dil, bias, relu, mask, csum, stride);
 }
 
 template <int TN, bool SPLIT, bool PAIR, int MT = 1>

@@ -185,6 +185,12 @@ CONV_CASES = [  # B, C, H, W, O, kh, kw, pad, stride, dil
     (3, 32, 14, 14, 256, 3, 3, 1, 1, 1),    # 14x14: 9 + 5 rows
     (2, 512, 7, 7, 512, 3, 3, 1, 1, 1),     # ResNet-style deep layer
     (4, 32, 5, 6, 32, 3, 3, 1, 1, 1),       # 5x6
+    # strided convolutions: tensor-core forward (TMA boxes with element stride), CUDA-core dgrad / wgrad
+    (2, 32, 33, 33, 64, 3, 3, 1, 2, 1),
+    (2, 64, 56, 56, 128, 3, 3, 1, 2, 1),    # ResNet stage transition
+    (3, 32, 17, 20, 32, 3, 3, 0, 2, 1),
+    (2, 32, 40, 40, 32, 3, 3, 1, 3, 1),     # stride 3
+    (2, 64, 14, 14, 64, 1, 1, 0, 2, 1),     # 1x1 stride-2 projection
 ]
 
 
