@@ -304,7 +304,7 @@ extern "C" int agb_conv2d_wgrad_f32(agb_ctx* ctx, const agb_tensor* img, const a
   AGB_CHECK(agb_is_contig(gw), AGB_ERR_UNSUPPORTED, "conv2d_filter_grad: the filter gradient must be C-contiguous");
   if (agb_numel(gw) == 0) return AGB_OK;
   AgbProfScope prof(ctx, AGB_PROF_CONV_WGRAD, 2.0 * (double)agb_numel(gr) * g.C * g.kh * g.kw);
-  if (ctx->math_mode != AGB_MATH_FP32 && agb_tc_conv_eligible(g.C, g.O, g.kh, g.kw, stride, g.yw)) {
+  if (ctx->math_mode != AGB_MATH_FP32 && agb_tc_conv_fprop_eligible(g.C, g.O, g.kh, g.kw, stride, g.yw)) {       // strides 1..4
     LayoutTmp li(ctx), lg(ctx);
     AGB_TRY(li.input(img, true)); AGB_TRY(lg.input(gr, true));
     int r = agb_tc_conv_wgrad(ctx, ctx->math_mode, li.view.ptr, lg.view.ptr, gw->ptr, g.B, g.C, g.H, g.W, g.O, g.kh, g.kw, pad, stride, dilation);

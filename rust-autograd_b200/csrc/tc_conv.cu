@@ -147,7 +147,7 @@ template <int TN_, bool SPLIT_, bool PAIR_, int MT_ = 1> struct ConvWgradPol {
   static constexpr int TN = TN_, MT = MT_; static constexpr bool SPLIT = SPLIT_, P_MN = true, Q_MN = true;
   static constexpr int OCC = (SPLIT_ || TN_ > 128 || MT_ > 1) ? 1 : 2;
   static_assert(!(PAIR_ && MT_ > 1), "tap pairing within one M-tile and two M-tiles are alternatives");
-  struct Params { CUtensorMap tmX, tmG; float* gw; int C, O, T, kw, pad, dil, yh, xblocks, kb_total, kb_per_split; MnDescCfg mnc; };
+  struct Params { CUtensorMap tmX, tmG; float* gw; int C, O, T, kw, pad, dil, stride, yh, xblocks, kb_total, kb_per_split; MnDescCfg mnc; };
   struct Tile { int c0, tapA, tapB, o0, q0, q1, c1; };       // MT == 2: unit 0 = (tapA, c0), unit 1 = (tapB, c1)
   __device__ static Tile tile(const Params& p, uint3 blk) {
     Tile t; t.o0 = (int)blk.y * TN; t.c1 = 0;
@@ -167,10 +167,10 @@ template <int TN_, bool SPLIT_, bool PAIR_, int MT_ = 1> struct ConvWgradPol {
     const int q = t.q0 + kb; const int xb = q % p.xblocks; const int r = q / p.xblocks; const int oy = r % p.yh, b = r / p.yh;
     const int ox0 = xb * 32;
     const int iA = t.tapA / p.kw, jA = t.tapA - iA * p.kw;
-    const int xA = ox0 + jA * p.dil - p.pad, yA = oy + iA * p.dil - p.pad;
+    const int xA = ox0 * p.stride + jA * p.dil - p.pad, yA = oy * p.stride + iA * p.dil - p.pad;       // strided conv: the x box walks w with element stride s
     if (PAIR_) {      // lanes 0-63: channels 0..63 at tap A, lanes 64-127: channels 0..63 at tap B
       int xB = xA, yB = yA, cB = p.C + 64;                                   // tap B absent (odd tap count): fully out of bounds = zero rows
-      if (t.tapB < p.T) { const int iB = t.tapB / p.kw, jB = t.tapB - iB * p.kw; xB = ox0 + jB * p.dil - p.pad; yB = oy + iB * p.dil - p.pad; cB = 0; }
+      if (t.tapB < p.T) { const int iB = t.tapB / p.kw, jB = t.tapB - iB * p.kw; xB = ox0 * p.stride + jB * p.dil - p.pad; yB = oy * p.stride + iB * p.dil - p.pad; cB = 0; }
       tma_load_4d(pP, &p.tmX, bar, 0, xA, yA, b);
       tma_load_4d(pP + 4096, &p.tmX, bar, 32, xA, yA, b);
       tma_load_4d(pP + 8192, &p.tmX, bar, cB, xB, yB, b);
@@ -180,7 +180,7 @@ template <int TN_, bool SPLIT_, bool PAIR_, int MT_ = 1> struct ConvWgradPol {
       for (int g = 0; g < 4; g++) tma_load_4d(pP + g * 4096, &p.tmX, bar, t.c0 + 32 * g, xA, yA, b);
       if (MT == 2) {
         int xB = xA, yB = yA, cB = p.C + 128;                                // absent unit: fully out of bounds = zero rows
-        if (t.tapB < p.T) { const int iB = t.tapB / p.kw, jB = t.tapB - iB * p.kw; xB = ox0 + jB * p.dil - p.pad; yB = oy + iB * p.dil - p.pad; cB = t.c1; }
+        if (t.tapB < p.T) { const int iB = t.tapB / p.kw, jB = t.tapB - iB * p.kw; xB = ox0 * p.stride + jB * p.dil - p.pad; yB = oy * p.stride + iB * p.dil - p.pad; cB = t.c1; }
 #pragma unroll
         for (int g = 0; g < 4; g++) tma_load_4d(pP + 16384 + g * 4096, &p.tmX, bar, cB + 32 * g, xB, yB, b);
       }
@@ -298,10 +298,17 @@ int agb_tc_conv_fprop(agb_ctx* ctx, int mode, const float* x, const float* w, fl
 }
 
 template <int TN, bool SPLIT, bool PAIR, int MT = 1>
-static int wgrad_launch(agb_ctx* ctx, const float* img, const float* g, float* gw, int B, int C, int H, int W, int O, int yh, int yw, int kh, int kw, int pad, int dil) {
+static int wgrad_launch(agb_ctx* ctx, const float* img, const float* g, float* gw, int B, int C, int H, int W, int O, int yh, int yw, int kh, int kw, int pad, int dil, int stride = 1) {
   using Pol = ConvWgradPol<TN, SPLIT, PAIR, MT>;
   typename Pol::Params p;
-  AGB_TRY(make_cl_map(&p.tmX, img, B, C, H, W, 32, 32, 1, true));
+  {
+    uint64_t dims[4] = {(uint64_t)C, (uint64_t)W, (uint64_t)H, (uint64_t)B};
+    uint64_t str[3] = {(uint64_t)C * 4, (uint64_t)W * C * 4, (uint64_t)H * W * C * 4};
+    const uint32_t su = (uint32_t)stride;
+    uint32_t box[4] = {32, 31 * su + 1, 1, 1}, es[4] = {1, su, 1, 1};
+    AGB_TRY(agb_make_tmap(&p.tmX, img, 4, dims, str, box, true, stride > 1 ? es : nullptr));
+  }
+  p.stride = stride;
   AGB_TRY(make_cl_map(&p.tmG, g, B, O, yh, yw, 32, 32, 1, true));
   const int T = kh * kw;
   p.gw = gw; p.C = C; p.O = O; p.T = T; p.kw = kw; p.pad = pad; p.dil = dil; p.yh = yh; p.xblocks = (yw + 31) / 32;
@@ -323,23 +330,23 @@ static int wgrad_launch(agb_ctx* ctx, const float* img, const float* g, float* g
 // wgrad on channels-last buffers: img [B,H,W,C] (the im2col'd operand), g [B,yh,yw,O] -> gw [O,C,kh,kw] (plain)
 int agb_tc_conv_wgrad(agb_ctx* ctx, int mode, const float* img, const float* g, float* gw, int B, int C, int H, int W, int O, int kh, int kw,
                       int pad, int stride, int dil) {
-  const int yh = H + 2 * pad - (dil * (kh - 1) + 1) + 1, yw = W + 2 * pad - (dil * (kw - 1) + 1) + 1;
-  if (yh < 1 || yw < 1 || !agb_tc_conv_eligible(C, O, kh, kw, stride, yw)) return AGB_ERR_UNSUPPORTED;
+  const int yh = (H + 2 * pad - (dil * (kh - 1) + 1)) / stride + 1, yw = (W + 2 * pad - (dil * (kw - 1) + 1)) / stride + 1;
+  if (yh < 1 || yw < 1 || !agb_tc_conv_fprop_eligible(C, O, kh, kw, stride, yw)) return AGB_ERR_UNSUPPORTED;
   if ((((uintptr_t)img | (uintptr_t)g) & 15) != 0) return AGB_ERR_UNSUPPORTED;
   const bool split = mode == AGB_MATH_3XTF32;
-  if (!split) {       // narrow layers: all taps per CTA from one haloed window (tc_conv_wgrad_taps.cu)
+  if (!split && stride == 1) {       // narrow layers: all taps per CTA from one haloed window (tc_conv_wgrad_taps.cu)
     int r = agb_tc_conv_wgrad_taps(ctx, img, g, gw, B, C, H, W, O, yh, yw, kh, kw, pad, dil);
     if (r != AGB_ERR_UNSUPPORTED) return r;
   }
   const bool pair = C <= 64;
-#define WG(TN_, SP_) (pair ? wgrad_launch<TN_, SP_, true>(ctx, img, g, gw, B, C, H, W, O, yh, yw, kh, kw, pad, dil) \
-                           : wgrad_launch<TN_, SP_, false>(ctx, img, g, gw, B, C, H, W, O, yh, yw, kh, kw, pad, dil))
+#define WG(TN_, SP_) (pair ? wgrad_launch<TN_, SP_, true>(ctx, img, g, gw, B, C, H, W, O, yh, yw, kh, kw, pad, dil, stride) \
+                           : wgrad_launch<TN_, SP_, false>(ctx, img, g, gw, B, C, H, W, O, yh, yw, kh, kw, pad, dil, stride))
   if (split) { if (O > 64) return WG(128, true); return WG(64, true); }
   static int m2 = -1;
   if (m2 < 0) { const char* e = getenv("AGB_WGRAD_M2"); m2 = (e && e[0] == '0') ? 0 : 1; }
   // measured (B200, B = 256): C256/O256 0.66 -> 0.54 ms, C128/O256 0.37 -> 0.32 ms; with TN = 128 the one-M-tile kernel at two CTAs
   // per SM is faster (0.57 vs 0.78 ms), so only the 256-wide tiles pair up
-  if (m2 && !pair && O > 128) return wgrad_launch<256, false, false, 2>(ctx, img, g, gw, B, C, H, W, O, yh, yw, kh, kw, pad, dil);
+  if (m2 && !pair && O > 128) return wgrad_launch<256, false, false, 2>(ctx, img, g, gw, B, C, H, W, O, yh, yw, kh, kw, pad, dil, stride);
   if (O > 128) return WG(256, false);
   if (O > 64) return WG(128, false);
   return WG(64, false);

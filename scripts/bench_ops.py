@@ -87,6 +87,19 @@ def main():
             row("conv2d_transpose_" + tag, timeit(dev, lambda: ffi.check(lib.agb_conv2d_dgrad_f32(dev.ctx, gy.desc(), w.desc(), gx.desc(), 1, 1, 1)), iters=5, flush=False), flops=fl)
             row("conv2d_filter_grad_" + tag, timeit(dev, lambda: ffi.check(lib.agb_conv2d_wgrad_f32(dev.ctx, x.desc(), gy.desc(), gw.desc(), 1, 1, 1)), iters=5, flush=False), flops=fl)
             x = gy = y = gx = None
+    # stride-2 stage transitions (ResNet-shaped): forward and filter gradient on the tensor cores, dgrad on the CUDA cores
+    dev.set_math_mode(1)
+    for (B, Cc, H, O) in ((32, 64, 56, 128), (32, 128, 28, 256), (32, 256, 14, 512)):
+        Ho = (H + 2 - 3) // 2 + 1
+        x, gy = cl(dev, (B, Cc, H, H)), cl(dev, (B, O, Ho, Ho))
+        y, gx = cl(dev, (B, O, Ho, Ho)), cl(dev, (B, Cc, H, H))
+        w, gw = dev.fill((O, Cc, 3, 3), 0.01), dev.empty((O, Cc, 3, 3))
+        fl = 2.0 * B * O * Ho * Ho * Cc * 9
+        tag = "tf32_s2_B%d_C%d_H%d_O%d" % (B, Cc, H, O)
+        row("conv2d_fprop_" + tag, timeit(dev, lambda: ffi.check(lib.agb_conv2d_fprop_f32(dev.ctx, x.desc(), w.desc(), y.desc(), 1, 2, 1)), iters=5, flush=False), flops=fl)
+        row("conv2d_transpose_" + tag, timeit(dev, lambda: ffi.check(lib.agb_conv2d_dgrad_f32(dev.ctx, gy.desc(), w.desc(), gx.desc(), 1, 2, 1)), iters=5, flush=False), flops=fl)
+        row("conv2d_filter_grad_" + tag, timeit(dev, lambda: ffi.check(lib.agb_conv2d_wgrad_f32(dev.ctx, x.desc(), gy.desc(), gw.desc(), 1, 2, 1)), iters=5, flush=False), flops=fl)
+        x = gy = y = gx = None
     # first layer (C = 3, warp-MMA kernels), max-pool forward / gather-form backward with the ReLU gate, long softmax rows
     for mode, nm in ((1, "tf32"), (0, "3xtf32"), (2, "fp32")):
         dev.set_math_mode(mode)
