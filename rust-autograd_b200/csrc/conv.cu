@@ -16,6 +16,8 @@
 // tcgen05 kernels (tc_conv.cu): operate on channels-last activation buffers
 int agb_tc_conv_fprop(agb_ctx* ctx, int mode, const float* x, const float* w, float* y,
                       int B, int C, int H, int W, int O, int kh, int kw, int pad, int stride, int dil, int flip_transpose, const float* bias, int relu, const float* mask, float* csum, float* pool_y, int* pool_idx);
+int agb_tc_conv_dgrad_strided(agb_ctx* ctx, int mode, const float* gy, const float* w, float* gx, int B, int O, int yh, int yw, int C, int H, int W,
+                              int kh, int kw, int pad, int stride, int dil, const float* mask, float* csum);
 int agb_tc_conv_wgrad(agb_ctx* ctx, int mode, const float* img, const float* g, float* gw,
                       int B, int C, int H, int W, int O, int kh, int kw, int pad, int stride, int dil);
 bool agb_tc_conv_eligible(int C, int O, int kh, int kw, int stride, int yw);
@@ -288,6 +290,22 @@ extern "C" int agb_conv2d_dgrad_fused_f32(agb_ctx* ctx, const agb_tensor* gy, co
     if (r != AGB_ERR_UNSUPPORTED) return r;
   }
   prof.set_cls(AGB_PROF_CONV_SIMT);
+  if (ctx->math_mode == AGB_MATH_TF32 && stride > 1) {       // strided dgrad: s*s unit-stride phase convolutions on the tensor cores
+    LayoutTmp lg(ctx), lx(ctx);
+    AGB_TRY(lg.input(gy, true)); AGB_TRY(lx.output(gx, true));
+    const bool in_place = lx.view.ptr == gx->ptr;
+    const bool fuse = same_strides && in_place && ((((uintptr_t)mask_src->ptr) & 15) == 0);
+    const bool fuse_sum = chan_sum != nullptr && in_place && (mask_src == nullptr || fuse);
+    if (fuse_sum) AGB_TRY(agb_memset0(ctx, chan_sum, (size_t)g.C * sizeof(float)));
+    int r = agb_tc_conv_dgrad_strided(ctx, ctx->math_mode, lg.view.ptr, w->ptr, lx.view.ptr, g.B, g.O, g.yh, g.yw, g.C, g.H, g.W, g.kh, g.kw, pad, stride, dilation,
+                                      fuse ? mask_src->ptr : nullptr, fuse_sum ? chan_sum : nullptr);
+    if (r == AGB_OK) {
+      AGB_TRY(lx.finish()); AGB_TRY(lg.finish());
+      if (!fuse) AGB_TRY(apply_relu_mask(ctx, mask_src, gx));
+      return (chan_sum != nullptr && !fuse_sum) ? channel_sums(ctx, gx, chan_sum) : AGB_OK;
+    }
+    if (r != AGB_ERR_UNSUPPORTED) return r;
+  }
   LayoutTmp lg(ctx), lx(ctx);
   AGB_TRY(lg.input(gy, false)); AGB_TRY(lx.output(gx, false));
   int64_t K = (int64_t)g.O * g.kh * g.kw;

@@ -20,6 +20,7 @@
 //   (channels contiguous): [32 px][32 ch] TMA boxes {32 c, 32 w, 1, 1} (128B_BASE32B swizzle).  With C == 64 two taps share
 //   the 128 lanes.  Split-K over (b, oy) across CTAs, fp32 `red.global.add` into the zeroed gw.
 #include "tc_tile.cuh"
+#include <vector>
 
 // ------------------------------------------------------------------------------------------------ filter repack
 // mode 0 (fprop): wr[t][o][c] = w[o][c][t];  mode 1 (dgrad): wr[T-1-t][c][o] = w[o][c][t]   (rows = output channel of the GEMM)
@@ -34,6 +35,7 @@ __global__ void __launch_bounds__(256) repack_filter_kernel(const float* __restr
 }
 
 // ------------------------------------------------------------------------------------------------ fprop / dgrad policy
+#define AGB_CONV_MAX_TAPS 64
 // MT_ = 2: the CTA owns an 8x32 pixel patch = two 128-lane M-tiles (rows 0-3 / 4-7, ONE {32 c, 32 w, 8 h} box per k-block) that
 // share every filter tile: 1.33x (TN 128) / 1.5x (TN 256) fewer bytes through L2 -> smem per output, the bound of these kernels.
 template <int TN_, bool SPLIT_, int MT_ = 1> struct ConvFpropPol {
@@ -42,14 +44,22 @@ template <int TN_, bool SPLIT_, int MT_ = 1> struct ConvFpropPol {
   // The 128 lanes of an M-tile are a {bw w, bh h, bb images} pixel box (TMA writes box elements in exactly that order): 32x4x1 for
   // maps at least 32 wide; narrow maps take whole rows and, when a whole image is smaller than the tile, several images
   // (14x14 -> 14x9x1, 7x7 -> 7x7x2).  Lanes past bw*bh*bb read stale shared memory and are never stored.
-  struct Params { CUtensorMap tmX, tmW; float* y; const float* bias; const float* mask; float* csum; int relu; int B, Cout, yh, yw, kw, pad, dil, stride, tiles_x, tiles_y, cblocks, taps;
-                  int bw, bh, bb; uint32_t p_bytes; MnDescCfg mnc; };
+  struct Params { CUtensorMap tmX, tmW; float* y; const float* bias; const float* mask; float* csum; int relu; int B, Cout, yh, yw, stride, tiles_x, tiles_y, cblocks, taps;
+                  int bw, bh, bb; uint32_t p_bytes; MnDescCfg mnc;
+                  // tap k of the k-loop: input box origin = tile origin * stride + (dx[k], dy[k]), filter slice wt[k] of the repacked filter
+                  short dy[AGB_CONV_MAX_TAPS], dx[AGB_CONV_MAX_TAPS], wt[AGB_CONV_MAX_TAPS];
+                  // output pixel (oy, ox) of the tile grid lands at (oy * os + oyo, ox * os + oxo) of a [B, YH, YW, Cout] tensor
+                  // (identity for convolutions; the s*s phases of a strided dgrad write interleaved sub-grids)
+                  int os, oyo, oxo, YH, YW; };
   struct Tile { int b, oy0, ox0, o0; };
   __device__ static Tile tile(const Params& p, uint3 blk) {
     int bx = (int)blk.x; int tx = bx % p.tiles_x; int r = bx / p.tiles_x; int ty = r % p.tiles_y;
     return Tile{(r / p.tiles_y) * p.bb, ty * p.bh * MT, tx * p.bw, (int)blk.y * TN};
   }
   __device__ static uint32_t p_bytes(const Params& p, uint32_t) { return p.p_bytes; }
+  __device__ static int64_t out_offset(const Params& p, int b, int oy, int ox) {
+    return (((int64_t)b * p.YH + (oy * p.os + p.oyo)) * p.YW + (ox * p.os + p.oxo)) * p.Cout;
+  }
   // lane -> pixel of M-tile mt
   __device__ static bool pixel(const Params& p, const Tile& t, int mt, int lane, int& b, int& oy, int& ox) {
     const int w = lane % p.bw, q = lane / p.bw, h = q % p.bh, bi = q / p.bh;
@@ -59,9 +69,9 @@ template <int TN_, bool SPLIT_, int MT_ = 1> struct ConvFpropPol {
   __device__ static int num_kblocks(const Params& p, const Tile&) { return p.taps * p.cblocks; }
   __device__ static void prefetch(const Params& p) { tma_prefetch_desc(&p.tmX); tma_prefetch_desc(&p.tmW); }
   __device__ static void load(const Params& p, const Tile& t, int kb, uint8_t* pP, uint8_t* pQ, uint64_t* bar) {
-    const int tap = kb / p.cblocks, cb = kb - tap * p.cblocks; const int i = tap / p.kw, j = tap - i * p.kw;
-    tma_load_4d(pP, &p.tmX, bar, cb * 32, t.ox0 * p.stride + j * p.dil - p.pad, t.oy0 * p.stride + i * p.dil - p.pad, t.b);     // dims {c, w, h, b}; a strided
-    tma_load_3d(pQ, &p.tmW, bar, cb * 32, t.o0, tap);                                                                             // conv walks the box with element stride s
+    const int tap = kb / p.cblocks, cb = kb - tap * p.cblocks;
+    tma_load_4d(pP, &p.tmX, bar, cb * 32, t.ox0 * p.stride + p.dx[tap], t.oy0 * p.stride + p.dy[tap], t.b);     // dims {c, w, h, b}; a strided conv walks
+    tma_load_3d(pQ, &p.tmW, bar, cb * 32, t.o0, p.wt[tap]);                                                      // the box with element stride s
   }
   // dgrad + ReLU backward of the layer below: bit j of pre[c] = (mask_src[pixel, o0 + 32c + j] > 0).  Read while the MMAs run, so the
   // strided (one pixel per thread) loads cost no epilogue latency; default-cached so both halves of a 32-byte sector are used.
@@ -71,7 +81,7 @@ template <int TN_, bool SPLIT_, int MT_ = 1> struct ConvFpropPol {
     for (int mt = 0; mt < MT; mt++) {
       int b, oy, ox;
       const bool in = pixel(p, t, mt, lane, b, oy, ox);
-      const float* m = p.mask + (((int64_t)(in ? b : 0) * p.yh + (in ? oy : 0)) * p.yw + (in ? ox : 0)) * p.Cout + t.o0;
+      const float* m = p.mask + out_offset(p, in ? b : 0, in ? oy : 0, in ? ox : 0) + t.o0;
 #pragma unroll
       for (int c = 0; c < TN / 32; c++) {
         uint32_t bits = 0;
@@ -95,7 +105,7 @@ template <int TN_, bool SPLIT_, int MT_ = 1> struct ConvFpropPol {
     const bool in = pixel(p, t, mt, lane, b, oy, ox);
     if (!in && p.csum == nullptr) return;
     const int o = t.o0 + c0;
-    float* dst = p.y + (((int64_t)(in ? b : 0) * p.yh + (in ? oy : 0)) * p.yw + (in ? ox : 0)) * p.Cout + o;
+    float* dst = p.y + out_offset(p, in ? b : 0, in ? oy : 0, in ? ox : 0) + o;
     // fused epilogue: per-channel bias and ReLU applied to the accumulator registers, so the
     // pre-activation tensors of conv -> add -> relu never travel through HBM
     float r[32];
@@ -223,11 +233,15 @@ bool agb_tc_conv_eligible(int C, int O, int kh, int kw, int stride, int yw) {
   return stride == 1 && kh == kw && C >= 32 && C % 4 == 0 && O >= 32 && O % 4 == 0 && yw >= 4;       // narrow maps: see ConvFpropPol::Params (whole rows / several images per tile)
 }
 
+// strided-dgrad phase: explicit tap list and interleaved output sub-grid (nullptr = an ordinary convolution)
+struct ConvPhase { int ntaps; short dy[AGB_CONV_MAX_TAPS], dx[AGB_CONV_MAX_TAPS], wt[AGB_CONV_MAX_TAPS]; int os, oyo, oxo, YH, YW; };
+
 template <int TN, bool SPLIT, int MT = 1>
 static int fprop_launch(agb_ctx* ctx, const float* x, const float* wr, float* y, int B, int Cin, int H, int W, int Cout, int yh, int yw, int kh, int kw,
-                        int pad, int dil, const float* bias, int relu, const float* mask, float* csum, int stride = 1) {
+                        int pad, int dil, const float* bias, int relu, const float* mask, float* csum, int stride = 1, const ConvPhase* ph = nullptr) {
   using Pol = ConvFpropPol<TN, SPLIT, MT>;
   typename Pol::Params p;
+  if (kh * kw > AGB_CONV_MAX_TAPS) return AGB_ERR_UNSUPPORTED;
   int bw = 32, bh = 4, bb = 1;
   if (yw < 32) { bw = yw; bh = yh < 128 / bw ? yh : 128 / bw; bb = bh == yh ? 128 / (bw * bh) : 1; if (bb > B) bb = B; if (bb < 1) bb = 1; }
   if (MT > 1 && (bw != 32 || bb != 1)) return AGB_ERR_UNSUPPORTED;
@@ -246,8 +260,15 @@ static int fprop_launch(agb_ctx* ctx, const float* x, const float* wr, float* y,
     uint32_t box[3] = {32, (uint32_t)TN, 1};
     AGB_TRY(agb_make_tmap(&p.tmW, wr, 3, dims, str, box, false));
   }
-  p.y = y; p.bias = bias; p.mask = mask; p.csum = csum; p.relu = relu; p.Cout = Cout; p.yh = yh; p.yw = yw; p.kw = kw; p.pad = pad; p.dil = dil;
-  p.tiles_x = (yw + bw - 1) / bw; p.tiles_y = (yh + bh * MT - 1) / (bh * MT); p.cblocks = (Cin + 31) / 32; p.taps = kh * kw; p.mnc = agb_mn_cfg();
+  p.y = y; p.bias = bias; p.mask = mask; p.csum = csum; p.relu = relu; p.Cout = Cout; p.yh = yh; p.yw = yw;
+  p.tiles_x = (yw + bw - 1) / bw; p.tiles_y = (yh + bh * MT - 1) / (bh * MT); p.cblocks = (Cin + 31) / 32; p.mnc = agb_mn_cfg();
+  if (ph == nullptr) {
+    p.taps = kh * kw; p.os = 1; p.oyo = 0; p.oxo = 0; p.YH = yh; p.YW = yw;
+    for (int t = 0; t < p.taps; t++) { p.dy[t] = (short)((t / kw) * dil - pad); p.dx[t] = (short)((t % kw) * dil - pad); p.wt[t] = (short)t; }
+  } else {
+    p.taps = ph->ntaps; p.os = ph->os; p.oyo = ph->oyo; p.oxo = ph->oxo; p.YH = ph->YH; p.YW = ph->YW;
+    for (int t = 0; t < p.taps; t++) { p.dy[t] = ph->dy[t]; p.dx[t] = ph->dx[t]; p.wt[t] = ph->wt[t]; }
+  }
   int64_t nb = (int64_t)p.tiles_x * p.tiles_y * ((B + bb - 1) / bb);
   if (nb > 2147483647ll) return AGB_ERR_UNSUPPORTED;
   dim3 grid((unsigned)nb, (unsigned)((Cout + TN - 1) / TN), 1);
@@ -295,6 +316,53 @@ int agb_tc_conv_fprop(agb_ctx* ctx, int mode, const float* x, const float* w, fl
   if (O > 64) return tall ? fprop_launch<128, false, 2>(ctx, x, wr, y, B, C, H, W, O, yh, yw, kh, kw, epad, dil, bias, relu, mask, csum)
                           : fprop_launch<128, false>(ctx, x, wr, y, B, C, H, W, O, yh, yw, kh, kw, epad, dil, bias, relu, mask, csum, stride);
   return fprop_launch<64, false>(ctx, x, wr, y, B, C, H, W, O, yh, yw, kh, kw, epad, dil, bias, relu, mask, csum, stride);
+}
+
+// Strided dgrad (Conv2DTranspose::compute, conv2d_transpose.rs:89-247, stride s > 1) as s*s unit-stride convolutions over gy:
+//   gx[b, c, s u + py, s v + px] = sum over the taps (i, j) with (py + p - i d) % s == 0 and (px + p - j d) % s == 0 of
+//                                  sum_o gy[b, o, u + (py + p - i d)/s, v + (px + p - j d)/s] * w[o, c, i, j]
+// Each phase (py, px) is one launch of the per-tap tile kernel with its own tap list, writing an interleaved sub-grid of gx
+// (epilogue mask / channel sums address the same sub-grid).  gy [B,yh,yw,O] and gx [B,H,W,C] channels-last, w [O,C,kh,kw] plain.
+int agb_tc_conv_dgrad_strided(agb_ctx* ctx, int mode, const float* gy, const float* w, float* gx, int B, int O, int yh, int yw, int C, int H, int W,
+                              int kh, int kw, int pad, int stride, int dil, const float* mask, float* csum) {
+  const int s = stride, T = kh * kw;
+  if (s < 2 || s > 4 || T > AGB_CONV_MAX_TAPS || mode == AGB_MATH_3XTF32) return AGB_ERR_UNSUPPORTED;
+  if (!agb_tc_conv_eligible(O, C, kh, kw, 1, (W + s - 1) / s) || (((uintptr_t)gy | (uintptr_t)gx) & 15) != 0) return AGB_ERR_UNSUPPORTED;
+  // floor division helper for possibly negative numerators
+  auto fdiv = [](int a, int b) { return a >= 0 ? a / b : -((-a + b - 1) / b); };
+  std::vector<ConvPhase> phases;
+  bool empty_phase = false;
+  for (int py = 0; py < s && py < H; py++)
+    for (int px = 0; px < s && px < W; px++) {
+      ConvPhase ph; ph.ntaps = 0; ph.os = s; ph.oyo = py; ph.oxo = px; ph.YH = H; ph.YW = W;
+      for (int i = 0; i < kh; i++) {
+        if (((py + pad - i * dil) % s + s) % s != 0) continue;
+        for (int j = 0; j < kw; j++) {
+          if (((px + pad - j * dil) % s + s) % s != 0) continue;
+          ph.dy[ph.ntaps] = (short)fdiv(py + pad - i * dil, s); ph.dx[ph.ntaps] = (short)fdiv(px + pad - j * dil, s);
+          ph.wt[ph.ntaps] = (short)(T - 1 - (i * kw + j));            // the dgrad repack stores tap t at slot T-1-t
+          ph.ntaps++;
+        }
+      }
+      if (ph.ntaps == 0) empty_phase = true; else phases.push_back(ph);
+    }
+  float* wr = nullptr;
+  AGB_TRY(agb_scratch(ctx, (size_t)T * O * C * sizeof(float), (void**)&wr));
+  {
+    int64_t n = (int64_t)O * C * T;
+    repack_filter_kernel<<<agb_grid_for(n, 256, ctx->sm_count, 4), 256, 0, ctx->stream>>>(w, wr, O, C, T, 1);      // wr[T-1-t][c][o]
+    AGB_LAUNCHED(ctx);
+  }
+  if (empty_phase) AGB_TRY(agb_memset0(ctx, gx, (size_t)B * H * W * C * sizeof(float)));                              // filter smaller than the stride: untouched pixels are 0
+  for (const ConvPhase& ph : phases) {
+    const int uh = (H - ph.oyo + s - 1) / s, uw = (W - ph.oxo + s - 1) / s;      // size of this phase's sub-grid
+    int r;
+    if (C > 128) r = fprop_launch<256, false>(ctx, gy, wr, gx, B, O, yh, yw, C, uh, uw, kh, kw, 0, dil, nullptr, 0, mask, csum, 1, &ph);
+    else if (C > 64) r = fprop_launch<128, false>(ctx, gy, wr, gx, B, O, yh, yw, C, uh, uw, kh, kw, 0, dil, nullptr, 0, mask, csum, 1, &ph);
+    else r = fprop_launch<64, false>(ctx, gy, wr, gx, B, O, yh, yw, C, uh, uw, kh, kw, 0, dil, nullptr, 0, mask, csum, 1, &ph);
+    if (r != AGB_OK) return r;
+  }
+  return AGB_OK;
 }
 
 template <int TN, bool SPLIT, bool PAIR, int MT = 1>

@@ -92,7 +92,8 @@ def main():
     for (B, Cc, H, O) in ((32, 64, 56, 128), (32, 128, 28, 256), (32, 256, 14, 512)):
         Ho = (H + 2 - 3) // 2 + 1
         x, gy = cl(dev, (B, Cc, H, H)), cl(dev, (B, O, Ho, Ho))
-        y, gx = cl(dev, (B, O, Ho, Ho)), cl(dev, (B, Cc, H, H))
+        Hx = 2 * (Ho - 1) - 2 + 3            # conv2d_transpose output size follows the reference formula (conv2d_transpose.rs:55-56)
+        y, gx = cl(dev, (B, O, Ho, Ho)), cl(dev, (B, Cc, Hx, Hx))
         w, gw = dev.fill((O, Cc, 3, 3), 0.01), dev.empty((O, Cc, 3, 3))
         fl = 2.0 * B * O * Ho * Ho * Cc * 9
         tag = "tf32_s2_B%d_C%d_H%d_O%d" % (B, Cc, H, O)

@@ -254,6 +254,28 @@ def test_conv2d_fused_epilogues_vs_oracle(dev, case, cl, mode):
     assert rel_err(cs2.numpy(), gx2.numpy().astype(np.float64).sum(axis=(0, 2, 3))) <= 1e-5
 
 
+@pytest.mark.parametrize("cl", [False, True])
+@pytest.mark.parametrize("case", [(2, 64, 28, 28, 32, 3, 3, 1, 2, 1), (3, 32, 15, 18, 96, 3, 3, 0, 2, 1), (2, 32, 20, 20, 32, 1, 1, 0, 2, 1), (2, 32, 26, 26, 160, 3, 3, 1, 3, 1)])
+def test_strided_dgrad_phases_with_mask_and_channel_sums(dev, case, cl):
+    """stride-s conv2d_transpose = s*s unit-stride phase convolutions on the tensor cores (TF32 mode), with the ReLU mask and the
+    per-channel sums in the epilogue; a 1x1 stride-2 filter leaves three of four phases empty (zeros)."""
+    dev.set_math_mode(1)
+    B, C, H, W, O, kh, kw, pad, stride, dil = case
+    rng = np.random.default_rng(sum(case))
+    w = (rng.standard_normal((O, C, kh, kw)) * 0.1).astype(np.float32)
+    yh, yw = (H + 2 * pad - (dil * (kh - 1) + 1)) // stride + 1, (W + 2 * pad - (dil * (kw - 1) + 1)) // stride + 1
+    gy = rng.standard_normal((B, O, yh, yw)).astype(np.float32)
+    gx_plain = R.conv2d_transpose(gy, w, pad, stride, dil)
+    mask_src = rng.standard_normal(gx_plain.shape).astype(np.float32)
+    up = dev.upload_channels_last if cl else dev.upload
+    gx, cs = dev.conv2d_transpose(up(gy), dev.upload(w), pad, stride, dil, mask_src=up(mask_src), channels_last=cl, chan_sum=True)
+    gx = gx.numpy()
+    assert gx.shape == gx_plain.shape
+    assert rel_err(gx, gx_plain * (mask_src > 0)) <= TOL[1]
+    assert rel_err(cs.numpy(), gx.astype(np.float64).sum(axis=(0, 2, 3))) <= 1e-5
+    assert rel_err(dev.conv2d_transpose(up(gy), dev.upload(w), pad, stride, dil, channels_last=cl).numpy(), gx_plain) <= TOL[1]
+
+
 @pytest.mark.parametrize("mode", MODES)
 @pytest.mark.parametrize("case", [(2, 1, 28, 28, 32, 3, 3, 1, 1, 1), (2, 3, 32, 32, 64, 3, 3, 1, 1, 1), (3, 3, 17, 13, 48, 3, 3, 1, 2, 1), (2, 2, 11, 11, 24, 3, 3, 2, 1, 2),
                                   (1, 4, 9, 9, 8, 2, 2, 0, 1, 1), (2, 3, 20, 20, 200, 3, 3, 1, 1, 1), (5, 1, 6, 6, 10, 5, 5, 2, 1, 1)])
