@@ -62,7 +62,9 @@ template <int TN_, bool SPLIT_, int MT_ = 1> struct ConvFpropPol {
   }
   // lane -> pixel of M-tile mt
   __device__ static bool pixel(const Params& p, const Tile& t, int mt, int lane, int& b, int& oy, int& ox) {
-    const int w = lane % p.bw, q = lane / p.bw, h = q % p.bh, bi = q / p.bh;
+    int w, h, bi;
+    if (p.bw == 32) { w = lane & 31; h = lane >> 5; bi = 0; }          // the common 32x4x1 box: no divisions in the epilogue
+    else { w = lane % p.bw; const int q = lane / p.bw; h = q % p.bh; bi = q / p.bh; }
     b = t.b + bi; oy = t.oy0 + p.bh * mt + h; ox = t.ox0 + w;
     return bi < p.bb && b < p.B && oy < p.yh && ox < p.yw;
   }
