@@ -136,6 +136,10 @@ static NdArray run_dgrad(Device* dev, const Lazy& L, const NdArray* mask_src) {
   int64_t xh = p.stride * (gy.shape[2] - 1) - 2 * p.pad + (p.dilation * (w.shape[2] - 1) + 1);     // follows the code (conv2d_transpose.rs:55-56)
   int64_t xw = p.stride * (gy.shape[3] - 1) - 2 * p.pad + (p.dilation * (w.shape[3] - 1) + 1);
   bool cl = p.stride == 1 && agb_conv_prefers_channels_last((int)w.shape[0], (int)w.shape[1], (int)w.shape[2], (int)w.shape[3], 1, (int)xw);
+  if (p.stride > 1 && p.stride <= 4) {       // strided dgrad runs as phase convolutions on the tensor cores in TF32 mode: keep gx channels-last there
+    int mode = 0; agb_get_math_mode(dev->ctx, &mode);
+    cl = mode == AGB_MATH_TF32 && agb_conv_prefers_channels_last((int)w.shape[0], (int)w.shape[1], (int)w.shape[2], (int)w.shape[3], 1, (int)((xw + p.stride - 1) / p.stride));
+  }
   if (mask_src) cl = !mask_src->is_contiguous();          // write gx in the mask's memory order so the epilogue can read it in place
   NdArray gx = act_empty(dev, {gy.shape[0], w.shape[1], xh, xw}, cl);
   agb_tensor tg = gy.desc(), tw = w.desc(), tx = gx.desc(), tm;

@@ -215,6 +215,47 @@ def test_channels_last_network_matches_oracle(ag):
                 assert l2 <= 1e-1, (mode, a.shape, l2)
 
 
+def test_strided_conv_network_matches_oracle(ag):
+    """ResNet-style stage transition through the evaluator: conv3x3 stride 2 + bias + ReLU -> conv3x3 + bias + ReLU -> conv1x1 stride 2
+    -> mean.  In TF32 mode the strided forward / filter-gradient kernels and the phase-decomposed strided dgrad (with the fused
+    ReLU mask and bias-gradient sums) run on the tensor cores; loss and all gradients against the oracle."""
+    from rust_autograd_b200 import ffi
+    rng0 = np.random.default_rng(11)
+    x = rng0.standard_normal((4, 32, 21, 21)).astype(np.float32)      # 21: the reference's dgrad size formula (conv2d_transpose.rs:55-56) inverts the forward one only when (H + 2p - k) % s == 0
+    ws = [(rng0.standard_normal(sh) * 0.1).astype(np.float32) for sh in ((64, 32, 3, 3), (64, 64, 3, 3), (32, 64, 1, 1))]
+    bs = [(rng0.standard_normal((1, c, 1, 1)) * 0.1).astype(np.float32) for c in (64, 64)]
+
+    def run(mod, mode):
+        env = mod.VariableEnvironment()
+        if mode is not None:
+            ffi.check(ffi.load_library().agb_set_math_mode(env.agb_ctx(), mode))
+        vw = [env.slot().set(w) for w in ws]
+        vb = [env.slot().set(b) for b in bs]
+
+        def body(g):
+            xt = g.placeholder("x", [-1, 32, 21, 21])
+            tw, tb = [g.variable(v) for v in vw], [g.variable(v) for v in vb]
+            h = mod.relu(mod.conv2d(xt, tw[0], 1, 2) + tb[0])
+            h = mod.relu(mod.conv2d(h, tw[1], 1, 1) + tb[1])
+            z = mod.conv2d(h, tw[2], 0, 2)
+            loss = mod.reduce_mean(mod.square(z), [0, 1, 2, 3], False)
+            grads = mod.grad([loss], tw + tb + [xt])
+            return [r.unwrap() for r in g.evaluator().push(loss).extend(grads).feed("x", x).run()]
+        out = env.run(body)
+        env.close()
+        return out
+    ref = run(OG, None)
+    for mode, tol in ((0, 5e-5), (1, 2e-2)):
+        got = run(ag, mode)
+        assert len(got) == len(ref) == 7
+        for k, (a, b) in enumerate(zip(got, ref)):
+            if mode == 0 or k == 0:
+                assert rel(a, b) <= tol, (mode, k, rel(a, b))
+            else:        # TF32: ReLU masks may flip for pre-activations within rounding of 0 -> compare in relative L2
+                l2 = float(np.linalg.norm(np.asarray(a, np.float64) - b) / max(np.linalg.norm(b), 1e-12))
+                assert l2 <= 5e-2, (mode, k, l2)
+
+
 def test_lstm_language_model_matches_oracle(ag):
     """examples/lstm_lm.rs unrolled LSTM LM (gather, two gate GEMMs, slices, sigmoid/tanh cell, prediction GEMM, sparse xent, add_n) at a
     size where the tensor-core GEMMs engage (batch 32, dim 64, vocab 96, 5 steps): loss and all five parameter gradients vs the oracle."""
