@@ -218,6 +218,23 @@ int  agb_binary(agb_ctx* ctx, int op, float p0, float p1, const agb_tensor* a, c
 /* AddN::compute (array_ops.rs:503-528): y = xs[0] + ... + xs[n-1], all same shape, left fold */
 int  agb_add_n(agb_ctx* ctx, int n, const agb_tensor* const* xs, agb_tensor* y);
 int  agb_fill(agb_ctx* ctx, agb_tensor* y, float value);
+/* Fused elementwise program: one launch evaluates a small DAG of the unary / binary functors above over a
+ * [rows, cols] index space and writes up to AGB_FUSE_MAX_OUT of its values.  It replaces a chain of ndarray `map` / `Zip` passes
+ * such as the backward compositions gy * (y - square(y)) (activation_ops.rs:150) or gy * (1 - square(y)) (math_ops.rs:854-858) and
+ * the LSTM cell sigmoid(f) * c + sigmoid(i) * tanh(g) (examples/lstm_lm.rs:36-45); every instruction applies the SAME functor as
+ * agb_unary / agb_binary, so the values are bit-identical to the unfused sequence.
+ * Leaf l is read at ptr + r * pitch + c * cstride (pitch / cstride 0 = broadcast, pitch != cols = a sliced view) into register
+ * `reg`; instruction i computes regs[dst] = f(regs[a], regs[b] or imm); output o stores regs[reg] at ptr + r * pitch + c. */
+#define AGB_FUSE_MAX_LEAVES 12
+#define AGB_FUSE_MAX_INSTR 48
+#define AGB_FUSE_MAX_OUT 8
+#define AGB_FUSE_REGS 32
+enum agb_fuse_kind { AGB_F_UNARY = 0 /* f(a; p0) */, AGB_F_BINARY /* f(a, b) */, AGB_F_BINARY_IMM_B /* f(a, p0) */, AGB_F_BINARY_IMM_A /* f(p0, b) */ };
+typedef struct agb_fuse_leaf { const float* ptr; int64_t pitch, cstride; int32_t reg; } agb_fuse_leaf;
+typedef struct agb_fuse_instr { int32_t kind, op, dst, a, b; float p0; } agb_fuse_instr;
+typedef struct agb_fuse_out { float* ptr; int64_t pitch; int32_t reg; } agb_fuse_out;
+int  agb_fused_ewise(agb_ctx* ctx, int64_t rows, int64_t cols, int n_leaves, const agb_fuse_leaf* leaves,
+                     int n_instr, const agb_fuse_instr* instr, int n_out, const agb_fuse_out* outs);
 /* dst (any strides, e.g. a sliced region of a larger buffer) <- src (any strides), same shape.
  * Serves deep_copy, Concat/Tile, SliceGrad/SplitGrad (array_ops.rs:576-825), MaybeBroadcast. */
 int  agb_copy_strided(agb_ctx* ctx, const agb_tensor* src, agb_tensor* dst);

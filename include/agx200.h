@@ -48,6 +48,9 @@ int agx_env_var_ptr(agx_env* env, int vid, float** dptr);                       
 int agx_env_save(agx_env* env, const char* path);                                    /* JSON, src/variable.rs:549-598 */
 int agx_env_load(agx_env* env, const char* path);
 int agx_env_set_data_parallel(agx_env* env, int rank, int world, const void* nccl_id128);
+/* Deferred elementwise expressions (engine/fuse.cc): on by default.  Chains of unary / binary / compare / small AddN
+ * nodes run as ONE agb_fused_ewise launch; off = one launch per node.  Values are bit-identical either way. */
+int agx_env_set_fusion(agx_env* env, int on);
 
 /* ---- Graph construction ---- */
 int agx_graph_new(agx_env* env, agx_graph** out);

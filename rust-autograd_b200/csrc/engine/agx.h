@@ -50,6 +50,7 @@ typedef std::vector<int64_t> Shape;
 struct NdArray;
 struct Im2colRef;                 // virtual `cols` tensor (Conv2D output #1), see ops_nn.cc
 struct PoolRef;                   // (max-pool index buffers) the pooled forward output + identity of the pooled input, see ops_nn.cc
+struct ExprNode;                  // deferred elementwise expression (fuse.cc): value = one instruction of a fused program
 struct Lazy;                      // deferred epilogue (conv [+bias] awaiting a ReLU, "x > 0" mask awaiting a multiply), see ops_nn.cc
 
 // f32 array: a strided view on an HBM block and/or a small contiguous host vector.
@@ -69,6 +70,9 @@ struct NdArray {
                                        // pool-backward epilogues; MaybeReduceSum (the bias gradient) takes it instead of re-reading the tensor
   std::shared_ptr<Lazy> lazy;     // value not computed yet: only `shape` is valid.  ComputeContext::input() materialises it unless the
                                   // consuming op declared accept_lazy (the ops that can fuse it into their own kernel)
+
+  std::shared_ptr<ExprNode> expr; // pending elementwise expression (fuse.cc): only `shape` is valid until a consumer that needs memory compiles
+                                  // the DAG into one fused launch.  ComputeContext::input() materialises it unless the op declared accept_expr
 
   int ndim() const { return (int)shape.size(); }
   int64_t size() const { int64_t n = 1; for (auto d : shape) n *= d; return n; }
@@ -118,6 +122,8 @@ struct Op {                       // trait Op (src/op.rs:90-101)
   virtual const char* name() const = 0;
   virtual void compute(ComputeContext& ctx) = 0;     // throws OpError for Err(..), Panic for panics
   virtual void grad(GradientContext& ctx) = 0;
+  virtual bool metadata_only() const { return false; }   // Shape / Rank / Size: read the input's shape, never its values
+  virtual bool mutates_now() const { return false; }     // Assign: writes a variable in the middle of the traversal (optimizer ops are deferred)
 };
 
 struct IncomingTensor { TensorID id; bool allow_mut; int array_selector; };   // src/tensor.rs:542-550
@@ -178,6 +184,7 @@ struct ComputeContext {           // src/op.rs:186-309
   Device* dev; Evaluation* run; TensorID node;
   bool accept_i32 = false;        // set by ops that consume int32 index buffers natively
   bool accept_lazy = false;       // set by ops that fuse a deferred producer (AddOp / ReLU / greater / MulOp / Shape)
+  bool accept_expr = false;       // set by ops that extend (or pass through) a pending elementwise expression
   NdArray input(int i);           // each input may be taken once (:206-233)
   NdArray input_mut(int i);       // only RdWrVariable edges (:239-259)
   int num_inputs() const { return (int)xs.size(); }
@@ -204,6 +211,7 @@ std::vector<Tensor> compute_gradients(const std::vector<Tensor>& ys, const std::
 // ---------------------------------------------------------------------------------------------- variables
 struct VariableEnvironment {      // src/variable.rs:152-155: Vec<RefCell<NdArray>> -> arrays resident in HBM
   Device* dev; bool owns_dev = false;
+  bool fuse_elementwise = true;   // deferred elementwise expressions (fuse.cc); off = one launch per op, same values
   std::vector<NdArray> array_list;
   std::vector<std::pair<std::string, std::string>> names;        // index = VariableID: (namespace, name)
   std::map<std::pair<std::string, std::string>, int> name_to_id;
@@ -229,6 +237,10 @@ struct Evaluation {
   Graph* graph; Device* dev;
   std::vector<PendingUpdate> pending;     // optimizer ops of this run: flushed as ONE multi-tensor launch after all grads exist
   uint64_t dropout_calls = 0;
+  bool fuse = false;                      // elementwise fusion enabled for this run
+  std::vector<int> consumers;             // per node id: consuming edges inside this evaluation (+1 per request as a target); metadata-only
+                                          // consumers (Shape / Rank / Size) are not counted
+  int consumers_of(TensorID id) const { return id >= 0 && id < (int)consumers.size() && consumers[id] > 0 ? consumers[id] : 1; }
 };
 
 // Graph::eval (src/evaluation.rs:252-362): DFS post-order, memo table, placeholders from feeds, variables from env.
@@ -294,6 +306,16 @@ std::vector<int64_t> as_ints(Device* dev, NdArray& a);
 inline bool is_scalar_shape(const Shape& s) { return s.empty() || (s.size() == 1 && s[0] == 0); }   // ndarray_ext.rs:120-122
 inline int normalize_negative_axis(int64_t axis, int ndim) { return (int)(axis < 0 ? ndim + axis : axis); }
 NdArray materialize_lazy(Device* dev, const NdArray& a);      // runs the deferred producer un-fused (always correct)
+// fuse.cc: each returns an array with `expr` set, or an invalid array (no expr) when the op cannot join a fused program
+NdArray expr_unary(ComputeContext& c, int op, float p0, NdArray x);
+NdArray expr_binary(ComputeContext& c, int op, NdArray a, NdArray b);
+NdArray expr_binary_imm(ComputeContext& c, int op, NdArray x, float imm, bool imm_is_lhs);
+NdArray expr_passthrough(ComputeContext& c, const NdArray& x);
+NdArray expr_materialize(Device* dev, const NdArray& x);
+bool expr_has_value(const NdArray& x);
+NdArray expr_pad(ComputeContext& c, const Shape& full, const std::vector<int64_t>& start, NdArray gy);
+bool expr_sum_pads(ComputeContext& c, const std::vector<NdArray>& xs, NdArray* out);
+bool expr_materialize_into(Device* dev, const NdArray& x, NdArray dest);
 Op* make_optimizer_op(int kind, float h0, float h1, float h2, float h3);
 void flush_pending_updates(Evaluation& run, VariableEnvironment* env);
 

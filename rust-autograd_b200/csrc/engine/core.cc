@@ -214,6 +214,7 @@ NdArray ComputeContext::input(int i) {
   if (x.kind == InputKind::RdWrVariable) throw Panic("Bad op impl: cannot perform mutable borrowing for input. Use input_mut() instead.");
   if (x.taken) throw Panic("Bad op impl: input()/input_mut() cannot be called twice");
   x.taken = true;
+  if (x.arr.expr && (!accept_expr || expr_has_value(x.arr))) return expr_materialize(dev, x.arr);
   if (x.arr.lazy && !accept_lazy) return materialize_lazy(dev, x.arr);
   if (x.arr.i32 && !accept_i32) return dev->i32_to_f32(x.arr);
   return x.arr;
@@ -346,6 +347,19 @@ std::vector<EvalResult> eval(Graph* g, const std::vector<Tensor>& targets, const
   };
   std::vector<std::pair<TensorID, bool>> st; st.reserve(1 << 10);
   for (auto& t : targets) { if (t.graph != g) throw Panic("Detected tensors belonging to different graphs"); st.push_back({t.id, false}); }
+  run.fuse = env->fuse_elementwise;
+  if (run.fuse) {         // pre-pass for fuse.cc: how many consumers will read each node's VALUES in this evaluation
+    run.consumers.assign(g->node_set.size(), 0);
+    std::vector<char> seen(g->node_set.size(), 0); std::vector<TensorID> todo;
+    for (auto& t : targets) { run.consumers[t.id]++; if (!seen[t.id]) { seen[t.id] = 1; todo.push_back(t.id); } }
+    while (!todo.empty()) {
+      TensorInternal& n = g->inner(todo.back()); todo.pop_back();
+      if (n.is_placeholder || n.is_variable()) continue;
+      const bool meta_only = n.op && n.op->metadata_only();
+      if (n.op && n.op->mutates_now()) run.fuse = false;      // a pending expression must never read a variable after an Assign of the same run
+      for (auto& c : n.incoming_nodes) { if (!meta_only) run.consumers[c.id]++; if (!seen[c.id]) { seen[c.id] = 1; todo.push_back(c.id); } }
+    }
+  }
   while (!st.empty()) {
     auto [id, visit] = st.back(); st.pop_back();
     if (visit) {
@@ -377,6 +391,8 @@ std::vector<EvalResult> eval(Graph* g, const std::vector<Tensor>& targets, const
       for (auto& c : g->inner(id).incoming_nodes) if (!would_not_visit(c.id)) st.push_back({c.id, false});
     }
   }
+  // pending elementwise expressions among the targets read the variables' CURRENT values: compute them before the optimizer writes
+  for (auto& t : targets) { auto it = storage.find(t.id); if (it != storage.end() && it->second.ok) for (auto& y : it->second.ys) if (y.expr) y = expr_materialize(dev, y); }
   // all gradients of this run exist now: (allreduce +) ONE fused multi-tensor optimizer launch (north_star item 5)
   flush_pending_updates(run, env);
 

@@ -1,0 +1,285 @@
+// fuse.cc — deferred elementwise expressions ("elementwise fusion of backward chains produced by Op::grad
+// compositions ... must keep unfused intermediates available when a test evaluates them").
+//
+// The reference evaluates every node of a composition such as  gy * (y - square(y))  (Sigmoid::grad, activation_ops.rs:150),
+// gy * (1 - square(y))  (Tanh::grad, math_ops.rs:854-858)  or the LSTM cell  sigmoid(f) * c + sigmoid(i) * tanh(g)
+// (examples/lstm_lm.rs:36-45) as its own ndarray pass.  Here the unary / binary / compare / small AddN ops return an EXPRESSION
+// array (shape only, `NdArray::expr`) instead of launching; the first consumer that needs memory (a GEMM, a reduction, a slice, the
+// user) compiles the pending DAG into one `agb_fused_ewise` program:
+//   * leaves are the device arrays the DAG reads — sliced and row/column-broadcast views are read in place;
+//   * every node with more than one consumer in this evaluation (counted by eval()'s pre-pass; the forward values the backward
+//     pass re-reads) is stored as an extra output of the same launch, so nothing is ever recomputed and every intermediate of the
+//     reference graph stays observable;
+//   * each instruction is the functor the single-op kernel applies, so fused and unfused runs are bit-identical.
+// Programs are bounded (AGB_FUSE_MAX_*); an operand sub-DAG that would overflow is materialised first and becomes a leaf.
+#include "agx.h"
+#include <algorithm>
+#include <unordered_map>
+
+namespace agx {
+
+struct ExprNode {
+  int kind = AGB_F_UNARY, op = 0; float p0 = 0.f;
+  NdArray a, b;                 // operands: an expression (a.expr) of this node's shape, or a device array broadcastable to it
+  Shape shape;
+  int consumers = 1;            // consuming edges in this evaluation (+1 when the node is a requested target)
+  int n_instr = 1, n_leaves = 0, n_multi = 0;     // upper bounds over the not-yet-computed part of the DAG below (shared nodes count twice)
+  NdArray value; bool has_value = false;
+  std::vector<int64_t> pad_start;     // kind == kPad (SliceGrad / SplitGrad): `a` (any shape-compatible array or expression) placed at this offset of a
+                                      // zero array of `shape`.  Never part of a program: materialised on its own, or summed in place by AddN
+};
+
+namespace {
+const int kPad = 100;
+void materialize_node(Device* dev, ExprNode* n, NdArray* dest = nullptr);
+const int64_t kMaxFusedElems = (int64_t)1 << 24;     // beyond this a pass is bandwidth-bound anyway and the vectorised single-op kernels are used
+
+bool unvalued(const NdArray& x) { return x.expr && !x.expr->has_value; }
+const NdArray& resolved(const NdArray& x) { return x.expr ? x.expr->value : x; }
+
+// a leaf read as ptr + r * pitch + c * cstride over [rows, cols] = [prod(shape[:-1]), shape[-1]]
+bool as_2d(const NdArray& leaf, const Shape& out, int64_t& pitch, int64_t& cs) {
+  pitch = 0; cs = 0;
+  if (leaf.size() == 1) return true;
+  if (leaf.ndim() != (int)out.size()) return false;
+  const int n = (int)out.size();
+  for (int d = 0; d < n; d++) if (leaf.shape[d] != out[d] && leaf.shape[d] != 1) return false;
+  auto eff = [&](int d) { return leaf.shape[d] == 1 ? (int64_t)0 : leaf.stride[d]; };
+  if (out[n - 1] != 1) cs = eff(n - 1);
+  bool first = true; int64_t expected = 0;
+  for (int d = n - 2; d >= 0; d--) {
+    if (out[d] == 1) continue;
+    if (first) { pitch = eff(d); expected = pitch * out[d]; first = false; }
+    else { if (eff(d) != expected) return false; expected *= out[d]; }
+  }
+  return true;
+}
+
+bool leaf_ok(Device* dev, NdArray& x, const Shape& out) {
+  if (x.lazy || x.i32 || x.virt) return false;
+  if (!x.on_device()) { if (!x.has_host()) return false; dev->ensure_device(x); }
+  int64_t p, c; return as_2d(x, out, p, c);
+}
+
+// value ids: [0, n_leaves) leaves, then one per instruction
+struct Compiler {
+  Device* dev; ExprNode* root; const Shape& shape;
+  std::vector<ExprNode*> order; std::unordered_map<ExprNode*, int> instr_of;
+  struct Leaf { NdArray arr; int64_t pitch, cs; };
+  std::vector<Leaf> leaves;
+  bool ok = true;
+  Compiler(Device* d, ExprNode* r) : dev(d), root(r), shape(r->shape) {}
+  void visit(ExprNode* n) {
+    if (instr_of.count(n)) return;
+    if (unvalued(n->a)) visit(n->a.expr.get());
+    if (n->kind == AGB_F_BINARY && unvalued(n->b)) visit(n->b.expr.get());
+    instr_of[n] = (int)order.size(); order.push_back(n);
+  }
+  int leaf_id(const NdArray& x) {
+    int64_t p, c;
+    if (!as_2d(x, shape, p, c)) { ok = false; return 0; }
+    for (size_t i = 0; i < leaves.size(); i++) if (leaves[i].arr.dptr == x.dptr && leaves[i].pitch == p && leaves[i].cs == c) return (int)i;
+    leaves.push_back(Leaf{x, p, c}); return (int)leaves.size() - 1;
+  }
+};
+
+bool run_program(Device* dev, ExprNode* root, NdArray* root_dest) {
+  Compiler C(dev, root);
+  C.visit(root);
+  const int I = (int)C.order.size();
+  if (I > AGB_FUSE_MAX_INSTR) return false;
+  // operands -> value ids (leaves first; instruction k is value L + k, fixed up once L is known)
+  struct Opnd { bool leaf; int id; };
+  std::vector<Opnd> oa(I), ob(I);
+  auto operand = [&](const NdArray& x) { if (unvalued(x)) return Opnd{false, C.instr_of[x.expr.get()]}; return Opnd{true, C.leaf_id(resolved(x))}; };
+  for (int k = 0; k < I; k++) {
+    ExprNode* n = C.order[k];
+    if (n->kind != AGB_F_BINARY_IMM_A) oa[k] = operand(n->a); else oa[k] = Opnd{true, -1};
+    if (n->kind == AGB_F_BINARY) ob[k] = operand(n->b); else if (n->kind == AGB_F_BINARY_IMM_A) ob[k] = operand(n->a); else ob[k] = Opnd{true, -1};
+  }
+  const int L = (int)C.leaves.size();
+  if (!C.ok || L > AGB_FUSE_MAX_LEAVES) return false;
+  // outputs: the root + every other node somebody else will read
+  std::vector<int> outs; outs.push_back(I - 1);
+  for (int k = 0; k < I - 1 && (int)outs.size() < AGB_FUSE_MAX_OUT; k++) if (C.order[k]->consumers > 1) outs.push_back(k);
+  std::vector<char> is_out(I, 0); for (int k : outs) is_out[k] = 1;
+  // linear-scan register allocation
+  const int V = L + I;
+  auto vid = [&](const Opnd& o) { return o.id < 0 ? -1 : (o.leaf ? o.id : L + o.id); };
+  std::vector<int> last(V, -1), reg(V, -1); std::vector<char> released(V, 0);
+  for (int k = 0; k < I; k++) { int x = vid(oa[k]), y = vid(ob[k]); if (x >= 0) last[x] = k; if (y >= 0) last[y] = k; }
+  std::vector<int> free_regs; for (int r = AGB_FUSE_REGS - 1; r >= 0; r--) free_regs.push_back(r);
+  for (int l = 0; l < L; l++) { reg[l] = free_regs.back(); free_regs.pop_back(); }
+  std::vector<agb_fuse_instr> code(I);
+  for (int k = 0; k < I; k++) {
+    ExprNode* n = C.order[k];
+    int x = vid(oa[k]), y = vid(ob[k]);
+    agb_fuse_instr& ins = code[k];
+    ins.kind = n->kind; ins.op = n->op; ins.p0 = n->p0; ins.a = x >= 0 ? reg[x] : 0; ins.b = y >= 0 ? reg[y] : 0;
+    auto release = [&](int v) { if (v >= 0 && last[v] == k && !released[v] && !(v >= L && is_out[v - L])) { free_regs.push_back(reg[v]); released[v] = 1; } };
+    release(x); if (y != x) release(y);
+    if (free_regs.empty()) return false;
+    reg[L + k] = free_regs.back(); free_regs.pop_back();
+    ins.dst = reg[L + k];
+    if (last[L + k] < 0 && !is_out[k]) { free_regs.push_back(reg[L + k]); }      // dead value (cannot happen for a DAG reachable from the root)
+  }
+  // launch
+  const int nd = (int)root->shape.size();
+  int64_t cols = nd == 0 ? 1 : root->shape[nd - 1], total = 1; for (auto d : root->shape) total *= d;
+  int64_t rows = cols == 0 ? 0 : total / cols;
+  bool flat = root_dest == nullptr;
+  for (auto& lf : C.leaves) if (!((lf.pitch == 0 && lf.cs == 0) || (lf.cs == 1 && (lf.pitch == cols || rows == 1)))) flat = false;
+  std::vector<agb_fuse_leaf> lv(L);
+  for (int l = 0; l < L; l++) { lv[l].ptr = C.leaves[l].arr.dptr; lv[l].pitch = flat ? 0 : C.leaves[l].pitch; lv[l].cstride = C.leaves[l].cs; lv[l].reg = reg[l]; }
+  std::vector<agb_fuse_out> ov(outs.size()); std::vector<NdArray> values(outs.size());
+  for (size_t o = 0; o < outs.size(); o++) {
+    if (o == 0 && root_dest) { int64_t p, cs; as_2d(*root_dest, root->shape, p, cs); values[o] = *root_dest; ov[o].pitch = p; }
+    else { values[o] = dev->empty(root->shape); ov[o].pitch = flat ? 0 : cols; }
+    ov[o].ptr = values[o].dptr; ov[o].reg = code[outs[o]].dst;
+  }
+  check_status(agb_fused_ewise(dev->ctx, flat ? 1 : rows, flat ? total : cols, L, lv.data(), I, code.data(), (int)ov.size(), ov.data()));
+  for (size_t o = 0; o < outs.size(); o++) {
+    ExprNode* n = C.order[outs[o]];
+    n->value = values[o]; n->has_value = true; n->a = NdArray(); n->b = NdArray();      // operands are no longer needed
+  }
+  return true;
+}
+
+NdArray pad_region(const NdArray& full, const std::vector<int64_t>& start, const Shape& part) {
+  NdArray r = full;
+  for (int k = 0; k < full.ndim(); k++) r = r.sliced(k, start[k], part[k]);
+  return r;
+}
+void write_region(Device* dev, NdArray src, NdArray region) {      // region <- src: a pending expression is computed straight into it
+  if (unvalued(src) && expr_materialize_into(dev, src, region)) return;
+  if (src.expr) src = expr_materialize(dev, src);
+  dev->ensure_device(src);
+  agb_tensor ts = src.desc(), td = region.desc();
+  check_status(agb_copy_strided(dev->ctx, &ts, &td));
+}
+
+void materialize_node(Device* dev, ExprNode* n, NdArray* dest) {
+  if (n->has_value) return;
+  if (n->kind == kPad) {
+    NdArray gx = dev->zeros(n->shape);
+    write_region(dev, n->a, pad_region(gx, n->pad_start, n->a.shape));
+    n->value = gx; n->has_value = true; n->a = NdArray();
+    return;
+  }
+  if (run_program(dev, n, dest)) return;
+  // the DAG does not fit one program (registers / leaves / instructions): compute the operands first, then this node alone
+  if (unvalued(n->a)) materialize_node(dev, n->a.expr.get());
+  if (n->kind == AGB_F_BINARY && unvalued(n->b)) materialize_node(dev, n->b.expr.get());
+  if (!run_program(dev, n, dest)) throw Panic("fused elementwise: a single instruction does not fit a program");
+}
+
+void account(ExprNode* n) {
+  auto add = [&](const NdArray& x) {
+    if (unvalued(x)) { n->n_instr += x.expr->n_instr; n->n_leaves += x.expr->n_leaves; n->n_multi += x.expr->n_multi; }
+    else n->n_leaves += 1;
+  };
+  n->n_instr = 1; n->n_leaves = 0; n->n_multi = n->consumers > 1 ? 1 : 0;
+  add(n->a); if (n->kind == AGB_F_BINARY) add(n->b);
+}
+
+NdArray finish(ComputeContext& c, std::shared_ptr<ExprNode> n) {
+  n->consumers = c.run->consumers_of(c.node);
+  account(n.get());
+  // keep the pending DAG inside one program: materialise the larger operand first when the bounds would overflow
+  for (int round = 0; round < 2; round++) {
+    if (n->n_instr <= AGB_FUSE_MAX_INSTR - 8 && n->n_leaves <= AGB_FUSE_MAX_LEAVES - 1 && n->n_multi <= AGB_FUSE_MAX_OUT - 1) break;
+    NdArray* big = nullptr;
+    if (unvalued(n->a)) big = &n->a;
+    if (n->kind == AGB_F_BINARY && unvalued(n->b) && (!big || n->b.expr->n_instr > n->a.expr->n_instr)) big = &n->b;
+    if (!big) break;
+    materialize_node(c.dev, big->expr.get());
+    account(n.get());
+  }
+  NdArray r; r.shape = n->shape; r.stride = NdArray::contiguous_strides(r.shape); r.expr = n;
+  return r;
+}
+
+bool operand_ok(Device* dev, NdArray& x, const Shape& out) {
+  if (unvalued(x) && x.expr->kind == kPad) materialize_node(dev, x.expr.get());       // a padded slice gradient is memory, not an instruction
+  if (x.expr) { if (x.expr->has_value) { NdArray v = x.expr->value; return leaf_ok(dev, v, out); } return x.shape == out; }
+  return leaf_ok(dev, x, out);
+}
+bool size_ok(const Shape& s) { int64_t n = 1; for (auto d : s) n *= d; return n >= 1 && n <= kMaxFusedElems && s.size() <= 6; }
+}  // namespace
+
+NdArray expr_unary(ComputeContext& c, int op, float p0, NdArray x) {
+  if (!c.run->fuse || op == AGB_U_CLIP || op < 0 || op >= AGB_U_COUNT || !size_ok(x.shape) || !operand_ok(c.dev, x, x.shape)) return NdArray();
+  auto n = std::make_shared<ExprNode>(); n->kind = AGB_F_UNARY; n->op = op; n->p0 = p0; n->a = x; n->shape = x.shape;
+  return finish(c, n);
+}
+NdArray expr_binary(ComputeContext& c, int op, NdArray a, NdArray b) {
+  if (!c.run->fuse || op < 0 || op > AGB_B_MIN || a.ndim() != b.ndim()) return NdArray();
+  Shape out(a.shape.size());
+  for (size_t i = 0; i < out.size(); i++) {
+    if (a.shape[i] != b.shape[i] && a.shape[i] != 1 && b.shape[i] != 1) return NdArray();
+    out[i] = a.shape[i] == 1 ? b.shape[i] : a.shape[i];
+  }
+  if (!size_ok(out) || !operand_ok(c.dev, a, out) || !operand_ok(c.dev, b, out)) return NdArray();
+  auto n = std::make_shared<ExprNode>(); n->kind = AGB_F_BINARY; n->op = op; n->a = a; n->b = b; n->shape = out;
+  return finish(c, n);
+}
+NdArray expr_binary_imm(ComputeContext& c, int op, NdArray x, float imm, bool imm_is_lhs) {
+  if (!c.run->fuse || op < 0 || op > AGB_B_MIN || !size_ok(x.shape) || !operand_ok(c.dev, x, x.shape)) return NdArray();
+  auto n = std::make_shared<ExprNode>(); n->kind = imm_is_lhs ? AGB_F_BINARY_IMM_A : AGB_F_BINARY_IMM_B; n->op = op; n->p0 = imm; n->a = x; n->shape = x.shape;
+  return finish(c, n);
+}
+// a view op (MaybeReduceSum / Identity with nothing to do) hands the same pending node to ITS consumers
+NdArray expr_passthrough(ComputeContext& c, const NdArray& x) {
+  if (x.expr && !x.expr->has_value) { x.expr->consumers += c.run->consumers_of(c.node) - 1; if (x.expr->consumers > 1 && x.expr->n_multi == 0) x.expr->n_multi = 1; }
+  return x;
+}
+// SliceGrad / SplitGrad (array_ops.rs:726-749,803-825): zeros(full) with `gy` assigned at `start`, deferred so that AddN can sum
+// the disjoint pieces of one gradient (the 4 gate slices of the LSTM pre-activation) by writing them side by side
+NdArray expr_pad(ComputeContext& c, const Shape& full, const std::vector<int64_t>& start, NdArray gy) {
+  if (!c.run->fuse || full.size() != gy.shape.size() || full.empty() || gy.lazy || gy.i32) return NdArray();
+  if (!gy.expr && !gy.on_device()) { if (!gy.has_host()) return NdArray(); c.dev->ensure_device(gy); }
+  auto n = std::make_shared<ExprNode>(); n->kind = kPad; n->a = gy; n->shape = full; n->pad_start = start;
+  n->consumers = c.run->consumers_of(c.node); n->n_instr = 0; n->n_leaves = 1; n->n_multi = 0;
+  NdArray r; r.shape = full; r.stride = NdArray::contiguous_strides(full); r.expr = n;
+  return r;
+}
+// AddN over padded pieces that differ along ONE axis and do not overlap: one buffer, every piece written in place
+bool expr_sum_pads(ComputeContext& c, const std::vector<NdArray>& xs, NdArray* out) {
+  if (xs.size() < 2) return false;
+  for (auto& x : xs) if (!unvalued(x) || x.expr->kind != kPad || x.shape != xs[0].shape) return false;
+  const Shape& full = xs[0].shape; const int nd = (int)full.size();
+  int axis = -1;
+  for (auto& x : xs) for (int k = 0; k < nd; k++) {
+    if (x.expr->pad_start[k] == 0 && x.expr->a.shape[k] == full[k]) continue;
+    if (axis >= 0 && axis != k) return false;
+    axis = k;
+  }
+  if (axis < 0) return false;
+  std::vector<std::pair<int64_t, int64_t>> spans;
+  for (auto& x : xs) spans.push_back({x.expr->pad_start[axis], x.expr->a.shape[axis]});
+  std::sort(spans.begin(), spans.end());
+  int64_t at = 0; bool covered = true;
+  for (auto& sp : spans) { if (sp.first < at) return false; if (sp.first > at) covered = false; at = sp.first + sp.second; }
+  if (at != full[axis]) covered = false;
+  NdArray y = covered ? c.dev->empty(full) : c.dev->zeros(full);
+  for (auto& x : xs) write_region(c.dev, x.expr->a, pad_region(y, x.expr->pad_start, x.expr->a.shape));
+  *out = y;
+  return true;
+}
+bool expr_has_value(const NdArray& x) { return x.expr && x.expr->has_value; }
+NdArray expr_materialize(Device* dev, const NdArray& x) {
+  if (!x.expr) return x;
+  materialize_node(dev, x.expr.get());
+  return x.expr->value;
+}
+// SliceGrad: the pending value is written straight into its region of the zero-filled gradient
+bool expr_materialize_into(Device* dev, const NdArray& x, NdArray dest) {
+  if (!x.expr || x.expr->has_value || dest.shape != x.shape) return false;
+  const int nd = dest.ndim();
+  if (nd == 0 || (dest.shape[nd - 1] != 1 && dest.stride[nd - 1] != 1)) return false;
+  int64_t p, cs; if (!as_2d(dest, dest.shape, p, cs)) return false;
+  materialize_node(dev, x.expr.get(), &dest);
+  return true;
+}
+
+}  // namespace agx

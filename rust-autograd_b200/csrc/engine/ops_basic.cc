@@ -30,6 +30,7 @@ static agb_tensor permuted_desc(const agb_tensor& t, const std::vector<int>& ord
   agb_tensor r = t; for (int i = 0; i < t.rank; i++) { r.shape[i] = t.shape[order[i]]; r.stride[i] = t.stride[order[i]]; } return r;
 }
 static NdArray dev_unary(Device* d, int op, NdArray x, float p0 = 0.f, float p1 = 0.f) {
+  if (x.expr) x = expr_materialize(d, x);
   d->ensure_device(x);
   std::vector<int> order;
   if (x.dense_order(order) && !is_identity(order)) {          // dense but permuted: run on the flat memory, keep the strides
@@ -64,6 +65,8 @@ static agb_tensor broadcast_desc(const NdArray& a, const Shape& out) {
   return t;
 }
 static NdArray dev_binary(Device* d, int op, NdArray a, NdArray b, float p0 = 0.f, float p1 = 0.f, const char* who = "binary op") {
+  if (a.expr) a = expr_materialize(d, a);
+  if (b.expr) b = expr_materialize(d, b);
   d->ensure_device(a); d->ensure_device(b);
   Shape out = broadcast_shape(a.shape, b.shape, who);
   agb_tensor ta = broadcast_desc(a, out), tb = broadcast_desc(b, out);
@@ -228,18 +231,21 @@ Tensor T::ones(Graph* g, Tensor shape) { auto* op = new FillOp(); op->v = 1.f; r
 // ================================================================================================ metadata ops (host)
 struct ShapeOp : Op {                  // array_ops.rs:148-159
   const char* name() const override { return REFNAME("array_ops", "Shape"); }
-  void compute(ComputeContext& c) override { c.accept_lazy = true; NdArray x = c.input(0); std::vector<float> v; for (auto s : x.shape) v.push_back((float)s); c.append_output(NdArray::from_host({(int64_t)v.size()}, v, true)); }
+  void compute(ComputeContext& c) override { c.accept_lazy = true; c.accept_expr = true; NdArray x = c.input(0); std::vector<float> v; for (auto s : x.shape) v.push_back((float)s); c.append_output(NdArray::from_host({(int64_t)v.size()}, v, true)); }
   void grad(GradientContext& c) override { c.append_none(); }
+  bool metadata_only() const override { return true; }
 };
 struct RankOp : Op {
   const char* name() const override { return REFNAME("array_ops", "Rank"); }
-  void compute(ComputeContext& c) override { c.append_output(NdArray::scalar_host((float)c.input(0).ndim(), true)); }
+  void compute(ComputeContext& c) override { c.accept_lazy = true; c.accept_expr = true; c.append_output(NdArray::scalar_host((float)c.input(0).ndim(), true)); }
   void grad(GradientContext& c) override { c.append_none(); }
+  bool metadata_only() const override { return true; }
 };
 struct SizeOp : Op {
   const char* name() const override { return REFNAME("array_ops", "Size"); }
-  void compute(ComputeContext& c) override { c.append_output(NdArray::scalar_host((float)c.input(0).size(), true)); }
+  void compute(ComputeContext& c) override { c.accept_lazy = true; c.accept_expr = true; c.append_output(NdArray::scalar_host((float)c.input(0).size(), true)); }
   void grad(GradientContext& c) override { c.append_none(); }
+  bool metadata_only() const override { return true; }
 };
 struct InferBinOpShape : Op {          // array_ops.rs:107-146
   const char* name() const override { return REFNAME("array_ops", "InferBinOpShape"); }
@@ -280,7 +286,11 @@ static Tensor infer_bin_op_shape(Graph* g, Tensor sa, Tensor sb) { return Tensor
 // ================================================================================================ pass-through ops
 struct IdentityOp : Op {               // activation_ops.rs:169-181 (also nth_tensor)
   const char* name() const override { return REFNAME("activation_ops", "Identity"); }
-  void compute(ComputeContext& c) override { c.accept_i32 = true; c.append_output_view(c.input(0)); }
+  void compute(ComputeContext& c) override {
+    c.accept_i32 = true; c.accept_expr = true; NdArray x = c.input(0);
+    if (x.expr) { c.append_output(expr_passthrough(c, x)); return; }       // the same pending expression, now with this node's consumers too
+    c.append_output_view(x);
+  }
   void grad(GradientContext& c) override { c.append_input_grad(c.output_grad()); }
 };
 struct StopGradient : Op {             // gradient_ops.rs:4-16
@@ -326,9 +336,11 @@ struct BinArith : Op {                 // AddOp/SubOp/MulOp/DivOp, binary_ops.rs
     return kind == AGB_B_ADD ? REFNAME("binary_ops", "AddOp") : kind == AGB_B_SUB ? REFNAME("binary_ops", "SubOp") : kind == AGB_B_MUL ? REFNAME("binary_ops", "MulOp") : REFNAME("binary_ops", "DivOp");
   }
   void compute(ComputeContext& c) override {
-    c.accept_lazy = (kind == AGB_B_ADD || kind == AGB_B_MUL);
+    c.accept_lazy = (kind == AGB_B_ADD || kind == AGB_B_MUL); c.accept_expr = true;
     NdArray a = c.input(0), b = c.input(1);
     if (a.lazy || b.lazy) {
+      if (a.expr) a = expr_materialize(c.dev, a);
+      if (b.expr) b = expr_materialize(c.dev, b);
       if (kind == AGB_B_ADD) {            // Conv2D + bias[1,O,1,1]: stays deferred, the bias joins the conv epilogue
         NdArray bb = lazy_is_conv(a) ? b : a; if (!bb.lazy) c.dev->ensure_device(bb);
         NdArray r = lazy_is_conv(a) && !b.lazy ? lazy_conv_add_bias(a, bb) : (lazy_is_conv(b) && !a.lazy ? lazy_conv_add_bias(b, bb) : NdArray());
@@ -349,18 +361,21 @@ struct BinArith : Op {                 // AddOp/SubOp/MulOp/DivOp, binary_ops.rs
     }
     if (all_meta(a) && all_meta(b)) { c.append_output(host_binary(kind, a, b)); return; }
     float s;
+    // every device path first tries to join a pending elementwise expression (fuse.cc); the single-op kernel is the fallback
+    auto unary = [&](int op, const NdArray& x, float p) { NdArray r = expr_unary(c, op, p, x); return r.expr ? r : dev_unary(c.dev, op, x, p); };
     const bool a_sc = a.ndim() == 0 && scalar_value(a, &s);
     if (a_sc && b.size() != 1) {       // scalar (op) tensor fast paths: the scalar travels as a kernel parameter
-      NdArray y = kind == AGB_B_ADD ? dev_unary(c.dev, AGB_U_ADD_SCALAR, b, s) : kind == AGB_B_SUB ? dev_unary(c.dev, AGB_U_RSUB_SCALAR, b, s)
-                : kind == AGB_B_MUL ? dev_unary(c.dev, AGB_U_SCALE, b, s) : dev_unary(c.dev, AGB_U_RDIV_SCALAR, b, s);
+      NdArray y = kind == AGB_B_ADD ? unary(AGB_U_ADD_SCALAR, b, s) : kind == AGB_B_SUB ? unary(AGB_U_RSUB_SCALAR, b, s)
+                : kind == AGB_B_MUL ? unary(AGB_U_SCALE, b, s) : unary(AGB_U_RDIV_SCALAR, b, s);
       c.append_output(y); return;
     }
     const bool b_sc = (b.ndim() == 0 || (kind == AGB_B_DIV && b.ndim() == 1 && b.shape[0] == 1)) && scalar_value(b, &s);
     if (b_sc && !(all_meta(a))) {
-      NdArray y = kind == AGB_B_ADD ? dev_unary(c.dev, AGB_U_ADD_SCALAR, a, s) : kind == AGB_B_SUB ? dev_unary(c.dev, AGB_U_ADD_SCALAR, a, -s)
-                : kind == AGB_B_MUL ? dev_unary(c.dev, AGB_U_SCALE, a, s) : dev_unary(c.dev, AGB_U_SCALE, a, 1.0f / s);   // Div by scalar = multiply by reciprocal (:251-255)
+      NdArray y = kind == AGB_B_ADD ? unary(AGB_U_ADD_SCALAR, a, s) : kind == AGB_B_SUB ? unary(AGB_U_ADD_SCALAR, a, -s)
+                : kind == AGB_B_MUL ? unary(AGB_U_SCALE, a, s) : unary(AGB_U_SCALE, a, 1.0f / s);   // Div by scalar = multiply by reciprocal (:251-255)
       c.append_output(y); return;
     }
+    if (a.ndim() == b.ndim() && a.ndim() > 0) { NdArray r = expr_binary(c, kind, a, b); if (r.expr) { c.append_output(r); return; } }
     c.append_output(dev_binary(c.dev, kind, a, b, 0.f, 0.f, name()));
   }
   void grad(GradientContext& c) override {
@@ -388,9 +403,11 @@ struct MaybeBroadcast;
 struct MaybeReduceSum : Op {           // binary_ops.rs:39-105
   const char* name() const override { return REFNAME("binary_ops", "MaybeReduceSum"); }
   void compute(ComputeContext& c) override {
+    c.accept_expr = true;
     NdArray gy = c.input(0), sh = c.input(1);
     Shape orig_ = as_shape(c.dev, sh);
-    if (orig_ == gy.shape) { c.append_output_view(gy); return; }
+    if (orig_ == gy.shape) { if (gy.expr) c.append_output(expr_passthrough(c, gy)); else c.append_output_view(gy); return; }
+    if (gy.expr) gy = expr_materialize(c.dev, gy);
     bool target_scalar = is_scalar_shape(orig_);
     Shape orig = target_scalar ? Shape(gy.shape.size(), 1) : orig_;
     if (orig == gy.shape) { c.append_output_view(d_reshape(c, gy, orig_)); return; }
@@ -462,13 +479,14 @@ struct UnaryOp : Op {
   const UnaryInfo* info; float p0;
   const char* name() const override { return info->ref; }
   void compute(ComputeContext& c) override {
-    c.accept_lazy = info->op == AGB_U_RELU;
+    c.accept_lazy = info->op == AGB_U_RELU; c.accept_expr = true;
     NdArray x = c.input(0);
     if (x.lazy) {
       if (lazy_is_conv(x)) { NdArray y = lazy_conv_relu(c.dev, x); if (y.lazy) { c.append_output(y); return; } }      // stays deferred (ops_nn.cc)
       x = materialize_lazy(c.dev, x);
     }
     if (info->op == AGB_U_NEG && all_meta(x)) { std::vector<float> v = *x.host; for (auto& e : v) e = -e; c.append_output(NdArray::from_host(x.shape, v, true)); return; }
+    if (!all_meta(x)) { NdArray r = expr_unary(c, info->op, p0, x); if (r.expr) { c.append_output(r); return; } }
     c.append_output(dev_unary(c.dev, info->op, x, p0));
   }
   void grad(GradientContext& c) override {
@@ -550,9 +568,9 @@ struct CmpOp : Op {                    // impl_cmp_op!, math_ops.rs:86-184
   const CmpInfo* info;
   const char* name() const override { return info->ref; }
   void compute(ComputeContext& c) override {
-    c.accept_lazy = info->op == AGB_B_GT;
+    c.accept_lazy = info->op == AGB_B_GT; c.accept_expr = true;
     NdArray a = c.input(0), b = c.input(1);
-    if (info->op == AGB_B_GT) {          // greater(x, scalar 0): the ReLU-gradient mask; deferred until its multiply arrives
+    if (info->op == AGB_B_GT && !a.expr && !b.expr) {          // greater(x, scalar 0): the ReLU-gradient mask; deferred until its multiply arrives
       float z;
       if (!b.lazy && b.ndim() == 0 && scalar_value(b, &z) && z == 0.0f && a.ndim() > 0 && (a.lazy || a.on_device())) {
         NdArray r = lazy_gt0_mask(a);
@@ -566,6 +584,18 @@ struct CmpOp : Op {                    // impl_cmp_op!, math_ops.rs:86-184
       if (a.ndim() != b.ndim()) throw Panic(std::string("Tensor ranks mismatch: ") + info->ref);
       if (a.size() > b.size()) throw Panic(std::string("Tensor ranks mismatch: ") + info->ref);     // only lhs -> rhs broadcasting (:134-148)
       if (a.size() == b.size() && a.shape != b.shape) throw Panic(std::string("shape mismatch: ") + info->ref);
+    }
+    if (a.lazy) a = materialize_lazy(c.dev, a);
+    if (b.lazy) b = materialize_lazy(c.dev, b);
+    if (!as && !bs && !(all_meta(a) && all_meta(b))) {
+      NdArray r = expr_binary(c, info->op, a, b);
+      if (r.expr) { c.append_output(r); return; }
+    } else if (as != bs && a.ndim() + b.ndim() > 0) {            // compare against a host-known scalar: it travels as an immediate
+      float sv; const NdArray& sc = as ? a : b; const NdArray& full = as ? b : a;
+      if (sc.ndim() == 0 && scalar_value(sc, &sv) && full.ndim() > 0 && !all_meta(full)) {
+        NdArray r = expr_binary_imm(c, info->op, full, sv, as);
+        if (r.expr) { c.append_output(r); return; }
+      }
     }
     NdArray y = dev_binary(c.dev, info->op, a, b, 0.f, 0.f, info->ref);
     if (as && bs) y = y.reshaped(a.shape == Shape{0} ? Shape{} : a.shape);
@@ -590,8 +620,16 @@ struct AddN : Op {                     // array_ops.rs:503-535
   void compute(ComputeContext& c) override {
     int n = c.num_inputs();
     if (n == 1) { c.append_output_view(c.input(0)); return; }
+    c.accept_expr = true;
     std::vector<NdArray> xs; bool same = true, all_empty_scalars = true;
     for (int i = 0; i < n; i++) { xs.push_back(c.input(i)); if (xs[i].shape != xs[0].shape) same = false; if (!(xs[i].ndim() == 0 && xs[i].has_host() && !xs[i].on_device())) all_empty_scalars = false; }
+    if (same && !all_empty_scalars) { NdArray y; if (expr_sum_pads(c, xs, &y)) { c.append_output(y); return; } }
+    if (same && !all_empty_scalars && n <= 6 && xs[0].ndim() > 0) {      // a short sum joins the pending expression as the same left fold
+      NdArray acc = expr_binary(c, AGB_B_ADD, xs[0], xs[1]);
+      for (int i = 2; i < n && acc.expr; i++) acc = expr_binary(c, AGB_B_ADD, acc, xs[i]);
+      if (acc.expr) { c.append_output(acc); return; }
+    }
+    for (auto& x : xs) if (x.expr) x = expr_materialize(c.dev, x);
     if (all_empty_scalars) {           // sum of optimizer-op placeholders (get_update_op = add_n(update_ops), optimizers/mod.rs:87-98)
       float s = 0.f; for (auto& x : xs) s += (*x.host)[0];
       c.append_output(NdArray::scalar_host(s)); return;
@@ -949,12 +987,22 @@ struct SliceGrad : Op {                // SliceGrad / SplitGrad, array_ops.rs:72
   std::vector<SliceElem> indices; int split_axis = -1000; int64_t s0 = 0, s1 = 0; bool is_split = false;
   const char* name() const override { return is_split ? REFNAME("array_ops", "SplitGrad") : REFNAME("array_ops", "SliceGrad"); }
   void compute(ComputeContext& c) override {
-    NdArray x = c.input(0), gy = on_dev(c.dev, c.input(1));
-    NdArray gx = c.dev->zeros(x.shape);
+    c.accept_expr = true; c.accept_lazy = true;
+    NdArray x = c.input(0), gy = c.input(1);          // x: only its shape is used
+    if (gy.lazy) gy = materialize_lazy(c.dev, gy);
     std::vector<SliceElem> idx = indices;
     if (is_split) { int ax = normalize_negative_axis(split_axis, x.ndim()); idx.assign(x.ndim(), SliceElem{0, false, 0}); idx[ax] = SliceElem{s0, true, s1}; }
+    if ((int)idx.size() == x.ndim() && x.ndim() == gy.ndim()) {      // deferred: AddN may sum the pieces of one gradient in place (fuse.cc)
+      std::vector<int64_t> start(x.ndim()); bool match = true;
+      for (int k = 0; k < x.ndim(); k++) { int64_t s, n; resolve_slice(idx[k], x.shape[k], s, n); start[k] = s; if (n != gy.shape[k]) match = false; }
+      if (match) { NdArray r = expr_pad(c, x.shape, start, gy); if (r.expr) { c.append_output(r); return; } }
+    }
+    NdArray gx = c.dev->zeros(x.shape);
     NdArray region = apply_slices(c.dev, gx, idx);
     if (region.shape != gy.shape) throw Panic("SliceGrad: gradient shape does not match the sliced region");
+    if (gy.expr && expr_materialize_into(c.dev, gy, region)) { c.append_output(gx); return; }       // the fused program writes the region directly
+    if (gy.expr) gy = expr_materialize(c.dev, gy);
+    c.dev->ensure_device(gy);
     agb_tensor ts = gy.desc(), td = region.desc();
     check_status(agb_copy_strided(c.dev->ctx, &ts, &td));
     c.append_output(gx);
@@ -1132,6 +1180,7 @@ struct Assign : Op {                   // array_ops.rs:94-105: device copy into 
     c.append_empty_output();
   }
   void grad(GradientContext& c) override { c.append_none(); c.append_none(); }
+  bool mutates_now() const override { return true; }
 };
 Tensor T::assign(Tensor x, Tensor y) { return TensorBuilder(x.graph).append_input(x, true).append_input(y, false).build(new Assign()); }
 

@@ -393,6 +393,87 @@ extern "C" int agb_add_n(agb_ctx* ctx, int n, const agb_tensor* const* xs, agb_t
   return AGB_OK;
 }
 
+// ----------------------------------------------------------------------------------------------
+// fused elementwise program: a small register machine per element.  The host (engine/fuse.cc) compiles a
+// DAG of deferred unary / binary ops into <= 48 instructions over <= 32 registers; every thread keeps its register file in its
+// own shared-memory column (conflict-free, no synchronisation), loads all leaves up front (independent loads in flight), runs the
+// program with the same functors as the single-op kernels and stores the requested registers.  One launch replaces the whole
+// chain, and sliced / broadcast operands are read in place (no deep copy first).
+// ----------------------------------------------------------------------------------------------
+struct FuseParams {
+  int n_leaves, n_instr, n_out;
+  int64_t cols, total;
+  const float* lptr[AGB_FUSE_MAX_LEAVES]; int64_t lpitch[AGB_FUSE_MAX_LEAVES], lcs[AGB_FUSE_MAX_LEAVES];
+  float* optr[AGB_FUSE_MAX_OUT]; int64_t opitch[AGB_FUSE_MAX_OUT];
+  uint32_t code[AGB_FUSE_MAX_INSTR];      // kind (2 bits) | op (6) | dst (5) | a (5) | b (5)
+  float imm[AGB_FUSE_MAX_INSTR];
+  uint8_t lreg[AGB_FUSE_MAX_LEAVES], oreg[AGB_FUSE_MAX_OUT];
+};
+
+__global__ void __launch_bounds__(256) fused_ewise_kernel(const __grid_constant__ FuseParams P) {
+  __shared__ float R[AGB_FUSE_REGS][256];
+  const int t = threadIdx.x;
+  const int64_t stride = (int64_t)gridDim.x * 256;
+  for (int64_t i = blockIdx.x * (int64_t)256 + t; i < P.total; i += stride) {
+    int64_t r, c;
+    if (P.cols == P.total) { r = 0; c = i; }
+    else if (P.total < (int64_t)0x7fffffff) { r = (uint32_t)i / (uint32_t)P.cols; c = i - r * P.cols; }
+    else { r = i / P.cols; c = i - r * P.cols; }
+    float v[AGB_FUSE_MAX_LEAVES];
+#pragma unroll
+    for (int l = 0; l < AGB_FUSE_MAX_LEAVES; l++) if (l < P.n_leaves) v[l] = __ldg(P.lptr[l] + r * P.lpitch[l] + c * P.lcs[l]);
+#pragma unroll
+    for (int l = 0; l < AGB_FUSE_MAX_LEAVES; l++) if (l < P.n_leaves) R[P.lreg[l]][t] = v[l];
+    for (int k = 0; k < P.n_instr; k++) {
+      const uint32_t w = P.code[k];
+      const int kind = w & 3, op = (w >> 2) & 63;
+      const float p0 = P.imm[k];
+      float a = R[(w >> 13) & 31][t], b = R[(w >> 18) & 31][t], y;
+      if (kind == AGB_F_UNARY) y = unary_apply(op, a, p0, 0.0f);
+      else {
+        if (kind == AGB_F_BINARY_IMM_B) b = p0; else if (kind == AGB_F_BINARY_IMM_A) a = p0;
+        y = binary_apply(op, a, b, 0.0f, 0.0f);
+      }
+      R[(w >> 8) & 31][t] = y;
+    }
+    for (int o = 0; o < P.n_out; o++) P.optr[o][r * P.opitch[o] + c] = R[P.oreg[o]][t];
+  }
+}
+
+extern "C" int agb_fused_ewise(agb_ctx* ctx, int64_t rows, int64_t cols, int n_leaves, const agb_fuse_leaf* leaves,
+                               int n_instr, const agb_fuse_instr* instr, int n_out, const agb_fuse_out* outs) {
+  AGB_CHECK(rows >= 0 && cols >= 0, AGB_ERR_INVALID_DIMS, "agb_fused_ewise: negative extent");
+  AGB_CHECK(n_leaves >= 0 && n_leaves <= AGB_FUSE_MAX_LEAVES && n_instr >= 1 && n_instr <= AGB_FUSE_MAX_INSTR && n_out >= 1 && n_out <= AGB_FUSE_MAX_OUT,
+            AGB_ERR_INVALID_DIMS, "agb_fused_ewise: program too large (%d leaves, %d instructions, %d outputs)", n_leaves, n_instr, n_out);
+  FuseParams P; memset(&P, 0, sizeof(P));
+  P.n_leaves = n_leaves; P.n_instr = n_instr; P.n_out = n_out; P.cols = cols; P.total = rows * cols;
+  bool written[AGB_FUSE_REGS] = {false};
+  for (int l = 0; l < n_leaves; l++) {
+    AGB_CHECK(leaves[l].ptr != nullptr && leaves[l].reg >= 0 && leaves[l].reg < AGB_FUSE_REGS, AGB_ERR_INVALID_DIMS, "agb_fused_ewise: bad leaf %d", l);
+    P.lptr[l] = leaves[l].ptr; P.lpitch[l] = leaves[l].pitch; P.lcs[l] = leaves[l].cstride; P.lreg[l] = (uint8_t)leaves[l].reg; written[leaves[l].reg] = true;
+  }
+  for (int k = 0; k < n_instr; k++) {
+    const agb_fuse_instr& I = instr[k];
+    AGB_CHECK(I.kind >= AGB_F_UNARY && I.kind <= AGB_F_BINARY_IMM_A, AGB_ERR_UNSUPPORTED, "agb_fused_ewise: instruction %d: bad kind %d", k, I.kind);
+    AGB_CHECK(I.op >= 0 && I.op < (I.kind == AGB_F_UNARY ? (int)AGB_U_COUNT : (int)AGB_B_MIN + 1) && !(I.kind == AGB_F_UNARY && I.op == AGB_U_CLIP), AGB_ERR_UNSUPPORTED,
+              "agb_fused_ewise: instruction %d: op %d is not fusable", k, I.op);
+    AGB_CHECK(I.dst >= 0 && I.dst < AGB_FUSE_REGS && I.a >= 0 && I.a < AGB_FUSE_REGS && I.b >= 0 && I.b < AGB_FUSE_REGS, AGB_ERR_INVALID_DIMS, "agb_fused_ewise: instruction %d: register out of range", k);
+    const bool need_a = I.kind != AGB_F_BINARY_IMM_A, need_b = I.kind == AGB_F_BINARY || I.kind == AGB_F_BINARY_IMM_A;
+    AGB_CHECK((!need_a || written[I.a]) && (!need_b || written[I.b]), AGB_ERR_INVALID_DIMS, "agb_fused_ewise: instruction %d reads a register nothing wrote", k);
+    written[I.dst] = true;
+    P.code[k] = (uint32_t)I.kind | ((uint32_t)I.op << 2) | ((uint32_t)I.dst << 8) | ((uint32_t)I.a << 13) | ((uint32_t)I.b << 18);
+    P.imm[k] = I.p0;
+  }
+  for (int o = 0; o < n_out; o++) {
+    AGB_CHECK(outs[o].ptr != nullptr && outs[o].reg >= 0 && outs[o].reg < AGB_FUSE_REGS && written[outs[o].reg], AGB_ERR_INVALID_DIMS, "agb_fused_ewise: bad output %d", o);
+    P.optr[o] = outs[o].ptr; P.opitch[o] = outs[o].pitch; P.oreg[o] = (uint8_t)outs[o].reg;
+  }
+  if (P.total == 0) return AGB_OK;
+  fused_ewise_kernel<<<agb_grid_for(P.total, 256, ctx->sm_count, 6), 256, 0, ctx->stream>>>(P);
+  AGB_LAUNCHED(ctx);
+  return AGB_OK;
+}
+
 __global__ void __launch_bounds__(256) fill_kernel(float* __restrict__ y, int64_t n, float v) {
   int64_t tid = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
   int64_t stride = (int64_t)gridDim.x * blockDim.x;

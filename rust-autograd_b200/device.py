@@ -182,6 +182,25 @@ class Device:
         ffi.check(self.lib.agb_add_n(self.ctx, len(xs), arr, y.desc()))
         return y
 
+    def fused_ewise(self, rows, cols, leaves, program, out_regs):
+        """agb_fused_ewise: `leaves` = [(2-D DArray view broadcastable to [rows, cols], reg)], `program` = [(kind, op name, dst, a, b, p0)],
+        `out_regs` = registers to store; returns one contiguous [rows, cols] array per output register."""
+        lv = (ffi.AgbFuseLeaf * max(len(leaves), 1))()
+        for i, (x, reg) in enumerate(leaves):
+            assert x.ndim == 2
+            pitch = 0 if x.shape[0] == 1 and rows != 1 else x.strides[0]
+            cs = 0 if x.shape[1] == 1 and cols != 1 else x.strides[1]
+            lv[i] = ffi.AgbFuseLeaf(x.ptr, pitch, cs, reg)
+        ins = (ffi.AgbFuseInstr * len(program))()
+        for i, (kind, op, dst, a, b, p0) in enumerate(program):
+            ins[i] = ffi.AgbFuseInstr(kind, (ffi.U if kind == ffi.F_UNARY else ffi.B)[op], dst, a, b, p0)
+        ys = [self.empty((rows, cols)) for _ in out_regs]
+        outs = (ffi.AgbFuseOut * len(out_regs))()
+        for i, (y, reg) in enumerate(zip(ys, out_regs)):
+            outs[i] = ffi.AgbFuseOut(y.ptr, cols, reg)
+        ffi.check(self.lib.agb_fused_ewise(self.ctx, rows, cols, len(leaves), lv, len(program), ins, len(out_regs), outs))
+        return ys
+
     def fill(self, shape, v):
         y = self.empty(shape)
         ffi.check(self.lib.agb_fill(self.ctx, y.desc(), v))

@@ -33,6 +33,21 @@ class AgbTensor(C.Structure):
     _fields_ = [("ptr", C.c_void_p), ("rank", C.c_int32), ("shape", C.c_int64 * MAX_RANK), ("stride", C.c_int64 * MAX_RANK)]
 
 
+class AgbFuseLeaf(C.Structure):
+    _fields_ = [("ptr", C.c_void_p), ("pitch", C.c_int64), ("cstride", C.c_int64), ("reg", C.c_int32)]
+
+
+class AgbFuseInstr(C.Structure):
+    _fields_ = [("kind", C.c_int32), ("op", C.c_int32), ("dst", C.c_int32), ("a", C.c_int32), ("b", C.c_int32), ("p0", C.c_float)]
+
+
+class AgbFuseOut(C.Structure):
+    _fields_ = [("ptr", C.c_void_p), ("pitch", C.c_int64), ("reg", C.c_int32)]
+
+
+F_UNARY, F_BINARY, F_BINARY_IMM_B, F_BINARY_IMM_A = 0, 1, 2, 3
+
+
 class OpError(RuntimeError):
     """Mirrors ``OpError`` (reference ``src/op.rs:67-73``); ``code`` is the C status."""
     NAMES = {1: "NdArrayError", 2: "IncompatibleShape", 3: "TypeUnsupported", 4: "InvalidDims", 5: "OutOfBounds",
@@ -70,7 +85,8 @@ SIGNATURES = {
     "agb_maxpool2d_gradgrad": [_P, _T, _P, _P, _T],
     "agb_convert_i32_f32": [_P, _P, _P, _i64],
     "agb_unary": [_P, _i, _f, _f, _T, _T], "agb_binary": [_P, _i, _f, _f, _T, _T, _T],
-    "agb_add_n": [_P, _i, C.POINTER(_T), _T], "agb_fill": [_P, _T, _f], "agb_copy_strided": [_P, _T, _T],
+    "agb_add_n": [_P, _i, C.POINTER(_T), _T], "agb_fill": [_P, _T, _f],
+    "agb_fused_ewise": [_P, _i64, _i64, _i, _P, _i, _P, _i, _P], "agb_copy_strided": [_P, _T, _T],
     "agb_dropout": [_P, _T, _T, _T, _f, _u64, _u64],
     "agb_reduce": [_P, _i, _P, _P, _i64, _i64, _i64], "agb_argreduce": [_P, _i, _P, _P, _i64, _i64, _i64],
     "agb_softmax": [_P, _P, _P, _i64, _i64, _i64], "agb_log_softmax": [_P, _P, _P, _i64, _i64, _i64],

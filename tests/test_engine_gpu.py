@@ -285,6 +285,51 @@ def test_lstm_language_model_matches_oracle(ag):
             assert rel(a, b) <= tol, (mode, np.asarray(a).shape, rel(a, b))
 
 
+def test_elementwise_fusion_is_bit_identical_and_saves_launches(ag):
+    """engine/fuse.cc: the LSTM language model's forward + backward with deferred elementwise expressions ON (default)
+    and OFF give bit-identical loss, gradients and observable intermediates (every instruction of a fused program is the functor of the
+    single-op kernel), while the fused run needs far fewer launches."""
+    import ctypes as C
+    from rust_autograd_b200 import ffi, workloads as W
+    D, V, S, B = 64, 96, 6, 32
+    sents = np.random.default_rng(3).integers(0, V, (B, S)).astype(np.float32)
+
+    def run(fuse):
+        env = ag.VariableEnvironment()
+        env.set_fusion(fuse)
+        ffi.check(ffi.load_library().agb_set_math_mode(env.agb_ctx(), 2))        # exact fp32 GEMMs: deterministic, no split-K atomics
+        W.lstm_init(env, np.random.default_rng(0), D, V, scale=0.2)
+        n0, n1 = C.c_int64(), C.c_int64()
+
+        def body(g):
+            loss, _ = W.lstm_loss(ag, g, D, S)
+            vs = [g.variable(k) for k in ("wx", "wh", "b", "lookup_table", "w_pred")]
+            grads = ag.grad([loss], vs)
+            # a composition evaluated for its own sake + one of its interior nodes: both must stay observable
+            x = g.placeholder("z", [B, D])
+            y = ag.tanh(x)
+            inner = ag.square(y)
+            outer = ag.grad([ag.sigmoid(y) * 3.0 + y], [x])[0]
+            ffi.check(ffi.load_library().agb_launch_count(env.agb_ctx(), C.byref(n0)))
+            out = [r_.unwrap() for r_ in g.evaluator().push(loss).extend(grads).extend([inner, outer, y]).feed("sents", sents)
+                   .feed("z", np.linspace(-2, 2, B * D, dtype=np.float32).reshape(B, D)).run()]
+            ffi.check(ffi.load_library().agb_launch_count(env.agb_ctx(), C.byref(n1)))
+            return out
+        out = env.run(body)
+        env.close()
+        return out, n1.value - n0.value
+    fused, n_fused = run(True)
+    plain, n_plain = run(False)
+    assert len(fused) == len(plain) == 9
+    for k, (a, b) in enumerate(zip(fused, plain)):
+        if k == 4:      # the embedding gradient is an atomic scatter-add (GatherGrad): its summation order differs from run to run
+            assert rel(a, b) <= 1e-6
+        else:
+            assert np.array_equal(np.asarray(a), np.asarray(b)), k
+    assert n_fused < 0.6 * n_plain, (n_fused, n_plain)
+    print("launches fused/plain:", n_fused, n_plain)
+
+
 def test_training_reduces_loss_and_checkpoint_roundtrip(ag, tmp_path):
     """examples/mlp_mnist.rs flow on synthetic data + VariableEnvironment::save/load (src/variable.rs:470-598, test :810-840)."""
     from rust_autograd_b200 import workloads as W

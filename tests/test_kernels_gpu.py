@@ -457,6 +457,54 @@ def test_add_n_fill_copy_dropout(dev):
     assert set(np.unique(m)) == {0.0, 1.0} and abs(m.mean() - 0.75) < 5e-3 and np.array_equal(y.numpy(), m)
 
 
+def test_fused_ewise_lstm_cell_matches_single_op_kernels(dev):
+    """agb_fused_ewise on the LSTM cell (examples/lstm_lm.rs:36-45): gates are sliced views of one [B, 4D] buffer (read in place, pitch 4D),
+    the bias is a row broadcast, outputs i, f, o, g, c', tanh(c'), h from ONE launch: bit-identical to the chain of agb_unary / agb_binary
+    launches it replaces, and within 1e-6 of the oracle."""
+    from rust_autograd_b200 import ffi
+    rng = np.random.default_rng(21)
+    B, D = 37, 48
+    xh = rng.standard_normal((B, 4 * D)).astype(np.float32)
+    bias = rng.standard_normal((1, 4 * D)).astype(np.float32)
+    c0 = rng.standard_normal((B, D)).astype(np.float32)
+    dxh, db, dc = dev.upload(xh), dev.upload(bias), dev.upload(c0)
+    # registers: 0..3 gate slices of xh, 4..7 bias slices, 8 c
+    leaves = [(dxh.slice(1, k * D, (k + 1) * D), k) for k in range(4)] + [(db.slice(1, k * D, (k + 1) * D), 4 + k) for k in range(4)] + [(dc, 8)]
+    U, Bn = ffi.F_UNARY, ffi.F_BINARY
+    prog = [(Bn, "add", 9, 0, 4, 0.0), (Bn, "add", 10, 1, 5, 0.0), (Bn, "add", 11, 2, 6, 0.0), (Bn, "add", 12, 3, 7, 0.0),
+            (U, "sigmoid", 13, 9, 0, 0.0), (U, "sigmoid", 14, 10, 0, 0.0), (U, "tanh", 15, 11, 0, 0.0), (U, "sigmoid", 16, 12, 0, 0.0),
+            (Bn, "mul", 17, 14, 8, 0.0), (Bn, "mul", 18, 13, 15, 0.0), (Bn, "add", 19, 17, 18, 0.0),
+            (U, "tanh", 20, 19, 0, 0.0), (Bn, "mul", 21, 16, 20, 0.0),
+            (ffi.F_BINARY_IMM_A, "sub", 22, 0, 20, 1.0), (ffi.F_BINARY_IMM_B, "gt", 23, 21, 0, 0.0), (U, "scale", 24, 21, 0, 0.5)]
+    outs = dev.fused_ewise(B, D, leaves, prog, [13, 14, 16, 15, 19, 20, 21, 22])
+    pre = dev.binary("add", dxh, db)
+    i_, f_, g_, o_ = (dev.copy(pre.slice(1, k * D, (k + 1) * D)) for k in range(4))
+    i, f, g, o = dev.unary("sigmoid", i_), dev.unary("sigmoid", f_), dev.unary("tanh", g_), dev.unary("sigmoid", o_)
+    c1 = dev.binary("add", dev.binary("mul", f, dc), dev.binary("mul", i, g))
+    tc = dev.unary("tanh", c1)
+    h = dev.binary("mul", o, tc)
+    one_minus = dev.unary("rsub_scalar", tc, 1.0)
+    for got, want in zip(outs, [i, f, o, g, c1, tc, h, one_minus]):
+        assert np.array_equal(got.numpy(), want.numpy())
+    sig = lambda v: R.unary("sigmoid", v)
+    p = (xh.astype(np.float64) + bias).astype(np.float32)
+    c_ref = sig(p[:, D:2 * D]).astype(np.float64) * c0 + sig(p[:, :D]).astype(np.float64) * np.tanh(p[:, 2 * D:3 * D].astype(np.float64))
+    close(outs[4].numpy(), c_ref, 1e-6)
+    close(outs[6].numpy(), sig(p[:, 3 * D:]).astype(np.float64) * np.tanh(c_ref), 1e-6)
+    # immediates on either side, compare ops, column broadcast ([B,1] leaf), single row
+    col = dev.upload(rng.standard_normal((B, 1)).astype(np.float32))
+    y, = dev.fused_ewise(B, D, [(dc, 0), (col, 1)], [(Bn, "mul", 2, 0, 1, 0.0), (ffi.F_BINARY_IMM_B, "gt", 3, 2, 0, 0.0), (Bn, "mul", 4, 3, 0, 0.0)], [4])
+    cc = col.numpy()
+    assert np.array_equal(y.numpy(), ((c0 * cc) > 0).astype(np.float32) * c0)
+    y, = dev.fused_ewise(1, B * D, [(dc.reshape((1, B * D)), 5)], [(U, "square", 6, 5, 0, 0.0)], [6])
+    assert np.array_equal(y.numpy().reshape(B, D), c0 * c0)
+    # malformed programs are rejected on the host, before any launch
+    with pytest.raises(ffi.OpError):
+        dev.fused_ewise(B, D, [(dc, 0)], [(Bn, "add", 1, 0, 7, 0.0)], [1])          # reads a register nothing wrote
+    with pytest.raises(ffi.OpError):
+        dev.fused_ewise(B, D, [(dc, 0)], [(U, "clip", 1, 0, 0, 0.0)], [1])          # two-parameter op
+
+
 # ------------------------------------------------------------------------------------------------ reductions
 @pytest.mark.parametrize("k", KATS["reduce"])
 def test_reduce_kats(dev, k):
