@@ -238,6 +238,11 @@ int  agb_fused_ewise(agb_ctx* ctx, int64_t rows, int64_t cols, int n_leaves, con
 /* dst (any strides, e.g. a sliced region of a larger buffer) <- src (any strides), same shape.
  * Serves deep_copy, Concat/Tile, SliceGrad/SplitGrad (array_ops.rs:576-825), MaybeBroadcast. */
 int  agb_copy_strided(agb_ctx* ctx, const agb_tensor* src, agb_tensor* dst);
+/* dst[s * rows + r, :] = srcs[s][r, :]: n equally-shaped row blocks (unit column stride, row pitch src_pitch[s]) stacked into one
+ * contiguous [n * rows, cols] matrix, one launch per 64 blocks (Concat along axis 0, array_ops.rs:576-620).  The engine uses it to turn
+ * the per-time-step weight-gradient GEMMs of an unrolled RNN, sum_t A_t^T * G_t (gradient accumulation by AddN, gradient.rs:168-173), into
+ * ONE long-K GEMM.  cols and every pitch must be multiples of 4, pointers 16-byte aligned. */
+int  agb_concat_rows(agb_ctx* ctx, int n, const float* const* srcs, const int64_t* src_pitch, int64_t rows, int64_t cols, float* dst);
 /* Dropout::compute (random_ops.rs:218-237): train: y = x*mask (NOT rescaled); mask is supplied in
  * `mask` when seed==0, otherwise generated on device (Philox, (seed,offset)) and written to `mask`. */
 int  agb_dropout(agb_ctx* ctx, const agb_tensor* x, agb_tensor* y, agb_tensor* mask,

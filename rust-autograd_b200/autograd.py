@@ -532,7 +532,8 @@ class VariableEnvironment:
         _check(lib().agx_env_set_data_parallel(self.h, rank, world, buf))
 
     def set_fusion(self, on):
-        """Deferred elementwise expressions (engine/fuse.cc): on by default; off = one launch per node, bit-identical values."""
+        """Deferred elementwise expressions (engine/fuse.cc): on by default; off = one launch per node (elementwise values bit-identical; summed
+        weight-gradient GEMMs differ by fp32 reassociation)."""
         _check(lib().agx_env_set_fusion(self.h, 1 if on else 0))
 
     def run(self, f):

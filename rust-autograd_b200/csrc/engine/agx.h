@@ -123,6 +123,7 @@ struct Op {                       // trait Op (src/op.rs:90-101)
   virtual void compute(ComputeContext& ctx) = 0;     // throws OpError for Err(..), Panic for panics
   virtual void grad(GradientContext& ctx) = 0;
   virtual bool metadata_only() const { return false; }   // Shape / Rank / Size: read the input's shape, never its values
+  virtual bool sums_inputs() const { return false; }     // AddN: lets a producer defer itself so that the sum can absorb it (fuse.cc)
   virtual bool mutates_now() const { return false; }     // Assign: writes a variable in the middle of the traversal (optimizer ops are deferred)
 };
 
@@ -240,6 +241,8 @@ struct Evaluation {
   bool fuse = false;                      // elementwise fusion enabled for this run
   std::vector<int> consumers;             // per node id: consuming edges inside this evaluation (+1 per request as a target); metadata-only
                                           // consumers (Shape / Rank / Size) are not counted
+  std::vector<int> sole_consumer;         // per node id: the one node that reads it (-1 none yet, -2 several / a target)
+  bool sole_consumer_sums(TensorID id) const;    // true when the node's only reader in this evaluation is an AddN
   int consumers_of(TensorID id) const { return id >= 0 && id < (int)consumers.size() && consumers[id] > 0 ? consumers[id] : 1; }
 };
 
@@ -315,6 +318,8 @@ NdArray expr_materialize(Device* dev, const NdArray& x);
 bool expr_has_value(const NdArray& x);
 NdArray expr_pad(ComputeContext& c, const Shape& full, const std::vector<int64_t>& start, NdArray gy);
 bool expr_sum_pads(ComputeContext& c, const std::vector<NdArray>& xs, NdArray* out);
+NdArray expr_gemm_ta(ComputeContext& c, NdArray a, NdArray b);                 // deferred A^T * B whose only reader is an AddN
+bool expr_sum_gemms(ComputeContext& c, const std::vector<NdArray>& xs, NdArray* out);
 bool expr_materialize_into(Device* dev, const NdArray& x, NdArray dest);
 Op* make_optimizer_op(int kind, float h0, float h1, float h2, float h3);
 void flush_pending_updates(Evaluation& run, VariableEnvironment* env);

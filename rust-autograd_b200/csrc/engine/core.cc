@@ -337,6 +337,12 @@ NdArray find_placeholder_value(const std::vector<Feed>& feeds, Graph* g, TensorI
 }
 }  // namespace
 
+bool Evaluation::sole_consumer_sums(TensorID id) const {
+  if (id < 0 || id >= (int)sole_consumer.size() || sole_consumer[id] < 0) return false;
+  TensorInternal& n = graph->inner(sole_consumer[id]);
+  return n.op && n.op->sums_inputs();
+}
+
 std::vector<EvalResult> eval(Graph* g, const std::vector<Tensor>& targets, const std::vector<Feed>& feeds, bool fetch_to_host) {
   VariableEnvironment* env = g->env; Device* dev = env->dev;
   std::unordered_map<TensorID, Stored> storage;
@@ -349,7 +355,8 @@ std::vector<EvalResult> eval(Graph* g, const std::vector<Tensor>& targets, const
   for (auto& t : targets) { if (t.graph != g) throw Panic("Detected tensors belonging to different graphs"); st.push_back({t.id, false}); }
   run.fuse = env->fuse_elementwise;
   if (run.fuse) {         // pre-pass for fuse.cc: how many consumers will read each node's VALUES in this evaluation
-    run.consumers.assign(g->node_set.size(), 0);
+    run.consumers.assign(g->node_set.size(), 0); run.sole_consumer.assign(g->node_set.size(), -1);
+    for (auto& t : targets) run.sole_consumer[t.id] = -2;
     std::vector<char> seen(g->node_set.size(), 0); std::vector<TensorID> todo;
     for (auto& t : targets) { run.consumers[t.id]++; if (!seen[t.id]) { seen[t.id] = 1; todo.push_back(t.id); } }
     while (!todo.empty()) {
@@ -357,7 +364,10 @@ std::vector<EvalResult> eval(Graph* g, const std::vector<Tensor>& targets, const
       if (n.is_placeholder || n.is_variable()) continue;
       const bool meta_only = n.op && n.op->metadata_only();
       if (n.op && n.op->mutates_now()) run.fuse = false;      // a pending expression must never read a variable after an Assign of the same run
-      for (auto& c : n.incoming_nodes) { if (!meta_only) run.consumers[c.id]++; if (!seen[c.id]) { seen[c.id] = 1; todo.push_back(c.id); } }
+      for (auto& c : n.incoming_nodes) {
+        if (!meta_only) { run.consumers[c.id]++; run.sole_consumer[c.id] = run.sole_consumer[c.id] == -1 ? n.id : -2; }
+        if (!seen[c.id]) { seen[c.id] = 1; todo.push_back(c.id); }
+      }
     }
   }
   while (!st.empty()) {

@@ -30,7 +30,7 @@ struct ExprNode {
 };
 
 namespace {
-const int kPad = 100;
+const int kPad = 100, kGemmTA = 101;     // nodes that are memory, not instructions: never part of a program
 void materialize_node(Device* dev, ExprNode* n, NdArray* dest = nullptr);
 const int64_t kMaxFusedElems = (int64_t)1 << 24;     // beyond this a pass is bandwidth-bound anyway and the vectorised single-op kernels are used
 
@@ -160,6 +160,13 @@ void write_region(Device* dev, NdArray src, NdArray region) {      // region <- 
 
 void materialize_node(Device* dev, ExprNode* n, NdArray* dest) {
   if (n->has_value) return;
+  if (n->kind == kGemmTA) {
+    NdArray y = dev->empty(n->shape);
+    agb_tensor da = n->a.desc(), db = n->b.desc(), dy = y.desc();
+    check_status(agb_gemm_f32(dev->ctx, 1, 0, &da, &db, &dy, 0.0f));
+    n->value = y; n->has_value = true; n->a = NdArray(); n->b = NdArray();
+    return;
+  }
   if (n->kind == kPad) {
     NdArray gx = dev->zeros(n->shape);
     write_region(dev, n->a, pad_region(gx, n->pad_start, n->a.shape));
@@ -200,7 +207,7 @@ NdArray finish(ComputeContext& c, std::shared_ptr<ExprNode> n) {
 }
 
 bool operand_ok(Device* dev, NdArray& x, const Shape& out) {
-  if (unvalued(x) && x.expr->kind == kPad) materialize_node(dev, x.expr.get());       // a padded slice gradient is memory, not an instruction
+  if (unvalued(x) && x.expr->kind >= kPad) materialize_node(dev, x.expr.get());       // a padded slice gradient is memory, not an instruction
   if (x.expr) { if (x.expr->has_value) { NdArray v = x.expr->value; return leaf_ok(dev, v, out); } return x.shape == out; }
   return leaf_ok(dev, x, out);
 }
@@ -263,6 +270,33 @@ bool expr_sum_pads(ComputeContext& c, const std::vector<NdArray>& xs, NdArray* o
   if (at != full[axis]) covered = false;
   NdArray y = covered ? c.dev->empty(full) : c.dev->zeros(full);
   for (auto& x : xs) write_region(c.dev, x.expr->a, pad_region(y, x.expr->pad_start, x.expr->a.shape));
+  *out = y;
+  return true;
+}
+NdArray expr_gemm_ta(ComputeContext& c, NdArray a, NdArray b) {
+  if (a.ndim() != 2 || b.ndim() != 2 || !a.on_device() || !b.on_device() || a.shape[0] != b.shape[0] || a.lazy || b.lazy || a.i32 || b.i32) return NdArray();
+  auto n = std::make_shared<ExprNode>(); n->kind = kGemmTA; n->a = a; n->b = b; n->shape = {a.shape[1], b.shape[1]};
+  n->consumers = 1; n->n_instr = 0; n->n_leaves = 1; n->n_multi = 0;
+  NdArray r; r.shape = n->shape; r.stride = NdArray::contiguous_strides(r.shape); r.expr = n;
+  return r;
+}
+// AddN over deferred A_t^T * G_t terms of one shape: stack the A_t and the G_t (one launch each per 64 terms) and run one GEMM with
+// K = sum of the terms' K.  The result differs from the term-by-term sum only by fp32 reassociation.
+bool expr_sum_gemms(ComputeContext& c, const std::vector<NdArray>& xs, NdArray* out) {
+  if (xs.size() < 2) return false;
+  for (auto& x : xs) if (!unvalued(x) || x.expr->kind != kGemmTA || x.expr->a.shape != xs[0].expr->a.shape || x.expr->b.shape != xs[0].expr->b.shape) return false;
+  auto stackable = [](const NdArray& t) { return t.stride[1] == 1 && t.stride[0] % 4 == 0 && t.shape[1] % 4 == 0 && (((uintptr_t)t.dptr) & 15) == 0; };
+  for (auto& x : xs) if (!stackable(x.expr->a) || !stackable(x.expr->b)) return false;
+  const int n = (int)xs.size();
+  const int64_t k = xs[0].expr->a.shape[0], M = xs[0].expr->a.shape[1], N = xs[0].expr->b.shape[1];
+  NdArray A = c.dev->empty({n * k, M}), B = c.dev->empty({n * k, N});
+  std::vector<const float*> pa(n), pb(n); std::vector<int64_t> sa(n), sb(n);
+  for (int i = 0; i < n; i++) { pa[i] = xs[i].expr->a.dptr; sa[i] = xs[i].expr->a.stride[0]; pb[i] = xs[i].expr->b.dptr; sb[i] = xs[i].expr->b.stride[0]; }
+  check_status(agb_concat_rows(c.dev->ctx, n, pa.data(), sa.data(), k, M, A.dptr));
+  check_status(agb_concat_rows(c.dev->ctx, n, pb.data(), sb.data(), k, N, B.dptr));
+  NdArray y = c.dev->empty({M, N});
+  agb_tensor da = A.desc(), db = B.desc(), dy = y.desc();
+  check_status(agb_gemm_f32(c.dev->ctx, 1, 0, &da, &db, &dy, 0.0f));
   *out = y;
   return true;
 }

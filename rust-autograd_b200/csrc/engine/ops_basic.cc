@@ -623,7 +623,7 @@ struct AddN : Op {                     // array_ops.rs:503-535
     c.accept_expr = true;
     std::vector<NdArray> xs; bool same = true, all_empty_scalars = true;
     for (int i = 0; i < n; i++) { xs.push_back(c.input(i)); if (xs[i].shape != xs[0].shape) same = false; if (!(xs[i].ndim() == 0 && xs[i].has_host() && !xs[i].on_device())) all_empty_scalars = false; }
-    if (same && !all_empty_scalars) { NdArray y; if (expr_sum_pads(c, xs, &y)) { c.append_output(y); return; } }
+    if (same && !all_empty_scalars) { NdArray y; if (expr_sum_pads(c, xs, &y) || expr_sum_gemms(c, xs, &y)) { c.append_output(y); return; } }
     if (same && !all_empty_scalars && n <= 6 && xs[0].ndim() > 0) {      // a short sum joins the pending expression as the same left fold
       NdArray acc = expr_binary(c, AGB_B_ADD, xs[0], xs[1]);
       for (int i = 2; i < n && acc.expr; i++) acc = expr_binary(c, AGB_B_ADD, acc, xs[i]);
@@ -657,6 +657,7 @@ struct AddN : Op {                     // array_ops.rs:503-535
     c.append_output(acc);
   }
   void grad(GradientContext& c) override { for (int i = 0; i < c.num_inputs(); i++) c.append_input_grad(c.output_grad()); }
+  bool sums_inputs() const override { return true; }
 };
 Tensor T::add_n(const std::vector<Tensor>& xs) {
   if (xs.empty()) throw Panic("add_n: empty input");

@@ -26,6 +26,9 @@ struct MatMul : Op {                   // dot_ops.rs:554-629.  Transposes = stri
       if (!collapsible(a)) a = c.dev->copy(a);
       if (!collapsible(b)) b = c.dev->copy(b);
     }
+    // one term of a gradient accumulation sum_t A_t^T * G_t (MatMul::grad under AddN, gradient.rs:168-173): deferred, so that the sum
+    // runs as ONE long-K GEMM over the stacked operands instead of T short ones plus an add (fuse.cc)
+    if (!batched && ta && !tb && c.run->fuse && c.run->sole_consumer_sums(c.node)) { NdArray r = expr_gemm_ta(c, a, b); if (r.expr) { c.append_output(r); return; } }
     int R = a.ndim();
     int64_t m = ta ? a.shape[R - 1] : a.shape[R - 2], n = tb ? b.shape[R - 2] : b.shape[R - 1];
     Shape out(a.shape.begin(), a.shape.end() - 2); out.push_back(m); out.push_back(n);

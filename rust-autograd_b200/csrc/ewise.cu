@@ -394,6 +394,39 @@ extern "C" int agb_add_n(agb_ctx* ctx, int n, const agb_tensor* const* xs, agb_t
 }
 
 // ----------------------------------------------------------------------------------------------
+// stack n row blocks into one matrix (pointer table in the kernel parameters, blockIdx.y = block)
+// ----------------------------------------------------------------------------------------------
+#define AGB_CONCAT_MAX 64
+struct ConcatParams { const float* src[AGB_CONCAT_MAX]; int64_t pitch[AGB_CONCAT_MAX]; };
+__global__ void __launch_bounds__(256) concat_rows_kernel(const __grid_constant__ ConcatParams P, int64_t rows, int64_t cols4, float* __restrict__ dst) {
+  const int s = blockIdx.y;
+  const float* __restrict__ src = P.src[s]; const int64_t pitch = P.pitch[s];
+  float* d = dst + (int64_t)s * rows * cols4 * 4;
+  const int64_t total = rows * cols4, stride = (int64_t)gridDim.x * 256;
+  for (int64_t i = blockIdx.x * (int64_t)256 + threadIdx.x; i < total; i += stride) {
+    const int64_t r = i / cols4, c = i - r * cols4;
+    *reinterpret_cast<float4*>(d + 4 * i) = ldg_stream4(src + r * pitch + 4 * c);      // plain store: the GEMM that follows reads it from L2
+  }
+}
+extern "C" int agb_concat_rows(agb_ctx* ctx, int n, const float* const* srcs, const int64_t* src_pitch, int64_t rows, int64_t cols, float* dst) {
+  AGB_CHECK(n >= 1 && rows >= 0 && cols >= 0, AGB_ERR_INVALID_DIMS, "agb_concat_rows: bad extents");
+  AGB_CHECK(cols % 4 == 0 && (((uintptr_t)dst) & 15) == 0, AGB_ERR_UNSUPPORTED, "agb_concat_rows: cols must be a multiple of 4 and dst 16-byte aligned");
+  for (int i = 0; i < n; i++)
+    AGB_CHECK(srcs[i] != nullptr && (((uintptr_t)srcs[i]) & 15) == 0 && src_pitch[i] % 4 == 0, AGB_ERR_UNSUPPORTED, "agb_concat_rows: block %d is not 16-byte aligned / pitch %% 4 != 0", i);
+  if (rows * cols == 0) return AGB_OK;
+  AgbProfScope prof(ctx, AGB_PROF_EWISE, 8.0 * (double)n * rows * cols);
+  for (int base = 0; base < n; base += AGB_CONCAT_MAX) {
+    const int m = n - base < AGB_CONCAT_MAX ? n - base : AGB_CONCAT_MAX;
+    ConcatParams P; memset(&P, 0, sizeof(P));
+    for (int i = 0; i < m; i++) { P.src[i] = srcs[base + i]; P.pitch[i] = src_pitch[base + i]; }
+    int gx = agb_grid_for(rows * cols / 4, 256, ctx->sm_count, 8); gx = (gx + m - 1) / m; if (gx < 1) gx = 1;
+    concat_rows_kernel<<<dim3(gx, m), 256, 0, ctx->stream>>>(P, rows, cols / 4, dst + (int64_t)base * rows * cols);
+    AGB_LAUNCHED(ctx);
+  }
+  return AGB_OK;
+}
+
+// ----------------------------------------------------------------------------------------------
 // fused elementwise program: a small register machine per element.  The host (engine/fuse.cc) compiles a
 // DAG of deferred unary / binary ops into <= 48 instructions over <= 32 registers; every thread keeps its register file in its
 // own shared-memory column (conflict-free, no synchronisation), loads all leaves up front (independent loads in flight), runs the
@@ -469,6 +502,7 @@ extern "C" int agb_fused_ewise(agb_ctx* ctx, int64_t rows, int64_t cols, int n_l
     P.optr[o] = outs[o].ptr; P.opitch[o] = outs[o].pitch; P.oreg[o] = (uint8_t)outs[o].reg;
   }
   if (P.total == 0) return AGB_OK;
+  AgbProfScope prof(ctx, AGB_PROF_EWISE, 4.0 * (double)P.total * (n_leaves + n_out));
   fused_ewise_kernel<<<agb_grid_for(P.total, 256, ctx->sm_count, 6), 256, 0, ctx->stream>>>(P);
   AGB_LAUNCHED(ctx);
   return AGB_OK;

@@ -201,6 +201,15 @@ class Device:
         ffi.check(self.lib.agb_fused_ewise(self.ctx, rows, cols, len(leaves), lv, len(program), ins, len(out_regs), outs))
         return ys
 
+    def concat_rows(self, xs):
+        """agb_concat_rows: equally-shaped 2-D blocks (unit column stride) stacked along axis 0 in one launch."""
+        rows, cols = xs[0].shape
+        y = self.empty((len(xs) * rows, cols))
+        ptrs = (C.c_void_p * len(xs))(*[x.ptr for x in xs])
+        pitch = (C.c_int64 * len(xs))(*[x.strides[0] for x in xs])
+        ffi.check(self.lib.agb_concat_rows(self.ctx, len(xs), ptrs, pitch, rows, cols, y.ptr))
+        return y
+
     def fill(self, shape, v):
         y = self.empty(shape)
         ffi.check(self.lib.agb_fill(self.ctx, y.desc(), v))

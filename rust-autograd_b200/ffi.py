@@ -87,6 +87,7 @@ SIGNATURES = {
     "agb_unary": [_P, _i, _f, _f, _T, _T], "agb_binary": [_P, _i, _f, _f, _T, _T, _T],
     "agb_add_n": [_P, _i, C.POINTER(_T), _T], "agb_fill": [_P, _T, _f],
     "agb_fused_ewise": [_P, _i64, _i64, _i, _P, _i, _P, _i, _P], "agb_copy_strided": [_P, _T, _T],
+    "agb_concat_rows": [_P, _i, _P, _P, _i64, _i64, _P],
     "agb_dropout": [_P, _T, _T, _T, _f, _u64, _u64],
     "agb_reduce": [_P, _i, _P, _P, _i64, _i64, _i64], "agb_argreduce": [_P, _i, _P, _P, _i64, _i64, _i64],
     "agb_softmax": [_P, _P, _P, _i64, _i64, _i64], "agb_log_softmax": [_P, _P, _P, _i64, _i64, _i64],

@@ -64,6 +64,20 @@ def run(name, init, loss_fn, feeds, mode, steps=200, warm=20):
     dt = (time.time() - t0) / steps
     row.update({"graph_us_per_step": dt * 1e6, "graph_samples_per_s": b / dt})
     sg.close()
+    if "--profile" in sys.argv:      # where the eager step's device time goes: event pairs around every call of each kernel class (agb_prof_*)
+        names = ["gemm", "conv_fprop", "conv_dgrad", "conv_wgrad", "ewise", "reduce", "softmax", "pool", "optim"]
+        ffi.check(lib.agb_prof_enable(ctx, 1)); ffi.check(lib.agb_prof_reset(ctx))
+        n = 3
+        for _ in range(n):
+            step()
+        prof = {}
+        for i, nm in enumerate(names):
+            ms, calls, work = C.c_double(), C.c_int64(), C.c_double()
+            ffi.check(lib.agb_prof_collect(ctx, i, C.byref(ms), C.byref(calls), C.byref(work)))
+            if calls.value:
+                prof[nm] = {"ms_per_step": ms.value / n, "calls_per_step": calls.value / n, "work_per_s": work.value / max(ms.value, 1e-9) * 1e3}
+        ffi.check(lib.agb_prof_enable(ctx, 0))
+        row["profile"] = prof
     print(json.dumps(row), flush=True)
     g.close(); env.close()
 
@@ -72,7 +86,7 @@ def main():
     rng = np.random.default_rng(0)
     B = 200
     x = rng.uniform(size=(B, 784)).astype(np.float32); y = rng.integers(0, 10, (B, 1)).astype(np.float32)
-    for mode in (0, 1):
+    for mode in ((0, 1) if "--lstm-only" not in sys.argv else ()):
         run("mlp_mnist_b200", W.mlp_init, W.mlp_loss, {"x": x, "y": y}, mode)
         run("cnn_mnist_b200", W.cnn_mnist_init, lambda T, g: W.cnn_mnist_loss(T, g, train=True), {"x": x, "y": y}, mode)
     # LSTM language model: batch 128 x seq 64, hidden 1024, vocab 8192 -> 0.81 TFLOP per step

@@ -457,6 +457,17 @@ def test_add_n_fill_copy_dropout(dev):
     assert set(np.unique(m)) == {0.0, 1.0} and abs(m.mean() - 0.75) < 5e-3 and np.array_equal(y.numpy(), m)
 
 
+def test_concat_rows(dev):
+    """agb_concat_rows: 70 blocks (two launches of the 64-entry pointer table), contiguous and sliced (pitch != cols) sources."""
+    rng = np.random.default_rng(5)
+    big = rng.standard_normal((24, 96)).astype(np.float32)
+    dbig = dev.upload(big)
+    xs = [rng.standard_normal((24, 32)).astype(np.float32) for _ in range(69)]
+    ds = [dev.upload(x) for x in xs] + [dbig.slice(1, 32, 64)]
+    got = dev.concat_rows(ds).numpy()
+    assert np.array_equal(got, np.concatenate(xs + [big[:, 32:64]], axis=0))
+
+
 def test_fused_ewise_lstm_cell_matches_single_op_kernels(dev):
     """agb_fused_ewise on the LSTM cell (examples/lstm_lm.rs:36-45): gates are sliced views of one [B, 4D] buffer (read in place, pitch 4D),
     the bias is a row broadcast, outputs i, f, o, g, c', tanh(c'), h from ONE launch: bit-identical to the chain of agb_unary / agb_binary
