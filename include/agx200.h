@@ -49,8 +49,9 @@ int agx_env_save(agx_env* env, const char* path);                               
 int agx_env_load(agx_env* env, const char* path);
 int agx_env_set_data_parallel(agx_env* env, int rank, int world, const void* nccl_id128);
 /* Deferred elementwise expressions (engine/fuse.cc): on by default.  Chains of unary / binary / compare / small AddN
- * nodes run as ONE agb_fused_ewise launch, slice gradients are summed in place, and a gradient accumulation sum_t A_t^T * G_t runs as one
- * long-K GEMM; off = one launch per node.  Elementwise values are bit-identical either way; the summed GEMM differs by fp32 reassociation. */
+ * nodes run as ONE agb_fused_ewise launch, slice gradients are summed in place, a gradient accumulation sum_t A_t^T * G_t runs as one
+ * long-K GEMM, and independent MatMuls against one weight (the time steps of an unrolled RNN) run as one row-stacked GEMM; off = one
+ * launch per node.  Elementwise values are bit-identical either way; the regrouped GEMMs differ by fp32 reassociation. */
 int agx_env_set_fusion(agx_env* env, int on);
 
 /* ---- Graph construction ---- */

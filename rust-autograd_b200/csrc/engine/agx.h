@@ -123,6 +123,7 @@ struct Op {                       // trait Op (src/op.rs:90-101)
   virtual void compute(ComputeContext& ctx) = 0;     // throws OpError for Err(..), Panic for panics
   virtual void grad(GradientContext& ctx) = 0;
   virtual bool metadata_only() const { return false; }   // Shape / Rank / Size: read the input's shape, never its values
+  virtual bool plain_matmul(bool* tb) const { return false; }   // MatMul (2-D, lhs not transposed): rows of several such products with one rhs can be stacked
   virtual bool sums_inputs() const { return false; }     // AddN: lets a producer defer itself so that the sum can absorb it (fuse.cc)
   virtual bool mutates_now() const { return false; }     // Assign: writes a variable in the middle of the traversal (optimizer ops are deferred)
 };

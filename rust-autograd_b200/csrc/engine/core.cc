@@ -1,5 +1,6 @@
 // core.cc — arrays, graph, reverse-mode gradient builder, evaluator, variable environment (see agx.h for the reference map).
 #include "agx.h"
+#include <map>
 #include <algorithm>
 #include <queue>
 #include <sstream>
@@ -354,10 +355,11 @@ std::vector<EvalResult> eval(Graph* g, const std::vector<Tensor>& targets, const
   std::vector<std::pair<TensorID, bool>> st; st.reserve(1 << 10);
   for (auto& t : targets) { if (t.graph != g) throw Panic("Detected tensors belonging to different graphs"); st.push_back({t.id, false}); }
   run.fuse = env->fuse_elementwise;
+  std::vector<char> seen;      // nodes this evaluation will compute
   if (run.fuse) {         // pre-pass for fuse.cc: how many consumers will read each node's VALUES in this evaluation
     run.consumers.assign(g->node_set.size(), 0); run.sole_consumer.assign(g->node_set.size(), -1);
     for (auto& t : targets) run.sole_consumer[t.id] = -2;
-    std::vector<char> seen(g->node_set.size(), 0); std::vector<TensorID> todo;
+    seen.assign(g->node_set.size(), 0); std::vector<TensorID> todo;
     for (auto& t : targets) { run.consumers[t.id]++; if (!seen[t.id]) { seen[t.id] = 1; todo.push_back(t.id); } }
     while (!todo.empty()) {
       TensorInternal& n = g->inner(todo.back()); todo.pop_back();
@@ -370,10 +372,97 @@ std::vector<EvalResult> eval(Graph* g, const std::vector<Tensor>& targets, const
       }
     }
   }
+  // ---- row-stacked MatMuls (the contraction side): an unrolled RNN multiplies T different [B, k] inputs by the SAME
+  // weight (lstm_lm.rs:30-35,48: x_t * wx, h_t * w_pred, and their MatMul::grad counterparts gy_t * W^T).  Members whose lhs does not depend on
+  // another member's product are evaluated together: when the traversal first reaches one, the lhs of ALL of them are scheduled first, the
+  // rows are stacked (agb_concat_rows) and ONE [T*B, k] x W GEMM fills every member's output (row blocks of one buffer).  Per-row
+  // arithmetic is unchanged; a 128-row GEMM cannot fill 148 SMs, a 8064-row one runs at the large-GEMM rate.
+  struct RowBatch { std::vector<TensorID> members; TensorID weight; bool tb; bool expanded = false, done = false; };
+  std::vector<RowBatch> batches; std::vector<int> batch_of;
+  if (run.fuse) {
+    const size_t N = g->node_set.size();
+    std::map<std::pair<TensorID, bool>, int> key2group; std::vector<RowBatch> groups; std::vector<int> group_of(N, -1);
+    bool ordered = true;
+    for (size_t id = 0; id < N; id++) {
+      if (!seen[id]) continue;                                    // not part of this evaluation
+      TensorInternal& n = g->inner((TensorID)id); bool tb = false;
+      if (n.is_placeholder || n.is_variable() || !n.op) continue;
+      for (auto& c : n.incoming_nodes) if (c.id >= (TensorID)id) ordered = false;      // (control_dependencies rewiring) no stacking then
+      if (!n.op->plain_matmul(&tb) || n.incoming_nodes.size() != 2 || !g->inner(n.incoming_nodes[1].id).is_variable()) continue;
+      auto key = std::make_pair(n.incoming_nodes[1].id, tb);
+      auto it = key2group.find(key);
+      if (it == key2group.end()) { if (groups.size() >= 64) continue; it = key2group.insert({key, (int)groups.size()}).first; RowBatch b; b.weight = key.first; b.tb = tb; groups.push_back(b); }
+      groups[it->second].members.push_back((TensorID)id); group_of[id] = it->second;
+    }
+    if (ordered && !groups.empty()) {
+      std::vector<uint64_t> dep(N, 0);                            // bit q: the node's value depends on a product of group q
+      for (size_t id = 0; id < N; id++) {
+        if (!seen[id]) continue;
+        TensorInternal& n = g->inner((TensorID)id);
+        if (n.is_placeholder || n.is_variable()) continue;
+        uint64_t d = 0;
+        for (auto& c : n.incoming_nodes) { d |= dep[c.id]; if (group_of[c.id] >= 0) d |= 1ull << group_of[c.id]; }
+        dep[id] = d;
+      }
+      batch_of.assign(N, -1);
+      for (size_t q = 0; q < groups.size(); q++) {
+        RowBatch b; b.weight = groups[q].weight; b.tb = groups[q].tb;
+        for (TensorID m : groups[q].members) {
+          TensorID a = g->inner(m).incoming_nodes[0].id;
+          uint64_t d = dep[a] | (group_of[a] >= 0 ? 1ull << group_of[a] : 0);
+          if (!((d >> q) & 1)) b.members.push_back(m);
+        }
+        if (b.members.size() >= 2) { for (TensorID m : b.members) batch_of[m] = (int)batches.size(); batches.push_back(b); }
+      }
+    }
+  }
+  auto fetch = [&](const IncomingTensor& in, NdArray* out) {      // the value an op would receive through ComputeContext::input
+    TensorInternal& x = g->inner(in.id);
+    if (x.is_placeholder) *out = find_placeholder_value(feeds, g, in.id);
+    else if (x.is_variable()) *out = env->array_list[x.variable_id.v];
+    else {
+      auto it = storage.find(in.id);
+      if (it == storage.end() || !it->second.ok || in.array_selector >= (int)it->second.ys.size()) return false;
+      *out = it->second.ys[in.array_selector];
+    }
+    if (out->expr) *out = expr_materialize(dev, *out);
+    if (out->lazy) *out = materialize_lazy(dev, *out);
+    if (out->i32 || out->virt) return false;
+    dev->ensure_device(*out);
+    return out->on_device();
+  };
+  auto run_row_batch = [&](RowBatch& b) {
+    std::vector<TensorID> ms; std::vector<NdArray> as; NdArray w;
+    if (!fetch(IncomingTensor{b.weight, false, 0}, &w) || w.ndim() != 2) return false;
+    for (TensorID m : b.members) {
+      if (storage.count(m)) continue;
+      NdArray a;
+      if (!fetch(g->inner(m).incoming_nodes[0], &a) || a.ndim() != 2) continue;
+      if (!as.empty() && a.shape != as[0].shape) continue;
+      if (a.stride[1] != 1 || a.stride[0] % 4 != 0 || a.shape[1] % 4 != 0 || (((uintptr_t)a.dptr) & 15) != 0) continue;
+      ms.push_back(m); as.push_back(a);
+    }
+    if (ms.size() < 2) return false;
+    const int64_t rows = as[0].shape[0], k = as[0].shape[1], ncol = b.tb ? w.shape[0] : w.shape[1];
+    if ((b.tb ? w.shape[1] : w.shape[0]) != k || rows == 0 || k == 0 || ncol == 0) return false;      // the members raise their own shape errors
+    const int n = (int)ms.size();
+    NdArray A = dev->empty({n * rows, k}), Y = dev->empty({n * rows, ncol});
+    std::vector<const float*> ps(n); std::vector<int64_t> pitch(n);
+    for (int i = 0; i < n; i++) { ps[i] = as[i].dptr; pitch[i] = as[i].stride[0]; }
+    check_status(agb_concat_rows(dev->ctx, n, ps.data(), pitch.data(), rows, k, A.dptr));
+    agb_tensor da = A.desc(), dw = w.desc(), dy = Y.desc();
+    check_status(agb_gemm_f32(dev->ctx, 0, b.tb ? 1 : 0, &da, &dw, &dy, 0.0f));
+    for (int i = 0; i < n; i++) { Stored o; o.ys.push_back(Y.sliced(0, i * rows, rows)); storage[ms[i]] = std::move(o); }
+    return true;
+  };
   while (!st.empty()) {
     auto [id, visit] = st.back(); st.pop_back();
     if (visit) {
       if (would_not_visit(id)) continue;
+      if (!batch_of.empty() && batch_of[id] >= 0 && !batches[batch_of[id]].done) {
+        RowBatch& b = batches[batch_of[id]]; b.done = true;
+        if (run_row_batch(b) && storage.count(id)) continue;
+      }
       TensorInternal& n = g->inner(id);
       Stored out;
       ComputeContext ctx; ctx.dev = dev; ctx.run = &run; ctx.node = id;
@@ -399,6 +488,10 @@ std::vector<EvalResult> eval(Graph* g, const std::vector<Tensor>& targets, const
     } else {
       st.push_back({id, true});
       for (auto& c : g->inner(id).incoming_nodes) if (!would_not_visit(c.id)) st.push_back({c.id, false});
+      if (!batch_of.empty() && batch_of[id] >= 0 && !batches[batch_of[id]].expanded) {       // schedule the lhs of every member of the stack first
+        RowBatch& b = batches[batch_of[id]]; b.expanded = true;
+        for (TensorID m : b.members) { TensorID a = g->inner(m).incoming_nodes[0].id; if (m != id && !would_not_visit(a)) st.push_back({a, false}); }
+      }
     }
   }
   // pending elementwise expressions among the targets read the variables' CURRENT values: compute them before the optimizer writes

@@ -37,6 +37,7 @@ struct MatMul : Op {                   // dot_ops.rs:554-629.  Transposes = stri
     check_status(agb_gemm_f32(c.dev->ctx, ta ? 1 : 0, tb ? 1 : 0, &da, &db, &dy, 0.0f));
     c.append_output(y);
   }
+  bool plain_matmul(bool* tb_) const override { if (batched || ta) return false; *tb_ = tb; return true; }
   void grad(GradientContext& c) override {       // dot_ops.rs:608-628,697-717: the forward op's own flags are ignored (sic)
     Tensor gy = c.output_grad();
     auto mk = [&](Tensor l, Tensor r, bool tl, bool tr) { auto* op = new MatMul(); op->ta = tl; op->tb = tr; op->batched = batched; return TensorBuilder(c.graph()).append_input(l, false).append_input(r, false).build(op); };

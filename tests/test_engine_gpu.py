@@ -287,8 +287,9 @@ def test_lstm_language_model_matches_oracle(ag):
 
 def test_elementwise_fusion_is_bit_identical_and_saves_launches(ag):
     """engine/fuse.cc: the LSTM language model's forward + backward with deferred elementwise expressions ON (default)
-    and OFF give bit-identical loss, bias gradient and observable intermediates (every instruction of a fused program is the functor of the
-    single-op kernel; weight gradients agree to fp32 reassociation), while the fused run needs far fewer launches."""
+    and OFF: elementwise compositions and their observable intermediates are bit-identical (every instruction of a fused program is the functor
+    of the single-op kernel); loss and gradients, which pass through row-stacked / long-K GEMMs when fused, agree to fp32 reassociation (2e-6);
+    the fused run needs far fewer launches."""
     import ctypes as C
     from rust_autograd_b200 import ffi, workloads as W
     D, V, S, B = 64, 96, 6, 32
@@ -322,9 +323,9 @@ def test_elementwise_fusion_is_bit_identical_and_saves_launches(ag):
     plain, n_plain = run(False)
     assert len(fused) == len(plain) == 9
     for k, (a, b) in enumerate(zip(fused, plain)):
-        if k in (1, 2, 4, 5):   # 4: the embedding gradient is an atomic scatter-add (GatherGrad), order differs from run to run; 1, 2, 5: the
-            assert rel(a, b) <= 2e-6   # weight gradients sum_t A_t^T G_t run as ONE long-K GEMM when fused: fp32 reassociation only
-        else:
+        if k < 6:       # through GEMMs: stacked rows / long-K sums pick other tile shapes and split-K factors => fp32 reassociation only
+            assert rel(a, b) <= 2e-6, (k, rel(a, b))
+        else:           # pure elementwise compositions: every fused instruction is the functor of the single-op kernel
             assert np.array_equal(np.asarray(a), np.asarray(b)), k
     assert n_fused < 0.6 * n_plain, (n_fused, n_plain)
     print("launches fused/plain:", n_fused, n_plain)
