@@ -202,7 +202,8 @@ enum { /* unary ops: math_ops.rs:277-1019, activation_ops.rs:113-226, array_ops.
   AGB_U_EXP10, AGB_U_SIN, AGB_U_COS, AGB_U_TAN, AGB_U_ASIN, AGB_U_ACOS, AGB_U_ATAN, AGB_U_SINH, AGB_U_COSH,
   AGB_U_TANH, AGB_U_ASINH, AGB_U_ACOSH, AGB_U_ATANH, AGB_U_SIGMOID, AGB_U_RELU, AGB_U_SOFTPLUS,
   AGB_U_ELU /*p0=alpha*/, AGB_U_CLIP /*p0=min,p1=max*/, AGB_U_SCALE /* x*p0 */, AGB_U_ADD_SCALAR /* x+p0 */,
-  AGB_U_RSUB_SCALAR /* p0-x */, AGB_U_RDIV_SCALAR /* p0/x */, AGB_U_COUNT
+  AGB_U_RSUB_SCALAR /* p0-x */, AGB_U_RDIV_SCALAR /* p0/x */,
+  AGB_U_LGAMMA /* ln|Gamma(x)| */, AGB_U_DIGAMMA /* d/dx ln Gamma(x) */ /* math_ops.rs:1021-1060, `special` 0.10 Gamma trait */, AGB_U_COUNT
 };
 enum { /* binary ops: binary_ops.rs:147-290, math_ops.rs:86-184, activation_ops.rs:204-226, array_ops.rs:556-574 */
   AGB_B_ADD = 0, AGB_B_SUB, AGB_B_MUL, AGB_B_DIV, AGB_B_EQ, AGB_B_NE, AGB_B_GT, AGB_B_LT, AGB_B_GE, AGB_B_LE,
@@ -282,6 +283,10 @@ int  agb_gather(agb_ctx* ctx, const float* param, const float* indices, float* o
                 int64_t pre, int64_t axis_len, int64_t post, int64_t n_idx, int normalize_negative);
 /* GatherGrad::compute (array_ops.rs:401-466): gx = 0; gx[:, idx[j], :] += gy[:, j, :] */
 int  agb_gather_grad(agb_ctx* ctx, const float* gy, const float* indices, float* gx,
+                     int64_t pre, int64_t axis_len, int64_t post, int64_t n_idx);
+/* the accumulation half of GatherGrad alone: gx[:, idx[j], :] += gy[:, j, :] with NO zero fill, so that a sum of GatherGrads of one
+ * table (an embedding looked up at every time step, gradient.rs:168-173) scatters into a single buffer */
+int  agb_scatter_add(agb_ctx* ctx, const float* gy, const float* indices, float* gx,
                      int64_t pre, int64_t axis_len, int64_t post, int64_t n_idx);
 
 /* ======================= optimizers ======================= */

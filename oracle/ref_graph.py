@@ -277,7 +277,7 @@ def _mk_unary(name):
 
 
 for _n in ["sin", "cos", "tan", "asin", "acos", "atan", "sinh", "cosh", "tanh", "asinh", "acosh", "atanh", "exp", "exp2", "exp10", "ln", "log2",
-           "log10", "sqrt", "neg", "abs", "sign", "floor", "ceil", "inv", "inv_sqrt", "square", "sigmoid", "relu", "softplus"]:
+           "log10", "sqrt", "neg", "abs", "sign", "floor", "ceil", "inv", "inv_sqrt", "square", "sigmoid", "relu", "softplus", "lgamma", "digamma"]:
     globals()[_n] = _mk_unary(_n)
 
 
@@ -678,6 +678,7 @@ def _grad_unary(y, gy):
         "inv_sqrt": lambda: S(-0.5) * pow(x, -1.5) * gy, "square": lambda: S(2.0) * x * gy,
         "sigmoid": lambda: gy * (y - square(y)), "relu": lambda: mul(greater(x, S(0.0)), gy),
         "softplus": lambda: gy * (exp(x) / (exp(x) + S(1.0))),
+        "lgamma": lambda: gy * digamma(x),                                               # math_ops.rs:1047-1052; Digamma: None (:1036-1039)
         "elu": lambda: Tensor(g, "ELUGrad", [x, gy], {"alpha": y.attrs["p"]}),
     }
     return [table[fn]()] if fn in table else [None]

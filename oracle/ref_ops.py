@@ -325,6 +325,9 @@ def unary(op, x, p0=0.0, p1=0.0):
             r = np.maximum(np.minimum(x, p1), p0)
         elif op == "scale":
             r = x * _f64(F32(p0))
+        elif op in ("lgamma", "digamma"):            # math_ops.rs:1021-1060: `special` 0.10 Gamma::{ln_gamma().0, digamma} (crate absent here);
+            from scipy import special as _sp         # restated with the same functions from scipy.special (ln|Gamma(x)|, psi(x))
+            r = _sp.gammaln(x) if op == "lgamma" else _sp.digamma(x)
         else:
             raise ValueError(op)
     return _f32(r)

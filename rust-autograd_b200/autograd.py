@@ -600,7 +600,7 @@ def _u(name):
 
 
 for _n in ["sin", "cos", "tan", "asin", "acos", "atan", "sinh", "cosh", "tanh", "asinh", "acosh", "atanh", "exp", "exp2", "exp10", "ln", "log2",
-           "log10", "sqrt", "neg", "abs", "sign", "floor", "ceil", "inv", "inv_sqrt", "square", "sigmoid", "relu", "softplus", "shape", "rank",
+           "log10", "sqrt", "neg", "abs", "sign", "floor", "ceil", "inv", "inv_sqrt", "square", "sigmoid", "relu", "softplus", "lgamma", "digamma", "shape", "rank",
            "size", "identity", "stop_gradient", "sum_all", "mean_all", "flatten"]:
     globals()[_n] = _u(_n)
 

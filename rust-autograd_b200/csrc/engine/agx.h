@@ -321,6 +321,8 @@ NdArray expr_pad(ComputeContext& c, const Shape& full, const std::vector<int64_t
 bool expr_sum_pads(ComputeContext& c, const std::vector<NdArray>& xs, NdArray* out);
 NdArray expr_gemm_ta(ComputeContext& c, NdArray a, NdArray b);                 // deferred A^T * B whose only reader is an AddN
 bool expr_sum_gemms(ComputeContext& c, const std::vector<NdArray>& xs, NdArray* out);
+NdArray expr_scatter(ComputeContext& c, const Shape& table, int axis, NdArray idx, NdArray gy);   // deferred GatherGrad whose only reader is an AddN
+bool expr_sum_scatters(ComputeContext& c, const std::vector<NdArray>& xs, NdArray* out);
 bool expr_materialize_into(Device* dev, const NdArray& x, NdArray dest);
 Op* make_optimizer_op(int kind, float h0, float h1, float h2, float h3);
 void flush_pending_updates(Evaluation& run, VariableEnvironment* env);

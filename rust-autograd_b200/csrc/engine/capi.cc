@@ -114,7 +114,7 @@ extern "C" int agx_call(agx_graph* gg, const char* fn_, const int* tensors, int 
   auto need = [&](int a, int b, int c) { if (nt < a || ni < b || nf < c) throw Panic("agx_call(" + fn + "): expected at least " + std::to_string(a) + " tensors, " + std::to_string(b) + " ints, " + std::to_string(c) + " floats"); };
   auto ints = [&](int from) { return std::vector<int64_t>(I + from, I + ni); };
   static const char* unary_names[] = {"sin", "cos", "tan", "asin", "acos", "atan", "sinh", "cosh", "tanh", "asinh", "acosh", "atanh", "exp", "exp2", "exp10", "ln", "log2",
-                                      "log10", "sqrt", "neg", "abs", "sign", "floor", "ceil", "inv", "inv_sqrt", "square", "sigmoid", "relu", "softplus"};
+                                      "log10", "sqrt", "neg", "abs", "sign", "floor", "ceil", "inv", "inv_sqrt", "square", "sigmoid", "relu", "softplus", "lgamma", "digamma"};
   static const char* cmp_names[] = {"equal", "not_equal", "greater", "lesser", "greater_equal", "lesser_equal", "maximum", "minimum"};
   bool done = false;
   for (auto u : unary_names) if (fn == u) { need(1, 0, 0); r = {T::unary(fn, t[0])}; done = true; }

@@ -30,7 +30,7 @@ struct ExprNode {
 };
 
 namespace {
-const int kPad = 100, kGemmTA = 101;     // nodes that are memory, not instructions: never part of a program
+const int kPad = 100, kGemmTA = 101, kScatter = 102;     // nodes that are memory, not instructions: never part of a program
 void materialize_node(Device* dev, ExprNode* n, NdArray* dest = nullptr);
 const int64_t kMaxFusedElems = (int64_t)1 << 24;     // beyond this a pass is bandwidth-bound anyway and the vectorised single-op kernels are used
 
@@ -160,6 +160,13 @@ void write_region(Device* dev, NdArray src, NdArray region) {      // region <- 
 
 void materialize_node(Device* dev, ExprNode* n, NdArray* dest) {
   if (n->has_value) return;
+  if (n->kind == kScatter) {      // GatherGrad on its own: zero table + scatter-add (array_ops.rs:401-466)
+    NdArray gx = dev->empty(n->shape);
+    int64_t pre = 1, post = 1; for (int k = 0; k < n->op; k++) pre *= n->shape[k]; for (int k = n->op + 1; k < (int)n->shape.size(); k++) post *= n->shape[k];
+    check_status(agb_gather_grad(dev->ctx, n->b.dptr, n->a.dptr, gx.dptr, pre, n->shape[n->op], post, n->a.size()));
+    n->value = gx; n->has_value = true; n->a = NdArray(); n->b = NdArray();
+    return;
+  }
   if (n->kind == kGemmTA) {
     NdArray y = dev->empty(n->shape);
     agb_tensor da = n->a.desc(), db = n->b.desc(), dy = y.desc();
@@ -298,6 +305,24 @@ bool expr_sum_gemms(ComputeContext& c, const std::vector<NdArray>& xs, NdArray* 
   agb_tensor da = A.desc(), db = B.desc(), dy = y.desc();
   check_status(agb_gemm_f32(c.dev->ctx, 1, 0, &da, &db, &dy, 0.0f));
   *out = y;
+  return true;
+}
+NdArray expr_scatter(ComputeContext& c, const Shape& table, int axis, NdArray idx, NdArray gy) {
+  if (!idx.on_device() || !gy.on_device() || !idx.is_contiguous() || !gy.is_contiguous() || axis < 0 || axis >= (int)table.size()) return NdArray();
+  auto n = std::make_shared<ExprNode>(); n->kind = kScatter; n->op = axis; n->a = idx; n->b = gy; n->shape = table;
+  n->consumers = 1; n->n_instr = 0; n->n_leaves = 1; n->n_multi = 0;
+  NdArray r; r.shape = table; r.stride = NdArray::contiguous_strides(table); r.expr = n;
+  return r;
+}
+// AddN over deferred GatherGrads of one table: ONE zero fill, every term scatter-adds into the same buffer
+bool expr_sum_scatters(ComputeContext& c, const std::vector<NdArray>& xs, NdArray* out) {
+  if (xs.size() < 2) return false;
+  for (auto& x : xs) if (!unvalued(x) || x.expr->kind != kScatter || x.expr->shape != xs[0].expr->shape || x.expr->op != xs[0].expr->op) return false;
+  const Shape& table = xs[0].expr->shape; const int ax = xs[0].expr->op;
+  int64_t pre = 1, post = 1; for (int k = 0; k < ax; k++) pre *= table[k]; for (int k = ax + 1; k < (int)table.size(); k++) post *= table[k];
+  NdArray gx = c.dev->zeros(table);
+  for (auto& x : xs) check_status(agb_scatter_add(c.dev->ctx, x.expr->b.dptr, x.expr->a.dptr, gx.dptr, pre, table[ax], post, x.expr->a.size()));
+  *out = gx;
   return true;
 }
 bool expr_has_value(const NdArray& x) { return x.expr && x.expr->has_value; }

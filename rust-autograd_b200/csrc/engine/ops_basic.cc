@@ -468,6 +468,7 @@ static const UnaryInfo UNARY[] = {
   {"square", AGB_U_SQUARE, REFNAME("math_ops", "Square")}, {"sigmoid", AGB_U_SIGMOID, REFNAME("activation_ops", "Sigmoid")},
   {"relu", AGB_U_RELU, REFNAME("activation_ops", "ReLU")}, {"softplus", AGB_U_SOFTPLUS, REFNAME("activation_ops", "Softplus")},
   {"elu", AGB_U_ELU, REFNAME("activation_ops", "ELU")},
+  {"lgamma", AGB_U_LGAMMA, REFNAME("math_ops", "Lgamma")}, {"digamma", AGB_U_DIGAMMA, REFNAME("math_ops", "Digamma")},      // math_ops.rs:1021-1060
 };
 struct ELUGrad : Op {                  // activation_ops.rs:204-226
   float alpha;
@@ -524,6 +525,7 @@ struct UnaryOp : Op {
       case AGB_U_SIGMOID: gx = mul(gy, sub(y, U("square", y))); break;
       case AGB_U_RELU: gx = mul(cmp("greater", x, S(0.f)), gy); break;
       case AGB_U_SOFTPLUS: { Tensor a = U("exp", x); gx = mul(gy, div(a, add(a, S(1.f)))); break; }
+      case AGB_U_LGAMMA: gx = mul(gy, U("digamma", x)); break;            // math_ops.rs:1047-1052 (Digamma itself has no gradient)
       case AGB_U_ELU: { auto* op = new ELUGrad(); op->alpha = p0; gx = TensorBuilder(g).append_input(x, false).append_input(gy, false).set_shape(shape(gy)).build(op); break; }
       default: c.append_none(); return;    // Sign / Floor / Ceil: None
     }
@@ -623,7 +625,7 @@ struct AddN : Op {                     // array_ops.rs:503-535
     c.accept_expr = true;
     std::vector<NdArray> xs; bool same = true, all_empty_scalars = true;
     for (int i = 0; i < n; i++) { xs.push_back(c.input(i)); if (xs[i].shape != xs[0].shape) same = false; if (!(xs[i].ndim() == 0 && xs[i].has_host() && !xs[i].on_device())) all_empty_scalars = false; }
-    if (same && !all_empty_scalars) { NdArray y; if (expr_sum_pads(c, xs, &y) || expr_sum_gemms(c, xs, &y)) { c.append_output(y); return; } }
+    if (same && !all_empty_scalars) { NdArray y; if (expr_sum_pads(c, xs, &y) || expr_sum_gemms(c, xs, &y) || expr_sum_scatters(c, xs, &y)) { c.append_output(y); return; } }
     if (same && !all_empty_scalars && n <= 6 && xs[0].ndim() > 0) {      // a short sum joins the pending expression as the same left fold
       NdArray acc = expr_binary(c, AGB_B_ADD, xs[0], xs[1]);
       for (int i = 2; i < n && acc.expr; i++) acc = expr_binary(c, AGB_B_ADD, acc, xs[i]);
@@ -1103,6 +1105,7 @@ struct GatherGrad : Op {               // array_ops.rs:401-474
     NdArray idx = c.dev->contiguous(on_dev(c.dev, c.input(0))), param = c.input(1), gy = c.dev->contiguous(on_dev(c.dev, c.input(2)));
     int ax = normalize_negative_axis(axis, param.ndim());
     int64_t pre = 1, post = 1; for (int k = 0; k < ax; k++) pre *= param.shape[k]; for (int k = ax + 1; k < param.ndim(); k++) post *= param.shape[k];
+    if (c.run->fuse && c.run->sole_consumer_sums(c.node)) { NdArray r = expr_scatter(c, param.shape, ax, idx, gy); if (r.expr) { c.append_output(r); return; } }
     NdArray gx = c.dev->empty(param.shape);
     check_status(agb_gather_grad(c.dev->ctx, gy.dptr, idx.dptr, gx.dptr, pre, param.shape[ax], post, idx.size()));
     c.append_output(gx);

@@ -15,6 +15,20 @@
 // ----------------------------------------------------------------------------------------------
 // functors
 // ----------------------------------------------------------------------------------------------
+// digamma (the `special` crate's Gamma::digamma, math_ops.rs:1029): reflection for x <= 0, recurrence up to x >= 6, then the
+// asymptotic series; evaluated in double (the op is bandwidth-bound) and rounded once
+__device__ __noinline__ float digamma_apply(float xf) {
+  double x = (double)xf, r = 0.0;
+  if (x <= 0.0) {
+    if (x == floor(x)) return __int_as_float(0x7fc00000);      // poles
+    r = -3.14159265358979323846 / tan(3.14159265358979323846 * x); x = 1.0 - x;
+  }
+  while (x < 6.0) { r -= 1.0 / x; x += 1.0; }
+  const double f = 1.0 / (x * x);
+  r += log(x) - 0.5 / x - f * (1.0 / 12.0 - f * (1.0 / 120.0 - f * (1.0 / 252.0 - f * (1.0 / 240.0 - f * (1.0 / 132.0)))));
+  return (float)r;
+}
+
 __device__ __forceinline__ float unary_apply(int op, float x, float p0, float p1) {
   switch (op) {
     case AGB_U_COPY: return x;
@@ -55,6 +69,8 @@ __device__ __forceinline__ float unary_apply(int op, float x, float p0, float p1
     case AGB_U_ADD_SCALAR: return x + p0;
     case AGB_U_RSUB_SCALAR: return p0 - x;
     case AGB_U_RDIV_SCALAR: return p0 / x;
+    case AGB_U_LGAMMA: return lgammaf(x);                              // ln_gamma().0 = ln|Gamma(x)|
+    case AGB_U_DIGAMMA: return digamma_apply(x);
   }
   return x;
 }
@@ -503,7 +519,7 @@ extern "C" int agb_fused_ewise(agb_ctx* ctx, int64_t rows, int64_t cols, int n_l
   }
   if (P.total == 0) return AGB_OK;
   AgbProfScope prof(ctx, AGB_PROF_EWISE, 4.0 * (double)P.total * (n_leaves + n_out));
-  fused_ewise_kernel<<<agb_grid_for(P.total, 256, ctx->sm_count, 6), 256, 0, ctx->stream>>>(P);
+  fused_ewise_kernel<<<agb_grid_occ(ctx, fused_ewise_kernel, P.total, 256), 256, 0, ctx->stream>>>(P);
   AGB_LAUNCHED(ctx);
   return AGB_OK;
 }

@@ -309,13 +309,17 @@ __global__ void __launch_bounds__(256) gather_grad_kernel(const float* __restric
     atomicAdd(gx + (p * axis_len + k) * post + q, __ldg(gy + o));
   }
 }
-extern "C" int agb_gather_grad(agb_ctx* ctx, const float* gy, const float* indices, float* gx,
+extern "C" int agb_scatter_add(agb_ctx* ctx, const float* gy, const float* indices, float* gx,
                                int64_t pre, int64_t axis_len, int64_t post, int64_t n_idx) {
-  AGB_TRY(agb_memset0(ctx, gx, pre * axis_len * post * sizeof(float)));
   int64_t n = pre * n_idx * post; if (n == 0) return AGB_OK;
   gather_grad_kernel<<<agb_grid_for(n, 256, ctx->sm_count, 8), 256, 0, ctx->stream>>>(gy, indices, gx, pre, axis_len, post, n_idx, ctx->dev_err);
   AGB_LAUNCHED(ctx);
   return AGB_OK;
+}
+extern "C" int agb_gather_grad(agb_ctx* ctx, const float* gy, const float* indices, float* gx,
+                               int64_t pre, int64_t axis_len, int64_t post, int64_t n_idx) {
+  AGB_TRY(agb_memset0(ctx, gx, pre * axis_len * post * sizeof(float)));
+  return agb_scatter_add(ctx, gy, indices, gx, pre, axis_len, post, n_idx);
 }
 
 __global__ void __launch_bounds__(256) i32_to_f32_kernel(const int32_t* __restrict__ s, float* __restrict__ d, int64_t n) {

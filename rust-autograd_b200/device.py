@@ -401,6 +401,13 @@ class Device:
         ffi.check(self.lib.agb_gather_grad(self.ctx, gy.ptr, indices.ptr, gx.ptr, pre, al, post, indices.size))
         return gx
 
+    def scatter_add(self, gx, gy, indices, axis):
+        """agb_scatter_add: gx[:, idx[j], :] += gy[:, j, :] in place (GatherGrad without its zero fill)."""
+        axis %= len(gx.shape)
+        pre, al, post = self._axis_view(tuple(gx.shape), axis)
+        ffi.check(self.lib.agb_scatter_add(self.ctx, gy.ptr, indices.ptr, gx.ptr, pre, al, post, indices.size))
+        return gx
+
     def dropout(self, x, ratio, mask=None, seed=0, offset=0):
         y = self.empty(x.shape)
         m = mask if mask is not None else self.empty(x.shape)

@@ -20,7 +20,7 @@ MATH_3XTF32, MATH_TF32, MATH_FP32 = 0, 1, 2
 
 U_OPS = ["copy", "abs", "neg", "square", "inv", "invsqrt", "sign", "floor", "ceil", "sqrt", "pow", "ln", "log2", "log10",
          "exp", "exp2", "exp10", "sin", "cos", "tan", "asin", "acos", "atan", "sinh", "cosh", "tanh", "asinh", "acosh",
-         "atanh", "sigmoid", "relu", "softplus", "elu", "clip", "scale", "add_scalar", "rsub_scalar", "rdiv_scalar"]
+         "atanh", "sigmoid", "relu", "softplus", "elu", "clip", "scale", "add_scalar", "rsub_scalar", "rdiv_scalar", "lgamma", "digamma"]
 B_OPS = ["add", "sub", "mul", "div", "eq", "ne", "gt", "lt", "ge", "le", "max", "min", "elu_grad", "clip_grad",
          "sigmoid_xent", "relu_grad"]
 R_OPS = ["sum", "mean", "prod", "min", "max"]
@@ -94,7 +94,7 @@ SIGNATURES = {
     "agb_logsumexp": [_P, _P, _P, _i64, _i64, _i64],
     "agb_sparse_xent_fwd": [_P, _P, _P, _P, _P, _i64, _i64], "agb_sparse_xent_bwd": [_P, _P, _P, _P, _i64, _P, _i64, _i64],
     "agb_softmax_xent_fwd": [_P, _P, _P, _P, _P, _i64, _i64],
-    "agb_gather": [_P, _P, _P, _P, _i64, _i64, _i64, _i64, _i], "agb_gather_grad": [_P, _P, _P, _P, _i64, _i64, _i64, _i64],
+    "agb_gather": [_P, _P, _P, _P, _i64, _i64, _i64, _i64, _i], "agb_gather_grad": [_P, _P, _P, _P, _i64, _i64, _i64, _i64], "agb_scatter_add": [_P, _P, _P, _P, _i64, _i64, _i64, _i64],
     "agb_multi_tensor_adam": [_P, _i, C.POINTER(_P), C.POINTER(_P), C.POINTER(_P), C.POINTER(_P), C.POINTER(_P),
                               C.POINTER(_i64), _f, _f, _f, _f, _f],
     "agb_multi_tensor_sgd": [_P, _i, C.POINTER(_P), C.POINTER(_P), C.POINTER(_i64), _f, _f],

@@ -45,7 +45,7 @@ for _n, _lo, _hi, _tol in [("asinh", 0., 0.2, 1e-3), ("acosh", 1.1, 1.3, 1e-3), 
                            ("cos", 0., 0.2, 1e-3), ("tan", 0., 0.2, 1e-2), ("sqrt", 0.9, 1.1, 1e-3), ("exp", 0.9, 1.1, 1e-2), ("ln", 1., 1.1, 1e-2),
                            ("abs", 0.2, 1.0, 1e-3), ("neg", -1., 1., 1e-3), ("square", -1., 1., 1e-3), ("inv", 0.5, 1.5, 1e-3), ("sigmoid", -1., 1., 1e-3),
                            ("softplus", -1., 1., 1e-3), ("exp2", 0.5, 1., 1e-2), ("exp10", 0., 0.3, 1e-2), ("log2", 1., 2., 1e-3), ("log10", 1., 2., 1e-3),
-                           ("inv_sqrt", 0.5, 1.5, 1e-3)]:
+                           ("inv_sqrt", 0.5, 1.5, 1e-3), ("lgamma", 1., 1.01, 1e-3)]:     # lgamma: :858-876 (f64 there)
     CASES.append(_u(_n, _lo, _hi, tol=_tol))
 
 

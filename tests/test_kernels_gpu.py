@@ -380,7 +380,7 @@ UNARY = {"abs": (-3, 3), "neg": (-3, 3), "square": (-3, 3), "inv": (0.5, 3), "in
          "ceil": (-3, 3), "sqrt": (0.1, 9), "ln": (0.1, 9), "log2": (0.1, 9), "log10": (0.1, 9), "exp": (-3, 3), "exp2": (-3, 3),
          "exp10": (-2, 2), "sin": (-3, 3), "cos": (-3, 3), "tan": (-1, 1), "asin": (-0.9, 0.9), "acos": (-0.9, 0.9), "atan": (-3, 3),
          "sinh": (-3, 3), "cosh": (-3, 3), "tanh": (-3, 3), "asinh": (-3, 3), "acosh": (1.1, 5), "atanh": (-0.9, 0.9),
-         "sigmoid": (-6, 6), "relu": (-3, 3), "softplus": (-6, 6)}
+         "sigmoid": (-6, 6), "relu": (-3, 3), "softplus": (-6, 6), "lgamma": (0.1, 30), "digamma": (0.1, 30)}
 
 
 @pytest.mark.parametrize("op", sorted(UNARY))
@@ -393,6 +393,15 @@ def test_unary_vs_oracle(dev, op):
     close(y, R.unary(op, x), 1e-5)
     yt = dev.unary(op, dev.upload(x).transpose()).numpy()        # strided input view
     close(yt, R.unary(op, x.T), 1e-5)
+
+
+def test_gamma_functions_negative_arguments(dev):
+    """Lgamma / Digamma (math_ops.rs:1021-1060) left of zero, away from the poles: ln|Gamma(x)| and the reflected digamma."""
+    rng = np.random.default_rng(12)
+    x = (-rng.integers(0, 5, 4000) - rng.uniform(0.15, 0.85, 4000)).astype(np.float32)
+    d = dev.upload(x)
+    close(dev.unary("lgamma", d).numpy(), R.unary("lgamma", x), 1e-4)
+    close(dev.unary("digamma", d).numpy(), R.unary("digamma", x), 1e-5)
 
 
 def test_unary_param_ops(dev):
@@ -610,6 +619,11 @@ def test_gather_family_bit_exact(dev, pshape, ishape, axis):
     gy = rng.integers(-3, 4, ref.shape).astype(np.float32)
     gx = dev.gather_grad(dev.upload(gy), dev.upload(idx), pshape, axis).numpy()
     assert np.array_equal(gx, R.gather_grad(idx, pshape, gy, axis))
+    # two scatter-adds into one zero table == the sum of two GatherGrads (integer-valued data: exact in any order)
+    acc = dev.fill(pshape, 0.0)
+    dev.scatter_add(acc, dev.upload(gy), dev.upload(idx), axis)
+    dev.scatter_add(acc, dev.upload(2 * gy), dev.upload(idx), axis)
+    assert np.array_equal(acc.numpy(), 3 * R.gather_grad(idx, pshape, gy, axis))
 
 
 # ------------------------------------------------------------------------------------------------ optimizers
