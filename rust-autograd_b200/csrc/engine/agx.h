@@ -102,6 +102,9 @@ struct Device {                   // thin C++ handle on the kernel C ABI context
   void ensure_device(NdArray& a);               // upload the host copy if there is no device copy yet
   const std::vector<float>& ensure_host(NdArray& a);   // D2H (+ stream sync) if there is no host copy yet
   NdArray contiguous(const NdArray& a);         // materialise a strided view (reference: ndarray_ext::deep_copy)
+  // deep copies of SMALL strided views made during the current evaluation (label / token-id columns sliced out of one feed are consumed by a
+  // forward op and again by its gradient op): the second request reuses the first copy.  Cleared by eval() and by Assign.
+  std::vector<std::pair<NdArray, NdArray>> small_copies;
   NdArray i32_to_f32(const NdArray& a);         // float copy of an int32 index buffer
   NdArray copy(const NdArray& a);
   void sync();

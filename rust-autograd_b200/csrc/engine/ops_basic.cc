@@ -1177,6 +1177,7 @@ Tensor T::access_elem(Tensor x, int64_t i) { auto* op = new IndexOp(); op->index
 struct Assign : Op {                   // array_ops.rs:94-105: device copy into the variable
   const char* name() const override { return REFNAME("array_ops", "Assign"); }
   void compute(ComputeContext& c) override {
+    c.dev->small_copies.clear();
     NdArray dst = c.input_mut(0), src = on_dev(c.dev, c.input(1));
     if (dst.shape != src.shape) src = dev_broadcast_to(c.dev, src, dst.shape);
     agb_tensor ts = src.desc(), td = dst.desc();

@@ -536,6 +536,7 @@ struct UpdateOp : Op {
 void flush_pending_updates(Evaluation& run, VariableEnvironment* env) {
   if (run.pending.empty()) return;
   Device* dev = run.dev;
+  dev->small_copies.clear();          // the variables are about to change: no cached copy of a view may outlive this point
   float gscale = 1.0f;
   if (env->world > 1) {
     // data parallel: pack all gradients into one contiguous arena, ONE NCCL all-reduce (sum), read them back
