@@ -248,6 +248,13 @@ int  agb_concat_rows(agb_ctx* ctx, int n, const float* const* srcs, const int64_
  * `mask` when seed==0, otherwise generated on device (Philox, (seed,offset)) and written to `mask`. */
 int  agb_dropout(agb_ctx* ctx, const agb_tensor* x, agb_tensor* y, agb_tensor* mask,
                  float ratio, uint64_t seed, uint64_t offset);
+/* The random_* generator ops (random_ops.rs:6-214; ArrayRng::{random_uniform, random_normal, bernoulli, exponential, log_normal, gamma},
+ * ndarray_ext.rs:276-388) on the device: y is filled from the counter stream Philox-4x32-10(key = seed, counter = (element, offset)),
+ * so a call is reproducible from (seed, offset) and independent of the launch geometry.  The reference's XorShift stream is
+ * parity-unpinned; distributions and parameter meaning follow rand_distr 0.4: Uniform [p0, p1), Normal(mean p0, std p1),
+ * Bernoulli = (U[0,1) < p0) as 0/1, Exp(rate p0), LogNormal(mu p0, sigma p1), Gamma(shape p0, scale p1) by Marsaglia-Tsang. */
+enum agb_rand_kind { AGB_RAND_UNIFORM = 0, AGB_RAND_NORMAL, AGB_RAND_BERNOULLI, AGB_RAND_EXP, AGB_RAND_LOGNORMAL, AGB_RAND_GAMMA, AGB_RAND_COUNT };
+int  agb_random(agb_ctx* ctx, int kind, float p0, float p1, uint64_t seed, uint64_t offset, agb_tensor* y);
 
 /* ======================= reductions ======================= */
 enum { AGB_R_SUM = 0, AGB_R_MEAN, AGB_R_PROD, AGB_R_MIN, AGB_R_MAX };

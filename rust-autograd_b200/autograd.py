@@ -661,6 +661,21 @@ def conv2d_transpose(x, w, pad, stride): return _call(x.graph, "conv2d_transpose
 def dilated_conv2d_transpose(x, w, pad, stride, dilate): return _call(x.graph, "dilated_conv2d_transpose", [x, w], [pad, stride, dilate])
 def max_pool2d(x, pool_size, pad, stride): return _call(x.graph, "max_pool2d", [x], [pool_size, pad, stride])
 def dropout(x, dropout_ratio, train, seed=0): return _call(x.graph, "dropout", [x], [int(train), int(seed)], [dropout_ratio])
+
+
+# random_* generator ops (src/tensor_ops/mod.rs:2426-2676).  `seed=0` = the crate's default rng (fixed seed, ndarray_ext.rs:250-264); the
+# `_rng` variants of the reference take an ArrayRng, here a seed.  Values come from a device Philox stream (parity-unpinned).
+def _rand(kind, shape, g, p0, p1, seed): return _call(g, "random", [as_tensor(shape, g)], [kind, int(seed)], [float(p0), float(p1)])
+def random_uniform(shape, min, max, g, seed=0): return _rand(0, shape, g, min, max, seed)
+def random_normal(shape, mean, stddev, g, seed=0): return _rand(1, shape, g, mean, stddev, seed)
+def standard_uniform(shape, g, seed=0): return _rand(0, shape, g, 0.0, 1.0, seed)
+def standard_normal(shape, g, seed=0): return _rand(1, shape, g, 0.0, 1.0, seed)
+def bernoulli(shape, p, g, seed=0): return _rand(2, shape, g, p, 0.0, seed)
+def random_exp(shape, lambda_, g, seed=0): return _rand(3, shape, g, lambda_, 0.0, seed)
+def log_normal(shape, mean, stddev, g, seed=0): return _rand(4, shape, g, mean, stddev, seed)
+def gamma(shape, shape_param, scale, g, seed=0): return _rand(5, shape, g, shape_param, scale, seed)
+
+
 def normalize(x, axes): return _call(x.graph, "normalize", [x, as_tensor(axes, x.graph)])
 def batch_norm(x, scale, shift): return _call(x.graph, "batch_norm", [x, scale, shift])
 def control_dependencies(x, deps): return _call(x.graph, "control_dependencies", [x] + list(deps))

@@ -298,6 +298,7 @@ Tensor conv2d(Tensor x, Tensor w, int pad, int stride, int dilation);
 Tensor conv2d_transpose(Tensor x, Tensor w, int pad, int stride, int dilation);
 Tensor max_pool2d(Tensor x, int size, int pad, int stride);
 Tensor dropout(Tensor x, float ratio, bool train, uint64_t seed);
+Tensor random(Graph* g, int kind, Tensor shape, float p0, float p1, uint64_t seed);   // random_normal .. gamma (:2426-2676); kind = agb_rand_kind
 Tensor assign(Tensor x, Tensor y); Tensor control_dependencies(Tensor x, const std::vector<Tensor>& deps);
 Tensor hook(Tensor x, std::function<void(const NdArray&, const std::vector<float>&)> f);   // Tensor::raw_hook: D2H sync point
 std::vector<Tensor> grad(const std::vector<Tensor>& ys, const std::vector<Tensor>& xs);          // :94-114

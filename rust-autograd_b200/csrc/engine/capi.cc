@@ -175,6 +175,7 @@ extern "C" int agx_call(agx_graph* gg, const char* fn_, const int* tensors, int 
   else if (fn == "dilated_conv2d_transpose") { need(2, 3, 0); r = {T::conv2d_transpose(t[0], t[1], (int)I[0], (int)I[1], (int)I[2])}; }
   else if (fn == "max_pool2d") { need(1, 3, 0); r = {T::max_pool2d(t[0], (int)I[0], (int)I[1], (int)I[2])}; }
   else if (fn == "dropout") { need(1, 1, 1); r = {T::dropout(t[0], (float)F[0], I[0] != 0, ni > 1 ? (uint64_t)I[1] : 0)}; }
+  else if (fn == "random") { need(1, 2, 2); r = {T::random(g, (int)I[0], t[0], (float)F[0], (float)F[1], (uint64_t)I[1])}; }      // ints: agb_rand_kind, seed (0 = the default rng)
   else if (fn == "normalize") { need(2, 0, 0); r = {T::normalize(t[0], t[1])}; }
   else if (fn == "batch_norm") { need(3, 0, 0); r = {T::batch_norm(t[0], t[1], t[2])}; }
   else if (fn == "assign") { need(2, 0, 0); r = {T::assign(t[0], t[1])}; }

@@ -509,6 +509,32 @@ struct Dropout : Op {                  // random_ops.rs:218-245: NOT inverted; o
 };
 Tensor T::dropout(Tensor x, float ratio, bool train, uint64_t seed) { auto* op = new Dropout(); op->ratio = ratio; op->train = train; op->seed = seed; return TensorBuilder(x.graph).append_input(x, false).build(op); }
 
+// random_ops.rs:6-214: RandomNormal / RandomUniform / StandardNormal / StandardUniform / Bernoulli / Exponential / LogNormal / Gamma.
+// The op owns its stream position like the reference's ArrayRng (RefCell<R>): every evaluation of the SAME node continues the stream,
+// a node built with the default rng starts from the crate's fixed default seed (ndarray_ext.rs:250-264), so two default-constructed
+// nodes draw the same values (as there).  Stream values are parity-unpinned: device Philox instead of XorShift.
+struct RandomOp : Op {
+  int kind; float p0, p1; uint64_t seed; uint64_t calls = 0;
+  const char* name() const override {
+    static const char* N[] = {REFNAME("random_ops", "RandomUniform"), REFNAME("random_ops", "RandomNormal"), REFNAME("random_ops", "Bernoulli"),
+                              REFNAME("random_ops", "Exponential"), REFNAME("random_ops", "LogNormal"), REFNAME("random_ops", "Gamma")};
+    return N[kind];
+  }
+  void compute(ComputeContext& c) override {
+    NdArray sh = c.input(0);
+    NdArray y = c.dev->empty(as_shape(c.dev, sh));
+    agb_tensor ty = y.desc();
+    check_status(agb_random(c.dev->ctx, kind, p0, p1, seed ? seed : 0x5EEDull, calls++, &ty));
+    c.append_output(y);
+  }
+  void grad(GradientContext& c) override { c.append_none(); }
+};
+Tensor T::random(Graph* g, int kind, Tensor shape, float p0, float p1, uint64_t seed) {
+  if (kind < 0 || kind >= AGB_RAND_COUNT) throw Panic("random: unknown distribution");
+  auto* op = new RandomOp(); op->kind = kind; op->p0 = p0; op->p1 = p1; op->seed = seed;
+  return TensorBuilder(g).append_input(shape, false).set_shape(shape).build(op);
+}
+
 // ================================================================================================ optimizer update ops
 // One op node per variable as in the reference (AdamOp inputs: param(mut), grad, m(mut), v(mut), t(mut); adam.rs:11-58), but
 // compute() only REGISTERS the update; Graph::eval flushes all registered updates of the run as a single fused multi-tensor

@@ -595,3 +595,72 @@ extern "C" int agb_dropout(agb_ctx* ctx, const agb_tensor* x, agb_tensor* y, agb
   AGB_LAUNCHED(ctx);
   return AGB_OK;
 }
+
+// ----------------------------------------------------------------------------------------------
+// random_* generator ops (random_ops.rs:6-214): counter-based, 4 elements per Philox call; Gamma is a per-element rejection loop on its
+// own counter sub-space (word 3 = 0x80000000 | iteration)
+// ----------------------------------------------------------------------------------------------
+__device__ __forceinline__ float u01_co(uint32_t x) { return (x >> 8) * (1.0f / 16777216.0f); }             // [0, 1)
+__device__ __forceinline__ float u01_oc(uint32_t x) { return ((x >> 8) + 1u) * (1.0f / 16777216.0f); }      // (0, 1]
+__device__ __forceinline__ void box_muller(uint32_t a, uint32_t b, float& z0, float& z1) {
+  float r = sqrtf(-2.0f * logf(u01_oc(a))), s, c;
+  sincospif(2.0f * u01_co(b), &s, &c);
+  z0 = r * c; z1 = r * s;
+}
+__device__ float gamma_sample(int64_t elem, float k, float scale, uint64_t seed, uint32_t off) {
+  const uint2 key = make_uint2((uint32_t)seed, (uint32_t)(seed >> 32));
+  float boost = 1.0f;
+  const bool small = k < 1.0f;
+  const float kk = small ? k + 1.0f : k;
+  const float d = kk - 1.0f / 3.0f, c = rsqrtf(9.0f * d);
+  for (uint32_t it = 0; it < 64; it++) {
+    uint4 r = philox4x32_10(make_uint4((uint32_t)elem, (uint32_t)((uint64_t)elem >> 32), off, 0x80000000u | it), key);
+    if (it == 0 && small) boost = powf(u01_oc(r.w), 1.0f / k);          // Gamma(k) = Gamma(k + 1) * U^(1/k)
+    float z, unused; box_muller(r.x, r.y, z, unused);
+    float v = 1.0f + c * z;
+    if (v <= 0.0f) continue;
+    v = v * v * v;
+    if (logf(u01_oc(r.z)) < 0.5f * z * z + d - d * v + d * logf(v)) return d * v * scale * boost;
+  }
+  return d * scale * boost;      // (probability ~ 1e-30) the mode
+}
+__global__ void __launch_bounds__(256) random_kernel(float* __restrict__ y, int64_t n, int kind, float p0, float p1, uint64_t seed, uint64_t offset) {
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x, n4 = (n + 3) >> 2;
+  const uint2 key = make_uint2((uint32_t)seed, (uint32_t)(seed >> 32));
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n4; i += stride) {
+    float v[4];
+    if (kind == AGB_RAND_GAMMA) {
+#pragma unroll
+      for (int k = 0; k < 4; k++) v[k] = 4 * i + k < n ? gamma_sample(4 * i + k, p0, p1, seed, (uint32_t)offset) : 0.0f;
+    } else {
+      uint4 r = philox4x32_10(make_uint4((uint32_t)i, (uint32_t)((uint64_t)i >> 32), (uint32_t)offset, (uint32_t)(offset >> 32) & 0x7fffffffu), key);
+      const uint32_t rr[4] = {r.x, r.y, r.z, r.w};
+      if (kind == AGB_RAND_NORMAL || kind == AGB_RAND_LOGNORMAL) {
+        box_muller(r.x, r.y, v[0], v[1]); box_muller(r.z, r.w, v[2], v[3]);
+#pragma unroll
+        for (int k = 0; k < 4; k++) { v[k] = p0 + p1 * v[k]; if (kind == AGB_RAND_LOGNORMAL) v[k] = expf(v[k]); }
+      } else {
+#pragma unroll
+        for (int k = 0; k < 4; k++) {
+          if (kind == AGB_RAND_UNIFORM) { v[k] = p0 + (p1 - p0) * u01_co(rr[k]); if (v[k] >= p1 && p1 > p0) v[k] = p0; }     // rounding must not reach the open end
+          else if (kind == AGB_RAND_BERNOULLI) v[k] = u01_co(rr[k]) < p0 ? 1.0f : 0.0f;
+          else v[k] = -logf(u01_oc(rr[k])) / p0;
+        }
+      }
+    }
+#pragma unroll
+    for (int k = 0; k < 4; k++) if (4 * i + k < n) y[4 * i + k] = v[k];
+  }
+}
+extern "C" int agb_random(agb_ctx* ctx, int kind, float p0, float p1, uint64_t seed, uint64_t offset, agb_tensor* y) {
+  AGB_CHECK(kind >= 0 && kind < AGB_RAND_COUNT, AGB_ERR_UNSUPPORTED, "agb_random: unknown distribution %d", kind);
+  AGB_CHECK(agb_is_contig(y), AGB_ERR_UNSUPPORTED, "agb_random: output must be contiguous");
+  if (kind == AGB_RAND_NORMAL || kind == AGB_RAND_LOGNORMAL) AGB_CHECK(p1 >= 0.0f, AGB_ERR_INVALID_DIMS, "agb_random: standard deviation must be >= 0");     // Normal::new(..).unwrap() panics
+  if (kind == AGB_RAND_EXP) AGB_CHECK(p0 > 0.0f, AGB_ERR_INVALID_DIMS, "agb_random: exponential rate must be > 0");
+  if (kind == AGB_RAND_GAMMA) AGB_CHECK(p0 > 0.0f && p1 > 0.0f, AGB_ERR_INVALID_DIMS, "agb_random: gamma shape and scale must be > 0");
+  if (kind == AGB_RAND_UNIFORM) AGB_CHECK(p0 < p1, AGB_ERR_INVALID_DIMS, "agb_random: uniform range must satisfy low < high");                              // Uniform::new panics otherwise
+  const int64_t n = agb_numel(y); if (n == 0) return AGB_OK;
+  random_kernel<<<agb_grid_for((n + 3) / 4, 256, ctx->sm_count, 8), 256, 0, ctx->stream>>>(y->ptr, n, kind, p0, p1, seed, offset);
+  AGB_LAUNCHED(ctx);
+  return AGB_OK;
+}

@@ -401,6 +401,12 @@ class Device:
         ffi.check(self.lib.agb_gather_grad(self.ctx, gy.ptr, indices.ptr, gx.ptr, pre, al, post, indices.size))
         return gx
 
+    def random(self, kind, shape, p0=0.0, p1=1.0, seed=1, offset=0):
+        """agb_random: uniform [p0, p1) / normal(p0, p1) / bernoulli(p0) / exp(rate p0) / log_normal(p0, p1) / gamma(shape p0, scale p1)."""
+        y = self.empty(shape)
+        ffi.check(self.lib.agb_random(self.ctx, ffi.RAND[kind], p0, p1, seed, offset, y.desc()))
+        return y
+
     def scatter_add(self, gx, gy, indices, axis):
         """agb_scatter_add: gx[:, idx[j], :] += gy[:, j, :] in place (GatherGrad without its zero fill)."""
         axis %= len(gx.shape)

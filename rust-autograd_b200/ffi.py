@@ -24,6 +24,7 @@ U_OPS = ["copy", "abs", "neg", "square", "inv", "invsqrt", "sign", "floor", "cei
 B_OPS = ["add", "sub", "mul", "div", "eq", "ne", "gt", "lt", "ge", "le", "max", "min", "elu_grad", "clip_grad",
          "sigmoid_xent", "relu_grad"]
 R_OPS = ["sum", "mean", "prod", "min", "max"]
+RAND = {n: i for i, n in enumerate(["uniform", "normal", "bernoulli", "exp", "log_normal", "gamma"])}
 U = {n: i for i, n in enumerate(U_OPS)}
 B = {n: i for i, n in enumerate(B_OPS)}
 R = {n: i for i, n in enumerate(R_OPS)}
@@ -88,7 +89,7 @@ SIGNATURES = {
     "agb_add_n": [_P, _i, C.POINTER(_T), _T], "agb_fill": [_P, _T, _f],
     "agb_fused_ewise": [_P, _i64, _i64, _i, _P, _i, _P, _i, _P], "agb_copy_strided": [_P, _T, _T],
     "agb_concat_rows": [_P, _i, _P, _P, _i64, _i64, _P],
-    "agb_dropout": [_P, _T, _T, _T, _f, _u64, _u64],
+    "agb_dropout": [_P, _T, _T, _T, _f, _u64, _u64], "agb_random": [_P, _i, _f, _f, _u64, _u64, _T],
     "agb_reduce": [_P, _i, _P, _P, _i64, _i64, _i64], "agb_argreduce": [_P, _i, _P, _P, _i64, _i64, _i64],
     "agb_softmax": [_P, _P, _P, _i64, _i64, _i64], "agb_log_softmax": [_P, _P, _P, _i64, _i64, _i64],
     "agb_logsumexp": [_P, _P, _P, _i64, _i64, _i64],

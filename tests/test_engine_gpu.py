@@ -331,6 +331,35 @@ def test_elementwise_fusion_is_bit_identical_and_saves_launches(ag):
     print("launches fused/plain:", n_fused, n_plain)
 
 
+def test_random_ops_through_the_graph(ag):
+    """random_* constructors (mod.rs:2426-2676): shapes, ranges, a != b for two evaluations of the same node (tests/test_array_gen.rs:4-40: the
+    op's rng advances), equal values for two default-rng nodes (the crate seeds every default ArrayRng identically, ndarray_ext.rs:250-264),
+    no gradient (random_ops.rs: every grad appends None)."""
+    env = ag.VariableEnvironment()
+
+    def body(g):
+        u = ag.random_uniform([3, 1000], 0.0, 1.0, g)
+        u2 = ag.standard_uniform([3, 1000], g)
+        nrm = ag.random_normal([2000], 3.0, 0.5, g, seed=11)
+        outs = {"u": u.eval(g), "u_again": u.eval(g), "u2": u2.eval(g), "n": nrm.eval(g), "sn": ag.standard_normal([5, 7], g).eval(g),
+                "b": ag.bernoulli([4000], 0.25, g).eval(g), "e": ag.random_exp([4000], 2.0, g).eval(g),
+                "ln": ag.log_normal([4000], 0.0, 0.25, g).eval(g), "ga": ag.gamma([4000], 2.0, 2.0, g).eval(g)}
+        x = g.placeholder("x", [3, 1000])
+        y = x * u
+        outs["gx"] = ag.grad([y], [x])[0].eval(g, {"x": np.ones((3, 1000), np.float32)})
+        return outs
+    o = env.run(body)
+    env.close()
+    assert o["u"].shape == (3, 1000) and o["sn"].shape == (5, 7)
+    assert np.abs(o["u"] - 0.5).max() <= 0.5 and not np.array_equal(o["u"], o["u_again"])
+    assert np.array_equal(o["u"], o["u2"])                       # two default-rng nodes: same stream from the same fixed seed
+    assert abs(o["n"].mean() - 3.0) < 0.06 and abs(o["n"].std() - 0.5) < 0.05
+    assert set(np.unique(o["b"])) == {0.0, 1.0} and abs(o["b"].mean() - 0.25) < 0.04
+    assert (o["e"] >= 0).all() and abs(o["e"].mean() - 0.5) < 0.05
+    assert (o["ln"] > 0).all() and (o["ga"] > 0).all() and abs(o["ga"].mean() - 4.0) < 0.3
+    assert o["gx"].shape == (3, 1000) and np.abs(o["gx"] - 0.5).max() <= 0.5      # d(x*u)/dx = u (a later draw of the same node)
+
+
 def test_training_reduces_loss_and_checkpoint_roundtrip(ag, tmp_path):
     """examples/mlp_mnist.rs flow on synthetic data + VariableEnvironment::save/load (src/variable.rs:470-598, test :810-840)."""
     from rust_autograd_b200 import workloads as W

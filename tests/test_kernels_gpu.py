@@ -525,6 +525,38 @@ def test_fused_ewise_lstm_cell_matches_single_op_kernels(dev):
         dev.fused_ewise(B, D, [(dc, 0)], [(U, "clip", 1, 0, 0, 0.0)], [1])          # two-parameter op
 
 
+def test_random_generators_moments_and_reproducibility(dev):
+    """agb_random (random_ops.rs:6-214, ndarray_ext.rs:276-388).  The reference's stream is parity-unpinned and its tests only check range
+    and a != b (tests/test_array_gen.rs:4-40): here range, first two moments on 2^20 samples (4 sigma of the estimator), reproducibility from
+    (seed, offset), and independence of offsets / seeds."""
+    n = 1 << 20
+    cases = [("uniform", -2.0, 3.0, 0.5, 25.0 / 12), ("normal", 1.5, 2.0, 1.5, 4.0), ("bernoulli", 0.3, 0.0, 0.3, 0.21), ("exp", 2.0, 0.0, 0.5, 0.25),
+             ("log_normal", 0.1, 0.5, float(np.exp(0.1 + 0.125)), float((np.exp(0.25) - 1) * np.exp(0.2 + 0.25))),
+             ("gamma", 2.5, 1.5, 3.75, 5.625), ("gamma", 0.4, 2.0, 0.8, 1.6)]
+    for kind, p0, p1, mean, var in cases:
+        a = dev.random(kind, (n,), p0, p1, seed=7, offset=3).numpy().astype(np.float64)
+        assert np.isfinite(a).all(), kind
+        assert abs(a.mean() - mean) <= 4 * np.sqrt(var / n) + 1e-6, (kind, a.mean(), mean)
+        kurt_bound = 0.05 if kind in ("log_normal", "gamma") else 0.02       # heavier tails: looser variance estimate
+        assert abs(a.var() - var) <= kurt_bound * var, (kind, a.var(), var)
+        assert np.array_equal(a, dev.random(kind, (n,), p0, p1, seed=7, offset=3).numpy()), kind          # reproducible
+        b = dev.random(kind, (n,), p0, p1, seed=7, offset=4).numpy()
+        c_ = dev.random(kind, (n,), p0, p1, seed=8, offset=3).numpy()
+        assert (a != b).mean() > (0.3 if kind == "bernoulli" else 0.99) and (a != c_).mean() > (0.3 if kind == "bernoulli" else 0.99), kind
+    u = dev.random("uniform", (n,), 0.0, 1.0, seed=1).numpy()
+    assert u.min() >= 0.0 and u.max() < 1.0
+    assert set(np.unique(dev.random("bernoulli", (4096,), 0.5, 0.0, seed=1).numpy())) == {0.0, 1.0}
+    assert (dev.random("exp", (n,), 1.0, 0.0, seed=2).numpy() >= 0).all() and (dev.random("gamma", (n,), 0.5, 1.0, seed=2).numpy() > 0).all()
+    # odd sizes / shapes, launch-geometry independence: a prefix of a longer draw equals the shorter draw
+    s = dev.random("normal", (1001,), 0.0, 1.0, seed=5).numpy()
+    assert np.array_equal(s, dev.random("normal", (4003,), 0.0, 1.0, seed=5).numpy()[:1001])
+    from rust_autograd_b200 import ffi
+    with pytest.raises(ffi.OpError):
+        dev.random("uniform", (8,), 1.0, 1.0)          # Uniform::new(low, high) requires low < high
+    with pytest.raises(ffi.OpError):
+        dev.random("gamma", (8,), -1.0, 1.0)
+
+
 # ------------------------------------------------------------------------------------------------ reductions
 @pytest.mark.parametrize("k", KATS["reduce"])
 def test_reduce_kats(dev, k):
