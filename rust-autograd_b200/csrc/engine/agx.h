@@ -245,6 +245,8 @@ struct Evaluation {
   bool fuse = false;                      // elementwise fusion enabled for this run
   std::vector<int> consumers;             // per node id: consuming edges inside this evaluation (+1 per request as a target); metadata-only
                                           // consumers (Shape / Rank / Size) are not counted
+  struct RowStack { std::vector<const float*> key; std::vector<NdArray> parts; NdArray stacked; };      // `parts` pins the blocks: their addresses cannot be recycled while the stack is cached
+  std::vector<RowStack> row_stacks;       // stacked operands built in this run (the same G_t stack serves both weight gradients and the bias gradient)
   std::vector<int> sole_consumer;         // per node id: the one node that reads it (-1 none yet, -2 several / a target)
   bool sole_consumer_sums(TensorID id) const;    // true when the node's only reader in this evaluation is an AddN
   int consumers_of(TensorID id) const { return id >= 0 && id < (int)consumers.size() && consumers[id] > 0 ? consumers[id] : 1; }
@@ -327,6 +329,10 @@ NdArray expr_gemm_ta(ComputeContext& c, NdArray a, NdArray b);                 /
 bool expr_sum_gemms(ComputeContext& c, const std::vector<NdArray>& xs, NdArray* out);
 NdArray expr_scatter(ComputeContext& c, const Shape& table, int axis, NdArray idx, NdArray gy);   // deferred GatherGrad whose only reader is an AddN
 bool expr_sum_scatters(ComputeContext& c, const std::vector<NdArray>& xs, NdArray* out);
+NdArray expr_colsum(ComputeContext& c, NdArray gy, const Shape& target);       // deferred MaybeReduceSum [R, N] -> [1, N] whose only reader is an AddN
+bool expr_sum_colsums(ComputeContext& c, const std::vector<NdArray>& xs, NdArray* out);
+bool stackable(const NdArray& t);                                                                   // 2-D, unit column stride, 16-byte aligned rows
+NdArray stack_rows(Evaluation& run, Device* dev, const std::vector<NdArray>& parts);              // agb_concat_rows, remembered for the rest of the run
 bool expr_materialize_into(Device* dev, const NdArray& x, NdArray dest);
 Op* make_optimizer_op(int kind, float h0, float h1, float h2, float h3);
 void flush_pending_updates(Evaluation& run, VariableEnvironment* env);

@@ -447,17 +447,14 @@ std::vector<EvalResult> eval(Graph* g, const std::vector<Tensor>& targets, const
       NdArray a;
       if (!fetch(g->inner(m).incoming_nodes[0], &a) || a.ndim() != 2) continue;
       if (!as.empty() && a.shape != as[0].shape) continue;
-      if (a.stride[1] != 1 || a.stride[0] % 4 != 0 || a.shape[1] % 4 != 0 || (((uintptr_t)a.dptr) & 15) != 0) continue;
+      if (!stackable(a)) continue;
       ms.push_back(m); as.push_back(a);
     }
     if (ms.size() < 2) return false;
     const int64_t rows = as[0].shape[0], k = as[0].shape[1], ncol = b.tb ? w.shape[0] : w.shape[1];
     if ((b.tb ? w.shape[1] : w.shape[0]) != k || rows == 0 || k == 0 || ncol == 0) return false;      // the members raise their own shape errors
     const int n = (int)ms.size();
-    NdArray A = dev->empty({n * rows, k}), Y = dev->empty({n * rows, ncol});
-    std::vector<const float*> ps(n); std::vector<int64_t> pitch(n);
-    for (int i = 0; i < n; i++) { ps[i] = as[i].dptr; pitch[i] = as[i].stride[0]; }
-    check_status(agb_concat_rows(dev->ctx, n, ps.data(), pitch.data(), rows, k, A.dptr));
+    NdArray A = stack_rows(run, dev, as), Y = dev->empty({n * rows, ncol});
     agb_tensor da = A.desc(), dw = w.desc(), dy = Y.desc();
     check_status(agb_gemm_f32(dev->ctx, 0, b.tb ? 1 : 0, &da, &dw, &dy, 0.0f));
     for (int i = 0; i < n; i++) { Stored o; o.ys.push_back(Y.sliced(0, i * rows, rows)); storage[ms[i]] = std::move(o); }

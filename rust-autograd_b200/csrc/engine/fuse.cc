@@ -30,7 +30,7 @@ struct ExprNode {
 };
 
 namespace {
-const int kPad = 100, kGemmTA = 101, kScatter = 102;     // nodes that are memory, not instructions: never part of a program
+const int kPad = 100, kGemmTA = 101, kScatter = 102, kColSum = 103;     // nodes that are memory, not instructions: never part of a program
 void materialize_node(Device* dev, ExprNode* n, NdArray* dest = nullptr);
 const int64_t kMaxFusedElems = (int64_t)1 << 24;     // beyond this a pass is bandwidth-bound anyway and the vectorised single-op kernels are used
 
@@ -160,6 +160,12 @@ void write_region(Device* dev, NdArray src, NdArray region) {      // region <- 
 
 void materialize_node(Device* dev, ExprNode* n, NdArray* dest) {
   if (n->has_value) return;
+  if (n->kind == kColSum) {       // MaybeReduceSum on its own: sum over the rows
+    NdArray y = dev->empty(n->shape);
+    check_status(agb_reduce(dev->ctx, AGB_R_SUM, n->a.dptr, y.dptr, 1, n->a.shape[0], n->a.shape[1]));
+    n->value = y; n->has_value = true; n->a = NdArray();
+    return;
+  }
   if (n->kind == kScatter) {      // GatherGrad on its own: zero table + scatter-add (array_ops.rs:401-466)
     NdArray gx = dev->empty(n->shape);
     int64_t pre = 1, post = 1; for (int k = 0; k < n->op; k++) pre *= n->shape[k]; for (int k = n->op + 1; k < (int)n->shape.size(); k++) post *= n->shape[k];
@@ -280,6 +286,35 @@ bool expr_sum_pads(ComputeContext& c, const std::vector<NdArray>& xs, NdArray* o
   *out = y;
   return true;
 }
+// rows of equally-shaped 2-D blocks stacked into one matrix (one launch per 64 blocks); the stack is remembered for the rest of the run
+bool stackable(const NdArray& t) { return t.ndim() == 2 && t.stride[1] == 1 && t.stride[0] % 4 == 0 && t.shape[1] % 4 == 0 && (((uintptr_t)t.dptr) & 15) == 0; }
+NdArray stack_rows(Evaluation& run, Device* dev, const std::vector<NdArray>& parts) {
+  std::vector<const float*> ps(parts.size()); std::vector<int64_t> pitch(parts.size());
+  for (size_t i = 0; i < parts.size(); i++) { ps[i] = parts[i].dptr; pitch[i] = parts[i].stride[0]; }
+  for (auto& e : run.row_stacks) if (e.key == ps && e.stacked.shape[1] == parts[0].shape[1] && e.parts[0].shape == parts[0].shape) return e.stacked;
+  NdArray S = dev->empty({(int64_t)parts.size() * parts[0].shape[0], parts[0].shape[1]});
+  check_status(agb_concat_rows(dev->ctx, (int)parts.size(), ps.data(), pitch.data(), parts[0].shape[0], parts[0].shape[1], S.dptr));
+  run.row_stacks.push_back(Evaluation::RowStack{ps, parts, S});
+  return S;
+}
+NdArray expr_colsum(ComputeContext& c, NdArray gy, const Shape& target) {
+  if (gy.ndim() != 2 || target.size() != 2 || target[0] != 1 || target[1] != gy.shape[1] || gy.shape[0] < 2 || !gy.on_device() || !gy.is_contiguous() || gy.lazy || gy.i32) return NdArray();
+  auto n = std::make_shared<ExprNode>(); n->kind = kColSum; n->a = gy; n->shape = target;
+  n->consumers = 1; n->n_instr = 0; n->n_leaves = 1; n->n_multi = 0;
+  NdArray r; r.shape = target; r.stride = NdArray::contiguous_strides(target); r.expr = n;
+  return r;
+}
+// AddN over deferred row sums of equally-shaped blocks (the bias gradient of an unrolled RNN): ONE reduction over the stacked rows
+bool expr_sum_colsums(ComputeContext& c, const std::vector<NdArray>& xs, NdArray* out) {
+  if (xs.size() < 2) return false;
+  std::vector<NdArray> parts;
+  for (auto& x : xs) { if (!unvalued(x) || x.expr->kind != kColSum || x.expr->a.shape != xs[0].expr->a.shape || !stackable(x.expr->a)) return false; parts.push_back(x.expr->a); }
+  NdArray S = stack_rows(*c.run, c.dev, parts);
+  NdArray y = c.dev->empty(xs[0].expr->shape);
+  check_status(agb_reduce(c.dev->ctx, AGB_R_SUM, S.dptr, y.dptr, 1, S.shape[0], S.shape[1]));
+  *out = y;
+  return true;
+}
 NdArray expr_gemm_ta(ComputeContext& c, NdArray a, NdArray b) {
   if (a.ndim() != 2 || b.ndim() != 2 || !a.on_device() || !b.on_device() || a.shape[0] != b.shape[0] || a.lazy || b.lazy || a.i32 || b.i32) return NdArray();
   auto n = std::make_shared<ExprNode>(); n->kind = kGemmTA; n->a = a; n->b = b; n->shape = {a.shape[1], b.shape[1]};
@@ -292,15 +327,10 @@ NdArray expr_gemm_ta(ComputeContext& c, NdArray a, NdArray b) {
 bool expr_sum_gemms(ComputeContext& c, const std::vector<NdArray>& xs, NdArray* out) {
   if (xs.size() < 2) return false;
   for (auto& x : xs) if (!unvalued(x) || x.expr->kind != kGemmTA || x.expr->a.shape != xs[0].expr->a.shape || x.expr->b.shape != xs[0].expr->b.shape) return false;
-  auto stackable = [](const NdArray& t) { return t.stride[1] == 1 && t.stride[0] % 4 == 0 && t.shape[1] % 4 == 0 && (((uintptr_t)t.dptr) & 15) == 0; };
-  for (auto& x : xs) if (!stackable(x.expr->a) || !stackable(x.expr->b)) return false;
-  const int n = (int)xs.size();
-  const int64_t k = xs[0].expr->a.shape[0], M = xs[0].expr->a.shape[1], N = xs[0].expr->b.shape[1];
-  NdArray A = c.dev->empty({n * k, M}), B = c.dev->empty({n * k, N});
-  std::vector<const float*> pa(n), pb(n); std::vector<int64_t> sa(n), sb(n);
-  for (int i = 0; i < n; i++) { pa[i] = xs[i].expr->a.dptr; sa[i] = xs[i].expr->a.stride[0]; pb[i] = xs[i].expr->b.dptr; sb[i] = xs[i].expr->b.stride[0]; }
-  check_status(agb_concat_rows(c.dev->ctx, n, pa.data(), sa.data(), k, M, A.dptr));
-  check_status(agb_concat_rows(c.dev->ctx, n, pb.data(), sb.data(), k, N, B.dptr));
+  std::vector<NdArray> as, bs;
+  for (auto& x : xs) { if (!stackable(x.expr->a) || !stackable(x.expr->b)) return false; as.push_back(x.expr->a); bs.push_back(x.expr->b); }
+  const int64_t M = xs[0].expr->a.shape[1], N = xs[0].expr->b.shape[1];
+  NdArray A = stack_rows(*c.run, c.dev, as), B = stack_rows(*c.run, c.dev, bs);
   NdArray y = c.dev->empty({M, N});
   agb_tensor da = A.desc(), db = B.desc(), dy = y.desc();
   check_status(agb_gemm_f32(c.dev->ctx, 1, 0, &da, &db, &dy, 0.0f));

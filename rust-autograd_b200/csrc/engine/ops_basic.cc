@@ -418,6 +418,7 @@ struct MaybeReduceSum : Op {           // binary_ops.rs:39-105
       else if (orig[i] != gy.shape[i]) throw Panic("bug of MaybeReduceSum probably");
     }
     Shape fin = orig_.size() == 1 && orig_[0] == 0 ? Shape{} : orig_;     // shape [0] (scalar_shape) denotes a 0-d target
+    if (c.run->fuse && c.run->sole_consumer_sums(c.node) && axes == std::vector<int>({0})) { NdArray r = expr_colsum(c, on_dev(c.dev, gy), fin); if (r.expr) { c.append_output(r); return; } }
     if (gy.chan_sum && gy.ndim() == 4 && axes == std::vector<int>({0, 2, 3}) && gy.chan_sum->size() == gy.shape[1]) {
       c.append_output(gy.chan_sum->reshaped(fin)); return;               // bias gradient already produced by the fused epilogue that wrote gy
     }
@@ -625,7 +626,7 @@ struct AddN : Op {                     // array_ops.rs:503-535
     c.accept_expr = true;
     std::vector<NdArray> xs; bool same = true, all_empty_scalars = true;
     for (int i = 0; i < n; i++) { xs.push_back(c.input(i)); if (xs[i].shape != xs[0].shape) same = false; if (!(xs[i].ndim() == 0 && xs[i].has_host() && !xs[i].on_device())) all_empty_scalars = false; }
-    if (same && !all_empty_scalars) { NdArray y; if (expr_sum_pads(c, xs, &y) || expr_sum_gemms(c, xs, &y) || expr_sum_scatters(c, xs, &y)) { c.append_output(y); return; } }
+    if (same && !all_empty_scalars) { NdArray y; if (expr_sum_pads(c, xs, &y) || expr_sum_gemms(c, xs, &y) || expr_sum_scatters(c, xs, &y) || expr_sum_colsums(c, xs, &y)) { c.append_output(y); return; } }
     if (same && !all_empty_scalars && n <= 6 && xs[0].ndim() > 0) {      // a short sum joins the pending expression as the same left fold
       NdArray acc = expr_binary(c, AGB_B_ADD, xs[0], xs[1]);
       for (int i = 2; i < n && acc.expr; i++) acc = expr_binary(c, AGB_B_ADD, acc, xs[i]);

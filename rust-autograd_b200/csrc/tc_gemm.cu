@@ -18,6 +18,7 @@
 //
 // Replaces matrixmultiply::sgemm / cblas_sgemm behind MatMul and BatchMatMul
 // (reference src/tensor_ops/dot_ops.rs:383-422, 142-380).
+#include <stdlib.h>
 #include "tc_tile.cuh"
 
 template <int TN_, bool P_MN_, bool Q_MN_, bool SPLIT_> struct GemmPol {
@@ -92,7 +93,9 @@ static int tc_launch(agb_ctx* ctx, const CUtensorMap& tmP, const CUtensorMap& tm
   int64_t tiles = (int64_t)gx * gy * batch, cap = (int64_t)ctx->sm_count * Pol::OCC;
   int splits = 1;
   if (tiles * 2 <= cap && kb_total >= 8 && ldc == NL && (batch == 1 || bsc == (int64_t)NC * NL)) {
-    int64_t s = cap / tiles; if (s > kb_total / 4) s = kb_total / 4; if (s > 1) splits = (int)s;
+    static const int min_kb = [] { const char* e = getenv("AGB_GEMM_SPLIT_MIN_KB"); int v = e ? atoi(e) : 4; return v < 1 ? 1 : v; }();      // tuning knob (k-blocks per split)
+    static const int occ_cap = [] { const char* e = getenv("AGB_GEMM_SPLIT_WAVES_X2"); int v = e ? atoi(e) : 2; return v < 1 ? 1 : v; }();     // cap = SMs * OCC * v / 2
+    int64_t s = cap * occ_cap / 2 / tiles; if (s > kb_total / min_kb) s = kb_total / min_kb; if (s > 1) splits = (int)s;
   }
   int kb_per = (kb_total + splits - 1) / splits; splits = (kb_total + kb_per - 1) / kb_per;
   if ((int64_t)batch * splits > 65535) { splits = 1; kb_per = kb_total; }
