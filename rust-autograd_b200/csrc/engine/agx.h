@@ -111,7 +111,7 @@ struct Device {                   // thin C++ handle on the kernel C ABI context
 };
 
 // ---------------------------------------------------------------------------------------------- graph
-struct Graph; struct Context; struct VariableEnvironment; struct ComputeContext; struct GradientContext;
+struct Graph; struct Context; struct VariableEnvironment; struct ComputeContext; struct GradientContext; struct Evaluation;
 typedef int TensorID;
 struct VariableID { int v = -1; bool valid() const { return v >= 0; } };
 
@@ -127,6 +127,11 @@ struct Op {                       // trait Op (src/op.rs:90-101)
   virtual void grad(GradientContext& ctx) = 0;
   virtual bool metadata_only() const { return false; }   // Shape / Rank / Size: read the input's shape, never its values
   virtual bool plain_matmul(bool* tb) const { return false; }   // MatMul (2-D, lhs not transposed): rows of several such products with one rhs can be stacked
+  // Row-wise ops (every output row depends only on the same row of the inputs): nodes with the same non-null stack_key whose inputs do not
+  // depend on each other may be computed together on stacked rows.  ins[m] / outs[m] = the inputs / outputs of member m; false = not
+  // applicable (the members then run on their own and raise their own errors).
+  virtual const char* stack_key() const { return nullptr; }
+  virtual bool compute_stacked(Device* dev, Evaluation& run, const std::vector<std::vector<NdArray>>& ins, std::vector<std::vector<NdArray>>* outs) { return false; }
   virtual bool sums_inputs() const { return false; }     // AddN: lets a producer defer itself so that the sum can absorb it (fuse.cc)
   virtual bool mutates_now() const { return false; }     // Assign: writes a variable in the middle of the traversal (optimizer ops are deferred)
 };
@@ -332,7 +337,8 @@ bool expr_sum_scatters(ComputeContext& c, const std::vector<NdArray>& xs, NdArra
 NdArray expr_colsum(ComputeContext& c, NdArray gy, const Shape& target);       // deferred MaybeReduceSum [R, N] -> [1, N] whose only reader is an AddN
 bool expr_sum_colsums(ComputeContext& c, const std::vector<NdArray>& xs, NdArray* out);
 bool stackable(const NdArray& t);                                                                   // 2-D, unit column stride, 16-byte aligned rows
-NdArray stack_rows(Evaluation& run, Device* dev, const std::vector<NdArray>& parts);              // agb_concat_rows, remembered for the rest of the run
+NdArray stack_rows(Evaluation& run, Device* dev, const std::vector<NdArray>& parts);
+NdArray stack_vectors(Evaluation& run, Device* dev, const std::vector<NdArray>& parts);          // n vectors of B elements -> contiguous [n * B]              // agb_concat_rows, remembered for the rest of the run
 bool expr_materialize_into(Device* dev, const NdArray& x, NdArray dest);
 Op* make_optimizer_op(int kind, float h0, float h1, float h2, float h3);
 void flush_pending_updates(Evaluation& run, VariableEnvironment* env);

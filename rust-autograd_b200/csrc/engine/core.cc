@@ -1,6 +1,7 @@
 // core.cc — arrays, graph, reverse-mode gradient builder, evaluator, variable environment (see agx.h for the reference map).
 #include "agx.h"
 #include <map>
+#include <tuple>
 #include <algorithm>
 #include <queue>
 #include <sstream>
@@ -385,21 +386,25 @@ std::vector<EvalResult> eval(Graph* g, const std::vector<Tensor>& targets, const
   // another member's product are evaluated together: when the traversal first reaches one, the lhs of ALL of them are scheduled first, the
   // rows are stacked (agb_concat_rows) and ONE [T*B, k] x W GEMM fills every member's output (row blocks of one buffer).  Per-row
   // arithmetic is unchanged; a 128-row GEMM cannot fill 148 SMs, a 8064-row one runs at the large-GEMM rate.
-  struct RowBatch { std::vector<TensorID> members; TensorID weight; bool tb; bool expanded = false, done = false; };
+  // The same scheduling serves row-wise ops that declare a stack_key (the per-step softmax cross-entropy and its gradient): one launch over
+  // the stacked rows instead of T (Op::compute_stacked).
+  struct RowBatch { std::vector<TensorID> members; TensorID weight; bool tb; bool generic = false; bool expanded = false, done = false; };
   std::vector<RowBatch> batches; std::vector<int> batch_of;
   if (run.fuse) {
     const size_t N = g->node_set.size();
-    std::map<std::pair<TensorID, bool>, int> key2group; std::vector<RowBatch> groups; std::vector<int> group_of(N, -1);
+    std::map<std::tuple<std::string, TensorID, bool>, int> key2group; std::vector<RowBatch> groups; std::vector<int> group_of(N, -1);
     bool ordered = true;
     for (size_t id = 0; id < N; id++) {
       if (!seen[id]) continue;                                    // not part of this evaluation
       TensorInternal& n = g->inner((TensorID)id); bool tb = false;
       if (n.is_placeholder || n.is_variable() || !n.op) continue;
       for (auto& c : n.incoming_nodes) if (c.id >= (TensorID)id) ordered = false;      // (control_dependencies rewiring) no stacking then
-      if (!n.op->plain_matmul(&tb) || n.incoming_nodes.size() != 2 || !g->inner(n.incoming_nodes[1].id).is_variable()) continue;
-      auto key = std::make_pair(n.incoming_nodes[1].id, tb);
+      std::tuple<std::string, TensorID, bool> key; bool generic = false;
+      if (n.op->plain_matmul(&tb) && n.incoming_nodes.size() == 2 && g->inner(n.incoming_nodes[1].id).is_variable()) key = std::make_tuple(std::string(), n.incoming_nodes[1].id, tb);
+      else if (n.op->stack_key() && !n.incoming_nodes.empty()) { key = std::make_tuple(std::string(n.op->stack_key()), (TensorID)-1, false); generic = true; }
+      else continue;
       auto it = key2group.find(key);
-      if (it == key2group.end()) { if (groups.size() >= 64) continue; it = key2group.insert({key, (int)groups.size()}).first; RowBatch b; b.weight = key.first; b.tb = tb; groups.push_back(b); }
+      if (it == key2group.end()) { if (groups.size() >= 64) continue; it = key2group.insert({key, (int)groups.size()}).first; RowBatch b; b.weight = std::get<1>(key); b.tb = tb; b.generic = generic; groups.push_back(b); }
       groups[it->second].members.push_back((TensorID)id); group_of[id] = it->second;
     }
     if (ordered && !groups.empty()) {
@@ -414,17 +419,17 @@ std::vector<EvalResult> eval(Graph* g, const std::vector<Tensor>& targets, const
       }
       batch_of.assign(N, -1);
       for (size_t q = 0; q < groups.size(); q++) {
-        RowBatch b; b.weight = groups[q].weight; b.tb = groups[q].tb;
+        RowBatch b; b.weight = groups[q].weight; b.tb = groups[q].tb; b.generic = groups[q].generic;
         for (TensorID m : groups[q].members) {
-          TensorID a = g->inner(m).incoming_nodes[0].id;
-          uint64_t d = dep[a] | (group_of[a] >= 0 ? 1ull << group_of[a] : 0);
+          uint64_t d = 0; auto& ins = g->inner(m).incoming_nodes;
+          for (size_t k = 0; k < (b.generic ? ins.size() : 1); k++) { TensorID a = ins[k].id; d |= dep[a] | (group_of[a] >= 0 ? 1ull << group_of[a] : 0); }
           if (!((d >> q) & 1)) b.members.push_back(m);
         }
         if (b.members.size() >= 2) { for (TensorID m : b.members) batch_of[m] = (int)batches.size(); batches.push_back(b); }
       }
     }
   }
-  auto fetch = [&](const IncomingTensor& in, NdArray* out) {      // the value an op would receive through ComputeContext::input
+  auto fetch = [&](const IncomingTensor& in, NdArray* out, bool need_device = true) {      // the value an op would receive through ComputeContext::input
     TensorInternal& x = g->inner(in.id);
     if (x.is_placeholder) *out = find_placeholder_value(feeds, g, in.id);
     else if (x.is_variable()) *out = env->array_list[x.variable_id.v];
@@ -436,6 +441,7 @@ std::vector<EvalResult> eval(Graph* g, const std::vector<Tensor>& targets, const
     if (out->expr) *out = expr_materialize(dev, *out);
     if (out->lazy) *out = materialize_lazy(dev, *out);
     if (out->i32 || out->virt) return false;
+    if (!need_device) return true;                    // (host-known scalars stay on the host, like ComputeContext::input)
     dev->ensure_device(*out);
     return out->on_device();
   };
@@ -460,13 +466,27 @@ std::vector<EvalResult> eval(Graph* g, const std::vector<Tensor>& targets, const
     for (int i = 0; i < n; i++) { Stored o; o.ys.push_back(Y.sliced(0, i * rows, rows)); storage[ms[i]] = std::move(o); }
     return true;
   };
+  auto run_stacked_ops = [&](RowBatch& b) {
+    std::vector<TensorID> ms; std::vector<std::vector<NdArray>> ins;
+    for (TensorID m : b.members) {
+      if (storage.count(m)) continue;
+      std::vector<NdArray> xs; bool ok = true;
+      for (auto& in : g->inner(m).incoming_nodes) { NdArray a; if (!fetch(in, &a, false)) { ok = false; break; } xs.push_back(a); }
+      if (ok) { ms.push_back(m); ins.push_back(std::move(xs)); }
+    }
+    if (ms.size() < 2) return false;
+    std::vector<std::vector<NdArray>> outs;
+    if (!g->inner(ms[0]).op->compute_stacked(dev, run, ins, &outs) || outs.size() != ms.size()) return false;
+    for (size_t i = 0; i < ms.size(); i++) { Stored o; o.ys = std::move(outs[i]); storage[ms[i]] = std::move(o); }
+    return true;
+  };
   while (!st.empty()) {
     auto [id, visit] = st.back(); st.pop_back();
     if (visit) {
       if (would_not_visit(id)) continue;
       if (!batch_of.empty() && batch_of[id] >= 0 && !batches[batch_of[id]].done) {
         RowBatch& b = batches[batch_of[id]]; b.done = true;
-        if (run_row_batch(b) && storage.count(id)) continue;
+        if ((b.generic ? run_stacked_ops(b) : run_row_batch(b)) && storage.count(id)) continue;
       }
       TensorInternal& n = g->inner(id);
       Stored out;
@@ -495,7 +515,11 @@ std::vector<EvalResult> eval(Graph* g, const std::vector<Tensor>& targets, const
       for (auto& c : g->inner(id).incoming_nodes) if (!would_not_visit(c.id)) st.push_back({c.id, false});
       if (!batch_of.empty() && batch_of[id] >= 0 && !batches[batch_of[id]].expanded) {       // schedule the lhs of every member of the stack first
         RowBatch& b = batches[batch_of[id]]; b.expanded = true;
-        for (TensorID m : b.members) { TensorID a = g->inner(m).incoming_nodes[0].id; if (m != id && !would_not_visit(a)) st.push_back({a, false}); }
+        for (TensorID m : b.members) {
+          if (m == id) continue;
+          auto& ins = g->inner(m).incoming_nodes;
+          for (size_t k = 0; k < (b.generic ? ins.size() : 1); k++) if (!would_not_visit(ins[k].id)) st.push_back({ins[k].id, false});
+        }
       }
     }
   }

@@ -291,11 +291,42 @@ bool stackable(const NdArray& t) { return t.ndim() == 2 && t.stride[1] == 1 && t
 NdArray stack_rows(Evaluation& run, Device* dev, const std::vector<NdArray>& parts) {
   std::vector<const float*> ps(parts.size()); std::vector<int64_t> pitch(parts.size());
   for (size_t i = 0; i < parts.size(); i++) { ps[i] = parts[i].dptr; pitch[i] = parts[i].stride[0]; }
+  {   // consecutive row blocks of ONE buffer (slices of a stacked GEMM / stacked op output): the stack is a view, nothing is copied
+    bool consecutive = parts[0].buf != nullptr && parts[0].stride[0] == parts[0].shape[1];
+    const int64_t block = parts[0].shape[0] * parts[0].shape[1];
+    for (size_t i = 1; consecutive && i < parts.size(); i++) consecutive = parts[i].buf == parts[0].buf && parts[i].dptr == parts[0].dptr + (int64_t)i * block && parts[i].stride[0] == parts[i].shape[1];
+    if (consecutive) { NdArray v = parts[0]; v.shape[0] = (int64_t)parts.size() * parts[0].shape[0]; v.host.reset(); v.chan_sum.reset(); return v; }
+  }
   for (auto& e : run.row_stacks) if (e.key == ps && e.stacked.shape[1] == parts[0].shape[1] && e.parts[0].shape == parts[0].shape) return e.stacked;
   NdArray S = dev->empty({(int64_t)parts.size() * parts[0].shape[0], parts[0].shape[1]});
   check_status(agb_concat_rows(dev->ctx, (int)parts.size(), ps.data(), pitch.data(), parts[0].shape[0], parts[0].shape[1], S.dptr));
   run.row_stacks.push_back(Evaluation::RowStack{ps, parts, S});
   return S;
+}
+// per-member vectors (labels [B] or [B, 1], any strides) -> one contiguous [n * B] vector; evenly spaced column views of one array (the
+// token-id columns of one feed) take a single strided copy
+NdArray stack_vectors(Evaluation& run, Device* dev, const std::vector<NdArray>& parts) {
+  const int n = (int)parts.size(); const int64_t B = parts[0].size();
+  std::vector<const float*> ps(n); for (int i = 0; i < n; i++) ps[i] = parts[i].dptr;
+  for (auto& e : run.row_stacks) if (e.key == ps && e.stacked.ndim() == 1 && e.stacked.shape[0] == n * B && e.parts[0].shape == parts[0].shape && e.parts[0].stride == parts[0].stride) return e.stacked;
+  auto step_of = [](const NdArray& t) { for (int k = 0; k < t.ndim(); k++) if (t.shape[k] != 1) return t.stride[k]; return (int64_t)1; };
+  const int64_t s0 = step_of(parts[0]), delta = n > 1 ? parts[1].dptr - parts[0].dptr : 0;
+  bool even = true;
+  for (int i = 0; i < n && even; i++) even = parts[i].size() == B && step_of(parts[i]) == s0 && parts[i].dptr - parts[0].dptr == (int64_t)i * delta && parts[i].buf == parts[0].buf;
+  NdArray L = dev->empty({n * B});
+  if (even) {
+    agb_tensor ts, td; ts.ptr = parts[0].dptr; ts.rank = 2; ts.shape[0] = n; ts.shape[1] = B; ts.stride[0] = delta; ts.stride[1] = s0;
+    td.ptr = L.dptr; td.rank = 2; td.shape[0] = n; td.shape[1] = B; td.stride[0] = B; td.stride[1] = 1;
+    check_status(agb_copy_strided(dev->ctx, &ts, &td));
+  } else {
+    for (int i = 0; i < n; i++) {
+      agb_tensor ts, td; ts.ptr = parts[i].dptr; ts.rank = 1; ts.shape[0] = B; ts.stride[0] = step_of(parts[i]);
+      td.ptr = L.dptr + (int64_t)i * B; td.rank = 1; td.shape[0] = B; td.stride[0] = 1;
+      check_status(agb_copy_strided(dev->ctx, &ts, &td));
+    }
+  }
+  run.row_stacks.push_back(Evaluation::RowStack{ps, parts, L});
+  return L;
 }
 NdArray expr_colsum(ComputeContext& c, NdArray gy, const Shape& target) {
   if (gy.ndim() != 2 || target.size() != 2 || target[0] != 1 || target[1] != gy.shape[1] || gy.shape[0] < 2 || !gy.on_device() || !gy.is_contiguous() || gy.lazy || gy.i32) return NdArray();

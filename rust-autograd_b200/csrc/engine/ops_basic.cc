@@ -831,6 +831,30 @@ struct SparseSoftmaxCrossEntropyGrad : Op {   // xent_ops.rs:139-158
     c.append_output(gx);
   }
   void grad(GradientContext& c) override { c.append_none(); c.append_none(); }
+  // T time steps of an unrolled RNN: one launch over the stacked rows (the log_x blocks are slices of the stacked forward output)
+  const char* stack_key() const override { return "sparse_xent_grad"; }
+  bool compute_stacked(Device* dev, Evaluation& run, const std::vector<std::vector<NdArray>>& ins, std::vector<std::vector<NdArray>>* outs) override {
+    std::vector<NdArray> xs, ts; const NdArray& gy0 = ins[0][2];
+    for (auto& in : ins) {
+      if (in.size() != 3 || !in[0].on_device() || in[0].ndim() != 2 || in[0].shape != ins[0][0].shape || !stackable(in[0]) || in[1].size() != in[0].shape[0] || !in[1].on_device()) return false;
+      if (in[2].dptr != gy0.dptr || in[2].shape != gy0.shape || in[2].stride != gy0.stride || in[2].host != gy0.host) return false;      // one upstream gradient (the same array) for all
+      xs.push_back(in[0]); ts.push_back(in[1]);
+    }
+    const int64_t n = (int64_t)ins.size(), B = xs[0].shape[0], C = xs[0].shape[1];
+    float v; NdArray gyd;
+    if (scalar_value(gy0, &v)) gyd = dev->full({1}, v);
+    else if (gy0.size() == 1) gyd = dev->contiguous(on_dev(dev, gy0));
+    else if (gy0.size() == B) {      // the same [B, 1] gradient for every step: tiled once
+      NdArray g1 = dev->contiguous(on_dev(dev, gy0)); gyd = dev->empty({n * B});
+      agb_tensor ts_, td; ts_.ptr = g1.dptr; ts_.rank = 2; ts_.shape[0] = n; ts_.shape[1] = B; ts_.stride[0] = 0; ts_.stride[1] = 1;
+      td.ptr = gyd.dptr; td.rank = 2; td.shape[0] = n; td.shape[1] = B; td.stride[0] = B; td.stride[1] = 1;
+      check_status(agb_copy_strided(dev->ctx, &ts_, &td));
+    } else return false;
+    NdArray X = stack_rows(run, dev, xs), L = stack_vectors(run, dev, ts), gx = dev->empty({n * B, C});
+    check_status(agb_sparse_xent_bwd(dev->ctx, X.dptr, L.dptr, gyd.dptr, gyd.size(), gx.dptr, n * B, C));
+    for (int64_t i = 0; i < n; i++) outs->push_back({gx.sliced(0, i * B, B)});
+    return true;
+  }
 };
 struct SparseSoftmaxCrossEntropy : Op {       // xent_ops.rs:63-137
   const char* name() const override { return REFNAME("xent_ops", "SparseSoftmaxCrossEntropy"); }
@@ -845,6 +869,21 @@ struct SparseSoftmaxCrossEntropy : Op {       // xent_ops.rs:63-137
     NdArray loss = c.dev->empty({B, 1}), log_x = c.dev->empty({B, C});
     check_status(agb_sparse_xent_fwd(c.dev->ctx, x.dptr, t.dptr, loss.dptr, log_x.dptr, B, C));
     c.append_output(loss); c.append_output(log_x);
+  }
+  const char* stack_key() const override { return "sparse_xent"; }
+  bool compute_stacked(Device* dev, Evaluation& run, const std::vector<std::vector<NdArray>>& ins, std::vector<std::vector<NdArray>>* outs) override {
+    std::vector<NdArray> xs, ts;
+    for (auto& in : ins) {
+      if (in.size() != 2 || !in[0].on_device() || in[0].ndim() != 2 || in[0].shape != ins[0][0].shape || !stackable(in[0]) || !in[1].on_device()) return false;
+      if (!(in[1].ndim() == 1 || (in[1].ndim() == 2 && in[1].shape[1] == 1)) || in[1].size() != in[0].shape[0]) return false;      // the members raise their own errors
+      xs.push_back(in[0]); ts.push_back(in[1]);
+    }
+    const int64_t n = (int64_t)ins.size(), B = xs[0].shape[0], C = xs[0].shape[1];
+    NdArray X = stack_rows(run, dev, xs), L = stack_vectors(run, dev, ts);
+    NdArray loss = dev->empty({n * B, 1}), log_x = dev->empty({n * B, C});
+    check_status(agb_sparse_xent_fwd(dev->ctx, X.dptr, L.dptr, loss.dptr, log_x.dptr, n * B, C));
+    for (int64_t i = 0; i < n; i++) outs->push_back({loss.sliced(0, i * B, B), log_x.sliced(0, i * B, B)});
+    return true;
   }
   void grad(GradientContext& c) override {
     using namespace T; Graph* g = c.graph();
