@@ -169,7 +169,8 @@ void materialize_node(Device* dev, ExprNode* n, NdArray* dest) {
   if (n->kind == kScatter) {      // GatherGrad on its own: zero table + scatter-add (array_ops.rs:401-466)
     NdArray gx = dev->empty(n->shape);
     int64_t pre = 1, post = 1; for (int k = 0; k < n->op; k++) pre *= n->shape[k]; for (int k = n->op + 1; k < (int)n->shape.size(); k++) post *= n->shape[k];
-    check_status(agb_gather_grad(dev->ctx, n->b.dptr, n->a.dptr, gx.dptr, pre, n->shape[n->op], post, n->a.size()));
+    NdArray idx = dev->contiguous(n->a);
+    check_status(agb_gather_grad(dev->ctx, n->b.dptr, idx.dptr, gx.dptr, pre, n->shape[n->op], post, idx.size()));
     n->value = gx; n->has_value = true; n->a = NdArray(); n->b = NdArray();
     return;
   }
@@ -369,7 +370,7 @@ bool expr_sum_gemms(ComputeContext& c, const std::vector<NdArray>& xs, NdArray* 
   return true;
 }
 NdArray expr_scatter(ComputeContext& c, const Shape& table, int axis, NdArray idx, NdArray gy) {
-  if (!idx.on_device() || !gy.on_device() || !idx.is_contiguous() || !gy.is_contiguous() || axis < 0 || axis >= (int)table.size()) return NdArray();
+  if (!idx.on_device() || !gy.on_device() || !gy.is_contiguous() || axis < 0 || axis >= (int)table.size()) return NdArray();      // idx: any strided view
   auto n = std::make_shared<ExprNode>(); n->kind = kScatter; n->op = axis; n->a = idx; n->b = gy; n->shape = table;
   n->consumers = 1; n->n_instr = 0; n->n_leaves = 1; n->n_multi = 0;
   NdArray r; r.shape = table; r.stride = NdArray::contiguous_strides(table); r.expr = n;
@@ -382,7 +383,25 @@ bool expr_sum_scatters(ComputeContext& c, const std::vector<NdArray>& xs, NdArra
   const Shape& table = xs[0].expr->shape; const int ax = xs[0].expr->op;
   int64_t pre = 1, post = 1; for (int k = 0; k < ax; k++) pre *= table[k]; for (int k = ax + 1; k < (int)table.size(); k++) post *= table[k];
   NdArray gx = c.dev->zeros(table);
-  for (auto& x : xs) check_status(agb_scatter_add(c.dev->ctx, x.expr->b.dptr, x.expr->a.dptr, gx.dptr, pre, table[ax], post, x.expr->a.size()));
+  {   // token-id vectors and gradient row blocks that stack (the gy_t are slices of one stacked GEMM output): ONE scatter-add for all terms
+    bool vec = ax == 0 && pre == 1 && post % 4 == 0;
+    std::vector<NdArray> ids, gys;
+    for (auto& x : xs) {
+      const NdArray& id = x.expr->a; int nontrivial = 0; for (auto d : id.shape) if (d != 1) nontrivial++;
+      if (nontrivial > 1 || id.shape != xs[0].expr->a.shape || x.expr->b.size() != id.size() * post) vec = false;
+      if (!vec) break;
+      NdArray g2 = x.expr->b; g2.shape = {id.size(), post}; g2.stride = {post, 1};       // contiguous [B, ..., post] viewed as [B, post]
+      if (!stackable(g2)) { vec = false; break; }
+      ids.push_back(id); gys.push_back(g2);
+    }
+    if (vec) {
+      NdArray L = stack_vectors(*c.run, c.dev, ids), G = stack_rows(*c.run, c.dev, gys);
+      check_status(agb_scatter_add(c.dev->ctx, G.dptr, L.dptr, gx.dptr, 1, table[0], post, L.size()));
+      *out = gx;
+      return true;
+    }
+  }
+  for (auto& x : xs) { NdArray idx = c.dev->contiguous(x.expr->a); check_status(agb_scatter_add(c.dev->ctx, x.expr->b.dptr, idx.dptr, gx.dptr, pre, table[ax], post, idx.size())); }
   *out = gx;
   return true;
 }

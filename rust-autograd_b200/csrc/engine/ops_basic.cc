@@ -1142,10 +1142,11 @@ struct GatherGrad : Op {               // array_ops.rs:401-474
   int axis;
   const char* name() const override { return REFNAME("array_ops", "GatherGrad"); }
   void compute(ComputeContext& c) override {
-    NdArray idx = c.dev->contiguous(on_dev(c.dev, c.input(0))), param = c.input(1), gy = c.dev->contiguous(on_dev(c.dev, c.input(2)));
+    NdArray idx_view = on_dev(c.dev, c.input(0)), param = c.input(1), gy = c.dev->contiguous(on_dev(c.dev, c.input(2)));
     int ax = normalize_negative_axis(axis, param.ndim());
+    if (c.run->fuse && c.run->sole_consumer_sums(c.node)) { NdArray r = expr_scatter(c, param.shape, ax, idx_view, gy); if (r.expr) { c.append_output(r); return; } }
+    NdArray idx = c.dev->contiguous(idx_view);
     int64_t pre = 1, post = 1; for (int k = 0; k < ax; k++) pre *= param.shape[k]; for (int k = ax + 1; k < param.ndim(); k++) post *= param.shape[k];
-    if (c.run->fuse && c.run->sole_consumer_sums(c.node)) { NdArray r = expr_scatter(c, param.shape, ax, idx, gy); if (r.expr) { c.append_output(r); return; } }
     NdArray gx = c.dev->empty(param.shape);
     check_status(agb_gather_grad(c.dev->ctx, gy.dptr, idx.dptr, gx.dptr, pre, param.shape[ax], post, idx.size()));
     c.append_output(gx);
@@ -1172,6 +1173,26 @@ struct Gather : Op {                   // array_ops.rs:353-399; inputs are (indi
     NdArray y = c.dev->empty(out);
     check_status(agb_gather(c.dev->ctx, param.dptr, idx.dptr, y.dptr, pre, param.shape[ax], post, idx.size(), normalize ? 1 : 0));
     c.append_output(y);
+  }
+  // the embedding lookups of an unrolled RNN: one gather with the stacked token ids; its row blocks are already the stacked lhs of x_t * wx
+  const char* stack_key() const override { return axis == 0 ? (normalize ? "gather0n" : "gather0") : nullptr; }
+  bool compute_stacked(Device* dev, Evaluation& run, const std::vector<std::vector<NdArray>>& ins, std::vector<std::vector<NdArray>>* outs) override {
+    std::vector<NdArray> ids; const NdArray& p0 = ins[0][1];
+    if (!p0.on_device() || p0.ndim() < 2 || !p0.is_contiguous() || p0.meta) return false;
+    for (auto& in : ins) {
+      if (in.size() != 2 || !in[0].on_device() || in[0].meta || in[0].shape != ins[0][0].shape || in[0].size() == 0) return false;
+      if (in[1].dptr != p0.dptr || in[1].shape != p0.shape || in[1].stride != p0.stride) return false;      // one table for all
+      int nontrivial = 0; for (auto d : in[0].shape) if (d != 1) nontrivial++;
+      if (nontrivial > 1) return false;                                                                     // ids as a vector ([B] / [B, 1]) only
+      ids.push_back(in[0]);
+    }
+    const int64_t n = (int64_t)ins.size(), B = ids[0].size();
+    int64_t post = 1; for (int k = 1; k < p0.ndim(); k++) post *= p0.shape[k];
+    NdArray L = stack_vectors(run, dev, ids), y = dev->empty({n * B, post});
+    check_status(agb_gather(dev->ctx, p0.dptr, L.dptr, y.dptr, 1, p0.shape[0], post, n * B, normalize ? 1 : 0));
+    Shape out(ids[0].shape); out.insert(out.end(), p0.shape.begin() + 1, p0.shape.end());
+    for (int64_t i = 0; i < n; i++) outs->push_back({y.sliced(0, i * B, B).reshaped(out)});
+    return true;
   }
   void grad(GradientContext& c) override {
     Tensor x = c.input(0), x1 = c.input(1);
