@@ -226,7 +226,7 @@ int  agb_fill(agb_ctx* ctx, agb_tensor* y, float value);
  * agb_unary / agb_binary, so the values are bit-identical to the unfused sequence.
  * Leaf l is read at ptr + r * pitch + c * cstride (pitch / cstride 0 = broadcast, pitch != cols = a sliced view) into register
  * `reg`; instruction i computes regs[dst] = f(regs[a], regs[b] or imm); output o stores regs[reg] at ptr + r * pitch + c. */
-#define AGB_FUSE_MAX_LEAVES 12
+#define AGB_FUSE_MAX_LEAVES 16
 #define AGB_FUSE_MAX_INSTR 48
 #define AGB_FUSE_MAX_OUT 8
 #define AGB_FUSE_REGS 32

@@ -328,6 +328,7 @@ NdArray expr_binary_imm(ComputeContext& c, int op, NdArray x, float imm, bool im
 NdArray expr_passthrough(ComputeContext& c, const NdArray& x);
 NdArray expr_materialize(Device* dev, const NdArray& x);
 bool expr_has_value(const NdArray& x);
+NdArray expr_slice(ComputeContext& c, const NdArray& x, const std::vector<int64_t>& start, const std::vector<int64_t>& len);   // slice of a pending expression = the expression over sliced leaves
 NdArray expr_pad(ComputeContext& c, const Shape& full, const std::vector<int64_t>& start, NdArray gy);
 bool expr_sum_pads(ComputeContext& c, const std::vector<NdArray>& xs, NdArray* out);
 NdArray expr_gemm_ta(ComputeContext& c, NdArray a, NdArray b);                 // deferred A^T * B whose only reader is an AddN

@@ -14,6 +14,7 @@
 // Programs are bounded (AGB_FUSE_MAX_*); an operand sub-DAG that would overflow is materialised first and becomes a leaf.
 #include "agx.h"
 #include <algorithm>
+#include <functional>
 #include <unordered_map>
 
 namespace agx {
@@ -83,9 +84,13 @@ struct Compiler {
   }
 };
 
-bool run_program(Device* dev, ExprNode* root, NdArray* root_dest) {
+// One launch for the DAG below `roots` (all of one shape).  dests[i] with a device pointer = root i is written there (a strided region of
+// a larger buffer); otherwise a fresh array is allocated.
+bool run_program(Device* dev, const std::vector<ExprNode*>& roots, const std::vector<NdArray>& dests) {
+  ExprNode* root = roots[0];
+  if ((int)roots.size() > AGB_FUSE_MAX_OUT) return false;
   Compiler C(dev, root);
-  C.visit(root);
+  for (ExprNode* r : roots) { if (r->shape != root->shape || r->has_value || r->kind >= kPad) return false; C.visit(r); }
   const int I = (int)C.order.size();
   if (I > AGB_FUSE_MAX_INSTR) return false;
   // operands -> value ids (leaves first; instruction k is value L + k, fixed up once L is known)
@@ -100,9 +105,9 @@ bool run_program(Device* dev, ExprNode* root, NdArray* root_dest) {
   const int L = (int)C.leaves.size();
   if (!C.ok || L > AGB_FUSE_MAX_LEAVES) return false;
   // outputs: the root + every other node somebody else will read
-  std::vector<int> outs; outs.push_back(I - 1);
-  for (int k = 0; k < I - 1 && (int)outs.size() < AGB_FUSE_MAX_OUT; k++) if (C.order[k]->consumers > 1) outs.push_back(k);
-  std::vector<char> is_out(I, 0); for (int k : outs) is_out[k] = 1;
+  std::vector<int> outs; std::vector<char> is_out(I, 0); bool any_dest = false;
+  for (size_t i = 0; i < roots.size(); i++) { int k = C.instr_of[roots[i]]; if (is_out[k]) return false; is_out[k] = 1; outs.push_back(k); if (dests[i].on_device()) any_dest = true; }
+  for (int k = 0; k < I && (int)outs.size() < AGB_FUSE_MAX_OUT; k++) if (!is_out[k] && C.order[k]->consumers > 1) { is_out[k] = 1; outs.push_back(k); }
   // linear-scan register allocation
   const int V = L + I;
   auto vid = [&](const Opnd& o) { return o.id < 0 ? -1 : (o.leaf ? o.id : L + o.id); };
@@ -127,13 +132,13 @@ bool run_program(Device* dev, ExprNode* root, NdArray* root_dest) {
   const int nd = (int)root->shape.size();
   int64_t cols = nd == 0 ? 1 : root->shape[nd - 1], total = 1; for (auto d : root->shape) total *= d;
   int64_t rows = cols == 0 ? 0 : total / cols;
-  bool flat = root_dest == nullptr;
+  bool flat = !any_dest;
   for (auto& lf : C.leaves) if (!((lf.pitch == 0 && lf.cs == 0) || (lf.cs == 1 && (lf.pitch == cols || rows == 1)))) flat = false;
   std::vector<agb_fuse_leaf> lv(L);
   for (int l = 0; l < L; l++) { lv[l].ptr = C.leaves[l].arr.dptr; lv[l].pitch = flat ? 0 : C.leaves[l].pitch; lv[l].cstride = C.leaves[l].cs; lv[l].reg = reg[l]; }
   std::vector<agb_fuse_out> ov(outs.size()); std::vector<NdArray> values(outs.size());
   for (size_t o = 0; o < outs.size(); o++) {
-    if (o == 0 && root_dest) { int64_t p, cs; as_2d(*root_dest, root->shape, p, cs); values[o] = *root_dest; ov[o].pitch = p; }
+    if (o < roots.size() && dests[o].on_device()) { int64_t p, cs; as_2d(dests[o], root->shape, p, cs); values[o] = dests[o]; ov[o].pitch = p; }
     else { values[o] = dev->empty(root->shape); ov[o].pitch = flat ? 0 : cols; }
     ov[o].ptr = values[o].dptr; ov[o].reg = code[outs[o]].dst;
   }
@@ -187,11 +192,12 @@ void materialize_node(Device* dev, ExprNode* n, NdArray* dest) {
     n->value = gx; n->has_value = true; n->a = NdArray();
     return;
   }
-  if (run_program(dev, n, dest)) return;
+  const std::vector<ExprNode*> roots{n}; const std::vector<NdArray> dests{dest ? *dest : NdArray()};
+  if (run_program(dev, roots, dests)) return;
   // the DAG does not fit one program (registers / leaves / instructions): compute the operands first, then this node alone
   if (unvalued(n->a)) materialize_node(dev, n->a.expr.get());
   if (n->kind == AGB_F_BINARY && unvalued(n->b)) materialize_node(dev, n->b.expr.get());
-  if (!run_program(dev, n, dest)) throw Panic("fused elementwise: a single instruction does not fit a program");
+  if (!run_program(dev, roots, dests)) throw Panic("fused elementwise: a single instruction does not fit a program");
 }
 
 void account(ExprNode* n) {
@@ -283,7 +289,18 @@ bool expr_sum_pads(ComputeContext& c, const std::vector<NdArray>& xs, NdArray* o
   for (auto& sp : spans) { if (sp.first < at) return false; if (sp.first > at) covered = false; at = sp.first + sp.second; }
   if (at != full[axis]) covered = false;
   NdArray y = covered ? c.dev->empty(full) : c.dev->zeros(full);
-  for (auto& x : xs) write_region(c.dev, x.expr->a, pad_region(y, x.expr->pad_start, x.expr->a.shape));
+  // pieces that are pending expressions of one shape (the four gate gradients share most of their DAG): ONE program with several roots,
+  // each stored into its own region
+  std::vector<ExprNode*> roots; std::vector<NdArray> dests; std::vector<char> in_prog(xs.size(), 0);
+  for (size_t i = 0; i < xs.size(); i++) {
+    const NdArray& src = xs[i].expr->a;
+    NdArray region = pad_region(y, xs[i].expr->pad_start, src.shape);
+    int64_t p, cs; const int nd = region.ndim();
+    if (unvalued(src) && src.expr->kind < kPad && (roots.empty() || src.expr->shape == roots[0]->shape) && nd > 0 && (region.shape[nd - 1] == 1 || region.stride[nd - 1] == 1) &&
+        as_2d(region, region.shape, p, cs) && std::find(roots.begin(), roots.end(), src.expr.get()) == roots.end()) { roots.push_back(src.expr.get()); dests.push_back(region); in_prog[i] = 1; }
+  }
+  if (roots.size() < 2 || !run_program(c.dev, roots, dests)) std::fill(in_prog.begin(), in_prog.end(), 0);
+  for (size_t i = 0; i < xs.size(); i++) if (!in_prog[i]) write_region(c.dev, xs[i].expr->a, pad_region(y, xs[i].expr->pad_start, xs[i].expr->a.shape));
   *out = y;
   return true;
 }
@@ -404,6 +421,38 @@ bool expr_sum_scatters(ComputeContext& c, const std::vector<NdArray>& xs, NdArra
   for (auto& x : xs) { NdArray idx = c.dev->contiguous(x.expr->a); check_status(agb_scatter_add(c.dev->ctx, x.expr->b.dptr, idx.dptr, gx.dptr, pre, table[ax], post, idx.size())); }
   *out = gx;
   return true;
+}
+// Slice of a pending expression: elementwise ops commute with slicing, so the slice is the same (small) expression over sliced leaves and
+// the full-size value (the LSTM pre-activation x*wx + h*wh + b, consumed only through its four gate slices) is never written.
+NdArray expr_slice(ComputeContext& c, const NdArray& x, const std::vector<int64_t>& start, const std::vector<int64_t>& len) {
+  if (!c.run->fuse || !unvalued(x) || x.expr->kind >= kPad || x.expr->n_instr > 8 || (int)start.size() != x.ndim()) return NdArray();
+  for (auto l : len) if (l <= 0) return NdArray();
+  Shape part(len.begin(), len.end());
+  bool ok = true; ExprNode* top = x.expr.get();
+  std::function<NdArray(const NdArray&)> clone = [&](const NdArray& o) -> NdArray {
+    if (!ok) return NdArray();
+    if (unvalued(o)) {
+      ExprNode* s = o.expr.get();
+      if (s->kind >= kPad || s->shape != x.shape || (s != top && s->consumers > 1)) { ok = false; return NdArray(); }      // an interior node somebody else reads: keep it whole
+      auto n = std::make_shared<ExprNode>(); n->kind = s->kind; n->op = s->op; n->p0 = s->p0; n->shape = part; n->consumers = 1;
+      n->a = clone(s->a); if (s->kind == AGB_F_BINARY) n->b = clone(s->b);
+      if (!ok) return NdArray();
+      account(n.get());
+      NdArray r; r.shape = part; r.stride = NdArray::contiguous_strides(part); r.expr = n;
+      return r;
+    }
+    NdArray leaf = resolved(o);
+    if (leaf.size() == 1) return leaf;
+    if (leaf.ndim() != x.ndim()) { ok = false; return NdArray(); }
+    for (int k = 0; k < leaf.ndim(); k++) if (leaf.shape[k] != 1) leaf = leaf.sliced(k, start[k], len[k]);
+    leaf.host.reset(); leaf.chan_sum.reset();
+    return leaf;
+  };
+  NdArray r = clone(x);
+  if (!ok || !r.expr) return NdArray();
+  r.expr->consumers = c.run->consumers_of(c.node);
+  account(r.expr.get());
+  return r;
 }
 bool expr_has_value(const NdArray& x) { return x.expr && x.expr->has_value; }
 NdArray expr_materialize(Device* dev, const NdArray& x) {

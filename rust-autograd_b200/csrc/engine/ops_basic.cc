@@ -1056,9 +1056,19 @@ struct SliceOp : Op {                  // Slice / Split, array_ops.rs:698-724,78
   std::vector<SliceElem> indices; int split_axis = -1000; int64_t s0 = 0, s1 = 0; bool is_split = false;
   const char* name() const override { return is_split ? REFNAME("array_ops", "Split") : REFNAME("array_ops", "Slice"); }
   void compute(ComputeContext& c) override {
+    c.accept_expr = true;
     NdArray x = c.input(0);
     std::vector<SliceElem> idx = indices;
     if (is_split) { int ax = normalize_negative_axis(split_axis, x.ndim()); if (ax < 0 || ax >= x.ndim()) throw Panic("Wrong split axis"); idx.assign(x.ndim(), SliceElem{0, false, 0}); idx[ax] = SliceElem{s0, true, s1}; }
+    if (x.expr) {                        // a slice of a pending expression stays pending (fuse.cc); otherwise the value is needed now
+      if ((int)idx.size() == x.ndim()) {
+        std::vector<int64_t> st(x.ndim()), ln(x.ndim());
+        for (int k = 0; k < x.ndim(); k++) resolve_slice(idx[k], x.shape[k], st[k], ln[k]);
+        NdArray r = expr_slice(c, x, st, ln);
+        if (r.expr) { c.append_output(r); return; }
+      }
+      x = expr_materialize(c.dev, x);
+    }
     c.append_output_view(apply_slices(c.dev, x, idx));
   }
   void grad(GradientContext& c) override {
