@@ -459,7 +459,7 @@ struct FuseParams {
   uint8_t lreg[AGB_FUSE_MAX_LEAVES], oreg[AGB_FUSE_MAX_OUT];
 };
 
-__global__ void __launch_bounds__(256) fused_ewise_kernel(const __grid_constant__ FuseParams P) {
+__global__ void __launch_bounds__(256, 4) fused_ewise_kernel(const __grid_constant__ FuseParams P) {
   __shared__ float R[AGB_FUSE_REGS][256];
   const int t = threadIdx.x;
   const int64_t stride = (int64_t)gridDim.x * 256;
@@ -473,17 +473,21 @@ __global__ void __launch_bounds__(256) fused_ewise_kernel(const __grid_constant_
     for (int l = 0; l < AGB_FUSE_MAX_LEAVES; l++) if (l < P.n_leaves) v[l] = __ldg(P.lptr[l] + r * P.lpitch[l] + c * P.lcs[l]);
 #pragma unroll
     for (int l = 0; l < AGB_FUSE_MAX_LEAVES; l++) if (l < P.n_leaves) R[P.lreg[l]][t] = v[l];
+    float prev = 0.0f; int prev_dst = -1;          // the previous result is forwarded in a register: a dependent chain does not wait for its own store
     for (int k = 0; k < P.n_instr; k++) {
       const uint32_t w = P.code[k];
-      const int kind = w & 3, op = (w >> 2) & 63;
+      const int kind = w & 3, op = (w >> 2) & 63, ia = (w >> 13) & 31, ib = (w >> 18) & 31;
       const float p0 = P.imm[k];
-      float a = R[(w >> 13) & 31][t], b = R[(w >> 18) & 31][t], y;
+      float a, b, y;
+      if (ia == prev_dst) a = prev; else a = R[ia][t];                 // (warp-uniform branches)
+      if (kind != AGB_F_BINARY && kind != AGB_F_BINARY_IMM_A) b = 0.0f; else if (ib == prev_dst) b = prev; else b = R[ib][t];
       if (kind == AGB_F_UNARY) y = unary_apply(op, a, p0, 0.0f);
       else {
         if (kind == AGB_F_BINARY_IMM_B) b = p0; else if (kind == AGB_F_BINARY_IMM_A) a = p0;
         y = binary_apply(op, a, b, 0.0f, 0.0f);
       }
-      R[(w >> 8) & 31][t] = y;
+      prev_dst = (w >> 8) & 31; prev = y;
+      R[prev_dst][t] = y;
     }
     for (int o = 0; o < P.n_out; o++) P.optr[o][r * P.opitch[o] + c] = R[P.oreg[o]][t];
   }
