@@ -37,19 +37,26 @@ static int simt_gemm(agb_ctx* ctx, const float* A, const float* B, float* C, int
   // SMs, fp32 atomics into the (zeroed) result
   int64_t tile = (M >= 96 && N >= 96) ? 128 : 64;
   int64_t tiles = ((M + tile - 1) / tile) * ((N + tile - 1) / tile);
-  if (batch == 1 && K >= 2048 && tiles * 2 <= ctx->sm_count) {
+  if (batch == 1 && K >= 512 && tiles * 2 <= ctx->sm_count) {       // (K >= 512: the 200 x 784 x 10 softmax-regression GEMM ran 73 us on 4 CTAs)
     int64_t splits = (2 * (int64_t)ctx->sm_count + tiles - 1) / tiles;
-    int64_t kchunk = (K + splits - 1) / splits; kchunk = (kchunk + 15) / 16 * 16; if (kchunk < 256) kchunk = 256;
+    int64_t kchunk = (K + splits - 1) / splits; kchunk = (kchunk + 15) / 16 * 16; if (kchunk < 128) kchunk = 128;
     splits = (K + kchunk - 1) / kchunk;
     if (splits > 1 && splits <= 65535) {
-      if (beta == 0.0f) AGB_TRY(agb_memset0(ctx, C, (size_t)M * N * sizeof(float)));
+      // small outputs: every split stores its partial product, one reduction adds them in a fixed order (deterministic, and the same
+      // number of graph nodes as zero-fill + atomics); large outputs keep the atomic accumulation
+      float* part = nullptr;
+      if (beta == 0.0f && splits * M * N <= (1ll << 22)) { void* pv = nullptr; AGB_TRY(agb_alloc(ctx, (size_t)(splits * M * N) * sizeof(float), &pv)); part = (float*)pv; }
+      if (!part && beta == 0.0f) AGB_TRY(agb_memset0(ctx, C, (size_t)M * N * sizeof(float)));
       StoreC ca{C, N, 0, 1, 1};
+      if (part) ca = StoreC{part, N, M * N, 0, 0};
+      struct Finish { agb_ctx* ctx; float* part; float* C; int64_t splits, mn;
+        int operator()(int r) const { if (!part) return r; if (r == AGB_OK) r = agb_reduce(ctx, AGB_R_SUM, part, C, 1, splits, mn); agb_free(ctx, part); return r; } } finish{ctx, part, C, splits, M * N};
       int r;
       if (a_kc && !b_kc) r = simt_gemm_launch(ctx, StridedA{A, rsa, csa, kchunk * csa, kchunk, K}, StridedB{B, rsb, csb, kchunk * rsb, kchunk, K}, ca, M, N, kchunk, splits);
       else if (a_kc && b_kc) r = simt_gemm_launch(ctx, StridedA{A, rsa, csa, kchunk * csa, kchunk, K}, StridedB_K{B, rsb, csb, kchunk * rsb, kchunk, K}, ca, M, N, kchunk, splits);
       else if (!a_kc && !b_kc) r = simt_gemm_launch(ctx, StridedA_M{A, rsa, csa, kchunk * csa, kchunk, K}, StridedB{B, rsb, csb, kchunk * rsb, kchunk, K}, ca, M, N, kchunk, splits);
       else r = simt_gemm_launch(ctx, StridedA_M{A, rsa, csa, kchunk * csa, kchunk, K}, StridedB_K{B, rsb, csb, kchunk * rsb, kchunk, K}, ca, M, N, kchunk, splits);
-      return r;
+      return finish(r);
     }
   }
   for (int64_t z0 = 0; z0 < batch; z0 += 65535) {
