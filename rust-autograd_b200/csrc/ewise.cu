@@ -493,6 +493,105 @@ __global__ void __launch_bounds__(256, 4) fused_ewise_kernel(const __grid_consta
   }
 }
 
+// The same machine with E elements per thread: the program is decoded and dispatched ONCE per instruction for E values, which is what
+// bounds the one-element kernel on mid-sized tensors (issue-bound: ~40 SASS instructions of decode + dispatch per interpreted instruction
+// against 1 for an add).  Register file = dynamic shared memory [nreg][E][256]; leaves are fetched four at a time (4 * E loads in flight).
+#define AGB_FUSE_UNARY_OPS(X) X(AGB_U_COPY) X(AGB_U_ABS) X(AGB_U_NEG) X(AGB_U_SQUARE) X(AGB_U_INV) X(AGB_U_INVSQRT) X(AGB_U_SIGN) X(AGB_U_FLOOR) \
+  X(AGB_U_CEIL) X(AGB_U_SQRT) X(AGB_U_POW) X(AGB_U_LN) X(AGB_U_LOG2) X(AGB_U_LOG10) X(AGB_U_EXP) X(AGB_U_EXP2) X(AGB_U_EXP10) X(AGB_U_SIN) \
+  X(AGB_U_COS) X(AGB_U_TAN) X(AGB_U_ASIN) X(AGB_U_ACOS) X(AGB_U_ATAN) X(AGB_U_SINH) X(AGB_U_COSH) X(AGB_U_TANH) X(AGB_U_ASINH) X(AGB_U_ACOSH) \
+  X(AGB_U_ATANH) X(AGB_U_SIGMOID) X(AGB_U_RELU) X(AGB_U_SOFTPLUS) X(AGB_U_ELU) X(AGB_U_SCALE) X(AGB_U_ADD_SCALAR) X(AGB_U_RSUB_SCALAR) \
+  X(AGB_U_RDIV_SCALAR) X(AGB_U_LGAMMA) X(AGB_U_DIGAMMA)
+#define AGB_FUSE_BINARY_OPS(X) X(AGB_B_ADD) X(AGB_B_SUB) X(AGB_B_MUL) X(AGB_B_DIV) X(AGB_B_EQ) X(AGB_B_NE) X(AGB_B_GT) X(AGB_B_LT) X(AGB_B_GE) \
+  X(AGB_B_LE) X(AGB_B_MAX) X(AGB_B_MIN)
+
+template <int E>
+__global__ void __launch_bounds__(256) fused_ewise_kernel_e(const __grid_constant__ FuseParams P) {
+  extern __shared__ float Rf[];                        // [nreg][E][256]
+  const int t = threadIdx.x;
+  const int64_t chunk = 256 * E;
+#define RF(reg, j) Rf[((reg) * E + (j)) * 256 + t]
+  for (int64_t base = blockIdx.x * chunk; base < P.total; base += (int64_t)gridDim.x * chunk) {
+    uint32_t r[E], c[E]; bool ok[E];
+#pragma unroll
+    for (int j = 0; j < E; j++) {
+      const int64_t i = base + j * 256 + t;
+      ok[j] = i < P.total;
+      const uint32_t ii = ok[j] ? (uint32_t)i : 0u;                     // out-of-range slots read element 0 and store nothing (total < 2^31 on this path)
+      if (P.cols == P.total) { r[j] = 0; c[j] = ii; } else { r[j] = ii / (uint32_t)P.cols; c[j] = ii - r[j] * (uint32_t)P.cols; }
+    }
+    for (int l0 = 0; l0 < P.n_leaves; l0 += 4) {
+      float v[4][E];
+#pragma unroll
+      for (int q = 0; q < 4; q++) if (l0 + q < P.n_leaves) {
+        const float* p = P.lptr[l0 + q]; const int64_t pitch = P.lpitch[l0 + q], cs = P.lcs[l0 + q];
+#pragma unroll
+        for (int j = 0; j < E; j++) v[q][j] = __ldg(p + (int64_t)r[j] * pitch + (int64_t)c[j] * cs);
+      }
+#pragma unroll
+      for (int q = 0; q < 4; q++) if (l0 + q < P.n_leaves) {
+        const int reg = P.lreg[l0 + q];
+#pragma unroll
+        for (int j = 0; j < E; j++) RF(reg, j) = v[q][j];
+      }
+    }
+    float prev[E]; int prev_dst = -1;
+#pragma unroll
+    for (int j = 0; j < E; j++) prev[j] = 0.0f;
+    for (int k = 0; k < P.n_instr; k++) {
+      const uint32_t w = P.code[k];
+      const int kind = w & 3, op = (w >> 2) & 63, ia = (w >> 13) & 31, ib = (w >> 18) & 31, dst = (w >> 8) & 31;
+      const float p0 = P.imm[k];
+      float a[E], b[E], y[E];
+      if (kind == AGB_F_BINARY_IMM_A) {
+#pragma unroll
+        for (int j = 0; j < E; j++) a[j] = p0;
+      } else if (ia == prev_dst) {
+#pragma unroll
+        for (int j = 0; j < E; j++) a[j] = prev[j];
+      } else {
+#pragma unroll
+        for (int j = 0; j < E; j++) a[j] = RF(ia, j);
+      }
+      if (kind == AGB_F_BINARY || kind == AGB_F_BINARY_IMM_A) {
+        if (ib == prev_dst) {
+#pragma unroll
+          for (int j = 0; j < E; j++) b[j] = prev[j];
+        } else {
+#pragma unroll
+          for (int j = 0; j < E; j++) b[j] = RF(ib, j);
+        }
+      } else {
+#pragma unroll
+        for (int j = 0; j < E; j++) b[j] = p0;                          // AGB_F_BINARY_IMM_B (unused by unary ops)
+      }
+      if (kind == AGB_F_UNARY) {
+        switch (op) {
+#define X(OP) case OP: _Pragma("unroll") for (int j = 0; j < E; j++) y[j] = unary_apply(OP, a[j], p0, 0.0f); break;
+          AGB_FUSE_UNARY_OPS(X)
+#undef X
+          default: _Pragma("unroll") for (int j = 0; j < E; j++) y[j] = a[j]; break;
+        }
+      } else {
+        switch (op) {
+#define X(OP) case OP: _Pragma("unroll") for (int j = 0; j < E; j++) y[j] = binary_apply(OP, a[j], b[j], 0.0f, 0.0f); break;
+          AGB_FUSE_BINARY_OPS(X)
+#undef X
+          default: _Pragma("unroll") for (int j = 0; j < E; j++) y[j] = 0.0f; break;
+        }
+      }
+#pragma unroll
+      for (int j = 0; j < E; j++) { RF(dst, j) = y[j]; prev[j] = y[j]; }
+      prev_dst = dst;
+    }
+    for (int o = 0; o < P.n_out; o++) {
+      float* q = P.optr[o]; const int64_t pitch = P.opitch[o]; const int reg = P.oreg[o];
+#pragma unroll
+      for (int j = 0; j < E; j++) if (ok[j]) q[(int64_t)r[j] * pitch + c[j]] = RF(reg, j);
+    }
+  }
+#undef RF
+}
+
 extern "C" int agb_fused_ewise(agb_ctx* ctx, int64_t rows, int64_t cols, int n_leaves, const agb_fuse_leaf* leaves,
                                int n_instr, const agb_fuse_instr* instr, int n_out, const agb_fuse_out* outs) {
   AGB_CHECK(rows >= 0 && cols >= 0, AGB_ERR_INVALID_DIMS, "agb_fused_ewise: negative extent");
@@ -523,6 +622,20 @@ extern "C" int agb_fused_ewise(agb_ctx* ctx, int64_t rows, int64_t cols, int n_l
   }
   if (P.total == 0) return AGB_OK;
   AgbProfScope prof(ctx, AGB_PROF_EWISE, 4.0 * (double)P.total * (n_leaves + n_out));
+  if (P.total >= (1 << 15) && P.total < (int64_t)0x7fffffff) {        // enough work to amortise the dispatch over 4 elements per thread
+    constexpr int E = 4;
+    int nreg = 0;
+    for (int l = 0; l < n_leaves; l++) nreg = leaves[l].reg + 1 > nreg ? leaves[l].reg + 1 : nreg;
+    for (int k = 0; k < n_instr; k++) nreg = instr[k].dst + 1 > nreg ? instr[k].dst + 1 : nreg;
+    const size_t smem = (size_t)nreg * E * 256 * sizeof(float);
+    static bool attr = false;
+    if (!attr) { AGB_CUDA(cudaFuncSetAttribute(fused_ewise_kernel_e<E>, cudaFuncAttributeMaxDynamicSharedMemorySize, AGB_FUSE_REGS * E * 256 * (int)sizeof(float))); attr = true; }
+    int nb = 0;
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, fused_ewise_kernel_e<E>, 256, smem) != cudaSuccess || nb < 1) nb = 1;
+    fused_ewise_kernel_e<E><<<agb_grid_for((P.total + E - 1) / E, 256, ctx->sm_count, nb), 256, smem, ctx->stream>>>(P);
+    AGB_LAUNCHED(ctx);
+    return AGB_OK;
+  }
   fused_ewise_kernel<<<agb_grid_occ(ctx, fused_ewise_kernel, P.total, 256), 256, 0, ctx->stream>>>(P);
   AGB_LAUNCHED(ctx);
   return AGB_OK;

@@ -292,7 +292,7 @@ def test_elementwise_fusion_is_bit_identical_and_saves_launches(ag):
     the fused run needs far fewer launches."""
     import ctypes as C
     from rust_autograd_b200 import ffi, workloads as W
-    D, V, S, B = 64, 96, 6, 32
+    D, V, S, B = 256, 96, 6, 128           # [B, D] = 2^15 elements: the cell programs take the four-elements-per-thread kernel
     sents = np.random.default_rng(3).integers(0, V, (B, S)).astype(np.float32)
 
     def run(fuse):

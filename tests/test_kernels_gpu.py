@@ -477,13 +477,13 @@ def test_concat_rows(dev):
     assert np.array_equal(got, np.concatenate(xs + [big[:, 32:64]], axis=0))
 
 
-def test_fused_ewise_lstm_cell_matches_single_op_kernels(dev):
+@pytest.mark.parametrize("B,D", [(37, 48), (301, 128)])      # one element per thread / four elements per thread (>= 2^15 elements, ragged tail)
+def test_fused_ewise_lstm_cell_matches_single_op_kernels(dev, B, D):
     """agb_fused_ewise on the LSTM cell (examples/lstm_lm.rs:36-45): gates are sliced views of one [B, 4D] buffer (read in place, pitch 4D),
     the bias is a row broadcast, outputs i, f, o, g, c', tanh(c'), h from ONE launch: bit-identical to the chain of agb_unary / agb_binary
-    launches it replaces, and within 1e-6 of the oracle."""
+    launches it replaces, and within 1e-5 of the oracle."""
     from rust_autograd_b200 import ffi
     rng = np.random.default_rng(21)
-    B, D = 37, 48
     xh = rng.standard_normal((B, 4 * D)).astype(np.float32)
     bias = rng.standard_normal((1, 4 * D)).astype(np.float32)
     c0 = rng.standard_normal((B, D)).astype(np.float32)
@@ -509,8 +509,8 @@ def test_fused_ewise_lstm_cell_matches_single_op_kernels(dev):
     sig = lambda v: R.unary("sigmoid", v)
     p = (xh.astype(np.float64) + bias).astype(np.float32)
     c_ref = sig(p[:, D:2 * D]).astype(np.float64) * c0 + sig(p[:, :D]).astype(np.float64) * np.tanh(p[:, 2 * D:3 * D].astype(np.float64))
-    close(outs[4].numpy(), c_ref, 1e-6)
-    close(outs[6].numpy(), sig(p[:, 3 * D:]).astype(np.float64) * np.tanh(c_ref), 1e-6)
+    close(outs[4].numpy(), c_ref, 1e-5)            # the north_star tolerance for elementwise kernels (sums with cancellation near 0)
+    close(outs[6].numpy(), sig(p[:, 3 * D:]).astype(np.float64) * np.tanh(c_ref), 1e-5)
     # immediates on either side, compare ops, column broadcast ([B,1] leaf), single row
     col = dev.upload(rng.standard_normal((B, 1)).astype(np.float32))
     y, = dev.fused_ewise(B, D, [(dc, 0), (col, 1)], [(Bn, "mul", 2, 0, 1, 0.0), (ffi.F_BINARY_IMM_B, "gt", 3, 2, 0, 0.0), (Bn, "mul", 4, 3, 0, 0.0)], [4])
