@@ -537,10 +537,11 @@ __global__ void __launch_bounds__(256) fused_ewise_kernel_e(const __grid_constan
     float prev[E]; int prev_dst = -1;
 #pragma unroll
     for (int j = 0; j < E; j++) prev[j] = 0.0f;
+    uint32_t w_next = P.code[0]; float p_next = P.imm[0];
     for (int k = 0; k < P.n_instr; k++) {
-      const uint32_t w = P.code[k];
+      const uint32_t w = w_next; const float p0 = p_next;
+      if (k + 1 < P.n_instr) { w_next = P.code[k + 1]; p_next = P.imm[k + 1]; }        // the next instruction word is fetched under this instruction
       const int kind = w & 3, op = (w >> 2) & 63, ia = (w >> 13) & 31, ib = (w >> 18) & 31, dst = (w >> 8) & 31;
-      const float p0 = P.imm[k];
       float a[E], b[E], y[E];
       if (kind == AGB_F_BINARY_IMM_A) {
 #pragma unroll
@@ -592,6 +593,21 @@ __global__ void __launch_bounds__(256) fused_ewise_kernel_e(const __grid_constan
 #undef RF
 }
 
+template <int E>
+static int launch_fused_e(agb_ctx* ctx, const FuseParams& P, int n_leaves, const agb_fuse_leaf* leaves, int n_instr, const agb_fuse_instr* instr) {
+  int nreg = 0;
+  for (int l = 0; l < n_leaves; l++) nreg = leaves[l].reg + 1 > nreg ? leaves[l].reg + 1 : nreg;
+  for (int k = 0; k < n_instr; k++) nreg = instr[k].dst + 1 > nreg ? instr[k].dst + 1 : nreg;
+  const size_t smem = (size_t)nreg * E * 256 * sizeof(float);
+  static bool attr = false;
+  if (!attr) { AGB_CUDA(cudaFuncSetAttribute(fused_ewise_kernel_e<E>, cudaFuncAttributeMaxDynamicSharedMemorySize, AGB_FUSE_REGS * E * 256 * (int)sizeof(float))); attr = true; }
+  int nb = 0;
+  if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, fused_ewise_kernel_e<E>, 256, smem) != cudaSuccess || nb < 1) nb = 1;
+  fused_ewise_kernel_e<E><<<agb_grid_for((P.total + E - 1) / E, 256, ctx->sm_count, nb), 256, smem, ctx->stream>>>(P);
+  AGB_LAUNCHED(ctx);
+  return AGB_OK;
+}
+
 extern "C" int agb_fused_ewise(agb_ctx* ctx, int64_t rows, int64_t cols, int n_leaves, const agb_fuse_leaf* leaves,
                                int n_instr, const agb_fuse_instr* instr, int n_out, const agb_fuse_out* outs) {
   AGB_CHECK(rows >= 0 && cols >= 0, AGB_ERR_INVALID_DIMS, "agb_fused_ewise: negative extent");
@@ -622,19 +638,10 @@ extern "C" int agb_fused_ewise(agb_ctx* ctx, int64_t rows, int64_t cols, int n_l
   }
   if (P.total == 0) return AGB_OK;
   AgbProfScope prof(ctx, AGB_PROF_EWISE, 4.0 * (double)P.total * (n_leaves + n_out));
-  if (P.total >= (1 << 15) && P.total < (int64_t)0x7fffffff) {        // enough work to amortise the dispatch over 4 elements per thread
-    constexpr int E = 4;
-    int nreg = 0;
-    for (int l = 0; l < n_leaves; l++) nreg = leaves[l].reg + 1 > nreg ? leaves[l].reg + 1 : nreg;
-    for (int k = 0; k < n_instr; k++) nreg = instr[k].dst + 1 > nreg ? instr[k].dst + 1 : nreg;
-    const size_t smem = (size_t)nreg * E * 256 * sizeof(float);
-    static bool attr = false;
-    if (!attr) { AGB_CUDA(cudaFuncSetAttribute(fused_ewise_kernel_e<E>, cudaFuncAttributeMaxDynamicSharedMemorySize, AGB_FUSE_REGS * E * 256 * (int)sizeof(float))); attr = true; }
-    int nb = 0;
-    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, fused_ewise_kernel_e<E>, 256, smem) != cudaSuccess || nb < 1) nb = 1;
-    fused_ewise_kernel_e<E><<<agb_grid_for((P.total + E - 1) / E, 256, ctx->sm_count, nb), 256, smem, ctx->stream>>>(P);
-    AGB_LAUNCHED(ctx);
-    return AGB_OK;
+  if (P.total >= (1 << 15) && P.total < (int64_t)0x7fffffff) {        // enough work to amortise the dispatch over several elements per thread
+    static const int e_sel = [] { const char* e = getenv("AGB_FUSE_E"); return e ? atoi(e) : 2; }();       // tuning knob: elements per thread (2: 3.5 warps per scheduler on a [128, 1024] cell; 4 leaves 1.7)
+    if (e_sel == 4) return launch_fused_e<4>(ctx, P, n_leaves, leaves, n_instr, instr);
+    if (e_sel != 1) return launch_fused_e<2>(ctx, P, n_leaves, leaves, n_instr, instr);
   }
   fused_ewise_kernel<<<agb_grid_occ(ctx, fused_ewise_kernel, P.total, 256), 256, 0, ctx->stream>>>(P);
   AGB_LAUNCHED(ctx);
