@@ -462,7 +462,7 @@ NdArray expr_materialize(Device* dev, const NdArray& x) {
 }
 // SliceGrad: the pending value is written straight into its region of the zero-filled gradient
 bool expr_materialize_into(Device* dev, const NdArray& x, NdArray dest) {
-  if (!x.expr || x.expr->has_value || dest.shape != x.shape) return false;
+  if (!x.expr || x.expr->has_value || x.expr->kind >= kPad || dest.shape != x.shape) return false;      // (memory nodes produce their own buffer)
   const int nd = dest.ndim();
   if (nd == 0 || (dest.shape[nd - 1] != 1 && dest.stride[nd - 1] != 1)) return false;
   int64_t p, cs; if (!as_2d(dest, dest.shape, p, cs)) return false;

@@ -331,6 +331,33 @@ def test_elementwise_fusion_is_bit_identical_and_saves_launches(ag):
     print("launches fused/plain:", n_fused, n_plain)
 
 
+def test_nested_slice_gradients_and_pending_pieces_match_oracle(ag):
+    """Slices of pending expressions, SliceGrad of a pending SliceGrad (a memory node, never written through a region), AddN over slice
+    gradients that overlap / leave gaps (zero fill + separate adds) and over disjoint covering pieces (written side by side): loss and
+    gradient against the oracle."""
+    x0 = np.random.default_rng(4).standard_normal((6, 8)).astype(np.float32)
+
+    def run(mod):
+        env = mod.VariableEnvironment()
+        v = env.slot().set(x0)
+
+        def body(g):
+            x = g.variable(v)
+            e = mod.tanh(x * 2.0) + x                                  # pending expression, read only through slices
+            inner = mod.slice(mod.slice(e, [0, 2], [-1, 7]), [1, 1], [5, 4])      # slice of a slice
+            left, right = mod.slice(e, [0, 0], [-1, 4]), mod.slice(e, [0, 4], [-1, 8])   # disjoint, covering
+            over = mod.slice(e, [0, 2], [-1, 6])                        # overlaps both
+            loss = mod.sum_all(mod.square(inner)) + mod.sum_all(left * right) + mod.sum_all(mod.sigmoid(over))
+            gx = mod.grad([loss], [x])[0]
+            return [r.unwrap() for r in g.evaluator().push(loss).push(gx).push(inner).run()]
+        out = env.run(body)
+        env.close()
+        return out
+    got, ref = run(ag), run(OG)
+    for a, b in zip(got, ref):
+        assert rel(a, b) <= 1e-5, rel(a, b)
+
+
 def test_random_ops_through_the_graph(ag):
     """random_* constructors (mod.rs:2426-2676): shapes, ranges, a != b for two evaluations of the same node (tests/test_array_gen.rs:4-40: the
     op's rng advances), equal values for two default-rng nodes (the crate seeds every default ArrayRng identically, ndarray_ext.rs:250-264),
