@@ -76,6 +76,16 @@ static NdArray dev_binary(Device* d, int op, NdArray a, NdArray b, float p0 = 0.
   if (a.shape == out && a.dense_order(order) && !is_identity(order)) dom = &a;
   else if (b.shape == out && b.dense_order(order) && !is_identity(order)) dom = &b;
   if (dom) {
+    // the other operand is a smaller dense array in a DIFFERENT memory order (cnn_mnist.rs:36-45 adds full-map biases [1, C, H, W] to
+    // channels-last activations): re-lay it once in the dominant order so that the add collapses to a vectorised row-broadcast pass
+    NdArray* oth = dom == &a ? &b : &a; std::vector<int> oo; int nontrivial = 0;
+    for (auto dd : oth->shape) if (dd != 1) nontrivial++;
+    if (oth->ndim() == (int)out.size() && nontrivial > 1 && oth->size() < dom->size() && oth->size() <= (1 << 22) && oth->dense_order(oo) && oo != order) {
+      NdArray t = d->empty_ordered(oth->shape, order);
+      agb_tensor ts = oth->desc(), td = t.desc();
+      check_status(agb_copy_strided(d->ctx, &ts, &td));
+      *oth = t; ta = broadcast_desc(a, out); tb = broadcast_desc(b, out);
+    }
     NdArray y = d->empty_ordered(out, order);
     agb_tensor pa = permuted_desc(ta, order), pb = permuted_desc(tb, order), py = permuted_desc(y.desc(), order);
     check_status(agb_binary(d->ctx, op, p0, p1, &pa, &pb, &py));
