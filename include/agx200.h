@@ -53,6 +53,9 @@ int agx_env_set_data_parallel(agx_env* env, int rank, int world, const void* ncc
  * long-K GEMM, and independent MatMuls against one weight (the time steps of an unrolled RNN) run as one row-stacked GEMM; off = one
  * launch per node.  Elementwise values are bit-identical either way; the regrouped GEMMs differ by fp32 reassociation. */
 int agx_env_set_fusion(agx_env* env, int on);
+/* Host-only self test of the fused-program compiler (no device needed; run by the CPU test suite): `n_cases` random expression DAGs are
+ * compiled and their instruction streams interpreted on the host; returns 0 when every stored register reproduces its node's value. */
+int agx_fuse_selftest(int n_cases, unsigned seed, int* n_compiled);
 
 /* ---- Graph construction ---- */
 int agx_graph_new(agx_env* env, agx_graph** out);

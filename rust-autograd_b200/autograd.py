@@ -33,7 +33,7 @@ SIGNATURES = {
     "agx_env_set": [_P, C.c_char_p, C.c_char_p, _P, _pi64, _i, _pi], "agx_env_find": [_P, C.c_char_p, C.c_char_p, _pi],
     "agx_env_var_count": [_P, _pi], "agx_env_var_ids": [_P, C.c_char_p, _pi, _i, _pi], "agx_env_var_shape": [_P, _i, _pi64, _pi],
     "agx_env_get": [_P, _i, _P, _i64], "agx_env_put": [_P, _i, _P, _i64], "agx_env_var_ptr": [_P, _i, C.POINTER(_P)],
-    "agx_env_save": [_P, C.c_char_p], "agx_env_load": [_P, C.c_char_p], "agx_env_set_data_parallel": [_P, _i, _i, _P], "agx_env_set_fusion": [_P, _i],
+    "agx_env_save": [_P, C.c_char_p], "agx_env_load": [_P, C.c_char_p], "agx_env_set_data_parallel": [_P, _i, _i, _P], "agx_env_set_fusion": [_P, _i], "agx_fuse_selftest": [_i, C.c_uint, C.POINTER(C.c_int)],
     "agx_graph_new": [_P, C.POINTER(_P)], "agx_graph_free": [_P], "agx_graph_clear": [_P], "agx_graph_size": [_P, _pi],
     "agx_placeholder": [_P, C.c_char_p, _pi64, _i, _pi], "agx_variable": [_P, _i, _pi], "agx_variable_by_name": [_P, C.c_char_p, C.c_char_p, _pi],
     "agx_convert_to_tensor": [_P, _P, _pi64, _i, _pi],

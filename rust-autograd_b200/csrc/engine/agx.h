@@ -337,6 +337,7 @@ NdArray expr_scatter(ComputeContext& c, const Shape& table, int axis, NdArray id
 bool expr_sum_scatters(ComputeContext& c, const std::vector<NdArray>& xs, NdArray* out);
 NdArray expr_colsum(ComputeContext& c, NdArray gy, const Shape& target);       // deferred MaybeReduceSum [R, N] -> [1, N] whose only reader is an AddN
 bool expr_sum_colsums(ComputeContext& c, const std::vector<NdArray>& xs, NdArray* out);
+int fuse_selftest(int n_cases, uint32_t seed, int* n_compiled);                                 // host-only check of the program compiler (0 = ok)
 bool stackable(const NdArray& t);                                                                   // 2-D, unit column stride, 16-byte aligned rows
 NdArray stack_rows(Evaluation& run, Device* dev, const std::vector<NdArray>& parts);
 NdArray stack_vectors(Evaluation& run, Device* dev, const std::vector<NdArray>& parts);          // n vectors of B elements -> contiguous [n * B]              // agb_concat_rows, remembered for the rest of the run

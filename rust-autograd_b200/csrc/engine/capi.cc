@@ -85,6 +85,7 @@ extern "C" int agx_env_save(agx_env* env, const char* path) {
 extern "C" int agx_env_load(agx_env* env, const char* path) {
   AGX_TRY std::ifstream f(path); if (!f) throw OpError(AGB_ERR_NDARRAY, std::string("load: cannot open ") + path); std::stringstream ss; ss << f.rdbuf(); env->env->load_json(ss.str()); AGX_CATCH
 }
+extern "C" int agx_fuse_selftest(int n_cases, unsigned seed, int* n_compiled) { AGX_TRY return fuse_selftest(n_cases, seed, n_compiled); AGX_CATCH }
 extern "C" int agx_env_set_fusion(agx_env* env, int on) { AGX_TRY env->env->fuse_elementwise = on != 0; AGX_CATCH }
 extern "C" int agx_env_set_data_parallel(agx_env* env, int rank, int world, const void* id) {
   AGX_TRY if (world > 1) check_status(agb_nccl_init(env->env->dev->ctx, rank, world, id)); env->env->rank = rank; env->env->world = world; AGX_CATCH

@@ -14,6 +14,7 @@
 // Programs are bounded (AGB_FUSE_MAX_*); an operand sub-DAG that would overflow is materialised first and becomes a leaf.
 #include "agx.h"
 #include <algorithm>
+#include <math.h>
 #include <functional>
 #include <unordered_map>
 
@@ -84,12 +85,17 @@ struct Compiler {
   }
 };
 
-// One launch for the DAG below `roots` (all of one shape).  dests[i] with a device pointer = root i is written there (a strided region of
-// a larger buffer); otherwise a fresh array is allocated.
-bool run_program(Device* dev, const std::vector<ExprNode*>& roots, const std::vector<NdArray>& dests) {
+struct Compiled {
+  std::vector<ExprNode*> order;            // instruction k computes order[k]
+  std::vector<NdArray> leaf_arrays; std::vector<agb_fuse_leaf> leaves;     // leaves[l].pitch is the 2-D pitch (the launcher may flatten)
+  std::vector<agb_fuse_instr> code;
+  std::vector<int> outs;                   // instruction indices stored: the roots first, then the other multi-consumer nodes
+};
+// host-only half: DAG -> leaves, instructions, registers, outputs (no device call; exercised on the CPU by agx_fuse_selftest)
+bool compile_program(const std::vector<ExprNode*>& roots, Compiled* out) {
   ExprNode* root = roots[0];
   if ((int)roots.size() > AGB_FUSE_MAX_OUT) return false;
-  Compiler C(dev, root);
+  Compiler C(nullptr, root);
   for (ExprNode* r : roots) { if (r->shape != root->shape || r->has_value || r->kind >= kPad) return false; C.visit(r); }
   const int I = (int)C.order.size();
   if (I > AGB_FUSE_MAX_INSTR) return false;
@@ -105,8 +111,8 @@ bool run_program(Device* dev, const std::vector<ExprNode*>& roots, const std::ve
   const int L = (int)C.leaves.size();
   if (!C.ok || L > AGB_FUSE_MAX_LEAVES) return false;
   // outputs: the root + every other node somebody else will read
-  std::vector<int> outs; std::vector<char> is_out(I, 0); bool any_dest = false;
-  for (size_t i = 0; i < roots.size(); i++) { int k = C.instr_of[roots[i]]; if (is_out[k]) return false; is_out[k] = 1; outs.push_back(k); if (dests[i].on_device()) any_dest = true; }
+  std::vector<int> outs; std::vector<char> is_out(I, 0);
+  for (size_t i = 0; i < roots.size(); i++) { int k = C.instr_of[roots[i]]; if (is_out[k]) return false; is_out[k] = 1; outs.push_back(k); }
   for (int k = 0; k < I && (int)outs.size() < AGB_FUSE_MAX_OUT; k++) if (!is_out[k] && C.order[k]->consumers > 1) { is_out[k] = 1; outs.push_back(k); }
   // linear-scan register allocation
   const int V = L + I;
@@ -128,14 +134,29 @@ bool run_program(Device* dev, const std::vector<ExprNode*>& roots, const std::ve
     ins.dst = reg[L + k];
     if (last[L + k] < 0 && !is_out[k]) { free_regs.push_back(reg[L + k]); }      // dead value (cannot happen for a DAG reachable from the root)
   }
+  out->order = C.order; out->code = code; out->outs = outs;
+  out->leaves.resize(L); out->leaf_arrays.resize(L);
+  for (int l = 0; l < L; l++) { out->leaf_arrays[l] = C.leaves[l].arr; out->leaves[l].ptr = C.leaves[l].arr.dptr; out->leaves[l].pitch = C.leaves[l].pitch; out->leaves[l].cstride = C.leaves[l].cs; out->leaves[l].reg = reg[l]; }
+  return true;
+}
+
+// One launch for the DAG below `roots` (all of one shape).  dests[i] with a device pointer = root i is written there (a strided region of
+// a larger buffer); otherwise a fresh array is allocated.
+bool run_program(Device* dev, const std::vector<ExprNode*>& roots, const std::vector<NdArray>& dests) {
+  Compiled P;
+  if (!compile_program(roots, &P)) return false;
+  ExprNode* root = roots[0];
+  const int L = (int)P.leaves.size(), I = (int)P.code.size();
+  const std::vector<int>& outs = P.outs; const std::vector<agb_fuse_instr>& code = P.code;
+  bool any_dest = false; for (auto& d : dests) if (d.on_device()) any_dest = true;
   // launch
   const int nd = (int)root->shape.size();
   int64_t cols = nd == 0 ? 1 : root->shape[nd - 1], total = 1; for (auto d : root->shape) total *= d;
   int64_t rows = cols == 0 ? 0 : total / cols;
   bool flat = !any_dest;
-  for (auto& lf : C.leaves) if (!((lf.pitch == 0 && lf.cs == 0) || (lf.cs == 1 && (lf.pitch == cols || rows == 1)))) flat = false;
-  std::vector<agb_fuse_leaf> lv(L);
-  for (int l = 0; l < L; l++) { lv[l].ptr = C.leaves[l].arr.dptr; lv[l].pitch = flat ? 0 : C.leaves[l].pitch; lv[l].cstride = C.leaves[l].cs; lv[l].reg = reg[l]; }
+  for (auto& lf : P.leaves) if (!((lf.pitch == 0 && lf.cstride == 0) || (lf.cstride == 1 && (lf.pitch == cols || rows == 1)))) flat = false;
+  std::vector<agb_fuse_leaf> lv = P.leaves;
+  if (flat) for (auto& lf : lv) lf.pitch = 0;
   std::vector<agb_fuse_out> ov(outs.size()); std::vector<NdArray> values(outs.size());
   for (size_t o = 0; o < outs.size(); o++) {
     if (o < roots.size() && dests[o].on_device()) { int64_t p, cs; as_2d(dests[o], root->shape, p, cs); values[o] = dests[o]; ov[o].pitch = p; }
@@ -144,7 +165,7 @@ bool run_program(Device* dev, const std::vector<ExprNode*>& roots, const std::ve
   }
   check_status(agb_fused_ewise(dev->ctx, flat ? 1 : rows, flat ? total : cols, L, lv.data(), I, code.data(), (int)ov.size(), ov.data()));
   for (size_t o = 0; o < outs.size(); o++) {
-    ExprNode* n = C.order[outs[o]];
+    ExprNode* n = P.order[outs[o]];
     n->value = values[o]; n->has_value = true; n->a = NdArray(); n->b = NdArray();      // operands are no longer needed
   }
   return true;
@@ -468,6 +489,76 @@ bool expr_materialize_into(Device* dev, const NdArray& x, NdArray dest) {
   int64_t p, cs; if (!as_2d(dest, dest.shape, p, cs)) return false;
   materialize_node(dev, x.expr.get(), &dest);
   return true;
+}
+
+// ---- host-only self test of the program compiler (tests/test_abi.py, no device needed): random DAGs over fake leaves are compiled and the
+// instruction stream is interpreted on the host for one element; every stored register must equal the direct evaluation of its node.
+int fuse_selftest(int n_cases, uint32_t seed, int* n_compiled) {
+  uint32_t st = seed ? seed : 1u;
+  auto rnd = [&]() { st ^= st << 13; st ^= st >> 17; st ^= st << 5; return st; };
+  auto frand = [&]() { return (float)((int)(rnd() % 2001) - 1000) / 500.0f; };
+  const int u_ops[] = {AGB_U_NEG, AGB_U_SQUARE, AGB_U_ABS, AGB_U_SCALE, AGB_U_ADD_SCALAR, AGB_U_RSUB_SCALAR};
+  const int b_ops[] = {AGB_B_ADD, AGB_B_SUB, AGB_B_MUL, AGB_B_MAX, AGB_B_GT};
+  auto un = [](int op, float a, float p) { return op == AGB_U_NEG ? -a : op == AGB_U_SQUARE ? a * a : op == AGB_U_ABS ? fabsf(a) : op == AGB_U_SCALE ? a * p : op == AGB_U_ADD_SCALAR ? a + p : p - a; };
+  auto bi = [](int op, float a, float b) { return op == AGB_B_ADD ? a + b : op == AGB_B_SUB ? a - b : op == AGB_B_MUL ? a * b : op == AGB_B_MAX ? (a > b ? a : b) : (a > b ? 1.0f : 0.0f); };
+  int compiled = 0;
+  for (int cs = 0; cs < n_cases; cs++) {
+    const Shape shape{4, 8};
+    const int n_leaf = 1 + (int)(rnd() % 24), n_node = 1 + (int)(rnd() % 90);     // some cases exceed the program bounds and must be refused
+    std::vector<NdArray> leaves(n_leaf); std::vector<float> leaf_val(n_leaf);
+    for (int l = 0; l < n_leaf; l++) { leaves[l].shape = shape; leaves[l].stride = NdArray::contiguous_strides(shape); leaves[l].dptr = (float*)(uintptr_t)(0x10000 * (l + 1)); leaf_val[l] = frand(); }
+    std::vector<NdArray> nodes; std::vector<float> node_val;          // expression arrays in creation order
+    auto pick = [&](float* v) -> NdArray {                            // an earlier node (preferably a recent one) or a leaf
+      if (!nodes.empty() && rnd() % 5 != 0) { size_t k = nodes.size() - 1 - rnd() % std::min<size_t>(nodes.size(), 6); *v = node_val[k]; return nodes[k]; }
+      int l = (int)(rnd() % n_leaf); *v = leaf_val[l]; return leaves[l];
+    };
+    for (int k = 0; k < n_node; k++) {
+      auto n = std::make_shared<ExprNode>(); n->shape = shape; n->consumers = rnd() % 4 == 0 ? 2 : 1;
+      float va, vb, val; const int f8 = (int)(rnd() % 8), form = f8 < 4 ? 1 : f8 < 6 ? 0 : f8 - 4;      // half of the nodes are binary
+      if (form == 0) { n->kind = AGB_F_UNARY; n->op = u_ops[rnd() % 6]; n->p0 = frand(); n->a = pick(&va); val = un(n->op, va, n->p0); }
+      else if (form == 1) { n->kind = AGB_F_BINARY; n->op = b_ops[rnd() % 5]; n->a = pick(&va); n->b = pick(&vb); val = bi(n->op, va, vb); }
+      else if (form == 2) { n->kind = AGB_F_BINARY_IMM_B; n->op = b_ops[rnd() % 5]; n->p0 = frand(); n->a = pick(&va); val = bi(n->op, va, n->p0); }
+      else { n->kind = AGB_F_BINARY_IMM_A; n->op = b_ops[rnd() % 5]; n->p0 = frand(); n->a = pick(&va); val = bi(n->op, n->p0, va); }
+      NdArray r; r.shape = shape; r.stride = NdArray::contiguous_strides(shape); r.expr = n;
+      nodes.push_back(r); node_val.push_back(val);
+    }
+    std::vector<ExprNode*> roots{nodes.back().expr.get()};
+    if (n_node > 3 && rnd() % 2) roots.push_back(nodes[n_node - 2].expr.get());       // a second root (it may also be an operand of the first)
+    Compiled P;
+    if (!compile_program(roots, &P)) continue;                        // too many leaves / registers / outputs: the evaluator would split
+    compiled++;
+    if ((int)P.leaves.size() > AGB_FUSE_MAX_LEAVES || (int)P.code.size() > AGB_FUSE_MAX_INSTR || (int)P.outs.size() > AGB_FUSE_MAX_OUT) return 10;
+    float regs[AGB_FUSE_REGS]; bool live[AGB_FUSE_REGS] = {false};
+    for (size_t l = 0; l < P.leaves.size(); l++) {
+      int idx = (int)((uintptr_t)P.leaves[l].ptr / 0x10000) - 1;
+      if (P.leaves[l].reg < 0 || P.leaves[l].reg >= AGB_FUSE_REGS || live[P.leaves[l].reg]) return 11;          // two leaves in one register
+      regs[P.leaves[l].reg] = leaf_val[idx]; live[P.leaves[l].reg] = true;
+    }
+    std::unordered_map<ExprNode*, float> expect;
+    for (int k = 0; k < n_node; k++) expect[nodes[k].expr.get()] = node_val[k];
+    for (size_t k = 0; k < P.code.size(); k++) {
+      const agb_fuse_instr& in = P.code[k];
+      if (in.dst < 0 || in.dst >= AGB_FUSE_REGS) return 12;
+      float a = regs[in.a], b = regs[in.b], y;
+      if (in.kind == AGB_F_UNARY) y = un(in.op, a, in.p0);
+      else if (in.kind == AGB_F_BINARY) y = bi(in.op, a, b);
+      else if (in.kind == AGB_F_BINARY_IMM_B) y = bi(in.op, a, in.p0);
+      else y = bi(in.op, in.p0, b);
+      regs[in.dst] = y;
+      if (y != expect[P.order[k]] && !(y != y && expect[P.order[k]] != expect[P.order[k]])) return 13;           // an operand register was clobbered
+    }
+    for (size_t o = 0; o < P.outs.size(); o++) {
+      const float got = regs[P.code[P.outs[o]].dst], want = expect[P.order[P.outs[o]]];
+      if (got != want && !(got != got && want != want)) return 14;                                               // a stored register was reused before the end
+    }
+    for (size_t i = 0; i < roots.size(); i++) if (P.order[P.outs[i]] != roots[i]) return 15;
+    for (size_t k = 0; k + 1 < P.order.size(); k++) {                 // every other multi-consumer node is stored (while there is room)
+      bool stored = false; for (int o : P.outs) if (o == (int)k) stored = true;
+      if (P.order[k]->consumers > 1 && !stored && (int)P.outs.size() < AGB_FUSE_MAX_OUT) return 16;
+    }
+  }
+  if (n_compiled) *n_compiled = compiled;
+  return 0;
 }
 
 }  // namespace agx

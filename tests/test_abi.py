@@ -55,3 +55,18 @@ def test_error_codes_mirror_op_error():
     """src/op.rs:67-73: five OpError variants -> codes 1..5"""
     from rust_autograd_b200 import ffi
     assert [ffi.OpError.NAMES[i] for i in range(1, 6)] == ["NdArrayError", "IncompatibleShape", "TypeUnsupported", "InvalidDims", "OutOfBounds"]
+
+
+def test_fused_program_compiler_on_the_host():
+    """engine/fuse.cc: random expression DAGs (unary / binary / immediate forms, shared sub-expressions, multi-consumer nodes, two roots) are
+    compiled into agb_fused_ewise programs and interpreted on the host: every stored register must hold its node's value (register
+    allocation never clobbers a live value, leaves are deduplicated, roots come first, oversized DAGs are refused).  No device needed."""
+    import ctypes as C
+    from rust_autograd_b200 import autograd as ag
+    n = C.c_int()
+    total = 0
+    for seed in (1, 7, 2026, 99991):
+        assert ag.lib().agx_fuse_selftest(3000, seed, C.byref(n)) == 0, seed
+        assert 0 < n.value <= 3000
+        total += n.value
+    assert total < 4 * 3000          # some DAGs exceeded the leaf / register / output bounds and were refused
