@@ -53,6 +53,25 @@ int agx_env_set_data_parallel(agx_env* env, int rank, int world, const void* ncc
  * long-K GEMM, and independent MatMuls against one weight (the time steps of an unrolled RNN) run as one row-stacked GEMM; off = one
  * launch per node.  Elementwise values are bit-identical either way; the regrouped GEMMs differ by fp32 reassociation. */
 int agx_env_set_fusion(agx_env* env, int on);
+/* ---- host-callback ops (class C): user-defined ops and hooks.  The reference's `Op` trait is public API (src/op.rs:1-48,90-101;
+ * tests/test_core.rs:6-36) and its compute() works on ndarray views, so a user op here sees HOST copies of its inputs (an explicit D2H
+ * synchronisation point, like HookOp / MapOp) and hands host arrays back; they re-enter HBM when a device kernel consumes them. */
+typedef struct agx_host_array { const float* data; const int64_t* shape; int rank; } agx_host_array;
+typedef struct agx_out agx_out;
+/* Op::compute: append outputs with agx_out_append (several = a multi-output op, selected by nth_tensor); return 0, or 1..5 = an OpError
+ * variant (op.rs:67-73) with the message set by agx_out_error. */
+typedef int (*agx_compute_fn)(void* user, const agx_host_array* inputs, int n_inputs, agx_out* out);
+int agx_out_append(agx_out* out, const float* data, const int64_t* shape, int rank);
+int agx_out_error(agx_out* out, const char* message);
+/* Op::grad: called while T::grad builds the backward graph; gxs[i] = tensor id of the gradient for input i, or -1 for None. */
+typedef void (*agx_grad_fn)(void* user, agx_graph* g, const int* inputs, int n_inputs, int y, int gy, int* gxs);
+/* Tensor::builder(g).append_input(..).build(op).  grad == NULL: every input gradient is None.  The callbacks must outlive the graph. */
+int agx_custom_op(agx_graph* g, const char* name, const int* inputs, int n_inputs, agx_compute_fn compute, agx_grad_fn grad, void* user, int* tid);
+/* HookOp (hook_ops.rs:5-31; Tensor::{raw_hook, show, show_shape, print}, tensor.rs:198-320): identity node that runs a callback on the
+ * host value when it is evaluated.  kind 0 = raw_hook (fn), 1 = show, 2 = show_shape, 3 = print(text); 1..3 write to stderr. */
+typedef void (*agx_hook_fn)(void* user, const agx_host_array* value);
+int agx_hook(agx_graph* g, int tensor, int kind, const char* text, agx_hook_fn fn, void* user, int* tid);
+
 /* Host-only self test of the fused-program compiler (no device needed; run by the CPU test suite): `n_cases` random expression DAGs are
  * compiled and their instruction streams interpreted on the host; returns 0 when every stored register reproduces its node's value. */
 int agx_fuse_selftest(int n_cases, unsigned seed, int* n_compiled);

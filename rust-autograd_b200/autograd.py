@@ -34,6 +34,8 @@ SIGNATURES = {
     "agx_env_var_count": [_P, _pi], "agx_env_var_ids": [_P, C.c_char_p, _pi, _i, _pi], "agx_env_var_shape": [_P, _i, _pi64, _pi],
     "agx_env_get": [_P, _i, _P, _i64], "agx_env_put": [_P, _i, _P, _i64], "agx_env_var_ptr": [_P, _i, C.POINTER(_P)],
     "agx_env_save": [_P, C.c_char_p], "agx_env_load": [_P, C.c_char_p], "agx_env_set_data_parallel": [_P, _i, _i, _P], "agx_env_set_fusion": [_P, _i], "agx_fuse_selftest": [_i, C.c_uint, C.POINTER(C.c_int)],
+    "agx_out_append": [_P, _P, _P, _i], "agx_out_error": [_P, C.c_char_p], "agx_custom_op": [_P, C.c_char_p, _P, _i, _P, _P, _P, C.POINTER(_i)],
+    "agx_hook": [_P, _i, _i, C.c_char_p, _P, _P, C.POINTER(_i)],
     "agx_graph_new": [_P, C.POINTER(_P)], "agx_graph_free": [_P], "agx_graph_clear": [_P], "agx_graph_size": [_P, _pi],
     "agx_placeholder": [_P, C.c_char_p, _pi64, _i, _pi], "agx_variable": [_P, _i, _pi], "agx_variable_by_name": [_P, C.c_char_p, C.c_char_p, _pi],
     "agx_convert_to_tensor": [_P, _P, _pi64, _i, _pi],
@@ -123,6 +125,23 @@ class Tensor:
     def eval(self, ctx=None, feeds=None):
         """Tensor::eval (src/tensor.rs:94-99): Result -> value or raises EvalError."""
         return (ctx or self.graph).evaluator().push(self).feeds(feeds).run()[0].unwrap()
+
+    # hooks (src/tensor.rs:198-320 -> hook_ops.rs:5-31): identity nodes that show the HOST value when evaluated (explicit D2H sync point)
+    def _hook(self, kind, text=None, fn=None):
+        cb = None
+        if fn is not None:
+            def tramp(_user, arr):
+                fn(_host_array(arr.contents))
+            cb = _HOOK_FN(tramp)
+            self.graph._keep.append(cb)
+        t = C.c_int()
+        _check(lib().agx_hook(self.graph.h, self.id, kind, text.encode() if text else None, C.cast(cb, C.c_void_p) if cb else None, None, C.byref(t)))
+        return Tensor(self.graph, t.value)
+
+    def raw_hook(self, fn): return self._hook(0, fn=fn)
+    def show(self): return self._hook(1)
+    def show_shape(self): return self._hook(2)
+    def print(self, what): return self._hook(3, text=str(what))
 
     def op_name(self):
         buf = C.create_string_buffer(256)
@@ -384,6 +403,7 @@ class Context:
         h = C.c_void_p()
         _check(lib().agx_graph_new(env.h, C.byref(h)))
         self.h = h
+        self._keep = []        # ctypes callbacks / Python ops of user-defined nodes and hooks: must outlive the graph
 
     def close(self):
         if self.h:
@@ -560,6 +580,96 @@ def _graph_of(tensors):
         if isinstance(t, Tensor):
             return t.graph
     raise Panic("no tensor argument to take the graph from")
+
+
+# ---- user-defined ops (the public `Op` trait, src/op.rs:1-48,90-101; tests/test_core.rs:6-36) through the host-callback ABI
+class _HostArray(C.Structure):
+    _fields_ = [("data", C.POINTER(C.c_float)), ("shape", C.POINTER(C.c_int64)), ("rank", C.c_int)]
+
+
+_COMPUTE_FN = C.CFUNCTYPE(C.c_int, C.c_void_p, C.POINTER(_HostArray), C.c_int, C.c_void_p)
+_GRAD_FN = C.CFUNCTYPE(None, C.c_void_p, C.c_void_p, C.POINTER(C.c_int), C.c_int, C.c_int, C.c_int, C.POINTER(C.c_int))
+_HOOK_FN = C.CFUNCTYPE(None, C.c_void_p, C.POINTER(_HostArray))
+
+
+def _host_array(h):
+    shape = tuple(h.shape[i] for i in range(h.rank))
+    n = int(np.prod(shape)) if shape else 1
+    return np.ctypeslib.as_array(h.data, shape=(n,)).reshape(shape).copy() if n else np.zeros(shape, np.float32)
+
+
+class OpError(Exception):
+    """Raise from Op.compute to return Err(OpError::..) (op.rs:67-73): code 1..5."""
+
+    def __init__(self, code, msg):
+        self.code, self.msg = int(code), str(msg)
+        super().__init__(msg)
+
+
+class ComputeContext:
+    """op::ComputeContext (src/op.rs:186-309) for a user-defined op: inputs arrive as host ndarrays."""
+
+    def __init__(self, inputs, out):
+        self._inputs, self._out = inputs, out
+
+    def num_inputs(self): return len(self._inputs)
+    def input(self, i): return self._inputs[i]
+
+    def append_output(self, arr):
+        a = _f32c(arr)
+        _check(lib().agx_out_append(self._out, a.ctypes.data, _i64s(a.shape), a.ndim))
+
+
+class GradientContext:
+    """op::GradientContext (src/op.rs:342-434)."""
+
+    def __init__(self, g, inputs, y, gy):
+        self.g, self._inputs, self._y, self._gy, self.gxs = g, inputs, y, gy, []
+
+    def graph(self): return self.g
+    def num_inputs(self): return len(self._inputs)
+    def input(self, i): return self._inputs[i]
+    def output(self): return self._y
+    def output_grad(self): return self._gy
+    def append_input_grad(self, gx): self.gxs.append(gx)
+
+
+class Op:
+    """trait Op (src/op.rs:90-101): subclass with name() / compute(ctx) / grad(ctx); build nodes with `build_op`."""
+
+    def name(self): return type(self).__name__
+    def compute(self, ctx): raise NotImplementedError
+    def grad(self, ctx):
+        for _ in range(ctx.num_inputs()):
+            ctx.append_input_grad(None)
+
+
+def build_op(g, op, inputs=()):
+    """Tensor::builder(g).append_input(x, false)...build(op) (src/tensor.rs:609-803) for a Python `Op`."""
+    inputs = list(inputs)
+
+    def compute(_user, arrs, n, out):
+        try:
+            op.compute(ComputeContext([_host_array(arrs[i]) for i in range(n)], out))
+            return 0
+        except OpError as e:
+            lib().agx_out_error(out, e.msg.encode())
+            return e.code
+        except Exception as e:          # a panic must not cross the FFI boundary (SURVEY 8b): reported as NdArrayError
+            lib().agx_out_error(out, ("%s: %s" % (type(e).__name__, e)).encode())
+            return 1
+
+    def grad(_user, _g, ins, n, y, gy, gxs):
+        ctx = GradientContext(g, [Tensor(g, ins[i]) for i in range(n)], Tensor(g, y), Tensor(g, gy))
+        op.grad(ctx)
+        for i in range(n):
+            gx = ctx.gxs[i] if i < len(ctx.gxs) else None
+            gxs[i] = gx.id if gx is not None else -1
+    c_fn, g_fn = _COMPUTE_FN(compute), _GRAD_FN(grad)
+    g._keep.extend([c_fn, g_fn, op])
+    t = C.c_int()
+    _check(lib().agx_custom_op(g.h, op.name().encode(), _ints([x.id for x in inputs]), len(inputs), C.cast(c_fn, C.c_void_p), C.cast(g_fn, C.c_void_p), None, C.byref(t)))
+    return Tensor(g, t.value)
 
 
 def _call(g, fn, tensors=(), ints=(), floats=(), multi=False):

@@ -187,6 +187,70 @@ extern "C" int agx_call(agx_graph* gg, const char* fn_, const int* tensors, int 
   AGX_CATCH
 }
 
+// ================================================================================================ host-callback ops
+struct agx_out { std::vector<NdArray> ys; std::string err; };
+extern "C" int agx_out_append(agx_out* out, const float* data, const int64_t* shape, int rank) {
+  AGX_TRY Shape s(shape, shape + rank); int64_t n = 1; for (auto d : s) n *= d;
+  out->ys.push_back(NdArray::from_host(s, std::vector<float>(data, data + n))); AGX_CATCH
+}
+extern "C" int agx_out_error(agx_out* out, const char* message) { AGX_TRY out->err = message ? message : ""; AGX_CATCH }
+namespace {
+struct HostView { std::vector<float> data; Shape shape; agx_host_array view() const { return agx_host_array{data.data(), shape.data(), (int)shape.size()}; } };
+HostView host_view(Device* dev, NdArray x) {          // D2H (+ stream sync) of a possibly strided device view, in logical (C) order
+  HostView h; h.shape = x.shape;
+  if (x.on_device() && !x.has_host() && !x.is_contiguous()) x = dev->contiguous(x);
+  h.data = dev->ensure_host(x);
+  return h;
+}
+struct CustomOp : Op {                 // a user-defined Op (src/op.rs:90-101) whose compute / grad live behind C callbacks
+  std::string nm; agx_compute_fn fc; agx_grad_fn fg; void* user; agx_graph* owner;
+  const char* name() const override { return nm.c_str(); }
+  void compute(ComputeContext& c) override {
+    std::vector<HostView> hs; std::vector<agx_host_array> views;
+    for (int i = 0; i < c.num_inputs(); i++) hs.push_back(host_view(c.dev, c.input(i)));
+    for (auto& h : hs) views.push_back(h.view());
+    agx_out out;
+    int code = fc(user, views.data(), (int)views.size(), &out);
+    if (code != 0) throw OpError(code >= 1 && code <= 5 ? code : AGB_ERR_NDARRAY, nm + ": " + (out.err.empty() ? "compute failed" : out.err));
+    if (out.ys.empty()) throw Panic("Bad op implementation: empty return value");
+    for (auto& y : out.ys) c.append_output(y);
+  }
+  void grad(GradientContext& c) override {
+    const int n = c.num_inputs();
+    if (!fg) { for (int i = 0; i < n; i++) c.append_none(); return; }
+    std::vector<int> ins, gxs(n, -1);
+    for (int i = 0; i < n; i++) ins.push_back(c.input(i).id);
+    fg(user, owner, ins.data(), n, c.output().id, c.output_grad().id, gxs.data());
+    for (int i = 0; i < n; i++) { if (gxs[i] < 0) c.append_none(); else c.append_input_grad(c.graph()->tensor(gxs[i])); }
+  }
+};
+}  // namespace
+extern "C" int agx_custom_op(agx_graph* g, const char* name, const int* inputs, int n_inputs, agx_compute_fn compute, agx_grad_fn grad, void* user, int* tid) {
+  AGX_TRY
+  if (!compute) throw Panic("agx_custom_op: compute callback is NULL");
+  auto* op = new CustomOp(); op->nm = name ? name : "CustomOp"; op->fc = compute; op->fg = grad; op->user = user; op->owner = g;
+  TensorBuilder b(&g->g);
+  for (auto& t : tv(g, inputs, n_inputs)) b.append_input(t, false);
+  *tid = b.build(op).id;
+  AGX_CATCH
+}
+extern "C" int agx_hook(agx_graph* g, int tensor, int kind, const char* text, agx_hook_fn fn, void* user, int* tid) {
+  AGX_TRY
+  if (kind < 0 || kind > 3 || (kind == 0 && !fn)) throw Panic("agx_hook: bad hook kind / missing callback");
+  std::string prefix = text ? text : "";
+  Tensor x = tv(g, &tensor, 1)[0];
+  *tid = T::hook(x, [kind, prefix, fn, user](const NdArray& a, const std::vector<float>& h) {
+    if (kind == 0) { agx_host_array v{h.data(), a.shape.data(), (int)a.shape.size()}; fn(user, &v); return; }
+    if (kind == 3) fprintf(stderr, "%s\n", prefix.c_str());
+    fprintf(stderr, "[");
+    for (size_t i = 0; i < a.shape.size(); i++) fprintf(stderr, "%s%lld", i ? ", " : "", (long long)a.shape[i]);
+    fprintf(stderr, "]");
+    if (kind != 2) { fprintf(stderr, " ["); for (size_t i = 0; i < h.size() && i < 64; i++) fprintf(stderr, "%s%g", i ? ", " : "", h[i]); fprintf(stderr, h.size() > 64 ? ", ...]" : "]"); }
+    fprintf(stderr, "\n");
+  }).id;
+  AGX_CATCH
+}
+
 extern "C" int agx_grad(agx_graph* g, const int* ys, int ny, const int* xs, int nx, const int* gys, int* out) {
   AGX_TRY
   std::vector<Tensor> r = gys ? T::grad_with_default(tv(g, ys, ny), tv(g, xs, nx), tv(g, gys, ny)) : T::grad(tv(g, ys, ny), tv(g, xs, nx));

@@ -358,6 +358,68 @@ def test_nested_slice_gradients_and_pending_pieces_match_oracle(ag):
         assert rel(a, b) <= 1e-5, rel(a, b)
 
 
+def test_core_user_defined_op_hooks_and_graph_limit(ag, capfd):
+    """tests/test_core.rs re-hosted: a user-defined multi-output Op + nth_tensor (:6-36), hooks show / show_shape / print / raw_hook (:38-71, the
+    callback sees the host value), second-order gradients through placeholders (:48-70), the 500 000-node panic (:72-84); plus a user op with
+    a gradient of its own and an Err(OpError) from compute (op.rs:67-73) propagating to the evaluation result."""
+    class MultiOutputOp(ag.Op):
+        def compute(self, ctx):
+            ctx.append_output(np.zeros((2, 3), np.float32))
+            ctx.append_output(np.full((1, 3), 2.0, np.float32))
+
+    class Cube(ag.Op):                       # y = x^3 on the host; grad = 3 x^2 gy built from tensor_ops
+        def compute(self, ctx):
+            ctx.append_output(ctx.input(0) ** 3)
+
+        def grad(self, ctx):
+            x = ctx.input(0)
+            ctx.append_input_grad(ctx.output_grad() * 3.0 * x * x)
+
+    class Failing(ag.Op):
+        def compute(self, ctx):
+            raise ag.OpError(2, "shapes do not fit")
+
+    env = ag.VariableEnvironment()
+    seen = []
+
+    def body(g):
+        a = ag.build_op(g, MultiOutputOp())
+        c = ag.exp(ag.nth_tensor(a, 1))
+        assert np.allclose(c.eval(g), np.exp(2.0)) and c.eval(g).shape == (1, 3)
+        ones = ag.ones([4, 2], g).show()
+        zs = ag.zeros([2, 3], g).show_shape()
+        mm = ag.matmul(ones, zs).print("aaa").raw_hook(lambda v: seen.append(v.copy()))
+        assert np.array_equal(mm.eval(g), np.zeros((4, 3), np.float32))
+        x, y = g.placeholder("x", []), g.placeholder("y", [])
+        z = 2.0 * x * x + 3.0 * y + 1.0
+        assert float(ag.grad([z], [y])[0].eval(g)) == 3.0
+        gx = ag.grad([z], [x])[0]
+        assert float(gx.eval(g, {"x": np.float32(2.0)})) == 8.0
+        assert float(ag.grad([gx], [x])[0].eval(g)) == 4.0
+        xv = g.placeholder("v", [5])
+        cube = ag.build_op(g, Cube(), [xv])
+        v0 = np.arange(5, dtype=np.float32)
+        got = [r.unwrap() for r in g.evaluator().push(cube).extend(ag.grad([ag.sum_all(cube)], [xv])).feed("v", v0).run()]
+        assert np.array_equal(got[0], v0 ** 3) and np.allclose(got[1], 3 * v0 ** 2)
+        bad = ag.build_op(g, Failing(), [xv]) * 2.0           # the error reaches dependents (evaluation.rs:202-211)
+        res = g.evaluator().push(bad).feed("v", v0).run()[0]
+        with pytest.raises(ag.EvalError) as e:
+            res.unwrap()
+        assert e.value.code == 2 and "shapes do not fit" in str(e.value)
+    env.run(body)
+    err = capfd.readouterr().err
+    assert "aaa" in err and "[4, 2]" in err and "[2, 3]" in err
+    assert len(seen) == 1 and seen[0].shape == (4, 3)
+
+    def too_many(g):
+        x = g.placeholder("x", [3])
+        for _ in range(130000):                  # 4 nodes per iteration -> past NUM_NODES_CRITICAL = 500 000 (graph.rs:36-41)
+            _ = 2.0 * x / 2.0
+    with pytest.raises(ag.Panic):
+        env.run(too_many)
+    env.close()
+
+
 def test_random_ops_through_the_graph(ag):
     """random_* constructors (mod.rs:2426-2676): shapes, ranges, a != b for two evaluations of the same node (tests/test_array_gen.rs:4-40: the
     op's rng advances), equal values for two default-rng nodes (the crate seeds every default ArrayRng identically, ndarray_ext.rs:250-264),
