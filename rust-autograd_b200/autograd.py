@@ -138,6 +138,7 @@ class Tensor:
         _check(lib().agx_hook(self.graph.h, self.id, kind, text.encode() if text else None, C.cast(cb, C.c_void_p) if cb else None, None, C.byref(t)))
         return Tensor(self.graph, t.value)
 
+    def map(self, f): return map(self, f)
     def raw_hook(self, fn): return self._hook(0, fn=fn)
     def show(self): return self._hook(1)
     def show_shape(self): return self._hook(2)
@@ -670,6 +671,18 @@ def build_op(g, op, inputs=()):
     t = C.c_int()
     _check(lib().agx_custom_op(g.h, op.name().encode(), _ints([x.id for x in inputs]), len(inputs), C.cast(c_fn, C.c_void_p), C.cast(g_fn, C.c_void_p), None, C.byref(t)))
     return Tensor(g, t.value)
+
+
+class _MapOp(Op):
+    """higher_order_ops.rs:5-36 MapOp: y = f(x) on the host value, no gradient."""
+
+    def __init__(self, f): self.f = f
+    def name(self): return "MapOp"
+    def compute(self, ctx): ctx.append_output(self.f(ctx.input(0)))
+
+
+def map(x, f):  # noqa: A001  (the reference's name: tensor_ops::map, mod.rs:2931-2945)
+    return build_op(x.graph, _MapOp(f), [x])
 
 
 def _call(g, fn, tensors=(), ints=(), floats=(), multi=False):

@@ -401,6 +401,8 @@ def test_core_user_defined_op_hooks_and_graph_limit(ag, capfd):
         v0 = np.arange(5, dtype=np.float32)
         got = [r.unwrap() for r in g.evaluator().push(cube).extend(ag.grad([ag.sum_all(cube)], [xv])).feed("v", v0).run()]
         assert np.array_equal(got[0], v0 ** 3) and np.allclose(got[1], 3 * v0 ** 2)
+        mapped = (xv * 2.0).map(lambda a: a[::-1] + 1.0)          # MapOp (higher_order_ops.rs): host function of the value
+        assert np.array_equal(mapped.eval(g, {"v": v0}), (v0 * 2.0)[::-1] + 1.0)
         bad = ag.build_op(g, Failing(), [xv]) * 2.0           # the error reaches dependents (evaluation.rs:202-211)
         res = g.evaluator().push(bad).feed("v", v0).run()[0]
         with pytest.raises(ag.EvalError) as e:
