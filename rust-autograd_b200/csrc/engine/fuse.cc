@@ -34,7 +34,8 @@ struct ExprNode {
 namespace {
 const int kPad = 100, kGemmTA = 101, kScatter = 102, kColSum = 103;     // nodes that are memory, not instructions: never part of a program
 void materialize_node(Device* dev, ExprNode* n, NdArray* dest = nullptr);
-const int64_t kMaxFusedElems = (int64_t)1 << 24;     // beyond this a pass is bandwidth-bound anyway and the vectorised single-op kernels are used
+const int64_t kMaxFusedElems = (int64_t)1 << 21;     // the interpreter sustains ~1.5 TB/s of operand traffic: measured break-even with the vectorised
+                                                     // single-op kernels is ~2^22 elements for a 3-instruction chain (profiles/ops_r1.jsonl), above it they win
 
 bool unvalued(const NdArray& x) { return x.expr && !x.expr->has_value; }
 const NdArray& resolved(const NdArray& x) { return x.expr ? x.expr->value : x; }
