@@ -726,6 +726,9 @@ for _n in ["sin", "cos", "tan", "asin", "acos", "atan", "sinh", "cosh", "tanh", 
            "log10", "sqrt", "neg", "abs", "sign", "floor", "ceil", "inv", "inv_sqrt", "square", "sigmoid", "relu", "softplus", "lgamma", "digamma", "shape", "rank",
            "size", "identity", "stop_gradient", "sum_all", "mean_all", "flatten"]:
     globals()[_n] = _u(_n)
+# the reference exports the gamma functions per float type (mod.rs:488-538); the device arithmetic is f32 for both spellings
+lgamma_f32 = lgamma_f64 = globals()["lgamma"]
+digamma_f32 = digamma_f64 = globals()["digamma"]
 
 
 def _b(name):
@@ -799,9 +802,41 @@ def log_normal(shape, mean, stddev, g, seed=0): return _rand(4, shape, g, mean, 
 def gamma(shape, shape_param, scale, g, seed=0): return _rand(5, shape, g, shape_param, scale, seed)
 
 
+random_gamma = gamma                         # the reference's name (mod.rs:2639)
+
+
+class ArrayRng:
+    """ndarray_ext::ArrayRng (ndarray_ext.rs:243-264) as far as the graph API needs it: a seed for the `_rng` constructors.  The default is
+    the crate's fixed default seed; the values come from the device Philox stream (parity-unpinned)."""
+
+    def __init__(self, seed=0):
+        self.seed = int(seed)
+
+    @staticmethod
+    def default():
+        return ArrayRng(0)
+
+
+def _seed_of(arr_rng): return arr_rng.seed if isinstance(arr_rng, ArrayRng) else int(arr_rng)
+def random_uniform_rng(arr_rng, shape, min, max, g): return random_uniform(shape, min, max, g, _seed_of(arr_rng))
+def random_normal_rng(arr_rng, shape, mean, stddev, g): return random_normal(shape, mean, stddev, g, _seed_of(arr_rng))
+def standard_uniform_rng(arr_rng, shape, g): return standard_uniform(shape, g, _seed_of(arr_rng))
+def standard_normal_rng(arr_rng, shape, g): return standard_normal(shape, g, _seed_of(arr_rng))
+def bernoulli_rng(arr_rng, shape, p, g): return bernoulli(shape, p, g, _seed_of(arr_rng))
+def random_exp_rng(arr_rng, shape, lambda_, g): return random_exp(shape, lambda_, g, _seed_of(arr_rng))
+def log_normal_rng(arr_rng, shape, mean, stddev, g): return log_normal(shape, mean, stddev, g, _seed_of(arr_rng))
+def random_gamma_rng(arr_rng, shape, shape_param, scale, g): return gamma(shape, shape_param, scale, g, _seed_of(arr_rng))
+def dropout_rng(x, dropout_ratio, train, rng): return dropout(x, dropout_ratio, train, _seed_of(rng) or 0x5EED + 1)
+
+
 def normalize(x, axes): return _call(x.graph, "normalize", [x, as_tensor(axes, x.graph)])
 def batch_norm(x, scale, shift): return _call(x.graph, "batch_norm", [x, scale, shift])
 def control_dependencies(x, deps): return _call(x.graph, "control_dependencies", [x] + list(deps))
+
+
+def _hessian_vector_product(ys, xs, vectors):
+    """(Experimental in the reference) mod.rs:218-236: grad of sum_i grad(ys, xs)[i] * vectors[i] with respect to xs."""
+    return grad([gx * v for gx, v in zip(grad(ys, xs), vectors)], xs)
 
 
 def grad(ys, xs):

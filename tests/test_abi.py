@@ -70,3 +70,28 @@ def test_fused_program_compiler_on_the_host():
         assert 0 < n.value <= 3000
         total += n.value
     assert total < 4 * 3000          # some DAGs exceeded the leaf / register / output bounds and were refused
+
+
+REFERENCE_TENSOR_OPS = """_hessian_vector_product abs acos acosh add add_n argmax argmin asin asinh assign atan atanh batch_matmul batch_matmul_t batch_norm
+bernoulli bernoulli_rng ceil clip concat control_dependencies conv2d conv2d_transpose convert_to_tensor cos cosh digamma_f32 digamma_f64 dilated_conv2d
+dilated_conv2d_transpose div dropout dropout_rng elu equal exp exp10 exp2 expand_dims flatten floor gather gather_common grad grad_with_default greater
+greater_equal identity inv inv_sqrt jacobians leaky_relu lesser lesser_equal lgamma_f32 lgamma_f64 ln log10 log2 log_normal log_normal_rng log_softmax map
+matmul max_pool2d maximum mean_all mean_squared_error minimum mul neg normalize not_equal nth_tensor ones pow random_exp random_exp_rng random_gamma
+random_gamma_rng random_normal random_normal_rng random_uniform random_uniform_rng rank reduce_logsumexp reduce_max reduce_mean reduce_min reduce_prod
+reduce_sum reduce_variance relu reshape scalar setdiff1d shape sigmoid sigmoid_cross_entropy sign sin sinh size slice softmax softmax_cross_entropy softplus
+sparse_softmax_cross_entropy split sqrt square squeeze standard_normal standard_normal_rng standard_uniform standard_uniform_rng stop_gradient sub sum_all tan
+tanh tensordot tile transpose zeros""".split()
+
+
+def test_python_view_exposes_every_tensor_ops_constructor():
+    """Every `pub fn` of the reference's src/tensor_ops/mod.rs (126 names, listed above so that the test does not need the reference tree) has a
+    same-named constructor in the Python view of the graph-level ABI, plus the Tensor methods of src/tensor.rs (eval, show, show_shape, print,
+    raw_hook, map, access_elem) and the optimizers of src/optimizers."""
+    from rust_autograd_b200 import autograd as ag
+    assert len(REFERENCE_TENSOR_OPS) == 126
+    missing = [n for n in REFERENCE_TENSOR_OPS if not callable(getattr(ag, n, None))]
+    assert not missing, missing
+    for m in ("eval", "show", "show_shape", "print", "raw_hook", "map", "access_elem"):
+        assert callable(getattr(ag.Tensor, m, None)), m
+    for o in ("Adam", "SGD", "MomentumSGD", "AdaGrad"):
+        assert hasattr(ag.optimizers, o), o

@@ -422,6 +422,30 @@ def test_core_user_defined_op_hooks_and_graph_limit(ag, capfd):
     env.close()
 
 
+def test_hessian_vector_product_and_typed_aliases(ag):
+    """`_hessian_vector_product` (mod.rs:218-236) on f(x) = sum(x^3): H = diag(6x), so H v = 6 x v; the per-type gamma spellings
+    (lgamma_f32 / digamma_f32, mod.rs:488-538) and the `_rng` constructors taking an ArrayRng (mod.rs:2441-2676)."""
+    from scipy import special
+    env = ag.VariableEnvironment()
+    x0 = np.linspace(0.5, 2.0, 12, dtype=np.float32).reshape(3, 4)
+    v0 = np.linspace(-1.0, 1.0, 12, dtype=np.float32).reshape(3, 4)
+    vx = env.slot().set(x0)
+
+    def body(g):
+        x, v = g.variable(vx), g.placeholder("v", [3, 4])
+        f = ag.sum_all(x * x * x)
+        hv = ag._hessian_vector_product([f], [x], [v])[0]
+        lg, dg = ag.lgamma_f32(x), ag.digamma_f32(x)
+        a = ag.random_gamma_rng(ag.ArrayRng(5), [64], 2.0, 1.5, g)
+        b = ag.random_gamma([64], 2.0, 1.5, g, seed=5)
+        return [r.unwrap() for r in g.evaluator().extend([hv, lg, dg, a, b]).feed("v", v0).run()]
+    hv, lg, dg, a, b = env.run(body)
+    env.close()
+    assert rel(hv, 6.0 * x0 * v0) <= 1e-5
+    assert rel(lg, special.gammaln(x0.astype(np.float64))) <= 1e-5 and rel(dg, special.digamma(x0.astype(np.float64))) <= 1e-5
+    assert np.array_equal(a, b) and (a > 0).all()
+
+
 def test_random_ops_through_the_graph(ag):
     """random_* constructors (mod.rs:2426-2676): shapes, ranges, a != b for two evaluations of the same node (tests/test_array_gen.rs:4-40: the
     op's rng advances), equal values for two default-rng nodes (the crate seeds every default ArrayRng identically, ndarray_ext.rs:250-264),
