@@ -422,6 +422,49 @@ def test_core_user_defined_op_hooks_and_graph_limit(ag, capfd):
     env.close()
 
 
+def test_assign_control_dependencies_and_jacobians(ag):
+    """`assign` (mod.rs:2977-2995, array_ops.rs:94-105: the variable is overwritten in the middle of the traversal, which switches the deferred
+    expressions off for that run), `control_dependencies` (mod.rs:2951-2971: the assignment runs before the read) and `jacobians`
+    (mod.rs:160-217: [y size, x size] per input, doc example with matmul)."""
+    env = ag.VariableEnvironment()
+    a0 = np.array([[0.5, -1.0], [2.0, 0.25]], np.float32)
+    va = env.slot().set(a0)
+
+    def first(g):
+        x = g.variable(va)
+        ag.assign(x, ag.tanh(x * 2.0) + 1.0).eval(g)
+    env.run(first)
+    a1 = np.tanh(a0.astype(np.float64) * 2.0) + 1.0
+    assert rel(env.get_array_by_id(va), a1) <= 1e-6
+
+    def second(g):
+        x = g.variable(va)
+        w = ag.assign(x, ag.zeros([2, 2], g))
+        y = x + 1.0
+        return ag.control_dependencies(y, [w]).eval(g)
+    assert np.array_equal(env.run(second), np.ones((2, 2), np.float32))
+    assert np.array_equal(env.get_array_by_id(va), np.zeros((2, 2), np.float32))
+
+    rng = np.random.default_rng(2)
+    am, bm = rng.standard_normal((4, 2)).astype(np.float32), rng.standard_normal((2, 3)).astype(np.float32)
+    v1, v2 = env.slot().set(am), env.slot().set(bm)
+
+    def third(g):
+        a, b = g.variable(v1), g.variable(v2)
+        j = ag.jacobians(ag.matmul(a, b), [a, b], 12)
+        return [t.eval(g) for t in j]
+    ja, jb = env.run(third)
+    env.close()
+    ja_ref, jb_ref = np.zeros((12, 8), np.float32), np.zeros((12, 6), np.float32)
+    for i in range(4):
+        for k in range(3):
+            for j in range(2):
+                ja_ref[i * 3 + k, i * 2 + j] = bm[j, k]          # d c[i,k] / d a[i,j] = b[j,k]
+                jb_ref[i * 3 + k, j * 3 + k] = am[i, j]          # d c[i,k] / d b[j,k] = a[i,j]
+    assert ja.shape == (12, 8) and jb.shape == (12, 6)
+    assert rel(ja, ja_ref) <= 1e-6 and rel(jb, jb_ref) <= 1e-6
+
+
 def test_hessian_vector_product_and_typed_aliases(ag):
     """`_hessian_vector_product` (mod.rs:218-236) on f(x) = sum(x^3): H = diag(6x), so H v = 6 x v; the per-type gamma spellings
     (lgamma_f32 / digamma_f32, mod.rs:488-538) and the `_rng` constructors taking an ArrayRng (mod.rs:2441-2676)."""
