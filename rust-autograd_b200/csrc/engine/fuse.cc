@@ -558,6 +558,29 @@ int fuse_selftest(int n_cases, uint32_t seed, int* n_compiled) {
       if (P.order[k]->consumers > 1 && !stored && (int)P.outs.size() < AGB_FUSE_MAX_OUT) return 16;
     }
   }
+  // leaf addressing: whenever as_2d accepts a (sliced / broadcast / squeezed) view, ptr + r * pitch + c * cstride must hit exactly the element
+  // the strided view holds at the output's multi-index
+  for (int cs = 0; cs < n_cases; cs++) {
+    const int nd = 1 + (int)(rnd() % 4);
+    Shape base(nd), out(nd); NdArray leaf;
+    for (int k = 0; k < nd; k++) { base[k] = 1 + (int64_t)(rnd() % 5); out[k] = base[k]; }
+    leaf.shape = base; leaf.stride = NdArray::contiguous_strides(base); leaf.dptr = (float*)(uintptr_t)0x100000;
+    int64_t off0 = 0;
+    for (int k = 0; k < nd; k++) {
+      const uint32_t what = rnd() % 4;
+      if (what == 0 && base[k] > 1) { int64_t s0 = (int64_t)(rnd() % base[k]), ln = 1 + (int64_t)(rnd() % (base[k] - s0)); off0 += s0 * leaf.stride[k]; leaf.shape[k] = ln; out[k] = ln; }   // slice
+      else if (what == 1) { leaf.shape[k] = 1; out[k] = 1 + (int64_t)(rnd() % 4); }                                                                                        // broadcast axis
+    }
+    leaf.dptr += off0;
+    int64_t pitch, cst;
+    if (!as_2d(leaf, out, pitch, cst)) continue;
+    const int64_t cols = out[nd - 1]; int64_t total = 1; for (auto d : out) total *= d;
+    for (int64_t i = 0; i < total; i++) {
+      int64_t rem = i, want = 0;
+      for (int k = nd - 1; k >= 0; k--) { const int64_t idx = rem % out[k]; rem /= out[k]; if (leaf.shape[k] != 1) want += idx * leaf.stride[k]; }
+      if (want != (i / cols) * pitch + (i % cols) * cst) return 20;
+    }
+  }
   if (n_compiled) *n_compiled = compiled;
   return 0;
 }

@@ -60,7 +60,8 @@ def test_error_codes_mirror_op_error():
 def test_fused_program_compiler_on_the_host():
     """engine/fuse.cc: random expression DAGs (unary / binary / immediate forms, shared sub-expressions, multi-consumer nodes, two roots) are
     compiled into agb_fused_ewise programs and interpreted on the host: every stored register must hold its node's value (register
-    allocation never clobbers a live value, leaves are deduplicated, roots come first, oversized DAGs are refused).  No device needed."""
+    allocation never clobbers a live value, leaves are deduplicated, roots come first, oversized DAGs are refused); the second half checks the
+    leaf addressing ptr + r * pitch + c * cstride against the strided view it stands for on random sliced / broadcast views.  No device needed."""
     import ctypes as C
     from rust_autograd_b200 import autograd as ag
     n = C.c_int()
