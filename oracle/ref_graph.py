@@ -609,6 +609,8 @@ COMPUTE = {
     "Rank": lambda n, ins, _: [np.asarray(float(np.asarray(ins[0]).ndim))],
     "Size": lambda n, ins, _: [np.asarray(float(np.asarray(ins[0]).size))],
     "Identity": lambda n, ins, _: [ins[0]], "StopGradient": lambda n, ins, _: [ins[0]],
+    "SetDiff1D": lambda n, ins, _: [np.asarray(sorted(set(np.asarray(ins[0]).ravel().tolist()) - set(np.asarray(ins[1]).ravel().tolist())), dtype=R.OUT_DTYPE)],
+    "Map": lambda n, ins, _: [np.asarray(n.attrs["f"](np.asarray(ins[0])), dtype=R.OUT_DTYPE)],
     "Bin": _c_bin, "Unary": _c_unary, "Reduce": _c_reduce,
     "Clip": lambda n, ins, _: [R.unary("clip", ins[0], n.attrs["lo"], n.attrs["hi"])],
     "ClipGrad": lambda n, ins, _: [R.clip_grad(ins[0], ins[1], n.attrs["lo"], n.attrs["hi"])],
@@ -848,6 +850,15 @@ def grad(ys, xs):
 def grad_with_default(ys, xs, ys_grads):
     gs = compute_gradients(list(ys), xs, list(ys_grads))
     return [gx if gx is not None else zeros(shape(x), x.graph) for x, gx in zip(xs, gs)]
+
+
+def _hessian_vector_product(ys, xs, vectors):
+    """tensor_ops/mod.rs:218-236"""
+    return grad([gx * v for gx, v in zip(grad(ys, xs), vectors)], xs)
+
+
+def setdiff1d(a, b): return Tensor(a.graph, "SetDiff1D", [a, b], differentiable=False)       # mod.rs:2044-2057, array_ops.rs:241-279
+def map(x, f): return Tensor(x.graph, "Map", [x], {"f": f}, differentiable=False)            # noqa: A001  mod.rs:2931-2945, higher_order_ops.rs:5-36
 
 
 def jacobians(y, xs, objective_len):

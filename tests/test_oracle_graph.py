@@ -91,3 +91,28 @@ def test_eval_semantics():
         r = g.evaluator().push(bad + x).feed("a", np.ones((3, 2))).run()
         assert not r[0].is_ok() and r[0].err.kind == "IncompatibleShape"               # errors propagate to dependents (:202-211)
     env.run(body)
+
+
+def test_oracle_hessian_vector_product_setdiff_map():
+    """Oracle restatements of `_hessian_vector_product` (mod.rs:218-236), `setdiff1d` (doc example mod.rs:2044-2057) and `map`
+    (higher_order_ops.rs:5-36): H v of f = sum(x^3) is 6 x v; the HVP also matches a central difference of the gradient."""
+    from oracle import ref_graph as OG
+    x0 = np.linspace(0.5, 2.0, 12).reshape(3, 4)
+    v0 = np.linspace(-1.0, 1.0, 12).reshape(3, 4)
+    env = OG.VariableEnvironment()
+    vx = env.slot().set(x0)
+
+    def body(g):
+        x, v = g.variable(vx), g.placeholder("v", [3, 4])
+        f = OG.sum_all(x * x * x)
+        hv = OG._hessian_vector_product([f], [x], [v])[0]
+        sd = OG.setdiff1d(OG.convert_to_tensor(np.array([4., 1., 5., 2., 3., 6.]), g), OG.convert_to_tensor(np.array([1., 3., 5.]), g))
+        mp = OG.map(x * 2.0, lambda a: a[::-1] + 1.0)
+        return [r.unwrap() for r in g.evaluator().extend([hv, sd, mp]).feed("v", v0).run()]
+    hv, sd, mp = env.run(body)
+    assert np.allclose(hv, 6.0 * x0 * v0, rtol=1e-5)
+    eps = 1e-4
+    fd = (3.0 * (x0 + eps * v0) ** 2 - 3.0 * (x0 - eps * v0) ** 2) / (2 * eps)       # d/d eps of grad f(x + eps v)
+    assert np.allclose(hv, fd, rtol=1e-3)
+    assert np.asarray(sd).tolist() == [2., 4., 6.]
+    assert np.allclose(mp, (x0 * 2.0)[::-1] + 1.0, rtol=1e-6)
