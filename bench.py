@@ -7,8 +7,14 @@ One process per GPU (torchrun for N > 1).  Prints ONE JSON line on rank 0.
   value     whole-job samples/s with the batch already resident in HBM (CUDA events on the library's own stream, max over ranks)
   e2e       the same step driven through the public graph API with HOST feeds: H2D of the batch and D2H of the loss inside the timed region
   roofline  the dominant kernel class (conv implicit GEMM) timed live with CUDA event pairs around every call (agb_prof_*)
-  cpu_baseline  the oracle (CPU restatement of the reference, numpy/OpenBLAS) on a bounded sample of the same workload
---impl reference times that oracle alone (the Rust crate cannot be built in this image: no cargo/rustc).
+  cpu_baseline  the f32 C restatement of the reference's default-build CPU path (oracle/cpu_ref.c: im2col + one sgemm per sample in parallel
+            over samples, sequential filter gradient, single-thread elementwise / pooling / Adam) on a bounded sample of the same workload
+  modes     the same step in the f32-faithful 3xTF32 mode (the mode that matches the reference's f32 arithmetic to 1e-5)
+  parity    loss / gradients of a batch-4 sample of the same network on the GPU (both modes) against the numpy oracle
+  micro     GEMM 8192^3 (TF32, 3xTF32), reduce_sum / softmax over 2^28 elements, Adam 2^26: TFLOP/s, GB/s and roofline fractions
+  configs   BASELINE configs[0..2] (MLP-MNIST, CNN-MNIST, LSTM LM): us per step, eager and replayed as a step graph
+--impl reference times that C restatement alone with --steps / --warmup honoured (the Rust crate cannot be built in this image: no
+cargo/rustc; kind = "port").
 """
 import argparse
 import json
@@ -66,61 +72,92 @@ class ClockSampler(threading.Thread):
         return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None, "reasons": reasons, "samples": len(sm)}
 
 
-# ------------------------------------------------------------------------------------------------ reference arm (oracle on host cores)
-def run_reference(args, rank):
-    if rank != 0:
-        return
-    from oracle import ref_graph as OG
+# ------------------------------------------------------------------------------------------------ reference arm (f32 C port on host cores)
+def _cpu_trainer(batch):
+    from oracle import cpu_ref as CR
     from rust_autograd_b200 import workloads as W
     rng = np.random.default_rng(0)
-    bs = args.cpu_batch
-    env = OG.VariableEnvironment()
-    W.vgg_init(env, rng)
-    adam = OG.optimizers.Adam.default("adam", env.default_namespace().current_var_ids(), env)
-    x = rng.standard_normal((bs, 3, 128, 128)).astype(np.float32)
-    y = rng.integers(0, 10, (bs, 1)).astype(np.float32)
+    tr = CR.VggTrainer(CR.vgg_params(rng), W.VGG_LAYERS, 128)
+    x = rng.standard_normal((batch, 3, 128, 128)).astype(np.float32)
+    y = rng.integers(0, 10, (batch, 1)).astype(np.float32)
+    return CR, tr, x, y
 
-    def step(g):
-        loss, _ = W.vgg_loss(OG, g)
-        params, grads = OG.optimizers.grad_helper([loss], g.default_namespace())
-        upd = adam.get_update_op(params, grads, g)
-        return float(np.asarray(g.evaluator().push(loss).push(upd).feed("x", x).feed("y", y).run()[0].unwrap()).ravel()[0])
-    for _ in range(args.warmup_ref):
-        env.run(step)
+
+def run_reference(args, rank):
+    """The reference's own CPU algorithm for the path (f32, oracle/cpu_ref.c), all host threads it can use (one task per sample for
+    conv / conv_transpose like rayon in the reference; everything else single-threaded like the reference), on a `--cpu-batch`-sample
+    slice of the same VGG step.  --steps / --warmup are honoured; a wall-clock cap (REF_BUDGET_S) only trims a run that would not end
+    within a few minutes, and says so."""
+    if rank != 0:
+        return
+    CR, tr, x, y = _cpu_trainer(args.cpu_batch)
+    budget = float(os.environ.get("REF_BUDGET_S", "240"))
+    t_begin = time.time()
+    warm_done = 0
+    for _ in range(max(args.warmup, 1)):
+        tr.step(x, y)
+        warm_done += 1
+        if time.time() - t_begin > budget / 4:
+            break
+    per = (time.time() - t_begin) / warm_done
+    steps = max(1, min(args.steps, int((budget - (time.time() - t_begin)) / max(per, 1e-6))))
     t0 = time.time()
-    for _ in range(args.steps_ref):
-        env.run(step)
-    dt = (time.time() - t0) / args.steps_ref
-    cores = os.cpu_count()
-    sample = "oracle (numpy/OpenBLAS restatement of the reference CPU path) on batch %d of the VGG stack, %d step(s)" % (bs, args.steps_ref)
-    v = bs / dt
-    print(json.dumps({"impl": "reference", "metric": METRIC, "value": v, "unit": "samples/s", "n_gpus": args.gpus, "steps": args.steps_ref, "warmup": args.warmup_ref,
+    loss = None
+    for _ in range(steps):
+        loss, _ = tr.step(x, y)
+    dt = (time.time() - t0) / steps
+    cores = CR.load().cr_threads()
+    sample = ("f32 C port of the reference CPU path (%s), batch %d of the VGG stack per step, %d timed step(s) after %d warm-up%s"
+              % (CR.SGEMM_BACKEND, args.cpu_batch, steps, warm_done, "" if steps == args.steps else " (trimmed from --steps %d by the %.0f s budget)" % (args.steps, budget)))
+    v = args.cpu_batch / dt
+    print(json.dumps({"impl": "reference", "metric": METRIC, "value": v, "unit": "samples/s", "n_gpus": args.gpus, "steps": steps, "warmup": warm_done,
                       "ms_per_step": dt * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-                      "config": {"workload": WORKLOAD, "sample_batch": bs},
+                      "config": {"workload": WORKLOAD, "sample_batch": args.cpu_batch, "optimizer": "adam", "last_loss": loss},
                       "cpu_baseline": {"value": v, "unit": "samples/s", "cores": cores, "kind": "port", "sample": sample},
                       "e2e": {"value": v, "unit": "samples/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}), flush=True)
 
 
-def cpu_baseline(batch, steps=1):
+def cpu_baseline(batch, steps=2):
+    CR, tr, x, y = _cpu_trainer(batch)
+    tr.step(x, y)
+    t0 = time.time()
+    for _ in range(steps):
+        tr.step(x, y)
+    dt = (time.time() - t0) / steps
+    return {"value": batch / dt, "unit": "samples/s", "cores": CR.load().cr_threads(), "kind": "port",
+            "sample": "f32 C port of the reference CPU path (%s; conv parallel over samples, the rest single-threaded like the reference), batch %d of the same "
+                      "VGG stack, %d timed step(s) after 1 warm-up, %.1f s" % (CR.SGEMM_BACKEND, batch, steps, dt * steps)}
+
+
+def parity_block(ag, ffi, lib, device, batch=4):
+    """The same network on a batch-`batch` sample: GPU (3xTF32 and TF32) vs the numpy oracle, forward loss and all 16 gradients."""
     from oracle import ref_graph as OG
     from rust_autograd_b200 import workloads as W
-    rng = np.random.default_rng(0)
-    env = OG.VariableEnvironment()
-    W.vgg_init(env, rng)
-    adam = OG.optimizers.Adam.default("adam", env.default_namespace().current_var_ids(), env)
+    rng = np.random.default_rng(17)
     x = rng.standard_normal((batch, 3, 128, 128)).astype(np.float32)
     y = rng.integers(0, 10, (batch, 1)).astype(np.float32)
 
-    def step(g):
-        loss, _ = W.vgg_loss(OG, g)
-        params, grads = OG.optimizers.grad_helper([loss], g.default_namespace())
-        g.evaluator().push(loss).push(adam.get_update_op(params, grads, g)).feed("x", x).feed("y", y).run()[0].unwrap()
-    t0 = time.time()
-    for _ in range(steps):
-        env.run(step)
-    dt = (time.time() - t0) / steps
-    return {"value": batch / dt, "unit": "samples/s", "cores": os.cpu_count(), "kind": "port",
-            "sample": "oracle (numpy/OpenBLAS restatement of the reference CPU path), batch %d of the same VGG stack, %d step(s), %.1f s" % (batch, steps, dt * steps)}
+    def run(mod, mode):
+        env = mod.VariableEnvironment(device) if mod is ag else mod.VariableEnvironment()
+        if mode is not None:
+            ffi.check(lib.agb_set_math_mode(env.agb_ctx(), mode))
+        W.vgg_init(env, np.random.default_rng(0))
+
+        def body(g):
+            loss, _ = W.vgg_loss(mod, g)
+            params, grads = mod.optimizers.grad_helper([loss], g.default_namespace())
+            return [np.asarray(r.unwrap(), np.float64) for r in g.evaluator().push(loss).extend(grads).feed("x", x).feed("y", y).run()]
+        out = env.run(body)
+        env.close()
+        return out
+    ref = run(OG, None)
+    res = {"sample_batch": batch, "oracle": "oracle/ref_graph.py (numpy, f64 accumulation)"}
+    for mode, nm in ((0, "3xtf32"), (1, "tf32")):
+        got = run(ag, mode)
+        res[nm] = {"loss_rel": float(abs(got[0] - ref[0]).max() / abs(ref[0]).max()),
+                   "max_grad_rel": float(max(np.abs(a - b).max() / max(np.abs(b).max(), 1e-30) for a, b in zip(got[1:], ref[1:]))),
+                   "max_grad_rel_l2": float(max(np.linalg.norm(a - b) / max(np.linalg.norm(b), 1e-30) for a, b in zip(got[1:], ref[1:])))}
+    return res
 
 
 # ------------------------------------------------------------------------------------------------ our arm
@@ -132,10 +169,9 @@ def main():
     ap.add_argument("--impl", default="ours")
     ap.add_argument("--mode", default="tf32", choices=["tf32", "3xtf32", "fp32"])
     ap.add_argument("--batch", type=int, default=256, help="per-GPU batch")
-    ap.add_argument("--cpu-batch", type=int, default=4)
-    ap.add_argument("--steps-ref", type=int, default=2)
-    ap.add_argument("--warmup-ref", type=int, default=1)
+    ap.add_argument("--cpu-batch", type=int, default=32, help="samples per step of the CPU reference arm / cpu_baseline")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-extras", action="store_true", help="skip the modes / parity / micro / configs blocks (ncu captures)")
     args = ap.parse_args()
     rank, world, local = int(os.environ.get("RANK", 0)), int(os.environ.get("WORLD_SIZE", 1)), int(os.environ.get("LOCAL_RANK", 0))
     if args.impl == "reference":
@@ -264,9 +300,32 @@ def main():
             prof[nm] = {"ms": t.value, "calls": n.value, "work": w.value}
     ffi.check(lib.agb_prof_reset(ctx))
     # ---- leg 2: end to end through the public API with host feeds
+    e2e_state["losses"] = []
     e2e_ms, e2e_wall, _ = timed(step_e2e, args.steps, 1, e2e_drain)
     e2e_time = max(e2e_ms, e2e_wall)       # the D2H of the loss serialises host and device: wall time is the honest figure
+    timed_losses = e2e_state["losses"][1:]  # [0] belongs to the warm-up step
+    # ---- leg 3: the same resident step in the other tensor-core mode (3xTF32 = the f32-faithful mode; TF32 when --mode 3xtf32)
+    other = None
+    if not args.no_extras and args.mode in ("tf32", "3xtf32"):
+        other_mode = "3xtf32" if args.mode == "tf32" else "tf32"
+        ffi.check(lib.agb_set_math_mode(ctx, {"3xtf32": 0, "tf32": 1}[other_mode]))
+        o_steps = max(3, args.steps // 2)
+        o_ms, _, _ = timed(step_resident, o_steps, 3)
+        other = {"mode": other_mode, "steps": o_steps, "ms_per_step": o_ms / o_steps, "value": world * B * o_steps / (o_ms / 1e3), "unit": "samples/s"}
+        ffi.check(lib.agb_set_math_mode(ctx, {"3xtf32": 0, "tf32": 1, "fp32": 2}[args.mode]))
     sampler.stop_flag = True
+    # ---- data-parallel invariant: every rank holds bit-identical variables after the timed steps
+    dp_check = None
+    if world > 1:
+        import zlib
+        n_vars = len(env.default_namespace().current_var_ids())
+        crc = 0
+        for vid in range(n_vars):
+            crc = zlib.crc32(np.ascontiguousarray(env.get_array_by_id(vid)).tobytes(), crc)
+        t = torch.tensor([crc], dtype=torch.int64, device="cuda")
+        allc = [torch.zeros_like(t) for _ in range(world)]
+        dist.all_gather(allc, t)
+        dp_check = {"weights_crc32_equal_across_ranks": len({int(c.item()) for c in allc}) == 1, "variables": n_vars}
 
     if rank == 0:
         pk = peaks()
@@ -282,7 +341,9 @@ def main():
             d_ms = sum(v["ms"] for v in dom); d_w = sum(v["work"] for v in dom); d_n = sum(v["calls"] for v in dom)
             tot_ms = sum(v["ms"] for v in conv.values()); tot_w = sum(v["work"] for v in conv.values())
             achieved = d_w / (d_ms / 1e3) / 1e12
-            tf32_peak = pk["bf16_tflops_sustained"] / 2.0
+            peak_div = 3.0 if args.mode == "3xtf32" else 1.0          # 3xTF32 issues three MMAs per product: useful-FLOP ceiling = 1/3
+            tf32_peak = pk["bf16_tflops_sustained"] / 2.0 / peak_div
+            tf32_burst = pk["bf16_tflops"] / 2.0 / peak_div
             traffic, traffic_src = None, None
             tpath = os.path.join(ROOT, "profiles", "ncu_conv_traffic.json")     # dram bytes per launch from the committed ncu --set full capture
             if os.path.exists(tpath) and world == 1:
@@ -291,7 +352,8 @@ def main():
                     traffic, traffic_src = tj["dram_bytes_per_launch"], tj["source"]
             roof = {"bound": "tensor", "kernel": "tc_tile_persist_kernel<ConvFpropPol> + conv_rows_kernel + conv_cols_kernel (tcgen05 implicit-GEMM conv: fprop + dgrad, %s)" % args.mode,
                     "achieved": achieved, "peak": tf32_peak, "unit": "TFLOP/s", "frac": achieved / tf32_peak, "traffic": traffic, "traffic_source": traffic_src,
-                    "peak_source": "%s bf16 sustained / 2 (dense TF32 = half the bf16 rate), MEASURED_PEAKS.json" % pk["src"],
+                    "peak_source": "%s bf16 sustained / 2 (dense TF32 = half the bf16 rate; the kernel is timed inside a long step), MEASURED_PEAKS.json" % pk["src"],
+                    "peak_burst": tf32_burst, "frac_burst": achieved / tf32_burst,
                     "per_launch_ms": d_ms / d_n, "flops_per_launch": d_w / d_n, "launches_per_step": d_n / args.steps,
                     "share_of_step": d_ms / max(prof_ms, 1e-9),
                     "all_conv": {"achieved": tot_w / (tot_ms / 1e3) / 1e12, "share_of_step": tot_ms / max(prof_ms, 1e-9)},
@@ -304,7 +366,22 @@ def main():
                "e2e": {"value": e2e_value, "unit": "samples/s", "h2d_bytes_per_step": int(xs[0].nbytes + ys[0].nbytes), "d2h_bytes_per_step": 4,
                        "ms_per_step": e2e_time / args.steps},
                "gpu_launches": int(launches), "clocks": sampler.summary(), "roofline": roof,
-               "model_tflops": W.vgg_flops_per_sample() * B / (step_ms / 1e3) / 1e12}
+               "model_tflops": W.vgg_flops_per_sample() * B / (step_ms / 1e3) / 1e12,
+               "losses": {"first": timed_losses[0] if timed_losses else None, "last": timed_losses[-1] if timed_losses else None, "n": len(timed_losses),
+                          "note": "rank 0's loss of the first / last timed e2e step (random labels: the value only shows the step trains and is finite)"}}
+        if other is not None:
+            out["modes"] = {other["mode"]: other}
+        if dp_check is not None:
+            out["dp_check"] = dp_check
+        if world == 1 and not args.no_extras:
+            ffi.check(lib.agb_sync(ctx)); pf.close(); g.close(); env.close()      # release the training arena before the side blocks allocate their own
+            for key, fn in (("parity", lambda: parity_block(ag, ffi, lib, local)),
+                            ("micro", lambda: __import__("scripts.bench_micro", fromlist=["run"]).run(pk, local)),
+                            ("configs", lambda: __import__("scripts.bench_configs", fromlist=["small_configs"]).small_configs(local))):
+                try:
+                    out[key] = fn()
+                except Exception as e:      # side blocks never take the headline down
+                    out[key] = {"error": repr(e)}
         if not args.no_cpu_baseline and world == 1:
             try:
                 out["cpu_baseline"] = cpu_baseline(args.cpu_batch)

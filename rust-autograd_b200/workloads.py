@@ -35,11 +35,19 @@ def cnn_mnist_init(env, rng):
     ns.slot().name("b3").set(np.zeros((1, 10), np.float32))
 
 
-def cnn_mnist_logits(T, g, train, masks=None):
+def cnn_mnist_logits(T, g, train, masks=None, taps=None):
+    """`taps` (a dict) collects the three dropout nodes so a parity test can read the device masks back (nth_tensor(d, 1)) and hand them to
+    the oracle through `masks` (the RNG streams are parity-unpinned)."""
     def drop(t, i):
         if masks is not None:
-            return T.dropout(t, 0.25, train, mask=masks[i])      # oracle: explicit mask
-        return T.dropout(t, 0.25, train) if train is not None else t
+            d = T.dropout(t, 0.25, train, mask=masks[i])         # oracle: explicit mask
+        elif train is not None:
+            d = T.dropout(t, 0.25, train)
+        else:
+            return t
+        if taps is not None:
+            taps["drop%d" % i] = d
+        return d
     x = g.placeholder("x", [-1, 28 * 28]).reshape([-1, 1, 28, 28])
     z1 = T.conv2d(x, g.variable("w1"), 1, 1) + g.variable("b1")
     z2 = drop(T.max_pool2d(T.relu(z1), 2, 0, 2), 0)
@@ -49,8 +57,8 @@ def cnn_mnist_logits(T, g, train, masks=None):
     return drop(T.matmul(z5, g.variable("w3")) + g.variable("b3"), 2)
 
 
-def cnn_mnist_loss(T, g, train=True, masks=None):
-    logits = cnn_mnist_logits(T, g, train, masks)
+def cnn_mnist_loss(T, g, train=True, masks=None, taps=None):
+    logits = cnn_mnist_logits(T, g, train, masks, taps)
     return T.reduce_mean(T.sparse_softmax_cross_entropy(logits, g.placeholder("y", [-1, 1])), [0], False), logits
 
 
@@ -104,12 +112,15 @@ def vgg_init(env, rng, size=128, classes=10, layers=VGG_LAYERS):
     return c_last * h * h
 
 
-def vgg_loss(T, g, size=128, layers=VGG_LAYERS):
+def vgg_loss(T, g, size=128, layers=VGG_LAYERS, taps=None):
+    """`taps` (a dict) collects the max-pool nodes: parity tests compare their argmax outputs (nth_tensor(p, 1)) bit for bit."""
     x, y = g.placeholder("x", [-1, 3, size, size]), g.placeholder("y", [-1, 1])
     h, i, c_last, t = size, 0, 3, x
     for l in layers:
         if l == "pool":
             t = T.max_pool2d(t, 2, 0, 2)
+            if taps is not None:
+                taps["pool%d" % len(taps)] = t
             h //= 2
             continue
         t = T.relu(T.conv2d(t, g.variable("conv%d_w" % i), 1, 1) + g.variable("conv%d_b" % i))

@@ -12,8 +12,8 @@ sys.path.insert(0, ROOT)
 from rust_autograd_b200 import autograd as ag, ffi, workloads as W  # noqa: E402
 
 
-def run(name, init, loss_fn, feeds, mode, steps=200, warm=20):
-    env = ag.VariableEnvironment()
+def run(name, init, loss_fn, feeds, mode, steps=200, warm=20, device=0, emit=True):
+    env = ag.VariableEnvironment(device)
     lib, ctx = ffi.load_library(), env.agb_ctx()
     ffi.check(lib.agb_set_math_mode(ctx, mode))
     init(env, np.random.default_rng(0))
@@ -78,8 +78,25 @@ def run(name, init, loss_fn, feeds, mode, steps=200, warm=20):
                 prof[nm] = {"ms_per_step": ms.value / n, "calls_per_step": calls.value / n, "work_per_s": work.value / max(ms.value, 1e-9) * 1e3}
         ffi.check(lib.agb_prof_enable(ctx, 0))
         row["profile"] = prof
-    print(json.dumps(row), flush=True)
+    if emit:
+        print(json.dumps(row), flush=True)
     g.close(); env.close()
+    return row
+
+
+def small_configs(device=0, mode=1, lstm_steps=5):
+    """bench.py's "configs" block: BASELINE configs[0..2] on one GPU, eager and replayed as a step graph (us per step)."""
+    rng = np.random.default_rng(0)
+    B = 200
+    x = rng.uniform(size=(B, 784)).astype(np.float32); y = rng.integers(0, 10, (B, 1)).astype(np.float32)
+    D, V, S, Bl = 1024, 8192, 64, 128
+    sents = rng.integers(0, V, (Bl, S)).astype(np.float32)
+    rows = [run("mlp_mnist_b200", W.mlp_init, W.mlp_loss, {"x": x, "y": y}, mode, steps=100, warm=10, device=device, emit=False),
+            run("cnn_mnist_b200", W.cnn_mnist_init, lambda T, g: W.cnn_mnist_loss(T, g, train=True), {"x": x, "y": y}, mode, steps=100, warm=10, device=device, emit=False),
+            run("lstm_lm_b128_s64_d1024_v8192", lambda env, r: W.lstm_init(env, r, D, V), lambda T, g: W.lstm_loss(T, g, D, S), {"sents": sents}, mode,
+                steps=lstm_steps, warm=3, device=device, emit=False)]
+    return {r["config"]: {"eager_us_per_step": r["us_per_step"], "graph_us_per_step": r["graph_us_per_step"], "graph_samples_per_s": r["graph_samples_per_s"],
+                          "launches_per_step": r["launches_per_step"], "mode": r["mode"]} for r in rows}
 
 
 def main():

@@ -1,0 +1,202 @@
+"""-m gpu parity tests at the geometry the benchmarks time (VERDICT r1 "next" #1): the evaluator paths behind the headline numbers —
+conv_rows + fused 2x2 pool epilogue, conv_cols, per-tap 256-wide tiles, all-taps filter gradient, masked dgrad with bias side sums at
+128^2 / 64^2 / 32^2; the CNN-MNIST example at batch 200; the LSTM language model at hidden 1024 / vocab 8192 with row-stacked and
+long-K GEMMs — compared with the oracle (oracle/ref_graph.py) on the same seeded inputs, in both tensor-core modes.
+
+Tolerances (BASELINE.json north_star): 3xTF32 f32 tensors <= 2e-5 of the tensor's largest magnitude (1e-5 per contraction, graph depth
+doubles it); TF32 loss / logits <= 1e-2, gradients in relative L2 (forward rounding legitimately flips ReLU masks and pool argmaxes of
+pre-activations within rounding of a tie).  Pool argmax indices: exact except at near-ties (the two candidates differ by <= 1e-5 of the
+map's largest value), and those must be rarer than 1e-4 of the windows in 3xTF32 mode."""
+import numpy as np
+import pytest
+
+from oracle import ref_graph as OG
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def ag():
+    from rust_autograd_b200 import autograd
+    return autograd
+
+
+def rel(got, ref):
+    got, ref = np.asarray(got, np.float64), np.asarray(ref, np.float64)
+    assert got.shape == ref.shape, (got.shape, ref.shape)
+    return float(np.abs(got - ref).max() / max(np.abs(ref).max(), 1e-30))
+
+
+def rel_l2(got, ref):
+    got, ref = np.asarray(got, np.float64), np.asarray(ref, np.float64)
+    return float(np.linalg.norm(got - ref) / max(np.linalg.norm(ref), 1e-30))
+
+
+def set_mode(env, mode):
+    from rust_autograd_b200 import ffi
+    ffi.check(ffi.load_library().agb_set_math_mode(env.agb_ctx(), mode))
+
+
+# ------------------------------------------------------------------------------------------------ VGG stack at the bench geometry
+def _vgg_run(mod, mode, x, y):
+    from rust_autograd_b200 import workloads as W
+    env = mod.VariableEnvironment()
+    if mode is not None:
+        set_mode(env, mode)
+    W.vgg_init(env, np.random.default_rng(0))
+
+    def body(g):
+        taps = {}
+        loss, logits = W.vgg_loss(mod, g, taps=taps)
+        params, grads = mod.optimizers.grad_helper([loss], g.default_namespace())
+        pools = [taps[k] for k in sorted(taps)]
+        idx = [mod.nth_tensor(p, 1) for p in pools]
+        out = g.evaluator().push(loss).push(logits).extend(grads).extend(pools).extend(idx).feed("x", x).feed("y", y).run()
+        return [np.asarray(r.unwrap()) for r in out], len(grads), len(pools)
+    try:
+        return env.run(body)
+    finally:
+        env.close()
+
+
+@pytest.fixture(scope="module")
+def vgg_reference():
+    rng = np.random.default_rng(3)
+    x = rng.standard_normal((8, 3, 128, 128)).astype(np.float32)
+    y = rng.integers(0, 10, (8, 1)).astype(np.float32)
+    return x, y, _vgg_run(OG, None, x, y)
+
+
+@pytest.mark.parametrize("mode", [0, 1], ids=["3xtf32", "tf32"])
+def test_vgg_bench_geometry_matches_oracle(ag, vgg_reference, mode):
+    """workloads.vgg_loss at 3x128x128 (the bench's graph: examples/cnn_mnist.rs:36-51 widened to configs[3]), batch 8: loss, logits, all
+    16 parameter gradients, the three pooled maps and their argmax indices (max_pool2d.rs:21-88)."""
+    x, y, (ref, ng, npool) = vgg_reference
+    got, ng2, npool2 = _vgg_run(ag, mode, x, y)
+    assert (ng, npool) == (ng2, npool2) == (16, 3) and len(got) == len(ref)
+    tol = 2e-5 if mode == 0 else 1e-2
+    assert rel(got[0], ref[0]) <= tol and rel(got[1], ref[1]) <= tol, (rel(got[0], ref[0]), rel(got[1], ref[1]))
+    for k in range(2, 2 + ng):
+        if mode == 0:
+            assert rel(got[k], ref[k]) <= tol, (k, got[k].shape, rel(got[k], ref[k]))
+        else:
+            assert rel_l2(got[k], ref[k]) <= 1e-1, (k, got[k].shape, rel_l2(got[k], ref[k]))
+    for k in range(npool):
+        pv, pr = got[2 + ng + k], ref[2 + ng + k]
+        iv, ir = got[2 + ng + npool + k], ref[2 + ng + npool + k]
+        assert rel(pv, pr) <= tol, (k, rel(pv, pr))
+        bad = iv != ir
+        frac = float(bad.mean())
+        assert frac <= (1e-4 if mode == 0 else 2e-2), (k, frac)
+        if bad.any():          # every differing argmax is a near-tie: the winners' values agree
+            assert float(np.abs(pv[bad].astype(np.float64) - pr[bad]).max()) <= (1e-5 if mode == 0 else 1e-2) * float(np.abs(pr).max()), k
+
+
+def test_vgg_training_steps_match_oracle(ag):
+    """Three Adam steps of the bench graph (64x64 images, batch 4: the oracle does this in seconds): per-step losses and every
+    variable incl. optimizer state after the last step (optimizers/mod.rs:66-82, adam.rs:11-58)."""
+    from rust_autograd_b200 import workloads as W
+    rng = np.random.default_rng(7)
+    xs = [rng.standard_normal((4, 3, 64, 64)).astype(np.float32) for _ in range(3)]
+    ys = [rng.integers(0, 10, (4, 1)).astype(np.float32) for _ in range(3)]
+
+    def train(mod, mode):
+        env = mod.VariableEnvironment()
+        if mode is not None:
+            set_mode(env, mode)
+        W.vgg_init(env, np.random.default_rng(0), size=64)
+        adam = mod.optimizers.Adam.default("adam", env.default_namespace().current_var_ids(), env)
+        losses = []
+        for x, y in zip(xs, ys):
+            def step(g):
+                loss, _ = W.vgg_loss(mod, g, size=64)
+                params, grads = mod.optimizers.grad_helper([loss], g.default_namespace())
+                r = g.evaluator().push(loss).push(adam.get_update_op(params, grads, g)).feed("x", x).feed("y", y).run()
+                losses.append(float(np.asarray(r[0].unwrap()).ravel()[0]))
+            env.run(step)
+        n = len(env.default_namespace().current_var_ids()) + len(env.namespace("adam").current_var_ids())
+        out = [np.asarray(env.get_array_by_id(i)).copy() for i in range(n)]
+        env.close()
+        return losses, out
+    l_ref, v_ref = train(OG, None)
+    l_got, v_got = train(ag, 0)
+    assert np.allclose(l_got, l_ref, rtol=2e-5, atol=0), (l_got, l_ref)
+    assert len(v_got) == len(v_ref)
+    for k, (a, b) in enumerate(zip(v_got, v_ref)):
+        # Adam's first steps move every weight by ~alpha * g / (|g| + eps): entries whose gradient is ~eps-sized amplify a 1e-6 gradient
+        # difference, so the bound is on the update relative to alpha (1e-3), not on the weight's magnitude alone
+        assert float(np.abs(a.astype(np.float64) - b).max()) <= 2e-5 * max(float(np.abs(b).max()), 1.0) + 2e-5, (k, a.shape)
+
+
+# ------------------------------------------------------------------------------------------------ CNN-MNIST at batch 200 (configs[1])
+@pytest.mark.parametrize("mode", [0, 1], ids=["3xtf32", "tf32"])
+def test_cnn_mnist_batch200_matches_oracle(ag, mode):
+    """examples/cnn_mnist.rs:36-115 at BASELINE's batch 200 with dropout in training mode: the device masks are read back
+    (nth_tensor(dropout, 1), random_ops.rs:218-245) and handed to the oracle; loss, logits and the six gradients."""
+    from rust_autograd_b200 import workloads as W
+    rng = np.random.default_rng(5)
+    x = rng.uniform(0, 1, (200, 784)).astype(np.float32)
+    y = rng.integers(0, 10, (200, 1)).astype(np.float32)
+
+    env = ag.VariableEnvironment()
+    set_mode(env, mode)
+    W.cnn_mnist_init(env, np.random.default_rng(0))
+
+    def body(g):
+        taps = {}
+        loss, logits = W.cnn_mnist_loss(ag, g, train=True, taps=taps)
+        params, grads = ag.optimizers.grad_helper([loss], g.default_namespace())
+        masks = [ag.nth_tensor(taps["drop%d" % i], 1) for i in range(3)]
+        r = g.evaluator().push(loss).push(logits).extend(grads).extend(masks).feed("x", x).feed("y", y).run()
+        return [np.asarray(v.unwrap()) for v in r]
+    got = env.run(body)
+    env.close()
+    masks = got[-3:]
+    for m in masks:
+        assert set(np.unique(m)) <= {0.0, 1.0} and abs(float(m.mean()) - 0.75) < 0.02
+
+    renv = OG.VariableEnvironment()
+    W.cnn_mnist_init(renv, np.random.default_rng(0))
+
+    def rbody(g):
+        loss, logits = W.cnn_mnist_loss(OG, g, train=True, masks=masks)
+        params, grads = OG.optimizers.grad_helper([loss], g.default_namespace())
+        return [np.asarray(v.unwrap()) for v in g.evaluator().push(loss).push(logits).extend(grads).feed("x", x).feed("y", y).run()]
+    ref = renv.run(rbody)
+    assert len(ref) == 8
+    tol = 2e-5 if mode == 0 else 1e-2
+    for k, (a, b) in enumerate(zip(got[:8], ref)):
+        if mode == 0 or k < 2:
+            assert rel(a, b) <= tol, (k, a.shape, rel(a, b))
+        else:
+            assert rel_l2(a, b) <= 5e-2, (k, a.shape, rel_l2(a, b))
+
+
+# ------------------------------------------------------------------------------------------------ LSTM LM at hidden 1024 / vocab 8192 (configs[2])
+@pytest.mark.parametrize("mode", [0, 1], ids=["3xtf32", "tf32"])
+def test_lstm_lm_full_width_matches_oracle(ag, mode):
+    """examples/lstm_lm.rs:18-125 at the benchmarked width (batch 128, hidden 1024, vocab 8192), 9 tokens = 8 unrolled steps, so the
+    evaluator's row-stacked x*wx / h*w_pred products, the long-K weight-gradient GEMMs, the stacked cross-entropy and the fused cell
+    programs all engage: loss and the five parameter gradients."""
+    from rust_autograd_b200 import workloads as W
+    D, V, S, B = 1024, 8192, 9, 128
+    sents = np.random.default_rng(9).integers(0, V, (B, S)).astype(np.float32)
+
+    def run(mod, m):
+        env = mod.VariableEnvironment()
+        if m is not None:
+            set_mode(env, m)
+        W.lstm_init(env, np.random.default_rng(0), D, V, scale=0.05)
+
+        def body(g):
+            loss, _ = W.lstm_loss(mod, g, D, S)
+            vs = [g.variable(k) for k in ("wx", "wh", "b", "lookup_table", "w_pred")]
+            return [np.asarray(r.unwrap()) for r in g.evaluator().push(loss).extend(mod.grad([loss], vs)).feed("sents", sents).run()]
+        try:
+            return env.run(body)
+        finally:
+            env.close()
+    ref, got = run(OG, None), run(ag, mode)
+    assert len(got) == len(ref) == 6
+    for k, (a, b) in enumerate(zip(got, ref)):
+        assert rel(a, b) <= (5e-5 if mode == 0 else 2e-2), (mode, k, a.shape, rel(a, b))
