@@ -383,6 +383,23 @@ def dilated_conv2d(x, w, pad, stride, dilate): return Tensor(x.graph, "Conv2D", 
 def conv2d_transpose(x, w, pad, stride): return dilated_conv2d_transpose(x, w, pad, stride, 1)
 def dilated_conv2d_transpose(x, w, pad, stride, dilate): return Tensor(x.graph, "Conv2DTranspose", [x, w], {"p": (pad, stride, dilate)})
 def max_pool2d(x, pool_size, pad, stride): return Tensor(x.graph, "MaxPool2D", [x], {"size": pool_size, "pad": pad, "stride": stride})
+
+
+# ---- forced discrete decisions (parity-test tooling, not reference API) -------------------------------------------------------------
+# ReLU masks and max-pool argmaxes make a network's gradient a DISCONTINUOUS function of its forward values: one pre-activation within
+# rounding of 0, or two window candidates within rounding of each other, and two correct implementations route a gradient value
+# differently; after the sqrt(N) cancellation inside a filter gradient a single such flip is a 1e-3 relative difference (measured: the
+# f32 C port of the reference against this f64 oracle, VGG stack at 128x128).  The full-size parity tests therefore (1) check that the
+# device's decisions equal the oracle's except at verified near-ties, and (2) compare gradients with the oracle evaluated UNDER THE
+# DEVICE'S DECISIONS, where everything left is rounding.
+def relu_forced(x, mask):
+    """relu with the 0/1 mask given: y = x * mask, dy/dx = mask (activation_ops.rs:154-166 with `greater(x, 0)` replaced by `mask`)"""
+    return Tensor(x.graph, "ReLUForced", [x], {"mask": np.asarray(mask, dtype=R.OUT_DTYPE)})
+
+
+def max_pool2d_forced(x, idx, pool_size, pad, stride):
+    """max_pool2d with the argmax offsets given (flat offsets into the whole input, max_pool2d.rs:61): y = x.flat[idx]; backward unchanged"""
+    return Tensor(x.graph, "MaxPool2DForced", [x], {"size": pool_size, "pad": pad, "stride": stride, "idx": np.asarray(idx).astype(np.int64)})
 def dropout(x, ratio, train, seed=0, mask=None): return Tensor(x.graph, "Dropout", [x], {"ratio": ratio, "train": train, "mask": mask})
 
 
@@ -644,6 +661,8 @@ COMPUTE = {
     "MaxPool2DGrad": lambda n, ins, _: [R.max_pool2d_grad(ins[0], ins[1], n.attrs["size"], n.attrs["pad"], n.attrs["stride"])],
     "MaxPool2DGradGrad": lambda n, ins, _: [R.max_pool2d_grad_grad(ins[0], ins[1], n.attrs["size"], n.attrs["pad"], n.attrs["stride"])],
     "Dropout": _c_dropout, "Update": _c_update,
+    "ReLUForced": lambda n, ins, _: [(np.asarray(ins[0]) * n.attrs["mask"]).astype(R.OUT_DTYPE)],
+    "MaxPool2DForced": lambda n, ins, _: [np.asarray(ins[0]).ravel()[n.attrs["idx"]], n.attrs["idx"].astype(R.OUT_DTYPE)],
 }
 
 
@@ -787,6 +806,8 @@ GRAD = {
     "MaxPool2D": lambda y, gy: [Tensor(y.graph, "MaxPool2DGrad", [gy, nth_tensor(y, 1)], dict(y.attrs))],
     "MaxPool2DGrad": lambda y, gy: [Tensor(y.graph, "MaxPool2DGradGrad", [gy, y.inputs[1]], dict(y.attrs)), None],
     "Dropout": lambda y, gy: [gy * nth_tensor(y, 1)],
+    "ReLUForced": lambda y, gy: [gy * convert_to_tensor(y.attrs["mask"], y.graph)],
+    "MaxPool2DForced": lambda y, gy: [Tensor(y.graph, "MaxPool2DGrad", [gy, nth_tensor(y, 1)], {k: y.attrs[k] for k in ("size", "pad", "stride")})],
 }
 
 

@@ -36,6 +36,14 @@ struct agb_ctx {
   int rank = 0, world = 1;
   bool capturing = false;
   int pinned_graphs = 0;            // live agx_step graphs: the arena must not return blocks to the driver while they exist
+  // Private memory of instantiated graphs.  A CUDA graph keeps the RAW addresses of every arena block its kernels touch; once the
+  // capture ends those blocks would sit in the free list and the next eager allocation could receive one while a replay still writes
+  // it.  Every block handed out during a capture is therefore recorded (`capture_blocks`); agb_graph_end moves them out of the free
+  // list into the graph's reservation (blocks still live at that point follow when they are freed: `reserve_on_free`), and
+  // agb_graph_destroy returns them.
+  std::vector<void*> capture_blocks;
+  struct GraphRes { agb_ctx* ctx; void* exec; std::vector<void*> blocks; };
+  std::unordered_map<void*, GraphRes*> reserve_on_free;
   // live profiler (agb_prof_*): event pairs per profiled entry-point call
   bool prof_on = false;
   struct ProfRec { int cls; cudaEvent_t a, b; double work; };

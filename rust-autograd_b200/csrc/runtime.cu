@@ -4,6 +4,7 @@
 // (`src/variable.rs:152-155`): variables and intermediates live in HBM.
 #include "common.cuh"
 #include <stdarg.h>
+#include <algorithm>
 #include <dlfcn.h>
 
 static thread_local char g_err[1024] = "";
@@ -87,6 +88,7 @@ extern "C" int agb_alloc(agb_ctx* ctx, size_t bytes, void** out) {
     ctx->free_blocks.erase(it);
     ctx->cached_bytes -= got; ctx->live_bytes += got; ctx->is_live[p] = true;
     if (ctx->live_bytes > ctx->peak_bytes) ctx->peak_bytes = ctx->live_bytes;
+    if (ctx->capturing) ctx->capture_blocks.push_back(p);
     *out = p; return AGB_OK;
   }
   AGB_CHECK(!ctx->capturing, AGB_ERR_CUDA, "arena growth during graph capture; run the step eagerly (twice) first");
@@ -109,7 +111,10 @@ extern "C" int agb_free(agb_ctx* ctx, void* ptr) {
   AGB_CHECK(it != ctx->block_size.end(), AGB_ERR_INVALID_DIMS, "agb_free: pointer %p not owned by this context", ptr);
   AGB_CHECK(ctx->is_live[ptr], AGB_ERR_INVALID_DIMS, "agb_free: double free of %p", ptr);
   ctx->is_live[ptr] = false;
-  ctx->live_bytes -= it->second; ctx->cached_bytes += it->second;
+  ctx->live_bytes -= it->second;
+  auto rs = ctx->reserve_on_free.find(ptr);
+  if (rs != ctx->reserve_on_free.end()) { rs->second->blocks.push_back(ptr); ctx->reserve_on_free.erase(rs); return AGB_OK; }      // stays private to the graph that uses it
+  ctx->cached_bytes += it->second;
   ctx->free_blocks.insert({it->second, ptr});
   return AGB_OK;
 }
@@ -244,22 +249,46 @@ extern "C" int agb_event_elapsed_ms(void* a, void* b, float* ms) {
 // ---- CUDA graphs ----
 extern "C" int agb_graph_begin(agb_ctx* ctx) {
   AGB_CUDA(cudaStreamBeginCapture(ctx->stream, cudaStreamCaptureModeThreadLocal));
-  ctx->capturing = true; return AGB_OK;
+  ctx->capturing = true; ctx->capture_blocks.clear(); return AGB_OK;
 }
+// The handle owns the executable graph AND the arena blocks its kernels address (see agb_ctx::capture_blocks): they leave the free list
+// here and come back in agb_graph_destroy, so no later allocation can alias memory a replay writes.
 extern "C" int agb_graph_end(agb_ctx* ctx, void** graph_exec) {
   cudaGraph_t g = nullptr; ctx->capturing = false;
-  if (graph_exec == nullptr) { cudaStreamEndCapture(ctx->stream, &g); if (g) cudaGraphDestroy(g); cudaGetLastError(); return AGB_OK; }     // abort
+  if (graph_exec == nullptr) { cudaStreamEndCapture(ctx->stream, &g); if (g) cudaGraphDestroy(g); cudaGetLastError(); ctx->capture_blocks.clear(); return AGB_OK; }     // abort
   AGB_CUDA(cudaStreamEndCapture(ctx->stream, &g));
   cudaGraphExec_t ge = nullptr;
-  AGB_CUDA(cudaGraphInstantiate(&ge, g, 0));
+  cudaError_t e = cudaGraphInstantiate(&ge, g, 0);
   cudaGraphDestroy(g);
-  *graph_exec = ge; return AGB_OK;
+  if (e != cudaSuccess) { ctx->capture_blocks.clear(); return agb_cuda_fail(e, "cudaGraphInstantiate", __FILE__, __LINE__); }
+  auto* res = new agb_ctx::GraphRes{ctx, (void*)ge, {}};
+  std::sort(ctx->capture_blocks.begin(), ctx->capture_blocks.end());
+  ctx->capture_blocks.erase(std::unique(ctx->capture_blocks.begin(), ctx->capture_blocks.end()), ctx->capture_blocks.end());
+  for (void* p : ctx->capture_blocks) {
+    if (ctx->reserve_on_free.count(p)) continue;                                  // already promised to an older graph
+    if (ctx->is_live[p]) { ctx->reserve_on_free[p] = res; continue; }            // still held by the caller: joins the reservation when freed
+    const size_t sz = ctx->block_size[p];
+    auto range = ctx->free_blocks.equal_range(sz);
+    for (auto it = range.first; it != range.second; ++it) if (it->second == p) { ctx->free_blocks.erase(it); ctx->cached_bytes -= sz; res->blocks.push_back(p); break; }
+  }
+  ctx->capture_blocks.clear();
+  *graph_exec = res; return AGB_OK;
 }
 extern "C" int agb_arena_pin(agb_ctx* ctx, int delta) { ctx->pinned_graphs += delta; if (ctx->pinned_graphs < 0) ctx->pinned_graphs = 0; return AGB_OK; }
 extern "C" int agb_graph_launch(agb_ctx* ctx, void* graph_exec) {
-  AGB_CUDA(cudaGraphLaunch((cudaGraphExec_t)graph_exec, ctx->stream)); return AGB_OK;
+  AGB_CUDA(cudaGraphLaunch((cudaGraphExec_t)((agb_ctx::GraphRes*)graph_exec)->exec, ctx->stream)); return AGB_OK;
 }
-extern "C" int agb_graph_destroy(void* graph_exec) { AGB_CUDA(cudaGraphExecDestroy((cudaGraphExec_t)graph_exec)); return AGB_OK; }
+extern "C" int agb_graph_destroy(void* graph_exec) {
+  if (!graph_exec) return AGB_OK;
+  auto* res = (agb_ctx::GraphRes*)graph_exec; agb_ctx* ctx = res->ctx;
+  cudaStreamSynchronize(ctx->stream);                                             // a replay may still be running on the blocks given back below
+  cudaError_t e = cudaGraphExecDestroy((cudaGraphExec_t)res->exec);
+  for (auto it = ctx->reserve_on_free.begin(); it != ctx->reserve_on_free.end();) { if (it->second == res) it = ctx->reserve_on_free.erase(it); else ++it; }
+  for (void* p : res->blocks) { const size_t sz = ctx->block_size[p]; ctx->cached_bytes += sz; ctx->free_blocks.insert({sz, p}); }
+  delete res;
+  if (e != cudaSuccess) return agb_cuda_fail(e, "cudaGraphExecDestroy", __FILE__, __LINE__);
+  return AGB_OK;
+}
 
 // ---- NCCL (dlopen'ed so the library loads on boxes without it; torch's bundled copy is reused when
 //      torch is already imported in the process) ----

@@ -112,18 +112,24 @@ def vgg_init(env, rng, size=128, classes=10, layers=VGG_LAYERS):
     return c_last * h * h
 
 
-def vgg_loss(T, g, size=128, layers=VGG_LAYERS, taps=None):
-    """`taps` (a dict) collects the max-pool nodes: parity tests compare their argmax outputs (nth_tensor(p, 1)) bit for bit."""
+def vgg_loss(T, g, size=128, layers=VGG_LAYERS, taps=None, forced=None):
+    """`taps` (a dict) collects the ReLU and max-pool nodes ("relu%d", "pool%d") so parity tests can read the activations and the argmax
+    outputs (nth_tensor(p, 1)).  `forced` (oracle only: {"relu%d": 0/1 mask, "pool%d": argmax offsets}) evaluates the network under given
+    discrete decisions (oracle/ref_graph.py relu_forced / max_pool2d_forced)."""
     x, y = g.placeholder("x", [-1, 3, size, size]), g.placeholder("y", [-1, 1])
-    h, i, c_last, t = size, 0, 3, x
+    h, i, c_last, t, n_pool = size, 0, 3, x, 0
     for l in layers:
         if l == "pool":
-            t = T.max_pool2d(t, 2, 0, 2)
+            t = T.max_pool2d(t, 2, 0, 2) if forced is None else T.max_pool2d_forced(t, forced["pool%d" % n_pool], 2, 0, 2)
             if taps is not None:
-                taps["pool%d" % len(taps)] = t
+                taps["pool%d" % n_pool] = t
             h //= 2
+            n_pool += 1
             continue
-        t = T.relu(T.conv2d(t, g.variable("conv%d_w" % i), 1, 1) + g.variable("conv%d_b" % i))
+        z = T.conv2d(t, g.variable("conv%d_w" % i), 1, 1) + g.variable("conv%d_b" % i)
+        t = T.relu(z) if forced is None else T.relu_forced(z, forced["relu%d" % i])
+        if taps is not None:
+            taps["relu%d" % i] = t
         i, c_last = i + 1, l[1]
     logits = T.matmul(T.reshape(t, [-1, c_last * h * h]), g.variable("fc_w")) + g.variable("fc_b")
     return T.reduce_mean(T.sparse_softmax_cross_entropy(logits, y), [0], False), logits

@@ -38,63 +38,36 @@ def set_mode(env, mode):
 
 
 # ------------------------------------------------------------------------------------------------ VGG stack at the bench geometry
-def _vgg_run(mod, mode, x, y):
-    from rust_autograd_b200 import workloads as W
-    env = mod.VariableEnvironment()
-    if mode is not None:
-        set_mode(env, mode)
-    W.vgg_init(env, np.random.default_rng(0))
-
-    def body(g):
-        taps = {}
-        loss, logits = W.vgg_loss(mod, g, taps=taps)
-        params, grads = mod.optimizers.grad_helper([loss], g.default_namespace())
-        pools = [taps[k] for k in sorted(taps)]
-        idx = [mod.nth_tensor(p, 1) for p in pools]
-        out = g.evaluator().push(loss).push(logits).extend(grads).extend(pools).extend(idx).feed("x", x).feed("y", y).run()
-        return [np.asarray(r.unwrap()) for r in out], len(grads), len(pools)
-    try:
-        return env.run(body)
-    finally:
-        env.close()
-
-
-@pytest.fixture(scope="module")
-def vgg_reference():
-    rng = np.random.default_rng(3)
-    x = rng.standard_normal((8, 3, 128, 128)).astype(np.float32)
-    y = rng.integers(0, 10, (8, 1)).astype(np.float32)
-    return x, y, _vgg_run(OG, None, x, y)
+_VGG_CACHE = {}
 
 
 @pytest.mark.parametrize("mode", [0, 1], ids=["3xtf32", "tf32"])
-def test_vgg_bench_geometry_matches_oracle(ag, vgg_reference, mode):
-    """workloads.vgg_loss at 3x128x128 (the bench's graph: examples/cnn_mnist.rs:36-51 widened to configs[3]), batch 8: loss, logits, all
-    16 parameter gradients, the three pooled maps and their argmax indices (max_pool2d.rs:21-88)."""
-    x, y, (ref, ng, npool) = vgg_reference
-    got, ng2, npool2 = _vgg_run(ag, mode, x, y)
-    assert (ng, npool) == (ng2, npool2) == (16, 3) and len(got) == len(ref)
+def test_vgg_bench_geometry_matches_oracle(ag, mode):
+    """workloads.vgg_loss at 3x128x128 (the bench's graph: examples/cnn_mnist.rs:36-51 widened to configs[3]), batch 8, through the protocol
+    of oracle/parity.py: (1) every ReLU mask and pool argmax (max_pool2d.rs:21-88) equals the oracle's except at verified near-ties;
+    (2) loss, logits and all 16 parameter gradients equal the oracle evaluated under the device's decisions.  The device run whose
+    gradients are compared requests exactly what a training step requests, so conv_rows + fused pool epilogue, conv_cols, the 256-wide
+    per-tap tiles, the all-taps filter gradient and the masked dgrad with bias side sums are the kernels under test."""
+    from oracle import parity as P
+    rng = np.random.default_rng(3)
+    x = rng.standard_normal((8, 3, 128, 128)).astype(np.float32)
+    y = rng.integers(0, 10, (8, 1)).astype(np.float32)
+    res, _VGG_CACHE["ref"] = P.vgg_parity(ag, set_mode, mode, x, y, ref_unforced=_VGG_CACHE.get("ref"))
     tol = 2e-5 if mode == 0 else 1e-2
-    assert rel(got[0], ref[0]) <= tol and rel(got[1], ref[1]) <= tol, (rel(got[0], ref[0]), rel(got[1], ref[1]))
-    for k in range(2, 2 + ng):
-        if mode == 0:
-            assert rel(got[k], ref[k]) <= tol, (k, got[k].shape, rel(got[k], ref[k]))
-        else:
-            assert rel_l2(got[k], ref[k]) <= 1e-1, (k, got[k].shape, rel_l2(got[k], ref[k]))
-    for k in range(npool):
-        pv, pr = got[2 + ng + k], ref[2 + ng + k]
-        iv, ir = got[2 + ng + npool + k], ref[2 + ng + npool + k]
-        assert rel(pv, pr) <= tol, (k, rel(pv, pr))
-        bad = iv != ir
-        frac = float(bad.mean())
-        assert frac <= (1e-4 if mode == 0 else 2e-2), (k, frac)
-        if bad.any():          # every differing argmax is a near-tie: the winners' values agree
-            assert float(np.abs(pv[bad].astype(np.float64) - pr[bad]).max()) <= (1e-5 if mode == 0 else 1e-2) * float(np.abs(pr).max()), k
+    assert res["forward_independent_of_targets"]
+    d = res["decisions"]
+    assert d["mismatches_are_near_ties"], d
+    assert d["relu_mismatch_frac"] <= (1e-5 if mode == 0 else 5e-3) and d["pool_mismatch_frac"] <= (1e-4 if mode == 0 else 2e-2), d
+    assert res["loss_rel"] <= tol and res["logits_rel"] <= tol, res
+    assert len(res["grad_rel"]) == 16 and res["max_grad_rel"] <= tol, res["grad_rel"]
 
 
-def test_vgg_training_steps_match_oracle(ag):
-    """Three Adam steps of the bench graph (64x64 images, batch 4: the oracle does this in seconds): per-step losses and every
-    variable incl. optimizer state after the last step (optimizers/mod.rs:66-82, adam.rs:11-58)."""
+def test_vgg_training_steps_track_oracle(ag):
+    """Three Adam steps of the bench graph (64x64 images, batch 4: the oracle does this in seconds; optimizers/mod.rs:66-82, adam.rs:11-58).
+    The per-step losses are continuous in the weights and must agree to 1e-4.  The weights themselves are compared in relative L2: a single
+    near-tie decision (see oracle/parity.py) changes the sign of a few near-zero gradient entries, and Adam's normalised first steps move
+    such an entry by +-alpha regardless of its size, so an entry-wise bound tighter than 2 * alpha * steps is not a property of the
+    algorithm; bit-level Adam parity incl. state is pinned on smooth graphs (test_optimizers_match_oracle, test_kernels_gpu adam tests)."""
     from rust_autograd_b200 import workloads as W
     rng = np.random.default_rng(7)
     xs = [rng.standard_normal((4, 3, 64, 64)).astype(np.float32) for _ in range(3)]
@@ -114,18 +87,22 @@ def test_vgg_training_steps_match_oracle(ag):
                 r = g.evaluator().push(loss).push(adam.get_update_op(params, grads, g)).feed("x", x).feed("y", y).run()
                 losses.append(float(np.asarray(r[0].unwrap()).ravel()[0]))
             env.run(step)
-        n = len(env.default_namespace().current_var_ids()) + len(env.namespace("adam").current_var_ids())
+        n_w = len(env.default_namespace().current_var_ids())
+        n = n_w + len(env.namespace("adam").current_var_ids())
         out = [np.asarray(env.get_array_by_id(i)).copy() for i in range(n)]
         env.close()
-        return losses, out
-    l_ref, v_ref = train(OG, None)
-    l_got, v_got = train(ag, 0)
-    assert np.allclose(l_got, l_ref, rtol=2e-5, atol=0), (l_got, l_ref)
+        return losses, out, n_w
+    l_ref, v_ref, n_w = train(OG, None)
+    l_got, v_got, _ = train(ag, 0)
+    assert np.allclose(l_got, l_ref, rtol=1e-4, atol=0), (l_got, l_ref)
     assert len(v_got) == len(v_ref)
     for k, (a, b) in enumerate(zip(v_got, v_ref)):
-        # Adam's first steps move every weight by ~alpha * g / (|g| + eps): entries whose gradient is ~eps-sized amplify a 1e-6 gradient
-        # difference, so the bound is on the update relative to alpha (1e-3), not on the weight's magnitude alone
-        assert float(np.abs(a.astype(np.float64) - b).max()) <= 2e-5 * max(float(np.abs(b).max()), 1.0) + 2e-5, (k, a.shape)
+        if b.size == 1:                                   # the "{vid}t" step counters: exact
+            assert np.array_equal(a, b), k
+        elif k < n_w:                                     # weights: every entry within the three steps' travel, and close in L2
+            assert float(np.abs(a.astype(np.float64) - b).max()) <= 6.1e-3 and rel_l2(a, b) <= 2e-3, (k, a.shape, rel_l2(a, b))
+        else:                                             # Adam moments: linear in the gradients
+            assert rel_l2(a, b) <= 2e-2, (k, a.shape, rel_l2(a, b))
 
 
 # ------------------------------------------------------------------------------------------------ CNN-MNIST at batch 200 (configs[1])

@@ -116,3 +116,16 @@ def test_oracle_hessian_vector_product_setdiff_map():
     assert np.allclose(hv, fd, rtol=1e-3)
     assert np.asarray(sd).tolist() == [2., 4., 6.]
     assert np.allclose(mp, (x0 * 2.0)[::-1] + 1.0, rtol=1e-6)
+
+
+def test_parity_protocol_is_self_consistent():
+    """oracle/parity.py with the oracle standing in for the device: its own decisions forced back in reproduce the unforced run exactly,
+    so any difference the GPU tests see under forced decisions is the device's rounding, not the protocol."""
+    import numpy as np
+    from oracle import parity as P, ref_graph as OG
+    rng = np.random.default_rng(3)
+    x = rng.standard_normal((2, 3, 32, 32)).astype(np.float32)
+    y = rng.integers(0, 10, (2, 1)).astype(np.float32)
+    res, _ = P.vgg_parity(OG, lambda env, m: None, 0, x, y, size=32)
+    assert res["max_grad_rel"] == 0.0 and res["loss_rel"] == 0.0 and res["max_grad_rel_unforced"] == 0.0
+    assert res["decisions"] == {"relu_mismatch_frac": 0.0, "pool_mismatch_frac": 0.0, "mismatches_are_near_ties": True}
