@@ -5,7 +5,6 @@
 #pragma once
 #include "common.cuh"
 #include <cuda.h>
-#include <stdlib.h>
 
 // ------------------------------------------------------------------ host: tensor maps
 typedef CUresult (*PFN_encodeTiled)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
@@ -142,18 +141,10 @@ __host__ __device__ constexpr uint32_t umma_idesc_tf32(int M, int N, int a_mn_ma
 __device__ __forceinline__ uint64_t umma_desc_kmajor(uint32_t tile_saddr, int kstep /*0..3*/) {
   return umma_smem_desc(tile_saddr + kstep * 32, 16, 1024);
 }
-struct MnDescCfg { uint32_t lbo, sbo, layout, kadv; };     // bring-up knob (AGB_MN_VARIANT); defaults = the documented layout
+struct MnDescCfg { uint32_t lbo, sbo, layout, kadv; };     // MN-major operand descriptor fields (bytes): LBO between 32-mn boxes, SBO between 4-k-row atoms, layout 128B_BASE32B, bytes per K = 8 step
 static inline MnDescCfg agb_mn_cfg(bool* atom32 = nullptr) {
-  static MnDescCfg c = {4096, 512, 1, 1024}; static bool a32 = true; static bool init = false;
-  if (!init) {
-    init = true;
-    if (const char* e = getenv("AGB_MN_VARIANT")) {
-      unsigned l, s, t, k, a;
-      if (sscanf(e, "%u,%u,%u,%u,%u", &l, &s, &t, &k, &a) == 5) { c = {l, s, t, k}; a32 = a != 0; }
-    }
-  }
-  if (atom32) *atom32 = a32;
-  return c;
+  if (atom32) *atom32 = true;                             // tensor maps of MN-major operands use SWIZZLE_128B_ATOM_32B
+  return MnDescCfg{4096, 512, 1, 1024};
 }
 __device__ __forceinline__ uint64_t umma_desc_mnmajor(uint32_t tile_saddr, int kstep /*0..3*/, MnDescCfg c) {
   return umma_smem_desc(tile_saddr + kstep * c.kadv, c.lbo, c.sbo, c.layout);

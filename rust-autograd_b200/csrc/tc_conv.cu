@@ -24,13 +24,17 @@
 
 // ------------------------------------------------------------------------------------------------ filter repack
 // mode 0 (fprop): wr[t][o][c] = w[o][c][t];  mode 1 (dgrad): wr[T-1-t][c][o] = w[o][c][t]   (rows = output channel of the GEMM)
-__global__ void __launch_bounds__(256) repack_filter_kernel(const float* __restrict__ w, float* __restrict__ wr, int O, int C, int T, int mode) {
+// wr_lo != nullptr (3xTF32): the filter arrives pre-split — wr = rna_tf32(w), wr_lo = rna_tf32(w - wr) in the same layout — so the per-tap
+// kernel streams both planes by TMA and splits only the activations in shared memory (a round-to-nearest split on this side keeps the
+// dropped lo*lo term free of a sign bias, see tc_tile.cuh).
+__global__ void __launch_bounds__(256) repack_filter_kernel(const float* __restrict__ w, float* __restrict__ wr, float* __restrict__ wr_lo, int O, int C, int T, int mode) {
   int64_t n = (int64_t)O * C * T;
   for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
     int t = (int)(i % T); int64_t r = i / T; int c = (int)(r % C); int o = (int)(r / C);
     float v = __ldg(w + i);
-    if (mode == 0) wr[((int64_t)t * O + o) * C + c] = v;
-    else wr[((int64_t)(T - 1 - t) * C + c) * O + o] = v;
+    const int64_t d = mode == 0 ? ((int64_t)t * O + o) * C + c : ((int64_t)(T - 1 - t) * C + c) * O + o;
+    if (wr_lo != nullptr) { const float h = tf32_rna(v); wr[d] = h; wr_lo[d] = tf32_rna(v - h); }
+    else wr[d] = v;
   }
 }
 
@@ -39,12 +43,12 @@ __global__ void __launch_bounds__(256) repack_filter_kernel(const float* __restr
 // MT_ = 2: the CTA owns an 8x32 pixel patch = two 128-lane M-tiles (rows 0-3 / 4-7, ONE {32 c, 32 w, 8 h} box per k-block) that
 // share every filter tile: 1.33x (TN 128) / 1.5x (TN 256) fewer bytes through L2 -> smem per output, the bound of these kernels.
 template <int TN_, bool SPLIT_, int MT_ = 1> struct ConvFpropPol {
-  static constexpr int TN = TN_, MT = MT_; static constexpr bool SPLIT = SPLIT_, P_MN = false, Q_MN = false;
+  static constexpr int TN = TN_, MT = MT_; static constexpr bool SPLIT = SPLIT_, P_MN = false, Q_MN = false, Q_PRESPLIT = SPLIT_;
   static constexpr int OCC = (SPLIT_ || TN_ > 128 || MT_ > 1) ? 1 : 2;
   // The 128 lanes of an M-tile are a {bw w, bh h, bb images} pixel box (TMA writes box elements in exactly that order): 32x4x1 for
   // maps at least 32 wide; narrow maps take whole rows and, when a whole image is smaller than the tile, several images
   // (14x14 -> 14x9x1, 7x7 -> 7x7x2).  Lanes past bw*bh*bb read stale shared memory and are never stored.
-  struct Params { CUtensorMap tmX, tmW; float* y; const float* bias; const float* mask; float* csum; int relu; int B, Cout, yh, yw, stride, tiles_x, tiles_y, cblocks, taps;
+  struct Params { CUtensorMap tmX, tmW, tmWlo; float* y; const float* bias; const float* mask; float* csum; int relu; int B, Cout, yh, yw, stride, tiles_x, tiles_y, cblocks, taps;
                   int bw, bh, bb; uint32_t p_bytes; MnDescCfg mnc;
                   // tap k of the k-loop: input box origin = tile origin * stride + (dx[k], dy[k]), filter slice wt[k] of the repacked filter
                   short dy[AGB_CONV_MAX_TAPS], dx[AGB_CONV_MAX_TAPS], wt[AGB_CONV_MAX_TAPS];
@@ -69,11 +73,15 @@ template <int TN_, bool SPLIT_, int MT_ = 1> struct ConvFpropPol {
     return bi < p.bb && b < p.B && oy < p.yh && ox < p.yw;
   }
   __device__ static int num_kblocks(const Params& p, const Tile&) { return p.taps * p.cblocks; }
-  __device__ static void prefetch(const Params& p) { tma_prefetch_desc(&p.tmX); tma_prefetch_desc(&p.tmW); }
+  __device__ static void prefetch(const Params& p) { tma_prefetch_desc(&p.tmX); tma_prefetch_desc(&p.tmW); if (SPLIT) tma_prefetch_desc(&p.tmWlo); }
   __device__ static void load(const Params& p, const Tile& t, int kb, uint8_t* pP, uint8_t* pQ, uint64_t* bar) {
     const int tap = kb / p.cblocks, cb = kb - tap * p.cblocks;
     tma_load_4d(pP, &p.tmX, bar, cb * 32, t.ox0 * p.stride + p.dx[tap], t.oy0 * p.stride + p.dy[tap], t.b);     // dims {c, w, h, b}; a strided conv walks
     tma_load_3d(pQ, &p.tmW, bar, cb * 32, t.o0, p.wt[tap]);                                                      // the box with element stride s
+  }
+  __device__ static void load_q_lo(const Params& p, const Tile& t, int kb, uint8_t* pQlo, uint64_t* bar) {          // 3xTF32: the pre-split filter's low plane
+    const int tap = kb / p.cblocks, cb = kb - tap * p.cblocks;
+    tma_load_3d(pQlo, &p.tmWlo, bar, cb * 32, t.o0, p.wt[tap]);
   }
   // dgrad + ReLU backward of the layer below: bit j of pre[c] = (mask_src[pixel, o0 + 32c + j] > 0).  Read while the MMAs run, so the
   // strided (one pixel per thread) loads cost no epilogue latency; default-cached so both halves of a 32-byte sector are used.
@@ -156,7 +164,7 @@ template <int TN_, bool SPLIT_, int MT_ = 1> struct ConvFpropPol {
 // MT_ = 2 (non-PAIR): the CTA owns two (tap, 128-channel tile) units — two M-tiles that share every gy tile, so gy is pulled from
 // L2 half as often (the TN = 256 wgrad moved 48 KB per 4 MMAs: bound by L2 -> smem ingest at 43 % tensor activity).
 template <int TN_, bool SPLIT_, bool PAIR_, int MT_ = 1> struct ConvWgradPol {
-  static constexpr int TN = TN_, MT = MT_; static constexpr bool SPLIT = SPLIT_, P_MN = true, Q_MN = true;
+  static constexpr int TN = TN_, MT = MT_; static constexpr bool SPLIT = SPLIT_, P_MN = true, Q_MN = true, Q_PRESPLIT = false;
   static constexpr int OCC = (SPLIT_ || TN_ > 128 || MT_ > 1) ? 1 : 2;
   static_assert(!(PAIR_ && MT_ > 1), "tap pairing within one M-tile and two M-tiles are alternatives");
   struct Params { CUtensorMap tmX, tmG; float* gw; int C, O, T, kw, pad, dil, stride, yh, xblocks, kb_total, kb_per_split; MnDescCfg mnc; };
@@ -261,6 +269,8 @@ static int fprop_launch(agb_ctx* ctx, const float* x, const float* wr, float* y,
     uint64_t str[2] = {(uint64_t)Cin * 4, (uint64_t)Cin * Cout * 4};
     uint32_t box[3] = {32, (uint32_t)TN, 1};
     AGB_TRY(agb_make_tmap(&p.tmW, wr, 3, dims, str, box, false));
+    if (SPLIT) AGB_TRY(agb_make_tmap(&p.tmWlo, wr + (size_t)kh * kw * Cout * Cin, 3, dims, str, box, false));      // the low plane follows the repacked filter (repack_filter_kernel)
+    else p.tmWlo = p.tmW;
   }
   p.y = y; p.bias = bias; p.mask = mask; p.csum = csum; p.relu = relu; p.Cout = Cout; p.yh = yh; p.yw = yw;
   p.tiles_x = (yw + bw - 1) / bw; p.tiles_y = (yh + bh * MT - 1) / (bh * MT); p.cblocks = (Cin + 31) / 32; p.mnc = agb_mn_cfg();
@@ -288,16 +298,17 @@ int agb_tc_conv_fprop(agb_ctx* ctx, int mode, const float* x, const float* w, fl
   if (yh < 1 || yw < 1 || stride < 1 || stride > 4 || (stride > 1 && flip_transpose) || !agb_tc_conv_eligible(C, O, kh, kw, 1, yw)) return AGB_ERR_UNSUPPORTED;
   if ((((uintptr_t)x | (uintptr_t)y) & 15) != 0) return AGB_ERR_UNSUPPORTED;
   const int T = kh * kw;
+  const bool split = mode == AGB_MATH_3XTF32;
   float* wr = nullptr;
-  AGB_TRY(agb_scratch(ctx, (size_t)T * O * C * sizeof(float), (void**)&wr));
+  AGB_TRY(agb_scratch(ctx, (size_t)T * O * C * sizeof(float) * (split ? 2 : 1), (void**)&wr));
   {
     int64_t n = (int64_t)O * C * T;
+    float* wr_lo = split ? wr + n : nullptr;
     // fprop: w is [O][C][T] -> wr[t][O][C];  dgrad: w is [C(in)][O(out)][T] -> wr[T-1-t][O(out)][C(in)]
-    if (!flip_transpose) repack_filter_kernel<<<agb_grid_for(n, 256, ctx->sm_count, 4), 256, 0, ctx->stream>>>(w, wr, O, C, T, 0);
-    else repack_filter_kernel<<<agb_grid_for(n, 256, ctx->sm_count, 4), 256, 0, ctx->stream>>>(w, wr, C, O, T, 1);
+    if (!flip_transpose) repack_filter_kernel<<<agb_grid_for(n, 256, ctx->sm_count, 4), 256, 0, ctx->stream>>>(w, wr, wr_lo, O, C, T, 0);
+    else repack_filter_kernel<<<agb_grid_for(n, 256, ctx->sm_count, 4), 256, 0, ctx->stream>>>(w, wr, wr_lo, C, O, T, 1);
     AGB_LAUNCHED(ctx);
   }
-  const bool split = mode == AGB_MATH_3XTF32;
   if ((split || stride > 1) && pool_y != nullptr) return AGB_ERR_UNSUPPORTED;
   if (!split && stride == 1) {       // wide feature maps: persistent halo-reusing kernel (tc_conv_rows.cu), 3x less L2 -> smem traffic
     int r = agb_tc_conv_rows(ctx, x, wr, y, B, C, H, W, O, yh, yw, kh, kw, epad, dil, bias, relu, mask, csum, pool_y, pool_idx);
@@ -352,7 +363,7 @@ int agb_tc_conv_dgrad_strided(agb_ctx* ctx, int mode, const float* gy, const flo
   AGB_TRY(agb_scratch(ctx, (size_t)T * O * C * sizeof(float), (void**)&wr));
   {
     int64_t n = (int64_t)O * C * T;
-    repack_filter_kernel<<<agb_grid_for(n, 256, ctx->sm_count, 4), 256, 0, ctx->stream>>>(w, wr, O, C, T, 1);      // wr[T-1-t][c][o]
+    repack_filter_kernel<<<agb_grid_for(n, 256, ctx->sm_count, 4), 256, 0, ctx->stream>>>(w, wr, nullptr, O, C, T, 1);      // wr[T-1-t][c][o]
     AGB_LAUNCHED(ctx);
   }
   if (empty_phase) AGB_TRY(agb_memset0(ctx, gx, (size_t)B * H * W * C * sizeof(float)));                              // filter smaller than the stride: untouched pixels are 0

@@ -12,21 +12,21 @@
 // Both operand majors are supported natively (no transposed copies): a K-major tile is one TMA box
 // [rows x 32 k]; an MN-major tile is rows/32 boxes of [32 k x 32 rows] (UMMA MN-major SWIZZLE_128B canonical layout).
 //
-// 3xTF32 (f32-faithful) mode: four extra warps split every landed tile in place into hi = rna_tf32(x) and
-// lo = rna_tf32(x - hi) (second smem buffer), then the issuing thread runs lo*hi + hi*lo + hi*hi; partial sums are
-// promoted to fp32 registers every 256 k (tc_tile.cuh).  The kernel body lives in tc_tile.cuh (shared with tc_conv.cu).
+// 3xTF32 (f32-faithful) mode: four extra warps write lo = rna_tf32(x - trunc_tf32(x)) of every landed tile to a second smem
+// buffer (the tensor core itself truncates the raw tile to hi), then the issuing thread runs lo*hi + hi*lo + hi*hi; partial sums
+// are promoted to fp32 registers every 64 k (tc_tile.cuh).  The kernel bodies live in tc_tile.cuh (shared with tc_conv.cu).
 //
 // Replaces matrixmultiply::sgemm / cblas_sgemm behind MatMul and BatchMatMul
 // (reference src/tensor_ops/dot_ops.rs:383-422, 142-380).
 #include <stdlib.h>
 #include "tc_tile.cuh"
 
-template <int TN_, bool P_MN_, bool Q_MN_, bool SPLIT_> struct GemmPol {
-  static constexpr int TN = TN_, MT = 1; static constexpr bool SPLIT = SPLIT_, P_MN = P_MN_, Q_MN = Q_MN_;
+template <int TN_, bool P_MN_, bool Q_MN_, bool SPLIT_, bool QPRE_ = false> struct GemmPol {
+  static constexpr int TN = TN_, MT = 1; static constexpr bool SPLIT = SPLIT_, P_MN = P_MN_, Q_MN = Q_MN_, Q_PRESPLIT = QPRE_;
   static constexpr int OCC = (SPLIT_ || TN_ > 128) ? 1 : 2;
   // splits > 1: split-K for problems with too few output tiles to fill the machine (e.g. the LSTM's 128 x 1024 x 8192 dgrad GEMM is
   // 8 tiles): grid.z = batch * splits, every CTA reduces kb_per_split k-blocks and adds its partial with red.global.add (C pre-zeroed)
-  struct Params { CUtensorMap tmP, tmQ; float* C; int NL, NC, K; int64_t ldc, bsc; int accumulate; int splits, kb_per_split; MnDescCfg mnc; };
+  struct Params { CUtensorMap tmP, tmQ, tmQlo; float* C; int NL, NC, K; int64_t ldc, bsc; int accumulate; int splits, kb_per_split; MnDescCfg mnc; };
   struct Tile { int lane0, col0, bz, kb0, nkb; };
   __device__ static Tile tile(const Params& p, uint3 blk) {
     const int kb_total = (p.K + TC_BK - 1) / TC_BK;
@@ -36,14 +36,19 @@ template <int TN_, bool P_MN_, bool Q_MN_, bool SPLIT_> struct GemmPol {
   }
   __device__ static int num_kblocks(const Params&, const Tile& t) { return t.nkb; }
   __device__ static uint32_t p_bytes(const Params&, uint32_t full) { return full; }
-  __device__ static void prefetch(const Params& p) { tma_prefetch_desc(&p.tmP); tma_prefetch_desc(&p.tmQ); }
+  __device__ static void prefetch(const Params& p) { tma_prefetch_desc(&p.tmP); tma_prefetch_desc(&p.tmQ); if (QPRE_) tma_prefetch_desc(&p.tmQlo); }
+  __device__ static void load_q(const CUtensorMap* tm, const Tile& t, int kb, uint8_t* pQ, uint64_t* bar) {
+    const int k0 = (t.kb0 + kb) * TC_BK;
+    if (Q_MN) { for (int j = 0; j < TN / 32; j++) tma_load_3d(pQ + j * 4096, tm, bar, t.col0 + 32 * j, k0, t.bz); }
+    else tma_load_3d(pQ, tm, bar, k0, t.col0, t.bz);
+  }
   __device__ static void load(const Params& p, const Tile& t, int kb, uint8_t* pP, uint8_t* pQ, uint64_t* bar) {
     const int k0 = (t.kb0 + kb) * TC_BK;
     if (P_MN) { for (int j = 0; j < TC_LANES / 32; j++) tma_load_3d(pP + j * 4096, &p.tmP, bar, t.lane0 + 32 * j, k0, t.bz); }
     else tma_load_3d(pP, &p.tmP, bar, k0, t.lane0, t.bz);
-    if (Q_MN) { for (int j = 0; j < TN / 32; j++) tma_load_3d(pQ + j * 4096, &p.tmQ, bar, t.col0 + 32 * j, k0, t.bz); }
-    else tma_load_3d(pQ, &p.tmQ, bar, k0, t.col0, t.bz);
+    load_q(&p.tmQ, t, kb, pQ, bar);
   }
+  __device__ static void load_q_lo(const Params& p, const Tile& t, int kb, uint8_t* pQlo, uint64_t* bar) { load_q(&p.tmQlo, t, kb, pQlo, bar); }       // 3xTF32 with the Q operand pre-split in global memory
   // thread `lane` owns C column n = lane0 + lane; v[j] belongs to C row m = col0 + c0 + j: a warp stores 32 consecutive
   // floats of one C row per instruction (128-byte coalesced), no shared-memory staging
   __device__ static void pre_epilogue(const Params&, const Tile&, int, uint32_t*) {}
@@ -83,10 +88,10 @@ static int tc_make_map(CUtensorMap* m, const TcOperand& o, int64_t K, int64_t ba
   return agb_make_tmap(m, o.p, 3, dims, strides, box, mn_major && a32);
 }
 
-template <int TN, bool P_MN, bool Q_MN, bool SPLIT>
-static int tc_launch(agb_ctx* ctx, const CUtensorMap& tmP, const CUtensorMap& tmQ, float* C, int NL, int NC, int K, int64_t ldc, int64_t bsc,
+template <int TN, bool P_MN, bool Q_MN, bool SPLIT, bool QPRE = false>
+static int tc_launch(agb_ctx* ctx, const CUtensorMap& tmP, const CUtensorMap& tmQ, const CUtensorMap* tmQlo, float* C, int NL, int NC, int K, int64_t ldc, int64_t bsc,
                      int64_t batch, int accumulate) {
-  using Pol = GemmPol<TN, P_MN, Q_MN, SPLIT>;
+  using Pol = GemmPol<TN, P_MN, Q_MN, SPLIT, QPRE>;
   const int gx = (NL + TC_LANES - 1) / TC_LANES, gy = (NC + TN - 1) / TN;
   const int kb_total = (K + TC_BK - 1) / TC_BK;
   // split-K when the output tiles cannot fill the machine and there is K to share (>= 4 k-blocks per split)
@@ -100,18 +105,29 @@ static int tc_launch(agb_ctx* ctx, const CUtensorMap& tmP, const CUtensorMap& tm
   int kb_per = (kb_total + splits - 1) / splits; splits = (kb_total + kb_per - 1) / kb_per;
   if ((int64_t)batch * splits > 65535) { splits = 1; kb_per = kb_total; }
   if (splits > 1 && !accumulate) AGB_TRY(agb_memset0(ctx, C, (size_t)batch * NC * NL * sizeof(float)));
-  typename Pol::Params prm{tmP, tmQ, C, NL, NC, K, ldc, bsc, accumulate, splits, kb_per, agb_mn_cfg()};
+  typename Pol::Params prm{tmP, tmQ, tmQlo ? *tmQlo : tmQ, C, NL, NC, K, ldc, bsc, accumulate, splits, kb_per, agb_mn_cfg()};
   dim3 grid(gx, gy, (unsigned)(batch * splits));
   return tc_tile_launch<Pol>(ctx, prm, grid);
 }
 
-template <int TN, bool SPLIT>
-static int tc_dispatch_major(agb_ctx* ctx, bool pmn, bool qmn, const CUtensorMap& tmP, const CUtensorMap& tmQ, float* C, int NL, int NC, int K,
+template <int TN, bool SPLIT, bool QPRE = false>
+static int tc_dispatch_major(agb_ctx* ctx, bool pmn, bool qmn, const CUtensorMap& tmP, const CUtensorMap& tmQ, const CUtensorMap* tmQlo, float* C, int NL, int NC, int K,
                              int64_t ldc, int64_t bsc, int64_t batch, int acc) {
-  if (!pmn && !qmn) return tc_launch<TN, false, false, SPLIT>(ctx, tmP, tmQ, C, NL, NC, K, ldc, bsc, batch, acc);
-  if (!pmn && qmn) return tc_launch<TN, false, true, SPLIT>(ctx, tmP, tmQ, C, NL, NC, K, ldc, bsc, batch, acc);
-  if (pmn && !qmn) return tc_launch<TN, true, false, SPLIT>(ctx, tmP, tmQ, C, NL, NC, K, ldc, bsc, batch, acc);
-  return tc_launch<TN, true, true, SPLIT>(ctx, tmP, tmQ, C, NL, NC, K, ldc, bsc, batch, acc);
+  if (!pmn && !qmn) return tc_launch<TN, false, false, SPLIT, QPRE>(ctx, tmP, tmQ, tmQlo, C, NL, NC, K, ldc, bsc, batch, acc);
+  if (!pmn && qmn) return tc_launch<TN, false, true, SPLIT, QPRE>(ctx, tmP, tmQ, tmQlo, C, NL, NC, K, ldc, bsc, batch, acc);
+  if (pmn && !qmn) return tc_launch<TN, true, false, SPLIT, QPRE>(ctx, tmP, tmQ, tmQlo, C, NL, NC, K, ldc, bsc, batch, acc);
+  return tc_launch<TN, true, true, SPLIT, QPRE>(ctx, tmP, tmQ, tmQlo, C, NL, NC, K, ldc, bsc, batch, acc);
+}
+
+// 3xTF32: hi = rna_tf32(x), lo = rna_tf32(x - hi) planes of a dense operand, written once to scratch when the operand is re-read by
+// enough lane tiles to pay for the pass (12 bytes per element against 48 KB of shared-memory traffic per k-block and CTA saved)
+__global__ void __launch_bounds__(256) presplit_kernel(const float4* __restrict__ x, float4* __restrict__ hi, float4* __restrict__ lo, int64_t n4) {
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n4; i += (int64_t)gridDim.x * blockDim.x) {
+    const float4 v = __ldg(x + i); float4 h, l;
+    h.x = tf32_rna(v.x); h.y = tf32_rna(v.y); h.z = tf32_rna(v.z); h.w = tf32_rna(v.w);
+    l.x = tf32_rna(v.x - h.x); l.y = tf32_rna(v.y - h.y); l.z = tf32_rna(v.z - h.z); l.w = tf32_rna(v.w - h.w);
+    hi[i] = h; lo[i] = l;
+  }
 }
 
 // C[m,n] = op(A)[m,k] . op(B)[k,n];  (rsa, csa) strides of op(A) over (m, k), (rsb, csb) strides of op(B) over (k, n)
@@ -133,10 +149,25 @@ int agb_tc_gemm(agb_ctx* ctx, int mode, const float* A, const float* B, float* C
   r = tc_make_map(&tmQ, Q, K, batch, qmn, TN); if (r != AGB_OK) return r;
   const int acc = beta != 0.0f;
   if (split) {
-    if (TN == 128) return tc_dispatch_major<128, true>(ctx, pmn, qmn, tmP, tmQ, C, (int)N, (int)M, (int)K, N, bsc, batch, acc);
-    return tc_dispatch_major<64, true>(ctx, pmn, qmn, tmP, tmQ, C, (int)N, (int)M, (int)K, N, bsc, batch, acc);
+    // Q = op(A) is re-read by every one of the N/128 lane tiles: pre-split it once in global memory when it is dense and N is large
+    const int64_t qn = M * K * batch;
+    const bool q_dense = qn % 4 == 0 && (batch == 1 || Q.bs == M * K) && (qmn ? (Q.ks == M) : (Q.rs == K));
+    if (q_dense && N >= 512 && qn <= (1ll << 31)) {
+      float* planes = nullptr;
+      AGB_TRY(agb_scratch(ctx, (size_t)qn * 2 * sizeof(float), (void**)&planes));
+      presplit_kernel<<<agb_grid_for(qn / 4, 256, ctx->sm_count, 8), 256, 0, ctx->stream>>>((const float4*)A, (float4*)planes, (float4*)(planes + qn), qn / 4);
+      AGB_LAUNCHED(ctx);
+      CUtensorMap tmQh, tmQl;
+      TcOperand Qh = Q, Ql = Q; Qh.p = planes; Ql.p = planes + qn;
+      r = tc_make_map(&tmQh, Qh, K, batch, qmn, TN); if (r != AGB_OK) return r;
+      r = tc_make_map(&tmQl, Ql, K, batch, qmn, TN); if (r != AGB_OK) return r;
+      if (TN == 128) return tc_dispatch_major<128, true, true>(ctx, pmn, qmn, tmP, tmQh, &tmQl, C, (int)N, (int)M, (int)K, N, bsc, batch, acc);
+      return tc_dispatch_major<64, true, true>(ctx, pmn, qmn, tmP, tmQh, &tmQl, C, (int)N, (int)M, (int)K, N, bsc, batch, acc);
+    }
+    if (TN == 128) return tc_dispatch_major<128, true>(ctx, pmn, qmn, tmP, tmQ, nullptr, C, (int)N, (int)M, (int)K, N, bsc, batch, acc);
+    return tc_dispatch_major<64, true>(ctx, pmn, qmn, tmP, tmQ, nullptr, C, (int)N, (int)M, (int)K, N, bsc, batch, acc);
   }
-  if (TN == 256) return tc_dispatch_major<256, false>(ctx, pmn, qmn, tmP, tmQ, C, (int)N, (int)M, (int)K, N, bsc, batch, acc);
-  if (TN == 128) return tc_dispatch_major<128, false>(ctx, pmn, qmn, tmP, tmQ, C, (int)N, (int)M, (int)K, N, bsc, batch, acc);
-  return tc_dispatch_major<64, false>(ctx, pmn, qmn, tmP, tmQ, C, (int)N, (int)M, (int)K, N, bsc, batch, acc);
+  if (TN == 256) return tc_dispatch_major<256, false>(ctx, pmn, qmn, tmP, tmQ, nullptr, C, (int)N, (int)M, (int)K, N, bsc, batch, acc);
+  if (TN == 128) return tc_dispatch_major<128, false>(ctx, pmn, qmn, tmP, tmQ, nullptr, C, (int)N, (int)M, (int)K, N, bsc, batch, acc);
+  return tc_dispatch_major<64, false>(ctx, pmn, qmn, tmP, tmQ, nullptr, C, (int)N, (int)M, (int)K, N, bsc, batch, acc);
 }

@@ -7,19 +7,29 @@
 //               into a multi-stage mbarrier ring (128-byte swizzled tiles, zero fill out of bounds)
 //   warp 1      allocates TMEM, then ONE thread issues `tcgen05.mma.kind::tf32` (K = 8 per instruction) and
 //               `tcgen05.commit`s ring slots back to the producer and accumulators to the drain warps
-//   warps 2-5   SPLIT (3xTF32) only: split every landed tile in place into hi = rna_tf32(x), lo = rna_tf32(x - hi);
-//               the issuer then runs lo*hi + hi*lo + hi*hi (dropped lo*lo ~ 2^-22)
+//   warps 2-5   SPLIT (3xTF32) only: the tensor core TRUNCATES an fp32 operand to tf32 (the low 13 mantissa bits are ignored), so the
+//               landed tile itself serves as hi = trunc_tf32(x); the splitters only write lo = rna_tf32(x - trunc_tf32(x)) (exact
+//               difference) to a second buffer — one read and ONE write per element, the tile engine's scarce resource in this mode
+//               being shared-memory bandwidth (an N = 128 MMA already reads 128 B/clk).  An operand that is tiny and re-read by many
+//               CTAs (a convolution's repacked filter) arrives pre-split instead: Pol::Q_PRESPLIT, its lo plane is a second TMA load.
+//               The issuer runs lo*hi + hi*lo into one accumulator and hi*hi into another (dropped lo*lo ~ 2^-22): the tensor core
+//               truncates on every accumulate, so keeping the small cross terms out of the main sum leaves it one truncation per
+//               K = 8 step instead of three (measured bias on positive operands, relative to the sum: -2.4e-6 with everything in one
+//               accumulator and 256-k chunks, -1.1e-6 with 64-k chunks; scripts/bias_probe.py)
 //   last 4      drain/epilogue: `tcgen05.ld` the accumulator and hand 32-column strips to the Policy's store functor
 //
 // fp32-faithful accumulation (SPLIT): the tensor core adds into the TMEM accumulator with truncation, which biases long
-// sums toward zero (measured on B200: relative bias ~5e-9 * K, i.e. 1e-4 at K = 16k).  The 3xTF32 mode therefore
-// accumulates at most TC_KC k-blocks (256 k) per TMEM buffer, ping-pongs two buffers, and the drain warps add each finished
-// chunk into fp32 registers with round-to-nearest CUDA-core adds while the tensor core works on the other buffer.
+// sums toward zero (measured on B200: relative bias ~5e-9 * K, i.e. 1e-4 at K = 16k; ~half an ulp of the running sum per MMA,
+// and the two small cross terms of 3xTF32 pay it too).  The bias is coherent across output elements, so a reduction over the
+// GEMM's output (a bias gradient summing 1024 rows) accumulates it: with 256-k chunks the LSTM LM's bias gradient was 1.1e-4 off
+// the oracle while every GEMM output was within 1e-5.  The 3xTF32 mode therefore accumulates at most TC_KC k-blocks (64 k = 24
+// MMAs) per TMEM buffer, ping-pongs two buffers, and the drain warps add each finished chunk into fp32 registers with
+// round-to-nearest CUDA-core adds while the tensor core works on the other buffer.
 #pragma once
 #include "tc_common.cuh"
 
 #define TC_LANES 128
-#define TC_KC 8            // k-blocks per TMEM accumulation chunk in SPLIT mode (8 * 32 = 256 k)
+#define TC_KC 2            // k-blocks per TMEM accumulation chunk in SPLIT mode (2 * 32 = 64 k)
 
 // OCC = CTAs co-resident per SM.  Two co-resident CTAs overlap one CTA's prologue / epilogue (TMEM drain, global stores) with the
 // other's MMA main loop without a persistent tile scheduler; the ring depth is what fits in 1/OCC of the 227 KB shared memory.
@@ -40,7 +50,8 @@ template <int TN, bool SPLIT, int OCC = 1, int MT = 1> struct TcCfg {
 };
 
 // Policy interface:
-//   static constexpr int TN, OCC; static constexpr bool SPLIT, P_MN, Q_MN;
+//   static constexpr int TN, OCC; static constexpr bool SPLIT, P_MN, Q_MN, Q_PRESPLIT;
+//   (Q_PRESPLIT) __device__ static void load_q_lo(const Params&, const Tile&, int kb, uint8_t* pQlo, uint64_t* bar);
 //   struct Params { ... CUtensorMap members ...; MnDescCfg mnc; };
 //   struct Tile { ... };                                               per-CTA coordinates
 //   __device__ static Tile tile(const Params&, uint3 blk);             blk = block coordinates in the logical grid
@@ -49,17 +60,19 @@ template <int TN, bool SPLIT, int OCC = 1, int MT = 1> struct TcCfg {
 //   __device__ static void load(const Params&, const Tile&, int kb, uint8_t* pP, uint8_t* pQ, uint64_t* bar);   one thread
 //   __device__ static void store(const Params&, const Tile&, int lane /*0..127*/, int c0 /*0..TN-32*/, const float* v /*[32]*/);
 template <class Pol>
-__global__ void __launch_bounds__(TcCfg<Pol::TN, Pol::SPLIT, Pol::OCC, Pol::MT>::THREADS, Pol::OCC) tc_tile_kernel(const __grid_constant__ typename Pol::Params prm) {
-  constexpr int TN = Pol::TN; constexpr bool SPLIT = Pol::SPLIT, P_MN = Pol::P_MN, Q_MN = Pol::Q_MN;
+__global__ void __launch_bounds__(TcCfg<Pol::TN, false, Pol::OCC, Pol::MT>::THREADS, Pol::OCC) tc_tile_kernel(const __grid_constant__ typename Pol::Params prm) {
+  // one output tile per CTA, single-pass (TF32) mode: the fallback of the persistent kernel below (AGB_TC_PERSIST=0, > 2^31 tiles)
+  constexpr int TN = Pol::TN; constexpr bool P_MN = Pol::P_MN, Q_MN = Pol::Q_MN;
   constexpr int MT = Pol::MT;
-  using Cfg = TcCfg<TN, SPLIT, Pol::OCC, MT>;
+  static_assert(!Pol::SPLIT, "3xTF32 runs on tc_tile_split_kernel");
+  using Cfg = TcCfg<TN, false, Pol::OCC, MT>;
   constexpr int S = Cfg::STAGES;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
   uint64_t* bars = (uint64_t*)(smem + S * Cfg::STAGE_BYTES);
-  uint64_t* full = bars; uint64_t* ready = bars + S; uint64_t* empty = bars + 2 * S;
-  uint64_t* acc_full = bars + 3 * S; uint64_t* acc_empty = bars + 3 * S + 2;
-  uint32_t* tmem_slot = (uint32_t*)(bars + 3 * S + 4);
+  uint64_t* full = bars; uint64_t* empty = bars + S;
+  uint64_t* acc_full = bars + 2 * S;
+  uint32_t* tmem_slot = (uint32_t*)(bars + 2 * S + 1);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const typename Pol::Tile tl = Pol::tile(prm, blockIdx);
@@ -67,8 +80,8 @@ __global__ void __launch_bounds__(TcCfg<Pol::TN, Pol::SPLIT, Pol::OCC, Pol::MT>:
 
   if (warp == 0 && lane == 0) {
     Pol::prefetch(prm);
-    for (int s = 0; s < S; s++) { mbar_init(&full[s], 1); mbar_init(&ready[s], 128); mbar_init(&empty[s], 1); }
-    for (int b = 0; b < 2; b++) { mbar_init(&acc_full[b], 1); mbar_init(&acc_empty[b], 128); }
+    for (int s = 0; s < S; s++) { mbar_init(&full[s], 1); mbar_init(&empty[s], 1); }
+    mbar_init(&acc_full[0], 1);
     fence_barrier_init();
   }
   if (warp == 1) { tmem_alloc(tmem_slot, Cfg::TMEM_COLS); tmem_relinquish(); }
@@ -104,58 +117,23 @@ __global__ void __launch_bounds__(TcCfg<Pol::TN, Pol::SPLIT, Pol::OCC, Pol::MT>:
     const uint32_t smem0 = smem_u32(smem) >> 4;
     int s = 0; uint32_t ph = 0;
     for (int kb = 0; kb < nk; kb++) {
-      uint32_t tacc = tmem_base; bool first = (kb == 0);
-      if (SPLIT) {
-        const int chunk = kb / TC_KC, buf = chunk & 1;
-        tacc = tmem_base + (uint32_t)(buf * TN);
-        first = (kb % TC_KC) == 0;
-        if (first) { mbar_wait(&acc_empty[buf], (uint32_t)(((chunk >> 1) & 1) ^ 1)); tc_fence_after(); }
-      }
-      mbar_wait(SPLIT ? &ready[s] : &full[s], ph);
+      mbar_wait(&full[s], ph);
       tc_fence_after();
       if (elect_one()) {
         const uint32_t st = smem0 + (uint32_t)s * (Cfg::STAGE_BYTES >> 4);
         const uint32_t aP = st + loP, aQ = st + (Cfg::P_BYTES >> 4) + loQ;
-        const uint32_t aPl = aP + ((Cfg::P_BYTES + Cfg::Q_BYTES) >> 4), aQl = aQ + ((Cfg::P_BYTES + Cfg::Q_BYTES) >> 4);
 #pragma unroll
         for (int k = 0; k < TC_BK / 8; k++) {
-          const uint64_t dP = umma_desc_pack(aP + k * stepP, hiP), dQ = umma_desc_pack(aQ + k * stepQ, hiQ);
-          if (SPLIT) {
-            const uint64_t dPl = umma_desc_pack(aPl + k * stepP, hiP), dQl = umma_desc_pack(aQl + k * stepQ, hiQ);
-            umma_tf32(tacc, dPl, dQ, idesc, !(first && k == 0));
-            umma_tf32(tacc, dP, dQl, idesc, 1);
-            umma_tf32(tacc, dP, dQ, idesc, 1);
-          } else {
+          const uint64_t dQ = umma_desc_pack(aQ + k * stepQ, hiQ);
 #pragma unroll
-            for (int mt = 0; mt < MT; mt++)
-              umma_tf32(tacc + (uint32_t)(mt * TN), umma_desc_pack(aP + (uint32_t)(mt * ((TC_LANES * TC_BK * 4) >> 4)) + k * stepP, hiP), dQ, idesc, !(first && k == 0));
-          }
+          for (int mt = 0; mt < MT; mt++)
+            umma_tf32(tmem_base + (uint32_t)(mt * TN), umma_desc_pack(aP + (uint32_t)(mt * ((TC_LANES * TC_BK * 4) >> 4)) + k * stepP, hiP), dQ, idesc, !(kb == 0 && k == 0));
         }
         umma_commit(&empty[s]);            // ring slot reusable once these MMAs have read it
-        if (SPLIT) { if ((kb % TC_KC) == TC_KC - 1 || kb == nk - 1) umma_commit(&acc_full[(kb / TC_KC) & 1]); }
-        else if (kb == nk - 1) umma_commit(&acc_full[0]);
+        if (kb == nk - 1) umma_commit(&acc_full[0]);
       }
       __syncwarp();
       if (++s == S) { s = 0; ph ^= 1; }
-    }
-  } else if (SPLIT && warp < 6) {
-    // ===================== splitter (3xTF32) =====================
-    const int t = threadIdx.x - 64;        // 0..127
-    for (int kb = 0; kb < nk; kb++) {
-      const int s = kb % S; const uint32_t ph = (kb / S) & 1;
-      mbar_wait(&full[s], ph);
-      float4* hi = (float4*)(smem + s * Cfg::STAGE_BYTES);
-      float4* lo = (float4*)(smem + s * Cfg::STAGE_BYTES + Cfg::P_BYTES + Cfg::Q_BYTES);
-      constexpr int N4 = (Cfg::P_BYTES + Cfg::Q_BYTES) / 16;
-#pragma unroll 4
-      for (int i = t; i < N4; i += 128) {
-        float4 x = hi[i], h, l;
-        h.x = tf32_rna(x.x); h.y = tf32_rna(x.y); h.z = tf32_rna(x.z); h.w = tf32_rna(x.w);
-        l.x = tf32_rna(x.x - h.x); l.y = tf32_rna(x.y - h.y); l.z = tf32_rna(x.z - h.z); l.w = tf32_rna(x.w - h.w);
-        hi[i] = h; lo[i] = l;
-      }
-      fence_proxy_async();               // generic-proxy writes -> visible to the tensor core (async proxy)
-      mbar_arrive(&ready[s]);
     }
   } else {
     // ===================== drain / epilogue =====================
@@ -165,31 +143,7 @@ __global__ void __launch_bounds__(TcCfg<Pol::TN, Pol::SPLIT, Pol::OCC, Pol::MT>:
     // per-thread epilogue side input (e.g. the ReLU mask bits of the dgrad epilogue), fetched while the MMAs are still running
     uint32_t pre[MT * (TN / 32)];
     Pol::pre_epilogue(prm, tl, row, pre);
-    if (SPLIT) {
-      float racc[TN];
-#pragma unroll
-      for (int j = 0; j < TN; j++) racc[j] = 0.0f;
-      const int nchunks = (nk + TC_KC - 1) / TC_KC;
-      for (int c = 0; c < nchunks; c++) {
-        const int buf = c & 1;
-        mbar_wait(&acc_full[buf], (uint32_t)((c >> 1) & 1));
-        tc_fence_after();
-#pragma unroll
-        for (int c0 = 0; c0 < TN; c0 += 32) {
-          float v[32];
-          tmem_ld32(tlane + (uint32_t)(buf * TN + c0), v);
-          tmem_ld_wait();
-#pragma unroll
-          for (int j = 0; j < 32; j++) racc[c0 + j] += v[j];
-        }
-        tc_fence_before();
-        mbar_arrive(&acc_empty[buf]);
-      }
-      if (nk > 0) {
-#pragma unroll
-        for (int c0 = 0; c0 < TN; c0 += 32) Pol::store(prm, tl, 0, row, c0, &racc[c0], pre[c0 / 32]);
-      }
-    } else if (nk > 0) {
+    if (nk > 0) {
       mbar_wait(&acc_full[0], 0);
       tc_fence_after();
 #pragma unroll
@@ -207,6 +161,203 @@ __global__ void __launch_bounds__(TcCfg<Pol::TN, Pol::SPLIT, Pol::OCC, Pol::MT>:
   tc_fence_before();
   __syncthreads();
   if (warp == 1) tmem_dealloc(tmem_base, Cfg::TMEM_COLS);
+}
+
+// ------------------------------------------------------------------------------------------------ 3xTF32 (f32-faithful) persistent kernel
+// Warps: 0 TMA producer, 1 MMA issuer, 2-5 splitters, 6-9 drain.  Persistent over the logical grid like tc_tile_persist_kernel; the two
+// TMEM accumulator buffers ping-pong per CHUNK (TC_KC k-blocks), the chunk counter runs on across tiles, and the drain warps keep the
+// tile's fp32 partial sums in registers (TN <= 128) until its last chunk, then run the Policy's epilogue while the issuer already works
+// on the next tile's first two chunks.
+template <class Pol>
+__global__ void __launch_bounds__(320, 1) tc_tile_split_kernel(const __grid_constant__ typename Pol::Params prm, const uint3 lgrid, const int kc /* k-blocks per TMEM chunk */, const int order) {
+  constexpr int TN = Pol::TN; constexpr bool P_MN = Pol::P_MN, Q_MN = Pol::Q_MN;
+  static_assert(Pol::SPLIT && Pol::MT == 1 && TN <= 128, "3xTF32: one M-tile, TN fp32 partial sums per drain thread");
+  constexpr bool QPRE = Pol::Q_PRESPLIT;                 // Q's lo plane comes from global memory (second TMA load), only P is split here
+  using Cfg = TcCfg<TN, true, 1, 1>;
+  constexpr int S = Cfg::STAGES;
+  constexpr int LO_OFF = Cfg::P_BYTES + Cfg::Q_BYTES;    // stage = [P | Q | P_lo | Q_lo]
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
+  uint64_t* bars = (uint64_t*)(smem + S * Cfg::STAGE_BYTES);
+  uint64_t* full = bars; uint64_t* ready = bars + S; uint64_t* empty = bars + 2 * S;
+  uint64_t* acc_full = bars + 3 * S; uint64_t* acc_empty = bars + 3 * S + 2;
+  uint32_t* tmem_slot = (uint32_t*)(bars + 3 * S + 4);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const uint32_t total = lgrid.x * lgrid.y * lgrid.z;
+
+  if (warp == 0 && lane == 0) {
+    Pol::prefetch(prm);
+    for (int s = 0; s < S; s++) { mbar_init(&full[s], 1); mbar_init(&ready[s], 128); mbar_init(&empty[s], 1); }
+    for (int b = 0; b < 2; b++) { mbar_init(&acc_full[b], 1); mbar_init(&acc_empty[b], 128); }
+    fence_barrier_init();
+  }
+  if (warp == 1) { tmem_alloc(tmem_slot, 4 * TN); tmem_relinquish(); }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+  auto blk_of = [&](uint32_t t) { uint3 b; b.x = t % lgrid.x; const uint32_t r = t / lgrid.x; b.y = r % lgrid.y; b.z = r / lgrid.y; return b; };
+
+  if (warp == 0) {
+    // ===================== TMA producer =====================
+    if (lane == 0) {
+      int s = 0; uint32_t ph = 0;
+      for (uint32_t t = blockIdx.x; t < total; t += gridDim.x) {
+        const typename Pol::Tile tl = Pol::tile(prm, blk_of(t));
+        const int nk = Pol::num_kblocks(prm, tl);
+        for (int kb = 0; kb < nk; kb++) {
+          mbar_wait(&empty[s], ph ^ 1);
+          uint8_t* st = smem + s * Cfg::STAGE_BYTES;
+          mbar_expect_tx(&full[s], Pol::p_bytes(prm, Cfg::P_BYTES) + Cfg::Q_BYTES * (QPRE ? 2 : 1));
+          Pol::load(prm, tl, kb, st, st + Cfg::P_BYTES, &full[s]);
+          if constexpr (QPRE) Pol::load_q_lo(prm, tl, kb, st + LO_OFF + Cfg::P_BYTES, &full[s]);
+          if (++s == S) { s = 0; ph ^= 1; }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ===================== MMA issuer (converged warp, elected lane; see tc_tile_kernel) =====================
+    constexpr uint32_t idesc = umma_idesc_tf32(TC_LANES, TN, P_MN ? 1 : 0, Q_MN ? 1 : 0);
+    const MnDescCfg mnc = prm.mnc;
+    const uint32_t hiK = (1024u >> 4) | (1u << 14) | (2u << 29), loK = (16u >> 4) << 16, stepK = 32u >> 4;
+    const uint32_t hiM = (mnc.sbo >> 4) | (1u << 14) | (mnc.layout << 29), loM = (mnc.lbo >> 4) << 16, stepM = mnc.kadv >> 4;
+    const uint32_t hiP = P_MN ? hiM : hiK, loP = P_MN ? loM : loK, stepP = P_MN ? stepM : stepK;
+    const uint32_t hiQ = Q_MN ? hiM : hiK, loQ = Q_MN ? loM : loK, stepQ = Q_MN ? stepM : stepK;
+    const uint32_t smem0 = smem_u32(smem) >> 4;
+    int s = 0; uint32_t ph = 0, ch = 0, ti = 0;          // ch: chunks issued so far by this CTA (all tiles); ti: tiles
+    for (uint32_t t = blockIdx.x; t < total; t += gridDim.x) {
+      const typename Pol::Tile tl = Pol::tile(prm, blk_of(t));
+      const int nk = Pol::num_kblocks(prm, tl);
+      if (nk <= 0) continue;
+      // TMEM: [main 0 | main 1 | cross 0 | cross 1].  The hi*hi sums ping-pong per chunk; the cross-term sums (2^-11 of the magnitude:
+      // their truncation does not matter) run over the whole tile, one buffer per tile parity.  No barrier of their own: the drain reads
+      // cross(t) before it releases the tile's last main chunk, and tile t+2 cannot start before that release.
+      const uint32_t tcross = tmem_base + (uint32_t)((2 + (ti & 1)) * TN);
+      ti++;
+      for (int kb = 0; kb < nk; kb++) {
+        const bool first = (kb % kc) == 0, last = (kb % kc) == kc - 1 || kb == nk - 1;
+        const uint32_t buf = ch & 1;
+        if (first) { mbar_wait(&acc_empty[buf], ((ch >> 1) & 1) ^ 1); tc_fence_after(); }
+        mbar_wait(&ready[s], ph);
+        tc_fence_after();
+        if (elect_one()) {
+          const uint32_t tacc = tmem_base + buf * (uint32_t)TN;
+          const uint32_t st = smem0 + (uint32_t)s * (Cfg::STAGE_BYTES >> 4);
+          const uint32_t aP = st + loP, aQ = st + (Cfg::P_BYTES >> 4) + loQ;
+          const uint32_t aPl = aP + (LO_OFF >> 4), aQl = aQ + (LO_OFF >> 4);
+          if (order == 0) {
+#pragma unroll
+            for (int k = 0; k < TC_BK / 8; k++) {
+              const uint64_t dP = umma_desc_pack(aP + k * stepP, hiP), dQ = umma_desc_pack(aQ + k * stepQ, hiQ);
+              const uint64_t dPl = umma_desc_pack(aPl + k * stepP, hiP), dQl = umma_desc_pack(aQl + k * stepQ, hiQ);
+              umma_tf32(tcross, dPl, dQ, idesc, !(kb == 0 && k == 0));
+              umma_tf32(tcross, dP, dQl, idesc, 1);
+              umma_tf32(tacc, dP, dQ, idesc, !(first && k == 0));
+            }
+          } else {
+#pragma unroll
+            for (int k = 0; k < TC_BK / 8; k++) umma_tf32(tacc, umma_desc_pack(aP + k * stepP, hiP), umma_desc_pack(aQ + k * stepQ, hiQ), idesc, !(first && k == 0));
+#pragma unroll
+            for (int k = 0; k < TC_BK / 8; k++) {
+              umma_tf32(tcross, umma_desc_pack(aPl + k * stepP, hiP), umma_desc_pack(aQ + k * stepQ, hiQ), idesc, !(kb == 0 && k == 0));
+              umma_tf32(tcross, umma_desc_pack(aP + k * stepP, hiP), umma_desc_pack(aQl + k * stepQ, hiQ), idesc, 1);
+            }
+          }
+          umma_commit(&empty[s]);
+          if (last) umma_commit(&acc_full[buf]);
+        }
+        __syncwarp();
+        if (last) ch++;
+        if (++s == S) { s = 0; ph ^= 1; }
+      }
+    }
+  } else if (warp < 6) {
+    // ===================== splitters =====================
+    const int tid = threadIdx.x - 64;        // 0..127
+    int s = 0; uint32_t ph = 0;
+    for (uint32_t t = blockIdx.x; t < total; t += gridDim.x) {
+      const typename Pol::Tile tl = Pol::tile(prm, blk_of(t));
+      const int nk = Pol::num_kblocks(prm, tl);
+      for (int kb = 0; kb < nk; kb++) {
+        mbar_wait(&full[s], ph);
+        float4* hi = (float4*)(smem + s * Cfg::STAGE_BYTES);
+        float4* lo = (float4*)(smem + s * Cfg::STAGE_BYTES + LO_OFF);
+        constexpr int NP4 = Cfg::P_BYTES / 16, NQ4 = Cfg::Q_BYTES / 16;
+#pragma unroll 4
+        for (int i = tid; i < NP4; i += 128) {             // P: one read, one write (the hardware truncates the raw tile to hi)
+          const float4 x = hi[i]; float4 l;
+          l.x = tf32_rna(x.x - __uint_as_float(__float_as_uint(x.x) & 0xFFFFE000u));
+          l.y = tf32_rna(x.y - __uint_as_float(__float_as_uint(x.y) & 0xFFFFE000u));
+          l.z = tf32_rna(x.z - __uint_as_float(__float_as_uint(x.z) & 0xFFFFE000u));
+          l.w = tf32_rna(x.w - __uint_as_float(__float_as_uint(x.w) & 0xFFFFE000u));
+          lo[i] = l;
+        }
+        if constexpr (!QPRE) {
+          // Q: rounded hi written back + signed lo.  P's lo always has the sign of its value (truncation), so with a truncated Q the dropped
+          // lo*lo term would have the sign of the product — a coherent 2^-22 bias toward zero; a round-to-nearest split on ONE side removes it.
+#pragma unroll 4
+          for (int i = NP4 + tid; i < NP4 + NQ4; i += 128) {
+            const float4 x = hi[i]; float4 h, l;
+            h.x = tf32_rna(x.x); h.y = tf32_rna(x.y); h.z = tf32_rna(x.z); h.w = tf32_rna(x.w);
+            l.x = tf32_rna(x.x - h.x); l.y = tf32_rna(x.y - h.y); l.z = tf32_rna(x.z - h.z); l.w = tf32_rna(x.w - h.w);
+            hi[i] = h; lo[i] = l;
+          }
+        }
+        fence_proxy_async();               // generic-proxy writes -> visible to the tensor core (async proxy)
+        mbar_arrive(&ready[s]);
+        if (++s == S) { s = 0; ph ^= 1; }
+      }
+    }
+  } else {
+    // ===================== drain / epilogue =====================
+    const int q = warp & 3;
+    const int row = 32 * q + lane;
+    const uint32_t tlane = tmem_base + ((uint32_t)(32 * q) << 16);
+    uint32_t ch = 0, ti = 0;
+    for (uint32_t t = blockIdx.x; t < total; t += gridDim.x) {
+      const typename Pol::Tile tl = Pol::tile(prm, blk_of(t));
+      const int nk = Pol::num_kblocks(prm, tl);
+      if (nk <= 0) continue;
+      uint32_t pre[TN / 32];
+      Pol::pre_epilogue(prm, tl, row, pre);
+      float racc[TN];
+#pragma unroll
+      for (int j = 0; j < TN; j++) racc[j] = 0.0f;
+      const int nchunks = (nk + kc - 1) / kc;
+      const uint32_t tcross = tlane + (uint32_t)((2 + (ti & 1)) * TN);
+      ti++;
+      for (int c = 0; c < nchunks; c++, ch++) {
+        const uint32_t buf = ch & 1;
+        mbar_wait(&acc_full[buf], (ch >> 1) & 1);
+        tc_fence_after();
+#pragma unroll
+        for (int c0 = 0; c0 < TN; c0 += 32) {
+          float v[32];
+          tmem_ld32(tlane + buf * (uint32_t)TN + (uint32_t)c0, v);
+          tmem_ld_wait();
+#pragma unroll
+          for (int j = 0; j < 32; j++) racc[c0 + j] += v[j];
+        }
+        if (c == nchunks - 1) {            // the tile's cross-term sums, complete with the last chunk (same commit)
+#pragma unroll
+          for (int c0 = 0; c0 < TN; c0 += 32) {
+            float v[32];
+            tmem_ld32(tcross + (uint32_t)c0, v);
+            tmem_ld_wait();
+#pragma unroll
+            for (int j = 0; j < 32; j++) racc[c0 + j] += v[j];
+          }
+        }
+        tc_fence_before();
+        mbar_arrive(&acc_empty[buf]);
+      }
+#pragma unroll
+      for (int c0 = 0; c0 < TN; c0 += 32) Pol::store(prm, tl, 0, row, c0, &racc[c0], pre[c0 / 32]);
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) tmem_dealloc(tmem_base, 4 * TN);
 }
 
 // ------------------------------------------------------------------------------------------------ persistent variant
@@ -339,26 +490,36 @@ tc_tile_persist_kernel(const __grid_constant__ typename Pol::Params prm, const u
 
 template <class Pol>
 static int tc_tile_launch(agb_ctx* ctx, const typename Pol::Params& prm, dim3 grid) {
-  using Cfg = TcCfg<Pol::TN, Pol::SPLIT, Pol::OCC, Pol::MT>;
-  static bool attr = false;
-  if (!attr) { AGB_CUDA(cudaFuncSetAttribute(tc_tile_kernel<Pol>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM)); attr = true; }
-  static int persist = -1;
-  if (persist < 0) { const char* e = getenv("AGB_TC_PERSIST"); persist = (e && e[0] == '0') ? 0 : 1; }
-  if constexpr (!Pol::SPLIT) {
-    if (persist) {
+  const uint64_t total = (uint64_t)grid.x * grid.y * grid.z;
+  if constexpr (Pol::SPLIT) {
+    using Cfg = TcCfg<Pol::TN, true, 1, 1>;
+    static bool attr = false;
+    if (!attr) { AGB_CUDA(cudaFuncSetAttribute(tc_tile_split_kernel<Pol>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM)); attr = true; }
+    if (total >= (1ull << 31)) return AGB_ERR_UNSUPPORTED;
+    const unsigned n = (unsigned)(total < (uint64_t)ctx->sm_count ? total : (uint64_t)ctx->sm_count);
+    if (n == 0) return AGB_OK;
+    static const int kc = [] { const char* e = getenv("AGB_SPLIT_KC"); int v = e ? atoi(e) : TC_KC; return v < 1 ? 1 : v; }();      // tuning knob: k-blocks per TMEM accumulation chunk
+    static const int order = [] { const char* e = getenv("AGB_SPLIT_ORDER"); return e ? atoi(e) : 0; }();
+    tc_tile_split_kernel<Pol><<<n, 320, Cfg::SMEM, ctx->stream>>>(prm, make_uint3(grid.x, grid.y, grid.z), kc, order);
+    AGB_LAUNCHED(ctx);
+    return AGB_OK;
+  } else {
+    using Cfg = TcCfg<Pol::TN, false, Pol::OCC, Pol::MT>;
+    static int persist = -1;
+    if (persist < 0) { const char* e = getenv("AGB_TC_PERSIST"); persist = (e && e[0] == '0') ? 0 : 1; }
+    if (persist && total < (1ull << 31)) {
       static bool attr2 = false;
       if (!attr2) { AGB_CUDA(cudaFuncSetAttribute(tc_tile_persist_kernel<Pol>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM)); attr2 = true; }
-      const uint64_t total = (uint64_t)grid.x * grid.y * grid.z;
-      if (total < (1ull << 31)) {
-        const uint64_t cap = (uint64_t)ctx->sm_count * Pol::OCC;
-        const unsigned n = (unsigned)(total < cap ? total : cap);
-        tc_tile_persist_kernel<Pol><<<n, Cfg::THREADS, Cfg::SMEM, ctx->stream>>>(prm, make_uint3(grid.x, grid.y, grid.z));
-        AGB_LAUNCHED(ctx);
-        return AGB_OK;
-      }
+      const uint64_t cap = (uint64_t)ctx->sm_count * Pol::OCC;
+      const unsigned n = (unsigned)(total < cap ? total : cap);
+      tc_tile_persist_kernel<Pol><<<n, Cfg::THREADS, Cfg::SMEM, ctx->stream>>>(prm, make_uint3(grid.x, grid.y, grid.z));
+      AGB_LAUNCHED(ctx);
+      return AGB_OK;
     }
+    static bool attr = false;
+    if (!attr) { AGB_CUDA(cudaFuncSetAttribute(tc_tile_kernel<Pol>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM)); attr = true; }
+    tc_tile_kernel<Pol><<<grid, Cfg::THREADS, Cfg::SMEM, ctx->stream>>>(prm);
+    AGB_LAUNCHED(ctx);
+    return AGB_OK;
   }
-  tc_tile_kernel<Pol><<<grid, Cfg::THREADS, Cfg::SMEM, ctx->stream>>>(prm);
-  AGB_LAUNCHED(ctx);
-  return AGB_OK;
 }
