@@ -255,6 +255,14 @@ int  agb_dropout(agb_ctx* ctx, const agb_tensor* x, agb_tensor* y, agb_tensor* m
  * Bernoulli = (U[0,1) < p0) as 0/1, Exp(rate p0), LogNormal(mu p0, sigma p1), Gamma(shape p0, scale p1) by Marsaglia-Tsang. */
 enum agb_rand_kind { AGB_RAND_UNIFORM = 0, AGB_RAND_NORMAL, AGB_RAND_BERNOULLI, AGB_RAND_EXP, AGB_RAND_LOGNORMAL, AGB_RAND_GAMMA, AGB_RAND_COUNT };
 int  agb_random(agb_ctx* ctx, int kind, float p0, float p1, uint64_t seed, uint64_t offset, agb_tensor* y);
+/* The same generators with the stream position kept in device memory: `cell` points to agb_stream_cell_bytes() zero-initialised bytes
+ * owned by the caller (one cell per op instance).  Every call draws from position *cell and advances it ON THE DEVICE, so an op that is
+ * evaluated repeatedly continues its stream like the reference's ArrayRng (RefCell<R>, ndarray_ext.rs:250-264; Dropout's rng,
+ * random_ops.rs:218-245) — including under CUDA-graph replay, where host-side kernel arguments are frozen at capture.  cell == NULL
+ * behaves like the plain entry points. */
+int  agb_stream_cell_bytes(void);
+int  agb_dropout_stream(agb_ctx* ctx, const agb_tensor* x, agb_tensor* y, agb_tensor* mask, float ratio, uint64_t seed, uint64_t offset, uint32_t* cell);
+int  agb_random_stream(agb_ctx* ctx, int kind, float p0, float p1, uint64_t seed, uint64_t offset, uint32_t* cell, agb_tensor* y);
 
 /* ======================= reductions ======================= */
 enum { AGB_R_SUM = 0, AGB_R_MEAN, AGB_R_PROD, AGB_R_MIN, AGB_R_MAX };

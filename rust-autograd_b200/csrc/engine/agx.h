@@ -91,8 +91,18 @@ struct NdArray {
   NdArray sliced(int axis, int64_t start, int64_t len) const;
 };
 
+// Device-resident stream positions of the random ops (agb_*_stream): one 8-byte cell per op instance, carved from pooled arena blocks.
+// The pool outlives neither the context nor its users' handles: `alive` goes false when the Device dies, handles then do nothing.
+struct StreamCellPool { agb_ctx* ctx = nullptr; bool alive = true; std::vector<uint32_t*> free_cells; std::vector<void*> blocks; };
+struct StreamCell {
+  std::shared_ptr<StreamCellPool> pool; uint32_t* ptr = nullptr;
+  ~StreamCell() { if (pool && pool->alive && ptr) pool->free_cells.push_back(ptr); }
+};
+
 struct Device {                   // thin C++ handle on the kernel C ABI context
   agb_ctx* ctx = nullptr;
+  std::shared_ptr<StreamCellPool> stream_cells;
+  std::shared_ptr<StreamCell> new_stream_cell();     // zeroed on the stream before it is handed out
   explicit Device(int index);
   ~Device();
   NdArray empty(const Shape& s);
@@ -246,7 +256,6 @@ struct PendingUpdate { int kind; float h[4]; NdArray p, g, s0, s1, t; };
 struct Evaluation {
   Graph* graph; Device* dev;
   std::vector<PendingUpdate> pending;     // optimizer ops of this run: flushed as ONE multi-tensor launch after all grads exist
-  uint64_t dropout_calls = 0;
   bool fuse = false;                      // elementwise fusion enabled for this run
   std::vector<int> consumers;             // per node id: consuming edges inside this evaluation (+1 per request as a target); metadata-only
                                           // consumers (Shape / Rank / Size) are not counted

@@ -80,7 +80,7 @@ extern "C" int agx_env_get(agx_env* env, int vid, float* out, int64_t cap) {
 extern "C" int agx_env_put(agx_env* env, int vid, const float* data, int64_t n) { AGX_TRY env->env->put(VariableID{vid}, data, (size_t)n); AGX_CATCH }
 extern "C" int agx_env_var_ptr(agx_env* env, int vid, float** dptr) { AGX_TRY *dptr = env->env->array_list.at(vid).dptr; AGX_CATCH }
 extern "C" int agx_env_save(agx_env* env, const char* path) {
-  AGX_TRY std::ofstream f(path); if (!f) throw OpError(AGB_ERR_NDARRAY, std::string("save: cannot open ") + path); f << env->env->save_json(); AGX_CATCH
+  AGX_TRY std::ofstream f(path); if (!f) throw OpError(AGB_ERR_NDARRAY, std::string("save: cannot open ") + path); f << env->env->save_json(); f.flush(); if (!f.good()) throw OpError(AGB_ERR_NDARRAY, std::string("save: write failed: ") + path); AGX_CATCH
 }
 extern "C" int agx_env_load(agx_env* env, const char* path) {
   AGX_TRY std::ifstream f(path); if (!f) throw OpError(AGB_ERR_NDARRAY, std::string("load: cannot open ") + path); std::stringstream ss; ss << f.rdbuf(); env->env->load_json(ss.str()); AGX_CATCH

@@ -1,5 +1,7 @@
 // core.cc — arrays, graph, reverse-mode gradient builder, evaluator, variable environment (see agx.h for the reference map).
 #include "agx.h"
+#include <cmath>
+#include <limits>
 #include <map>
 #include <tuple>
 #include <algorithm>
@@ -71,8 +73,19 @@ NdArray NdArray::sliced(int axis, int64_t start, int64_t len) const {
   return r;
 }
 
-Device::Device(int index) { check_status(agb_init(index, &ctx)); }
-Device::~Device() { if (ctx) agb_destroy(ctx); }
+Device::Device(int index) { check_status(agb_init(index, &ctx)); stream_cells = std::make_shared<StreamCellPool>(); stream_cells->ctx = ctx; }
+Device::~Device() { if (stream_cells) { stream_cells->alive = false; stream_cells->free_cells.clear(); } if (ctx) agb_destroy(ctx); }      // agb_destroy releases the pool's arena blocks with everything else
+std::shared_ptr<StreamCell> Device::new_stream_cell() {
+  StreamCellPool& p = *stream_cells;
+  if (p.free_cells.empty()) {
+    const size_t cell = (size_t)agb_stream_cell_bytes(), n = 512;
+    void* blk = nullptr; check_status(agb_alloc(ctx, cell * n, &blk)); p.blocks.push_back(blk);
+    for (size_t i = 0; i < n; i++) p.free_cells.push_back((uint32_t*)((char*)blk + i * cell));
+  }
+  auto c = std::make_shared<StreamCell>(); c->pool = stream_cells; c->ptr = p.free_cells.back(); p.free_cells.pop_back();
+  check_status(agb_memset0(ctx, c->ptr, (size_t)agb_stream_cell_bytes()));
+  return c;
+}
 NdArray Device::empty(const Shape& s) {
   NdArray a; a.shape = s; a.stride = NdArray::contiguous_strides(s);
   a.buf = std::make_shared<Buffer>(ctx, (size_t)std::max<int64_t>(a.size(), 1) * sizeof(float)); a.dptr = a.buf->ptr;
@@ -588,6 +601,15 @@ void VariableEnvironment::put(VariableID v, const float* data, size_t n) {
 
 // JSON checkpoint in the reference's serde layout (variable.rs:549-598; ndarray's {"v":1,"dim":[..],"data":[..]}),
 // names serialised as "namespacename" (variable.rs:225-229).
+static std::string json_escape(const std::string& in) {
+  std::string r; char buf[8];
+  for (unsigned char c : in) {
+    if (c == '"' || c == '\\') { r.push_back('\\'); r.push_back((char)c); }
+    else if (c < 0x20) { snprintf(buf, sizeof(buf), "\\u%04x", (unsigned)c); r += buf; }
+    else r.push_back((char)c);
+  }
+  return r;
+}
 std::string VariableEnvironment::save_json() {
   std::ostringstream o; o.precision(9);
   o << "{\"array_list\":[";
@@ -597,14 +619,14 @@ std::string VariableEnvironment::save_json() {
     o << "{\"v\":1,\"dim\":[";
     for (size_t d = 0; d < array_list[i].shape.size(); d++) { if (d) o << ","; o << array_list[i].shape[d]; }
     o << "],\"data\":[";
-    for (size_t k = 0; k < h.size(); k++) { if (k) o << ","; o << h[k]; }
+    for (size_t k = 0; k < h.size(); k++) { if (k) o << ","; if (std::isfinite(h[k])) o << h[k]; else o << "null"; }      // serde_json writes non-finite floats as null
     o << "]}";
   }
   o << "],\"name_to_id\":{";
   bool first = true;
   for (auto& kv : name_to_id) {
     if (!first) o << ","; first = false;
-    o << "\"" << kv.first.first << "\\u0001" << kv.first.second << "\":" << kv.second;
+    o << "\"" << json_escape(kv.first.first) << "\\u0001" << json_escape(kv.first.second) << "\":" << kv.second;
   }
   o << "}}";
   return o.str();
@@ -626,7 +648,7 @@ struct JsonCur {
     }
     expect('"'); return r;
   }
-  double num() { ws(); size_t j = i; while (j < s.size() && (isdigit((unsigned char)s[j]) || strchr("+-.eE", s[j]))) j++; double v = atof(s.substr(i, j - i).c_str()); i = j; return v; }
+  double num() { ws(); if (s.compare(i, 4, "null") == 0) { i += 4; return std::numeric_limits<double>::quiet_NaN(); } size_t j = i; while (j < s.size() && (isdigit((unsigned char)s[j]) || strchr("+-.eE", s[j]))) j++; double v = atof(s.substr(i, j - i).c_str()); i = j; return v; }
 };
 }  // namespace
 
@@ -667,6 +689,7 @@ void VariableEnvironment::load_json(const std::string& js) {
   }
   dev->sync();
   for (auto& kv : ids) {
+    if (kv.second < 0 || kv.second >= (int)arrays.size()) throw OpError(AGB_ERR_NDARRAY, "load: name_to_id refers to a variable id outside array_list");
     size_t p = kv.first.find('\x01');
     std::string ns = p == std::string::npos ? "" : kv.first.substr(0, p), nm = p == std::string::npos ? kv.first : kv.first.substr(p + 1);
     name_to_id[{ns, nm}] = kv.second;

@@ -493,16 +493,19 @@ Tensor T::max_pool2d(Tensor x, int size, int pad, int stride) { auto* op = new M
 
 // ================================================================================================ dropout
 struct Dropout : Op {                  // random_ops.rs:218-245: NOT inverted; outputs (y, mask); eval mode scales by (1 - ratio)
-  float ratio; bool train; uint64_t seed;
+  float ratio; bool train; uint64_t seed; std::shared_ptr<StreamCell> cell;
   const char* name() const override { return REFNAME("random_ops", "Dropout"); }
   void compute(ComputeContext& c) override {
     NdArray x = c.dev->contiguous(on_dev(c.dev, c.input(0)));
     if (!train) { NdArray y = c.dev->empty(x.shape); agb_tensor tx = x.desc(), ty = y.desc(); check_status(agb_unary(c.dev->ctx, AGB_U_SCALE, 1.0f - ratio, 0.f, &tx, &ty)); c.append_output(y); return; }
     NdArray y = c.dev->empty(x.shape), mask = c.dev->empty(x.shape);
     agb_tensor tx = x.desc(), ty = y.desc(), tm = mask.desc();
-    // The reference re-seeds a XorShift stream with a constant at every op construction (mod.rs:2895-2905), so every step
-    // draws the same mask; that stream is parity-unpinned.  Here: device Philox keyed by (seed, node id).
-    check_status(agb_dropout(c.dev->ctx, &tx, &ty, &tm, ratio, seed ? seed : 0x5EEDull, (uint64_t)c.node << 32));
+    // The reference seeds a XorShift stream with a constant at every op CONSTRUCTION (mod.rs:2895-2905) and the op's rng then advances with
+    // every evaluation: a graph rebuilt per step draws the same mask every step, a persistent graph (or a replayed step graph) a fresh one.
+    // Same here: device Philox keyed by (seed, node id, evaluations of this op instance so far); the count lives in device memory so that
+    // CUDA-graph replays advance it too.  The stream's values are parity-unpinned.
+    if (!cell) cell = c.dev->new_stream_cell();
+    check_status(agb_dropout_stream(c.dev->ctx, &tx, &ty, &tm, ratio, seed ? seed : 0x5EEDull, (uint64_t)c.node << 32, cell->ptr));
     c.append_output(y); c.append_output(mask);
   }
   void grad(GradientContext& c) override { c.append_input_grad(T::mul(c.output_grad(), T::nth_tensor(c.output(), 1))); }
@@ -514,7 +517,7 @@ Tensor T::dropout(Tensor x, float ratio, bool train, uint64_t seed) { auto* op =
 // a node built with the default rng starts from the crate's fixed default seed (ndarray_ext.rs:250-264), so two default-constructed
 // nodes draw the same values (as there).  Stream values are parity-unpinned: device Philox instead of XorShift.
 struct RandomOp : Op {
-  int kind; float p0, p1; uint64_t seed; uint64_t calls = 0;
+  int kind; float p0, p1; uint64_t seed; std::shared_ptr<StreamCell> cell;
   const char* name() const override {
     static const char* N[] = {REFNAME("random_ops", "RandomUniform"), REFNAME("random_ops", "RandomNormal"), REFNAME("random_ops", "Bernoulli"),
                               REFNAME("random_ops", "Exponential"), REFNAME("random_ops", "LogNormal"), REFNAME("random_ops", "Gamma")};
@@ -524,7 +527,8 @@ struct RandomOp : Op {
     NdArray sh = c.input(0);
     NdArray y = c.dev->empty(as_shape(c.dev, sh));
     agb_tensor ty = y.desc();
-    check_status(agb_random(c.dev->ctx, kind, p0, p1, seed ? seed : 0x5EEDull, calls++, &ty));
+    if (!cell) cell = c.dev->new_stream_cell();       // evaluations so far, kept on the device (advances under CUDA-graph replay too)
+    check_status(agb_random_stream(c.dev->ctx, kind, p0, p1, seed ? seed : 0x5EEDull, 0, cell->ptr, &ty));
     c.append_output(y);
   }
   void grad(GradientContext& c) override { c.append_none(); }

@@ -685,15 +685,28 @@ __device__ __forceinline__ uint4 philox4x32_10(uint4 ctr, uint2 key) {
   }
   return ctr;
 }
+// Stream position kept ON THE DEVICE (cell[0] = evaluations so far, cell[1] = block ticket): an op instance that is evaluated repeatedly
+// continues its stream like the reference's ArrayRng (RefCell<R>, ndarray_ext.rs:250-264) — also when the evaluation is a replayed CUDA
+// graph, whose kernel arguments are frozen at capture.  Every block reads cell[0] when it starts; the block that finishes last advances it.
+__device__ __forceinline__ uint32_t stream_pos_begin(const uint32_t* cell) { return cell ? *(const volatile uint32_t*)cell : 0u; }
+__device__ __forceinline__ void stream_pos_end(uint32_t* cell, uint32_t pos) {
+  if (cell == nullptr) return;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    __threadfence();
+    if (atomicInc(cell + 1, gridDim.x - 1) == gridDim.x - 1) { cell[0] = pos + 1; __threadfence(); }
+  }
+}
 __global__ void __launch_bounds__(256) dropout_gen_kernel(const float* __restrict__ x, float* __restrict__ y,
                                                           float* __restrict__ mask, int64_t n, float keep,
-                                                          uint64_t seed, uint64_t offset) {
+                                                          uint64_t seed, uint64_t offset, uint32_t* cell) {
   int64_t tid = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
   int64_t stride = (int64_t)gridDim.x * blockDim.x;
   int64_t n4 = (n + 3) >> 2;
+  const uint32_t pos = stream_pos_begin(cell);
   for (int64_t i = tid; i < n4; i += stride) {
     uint64_t c = offset + (uint64_t)i;
-    uint4 r = philox4x32_10(make_uint4((uint32_t)c, (uint32_t)(c >> 32), 0u, 0u), make_uint2((uint32_t)seed, (uint32_t)(seed >> 32)));
+    uint4 r = philox4x32_10(make_uint4((uint32_t)c, (uint32_t)(c >> 32), pos, 0u), make_uint2((uint32_t)seed, (uint32_t)(seed >> 32)));
     uint32_t rr[4] = {r.x, r.y, r.z, r.w};
 #pragma unroll
     for (int k = 0; k < 4; k++) {
@@ -705,8 +718,13 @@ __global__ void __launch_bounds__(256) dropout_gen_kernel(const float* __restric
       }
     }
   }
+  stream_pos_end(cell, pos);
 }
+extern "C" int agb_stream_cell_bytes(void) { return 8; }
 extern "C" int agb_dropout(agb_ctx* ctx, const agb_tensor* x, agb_tensor* y, agb_tensor* mask, float ratio, uint64_t seed, uint64_t offset) {
+  return agb_dropout_stream(ctx, x, y, mask, ratio, seed, offset, nullptr);
+}
+extern "C" int agb_dropout_stream(agb_ctx* ctx, const agb_tensor* x, agb_tensor* y, agb_tensor* mask, float ratio, uint64_t seed, uint64_t offset, uint32_t* cell) {
   AGB_CHECK(agb_is_contig(x) && agb_is_contig(y) && agb_is_contig(mask), AGB_ERR_UNSUPPORTED, "agb_dropout: tensors must be contiguous");
   int64_t n = agb_numel(x);
   AGB_CHECK(agb_numel(y) == n && agb_numel(mask) == n, AGB_ERR_INCOMPATIBLE_SHAPE, "agb_dropout: size mismatch");
@@ -715,7 +733,7 @@ extern "C" int agb_dropout(agb_ctx* ctx, const agb_tensor* x, agb_tensor* y, agb
     agb_tensor xm = *x, mm = *mask, ym = *y;
     return agb_binary(ctx, AGB_B_MUL, 0.f, 0.f, &mm, &xm, &ym);    // mask * x
   }
-  dropout_gen_kernel<<<agb_grid_for((n + 3) / 4, 256, ctx->sm_count, 8), 256, 0, ctx->stream>>>(x->ptr, y->ptr, mask->ptr, n, 1.0f - ratio, seed, offset);
+  dropout_gen_kernel<<<agb_grid_for((n + 3) / 4, 256, ctx->sm_count, 8), 256, 0, ctx->stream>>>(x->ptr, y->ptr, mask->ptr, n, 1.0f - ratio, seed, offset, cell);
   AGB_LAUNCHED(ctx);
   return AGB_OK;
 }
@@ -748,9 +766,11 @@ __device__ float gamma_sample(int64_t elem, float k, float scale, uint64_t seed,
   }
   return d * scale * boost;      // (probability ~ 1e-30) the mode
 }
-__global__ void __launch_bounds__(256) random_kernel(float* __restrict__ y, int64_t n, int kind, float p0, float p1, uint64_t seed, uint64_t offset) {
+__global__ void __launch_bounds__(256) random_kernel(float* __restrict__ y, int64_t n, int kind, float p0, float p1, uint64_t seed, uint64_t offset, uint32_t* cell) {
   const int64_t stride = (int64_t)gridDim.x * blockDim.x, n4 = (n + 3) >> 2;
   const uint2 key = make_uint2((uint32_t)seed, (uint32_t)(seed >> 32));
+  const uint32_t pos = stream_pos_begin(cell);
+  offset += pos;                                           // the op's evaluations so far (device-resident stream position)
   for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n4; i += stride) {
     float v[4];
     if (kind == AGB_RAND_GAMMA) {
@@ -775,8 +795,12 @@ __global__ void __launch_bounds__(256) random_kernel(float* __restrict__ y, int6
 #pragma unroll
     for (int k = 0; k < 4; k++) if (4 * i + k < n) y[4 * i + k] = v[k];
   }
+  stream_pos_end(cell, pos);
 }
 extern "C" int agb_random(agb_ctx* ctx, int kind, float p0, float p1, uint64_t seed, uint64_t offset, agb_tensor* y) {
+  return agb_random_stream(ctx, kind, p0, p1, seed, offset, nullptr, y);
+}
+extern "C" int agb_random_stream(agb_ctx* ctx, int kind, float p0, float p1, uint64_t seed, uint64_t offset, uint32_t* cell, agb_tensor* y) {
   AGB_CHECK(kind >= 0 && kind < AGB_RAND_COUNT, AGB_ERR_UNSUPPORTED, "agb_random: unknown distribution %d", kind);
   AGB_CHECK(agb_is_contig(y), AGB_ERR_UNSUPPORTED, "agb_random: output must be contiguous");
   if (kind == AGB_RAND_NORMAL || kind == AGB_RAND_LOGNORMAL) AGB_CHECK(p1 >= 0.0f, AGB_ERR_INVALID_DIMS, "agb_random: standard deviation must be >= 0");     // Normal::new(..).unwrap() panics
@@ -784,7 +808,7 @@ extern "C" int agb_random(agb_ctx* ctx, int kind, float p0, float p1, uint64_t s
   if (kind == AGB_RAND_GAMMA) AGB_CHECK(p0 > 0.0f && p1 > 0.0f, AGB_ERR_INVALID_DIMS, "agb_random: gamma shape and scale must be > 0");
   if (kind == AGB_RAND_UNIFORM) AGB_CHECK(p0 < p1, AGB_ERR_INVALID_DIMS, "agb_random: uniform range must satisfy low < high");                              // Uniform::new panics otherwise
   const int64_t n = agb_numel(y); if (n == 0) return AGB_OK;
-  random_kernel<<<agb_grid_for((n + 3) / 4, 256, ctx->sm_count, 8), 256, 0, ctx->stream>>>(y->ptr, n, kind, p0, p1, seed, offset);
+  random_kernel<<<agb_grid_for((n + 3) / 4, 256, ctx->sm_count, 8), 256, 0, ctx->stream>>>(y->ptr, n, kind, p0, p1, seed, offset, cell);
   AGB_LAUNCHED(ctx);
   return AGB_OK;
 }

@@ -73,6 +73,14 @@ extern "C" int agb_set_math_mode(agb_ctx* ctx, int mode) {
 extern "C" int agb_get_math_mode(agb_ctx* ctx, int* mode) { *mode = ctx->math_mode; return AGB_OK; }
 extern "C" int agb_launch_count(agb_ctx* ctx, int64_t* out) { *out = ctx->launches; return AGB_OK; }
 
+// One process drives one GPU, but nothing stops a process from holding contexts on several devices: the calls that would
+// silently act on the WRONG device (cudaMalloc lands on whichever device is current) make the context's device current first.  Kernel
+// launches go to ctx->stream and fail loudly (invalid resource handle) if another device is current.
+static inline void agb_use_device(agb_ctx* ctx) {
+  int cur = -1;
+  if (cudaGetDevice(&cur) != cudaSuccess || cur != ctx->device) cudaSetDevice(ctx->device);
+}
+
 static size_t round_block(size_t bytes) {
   if (bytes == 0) bytes = 1;
   if (bytes <= (1u << 20)) return (bytes + 511) & ~(size_t)511;              // 512 B granules
@@ -92,6 +100,7 @@ extern "C" int agb_alloc(agb_ctx* ctx, size_t bytes, void** out) {
     *out = p; return AGB_OK;
   }
   AGB_CHECK(!ctx->capturing, AGB_ERR_CUDA, "arena growth during graph capture; run the step eagerly (twice) first");
+  agb_use_device(ctx);
   void* p = nullptr;
   cudaError_t e = cudaMalloc(&p, sz);
   if (e != cudaSuccess) {   // give cached memory back and retry once
@@ -127,6 +136,7 @@ extern "C" int agb_mem_stats(agb_ctx* ctx, size_t* live, size_t* cached, size_t*
 int agb_scratch(agb_ctx* ctx, size_t bytes, void** out) {
   if (bytes > ctx->scratch_bytes) {
     AGB_CHECK(!ctx->capturing, AGB_ERR_CUDA, "scratch growth during graph capture; run the step once eagerly first");
+    agb_use_device(ctx);
     if (ctx->scratch) { AGB_CUDA(cudaStreamSynchronize(ctx->stream)); AGB_CUDA(cudaFree(ctx->scratch)); }
     size_t sz = bytes < (8u << 20) ? (8u << 20) : round_block(bytes);
     AGB_CUDA(cudaMalloc(&ctx->scratch, sz)); ctx->scratch_bytes = sz;
@@ -201,7 +211,8 @@ extern "C" int agb_sync(agb_ctx* ctx) {
   int flag = 0;
   AGB_CUDA(cudaMemcpy(&flag, ctx->dev_err, sizeof(int), cudaMemcpyDeviceToHost));
   if (flag) {
-    cudaMemset(ctx->dev_err, 0, sizeof(int));
+    cudaMemsetAsync(ctx->dev_err, 0, sizeof(int), ctx->stream);      // ordered with the kernels that set it (the legacy stream is not)
+    cudaStreamSynchronize(ctx->stream);
     agb_set_error("device-side index check failed (code %d): label / gather index out of range", flag);
     return AGB_ERR_OUT_OF_BOUNDS;
   }
@@ -215,6 +226,7 @@ __global__ void flush_kernel(float4* p, size_t n4) {
 }
 extern "C" int agb_flush_l2(agb_ctx* ctx) {
   const size_t bytes = 256u << 20;   // 256 MiB > 126 MB L2
+  if (!ctx->flush_buf) agb_use_device(ctx);
   if (!ctx->flush_buf) { AGB_CUDA(cudaMalloc(&ctx->flush_buf, bytes)); ctx->flush_bytes = bytes; }
   flush_kernel<<<ctx->sm_count * 4, 256, 0, ctx->stream>>>((float4*)ctx->flush_buf, bytes / 16);
   AGB_CUDA(cudaPeekAtLastError());

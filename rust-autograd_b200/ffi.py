@@ -90,6 +90,7 @@ SIGNATURES = {
     "agb_fused_ewise": [_P, _i64, _i64, _i, _P, _i, _P, _i, _P], "agb_copy_strided": [_P, _T, _T],
     "agb_concat_rows": [_P, _i, _P, _P, _i64, _i64, _P],
     "agb_dropout": [_P, _T, _T, _T, _f, _u64, _u64], "agb_random": [_P, _i, _f, _f, _u64, _u64, _T],
+    "agb_stream_cell_bytes": [], "agb_dropout_stream": [_P, _T, _T, _T, _f, _u64, _u64, _P], "agb_random_stream": [_P, _i, _f, _f, _u64, _u64, _P, _T],
     "agb_reduce": [_P, _i, _P, _P, _i64, _i64, _i64], "agb_argreduce": [_P, _i, _P, _P, _i64, _i64, _i64],
     "agb_softmax": [_P, _P, _P, _i64, _i64, _i64], "agb_log_softmax": [_P, _P, _P, _i64, _i64, _i64],
     "agb_logsumexp": [_P, _P, _P, _i64, _i64, _i64],

@@ -653,3 +653,56 @@ def test_dropout_semantics(ag):
         assert np.allclose(ag.dropout(x, 0.25, False).eval(g), 0.75)
     env.run(body)
     env.close()
+
+
+def test_dropout_stream_advances_per_evaluation_and_under_graph_replay(ag):
+    """The op's rng belongs to the op INSTANCE (random_ops.rs:218-245, seeded at construction mod.rs:2895-2905): evaluating the same node
+    again draws a fresh mask, a graph rebuilt from scratch draws the first mask again, and a captured step graph keeps advancing on every
+    replay (the stream position lives in device memory, agb_dropout_stream) instead of freezing the mask baked in at capture."""
+    import ctypes as C
+    from rust_autograd_b200 import ffi
+    env = ag.VariableEnvironment()
+    v = env.slot().set(np.ones((64, 64)))
+    w = env.slot().set(np.zeros((64, 64)))
+
+    def first_two(g):
+        d = ag.dropout(g.variable(v), 0.25, True)
+        return d.eval(g), d.eval(g)
+    a0, a1 = env.run(first_two)
+    b0, _ = env.run(first_two)
+    assert not np.array_equal(a0, a1) and abs(a1.mean() - 0.75) < 0.05
+    assert np.array_equal(a0, b0)                              # same construction-time seed, stream position 0 again
+    g = ag.Context(env)
+    d = ag.dropout(g.variable(v), 0.25, True)
+    r = ag.random_uniform([64, 64], 0.0, 1.0, g)
+    step = g.evaluator().push(ag.assign(g.variable(w), d * r)).capture()
+    seen = []
+    for _ in range(3):
+        step.launch()
+        ffi.check(ffi.load_library().agb_sync(env.agb_ctx()))
+        seen.append(env.get_array_by_id(1).copy())
+    step.close(); g.close(); env.close()
+    assert not np.array_equal(seen[0], seen[1]) and not np.array_equal(seen[1], seen[2])
+    assert not np.array_equal(seen[0] > 0, seen[1] > 0)        # the mask itself changed, not only the uniform factor
+
+
+def test_checkpoint_is_valid_json_for_odd_names_and_non_finite_values(ag, tmp_path):
+    """variable.rs:549-598 writes through serde_json: names are escaped and non-finite floats become null.  The file must parse as
+    JSON and load back (null -> NaN); a name_to_id entry pointing outside array_list is rejected."""
+    env = ag.VariableEnvironment()
+    env.slot().name('we"ird\\name\twith\ncontrol').set(np.array([[1.5, np.nan], [np.inf, -2.0]]))
+    env.namespace("ns").slot().name("b").set(np.array([3.0]))
+    path = str(tmp_path / "ckpt.json")
+    env.save(path)
+    js = json.load(open(path))                          # valid JSON (nan / inf would not parse strictly)
+    assert js["array_list"][0]["data"] == [1.5, None, None, -2.0] and len(js["name_to_id"]) == 2
+    env2 = ag.VariableEnvironment.load(path)
+    a = env2.get_array_by_id(0)
+    assert a[0, 0] == 1.5 and a[1, 1] == -2.0 and np.isnan(a[0, 1]) and np.isnan(a[1, 0])
+    assert np.array_equal(env2.namespace("ns").get_array_by_name("b"), np.array([3.0], np.float32))
+    assert env2.default_namespace().get_array_by_name('we"ird\\name\twith\ncontrol') is not None
+    js["name_to_id"]["bad"] = 7
+    json.dump(js, open(path, "w"))
+    with pytest.raises(Exception):
+        ag.VariableEnvironment.load(path)
+    env.close(); env2.close()
