@@ -43,7 +43,7 @@ __global__ void __launch_bounds__(256) repack_filter_kernel(const float* __restr
 // MT_ = 2: the CTA owns an 8x32 pixel patch = two 128-lane M-tiles (rows 0-3 / 4-7, ONE {32 c, 32 w, 8 h} box per k-block) that
 // share every filter tile: 1.33x (TN 128) / 1.5x (TN 256) fewer bytes through L2 -> smem per output, the bound of these kernels.
 template <int TN_, bool SPLIT_, int MT_ = 1> struct ConvFpropPol {
-  static constexpr int TN = TN_, MT = MT_; static constexpr bool SPLIT = SPLIT_, P_MN = false, Q_MN = false, Q_PRESPLIT = SPLIT_;
+  static constexpr int TN = TN_, MT = MT_; static constexpr bool SPLIT = SPLIT_, P_MN = false, Q_MN = false, Q_PRESPLIT = SPLIT_, PAIR2 = false;
   static constexpr int OCC = (SPLIT_ || TN_ > 128 || MT_ > 1) ? 1 : 2;
   // The 128 lanes of an M-tile are a {bw w, bh h, bb images} pixel box (TMA writes box elements in exactly that order): 32x4x1 for
   // maps at least 32 wide; narrow maps take whole rows and, when a whole image is smaller than the tile, several images
@@ -164,7 +164,7 @@ template <int TN_, bool SPLIT_, int MT_ = 1> struct ConvFpropPol {
 // MT_ = 2 (non-PAIR): the CTA owns two (tap, 128-channel tile) units — two M-tiles that share every gy tile, so gy is pulled from
 // L2 half as often (the TN = 256 wgrad moved 48 KB per 4 MMAs: bound by L2 -> smem ingest at 43 % tensor activity).
 template <int TN_, bool SPLIT_, bool PAIR_, int MT_ = 1> struct ConvWgradPol {
-  static constexpr int TN = TN_, MT = MT_; static constexpr bool SPLIT = SPLIT_, P_MN = true, Q_MN = true, Q_PRESPLIT = false;
+  static constexpr int TN = TN_, MT = MT_; static constexpr bool SPLIT = SPLIT_, P_MN = true, Q_MN = true, Q_PRESPLIT = false, PAIR2 = false;
   static constexpr int OCC = (SPLIT_ || TN_ > 128 || MT_ > 1) ? 1 : 2;
   static_assert(!(PAIR_ && MT_ > 1), "tap pairing within one M-tile and two M-tiles are alternatives");
   struct Params { CUtensorMap tmX, tmG; float* gw; int C, O, T, kw, pad, dil, stride, yh, xblocks, kb_total, kb_per_split; MnDescCfg mnc; };

@@ -24,9 +24,10 @@
 template <int TN_, bool P_MN_, bool Q_MN_, bool SPLIT_, bool QPRE_ = false> struct GemmPol {
   static constexpr int TN = TN_, MT = 1; static constexpr bool SPLIT = SPLIT_, P_MN = P_MN_, Q_MN = Q_MN_, Q_PRESPLIT = QPRE_;
   static constexpr int OCC = (SPLIT_ || TN_ > 128) ? 1 : 2;
+  static constexpr bool PAIR2 = !SPLIT_ && TN_ == 256;       // CTA pairs: tmQh = the Q map with TN / 2 rows per box
   // splits > 1: split-K for problems with too few output tiles to fill the machine (e.g. the LSTM's 128 x 1024 x 8192 dgrad GEMM is
   // 8 tiles): grid.z = batch * splits, every CTA reduces kb_per_split k-blocks and adds its partial with red.global.add (C pre-zeroed)
-  struct Params { CUtensorMap tmP, tmQ, tmQlo; float* C; int NL, NC, K; int64_t ldc, bsc; int accumulate; int splits, kb_per_split; MnDescCfg mnc; };
+  struct Params { CUtensorMap tmP, tmQ, tmQlo /* 3xTF32: lo plane; CTA pairs: half-height Q boxes */; float* C; int NL, NC, K; int64_t ldc, bsc; int accumulate; int splits, kb_per_split; MnDescCfg mnc; };
   struct Tile { int lane0, col0, bz, kb0, nkb; };
   __device__ static Tile tile(const Params& p, uint3 blk) {
     const int kb_total = (p.K + TC_BK - 1) / TC_BK;
@@ -49,6 +50,14 @@ template <int TN_, bool P_MN_, bool Q_MN_, bool SPLIT_, bool QPRE_ = false> stru
     load_q(&p.tmQ, t, kb, pQ, bar);
   }
   __device__ static void load_q_lo(const Params& p, const Tile& t, int kb, uint8_t* pQlo, uint64_t* bar) { load_q(&p.tmQlo, t, kb, pQlo, bar); }       // 3xTF32 with the Q operand pre-split in global memory
+  // CTA pair: this CTA's 128 P rows + its half of the Q rows, completing on the leader's barrier
+  __device__ static void load2(const Params& p, const Tile& t, int kb, uint8_t* pP, uint8_t* pQ, uint32_t bar, int rank) {
+    const int k0 = (t.kb0 + kb) * TC_BK, c0 = t.col0 + rank * (TN / 2);
+    if (P_MN) { for (int j = 0; j < TC_LANES / 32; j++) tma_load_3d_2sm(pP + j * 4096, &p.tmP, bar, t.lane0 + 32 * j, k0, t.bz); }
+    else tma_load_3d_2sm(pP, &p.tmP, bar, k0, t.lane0, t.bz);
+    if (Q_MN) { for (int j = 0; j < TN / 64; j++) tma_load_3d_2sm(pQ + j * 4096, &p.tmQlo, bar, c0 + 32 * j, k0, t.bz); }
+    else tma_load_3d_2sm(pQ, &p.tmQlo, bar, k0, c0, t.bz);
+  }
   // thread `lane` owns C column n = lane0 + lane; v[j] belongs to C row m = col0 + c0 + j: a warp stores 32 consecutive
   // floats of one C row per instruction (128-byte coalesced), no shared-memory staging
   __device__ static void pre_epilogue(const Params&, const Tile&, int, uint32_t*) {}
@@ -130,16 +139,56 @@ __global__ void __launch_bounds__(256) presplit_kernel(const float4* __restrict_
   }
 }
 
+// A thin operand whose contiguous extent is not a multiple of 4 floats (the [65536, 10] classifier weight of a CNN, its [256, 10]
+// logits gradient) breaks TMA's 16-byte pitch rule.  Such an operand is tiny next to the other one, so it is copied once per call into
+// scratch with the pitch rounded up to 16 floats (zero padded) and the GEMM runs on the tensor cores instead of the CUDA-core path
+// (VGG classifier, batch 256: forward + two gradients 229 us -> the three calls are bound by streaming the 67 MB activation once each).
+__global__ void __launch_bounds__(256) pad_pitch_kernel(const float* __restrict__ src, float* __restrict__ dst, int64_t outer, int inner, int64_t src_pitch, int dst_pitch) {
+  const int64_t n = outer * dst_pitch;
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t o = i / dst_pitch; const int j = (int)(i - o * dst_pitch);
+    dst[i] = j < inner ? __ldg(src + o * src_pitch + j) : 0.0f;
+  }
+}
+// returns true when `o` was re-pointed at a padded copy (scratch cursor advanced)
+static bool tc_pad_thin(agb_ctx* ctx, TcOperand& o, int64_t K, float*& cursor, int* status) {
+  *status = AGB_OK;
+  int64_t outer, inner, pitch; bool k_inner;
+  if (o.ks == 1 && o.rs >= K) { outer = o.rows; inner = K; pitch = o.rs; k_inner = true; }           // K contiguous
+  else if (o.rs == 1 && o.ks >= o.rows) { outer = K; inner = o.rows; pitch = o.ks; k_inner = false; } // rows contiguous
+  else return false;
+  if ((pitch % 4 == 0 && ((uintptr_t)o.p & 15) == 0) || inner > 64) return false;
+  const int dp = (int)((inner + 15) / 16 * 16);
+  pad_pitch_kernel<<<agb_grid_for(outer * dp, 256, ctx->sm_count, 8), 256, 0, ctx->stream>>>(o.p, cursor, outer, (int)inner, pitch, dp);
+  ctx->launches++;
+  o.p = cursor; cursor += outer * dp;
+  if (k_inner) o.rs = dp; else o.ks = dp;
+  return true;
+}
+
 // C[m,n] = op(A)[m,k] . op(B)[k,n];  (rsa, csa) strides of op(A) over (m, k), (rsb, csb) strides of op(B) over (k, n)
 int agb_tc_gemm(agb_ctx* ctx, int mode, const float* A, const float* B, float* C, int64_t M, int64_t N, int64_t K, int64_t batch,
                 int64_t rsa, int64_t csa, int64_t bsa, int64_t rsb, int64_t csb, int64_t bsb, int64_t bsc, float beta) {
   // worth a 128-lane tile?  (tiny problems stay on the CUDA-core path, which is also exact fp32)
-  if (N < 64 || M < 16 || K < 32) return AGB_ERR_UNSUPPORTED;
+  const bool thin_big = batch == 1 && M >= 16 && (double)M * (double)N * (double)K >= (double)(1 << 26) && (N < 64 || K < 32);
+  if ((N < 64 || M < 16 || K < 32) && !thin_big) return AGB_ERR_UNSUPPORTED;
   if (M > (1ll << 30) || N > (1ll << 30) || K > (1ll << 30) || batch > 65535) return AGB_ERR_UNSUPPORTED;
   if (((uintptr_t)C & 15) != 0) return AGB_ERR_UNSUPPORTED;
   TcOperand P{B, N, csb, rsb, bsb};     // lanes = n : P[n, k] = op(B)[k, n]
   TcOperand Q{A, M, rsa, csa, bsa};     // cols  = m : Q[m, k] = op(A)[m, k]
   bool pmn, qmn;
+  float* pad_base = nullptr; size_t pad_floats = 0;
+  if (thin_big) {        // padded copies of the thin operand(s): at most 64 floats of pitch per outer index
+    bool p_ok = tc_operand_ok(P, K, batch, pmn), q_ok = tc_operand_ok(Q, K, batch, qmn);
+    if (!p_ok) pad_floats += (size_t)((P.ks == 1 ? P.rows : K)) * 64;
+    if (!q_ok) pad_floats += (size_t)((Q.ks == 1 ? Q.rows : K)) * 64;
+    if (pad_floats) {
+      AGB_TRY(agb_scratch(ctx, pad_floats * sizeof(float), (void**)&pad_base));
+      float* cur = pad_base; int st;
+      if (!p_ok) { tc_pad_thin(ctx, P, K, cur, &st); AGB_TRY(st); }
+      if (!q_ok) { tc_pad_thin(ctx, Q, K, cur, &st); AGB_TRY(st); }
+    }
+  }
   if (!tc_operand_ok(P, K, batch, pmn) || !tc_operand_ok(Q, K, batch, qmn)) return AGB_ERR_UNSUPPORTED;
   const bool split = (mode == AGB_MATH_3XTF32);
   // 256-wide tiles (one CTA per SM, 128 KB epilogue per tile) only pay off when the k-loop is long enough to hide the epilogue behind it
@@ -152,7 +201,7 @@ int agb_tc_gemm(agb_ctx* ctx, int mode, const float* A, const float* B, float* C
     // Q = op(A) is re-read by every one of the N/128 lane tiles: pre-split it once in global memory when it is dense and N is large
     const int64_t qn = M * K * batch;
     const bool q_dense = qn % 4 == 0 && (batch == 1 || Q.bs == M * K) && (qmn ? (Q.ks == M) : (Q.rs == K));
-    if (q_dense && N >= 512 && qn <= (1ll << 31)) {
+    if (q_dense && N >= 512 && qn <= (1ll << 31) && pad_base == nullptr) {
       float* planes = nullptr;
       AGB_TRY(agb_scratch(ctx, (size_t)qn * 2 * sizeof(float), (void**)&planes));
       presplit_kernel<<<agb_grid_for(qn / 4, 256, ctx->sm_count, 8), 256, 0, ctx->stream>>>((const float4*)A, (float4*)planes, (float4*)(planes + qn), qn / 4);
@@ -167,7 +216,11 @@ int agb_tc_gemm(agb_ctx* ctx, int mode, const float* A, const float* B, float* C
     if (TN == 128) return tc_dispatch_major<128, true>(ctx, pmn, qmn, tmP, tmQ, nullptr, C, (int)N, (int)M, (int)K, N, bsc, batch, acc);
     return tc_dispatch_major<64, true>(ctx, pmn, qmn, tmP, tmQ, nullptr, C, (int)N, (int)M, (int)K, N, bsc, batch, acc);
   }
-  if (TN == 256) return tc_dispatch_major<256, false>(ctx, pmn, qmn, tmP, tmQ, nullptr, C, (int)N, (int)M, (int)K, N, bsc, batch, acc);
+  if (TN == 256) {
+    CUtensorMap tmQhalf;        // CTA pairs: each CTA of a pair loads TN / 2 rows of the Q tile
+    r = tc_make_map(&tmQhalf, Q, K, batch, qmn, TN / 2); if (r != AGB_OK) return r;
+    return tc_dispatch_major<256, false>(ctx, pmn, qmn, tmP, tmQ, &tmQhalf, C, (int)N, (int)M, (int)K, N, bsc, batch, acc);
+  }
   if (TN == 128) return tc_dispatch_major<128, false>(ctx, pmn, qmn, tmP, tmQ, nullptr, C, (int)N, (int)M, (int)K, N, bsc, batch, acc);
   return tc_dispatch_major<64, false>(ctx, pmn, qmn, tmP, tmQ, nullptr, C, (int)N, (int)M, (int)K, N, bsc, batch, acc);
 }

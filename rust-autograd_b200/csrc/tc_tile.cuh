@@ -50,7 +50,8 @@ template <int TN, bool SPLIT, int OCC = 1, int MT = 1> struct TcCfg {
 };
 
 // Policy interface:
-//   static constexpr int TN, OCC; static constexpr bool SPLIT, P_MN, Q_MN, Q_PRESPLIT;
+//   static constexpr int TN, OCC; static constexpr bool SPLIT, P_MN, Q_MN, Q_PRESPLIT, PAIR2;
+//   (PAIR2) __device__ static void load2(const Params&, const Tile&, int kb, uint8_t* pP, uint8_t* pQhalf, uint32_t leader_bar, int rank);
 //   (Q_PRESPLIT) __device__ static void load_q_lo(const Params&, const Tile&, int kb, uint8_t* pQlo, uint64_t* bar);
 //   struct Params { ... CUtensorMap members ...; MnDescCfg mnc; };
 //   struct Tile { ... };                                               per-CTA coordinates
@@ -488,6 +489,130 @@ tc_tile_persist_kernel(const __grid_constant__ typename Pol::Params prm, const u
   if (warp == 1) tmem_dealloc(tmem_base, TCOLS);
 }
 
+// ------------------------------------------------------------------------------------------------ CTA-pair variant (cta_group::2)
+// Single-pass (TF32) tiles of TN = 256: a cluster of two CTAs (the two SMs of a TPC) owns TWO adjacent M-tiles of the logical grid
+// (blk.x = 2 * pair_tile + rank) and runs them as one M = 256 MMA.  Each CTA loads its own 128 P rows and HALF of the Q rows (Pol::load2:
+// TN / 2 rows at rank * TN / 2), so the Q bytes a CTA pulls through L2 -> shared memory per output halve and a stage is 32 KB (6-deep ring
+// with two 256-column TMEM accumulator sets per CTA) — the one-CTA TN = 256 kernel moves 48 KB per 4 MMAs (94 B/clk against the ~50 B/clk
+// an SM can ingest; measured 65-72 % tensor-pipe activity).  The leader issues; both producers' TMA bytes land on the leader's `full`
+// barrier; commits are multicast to both CTAs' `empty` / `acc_full`; both CTAs' drain warps release the leader's `acc_empty`.
+template <class Pol>
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(192, 1)
+tc_tile_pair_kernel(const __grid_constant__ typename Pol::Params prm, const uint3 lgrid) {
+  constexpr int TN = Pol::TN; constexpr bool P_MN = Pol::P_MN, Q_MN = Pol::Q_MN;
+  static_assert(!Pol::SPLIT && Pol::MT == 1 && TN == 256, "CTA pairs serve the single-pass 256-wide tiles");
+  constexpr int P_BYTES = TC_LANES * TC_BK * 4, QH_BYTES = (TN / 2) * TC_BK * 4, STAGE = P_BYTES + QH_BYTES;
+  constexpr int S = 6;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
+  uint64_t* bars = (uint64_t*)(smem + S * STAGE);
+  uint64_t* full = bars; uint64_t* empty = bars + S;
+  uint64_t* acc_full = bars + 2 * S; uint64_t* acc_empty = bars + 2 * S + 2;
+  uint32_t* tmem_slot = (uint32_t*)(bars + 2 * S + 4);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const uint32_t rank = cluster_ctarank();
+  const uint32_t xpairs = (lgrid.x + 1) / 2, total = xpairs * lgrid.y * lgrid.z;
+  const uint32_t pair_id = blockIdx.x >> 1, npairs = gridDim.x >> 1;
+
+  if (warp == 0 && lane == 0) {
+    Pol::prefetch(prm);
+    for (int s = 0; s < S; s++) { mbar_init(&full[s], 1); mbar_init(&empty[s], 1); }
+    for (int b = 0; b < 2; b++) { mbar_init(&acc_full[b], 1); mbar_init(&acc_empty[b], 256); }
+    fence_barrier_init();
+  }
+  if (warp == 1) { tmem_alloc2(tmem_slot, 512); tmem_relinquish2(); }
+  tc_fence_before();
+  cluster_sync_all();                // barriers of BOTH CTAs are initialised before anybody signals across
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+  auto blk_of = [&](uint32_t t) { uint3 b; b.x = 2 * (t % xpairs) + rank; const uint32_t r = t / xpairs; b.y = r % lgrid.y; b.z = r / lgrid.y; return b; };
+
+  if (warp == 0) {
+    // ===================== TMA producer (both CTAs) =====================
+    if (lane == 0) {
+      int s = 0; uint32_t ph = 0;
+      for (uint32_t t = pair_id; t < total; t += npairs) {
+        const typename Pol::Tile tl = Pol::tile(prm, blk_of(t));
+        const int nk = Pol::num_kblocks(prm, tl);
+        for (int kb = 0; kb < nk; kb++) {
+          mbar_wait(&empty[s], ph ^ 1);
+          uint8_t* st = smem + s * STAGE;
+          if (rank == 0) mbar_expect_tx(&full[s], 2 * (Pol::p_bytes(prm, P_BYTES) + QH_BYTES));
+          Pol::load2(prm, tl, kb, st, st + P_BYTES, mapa_shared(smem_u32(&full[s]), 0), (int)rank);
+          if (++s == S) { s = 0; ph ^= 1; }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ===================== MMA issuer (leader CTA only) =====================
+    if (rank == 0) {
+      constexpr uint32_t idesc = umma_idesc_tf32(2 * TC_LANES, TN, P_MN ? 1 : 0, Q_MN ? 1 : 0);
+      const MnDescCfg mnc = prm.mnc;
+      const uint32_t hiK = (1024u >> 4) | (1u << 14) | (2u << 29), loK = (16u >> 4) << 16, stepK = 32u >> 4;
+      const uint32_t hiM = (mnc.sbo >> 4) | (1u << 14) | (mnc.layout << 29), loM = (mnc.lbo >> 4) << 16, stepM = mnc.kadv >> 4;
+      const uint32_t hiP = P_MN ? hiM : hiK, loP = P_MN ? loM : loK, stepP = P_MN ? stepM : stepK;
+      const uint32_t hiQ = Q_MN ? hiM : hiK, loQ = Q_MN ? loM : loK, stepQ = Q_MN ? stepM : stepK;
+      const uint32_t smem0 = smem_u32(smem) >> 4;
+      int s = 0; uint32_t ph = 0, ti = 0;
+      for (uint32_t t = pair_id; t < total; t += npairs) {
+        const typename Pol::Tile tl = Pol::tile(prm, blk_of(t));
+        const int nk = Pol::num_kblocks(prm, tl);
+        if (nk <= 0) continue;
+        const uint32_t ab = ti & 1;
+        mbar_wait(&acc_empty[ab], ((ti >> 1) & 1) ^ 1);
+        tc_fence_after();
+        const uint32_t tacc = tmem_base + ab * (uint32_t)TN;
+        for (int kb = 0; kb < nk; kb++) {
+          mbar_wait(&full[s], ph);
+          tc_fence_after();
+          if (elect_one()) {
+            const uint32_t st = smem0 + (uint32_t)s * (STAGE >> 4);
+            const uint32_t aP = st + loP, aQ = st + (P_BYTES >> 4) + loQ;
+#pragma unroll
+            for (int k = 0; k < TC_BK / 8; k++)
+              umma_tf32_2cta(tacc, umma_desc_pack(aP + k * stepP, hiP), umma_desc_pack(aQ + k * stepQ, hiQ), idesc, !(kb == 0 && k == 0));
+            umma_commit_2cta(&empty[s], 3);
+            if (kb == nk - 1) umma_commit_2cta(&acc_full[ab], 3);
+          }
+          __syncwarp();
+          if (++s == S) { s = 0; ph ^= 1; }
+        }
+        ti++;
+      }
+    }
+  } else {
+    // ===================== drain / epilogue (both CTAs, each its own 128 lanes) =====================
+    const int q = warp & 3;
+    const int row = 32 * q + lane;
+    const uint32_t tlane = tmem_base + ((uint32_t)(32 * q) << 16);
+    const uint32_t rel0 = mapa_shared(smem_u32(&acc_empty[0]), 0), rel1 = mapa_shared(smem_u32(&acc_empty[1]), 0);
+    uint32_t ti = 0;
+    for (uint32_t t = pair_id; t < total; t += npairs) {
+      const typename Pol::Tile tl = Pol::tile(prm, blk_of(t));
+      const int nk = Pol::num_kblocks(prm, tl);
+      if (nk <= 0) continue;
+      uint32_t pre[TN / 32];
+      Pol::pre_epilogue(prm, tl, row, pre);
+      const uint32_t ab = ti & 1;
+      mbar_wait(&acc_full[ab], (ti >> 1) & 1);
+      tc_fence_after();
+#pragma unroll
+      for (int c0 = 0; c0 < TN; c0 += 32) {
+        float v[32];
+        tmem_ld32(tlane + ab * (uint32_t)TN + (uint32_t)c0, v);
+        tmem_ld_wait();
+        Pol::store(prm, tl, 0, row, c0, v, pre[c0 / 32]);
+      }
+      tc_fence_before();
+      mbar_arrive_cluster(ab ? rel1 : rel0);
+      ti++;
+    }
+  }
+  tc_fence_before();
+  cluster_sync_all();                // nobody leaves (or frees TMEM) while the peer may still read its shared memory / signal its barriers
+  if (warp == 1) tmem_dealloc2(tmem_base, 512);
+}
+
 template <class Pol>
 static int tc_tile_launch(agb_ctx* ctx, const typename Pol::Params& prm, dim3 grid) {
   const uint64_t total = (uint64_t)grid.x * grid.y * grid.z;
@@ -505,6 +630,20 @@ static int tc_tile_launch(agb_ctx* ctx, const typename Pol::Params& prm, dim3 gr
     return AGB_OK;
   } else {
     using Cfg = TcCfg<Pol::TN, false, Pol::OCC, Pol::MT>;
+    if constexpr (Pol::PAIR2) {           // CTA pairs (cta_group::2): the policy provides load2 and half-Q tensor maps
+      static const int pair_on = [] { const char* e = getenv("AGB_TC_PAIR"); return (e && e[0] == '0') ? 0 : 1; }();
+      const uint64_t ptotal = (uint64_t)((grid.x + 1) / 2) * grid.y * grid.z;
+      if (pair_on && ptotal < (1ull << 31) && ptotal >= 1) {
+        constexpr int SMEM2 = 6 * (TC_LANES * TC_BK * 4 + (Pol::TN / 2) * TC_BK * 4) + 1024 + 256;
+        static bool attr3 = false;
+        if (!attr3) { AGB_CUDA(cudaFuncSetAttribute(tc_tile_pair_kernel<Pol>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM2)); attr3 = true; }
+        const uint64_t cap = (uint64_t)(ctx->sm_count / 2);
+        const unsigned np = (unsigned)(ptotal < cap ? ptotal : cap);
+        tc_tile_pair_kernel<Pol><<<2 * np, 192, SMEM2, ctx->stream>>>(prm, make_uint3(grid.x, grid.y, grid.z));
+        AGB_LAUNCHED(ctx);
+        return AGB_OK;
+      }
+    }
     static int persist = -1;
     if (persist < 0) { const char* e = getenv("AGB_TC_PERSIST"); persist = (e && e[0] == '0') ? 0 : 1; }
     if (persist && total < (1ull << 31)) {
