@@ -68,6 +68,12 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
     if (clock64() - t0 > 4000000000ll) { printf("agb200: mbarrier wait timed out (block %d,%d,%d thread %d)\n", blockIdx.x, blockIdx.y, blockIdx.z, threadIdx.x); __trap(); }
   }
 }
+// one lane polls, the warp waits at the convergence point: 32x fewer shared-memory probes than every thread spinning on the barrier
+// (the splitter and drain warps of the 3xTF32 kernels are 256 threads that would otherwise poll next to the tensor core's operand reads)
+__device__ __forceinline__ void mbar_wait_warp(uint64_t* bar, uint32_t parity) {
+  if ((threadIdx.x & 31) == 0) mbar_wait(bar, parity);
+  __syncwarp();
+}
 __device__ __forceinline__ void tma_prefetch_desc(const void* tmap) {
   asm volatile("prefetch.tensormap [%0];" :: "l"(tmap) : "memory");
 }

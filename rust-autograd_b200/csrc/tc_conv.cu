@@ -43,12 +43,14 @@ __global__ void __launch_bounds__(256) repack_filter_kernel(const float* __restr
 // MT_ = 2: the CTA owns an 8x32 pixel patch = two 128-lane M-tiles (rows 0-3 / 4-7, ONE {32 c, 32 w, 8 h} box per k-block) that
 // share every filter tile: 1.33x (TN 128) / 1.5x (TN 256) fewer bytes through L2 -> smem per output, the bound of these kernels.
 template <int TN_, bool SPLIT_, int MT_ = 1> struct ConvFpropPol {
-  static constexpr int TN = TN_, MT = MT_; static constexpr bool SPLIT = SPLIT_, P_MN = false, Q_MN = false, Q_PRESPLIT = SPLIT_, PAIR2 = false;
+  static constexpr int TN = TN_, MT = MT_; static constexpr bool SPLIT = SPLIT_, P_MN = false, Q_MN = false, Q_PRESPLIT = SPLIT_;
+  static constexpr bool SPLIT_PAIR2 = SPLIT_ && TN_ == 128 && MT_ == 1;      // 3xTF32 CTA pairs (tc_tile_split_pair_kernel): tmWh / tmWlh = 64-row boxes of the filter's hi / lo planes
+  static constexpr bool PAIR2 = !SPLIT_ && TN_ == 256 && MT_ == 1;      // CTA pairs (tc_tile_pair_kernel): two adjacent pixel tiles, each CTA streams half of the filter rows (tmWlo = half-height boxes)
   static constexpr int OCC = (SPLIT_ || TN_ > 128 || MT_ > 1) ? 1 : 2;
   // The 128 lanes of an M-tile are a {bw w, bh h, bb images} pixel box (TMA writes box elements in exactly that order): 32x4x1 for
   // maps at least 32 wide; narrow maps take whole rows and, when a whole image is smaller than the tile, several images
   // (14x14 -> 14x9x1, 7x7 -> 7x7x2).  Lanes past bw*bh*bb read stale shared memory and are never stored.
-  struct Params { CUtensorMap tmX, tmW, tmWlo; float* y; const float* bias; const float* mask; float* csum; int relu; int B, Cout, yh, yw, stride, tiles_x, tiles_y, cblocks, taps;
+  struct Params { CUtensorMap tmX, tmW, tmWlo, tmWh, tmWlh; float* y; const float* bias; const float* mask; float* csum; int relu; int B, Cout, yh, yw, stride, tiles_x, tiles_y, cblocks, taps;
                   int bw, bh, bb; uint32_t p_bytes; MnDescCfg mnc;
                   // tap k of the k-loop: input box origin = tile origin * stride + (dx[k], dy[k]), filter slice wt[k] of the repacked filter
                   short dy[AGB_CONV_MAX_TAPS], dx[AGB_CONV_MAX_TAPS], wt[AGB_CONV_MAX_TAPS];
@@ -82,6 +84,17 @@ template <int TN_, bool SPLIT_, int MT_ = 1> struct ConvFpropPol {
   __device__ static void load_q_lo(const Params& p, const Tile& t, int kb, uint8_t* pQlo, uint64_t* bar) {          // 3xTF32: the pre-split filter's low plane
     const int tap = kb / p.cblocks, cb = kb - tap * p.cblocks;
     tma_load_3d(pQlo, &p.tmWlo, bar, cb * 32, t.o0, p.wt[tap]);
+  }
+  __device__ static void load_sp2(const Params& p, const Tile& t, int kb, uint8_t* pP, uint8_t* pQh, uint8_t* pQl, uint64_t* bar, int rank) {     // 3xTF32 CTA pair: own pixels + half of the filter rows, both planes
+    const int tap = kb / p.cblocks, cb = kb - tap * p.cblocks;
+    tma_load_4d(pP, &p.tmX, bar, cb * 32, t.ox0 * p.stride + p.dx[tap], t.oy0 * p.stride + p.dy[tap], t.b);
+    tma_load_3d(pQh, &p.tmWh, bar, cb * 32, t.o0 + rank * (TN / 2), p.wt[tap]);
+    tma_load_3d(pQl, &p.tmWlh, bar, cb * 32, t.o0 + rank * (TN / 2), p.wt[tap]);
+  }
+  __device__ static void load2(const Params& p, const Tile& t, int kb, uint8_t* pP, uint8_t* pQ, uint32_t bar, int rank) {     // CTA pair: own pixels + half of the filter rows
+    const int tap = kb / p.cblocks, cb = kb - tap * p.cblocks;
+    tma_load_4d_2sm(pP, &p.tmX, bar, cb * 32, t.ox0 * p.stride + p.dx[tap], t.oy0 * p.stride + p.dy[tap], t.b);
+    tma_load_3d_2sm(pQ, &p.tmWlo, bar, cb * 32, t.o0 + rank * (TN / 2), p.wt[tap]);
   }
   // dgrad + ReLU backward of the layer below: bit j of pre[c] = (mask_src[pixel, o0 + 32c + j] > 0).  Read while the MMAs run, so the
   // strided (one pixel per thread) loads cost no epilogue latency; default-cached so both halves of a 32-byte sector are used.
@@ -164,7 +177,9 @@ template <int TN_, bool SPLIT_, int MT_ = 1> struct ConvFpropPol {
 // MT_ = 2 (non-PAIR): the CTA owns two (tap, 128-channel tile) units — two M-tiles that share every gy tile, so gy is pulled from
 // L2 half as often (the TN = 256 wgrad moved 48 KB per 4 MMAs: bound by L2 -> smem ingest at 43 % tensor activity).
 template <int TN_, bool SPLIT_, bool PAIR_, int MT_ = 1> struct ConvWgradPol {
-  static constexpr int TN = TN_, MT = MT_; static constexpr bool SPLIT = SPLIT_, P_MN = true, Q_MN = true, Q_PRESPLIT = false, PAIR2 = false;
+  static constexpr int TN = TN_, MT = MT_; static constexpr bool SPLIT = SPLIT_, P_MN = true, Q_MN = true, Q_PRESPLIT = false;
+  static constexpr bool SPLIT_PAIR2 = false;
+  static constexpr bool PAIR2 = !SPLIT_ && TN_ == 256 && MT_ == 1 && !PAIR_;      // CTA pairs: two (tap, 128-channel tile) units share every gy tile, each CTA streams half of its columns
   static constexpr int OCC = (SPLIT_ || TN_ > 128 || MT_ > 1) ? 1 : 2;
   static_assert(!(PAIR_ && MT_ > 1), "tap pairing within one M-tile and two M-tiles are alternatives");
   struct Params { CUtensorMap tmX, tmG; float* gw; int C, O, T, kw, pad, dil, stride, yh, xblocks, kb_total, kb_per_split; MnDescCfg mnc; };
@@ -207,6 +222,16 @@ template <int TN_, bool SPLIT_, bool PAIR_, int MT_ = 1> struct ConvWgradPol {
     }
 #pragma unroll
     for (int g = 0; g < TN / 32; g++) tma_load_4d(pQ + g * 4096, &p.tmG, bar, t.o0 + 32 * g, ox0, oy, b);
+  }
+  __device__ static void load2(const Params& p, const Tile& t, int kb, uint8_t* pP, uint8_t* pQ, uint32_t bar, int rank) {
+    const int q = t.q0 + kb; const int xb = q % p.xblocks; const int r = q / p.xblocks; const int oy = r % p.yh, b = r / p.yh;
+    const int ox0 = xb * 32;
+    const int iA = t.tapA / p.kw, jA = t.tapA - iA * p.kw;
+    const int xA = ox0 * p.stride + jA * p.dil - p.pad, yA = oy * p.stride + iA * p.dil - p.pad;
+#pragma unroll
+    for (int g = 0; g < 4; g++) tma_load_4d_2sm(pP + g * 4096, &p.tmX, bar, t.c0 + 32 * g, xA, yA, b);
+#pragma unroll
+    for (int g = 0; g < TN / 64; g++) tma_load_4d_2sm(pQ + g * 4096, &p.tmG, bar, t.o0 + rank * (TN / 2) + 32 * g, ox0, oy, b);
   }
   __device__ static void pre_epilogue(const Params&, const Tile&, int, uint32_t*) {}
   __device__ static void store(const Params& p, const Tile& t, int mt, int lane, int c0, const float* v, uint32_t) {
@@ -270,7 +295,14 @@ static int fprop_launch(agb_ctx* ctx, const float* x, const float* wr, float* y,
     uint32_t box[3] = {32, (uint32_t)TN, 1};
     AGB_TRY(agb_make_tmap(&p.tmW, wr, 3, dims, str, box, false));
     if (SPLIT) AGB_TRY(agb_make_tmap(&p.tmWlo, wr + (size_t)kh * kw * Cout * Cin, 3, dims, str, box, false));      // the low plane follows the repacked filter (repack_filter_kernel)
+    else if (Pol::PAIR2) { uint32_t hbox[3] = {32, (uint32_t)TN / 2, 1}; AGB_TRY(agb_make_tmap(&p.tmWlo, wr, 3, dims, str, hbox, false)); }
     else p.tmWlo = p.tmW;
+    p.tmWh = p.tmW; p.tmWlh = p.tmWlo;
+    if (Pol::SPLIT_PAIR2) {
+      uint32_t hbox[3] = {32, (uint32_t)TN / 2, 1};
+      AGB_TRY(agb_make_tmap(&p.tmWh, wr, 3, dims, str, hbox, false));
+      AGB_TRY(agb_make_tmap(&p.tmWlh, wr + (size_t)kh * kw * Cout * Cin, 3, dims, str, hbox, false));
+    }
   }
   p.y = y; p.bias = bias; p.mask = mask; p.csum = csum; p.relu = relu; p.Cout = Cout; p.yh = yh; p.yw = yw;
   p.tiles_x = (yw + bw - 1) / bw; p.tiles_y = (yh + bh * MT - 1) / (bh * MT); p.cblocks = (Cin + 31) / 32; p.mnc = agb_mn_cfg();
@@ -427,6 +459,9 @@ int agb_tc_conv_wgrad(agb_ctx* ctx, int mode, const float* img, const float* g, 
   if (m2 < 0) { const char* e = getenv("AGB_WGRAD_M2"); m2 = (e && e[0] == '0') ? 0 : 1; }
   // measured (B200, B = 256): C256/O256 0.66 -> 0.54 ms, C128/O256 0.37 -> 0.32 ms; with TN = 128 the one-M-tile kernel at two CTAs
   // per SM is faster (0.57 vs 0.78 ms), so only the 256-wide tiles pair up
+  // measured (B200, B = 256): CTA pairs lose to two M-tiles per CTA here (C256/O256 0.63 vs 0.55 ms, C128/O256 0.49 vs 0.32 ms): kept as an opt-in experiment
+  static const int pair2 = [] { const char* e = getenv("AGB_WGRAD_PAIR"); return (e && e[0] == '1') ? 1 : 0; }();
+  if (pair2 && !pair && O > 128) return wgrad_launch<256, false, false, 1>(ctx, img, g, gw, B, C, H, W, O, yh, yw, kh, kw, pad, dil, stride);      // CTA pairs (ConvWgradPol::PAIR2)
   if (m2 && !pair && O > 128) return wgrad_launch<256, false, false, 2>(ctx, img, g, gw, B, C, H, W, O, yh, yw, kh, kw, pad, dil, stride);
   if (O > 128) return WG(256, false);
   if (O > 64) return WG(128, false);

@@ -24,10 +24,11 @@
 template <int TN_, bool P_MN_, bool Q_MN_, bool SPLIT_, bool QPRE_ = false> struct GemmPol {
   static constexpr int TN = TN_, MT = 1; static constexpr bool SPLIT = SPLIT_, P_MN = P_MN_, Q_MN = Q_MN_, Q_PRESPLIT = QPRE_;
   static constexpr int OCC = (SPLIT_ || TN_ > 128) ? 1 : 2;
-  static constexpr bool PAIR2 = !SPLIT_ && TN_ == 256;       // CTA pairs: tmQh = the Q map with TN / 2 rows per box
+  static constexpr bool PAIR2 = !SPLIT_ && TN_ == 256;       // CTA pairs: tmQlo = the Q map with TN / 2 rows per box
+  static constexpr bool SPLIT_PAIR2 = SPLIT_ && QPRE_ && TN_ == 128;      // 3xTF32 CTA pairs: tmQh / tmQlh = half-height boxes of the hi / lo planes
   // splits > 1: split-K for problems with too few output tiles to fill the machine (e.g. the LSTM's 128 x 1024 x 8192 dgrad GEMM is
   // 8 tiles): grid.z = batch * splits, every CTA reduces kb_per_split k-blocks and adds its partial with red.global.add (C pre-zeroed)
-  struct Params { CUtensorMap tmP, tmQ, tmQlo /* 3xTF32: lo plane; CTA pairs: half-height Q boxes */; float* C; int NL, NC, K; int64_t ldc, bsc; int accumulate; int splits, kb_per_split; MnDescCfg mnc; };
+  struct Params { CUtensorMap tmP, tmQ, tmQlo /* 3xTF32: lo plane; CTA pairs: half-height Q boxes */, tmQh, tmQlh; float* C; int NL, NC, K; int64_t ldc, bsc; int accumulate; int splits, kb_per_split; MnDescCfg mnc; };
   struct Tile { int lane0, col0, bz, kb0, nkb; };
   __device__ static Tile tile(const Params& p, uint3 blk) {
     const int kb_total = (p.K + TC_BK - 1) / TC_BK;
@@ -50,6 +51,13 @@ template <int TN_, bool P_MN_, bool Q_MN_, bool SPLIT_, bool QPRE_ = false> stru
     load_q(&p.tmQ, t, kb, pQ, bar);
   }
   __device__ static void load_q_lo(const Params& p, const Tile& t, int kb, uint8_t* pQlo, uint64_t* bar) { load_q(&p.tmQlo, t, kb, pQlo, bar); }       // 3xTF32 with the Q operand pre-split in global memory
+  __device__ static void load_sp2(const Params& p, const Tile& t, int kb, uint8_t* pP, uint8_t* pQh, uint8_t* pQl, uint64_t* bar, int rank) {
+    const int k0 = (t.kb0 + kb) * TC_BK, c0 = t.col0 + rank * (TN / 2);
+    if (P_MN) { for (int j = 0; j < TC_LANES / 32; j++) tma_load_3d(pP + j * 4096, &p.tmP, bar, t.lane0 + 32 * j, k0, t.bz); }
+    else tma_load_3d(pP, &p.tmP, bar, k0, t.lane0, t.bz);
+    if (Q_MN) { for (int j = 0; j < TN / 64; j++) { tma_load_3d(pQh + j * 4096, &p.tmQh, bar, c0 + 32 * j, k0, t.bz); tma_load_3d(pQl + j * 4096, &p.tmQlh, bar, c0 + 32 * j, k0, t.bz); } }
+    else { tma_load_3d(pQh, &p.tmQh, bar, k0, c0, t.bz); tma_load_3d(pQl, &p.tmQlh, bar, k0, c0, t.bz); }
+  }
   // CTA pair: this CTA's 128 P rows + its half of the Q rows, completing on the leader's barrier
   __device__ static void load2(const Params& p, const Tile& t, int kb, uint8_t* pP, uint8_t* pQ, uint32_t bar, int rank) {
     const int k0 = (t.kb0 + kb) * TC_BK, c0 = t.col0 + rank * (TN / 2);
@@ -97,9 +105,10 @@ static int tc_make_map(CUtensorMap* m, const TcOperand& o, int64_t K, int64_t ba
   return agb_make_tmap(m, o.p, 3, dims, strides, box, mn_major && a32);
 }
 
+struct TcHalfMaps { CUtensorMap hi, lo; };       // 3xTF32 CTA pairs: TN / 2-row boxes of the pre-split Q planes
 template <int TN, bool P_MN, bool Q_MN, bool SPLIT, bool QPRE = false>
 static int tc_launch(agb_ctx* ctx, const CUtensorMap& tmP, const CUtensorMap& tmQ, const CUtensorMap* tmQlo, float* C, int NL, int NC, int K, int64_t ldc, int64_t bsc,
-                     int64_t batch, int accumulate) {
+                     int64_t batch, int accumulate, const TcHalfMaps* half = nullptr) {
   using Pol = GemmPol<TN, P_MN, Q_MN, SPLIT, QPRE>;
   const int gx = (NL + TC_LANES - 1) / TC_LANES, gy = (NC + TN - 1) / TN;
   const int kb_total = (K + TC_BK - 1) / TC_BK;
@@ -114,18 +123,18 @@ static int tc_launch(agb_ctx* ctx, const CUtensorMap& tmP, const CUtensorMap& tm
   int kb_per = (kb_total + splits - 1) / splits; splits = (kb_total + kb_per - 1) / kb_per;
   if ((int64_t)batch * splits > 65535) { splits = 1; kb_per = kb_total; }
   if (splits > 1 && !accumulate) AGB_TRY(agb_memset0(ctx, C, (size_t)batch * NC * NL * sizeof(float)));
-  typename Pol::Params prm{tmP, tmQ, tmQlo ? *tmQlo : tmQ, C, NL, NC, K, ldc, bsc, accumulate, splits, kb_per, agb_mn_cfg()};
+  typename Pol::Params prm{tmP, tmQ, tmQlo ? *tmQlo : tmQ, half ? half->hi : tmQ, half ? half->lo : tmQ, C, NL, NC, K, ldc, bsc, accumulate, splits, kb_per, agb_mn_cfg()};
   dim3 grid(gx, gy, (unsigned)(batch * splits));
   return tc_tile_launch<Pol>(ctx, prm, grid);
 }
 
 template <int TN, bool SPLIT, bool QPRE = false>
 static int tc_dispatch_major(agb_ctx* ctx, bool pmn, bool qmn, const CUtensorMap& tmP, const CUtensorMap& tmQ, const CUtensorMap* tmQlo, float* C, int NL, int NC, int K,
-                             int64_t ldc, int64_t bsc, int64_t batch, int acc) {
-  if (!pmn && !qmn) return tc_launch<TN, false, false, SPLIT, QPRE>(ctx, tmP, tmQ, tmQlo, C, NL, NC, K, ldc, bsc, batch, acc);
-  if (!pmn && qmn) return tc_launch<TN, false, true, SPLIT, QPRE>(ctx, tmP, tmQ, tmQlo, C, NL, NC, K, ldc, bsc, batch, acc);
-  if (pmn && !qmn) return tc_launch<TN, true, false, SPLIT, QPRE>(ctx, tmP, tmQ, tmQlo, C, NL, NC, K, ldc, bsc, batch, acc);
-  return tc_launch<TN, true, true, SPLIT, QPRE>(ctx, tmP, tmQ, tmQlo, C, NL, NC, K, ldc, bsc, batch, acc);
+                             int64_t ldc, int64_t bsc, int64_t batch, int acc, const TcHalfMaps* half = nullptr) {
+  if (!pmn && !qmn) return tc_launch<TN, false, false, SPLIT, QPRE>(ctx, tmP, tmQ, tmQlo, C, NL, NC, K, ldc, bsc, batch, acc, half);
+  if (!pmn && qmn) return tc_launch<TN, false, true, SPLIT, QPRE>(ctx, tmP, tmQ, tmQlo, C, NL, NC, K, ldc, bsc, batch, acc, half);
+  if (pmn && !qmn) return tc_launch<TN, true, false, SPLIT, QPRE>(ctx, tmP, tmQ, tmQlo, C, NL, NC, K, ldc, bsc, batch, acc, half);
+  return tc_launch<TN, true, true, SPLIT, QPRE>(ctx, tmP, tmQ, tmQlo, C, NL, NC, K, ldc, bsc, batch, acc, half);
 }
 
 // 3xTF32: hi = rna_tf32(x), lo = rna_tf32(x - hi) planes of a dense operand, written once to scratch when the operand is re-read by
@@ -210,7 +219,12 @@ int agb_tc_gemm(agb_ctx* ctx, int mode, const float* A, const float* B, float* C
       TcOperand Qh = Q, Ql = Q; Qh.p = planes; Ql.p = planes + qn;
       r = tc_make_map(&tmQh, Qh, K, batch, qmn, TN); if (r != AGB_OK) return r;
       r = tc_make_map(&tmQl, Ql, K, batch, qmn, TN); if (r != AGB_OK) return r;
-      if (TN == 128) return tc_dispatch_major<128, true, true>(ctx, pmn, qmn, tmP, tmQh, &tmQl, C, (int)N, (int)M, (int)K, N, bsc, batch, acc);
+      if (TN == 128) {
+        TcHalfMaps half;
+        r = tc_make_map(&half.hi, Qh, K, batch, qmn, TN / 2); if (r != AGB_OK) return r;
+        r = tc_make_map(&half.lo, Ql, K, batch, qmn, TN / 2); if (r != AGB_OK) return r;
+        return tc_dispatch_major<128, true, true>(ctx, pmn, qmn, tmP, tmQh, &tmQl, C, (int)N, (int)M, (int)K, N, bsc, batch, acc, &half);
+      }
       return tc_dispatch_major<64, true, true>(ctx, pmn, qmn, tmP, tmQh, &tmQl, C, (int)N, (int)M, (int)K, N, bsc, batch, acc);
     }
     if (TN == 128) return tc_dispatch_major<128, true>(ctx, pmn, qmn, tmP, tmQ, nullptr, C, (int)N, (int)M, (int)K, N, bsc, batch, acc);

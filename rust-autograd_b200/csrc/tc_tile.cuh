@@ -51,6 +51,7 @@ template <int TN, bool SPLIT, int OCC = 1, int MT = 1> struct TcCfg {
 
 // Policy interface:
 //   static constexpr int TN, OCC; static constexpr bool SPLIT, P_MN, Q_MN, Q_PRESPLIT, PAIR2;
+//   (SPLIT_PAIR2) __device__ static void load_sp2(const Params&, const Tile&, int kb, uint8_t* pP, uint8_t* pQh_hi, uint8_t* pQh_lo, uint64_t* bar, int rank);
 //   (PAIR2) __device__ static void load2(const Params&, const Tile&, int kb, uint8_t* pP, uint8_t* pQhalf, uint32_t leader_bar, int rank);
 //   (Q_PRESPLIT) __device__ static void load_q_lo(const Params&, const Tile&, int kb, uint8_t* pQlo, uint64_t* bar);
 //   struct Params { ... CUtensorMap members ...; MnDescCfg mnc; };
@@ -170,19 +171,20 @@ __global__ void __launch_bounds__(TcCfg<Pol::TN, false, Pol::OCC, Pol::MT>::THRE
 // tile's fp32 partial sums in registers (TN <= 128) until its last chunk, then run the Policy's epilogue while the issuer already works
 // on the next tile's first two chunks.
 template <class Pol>
-__global__ void __launch_bounds__(320, 1) tc_tile_split_kernel(const __grid_constant__ typename Pol::Params prm, const uint3 lgrid, const int kc /* k-blocks per TMEM chunk */, const int order) {
+__global__ void __launch_bounds__(320, 1) tc_tile_split_kernel(const __grid_constant__ typename Pol::Params prm, const uint3 lgrid, const int kc /* k-blocks per TMEM chunk */, const int order, const int poll /* 1: one lane per warp polls */, const int nstages) {
   constexpr int TN = Pol::TN; constexpr bool P_MN = Pol::P_MN, Q_MN = Pol::Q_MN;
   static_assert(Pol::SPLIT && Pol::MT == 1 && TN <= 128, "3xTF32: one M-tile, TN fp32 partial sums per drain thread");
   constexpr bool QPRE = Pol::Q_PRESPLIT;                 // Q's lo plane comes from global memory (second TMA load), only P is split here
   using Cfg = TcCfg<TN, true, 1, 1>;
-  constexpr int S = Cfg::STAGES;
+  constexpr int SMAX = Cfg::STAGES;
+  const int S = nstages > 0 && nstages < SMAX ? nstages : SMAX;
   constexpr int LO_OFF = Cfg::P_BYTES + Cfg::Q_BYTES;    // stage = [P | Q | P_lo | Q_lo]
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
-  uint64_t* bars = (uint64_t*)(smem + S * Cfg::STAGE_BYTES);
-  uint64_t* full = bars; uint64_t* ready = bars + S; uint64_t* empty = bars + 2 * S;
-  uint64_t* acc_full = bars + 3 * S; uint64_t* acc_empty = bars + 3 * S + 2;
-  uint32_t* tmem_slot = (uint32_t*)(bars + 3 * S + 4);
+  uint64_t* bars = (uint64_t*)(smem + SMAX * Cfg::STAGE_BYTES);
+  uint64_t* full = bars; uint64_t* ready = bars + SMAX; uint64_t* empty = bars + 2 * SMAX;
+  uint64_t* acc_full = bars + 3 * SMAX; uint64_t* acc_empty = bars + 3 * SMAX + 2;
+  uint32_t* tmem_slot = (uint32_t*)(bars + 3 * SMAX + 4);
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const uint32_t total = lgrid.x * lgrid.y * lgrid.z;
 
@@ -280,7 +282,7 @@ __global__ void __launch_bounds__(320, 1) tc_tile_split_kernel(const __grid_cons
       const typename Pol::Tile tl = Pol::tile(prm, blk_of(t));
       const int nk = Pol::num_kblocks(prm, tl);
       for (int kb = 0; kb < nk; kb++) {
-        mbar_wait(&full[s], ph);
+        if (poll) mbar_wait_warp(&full[s], ph); else mbar_wait(&full[s], ph);
         float4* hi = (float4*)(smem + s * Cfg::STAGE_BYTES);
         float4* lo = (float4*)(smem + s * Cfg::STAGE_BYTES + LO_OFF);
         constexpr int NP4 = Cfg::P_BYTES / 16, NQ4 = Cfg::Q_BYTES / 16;
@@ -329,7 +331,7 @@ __global__ void __launch_bounds__(320, 1) tc_tile_split_kernel(const __grid_cons
       ti++;
       for (int c = 0; c < nchunks; c++, ch++) {
         const uint32_t buf = ch & 1;
-        mbar_wait(&acc_full[buf], (ch >> 1) & 1);
+        if (poll) mbar_wait_warp(&acc_full[buf], (ch >> 1) & 1); else mbar_wait(&acc_full[buf], (ch >> 1) & 1);
         tc_fence_after();
 #pragma unroll
         for (int c0 = 0; c0 < TN; c0 += 32) {
@@ -613,6 +615,186 @@ tc_tile_pair_kernel(const __grid_constant__ typename Pol::Params prm, const uint
   if (warp == 1) tmem_dealloc2(tmem_base, 512);
 }
 
+// ------------------------------------------------------------------------------------------------ 3xTF32 on CTA pairs
+// The f32-faithful mode is bound by shared-memory bandwidth (an N = 128 MMA reads 128 B/clk, the splitters add to it).  A CTA pair
+// running M = 256 x N = 128 MMAs reads, per CTA and MMA, its own 128 P rows (4 KB) but only 64 Q rows (2 KB): 96 instead of 128 B/clk,
+// which leaves room for the splitters' P traffic.  Requires Pol::Q_PRESPLIT (both Q planes arrive by TMA, nothing to split on that side).
+// Warps per CTA: 0 producer, 1 issuer (leader only), 2-5 splitters, 6-9 drain.  Each CTA's loads complete on its OWN `full` barrier; its
+// splitters write P_lo and then one thread arrives on the LEADER's `ready` barrier (count 2), so `ready` = both CTAs' tiles landed and split.
+template <class Pol>
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(320, 1)
+tc_tile_split_pair_kernel(const __grid_constant__ typename Pol::Params prm, const uint3 lgrid, const int kc) {
+  constexpr int TN = Pol::TN; constexpr bool P_MN = Pol::P_MN, Q_MN = Pol::Q_MN;
+  static_assert(Pol::SPLIT && Pol::Q_PRESPLIT && Pol::MT == 1 && TN == 128, "3xTF32 CTA pairs: pre-split Q, 128-wide tiles");
+  constexpr int P_BYTES = TC_LANES * TC_BK * 4, QH_BYTES = (TN / 2) * TC_BK * 4;
+  constexpr int STAGE = 2 * P_BYTES + 2 * QH_BYTES;          // [P | Qh | P_lo | Qh_lo]
+  constexpr int LO_OFF = P_BYTES + QH_BYTES;
+  constexpr int S = 4;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
+  uint64_t* bars = (uint64_t*)(smem + S * STAGE);
+  uint64_t* full = bars; uint64_t* ready = bars + S; uint64_t* empty = bars + 2 * S;
+  uint64_t* acc_full = bars + 3 * S; uint64_t* acc_empty = bars + 3 * S + 2;
+  uint32_t* tmem_slot = (uint32_t*)(bars + 3 * S + 4);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const uint32_t rank = cluster_ctarank();
+  const uint32_t xpairs = (lgrid.x + 1) / 2, total = xpairs * lgrid.y * lgrid.z;
+  const uint32_t pair_id = blockIdx.x >> 1, npairs = gridDim.x >> 1;
+
+  if (warp == 0 && lane == 0) {
+    Pol::prefetch(prm);
+    for (int s = 0; s < S; s++) { mbar_init(&full[s], 1); mbar_init(&ready[s], 2); mbar_init(&empty[s], 1); }
+    for (int b = 0; b < 2; b++) { mbar_init(&acc_full[b], 1); mbar_init(&acc_empty[b], 256); }
+    fence_barrier_init();
+  }
+  if (warp == 1) { tmem_alloc2(tmem_slot, 512); tmem_relinquish2(); }
+  tc_fence_before();
+  cluster_sync_all();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+  auto blk_of = [&](uint32_t t) { uint3 b; b.x = 2 * (t % xpairs) + rank; const uint32_t r = t / xpairs; b.y = r % lgrid.y; b.z = r / lgrid.y; return b; };
+
+  if (warp == 0) {
+    // ===================== TMA producer (both CTAs, own barrier) =====================
+    if (lane == 0) {
+      int s = 0; uint32_t ph = 0;
+      for (uint32_t t = pair_id; t < total; t += npairs) {
+        const typename Pol::Tile tl = Pol::tile(prm, blk_of(t));
+        const int nk = Pol::num_kblocks(prm, tl);
+        for (int kb = 0; kb < nk; kb++) {
+          mbar_wait(&empty[s], ph ^ 1);
+          uint8_t* st = smem + s * STAGE;
+          mbar_expect_tx(&full[s], Pol::p_bytes(prm, P_BYTES) + 2 * QH_BYTES);
+          Pol::load_sp2(prm, tl, kb, st, st + P_BYTES, st + LO_OFF + P_BYTES, &full[s], (int)rank);
+          if (++s == S) { s = 0; ph ^= 1; }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ===================== MMA issuer (leader only) =====================
+    if (rank == 0) {
+      constexpr uint32_t idesc = umma_idesc_tf32(2 * TC_LANES, TN, P_MN ? 1 : 0, Q_MN ? 1 : 0);
+      const MnDescCfg mnc = prm.mnc;
+      const uint32_t hiK = (1024u >> 4) | (1u << 14) | (2u << 29), loK = (16u >> 4) << 16, stepK = 32u >> 4;
+      const uint32_t hiM = (mnc.sbo >> 4) | (1u << 14) | (mnc.layout << 29), loM = (mnc.lbo >> 4) << 16, stepM = mnc.kadv >> 4;
+      const uint32_t hiP = P_MN ? hiM : hiK, loP = P_MN ? loM : loK, stepP = P_MN ? stepM : stepK;
+      const uint32_t hiQ = Q_MN ? hiM : hiK, loQ = Q_MN ? loM : loK, stepQ = Q_MN ? stepM : stepK;
+      const uint32_t smem0 = smem_u32(smem) >> 4;
+      int s = 0; uint32_t ph = 0, ch = 0, ti = 0;
+      for (uint32_t t = pair_id; t < total; t += npairs) {
+        const typename Pol::Tile tl = Pol::tile(prm, blk_of(t));
+        const int nk = Pol::num_kblocks(prm, tl);
+        if (nk <= 0) continue;
+        const uint32_t tcross = tmem_base + (uint32_t)((2 + (ti & 1)) * TN);      // TMEM: [main 0 | main 1 | cross 0 | cross 1], see tc_tile_split_kernel
+        ti++;
+        for (int kb = 0; kb < nk; kb++) {
+          const bool first = (kb % kc) == 0, last = (kb % kc) == kc - 1 || kb == nk - 1;
+          const uint32_t buf = ch & 1;
+          if (first) { mbar_wait(&acc_empty[buf], ((ch >> 1) & 1) ^ 1); tc_fence_after(); }
+          mbar_wait(&ready[s], ph);
+          tc_fence_after();
+          if (elect_one()) {
+            const uint32_t tacc = tmem_base + buf * (uint32_t)TN;
+            const uint32_t st = smem0 + (uint32_t)s * (STAGE >> 4);
+            const uint32_t aP = st + loP, aQ = st + (P_BYTES >> 4) + loQ;
+            const uint32_t aPl = aP + (LO_OFF >> 4), aQl = aQ + (LO_OFF >> 4);
+#pragma unroll
+            for (int k = 0; k < TC_BK / 8; k++) {
+              const uint64_t dP = umma_desc_pack(aP + k * stepP, hiP), dQ = umma_desc_pack(aQ + k * stepQ, hiQ);
+              const uint64_t dPl = umma_desc_pack(aPl + k * stepP, hiP), dQl = umma_desc_pack(aQl + k * stepQ, hiQ);
+              umma_tf32_2cta(tcross, dPl, dQ, idesc, !(kb == 0 && k == 0));
+              umma_tf32_2cta(tcross, dP, dQl, idesc, 1);
+              umma_tf32_2cta(tacc, dP, dQ, idesc, !(first && k == 0));
+            }
+            umma_commit_2cta(&empty[s], 3);
+            if (last) umma_commit_2cta(&acc_full[buf], 3);
+          }
+          __syncwarp();
+          if (last) ch++;
+          if (++s == S) { s = 0; ph ^= 1; }
+        }
+      }
+    }
+  } else if (warp < 6) {
+    // ===================== splitters (both CTAs): P_lo = rna_tf32(P - trunc_tf32(P)) =====================
+    const int tid = threadIdx.x - 64;
+    const uint32_t ready0 = mapa_shared(smem_u32(&ready[0]), 0);
+    int s = 0; uint32_t ph = 0;
+    for (uint32_t t = pair_id; t < total; t += npairs) {
+      const typename Pol::Tile tl = Pol::tile(prm, blk_of(t));
+      const int nk = Pol::num_kblocks(prm, tl);
+      for (int kb = 0; kb < nk; kb++) {
+        mbar_wait(&full[s], ph);
+        const float4* hi = (const float4*)(smem + s * STAGE);
+        float4* lo = (float4*)(smem + s * STAGE + LO_OFF);
+#pragma unroll 4
+        for (int i = tid; i < P_BYTES / 16; i += 128) {
+          const float4 x = hi[i]; float4 l;
+          l.x = tf32_rna(x.x - __uint_as_float(__float_as_uint(x.x) & 0xFFFFE000u));
+          l.y = tf32_rna(x.y - __uint_as_float(__float_as_uint(x.y) & 0xFFFFE000u));
+          l.z = tf32_rna(x.z - __uint_as_float(__float_as_uint(x.z) & 0xFFFFE000u));
+          l.w = tf32_rna(x.w - __uint_as_float(__float_as_uint(x.w) & 0xFFFFE000u));
+          lo[i] = l;
+        }
+        fence_proxy_async();
+        asm volatile("bar.sync 1, 128;" ::: "memory");          // the four splitter warps of this CTA
+        if (tid == 0) mbar_arrive_cluster(ready0 + (uint32_t)s * 8u);
+        if (++s == S) { s = 0; ph ^= 1; }
+      }
+    }
+  } else {
+    // ===================== drain / epilogue (both CTAs) =====================
+    const int q = warp & 3;
+    const int row = 32 * q + lane;
+    const uint32_t tlane = tmem_base + ((uint32_t)(32 * q) << 16);
+    const uint32_t rel0 = mapa_shared(smem_u32(&acc_empty[0]), 0), rel1 = mapa_shared(smem_u32(&acc_empty[1]), 0);
+    uint32_t ch = 0, ti = 0;
+    for (uint32_t t = pair_id; t < total; t += npairs) {
+      const typename Pol::Tile tl = Pol::tile(prm, blk_of(t));
+      const int nk = Pol::num_kblocks(prm, tl);
+      if (nk <= 0) continue;
+      uint32_t pre[TN / 32];
+      Pol::pre_epilogue(prm, tl, row, pre);
+      float racc[TN];
+#pragma unroll
+      for (int j = 0; j < TN; j++) racc[j] = 0.0f;
+      const int nchunks = (nk + kc - 1) / kc;
+      const uint32_t tcross = tlane + (uint32_t)((2 + (ti & 1)) * TN);
+      ti++;
+      for (int c = 0; c < nchunks; c++, ch++) {
+        const uint32_t buf = ch & 1;
+        mbar_wait(&acc_full[buf], (ch >> 1) & 1);
+        tc_fence_after();
+#pragma unroll
+        for (int c0 = 0; c0 < TN; c0 += 32) {
+          float v[32];
+          tmem_ld32(tlane + buf * (uint32_t)TN + (uint32_t)c0, v);
+          tmem_ld_wait();
+#pragma unroll
+          for (int j = 0; j < 32; j++) racc[c0 + j] += v[j];
+        }
+        if (c == nchunks - 1) {
+#pragma unroll
+          for (int c0 = 0; c0 < TN; c0 += 32) {
+            float v[32];
+            tmem_ld32(tcross + (uint32_t)c0, v);
+            tmem_ld_wait();
+#pragma unroll
+            for (int j = 0; j < 32; j++) racc[c0 + j] += v[j];
+          }
+        }
+        tc_fence_before();
+        mbar_arrive_cluster(buf ? rel1 : rel0);
+      }
+#pragma unroll
+      for (int c0 = 0; c0 < TN; c0 += 32) Pol::store(prm, tl, 0, row, c0, &racc[c0], pre[c0 / 32]);
+    }
+  }
+  tc_fence_before();
+  cluster_sync_all();
+  if (warp == 1) tmem_dealloc2(tmem_base, 512);
+}
+
 template <class Pol>
 static int tc_tile_launch(agb_ctx* ctx, const typename Pol::Params& prm, dim3 grid) {
   const uint64_t total = (uint64_t)grid.x * grid.y * grid.z;
@@ -623,9 +805,29 @@ static int tc_tile_launch(agb_ctx* ctx, const typename Pol::Params& prm, dim3 gr
     if (total >= (1ull << 31)) return AGB_ERR_UNSUPPORTED;
     const unsigned n = (unsigned)(total < (uint64_t)ctx->sm_count ? total : (uint64_t)ctx->sm_count);
     if (n == 0) return AGB_OK;
+    if constexpr (Pol::SPLIT_PAIR2) {     // CTA pairs (pre-split Q, 128-wide tiles): see tc_tile_split_pair_kernel
+      // measured (B200): correct, but slower than the one-CTA kernel (GEMM 8192^3: 138 vs 186 useful TFLOP/s; VGG conv layers 125 vs 160-175): the
+      // 3xTF32 pipeline is bound by its depth (3-4 stages against a ~4300-clock stage round trip: ncu, AGB_SPLIT_STAGES=2 costs 27 %), and the
+      // cross-CTA ready / release handshakes lengthen that round trip.  Kept as an opt-in experiment.
+      static const int pair_on = [] { const char* e = getenv("AGB_TC_SPLIT_PAIR"); return (e && e[0] == '1') ? 1 : 0; }();
+      const uint64_t ptotal = (uint64_t)((grid.x + 1) / 2) * grid.y * grid.z;
+      if (pair_on && grid.x >= 2) {
+        constexpr int SMEM2 = 4 * (2 * TC_LANES * TC_BK * 4 + 2 * (Pol::TN / 2) * TC_BK * 4) + 1024 + 256;
+        static bool attr3 = false;
+        if (!attr3) { AGB_CUDA(cudaFuncSetAttribute(tc_tile_split_pair_kernel<Pol>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM2)); attr3 = true; }
+        static const int kc2 = [] { const char* e = getenv("AGB_SPLIT_KC"); int v = e ? atoi(e) : TC_KC; return v < 1 ? 1 : v; }();
+        const uint64_t cap = (uint64_t)(ctx->sm_count / 2);
+        const unsigned np = (unsigned)(ptotal < cap ? ptotal : cap);
+        tc_tile_split_pair_kernel<Pol><<<2 * np, 320, SMEM2, ctx->stream>>>(prm, make_uint3(grid.x, grid.y, grid.z), kc2);
+        AGB_LAUNCHED(ctx);
+        return AGB_OK;
+      }
+    }
     static const int kc = [] { const char* e = getenv("AGB_SPLIT_KC"); int v = e ? atoi(e) : TC_KC; return v < 1 ? 1 : v; }();      // tuning knob: k-blocks per TMEM accumulation chunk
     static const int order = [] { const char* e = getenv("AGB_SPLIT_ORDER"); return e ? atoi(e) : 0; }();
-    tc_tile_split_kernel<Pol><<<n, 320, Cfg::SMEM, ctx->stream>>>(prm, make_uint3(grid.x, grid.y, grid.z), kc, order);
+    static const int poll = [] { const char* e = getenv("AGB_SPLIT_POLL"); return e ? atoi(e) : 1; }();
+    static const int nst = [] { const char* e = getenv("AGB_SPLIT_STAGES"); return e ? atoi(e) : 0; }();
+    tc_tile_split_kernel<Pol><<<n, 320, Cfg::SMEM, ctx->stream>>>(prm, make_uint3(grid.x, grid.y, grid.z), kc, order, poll, nst);
     AGB_LAUNCHED(ctx);
     return AGB_OK;
   } else {
