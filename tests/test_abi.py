@@ -96,3 +96,25 @@ def test_python_view_exposes_every_tensor_ops_constructor():
         assert callable(getattr(ag.Tensor, m, None)), m
     for o in ("Adam", "SGD", "MomentumSGD", "AdaGrad"):
         assert hasattr(ag.optimizers, o), o
+
+
+def test_rust_bindings_are_in_sync_with_the_header():
+    """rust/src/tensor_ops/cuda_ffi.rs + rust/build.rs (the crate-side half of the boundary, generated by scripts/gen_rust_ffi.py): up to
+    date, one `pub fn` per header function with the same number of arguments as the ctypes prototype the tests call through."""
+    import subprocess
+    import sys
+    from rust_autograd_b200 import ffi
+    assert subprocess.run([sys.executable, os.path.join(ROOT, "scripts", "gen_rust_ffi.py"), "--check"]).returncode == 0, "run scripts/gen_rust_ffi.py"
+    rs = open(os.path.join(ROOT, "rust", "src", "tensor_ops", "cuda_ffi.rs")).read()
+    decl = {m.group(1): m.group(2) for m in re.finditer(r"pub fn (agb_[a-z0-9_]+)\((.*?)\) -> ", rs)}
+    assert set(decl) == set(_declared("agb200.h"))
+    for name, args in decl.items():
+        if name == "agb_last_error":
+            continue
+        n_rust = 0 if not args.strip() else len([a for a in args.split(", ") if ":" in a])
+        assert n_rust == len(ffi.SIGNATURES[name]), name
+    build = open(os.path.join(ROOT, "rust", "build.rs")).read()
+    for f in os.listdir(os.path.join(ROOT, "rust-autograd_b200", "csrc")):
+        if f.endswith(".cu"):
+            assert '"%s"' % f[:-3] in build, f
+    assert "arch=compute_100a,code=sm_100a" in build
