@@ -272,9 +272,11 @@ def main():
     # every profiled call: that pass feeds `roofline`, not `value`)
     ffi.check(lib.agb_prof_reset(ctx))
     dev_ms, wall_ms, launches = timed(step_resident, args.steps, args.warmup)
+    env.set_plan_cache(False)             # the per-call event pairs need eager launches (a replayed step graph is one opaque launch)
     ffi.check(lib.agb_prof_enable(ctx, 1)); ffi.check(lib.agb_prof_reset(ctx))
     prof_ms, _, _ = timed(step_resident, args.steps, 0)
     ffi.check(lib.agb_prof_enable(ctx, 0))
+    env.set_plan_cache(True)
     prof = {}
     names = ["gemm", "conv_fprop", "conv_dgrad", "conv_wgrad", "ewise", "reduce", "softmax", "pool", "optim",
              "conv_small_c_fprop", "conv_small_c_wgrad", "conv_simt"]
@@ -350,7 +352,7 @@ def main():
                           "flops_per_step_per_gpu": W.vgg_flops_per_sample() * B},
                "e2e": {"value": e2e_value, "unit": "samples/s", "h2d_bytes_per_step": int(xs[0].nbytes + ys[0].nbytes), "d2h_bytes_per_step": 4,
                        "ms_per_step": e2e_time / args.steps},
-               "gpu_launches": int(launches), "clocks": sampler.summary(), "roofline": roof,
+               "gpu_launches": int(launches), "plan_cache": env.plan_stats(), "clocks": sampler.summary(), "roofline": roof,
                "model_tflops": W.vgg_flops_per_sample() * B / (step_ms / 1e3) / 1e12,
                "losses": {"first": timed_losses[0] if timed_losses else None, "last": timed_losses[-1] if timed_losses else None, "n": len(timed_losses),
                           "note": "rank 0's loss of the first / last timed e2e step (random labels: the value only shows the step trains and is finite)"}}

@@ -326,6 +326,10 @@ int  agb_multi_tensor_adagrad(agb_ctx* ctx, int n, float* const* p, const float*
 int  agb_nccl_unique_id(void* id128);                           /* rank 0: fills 128 bytes */
 int  agb_nccl_init(agb_ctx* ctx, int rank, int world, const void* id128);
 int  agb_allreduce_sum(agb_ctx* ctx, float* buf, int64_t n);    /* in place, on ctx stream */
+/* overlapped form: the sum runs on the context's communication stream after the work enqueued so far; the compute stream continues and
+ * agb_allreduce_wait() orders it behind every bucket issued so far (call before the optimizer reads the sums). */
+int  agb_allreduce_sum_async(agb_ctx* ctx, float* buf, int64_t n);
+int  agb_allreduce_wait(agb_ctx* ctx);
 int  agb_nccl_destroy(agb_ctx* ctx);
 
 #ifdef __cplusplus

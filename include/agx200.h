@@ -36,6 +36,11 @@ const char* agx_last_error(void);
 /* ---- VariableEnvironment ---- */
 int agx_env_new(int device, agx_env** out);
 int agx_env_free(agx_env* env);
+/* Automatic step-plan cache: an evaluation seen for the third time with the same graph structure, targets and feed
+ * shapes is replayed from a CUDA graph captured at its second sight — also when the graph object was rebuilt in between, as the
+ * reference's training loops do (examples/mlp_mnist.rs:74).  On by default; results are the eager ones. */
+int agx_env_set_plan_cache(agx_env* env, int on);
+int agx_env_plan_stats(agx_env* env, int64_t* captures, int64_t* replays, int* live_plans);
 int agx_env_ctx(agx_env* env, agb_ctx** out);
 int agx_env_set(agx_env* env, const char* ns, const char* name, const float* data, const int64_t* shape, int rank, int* vid);   /* slot().name(..).set(..) */
 int agx_env_find(agx_env* env, const char* ns, const char* name, int* vid);          /* -1 when absent */

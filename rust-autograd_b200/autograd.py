@@ -33,7 +33,7 @@ SIGNATURES = {
     "agx_env_set": [_P, C.c_char_p, C.c_char_p, _P, _pi64, _i, _pi], "agx_env_find": [_P, C.c_char_p, C.c_char_p, _pi],
     "agx_env_var_count": [_P, _pi], "agx_env_var_ids": [_P, C.c_char_p, _pi, _i, _pi], "agx_env_var_shape": [_P, _i, _pi64, _pi],
     "agx_env_get": [_P, _i, _P, _i64], "agx_env_put": [_P, _i, _P, _i64], "agx_env_var_ptr": [_P, _i, C.POINTER(_P)],
-    "agx_env_save": [_P, C.c_char_p], "agx_env_load": [_P, C.c_char_p], "agx_env_set_data_parallel": [_P, _i, _i, _P], "agx_env_set_fusion": [_P, _i], "agx_fuse_selftest": [_i, C.c_uint, C.POINTER(C.c_int)],
+    "agx_env_save": [_P, C.c_char_p], "agx_env_load": [_P, C.c_char_p], "agx_env_set_data_parallel": [_P, _i, _i, _P], "agx_env_set_fusion": [_P, _i], "agx_env_set_plan_cache": [_P, _i], "agx_env_plan_stats": [_P, C.POINTER(C.c_int64), C.POINTER(C.c_int64), C.POINTER(C.c_int)], "agx_fuse_selftest": [_i, C.c_uint, C.POINTER(C.c_int)],
     "agx_out_append": [_P, _P, _P, _i], "agx_out_error": [_P, C.c_char_p], "agx_custom_op": [_P, C.c_char_p, _P, _i, _P, _P, _P, C.POINTER(_i)],
     "agx_hook": [_P, _i, _i, C.c_char_p, _P, _P, C.POINTER(_i)],
     "agx_graph_new": [_P, C.POINTER(_P)], "agx_graph_free": [_P], "agx_graph_clear": [_P], "agx_graph_size": [_P, _pi],
@@ -556,6 +556,16 @@ class VariableEnvironment:
         """Deferred elementwise expressions (engine/fuse.cc): on by default; off = one launch per node (elementwise values bit-identical; summed
         weight-gradient GEMMs differ by fp32 reassociation)."""
         _check(lib().agx_env_set_fusion(self.h, 1 if on else 0))
+
+    def set_plan_cache(self, on):
+        """Automatic step-plan cache (capi.cc): an evaluation seen for the third time with the same graph structure, targets and feed shapes
+        replays a CUDA graph captured at its second sight — also across graph objects rebuilt per step (env.run).  On by default."""
+        _check(lib().agx_env_set_plan_cache(self.h, 1 if on else 0))
+
+    def plan_stats(self):
+        c, r, n = C.c_int64(), C.c_int64(), C.c_int()
+        _check(lib().agx_env_plan_stats(self.h, C.byref(c), C.byref(r), C.byref(n)))
+        return {"captures": c.value, "replays": r.value, "live_plans": n.value}
 
     def run(self, f):
         """env.run(|g| ...) (src/variable.rs:670-683): a fresh graph per call."""

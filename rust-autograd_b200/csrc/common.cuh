@@ -34,6 +34,7 @@ struct agb_ctx {
   // nccl
   void* nccl_comm = nullptr;
   int rank = 0, world = 1;
+  cudaStream_t comm_stream = nullptr; cudaEvent_t comm_ready = nullptr, comm_done = nullptr; bool comm_pending = false;   // bucketed all-reduce overlapped with the rest of backward
   bool capturing = false;
   int pinned_graphs = 0;            // live agx_step graphs: the arena must not return blocks to the driver while they exist
   // Private memory of instantiated graphs.  A CUDA graph keeps the RAW addresses of every arena block its kernels touch; once the
@@ -42,7 +43,7 @@ struct agb_ctx {
   // list into the graph's reservation (blocks still live at that point follow when they are freed: `reserve_on_free`), and
   // agb_graph_destroy returns them.
   std::vector<void*> capture_blocks;
-  struct GraphRes { agb_ctx* ctx; void* exec; std::vector<void*> blocks; };
+  struct GraphRes { agb_ctx* ctx; void* exec; std::vector<void*> blocks; int64_t kernel_nodes = 0; };
   std::unordered_map<void*, GraphRes*> reserve_on_free;
   // live profiler (agb_prof_*): event pairs per profiled entry-point call
   bool prof_on = false;

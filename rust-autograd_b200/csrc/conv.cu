@@ -25,6 +25,8 @@ bool agb_tc_conv_fprop_eligible(int C, int O, int kh, int kw, int stride, int yw
 // direct kernels for very small input-channel counts (conv_small_c.cu)
 bool agb_small_c_eligible(int C, int O, int kh, int kw);
 int agb_small_c_fprop(agb_ctx* ctx, const float* x, const float* w, agb_tensor* y, int B, int C, int H, int W, int O, int kh, int kw, int yh, int yw, int pad, int stride, int dil, const float* bias, int relu);
+int agb_tc_conv_first(agb_ctx* ctx, int mode, const float* x, const float* w, float* y, int B, int C, int H, int W, int O, int kh, int kw, int yh, int yw,
+                      int pad, int stride, int dil, const float* bias, int relu);
 int agb_small_c_wgrad(agb_ctx* ctx, const float* x, const agb_tensor* gy, float* gw, int B, int C, int H, int W, int O, int kh, int kw, int yh, int yw, int pad, int stride, int dil);
 
 // ---- activation layouts.  A logical [B,C,H,W] tensor is accepted in two dense memory orders: NCHW (C-contiguous, the
@@ -169,6 +171,11 @@ extern "C" int agb_conv2d_fprop_fused_f32(agb_ctx* ctx, const agb_tensor* x, con
   }
   if (agb_small_c_eligible(g.C, g.O, g.kh, g.kw) && (is_nchw(y) || is_channels_last(y))) {
     LayoutTmp lx(ctx); AGB_TRY(lx.input(x, false));
+    if (is_channels_last(y) && !is_nchw(y)) {        // im2col tile built in shared memory + tcgen05 (tc_conv_first.cu): the first layer at the HBM rate
+      int r1 = agb_tc_conv_first(ctx, ctx->math_mode, lx.view.ptr, w->ptr, y->ptr, g.B, g.C, g.H, g.W, g.O, g.kh, g.kw, g.yh, g.yw, pad, stride, dilation, bias, relu);
+      if (r1 == AGB_OK) { prof.set_cls(AGB_PROF_CONV_SMALLC_FPROP); return lx.finish(); }
+      if (r1 != AGB_ERR_UNSUPPORTED) return r1;
+    }
     int r = agb_small_c_fprop(ctx, lx.view.ptr, w->ptr, y, g.B, g.C, g.H, g.W, g.O, g.kh, g.kw, g.yh, g.yw, pad, stride, dilation, bias, relu);
     if (r == AGB_OK) { prof.set_cls(AGB_PROF_CONV_SMALLC_FPROP); return lx.finish(); }
     if (r != AGB_ERR_UNSUPPORTED) return r;

@@ -96,13 +96,13 @@ struct NdArray {
 struct StreamCellPool { agb_ctx* ctx = nullptr; bool alive = true; std::vector<uint32_t*> free_cells; std::vector<void*> blocks; };
 struct StreamCell {
   std::shared_ptr<StreamCellPool> pool; uint32_t* ptr = nullptr;
-  ~StreamCell() { if (pool && pool->alive && ptr) pool->free_cells.push_back(ptr); }
+  ~StreamCell() { if (pool && pool->alive && ptr) { agb_memset0(pool->ctx, ptr, 8); pool->free_cells.push_back(ptr); } }   // cells are zero while they wait in the pool
 };
 
 struct Device {                   // thin C++ handle on the kernel C ABI context
   agb_ctx* ctx = nullptr;
   std::shared_ptr<StreamCellPool> stream_cells;
-  std::shared_ptr<StreamCell> new_stream_cell();     // zeroed on the stream before it is handed out
+  std::shared_ptr<StreamCell> new_stream_cell();     // cells in the pool are zero (zeroed when their block is created and when they are returned): acquiring one launches nothing, so it is safe inside a graph capture
   explicit Device(int index);
   ~Device();
   NdArray empty(const Shape& s);
@@ -144,6 +144,7 @@ struct Op {                       // trait Op (src/op.rs:90-101)
   virtual bool compute_stacked(Device* dev, Evaluation& run, const std::vector<std::vector<NdArray>>& ins, std::vector<std::vector<NdArray>>* outs) { return false; }
   virtual bool sums_inputs() const { return false; }     // AddN: lets a producer defer itself so that the sum can absorb it (fuse.cc)
   virtual bool mutates_now() const { return false; }     // Assign: writes a variable in the middle of the traversal (optimizer ops are deferred)
+  virtual std::shared_ptr<StreamCell> stream_cell() const { return nullptr; }   // random ops: the device-resident stream position (kept alive by cached step plans)
 };
 
 struct IncomingTensor { TensorID id; bool allow_mut; int array_selector; };   // src/tensor.rs:542-550
@@ -256,6 +257,9 @@ struct PendingUpdate { int kind; float h[4]; NdArray p, g, s0, s1, t; };
 struct Evaluation {
   Graph* graph; Device* dev;
   std::vector<PendingUpdate> pending;     // optimizer ops of this run: flushed as ONE multi-tensor launch after all grads exist
+  // data parallel: gradients are all-reduced in buckets on a communication stream as soon as enough of them exist, under the kernels that
+  // still compute the remaining ones (ops_nn.cc reduce_bucket); `ar_next` = first pending update not yet handed to NCCL
+  size_t ar_next = 0; std::vector<NdArray> ar_buckets;
   bool fuse = false;                      // elementwise fusion enabled for this run
   std::vector<int> consumers;             // per node id: consuming edges inside this evaluation (+1 per request as a target); metadata-only
                                           // consumers (Shape / Rank / Size) are not counted

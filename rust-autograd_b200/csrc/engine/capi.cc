@@ -4,14 +4,41 @@
 #include "agx.h"
 #include "../../../include/agx200.h"
 #include <fstream>
+#include <memory>
+#include <stdlib.h>
 #include <sstream>
 #include <string.h>
 
 using namespace agx;
+namespace agx { NdArray materialize_im2col(Device*, const NdArray&); }
 
-struct agx_env { VariableEnvironment* env; };
-struct agx_graph { Graph g; };
-struct agx_opt { Optimizer* o; };
+// ---- automatic step-plan cache -------------------------------------------------------------------------------------
+// The reference rebuilds its graph and re-walks it on every training step (examples/mlp_mnist.rs:74, cnn_mnist.rs:96).  Every call that
+// builds a node is folded into a running 128-bit signature of the graph; an evaluation is keyed by (signature, targets, feed keys and
+// shapes, math mode, fusion).  First sight of a key: eager.  Second sight: the feeds are staged into plan-owned device buffers, the
+// evaluation runs eagerly on them (that IS this step) and is then captured into a CUDA graph without executing.  From the third sight on
+// the plan is replayed: feeds are copied into the staging buffers (H2D or D2D), one graph launch, results are copied out of the graph's
+// private memory.  Graphs with host callbacks (custom ops, hooks), evaluations that need the host in the middle (capture fails: the plan
+// is marked bad and stays eager) and data-parallel runs are never cached.  agx_env_set_plan_cache(env, 0) / AGX_PLAN_CACHE=0 turn it off.
+struct PlanKey { uint64_t a, b; bool operator<(const PlanKey& o) const { return a != o.a ? a < o.a : b < o.b; } };
+struct Plan {
+  int sights = 0, failures = 0; bool bad = false; void* exec = nullptr; uint64_t last_use = 0, graph_serial = 0;
+  std::vector<NdArray> inputs; std::vector<Feed> feeds; std::vector<EvalResult> outs;
+  std::vector<std::shared_ptr<StreamCell>> cells;      // the captured ops' stream positions: alive (and not re-assigned) while the plan lives
+};
+struct agx_env { VariableEnvironment* env; bool plan_cache = true; uint64_t tick = 0; std::map<PlanKey, Plan> plans; int64_t replays = 0, captures = 0; };
+struct SigHash {
+  uint64_t a = 1469598103934665603ull, b = 0x9E3779B97F4A7C15ull;
+  void bytes(const void* p, size_t n) { const unsigned char* c = (const unsigned char*)p; for (size_t i = 0; i < n; i++) { a = (a ^ c[i]) * 1099511628211ull; b = (b + c[i] + 1) * 0xD6E8FEB86659FD93ull; b ^= b >> 32; } }
+  template <class T> void pod(const T& v) { bytes(&v, sizeof(T)); }
+  void str(const char* s) { size_t n = s ? strlen(s) : 0; pod(n); if (n) bytes(s, n); }
+};
+static uint64_t g_graph_serial = 0, g_opt_serial = 0;
+struct agx_graph { Graph g; agx_env* owner = nullptr; SigHash sig; bool cacheable = true; uint64_t serial = ++g_graph_serial; };
+struct agx_opt { Optimizer* o; uint64_t serial = ++g_opt_serial; };
+static void plan_free(Plan& p) { if (p.exec) { agb_graph_destroy(p.exec); p.exec = nullptr; } p.outs.clear(); p.feeds.clear(); p.inputs.clear(); p.cells.clear(); }
+static void plans_clear(agx_env* e) { for (auto& kv : e->plans) plan_free(kv.second); e->plans.clear(); }
+
 struct agx_results {
   std::vector<EvalResult> rs;
   // deferred fetch (agx_eval_launch / agx_results_fetch): pinned staging blocks of the in-flight D2H copies
@@ -61,7 +88,11 @@ static std::vector<Feed> fv(agx_graph* g, const agx_feed* feeds, int n) {
 
 // ================================================================================================ environment
 extern "C" int agx_env_new(int device, agx_env** out) { AGX_TRY *out = nullptr; auto* e = new agx_env(); e->env = new VariableEnvironment(device); *out = e; AGX_CATCH }
-extern "C" int agx_env_free(agx_env* env) { AGX_TRY if (env) { delete env->env; delete env; } AGX_CATCH }
+extern "C" int agx_env_free(agx_env* env) { AGX_TRY if (env) { plans_clear(env); delete env->env; delete env; } AGX_CATCH }
+extern "C" int agx_env_set_plan_cache(agx_env* env, int on) { AGX_TRY env->plan_cache = on != 0; if (!on) plans_clear(env); AGX_CATCH }
+extern "C" int agx_env_plan_stats(agx_env* env, int64_t* captures, int64_t* replays, int* live_plans) {
+  AGX_TRY if (captures) *captures = env->captures; if (replays) *replays = env->replays; if (live_plans) { int n = 0; for (auto& kv : env->plans) n += kv.second.exec != nullptr; *live_plans = n; } AGX_CATCH
+}
 extern "C" int agx_env_ctx(agx_env* env, agb_ctx** out) { AGX_TRY *out = env->env->dev->ctx; AGX_CATCH }
 extern "C" int agx_env_set(agx_env* env, const char* ns, const char* name, const float* data, const int64_t* shape, int rank, int* vid) {
   AGX_TRY *vid = env->env->set(ns ? ns : "", name, Shape(shape, shape + rank), data).v; AGX_CATCH
@@ -83,7 +114,7 @@ extern "C" int agx_env_save(agx_env* env, const char* path) {
   AGX_TRY std::ofstream f(path); if (!f) throw OpError(AGB_ERR_NDARRAY, std::string("save: cannot open ") + path); f << env->env->save_json(); f.flush(); if (!f.good()) throw OpError(AGB_ERR_NDARRAY, std::string("save: write failed: ") + path); AGX_CATCH
 }
 extern "C" int agx_env_load(agx_env* env, const char* path) {
-  AGX_TRY std::ifstream f(path); if (!f) throw OpError(AGB_ERR_NDARRAY, std::string("load: cannot open ") + path); std::stringstream ss; ss << f.rdbuf(); env->env->load_json(ss.str()); AGX_CATCH
+  AGX_TRY std::ifstream f(path); if (!f) throw OpError(AGB_ERR_NDARRAY, std::string("load: cannot open ") + path); std::stringstream ss; ss << f.rdbuf(); plans_clear(env); env->env->load_json(ss.str()); AGX_CATCH
 }
 extern "C" int agx_fuse_selftest(int n_cases, unsigned seed, int* n_compiled) { AGX_TRY return fuse_selftest(n_cases, seed, n_compiled); AGX_CATCH }
 extern "C" int agx_env_set_fusion(agx_env* env, int on) { AGX_TRY env->env->fuse_elementwise = on != 0; AGX_CATCH }
@@ -92,18 +123,22 @@ extern "C" int agx_env_set_data_parallel(agx_env* env, int rank, int world, cons
 }
 
 // ================================================================================================ graph
-extern "C" int agx_graph_new(agx_env* env, agx_graph** out) { AGX_TRY auto* g = new agx_graph(); g->g.env = env->env; g->g.node_set.reserve(512); *out = g; AGX_CATCH }
+extern "C" int agx_graph_new(agx_env* env, agx_graph** out) { AGX_TRY auto* g = new agx_graph(); g->g.env = env->env; g->owner = env; g->g.node_set.reserve(512); *out = g; AGX_CATCH }
 extern "C" int agx_graph_free(agx_graph* g) { AGX_TRY delete g; AGX_CATCH }
-extern "C" int agx_graph_clear(agx_graph* g) { AGX_TRY g->g.clear(); AGX_CATCH }
+extern "C" int agx_graph_clear(agx_graph* g) { AGX_TRY g->g.clear(); g->sig = SigHash(); g->cacheable = true; g->serial = ++g_graph_serial; AGX_CATCH }
 extern "C" int agx_graph_size(agx_graph* g, int* n) { AGX_TRY *n = (int)g->g.node_set.size(); AGX_CATCH }
 extern "C" int agx_placeholder(agx_graph* g, const char* name, const int64_t* shape, int rank, int* tid) {
-  AGX_TRY *tid = g->g.placeholder(name, std::vector<int64_t>(shape, shape + rank)).id; AGX_CATCH
+  AGX_TRY *tid = g->g.placeholder(name, std::vector<int64_t>(shape, shape + rank)).id;
+  g->sig.str("placeholder"); g->sig.str(name); g->sig.pod(rank); g->sig.bytes(shape, sizeof(int64_t) * rank); AGX_CATCH
 }
-extern "C" int agx_variable(agx_graph* g, int vid, int* tid) { AGX_TRY *tid = g->g.variable_by_id(VariableID{vid}).id; AGX_CATCH }
-extern "C" int agx_variable_by_name(agx_graph* g, const char* ns, const char* name, int* tid) { AGX_TRY *tid = g->g.variable_by_name(name, ns ? ns : "").id; AGX_CATCH }
+extern "C" int agx_variable(agx_graph* g, int vid, int* tid) { AGX_TRY *tid = g->g.variable_by_id(VariableID{vid}).id; g->sig.str("variable"); g->sig.pod(vid); g->sig.pod(*tid); AGX_CATCH }
+extern "C" int agx_variable_by_name(agx_graph* g, const char* ns, const char* name, int* tid) {
+  AGX_TRY *tid = g->g.variable_by_name(name, ns ? ns : "").id; g->sig.str("variable"); g->sig.pod(g->g.inner(*tid).variable_id.v); g->sig.pod(*tid); AGX_CATCH
+}
 extern "C" int agx_convert_to_tensor(agx_graph* g, const float* data, const int64_t* shape, int rank, int* tid) {
   AGX_TRY Shape s(shape, shape + rank); int64_t n = 1; for (auto d : s) n *= d;
-  *tid = T::convert_to_tensor(&g->g, s, std::vector<float>(data, data + n)).id; AGX_CATCH
+  *tid = T::convert_to_tensor(&g->g, s, std::vector<float>(data, data + n)).id;
+  g->sig.str("const"); g->sig.pod(rank); g->sig.bytes(shape, sizeof(int64_t) * rank); g->sig.bytes(data, sizeof(float) * (size_t)n); AGX_CATCH
 }
 extern "C" int agx_tensor_op_name(agx_graph* g, int tid, char* buf, int cap) { AGX_TRY snprintf(buf, cap, "%s", g->g.inner(tid).op->name()); AGX_CATCH }
 extern "C" int agx_tensor_variable_id(agx_graph* g, int tid, int* vid) { AGX_TRY *vid = g->g.inner(tid).variable_id.v; AGX_CATCH }
@@ -112,6 +147,7 @@ extern "C" int agx_call(agx_graph* gg, const char* fn_, const int* tensors, int 
   AGX_TRY
   Graph* g = &gg->g; std::string fn = fn_;
   std::vector<Tensor> t = tv(gg, tensors, nt); std::vector<Tensor> r;
+  gg->sig.str(fn_); gg->sig.pod(nt); gg->sig.bytes(tensors, sizeof(int) * nt); gg->sig.pod(ni); gg->sig.bytes(I, sizeof(int64_t) * ni); gg->sig.pod(nf); gg->sig.bytes(F, sizeof(double) * nf);
   auto need = [&](int a, int b, int c) { if (nt < a || ni < b || nf < c) throw Panic("agx_call(" + fn + "): expected at least " + std::to_string(a) + " tensors, " + std::to_string(b) + " ints, " + std::to_string(c) + " floats"); };
   auto ints = [&](int from) { return std::vector<int64_t>(I + from, I + ni); };
   static const char* unary_names[] = {"sin", "cos", "tan", "asin", "acos", "atan", "sinh", "cosh", "tanh", "asinh", "acosh", "atanh", "exp", "exp2", "exp10", "ln", "log2",
@@ -228,6 +264,7 @@ struct CustomOp : Op {                 // a user-defined Op (src/op.rs:90-101) w
 extern "C" int agx_custom_op(agx_graph* g, const char* name, const int* inputs, int n_inputs, agx_compute_fn compute, agx_grad_fn grad, void* user, int* tid) {
   AGX_TRY
   if (!compute) throw Panic("agx_custom_op: compute callback is NULL");
+  g->cacheable = false;                   // host callback inside the evaluation: never replayed from a captured plan
   auto* op = new CustomOp(); op->nm = name ? name : "CustomOp"; op->fc = compute; op->fg = grad; op->user = user; op->owner = g;
   TensorBuilder b(&g->g);
   for (auto& t : tv(g, inputs, n_inputs)) b.append_input(t, false);
@@ -238,6 +275,7 @@ extern "C" int agx_hook(agx_graph* g, int tensor, int kind, const char* text, ag
   AGX_TRY
   if (kind < 0 || kind > 3 || (kind == 0 && !fn)) throw Panic("agx_hook: bad hook kind / missing callback");
   std::string prefix = text ? text : "";
+  g->cacheable = false;                   // hooks run on the host in the middle of the evaluation
   Tensor x = tv(g, &tensor, 1)[0];
   *tid = T::hook(x, [kind, prefix, fn, user](const NdArray& a, const std::vector<float>& h) {
     if (kind == 0) { agx_host_array v{h.data(), a.shape.data(), (int)a.shape.size()}; fn(user, &v); return; }
@@ -255,26 +293,111 @@ extern "C" int agx_grad(agx_graph* g, const int* ys, int ny, const int* xs, int 
   AGX_TRY
   std::vector<Tensor> r = gys ? T::grad_with_default(tv(g, ys, ny), tv(g, xs, nx), tv(g, gys, ny)) : T::grad(tv(g, ys, ny), tv(g, xs, nx));
   for (int i = 0; i < nx; i++) out[i] = r[i].id;
+  g->sig.str("grad"); g->sig.pod(ny); g->sig.bytes(ys, sizeof(int) * ny); g->sig.pod(nx); g->sig.bytes(xs, sizeof(int) * nx); if (gys) g->sig.bytes(gys, sizeof(int) * ny);
   AGX_CATCH
 }
 extern "C" int agx_grad_helper(agx_graph* g, const int* losses, int n, const char* ns, int* vars, int* grads, int cap, int* nout) {
   AGX_TRY
   std::vector<Tensor> vs, gs; grad_helper(tv(g, losses, n), ns ? ns : "", &g->g, vs, gs);
+  g->sig.str("grad_helper"); g->sig.pod(n); g->sig.bytes(losses, sizeof(int) * n); g->sig.str(ns);
   *nout = (int)vs.size();
   for (int i = 0; i < (int)vs.size() && i < cap; i++) { vars[i] = vs[i].id; grads[i] = gs[i].id; }
   AGX_CATCH
 }
 
 // ================================================================================================ evaluation
+static bool plan_cache_enabled(agx_env* e) {
+  static const int env_on = [] { const char* v = getenv("AGX_PLAN_CACHE"); return (v && v[0] == '0') ? 0 : 1; }();
+  return e && e->plan_cache && env_on && e->env->world == 1;
+}
+// device-resident results of one evaluation, through the plan cache when the graph allows it (see the comment at struct Plan)
+static std::vector<EvalResult> eval_cached(agx_graph* g, const int* targets, int n, const agx_feed* feeds, int nfeeds) {
+  agx_env* owner = g->owner; VariableEnvironment* env = g->g.env; Device* dev = env->dev;
+  if (!plan_cache_enabled(owner) || !g->cacheable || n <= 0) return eval(&g->g, tv(g, targets, n), fv(g, feeds, nfeeds), false);
+  SigHash k = g->sig;
+  k.str("eval"); k.pod(g->g.node_set.size()); k.pod(n); k.bytes(targets, sizeof(int) * n); k.pod(nfeeds);
+  for (int i = 0; i < nfeeds; i++) { k.str(feeds[i].name); k.pod(feeds[i].tensor_id); k.pod(feeds[i].rank); k.bytes(feeds[i].shape, sizeof(int64_t) * feeds[i].rank); }
+  int mode = 0; agb_get_math_mode(dev->ctx, &mode); k.pod(mode); k.pod(env->fuse_elementwise);
+  Plan& p = owner->plans[PlanKey{k.a, k.b}];
+  p.last_use = ++owner->tick; p.sights++;
+  if (p.bad || p.sights == 1) return eval(&g->g, tv(g, targets, n), fv(g, feeds, nfeeds), false);
+  auto stage = [&]() {
+    for (int i = 0; i < nfeeds; i++) {
+      const size_t nb = (size_t)p.inputs[i].size() * sizeof(float);
+      if (!nb) continue;
+      if (feeds[i].on_device) check_status(agb_d2d(dev->ctx, p.inputs[i].dptr, feeds[i].data, nb));
+      else check_status(agb_h2d(dev->ctx, p.inputs[i].dptr, feeds[i].data, nb));
+    }
+  };
+  if (p.exec == nullptr) {
+    // ---- second sight: stage the feeds and CAPTURE the evaluation on the staged copies (nothing executes; every allocation must hit the
+    // arena's free list, which the first sight's eager run left holding exactly these block sizes); the replay below then IS this step.
+    // A capture that fails (arena miss, an op that needs the host mid-evaluation) executes nothing either: the step runs eagerly and the
+    // plan gets one more attempt on a warmer arena before it is marked bad.
+    if (p.inputs.empty()) {
+      for (int i = 0; i < nfeeds; i++) {
+        Feed f; f.by_name = feeds[i].name != nullptr; if (f.by_name) f.name = feeds[i].name; f.id = feeds[i].tensor_id;
+        f.value = dev->empty(Shape(feeds[i].shape, feeds[i].shape + feeds[i].rank));
+        p.inputs.push_back(f.value); p.feeds.push_back(std::move(f));
+      }
+    }
+    bool captured = false;
+    try {
+      check_status(agb_graph_begin(dev->ctx));
+      try {
+        p.outs = eval(&g->g, tv(g, targets, n), p.feeds, false);
+        for (auto& r : p.outs) if (!r.ok) throw OpError(r.err_code, r.err_msg);
+      } catch (...) { agb_graph_end(dev->ctx, nullptr); throw; }
+      check_status(agb_graph_end(dev->ctx, &p.exec));
+      for (auto& nd : g->g.node_set) if (nd && nd->op) { auto c = nd->op->stream_cell(); if (c) p.cells.push_back(c); }
+      p.graph_serial = g->serial; owner->captures++; captured = true;
+    } catch (const std::exception&) { p.outs.clear(); p.cells.clear(); if (p.exec) { agb_graph_destroy(p.exec); p.exec = nullptr; } }
+    while (owner->plans.size() > 8) {            // least-recently-used plans give their private memory back
+      auto victim = owner->plans.end();
+      for (auto it = owner->plans.begin(); it != owner->plans.end(); ++it) if (&it->second != &p && (victim == owner->plans.end() || it->second.last_use < victim->second.last_use)) victim = it;
+      if (victim == owner->plans.end()) break;
+      plan_free(victim->second); owner->plans.erase(victim);
+    }
+    if (!captured) {
+      if (++p.failures >= 2) { p.bad = true; plan_free(p); }
+      return eval(&g->g, tv(g, targets, n), fv(g, feeds, nfeeds), false);
+    }
+  }
+  // ---- replay
+  if (p.graph_serial != g->serial) {             // a graph REBUILT since the last replay: its random ops start their streams over, like freshly
+    for (auto& c : p.cells) check_status(agb_memset0(dev->ctx, c->ptr, (size_t)agb_stream_cell_bytes()));      // constructed ops do (mod.rs:2895-2905)
+    p.graph_serial = g->serial;
+  }
+  stage();
+  check_status(agb_graph_launch(dev->ctx, p.exec));
+  owner->replays++;
+  std::vector<EvalResult> rs;
+  for (auto& o : p.outs) {                       // results leave the graph's private memory before the next replay can overwrite them
+    EvalResult r = o;
+    if (r.ok && r.value.on_device() && !r.value.has_host() && !r.value.lazy && !r.value.expr && !r.value.virt) r.value = dev->copy(r.value);
+    rs.push_back(std::move(r));
+  }
+  return rs;
+}
+static void fetch_results(Device* dev, std::vector<EvalResult>& rs) {       // the tail of eval(.., fetch_to_host = true)
+  for (auto& r : rs) {
+    if (!r.ok) continue;
+    if (r.value.lazy) r.value = materialize_lazy(dev, r.value);
+    if (r.value.virt && !r.value.on_device() && !r.value.has_host()) r.value = materialize_im2col(dev, r.value);
+    dev->ensure_host(r.value);
+  }
+  dev->sync();      // surfaces device-side index errors (bad labels / gather ids) as OutOfBounds
+}
 extern "C" int agx_eval(agx_graph* g, const int* targets, int n, const agx_feed* feeds, int nfeeds, agx_results** out) {
-  AGX_TRY *out = nullptr; auto* r = new agx_results(); r->rs = eval(&g->g, tv(g, targets, n), fv(g, feeds, nfeeds), true); *out = r; AGX_CATCH
+  AGX_TRY *out = nullptr; auto* r = new agx_results(); std::unique_ptr<agx_results> guard(r);
+  r->rs = eval_cached(g, targets, n, feeds, nfeeds); fetch_results(g->g.env->dev, r->rs); *out = guard.release(); AGX_CATCH
 }
 // launch-only evaluation: every kernel of the run is enqueued, each result's D2H is queued on the copy stream into pinned memory,
 // and the call returns without a host sync; agx_results_fetch completes it later (after more work has been enqueued)
 extern "C" int agx_eval_launch(agx_graph* g, const int* targets, int n, const agx_feed* feeds, int nfeeds, agx_results** out) {
   AGX_TRY
   *out = nullptr; auto* r = new agx_results(); r->dev = g->g.env->dev;
-  r->rs = eval(&g->g, tv(g, targets, n), fv(g, feeds, nfeeds), false);
+  r->rs = eval_cached(g, targets, n, feeds, nfeeds);
   for (auto& e : r->rs) {
     void* pin = nullptr; void* ev = nullptr; size_t nb = 0;
     if (e.ok && !e.value.host && e.value.on_device()) {
@@ -333,7 +456,7 @@ extern "C" int agx_step_free(agx_step* s) { if (s) { agb_graph_destroy(s->exec);
 
 extern "C" int agx_run(agx_graph* g, const int* targets, int n, const agx_feed* feeds, int nfeeds) {
   AGX_TRY
-  std::vector<EvalResult> rs = eval(&g->g, tv(g, targets, n), fv(g, feeds, nfeeds), false);
+  std::vector<EvalResult> rs = eval_cached(g, targets, n, feeds, nfeeds);
   for (auto& r : rs) if (!r.ok) throw OpError(r.err_code, r.err_msg);
   AGX_CATCH
 }
@@ -365,12 +488,15 @@ extern "C" int agx_opt_adagrad(agx_env* env, const int* v, int n, const char* ns
   AGX_TRY auto* o = new agx_opt(); o->o = make_adagrad(env->env, vids(v, n), ns, lr); *out = o; AGX_CATCH
 }
 extern "C" int agx_opt_compute_updates(agx_opt* o, agx_graph* g, const int* params, const int* grads, int n, int* out) {
-  AGX_TRY std::vector<Tensor> r = o->o->compute_updates(tv(g, params, n), tv(g, grads, n), &g->g); for (int i = 0; i < n; i++) out[i] = r[i].id; AGX_CATCH
+  AGX_TRY std::vector<Tensor> r = o->o->compute_updates(tv(g, params, n), tv(g, grads, n), &g->g); for (int i = 0; i < n; i++) out[i] = r[i].id;
+  g->sig.str("opt_updates"); g->sig.pod(o->serial); g->sig.pod(n); g->sig.bytes(params, sizeof(int) * n); g->sig.bytes(grads, sizeof(int) * n); AGX_CATCH
 }
 extern "C" int agx_opt_get_update_op(agx_opt* o, agx_graph* g, const int* params, const int* grads, int n, int* tid) {
-  AGX_TRY *tid = o->o->get_update_op(tv(g, params, n), tv(g, grads, n), &g->g).id; AGX_CATCH
+  AGX_TRY *tid = o->o->get_update_op(tv(g, params, n), tv(g, grads, n), &g->g).id;
+  g->sig.str("opt_update_op"); g->sig.pod(o->serial); g->sig.pod(n); g->sig.bytes(params, sizeof(int) * n); g->sig.bytes(grads, sizeof(int) * n); AGX_CATCH
 }
 extern "C" int agx_opt_update(agx_opt* o, agx_graph* g, const int* params, const int* grads, int n, const agx_feed* feeds, int nfeeds) {
-  AGX_TRY o->o->update(tv(g, params, n), tv(g, grads, n), &g->g, fv(g, feeds, nfeeds)); AGX_CATCH
+  AGX_TRY o->o->update(tv(g, params, n), tv(g, grads, n), &g->g, fv(g, feeds, nfeeds));
+  g->sig.str("opt_update"); g->sig.pod(o->serial); g->sig.pod(n); g->sig.bytes(params, sizeof(int) * n); g->sig.bytes(grads, sizeof(int) * n); AGX_CATCH
 }
 extern "C" int agx_opt_free(agx_opt* o) { AGX_TRY if (o) { delete o->o; delete o; } AGX_CATCH }

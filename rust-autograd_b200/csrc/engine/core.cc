@@ -80,10 +80,10 @@ std::shared_ptr<StreamCell> Device::new_stream_cell() {
   if (p.free_cells.empty()) {
     const size_t cell = (size_t)agb_stream_cell_bytes(), n = 512;
     void* blk = nullptr; check_status(agb_alloc(ctx, cell * n, &blk)); p.blocks.push_back(blk);
+    check_status(agb_memset0(ctx, blk, cell * n));
     for (size_t i = 0; i < n; i++) p.free_cells.push_back((uint32_t*)((char*)blk + i * cell));
   }
   auto c = std::make_shared<StreamCell>(); c->pool = stream_cells; c->ptr = p.free_cells.back(); p.free_cells.pop_back();
-  check_status(agb_memset0(ctx, c->ptr, (size_t)agb_stream_cell_bytes()));
   return c;
 }
 NdArray Device::empty(const Shape& s) {

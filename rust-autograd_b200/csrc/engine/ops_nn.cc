@@ -494,6 +494,7 @@ Tensor T::max_pool2d(Tensor x, int size, int pad, int stride) { auto* op = new M
 // ================================================================================================ dropout
 struct Dropout : Op {                  // random_ops.rs:218-245: NOT inverted; outputs (y, mask); eval mode scales by (1 - ratio)
   float ratio; bool train; uint64_t seed; std::shared_ptr<StreamCell> cell;
+  std::shared_ptr<StreamCell> stream_cell() const override { return cell; }
   const char* name() const override { return REFNAME("random_ops", "Dropout"); }
   void compute(ComputeContext& c) override {
     NdArray x = c.dev->contiguous(on_dev(c.dev, c.input(0)));
@@ -518,6 +519,7 @@ Tensor T::dropout(Tensor x, float ratio, bool train, uint64_t seed) { auto* op =
 // nodes draw the same values (as there).  Stream values are parity-unpinned: device Philox instead of XorShift.
 struct RandomOp : Op {
   int kind; float p0, p1; uint64_t seed; std::shared_ptr<StreamCell> cell;
+  std::shared_ptr<StreamCell> stream_cell() const override { return cell; }
   const char* name() const override {
     static const char* N[] = {REFNAME("random_ops", "RandomUniform"), REFNAME("random_ops", "RandomNormal"), REFNAME("random_ops", "Bernoulli"),
                               REFNAME("random_ops", "Exponential"), REFNAME("random_ops", "LogNormal"), REFNAME("random_ops", "Gamma")};
@@ -545,6 +547,24 @@ Tensor T::random(Graph* g, int kind, Tensor shape, float p0, float p1, uint64_t 
 // kernel once every gradient exists (preceded by the NCCL gradient all-reduce in data-parallel runs).  This is the "clean"
 // ordering of SURVEY §3.5: every gradient is taken at the pre-update weights.
 enum { OPT_ADAM = 0, OPT_SGD = 1, OPT_MOMENTUM = 2, OPT_ADAGRAD = 3 };
+// Data parallel: the gradients registered so far and not yet reduced are packed into one arena and summed by ONE NCCL all-reduce on
+// the communication stream (agb_allreduce_sum_async), ordered after the kernels that produced them.  The evaluator reaches the update ops in
+// variable order, i.e. the early layers' gradients complete first while the late layers' filter gradients are still to be computed, so every
+// bucket but the last overlaps with compute (VGG stack: 9.6 MB of gradients = two buckets; only the second one is exposed).
+static const int64_t AR_BUCKET_BYTES = 4 << 20;
+static void reduce_bucket(Evaluation& run, Device* dev) {
+  if (run.ar_next >= run.pending.size()) return;
+  int64_t total = 0; for (size_t i = run.ar_next; i < run.pending.size(); i++) total += (run.pending[i].g.size() + 3) / 4 * 4;
+  NdArray arena = dev->empty({total}); int64_t off = 0;
+  for (size_t i = run.ar_next; i < run.pending.size(); i++) {
+    PendingUpdate& u = run.pending[i];
+    check_status(agb_d2d(dev->ctx, arena.dptr + off, u.g.dptr, (size_t)u.g.size() * sizeof(float)));
+    NdArray v = arena.sliced(0, off, u.g.size()); v.shape = u.g.shape; v.stride = NdArray::contiguous_strides(v.shape);
+    off += (u.g.size() + 3) / 4 * 4; u.g = v;
+  }
+  check_status(agb_allreduce_sum_async(dev->ctx, arena.dptr, total));
+  run.ar_buckets.push_back(arena); run.ar_next = run.pending.size();
+}
 struct UpdateOp : Op {
   int kind; float h[4];
   const char* name() const override {
@@ -558,6 +578,10 @@ struct UpdateOp : Op {
     if (kind == OPT_ADAM) { u.s0 = c.input_mut(2); u.s1 = c.input_mut(3); u.t = c.input_mut(4); }
     else if (kind != OPT_SGD) u.s0 = c.input_mut(2);
     c.run->pending.push_back(u);
+    if (c.run->graph->env->world > 1) {       // enough gradients for a bucket: start summing them while the remaining ones are still being computed
+      int64_t bytes = 0; for (size_t i = c.run->ar_next; i < c.run->pending.size(); i++) bytes += c.run->pending[i].g.size() * (int64_t)sizeof(float);
+      if (bytes >= AR_BUCKET_BYTES) reduce_bucket(*c.run, c.dev);
+    }
     c.append_empty_output();
   }
   void grad(GradientContext& c) override { for (int i = 0; i < c.num_inputs(); i++) c.append_none(); }
@@ -569,16 +593,10 @@ void flush_pending_updates(Evaluation& run, VariableEnvironment* env) {
   dev->small_copies.clear();          // the variables are about to change: no cached copy of a view may outlive this point
   float gscale = 1.0f;
   if (env->world > 1) {
-    // data parallel: pack all gradients into one contiguous arena, ONE NCCL all-reduce (sum), read them back
-    // scaled by 1/world inside the optimizer kernel
-    int64_t total = 0; for (auto& u : run.pending) total += (u.g.size() + 3) / 4 * 4;
-    NdArray arena = dev->empty({total}); int64_t off = 0;
-    for (auto& u : run.pending) {
-      check_status(agb_d2d(dev->ctx, arena.dptr + off, u.g.dptr, (size_t)u.g.size() * sizeof(float)));
-      NdArray v = arena.sliced(0, off, u.g.size()); v.shape = u.g.shape; v.stride = NdArray::contiguous_strides(v.shape);
-      off += (u.g.size() + 3) / 4 * 4; u.g = v;
-    }
-    check_status(agb_allreduce_sum(dev->ctx, arena.dptr, total));
+    // data parallel: the last bucket, then the compute stream waits for every bucket's sum; the optimizer kernel reads them
+    // scaled by 1/world
+    reduce_bucket(run, dev);
+    check_status(agb_allreduce_wait(dev->ctx));
     gscale = 1.0f / (float)env->world;
   }
   for (int kind = 0; kind < 4; kind++) {
@@ -598,7 +616,7 @@ void flush_pending_updates(Evaluation& run, VariableEnvironment* env) {
       i = j;
     }
   }
-  run.pending.clear();
+  run.pending.clear(); run.ar_buckets.clear(); run.ar_next = 0;
 }
 
 // ---- Optimizer trait (optimizers/mod.rs:49-99) ----

@@ -5,6 +5,7 @@
 #include "common.cuh"
 #include <stdarg.h>
 #include <algorithm>
+#include <vector>
 #include <dlfcn.h>
 
 static thread_local char g_err[1024] = "";
@@ -271,9 +272,20 @@ extern "C" int agb_graph_end(agb_ctx* ctx, void** graph_exec) {
   AGB_CUDA(cudaStreamEndCapture(ctx->stream, &g));
   cudaGraphExec_t ge = nullptr;
   cudaError_t e = cudaGraphInstantiate(&ge, g, 0);
+  int64_t kernel_nodes = 0;
+  {   // kernels per replay, for agb_launch_count (a replayed step launches them all without passing through AGB_LAUNCHED)
+    size_t nn = 0;
+    if (cudaGraphGetNodes(g, nullptr, &nn) == cudaSuccess && nn > 0) {
+      std::vector<cudaGraphNode_t> nodes(nn);
+      if (cudaGraphGetNodes(g, nodes.data(), &nn) == cudaSuccess)
+        for (size_t i = 0; i < nn; i++) { cudaGraphNodeType ty; if (cudaGraphNodeGetType(nodes[i], &ty) == cudaSuccess && ty == cudaGraphNodeTypeKernel) kernel_nodes++; }
+    }
+    cudaGetLastError();
+  }
   cudaGraphDestroy(g);
   if (e != cudaSuccess) { ctx->capture_blocks.clear(); return agb_cuda_fail(e, "cudaGraphInstantiate", __FILE__, __LINE__); }
   auto* res = new agb_ctx::GraphRes{ctx, (void*)ge, {}};
+  res->kernel_nodes = kernel_nodes;
   std::sort(ctx->capture_blocks.begin(), ctx->capture_blocks.end());
   ctx->capture_blocks.erase(std::unique(ctx->capture_blocks.begin(), ctx->capture_blocks.end()), ctx->capture_blocks.end());
   for (void* p : ctx->capture_blocks) {
@@ -288,7 +300,9 @@ extern "C" int agb_graph_end(agb_ctx* ctx, void** graph_exec) {
 }
 extern "C" int agb_arena_pin(agb_ctx* ctx, int delta) { ctx->pinned_graphs += delta; if (ctx->pinned_graphs < 0) ctx->pinned_graphs = 0; return AGB_OK; }
 extern "C" int agb_graph_launch(agb_ctx* ctx, void* graph_exec) {
-  AGB_CUDA(cudaGraphLaunch((cudaGraphExec_t)((agb_ctx::GraphRes*)graph_exec)->exec, ctx->stream)); return AGB_OK;
+  AGB_CUDA(cudaGraphLaunch((cudaGraphExec_t)((agb_ctx::GraphRes*)graph_exec)->exec, ctx->stream));
+  ctx->launches += ((agb_ctx::GraphRes*)graph_exec)->kernel_nodes;
+  return AGB_OK;
 }
 extern "C" int agb_graph_destroy(void* graph_exec) {
   if (!graph_exec) return AGB_OK;
@@ -351,7 +365,30 @@ extern "C" int agb_allreduce_sum(agb_ctx* ctx, float* buf, int64_t n) {
   ctx->launches++;
   return AGB_OK;
 }
+// Bucketed, overlapped form: the all-reduce of `buf` runs on the context's communication stream, ordered after everything enqueued on
+// the compute stream so far (the kernels that produced the bucket); the compute stream carries on with the rest of the backward pass.
+// agb_allreduce_wait makes the compute stream wait for every bucket issued so far (before the optimizer kernel reads the sums).
+extern "C" int agb_allreduce_sum_async(agb_ctx* ctx, float* buf, int64_t n) {
+  if (ctx->world <= 1) return AGB_OK;
+  AGB_CHECK(ctx->nccl_comm, AGB_ERR_NCCL, "agb_allreduce_sum_async: agb_nccl_init was not called");
+  if (!ctx->comm_stream) {
+    AGB_CUDA(cudaStreamCreateWithFlags(&ctx->comm_stream, cudaStreamNonBlocking));
+    AGB_CUDA(cudaEventCreateWithFlags(&ctx->comm_ready, cudaEventDisableTiming));
+    AGB_CUDA(cudaEventCreateWithFlags(&ctx->comm_done, cudaEventDisableTiming));
+  }
+  AGB_CUDA(cudaEventRecord(ctx->comm_ready, ctx->stream));
+  AGB_CUDA(cudaStreamWaitEvent(ctx->comm_stream, ctx->comm_ready, 0));
+  AGB_NCCL(g_nccl.ar(buf, buf, (size_t)n, 7, 0, ctx->nccl_comm, ctx->comm_stream));
+  AGB_CUDA(cudaEventRecord(ctx->comm_done, ctx->comm_stream));      // stream order: the latest record covers every earlier bucket
+  ctx->comm_pending = true; ctx->launches++;
+  return AGB_OK;
+}
+extern "C" int agb_allreduce_wait(agb_ctx* ctx) {
+  if (ctx->comm_pending) { AGB_CUDA(cudaStreamWaitEvent(ctx->stream, ctx->comm_done, 0)); ctx->comm_pending = false; }
+  return AGB_OK;
+}
 extern "C" int agb_nccl_destroy(agb_ctx* ctx) {
+  if (ctx->comm_stream) { cudaStreamSynchronize(ctx->comm_stream); cudaStreamDestroy(ctx->comm_stream); cudaEventDestroy(ctx->comm_ready); cudaEventDestroy(ctx->comm_done); ctx->comm_stream = nullptr; }
   if (ctx->nccl_comm && g_nccl.destroy) { g_nccl.destroy(ctx->nccl_comm); ctx->nccl_comm = nullptr; }
   return AGB_OK;
 }

@@ -23,7 +23,7 @@ static inline PFN_encodeTiled agb_get_encode() {
 // swizzle_atom32: false -> SWIZZLE_128B (16-byte chunks; K-major operands), true -> SWIZZLE_128B_ATOM_32B (32-byte chunks;
 // the only shared-memory layout tcgen05 accepts for MN-major TF32 operands, UMMA layout type 128B_BASE32B).
 static inline int agb_make_tmap(CUtensorMap* m, const void* base, int rank, const uint64_t* dims, const uint64_t* strides_bytes,
-                                const uint32_t* box, bool swizzle_atom32 = false, const uint32_t* elem_strides = nullptr) {
+                                const uint32_t* box, bool swizzle_atom32 = false, const uint32_t* elem_strides = nullptr, bool no_swizzle = false) {
   PFN_encodeTiled enc = agb_get_encode();
   AGB_CHECK(enc, AGB_ERR_CUDA, "cuTensorMapEncodeTiled is not available from the driver");
   cuuint64_t d[5], s[4]; cuuint32_t b[5], e[5];
@@ -31,7 +31,7 @@ static inline int agb_make_tmap(CUtensorMap* m, const void* base, int rank, cons
   for (int i = 0; i < rank; i++) { d[i] = dims[i]; b[i] = box[i]; e[i] = elem_strides ? elem_strides[i] : 1; }
   for (int i = 0; i + 1 < rank; i++) s[i] = strides_bytes[i];
   CUresult r = enc(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, (cuuint32_t)rank, const_cast<void*>(base), d, s, b, e,
-                   CU_TENSOR_MAP_INTERLEAVE_NONE, swizzle_atom32 ? CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B : CU_TENSOR_MAP_SWIZZLE_128B,
+                   CU_TENSOR_MAP_INTERLEAVE_NONE, no_swizzle ? CU_TENSOR_MAP_SWIZZLE_NONE : swizzle_atom32 ? CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B : CU_TENSOR_MAP_SWIZZLE_128B,
                    CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                    CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) { agb_set_error("cuTensorMapEncodeTiled failed with CUresult %d", (int)r); return AGB_ERR_UNSUPPORTED; }
@@ -85,6 +85,13 @@ __device__ __forceinline__ void tma_load_4d(void* dst, const void* tmap, uint64_
   asm volatile("cp.async.bulk.tensor.4d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];"
                :: "r"(smem_u32(dst)), "l"(tmap), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2), "r"(c3) : "memory");
 }
+// TMA store: shared-memory tile (layout = the tensor map's swizzle) -> global, bounds clipped by the hardware; bulk-group completion
+__device__ __forceinline__ void tma_store_4d(const void* tmap, const void* src, int c0, int c1, int c2, int c3) {
+  asm volatile("cp.async.bulk.tensor.4d.global.shared::cta.bulk_group [%0, {%2, %3, %4, %5}], [%1];"
+               :: "l"(tmap), "r"(smem_u32(src)), "r"(c0), "r"(c1), "r"(c2), "r"(c3) : "memory");
+}
+__device__ __forceinline__ void tma_store_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+template <int N> __device__ __forceinline__ void tma_store_wait_read() { asm volatile("cp.async.bulk.wait_group.read %0;" :: "n"(N) : "memory"); }
 __device__ __forceinline__ void red_add_f32(float* p, float v) { asm volatile("red.global.add.f32 [%0], %1;" :: "l"(p), "f"(v) : "memory"); }
 __device__ __forceinline__ void tmem_alloc(uint32_t* smem_dst, uint32_t ncols) {
   asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" :: "r"(smem_u32(smem_dst)), "r"(ncols) : "memory");

@@ -103,7 +103,7 @@ SIGNATURES = {
     "agb_multi_tensor_momentum": [_P, _i, C.POINTER(_P), C.POINTER(_P), C.POINTER(_P), C.POINTER(_i64), _f, _f, _f],
     "agb_multi_tensor_adagrad": [_P, _i, C.POINTER(_P), C.POINTER(_P), C.POINTER(_P), C.POINTER(_i64), _f, _f],
     "agb_nccl_unique_id": [_P], "agb_nccl_init": [_P, _i, _i, _P], "agb_allreduce_sum": [_P, _P, _i64],
-    "agb_nccl_destroy": [_P],
+    "agb_nccl_destroy": [_P], "agb_allreduce_sum_async": [_P, _P, _i64], "agb_allreduce_wait": [_P],
 }
 
 _lib = None

@@ -706,3 +706,78 @@ def test_checkpoint_is_valid_json_for_odd_names_and_non_finite_values(ag, tmp_pa
     with pytest.raises(Exception):
         ag.VariableEnvironment.load(path)
     env.close(); env2.close()
+
+
+# ------------------------------------------------------------------------------------------------ automatic step-plan cache
+@pytest.mark.parametrize("net", ["mlp", "cnn"])
+def test_plan_cache_replays_rebuilt_graphs_with_eager_results(ag, net):
+    """The reference's training loop rebuilds its graph every step (examples/mlp_mnist.rs:74, cnn_mnist.rs:96).  With the plan cache on, the
+    third and later steps replay a CUDA graph captured at the second one although every step hands in a NEW graph object and new feed
+    values; losses and final variables must equal the cache-off run (bit for bit for the MLP, whose kernels are deterministic; to the
+    split-K atomics' reassociation for the CNN, whose dropout masks — same construction-time seed in every rebuilt graph — repeat)."""
+    from rust_autograd_b200 import workloads as W
+    rng = np.random.default_rng(5)
+    xs = [rng.uniform(size=(64, 784)).astype(np.float32) for _ in range(8)]
+    ys = [rng.integers(0, 10, (64, 1)).astype(np.float32) for _ in range(8)]
+
+    def train(cache):
+        env = ag.VariableEnvironment()
+        env.set_plan_cache(cache)
+        (W.mlp_init if net == "mlp" else W.cnn_mnist_init)(env, np.random.default_rng(0))
+        adam = ag.optimizers.Adam.default("adam", env.default_namespace().current_var_ids(), env)
+        losses = []
+        for x, y in zip(xs, ys):
+            def step(g):
+                loss, _ = W.mlp_loss(ag, g) if net == "mlp" else W.cnn_mnist_loss(ag, g, train=True)
+                params, grads = ag.optimizers.grad_helper([loss], g.default_namespace())
+                r = g.evaluator().push(loss).push(adam.get_update_op(params, grads, g)).feed("x", x).feed("y", y).run()
+                losses.append(float(np.asarray(r[0].unwrap()).ravel()[0]))
+            env.run(step)
+        stats = env.plan_stats()
+        out = [env.get_array_by_id(i).copy() for i in range(len(env.default_namespace().current_var_ids()))]
+        env.close()
+        return losses, out, stats
+    l0, w0, s0 = train(False)
+    l1, w1, s1 = train(True)
+    assert s0 == {"captures": 0, "replays": 0, "live_plans": 0}
+    assert s1["captures"] == 1 and s1["replays"] == 7 and s1["live_plans"] == 1, s1      # first sight eager, second captured and replayed, then replays
+    if net == "mlp":
+        assert l0 == l1 and all(np.array_equal(a, b) for a, b in zip(w0, w1))
+    else:
+        assert np.allclose(l0, l1, rtol=1e-4) and all(rel(b, a) <= 1e-3 for a, b in zip(w0, w1))
+
+
+def test_plan_cache_keeps_stream_and_callback_semantics(ag):
+    """Replayed evaluations of ONE persistent graph keep advancing the random ops' streams exactly like eager evaluations do (the positions
+    live in device memory); graphs with host callbacks are never replayed; a changed feed shape is a different plan."""
+    def masks(cache):
+        env = ag.VariableEnvironment()
+        env.set_plan_cache(cache)
+        v = env.slot().set(np.ones((64, 64)))
+        g = ag.Context(env)
+        d = ag.dropout(g.variable(v), 0.25, True)
+        out = [d.eval(g).copy() for _ in range(5)]
+        st = env.plan_stats()
+        g.close(); env.close()
+        return out, st
+    m0, _ = masks(False)
+    m1, st = masks(True)
+    assert st["replays"] == 4 and all(np.array_equal(a, b) for a, b in zip(m0, m1))
+    assert not np.array_equal(m1[2], m1[3])
+    env = ag.VariableEnvironment()
+    g = ag.Context(env)
+    x = g.placeholder("x", [-1, 4])
+    seen = []
+    y = (x * 2.0).raw_hook(lambda a: seen.append(np.asarray(a).copy()))
+    for k in range(4):
+        assert np.array_equal(y.eval(g, {"x": np.full((3, 4), float(k), np.float32)}), np.full((3, 4), 2.0 * k, np.float32))
+    assert len(seen) == 4 and env.plan_stats()["captures"] == 0
+    g.close()
+    g = ag.Context(env)                                       # (a graph that holds a host callback anywhere is never cached: a fresh one)
+    x = g.placeholder("x", [-1, 4])
+    z = ag.square(x)
+    for k in range(4):
+        assert np.array_equal(z.eval(g, {"x": np.full((2, 4), float(k), np.float32)}), np.full((2, 4), float(k * k), np.float32))
+    assert np.array_equal(z.eval(g, {"x": np.full((5, 4), 3.0, np.float32)}), np.full((5, 4), 9.0, np.float32))      # new shape -> its own (eager) first sight
+    assert env.plan_stats()["replays"] == 3
+    g.close(); env.close()
