@@ -1,7 +1,7 @@
 """Op microbench sweep (BASELINE.json configs[4]): GEMM / batch_matmul M=N=K 256..8192, conv ResNet/VGG-shaped layers,
 reduce_sum / softmax over 2^20..2^30 elements, elementwise, Adam.  CUDA-event timing on the library's stream, L2 flushed
 between repetitions for the bandwidth kernels.  Roofline fractions use MEASURED_PEAKS.json (HBM copy GB/s; dense TF32 =
-bf16/2).  Output: gpurun_out/ops_r1.json (copied to profiles/)."""
+bf16/2).  Output: gpurun_out/ops_r2.json (copied to profiles/ as one JSON row per line)."""
 import ctypes as C
 import json
 import os
@@ -142,7 +142,7 @@ def main():
     p, g, m, v, t = dev.fill((n,), 1.0), dev.fill((n,), 0.5), dev.fill((n,), 0.0), dev.fill((n,), 0.0), dev.fill((1,), 1.0)
     row("adam_2^26", timeit(dev, lambda: dev.adam([p], [g], [m], [v], [t])), bytes_=28.0 * n)
     os.makedirs(os.path.join(ROOT, "gpurun_out"), exist_ok=True)
-    json.dump(out, open(os.path.join(ROOT, "gpurun_out", "ops_r1.json"), "w"), indent=1)
+    json.dump(out, open(os.path.join(ROOT, "gpurun_out", "ops_r2.json"), "w"), indent=1)
 
 
 if __name__ == "__main__":
