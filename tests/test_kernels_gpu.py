@@ -598,7 +598,8 @@ def test_argreduce_bit_exact_with_ties(dev, shape, axis):
 
 
 # ------------------------------------------------------------------------------------------------ softmax family
-@pytest.mark.parametrize("shape,axis", [((200, 10), 1), ((128, 8192), 1), ((7, 13, 5), 1), ((64, 100), 0), ((4, 40000), 1)])
+@pytest.mark.parametrize("shape,axis", [((200, 10), 1), ((128, 8192), 1), ((7, 13, 5), 1), ((64, 100), 0), ((4, 40000), 1),
+                                         ((37, 256), 1), ((19, 132), 1), ((50, 512), 1), ((9, 1024), 1), ((11, 1020), 1), ((5, 1023), 1), ((6, 12288), 1), ((3, 16384), 1), ((2, 16388), 1), ((3, 20000), 1), ((2, 100001), 1), ((2, 131072), 1), ((1, 140000), 1), ((5, 2048), 1), ((7, 128), 1)])
 def test_softmax_family_vs_oracle(dev, shape, axis):
     rng = np.random.default_rng(8)
     x = (rng.standard_normal(shape) * 4).astype(np.float32)
@@ -608,7 +609,7 @@ def test_softmax_family_vs_oracle(dev, shape, axis):
     close(dev.softmax_like("logsumexp", d, axis).numpy(), R.logsumexp(x, axis, True), 1e-5)
 
 
-@pytest.mark.parametrize("b,c", [(200, 10), (128, 8192), (1, 3), (1000, 1000)])
+@pytest.mark.parametrize("b,c", [(200, 10), (128, 8192), (1, 3), (1000, 1000), (77, 256), (31, 1024), (5, 16384), (3, 50000), (9, 2048)])
 def test_sparse_xent_vs_oracle(dev, b, c):
     rng = np.random.default_rng(b + c)
     x = (rng.standard_normal((b, c)) * 3).astype(np.float32)
