@@ -468,11 +468,17 @@ int agb_small_c_fprop(agb_ctx* ctx, const float* x, const float* w, agb_tensor* 
   return AGB_OK;
 }
 
+int agb_tc_conv_first_wgrad(agb_ctx* ctx, int mode, const float* x, const float* gy, float* gw, int B, int C, int H, int W, int O, int kh, int kw, int yh, int yw,
+                            int pad, int stride, int dil);
 // gy may be NCHW or channels-last; gw [O, C*kh*kw] contiguous
 int agb_small_c_wgrad(agb_ctx* ctx, const float* x, const agb_tensor* gy, float* gw, int B, int C, int H, int W, int O, int kh, int kw, int yh, int yw,
                       int pad, int stride, int dil) {
   SmallGeom g; fill_geom(g, B, C, H, W, O, kh, kw, yh, yw, pad, stride, dil, gy);
   const int K = C * kh * kw; const int64_t total = (int64_t)B * yh * yw;
+  if (ctx->math_mode == AGB_MATH_TF32 && gy->stride[1] == 1 && gy->stride[3] == O && gy->stride[2] == (int64_t)yw * O && gy->stride[0] == (int64_t)yh * yw * O) {
+    int r = agb_tc_conv_first_wgrad(ctx, ctx->math_mode, x, gy->ptr, gw, B, C, H, W, O, kh, kw, yh, yw, pad, stride, dil);      // tcgen05, gy by TMA (tc_conv_first.cu)
+    if (r != AGB_ERR_UNSUPPORTED) return r;
+  }
   if (ctx->math_mode != AGB_MATH_FP32 && K <= 32 && O <= 256) {       // warp-MMA path
     const int nslab = (O + 63) / 64, NT = (K + 7) / 8; const bool split = ctx->math_mode == AGB_MATH_3XTF32;
     if ((int64_t)C * H * W >= (1ll << 31) - (1 << 20)) return AGB_ERR_UNSUPPORTED;

@@ -12,8 +12,9 @@
 // clipped at the row end / channel count by the hardware) moves it to y — per-thread 16-byte global stores of a pixel-per-thread layout
 // touch 32 half-filled sectors per warp instruction and made the epilogue the bottleneck (ncu: builders and issuer waiting on it).
 //   warps 0-3  builders: build the A tile (and A_lo in 3xTF32 mode) from the staged rows, double buffered
-//   warp  4    TMA producer (lane 0) + MMA issuer (elected lane), TMEM accumulators double buffered
+//   warp  4    MMA issuer (elected lane), TMEM accumulators double buffered
 //   warps 5-8  epilogue: tcgen05.ld -> bias / ReLU -> y
+//   warp  9    TMA producer (lane 0)
 // 3xTF32: the filter is split once per CTA (hi = rna, lo = rna(w - hi)), the builders write lo = rna(v - trunc(v)) next to the raw tile
 // (the tensor core truncates the raw values itself) and the issuer runs lo*hi + hi*lo + hi*hi; with K <= 32 there are only 12
 // accumulating MMAs per output, no chunked promotion is needed.
@@ -33,7 +34,7 @@ struct FirstParams {
 };
 
 template <int TN, bool SPLIT>
-__global__ void __launch_bounds__(288, 2) conv_first_fprop_kernel(const __grid_constant__ FirstParams p) {
+__global__ void __launch_bounds__(320, 2) conv_first_fprop_kernel(const __grid_constant__ FirstParams p) {
   constexpr int A_BYTES = 128 * 128, B_BYTES = TN * 128;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
@@ -82,53 +83,58 @@ __global__ void __launch_bounds__(288, 2) conv_first_fprop_kernel(const __grid_c
 
   if (warp < 4) {
     // ===================== builders =====================
+    int koff[32];                                               // the tap table lives in registers: the gathers do not wait for a table lookup
+#pragma unroll
+    for (int k = 0; k < 32; k++) koff[k] = s_koff[k];
+    const uint32_t sA_u = smem_u32(sA), sAl_u = smem_u32(sAl), row_u = (uint32_t)tid * 128u;
     uint32_t it = 0;
     for (int64_t t = blockIdx.x; t < p.tiles; t += gridDim.x, it++) {
       const int buf = it & 1;
-      const int xb_i = it % CF_XS_STAGES; const float* xsb = xs + xb_i * p.xs_floats;
+      const int xb_i = it % CF_XS_STAGES; const float* xsb = xs + xb_i * p.xs_floats + tid * p.stride;
       mbar_wait(&x_full[xb_i], (it / CF_XS_STAGES) & 1);       // this tile's input rows have landed
       mbar_wait(&a_empty[buf], ((it >> 1) & 1) ^ 1);           // the MMAs that read this buffer two tiles ago are complete
-      uint8_t* A = sA + buf * A_BYTES; uint8_t* Al = sAl + buf * A_BYTES;
-      const int px = tid * p.stride;
+      const uint32_t A = sA_u + buf * A_BYTES + row_u, Al = sAl_u + buf * A_BYTES + row_u;
 #pragma unroll
       for (int ch = 0; ch < 8; ch++) {
         float4 v, l;
         float e[4];
 #pragma unroll
-        for (int q = 0; q < 4; q++) { const int ko = s_koff[ch * 4 + q]; e[q] = ko >= 0 ? xsb[ko + px] : 0.0f; }
+        for (int q = 0; q < 4; q++) { const int ko = koff[ch * 4 + q]; e[q] = ko >= 0 ? xsb[ko] : 0.0f; }
         v = make_float4(e[0], e[1], e[2], e[3]);
-        const int off = tid * 128 + ((ch ^ (tid & 7)) << 4);
-        *(float4*)(A + off) = v;
+        const uint32_t off = (uint32_t)((ch ^ (tid & 7)) << 4);
+        asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" :: "r"(A + off), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w) : "memory");
         if (SPLIT) {
           l.x = tf32_rna(v.x - __uint_as_float(__float_as_uint(v.x) & 0xFFFFE000u)); l.y = tf32_rna(v.y - __uint_as_float(__float_as_uint(v.y) & 0xFFFFE000u));
           l.z = tf32_rna(v.z - __uint_as_float(__float_as_uint(v.z) & 0xFFFFE000u)); l.w = tf32_rna(v.w - __uint_as_float(__float_as_uint(v.w) & 0xFFFFE000u));
-          *(float4*)(Al + off) = l;
+          asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" :: "r"(Al + off), "f"(l.x), "f"(l.y), "f"(l.z), "f"(l.w) : "memory");
         }
       }
       fence_proxy_async();
       mbar_arrive(&a_full[buf]);
       mbar_arrive(&x_empty[xb_i]);                             // the staged rows may be overwritten
     }
+  } else if (warp == 9) {
+    // ===================== TMA producer (its own warp: the tile decode and the ring wait stay off the issuer's instruction stream) =====================
+    if (lane == 0) {
+      const uint32_t x_bytes = (uint32_t)(p.C * p.kh * p.seg * 4);
+      const int shift = ((-p.pad) % 4 + 4) % 4;
+      uint32_t pi = 0;
+      for (int64_t t = blockIdx.x; t < p.tiles; t += gridDim.x, pi++) {
+        const int tx = (int)(t % p.tiles_x); const int64_t r = t / p.tiles_x; const int oy = (int)(r % p.yh), b = (int)(r / p.yh);
+        const uint32_t xi = pi % CF_XS_STAGES;
+        mbar_wait(&x_empty[xi], ((pi / CF_XS_STAGES) & 1) ^ 1);
+        mbar_expect_tx(&x_full[xi], x_bytes);
+        tma_load_4d(xs + xi * p.xs_floats, &p.tmX, &x_full[xi], tx * 128 * p.stride - p.pad - shift, oy * p.stride - p.pad, 0, b);
+      }
+    }
   } else if (warp == 4) {
     // ===================== MMA issuer =====================
     constexpr uint32_t idesc = umma_idesc_tf32(128, TN, 0, 0);
     const uint32_t hiK = (1024u >> 4) | (1u << 14) | (2u << 29), loK = (16u >> 4) << 16;
     const uint32_t aB = (smem_u32(sB) >> 4) + loK, aBl = (smem_u32(sBl) >> 4) + loK;
-    const uint32_t x_bytes = (uint32_t)(p.C * p.kh * p.seg * 4);
-    const int shift = ((-p.pad) % 4 + 4) % 4;
-    auto produce = [&](int64_t t, uint32_t pi) {              // stage tile t's input rows (lane 0)
-      const int tx = (int)(t % p.tiles_x); const int64_t r = t / p.tiles_x; const int oy = (int)(r % p.yh), b = (int)(r / p.yh);
-      const uint32_t xi = pi % CF_XS_STAGES;
-      mbar_wait(&x_empty[xi], ((pi / CF_XS_STAGES) & 1) ^ 1);
-      mbar_expect_tx(&x_full[xi], x_bytes);
-      tma_load_4d(xs + xi * p.xs_floats, &p.tmX, &x_full[xi], tx * 128 * p.stride - p.pad - shift, oy * p.stride - p.pad, 0, b);
-    };
-    uint32_t it = 0, pi = 0; int64_t tp = blockIdx.x;
-    if (lane == 0) for (; pi < CF_XS_STAGES - 1 && tp < p.tiles; pi++, tp += gridDim.x) produce(tp, pi);
+    uint32_t it = 0;
     for (int64_t t = blockIdx.x; t < p.tiles; t += gridDim.x, it++) {
       const uint32_t buf = it & 1;
-      if (lane == 0 && tp < p.tiles) { produce(tp, pi); pi++; tp += gridDim.x; }
-      __syncwarp();
       mbar_wait(&acc_empty[buf], ((it >> 1) & 1) ^ 1);
       mbar_wait(&a_full[buf], (it >> 1) & 1);
       tc_fence_after();
@@ -199,14 +205,16 @@ static int first_launch(agb_ctx* ctx, const FirstParams& p) {
   const int SMEM = SMEM_MAX - CF_XS_STAGES * (CF_XS_MAX_FLOATS - p.xs_floats) * 4;
   static bool attr = false;
   if (!attr) { AGB_CUDA(cudaFuncSetAttribute(conv_first_fprop_kernel<TN, SPLIT>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_MAX)); attr = true; }
-  static int occ = 0, occ_smem = 0;
-  if (occ_smem != SMEM) {      // co-resident CTAs overlap one's build / epilogue phases with the other's; they share the 512 TMEM columns
-    AGB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, conv_first_fprop_kernel<TN, SPLIT>, 288, SMEM)); if (occ < 1) occ = 1; if (occ * 2 * TN > 512) occ = 512 / (2 * TN);
-    occ_smem = SMEM;
-  }
+  // co-resident CTAs overlap one's build / epilogue phases with the other's (0.328 -> 0.203 ms on the 3 -> 64 @128x128 layer); they share the 512 TMEM
+  // columns.  Residency is computed here: cudaOccupancyMaxActiveBlocksPerMultiprocessor answers 1 for this kernel at 95 KB of dynamic shared memory
+  // although two CTAs are resident (ncu: launch__occupancy_limit_shared_mem = 2), which had left half of every SM idle.
+  static const int occ_env = [] { const char* e = getenv("AGB_CF_OCC"); return e ? atoi(e) : 0; }();
+  int occ = (227 * 1024) / (SMEM + 1024); if (occ > 2) occ = 2; if (occ < 1) occ = 1;
+  if (occ * 2 * TN > 512) occ = 512 / (2 * TN);
+  if (occ_env > 0) occ = occ_env;
   const int64_t cap = (int64_t)ctx->sm_count * occ;
   const unsigned n = (unsigned)(p.tiles < cap ? p.tiles : cap);
-  conv_first_fprop_kernel<TN, SPLIT><<<n, 288, SMEM, ctx->stream>>>(p);
+  conv_first_fprop_kernel<TN, SPLIT><<<n, 320, SMEM, ctx->stream>>>(p);
   AGB_LAUNCHED(ctx);
   return AGB_OK;
 }
@@ -241,4 +249,224 @@ int agb_tc_conv_first(agb_ctx* ctx, int mode, const float* x, const float* w, fl
   if (O <= 64) return split ? first_launch<64, true>(ctx, p) : first_launch<64, false>(ctx, p);
   if (O <= 128) return split ? first_launch<128, true>(ctx, p) : first_launch<128, false>(ctx, p);
   return split ? first_launch<256, true>(ctx, p) : first_launch<256, false>(ctx, p);
+}
+
+// =====================================================================================================================
+// First-layer FILTER GRADIENT on tcgen05: gw[o, k] = sum over pixels of gy[pixel, o] * patch[pixel, k], K = C*kh*kw <= 32.
+// The layer is bound by READING gy (1.07 GB at B = 256, 64 x 128 x 128) — the warp-MMA kernel of conv_small_c.cu gathered its fragments from
+// global memory at 0.41 of the HBM rate.  Here, per 128-pixel tile (a segment of one output row):
+//   * gy arrives by TMA as the MN-major A operand (M = o, K = pixel): one {32 o, 128 pixels} box per 32 channels, SWIZZLE_128B_ATOM_32B
+//     (the only MN-major TF32 layout, tc_common.cuh), a ring of up to 4 stages = up to 148 KB of loads in flight per SM;
+//   * the input rows arrive by the forward kernel's TMA box and 128 builder threads write the im2col tile [pixel][32 taps] — as an
+//     MN-major B operand (N = tap, K = pixel) it is the same 128-byte-row image the forward kernel builds, with the 32-byte-chunk swizzle;
+//   * 16 MMAs (M = 128 lanes of which O are used, N = 32, K = 8 pixels each) accumulate the tile into one of two TMEM buffers; four
+//     accumulator warps add every finished tile into fp32 REGISTERS (TMEM accumulation truncates, so nothing is left there for more
+//     than one tile), and at the end each CTA writes its [O, 32] partial sums to scratch.
+// A second tiny kernel adds the per-CTA partials in CTA order: no atomics, so the result is bit-reproducible run to run
+// (the reference's filter gradient is a sequential sum, conv2d.rs:631-734).
+// =====================================================================================================================
+struct FirstWgradParams {
+  CUtensorMap tmX;               // x as {W, H, C, B}, box {seg, kh (row step dil), C, 1}, no swizzle
+  CUtensorMap tmG;               // gy (channels-last) as {O, yw, yh, B}, box {32, 128, 1, 1}, SWIZZLE_128B_ATOM_32B
+  float* part;                   // [grid][128][32]
+  int B, C, H, W, O, kh, kw, pad, stride, dil, yh, yw, K;
+  int tiles_x, seg, xs_floats, nbox, stages; int64_t tiles;
+};
+
+#define CFW_MAX_STAGES 4
+#define CFW_THREADS 320          // warps 0-3 builders, 4 MMA issuer, 5-8 accumulators, 9 TMA producer
+__global__ void __launch_bounds__(CFW_THREADS, 1) conv_first_wgrad_kernel(const __grid_constant__ FirstWgradParams p) {
+  constexpr int BOX_BYTES = 128 * 128, P_BYTES = 128 * 128;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
+  const int a_stage = p.nbox * BOX_BYTES;
+  uint8_t* sA = smem;                                           // stages x nbox x [128 px][32 o]   (MN-major A, 32-byte-chunk swizzle)
+  uint8_t* sP = sA + p.stages * a_stage;                        // 2 x [128 px][32 taps]            (MN-major B, same swizzle)
+  float* xs = (float*)(sP + 2 * P_BYTES);                       // stages x [C][kh][seg]
+  uint64_t* bars = (uint64_t*)(xs + p.stages * p.xs_floats);
+  uint64_t* in_full = bars; uint64_t* in_empty = bars + CFW_MAX_STAGES; uint64_t* p_full = bars + 2 * CFW_MAX_STAGES; uint64_t* p_empty = p_full + 2;
+  uint64_t* acc_full = p_full + 4; uint64_t* acc_empty = p_full + 6;
+  uint32_t* tmem_slot = (uint32_t*)(p_full + 8);
+  __shared__ int s_koff[32];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, tid = threadIdx.x;
+  const int S = p.stages;
+
+  if (tid == 0) {
+    for (int b = 0; b < S; b++) { mbar_init(&in_full[b], 1); mbar_init(&in_empty[b], 1); }
+    for (int b = 0; b < 2; b++) { mbar_init(&p_full[b], 128); mbar_init(&p_empty[b], 1); mbar_init(&acc_full[b], 1); mbar_init(&acc_empty[b], 128); }
+    fence_barrier_init();
+    tma_prefetch_desc(&p.tmX); tma_prefetch_desc(&p.tmG);
+  }
+  if (tid < 32) {
+    const int k = tid, kk = p.kh * p.kw;
+    const int shift = ((-p.pad) % 4 + 4) % 4;
+    if (k < p.K) { const int c = k / kk, r = k - c * kk, i = r / p.kw, j = r - i * p.kw; s_koff[k] = (c * p.kh + i) * p.seg + j * p.dil + shift; }
+    else s_koff[k] = -1;
+  }
+  if (warp == 4) { tmem_alloc(tmem_slot, 64); tmem_relinquish(); }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp < 4) {
+    // ===================== builders: patches[pixel][tap] =====================
+    int koff[32];                                               // the tap table lives in registers: the gathers do not wait for a table lookup
+#pragma unroll
+    for (int k = 0; k < 32; k++) koff[k] = s_koff[k];
+    const uint32_t sP_u = smem_u32(sP), row_u = (uint32_t)tid * 128u;
+    uint32_t it = 0;
+    for (int64_t t = blockIdx.x; t < p.tiles; t += gridDim.x, it++) {
+      const int buf = it & 1, st = it % S;
+      const float* xsb = xs + st * p.xs_floats + tid * p.stride;
+      mbar_wait(&in_full[st], (it / S) & 1);
+      mbar_wait(&p_empty[buf], ((it >> 1) & 1) ^ 1);
+      const uint32_t Pt = sP_u + buf * P_BYTES + row_u;
+#pragma unroll
+      for (int ch = 0; ch < 8; ch++) {
+        const int c16 = ch ^ ((tid >> 2) & 1);                 // threads t and t+4 write different halves of a 32-byte chunk: conflict-free 16-byte stores
+        float e[4];
+#pragma unroll
+        for (int q = 0; q < 4; q++) { const int ko = (tid >> 2) & 1 ? koff[(ch ^ 1) * 4 + q] : koff[ch * 4 + q]; e[q] = ko >= 0 ? xsb[ko] : 0.0f; }
+        const uint32_t off = Pt + ((((c16 >> 1) ^ (tid & 3)) << 5) | ((c16 & 1) << 4));
+        asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" :: "r"(off), "f"(e[0]), "f"(e[1]), "f"(e[2]), "f"(e[3]) : "memory");
+      }
+      fence_proxy_async();
+      mbar_arrive(&p_full[buf]);
+    }
+  } else if (warp == 9) {
+    // ===================== TMA producer =====================
+    if (lane == 0) {
+      const uint32_t in_bytes = (uint32_t)(p.C * p.kh * p.seg * 4) + (uint32_t)a_stage;
+      const int shift = ((-p.pad) % 4 + 4) % 4;
+      uint32_t pi = 0;
+      for (int64_t t = blockIdx.x; t < p.tiles; t += gridDim.x, pi++) {
+        const int tx = (int)(t % p.tiles_x); const int64_t r = t / p.tiles_x; const int oy = (int)(r % p.yh), b = (int)(r / p.yh);
+        const uint32_t st = pi % S;
+        mbar_wait(&in_empty[st], ((pi / S) & 1) ^ 1);
+        mbar_expect_tx(&in_full[st], in_bytes);
+        tma_load_4d(xs + st * p.xs_floats, &p.tmX, &in_full[st], tx * 128 * p.stride - p.pad - shift, oy * p.stride - p.pad, 0, b);
+        for (int g = 0; g < p.nbox; g++) tma_load_4d(sA + st * a_stage + g * BOX_BYTES, &p.tmG, &in_full[st], 32 * g, tx * 128, oy, b);
+      }
+    }
+  } else if (warp == 4) {
+    // ===================== MMA issuer (nothing else: one warp's instruction stream per tile is the kernel's critical path) =====================
+    constexpr uint32_t idesc = umma_idesc_tf32(128, 32, 1, 1);
+    const uint32_t hi = (512u >> 4) | (1u << 14) | (1u << 29);           // SBO = 512 (4-pixel atoms), version 1, layout 128B_BASE32B
+    const uint32_t loA = ((uint32_t)BOX_BYTES >> 4) << 16, loB = (4096u >> 4) << 16;      // LBO: between 32-channel boxes (B has one box)
+    const uint32_t aA0 = (smem_u32(sA) >> 4) + loA, aB0 = (smem_u32(sP) >> 4) + loB;
+    uint32_t it = 0, st = 0;
+    for (int64_t t = blockIdx.x; t < p.tiles; t += gridDim.x, it++) {
+      const uint32_t buf = it & 1, ph = (it >> 1) & 1;
+      mbar_wait(&acc_empty[buf], ph ^ 1);
+      mbar_wait(&in_full[st], (it / S) & 1);
+      mbar_wait(&p_full[buf], ph);
+      tc_fence_after();
+      if (elect_one()) {
+        const uint32_t tacc = tmem_base + buf * 32u;
+        const uint32_t aA = aA0 + st * (uint32_t)(a_stage >> 4), aB = aB0 + buf * (uint32_t)(P_BYTES >> 4);
+#pragma unroll
+        for (int k = 0; k < 16; k++) umma_tf32(tacc, umma_desc_pack(aA + k * 64, hi), umma_desc_pack(aB + k * 64, hi), idesc, k != 0);      // 8 pixels = 1024 B per step
+        umma_commit(&in_empty[st]);
+        umma_commit(&p_empty[buf]);
+        umma_commit(&acc_full[buf]);
+      }
+      __syncwarp();
+      st = st + 1 == (uint32_t)S ? 0 : st + 1;
+    }
+  } else {
+    // ===================== accumulators: TMEM -> fp32 registers, once per tile =====================
+    const int q = warp & 3, row = 32 * q + lane;
+    const uint32_t tlane = tmem_base + ((uint32_t)(32 * q) << 16);
+    float acc[32];
+#pragma unroll
+    for (int j = 0; j < 32; j++) acc[j] = 0.0f;
+    uint32_t it = 0;
+    for (int64_t t = blockIdx.x; t < p.tiles; t += gridDim.x, it++) {
+      const uint32_t buf = it & 1;
+      mbar_wait(&acc_full[buf], (it >> 1) & 1);
+      tc_fence_after();
+      float v[32];
+      tmem_ld32(tlane + buf * 32u, v);
+      tmem_ld_wait();
+      tc_fence_before();
+      mbar_arrive(&acc_empty[buf]);
+#pragma unroll
+      for (int j = 0; j < 32; j++) acc[j] += v[j];
+    }
+    float4* dst = (float4*)(p.part + ((int64_t)blockIdx.x * 128 + row) * 32);
+#pragma unroll
+    for (int j = 0; j < 32; j += 4) dst[j >> 2] = make_float4(acc[j], acc[j + 1], acc[j + 2], acc[j + 3]);
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 4) tmem_dealloc(tmem_base, 64);
+}
+
+// gw[o, k] = sum over CTAs (in CTA order) of part[cta][o][k]
+__global__ void __launch_bounds__(256) conv_first_wgrad_reduce_kernel(const float* __restrict__ part, float* __restrict__ gw, int ncta, int O, int K) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= O * K) return;
+  const int o = i / K, k = i - o * K;
+  const float* src = part + o * 32 + k;
+  float s0 = 0.0f, s1 = 0.0f, s2 = 0.0f, s3 = 0.0f;
+  int c = 0;
+  for (; c + 3 < ncta; c += 4) {
+    s0 += __ldg(src + (int64_t)c * 4096); s1 += __ldg(src + (int64_t)(c + 1) * 4096); s2 += __ldg(src + (int64_t)(c + 2) * 4096); s3 += __ldg(src + (int64_t)(c + 3) * 4096);
+  }
+  for (; c < ncta; c++) s0 += __ldg(src + (int64_t)c * 4096);
+  gw[i] = (s0 + s1) + (s2 + s3);
+}
+
+// x NCHW-contiguous [B,C,H,W], gy channels-last dense [B,yh,yw,O], gw [O, C*kh*kw].  TF32 mode only (the 3xTF32 mode keeps the warp-MMA kernel).
+int agb_tc_conv_first_wgrad(agb_ctx* ctx, int mode, const float* x, const float* gy, float* gw, int B, int C, int H, int W, int O, int kh, int kw, int yh, int yw,
+                            int pad, int stride, int dil) {
+  static const int enabled = [] { const char* e = getenv("AGB_CONV_FIRST_WGRAD"); return (e && e[0] == '0') ? 0 : 1; }();
+  const int K = C * kh * kw;
+  const int shift = ((-pad) % 4 + 4) % 4;
+  const int seg = (127 * stride + (kw - 1) * dil + 1 + shift + 3) / 4 * 4;
+  if (!enabled || mode != AGB_MATH_TF32 || K > 32 || seg > 256 || C * kh * seg > CF_XS_MAX_FLOATS || (kh - 1) * dil + 1 > 256 || O > 128 || O % 4 != 0 || yw < 32 || W % 4 != 0)
+    return AGB_ERR_UNSUPPORTED;
+  if ((((uintptr_t)gy | (uintptr_t)x) & 15) != 0) return AGB_ERR_UNSUPPORTED;
+  FirstWgradParams p;
+  {
+    uint64_t dims[4] = {(uint64_t)W, (uint64_t)H, (uint64_t)C, (uint64_t)B};
+    uint64_t str[3] = {(uint64_t)W * 4, (uint64_t)H * W * 4, (uint64_t)C * H * W * 4};
+    uint32_t box[4] = {(uint32_t)seg, (uint32_t)((kh - 1) * dil + 1), (uint32_t)C, 1}, es[4] = {1, (uint32_t)dil, 1, 1};
+    AGB_TRY(agb_make_tmap(&p.tmX, x, 4, dims, str, box, false, dil > 1 ? es : nullptr, true));
+  }
+  {
+    uint64_t dims[4] = {(uint64_t)O, (uint64_t)yw, (uint64_t)yh, (uint64_t)B};
+    uint64_t str[3] = {(uint64_t)O * 4, (uint64_t)yw * O * 4, (uint64_t)yh * yw * O * 4};
+    uint32_t box[4] = {32, 128, 1, 1};
+    AGB_TRY(agb_make_tmap(&p.tmG, gy, 4, dims, str, box, true));
+  }
+  p.B = B; p.C = C; p.H = H; p.W = W; p.O = O; p.kh = kh; p.kw = kw; p.pad = pad; p.stride = stride; p.dil = dil; p.yh = yh; p.yw = yw; p.K = K;
+  p.tiles_x = (yw + 127) / 128; p.seg = seg; p.xs_floats = (C * kh * seg + 31) / 32 * 32; p.tiles = (int64_t)B * yh * p.tiles_x;
+  p.nbox = O <= 32 ? 1 : O <= 64 ? 2 : 4;
+  const int per_stage = p.nbox * 16384 + p.xs_floats * 4;
+  // measured (B200, 3 -> 64 @128x128, B = 256): one CTA per SM with a 4-deep ring 0.200 ms (0.86 of HBM); two co-resident CTAs with 2 stages each 0.251 ms
+  static const int st_env = [] { const char* e = getenv("AGB_CFW_STAGES"); return e ? atoi(e) : 0; }();
+  int stages = (227 * 1024 - 2 * 16384 - 2048) / per_stage;
+  if (st_env > 0) stages = st_env;
+  if (stages > CFW_MAX_STAGES) stages = CFW_MAX_STAGES;
+  if (stages < 2 || 1024 + stages * per_stage + 2 * 16384 + 512 > 227 * 1024) return AGB_ERR_UNSUPPORTED;
+  p.stages = stages;
+  int smem = 1024 + stages * per_stage + 2 * 16384 + 512;
+  const int reach = 1024 + (stages - 1) * p.nbox * 16384 + 4 * 16384;       // the M = 128 descriptor of the last stage reads four boxes: keep them inside the allocation
+  if (smem < reach) smem = reach;
+  static int attr_smem = 0;
+  if (attr_smem < smem) { AGB_CUDA(cudaFuncSetAttribute(conv_first_wgrad_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem)); attr_smem = smem; }
+  int occ = 1;
+  if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, conv_first_wgrad_kernel, CFW_THREADS, smem) != cudaSuccess || occ < 1) occ = 1;
+  if (occ > 2) occ = 2;
+  const int64_t cap = (int64_t)ctx->sm_count * occ;
+  const unsigned n = (unsigned)(p.tiles < cap ? p.tiles : cap);
+  float* part; AGB_TRY(agb_scratch(ctx, (size_t)n * 128 * 32 * sizeof(float), (void**)&part));
+  p.part = part;
+  conv_first_wgrad_kernel<<<n, CFW_THREADS, smem, ctx->stream>>>(p);
+  AGB_LAUNCHED(ctx);
+  conv_first_wgrad_reduce_kernel<<<(O * K + 255) / 256, 256, 0, ctx->stream>>>(part, gw, (int)n, O, K);
+  AGB_LAUNCHED(ctx);
+  return AGB_OK;
 }

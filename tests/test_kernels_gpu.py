@@ -279,7 +279,11 @@ def test_strided_dgrad_phases_with_mask_and_channel_sums(dev, case, cl):
 
 @pytest.mark.parametrize("mode", MODES)
 @pytest.mark.parametrize("case", [(2, 1, 28, 28, 32, 3, 3, 1, 1, 1), (2, 3, 32, 32, 64, 3, 3, 1, 1, 1), (3, 3, 17, 13, 48, 3, 3, 1, 2, 1), (2, 2, 11, 11, 24, 3, 3, 2, 1, 2),
-                                  (1, 4, 9, 9, 8, 2, 2, 0, 1, 1), (2, 3, 20, 20, 200, 3, 3, 1, 1, 1), (5, 1, 6, 6, 10, 5, 5, 2, 1, 1)])
+                                  (1, 4, 9, 9, 8, 2, 2, 0, 1, 1), (2, 3, 20, 20, 200, 3, 3, 1, 1, 1), (5, 1, 6, 6, 10, 5, 5, 2, 1, 1),
+                                  # geometries of the tcgen05 first-layer kernels (W % 4 == 0, output width >= 32): partial second 128-pixel strip, no padding, 128 channels,
+                                  # stride 2, dilation 2, 5x5 taps with 12 channels
+                                  (3, 3, 40, 160, 64, 3, 3, 1, 1, 1), (2, 3, 33, 136, 32, 3, 3, 0, 1, 1), (2, 4, 20, 64, 128, 2, 2, 0, 1, 1), (4, 3, 24, 132, 48, 3, 3, 1, 2, 1),
+                                  (2, 3, 24, 72, 96, 3, 3, 2, 1, 2), (3, 1, 36, 36, 12, 5, 5, 2, 1, 1), (9, 3, 64, 128, 64, 3, 3, 1, 1, 1)])
 def test_small_channel_conv_channels_last(dev, case, mode):
     """first-layer kernels (C <= 4): NCHW input, channels-last output / output-gradient, ragged pixel groups, O not a multiple of 64"""
     dev.set_math_mode(mode)
