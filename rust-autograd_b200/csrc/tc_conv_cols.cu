@@ -21,30 +21,35 @@
 struct ColsParams {
   CUtensorMap tmX, tmW;
   float* y; const float* bias; const float* mask; float* csum; int relu;
-  int Cout, yh, yw, kw, pad, dil, tiles_y, cblocks, taps, rm, copy_bytes, copy_stride, a_slot_bytes;
+  int Cout, yh, yw, kw, pad, dil, tiles_y, cblocks, taps, rm, copy_bytes, copy_stride, a_slot_bytes, nb /* filter ring depth, in stages of G taps */;
   long long num_tiles;
 };
 template <int TN> struct ColsCfg {
-  static constexpr int NB = 6;                                 // filter-tap ring depth
-  static constexpr int B_BYTES = TN * 64;                      // [TN o][16 c]
+  static constexpr int B_BYTES = TN * 64;                      // [TN o][16 c] per tap
   static constexpr int TMEM_COLS = 4 * TN;                     // 2 sets x 2 M-tiles
   static constexpr int THREADS = 256;                          // warps: 0 TMA-A, 1 MMA tile 0, 2-5 epilogue, 6 TMA-B, 7 MMA tile 1
 };
 
-template <int TN>
+// G = filter taps per ring stage.  G = 1: one tap per stage.  G = 3 (kw == 3): one filter ROW per stage, one TMA box {16 c, TN o, 3 taps} — the issuer
+// pays one barrier wait + one commit per 6 MMAs instead of per 2.  With N = 64 an MMA pair occupies the tensor pipe for ~67 clk while one trip
+// round the issuer's loop (wait, fence, elect, commit, counters) costs more than that: ncu showed the TN = 64 kernel at 34 % tensor-active with
+// the issuers 27 % of their time on b_full and the rest in loop overhead.
+#define COLS_NB_MAX 16
+template <int TN, int G>
 __global__ void __launch_bounds__(256, 1) conv_cols_kernel(const __grid_constant__ ColsParams p) {
   using Cfg = ColsCfg<TN>;
-  constexpr int NB = Cfg::NB;
+  constexpr int NB = COLS_NB_MAX;                              // barrier slots; p.nb stages are in use
+  constexpr int ST_BYTES = G * Cfg::B_BYTES;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
   uint8_t* sA = smem;                                          // [2][a_slot_bytes]: kw copies each
-  uint8_t* sB = smem + 2 * p.a_slot_bytes;                     // [NB][TN * 64]
-  uint64_t* bars = (uint64_t*)(sB + NB * Cfg::B_BYTES);
+  uint8_t* sB = smem + 2 * p.a_slot_bytes;                     // [p.nb][G][TN * 64]
+  uint64_t* bars = (uint64_t*)(sB + p.nb * ST_BYTES);
   uint64_t* a_full = bars; uint64_t* a_empty = bars + 2;
   uint64_t* b_full = bars + 4; uint64_t* b_empty = bars + 4 + NB;
   uint64_t* acc_full = bars + 4 + 2 * NB; uint64_t* acc_empty = bars + 6 + 2 * NB;
   uint32_t* tmem_slot = (uint32_t*)(bars + 8 + 2 * NB);
-  float* stage = (float*)((uint8_t*)bars + 256);               // [4 warps][32][36] epilogue transpose tiles
+  float* stage = (float*)((uint8_t*)bars + 512);               // [4 warps][32][36] epilogue transpose tiles
   float* csum_s = stage + 4 * 32 * 36;                         // [TN] per-channel sums of this CTA
   if ((int)threadIdx.x < TN) csum_s[threadIdx.x] = 0.0f;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -84,11 +89,11 @@ __global__ void __launch_bounds__(256, 1) conv_cols_kernel(const __grid_constant
       uint32_t bs = 0, bph = 0;
       for (long long t = blockIdx.x; t < p.num_tiles; t += gridDim.x)
         for (int cb = 0; cb < p.cblocks; cb++)
-          for (int tap = 0; tap < p.taps; tap++) {
+          for (int tap = 0; tap < p.taps; tap += G) {
             mbar_wait(&b_empty[bs], bph ^ 1);
-            mbar_expect_tx(&b_full[bs], Cfg::B_BYTES);
-            tma_load_3d(sB + bs * Cfg::B_BYTES, &p.tmW, &b_full[bs], cb * 16, 0, tap);
-            if (++bs == NB) { bs = 0; bph ^= 1; }
+            mbar_expect_tx(&b_full[bs], ST_BYTES);
+            tma_load_3d(sB + bs * ST_BYTES, &p.tmW, &b_full[bs], cb * 16, 0, tap);
+            if (++bs == (uint32_t)p.nb) { bs = 0; bph ^= 1; }
           }
     }
   } else if (warp == 1 || warp == 7) {
@@ -111,23 +116,27 @@ __global__ void __launch_bounds__(256, 1) conv_cols_kernel(const __grid_constant
         tc_fence_after();
         const uint32_t a0 = sA4 + as * ((uint32_t)p.a_slot_bytes >> 4);
         uint32_t arow = a0, atap = a0; int j = 0;                      // tap (i, j): copy j, window row i*d (+ this M-tile's first row)
-        for (int tap = 0; tap < p.taps; tap++) {
+        for (int tap = 0; tap < p.taps; tap += G) {
+          uint32_t at[G];
+#pragma unroll
+          for (int jj = 0; jj < G; jj++) { at[jj] = atap; if (++j == p.kw) { j = 0; arow += di4; atap = arow; } else atap += cp4; }
           mbar_wait(&b_full[bs], bph);
           tc_fence_after();
           if (elect_one()) {
-            const uint32_t q0 = sB4 + bs * (uint32_t)(Cfg::B_BYTES >> 4);
+            const uint32_t q0 = sB4 + bs * (uint32_t)(ST_BYTES >> 4);
 #pragma unroll
-            for (int ks = 0; ks < 2; ks++)
-              umma_tf32(tacc, umma_desc_pack(atap + ks * 2, hi), umma_desc_pack(q0 + ks * 2, hi), idesc, !(cb == 0 && tap == 0 && ks == 0));
+            for (int jj = 0; jj < G; jj++)
+#pragma unroll
+              for (int ks = 0; ks < 2; ks++)
+                umma_tf32(tacc, umma_desc_pack(at[jj] + ks * 2, hi), umma_desc_pack(q0 + jj * (uint32_t)(Cfg::B_BYTES >> 4) + ks * 2, hi), idesc, !(cb == 0 && tap == 0 && jj == 0 && ks == 0));
             umma_commit(&b_empty[bs]);
-            if (tap == p.taps - 1) {
+            if (tap + G >= p.taps) {
               umma_commit(&a_empty[as]);
               if (cb == p.cblocks - 1) umma_commit(&acc_full[acs]);
             }
           }
           __syncwarp();
-          if (++bs == NB) { bs = 0; bph ^= 1; }
-          if (++j == p.kw) { j = 0; arow += di4; atap = arow; } else atap += cp4;
+          if (++bs == (uint32_t)p.nb) { bs = 0; bph ^= 1; }
         }
       }
     }
@@ -229,12 +238,12 @@ __global__ void __launch_bounds__(256, 1) conv_cols_kernel(const __grid_constant
   if (warp == 1) tmem_dealloc(tmem_base, Cfg::TMEM_COLS);
 }
 
-template <int TN>
+template <int TN, int G>
 static int cols_launch(agb_ctx* ctx, ColsParams& p, size_t smem) {
   static bool attr = false;
-  if (!attr) { AGB_CUDA(cudaFuncSetAttribute(conv_cols_kernel<TN>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024)); attr = true; }
+  if (!attr) { AGB_CUDA(cudaFuncSetAttribute(conv_cols_kernel<TN, G>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024)); attr = true; }
   long long grid = p.num_tiles < ctx->sm_count ? p.num_tiles : ctx->sm_count;
-  conv_cols_kernel<TN><<<(unsigned)grid, ColsCfg<TN>::THREADS, smem, ctx->stream>>>(p);
+  conv_cols_kernel<TN, G><<<(unsigned)grid, ColsCfg<TN>::THREADS, smem, ctx->stream>>>(p);
   AGB_LAUNCHED(ctx);
   return AGB_OK;
 }
@@ -264,8 +273,14 @@ int agb_tc_conv_cols(agb_ctx* ctx, const float* x, const float* wr, float* y, in
   if (wrows > 256 || (int64_t)B * ((yh + rt - 1) / rt) < ctx->sm_count) return AGB_ERR_UNSUPPORTED;        // too few tiles to fill the machine
   p.copy_bytes = 64 * yw * wrows; p.copy_stride = (p.copy_bytes + 1023) & ~1023; p.a_slot_bytes = kw * p.copy_stride;
   const int TN = Cout > 64 ? 128 : 64;
-  const size_t smem = 2 * (size_t)p.a_slot_bytes + (size_t)ColsCfg<64>::NB * TN * 64 + 1024 + 256 + 4 * 32 * 36 * 4 + 128 * 4;
-  if (smem > 227 * 1024) return AGB_ERR_UNSUPPORTED;
+  static const int g_env = [] { const char* e = getenv("AGB_COLS_G"); return e ? atoi(e) : 0; }();
+  const int G = (kw == 3 && (g_env == 3 || (g_env == 0 && TN == 64))) ? 3 : 1;       // one filter row per ring stage where the ring can still be deep enough
+  const size_t fixed = 2 * (size_t)p.a_slot_bytes + 1024 + 512 + 4 * 32 * 36 * 4 + 128 * 4;
+  const size_t st_bytes = (size_t)G * TN * 64;
+  if (fixed + 2 * st_bytes > 227 * 1024) return AGB_ERR_UNSUPPORTED;
+  int nb = (int)((227 * 1024 - fixed) / st_bytes); if (nb > COLS_NB_MAX) nb = COLS_NB_MAX;
+  p.nb = nb;
+  const size_t smem = fixed + (size_t)nb * st_bytes;
   {
     uint64_t dims[4] = {(uint64_t)Cin, (uint64_t)W, (uint64_t)H, (uint64_t)B};
     uint64_t str[3] = {(uint64_t)Cin * 4, (uint64_t)W * Cin * 4, (uint64_t)H * W * Cin * 4};
@@ -275,11 +290,12 @@ int agb_tc_conv_cols(agb_ctx* ctx, const float* x, const float* wr, float* y, in
   {
     uint64_t dims[3] = {(uint64_t)Cin, (uint64_t)Cout, (uint64_t)(kh * kw)};
     uint64_t str[2] = {(uint64_t)Cin * 4, (uint64_t)Cin * Cout * 4};
-    uint32_t box[3] = {16, (uint32_t)TN, 1};
+    uint32_t box[3] = {16, (uint32_t)TN, (uint32_t)G};
     AGB_TRY(make_sw64_map(&p.tmW, wr, 3, dims, str, box));
   }
   p.y = y; p.bias = bias; p.mask = mask; p.csum = csum; p.relu = relu; p.Cout = Cout; p.yh = yh; p.yw = yw; p.kw = kw; p.pad = pad; p.dil = dil;
   p.tiles_y = (yh + rt - 1) / rt; p.cblocks = (Cin + 15) / 16; p.taps = kh * kw;
   p.num_tiles = (long long)B * p.tiles_y;
-  return TN == 64 ? cols_launch<64>(ctx, p, smem) : cols_launch<128>(ctx, p, smem);
+  if (G == 3) return TN == 64 ? cols_launch<64, 3>(ctx, p, smem) : cols_launch<128, 3>(ctx, p, smem);
+  return TN == 64 ? cols_launch<64, 1>(ctx, p, smem) : cols_launch<128, 1>(ctx, p, smem);
 }
