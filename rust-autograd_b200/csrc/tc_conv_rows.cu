@@ -29,25 +29,27 @@ struct RowsParams {
   CUtensorMap tmX, tmW;
   float* y; const float* bias; const float* mask; float* csum; int relu;
   float* pool_y; int* pool_idx; int ph, pw;      // fused max_pool2d(2, 0, 2): pooled output + int32 argmax (logical NCHW offsets into y), y itself not written
-  int Cout, yh, yw, kw, pad, dil, tiles_x, tiles_y, otiles, cblocks, taps, pitch, a_box_bytes, a_slot_bytes;
+  int Cout, yh, yw, kw, pad, dil, tiles_x, tiles_y, otiles, cblocks, taps, pitch, a_box_bytes, a_slot_bytes, nb /* filter ring depth in stages of G taps */;
   long long num_tiles;
 };
+#define ROWS_NB_MAX 8
 template <int TN> struct RowsCfg {
-  static constexpr int NB = TN <= 64 ? 6 : 4;                 // filter-tap ring depth
   static constexpr int B_BYTES = TN * 128;
   static constexpr int TMEM_COLS = 2 * ROWS_R * TN;            // 256 (TN = 64) / 512 (TN = 128)
   static constexpr int THREADS = 256;            // warps: 0 TMA-A, 1 MMA row 0, 2-5 epilogue, 6 TMA-B, 7 MMA row 1
 };
 
-template <int TN>
+// G = filter taps per ring stage (3 = one filter row per TMA box / barrier wait / commit when kw == 3: see tc_conv_cols.cu)
+template <int TN, int G>
 __global__ void __launch_bounds__(256, 1) conv_rows_kernel(const __grid_constant__ RowsParams p) {
   using Cfg = RowsCfg<TN>;
-  constexpr int NB = Cfg::NB, R = ROWS_R;
+  constexpr int NB = ROWS_NB_MAX, R = ROWS_R;                  // barrier slots; p.nb stages in use
+  constexpr int ST_BYTES = G * Cfg::B_BYTES;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
   uint8_t* sA = smem;                                          // [2][a_slot_bytes]
-  uint8_t* sB = smem + 2 * p.a_slot_bytes;                     // [NB][TN * 128]
-  uint64_t* bars = (uint64_t*)(sB + NB * Cfg::B_BYTES);
+  uint8_t* sB = smem + 2 * p.a_slot_bytes;                     // [p.nb][G][TN * 128]
+  uint64_t* bars = (uint64_t*)(sB + p.nb * ST_BYTES);
   uint64_t* a_full = bars; uint64_t* a_empty = bars + 2;
   uint64_t* b_full = bars + 4; uint64_t* b_empty = bars + 4 + NB;
   uint64_t* acc_full = bars + 4 + 2 * NB; uint64_t* acc_empty = bars + 6 + 2 * NB;
@@ -94,11 +96,11 @@ __global__ void __launch_bounds__(256, 1) conv_rows_kernel(const __grid_constant
       for (long long t = blockIdx.x; t < p.num_tiles; t += gridDim.x) {
         const int o0 = (int)(t % p.otiles) * TN;
         for (int cb = 0; cb < p.cblocks; cb++)
-          for (int tap = 0; tap < p.taps; tap++) {
+          for (int tap = 0; tap < p.taps; tap += G) {
             mbar_wait(&b_empty[bs], bph ^ 1);
-            mbar_expect_tx(&b_full[bs], Cfg::B_BYTES);
-            tma_load_3d(sB + bs * Cfg::B_BYTES, &p.tmW, &b_full[bs], cb * 32, o0, tap);
-            if (++bs == NB) { bs = 0; bph ^= 1; }
+            mbar_expect_tx(&b_full[bs], ST_BYTES);
+            tma_load_3d(sB + bs * ST_BYTES, &p.tmW, &b_full[bs], cb * 32, o0, tap);
+            if (++bs == (uint32_t)p.nb) { bs = 0; bph ^= 1; }
           }
       }
     }
@@ -126,23 +128,27 @@ __global__ void __launch_bounds__(256, 1) conv_rows_kernel(const __grid_constant
         tc_fence_after();
         const uint32_t a0 = sA4 + as * ((uint32_t)p.a_slot_bytes >> 4);
         uint32_t arow = a0, atap = a0; int j = 0;                      // window origin of tap (i, j) for this row
-        for (int tap = 0; tap < p.taps; tap++) {
+        for (int tap = 0; tap < p.taps; tap += G) {
+          uint32_t at[G];
+#pragma unroll
+          for (int jj = 0; jj < G; jj++) { at[jj] = atap; if (++j == p.kw) { j = 0; arow += di4; atap = arow; } else atap += dj4; }
           mbar_wait(&b_full[bs], bph);
           tc_fence_after();
           if (elect_one()) {
-            const uint32_t q0 = sB4 + bs * (uint32_t)(Cfg::B_BYTES >> 4);
+            const uint32_t q0 = sB4 + bs * (uint32_t)(ST_BYTES >> 4);
 #pragma unroll
-            for (int ks = 0; ks < 4; ks++)
-              umma_tf32(tacc, umma_desc_pack(atap + ks * 2, hi), umma_desc_pack(q0 + ks * 2, hi), idesc, !(cb == 0 && tap == 0 && ks == 0));
+            for (int jj = 0; jj < G; jj++)
+#pragma unroll
+              for (int ks = 0; ks < 4; ks++)
+                umma_tf32(tacc, umma_desc_pack(at[jj] + ks * 2, hi), umma_desc_pack(q0 + jj * (uint32_t)(Cfg::B_BYTES >> 4) + ks * 2, hi), idesc, !(cb == 0 && tap == 0 && jj == 0 && ks == 0));
             umma_commit(&b_empty[bs]);
-            if (tap == p.taps - 1) {
+            if (tap + G >= p.taps) {
               umma_commit(&a_empty[as]);
               if (cb == p.cblocks - 1) umma_commit(&acc_full[acs]);
             }
           }
           __syncwarp();
-          if (++bs == NB) { bs = 0; bph ^= 1; }
-          if (++j == p.kw) { j = 0; arow += di4; atap = arow; } else atap += dj4;
+          if (++bs == (uint32_t)p.nb) { bs = 0; bph ^= 1; }
         }
       }
     }
@@ -322,12 +328,12 @@ __global__ void __launch_bounds__(256, 1) conv_rows_kernel(const __grid_constant
   if (warp == 1) tmem_dealloc(tmem_base, Cfg::TMEM_COLS);
 }
 
-template <int TN>
+template <int TN, int G>
 static int rows_launch(agb_ctx* ctx, RowsParams& p, size_t smem) {
   static bool attr = false;
-  if (!attr) { AGB_CUDA(cudaFuncSetAttribute(conv_rows_kernel<TN>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024)); attr = true; }
+  if (!attr) { AGB_CUDA(cudaFuncSetAttribute(conv_rows_kernel<TN, G>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024)); attr = true; }
   long long grid = p.num_tiles < ctx->sm_count ? p.num_tiles : ctx->sm_count;
-  conv_rows_kernel<TN><<<(unsigned)grid, RowsCfg<TN>::THREADS, smem, ctx->stream>>>(p);
+  conv_rows_kernel<TN, G><<<(unsigned)grid, RowsCfg<TN>::THREADS, smem, ctx->stream>>>(p);
   AGB_LAUNCHED(ctx);
   return AGB_OK;
 }
@@ -345,9 +351,13 @@ int agb_tc_conv_rows(agb_ctx* ctx, const float* x, const float* wr, float* y, in
   RowsParams p;
   p.a_box_bytes = pitch * hrows * 128; p.a_slot_bytes = (p.a_box_bytes + 1023) & ~1023;
   const int TN = Cout > 64 ? 128 : 64;
-  const int nb = TN <= 64 ? RowsCfg<64>::NB : RowsCfg<128>::NB;
-  const size_t smem = 2 * (size_t)p.a_slot_bytes + (size_t)nb * TN * 128 + 1024 + 256 + 4 * 32 * 36 * 4 + 128 * 4;
-  if (smem > 227 * 1024) return AGB_ERR_UNSUPPORTED;
+  static const int g_env = [] { const char* e = getenv("AGB_ROWS_G"); return e ? atoi(e) : 0; }();
+  const int G = (kw == 3 && (g_env == 3 || (g_env == 0 && TN == 64))) ? 3 : 1;
+  const size_t fixed = 2 * (size_t)p.a_slot_bytes + 1024 + 256 + 4 * 32 * 36 * 4 + 128 * 4, st_bytes = (size_t)G * TN * 128;
+  if (fixed + 2 * st_bytes > 227 * 1024) return AGB_ERR_UNSUPPORTED;
+  int nb = (int)((227 * 1024 - fixed) / st_bytes); if (nb > ROWS_NB_MAX) nb = ROWS_NB_MAX;
+  p.nb = nb;
+  const size_t smem = fixed + (size_t)nb * st_bytes;
   {
     uint64_t dims[4] = {(uint64_t)Cin, (uint64_t)W, (uint64_t)H, (uint64_t)B};
     uint64_t str[3] = {(uint64_t)Cin * 4, (uint64_t)W * Cin * 4, (uint64_t)H * W * Cin * 4};
@@ -357,12 +367,13 @@ int agb_tc_conv_rows(agb_ctx* ctx, const float* x, const float* wr, float* y, in
   {
     uint64_t dims[3] = {(uint64_t)Cin, (uint64_t)Cout, (uint64_t)(kh * kw)};
     uint64_t str[2] = {(uint64_t)Cin * 4, (uint64_t)Cin * Cout * 4};
-    uint32_t box[3] = {32, (uint32_t)TN, 1};
+    uint32_t box[3] = {32, (uint32_t)TN, (uint32_t)G};
     AGB_TRY(agb_make_tmap(&p.tmW, wr, 3, dims, str, box, false));
   }
   p.y = y; p.bias = bias; p.mask = mask; p.csum = csum; p.relu = relu; p.pool_y = pool_y; p.pool_idx = pool_idx; p.ph = yh / 2; p.pw = yw / 2; p.Cout = Cout; p.yh = yh; p.yw = yw; p.kw = kw; p.pad = pad; p.dil = dil;
   p.tiles_x = (yw + 127) / 128; p.tiles_y = (yh + ROWS_R - 1) / ROWS_R; p.otiles = (Cout + TN - 1) / TN;
   p.cblocks = (Cin + 31) / 32; p.taps = kh * kw; p.pitch = pitch;
   p.num_tiles = (long long)B * p.tiles_x * p.tiles_y * p.otiles;
-  return TN == 64 ? rows_launch<64>(ctx, p, smem) : rows_launch<128>(ctx, p, smem);
+  if (G == 3) return TN == 64 ? rows_launch<64, 3>(ctx, p, smem) : rows_launch<128, 3>(ctx, p, smem);
+  return TN == 64 ? rows_launch<64, 1>(ctx, p, smem) : rows_launch<128, 1>(ctx, p, smem);
 }
