@@ -69,6 +69,13 @@ int  agb_device_count(int* out);
 int  agb_sm_count(agb_ctx* ctx, int* out);
 int  agb_set_math_mode(agb_ctx* ctx, int mode);
 int  agb_get_math_mode(agb_ctx* ctx, int* mode);
+/* Deterministic reductions (default ON).  Split-K partial sums (filter gradients, skinny GEMMs) and the per-channel side sums of the
+ * dgrad / pool-backward epilogues (bias gradients) are written to scratch and added in a fixed order instead of red.global.add in
+ * arrival order, so a training step is bit-reproducible run to run and a captured step equals the eager one — the reference's
+ * filter gradient is a sequential batch loop (conv2d.rs:631-734) and its reductions are sequential folds (reduction_ops.rs:54-108).
+ * 0 restores the atomic form (saves the partial-sum traffic: ~1 % of a VGG step). */
+int  agb_set_deterministic(agb_ctx* ctx, int on);
+int  agb_get_deterministic(agb_ctx* ctx, int* on);
 /* number of kernels this library has launched on ctx since agb_init (bench "gpu_launches") */
 int  agb_launch_count(agb_ctx* ctx, int64_t* out);
 

@@ -26,6 +26,8 @@ struct agb_ctx {
   size_t live_bytes = 0, cached_bytes = 0, peak_bytes = 0;
   // scratch for two-stage reductions / split-K / descriptor tables
   void* scratch = nullptr; size_t scratch_bytes = 0;
+  void* scratch2 = nullptr; size_t scratch2_bytes = 0;
+  std::vector<void*> retired_scratch;
   void* flush_buf = nullptr; size_t flush_bytes = 0;
   // optimizer descriptor-table cache (key = hash of pointer lists)
   std::unordered_map<uint64_t, void*> optim_tables;
@@ -36,6 +38,9 @@ struct agb_ctx {
   int rank = 0, world = 1;
   cudaStream_t comm_stream = nullptr; cudaEvent_t comm_ready = nullptr, comm_done = nullptr; bool comm_pending = false;   // bucketed all-reduce overlapped with the rest of backward
   bool capturing = false;
+  // deterministic reductions (default on): split-K partial sums and per-channel side sums go to scratch and are added in a fixed order instead of
+  // red.global.add / atomicAdd in arrival order, so a step is bit-reproducible run to run (the reference's loops are sequential: conv2d.rs:631-734)
+  int deterministic = 1;
   int pinned_graphs = 0;            // live agx_step graphs: the arena must not return blocks to the driver while they exist
   // Private memory of instantiated graphs.  A CUDA graph keeps the RAW addresses of every arena block its kernels touch; once the
   // capture ends those blocks would sit in the free list and the next eager allocation could receive one while a replay still writes
@@ -70,6 +75,13 @@ struct AgbProfScope {
 void agb_set_error(const char* fmt, ...);
 int  agb_cuda_fail(cudaError_t e, const char* what, const char* file, int line);
 int  agb_scratch(agb_ctx* ctx, size_t bytes, void** out);
+int  agb_scratch2(agb_ctx* ctx, size_t bytes, void** out);      // a second buffer: partial sums of the deterministic reductions (the first may hold repacked operands of the same call)
+// out[i] (+)= sum over k < nparts (in order) of part[k * stride + i]
+int  agb_reduce_partials(agb_ctx* ctx, const float* part, float* out, int nparts, int64_t n, int64_t stride, int accumulate);
+// many partials ([nparts][n], dense): 64 interleaved groups are added first, then the groups — both in a fixed order.  `part` must have room for
+// agb_reduce_partials2_floats(nparts, n) floats (padding to a multiple of 64 partials + the [64][n] group sums)
+static inline size_t agb_reduce_partials2_floats(int64_t nparts, int64_t n) { return (size_t)((nparts + 63) / 64 * 64 + 64) * (size_t)n; }
+int  agb_reduce_partials2(agb_ctx* ctx, float* part, int64_t nparts, int64_t n, float* out, int accumulate);
 
 #define AGB_CUDA(x) do { cudaError_t _e = (x); if (_e != cudaSuccess) return agb_cuda_fail(_e, #x, __FILE__, __LINE__); } while (0)
 #define AGB_CHECK(cond, code, ...) do { if (!(cond)) { agb_set_error(__VA_ARGS__); return (code); } } while (0)

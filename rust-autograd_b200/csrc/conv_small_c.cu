@@ -222,7 +222,7 @@ struct PixCursor {
 //      4 pixels x 32 B, every sector fully used.  B-fragments gather x through L1 (each x element is reused by kh*kw taps).
 template <int NT, bool SPLIT>
 __global__ void __launch_bounds__(128, 3) small_c_wgrad_mma_kernel(const float* __restrict__ x, const float* __restrict__ gy, float* __restrict__ gw,
-                                                                   SmallGeom g, int K, int nslab, int64_t groups_per_warp) {
+                                                                   SmallGeom g, int K, int nslab, int64_t groups_per_warp, float* __restrict__ part) {
   __shared__ float red[4][64][NT * 8 + 1];
   const int lane = threadIdx.x & 31, gq = lane >> 2, t = lane & 3, wib = threadIdx.x >> 5;
   for (int i = threadIdx.x; i < 4 * 64 * (NT * 8 + 1); i += blockDim.x) (&red[0][0][0])[i] = 0.0f;
@@ -303,6 +303,19 @@ __global__ void __launch_bounds__(128, 3) small_c_wgrad_mma_kernel(const float* 
         for (int j = 0; j < NT; j++) { bf[j][0] = bn[j][0]; bf[j][1] = bn[j][1]; }
       }
     }
+  }
+  if (part != nullptr) {         // deterministic mode: every warp stores its fragments as partial number wp; agb_reduce_partials2 adds them in order
+    float* d = part + wp * ((int64_t)g.O * K);
+#pragma unroll
+    for (int m = 0; m < 4; m++)
+#pragma unroll
+      for (int j = 0; j < NT; j++)
+#pragma unroll
+        for (int e = 0; e < 4; e++) {
+          const int o = slab * 64 + m * 16 + gq + (e >> 1) * 8, k = j * 8 + 2 * t + (e & 1);
+          if (o < g.O && k < K) d[(int64_t)o * K + k] = acc[m][j][e];
+        }
+    return;
   }
   // CTA-level reduction in shared memory, then one red.global.add per output element per CTA
   const int rs = slab & 3;       // nslab <= 4
@@ -483,17 +496,22 @@ int agb_small_c_wgrad(agb_ctx* ctx, const float* x, const agb_tensor* gy, float*
     const int nslab = (O + 63) / 64, NT = (K + 7) / 8; const bool split = ctx->math_mode == AGB_MATH_3XTF32;
     if ((int64_t)C * H * W >= (1ll << 31) - (1 << 20)) return AGB_ERR_UNSUPPORTED;
     const int64_t G = (total + 7) / 8;
-    AGB_TRY(agb_memset0(ctx, gw, (size_t)O * K * sizeof(float)));
     int64_t warps = 2ll * 12 * ctx->sm_count / nslab; if (warps < 1) warps = 1;      // 2 waves of 3 CTAs x 4 warps per SM
     int64_t gpw = (G + warps - 1) / warps; if (gpw < 8) gpw = 8;
     warps = (G + gpw - 1) / gpw;
-    const unsigned blocks = (unsigned)((warps * nslab + 3) / 4);
-#define SCW_LAUNCH(NT_, SP_) small_c_wgrad_mma_kernel<NT_, SP_><<<blocks, 128, 0, ctx->stream>>>(x, gy->ptr, gw, g, K, nslab, gpw)
+    unsigned blocks = (unsigned)((warps * nslab + 3) / 4);
+    while ((blocks * 4u) % (unsigned)nslab) blocks++;            // every partial (pixel range) has all its slabs
+    const int64_t nwp = (int64_t)blocks * 4 / nslab;
+    float* part = nullptr;
+    if (ctx->deterministic) AGB_TRY(agb_scratch2(ctx, agb_reduce_partials2_floats(nwp, (int64_t)O * K) * sizeof(float), (void**)&part));
+    else AGB_TRY(agb_memset0(ctx, gw, (size_t)O * K * sizeof(float)));
+#define SCW_LAUNCH(NT_, SP_) small_c_wgrad_mma_kernel<NT_, SP_><<<blocks, 128, 0, ctx->stream>>>(x, gy->ptr, gw, g, K, nslab, gpw, part)
 #define SCW_SW(NT_) do { if (split) SCW_LAUNCH(NT_, true); else SCW_LAUNCH(NT_, false); } while (0)
     switch (NT) { case 1: SCW_SW(1); break; case 2: SCW_SW(2); break; case 3: SCW_SW(3); break; default: SCW_SW(4); break; }
 #undef SCW_SW
 #undef SCW_LAUNCH
     AGB_LAUNCHED(ctx);
+    if (part) return agb_reduce_partials2(ctx, part, nwp, (int64_t)O * K, gw, 0);
     return AGB_OK;
   }
   if (O % 4 != 0 || O > 256 || K > 32) return AGB_ERR_UNSUPPORTED;       // 16 k-pairs per thread row

@@ -161,7 +161,7 @@ __global__ void __launch_bounds__(256) maxpool_bwd_tiled_kernel(const float* __r
 }
 // channels-last, C % 4 == 0, int32 indices: 4 channels per thread, 128-bit accesses
 __global__ void __launch_bounds__(256) maxpool_bwd_tiled_cl4_kernel(const float* __restrict__ gy, const int32_t* __restrict__ idx_i,
-                                                                    const float* __restrict__ gate, float* __restrict__ gx, float* __restrict__ csum,
+                                                                    const float* __restrict__ gate, float* __restrict__ gx, float* __restrict__ csum, float* __restrict__ csum_part,
                                                                     uint32_t n4, int C, int xh, int xw, int yh, int yw, int size) {
   const uint32_t c4n = (uint32_t)C >> 2;
   // csum != NULL (host guarantees 256 % c4n == 0): a thread meets the same 4 channels at every grid-stride step, so the per-channel
@@ -189,13 +189,15 @@ __global__ void __launch_bounds__(256) maxpool_bwd_tiled_cl4_kernel(const float*
       }
   }
   if (csum != nullptr) {
-    __shared__ float cs_s[1024];                       // C <= 1024
-    for (int i = threadIdx.x; i < C; i += blockDim.x) cs_s[i] = 0.0f;
+    __shared__ float4 cs_t[256];                       // every thread's four sums; channel c is then added over the threads that met it, in thread order
+    cs_t[threadIdx.x] = cs;
     __syncthreads();
-    const int c = (int)(threadIdx.x % c4n) * 4;
-    atomicAdd(cs_s + c, cs.x); atomicAdd(cs_s + c + 1, cs.y); atomicAdd(cs_s + c + 2, cs.z); atomicAdd(cs_s + c + 3, cs.w);
-    __syncthreads();
-    for (int i = threadIdx.x; i < C; i += blockDim.x) atomicAdd(csum + i, cs_s[i]);
+    for (int c = threadIdx.x; c < C; c += blockDim.x) {
+      float s = 0.0f;
+      for (uint32_t t = (uint32_t)c >> 2; t < 256; t += c4n) { const float4 v = cs_t[t]; s += (c & 3) == 0 ? v.x : (c & 3) == 1 ? v.y : (c & 3) == 2 ? v.z : v.w; }
+      if (csum_part != nullptr) csum_part[(size_t)blockIdx.x * C + c] = s;      // deterministic mode: per-CTA partials, added in CTA order by agb_reduce_partials
+      else atomicAdd(csum + c, s);
+    }
   }
 }
 // gy and the index buffer share one layout (either); gx may be NCHW or channels-last
@@ -229,10 +231,14 @@ extern "C" int agb_maxpool2d_bwd_fused(agb_ctx* ctx, const agb_tensor* gy, const
     if (gcl && idx_i32 && d.C % 4 == 0 && agb_numel(gx) < (1ll << 31) &&
         ((((uintptr_t)gy->ptr | (uintptr_t)gx->ptr | (uintptr_t)idx_i32 | (uintptr_t)gate) & 15) == 0)) {
       const bool fuse_sum = chan_sum != nullptr && d.C <= 1024 && 256 % (d.C / 4) == 0;
-      if (fuse_sum) AGB_TRY(agb_memset0(ctx, chan_sum, (size_t)d.C * sizeof(float)));
-      maxpool_bwd_tiled_cl4_kernel<<<agb_grid_occ(ctx, maxpool_bwd_tiled_cl4_kernel, n / 4, 256), 256, 0, ctx->stream>>>(gy->ptr, idx_i32, gate, gx->ptr, fuse_sum ? chan_sum : nullptr,
-                                                                                                       (uint32_t)(n / 4), d.C, d.xh, d.xw, d.yh, d.yw, size);
+      const int grid = agb_grid_occ(ctx, maxpool_bwd_tiled_cl4_kernel, n / 4, 256);
+      float* part = nullptr;
+      if (fuse_sum && ctx->deterministic) AGB_TRY(agb_scratch2(ctx, (size_t)grid * d.C * sizeof(float), (void**)&part));
+      if (fuse_sum && !part) AGB_TRY(agb_memset0(ctx, chan_sum, (size_t)d.C * sizeof(float)));
+      maxpool_bwd_tiled_cl4_kernel<<<grid, 256, 0, ctx->stream>>>(gy->ptr, idx_i32, gate, gx->ptr, fuse_sum ? chan_sum : nullptr, part,
+                                                                (uint32_t)(n / 4), d.C, d.xh, d.xw, d.yh, d.yw, size);
       AGB_LAUNCHED(ctx);
+      if (part) AGB_TRY(agb_reduce_partials(ctx, part, chan_sum, grid, d.C, d.C, 0));
       return (chan_sum != nullptr && !fuse_sum) ? pool_channel_sums(ctx, gx, true, chan_sum) : AGB_OK;
     } else if (gcl) maxpool_bwd_tiled_kernel<true><<<agb_grid_for(n, 256, ctx->sm_count, 8), 256, 0, ctx->stream>>>(gy->ptr, idx_f32, idx_i32, gate, gx->ptr, n, d, size);
     else maxpool_bwd_tiled_kernel<false><<<agb_grid_for(n, 256, ctx->sm_count, 8), 256, 0, ctx->stream>>>(gy->ptr, idx_f32, idx_i32, gate, gx->ptr, n, d, size);

@@ -3,6 +3,7 @@
 // per-run heap allocations (`src/evaluation.rs:183-223`) and of `VariableEnvironment` storage
 // (`src/variable.rs:152-155`): variables and intermediates live in HBM.
 #include "common.cuh"
+#include <stdlib.h>
 #include <stdarg.h>
 #include <algorithm>
 #include <vector>
@@ -35,6 +36,7 @@ extern "C" int agb_init(int device, agb_ctx** out) {
   AGB_CHECK(prop.major == 10, AGB_ERR_CUDA, "agb_init: device is sm_%d%d; this library is built for sm_100a only", prop.major, prop.minor);
   agb_ctx* ctx = new agb_ctx();
   ctx->device = device; ctx->sm_count = prop.multiProcessorCount;
+  if (const char* e = getenv("AGB_DETERMINISTIC")) ctx->deterministic = (e[0] == '0') ? 0 : 1;      // default on; agb_set_deterministic overrides
   AGB_CUDA(cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking));
   AGB_CUDA(cudaMalloc(&ctx->dev_err, sizeof(int)));
   AGB_CUDA(cudaMemsetAsync(ctx->dev_err, 0, sizeof(int), ctx->stream));
@@ -58,6 +60,8 @@ extern "C" int agb_destroy(agb_ctx* ctx) {
   for (auto& kv : ctx->block_size) cudaFree(kv.first);
   for (auto& kv : ctx->optim_tables) cudaFree(kv.second);
   if (ctx->scratch) cudaFree(ctx->scratch);
+  if (ctx->scratch2) cudaFree(ctx->scratch2);
+  for (void* p : ctx->retired_scratch) cudaFree(p);
   if (ctx->flush_buf) cudaFree(ctx->flush_buf);
   if (ctx->dev_err) cudaFree(ctx->dev_err);
   if (ctx->copy_stream) { cudaStreamSynchronize(ctx->copy_stream); cudaStreamDestroy(ctx->copy_stream); cudaStreamSynchronize(ctx->d2h_stream); cudaStreamDestroy(ctx->d2h_stream); cudaEventDestroy(ctx->stage_mark); cudaEventDestroy(ctx->stage_done); }
@@ -134,16 +138,52 @@ extern "C" int agb_mem_stats(agb_ctx* ctx, size_t* live, size_t* cached, size_t*
   return AGB_OK;
 }
 
-int agb_scratch(agb_ctx* ctx, size_t bytes, void** out) {
-  if (bytes > ctx->scratch_bytes) {
+static int scratch_grow(agb_ctx* ctx, void** buf, size_t* have, size_t bytes) {
+  if (bytes > *have) {
     AGB_CHECK(!ctx->capturing, AGB_ERR_CUDA, "scratch growth during graph capture; run the step once eagerly first");
     agb_use_device(ctx);
-    if (ctx->scratch) { AGB_CUDA(cudaStreamSynchronize(ctx->stream)); AGB_CUDA(cudaFree(ctx->scratch)); }
+    if (*buf) {
+      AGB_CUDA(cudaStreamSynchronize(ctx->stream));
+      if (ctx->pinned_graphs > 0) ctx->retired_scratch.push_back(*buf);      // an instantiated graph may hold this address: keep it alive until the context goes
+      else AGB_CUDA(cudaFree(*buf));
+    }
     size_t sz = bytes < (8u << 20) ? (8u << 20) : round_block(bytes);
-    AGB_CUDA(cudaMalloc(&ctx->scratch, sz)); ctx->scratch_bytes = sz;
+    AGB_CUDA(cudaMalloc(buf, sz)); *have = sz;
   }
-  *out = ctx->scratch; return AGB_OK;
+  return AGB_OK;
 }
+int agb_scratch(agb_ctx* ctx, size_t bytes, void** out) { AGB_TRY(scratch_grow(ctx, &ctx->scratch, &ctx->scratch_bytes, bytes)); *out = ctx->scratch; return AGB_OK; }
+int agb_scratch2(agb_ctx* ctx, size_t bytes, void** out) { AGB_TRY(scratch_grow(ctx, &ctx->scratch2, &ctx->scratch2_bytes, bytes)); *out = ctx->scratch2; return AGB_OK; }
+
+// ---- deterministic reductions -------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) reduce_partials_kernel(const float* __restrict__ part, float* __restrict__ out, int nparts, int64_t n, int64_t stride, int accumulate) {
+  const int64_t gs = (int64_t)gridDim.x * blockDim.x;
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += gs) {
+    const float* p = part + i;
+    float s0 = 0.0f, s1 = 0.0f, s2 = 0.0f, s3 = 0.0f;           // four independent chains (loads in flight); the grouping is fixed, so the sum is reproducible
+    int k = 0;
+    for (; k + 3 < nparts; k += 4) { s0 += __ldg(p + (int64_t)k * stride); s1 += __ldg(p + (int64_t)(k + 1) * stride); s2 += __ldg(p + (int64_t)(k + 2) * stride); s3 += __ldg(p + (int64_t)(k + 3) * stride); }
+    for (; k < nparts; k++) s0 += __ldg(p + (int64_t)k * stride);
+    const float s = (s0 + s1) + (s2 + s3);
+    out[i] = accumulate ? out[i] + s : s;
+  }
+}
+int agb_reduce_partials(agb_ctx* ctx, const float* part, float* out, int nparts, int64_t n, int64_t stride, int accumulate) {
+  if (n <= 0) return AGB_OK;
+  reduce_partials_kernel<<<agb_grid_for(n, 256, ctx->sm_count, 8), 256, 0, ctx->stream>>>(part, out, nparts, n, stride, accumulate);
+  AGB_LAUNCHED(ctx);
+  return AGB_OK;
+}
+int agb_reduce_partials2(agb_ctx* ctx, float* part, int64_t nparts, int64_t n, float* out, int accumulate) {
+  if (nparts <= 64) return agb_reduce_partials(ctx, part, out, (int)nparts, n, n, accumulate);
+  const int64_t pad = (nparts + 63) / 64 * 64;
+  if (pad > nparts) AGB_TRY(agb_memset0(ctx, part + nparts * n, (size_t)(pad - nparts) * n * sizeof(float)));
+  float* grp = part + pad * n;
+  AGB_TRY(agb_reduce_partials(ctx, part, grp, (int)(pad / 64), 64 * n, 64 * n, 0));        // group g = partials g, g + 64, g + 128, ...
+  return agb_reduce_partials(ctx, grp, out, 64, n, n, accumulate);
+}
+extern "C" int agb_set_deterministic(agb_ctx* ctx, int on) { ctx->deterministic = on ? 1 : 0; return AGB_OK; }
+extern "C" int agb_get_deterministic(agb_ctx* ctx, int* on) { *on = ctx->deterministic; return AGB_OK; }
 
 extern "C" int agb_host_alloc(size_t bytes, void** out) { AGB_CUDA(cudaMallocHost(out, bytes ? bytes : 1)); return AGB_OK; }
 extern "C" int agb_host_free(void* p) { if (p) AGB_CUDA(cudaFreeHost(p)); return AGB_OK; }

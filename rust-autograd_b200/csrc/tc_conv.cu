@@ -56,7 +56,8 @@ template <int TN_, bool SPLIT_, int MT_ = 1> struct ConvFpropPol {
                   short dy[AGB_CONV_MAX_TAPS], dx[AGB_CONV_MAX_TAPS], wt[AGB_CONV_MAX_TAPS];
                   // output pixel (oy, ox) of the tile grid lands at (oy * os + oyo, ox * os + oxo) of a [B, YH, YW, Cout] tensor
                   // (identity for convolutions; the s*s phases of a strided dgrad write interleaved sub-grids)
-                  int os, oyo, oxo, YH, YW; };
+                  int os, oyo, oxo, YH, YW;
+                  float* csum_part; };      // deterministic mode: slot (tile, M-tile, warp) stores its per-channel sums at csum_part[slot * Cout + channel]
   struct Tile { int b, oy0, ox0, o0; };
   __device__ static Tile tile(const Params& p, uint3 blk) {
     int bx = (int)blk.x; int tx = bx % p.tiles_x; int r = bx / p.tiles_x; int ty = r % p.tiles_y;
@@ -168,7 +169,12 @@ template <int TN_, bool SPLIT_, int MT_ = 1> struct ConvFpropPol {
           }
         }
       }
-      if (o + wl < p.Cout) red_add_f32(p.csum + o + wl, r[0]);
+      if (o + wl < p.Cout) {
+        if (p.csum_part != nullptr) {
+          const int64_t tlin = ((int64_t)(t.b / p.bb) * p.tiles_y + t.oy0 / (p.bh * MT)) * p.tiles_x + t.ox0 / p.bw;
+          p.csum_part[((tlin * MT + mt) * 4 + ((lane >> 5) & 3)) * p.Cout + o + wl] = r[0];
+        } else red_add_f32(p.csum + o + wl, r[0]);
+      }
     }
   }
 };
@@ -182,7 +188,7 @@ template <int TN_, bool SPLIT_, bool PAIR_, int MT_ = 1> struct ConvWgradPol {
   static constexpr bool PAIR2 = !SPLIT_ && TN_ == 256 && MT_ == 1 && !PAIR_;      // CTA pairs: two (tap, 128-channel tile) units share every gy tile, each CTA streams half of its columns
   static constexpr int OCC = (SPLIT_ || TN_ > 128 || MT_ > 1) ? 1 : 2;
   static_assert(!(PAIR_ && MT_ > 1), "tap pairing within one M-tile and two M-tiles are alternatives");
-  struct Params { CUtensorMap tmX, tmG; float* gw; int C, O, T, kw, pad, dil, stride, yh, xblocks, kb_total, kb_per_split; MnDescCfg mnc; };
+  struct Params { CUtensorMap tmX, tmG; float* gw; int C, O, T, kw, pad, dil, stride, yh, xblocks, kb_total, kb_per_split; MnDescCfg mnc; int64_t part_stride /* > 0: split z stores at gw + z * part_stride (deterministic mode) */; };
   struct Tile { int c0, tapA, tapB, o0, q0, q1, c1; };       // MT == 2: unit 0 = (tapA, c0), unit 1 = (tapB, c1)
   __device__ static Tile tile(const Params& p, uint3 blk) {
     Tile t; t.o0 = (int)blk.y * TN; t.c1 = 0;
@@ -240,8 +246,12 @@ template <int TN_, bool SPLIT_, bool PAIR_, int MT_ = 1> struct ConvWgradPol {
     else if (MT == 2 && mt == 1) { c = t.c1 + lane; tap = t.tapB; }
     else { c = t.c0 + lane; tap = t.tapA; }
     if (c >= p.C || tap >= p.T) return;
+    float* base = p.gw + (p.part_stride > 0 ? (int64_t)(t.q0 / p.kb_per_split) * p.part_stride : 0);
 #pragma unroll
-    for (int j = 0; j < 32; j++) { const int o = t.o0 + c0 + j; if (o < p.O) red_add_f32(p.gw + ((int64_t)o * p.C + c) * p.T + tap, v[j]); }
+    for (int j = 0; j < 32; j++) {
+      const int o = t.o0 + c0 + j;
+      if (o < p.O) { float* d = base + ((int64_t)o * p.C + c) * p.T + tap; if (p.part_stride > 0) *d = v[j]; else red_add_f32(d, v[j]); }
+    }
   }
 };
 
@@ -316,7 +326,13 @@ static int fprop_launch(agb_ctx* ctx, const float* x, const float* wr, float* y,
   int64_t nb = (int64_t)p.tiles_x * p.tiles_y * ((B + bb - 1) / bb);
   if (nb > 2147483647ll) return AGB_ERR_UNSUPPORTED;
   dim3 grid((unsigned)nb, (unsigned)((Cout + TN - 1) / TN), 1);
-  return tc_tile_launch<Pol>(ctx, p, grid);
+  // deterministic per-channel sums: one slot per (tile, M-tile, epilogue warp), added in a fixed order by two small reductions (64 interleaved groups, then the groups)
+  p.csum_part = nullptr;
+  const int64_t nparts = nb * MT * 4;
+  if (csum != nullptr && ctx->deterministic) AGB_TRY(agb_scratch2(ctx, agb_reduce_partials2_floats(nparts, Cout) * sizeof(float), (void**)&p.csum_part));
+  AGB_TRY(tc_tile_launch<Pol>(ctx, p, grid));
+  if (p.csum_part != nullptr) AGB_TRY(agb_reduce_partials2(ctx, p.csum_part, nparts, Cout, csum, 1));
+  return AGB_OK;
 }
 
 // fprop on channels-last buffers: x [B,H,W,C], w [O,C,kh,kw] (plain) -> y [B,yh,yw,O].  flip_transpose != 0: dgrad — `x` is gy
@@ -435,9 +451,14 @@ static int wgrad_launch(agb_ctx* ctx, const float* img, const float* g, float* g
   p.kb_per_split = (int)per;
   int splits = (int)((kb_total + per - 1) / per);
   if (splits > 65535) return AGB_ERR_UNSUPPORTED;
-  AGB_TRY(agb_memset0(ctx, gw, (size_t)O * C * T * sizeof(float)));
+  const int64_t n = (int64_t)O * C * T;
+  float* part = nullptr;
+  if (ctx->deterministic && splits > 1) AGB_TRY(agb_scratch2(ctx, (size_t)splits * n * sizeof(float), (void**)&part));
+  if (part) { p.gw = part; p.part_stride = n; } else { p.part_stride = 0; AGB_TRY(agb_memset0(ctx, gw, (size_t)n * sizeof(float))); }
   dim3 grid((unsigned)gx, (unsigned)gy_, (unsigned)splits);
-  return tc_tile_launch<Pol>(ctx, p, grid);
+  AGB_TRY(tc_tile_launch<Pol>(ctx, p, grid));
+  if (part) return agb_reduce_partials(ctx, part, gw, splits, n, n, 0);
+  return AGB_OK;
 }
 
 // wgrad on channels-last buffers: img [B,H,W,C] (the im2col'd operand), g [B,yh,yw,O] -> gw [O,C,kh,kw] (plain)

@@ -20,7 +20,7 @@
 
 struct ColsParams {
   CUtensorMap tmX, tmW;
-  float* y; const float* bias; const float* mask; float* csum; int relu;
+  float* y; const float* bias; const float* mask; float* csum; float* csum_part; int relu;
   int Cout, yh, yw, kw, pad, dil, tiles_y, cblocks, taps, rm, copy_bytes, copy_stride, a_slot_bytes, nb /* filter ring depth, in stages of G taps */;
   long long num_tiles;
 };
@@ -50,8 +50,8 @@ __global__ void __launch_bounds__(256, 1) conv_cols_kernel(const __grid_constant
   uint64_t* acc_full = bars + 4 + 2 * NB; uint64_t* acc_empty = bars + 6 + 2 * NB;
   uint32_t* tmem_slot = (uint32_t*)(bars + 8 + 2 * NB);
   float* stage = (float*)((uint8_t*)bars + 512);               // [4 warps][32][36] epilogue transpose tiles
-  float* csum_s = stage + 4 * 32 * 36;                         // [TN] per-channel sums of this CTA
-  if ((int)threadIdx.x < TN) csum_s[threadIdx.x] = 0.0f;
+  float* csum_s = stage + 4 * 32 * 36;                         // [4 epilogue warps][TN] per-channel sums of this CTA
+  for (int i = threadIdx.x; i < 4 * TN; i += blockDim.x) csum_s[i] = 0.0f;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
 
   if (warp == 0 && lane == 0) {
@@ -216,7 +216,7 @@ __global__ void __launch_bounds__(256, 1) conv_cols_kernel(const __grid_constant
       tc_fence_before();
       mbar_arrive(&acc_empty[acs]);
     }
-    if (p.csum != nullptr) {
+    if (p.csum != nullptr) {       // lanes with equal ch4 (4 per warp) -> this warp's slot of the CTA's sums (no atomics: the order of every addition is fixed)
 #pragma unroll
       for (int c = 0; c < TN / 32; c++) {
         float4 v = cs[c];
@@ -225,16 +225,17 @@ __global__ void __launch_bounds__(256, 1) conv_cols_kernel(const __grid_constant
           v.x += __shfl_xor_sync(0xffffffffu, v.x, off); v.y += __shfl_xor_sync(0xffffffffu, v.y, off);
           v.z += __shfl_xor_sync(0xffffffffu, v.z, off); v.w += __shfl_xor_sync(0xffffffffu, v.w, off);
         }
-        if (lane < 8) {
-          float* d = csum_s + 32 * c + 4 * ch4;
-          atomicAdd(d, v.x); atomicAdd(d + 1, v.y); atomicAdd(d + 2, v.z); atomicAdd(d + 3, v.w);
-        }
+        if (lane < 8) *(float4*)(csum_s + q * TN + 32 * c + 4 * ch4) = v;
       }
     }
   }
   tc_fence_before();
   __syncthreads();
-  if (p.csum != nullptr && (int)threadIdx.x < TN && (int)threadIdx.x < p.Cout) atomicAdd(p.csum + threadIdx.x, csum_s[threadIdx.x]);
+  if (p.csum != nullptr && (int)threadIdx.x < TN && (int)threadIdx.x < p.Cout) {
+    const float tot = (csum_s[threadIdx.x] + csum_s[TN + threadIdx.x]) + (csum_s[2 * TN + threadIdx.x] + csum_s[3 * TN + threadIdx.x]);
+    if (p.csum_part != nullptr) p.csum_part[(int64_t)blockIdx.x * TN + threadIdx.x] = tot;      // deterministic mode: per-CTA partials, added in CTA order by agb_reduce_partials
+    else atomicAdd(p.csum + threadIdx.x, tot);
+  }
   if (warp == 1) tmem_dealloc(tmem_base, Cfg::TMEM_COLS);
 }
 
@@ -275,7 +276,7 @@ int agb_tc_conv_cols(agb_ctx* ctx, const float* x, const float* wr, float* y, in
   const int TN = Cout > 64 ? 128 : 64;
   static const int g_env = [] { const char* e = getenv("AGB_COLS_G"); return e ? atoi(e) : 0; }();
   const int G = (kw == 3 && (g_env == 3 || (g_env == 0 && TN == 64))) ? 3 : 1;       // one filter row per ring stage where the ring can still be deep enough
-  const size_t fixed = 2 * (size_t)p.a_slot_bytes + 1024 + 512 + 4 * 32 * 36 * 4 + 128 * 4;
+  const size_t fixed = 2 * (size_t)p.a_slot_bytes + 1024 + 512 + 4 * 32 * 36 * 4 + 4 * 128 * 4;
   const size_t st_bytes = (size_t)G * TN * 64;
   if (fixed + 2 * st_bytes > 227 * 1024) return AGB_ERR_UNSUPPORTED;
   int nb = (int)((227 * 1024 - fixed) / st_bytes); if (nb > COLS_NB_MAX) nb = COLS_NB_MAX;
@@ -296,6 +297,12 @@ int agb_tc_conv_cols(agb_ctx* ctx, const float* x, const float* wr, float* y, in
   p.y = y; p.bias = bias; p.mask = mask; p.csum = csum; p.relu = relu; p.Cout = Cout; p.yh = yh; p.yw = yw; p.kw = kw; p.pad = pad; p.dil = dil;
   p.tiles_y = (yh + rt - 1) / rt; p.cblocks = (Cin + 15) / 16; p.taps = kh * kw;
   p.num_tiles = (long long)B * p.tiles_y;
-  if (G == 3) return TN == 64 ? cols_launch<64, 3>(ctx, p, smem) : cols_launch<128, 3>(ctx, p, smem);
-  return TN == 64 ? cols_launch<64, 1>(ctx, p, smem) : cols_launch<128, 1>(ctx, p, smem);
+  const int64_t ncta = p.num_tiles < ctx->sm_count ? p.num_tiles : ctx->sm_count;
+  p.csum_part = nullptr;
+  if (csum != nullptr && ctx->deterministic) AGB_TRY(agb_scratch2(ctx, (size_t)ncta * TN * sizeof(float), (void**)&p.csum_part));
+  int r;
+  if (G == 3) r = TN == 64 ? cols_launch<64, 3>(ctx, p, smem) : cols_launch<128, 3>(ctx, p, smem);
+  else r = TN == 64 ? cols_launch<64, 1>(ctx, p, smem) : cols_launch<128, 1>(ctx, p, smem);
+  if (r == AGB_OK && p.csum_part != nullptr) r = agb_reduce_partials(ctx, p.csum_part, csum, (int)ncta, Cout, TN, 1);
+  return r;
 }

@@ -102,12 +102,13 @@ __global__ void __launch_bounds__(320, 2) conv_first_fprop_kernel(const __grid_c
         for (int q = 0; q < 4; q++) { const int ko = koff[ch * 4 + q]; e[q] = ko >= 0 ? xsb[ko] : 0.0f; }
         v = make_float4(e[0], e[1], e[2], e[3]);
         const uint32_t off = (uint32_t)((ch ^ (tid & 7)) << 4);
-        asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" :: "r"(A + off), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w) : "memory");
-        if (SPLIT) {
-          l.x = tf32_rna(v.x - __uint_as_float(__float_as_uint(v.x) & 0xFFFFE000u)); l.y = tf32_rna(v.y - __uint_as_float(__float_as_uint(v.y) & 0xFFFFE000u));
-          l.z = tf32_rna(v.z - __uint_as_float(__float_as_uint(v.z) & 0xFFFFE000u)); l.w = tf32_rna(v.w - __uint_as_float(__float_as_uint(v.w) & 0xFFFFE000u));
+        if (SPLIT) {      // round-to-nearest split on BOTH operands (the builder writes the tile anyway, so hi costs nothing): a truncated hi leaves a lo of
+                          // up to 13 bits whose rounding to tf32 is a coherent 2^-21 error per product; with rna hi the lo fits tf32 exactly
+          const float4 h = make_float4(tf32_rna(v.x), tf32_rna(v.y), tf32_rna(v.z), tf32_rna(v.w));
+          l.x = tf32_rna(v.x - h.x); l.y = tf32_rna(v.y - h.y); l.z = tf32_rna(v.z - h.z); l.w = tf32_rna(v.w - h.w);
+          asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" :: "r"(A + off), "f"(h.x), "f"(h.y), "f"(h.z), "f"(h.w) : "memory");
           asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" :: "r"(Al + off), "f"(l.x), "f"(l.y), "f"(l.z), "f"(l.w) : "memory");
-        }
+        } else asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" :: "r"(A + off), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w) : "memory");
       }
       fence_proxy_async();
       mbar_arrive(&a_full[buf]);

@@ -27,7 +27,7 @@
 #define ROWS_R 2
 struct RowsParams {
   CUtensorMap tmX, tmW;
-  float* y; const float* bias; const float* mask; float* csum; int relu;
+  float* y; const float* bias; const float* mask; float* csum; float* csum_part; int relu;
   float* pool_y; int* pool_idx; int ph, pw;      // fused max_pool2d(2, 0, 2): pooled output + int32 argmax (logical NCHW offsets into y), y itself not written
   int Cout, yh, yw, kw, pad, dil, tiles_x, tiles_y, otiles, cblocks, taps, pitch, a_box_bytes, a_slot_bytes, nb /* filter ring depth in stages of G taps */;
   long long num_tiles;
@@ -55,8 +55,8 @@ __global__ void __launch_bounds__(256, 1) conv_rows_kernel(const __grid_constant
   uint64_t* acc_full = bars + 4 + 2 * NB; uint64_t* acc_empty = bars + 6 + 2 * NB;
   uint32_t* tmem_slot = (uint32_t*)(bars + 8 + 2 * NB);
   float* stage = (float*)((uint8_t*)bars + 256);               // [4 warps][32][36] epilogue transpose tiles
-  float* csum_s = stage + 4 * 32 * 36;                         // [TN] per-channel sums of this CTA
-  if ((int)threadIdx.x < TN) csum_s[threadIdx.x] = 0.0f;
+  float* csum_s = stage + 4 * 32 * 36;                         // [4 epilogue warps][TN] per-channel sums of this CTA
+  for (int i = threadIdx.x; i < 4 * TN; i += blockDim.x) csum_s[i] = 0.0f;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
 
   if (warp == 0 && lane == 0) {
@@ -306,7 +306,7 @@ __global__ void __launch_bounds__(256, 1) conv_rows_kernel(const __grid_constant
       tc_fence_before();
       mbar_arrive(&acc_empty[acs]);
     }
-    if (p.csum != nullptr) {       // lanes with equal ch4 (4 per warp) -> shared-memory sums of the CTA
+    if (p.csum != nullptr) {       // lanes with equal ch4 (4 per warp) -> this warp's slot of the CTA's sums (no atomics: the order of every addition is fixed)
 #pragma unroll
       for (int c = 0; c < TN / 32; c++) {
         float4 v = cs[c];
@@ -315,16 +315,17 @@ __global__ void __launch_bounds__(256, 1) conv_rows_kernel(const __grid_constant
           v.x += __shfl_xor_sync(0xffffffffu, v.x, off); v.y += __shfl_xor_sync(0xffffffffu, v.y, off);
           v.z += __shfl_xor_sync(0xffffffffu, v.z, off); v.w += __shfl_xor_sync(0xffffffffu, v.w, off);
         }
-        if (lane < 8) {
-          float* d = csum_s + 32 * c + 4 * ch4;
-          atomicAdd(d, v.x); atomicAdd(d + 1, v.y); atomicAdd(d + 2, v.z); atomicAdd(d + 3, v.w);
-        }
+        if (lane < 8) *(float4*)(csum_s + q * TN + 32 * c + 4 * ch4) = v;
       }
     }
   }
   tc_fence_before();
   __syncthreads();
-  if (p.csum != nullptr && (int)threadIdx.x < TN && (int)threadIdx.x < p.Cout) atomicAdd(p.csum + threadIdx.x, csum_s[threadIdx.x]);
+  if (p.csum != nullptr && (int)threadIdx.x < TN && (int)threadIdx.x < p.Cout) {
+    const float tot = (csum_s[threadIdx.x] + csum_s[TN + threadIdx.x]) + (csum_s[2 * TN + threadIdx.x] + csum_s[3 * TN + threadIdx.x]);
+    if (p.csum_part != nullptr) p.csum_part[(int64_t)blockIdx.x * TN + threadIdx.x] = tot;      // deterministic mode: per-CTA partials, added in CTA order by agb_reduce_partials
+    else atomicAdd(p.csum + threadIdx.x, tot);
+  }
   if (warp == 1) tmem_dealloc(tmem_base, Cfg::TMEM_COLS);
 }
 
@@ -353,7 +354,7 @@ int agb_tc_conv_rows(agb_ctx* ctx, const float* x, const float* wr, float* y, in
   const int TN = Cout > 64 ? 128 : 64;
   static const int g_env = [] { const char* e = getenv("AGB_ROWS_G"); return e ? atoi(e) : 0; }();
   const int G = (kw == 3 && (g_env == 3 || (g_env == 0 && TN == 64))) ? 3 : 1;
-  const size_t fixed = 2 * (size_t)p.a_slot_bytes + 1024 + 256 + 4 * 32 * 36 * 4 + 128 * 4, st_bytes = (size_t)G * TN * 128;
+  const size_t fixed = 2 * (size_t)p.a_slot_bytes + 1024 + 256 + 4 * 32 * 36 * 4 + 4 * 128 * 4, st_bytes = (size_t)G * TN * 128;
   if (fixed + 2 * st_bytes > 227 * 1024) return AGB_ERR_UNSUPPORTED;
   int nb = (int)((227 * 1024 - fixed) / st_bytes); if (nb > ROWS_NB_MAX) nb = ROWS_NB_MAX;
   p.nb = nb;
@@ -374,6 +375,12 @@ int agb_tc_conv_rows(agb_ctx* ctx, const float* x, const float* wr, float* y, in
   p.tiles_x = (yw + 127) / 128; p.tiles_y = (yh + ROWS_R - 1) / ROWS_R; p.otiles = (Cout + TN - 1) / TN;
   p.cblocks = (Cin + 31) / 32; p.taps = kh * kw; p.pitch = pitch;
   p.num_tiles = (long long)B * p.tiles_x * p.tiles_y * p.otiles;
-  if (G == 3) return TN == 64 ? rows_launch<64, 3>(ctx, p, smem) : rows_launch<128, 3>(ctx, p, smem);
-  return TN == 64 ? rows_launch<64, 1>(ctx, p, smem) : rows_launch<128, 1>(ctx, p, smem);
+  const int64_t ncta = p.num_tiles < ctx->sm_count ? p.num_tiles : ctx->sm_count;
+  p.csum_part = nullptr;
+  if (csum != nullptr && ctx->deterministic) AGB_TRY(agb_scratch2(ctx, (size_t)ncta * TN * sizeof(float), (void**)&p.csum_part));
+  int r;
+  if (G == 3) r = TN == 64 ? rows_launch<64, 3>(ctx, p, smem) : rows_launch<128, 3>(ctx, p, smem);
+  else r = TN == 64 ? rows_launch<64, 1>(ctx, p, smem) : rows_launch<128, 1>(ctx, p, smem);
+  if (r == AGB_OK && p.csum_part != nullptr) r = agb_reduce_partials(ctx, p.csum_part, csum, (int)ncta, Cout, TN, 1);
+  return r;
 }

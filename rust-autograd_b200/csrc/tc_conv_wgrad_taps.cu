@@ -22,6 +22,7 @@
 struct WTapsParams {
   CUtensorMap tmX, tmG;              // x: box {32 c, HP w, 1, 1}; gy: box {32 o, 32 w, 1, 1}  (SWIZZLE_128B_ATOM_32B)
   float* gw; int C, O, T, kh, kw, pad, dil, yh, xblocks, hp, kb_total, kb_per_cta, npair;
+  int64_t part_stride;               // > 0 (deterministic mode): CTA column x stores its partial sums at gw + x * part_stride, added in order by agb_reduce_partials
 };
 
 __global__ void __launch_bounds__(224, 1) conv_wgrad_taps_kernel(const __grid_constant__ WTapsParams p) {
@@ -118,7 +119,10 @@ __global__ void __launch_bounds__(224, 1) conv_wgrad_taps_kernel(const __grid_co
           tmem_ld_wait();
           if (i < p.kh && c < p.C) {
 #pragma unroll
-            for (int e = 0; e < 32; e++) { const int o = o0 + c0 + e; if (o < p.O) red_add_f32(p.gw + ((int64_t)o * p.C + c) * p.T + tap, v[e]); }
+            for (int e = 0; e < 32; e++) {
+              const int o = o0 + c0 + e;
+              if (o < p.O) { float* d = p.gw + ((int64_t)o * p.C + c) * p.T + tap; if (p.part_stride > 0) d[(int64_t)blockIdx.x * p.part_stride] = v[e]; else red_add_f32(d, v[e]); }
+            }
           }
         }
       }
@@ -159,10 +163,14 @@ int agb_tc_conv_wgrad_taps(agb_ctx* ctx, const float* img, const float* g, float
   int64_t ctas = ctx->sm_count / otiles; if (ctas > kb_total / 8) ctas = kb_total / 8; if (ctas < 1) ctas = 1;      // >= 8 k-blocks per CTA amortise the 36.9 K reds
   p.kb_per_cta = (int)((kb_total + ctas - 1) / ctas);
   ctas = (kb_total + p.kb_per_cta - 1) / p.kb_per_cta;
-  AGB_TRY(agb_memset0(ctx, gw, (size_t)O * C * p.T * sizeof(float)));
+  const int64_t n = (int64_t)O * C * p.T;
+  float* part = nullptr;
+  if (ctx->deterministic && ctas > 1) AGB_TRY(agb_scratch2(ctx, (size_t)ctas * n * sizeof(float), (void**)&part));
+  if (part) { p.gw = part; p.part_stride = n; } else { p.part_stride = 0; AGB_TRY(agb_memset0(ctx, gw, (size_t)n * sizeof(float))); }
   static bool attr = false;
   if (!attr) { AGB_CUDA(cudaFuncSetAttribute(conv_wgrad_taps_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024)); attr = true; }
   conv_wgrad_taps_kernel<<<dim3((unsigned)ctas, (unsigned)otiles), 224, smem, ctx->stream>>>(p);
   AGB_LAUNCHED(ctx);
+  if (part) return agb_reduce_partials(ctx, part, gw, (int)ctas, n, n, 0);
   return AGB_OK;
 }

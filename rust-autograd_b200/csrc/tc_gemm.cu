@@ -28,7 +28,7 @@ template <int TN_, bool P_MN_, bool Q_MN_, bool SPLIT_, bool QPRE_ = false> stru
   static constexpr bool SPLIT_PAIR2 = SPLIT_ && QPRE_ && TN_ == 128;      // 3xTF32 CTA pairs: tmQh / tmQlh = half-height boxes of the hi / lo planes
   // splits > 1: split-K for problems with too few output tiles to fill the machine (e.g. the LSTM's 128 x 1024 x 8192 dgrad GEMM is
   // 8 tiles): grid.z = batch * splits, every CTA reduces kb_per_split k-blocks and adds its partial with red.global.add (C pre-zeroed)
-  struct Params { CUtensorMap tmP, tmQ, tmQlo /* 3xTF32: lo plane; CTA pairs: half-height Q boxes */, tmQh, tmQlh; float* C; int NL, NC, K; int64_t ldc, bsc; int accumulate; int splits, kb_per_split; MnDescCfg mnc; };
+  struct Params { CUtensorMap tmP, tmQ, tmQlo /* 3xTF32: lo plane; CTA pairs: half-height Q boxes */, tmQh, tmQlh; float* C; int NL, NC, K; int64_t ldc, bsc; int accumulate; int splits, kb_per_split; MnDescCfg mnc; int64_t part_stride /* > 0: split ks stores its partial at C + ks * part_stride (deterministic mode) */; };
   struct Tile { int lane0, col0, bz, kb0, nkb; };
   __device__ static Tile tile(const Params& p, uint3 blk) {
     const int kb_total = (p.K + TC_BK - 1) / TC_BK;
@@ -78,7 +78,8 @@ template <int TN_, bool P_MN_, bool Q_MN_, bool SPLIT_, bool QPRE_ = false> stru
       const int m = t.col0 + c0 + j;
       if (m < p.NC) {
         float* q = cbase + (int64_t)m * p.ldc;
-        if (p.splits > 1) red_add_f32(q, v[j]); else *q = p.accumulate ? (*q + v[j]) : v[j];
+        if (p.splits > 1) { if (p.part_stride > 0) q[(int64_t)(t.kb0 / p.kb_per_split) * p.part_stride] = v[j]; else red_add_f32(q, v[j]); }
+        else *q = p.accumulate ? (*q + v[j]) : v[j];
       }
     }
   }
@@ -122,10 +123,15 @@ static int tc_launch(agb_ctx* ctx, const CUtensorMap& tmP, const CUtensorMap& tm
   }
   int kb_per = (kb_total + splits - 1) / splits; splits = (kb_total + kb_per - 1) / kb_per;
   if ((int64_t)batch * splits > 65535) { splits = 1; kb_per = kb_total; }
-  if (splits > 1 && !accumulate) AGB_TRY(agb_memset0(ctx, C, (size_t)batch * NC * NL * sizeof(float)));
-  typename Pol::Params prm{tmP, tmQ, tmQlo ? *tmQlo : tmQ, half ? half->hi : tmQ, half ? half->lo : tmQ, C, NL, NC, K, ldc, bsc, accumulate, splits, kb_per, agb_mn_cfg()};
+  const int64_t cn = (int64_t)batch * NC * NL;
+  float* part = nullptr;
+  if (splits > 1 && ctx->deterministic) AGB_TRY(agb_scratch2(ctx, (size_t)splits * cn * sizeof(float), (void**)&part));
+  if (splits > 1 && !accumulate && !part) AGB_TRY(agb_memset0(ctx, C, (size_t)cn * sizeof(float)));
+  typename Pol::Params prm{tmP, tmQ, tmQlo ? *tmQlo : tmQ, half ? half->hi : tmQ, half ? half->lo : tmQ, part ? part : C, NL, NC, K, ldc, bsc, accumulate, splits, kb_per, agb_mn_cfg(), part ? cn : 0};
   dim3 grid(gx, gy, (unsigned)(batch * splits));
-  return tc_tile_launch<Pol>(ctx, prm, grid);
+  AGB_TRY(tc_tile_launch<Pol>(ctx, prm, grid));
+  if (part) return agb_reduce_partials(ctx, part, C, splits, cn, cn, accumulate);
+  return AGB_OK;
 }
 
 template <int TN, bool SPLIT, bool QPRE = false>

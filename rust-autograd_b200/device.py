@@ -136,6 +136,9 @@ class Device:
     def set_math_mode(self, mode):
         ffi.check(self.lib.agb_set_math_mode(self.ctx, mode))
 
+    def set_deterministic(self, on):
+        ffi.check(self.lib.agb_set_deterministic(self.ctx, 1 if on else 0))
+
     def launch_count(self):
         v = C.c_int64()
         ffi.check(self.lib.agb_launch_count(self.ctx, C.byref(v)))

@@ -68,6 +68,7 @@ _f, _i, _i64, _u64, _sz = C.c_float, C.c_int, C.c_int64, C.c_uint64, C.c_size_t
 SIGNATURES = {
     "agb_init": [_i, C.POINTER(_P)], "agb_destroy": [_P], "agb_device_count": [C.POINTER(_i)],
     "agb_sm_count": [_P, C.POINTER(_i)], "agb_set_math_mode": [_P, _i], "agb_get_math_mode": [_P, C.POINTER(_i)],
+    "agb_set_deterministic": [_P, _i], "agb_get_deterministic": [_P, C.POINTER(_i)],
     "agb_launch_count": [_P, C.POINTER(_i64)],
     "agb_prof_enable": [_P, _i], "agb_prof_reset": [_P], "agb_prof_collect": [_P, _i, C.POINTER(C.c_double), C.POINTER(_i64), C.POINTER(C.c_double)],
     "agb_alloc": [_P, _sz, C.POINTER(_P)], "agb_free": [_P, _P], "agb_trim": [_P],

@@ -632,11 +632,8 @@ def test_step_graph_replay_matches_eager(ag, net):
         g.close(); env.close()
         return out
     a, b = train(False), train(True)
-    for u, v in zip(a, b):
-        if net == "mlp":
-            assert np.array_equal(u, v)
-        else:                          # split-K atomics in the conv filter gradients reorder fp32 sums from run to run
-            assert rel(v, u) <= 1e-4
+    for u, v in zip(a, b):             # deterministic reductions (the default): split-K filter gradients and bias-gradient side sums add in a fixed order
+        assert np.array_equal(u, v)
 
 
 def test_dropout_semantics(ag):

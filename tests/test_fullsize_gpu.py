@@ -78,7 +78,9 @@ def test_vgg_training_steps_track_oracle(ag):
         if mode is not None:
             set_mode(env, mode)
         W.vgg_init(env, np.random.default_rng(0), size=64)
-        adam = mod.optimizers.Adam.default("adam", env.default_namespace().current_var_ids(), env)
+        # alpha = 1e-4: with the default 1e-3 this random-label problem explodes (loss 6 -> 87 -> 19) and the third loss then hangs on which side of a
+        # near-tie a handful of step-2 decisions fell (both first-layer kernels are within 4e-7 of the oracle, yet their step-3 losses differ by 8e-4)
+        adam = mod.optimizers.Adam(1e-4, 1e-08, 0.9, 0.999, env.default_namespace().current_var_ids(), env, "adam")
         losses = []
         for x, y in zip(xs, ys):
             def step(g):
@@ -100,9 +102,9 @@ def test_vgg_training_steps_track_oracle(ag):
         if b.size == 1:                                   # the "{vid}t" step counters: exact
             assert np.array_equal(a, b), k
         elif k < n_w:                                     # weights: every entry within the three steps' travel, and close in L2
-            assert float(np.abs(a.astype(np.float64) - b).max()) <= 6.1e-3 and (b.size < 1024 or rel_l2(a, b) <= 5e-3), (k, a.shape, rel_l2(a, b))
-        else:                                             # Adam moments: linear in the gradients
-            assert rel_l2(a, b) <= 2e-2, (k, a.shape, rel_l2(a, b))
+            assert float(np.abs(a.astype(np.float64) - b).max()) <= 6.1e-4 and (b.size < 1024 or rel_l2(a, b) <= 5e-3), (k, a.shape, rel_l2(a, b))
+        else:                                             # Adam moments: linear in the UNFORCED gradients of three steps (near-tie ReLU / pool decisions differ: the
+            assert rel_l2(a, b) <= 5e-2, (k, a.shape, rel_l2(a, b))      # single-step gradients under forced decisions are pinned to 2e-5 in test_vgg_bench_geometry_matches_oracle)
 
 
 # ------------------------------------------------------------------------------------------------ CNN-MNIST at batch 200 (configs[1])

@@ -709,3 +709,85 @@ def test_reduce_sum_full_size_checksum(dev):
     assert np.array_equal(dev.reduce("sum", x2, 1).numpy(), np.full((1 << 14,), (1 << 14) * 0.5, np.float32))
     sm = dev.softmax_like("softmax", x2, 1)
     assert float(dev.reduce("sum", sm.reshape((n,)), 0).numpy()) == float(1 << 14)
+
+
+# ------------------------------------------------------------------------------------------------ deterministic reductions
+DET_CASES = [  # name, B, C, H, W, O, math mode
+    ("wgrad_taps_64_64", 40, 64, 32, 64, 64, 1), ("wgrad_tile_128_256", 16, 128, 32, 32, 256, 1), ("wgrad_tile_256_256_3x", 8, 256, 16, 32, 256, 0),
+    ("wgrad_pair_64_128", 24, 64, 32, 32, 128, 1), ("first_layer_tc", 9, 3, 64, 128, 64, 1), ("first_layer_mma_3x", 6, 3, 40, 44, 64, 0),
+]
+
+
+@pytest.mark.parametrize("case", DET_CASES, ids=[c[0] for c in DET_CASES])
+def test_filter_gradient_is_bit_reproducible(dev, case):
+    """The reference's filter gradient is a sequential sum (conv2d.rs:631-734): run to run it gives the same bits.  With deterministic
+    reductions on (the default) so do the split-K kernels here; the atomic form agrees with it to fp32 reassociation."""
+    _, B, C, H, W, O, mode = case
+    dev.set_math_mode(mode)
+    rng = np.random.default_rng(B + C + O)
+    x = rng.standard_normal((B, C, H, W)).astype(np.float32)
+    gy = rng.standard_normal((B, O, H, W)).astype(np.float32)
+    up = dev.upload if C <= 4 else dev.upload_channels_last
+    dx, dgy = up(x), dev.upload_channels_last(gy)
+    runs = [dev.conv2d_filter_grad(dx, dgy, (O, C, 3, 3), 1, 1, 1).numpy() for _ in range(3)]
+    assert np.array_equal(runs[0], runs[1]) and np.array_equal(runs[0], runs[2])
+    dev.set_deterministic(False)
+    try:
+        atomic = dev.conv2d_filter_grad(dx, dgy, (O, C, 3, 3), 1, 1, 1).numpy()
+    finally:
+        dev.set_deterministic(True)
+    assert rel_err(atomic, runs[0]) <= 2e-6
+    assert rel_err(runs[0], R.conv2d_filter_grad(x, gy, (O, C, 3, 3), 1, 1, 1)) <= TOL[mode]
+
+
+@pytest.mark.parametrize("case", [(2, 64, 8, 128, 64), (40, 64, 32, 32, 128), (38, 128, 16, 64, 64), (16, 256, 32, 32, 256), (3, 64, 14, 14, 48)],
+                         ids=["rows", "cols128", "cols64", "pair256", "per_tap"])
+def test_bias_gradient_side_sums_are_bit_reproducible(dev, case):
+    """per-channel sums of the masked dgrad epilogue (= the bias gradient of the layer below): same bits every run, and the atomic form
+    agrees to reassociation"""
+    dev.set_math_mode(1)
+    B, C, H, W, O = case
+    rng = np.random.default_rng(sum(case))
+    gy = rng.standard_normal((B, O, H, W)).astype(np.float32)
+    w = (rng.standard_normal((O, C, 3, 3)) * 0.1).astype(np.float32)
+    mask_src = rng.standard_normal((B, C, H, W)).astype(np.float32)
+    dgy, dw, dm = dev.upload_channels_last(gy), dev.upload(w), dev.upload_channels_last(mask_src)
+    runs = []
+    for _ in range(3):
+        gx, cs = dev.conv2d_transpose(dgy, dw, 1, 1, 1, mask_src=dm, channels_last=True, chan_sum=True)
+        runs.append((gx.numpy(), cs.numpy()))
+    assert all(np.array_equal(runs[0][0], r[0]) and np.array_equal(runs[0][1], r[1]) for r in runs[1:])
+    assert rel_err(runs[0][1], runs[0][0].astype(np.float64).sum(axis=(0, 2, 3))) <= 1e-5
+    dev.set_deterministic(False)
+    try:
+        _, cs_atomic = dev.conv2d_transpose(dgy, dw, 1, 1, 1, mask_src=dm, channels_last=True, chan_sum=True)
+        assert rel_err(cs_atomic.numpy(), runs[0][1]) <= 1e-5
+    finally:
+        dev.set_deterministic(True)
+
+
+def test_split_k_gemm_and_pool_sums_are_bit_reproducible(dev):
+    dev.set_math_mode(1)
+    rng = np.random.default_rng(3)
+    a = rng.standard_normal((128, 8192)).astype(np.float32)
+    b = rng.standard_normal((8192, 1024)).astype(np.float32)
+    da, db = dev.upload(a), dev.upload(b)
+    runs = [dev.gemm(da, db).numpy() for _ in range(3)]
+    assert np.array_equal(runs[0], runs[1]) and np.array_equal(runs[0], runs[2])
+    assert rel_err(runs[0], R.matmul(a, b)) <= TOL[1]
+    at = rng.standard_normal((4096, 256)).astype(np.float32)          # A^T B with a long K: the weight-gradient shape
+    bt = rng.standard_normal((4096, 64)).astype(np.float32)
+    dat, dbt = dev.upload(at), dev.upload(bt)
+    runs = [dev.gemm(dat, dbt, trans_a=True).numpy() for _ in range(3)]
+    assert np.array_equal(runs[0], runs[1]) and np.array_equal(runs[0], runs[2])
+    assert rel_err(runs[0], R.matmul(at, bt, True, False)) <= TOL[1]
+    # gated pool backward with per-channel sums
+    x = rng.standard_normal((6, 64, 32, 32)).astype(np.float32)
+    y, idx = dev.max_pool2d(dev.upload_channels_last(np.maximum(x, 0)), 2, 0, 2, int32_index=True)
+    gy = dev.upload_channels_last(rng.standard_normal((6, 64, 16, 16)).astype(np.float32))
+    runs = []
+    for _ in range(3):
+        gx, cs = dev.max_pool2d_grad(gy, idx, 2, 0, 2, gate=y, int32_index=True, chan_sum=True)
+        runs.append((gx.numpy(), cs.numpy()))
+    assert all(np.array_equal(runs[0][1], r[1]) for r in runs[1:])
+    assert rel_err(runs[0][1], runs[0][0].astype(np.float64).sum(axis=(0, 2, 3))) <= 1e-5
