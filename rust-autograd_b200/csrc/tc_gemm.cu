@@ -29,12 +29,12 @@ template <int TN_, bool P_MN_, bool Q_MN_, bool SPLIT_, bool QPRE_ = false> stru
   // splits > 1: split-K for problems with too few output tiles to fill the machine (e.g. the LSTM's 128 x 1024 x 8192 dgrad GEMM is
   // 8 tiles): grid.z = batch * splits, every CTA reduces kb_per_split k-blocks and adds its partial with red.global.add (C pre-zeroed)
   struct Params { CUtensorMap tmP, tmQ, tmQlo /* 3xTF32: lo plane; CTA pairs: half-height Q boxes */, tmQh, tmQlh; float* C; int NL, NC, K; int64_t ldc, bsc; int accumulate; int splits, kb_per_split; MnDescCfg mnc; int64_t part_stride /* > 0: split ks stores its partial at C + ks * part_stride (deterministic mode) */; };
-  struct Tile { int lane0, col0, bz, kb0, nkb; };
+  struct Tile { int lane0, col0, bz, kb0, nkb, ks; };
   __device__ static Tile tile(const Params& p, uint3 blk) {
     const int kb_total = (p.K + TC_BK - 1) / TC_BK;
     const int bz = (int)blk.z / p.splits, ks = (int)blk.z - bz * p.splits;
     const int kb0 = ks * p.kb_per_split;
-    return Tile{(int)blk.x * TC_LANES, (int)blk.y * TN, bz, kb0, max(0, min(p.kb_per_split, kb_total - kb0))};
+    return Tile{(int)blk.x * TC_LANES, (int)blk.y * TN, bz, kb0, max(0, min(p.kb_per_split, kb_total - kb0)), ks};
   }
   __device__ static int num_kblocks(const Params&, const Tile& t) { return t.nkb; }
   __device__ static uint32_t p_bytes(const Params&, uint32_t full) { return full; }
@@ -72,14 +72,13 @@ template <int TN_, bool P_MN_, bool Q_MN_, bool SPLIT_, bool QPRE_ = false> stru
   __device__ static void store(const Params& p, const Tile& t, int, int lane, int c0, const float* v, uint32_t) {
     const int n = t.lane0 + lane;
     if (n >= p.NL) return;
-    float* cbase = p.C + (int64_t)t.bz * p.bsc + n;
+    float* cbase = p.C + (int64_t)t.bz * p.bsc + n + (int64_t)t.ks * p.part_stride;      // part_stride > 0 (deterministic split-K): this split's own copy of C
 #pragma unroll
     for (int j = 0; j < 32; j++) {
       const int m = t.col0 + c0 + j;
       if (m < p.NC) {
         float* q = cbase + (int64_t)m * p.ldc;
-        if (p.splits > 1) { if (p.part_stride > 0) q[(int64_t)(t.kb0 / p.kb_per_split) * p.part_stride] = v[j]; else red_add_f32(q, v[j]); }
-        else *q = p.accumulate ? (*q + v[j]) : v[j];
+        if (p.splits > 1 && p.part_stride == 0) red_add_f32(q, v[j]); else *q = (p.accumulate && p.splits == 1) ? (*q + v[j]) : v[j];
       }
     }
   }
@@ -125,7 +124,10 @@ static int tc_launch(agb_ctx* ctx, const CUtensorMap& tmP, const CUtensorMap& tm
   if ((int64_t)batch * splits > 65535) { splits = 1; kb_per = kb_total; }
   const int64_t cn = (int64_t)batch * NC * NL;
   float* part = nullptr;
-  if (splits > 1 && ctx->deterministic) AGB_TRY(agb_scratch2(ctx, (size_t)splits * cn * sizeof(float), (void**)&part));
+  // deterministic split-K through per-split copies of C pays 2 x splits x |C| of traffic plus a launch: right for the small outputs split-K exists for
+  // (the classifier's [256, 10], weight gradients), wrong for a 128 x 4096 recurrence GEMM that lives on launch latency (measured: 12.3 -> 24.9 us).
+  // Above 4 MB of partials the sums stay on red.global.add (run-to-run differences of fp32 reassociation, like the embedding scatter-add).
+  if (splits > 1 && ctx->deterministic && (size_t)splits * cn * sizeof(float) <= (4u << 20)) AGB_TRY(agb_scratch2(ctx, (size_t)splits * cn * sizeof(float), (void**)&part));
   if (splits > 1 && !accumulate && !part) AGB_TRY(agb_memset0(ctx, C, (size_t)cn * sizeof(float)));
   typename Pol::Params prm{tmP, tmQ, tmQlo ? *tmQlo : tmQ, half ? half->hi : tmQ, half ? half->lo : tmQ, part ? part : C, NL, NC, K, ldc, bsc, accumulate, splits, kb_per, agb_mn_cfg(), part ? cn : 0};
   dim3 grid(gx, gy, (unsigned)(batch * splits));
