@@ -72,6 +72,164 @@ static int simt_gemm(agb_ctx* ctx, const float* A, const float* B, float* C, int
   return AGB_OK;
 }
 
+// ----------------------------------------------------------------------------------------------
+// Skinny GEMMs: one extent <= 16 next to a large operand — the classifier of the VGG stack (FC 65536 -> 10 at batch 256): forward
+// [256, 65536] x [65536, 10], weight gradient [65536, 256] x [256, 10], input gradient [256, 10] x [10, 65536].  They are one streaming pass over
+// the large operand (67 MB: ~10 us at the HBM rate); on the 128-lane tensor-core tiles they used 10 of 128 lanes or 10 of 32 k and took 56 / 44 /
+// 53 us behind padded copies.  Three CUDA-core kernels in exact fp32 FMA (dot_ops.rs:383-422 is an f32 sgemm):
+//   thin N, k contiguous in A   : CTA = 64 rows x 1024-k slice, B^T slice in shared memory, a warp walks 4 rows at a time (every 128-bit
+//                                 shared-memory read of B^T feeds 4 rows), per-slice partial sums added in slice order (deterministic)
+//   thin N, m contiguous in A   : thread per output row m, B in shared memory (broadcast reads), k sequential
+//   thin K                      : thread per output column n with its B column in registers, A in shared memory, coalesced stores of C
+// ----------------------------------------------------------------------------------------------
+#define SK_MAX 16
+#define SK_KSLICE 1024
+template <int NN>
+__global__ void __launch_bounds__(256) skinny_n_kcontig_kernel(const float* __restrict__ A, int64_t rsa, const float* __restrict__ B, int64_t rsb, int64_t csb,
+                                                               float* __restrict__ part, int M, int N, int64_t K) {
+  extern __shared__ __align__(16) float Wt[];                   // [NN][SK_KSLICE + 4]
+  constexpr int PITCH = SK_KSLICE + 4;
+  const int64_t k0 = (int64_t)blockIdx.x * SK_KSLICE;
+  const int kn = (int)min((int64_t)SK_KSLICE, K - k0);
+  for (int i = threadIdx.x; i < NN * SK_KSLICE; i += blockDim.x) {
+    int kk, n;
+    if (csb == 1) { kk = i / NN; n = i - kk * NN; } else { n = i / SK_KSLICE; kk = i - n * SK_KSLICE; }      // walk B in its contiguous direction
+    Wt[n * PITCH + kk] = (kk < kn && n < N) ? __ldg(B + (k0 + kk) * rsb + n * csb) : 0.0f;
+  }
+  __syncthreads();
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int row_base = blockIdx.y * 64 + warp * 8;
+#pragma unroll 1
+  for (int g = 0; g < 2; g++) {
+    const int r0 = row_base + g * 4;
+    if (r0 >= M) break;
+    float acc[4][NN];
+#pragma unroll
+    for (int j = 0; j < 4; j++)
+#pragma unroll
+      for (int n = 0; n < NN; n++) acc[j][n] = 0.0f;
+    const float* ap[4];
+#pragma unroll
+    for (int j = 0; j < 4; j++) ap[j] = A + (int64_t)min(r0 + j, M - 1) * rsa + k0;
+#pragma unroll 2
+    for (int kk = lane * 4; kk < kn; kk += 128) {
+      float4 a[4];
+#pragma unroll
+      for (int j = 0; j < 4; j++) a[j] = ldg_stream4(ap[j] + kk);
+#pragma unroll
+      for (int n = 0; n < NN; n++) {
+        const float4 w = *(const float4*)(Wt + n * PITCH + kk);
+#pragma unroll
+        for (int j = 0; j < 4; j++) acc[j][n] = fmaf(a[j].x, w.x, fmaf(a[j].y, w.y, fmaf(a[j].z, w.z, fmaf(a[j].w, w.w, acc[j][n]))));
+      }
+    }
+#pragma unroll
+    for (int j = 0; j < 4; j++)
+#pragma unroll
+      for (int n = 0; n < NN; n++) acc[j][n] = warp_sum(acc[j][n]);
+    if (lane == 0) {
+#pragma unroll
+      for (int j = 0; j < 4; j++)
+        if (r0 + j < M) {
+#pragma unroll
+          for (int n = 0; n < NN; n++) if (n < N) part[((int64_t)blockIdx.x * M + r0 + j) * N + n] = acc[j][n];
+        }
+    }
+  }
+}
+template <int NN>
+__global__ void __launch_bounds__(256) skinny_n_mcontig_kernel(const float* __restrict__ A, int64_t csa, const float* __restrict__ B, int64_t rsb, int64_t csb,
+                                                               float* __restrict__ C, int64_t M, int N, int K, int accumulate) {
+  __shared__ __align__(16) float Bs[256 * NN];                  // a chunk of up to 256 k
+  const int64_t m = blockIdx.x * (int64_t)256 + threadIdx.x;
+  float acc[NN];
+#pragma unroll
+  for (int n = 0; n < NN; n++) acc[n] = 0.0f;
+  for (int kc = 0; kc < K; kc += 256) {
+    const int kn = min(256, K - kc);
+    __syncthreads();
+    for (int i = threadIdx.x; i < kn * NN; i += blockDim.x) { const int kk = i / NN, n = i - kk * NN; Bs[i] = n < N ? __ldg(B + (int64_t)(kc + kk) * rsb + n * csb) : 0.0f; }
+    __syncthreads();
+    if (m < M) {
+      const float* ap = A + m + (int64_t)kc * csa;
+      int kk = 0;
+      for (; kk + 8 <= kn; kk += 8) {                           // eight independent loads in flight per thread
+        float a[8];
+#pragma unroll
+        for (int u = 0; u < 8; u++) a[u] = __ldg(ap + (int64_t)(kk + u) * csa);
+#pragma unroll
+        for (int u = 0; u < 8; u++)
+#pragma unroll
+          for (int n = 0; n < NN; n++) acc[n] = fmaf(a[u], Bs[(kk + u) * NN + n], acc[n]);
+      }
+      for (; kk < kn; kk++) {
+        const float a = __ldg(ap + (int64_t)kk * csa);
+#pragma unroll
+        for (int n = 0; n < NN; n++) acc[n] = fmaf(a, Bs[kk * NN + n], acc[n]);
+      }
+    }
+  }
+  if (m < M) {
+#pragma unroll
+    for (int n = 0; n < NN; n++) if (n < N) { float* c = C + m * N + n; *c = accumulate ? *c + acc[n] : acc[n]; }
+  }
+}
+__global__ void __launch_bounds__(256) skinny_k_kernel(const float* __restrict__ A, int64_t rsa, int64_t csa, const float* __restrict__ B, int64_t rsb, int64_t csb,
+                                                       float* __restrict__ C, int M, int64_t N, int K, int accumulate) {
+  __shared__ float As[32][SK_MAX];
+  const int64_t n = blockIdx.x * (int64_t)256 + threadIdx.x;
+  const int m0 = blockIdx.y * 32, mn = min(32, M - m0);
+  for (int i = threadIdx.x; i < 32 * SK_MAX; i += blockDim.x) { const int mm = i / SK_MAX, k = i - mm * SK_MAX; As[mm][k] = (mm < mn && k < K) ? __ldg(A + (int64_t)(m0 + mm) * rsa + k * csa) : 0.0f; }
+  __syncthreads();
+  if (n >= N) return;
+  float b[SK_MAX];
+#pragma unroll
+  for (int k = 0; k < SK_MAX; k++) b[k] = k < K ? __ldg(B + (int64_t)k * rsb + n * csb) : 0.0f;
+  for (int mm = 0; mm < mn; mm++) {
+    float s = 0.0f;
+#pragma unroll
+    for (int k = 0; k < SK_MAX; k++) s = fmaf(As[mm][k], b[k], s);
+    float* c = C + (int64_t)(m0 + mm) * N + n;
+    *c = accumulate ? *c + s : s;
+  }
+}
+// returns AGB_ERR_UNSUPPORTED when no skinny form applies
+static int skinny_gemm(agb_ctx* ctx, const float* A, const float* B, float* C, int64_t m, int64_t n, int64_t k, int64_t rsa, int64_t csa, int64_t rsb, int64_t csb, float beta) {
+  static const int enabled = [] { const char* e = getenv("AGB_SKINNY_GEMM"); return (e && e[0] == '0') ? 0 : 1; }();
+  if (!enabled || m >= (1ll << 31) || n >= (1ll << 31) || k >= (1ll << 31)) return AGB_ERR_UNSUPPORTED;
+  const int acc = beta != 0.0f;
+  if (n <= SK_MAX && m * k >= (1 << 18)) {
+    const int NN = n <= 4 ? 4 : n <= 8 ? 8 : n <= 12 ? 12 : 16;
+    if (csa == 1 && k >= 4 * SK_KSLICE && k % 4 == 0 && rsa % 4 == 0 && (((uintptr_t)A) & 15) == 0) {
+      const int64_t slices = (k + SK_KSLICE - 1) / SK_KSLICE;
+      float* part; AGB_TRY(agb_scratch2(ctx, (size_t)slices * m * n * sizeof(float), (void**)&part));
+      const dim3 grid((unsigned)slices, (unsigned)((m + 63) / 64));
+      const size_t smem = (size_t)NN * (SK_KSLICE + 4) * sizeof(float);
+#define SKA(NN_) do { static bool attr = false; if (!attr) { AGB_CUDA(cudaFuncSetAttribute(skinny_n_kcontig_kernel<NN_>, cudaFuncAttributeMaxDynamicSharedMemorySize, 16 * (SK_KSLICE + 4) * 4)); attr = true; } \
+                      skinny_n_kcontig_kernel<NN_><<<grid, 256, smem, ctx->stream>>>(A, rsa, B, rsb, csb, part, (int)m, (int)n, k); } while (0)
+      if (NN == 4) SKA(4); else if (NN == 8) SKA(8); else if (NN == 12) SKA(12); else SKA(16);
+#undef SKA
+      AGB_LAUNCHED(ctx);
+      return agb_reduce_partials(ctx, part, C, (int)slices, m * n, m * n, acc);
+    }
+    if (rsa == 1 && m >= 4096) {
+      const unsigned grid = (unsigned)((m + 255) / 256);
+      if (NN == 4) skinny_n_mcontig_kernel<4><<<grid, 256, 0, ctx->stream>>>(A, csa, B, rsb, csb, C, m, (int)n, (int)k, acc);
+      else if (NN == 8) skinny_n_mcontig_kernel<8><<<grid, 256, 0, ctx->stream>>>(A, csa, B, rsb, csb, C, m, (int)n, (int)k, acc);
+      else if (NN == 12) skinny_n_mcontig_kernel<12><<<grid, 256, 0, ctx->stream>>>(A, csa, B, rsb, csb, C, m, (int)n, (int)k, acc);
+      else skinny_n_mcontig_kernel<16><<<grid, 256, 0, ctx->stream>>>(A, csa, B, rsb, csb, C, m, (int)n, (int)k, acc);
+      AGB_LAUNCHED(ctx);
+      return AGB_OK;
+    }
+  }
+  if (k <= SK_MAX && m * n >= (1 << 18) && n >= 4096) {
+    skinny_k_kernel<<<dim3((unsigned)((n + 255) / 256), (unsigned)((m + 31) / 32)), 256, 0, ctx->stream>>>(A, rsa, csa, B, rsb, csb, C, (int)m, n, (int)k, acc);
+    AGB_LAUNCHED(ctx);
+    return AGB_OK;
+  }
+  return AGB_ERR_UNSUPPORTED;
+}
+
 extern "C" int agb_gemm_f32(agb_ctx* ctx, int trans_a, int trans_b, const agb_tensor* a, const agb_tensor* b, agb_tensor* c, float beta) {
   AGB_CHECK(a->rank >= 2 && b->rank >= 2, AGB_ERR_INCOMPATIBLE_SHAPE, "matmul: inputs must have ndim >= 2 (got %d and %d)", a->rank, b->rank);
   AGB_CHECK(a->rank == b->rank && c->rank == a->rank, AGB_ERR_INCOMPATIBLE_SHAPE, "matmul: rank mismatch: %d vs %d (out %d)", a->rank, b->rank, c->rank);
@@ -105,6 +263,10 @@ extern "C" int agb_gemm_f32(agb_ctx* ctx, int trans_a, int trans_b, const agb_te
   if (k == 0) { if (beta == 0.0f) return agb_memset0(ctx, c->ptr, agb_numel(c) * sizeof(float)); return AGB_OK; }
   AgbProfScope prof(ctx, AGB_PROF_GEMM, 2.0 * (double)m * (double)n * (double)k * (double)batch);
   int mode = ctx->math_mode;
+  if (batch == 1) {
+    int r = skinny_gemm(ctx, a->ptr, b->ptr, c->ptr, m, n, k, rsa, csa, rsb, csb, beta);
+    if (r != AGB_ERR_UNSUPPORTED) return r;
+  }
   if (mode != AGB_MATH_FP32) {
     int r = agb_tc_gemm(ctx, mode, a->ptr, b->ptr, c->ptr, m, n, k, batch, rsa, csa, bsa, rsb, csb, bsb, m * n, beta);
     if (r != AGB_ERR_UNSUPPORTED) return r;

@@ -791,3 +791,28 @@ def test_split_k_gemm_and_pool_sums_are_bit_reproducible(dev):
         runs.append((gx.numpy(), cs.numpy()))
     assert all(np.array_equal(runs[0][1], r[1]) for r in runs[1:])
     assert rel_err(runs[0][1], runs[0][0].astype(np.float64).sum(axis=(0, 2, 3))) <= 1e-5
+
+
+@pytest.mark.parametrize("mode", MODES)
+@pytest.mark.parametrize("case", [("fwd", 64, 8192, 10), ("fwd", 70, 5000, 3), ("fwd", 33, 16384, 16), ("wgrad", 300, 8192, 10), ("wgrad", 64, 5001, 7),
+                                  ("dgrad", 70, 8192, 10), ("dgrad", 256, 4100, 16)], ids=lambda c: "%s-%d-%d-%d" % c)
+def test_skinny_gemm_vs_oracle(dev, case, mode):
+    """the classifier GEMMs of a CNN (one extent <= 16 next to a large operand): dedicated streaming kernels in exact fp32 FMA, in every math mode"""
+    dev.set_math_mode(mode)
+    kind, b, feat, cls = case
+    rng = np.random.default_rng(b + feat + cls)
+    x = rng.standard_normal((b, feat)).astype(np.float32)
+    w = (rng.standard_normal((feat, cls)) * 0.05).astype(np.float32)
+    g = rng.standard_normal((b, cls)).astype(np.float32)
+    if kind == "fwd":
+        got, ref = dev.gemm(dev.upload(x), dev.upload(w)).numpy(), R.matmul(x, w)
+        prev = rng.standard_normal((b, cls)).astype(np.float32)
+        acc = dev.upload(prev)
+        dev.gemm(dev.upload(x), dev.upload(w), out=acc, beta=1.0)
+        assert rel_err(acc.numpy(), prev + ref) <= 1e-5
+    elif kind == "wgrad":
+        got, ref = dev.gemm(dev.upload(x), dev.upload(g), trans_a=True).numpy(), R.matmul(x, g, True, False)
+    else:
+        got, ref = dev.gemm(dev.upload(g), dev.upload(w), trans_b=True).numpy(), R.matmul(g, w, False, True)
+    assert got.shape == ref.shape
+    assert rel_err(got, ref) <= 1e-5
