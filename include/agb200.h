@@ -165,6 +165,14 @@ int  agb_conv2d_dgrad_f32(agb_ctx* ctx, const agb_tensor* gy, const agb_tensor* 
  * (MaybeReduceSum of the broadcast AddOp operand, binary_ops.rs:39-105), accumulated in the same epilogue. */
 int  agb_conv2d_dgrad_fused_f32(agb_ctx* ctx, const agb_tensor* gy, const agb_tensor* w, const agb_tensor* mask_src, float* chan_sum,
                                 agb_tensor* gx, int pad, int stride, int dilation);
+/* ReLU sign bits as a side channel of the two fused forms above (activation_ops.rs:161-166 needs only the SIGN of the activation): the forward
+ * writes 1 bit per element (channels-last order: word (pixel * O + o) / 32, bit o % 32; numel(y) / 32 words) next to y when the kernel that runs
+ * supports it (*bits_written = 1), and the masked dgrad reads those 4 bytes per pixel per 32 channels instead of 128 bytes of mask_src
+ * (2.1 GB less HBM traffic per VGG training step).  mask_src is still passed and is what every non-fusing path reads. */
+int  agb_conv2d_fprop_fused_bits_f32(agb_ctx* ctx, const agb_tensor* x, const agb_tensor* w, const float* bias, int relu, agb_tensor* y,
+                                     uint32_t* relu_bits, int* bits_written, int pad, int stride, int dilation);
+int  agb_conv2d_dgrad_fused_bits_f32(agb_ctx* ctx, const agb_tensor* gy, const agb_tensor* w, const agb_tensor* mask_src, const uint32_t* mask_bits,
+                                     float* chan_sum, agb_tensor* gx, int pad, int stride, int dilation);
 /* replaces Conv2DFilterGrad::compute (conv2d.rs:737-744) and Conv2DTransposeFilterGrad::compute
  * (conv2d_transpose.rs:433-451): gw[O,C,kh,kw] = sum_b g[b] (x) im2col(img[b]).
  * img [B,C,H,W] is the tensor that gets im2col'd, g [B,O,yh,yw] the one that multiplies it. */

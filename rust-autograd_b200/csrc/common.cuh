@@ -41,6 +41,9 @@ struct agb_ctx {
   // deterministic reductions (default on): split-K partial sums and per-channel side sums go to scratch and are added in a fixed order instead of
   // red.global.add / atomicAdd in arrival order, so a step is bit-reproducible run to run (the reference's loops are sequential: conv2d.rs:631-734)
   int deterministic = 1;
+  // ReLU sign bits (1 bit per element, channels-last order: word (pixel * C + c) / 32, bit c % 32) travelling next to an activation: the conv entry
+  // points set these for the launch they dispatch; kernels that can write / read the bits do and say so
+  uint32_t* bits_out = nullptr; const uint32_t* mask_bits = nullptr; int bits_written = 0, mask_bits_used = 0;
   int pinned_graphs = 0;            // live agx_step graphs: the arena must not return blocks to the driver while they exist
   // Private memory of instantiated graphs.  A CUDA graph keeps the RAW addresses of every arena block its kernels touch; once the
   // capture ends those blocks would sit in the free list and the next eager allocation could receive one while a replay still writes

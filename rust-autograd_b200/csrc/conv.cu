@@ -154,8 +154,24 @@ extern "C" int agb_conv2d_fprop_f32(agb_ctx* ctx, const agb_tensor* x, const agb
 }
 
 // y = [relu](conv(x, w) [+ bias[o]]): the fused form of Conv2D -> AddOp(bias [1,O,1,1]) -> ReLU (examples/cnn_mnist.rs:38-45)
+static int fprop_fused_impl(agb_ctx* ctx, const agb_tensor* x, const agb_tensor* w, const float* bias, int relu, agb_tensor* y, int pad, int stride, int dilation);
 extern "C" int agb_conv2d_fprop_fused_f32(agb_ctx* ctx, const agb_tensor* x, const agb_tensor* w, const float* bias, int relu, agb_tensor* y,
                                          int pad, int stride, int dilation) {
+  return fprop_fused_impl(ctx, x, w, bias, relu, y, pad, stride, dilation);
+}
+// the same with the SIGN BITS of the stored activation as a side output (1 bit per element in channels-last order: word (pixel * O + o) / 32,
+// bit o % 32): the mask of the ReLU backward, 1/32 of the bytes of the activation it would otherwise be read from.  *bits_written = 1 when the
+// kernel that ran wrote them (channels-last y, O % 32 == 0, a tensor-core kernel), else the buffer is untouched.
+extern "C" int agb_conv2d_fprop_fused_bits_f32(agb_ctx* ctx, const agb_tensor* x, const agb_tensor* w, const float* bias, int relu, agb_tensor* y,
+                                              uint32_t* relu_bits, int* bits_written, int pad, int stride, int dilation) {
+  const bool ok = relu_bits != nullptr && y->rank == 4 && y->shape[1] % 32 == 0 && is_channels_last(y) && !is_nchw(y) && ((((uintptr_t)relu_bits) & 3) == 0);
+  ctx->bits_out = ok ? relu_bits : nullptr; ctx->bits_written = 0;
+  const int r = fprop_fused_impl(ctx, x, w, bias, relu, y, pad, stride, dilation);
+  if (bits_written) *bits_written = (r == AGB_OK) ? ctx->bits_written : 0;
+  ctx->bits_out = nullptr; ctx->bits_written = 0;
+  return r;
+}
+static int fprop_fused_impl(agb_ctx* ctx, const agb_tensor* x, const agb_tensor* w, const float* bias, int relu, agb_tensor* y, int pad, int stride, int dilation) {
   ConvGeom g; AGB_TRY(check_geom("conv2d", x, w, pad, stride, dilation, g));
   AGB_CHECK(agb_is_contig(w), AGB_ERR_UNSUPPORTED, "conv2d: the filter must be C-contiguous");
   AGB_CHECK(y->rank == 4 && y->shape[0] == g.B && y->shape[1] == g.O && y->shape[2] == g.yh && y->shape[3] == g.yw, AGB_ERR_INCOMPATIBLE_SHAPE,
@@ -254,8 +270,22 @@ static int apply_relu_mask(agb_ctx* ctx, const agb_tensor* mask_src, agb_tensor*
   return r;
 }
 
+static int dgrad_fused_impl(agb_ctx* ctx, const agb_tensor* gy, const agb_tensor* w, const agb_tensor* mask_src, float* chan_sum, agb_tensor* gx, int pad, int stride, int dilation);
 extern "C" int agb_conv2d_dgrad_fused_f32(agb_ctx* ctx, const agb_tensor* gy, const agb_tensor* w, const agb_tensor* mask_src, float* chan_sum,
                                          agb_tensor* gx, int pad, int stride, int dilation) {
+  return dgrad_fused_impl(ctx, gy, w, mask_src, chan_sum, gx, pad, stride, dilation);
+}
+// the same with the sign bits of mask_src (agb_conv2d_fprop_fused_bits_f32) next to it: kernels that fuse the mask read 4 bytes per pixel per 32
+// channels instead of 128; every other path reads mask_src as before.  mask_bits must describe exactly mask_src (same buffer, channels-last).
+extern "C" int agb_conv2d_dgrad_fused_bits_f32(agb_ctx* ctx, const agb_tensor* gy, const agb_tensor* w, const agb_tensor* mask_src, const uint32_t* mask_bits,
+                                              float* chan_sum, agb_tensor* gx, int pad, int stride, int dilation) {
+  const bool ok = mask_bits != nullptr && mask_src != nullptr && mask_src->rank == 4 && mask_src->shape[1] % 32 == 0 && is_channels_last(mask_src) && !is_nchw(mask_src);
+  ctx->mask_bits = ok ? mask_bits : nullptr; ctx->mask_bits_used = 0;
+  const int r = dgrad_fused_impl(ctx, gy, w, mask_src, chan_sum, gx, pad, stride, dilation);
+  ctx->mask_bits = nullptr;
+  return r;
+}
+static int dgrad_fused_impl(agb_ctx* ctx, const agb_tensor* gy, const agb_tensor* w, const agb_tensor* mask_src, float* chan_sum, agb_tensor* gx, int pad, int stride, int dilation) {
   AGB_CHECK(gy->rank == 4, AGB_ERR_INCOMPATIBLE_SHAPE, "conv2d_transpose: Input must be 4D (got rank %d)", gy->rank);
   AGB_CHECK(w->rank == 4, AGB_ERR_INCOMPATIBLE_SHAPE, "conv2d_transpose: Filter must be 4D (got rank %d)", w->rank);
   AGB_CHECK(gy->shape[1] == w->shape[0], AGB_ERR_INCOMPATIBLE_SHAPE,

@@ -68,6 +68,9 @@ struct NdArray {
   std::shared_ptr<PoolRef> pool;
   std::shared_ptr<NdArray> chan_sum;   // (4-D activations gradients) per-channel sums over (b, h, w), produced for free by the fused dgrad /
                                        // pool-backward epilogues; MaybeReduceSum (the bias gradient) takes it instead of re-reading the tensor
+  std::shared_ptr<NdArray> relu_bits;  // (ReLU activations written by a fused conv kernel) the sign bits of exactly this buffer, numel / 32 words: the fused dgrad of
+                                       // the next layer reads them instead of the activation (agb_conv2d_*_bits_f32); `relu_bits_of` = the dptr they describe
+  const float* relu_bits_of = nullptr;
   std::shared_ptr<Lazy> lazy;     // value not computed yet: only `shape` is valid.  ComputeContext::input() materialises it unless the
                                   // consuming op declared accept_lazy (the ops that can fuse it into their own kernel)
 

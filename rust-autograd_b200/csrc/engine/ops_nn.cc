@@ -2,6 +2,7 @@
 // Reference files mirrored: tensor_ops/dot_ops.rs, tensor_ops/conv_ops/{conv2d,conv2d_transpose,max_pool2d}.rs,
 // tensor_ops/random_ops.rs:218-245, tensor_ops/gradient_descent_ops/*.rs, optimizers/*.rs.
 #include "agx.h"
+#include <cstdlib>
 #include <algorithm>
 
 namespace agx {
@@ -123,6 +124,7 @@ struct Lazy {
   NdArray src; std::shared_ptr<Lazy> src_lazy;    // kind 2: mask source as an array, or as a deferred ReLU node
   NdArray idx; int pool_size = 0, pool_stride = 0; // kind 4
   NdArray value; bool has_value = false;          // cache of the un-fused value
+  bool no_bits = false;                           // kind 1: the activation is being materialised for a max-pool (its ReLU backward is gated by the pooled output): no sign bits wanted
 };
 // activations enter the conv / pool entry points either NCHW-contiguous or channels-last; anything else is deep-copied
 static bool is_cl4(const NdArray& a) { std::vector<int> o; return a.ndim() == 4 && a.on_device() && a.dense_order(o) && o == std::vector<int>({0, 2, 3, 1}) && !a.is_contiguous(); }
@@ -151,6 +153,10 @@ static NdArray run_dgrad(Device* dev, const Lazy& L, const NdArray* mask_src) {
   // with the ReLU mask fused this is the gradient of a conv -> add(bias) -> relu layer's pre-activation: its per-channel sums
   // (the bias gradient) come out of the same epilogue
   NdArray cs; if (mask_src) cs = dev->empty({gx.shape[1]});
+  // sign bits of the mask source, when the forward kernel wrote them next to this very buffer
+  const uint32_t* bits = (mask_src && mask_src->relu_bits && mask_src->relu_bits_of == mask_src->dptr) ? (const uint32_t*)mask_src->relu_bits->dptr : nullptr;
+  if (bits) check_status(agb_conv2d_dgrad_fused_bits_f32(dev->ctx, &tg, &tw, &tm, bits, cs.dptr, &tx, p.pad, p.stride, p.dilation));
+  else
   check_status(agb_conv2d_dgrad_fused_f32(dev->ctx, &tg, &tw, mask_src ? &tm : nullptr, mask_src ? cs.dptr : nullptr, &tx, p.pad, p.stride, p.dilation));
   if (mask_src) gx.chan_sum = std::make_shared<NdArray>(cs);
   return gx;
@@ -179,6 +185,14 @@ static NdArray run_conv_fused(Device* dev, const Lazy& L, bool relu) {
   int64_t yw = (x.shape[3] + 2 * L.p.pad - (L.p.dilation * (w.shape[3] - 1) + 1)) / L.p.stride + 1;
   NdArray y = act_empty(dev, {x.shape[0], w.shape[0], yh, yw}, agb_conv_prefers_channels_last((int)x.shape[1], (int)w.shape[0], (int)w.shape[2], (int)w.shape[3], L.p.stride, (int)yw));
   agb_tensor tx = x.desc(), tw = w.desc(), ty = y.desc();
+  static const bool want_bits = [] { const char* e = getenv("AGX_RELU_BITS"); return !(e && e[0] == '0'); }();
+  if (want_bits && relu && !L.no_bits && y.shape[1] % 32 == 0 && is_cl4(y)) {       // a ReLU activation: let the kernel leave its sign bits next to it (1/32 of the bytes) for the masked dgrad
+    NdArray bits = dev->empty({(y.size() + 31) / 32});
+    int written = 0;
+    check_status(agb_conv2d_fprop_fused_bits_f32(dev->ctx, &tx, &tw, L.has_bias ? L.bias.dptr : nullptr, 1, &ty, (uint32_t*)bits.dptr, &written, L.p.pad, L.p.stride, L.p.dilation));
+    if (written) { y.relu_bits = std::make_shared<NdArray>(bits); y.relu_bits_of = y.dptr; }
+    return y;
+  }
   check_status(agb_conv2d_fprop_fused_f32(dev->ctx, &tx, &tw, L.has_bias ? L.bias.dptr : nullptr, relu ? 1 : 0, &ty, L.p.pad, L.p.stride, L.p.dilation));
   return y;
 }
@@ -470,6 +484,7 @@ struct MaxPool2D : Op {                // max_pool2d.rs:166-243
         }
         if (st != AGB_ERR_UNSUPPORTED) check_status(st);
       }
+      if (L.kind == 1 && L.relu_deferred && !L.has_value) L.no_bits = true;
       x = materialize_lazy(c.dev, x);
     }
     x = act_layout(c.dev, on_dev(c.dev, x));

@@ -42,7 +42,9 @@ __global__ void __launch_bounds__(256) repack_filter_kernel(const float* __restr
 #define AGB_CONV_MAX_TAPS 64
 // MT_ = 2: the CTA owns an 8x32 pixel patch = two 128-lane M-tiles (rows 0-3 / 4-7, ONE {32 c, 32 w, 8 h} box per k-block) that
 // share every filter tile: 1.33x (TN 128) / 1.5x (TN 256) fewer bytes through L2 -> smem per output, the bound of these kernels.
-template <int TN_, bool SPLIT_, int MT_ = 1> struct ConvFpropPol {
+// BITS_: the ReLU sign-bit side channel (mask read as bits / sign bits of the stored activation written).  A separate instantiation: with both mask forms in
+// one kernel the compiler scheduled the float-mask loads of the ordinary masked dgrad worse (0.57 -> 0.66 ms on the 256-wide layer).
+template <int TN_, bool SPLIT_, int MT_ = 1, bool BITS_ = false> struct ConvFpropPol {
   static constexpr int TN = TN_, MT = MT_; static constexpr bool SPLIT = SPLIT_, P_MN = false, Q_MN = false, Q_PRESPLIT = SPLIT_;
   static constexpr bool SPLIT_PAIR2 = SPLIT_ && TN_ == 128 && MT_ == 1;      // 3xTF32 CTA pairs (tc_tile_split_pair_kernel): tmWh / tmWlh = 64-row boxes of the filter's hi / lo planes
   static constexpr bool PAIR2 = !SPLIT_ && TN_ == 256 && MT_ == 1;      // CTA pairs (tc_tile_pair_kernel): two adjacent pixel tiles, each CTA streams half of the filter rows (tmWlo = half-height boxes)
@@ -57,6 +59,7 @@ template <int TN_, bool SPLIT_, int MT_ = 1> struct ConvFpropPol {
                   // output pixel (oy, ox) of the tile grid lands at (oy * os + oyo, ox * os + oxo) of a [B, YH, YW, Cout] tensor
                   // (identity for convolutions; the s*s phases of a strided dgrad write interleaved sub-grids)
                   int os, oyo, oxo, YH, YW;
+                  const uint32_t* mask_bits; uint32_t* bits_out;      // ReLU sign bits instead of mask_src (1 word per pixel per 32 channels) / of the stored activation
                   float* csum_part; };      // deterministic mode: slot (tile, M-tile, warp) stores its per-channel sums at csum_part[slot * Cout + channel]
   struct Tile { int b, oy0, ox0, o0; };
   __device__ static Tile tile(const Params& p, uint3 blk) {
@@ -105,12 +108,14 @@ template <int TN_, bool SPLIT_, int MT_ = 1> struct ConvFpropPol {
     for (int mt = 0; mt < MT; mt++) {
       int b, oy, ox;
       const bool in = pixel(p, t, mt, lane, b, oy, ox);
-      const float* m = p.mask + out_offset(p, in ? b : 0, in ? oy : 0, in ? ox : 0) + t.o0;
+      const int64_t moff = out_offset(p, in ? b : 0, in ? oy : 0, in ? ox : 0) + t.o0;
+      const float* m = p.mask + moff;
 #pragma unroll
       for (int c = 0; c < TN / 32; c++) {
         uint32_t bits = 0;
         const int o = t.o0 + 32 * c;
-        if (in && o + 32 <= p.Cout) {
+        if (BITS_ && p.mask_bits != nullptr) { if (in && o < p.Cout) bits = __ldg(p.mask_bits + ((moff + 32 * c) >> 5)); }      // Cout % 32 == 0 (host)
+        else if (in && o + 32 <= p.Cout) {
 #pragma unroll
           for (int j = 0; j < 32; j += 4) {
             const float4 mv = __ldg((const float4*)(m + 32 * c + j));
@@ -124,7 +129,11 @@ template <int TN_, bool SPLIT_, int MT_ = 1> struct ConvFpropPol {
       }
     }
   }
-  __device__ static void store(const Params& p, const Tile& t, int mt, int lane, int c0, const float* v, uint32_t pre) {
+  // `pre_io`: in = the ReLU-mask bits of this chunk (pre_epilogue); out = the sign bits of the stored chunk when bits_out is set.  The caller's words of one
+  // M-tile are consecutive, so the LAST chunk writes all of a pixel's words with 128-bit stores (one 4-byte store per chunk at a 32-byte pitch made
+  // every warp store touch 32 sectors and cost 0.3 ms per training step).
+  __device__ static void store(const Params& p, const Tile& t, int mt, int lane, int c0, const float* v, uint32_t& pre_io) {
+    const uint32_t pre = pre_io;
     int b, oy, ox;
     const bool in = pixel(p, t, mt, lane, b, oy, ox);
     if (!in && p.csum == nullptr) return;
@@ -150,6 +159,24 @@ template <int TN_, bool SPLIT_, int MT_ = 1> struct ConvFpropPol {
       } else {
 #pragma unroll
         for (int j = 0; j < 32; j++) if (o + j < p.Cout) dst[j] = r[j];
+      }
+    }
+    if (BITS_ && p.bits_out != nullptr) {
+      uint32_t sign = 0;
+#pragma unroll
+      for (int j = 0; j < 32; j++) sign |= (r[j] > 0.0f ? 1u : 0u) << j;
+      pre_io = sign;
+      const int nw = (min(TN, p.Cout - t.o0) + 31) >> 5, ci = c0 >> 5;
+      if (ci == nw - 1 && in) {
+        const uint32_t* pw = &pre_io - ci;                          // this M-tile's words 0 .. nw-1 (registers: every index is a compile-time constant after unrolling)
+        uint32_t* d = p.bits_out + ((out_offset(p, b, oy, ox) + t.o0) >> 5);
+        if ((nw & 3) == 0 && ((((uintptr_t)d) & 15) == 0)) {
+#pragma unroll
+          for (int q = 0; q < TN / 32; q += 4) if (q < nw) *(uint4*)(d + q) = make_uint4(pw[q], pw[q + 1], pw[q + 2], pw[q + 3]);
+        } else {
+#pragma unroll
+          for (int q = 0; q < TN / 32; q++) if (q < nw) d[q] = pw[q];
+        }
       }
     }
     if (p.csum != nullptr) {
@@ -240,7 +267,7 @@ template <int TN_, bool SPLIT_, bool PAIR_, int MT_ = 1> struct ConvWgradPol {
     for (int g = 0; g < TN / 64; g++) tma_load_4d_2sm(pQ + g * 4096, &p.tmG, bar, t.o0 + rank * (TN / 2) + 32 * g, ox0, oy, b);
   }
   __device__ static void pre_epilogue(const Params&, const Tile&, int, uint32_t*) {}
-  __device__ static void store(const Params& p, const Tile& t, int mt, int lane, int c0, const float* v, uint32_t) {
+  __device__ static void store(const Params& p, const Tile& t, int mt, int lane, int c0, const float* v, uint32_t&) {
     int c, tap;
     if (PAIR_) { c = lane & 63; tap = lane < 64 ? t.tapA : t.tapB; }
     else if (MT == 2 && mt == 1) { c = t.c1 + lane; tap = t.tapB; }
@@ -281,10 +308,21 @@ bool agb_tc_conv_eligible(int C, int O, int kh, int kw, int stride, int yw) {
 // strided-dgrad phase: explicit tap list and interleaved output sub-grid (nullptr = an ordinary convolution)
 struct ConvPhase { int ntaps; short dy[AGB_CONV_MAX_TAPS], dx[AGB_CONV_MAX_TAPS], wt[AGB_CONV_MAX_TAPS]; int os, oyo, oxo, YH, YW; };
 
+template <int TN, bool SPLIT, int MT, bool BITS>
+static int fprop_launch_impl(agb_ctx* ctx, const float* x, const float* wr, float* y, int B, int Cin, int H, int W, int Cout, int yh, int yw, int kh, int kw,
+                             int pad, int dil, const float* bias, int relu, const float* mask, float* csum, int stride, const ConvPhase* ph);
 template <int TN, bool SPLIT, int MT = 1>
 static int fprop_launch(agb_ctx* ctx, const float* x, const float* wr, float* y, int B, int Cin, int H, int W, int Cout, int yh, int yw, int kh, int kw,
                         int pad, int dil, const float* bias, int relu, const float* mask, float* csum, int stride = 1, const ConvPhase* ph = nullptr) {
-  using Pol = ConvFpropPol<TN, SPLIT, MT>;
+  // the sign-bit instantiation exists for the single-pass (TF32) one-M-tile kernels only
+  const bool bits = !SPLIT && MT == 1 && Cout % 32 == 0 && ph == nullptr && ((mask != nullptr && ctx->mask_bits != nullptr) || ctx->bits_out != nullptr);
+  if (bits) return fprop_launch_impl<TN, SPLIT, (SPLIT ? MT : 1), !SPLIT>(ctx, x, wr, y, B, Cin, H, W, Cout, yh, yw, kh, kw, pad, dil, bias, relu, mask, csum, stride, ph);
+  return fprop_launch_impl<TN, SPLIT, MT, false>(ctx, x, wr, y, B, Cin, H, W, Cout, yh, yw, kh, kw, pad, dil, bias, relu, mask, csum, stride, ph);
+}
+template <int TN, bool SPLIT, int MT, bool BITS>
+static int fprop_launch_impl(agb_ctx* ctx, const float* x, const float* wr, float* y, int B, int Cin, int H, int W, int Cout, int yh, int yw, int kh, int kw,
+                             int pad, int dil, const float* bias, int relu, const float* mask, float* csum, int stride, const ConvPhase* ph) {
+  using Pol = ConvFpropPol<TN, SPLIT, MT, BITS>;
   typename Pol::Params p;
   if (kh * kw > AGB_CONV_MAX_TAPS) return AGB_ERR_UNSUPPORTED;
   int bw = 32, bh = 4, bb = 1;
@@ -315,6 +353,11 @@ static int fprop_launch(agb_ctx* ctx, const float* x, const float* wr, float* y,
     }
   }
   p.y = y; p.bias = bias; p.mask = mask; p.csum = csum; p.relu = relu; p.Cout = Cout; p.yh = yh; p.yw = yw;
+  p.mask_bits = nullptr; p.bits_out = nullptr;
+  if (BITS && Cout % 32 == 0 && ph == nullptr) {
+    if (mask != nullptr && ctx->mask_bits != nullptr) { p.mask_bits = ctx->mask_bits; ctx->mask_bits_used = 1; }
+    if (ctx->bits_out != nullptr) { p.bits_out = ctx->bits_out; ctx->bits_written = 1; }
+  }
   p.tiles_x = (yw + bw - 1) / bw; p.tiles_y = (yh + bh * MT - 1) / (bh * MT); p.cblocks = (Cin + 31) / 32; p.mnc = agb_mn_cfg();
   if (ph == nullptr) {
     p.taps = kh * kw; p.os = 1; p.oyo = 0; p.oxo = 0; p.YH = yh; p.YW = yw;

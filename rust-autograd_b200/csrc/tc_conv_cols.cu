@@ -17,10 +17,11 @@
 //
 // Reference semantics: Conv2D::compute conv2d.rs:115-211, Conv2DTranspose::compute conv2d_transpose.rs:89-247.
 #include "tc_common.cuh"
+#include <stdlib.h>
 
 struct ColsParams {
   CUtensorMap tmX, tmW;
-  float* y; const float* bias; const float* mask; float* csum; float* csum_part; int relu;
+  float* y; const float* bias; const float* mask; const uint32_t* mask_bits; uint32_t* bits_out; float* csum; float* csum_part; int relu;
   int Cout, yh, yw, kw, pad, dil, tiles_y, cblocks, taps, rm, copy_bytes, copy_stride, a_slot_bytes, nb /* filter ring depth, in stages of G taps */;
   long long num_tiles;
 };
@@ -35,7 +36,9 @@ template <int TN> struct ColsCfg {
 // round the issuer's loop (wait, fence, elect, commit, counters) costs more than that: ncu showed the TN = 64 kernel at 34 % tensor-active with
 // the issuers 27 % of their time on b_full and the rest in loop overhead.
 #define COLS_NB_MAX 16
-template <int TN, int G>
+// MB: the ReLU sign-bit side channel (mask read as bits, sign bits of the output written) — its own instantiation, so the float-mask kernel keeps the
+// instruction schedule it had without it (with both forms in one kernel the ordinary masked dgrad lost 30 %)
+template <int TN, int G, bool MB, bool MBO>
 __global__ void __launch_bounds__(256, 1) conv_cols_kernel(const __grid_constant__ ColsParams p) {
   using Cfg = ColsCfg<TN>;
   constexpr int NB = COLS_NB_MAX;                              // barrier slots; p.nb stages are in use
@@ -155,7 +158,26 @@ __global__ void __launch_bounds__(256, 1) conv_cols_kernel(const __grid_constant
       const int oy0 = ty * rt;
       // pixel of (M-tile mt, strip position pl): row = oy0 + mt*rm + (32q + pl) / yw, column = (32q + pl) % yw
       uint32_t pre[2][TN / 32];
-      if (p.mask != nullptr) {
+      if (MB && p.mask_bits != nullptr) {        // sign bits written by the forward kernel: one word per pixel per 32 channels
+        const int cw = p.Cout >> 5;
+#pragma unroll
+        for (int mt = 0; mt < 2; mt++) {
+#pragma unroll
+          for (int c = 0; c < TN / 32; c++) {
+            const int cwi = min(c, cw - 1);
+            uint32_t wv[8];
+#pragma unroll
+            for (int k = 0; k < 8; k++) {
+              const int r = 32 * q + 4 * k + pl0; const int oy = min(oy0 + mt * p.rm + r / p.yw, p.yh - 1), ox = r % p.yw;
+              wv[k] = __ldg(p.mask_bits + (((long long)b * p.yh + oy) * p.yw + ox) * cw + cwi);
+            }
+            uint32_t bits = 0;
+#pragma unroll
+            for (int k = 0; k < 8; k++) bits |= ((wv[k] >> (4 * ch4)) & 15u) << (4 * k);
+            pre[mt][c] = bits;
+          }
+        }
+      } else if (p.mask != nullptr) {
 #pragma unroll
         for (int mt = 0; mt < 2; mt++) {
 #pragma unroll
@@ -185,6 +207,7 @@ __global__ void __launch_bounds__(256, 1) conv_cols_kernel(const __grid_constant
       tc_fence_after();
 #pragma unroll
       for (int mt = 0; mt < 2; mt++) {
+        uint32_t sgw[8][TN / 32];                                   // sign words of this lane group's 8 pixels (bits_out only)
 #pragma unroll
         for (int c = 0; c < TN / 32; c++) {
           float v[32];
@@ -209,8 +232,29 @@ __global__ void __launch_bounds__(256, 1) conv_cols_kernel(const __grid_constant
               *(float4*)(p.y + (((long long)b * p.yh + oy) * p.yw + ox) * p.Cout + o) = a;
               cs[c].x += a.x; cs[c].y += a.y; cs[c].z += a.z; cs[c].w += a.w;
             }
+            if (MBO && p.bits_out != nullptr) {       // sign bits of the stored activation: the 8 lanes of a pixel OR their nibbles into one word (warp-uniform branch)
+              uint32_t sg = ((a.x > 0.0f ? 1u : 0u) | (a.y > 0.0f ? 2u : 0u) | (a.z > 0.0f ? 4u : 0u) | (a.w > 0.0f ? 8u : 0u)) << (4 * ch4);
+              sg |= __shfl_xor_sync(0xffffffffu, sg, 1); sg |= __shfl_xor_sync(0xffffffffu, sg, 2); sg |= __shfl_xor_sync(0xffffffffu, sg, 4);
+              sgw[k][c] = sg;
+            }
           }
           __syncwarp();
+        }
+        if (MBO && p.bits_out != nullptr && ch4 == 0) {                    // one 8- / 16-byte store per pixel (all of its words when Cout == TN)
+          const int cw = p.Cout >> 5;
+#pragma unroll
+          for (int k = 0; k < 8; k++) {
+            const int r = 32 * q + 4 * k + pl0; const int oy = oy0 + mt * p.rm + r / p.yw, ox = r % p.yw;
+            if (oy < p.yh) {
+              uint32_t* d = p.bits_out + (((long long)b * p.yh + oy) * p.yw + ox) * cw;
+              if (TN == 128 && cw == 4) *(uint4*)d = make_uint4(sgw[k][0], sgw[k][1], sgw[k][2], sgw[k][3]);
+              else if (TN == 64 && cw == 2) *(uint2*)d = make_uint2(sgw[k][0], sgw[k][1]);
+              else {
+#pragma unroll
+                for (int c = 0; c < TN / 32; c++) if (c < cw) d[c] = sgw[k][c];
+              }
+            }
+          }
         }
       }
       tc_fence_before();
@@ -239,12 +283,12 @@ __global__ void __launch_bounds__(256, 1) conv_cols_kernel(const __grid_constant
   if (warp == 1) tmem_dealloc(tmem_base, Cfg::TMEM_COLS);
 }
 
-template <int TN, int G>
+template <int TN, int G, bool MB, bool MBO>
 static int cols_launch(agb_ctx* ctx, ColsParams& p, size_t smem) {
   static bool attr = false;
-  if (!attr) { AGB_CUDA(cudaFuncSetAttribute(conv_cols_kernel<TN, G>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024)); attr = true; }
+  if (!attr) { AGB_CUDA(cudaFuncSetAttribute(conv_cols_kernel<TN, G, MB, MBO>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024)); attr = true; }
   long long grid = p.num_tiles < ctx->sm_count ? p.num_tiles : ctx->sm_count;
-  conv_cols_kernel<TN, G><<<(unsigned)grid, ColsCfg<TN>::THREADS, smem, ctx->stream>>>(p);
+  conv_cols_kernel<TN, G, MB, MBO><<<(unsigned)grid, ColsCfg<TN>::THREADS, smem, ctx->stream>>>(p);
   AGB_LAUNCHED(ctx);
   return AGB_OK;
 }
@@ -300,9 +344,21 @@ int agb_tc_conv_cols(agb_ctx* ctx, const float* x, const float* wr, float* y, in
   const int64_t ncta = p.num_tiles < ctx->sm_count ? p.num_tiles : ctx->sm_count;
   p.csum_part = nullptr;
   if (csum != nullptr && ctx->deterministic) AGB_TRY(agb_scratch2(ctx, (size_t)ncta * TN * sizeof(float), (void**)&p.csum_part));
+  p.mask_bits = nullptr; p.bits_out = nullptr;
+  if (Cout % 32 == 0) {
+    if (mask != nullptr && ctx->mask_bits != nullptr) { p.mask_bits = ctx->mask_bits; ctx->mask_bits_used = 1; }
+    // measured (64 -> 128 @64x64, B = 256): writing the bits from this kernel's transposed epilogue costs 0.12 ms (the epilogue warps become the tile's
+    // critical path) and saves 0.14 ms in the next layer's masked dgrad: off by default (AGB_COLS_BITS=1); reading bits written by other kernels stays on
+    static const int prod = [] { const char* e = getenv("AGB_COLS_BITS"); return (e && e[0] == '1') ? 1 : 0; }();
+    if (prod && ctx->bits_out != nullptr) { p.bits_out = ctx->bits_out; ctx->bits_written = 1; }
+  }
   int r;
-  if (G == 3) r = TN == 64 ? cols_launch<64, 3>(ctx, p, smem) : cols_launch<128, 3>(ctx, p, smem);
-  else r = TN == 64 ? cols_launch<64, 1>(ctx, p, smem) : cols_launch<128, 1>(ctx, p, smem);
+#define AGB_COLS_DISPATCH(MB_, MBO_) do { if (G == 3) r = TN == 64 ? cols_launch<64, 3, MB_, MBO_>(ctx, p, smem) : cols_launch<128, 3, MB_, MBO_>(ctx, p, smem); \
+                                          else r = TN == 64 ? cols_launch<64, 1, MB_, MBO_>(ctx, p, smem) : cols_launch<128, 1, MB_, MBO_>(ctx, p, smem); } while (0)
+  if (p.bits_out != nullptr) AGB_COLS_DISPATCH(false, true);          // forward (no mask)
+  else if (p.mask_bits != nullptr) AGB_COLS_DISPATCH(true, false);
+  else AGB_COLS_DISPATCH(false, false);
+#undef AGB_COLS_DISPATCH
   if (r == AGB_OK && p.csum_part != nullptr) r = agb_reduce_partials(ctx, p.csum_part, csum, (int)ncta, Cout, TN, 1);
   return r;
 }

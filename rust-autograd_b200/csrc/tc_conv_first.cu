@@ -31,9 +31,10 @@ struct FirstParams {
   const float* w; float* y; const float* bias; int relu;
   int B, C, H, W, O, kh, kw, pad, stride, dil, yh, yw, K;
   int tiles_x, seg, xs_floats; int64_t tiles;
+  uint32_t* bits;                // optional: sign bits of the stored activation (O % 32 == 0), one word per pixel per 32 channels
 };
 
-template <int TN, bool SPLIT>
+template <int TN, bool SPLIT, bool BITS>
 __global__ void __launch_bounds__(320, 2) conv_first_fprop_kernel(const __grid_constant__ FirstParams p) {
   constexpr int A_BYTES = 128 * 128, B_BYTES = TN * 128;
   extern __shared__ uint8_t smem_raw[];
@@ -167,22 +168,27 @@ __global__ void __launch_bounds__(320, 2) conv_first_fprop_kernel(const __grid_c
       const uint32_t buf = it & 1;
       mbar_wait(&acc_full[buf], (it >> 1) & 1);
       tc_fence_after();
+      uint32_t signs[TN / 32];
 #pragma unroll
       for (int c0 = 0; c0 < TN; c0 += 32) {
         float v[32];
+        signs[c0 >> 5] = 0;
         tmem_ld32(tlane + buf * (uint32_t)TN + (uint32_t)c0, v);
         tmem_ld_wait();
         if (c0 < p.O) {                                         // (warp-uniform)
           uint8_t* stg = sY + (chunk & 1) * A_BYTES;
           if (leader) tma_store_wait_read<1>();                // the store that last read this staging buffer (two chunks ago) is done with it
           asm volatile("bar.sync 2, 128;" ::: "memory");
+          uint32_t sign = 0;
 #pragma unroll
           for (int j = 0; j < 32; j += 4) {
             float4 o4;
             o4.x = v[j] + sbias[c0 + j]; o4.y = v[j + 1] + sbias[c0 + j + 1]; o4.z = v[j + 2] + sbias[c0 + j + 2]; o4.w = v[j + 3] + sbias[c0 + j + 3];
             if (p.relu) { o4.x = fmaxf(o4.x, 0.0f); o4.y = fmaxf(o4.y, 0.0f); o4.z = fmaxf(o4.z, 0.0f); o4.w = fmaxf(o4.w, 0.0f); }
             *(float4*)(stg + row * 128 + (((j >> 2) ^ (row & 7)) << 4)) = o4;
+            if (BITS) sign |= ((o4.x > 0.0f ? 1u : 0u) | (o4.y > 0.0f ? 2u : 0u) | (o4.z > 0.0f ? 4u : 0u) | (o4.w > 0.0f ? 8u : 0u)) << j;
           }
+          signs[c0 >> 5] = sign;
           fence_proxy_async();
           asm volatile("bar.sync 2, 128;" ::: "memory");
           if (leader) { tma_store_4d(&p.tmY, stg, c0, tx * 128, oy, b); tma_store_commit(); }
@@ -191,6 +197,14 @@ __global__ void __launch_bounds__(320, 2) conv_first_fprop_kernel(const __grid_c
       }
       tc_fence_before();
       mbar_arrive(&acc_empty[buf]);
+      if (BITS && tx * 128 + row < p.yw) {          // the pixel's sign words, contiguous: 8 bytes per pixel at O = 64, consecutive pixels -> coalesced
+        uint32_t* d = p.bits + (((int64_t)b * p.yh + oy) * p.yw + tx * 128 + row) * (p.O >> 5);
+        if (TN == 64 && p.O == 64) *(uint2*)d = make_uint2(signs[0], signs[1]);
+        else {
+#pragma unroll
+          for (int c = 0; c < TN / 32; c++) if (32 * c < p.O) d[c] = signs[c];
+        }
+      }
     }
     if (leader) tma_store_wait_read<0>();
   }
@@ -199,13 +213,17 @@ __global__ void __launch_bounds__(320, 2) conv_first_fprop_kernel(const __grid_c
   if (warp == 4) tmem_dealloc(tmem_base, 2 * TN);
 }
 
+template <int TN, bool SPLIT, bool BITS>
+static int first_launch_impl(agb_ctx* ctx, const FirstParams& p);
 template <int TN, bool SPLIT>
-static int first_launch(agb_ctx* ctx, const FirstParams& p) {
+static int first_launch(agb_ctx* ctx, const FirstParams& p) { return p.bits != nullptr ? first_launch_impl<TN, SPLIT, true>(ctx, p) : first_launch_impl<TN, SPLIT, false>(ctx, p); }
+template <int TN, bool SPLIT, bool BITS>
+static int first_launch_impl(agb_ctx* ctx, const FirstParams& p) {
   constexpr int SMEM_MAX = (SPLIT ? 2 : 1) * (TN * 128 + 2 * 128 * 128) + 2 * 128 * 128 + CF_XS_STAGES * CF_XS_MAX_FLOATS * 4 + TN * 4 + 1024 + 256;
   static_assert(SMEM_MAX <= 227 * 1024, "first-layer tile does not fit shared memory");
   const int SMEM = SMEM_MAX - CF_XS_STAGES * (CF_XS_MAX_FLOATS - p.xs_floats) * 4;
   static bool attr = false;
-  if (!attr) { AGB_CUDA(cudaFuncSetAttribute(conv_first_fprop_kernel<TN, SPLIT>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_MAX)); attr = true; }
+  if (!attr) { AGB_CUDA(cudaFuncSetAttribute(conv_first_fprop_kernel<TN, SPLIT, BITS>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_MAX)); attr = true; }
   // co-resident CTAs overlap one's build / epilogue phases with the other's (0.328 -> 0.203 ms on the 3 -> 64 @128x128 layer); they share the 512 TMEM
   // columns.  Residency is computed here: cudaOccupancyMaxActiveBlocksPerMultiprocessor answers 1 for this kernel at 95 KB of dynamic shared memory
   // although two CTAs are resident (ncu: launch__occupancy_limit_shared_mem = 2), which had left half of every SM idle.
@@ -215,7 +233,7 @@ static int first_launch(agb_ctx* ctx, const FirstParams& p) {
   if (occ_env > 0) occ = occ_env;
   const int64_t cap = (int64_t)ctx->sm_count * occ;
   const unsigned n = (unsigned)(p.tiles < cap ? p.tiles : cap);
-  conv_first_fprop_kernel<TN, SPLIT><<<n, 320, SMEM, ctx->stream>>>(p);
+  conv_first_fprop_kernel<TN, SPLIT, BITS><<<n, 320, SMEM, ctx->stream>>>(p);
   AGB_LAUNCHED(ctx);
   return AGB_OK;
 }
@@ -244,6 +262,8 @@ int agb_tc_conv_first(agb_ctx* ctx, int mode, const float* x, const float* w, fl
     uint32_t box[4] = {32, 128, 1, 1};
     AGB_TRY(agb_make_tmap(&p.tmY, y, 4, dims, str, box, false));
   }
+  p.bits = nullptr;
+  if (ctx->bits_out != nullptr && O % 32 == 0) { p.bits = ctx->bits_out; ctx->bits_written = 1; }
   p.w = w; p.y = y; p.bias = bias; p.relu = relu; p.B = B; p.C = C; p.H = H; p.W = W; p.O = O; p.kh = kh; p.kw = kw; p.pad = pad; p.stride = stride;
   p.dil = dil; p.yh = yh; p.yw = yw; p.K = K; p.tiles_x = (yw + 127) / 128; p.seg = seg; p.xs_floats = (C * kh * seg + 31) / 32 * 32; p.tiles = (int64_t)B * yh * p.tiles_x;
   const bool split = mode == AGB_MATH_3XTF32;

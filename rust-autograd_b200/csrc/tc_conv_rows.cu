@@ -27,7 +27,7 @@
 #define ROWS_R 2
 struct RowsParams {
   CUtensorMap tmX, tmW;
-  float* y; const float* bias; const float* mask; float* csum; float* csum_part; int relu;
+  float* y; const float* bias; const float* mask; const uint32_t* mask_bits; uint32_t* bits_out; float* csum; float* csum_part; int relu;
   float* pool_y; int* pool_idx; int ph, pw;      // fused max_pool2d(2, 0, 2): pooled output + int32 argmax (logical NCHW offsets into y), y itself not written
   int Cout, yh, yw, kw, pad, dil, tiles_x, tiles_y, otiles, cblocks, taps, pitch, a_box_bytes, a_slot_bytes, nb /* filter ring depth in stages of G taps */;
   long long num_tiles;
@@ -40,7 +40,9 @@ template <int TN> struct RowsCfg {
 };
 
 // G = filter taps per ring stage (3 = one filter row per TMA box / barrier wait / commit when kw == 3: see tc_conv_cols.cu)
-template <int TN, int G>
+// MB: the ReLU sign-bit side channel (mask read as bits, sign bits of the output written) — its own instantiation, so the float-mask kernel keeps the
+// instruction schedule it had without it (with both forms in one kernel the ordinary masked dgrad lost 30 %)
+template <int TN, int G, bool MB>
 __global__ void __launch_bounds__(256, 1) conv_rows_kernel(const __grid_constant__ RowsParams p) {
   using Cfg = RowsCfg<TN>;
   constexpr int NB = ROWS_NB_MAX, R = ROWS_R;                  // barrier slots; p.nb stages in use
@@ -173,7 +175,25 @@ __global__ void __launch_bounds__(256, 1) conv_rows_kernel(const __grid_constant
       // ReLU-mask bits of the dgrad epilogue, fetched (coalesced) before the accumulator is ready:
       // bit 4 it + e of pre[r][c]  <=>  mask_src[b, oy0 + r, ox0 + 4 it + pl0, o0 + 32 c + 4 ch4 + e] > 0
       uint32_t pre[R][TN / 32];
-      if (p.mask != nullptr) {
+      if (MB && p.mask_bits != nullptr) {
+        // the mask as sign bits written by the forward kernel: one word per pixel per 32 channels (8 lanes share it) instead of 128 bytes
+        const int cw = p.Cout >> 5;
+#pragma unroll
+        for (int r = 0; r < R; r++) {
+          const long long prow = ((long long)b * p.yh + min(oy0 + r, p.yh - 1)) * p.yw;
+#pragma unroll
+          for (int c = 0; c < TN / 32; c++) {
+            const int cwi = min((o0 >> 5) + c, cw - 1);
+            uint32_t wv[8];
+#pragma unroll
+            for (int k = 0; k < 8; k++) wv[k] = __ldg(p.mask_bits + (prow + min(ox0 + 4 * k + pl0, p.yw - 1)) * cw + cwi);
+            uint32_t bits = 0;
+#pragma unroll
+            for (int k = 0; k < 8; k++) bits |= ((wv[k] >> (4 * ch4)) & 15u) << (4 * k);
+            pre[r][c] = bits;
+          }
+        }
+      } else if (p.mask != nullptr) {
         // pull the NEXT tile's mask lines into L2 now (one 128-byte line per 8 lanes): by the time that tile's epilogue starts, its
         // loads below hit L2 instead of waiting ~1.5 us on HBM with the accumulator already finished
         const long long tn = t + gridDim.x;
@@ -329,12 +349,12 @@ __global__ void __launch_bounds__(256, 1) conv_rows_kernel(const __grid_constant
   if (warp == 1) tmem_dealloc(tmem_base, Cfg::TMEM_COLS);
 }
 
-template <int TN, int G>
+template <int TN, int G, bool MB>
 static int rows_launch(agb_ctx* ctx, RowsParams& p, size_t smem) {
   static bool attr = false;
-  if (!attr) { AGB_CUDA(cudaFuncSetAttribute(conv_rows_kernel<TN, G>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024)); attr = true; }
+  if (!attr) { AGB_CUDA(cudaFuncSetAttribute(conv_rows_kernel<TN, G, MB>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024)); attr = true; }
   long long grid = p.num_tiles < ctx->sm_count ? p.num_tiles : ctx->sm_count;
-  conv_rows_kernel<TN, G><<<(unsigned)grid, RowsCfg<TN>::THREADS, smem, ctx->stream>>>(p);
+  conv_rows_kernel<TN, G, MB><<<(unsigned)grid, RowsCfg<TN>::THREADS, smem, ctx->stream>>>(p);
   AGB_LAUNCHED(ctx);
   return AGB_OK;
 }
@@ -378,9 +398,14 @@ int agb_tc_conv_rows(agb_ctx* ctx, const float* x, const float* wr, float* y, in
   const int64_t ncta = p.num_tiles < ctx->sm_count ? p.num_tiles : ctx->sm_count;
   p.csum_part = nullptr;
   if (csum != nullptr && ctx->deterministic) AGB_TRY(agb_scratch2(ctx, (size_t)ncta * TN * sizeof(float), (void**)&p.csum_part));
+  p.mask_bits = nullptr; p.bits_out = nullptr;
+  if (mask != nullptr && ctx->mask_bits != nullptr && Cout % 32 == 0) { p.mask_bits = ctx->mask_bits; ctx->mask_bits_used = 1; }
   int r;
-  if (G == 3) r = TN == 64 ? rows_launch<64, 3>(ctx, p, smem) : rows_launch<128, 3>(ctx, p, smem);
-  else r = TN == 64 ? rows_launch<64, 1>(ctx, p, smem) : rows_launch<128, 1>(ctx, p, smem);
+  const bool mb = p.mask_bits != nullptr || p.bits_out != nullptr;
+#define AGB_ROWS_DISPATCH(MB_) do { if (G == 3) r = TN == 64 ? rows_launch<64, 3, MB_>(ctx, p, smem) : rows_launch<128, 3, MB_>(ctx, p, smem); \
+                                    else r = TN == 64 ? rows_launch<64, 1, MB_>(ctx, p, smem) : rows_launch<128, 1, MB_>(ctx, p, smem); } while (0)
+  if (mb) AGB_ROWS_DISPATCH(true); else AGB_ROWS_DISPATCH(false);
+#undef AGB_ROWS_DISPATCH
   if (r == AGB_OK && p.csum_part != nullptr) r = agb_reduce_partials(ctx, p.csum_part, csum, (int)ncta, Cout, TN, 1);
   return r;
 }

@@ -69,7 +69,7 @@ template <int TN_, bool P_MN_, bool Q_MN_, bool SPLIT_, bool QPRE_ = false> stru
   // thread `lane` owns C column n = lane0 + lane; v[j] belongs to C row m = col0 + c0 + j: a warp stores 32 consecutive
   // floats of one C row per instruction (128-byte coalesced), no shared-memory staging
   __device__ static void pre_epilogue(const Params&, const Tile&, int, uint32_t*) {}
-  __device__ static void store(const Params& p, const Tile& t, int, int lane, int c0, const float* v, uint32_t) {
+  __device__ static void store(const Params& p, const Tile& t, int, int lane, int c0, const float* v, uint32_t&) {
     const int n = t.lane0 + lane;
     if (n >= p.NL) return;
     float* cbase = p.C + (int64_t)t.bz * p.bsc + n + (int64_t)t.ks * p.part_stride;      // part_stride > 0 (deterministic split-K): this split's own copy of C

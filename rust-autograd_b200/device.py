@@ -321,6 +321,19 @@ class Device:
             ffi.check(self.lib.agb_conv2d_fprop_fused_f32(self.ctx, x.desc(), w.desc(), bias.ptr if bias is not None else None, int(relu), y.desc(), pad, stride, dil))
         return y
 
+    def conv2d_relu_bits(self, x, w, pad=0, stride=1, dil=1, bias=None):
+        """relu(conv2d(x, w) [+ bias]) channels-last plus the sign bits of the result (numel / 32 words, None when the kernel that ran did not
+        write them): the 1/32-size mask the fused dgrad of the next layer reads instead of the activation"""
+        b, _, h, wd = x.shape
+        o, _, kh, kw = w.shape
+        shape = (b, o, self.conv_out(h, kh, pad, stride, dil), self.conv_out(wd, kw, pad, stride, dil))
+        y = self.empty_channels_last(shape)
+        bits = self.empty(((int(np.prod(shape)) + 31) // 32,))
+        written = C.c_int(0)
+        ffi.check(self.lib.agb_conv2d_fprop_fused_bits_f32(self.ctx, x.desc(), w.desc(), bias.ptr if bias is not None else None, 1, y.desc(), bits.ptr,
+                                                           C.byref(written), pad, stride, dil))
+        return y, (bits if written.value else None)
+
     def conv2d_pool(self, x, w, pad=0, stride=1, dil=1, bias=None, relu=True):
         """max_pool2d([relu](conv2d(x, w) [+ bias]), 2, 0, 2) in one kernel; returns (y_pooled, idx_int32) channels-last, or None when the
         fused kernel does not take the layer (AGB_ERR_UNSUPPORTED)"""
@@ -334,7 +347,7 @@ class Device:
         ffi.check(st)
         return y, idx
 
-    def conv2d_transpose(self, gy, w, pad=0, stride=1, dil=1, mask_src=None, channels_last=False, chan_sum=False):
+    def conv2d_transpose(self, gy, w, pad=0, stride=1, dil=1, mask_src=None, channels_last=False, chan_sum=False, mask_bits=None):
         """gx = conv2d_transpose(gy, w) [* (mask_src > 0)]; with chan_sum also returns sum_{b,h,w} gx as a [C] array"""
         b, _, yh, yw = gy.shape
         _, c, kh, kw = w.shape
@@ -345,8 +358,12 @@ class Device:
             ffi.check(self.lib.agb_conv2d_dgrad_f32(self.ctx, gy.desc(), w.desc(), gx.desc(), pad, stride, dil))
             return gx
         cs = self.empty((c,)) if chan_sum else None
-        ffi.check(self.lib.agb_conv2d_dgrad_fused_f32(self.ctx, gy.desc(), w.desc(), mask_src.desc() if mask_src is not None else None,
-                                                      cs.ptr if chan_sum else None, gx.desc(), pad, stride, dil))
+        if mask_bits is not None:
+            ffi.check(self.lib.agb_conv2d_dgrad_fused_bits_f32(self.ctx, gy.desc(), w.desc(), mask_src.desc(), mask_bits.ptr,
+                                                               cs.ptr if chan_sum else None, gx.desc(), pad, stride, dil))
+        else:
+            ffi.check(self.lib.agb_conv2d_dgrad_fused_f32(self.ctx, gy.desc(), w.desc(), mask_src.desc() if mask_src is not None else None,
+                                                          cs.ptr if chan_sum else None, gx.desc(), pad, stride, dil))
         return (gx, cs) if chan_sum else gx
 
     def conv2d_filter_grad(self, img, g, wshape, pad=0, stride=1, dil=1):

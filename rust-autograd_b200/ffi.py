@@ -10,7 +10,7 @@ import os
 import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "lib", "libagb200.so")
+LIB_PATH = os.environ.get("AGB200_LIB") or os.path.join(_HERE, "lib", "libagb200.so")      # AGB200_LIB: another build of the same library (A/B timing of two builds on one box)
 MAX_RANK = 8
 
 # status codes (include/agb200.h)
@@ -81,7 +81,8 @@ SIGNATURES = {
     "agb_graph_begin": [_P], "agb_graph_end": [_P, C.POINTER(_P)], "agb_graph_launch": [_P, _P], "agb_graph_destroy": [_P],
     "agb_gemm_f32": [_P, _i, _i, _T, _T, _T, _f],
     "agb_conv2d_fprop_f32": [_P, _T, _T, _T, _i, _i, _i], "agb_conv2d_fprop_fused_f32": [_P, _T, _T, _P, _i, _T, _i, _i, _i], "agb_conv2d_fprop_pool_f32": [_P, _T, _T, _P, _i, _T, _P, _i, _i, _i], "agb_conv2d_dgrad_f32": [_P, _T, _T, _T, _i, _i, _i],
-    "agb_conv2d_dgrad_fused_f32": [_P, _T, _T, _T, _P, _T, _i, _i, _i], "agb_maxpool2d_bwd_fused": [_P, _T, _P, _P, _P, _P, _T, _i, _i],
+    "agb_conv2d_dgrad_fused_f32": [_P, _T, _T, _T, _P, _T, _i, _i, _i],
+    "agb_conv2d_fprop_fused_bits_f32": [_P, _T, _T, _P, _i, _T, _P, C.POINTER(_i), _i, _i, _i], "agb_conv2d_dgrad_fused_bits_f32": [_P, _T, _T, _T, _P, _P, _T, _i, _i, _i], "agb_maxpool2d_bwd_fused": [_P, _T, _P, _P, _P, _P, _T, _i, _i],
     "agb_conv2d_wgrad_f32": [_P, _T, _T, _T, _i, _i, _i], "agb_conv_prefers_channels_last": [_i, _i, _i, _i, _i, _i], "agb_im2col_f32": [_P, _T, _T, _i, _i, _i, _i, _i],
     "agb_maxpool2d_fwd": [_P, _T, _T, _P, _P, _i, _i, _i], "agb_maxpool2d_bwd": [_P, _T, _P, _P, _T],
     "agb_maxpool2d_gradgrad": [_P, _T, _P, _P, _T],
@@ -120,6 +121,8 @@ def load_library():
                           "(there is no CPU fallback)" % LIB_PATH)
     lib = C.CDLL(LIB_PATH, mode=C.RTLD_GLOBAL)
     for name, args in SIGNATURES.items():
+        if not hasattr(lib, name) and os.environ.get("AGB200_LIB"):
+            continue                       # an older build under comparison may lack the newest entry points
         fn = getattr(lib, name)
         fn.argtypes = args
         fn.restype = C.c_int

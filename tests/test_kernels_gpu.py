@@ -816,3 +816,33 @@ def test_skinny_gemm_vs_oracle(dev, case, mode):
         got, ref = dev.gemm(dev.upload(g), dev.upload(w), trans_b=True).numpy(), R.matmul(g, w, False, True)
     assert got.shape == ref.shape
     assert rel_err(got, ref) <= 1e-5
+
+
+@pytest.mark.parametrize("case", [(4, 3, 64, 128, 64), (16, 256, 32, 32, 256), (3, 64, 14, 14, 128), (40, 128, 32, 32, 256)],
+                         ids=["first_layer->rows", "pair->pair", "per_tap->per_tap", "pair->pair(128->256)"])
+def test_relu_sign_bits_side_channel(dev, case):
+    """The fused conv + bias + ReLU kernels leave the SIGN BITS of their output next to it (1 bit per element, channels-last order), and the masked
+    dgrad of the next layer reads them instead of the activation (activation_ops.rs:161-166 needs only x > 0): the bits must be exactly (y > 0)
+    and the gradient exactly the one computed from the activation itself."""
+    dev.set_math_mode(1)
+    B, C, H, W, O = case
+    rng = np.random.default_rng(sum(case))
+    x = rng.standard_normal((B, C, H, W)).astype(np.float32)
+    w = (rng.standard_normal((O, C, 3, 3)) * 0.1).astype(np.float32)
+    bias = rng.standard_normal(O).astype(np.float32)
+    dx = dev.upload(x) if C <= 4 else dev.upload_channels_last(x)
+    y, bits = dev.conv2d_relu_bits(dx, dev.upload(w), 1, 1, 1, bias=dev.upload(bias))
+    assert bits is not None, "this layer runs on a kernel that writes the bits"
+    yv = y.numpy()                                                  # logical [B, O, H, W]
+    words = bits.numpy().view(np.uint32)
+    expect = np.packbits((yv.transpose(0, 2, 3, 1) > 0).reshape(-1, 32), axis=1, bitorder="little").view(np.uint32).ravel()
+    assert np.array_equal(words[:expect.size], expect)
+    # the next layer's masked dgrad: O -> O2 channels, gradient w.r.t. y
+    O2 = O
+    gy = rng.standard_normal((B, O2, H, W)).astype(np.float32)
+    w2 = (rng.standard_normal((O2, O, 3, 3)) * 0.1).astype(np.float32)
+    dgy, dw2 = dev.upload_channels_last(gy), dev.upload(w2)
+    gx_a, cs_a = dev.conv2d_transpose(dgy, dw2, 1, 1, 1, mask_src=y, channels_last=True, chan_sum=True)
+    gx_b, cs_b = dev.conv2d_transpose(dgy, dw2, 1, 1, 1, mask_src=y, channels_last=True, chan_sum=True, mask_bits=bits)
+    assert np.array_equal(gx_a.numpy(), gx_b.numpy()) and np.array_equal(cs_a.numpy(), cs_b.numpy())
+    assert rel_err(gx_b.numpy(), R.conv2d_transpose(gy, w2, 1, 1, 1) * (yv > 0)) <= TOL[1]
