@@ -126,8 +126,8 @@ static int tc_launch(agb_ctx* ctx, const CUtensorMap& tmP, const CUtensorMap& tm
   float* part = nullptr;
   // deterministic split-K through per-split copies of C pays 2 x splits x |C| of traffic plus a launch: right for the small outputs split-K exists for
   // (the classifier's [256, 10], weight gradients), wrong for a 128 x 4096 recurrence GEMM that lives on launch latency (measured: 12.3 -> 24.9 us).
-  // Above 4 MB of partials the sums stay on red.global.add (run-to-run differences of fp32 reassociation, like the embedding scatter-add).
-  if (splits > 1 && ctx->deterministic && (size_t)splits * cn * sizeof(float) <= (4u << 20)) AGB_TRY(agb_scratch2(ctx, (size_t)splits * cn * sizeof(float), (void**)&part));
+  // Above 1 MB of partials (a 512^3 product already pays +40 % for 4 MB of them) the sums stay on red.global.add (run-to-run differences of fp32 reassociation, like the embedding scatter-add).
+  if (splits > 1 && ctx->deterministic && (size_t)splits * cn * sizeof(float) <= (1u << 20)) AGB_TRY(agb_scratch2(ctx, (size_t)splits * cn * sizeof(float), (void**)&part));
   if (splits > 1 && !accumulate && !part) AGB_TRY(agb_memset0(ctx, C, (size_t)cn * sizeof(float)));
   typename Pol::Params prm{tmP, tmQ, tmQlo ? *tmQlo : tmQ, half ? half->hi : tmQ, half ? half->lo : tmQ, part ? part : C, NL, NC, K, ldc, bsc, accumulate, splits, kb_per, agb_mn_cfg(), part ? cn : 0};
   dim3 grid(gx, gy, (unsigned)(batch * splits));
