@@ -20,6 +20,7 @@
 //   (channels contiguous): [32 px][32 ch] TMA boxes {32 c, 32 w, 1, 1} (128B_BASE32B swizzle).  With C == 64 two taps share
 //   the 128 lanes.  Split-K over (b, oy) across CTAs, fp32 `red.global.add` into the zeroed gw.
 #include "tc_tile.cuh"
+#include <stdlib.h>
 #include <vector>
 
 // ------------------------------------------------------------------------------------------------ filter repack
@@ -215,7 +216,10 @@ template <int TN_, bool SPLIT_, bool PAIR_, int MT_ = 1> struct ConvWgradPol {
   static constexpr bool PAIR2 = !SPLIT_ && TN_ == 256 && MT_ == 1 && !PAIR_;      // CTA pairs: two (tap, 128-channel tile) units share every gy tile, each CTA streams half of its columns
   static constexpr int OCC = (SPLIT_ || TN_ > 128 || MT_ > 1) ? 1 : 2;
   static_assert(!(PAIR_ && MT_ > 1), "tap pairing within one M-tile and two M-tiles are alternatives");
-  struct Params { CUtensorMap tmX, tmG; float* gw; int C, O, T, kw, pad, dil, stride, yh, xblocks, kb_total, kb_per_split; MnDescCfg mnc; int64_t part_stride /* > 0: split z stores at gw + z * part_stride (deterministic mode) */; };
+  // tmX5 / tmG5 (wide = 1; C % 32 == 0 and O % 32 == 0): the channel axis split into {32, C / 32}, so ONE box {32 c, pixels, 4 blocks} lands as the four (TN / 32)
+  // consecutive 4 KB boxes the MMA descriptors expect — 3 TMA instructions per k-block instead of 16: ncu showed the producer warp 90 % busy issuing them
+  // (each cp.async.bulk.tensor of a lane-0 branch is an ELECT / uniform-branch waterfall) and the MMA issuer 20 % of its time waiting on `full`
+  struct Params { CUtensorMap tmX, tmG, tmX5, tmG5; int wide; float* gw; int C, O, T, kw, pad, dil, stride, yh, xblocks, kb_total, kb_per_split; MnDescCfg mnc; int64_t part_stride /* > 0: split z stores at gw + z * part_stride (deterministic mode) */; };
   struct Tile { int c0, tapA, tapB, o0, q0, q1, c1; };       // MT == 2: unit 0 = (tapA, c0), unit 1 = (tapB, c1)
   __device__ static Tile tile(const Params& p, uint3 blk) {
     Tile t; t.o0 = (int)blk.y * TN; t.c1 = 0;
@@ -236,6 +240,23 @@ template <int TN_, bool SPLIT_, bool PAIR_, int MT_ = 1> struct ConvWgradPol {
     const int ox0 = xb * 32;
     const int iA = t.tapA / p.kw, jA = t.tapA - iA * p.kw;
     const int xA = ox0 * p.stride + jA * p.dil - p.pad, yA = oy * p.stride + iA * p.dil - p.pad;       // strided conv: the x box walks w with element stride s
+    if (p.wide) {      // one box per operand tile (the channel axis as {32, blocks})
+      if (PAIR_) {
+        int xB = xA, yB = yA, cB = (p.C >> 5) + 2;                           // tap B absent: fully out of bounds = zero rows
+        if (t.tapB < p.T) { const int iB = t.tapB / p.kw, jB = t.tapB - iB * p.kw; xB = ox0 * p.stride + jB * p.dil - p.pad; yB = oy * p.stride + iB * p.dil - p.pad; cB = 0; }
+        tma_load_5d(pP, &p.tmX5, bar, 0, xA, 0, yA, b);
+        tma_load_5d(pP + 8192, &p.tmX5, bar, 0, xB, cB, yB, b);
+      } else {
+        tma_load_5d(pP, &p.tmX5, bar, 0, xA, t.c0 >> 5, yA, b);
+        if (MT == 2) {
+          int xB = xA, yB = yA, cB = (p.C >> 5) + 4;
+          if (t.tapB < p.T) { const int iB = t.tapB / p.kw, jB = t.tapB - iB * p.kw; xB = ox0 * p.stride + jB * p.dil - p.pad; yB = oy * p.stride + iB * p.dil - p.pad; cB = t.c1 >> 5; }
+          tma_load_5d(pP + 16384, &p.tmX5, bar, 0, xB, cB, yB, b);
+        }
+      }
+      tma_load_5d(pQ, &p.tmG5, bar, 0, ox0, t.o0 >> 5, oy, b);
+      return;
+    }
     if (PAIR_) {      // lanes 0-63: channels 0..63 at tap A, lanes 64-127: channels 0..63 at tap B
       int xB = xA, yB = yA, cB = p.C + 64;                                   // tap B absent (odd tap count): fully out of bounds = zero rows
       if (t.tapB < p.T) { const int iB = t.tapB / p.kw, jB = t.tapB - iB * p.kw; xB = ox0 * p.stride + jB * p.dil - p.pad; yB = oy * p.stride + iB * p.dil - p.pad; cB = 0; }
@@ -482,6 +503,24 @@ static int wgrad_launch(agb_ctx* ctx, const float* img, const float* g, float* g
   }
   p.stride = stride;
   AGB_TRY(make_cl_map(&p.tmG, g, B, O, yh, yw, 32, 32, 1, true));
+  static const int wide_env = [] { const char* e = getenv("AGB_WGRAD_WIDE"); return (e && e[0] == '0') ? 0 : 1; }();
+  p.wide = (wide_env && C % 32 == 0 && O % 32 == 0 && !Pol::PAIR2) ? 1 : 0;
+  p.tmX5 = p.tmX; p.tmG5 = p.tmG;
+  if (p.wide) {
+    const uint32_t su = (uint32_t)stride;
+    {   // x as {32 c, W, C / 32, H, B}
+      uint64_t dims[5] = {32, (uint64_t)W, (uint64_t)(C / 32), (uint64_t)H, (uint64_t)B};
+      uint64_t str[4] = {(uint64_t)C * 4, 128, (uint64_t)W * C * 4, (uint64_t)H * W * C * 4};
+      uint32_t box[5] = {32, 31 * su + 1, (uint32_t)(PAIR ? 2 : 4), 1, 1}, es[5] = {1, su, 1, 1, 1};
+      AGB_TRY(agb_make_tmap(&p.tmX5, img, 5, dims, str, box, true, stride > 1 ? es : nullptr));
+    }
+    {   // gy as {32 o, yw, O / 32, yh, B}
+      uint64_t dims[5] = {32, (uint64_t)yw, (uint64_t)(O / 32), (uint64_t)yh, (uint64_t)B};
+      uint64_t str[4] = {(uint64_t)O * 4, 128, (uint64_t)yw * O * 4, (uint64_t)yh * yw * O * 4};
+      uint32_t box[5] = {32, 32, (uint32_t)(TN / 32), 1, 1};
+      AGB_TRY(agb_make_tmap(&p.tmG5, g, 5, dims, str, box, true));
+    }
+  }
   const int T = kh * kw;
   p.gw = gw; p.C = C; p.O = O; p.T = T; p.kw = kw; p.pad = pad; p.dil = dil; p.yh = yh; p.xblocks = (yw + 31) / 32;
   int64_t kb_total = (int64_t)B * yh * p.xblocks;

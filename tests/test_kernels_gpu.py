@@ -769,14 +769,14 @@ def test_bias_gradient_side_sums_are_bit_reproducible(dev, case):
 def test_split_k_gemm_and_pool_sums_are_bit_reproducible(dev):
     dev.set_math_mode(1)
     rng = np.random.default_rng(3)
-    a = rng.standard_normal((128, 8192)).astype(np.float32)          # [128, 128] output, 8 MB of K: split-K with per-split copies of C (<= 4 MB of partials)
-    b = rng.standard_normal((8192, 128)).astype(np.float32)
+    a = rng.standard_normal((64, 8192)).astype(np.float32)           # [64, 32] output, long K: split-K with per-split copies of C (<= 1 MB of partials)
+    b = rng.standard_normal((8192, 32)).astype(np.float32)
     da, db = dev.upload(a), dev.upload(b)
     runs = [dev.gemm(da, db).numpy() for _ in range(3)]
     assert np.array_equal(runs[0], runs[1]) and np.array_equal(runs[0], runs[2])
     assert rel_err(runs[0], R.matmul(a, b)) <= TOL[1]
-    at = rng.standard_normal((4096, 256)).astype(np.float32)          # A^T B with a long K: the weight-gradient shape
-    bt = rng.standard_normal((4096, 64)).astype(np.float32)
+    at = rng.standard_normal((4096, 64)).astype(np.float32)           # A^T B with a long K: the weight-gradient shape
+    bt = rng.standard_normal((4096, 32)).astype(np.float32)
     dat, dbt = dev.upload(at), dev.upload(bt)
     runs = [dev.gemm(dat, dbt, trans_a=True).numpy() for _ in range(3)]
     assert np.array_equal(runs[0], runs[1]) and np.array_equal(runs[0], runs[2])
