@@ -28,7 +28,8 @@ template <int TN_, bool P_MN_, bool Q_MN_, bool SPLIT_, bool QPRE_ = false> stru
   static constexpr bool SPLIT_PAIR2 = SPLIT_ && QPRE_ && TN_ == 128;      // 3xTF32 CTA pairs: tmQh / tmQlh = half-height boxes of the hi / lo planes
   // splits > 1: split-K for problems with too few output tiles to fill the machine (e.g. the LSTM's 128 x 1024 x 8192 dgrad GEMM is
   // 8 tiles): grid.z = batch * splits, every CTA reduces kb_per_split k-blocks and adds its partial with red.global.add (C pre-zeroed)
-  struct Params { CUtensorMap tmP, tmQ, tmQlo /* 3xTF32: lo plane; CTA pairs: half-height Q boxes */, tmQh, tmQlh; float* C; int NL, NC, K; int64_t ldc, bsc; int accumulate; int splits, kb_per_split; MnDescCfg mnc; int64_t part_stride /* > 0: split ks stores its partial at C + ks * part_stride (deterministic mode) */; };
+  struct Params { CUtensorMap tmP, tmQ, tmQlo /* 3xTF32: lo plane; CTA pairs: half-height Q boxes */, tmQh, tmQlh; float* C; int NL, NC, K; int64_t ldc, bsc; int accumulate; int splits, kb_per_split; MnDescCfg mnc; int64_t part_stride /* > 0: split ks stores its partial at C + ks * part_stride (deterministic mode) */;
+                  CUtensorMap tmPw, tmQw; int widep, wideq; };      // MN-major operand with rows % 32 == 0: the row axis as {32, blocks}, ONE box per tile instead of one per 32 rows
   struct Tile { int lane0, col0, bz, kb0, nkb, ks; };
   __device__ static Tile tile(const Params& p, uint3 blk) {
     const int kb_total = (p.K + TC_BK - 1) / TC_BK;
@@ -46,9 +47,13 @@ template <int TN_, bool P_MN_, bool Q_MN_, bool SPLIT_, bool QPRE_ = false> stru
   }
   __device__ static void load(const Params& p, const Tile& t, int kb, uint8_t* pP, uint8_t* pQ, uint64_t* bar) {
     const int k0 = (t.kb0 + kb) * TC_BK;
-    if (P_MN) { for (int j = 0; j < TC_LANES / 32; j++) tma_load_3d(pP + j * 4096, &p.tmP, bar, t.lane0 + 32 * j, k0, t.bz); }
+    if (P_MN) {
+      if (p.widep) tma_load_4d(pP, &p.tmPw, bar, 0, k0, t.lane0 >> 5, t.bz);
+      else for (int j = 0; j < TC_LANES / 32; j++) tma_load_3d(pP + j * 4096, &p.tmP, bar, t.lane0 + 32 * j, k0, t.bz);
+    }
     else tma_load_3d(pP, &p.tmP, bar, k0, t.lane0, t.bz);
-    load_q(&p.tmQ, t, kb, pQ, bar);
+    if (Q_MN && p.wideq) tma_load_4d(pQ, &p.tmQw, bar, 0, k0, t.col0 >> 5, t.bz);
+    else load_q(&p.tmQ, t, kb, pQ, bar);
   }
   __device__ static void load_q_lo(const Params& p, const Tile& t, int kb, uint8_t* pQlo, uint64_t* bar) { load_q(&p.tmQlo, t, kb, pQlo, bar); }       // 3xTF32 with the Q operand pre-split in global memory
   __device__ static void load_sp2(const Params& p, const Tile& t, int kb, uint8_t* pP, uint8_t* pQh, uint8_t* pQl, uint64_t* bar, int rank) {
@@ -61,9 +66,15 @@ template <int TN_, bool P_MN_, bool Q_MN_, bool SPLIT_, bool QPRE_ = false> stru
   // CTA pair: this CTA's 128 P rows + its half of the Q rows, completing on the leader's barrier
   __device__ static void load2(const Params& p, const Tile& t, int kb, uint8_t* pP, uint8_t* pQ, uint32_t bar, int rank) {
     const int k0 = (t.kb0 + kb) * TC_BK, c0 = t.col0 + rank * (TN / 2);
-    if (P_MN) { for (int j = 0; j < TC_LANES / 32; j++) tma_load_3d_2sm(pP + j * 4096, &p.tmP, bar, t.lane0 + 32 * j, k0, t.bz); }
+    if (P_MN) {
+      if (p.widep) tma_load_4d_2sm(pP, &p.tmPw, bar, 0, k0, t.lane0 >> 5, t.bz);
+      else for (int j = 0; j < TC_LANES / 32; j++) tma_load_3d_2sm(pP + j * 4096, &p.tmP, bar, t.lane0 + 32 * j, k0, t.bz);
+    }
     else tma_load_3d_2sm(pP, &p.tmP, bar, k0, t.lane0, t.bz);
-    if (Q_MN) { for (int j = 0; j < TN / 64; j++) tma_load_3d_2sm(pQ + j * 4096, &p.tmQlo, bar, c0 + 32 * j, k0, t.bz); }
+    if (Q_MN) {
+      if (p.wideq) tma_load_4d_2sm(pQ, &p.tmQw, bar, 0, k0, c0 >> 5, t.bz);      // (the pair's wide Q map has TN / 2 rows per box)
+      else for (int j = 0; j < TN / 64; j++) tma_load_3d_2sm(pQ + j * 4096, &p.tmQlo, bar, c0 + 32 * j, k0, t.bz);
+    }
     else tma_load_3d_2sm(pQ, &p.tmQlo, bar, k0, c0, t.bz);
   }
   // thread `lane` owns C column n = lane0 + lane; v[j] belongs to C row m = col0 + c0 + j: a warp stores 32 consecutive
@@ -105,7 +116,17 @@ static int tc_make_map(CUtensorMap* m, const TcOperand& o, int64_t K, int64_t ba
   return agb_make_tmap(m, o.p, 3, dims, strides, box, mn_major && a32);
 }
 
-struct TcHalfMaps { CUtensorMap hi, lo; };       // 3xTF32 CTA pairs: TN / 2-row boxes of the pre-split Q planes
+struct TcHalfMaps { CUtensorMap hi, lo; };
+// wide maps of the MN-major operands of the current agb_tc_gemm call (set before the dispatch, read by tc_launch; single pass only)
+struct TcWide { CUtensorMap p, q; int hp = 0, hq = 0; };
+static thread_local TcWide g_tc_wide;
+static int tc_make_wide_map(CUtensorMap* m, const TcOperand& o, int64_t K, int64_t batch, int box_rows) {
+  uint64_t dims[4] = {32, (uint64_t)K, (uint64_t)(o.rows / 32), (uint64_t)batch};
+  uint64_t str[3] = {(uint64_t)o.ks * 4, 128, (uint64_t)((batch > 1 ? o.bs : o.ks * K) * 4)};
+  if (str[2] == 0) str[2] = 16;
+  uint32_t box[4] = {32, TC_BK, (uint32_t)(box_rows / 32), 1};
+  return agb_make_tmap(m, o.p, 4, dims, str, box, true);
+}       // 3xTF32 CTA pairs: TN / 2-row boxes of the pre-split Q planes
 template <int TN, bool P_MN, bool Q_MN, bool SPLIT, bool QPRE = false>
 static int tc_launch(agb_ctx* ctx, const CUtensorMap& tmP, const CUtensorMap& tmQ, const CUtensorMap* tmQlo, float* C, int NL, int NC, int K, int64_t ldc, int64_t bsc,
                      int64_t batch, int accumulate, const TcHalfMaps* half = nullptr) {
@@ -130,6 +151,11 @@ static int tc_launch(agb_ctx* ctx, const CUtensorMap& tmP, const CUtensorMap& tm
   if (splits > 1 && ctx->deterministic && (size_t)splits * cn * sizeof(float) <= (1u << 20)) AGB_TRY(agb_scratch2(ctx, (size_t)splits * cn * sizeof(float), (void**)&part));
   if (splits > 1 && !accumulate && !part) AGB_TRY(agb_memset0(ctx, C, (size_t)cn * sizeof(float)));
   typename Pol::Params prm{tmP, tmQ, tmQlo ? *tmQlo : tmQ, half ? half->hi : tmQ, half ? half->lo : tmQ, part ? part : C, NL, NC, K, ldc, bsc, accumulate, splits, kb_per, agb_mn_cfg(), part ? cn : 0};
+  prm.widep = 0; prm.wideq = 0; prm.tmPw = tmP; prm.tmQw = tmQ;
+  if (!SPLIT) {
+    if (P_MN && g_tc_wide.hp) { prm.tmPw = g_tc_wide.p; prm.widep = 1; }
+    if (Q_MN && g_tc_wide.hq) { prm.tmQw = g_tc_wide.q; prm.wideq = 1; }
+  }
   dim3 grid(gx, gy, (unsigned)(batch * splits));
   AGB_TRY(tc_tile_launch<Pol>(ctx, prm, grid));
   if (part) return agb_reduce_partials(ctx, part, C, splits, cn, cn, accumulate);
@@ -214,6 +240,12 @@ int agb_tc_gemm(agb_ctx* ctx, int mode, const float* A, const float* B, float* C
   int r = tc_make_map(&tmP, P, K, batch, pmn, TC_LANES); if (r != AGB_OK) return r;
   r = tc_make_map(&tmQ, Q, K, batch, qmn, TN); if (r != AGB_OK) return r;
   const int acc = beta != 0.0f;
+  g_tc_wide.hp = g_tc_wide.hq = 0;
+  static const int wide_env = [] { const char* e = getenv("AGB_GEMM_WIDE"); return (e && e[0] == '0') ? 0 : 1; }();
+  if (!split && wide_env) {
+    if (pmn && P.rows % 32 == 0 && tc_make_wide_map(&g_tc_wide.p, P, K, batch, TC_LANES) == AGB_OK) g_tc_wide.hp = 1;
+    if (qmn && Q.rows % 32 == 0 && tc_make_wide_map(&g_tc_wide.q, Q, K, batch, TN == 256 ? 128 : TN) == AGB_OK) g_tc_wide.hq = 1;      // CTA pairs: half of the Q tile per CTA
+  }
   if (split) {
     // Q = op(A) is re-read by every one of the N/128 lane tiles: pre-split it once in global memory when it is dense and N is large
     const int64_t qn = M * K * batch;
