@@ -152,10 +152,8 @@ static int tc_launch(agb_ctx* ctx, const CUtensorMap& tmP, const CUtensorMap& tm
   if (splits > 1 && !accumulate && !part) AGB_TRY(agb_memset0(ctx, C, (size_t)cn * sizeof(float)));
   typename Pol::Params prm{tmP, tmQ, tmQlo ? *tmQlo : tmQ, half ? half->hi : tmQ, half ? half->lo : tmQ, part ? part : C, NL, NC, K, ldc, bsc, accumulate, splits, kb_per, agb_mn_cfg(), part ? cn : 0};
   prm.widep = 0; prm.wideq = 0; prm.tmPw = tmP; prm.tmQw = tmQ;
-  if (!SPLIT) {
-    if (P_MN && g_tc_wide.hp) { prm.tmPw = g_tc_wide.p; prm.widep = 1; }
-    if (Q_MN && g_tc_wide.hq) { prm.tmQw = g_tc_wide.q; prm.wideq = 1; }
-  }
+  if (P_MN && g_tc_wide.hp) { prm.tmPw = g_tc_wide.p; prm.widep = 1; }
+  if (Q_MN && g_tc_wide.hq && !QPRE) { prm.tmQw = g_tc_wide.q; prm.wideq = 1; }      // (a pre-split Q comes from its hi / lo planes)
   dim3 grid(gx, gy, (unsigned)(batch * splits));
   AGB_TRY(tc_tile_launch<Pol>(ctx, prm, grid));
   if (part) return agb_reduce_partials(ctx, part, C, splits, cn, cn, accumulate);
@@ -242,7 +240,7 @@ int agb_tc_gemm(agb_ctx* ctx, int mode, const float* A, const float* B, float* C
   const int acc = beta != 0.0f;
   g_tc_wide.hp = g_tc_wide.hq = 0;
   static const int wide_env = [] { const char* e = getenv("AGB_GEMM_WIDE"); return (e && e[0] == '0') ? 0 : 1; }();
-  if (!split && wide_env) {
+  if (wide_env) {
     if (pmn && P.rows % 32 == 0 && tc_make_wide_map(&g_tc_wide.p, P, K, batch, TC_LANES) == AGB_OK) g_tc_wide.hp = 1;
     if (qmn && Q.rows % 32 == 0 && tc_make_wide_map(&g_tc_wide.q, Q, K, batch, TN == 256 ? 128 : TN) == AGB_OK) g_tc_wide.hq = 1;      // CTA pairs: half of the Q tile per CTA
   }
