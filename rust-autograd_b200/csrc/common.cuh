@@ -81,6 +81,8 @@ int  agb_scratch(agb_ctx* ctx, size_t bytes, void** out);
 int  agb_scratch2(agb_ctx* ctx, size_t bytes, void** out);      // a second buffer: partial sums of the deterministic reductions (the first may hold repacked operands of the same call)
 // out[i] (+)= sum over k < nparts (in order) of part[k * stride + i]
 int  agb_reduce_partials(agb_ctx* ctx, const float* part, float* out, int nparts, int64_t n, int64_t stride, int accumulate);
+// partials laid out [nparts][tap][o][c] -> gw[o][c][tap]
+int  agb_reduce_partials_wgrad(agb_ctx* ctx, const float* part, float* gw, int nparts, int O, int C, int T);
 // many partials ([nparts][n], dense): 64 interleaved groups are added first, then the groups — both in a fixed order.  `part` must have room for
 // agb_reduce_partials2_floats(nparts, n) floats (padding to a multiple of 64 partials + the [64][n] group sums)
 static inline size_t agb_reduce_partials2_floats(int64_t nparts, int64_t n) { return (size_t)((nparts + 63) / 64 * 64 + 64) * (size_t)n; }

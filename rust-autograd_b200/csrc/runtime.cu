@@ -158,7 +158,8 @@ int agb_scratch2(agb_ctx* ctx, size_t bytes, void** out) { AGB_TRY(scratch_grow(
 // ---- deterministic reductions -------------------------------------------------------------------------------------------
 // block = 32 consecutive elements x 8 partial groups: thread (e, g) adds partials g, g + 8, g + 16, ... of element e, the eight group sums are
 // added as a fixed tree.  (One thread per element walking all the partials was latency-bound: 23 us for the 2560 outputs of the classifier GEMM.)
-__global__ void __launch_bounds__(256) reduce_partials_kernel(const float* __restrict__ part, float* __restrict__ out, int nparts, int64_t n, int64_t stride, int accumulate) {
+// (pt > 0: the partials are laid out [tap][o][c] — coalesced drain stores of the filter-gradient kernels — and the sum goes to out[(o * pc + c) * pt + tap])
+__global__ void __launch_bounds__(256) reduce_partials_kernel(const float* __restrict__ part, float* __restrict__ out, int nparts, int64_t n, int64_t stride, int accumulate, int po, int pc, int pt) {
   __shared__ float sm[8][33];
   const int e = threadIdx.x & 31, g = threadIdx.x >> 5;
   for (int64_t base = (int64_t)blockIdx.x * 32; base < n; base += (int64_t)gridDim.x * 32) {
@@ -174,7 +175,9 @@ __global__ void __launch_bounds__(256) reduce_partials_kernel(const float* __res
     __syncthreads();
     if (g == 0 && i < n) {
       const float s = ((sm[0][e] + sm[1][e]) + (sm[2][e] + sm[3][e])) + ((sm[4][e] + sm[5][e]) + (sm[6][e] + sm[7][e]));
-      out[i] = accumulate ? out[i] + s : s;
+      int64_t oi = i;
+      if (pt > 0) { const int64_t oc = (int64_t)po * pc; const int tap = (int)(i / oc); const int64_t r = i - tap * oc; oi = r * pt + tap; }      // r = o * pc + c
+      out[oi] = accumulate ? out[oi] + s : s;
     }
     __syncthreads();
   }
@@ -182,7 +185,15 @@ __global__ void __launch_bounds__(256) reduce_partials_kernel(const float* __res
 int agb_reduce_partials(agb_ctx* ctx, const float* part, float* out, int nparts, int64_t n, int64_t stride, int accumulate) {
   if (n <= 0) return AGB_OK;
   int64_t blocks = (n + 31) / 32; const int64_t cap = (int64_t)ctx->sm_count * 16; if (blocks > cap) blocks = cap;
-  reduce_partials_kernel<<<(unsigned)blocks, 256, 0, ctx->stream>>>(part, out, nparts, n, stride, accumulate);
+  reduce_partials_kernel<<<(unsigned)blocks, 256, 0, ctx->stream>>>(part, out, nparts, n, stride, accumulate, 0, 0, 0);
+  AGB_LAUNCHED(ctx);
+  return AGB_OK;
+}
+int agb_reduce_partials_wgrad(agb_ctx* ctx, const float* part, float* gw, int nparts, int O, int C, int T) {
+  const int64_t n = (int64_t)O * C * T;
+  if (n <= 0) return AGB_OK;
+  int64_t blocks = (n + 31) / 32; const int64_t cap = (int64_t)ctx->sm_count * 16; if (blocks > cap) blocks = cap;
+  reduce_partials_kernel<<<(unsigned)blocks, 256, 0, ctx->stream>>>(part, gw, nparts, n, n, 0, O, C, T);
   AGB_LAUNCHED(ctx);
   return AGB_OK;
 }

@@ -294,11 +294,16 @@ template <int TN_, bool SPLIT_, bool PAIR_, int MT_ = 1> struct ConvWgradPol {
     else if (MT == 2 && mt == 1) { c = t.c1 + lane; tap = t.tapB; }
     else { c = t.c0 + lane; tap = t.tapA; }
     if (c >= p.C || tap >= p.T) return;
-    float* base = p.gw + (p.part_stride > 0 ? (int64_t)(t.q0 / p.kb_per_split) * p.part_stride : 0);
+    if (p.part_stride > 0) {       // deterministic mode: this split's partial, laid out [tap][o][c] so that a warp (32 consecutive c) stores 128 contiguous bytes
+      float* base = p.gw + (int64_t)(t.q0 / p.kb_per_split) * p.part_stride + (int64_t)tap * p.O * p.C + c;
+#pragma unroll
+      for (int j = 0; j < 32; j++) { const int o = t.o0 + c0 + j; if (o < p.O) base[(int64_t)o * p.C] = v[j]; }
+      return;
+    }
 #pragma unroll
     for (int j = 0; j < 32; j++) {
       const int o = t.o0 + c0 + j;
-      if (o < p.O) { float* d = base + ((int64_t)o * p.C + c) * p.T + tap; if (p.part_stride > 0) *d = v[j]; else red_add_f32(d, v[j]); }
+      if (o < p.O) red_add_f32(p.gw + ((int64_t)o * p.C + c) * p.T + tap, v[j]);
     }
   }
 };
@@ -539,7 +544,7 @@ static int wgrad_launch(agb_ctx* ctx, const float* img, const float* g, float* g
   if (part) { p.gw = part; p.part_stride = n; } else { p.part_stride = 0; AGB_TRY(agb_memset0(ctx, gw, (size_t)n * sizeof(float))); }
   dim3 grid((unsigned)gx, (unsigned)gy_, (unsigned)splits);
   AGB_TRY(tc_tile_launch<Pol>(ctx, p, grid));
-  if (part) return agb_reduce_partials(ctx, part, gw, splits, n, n, 0);
+  if (part) return agb_reduce_partials_wgrad(ctx, part, gw, splits, O, C, T);
   return AGB_OK;
 }
 

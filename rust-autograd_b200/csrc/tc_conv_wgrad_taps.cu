@@ -121,7 +121,10 @@ __global__ void __launch_bounds__(224, 1) conv_wgrad_taps_kernel(const __grid_co
 #pragma unroll
             for (int e = 0; e < 32; e++) {
               const int o = o0 + c0 + e;
-              if (o < p.O) { float* d = p.gw + ((int64_t)o * p.C + c) * p.T + tap; if (p.part_stride > 0) d[(int64_t)blockIdx.x * p.part_stride] = v[e]; else red_add_f32(d, v[e]); }
+              if (o < p.O) {
+                if (p.part_stride > 0) p.gw[(int64_t)blockIdx.x * p.part_stride + ((int64_t)tap * p.O + o) * p.C + c] = v[e];      // partials as [tap][o][c]: a warp stores 128 contiguous bytes
+                else red_add_f32(p.gw + ((int64_t)o * p.C + c) * p.T + tap, v[e]);
+              }
             }
           }
         }
@@ -171,6 +174,6 @@ int agb_tc_conv_wgrad_taps(agb_ctx* ctx, const float* img, const float* g, float
   if (!attr) { AGB_CUDA(cudaFuncSetAttribute(conv_wgrad_taps_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024)); attr = true; }
   conv_wgrad_taps_kernel<<<dim3((unsigned)ctas, (unsigned)otiles), 224, smem, ctx->stream>>>(p);
   AGB_LAUNCHED(ctx);
-  if (part) return agb_reduce_partials(ctx, part, gw, (int)ctas, n, n, 0);
+  if (part) return agb_reduce_partials_wgrad(ctx, part, gw, (int)ctas, O, C, p.T);
   return AGB_OK;
 }
