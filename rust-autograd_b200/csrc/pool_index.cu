@@ -326,9 +326,32 @@ __global__ void __launch_bounds__(256) gather_grad_kernel(const float* __restric
     atomicAdd(gx + (p * axis_len + k) * post + q, __ldg(gy + o));
   }
 }
+// rows of >= 4 floats (an embedding table): four values per thread, one 128-bit load and ONE vector reduction (red.global.add.v4.f32, sm_90+) instead of
+// four scalar atomics and four rounds of 64-bit index arithmetic
+__global__ void __launch_bounds__(256) gather_grad_v4_kernel(const float* __restrict__ gy, const float* __restrict__ indices,
+                                                             float* __restrict__ gx, int64_t pre, int64_t axis_len, int64_t post4,
+                                                             int64_t n_idx, int* err) {
+  const int64_t n4 = pre * n_idx * post4;
+  const int64_t gstride = (int64_t)gridDim.x * blockDim.x;
+  for (int64_t o = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; o < n4; o += gstride) {
+    const int64_t q4 = o % post4; const int64_t t = o / post4; const int64_t j = t % n_idx; const int64_t p = t / n_idx;
+    const float f = __ldg(indices + j);
+    int64_t k = (int64_t)f;
+    if (k < 0) k += axis_len;
+    if (k < 0 || k >= axis_len || f != f) { atomicExch(err, 2); continue; }
+    const float4 v = ldg_stream4(gy + 4 * o);
+    float* d = gx + ((p * axis_len + k) * post4 + q4) * 4;
+    asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" :: "l"(d), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w) : "memory");
+  }
+}
 extern "C" int agb_scatter_add(agb_ctx* ctx, const float* gy, const float* indices, float* gx,
                                int64_t pre, int64_t axis_len, int64_t post, int64_t n_idx) {
   int64_t n = pre * n_idx * post; if (n == 0) return AGB_OK;
+  if (post % 4 == 0 && ((((uintptr_t)gy | (uintptr_t)gx) & 15) == 0)) {
+    gather_grad_v4_kernel<<<agb_grid_for(n / 4, 256, ctx->sm_count, 8), 256, 0, ctx->stream>>>(gy, indices, gx, pre, axis_len, post / 4, n_idx, ctx->dev_err);
+    AGB_LAUNCHED(ctx);
+    return AGB_OK;
+  }
   gather_grad_kernel<<<agb_grid_for(n, 256, ctx->sm_count, 8), 256, 0, ctx->stream>>>(gy, indices, gx, pre, axis_len, post, n_idx, ctx->dev_err);
   AGB_LAUNCHED(ctx);
   return AGB_OK;
