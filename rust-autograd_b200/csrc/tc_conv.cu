@@ -533,7 +533,8 @@ static int wgrad_launch(agb_ctx* ctx, const float* img, const float* g, float* g
   p.kb_total = (int)kb_total; p.mnc = agb_mn_cfg();
   const int units = ((C + 127) / 128) * T;
   const int gx = PAIR ? (T + 1) / 2 : (MT == 2 ? (units + 1) / 2 : units), gy_ = (O + TN - 1) / TN;
-  int64_t want = 2ll * ctx->sm_count * Pol::OCC / ((int64_t)gx * gy_); if (want < 1) want = 1;
+  static const int waves_x2 = [] { const char* e = getenv("AGB_WGRAD_WAVES_X2"); int v = e ? atoi(e) : 2; return v < 1 ? 1 : v; }();      // tuning knob: split-K tiles per CTA slot, in halves (measured, 256->256 @32x32: one tile per slot 0.40 ms, two 0.47, one half 0.70)
+  int64_t want = (int64_t)waves_x2 * ctx->sm_count * Pol::OCC / (2 * (int64_t)gx * gy_); if (want < 1) want = 1;
   int64_t per = (kb_total + want - 1) / want; if (per < 16) per = 16; if (per > kb_total) per = kb_total;
   p.kb_per_split = (int)per;
   int splits = (int)((kb_total + per - 1) / per);
