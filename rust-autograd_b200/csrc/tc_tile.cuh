@@ -598,15 +598,25 @@ tc_tile_pair_kernel(const __grid_constant__ typename Pol::Params prm, const uint
       const uint32_t ab = ti & 1;
       mbar_wait(&acc_full[ab], (ti >> 1) & 1);
       tc_fence_after();
+      // software-pipelined drain: the tcgen05.ld of chunk c+1 is in flight while chunk c is stored (ncu on the 128 -> 256 layer: the drain warps were
+      // 94 % busy — the tile's critical path with only 36 k-blocks per tile — and a third of that was LDTM latency), and the accumulator set goes
+      // back to the MMA issuer as soon as its last chunk is in registers, before that chunk's stores
+      {
+        static_assert(TN % 64 == 0, "pair tiles are drained two chunks at a time");
+        const uint32_t tb = tlane + ab * (uint32_t)TN;
+        float va[32], vb[32];
+        tmem_ld32(tb, va);
 #pragma unroll
-      for (int c0 = 0; c0 < TN; c0 += 32) {
-        float v[32];
-        tmem_ld32(tlane + ab * (uint32_t)TN + (uint32_t)c0, v);
-        tmem_ld_wait();
-        Pol::store(prm, tl, 0, row, c0, v, pre[c0 / 32]);
+        for (int c0 = 0; c0 < TN; c0 += 64) {
+          tmem_ld_wait();
+          tmem_ld32(tb + (uint32_t)(c0 + 32), vb);
+          Pol::store(prm, tl, 0, row, c0, va, pre[c0 / 32]);
+          tmem_ld_wait();
+          if (c0 + 64 < TN) tmem_ld32(tb + (uint32_t)(c0 + 64), va);
+          else { tc_fence_before(); mbar_arrive_cluster(ab ? rel1 : rel0); }
+          Pol::store(prm, tl, 0, row, c0 + 32, vb, pre[c0 / 32 + 1]);
+        }
       }
-      tc_fence_before();
-      mbar_arrive_cluster(ab ? rel1 : rel0);
       ti++;
     }
   }
