@@ -471,18 +471,25 @@ tc_tile_persist_kernel(const __grid_constant__ typename Pol::Params prm, const u
       const uint32_t ab = ti % NACC;
       mbar_wait(&acc_full[ab], (ti / NACC) & 1);
       tc_fence_after();
+      {   // software-pipelined drain (see tc_tile_pair_kernel): chunk i + 1 is loaded from TMEM while chunk i is stored
+        constexpr int NCH = MT * (TN / 32);
+        const uint32_t tb = tlane + ab * (uint32_t)(MT * TN);
+        float va[32], vb[32];
+        tmem_ld32(tb, va);
 #pragma unroll
-      for (int mt = 0; mt < MT; mt++) {
-#pragma unroll
-        for (int c0 = 0; c0 < TN; c0 += 32) {
-          float v[32];
-          tmem_ld32(tlane + ab * (uint32_t)(MT * TN) + (uint32_t)(mt * TN + c0), v);
+        for (int i = 0; i < NCH; i += 2) {
           tmem_ld_wait();
-          Pol::store(prm, tl, mt, row, c0, v, pre[mt * (TN / 32) + c0 / 32]);
+          if (i + 1 < NCH) tmem_ld32(tb + (uint32_t)((i + 1) * 32), vb);
+          else { tc_fence_before(); mbar_arrive(&acc_empty[ab]); }
+          Pol::store(prm, tl, i / (TN / 32), row, (i % (TN / 32)) * 32, va, pre[i]);
+          if (i + 1 < NCH) {
+            tmem_ld_wait();
+            if (i + 2 < NCH) tmem_ld32(tb + (uint32_t)((i + 2) * 32), va);
+            else { tc_fence_before(); mbar_arrive(&acc_empty[ab]); }
+            Pol::store(prm, tl, (i + 1) / (TN / 32), row, ((i + 1) % (TN / 32)) * 32, vb, pre[i + 1]);
+          }
         }
       }
-      tc_fence_before();
-      mbar_arrive(&acc_empty[ab]);
       ti++;
     }
   }
