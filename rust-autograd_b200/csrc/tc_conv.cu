@@ -143,11 +143,23 @@ template <int TN_, bool SPLIT_, int MT_ = 1, bool BITS_ = false> struct ConvFpro
     // fused epilogue: per-channel bias and ReLU applied to the accumulator registers, so the
     // pre-activation tensors of conv -> add -> relu never travel through HBM
     float r[32];
+    if (p.bias != nullptr && o + 32 <= p.Cout && ((((uintptr_t)p.bias) & 15) == 0)) {       // eight 128-bit (warp-uniform) loads instead of 32 scalar ones: the drain is
+#pragma unroll                                                                               // the critical path of the short-K layers
+      for (int j = 0; j < 32; j += 4) {
+        const float4 b4 = __ldg((const float4*)(p.bias + o + j));
+        r[j] = v[j] + b4.x; r[j + 1] = v[j + 1] + b4.y; r[j + 2] = v[j + 2] + b4.z; r[j + 3] = v[j + 3] + b4.w;
+      }
+    } else {
 #pragma unroll
-    for (int j = 0; j < 32; j++) {
-      float a = v[j];
-      if (p.bias != nullptr && o + j < p.Cout) a += __ldg(p.bias + o + j);
-      r[j] = p.relu ? fmaxf(a, 0.0f) : a;
+      for (int j = 0; j < 32; j++) {
+        float a = v[j];
+        if (p.bias != nullptr && o + j < p.Cout) a += __ldg(p.bias + o + j);
+        r[j] = a;
+      }
+    }
+    if (p.relu) {
+#pragma unroll
+      for (int j = 0; j < 32; j++) r[j] = fmaxf(r[j], 0.0f);
     }
     if (p.mask != nullptr) {           // gx *= (mask_src > 0); 0*r keeps the NaN/Inf semantics of the un-fused multiply
 #pragma unroll
