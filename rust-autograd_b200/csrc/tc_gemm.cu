@@ -21,15 +21,17 @@
 #include <stdlib.h>
 #include "tc_tile.cuh"
 
-template <int TN_, bool P_MN_, bool Q_MN_, bool SPLIT_, bool QPRE_ = false> struct GemmPol {
-  static constexpr int TN = TN_, MT = 1; static constexpr bool SPLIT = SPLIT_, P_MN = P_MN_, Q_MN = Q_MN_, Q_PRESPLIT = QPRE_;
+template <int TN_, bool P_MN_, bool Q_MN_, bool SPLIT_, bool QPRE_ = false, bool PPRE_ = false> struct GemmPol {
+  static constexpr int TN = TN_, MT = 1; static constexpr bool SPLIT = SPLIT_, P_MN = P_MN_, Q_MN = Q_MN_, Q_PRESPLIT = QPRE_, P_PRESPLIT = PPRE_;
+  static_assert(!PPRE_ || QPRE_, "a pre-split P comes with a pre-split Q (no splitter warps at all)");
   static constexpr int OCC = (SPLIT_ || TN_ > 128) ? 1 : 2;
   static constexpr bool PAIR2 = !SPLIT_ && TN_ == 256;       // CTA pairs: tmQlo = the Q map with TN / 2 rows per box
-  static constexpr bool SPLIT_PAIR2 = SPLIT_ && QPRE_ && TN_ == 128;      // 3xTF32 CTA pairs: tmQh / tmQlh = half-height boxes of the hi / lo planes
+  static constexpr bool SPLIT_PAIR2 = SPLIT_ && QPRE_ && !PPRE_ && TN_ == 128;      // 3xTF32 CTA pairs: tmQh / tmQlh = half-height boxes of the hi / lo planes
   // splits > 1: split-K for problems with too few output tiles to fill the machine (e.g. the LSTM's 128 x 1024 x 8192 dgrad GEMM is
   // 8 tiles): grid.z = batch * splits, every CTA reduces kb_per_split k-blocks and adds its partial with red.global.add (C pre-zeroed)
   struct Params { CUtensorMap tmP, tmQ, tmQlo /* 3xTF32: lo plane; CTA pairs: half-height Q boxes */, tmQh, tmQlh; float* C; int NL, NC, K; int64_t ldc, bsc; int accumulate; int splits, kb_per_split; MnDescCfg mnc; int64_t part_stride /* > 0: split ks stores its partial at C + ks * part_stride (deterministic mode) */;
-                  CUtensorMap tmPw, tmQw; int widep, wideq; };      // MN-major operand with rows % 32 == 0: the row axis as {32, blocks}, ONE box per tile instead of one per 32 rows
+                  CUtensorMap tmPw, tmQw; int widep, wideq;
+                  CUtensorMap tmPlo, tmPwlo; };     // 3xTF32 with P pre-split in global memory: tmP / tmPw address the hi plane, these the lo plane      // MN-major operand with rows % 32 == 0: the row axis as {32, blocks}, ONE box per tile instead of one per 32 rows
   struct Tile { int lane0, col0, bz, kb0, nkb, ks; };
   __device__ static Tile tile(const Params& p, uint3 blk) {
     const int kb_total = (p.K + TC_BK - 1) / TC_BK;
@@ -39,19 +41,23 @@ template <int TN_, bool P_MN_, bool Q_MN_, bool SPLIT_, bool QPRE_ = false> stru
   }
   __device__ static int num_kblocks(const Params&, const Tile& t) { return t.nkb; }
   __device__ static uint32_t p_bytes(const Params&, uint32_t full) { return full; }
-  __device__ static void prefetch(const Params& p) { tma_prefetch_desc(&p.tmP); tma_prefetch_desc(&p.tmQ); if (QPRE_) tma_prefetch_desc(&p.tmQlo); }
+  __device__ static void prefetch(const Params& p) { tma_prefetch_desc(&p.tmP); tma_prefetch_desc(&p.tmQ); if (QPRE_) tma_prefetch_desc(&p.tmQlo); if (PPRE_) tma_prefetch_desc(&p.tmPlo); }
   __device__ static void load_q(const CUtensorMap* tm, const Tile& t, int kb, uint8_t* pQ, uint64_t* bar) {
     const int k0 = (t.kb0 + kb) * TC_BK;
     if (Q_MN) { for (int j = 0; j < TN / 32; j++) tma_load_3d(pQ + j * 4096, tm, bar, t.col0 + 32 * j, k0, t.bz); }
     else tma_load_3d(pQ, tm, bar, k0, t.col0, t.bz);
   }
+  __device__ static void load_p(const CUtensorMap* tm, const CUtensorMap* tmw, int wide, const Tile& t, int k0, uint8_t* pP, uint64_t* bar) {
+    if (P_MN) {
+      if (wide) tma_load_4d(pP, tmw, bar, 0, k0, t.lane0 >> 5, t.bz);
+      else for (int j = 0; j < TC_LANES / 32; j++) tma_load_3d(pP + j * 4096, tm, bar, t.lane0 + 32 * j, k0, t.bz);
+    }
+    else tma_load_3d(pP, tm, bar, k0, t.lane0, t.bz);
+  }
+  __device__ static void load_p_lo(const Params& p, const Tile& t, int kb, uint8_t* pPlo, uint64_t* bar) { load_p(&p.tmPlo, &p.tmPwlo, p.widep, t, (t.kb0 + kb) * TC_BK, pPlo, bar); }
   __device__ static void load(const Params& p, const Tile& t, int kb, uint8_t* pP, uint8_t* pQ, uint64_t* bar) {
     const int k0 = (t.kb0 + kb) * TC_BK;
-    if (P_MN) {
-      if (p.widep) tma_load_4d(pP, &p.tmPw, bar, 0, k0, t.lane0 >> 5, t.bz);
-      else for (int j = 0; j < TC_LANES / 32; j++) tma_load_3d(pP + j * 4096, &p.tmP, bar, t.lane0 + 32 * j, k0, t.bz);
-    }
-    else tma_load_3d(pP, &p.tmP, bar, k0, t.lane0, t.bz);
+    load_p(&p.tmP, &p.tmPw, p.widep, t, k0, pP, bar);
     if (Q_MN && p.wideq) tma_load_4d(pQ, &p.tmQw, bar, 0, k0, t.col0 >> 5, t.bz);
     else load_q(&p.tmQ, t, kb, pQ, bar);
   }
@@ -118,7 +124,7 @@ static int tc_make_map(CUtensorMap* m, const TcOperand& o, int64_t K, int64_t ba
 
 struct TcHalfMaps { CUtensorMap hi, lo; };
 // wide maps of the MN-major operands of the current agb_tc_gemm call (set before the dispatch, read by tc_launch; single pass only)
-struct TcWide { CUtensorMap p, q; int hp = 0, hq = 0; };
+struct TcWide { CUtensorMap p, q, plo; int hp = 0, hq = 0; };
 static thread_local TcWide g_tc_wide;
 static int tc_make_wide_map(CUtensorMap* m, const TcOperand& o, int64_t K, int64_t batch, int box_rows) {
   uint64_t dims[4] = {32, (uint64_t)K, (uint64_t)(o.rows / 32), (uint64_t)batch};
@@ -127,10 +133,10 @@ static int tc_make_wide_map(CUtensorMap* m, const TcOperand& o, int64_t K, int64
   uint32_t box[4] = {32, TC_BK, (uint32_t)(box_rows / 32), 1};
   return agb_make_tmap(m, o.p, 4, dims, str, box, true);
 }       // 3xTF32 CTA pairs: TN / 2-row boxes of the pre-split Q planes
-template <int TN, bool P_MN, bool Q_MN, bool SPLIT, bool QPRE = false>
+template <int TN, bool P_MN, bool Q_MN, bool SPLIT, bool QPRE = false, bool PPRE = false>
 static int tc_launch(agb_ctx* ctx, const CUtensorMap& tmP, const CUtensorMap& tmQ, const CUtensorMap* tmQlo, float* C, int NL, int NC, int K, int64_t ldc, int64_t bsc,
-                     int64_t batch, int accumulate, const TcHalfMaps* half = nullptr) {
-  using Pol = GemmPol<TN, P_MN, Q_MN, SPLIT, QPRE>;
+                     int64_t batch, int accumulate, const TcHalfMaps* half = nullptr, const CUtensorMap* tmPlo = nullptr) {
+  using Pol = GemmPol<TN, P_MN, Q_MN, SPLIT, QPRE, PPRE>;
   const int gx = (NL + TC_LANES - 1) / TC_LANES, gy = (NC + TN - 1) / TN;
   const int kb_total = (K + TC_BK - 1) / TC_BK;
   // split-K when the output tiles cannot fill the machine and there is K to share (>= 4 k-blocks per split)
@@ -153,6 +159,7 @@ static int tc_launch(agb_ctx* ctx, const CUtensorMap& tmP, const CUtensorMap& tm
   typename Pol::Params prm{tmP, tmQ, tmQlo ? *tmQlo : tmQ, half ? half->hi : tmQ, half ? half->lo : tmQ, part ? part : C, NL, NC, K, ldc, bsc, accumulate, splits, kb_per, agb_mn_cfg(), part ? cn : 0};
   prm.widep = 0; prm.wideq = 0; prm.tmPw = tmP; prm.tmQw = tmQ;
   if (P_MN && g_tc_wide.hp) { prm.tmPw = g_tc_wide.p; prm.widep = 1; }
+  prm.tmPlo = tmPlo ? *tmPlo : tmP; prm.tmPwlo = (PPRE && prm.widep) ? g_tc_wide.plo : prm.tmPw;
   if (Q_MN && g_tc_wide.hq && !QPRE) { prm.tmQw = g_tc_wide.q; prm.wideq = 1; }      // (a pre-split Q comes from its hi / lo planes)
   dim3 grid(gx, gy, (unsigned)(batch * splits));
   AGB_TRY(tc_tile_launch<Pol>(ctx, prm, grid));
@@ -160,13 +167,13 @@ static int tc_launch(agb_ctx* ctx, const CUtensorMap& tmP, const CUtensorMap& tm
   return AGB_OK;
 }
 
-template <int TN, bool SPLIT, bool QPRE = false>
+template <int TN, bool SPLIT, bool QPRE = false, bool PPRE = false>
 static int tc_dispatch_major(agb_ctx* ctx, bool pmn, bool qmn, const CUtensorMap& tmP, const CUtensorMap& tmQ, const CUtensorMap* tmQlo, float* C, int NL, int NC, int K,
-                             int64_t ldc, int64_t bsc, int64_t batch, int acc, const TcHalfMaps* half = nullptr) {
-  if (!pmn && !qmn) return tc_launch<TN, false, false, SPLIT, QPRE>(ctx, tmP, tmQ, tmQlo, C, NL, NC, K, ldc, bsc, batch, acc, half);
-  if (!pmn && qmn) return tc_launch<TN, false, true, SPLIT, QPRE>(ctx, tmP, tmQ, tmQlo, C, NL, NC, K, ldc, bsc, batch, acc, half);
-  if (pmn && !qmn) return tc_launch<TN, true, false, SPLIT, QPRE>(ctx, tmP, tmQ, tmQlo, C, NL, NC, K, ldc, bsc, batch, acc, half);
-  return tc_launch<TN, true, true, SPLIT, QPRE>(ctx, tmP, tmQ, tmQlo, C, NL, NC, K, ldc, bsc, batch, acc, half);
+                             int64_t ldc, int64_t bsc, int64_t batch, int acc, const TcHalfMaps* half = nullptr, const CUtensorMap* tmPlo = nullptr) {
+  if (!pmn && !qmn) return tc_launch<TN, false, false, SPLIT, QPRE, PPRE>(ctx, tmP, tmQ, tmQlo, C, NL, NC, K, ldc, bsc, batch, acc, half, tmPlo);
+  if (!pmn && qmn) return tc_launch<TN, false, true, SPLIT, QPRE, PPRE>(ctx, tmP, tmQ, tmQlo, C, NL, NC, K, ldc, bsc, batch, acc, half, tmPlo);
+  if (pmn && !qmn) return tc_launch<TN, true, false, SPLIT, QPRE, PPRE>(ctx, tmP, tmQ, tmQlo, C, NL, NC, K, ldc, bsc, batch, acc, half, tmPlo);
+  return tc_launch<TN, true, true, SPLIT, QPRE, PPRE>(ctx, tmP, tmQ, tmQlo, C, NL, NC, K, ldc, bsc, batch, acc, half, tmPlo);
 }
 
 // 3xTF32: hi = rna_tf32(x), lo = rna_tf32(x - hi) planes of a dense operand, written once to scratch when the operand is re-read by
@@ -249,14 +256,33 @@ int agb_tc_gemm(agb_ctx* ctx, int mode, const float* A, const float* B, float* C
     const int64_t qn = M * K * batch;
     const bool q_dense = qn % 4 == 0 && (batch == 1 || Q.bs == M * K) && (qmn ? (Q.ks == M) : (Q.rs == K));
     if (q_dense && N >= 512 && qn <= (1ll << 31) && pad_base == nullptr) {
+      // P = op(B)^T is re-read by every one of the M/TN column tiles: with M large it is pre-split too (hi = rna_tf32, lo planes), the kernel then has
+      // no splitter work at all and its shared memory carries only the TMA writes and the MMA reads (this mode is bound by shared-memory bandwidth)
+      const int64_t pn = N * K * batch;
+      const bool p_dense = pn % 4 == 0 && (batch == 1 || P.bs == N * K) && (pmn ? (P.ks == N) : (P.rs == K));
+      static const int ppre_env = [] { const char* e = getenv("AGB_GEMM_PPRE"); return (e && e[0] == '0') ? 0 : 1; }();
+      const bool ppre = ppre_env && p_dense && M >= 512 && pn <= (1ll << 28);
       float* planes = nullptr;
-      AGB_TRY(agb_scratch(ctx, (size_t)qn * 2 * sizeof(float), (void**)&planes));
+      AGB_TRY(agb_scratch(ctx, (size_t)(qn * 2 + (ppre ? pn * 2 : 0)) * sizeof(float), (void**)&planes));
       presplit_kernel<<<agb_grid_for(qn / 4, 256, ctx->sm_count, 8), 256, 0, ctx->stream>>>((const float4*)A, (float4*)planes, (float4*)(planes + qn), qn / 4);
       AGB_LAUNCHED(ctx);
-      CUtensorMap tmQh, tmQl;
+      CUtensorMap tmQh, tmQl, tmPh, tmPl;
       TcOperand Qh = Q, Ql = Q; Qh.p = planes; Ql.p = planes + qn;
       r = tc_make_map(&tmQh, Qh, K, batch, qmn, TN); if (r != AGB_OK) return r;
       r = tc_make_map(&tmQl, Ql, K, batch, qmn, TN); if (r != AGB_OK) return r;
+      if (ppre) {
+        float* pp = planes + 2 * qn;
+        presplit_kernel<<<agb_grid_for(pn / 4, 256, ctx->sm_count, 8), 256, 0, ctx->stream>>>((const float4*)B, (float4*)pp, (float4*)(pp + pn), pn / 4);
+        AGB_LAUNCHED(ctx);
+        TcOperand Ph = P, Pl = P; Ph.p = pp; Pl.p = pp + pn;
+        r = tc_make_map(&tmPh, Ph, K, batch, pmn, TC_LANES); if (r != AGB_OK) return r;
+        r = tc_make_map(&tmPl, Pl, K, batch, pmn, TC_LANES); if (r != AGB_OK) return r;
+        if (g_tc_wide.hp) {      // the wide (one box per tile) maps of the MN-major planes
+          if (tc_make_wide_map(&g_tc_wide.p, Ph, K, batch, TC_LANES) != AGB_OK || tc_make_wide_map(&g_tc_wide.plo, Pl, K, batch, TC_LANES) != AGB_OK) g_tc_wide.hp = 0;
+        }
+        if (TN == 128) return tc_dispatch_major<128, true, true, true>(ctx, pmn, qmn, tmPh, tmQh, &tmQl, C, (int)N, (int)M, (int)K, N, bsc, batch, acc, nullptr, &tmPl);
+        return tc_dispatch_major<64, true, true, true>(ctx, pmn, qmn, tmPh, tmQh, &tmQl, C, (int)N, (int)M, (int)K, N, bsc, batch, acc, nullptr, &tmPl);
+      }
       if (TN == 128) {
         TcHalfMaps half;
         r = tc_make_map(&half.hi, Qh, K, batch, qmn, TN / 2); if (r != AGB_OK) return r;

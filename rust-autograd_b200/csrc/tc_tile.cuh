@@ -12,10 +12,13 @@
 //               difference) to a second buffer — one read and ONE write per element, the tile engine's scarce resource in this mode
 //               being shared-memory bandwidth (an N = 128 MMA already reads 128 B/clk).  An operand that is tiny and re-read by many
 //               CTAs (a convolution's repacked filter) arrives pre-split instead: Pol::Q_PRESPLIT, its lo plane is a second TMA load.
-//               The issuer runs lo*hi + hi*lo into one accumulator and hi*hi into another (dropped lo*lo ~ 2^-22): the tensor core
-//               truncates on every accumulate, so keeping the small cross terms out of the main sum leaves it one truncation per
-//               K = 8 step instead of three (measured bias on positive operands, relative to the sum: -2.4e-6 with everything in one
-//               accumulator and 256-k chunks, -1.1e-6 with 64-k chunks; scripts/bias_probe.py)
+//               A dense GEMM operand that many tiles re-read is pre-split the same way (tc_gemm.cu); with both sides pre-split the splitters idle.
+//               The lo plane of Q lies directly behind Q in the stage, so the issuer runs ONE N = 2 TN instruction P.[Q | Q_lo] (hi*hi in TMEM
+//               columns [0, TN), hi*lo in [TN, 2 TN)) and one N = TN instruction P_lo.Q into [TN, 2 TN): P is read from shared memory twice per
+//               k-step instead of three times (20 instead of 24 KB for TN = 128) — shared-memory bandwidth is what bounds this mode (dropped lo*lo
+//               ~ 2^-22).  The tensor core truncates on every accumulate, so keeping the small cross terms out of the main sum leaves it one
+//               truncation per K = 8 step instead of three (measured bias on positive operands, relative to the sum: -2.4e-6 with everything in
+//               one accumulator and 256-k chunks, -1.1e-6 with 64-k chunks; scripts/bias_probe.py)
 //   last 4      drain/epilogue: `tcgen05.ld` the accumulator and hand 32-column strips to the Policy's store functor
 //
 // fp32-faithful accumulation (SPLIT): the tensor core adds into the TMEM accumulator with truncation, which biases long
@@ -23,9 +26,10 @@
 // and the two small cross terms of 3xTF32 pay it too).  The bias is coherent across output elements, so a reduction over the
 // GEMM's output (a bias gradient summing 1024 rows) accumulates it: with 256-k chunks the LSTM LM's bias gradient was 1.1e-4 off
 // the oracle while every GEMM output was within 1e-5.  The 3xTF32 mode therefore accumulates at most TC_KC k-blocks (64 k = 24
-// MMAs) per TMEM buffer, ping-pongs two buffers, and the drain warps add each finished chunk into fp32 registers with
-// round-to-nearest CUDA-core adds while the tensor core works on the other buffer.
+// MMAs) per TMEM buffer set (2 TN columns: main and cross sums), ping-pongs two sets, and the drain warps add each finished chunk into
+// fp32 registers with round-to-nearest CUDA-core adds while the tensor core works on the other set.
 #pragma once
+#include <type_traits>
 #include "tc_common.cuh"
 
 #define TC_LANES 128
@@ -167,18 +171,24 @@ __global__ void __launch_bounds__(TcCfg<Pol::TN, false, Pol::OCC, Pol::MT>::THRE
 
 // ------------------------------------------------------------------------------------------------ 3xTF32 (f32-faithful) persistent kernel
 // Warps: 0 TMA producer, 1 MMA issuer, 2-5 splitters, 6-9 drain.  Persistent over the logical grid like tc_tile_persist_kernel; the two
-// TMEM accumulator buffers ping-pong per CHUNK (TC_KC k-blocks), the chunk counter runs on across tiles, and the drain warps keep the
+// TMEM accumulator sets ([main | cross], 2 TN columns each) ping-pong per CHUNK (TC_KC k-blocks), the chunk counter runs on across tiles, and the drain warps keep the
 // tile's fp32 partial sums in registers (TN <= 128) until its last chunk, then run the Policy's epilogue while the issuer already works
 // on the next tile's first two chunks.
+template <class Pol, class = void> struct tc_p_presplit { static constexpr bool value = false; };
+template <class Pol> struct tc_p_presplit<Pol, std::enable_if_t<Pol::P_PRESPLIT || !Pol::P_PRESPLIT>> { static constexpr bool value = Pol::P_PRESPLIT; };
 template <class Pol>
-__global__ void __launch_bounds__(320, 1) tc_tile_split_kernel(const __grid_constant__ typename Pol::Params prm, const uint3 lgrid, const int kc /* k-blocks per TMEM chunk */, const int order, const int poll /* 1: one lane per warp polls */, const int nstages) {
+__global__ void __launch_bounds__(320, 1) tc_tile_split_kernel(const __grid_constant__ typename Pol::Params prm, const uint3 lgrid, const int kc /* k-blocks per TMEM chunk */, const int poll /* 1: one lane per warp polls */, const int nstages) {
   constexpr int TN = Pol::TN; constexpr bool P_MN = Pol::P_MN, Q_MN = Pol::Q_MN;
   static_assert(Pol::SPLIT && Pol::MT == 1 && TN <= 128, "3xTF32: one M-tile, TN fp32 partial sums per drain thread");
   constexpr bool QPRE = Pol::Q_PRESPLIT;                 // Q's lo plane comes from global memory (second TMA load), only P is split here
+  constexpr bool PPRE = tc_p_presplit<Pol>::value;       // P's planes too (Pol::load_p_lo): the splitter warps idle and the issuer waits for the TMA itself
+  static_assert(!PPRE || QPRE, "P pre-split implies Q pre-split");
   using Cfg = TcCfg<TN, true, 1, 1>;
   constexpr int SMAX = Cfg::STAGES;
   const int S = nstages > 0 && nstages < SMAX ? nstages : SMAX;
-  constexpr int LO_OFF = Cfg::P_BYTES + Cfg::Q_BYTES;    // stage = [P | Q | P_lo | Q_lo]
+  // stage = [P | Q | Q_lo | P_lo]: Q_lo directly behind Q, so ONE N = 2 TN instruction computes P.[Q | Q_lo] (the hi*hi sums and one cross term
+  // side by side in TMEM) and P is read from shared memory twice per k-step instead of three times — this mode is bound by shared-memory bandwidth
+  constexpr int QLO_OFF = Cfg::P_BYTES + Cfg::Q_BYTES, PLO_OFF = Cfg::P_BYTES + 2 * Cfg::Q_BYTES;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
   uint64_t* bars = (uint64_t*)(smem + SMAX * Cfg::STAGE_BYTES);
@@ -211,60 +221,46 @@ __global__ void __launch_bounds__(320, 1) tc_tile_split_kernel(const __grid_cons
         for (int kb = 0; kb < nk; kb++) {
           mbar_wait(&empty[s], ph ^ 1);
           uint8_t* st = smem + s * Cfg::STAGE_BYTES;
-          mbar_expect_tx(&full[s], Pol::p_bytes(prm, Cfg::P_BYTES) + Cfg::Q_BYTES * (QPRE ? 2 : 1));
+          mbar_expect_tx(&full[s], Pol::p_bytes(prm, Cfg::P_BYTES) * (PPRE ? 2 : 1) + Cfg::Q_BYTES * (QPRE ? 2 : 1));
           Pol::load(prm, tl, kb, st, st + Cfg::P_BYTES, &full[s]);
-          if constexpr (QPRE) Pol::load_q_lo(prm, tl, kb, st + LO_OFF + Cfg::P_BYTES, &full[s]);
+          if constexpr (QPRE) Pol::load_q_lo(prm, tl, kb, st + QLO_OFF, &full[s]);
+          if constexpr (PPRE) Pol::load_p_lo(prm, tl, kb, st + PLO_OFF, &full[s]);
           if (++s == S) { s = 0; ph ^= 1; }
         }
       }
     }
   } else if (warp == 1) {
     // ===================== MMA issuer (converged warp, elected lane; see tc_tile_kernel) =====================
-    constexpr uint32_t idesc = umma_idesc_tf32(TC_LANES, TN, P_MN ? 1 : 0, Q_MN ? 1 : 0);
+    constexpr uint32_t idesc = umma_idesc_tf32(TC_LANES, TN, P_MN ? 1 : 0, Q_MN ? 1 : 0);            // P_lo . Q
+    constexpr uint32_t idesc2 = umma_idesc_tf32(TC_LANES, 2 * TN, P_MN ? 1 : 0, Q_MN ? 1 : 0);       // P . [Q | Q_lo]
     const MnDescCfg mnc = prm.mnc;
     const uint32_t hiK = (1024u >> 4) | (1u << 14) | (2u << 29), loK = (16u >> 4) << 16, stepK = 32u >> 4;
     const uint32_t hiM = (mnc.sbo >> 4) | (1u << 14) | (mnc.layout << 29), loM = (mnc.lbo >> 4) << 16, stepM = mnc.kadv >> 4;
     const uint32_t hiP = P_MN ? hiM : hiK, loP = P_MN ? loM : loK, stepP = P_MN ? stepM : stepK;
     const uint32_t hiQ = Q_MN ? hiM : hiK, loQ = Q_MN ? loM : loK, stepQ = Q_MN ? stepM : stepK;
     const uint32_t smem0 = smem_u32(smem) >> 4;
-    int s = 0; uint32_t ph = 0, ch = 0, ti = 0;          // ch: chunks issued so far by this CTA (all tiles); ti: tiles
+    int s = 0; uint32_t ph = 0, ch = 0;                  // ch: chunks issued so far by this CTA (all tiles)
     for (uint32_t t = blockIdx.x; t < total; t += gridDim.x) {
       const typename Pol::Tile tl = Pol::tile(prm, blk_of(t));
       const int nk = Pol::num_kblocks(prm, tl);
       if (nk <= 0) continue;
-      // TMEM: [main 0 | main 1 | cross 0 | cross 1].  The hi*hi sums ping-pong per chunk; the cross-term sums (2^-11 of the magnitude:
-      // their truncation does not matter) run over the whole tile, one buffer per tile parity.  No barrier of their own: the drain reads
-      // cross(t) before it releases the tile's last main chunk, and tile t+2 cannot start before that release.
-      const uint32_t tcross = tmem_base + (uint32_t)((2 + (ti & 1)) * TN);
-      ti++;
+      // TMEM: two accumulator sets of 2 TN columns, ping-ponged per chunk: [hi*hi | hi*lo + lo*hi].  The cross-term sums are 2^-11 of the
+      // magnitude; they are promoted to the fp32 registers with their chunk like the main sums.
       for (int kb = 0; kb < nk; kb++) {
         const bool first = (kb % kc) == 0, last = (kb % kc) == kc - 1 || kb == nk - 1;
         const uint32_t buf = ch & 1;
         if (first) { mbar_wait(&acc_empty[buf], ((ch >> 1) & 1) ^ 1); tc_fence_after(); }
-        mbar_wait(&ready[s], ph);
+        mbar_wait(PPRE ? &full[s] : &ready[s], ph);
         tc_fence_after();
         if (elect_one()) {
-          const uint32_t tacc = tmem_base + buf * (uint32_t)TN;
+          const uint32_t tacc = tmem_base + buf * (uint32_t)(2 * TN);
           const uint32_t st = smem0 + (uint32_t)s * (Cfg::STAGE_BYTES >> 4);
-          const uint32_t aP = st + loP, aQ = st + (Cfg::P_BYTES >> 4) + loQ;
-          const uint32_t aPl = aP + (LO_OFF >> 4), aQl = aQ + (LO_OFF >> 4);
-          if (order == 0) {
+          const uint32_t aP = st + loP, aQ = st + (Cfg::P_BYTES >> 4) + loQ, aPl = aP + (PLO_OFF >> 4);
 #pragma unroll
-            for (int k = 0; k < TC_BK / 8; k++) {
-              const uint64_t dP = umma_desc_pack(aP + k * stepP, hiP), dQ = umma_desc_pack(aQ + k * stepQ, hiQ);
-              const uint64_t dPl = umma_desc_pack(aPl + k * stepP, hiP), dQl = umma_desc_pack(aQl + k * stepQ, hiQ);
-              umma_tf32(tcross, dPl, dQ, idesc, !(kb == 0 && k == 0));
-              umma_tf32(tcross, dP, dQl, idesc, 1);
-              umma_tf32(tacc, dP, dQ, idesc, !(first && k == 0));
-            }
-          } else {
-#pragma unroll
-            for (int k = 0; k < TC_BK / 8; k++) umma_tf32(tacc, umma_desc_pack(aP + k * stepP, hiP), umma_desc_pack(aQ + k * stepQ, hiQ), idesc, !(first && k == 0));
-#pragma unroll
-            for (int k = 0; k < TC_BK / 8; k++) {
-              umma_tf32(tcross, umma_desc_pack(aPl + k * stepP, hiP), umma_desc_pack(aQ + k * stepQ, hiQ), idesc, !(kb == 0 && k == 0));
-              umma_tf32(tcross, umma_desc_pack(aP + k * stepP, hiP), umma_desc_pack(aQl + k * stepQ, hiQ), idesc, 1);
-            }
+          for (int k = 0; k < TC_BK / 8; k++) {
+            const uint64_t dP = umma_desc_pack(aP + k * stepP, hiP), dQ = umma_desc_pack(aQ + k * stepQ, hiQ), dPl = umma_desc_pack(aPl + k * stepP, hiP);
+            umma_tf32(tacc, dP, dQ, idesc2, !(first && k == 0));          // columns [0, TN): P.Q, [TN, 2 TN): P.Q_lo (Q_lo's rows follow Q's at the same pitch)
+            umma_tf32(tacc + (uint32_t)TN, dPl, dQ, idesc, 1);            // += P_lo.Q
           }
           umma_commit(&empty[s]);
           if (last) umma_commit(&acc_full[buf]);
@@ -278,13 +274,13 @@ __global__ void __launch_bounds__(320, 1) tc_tile_split_kernel(const __grid_cons
     // ===================== splitters =====================
     const int tid = threadIdx.x - 64;        // 0..127
     int s = 0; uint32_t ph = 0;
-    for (uint32_t t = blockIdx.x; t < total; t += gridDim.x) {
+    for (uint32_t t = blockIdx.x; !PPRE && t < total; t += gridDim.x) {
       const typename Pol::Tile tl = Pol::tile(prm, blk_of(t));
       const int nk = Pol::num_kblocks(prm, tl);
       for (int kb = 0; kb < nk; kb++) {
         if (poll) mbar_wait_warp(&full[s], ph); else mbar_wait(&full[s], ph);
         float4* hi = (float4*)(smem + s * Cfg::STAGE_BYTES);
-        float4* lo = (float4*)(smem + s * Cfg::STAGE_BYTES + LO_OFF);
+        float4* plo = (float4*)(smem + s * Cfg::STAGE_BYTES + PLO_OFF);
         constexpr int NP4 = Cfg::P_BYTES / 16, NQ4 = Cfg::Q_BYTES / 16;
 #pragma unroll 4
         for (int i = tid; i < NP4; i += 128) {             // P: one read, one write (the hardware truncates the raw tile to hi)
@@ -293,17 +289,17 @@ __global__ void __launch_bounds__(320, 1) tc_tile_split_kernel(const __grid_cons
           l.y = tf32_rna(x.y - __uint_as_float(__float_as_uint(x.y) & 0xFFFFE000u));
           l.z = tf32_rna(x.z - __uint_as_float(__float_as_uint(x.z) & 0xFFFFE000u));
           l.w = tf32_rna(x.w - __uint_as_float(__float_as_uint(x.w) & 0xFFFFE000u));
-          lo[i] = l;
+          plo[i] = l;
         }
         if constexpr (!QPRE) {
           // Q: rounded hi written back + signed lo.  P's lo always has the sign of its value (truncation), so with a truncated Q the dropped
           // lo*lo term would have the sign of the product — a coherent 2^-22 bias toward zero; a round-to-nearest split on ONE side removes it.
 #pragma unroll 4
-          for (int i = NP4 + tid; i < NP4 + NQ4; i += 128) {
+          for (int i = NP4 + tid; i < NP4 + NQ4; i += 128) {          // Q_lo sits NQ4 float4 behind Q
             const float4 x = hi[i]; float4 h, l;
             h.x = tf32_rna(x.x); h.y = tf32_rna(x.y); h.z = tf32_rna(x.z); h.w = tf32_rna(x.w);
             l.x = tf32_rna(x.x - h.x); l.y = tf32_rna(x.y - h.y); l.z = tf32_rna(x.z - h.z); l.w = tf32_rna(x.w - h.w);
-            hi[i] = h; lo[i] = l;
+            hi[i] = h; hi[i + NQ4] = l;
           }
         }
         fence_proxy_async();               // generic-proxy writes -> visible to the tensor core (async proxy)
@@ -316,7 +312,7 @@ __global__ void __launch_bounds__(320, 1) tc_tile_split_kernel(const __grid_cons
     const int q = warp & 3;
     const int row = 32 * q + lane;
     const uint32_t tlane = tmem_base + ((uint32_t)(32 * q) << 16);
-    uint32_t ch = 0, ti = 0;
+    uint32_t ch = 0;
     for (uint32_t t = blockIdx.x; t < total; t += gridDim.x) {
       const typename Pol::Tile tl = Pol::tile(prm, blk_of(t));
       const int nk = Pol::num_kblocks(prm, tl);
@@ -327,29 +323,18 @@ __global__ void __launch_bounds__(320, 1) tc_tile_split_kernel(const __grid_cons
 #pragma unroll
       for (int j = 0; j < TN; j++) racc[j] = 0.0f;
       const int nchunks = (nk + kc - 1) / kc;
-      const uint32_t tcross = tlane + (uint32_t)((2 + (ti & 1)) * TN);
-      ti++;
       for (int c = 0; c < nchunks; c++, ch++) {
         const uint32_t buf = ch & 1;
         if (poll) mbar_wait_warp(&acc_full[buf], (ch >> 1) & 1); else mbar_wait(&acc_full[buf], (ch >> 1) & 1);
         tc_fence_after();
+        const uint32_t tacc = tlane + buf * (uint32_t)(2 * TN);
 #pragma unroll
-        for (int c0 = 0; c0 < TN; c0 += 32) {
+        for (int c0 = 0; c0 < 2 * TN; c0 += 32) {        // the chunk's hi*hi sums, then its cross-term sums: both added to the fp32 registers
           float v[32];
-          tmem_ld32(tlane + buf * (uint32_t)TN + (uint32_t)c0, v);
+          tmem_ld32(tacc + (uint32_t)c0, v);
           tmem_ld_wait();
 #pragma unroll
-          for (int j = 0; j < 32; j++) racc[c0 + j] += v[j];
-        }
-        if (c == nchunks - 1) {            // the tile's cross-term sums, complete with the last chunk (same commit)
-#pragma unroll
-          for (int c0 = 0; c0 < TN; c0 += 32) {
-            float v[32];
-            tmem_ld32(tcross + (uint32_t)c0, v);
-            tmem_ld_wait();
-#pragma unroll
-            for (int j = 0; j < 32; j++) racc[c0 + j] += v[j];
-          }
+          for (int j = 0; j < 32; j++) racc[(c0 & (TN - 1)) + j] += v[j];
         }
         tc_fence_before();
         mbar_arrive(&acc_empty[buf]);
@@ -841,10 +826,9 @@ static int tc_tile_launch(agb_ctx* ctx, const typename Pol::Params& prm, dim3 gr
       }
     }
     static const int kc = [] { const char* e = getenv("AGB_SPLIT_KC"); int v = e ? atoi(e) : TC_KC; return v < 1 ? 1 : v; }();      // tuning knob: k-blocks per TMEM accumulation chunk
-    static const int order = [] { const char* e = getenv("AGB_SPLIT_ORDER"); return e ? atoi(e) : 0; }();
     static const int poll = [] { const char* e = getenv("AGB_SPLIT_POLL"); return e ? atoi(e) : 1; }();
     static const int nst = [] { const char* e = getenv("AGB_SPLIT_STAGES"); return e ? atoi(e) : 0; }();
-    tc_tile_split_kernel<Pol><<<n, 320, Cfg::SMEM, ctx->stream>>>(prm, make_uint3(grid.x, grid.y, grid.z), kc, order, poll, nst);
+    tc_tile_split_kernel<Pol><<<n, 320, Cfg::SMEM, ctx->stream>>>(prm, make_uint3(grid.x, grid.y, grid.z), kc, poll, nst);
     AGB_LAUNCHED(ctx);
     return AGB_OK;
   } else {
