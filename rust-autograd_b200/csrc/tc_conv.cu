@@ -352,9 +352,10 @@ static int fprop_launch_impl(agb_ctx* ctx, const float* x, const float* wr, floa
 template <int TN, bool SPLIT, int MT = 1>
 static int fprop_launch(agb_ctx* ctx, const float* x, const float* wr, float* y, int B, int Cin, int H, int W, int Cout, int yh, int yw, int kh, int kw,
                         int pad, int dil, const float* bias, int relu, const float* mask, float* csum, int stride = 1, const ConvPhase* ph = nullptr) {
-  // the sign-bit instantiation exists for the single-pass (TF32) one-M-tile kernels only
-  const bool bits = !SPLIT && MT == 1 && Cout % 32 == 0 && ph == nullptr && ((mask != nullptr && ctx->mask_bits != nullptr) || ctx->bits_out != nullptr);
-  if (bits) return fprop_launch_impl<TN, SPLIT, (SPLIT ? MT : 1), !SPLIT>(ctx, x, wr, y, B, Cin, H, W, Cout, yh, yw, kh, kw, pad, dil, bias, relu, mask, csum, stride, ph);
+  // the sign-bit instantiation exists for the one-M-tile kernels (single-pass and 3xTF32: the masked dgrads of the f32-faithful step read 1.07 / 0.54 / 0.27 GB of float
+  // masks in their pre-epilogues, +0.2 .. 0.9 ms per layer over the unmasked kernel of the same shape)
+  const bool bits = MT == 1 && Cout % 32 == 0 && ph == nullptr && ((mask != nullptr && ctx->mask_bits != nullptr) || ctx->bits_out != nullptr);
+  if (bits) return fprop_launch_impl<TN, SPLIT, 1, true>(ctx, x, wr, y, B, Cin, H, W, Cout, yh, yw, kh, kw, pad, dil, bias, relu, mask, csum, stride, ph);
   return fprop_launch_impl<TN, SPLIT, MT, false>(ctx, x, wr, y, B, Cin, H, W, Cout, yh, yw, kh, kw, pad, dil, bias, relu, mask, csum, stride, ph);
 }
 template <int TN, bool SPLIT, int MT, bool BITS>

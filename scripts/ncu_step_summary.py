@@ -2,7 +2,9 @@
 a per-launch CSV (duration, DRAM bytes, L2->SM bytes, tensor-pipe %, DRAM %, registers, shared memory, grid) that fits the gpurun copy-back
 limit.  The .ncu-rep itself (hundreds of MB) stays on the box.
 
-    python scripts/ncu_step_summary.py [tf32|3xtf32] [out.csv]
+    python scripts/ncu_step_summary.py [tf32|3xtf32] [out.csv] [light]
+`light`: collect only the metrics of the summary (a handful of replay passes per kernel instead of the ~40 of `--set full`; the 3xTF32 step, 36 ms of kernels
+over multi-GB working sets, does not finish a full-set capture within minutes).
 The step runs eagerly (plan cache off) inside a cudaProfilerStart / Stop range after three warm-up steps."""
 import csv
 import os
@@ -14,7 +16,11 @@ mode = sys.argv[1] if len(sys.argv) > 1 else "tf32"
 out = sys.argv[2] if len(sys.argv) > 2 else os.path.join(ROOT, "gpurun_out", "ncu_step_%s.csv" % mode)
 rep = "/tmp/ncu_step_%s" % mode
 env = dict(os.environ, AGX_PLAN_CACHE="0")
-cmd = ["ncu", "--set", "full", "--clock-control", "none", "--profile-from-start", "off", "-f", "-o", rep,
+light = len(sys.argv) > 3 and sys.argv[3] == "light"
+METRICS = ("gpu__time_duration.sum,dram__bytes_read.sum,dram__bytes_write.sum,l1tex__m_xbar2l1tex_read_bytes.sum,"
+           "sm__pipe_tensor_cycles_active.avg.pct_of_peak_sustained_active,gpu__dram_throughput.avg.pct_of_peak_sustained_elapsed,"
+           "lts__throughput.avg.pct_of_peak_sustained_elapsed,sm__warps_active.avg.pct_of_peak_sustained_active")
+cmd = ["ncu"] + (["--metrics", METRICS] if light else ["--set", "full"]) + ["--clock-control", "none", "--profile-from-start", "off", "-f", "-o", rep,
        sys.executable, os.path.join(ROOT, "scripts", "one_step.py"), mode, "profile"]
 subprocess.run(cmd, check=True, env=env, cwd=ROOT, stdout=subprocess.DEVNULL, stderr=subprocess.DEVNULL)
 raw = subprocess.run(["ncu", "-i", rep + ".ncu-rep", "--page", "raw", "--csv"], capture_output=True, text=True, check=True).stdout
