@@ -222,8 +222,11 @@ template <int TN_, bool SPLIT_, int MT_ = 1, bool BITS_ = false> struct ConvFpro
 // ------------------------------------------------------------------------------------------------ wgrad policy
 // MT_ = 2 (non-PAIR): the CTA owns two (tap, 128-channel tile) units — two M-tiles that share every gy tile, so gy is pulled from
 // L2 half as often (the TN = 256 wgrad moved 48 KB per 4 MMAs: bound by L2 -> smem ingest at 43 % tensor activity).
-template <int TN_, bool SPLIT_, bool PAIR_, int MT_ = 1> struct ConvWgradPol {
-  static constexpr int TN = TN_, MT = MT_; static constexpr bool SPLIT = SPLIT_, P_MN = true, Q_MN = true, Q_PRESPLIT = false;
+// QPRE_ (3xTF32): gy arrives as hi = rna_tf32 / lo planes written once by agb_tc_presplit (12 B/element of HBM traffic) instead of being split per landed tile
+// (48 of the 192 KB a 128-wide stage moves through shared memory, the bound of this mode): pays when the tile count per gy element (C * taps / 128) is large.
+template <int TN_, bool SPLIT_, bool PAIR_, int MT_ = 1, bool QPRE_ = false> struct ConvWgradPol {
+  static constexpr int TN = TN_, MT = MT_; static constexpr bool SPLIT = SPLIT_, P_MN = true, Q_MN = true, Q_PRESPLIT = QPRE_;
+  static_assert(!QPRE_ || (SPLIT_ && !PAIR_ && MT_ == 1), "pre-split gy: the 3xTF32 one-M-tile kernel");
   static constexpr bool SPLIT_PAIR2 = false;
   static constexpr bool PAIR2 = !SPLIT_ && TN_ == 256 && MT_ == 1 && !PAIR_;      // CTA pairs: two (tap, 128-channel tile) units share every gy tile, each CTA streams half of its columns
   static constexpr int OCC = (SPLIT_ || TN_ > 128 || MT_ > 1) ? 1 : 2;
@@ -231,7 +234,7 @@ template <int TN_, bool SPLIT_, bool PAIR_, int MT_ = 1> struct ConvWgradPol {
   // tmX5 / tmG5 (wide = 1; C % 32 == 0 and O % 32 == 0): the channel axis split into {32, C / 32}, so ONE box {32 c, pixels, 4 blocks} lands as the four (TN / 32)
   // consecutive 4 KB boxes the MMA descriptors expect — 3 TMA instructions per k-block instead of 16: ncu showed the producer warp 90 % busy issuing them
   // (each cp.async.bulk.tensor of a lane-0 branch is an ELECT / uniform-branch waterfall) and the MMA issuer 20 % of its time waiting on `full`
-  struct Params { CUtensorMap tmX, tmG, tmX5, tmG5; int wide; float* gw; int C, O, T, kw, pad, dil, stride, yh, xblocks, kb_total, kb_per_split; MnDescCfg mnc; int64_t part_stride /* > 0: split z stores at gw + z * part_stride (deterministic mode) */; };
+  struct Params { CUtensorMap tmX, tmG, tmX5, tmG5, tmGl, tmG5l /* QPRE_: the lo plane of gy (tmG / tmG5 address the hi plane) */; int wide; float* gw; int C, O, T, kw, pad, dil, stride, yh, xblocks, kb_total, kb_per_split; MnDescCfg mnc; int64_t part_stride /* > 0: split z stores at gw + z * part_stride (deterministic mode) */; };
   struct Tile { int c0, tapA, tapB, o0, q0, q1, c1; };       // MT == 2: unit 0 = (tapA, c0), unit 1 = (tapB, c1)
   __device__ static Tile tile(const Params& p, uint3 blk) {
     Tile t; t.o0 = (int)blk.y * TN; t.c1 = 0;
@@ -246,7 +249,14 @@ template <int TN_, bool SPLIT_, bool PAIR_, int MT_ = 1> struct ConvWgradPol {
   }
   __device__ static int num_kblocks(const Params&, const Tile& t) { return t.q1 > t.q0 ? t.q1 - t.q0 : 0; }
   __device__ static uint32_t p_bytes(const Params&, uint32_t full) { return full; }
-  __device__ static void prefetch(const Params& p) { tma_prefetch_desc(&p.tmX); tma_prefetch_desc(&p.tmG); }
+  __device__ static void prefetch(const Params& p) { tma_prefetch_desc(&p.tmX); tma_prefetch_desc(&p.tmG); if (QPRE_) tma_prefetch_desc(&p.tmGl); }
+  __device__ static void load_q_lo(const Params& p, const Tile& t, int kb, uint8_t* pQlo, uint64_t* bar) {
+    const int q = t.q0 + kb; const int xb = q % p.xblocks; const int r = q / p.xblocks; const int oy = r % p.yh, b = r / p.yh;
+    const int ox0 = xb * 32;
+    if (p.wide) { tma_load_5d(pQlo, &p.tmG5l, bar, 0, ox0, t.o0 >> 5, oy, b); return; }
+#pragma unroll
+    for (int g = 0; g < TN / 32; g++) tma_load_4d(pQlo + g * 4096, &p.tmGl, bar, t.o0 + 32 * g, ox0, oy, b);
+  }
   __device__ static void load(const Params& p, const Tile& t, int kb, uint8_t* pP, uint8_t* pQ, uint64_t* bar) {
     const int q = t.q0 + kb; const int xb = q % p.xblocks; const int r = q / p.xblocks; const int oy = r % p.yh, b = r / p.yh;
     const int ox0 = xb * 32;
@@ -508,10 +518,19 @@ int agb_tc_conv_dgrad_strided(agb_ctx* ctx, int mode, const float* gy, const flo
   return AGB_OK;
 }
 
-template <int TN, bool SPLIT, bool PAIR, int MT = 1>
+int agb_tc_presplit(agb_ctx* ctx, const float* src, float* hi, float* lo, int64_t n);      // tc_gemm.cu
+template <int TN, bool SPLIT, bool PAIR, int MT = 1, bool QPRE = false>
 static int wgrad_launch(agb_ctx* ctx, const float* img, const float* g, float* gw, int B, int C, int H, int W, int O, int yh, int yw, int kh, int kw, int pad, int dil, int stride = 1) {
-  using Pol = ConvWgradPol<TN, SPLIT, PAIR, MT>;
+  using Pol = ConvWgradPol<TN, SPLIT, PAIR, MT, QPRE>;
   typename Pol::Params p;
+  const float* g_lo = g;
+  if (QPRE) {      // hi / lo planes of gy in scratch (this launcher uses scratch2 for its partials)
+    const int64_t gn = (int64_t)B * yh * yw * O;
+    float* planes = nullptr;
+    AGB_TRY(agb_scratch(ctx, (size_t)gn * 2 * sizeof(float), (void**)&planes));
+    AGB_TRY(agb_tc_presplit(ctx, g, planes, planes + gn, gn));
+    g = planes; g_lo = planes + gn;
+  }
   {
     uint64_t dims[4] = {(uint64_t)C, (uint64_t)W, (uint64_t)H, (uint64_t)B};
     uint64_t str[3] = {(uint64_t)C * 4, (uint64_t)W * C * 4, (uint64_t)H * W * C * 4};
@@ -521,9 +540,11 @@ static int wgrad_launch(agb_ctx* ctx, const float* img, const float* g, float* g
   }
   p.stride = stride;
   AGB_TRY(make_cl_map(&p.tmG, g, B, O, yh, yw, 32, 32, 1, true));
+  p.tmGl = p.tmG;
+  if (QPRE) AGB_TRY(make_cl_map(&p.tmGl, g_lo, B, O, yh, yw, 32, 32, 1, true));
   static const int wide_env = [] { const char* e = getenv("AGB_WGRAD_WIDE"); return (e && e[0] == '0') ? 0 : 1; }();
   p.wide = (wide_env && C % 32 == 0 && O % 32 == 0 && !Pol::PAIR2) ? 1 : 0;
-  p.tmX5 = p.tmX; p.tmG5 = p.tmG;
+  p.tmX5 = p.tmX; p.tmG5 = p.tmG; p.tmG5l = p.tmGl;
   if (p.wide) {
     const uint32_t su = (uint32_t)stride;
     {   // x as {32 c, W, C / 32, H, B}
@@ -537,6 +558,7 @@ static int wgrad_launch(agb_ctx* ctx, const float* img, const float* g, float* g
       uint64_t str[4] = {(uint64_t)O * 4, 128, (uint64_t)yw * O * 4, (uint64_t)yh * yw * O * 4};
       uint32_t box[5] = {32, 32, (uint32_t)(TN / 32), 1, 1};
       AGB_TRY(agb_make_tmap(&p.tmG5, g, 5, dims, str, box, true));
+      if (QPRE) AGB_TRY(agb_make_tmap(&p.tmG5l, g_lo, 5, dims, str, box, true));
     }
   }
   const int T = kh * kw;
@@ -576,7 +598,16 @@ int agb_tc_conv_wgrad(agb_ctx* ctx, int mode, const float* img, const float* g, 
   const bool pair = C <= 64;
 #define WG(TN_, SP_) (pair ? wgrad_launch<TN_, SP_, true>(ctx, img, g, gw, B, C, H, W, O, yh, yw, kh, kw, pad, dil, stride) \
                            : wgrad_launch<TN_, SP_, false>(ctx, img, g, gw, B, C, H, W, O, yh, yw, kh, kw, pad, dil, stride))
-  if (split) { if (O > 64) return WG(128, true); return WG(64, true); }
+  if (split) {
+    // pre-split gy where its planes (12 B/element once) cost well under the shared-memory traffic they save (~17 % of a kernel whose time grows with C * taps)
+    static const int qpre_env = [] { const char* e = getenv("AGB_WGRAD_QPRE"); return (e && e[0] == '0') ? 0 : 1; }();
+    const int64_t gn = (int64_t)B * yh * yw * O;
+    if (qpre_env && !pair && C * kh * kw >= 1152 && gn % 4 == 0 && gn <= (1ll << 30)) {
+      if (O > 64) return wgrad_launch<128, true, false, 1, true>(ctx, img, g, gw, B, C, H, W, O, yh, yw, kh, kw, pad, dil, stride);
+      return wgrad_launch<64, true, false, 1, true>(ctx, img, g, gw, B, C, H, W, O, yh, yw, kh, kw, pad, dil, stride);
+    }
+    if (O > 64) return WG(128, true); return WG(64, true);
+  }
   static int m2 = -1;
   if (m2 < 0) { const char* e = getenv("AGB_WGRAD_M2"); m2 = (e && e[0] == '0') ? 0 : 1; }
   // measured (B200, B = 256): C256/O256 0.66 -> 0.54 ms, C128/O256 0.37 -> 0.32 ms; with TN = 128 the one-M-tile kernel at two CTAs

@@ -187,6 +187,14 @@ __global__ void __launch_bounds__(256) presplit_kernel(const float4* __restrict_
   }
 }
 
+// (also the gy planes of the 3xTF32 filter gradient, tc_conv.cu); src / hi / lo 16-byte aligned, n % 4 == 0
+int agb_tc_presplit(agb_ctx* ctx, const float* src, float* hi, float* lo, int64_t n) {
+  if (n <= 0) return AGB_OK;
+  presplit_kernel<<<agb_grid_for(n / 4, 256, ctx->sm_count, 8), 256, 0, ctx->stream>>>((const float4*)src, (float4*)hi, (float4*)lo, n / 4);
+  AGB_LAUNCHED(ctx);
+  return AGB_OK;
+}
+
 // A thin operand whose contiguous extent is not a multiple of 4 floats (the [65536, 10] classifier weight of a CNN, its [256, 10]
 // logits gradient) breaks TMA's 16-byte pitch rule.  Such an operand is tiny next to the other one, so it is copied once per call into
 // scratch with the pitch rounded up to 16 floats (zero padded) and the GEMM runs on the tensor cores instead of the CUDA-core path
