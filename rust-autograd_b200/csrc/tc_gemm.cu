@@ -264,12 +264,12 @@ int agb_tc_gemm(agb_ctx* ctx, int mode, const float* A, const float* B, float* C
     const int64_t qn = M * K * batch;
     const bool q_dense = qn % 4 == 0 && (batch == 1 || Q.bs == M * K) && (qmn ? (Q.ks == M) : (Q.rs == K));
     if (q_dense && N >= 512 && qn <= (1ll << 31) && pad_base == nullptr) {
-      // P = op(B)^T is re-read by every one of the M/TN column tiles: with M large it is pre-split too (hi = rna_tf32, lo planes), the kernel then has
+      // P = op(B)^T is re-read by every one of the M/TN column tiles: with M large (>= 16 tiles) it is pre-split too (hi = rna_tf32, lo planes), the kernel then has
       // no splitter work at all and its shared memory carries only the TMA writes and the MMA reads (this mode is bound by shared-memory bandwidth)
       const int64_t pn = N * K * batch;
       const bool p_dense = pn % 4 == 0 && (batch == 1 || P.bs == N * K) && (pmn ? (P.ks == N) : (P.rs == K));
       static const int ppre_env = [] { const char* e = getenv("AGB_GEMM_PPRE"); return (e && e[0] == '0') ? 0 : 1; }();
-      const bool ppre = ppre_env && p_dense && M >= 512 && pn <= (1ll << 28);
+      const bool ppre = ppre_env && p_dense && M >= 2048 && pn <= (1ll << 28);      // measured: batch 64 x 512^3 +11 %, 16 x 1024^3 +3 % (slower), 2048^3 -5 %, 8192^3 -11 %
       float* planes = nullptr;
       AGB_TRY(agb_scratch(ctx, (size_t)(qn * 2 + (ppre ? pn * 2 : 0)) * sizeof(float), (void**)&planes));
       presplit_kernel<<<agb_grid_for(qn / 4, 256, ctx->sm_count, 8), 256, 0, ctx->stream>>>((const float4*)A, (float4*)planes, (float4*)(planes + qn), qn / 4);

@@ -60,6 +60,7 @@ def test_batch_matmul_kats(dev, k):
 
 GEMM_SHAPES = [(200, 10, 784), (784, 10, 200), (200, 784, 10), (128, 128, 128), (256, 512, 64), (130, 70, 33), (257, 129, 100),
                (512, 1024, 2048), (1, 1, 1), (5, 3, 7), (128, 4096, 1024), (1000, 1000, 1000), (64, 64, 32), (16, 64, 40),
+               (2048, 640, 96), (2304, 512, 64),        # M >= 2048, N >= 512, dense: both operands pre-split in global memory in 3xTF32 mode (no splitter warps)
                (256, 10, 65536), (64, 10, 5000),        # skinny classifier shapes: split-K path
                (65536, 10, 256), (256, 65536, 10), (300, 12, 40000), (32, 50000, 6)]     # the classifier's gradients: thin N / thin K with a 40-byte pitch (padded copies -> tcgen05)
 
